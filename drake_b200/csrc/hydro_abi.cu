@@ -1,0 +1,973 @@
+// Host side of libdrake_b200_hydro.so: the C-ABI declared in
+// include/drake_b200_hydro.h, asset preparation (per-element records, BVH),
+// the static geometry-pair list, kernel orchestration on one CUDA stream and
+// result export. No CPU implementation of the query exists in this library:
+// without a CUDA device every entry point fails with DBH_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/drake_b200_hydro.h"
+#include "hydro_kernels.cuh"
+
+using namespace dbh;
+
+namespace {
+
+thread_local std::string g_error;
+
+dbh_status Fail(dbh_status s, const std::string& msg) {
+  g_error = msg;
+  return s;
+}
+
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return Fail(DBH_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p{nullptr};
+  size_t n{0};
+  ~DevBuf() { reset(); }
+  void reset() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    reset();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
+};
+
+// ---------------------------------------------------------------------------
+// Asset preparation (host, set-up time only).
+struct HostAsset {
+  int type{0};
+  int num_vertices{0};
+  int num_elements{0};
+  int height{0};
+  std::vector<TetRec> tets;
+  std::vector<TetNormals> normals;
+  std::vector<TriRec> tris;
+  std::vector<BvhNode> nodes;
+  DevBuf<TetRec> d_tets;
+  DevBuf<TetNormals> d_normals;
+  DevBuf<TriRec> d_tris;
+  DevBuf<BvhNode> d_nodes;
+};
+
+struct Box {
+  double mn[3], mx[3];
+};
+
+// Aabb from min/max exactly as AabbMaker::Compute (aabb.cc:102-117).
+void BoxToNode(const Box& b, BvhNode* n) {
+  for (int k = 0; k < 3; ++k) {
+    n->c[k] = (b.mn[k] + b.mx[k]) / 2;
+    n->h[k] = b.mx[k] - n->c[k];
+  }
+}
+
+struct BuildItem {
+  int elem;
+  double centroid[3];
+};
+
+// Top-down median split on the longest box axis (the reference's strategy,
+// bvh.cc:32-104), one element per leaf, nodes in DFS pre-order.
+int BuildBvh(const std::vector<Box>& elem_boxes, std::vector<BuildItem>& items, int start, int end,
+             std::vector<BvhNode>* nodes, int depth, int* height) {
+  const int me = static_cast<int>(nodes->size());
+  nodes->emplace_back();
+  *height = std::max(*height, depth);
+  Box b = elem_boxes[items[start].elem];
+  for (int i = start + 1; i < end; ++i) {
+    const Box& e = elem_boxes[items[i].elem];
+    for (int k = 0; k < 3; ++k) {
+      b.mn[k] = std::min(b.mn[k], e.mn[k]);
+      b.mx[k] = std::max(b.mx[k], e.mx[k]);
+    }
+  }
+  BvhNode node{};
+  BoxToNode(b, &node);
+  if (end - start == 1) {
+    node.left = ~items[start].elem;
+    node.right = -1;
+    (*nodes)[me] = node;
+    return me;
+  }
+  int axis = 0;
+  if (node.h[1] > node.h[axis]) axis = 1;
+  if (node.h[2] > node.h[axis]) axis = 2;
+  const int mid = start + (end - start) / 2;
+  std::nth_element(items.begin() + start, items.begin() + mid, items.begin() + end,
+                   [axis](const BuildItem& x, const BuildItem& y) {
+                     if (x.centroid[axis] != y.centroid[axis]) return x.centroid[axis] < y.centroid[axis];
+                     return x.elem < y.elem;
+                   });
+  const int l = BuildBvh(elem_boxes, items, start, mid, nodes, depth + 1, height);
+  const int r = BuildBvh(elem_boxes, items, mid, end, nodes, depth + 1, height);
+  node.left = l;
+  node.right = r;
+  (*nodes)[me] = node;
+  return me;
+}
+
+template <int kVerts>
+void BuildAssetBvh(const double* verts, const int32_t* elems, int num_elems, HostAsset* a) {
+  std::vector<Box> boxes(num_elems);
+  std::vector<BuildItem> items(num_elems);
+  for (int e = 0; e < num_elems; ++e) {
+    Box b;
+    double c[3] = {0, 0, 0};
+    for (int k = 0; k < 3; ++k) {
+      b.mn[k] = std::numeric_limits<double>::infinity();
+      b.mx[k] = -std::numeric_limits<double>::infinity();
+    }
+    for (int v = 0; v < kVerts; ++v) {
+      const double* p = verts + 3 * elems[kVerts * e + v];
+      for (int k = 0; k < 3; ++k) {
+        b.mn[k] = std::min(b.mn[k], p[k]);
+        b.mx[k] = std::max(b.mx[k], p[k]);
+        c[k] += p[k];
+      }
+    }
+    boxes[e] = b;
+    items[e].elem = e;
+    for (int k = 0; k < 3; ++k) items[e].centroid[k] = c[k] / kVerts;
+  }
+  a->nodes.clear();
+  a->nodes.reserve(2 * static_cast<size_t>(num_elems));
+  a->height = 0;
+  BuildBvh(boxes, items, 0, num_elems, &a->nodes, 0, &a->height);
+}
+
+}  // namespace
+
+struct dbh_context {
+  int device{0};
+  cudaDeviceProp prop{};
+  std::vector<std::unique_ptr<HostAsset>> assets;
+  DevBuf<AssetDev> d_assets;
+  bool assets_dirty{true};
+
+  dbh_status UploadAssetTable() {
+    if (!assets_dirty) return DBH_OK;
+    std::vector<AssetDev> tab(assets.size());
+    for (size_t i = 0; i < assets.size(); ++i) {
+      const HostAsset& a = *assets[i];
+      tab[i].tets = a.d_tets.p;
+      tab[i].normals = a.d_normals.p;
+      tab[i].tris = a.d_tris.p;
+      tab[i].nodes = a.d_nodes.p;
+      tab[i].num_elements = a.num_elements;
+      tab[i].num_nodes = static_cast<int>(a.nodes.size());
+      tab[i].type = a.type;
+      tab[i].height = a.height;
+    }
+    CUDA_OK(d_assets.alloc(tab.size()));
+    CUDA_OK(cudaMemcpy(d_assets.p, tab.data(), tab.size() * sizeof(AssetDev), cudaMemcpyHostToDevice));
+    assets_dirty = false;
+    return DBH_OK;
+  }
+};
+
+struct dbh_batch {
+  dbh_context* ctx{nullptr};
+  cudaStream_t stream{nullptr};
+  int num_scenes{0}, num_geoms{0}, num_pairs{0};
+  std::vector<int32_t> scene_offsets;
+  std::vector<int32_t> geom_asset;
+  std::vector<int64_t> geom_id;
+  std::vector<PairRec> pairs;
+  dbh_batch_info info{};
+
+  // capacities (entries)
+  long long cap_frontier{0}, cap_cand{0}, cap_faces{0}, cap_verts{0}, cap_polys{0};
+
+  DevBuf<PairRec> d_pairs;
+  DevBuf<Xf> d_poses_own;
+  const Xf* d_poses{nullptr};
+  DevBuf<Xf> d_pair_X;
+  DevBuf<int4> d_frontier[2];
+  DevBuf<int4> d_cand_tri, d_cand_tet;
+  DevBuf<Counters> d_counters;
+  DevBuf<int> d_pair_polys, d_pair_verts, d_surf_index, d_surf_pair;
+  DevBuf<unsigned long long> d_pair_cursor;
+  DevBuf<long long> d_poly_off, d_vert_off, d_block_sums, d_surf_face_off, d_surf_vert_off;
+  DevBuf<int4> d_soup_hdr;
+  DevBuf<double> d_soup_v, d_soup_nhat;
+  DevBuf<double> d_face_f64, d_vert_f64, d_surf_f64;
+  DevBuf<int> d_face_i32;
+  Counters* h_counters{nullptr};  // pinned
+
+  int representation{DBH_POLYGON};
+  bool query_done{false};
+  bool timing{false};
+  cudaEvent_t ev[9]{};
+  float times_ms[8]{};
+
+  ~dbh_batch() {
+    if (h_counters) cudaFreeHost(h_counters);
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  dbh_status AllocWorkBuffers() {
+    CUDA_OK(d_frontier[0].ensure(cap_frontier));
+    CUDA_OK(d_frontier[1].ensure(cap_frontier));
+    CUDA_OK(d_cand_tri.ensure(info.num_soft_rigid_pairs ? cap_cand : 1));
+    CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_cand : 1));
+    CUDA_OK(d_soup_hdr.ensure(cap_polys));
+    CUDA_OK(d_soup_v.ensure(static_cast<size_t>(cap_polys) * kMaxPolyVerts * 4));
+    CUDA_OK(d_soup_nhat.ensure(static_cast<size_t>(cap_polys) * 3));
+    CUDA_OK(d_face_f64.ensure(static_cast<size_t>(cap_faces) * kNumFacePlanes));
+    CUDA_OK(d_face_i32.ensure(static_cast<size_t>(cap_faces) * kNumFaceIntPlanes));
+    CUDA_OK(d_vert_f64.ensure(static_cast<size_t>(cap_verts) * 4));
+    return DBH_OK;
+  }
+};
+
+extern "C" {
+
+const char* dbh_last_error(void) { return g_error.c_str(); }
+int32_t dbh_abi_version(void) { return 1000; }
+
+dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out) {
+  if (!out) return Fail(DBH_ERR_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return Fail(DBH_ERR_NO_DEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) +
+                                       "); this back end has no CPU fallback");
+  if (device_ordinal < 0 || device_ordinal >= count) return Fail(DBH_ERR_INVALID_ARGUMENT, "bad device ordinal");
+  auto ctx = std::make_unique<dbh_context>();
+  ctx->device = device_ordinal;
+  CUDA_OK(cudaSetDevice(device_ordinal));
+  CUDA_OK(cudaGetDeviceProperties(&ctx->prop, device_ordinal));
+  if (ctx->prop.major < 10)
+    return Fail(DBH_ERR_NO_DEVICE, "device is not sm_100 class; kernels are built for sm_100a only");
+  CUDA_OK(cudaFuncSetAttribute(k_clip_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_clip_tet, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
+  *out = ctx.release();
+  return DBH_OK;
+}
+
+void dbh_context_destroy(dbh_context* ctx) { delete ctx; }
+
+dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const double* verts, int32_t nt,
+                                       const int32_t* tets, const double* pressure, int32_t* asset_out) {
+  if (!ctx || !verts || !tets || !pressure || !asset_out || nv <= 0 || nt <= 0)
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "register_compliant_mesh: bad argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  for (int i = 0; i < 4 * nt; ++i)
+    if (tets[i] < 0 || tets[i] >= nv) return Fail(DBH_ERR_INVALID_ARGUMENT, "tet vertex index out of range");
+  auto a = std::make_unique<HostAsset>();
+  a->type = DBH_COMPLIANT;
+  a->num_vertices = nv;
+  a->num_elements = nt;
+  a->tets.resize(nt);
+  a->normals.resize(nt);
+  constexpr double kEps = std::numeric_limits<double>::epsilon();
+  for (int e = 0; e < nt; ++e) {
+    TetRec& r = a->tets[e];
+    D3 v[4];
+    double u[4];
+    for (int i = 0; i < 4; ++i) {
+      const int vi = tets[4 * e + i];
+      v[i] = load3(verts + 3 * vi);
+      u[i] = pressure[vi];
+      r.v[i][0] = v[i].x;
+      r.v[i][1] = v[i].y;
+      r.v[i][2] = v[i].z;
+    }
+    // MeshFieldLinear::CalcGradientField / VolumeMesh::MaybeCalcGradBarycentric
+    // (mesh_field_linear.h:440-478, volume_mesh.h:275-289,361-448).
+    D3 g = make_d3(0, 0, 0);
+    for (int i = 0; i < 4; ++i) {
+      const D3 V = v[i], A = v[(i + 1) % 4], B = v[(i + 2) % 4], C = v[(i + 3) % 4];
+      const D3 area_vector = cross(B - A, C - A);
+      const double signed_volume = dot(area_vector, V - A);
+      if (std::fabs(signed_volume) <= kEps)
+        return Fail(DBH_ERR_DEGENERATE_FIELD, "tetrahedron " + std::to_string(e) + " is degenerate");
+      g = g + u[i] * (area_vector / signed_volume);
+    }
+    r.grad[0] = g.x;
+    r.grad[1] = g.y;
+    r.grad[2] = g.z;
+    r.p_mo = u[0] - dot(g, v[0]);  // CalcValueAtMeshOrigin (mesh_field_linear.h:502-509)
+    // Inward normals (volume_mesh.cc:91-138).
+    const D3 ab = v[1] - v[0], ac = v[2] - v[0], ad = v[3] - v[0], bc = v[2] - v[1], bd = v[3] - v[1];
+    const D3 n[4] = {normalized(cross(bd, bc)), normalized(cross(ac, ad)), normalized(cross(ad, ab)),
+                     normalized(cross(ab, ac))};
+    for (int f = 0; f < 4; ++f) {
+      a->normals[e].n[f][0] = n[f].x;
+      a->normals[e].n[f][1] = n[f].y;
+      a->normals[e].n[f][2] = n[f].z;
+    }
+  }
+  BuildAssetBvh<4>(verts, tets, nt, a.get());
+  CUDA_OK(a->d_tets.alloc(nt));
+  CUDA_OK(a->d_normals.alloc(nt));
+  CUDA_OK(a->d_nodes.alloc(a->nodes.size()));
+  CUDA_OK(cudaMemcpy(a->d_tets.p, a->tets.data(), nt * sizeof(TetRec), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(a->d_normals.p, a->normals.data(), nt * sizeof(TetNormals), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(a->d_nodes.p, a->nodes.data(), a->nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+  ctx->assets.push_back(std::move(a));
+  ctx->assets_dirty = true;
+  *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
+  return DBH_OK;
+}
+
+dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* verts, int32_t nt,
+                                   const int32_t* tris, int32_t* asset_out) {
+  if (!ctx || !verts || !tris || !asset_out || nv <= 0 || nt <= 0)
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "register_rigid_mesh: bad argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  for (int i = 0; i < 3 * nt; ++i)
+    if (tris[i] < 0 || tris[i] >= nv) return Fail(DBH_ERR_INVALID_ARGUMENT, "triangle vertex index out of range");
+  auto a = std::make_unique<HostAsset>();
+  a->type = DBH_RIGID;
+  a->num_vertices = nv;
+  a->num_elements = nt;
+  a->tris.resize(nt);
+  for (int e = 0; e < nt; ++e) {
+    TriRec& r = a->tris[e];
+    D3 v[3];
+    for (int i = 0; i < 3; ++i) {
+      v[i] = load3(verts + 3 * tris[3 * e + i]);
+      r.v[i][0] = v[i].x;
+      r.v[i][1] = v[i].y;
+      r.v[i][2] = v[i].z;
+    }
+    // TriangleSurfaceMesh::ComputePositionDependentQuantities (triangle_surface_mesh.h:452-487).
+    const D3 c = cross(v[1] - v[0], v[2] - v[0]);
+    const double nm = norm(c);
+    const D3 n = (nm != 0.0) ? c / nm : c;
+    r.n[0] = n.x;
+    r.n[1] = n.y;
+    r.n[2] = n.z;
+  }
+  BuildAssetBvh<3>(verts, tris, nt, a.get());
+  CUDA_OK(a->d_tris.alloc(nt));
+  CUDA_OK(a->d_nodes.alloc(a->nodes.size()));
+  CUDA_OK(cudaMemcpy(a->d_tris.p, a->tris.data(), nt * sizeof(TriRec), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(a->d_nodes.p, a->nodes.data(), a->nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+  ctx->assets.push_back(std::move(a));
+  ctx->assets_dirty = true;
+  *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
+  return DBH_OK;
+}
+
+dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out) {
+  if (!ctx || !out || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_get_info: bad argument");
+  const HostAsset& a = *ctx->assets[asset];
+  std::memset(out, 0, sizeof(*out));
+  out->type = a.type;
+  out->num_vertices = a.num_vertices;
+  out->num_elements = a.num_elements;
+  out->num_bvh_nodes = static_cast<int>(a.nodes.size());
+  out->bvh_height = a.height;
+  for (int k = 0; k < 3; ++k) {
+    out->root_center[k] = a.nodes[0].c[k];
+    out->root_half_width[k] = a.nodes[0].h[k];
+  }
+  return DBH_OK;
+}
+
+dbh_status dbh_asset_get_derived(dbh_context* ctx, int32_t asset, double* g_or_n, double* at_Mo, double* inward) {
+  if (!ctx || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_get_derived: bad argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  HostAsset& a = *ctx->assets[asset];
+  // Read back from the device copies so tests see what the kernels see.
+  if (a.type == DBH_COMPLIANT) {
+    std::vector<TetRec> t(a.num_elements);
+    std::vector<TetNormals> n(a.num_elements);
+    CUDA_OK(cudaMemcpy(t.data(), a.d_tets.p, t.size() * sizeof(TetRec), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(n.data(), a.d_normals.p, n.size() * sizeof(TetNormals), cudaMemcpyDeviceToHost));
+    for (int e = 0; e < a.num_elements; ++e) {
+      if (g_or_n) std::memcpy(g_or_n + 3 * e, t[e].grad, 24);
+      if (at_Mo) at_Mo[e] = t[e].p_mo;
+      if (inward) std::memcpy(inward + 12 * e, n[e].n, 96);
+    }
+  } else {
+    std::vector<TriRec> t(a.num_elements);
+    CUDA_OK(cudaMemcpy(t.data(), a.d_tris.p, t.size() * sizeof(TriRec), cudaMemcpyDeviceToHost));
+    for (int e = 0; e < a.num_elements; ++e)
+      if (g_or_n) std::memcpy(g_or_n + 3 * e, t[e].n, 24);
+  }
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t* scene_offsets,
+                            const int32_t* geom_asset, const int64_t* geom_id, const uint8_t* geom_anchored,
+                            int32_t num_excluded, const int32_t* excluded_pairs, dbh_batch** out) {
+  if (!ctx || !out || num_scenes <= 0 || !scene_offsets || !geom_asset || !geom_id)
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_create: bad argument");
+  *out = nullptr;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  auto b = std::make_unique<dbh_batch>();
+  b->ctx = ctx;
+  b->num_scenes = num_scenes;
+  b->num_geoms = scene_offsets[num_scenes];
+  b->scene_offsets.assign(scene_offsets, scene_offsets + num_scenes + 1);
+  b->geom_asset.assign(geom_asset, geom_asset + b->num_geoms);
+  b->geom_id.assign(geom_id, geom_id + b->num_geoms);
+  const int num_assets = static_cast<int>(ctx->assets.size());
+  for (int g = 0; g < b->num_geoms; ++g)
+    if (geom_asset[g] < -1 || geom_asset[g] >= num_assets)
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_create: bad asset handle");
+  // Excluded pairs as a sorted list of (min, max) flat indices.
+  std::vector<std::pair<int, int>> excl;
+  for (int i = 0; i < num_excluded; ++i) {
+    int x = excluded_pairs[2 * i], y = excluded_pairs[2 * i + 1];
+    if (x > y) std::swap(x, y);
+    excl.emplace_back(x, y);
+  }
+  std::sort(excl.begin(), excl.end());
+  // Static geometry-pair list in (scene, id_M, id_N) order.
+  int max_levels = 1;
+  for (int s = 0; s < num_scenes; ++s) {
+    const int g0 = scene_offsets[s], g1 = scene_offsets[s + 1];
+    std::vector<int> order(g1 - g0);
+    for (int i = 0; i < g1 - g0; ++i) order[i] = g0 + i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return geom_id[x] < geom_id[y]; });
+    for (size_t i = 0; i < order.size(); ++i) {
+      for (size_t j = i + 1; j < order.size(); ++j) {
+        const int ga = order[i], gb = order[j];  // id(ga) < id(gb)
+        if (geom_id[ga] == geom_id[gb]) return Fail(DBH_ERR_INVALID_ARGUMENT, "duplicate geometry id in a scene");
+        if (geom_anchored && geom_anchored[ga] && geom_anchored[gb]) continue;
+        if (std::binary_search(excl.begin(), excl.end(), std::make_pair(std::min(ga, gb), std::max(ga, gb)))) continue;
+        PairRec pr{};
+        pr.scene = s;
+        pr.id_m = geom_id[ga];
+        pr.id_n = geom_id[gb];
+        const int ta = geom_asset[ga] < 0 ? DBH_UNDEFINED : ctx->assets[geom_asset[ga]]->type;
+        const int tb = geom_asset[gb] < 0 ? DBH_UNDEFINED : ctx->assets[geom_asset[gb]]->type;
+        pr.geom_a = ga;
+        pr.geom_b = gb;
+        if (ta == DBH_UNDEFINED || tb == DBH_UNDEFINED) {
+          pr.kind = kUnsupported;
+          ++b->info.num_unsupported_pairs;
+        } else if (ta == DBH_RIGID && tb == DBH_RIGID) {
+          pr.kind = kRigidRigid;
+          ++b->info.num_rigid_rigid_pairs;
+        } else if (ta == DBH_COMPLIANT && tb == DBH_COMPLIANT) {
+          pr.kind = kSoftSoft;  // smaller id is M / field0 (hydroelastic_calculator.cc:109-111)
+          ++b->info.num_soft_soft_pairs;
+        } else {
+          pr.kind = kSoftRigid;  // built as (S, R), swapped when id_R < id_S
+          if (ta == DBH_RIGID) {
+            pr.geom_a = gb;
+            pr.geom_b = ga;
+            pr.swapped = 1;
+          }
+          ++b->info.num_soft_rigid_pairs;
+        }
+        pr.asset_a = geom_asset[pr.geom_a];
+        pr.asset_b = geom_asset[pr.geom_b];
+        if (pr.kind <= kSoftSoft) {
+          max_levels = std::max(max_levels, std::max(ctx->assets[pr.asset_a]->height, ctx->assets[pr.asset_b]->height) + 1);
+        }
+        b->pairs.push_back(pr);
+      }
+    }
+  }
+  b->num_pairs = static_cast<int>(b->pairs.size());
+  b->info.num_scenes = num_scenes;
+  b->info.num_geometries = b->num_geoms;
+  b->info.num_geometry_pairs = b->num_pairs;
+  b->info.max_traversal_levels = max_levels;
+  if (max_levels > 62) return Fail(DBH_ERR_INVALID_ARGUMENT, "BVH too deep");
+
+  // Default capacities: a few entries per element of every pair; grown by
+  // the caller on DBH_ERR_CAPACITY.
+  long long est = 0;
+  for (const PairRec& pr : b->pairs)
+    if (pr.kind <= kSoftSoft)
+      est += 2ll * (ctx->assets[pr.asset_a]->num_elements + ctx->assets[pr.asset_b]->num_elements);
+  est = std::max(est, 1ll << 16);
+  b->cap_frontier = est;
+  b->cap_cand = est;
+  b->cap_polys = est / 2;
+  b->cap_faces = est * 2;
+  b->cap_verts = est * 3;
+
+  CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaMallocHost(&b->h_counters, sizeof(Counters)));
+  std::memset(b->h_counters, 0, sizeof(Counters));
+  for (auto& e : b->ev) CUDA_OK(cudaEventCreate(&e));
+  const size_t np = std::max(1, b->num_pairs);
+  CUDA_OK(b->d_pairs.alloc(np));
+  if (b->num_pairs)
+    CUDA_OK(cudaMemcpy(b->d_pairs.p, b->pairs.data(), b->num_pairs * sizeof(PairRec), cudaMemcpyHostToDevice));
+  CUDA_OK(b->d_poses_own.alloc(std::max(1, b->num_geoms)));
+  b->d_poses = b->d_poses_own.p;
+  CUDA_OK(b->d_pair_X.alloc(np));
+  CUDA_OK(b->d_counters.alloc(1));
+  CUDA_OK(b->d_pair_polys.alloc(np));
+  CUDA_OK(b->d_pair_verts.alloc(np));
+  CUDA_OK(b->d_pair_cursor.alloc(np));
+  CUDA_OK(b->d_surf_index.alloc(np + 1));
+  CUDA_OK(b->d_surf_pair.alloc(np));
+  CUDA_OK(b->d_poly_off.alloc(np + 1));
+  CUDA_OK(b->d_vert_off.alloc(np + 1));
+  CUDA_OK(b->d_surf_face_off.alloc(np + 1));
+  CUDA_OK(b->d_surf_vert_off.alloc(np + 1));
+  CUDA_OK(b->d_surf_f64.alloc(np * 4));
+  const int scan_blocks = (b->num_pairs + kScanTile - 1) / kScanTile;
+  CUDA_OK(b->d_block_sums.alloc(3 * std::max(1, scan_blocks)));
+  *out = b.release();
+  return DBH_OK;
+}
+
+void dbh_batch_destroy(dbh_batch* batch) { delete batch; }
+
+dbh_status dbh_batch_set_capacity(dbh_batch* b, int64_t max_bv_pairs, int64_t max_element_pairs, int64_t max_faces) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  if (max_bv_pairs > 0) b->cap_frontier = max_bv_pairs;
+  if (max_element_pairs > 0) b->cap_cand = max_element_pairs;
+  if (max_faces > 0) {
+    b->cap_polys = max_faces;
+    b->cap_faces = max_faces * 4;   // triangle rep: up to ~5 triangles per polygon on average
+    b->cap_verts = max_faces * 6;
+  }
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_get_info(dbh_batch* b, dbh_batch_info* out) {
+  if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_get_info: bad argument");
+  *out = b->info;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_set_poses_host(dbh_batch* b, const double* X_WGs) {
+  if (!b || !X_WGs) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_poses_host: bad argument");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  b->d_poses = b->d_poses_own.p;
+  CUDA_OK(cudaMemcpyAsync(b->d_poses_own.p, X_WGs, static_cast<size_t>(b->num_geoms) * sizeof(Xf),
+                          cudaMemcpyHostToDevice, b->stream));
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_set_poses_device(dbh_batch* b, const double* X_WGs_device) {
+  if (!b || !X_WGs_device) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_poses_device: bad argument");
+  b->d_poses = reinterpret_cast<const Xf*>(X_WGs_device);
+  return DBH_OK;
+}
+
+void* dbh_batch_stream(dbh_batch* b) { return b ? b->stream : nullptr; }
+
+dbh_status dbh_batch_enable_timing(dbh_batch* b, int32_t enabled) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  b->timing = enabled != 0;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_kind, int64_t* scene_stats_dev) {
+  if (!b || (representation != DBH_TRIANGLE && representation != DBH_POLYGON))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_query: bad argument");
+  dbh_context* ctx = b->ctx;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  if (dbh_status s = ctx->UploadAssetTable()) return s;
+  if (dbh_status s = b->AllocWorkBuffers()) return s;
+  b->representation = representation;
+  b->query_done = false;
+  cudaStream_t st = b->stream;
+  const int sms = ctx->prop.multiProcessorCount;
+  auto mark = [&](int i) {
+    if (b->timing) cudaEventRecord(b->ev[i], st);
+  };
+  mark(0);
+  CUDA_OK(cudaMemsetAsync(b->d_counters.p, 0, sizeof(Counters), st));
+  if (scene_stats_dev)
+    CUDA_OK(cudaMemsetAsync(scene_stats_dev, 0, static_cast<size_t>(b->num_scenes) * 6 * sizeof(int64_t), st));
+  if (b->num_pairs > 0) {
+    PairsArgs pa{};
+    pa.pairs = b->d_pairs.p;
+    pa.num_pairs = b->num_pairs;
+    pa.assets = ctx->d_assets.p;
+    pa.poses = b->d_poses;
+    pa.pair_X = b->d_pair_X.p;
+    pa.frontier0 = b->d_frontier[0].p;
+    pa.counters = b->d_counters.p;
+    pa.strict = query_kind == DBH_QUERY_STRICT;
+    pa.pair_polys = b->d_pair_polys.p;
+    pa.pair_verts = b->d_pair_verts.p;
+    pa.pair_cursor = b->d_pair_cursor.p;
+    if (b->num_pairs > b->cap_frontier) return Fail(DBH_ERR_CAPACITY, "frontier capacity below the pair count");
+    k_pairs<<<(b->num_pairs + 127) / 128, 128, 0, st>>>(pa);
+    mark(1);
+    // Dual-BVH traversal, one launch per level; counts stay on the device.
+    TraverseArgs ta{};
+    ta.pairs = b->d_pairs.p;
+    ta.pair_X = b->d_pair_X.p;
+    ta.assets = ctx->d_assets.p;
+    ta.cand_tri = b->d_cand_tri.p;
+    ta.cand_tet = b->d_cand_tet.p;
+    ta.cand_capacity = static_cast<unsigned long long>(b->cap_cand);
+    ta.out_capacity = static_cast<unsigned long long>(b->cap_frontier);
+    ta.counters = b->d_counters.p;
+    for (int level = 0; level < b->info.max_traversal_levels; ++level) {
+      ta.in = b->d_frontier[level & 1].p;
+      ta.out = b->d_frontier[(level + 1) & 1].p;
+      ta.level = level;
+      k_traverse<<<sms * 8, 256, 0, st>>>(ta);
+    }
+    mark(2);
+    ClipArgs ca{};
+    ca.pairs = b->d_pairs.p;
+    ca.pair_X = b->d_pair_X.p;
+    ca.assets = ctx->d_assets.p;
+    ca.soup.hdr = b->d_soup_hdr.p;
+    ca.soup.v = b->d_soup_v.p;
+    ca.soup.nhat = b->d_soup_nhat.p;
+    ca.soup.capacity = static_cast<unsigned long long>(b->cap_polys);
+    ca.pair_polys = b->d_pair_polys.p;
+    ca.pair_verts = b->d_pair_verts.p;
+    ca.counters = b->d_counters.p;
+    const int clip_blocks = sms * 3;
+    if (b->info.num_soft_rigid_pairs) {
+      ca.cand = b->d_cand_tri.p;
+      k_clip_tri<<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+    }
+    mark(3);
+    if (b->info.num_soft_soft_pairs) {
+      ca.cand = b->d_cand_tet.p;
+      k_clip_tet<<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+    }
+    mark(4);
+    ScanArgs sa{};
+    sa.pair_polys = b->d_pair_polys.p;
+    sa.pair_verts = b->d_pair_verts.p;
+    sa.num_pairs = b->num_pairs;
+    sa.poly_off = b->d_poly_off.p;
+    sa.vert_off = b->d_vert_off.p;
+    sa.surf_index = b->d_surf_index.p;
+    sa.block_sums = b->d_block_sums.p;
+    sa.num_blocks = (b->num_pairs + kScanTile - 1) / kScanTile;
+    sa.surf_pair = b->d_surf_pair.p;
+    sa.counters = b->d_counters.p;
+    k_scan_partials<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
+    k_scan_blocks<<<1, kScanThreads, 0, st>>>(sa);
+    k_scan_apply<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
+    mark(5);
+    PackArgs pk{};
+    pk.soup = ca.soup;
+    pk.pairs = b->d_pairs.p;
+    pk.assets = ctx->d_assets.p;
+    pk.poses = b->d_poses;
+    pk.poly_off = b->d_poly_off.p;
+    pk.vert_off = b->d_vert_off.p;
+    pk.pair_cursor = b->d_pair_cursor.p;
+    pk.representation = representation;
+    pk.face_f64 = b->d_face_f64.p;
+    pk.face_i32 = b->d_face_i32.p;
+    pk.face_stride = b->cap_faces;
+    pk.vert_f64 = b->d_vert_f64.p;
+    pk.vert_stride = b->cap_verts;
+    pk.counters = b->d_counters.p;
+    k_pack<<<sms * 8, 128, 0, st>>>(pk);
+    mark(6);
+    SurfaceArgs su{};
+    su.surf_pair = b->d_surf_pair.p;
+    su.pairs = b->d_pairs.p;
+    su.poly_off = b->d_poly_off.p;
+    su.vert_off = b->d_vert_off.p;
+    su.representation = representation;
+    su.face_f64 = b->d_face_f64.p;
+    su.face_stride = b->cap_faces;
+    su.surf_face_off = b->d_surf_face_off.p;
+    su.surf_vert_off = b->d_surf_vert_off.p;
+    su.surf_f64 = b->d_surf_f64.p;
+    su.surf_stride = std::max(1, b->num_pairs);
+    su.scene_stats = reinterpret_cast<long long*>(scene_stats_dev);
+    su.counters = b->d_counters.p;
+    k_surface<<<sms * 4, 128, 0, st>>>(su);
+    k_finalize<<<1, 32, 0, st>>>(su, b->num_pairs);
+    if (scene_stats_dev)
+      k_scene_stats<<<(b->num_pairs + 255) / 256, 256, 0, st>>>(b->d_pairs.p, b->num_pairs, b->d_pair_polys.p,
+                                                               reinterpret_cast<long long*>(scene_stats_dev));
+    mark(7);
+  }
+  CUDA_OK(cudaMemcpyAsync(b->h_counters, b->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  mark(8);
+  CUDA_OK(cudaGetLastError());
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_sync(dbh_batch* b) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  if (b->timing) {
+    // {pose+root, traversal, clip tri, clip tet, scan, pack, surface+finalize, total}
+    float t[8];
+    for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&t[i], b->ev[i], b->ev[i + 1]);
+    cudaEventElapsedTime(&t[7], b->ev[0], b->ev[8]);
+    std::memcpy(b->times_ms, t, sizeof(t));
+  }
+  const Counters& c = *b->h_counters;
+  if (c.error != 0) {
+    static const char* kWhere[] = {"",          "BV-pair frontier", "element-pair list", "polygon staging",
+                                   "tet-tri polygon > 8 vertices", "tet-tet polygon > 8 vertices", "face arrays",
+                                   "vertex arrays"};
+    if (c.error == DBH_ERR_CAPACITY) {
+      const int d = (c.error_detail >= 1 && c.error_detail <= 7) ? c.error_detail : 0;
+      return Fail(DBH_ERR_CAPACITY, std::string("device work list overflow: ") + kWhere[d]);
+    }
+    if (c.error == DBH_ERR_RIGID_RIGID)
+      return Fail(DBH_ERR_RIGID_RIGID, "rigid-rigid contact between geometries " +
+                                           std::to_string(b->pairs[c.error_detail].id_m) + " and " +
+                                           std::to_string(b->pairs[c.error_detail].id_n) +
+                                           " is not supported by the hydroelastic contact model");
+    if (c.error == DBH_ERR_UNSUPPORTED)
+      return Fail(DBH_ERR_UNSUPPORTED, "geometry pair " + std::to_string(c.error_detail) +
+                                           " has a geometry without a hydroelastic representation");
+    return Fail(static_cast<dbh_status>(c.error), "device-side failure " + std::to_string(c.error));
+  }
+  b->query_done = true;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_kernel_times_ms(dbh_batch* b, float* out8) {
+  if (!b || !out8) return Fail(DBH_ERR_INVALID_ARGUMENT, "kernel_times: bad argument");
+  std::memcpy(out8, b->times_ms, sizeof(b->times_ms));
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_result_sizes(dbh_batch* b, dbh_result_sizes* out) {
+  if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "result_sizes: bad argument");
+  if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
+  const Counters& c = *b->h_counters;
+  std::memset(out, 0, sizeof(*out));
+  out->num_surfaces = static_cast<int64_t>(c.surfaces);
+  out->num_faces = static_cast<int64_t>(c.faces);
+  out->num_vertices = static_cast<int64_t>(c.vertices);
+  out->num_polygons = static_cast<int64_t>(c.polys);
+  out->representation = b->representation;
+  out->face_data_ints = b->representation == DBH_POLYGON ? static_cast<int64_t>(c.polys + c.poly_verts)
+                                                         : 3 * static_cast<int64_t>(c.faces);
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
+  if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "stats: bad argument");
+  if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
+  const Counters& c = *b->h_counters;
+  std::memset(out, 0, sizeof(*out));
+  out->geometry_pairs_tested = static_cast<int64_t>(c.frontier[0]);
+  out->geometry_pairs_overlapping = static_cast<int64_t>(c.root_overlaps);
+  for (int l = 0; l < 64; ++l) out->bv_pair_tests += static_cast<int64_t>(c.frontier[l]);
+  out->tet_tri_pairs = static_cast<int64_t>(c.cand_tri);
+  out->tet_tet_pairs = static_cast<int64_t>(c.cand_tet);
+  out->polygons = static_cast<int64_t>(c.polys);
+  out->faces = static_cast<int64_t>(c.faces);
+  out->vertices = static_cast<int64_t>(c.vertices);
+  out->surfaces = static_cast<int64_t>(c.surfaces);
+  out->total_area = c.total_area;
+  // BV test 128 B; tet-tri pair 260 B in; tet-tet pair 392 B in;
+  // emitted n-gon 32 n + 96 (soft-rigid) / + 120 (soft-soft) out; pose 96 B per geometry.
+  // Triangle representation adds 32 B centroid vertex + n (12 + 24 + 8) B per polygon.
+  long long bytes = out->bv_pair_tests * 128 + out->tet_tri_pairs * 260 + out->tet_tet_pairs * 392 +
+                    static_cast<long long>(c.poly_verts) * 32 + out->polygons * 108 + 96ll * b->num_geoms;
+  if (b->representation == DBH_TRIANGLE) bytes += out->polygons * 32 + static_cast<long long>(c.poly_verts) * 44;
+  out->algorithmic_bytes = bytes;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_copy_candidates(dbh_batch* b, int32_t kind, int32_t* out_triples, int64_t* count) {
+  if (!b || !count || (kind != 0 && kind != 1)) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_candidates: bad argument");
+  if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  const int64_t n = static_cast<int64_t>(kind == 0 ? b->h_counters->cand_tri : b->h_counters->cand_tet);
+  *count = n;
+  if (!out_triples || n == 0) return DBH_OK;
+  std::vector<int4> tmp(n);
+  CUDA_OK(cudaMemcpy(tmp.data(), kind == 0 ? b->d_cand_tri.p : b->d_cand_tet.p, n * sizeof(int4),
+                     cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) {
+    out_triples[3 * i] = tmp[i].x;
+    out_triples[3 * i + 1] = tmp[i].y;
+    out_triples[3 * i + 2] = tmp[i].z;
+  }
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_copy_geometry_pairs(dbh_batch* b, int32_t* out) {
+  if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_geometry_pairs: bad argument");
+  for (int i = 0; i < b->num_pairs; ++i) {
+    out[4 * i] = b->pairs[i].scene;
+    out[4 * i + 1] = b->pairs[i].geom_a;
+    out[4 * i + 2] = b->pairs[i].geom_b;
+    out[4 * i + 3] = b->pairs[i].kind;
+  }
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_device_results(dbh_batch* b, dbh_device_results* out) {
+  if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "device_results: bad argument");
+  if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
+  out->surf_pair = b->d_surf_pair.p;
+  out->surf_face_offset = reinterpret_cast<const int64_t*>(b->d_surf_face_off.p);
+  out->surf_vertex_offset = reinterpret_cast<const int64_t*>(b->d_surf_vert_off.p);
+  out->surf_total_area = b->d_surf_f64.p;
+  out->surf_centroid = b->d_surf_f64.p + std::max(1, b->num_pairs);
+  out->surf_stride = std::max(1, b->num_pairs);
+  out->vertices = b->d_vert_f64.p;
+  out->vertex_stride = b->cap_verts;
+  out->face_f64 = b->d_face_f64.p;
+  out->face_stride = b->cap_faces;
+  out->face_i32 = b->d_face_i32.p;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_copy_results(dbh_batch* b, const dbh_result_buffers* buf) {
+  if (!b || !buf) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_results: bad argument");
+  if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  const Counters& c = *b->h_counters;
+  const int64_t ns = static_cast<int64_t>(c.surfaces), nf = static_cast<int64_t>(c.faces),
+                nv = static_cast<int64_t>(c.vertices);
+  const bool poly = b->representation == DBH_POLYGON;
+  // Surfaces.
+  std::vector<int> surf_pair(ns);
+  std::vector<long long> foff(ns + 1), voff(ns + 1);
+  std::vector<double> sf(4 * ns);
+  if (ns) {
+    CUDA_OK(cudaMemcpy(surf_pair.data(), b->d_surf_pair.p, ns * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; ++k)
+      CUDA_OK(cudaMemcpy(sf.data() + k * ns, b->d_surf_f64.p + static_cast<size_t>(k) * std::max(1, b->num_pairs),
+                         ns * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  CUDA_OK(cudaMemcpy(foff.data(), b->d_surf_face_off.p, (ns + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(voff.data(), b->d_surf_vert_off.p, (ns + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (int64_t s = 0; s < ns; ++s) {
+    const PairRec& pr = b->pairs[surf_pair[s]];
+    if (buf->surf_scene) buf->surf_scene[s] = pr.scene;
+    if (buf->surf_id_M) buf->surf_id_M[s] = pr.id_m;
+    if (buf->surf_id_N) buf->surf_id_N[s] = pr.id_n;
+    if (buf->surf_total_area) buf->surf_total_area[s] = sf[s];
+    if (buf->surf_centroid)
+      for (int k = 0; k < 3; ++k) buf->surf_centroid[3 * s + k] = sf[(k + 1) * ns + s];
+    if (buf->surf_flags) {
+      uint8_t f = 0;
+      if (pr.kind == kSoftSoft) {
+        f = 3;
+      } else {
+        f = pr.swapped ? (2 | 4) : 1;
+      }
+      buf->surf_flags[s] = f;
+    }
+  }
+  if (buf->surf_face_offset)
+    for (int64_t s = 0; s <= ns; ++s) buf->surf_face_offset[s] = foff[s];
+  if (buf->surf_vertex_offset)
+    for (int64_t s = 0; s <= ns; ++s) buf->surf_vertex_offset[s] = voff[s];
+  // Vertices.
+  if (nv && (buf->vertices || buf->pressures)) {
+    std::vector<double> tmp(nv);
+    for (int k = 0; k < 4; ++k) {
+      if (k < 3 && !buf->vertices) continue;
+      if (k == 3 && !buf->pressures) continue;
+      CUDA_OK(cudaMemcpy(tmp.data(), b->d_vert_f64.p + static_cast<size_t>(k) * b->cap_verts, nv * sizeof(double),
+                         cudaMemcpyDeviceToHost));
+      if (k < 3) {
+        for (int64_t i = 0; i < nv; ++i) buf->vertices[3 * i + k] = tmp[i];
+      } else {
+        std::memcpy(buf->pressures, tmp.data(), nv * sizeof(double));
+      }
+    }
+  }
+  // Faces.
+  if (nf) {
+    std::vector<double> tmp(nf);
+    auto plane = [&](int k) -> dbh_status {
+      CUDA_OK(cudaMemcpy(tmp.data(), b->d_face_f64.p + static_cast<size_t>(k) * b->cap_faces, nf * sizeof(double),
+                         cudaMemcpyDeviceToHost));
+      return DBH_OK;
+    };
+    auto vec3 = [&](double* dst, int k0) -> dbh_status {
+      if (!dst) return DBH_OK;
+      for (int k = 0; k < 3; ++k) {
+        if (dbh_status s = plane(k0 + k)) return s;
+        for (int64_t i = 0; i < nf; ++i) dst[3 * i + k] = tmp[i];
+      }
+      return DBH_OK;
+    };
+    if (buf->areas) {
+      if (dbh_status s = plane(kArea)) return s;
+      std::memcpy(buf->areas, tmp.data(), nf * sizeof(double));
+    }
+    if (buf->pressure_at_centroid) {
+      if (dbh_status s = plane(kEc)) return s;
+      std::memcpy(buf->pressure_at_centroid, tmp.data(), nf * sizeof(double));
+    }
+    if (dbh_status s = vec3(buf->normals, kNx)) return s;
+    if (dbh_status s = vec3(buf->centroids, kCx)) return s;
+    if (dbh_status s = vec3(buf->grad_eM, kGMx)) return s;
+    if (dbh_status s = vec3(buf->grad_eN, kGNx)) return s;
+    std::vector<int> itmp[kNumFaceIntPlanes];
+    auto iplane = [&](int k) -> dbh_status {
+      itmp[k].resize(nf);
+      CUDA_OK(cudaMemcpy(itmp[k].data(), b->d_face_i32.p + static_cast<size_t>(k) * b->cap_faces, nf * sizeof(int),
+                         cudaMemcpyDeviceToHost));
+      return DBH_OK;
+    };
+    if (buf->elem_M) {
+      if (dbh_status s = iplane(kElemA)) return s;
+      std::memcpy(buf->elem_M, itmp[kElemA].data(), nf * sizeof(int));
+    }
+    if (buf->elem_N) {
+      if (dbh_status s = iplane(kElemB)) return s;
+      std::memcpy(buf->elem_N, itmp[kElemB].data(), nf * sizeof(int));
+    }
+    if (buf->face_data) {
+      for (int k : {kI0, kI1, kI2})
+        if (dbh_status s = iplane(k)) return s;
+      if (poly) {
+        // |n|v0..vn-1| with surface-local indices; reversed when M and N were
+        // swapped (PolygonSurfaceMesh::ReverseFaceWinding, polygon_surface_mesh.cc:39-49).
+        if (dbh_status s = iplane(kPair)) return s;
+        int64_t w = 0;
+        for (int64_t f = 0; f < nf; ++f) {
+          const int n = itmp[kI0][f], vb = itmp[kI1][f];
+          const bool swapped = b->pairs[itmp[kPair][f]].swapped != 0;
+          buf->face_data[w++] = n;
+          if (!swapped) {
+            for (int k = 0; k < n; ++k) buf->face_data[w++] = vb + k;
+          } else {
+            for (int k = n - 1; k >= 0; --k) buf->face_data[w++] = vb + k;
+          }
+        }
+      } else {
+        for (int64_t f = 0; f < nf; ++f) {
+          buf->face_data[3 * f] = itmp[kI0][f];
+          buf->face_data[3 * f + 1] = itmp[kI1][f];
+          buf->face_data[3 * f + 2] = itmp[kI2][f];
+        }
+      }
+    }
+  }
+  return DBH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,960 @@
+// Device kernels of the B200 hydroelastic contact-surface pipeline (sm_100a).
+//
+//   k_pairs      pose composition X_MN = X_WM^-1 X_WN per geometry pair, level-0 frontier
+//   k_traverse   one level of the dual-BVH traversal (replaces Bvh::Collide, bvh.h:220-262)
+//   k_clip_tri   tet-triangle clipping (SurfaceVolumeIntersector::CalcContactPolygon,
+//                mesh_intersection.cc:321-382)
+//   k_clip_tet   tet-tet equilibrium-plane clipping (VolumeIntersector::CalcContactPolygon,
+//                field_intersection.cc:377-428)
+//   k_scan_*     per-pair face/vertex offsets (CSR) and surface compaction
+//   k_pack       per-polygon area / normal / centroid / pressure, world transform, id-order
+//                swap, final packed layout (PolyMeshBuilder/TriMeshBuilder + PolygonSurfaceMesh /
+//                TriangleSurfaceMesh derived quantities + TransformVertices + SwapMAndN)
+//   k_surface    per-surface total area and centroid
+//
+// All arithmetic is fp64 with the reference's operation order (hydro_math.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hydro_math.cuh"
+#include "hydro_types.h"
+
+namespace dbh {
+
+constexpr int kClipThreads = 128;
+constexpr double kCosAlphaDevice = -0.38268343236508973;  // cos(5*pi/8) as std::cos returns it
+
+// ---------------------------------------------------------------------------
+// Warp-aggregated append: every lane asks for `n` slots of a global list; one
+// atomic per warp. Returns the lane's first slot.
+__device__ __forceinline__ unsigned long long warp_append(unsigned long long* counter, int n) {
+  const unsigned mask = __activemask();
+  const int lane = threadIdx.x & 31;
+  int incl = n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int y = __shfl_up_sync(mask, incl, d);
+    if (lane >= d) incl += y;
+  }
+  // `mask` may be partial only at loop tails where whole trailing lanes are
+  // missing, so shfl_up from a missing lane never happens for active lanes
+  // below it... to stay safe we fall back to per-lane atomics on partial warps.
+  if (mask != 0xffffffffu) {
+    return n ? atomicAdd(counter, (unsigned long long)n) : 0ull;
+  }
+  const int total = __shfl_sync(mask, incl, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && total) base = atomicAdd(counter, (unsigned long long)total);
+  base = __shfl_sync(mask, base, 31);
+  return base + (unsigned long long)(incl - n);
+}
+
+__device__ __forceinline__ void raise_error(Counters* c, int status, int detail) {
+  if (atomicCAS(&c->error, 0, status) == 0) c->error_detail = detail;
+}
+
+// ---------------------------------------------------------------------------
+// k_pairs: one thread per potential geometry pair.
+struct PairsArgs {
+  const PairRec* pairs;
+  int num_pairs;
+  const AssetDev* assets;
+  const Xf* poses;       // X_WG per flat geometry index
+  Xf* pair_X;            // out: X_MN per pair
+  int4* frontier0;       // out: level-0 frontier
+  Counters* counters;
+  int strict;            // DBH_QUERY_STRICT
+  int* pair_polys;       // zeroed here
+  int* pair_verts;
+  unsigned long long* pair_cursor;  // hi 32: polygons placed, lo 32: polygon vertices placed
+};
+
+__global__ void k_pairs(PairsArgs a) {
+  // Launched with whole warps covering num_pairs rounded up to 32.
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool push = false;
+  if (p < a.num_pairs) {
+    a.pair_polys[p] = 0;
+    a.pair_verts[p] = 0;
+    a.pair_cursor[p] = 0ull;
+    const PairRec pr = a.pairs[p];
+    if (pr.kind == kUnsupported) {
+      if (a.strict) raise_error(a.counters, 7 /*DBH_ERR_UNSUPPORTED*/, p);
+    } else {
+      const Xf X_WA = a.poses[pr.geom_a];
+      const Xf X_WB = a.poses[pr.geom_b];
+      const Xf X_AB = invert_and_compose(X_WA, X_WB);
+      a.pair_X[p] = X_AB;
+      if (pr.kind == kRigidRigid) {
+        // Stand-in for the geometry-level broad phase (FCL tree,
+        // proximity_engine.cc:867-883): the pair only fails if the root boxes overlap.
+        if (a.strict) {
+          const BvhNode& na = a.assets[pr.asset_a].nodes[0];
+          const BvhNode& nb = a.assets[pr.asset_b].nodes[0];
+          const D3 t = xform_point(X_AB, load3(nb.c)) - load3(na.c);
+          if (boxes_overlap(na.h, nb.h, X_AB, t)) raise_error(a.counters, 6 /*DBH_ERR_RIGID_RIGID*/, p);
+        }
+      } else {
+        push = true;
+      }
+    }
+  }
+  const unsigned long long slot = warp_append(&a.counters->frontier[0], push ? 1 : 0);
+  if (push) a.frontier0[slot] = make_int4(p, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------
+// k_traverse: one thread per BV pair of the current level.
+struct TraverseArgs {
+  const int4* in;
+  int4* out;
+  int level;
+  unsigned long long out_capacity;
+  const PairRec* pairs;
+  const Xf* pair_X;
+  const AssetDev* assets;
+  int4* cand_tri;
+  int4* cand_tet;
+  unsigned long long cand_capacity;
+  Counters* counters;
+};
+
+__global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
+  const unsigned long long count = a.counters->frontier[a.level];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  // Keep whole warps in the loop so warp_append sees full masks.
+  const unsigned long long rounded = (count + 31ull) & ~31ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+    int n_children = 0;
+    bool emit = false;
+    int4 e = make_int4(0, 0, 0, 0);
+    int kind = 0;
+    int la = 0, ra = 0, lb = 0, rb = 0;
+    bool leaf_a = false, leaf_b = false, root_hit = false;
+    if (i < count) {
+      e = a.in[i];
+      const PairRec& pr = a.pairs[e.x];
+      kind = pr.kind;
+      const BvhNode* na = a.assets[pr.asset_a].nodes + e.y;
+      const BvhNode* nb = a.assets[pr.asset_b].nodes + e.z;
+      const Xf X = a.pair_X[e.x];
+      double ha[3] = {na->h[0], na->h[1], na->h[2]};
+      double hb[3] = {nb->h[0], nb->h[1], nb->h[2]};
+      la = na->left;
+      ra = na->right;
+      lb = nb->left;
+      rb = nb->right;
+      leaf_a = la < 0;
+      leaf_b = lb < 0;
+      // Aabb::HasOverlap (aabb.cc:16-33): t = X_GH * b.center - a.center.
+      const D3 t = xform_point(X, load3(nb->c)) - load3(na->c);
+      if (!(leaf_a && leaf_b)) {
+        // Internal tests are made strictly more permissive than the exact leaf
+        // predicate so rounding at an ancestor can never hide a passing leaf pair.
+        const double s =
+            1e-12 * (fabs(t.x) + fabs(t.y) + fabs(t.z) + ha[0] + ha[1] + ha[2] + hb[0] + hb[1] + hb[2]) + 1e-300;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          ha[k] += s;
+          hb[k] += s;
+        }
+      }
+      const bool overlap = boxes_overlap(ha, hb, X, t);
+      if (overlap) {
+        root_hit = (e.y == 0 && e.z == 0);
+        if (leaf_a && leaf_b) {
+          emit = true;
+        } else if (leaf_b) {
+          n_children = 2;
+        } else if (leaf_a) {
+          n_children = 2;
+        } else {
+          n_children = 4;
+        }
+      }
+    }
+    if (a.level == 0) {
+      const unsigned hits = __ballot_sync(0xffffffffu, root_hit);
+      if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&a.counters->root_overlaps, (unsigned long long)__popc(hits));
+    }
+    const unsigned long long slot = warp_append(&a.counters->frontier[a.level + 1], n_children);
+    if (n_children) {
+      if (slot + n_children > a.out_capacity) {
+        raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
+      } else if (leaf_b) {
+        a.out[slot] = make_int4(e.x, la, e.z, 0);
+        a.out[slot + 1] = make_int4(e.x, ra, e.z, 0);
+      } else if (leaf_a) {
+        a.out[slot] = make_int4(e.x, e.y, lb, 0);
+        a.out[slot + 1] = make_int4(e.x, e.y, rb, 0);
+      } else {
+        a.out[slot] = make_int4(e.x, la, lb, 0);
+        a.out[slot + 1] = make_int4(e.x, ra, lb, 0);
+        a.out[slot + 2] = make_int4(e.x, la, rb, 0);
+        a.out[slot + 3] = make_int4(e.x, ra, rb, 0);
+      }
+    }
+    const unsigned long long cslot_tri = warp_append(&a.counters->cand_tri, (emit && kind == kSoftRigid) ? 1 : 0);
+    const unsigned long long cslot_tet = warp_append(&a.counters->cand_tet, (emit && kind == kSoftSoft) ? 1 : 0);
+    if (emit) {
+      const unsigned long long cs = (kind == kSoftRigid) ? cslot_tri : cslot_tet;
+      if (cs >= a.cand_capacity) {
+        raise_error(a.counters, 5, 2);
+      } else {
+        int4* list = (kind == kSoftRigid) ? a.cand_tri : a.cand_tet;
+        list[cs] = make_int4(e.x, ~la, ~lb, 0);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-thread polygon scratch in shared memory: [buffer][slot][coord][thread],
+// so a warp's access to one (slot, coord) is a single conflict-free 256 B row
+// whatever slot each lane is on (the slot stride is a multiple of 128 B).
+struct PolyScratch {
+  double* base;  // &smem[threadIdx.x]
+  __device__ __forceinline__ double& at(int buf, int slot, int c) const {
+    return base[((buf * kMaxPolyVerts + slot) * 3 + c) * kClipThreads];
+  }
+  __device__ __forceinline__ double& dist(int slot) const {
+    return base[(2 * kMaxPolyVerts * 3 + slot) * kClipThreads];
+  }
+  __device__ __forceinline__ D3 get(int buf, int slot) const {
+    return D3{at(buf, slot, 0), at(buf, slot, 1), at(buf, slot, 2)};
+  }
+  __device__ __forceinline__ void set(int buf, int slot, D3 v) const {
+    at(buf, slot, 0) = v.x;
+    at(buf, slot, 1) = v.y;
+    at(buf, slot, 2) = v.z;
+  }
+};
+constexpr int kClipSmemDoublesPerThread = 2 * kMaxPolyVerts * 3 + kMaxPolyVerts;
+constexpr int kClipSmemBytes = kClipSmemDoublesPerThread * kClipThreads * 8;
+
+// RemoveNearlyDuplicateVertices (mesh_intersection.cc:121-170), in place.
+__device__ __forceinline__ int remove_nearly_duplicate(const PolyScratch& P, int buf, int n) {
+  if (n <= 1) return n;
+  const double kEpsSquared = 1e-14 * 1e-14;
+  int result = 0;
+  D3 kept = P.get(buf, 0);
+  for (int first = 1; first < n; ++first) {
+    const D3 q = P.get(buf, first);
+    const D3 d = kept - q;
+    if (!(dot(d, d) < kEpsSquared)) {
+      ++result;
+      if (result != first) P.set(buf, result, q);
+      kept = q;
+    }
+  }
+  n = result + 1;
+  if (n >= 3) {
+    const D3 d = P.get(buf, 0) - P.get(buf, n - 1);
+    if (dot(d, d) < kEpsSquared) --n;
+  }
+  return n;
+}
+
+// ClipPolygonByHalfSpace (mesh_intersection.cc:76-119) from `buf` into `1-buf`.
+// Half space: unit normal nh, displacement d (height = nh.p - d, inside <= 0).
+__device__ __forceinline__ int clip_by_half_space(const PolyScratch& P, int buf, int n, D3 nh, double d) {
+  for (int i = 0; i < n; ++i) P.dist(i) = dot(nh, P.get(buf, i)) - d;
+  int m = 0;
+  int prev = n - 1;
+  for (int i = 0; i < n; ++i) {
+    const double dc = P.dist(i), dp = P.dist(prev);
+    const bool cur_in = dc <= 0, prev_in = dp <= 0;
+    if (cur_in != prev_in) {
+      // CalcIntersection(current, previous, H): a = dist(current), b = dist(previous).
+      const double wa = dp / (dp - dc);
+      const double wb = 1.0 - wa;
+      const D3 cur = P.get(buf, i), pv = P.get(buf, prev);
+      if (m < kMaxPolyVerts) P.set(1 - buf, m, wa * cur + wb * pv);
+      ++m;
+    }
+    if (cur_in) {
+      if (m < kMaxPolyVerts) P.set(1 - buf, m, P.get(buf, i));
+      ++m;
+    }
+    prev = i;
+  }
+  return m;
+}
+
+// The staging soup of contact polygons (frame M of the first body).
+struct PolySoup {
+  int4* hdr;            // {pair, elem_a, elem_b, n}
+  double* v;            // [(slot*4 + c) * capacity + i], c = x, y, z, pressure
+  double* nhat;         // [c * capacity + i]: polygon normal in M (triangle rep needs it)
+  unsigned long long capacity;
+};
+
+struct ClipArgs {
+  const int4* cand;
+  const PairRec* pairs;
+  const Xf* pair_X;
+  const AssetDev* assets;
+  PolySoup soup;
+  int* pair_polys;
+  int* pair_verts;
+  Counters* counters;
+};
+
+__device__ __forceinline__ void emit_polygon(const ClipArgs& a, const PolyScratch& P, int buf, int n, int4 c, D3 grad,
+                                             double p_mo, D3 nhat) {
+  // One warp-aggregated atomic for the soup slot; per-pair counts by plain atomics.
+  const unsigned long long slot = warp_append(&a.counters->polys, n > 0 ? 1 : 0);
+  if (n <= 0) return;
+  if (slot >= a.soup.capacity) {
+    raise_error(a.counters, 5, 3);
+    return;
+  }
+  a.soup.hdr[slot] = make_int4(c.x, c.y, c.z, n);
+  for (int k = 0; k < n; ++k) {
+    const D3 p = P.get(buf, k);
+    a.soup.v[(k * 4 + 0) * a.soup.capacity + slot] = p.x;
+    a.soup.v[(k * 4 + 1) * a.soup.capacity + slot] = p.y;
+    a.soup.v[(k * 4 + 2) * a.soup.capacity + slot] = p.z;
+    // MeshFieldLinear::EvaluateCartesian (mesh_field_linear.h:349).
+    a.soup.v[(k * 4 + 3) * a.soup.capacity + slot] = dot(grad, p) + p_mo;
+  }
+  a.soup.nhat[0 * a.soup.capacity + slot] = nhat.x;
+  a.soup.nhat[1 * a.soup.capacity + slot] = nhat.y;
+  a.soup.nhat[2 * a.soup.capacity + slot] = nhat.z;
+  atomicAdd(&a.pair_polys[c.x], 1);
+  atomicAdd(&a.pair_verts[c.x], n);
+}
+
+// ---------------------------------------------------------------------------
+// k_clip_tri: one thread per (tet, triangle) candidate.
+__global__ void __launch_bounds__(kClipThreads) k_clip_tri(ClipArgs a) {
+  extern __shared__ double smem[];
+  const PolyScratch P{smem + threadIdx.x};
+  const unsigned long long count = a.counters->cand_tri;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long rounded = (count + 31ull) & ~31ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+    int n = 0;
+    int buf = 0;
+    int4 c = make_int4(0, 0, 0, 0);
+    D3 grad = make_d3(0, 0, 0), nhat_M = make_d3(0, 0, 0);
+    double p_mo = 0;
+    if (i < count) {
+      c = a.cand[i];
+      const PairRec& pr = a.pairs[c.x];
+      const TetRec& tet = a.assets[pr.asset_a].tets[c.y];
+      const TriRec& tri = a.assets[pr.asset_b].tris[c.z];
+      const Xf X = a.pair_X[c.x];
+      grad = load3(tet.grad);
+      p_mo = tet.p_mo;
+      // IsFaceNormalAlongPressureGradient (mesh_intersection.cc:266-288,
+      // contact_surface_utility.cc:336-354).
+      nhat_M = rot(X, load3(tri.n));
+      const double cos_theta = dot(normalized(grad), normalized(nhat_M));
+      if (cos_theta > kCosAlphaDevice) {
+        // ClipTriangleByTetrahedron (mesh_intersection.cc:176-264).
+        n = 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) P.set(0, k, xform_point(X, load3(tri.v[k])));
+        const int faces[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          if (n > 0) {
+            const D3 A = load3(tet.v[faces[f][0]]);
+            const D3 B = load3(tet.v[faces[f][1]]);
+            const D3 C = load3(tet.v[faces[f][2]]);
+            const D3 normal = cross(B - A, C - A);
+            const double mag = norm(normal);
+            if (mag < 1e-10) {  // Plane ctor throws (plane.cc:16-29)
+              raise_error(a.counters, 9 /*DBH_ERR_PLANE_NORMAL*/, c.x);
+              n = 0;
+            } else {
+              const D3 nh = normal / mag;
+              const double d = dot(nh, A);
+              n = clip_by_half_space(P, buf, n, nh, d);
+              if (n > kMaxPolyVerts) {
+                raise_error(a.counters, 5, 4);
+                n = 0;
+              }
+              buf = 1 - buf;
+            }
+          }
+        }
+        n = remove_nearly_duplicate(P, buf, n);
+        if (n < 3) n = 0;
+      }
+    }
+    emit_polygon(a, P, buf, n, c, grad, p_mo, nhat_M);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_clip_tet: one thread per (tet0, tet1) candidate.
+__global__ void __launch_bounds__(kClipThreads) k_clip_tet(ClipArgs a) {
+  extern __shared__ double smem[];
+  const PolyScratch P{smem + threadIdx.x};
+  const unsigned long long count = a.counters->cand_tet;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long rounded = (count + 31ull) & ~31ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+    int n = 0;
+    int buf = 0;
+    int4 c = make_int4(0, 0, 0, 0);
+    D3 grad0 = make_d3(0, 0, 0), nhat_M = make_d3(0, 0, 0);
+    double f0_Mo = 0;
+    if (i < count) {
+      c = a.cand[i];
+      const PairRec& pr = a.pairs[c.x];
+      const TetRec& tet0 = a.assets[pr.asset_a].tets[c.y];
+      const TetRec& tet1 = a.assets[pr.asset_b].tets[c.z];
+      const Xf X = a.pair_X[c.x];
+      // CalcEquilibriumPlane (field_intersection.cc:30-83).
+      grad0 = load3(tet0.grad);
+      f0_Mo = tet0.p_mo;
+      const D3 grad1_N = load3(tet1.grad);
+      const D3 grad1_M = rot(X, grad1_N);
+      const D3 p_NMo = -rot_t(X, make_d3(X.m[9], X.m[10], X.m[11]));
+      const double f1_Mo = dot(grad1_N, p_NMo) + tet1.p_mo;
+      const D3 n_M = grad0 - grad1_M;
+      const double magnitude = norm(n_M);
+      bool ok = magnitude > 0.0;
+      double displacement = 0;
+      if (ok) {
+        nhat_M = n_M / magnitude;
+        const D3 p_MQ = ((f1_Mo - f0_Mo) / magnitude) * nhat_M;
+        displacement = dot(nhat_M, p_MQ);
+        // IsPlaneNormalAlongPressureGradient x2 (field_intersection.cc:200-216,393-400).
+        ok = dot(nhat_M, normalized(grad0)) > kCosAlphaDevice;
+        if (ok) {
+          const D3 rev_N = rot_t(X, -nhat_M);
+          ok = dot(rev_N, normalized(grad1_N)) > kCosAlphaDevice;
+        }
+      }
+      if (ok) {
+        // SliceTetrahedronWithPlane (mesh_plane_intersection.cc:121-180).
+        double dist[4];
+        int code = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          dist[k] = dot(nhat_M, load3(tet0.v[k])) - displacement;
+          if (dist[k] > 0) code |= 1 << k;
+        }
+        // kMarchingTetsEdgeTable packed 4 bits per entry (0xF = none), edges kTetEdges.
+        const unsigned short kEdgeTable[16] = {0xFFFF, 0xF230, 0xF410, 0x1234, 0xF521, 0x1530, 0x4520, 0xF453,
+                                               0xF543, 0x0254, 0x0351, 0xF251, 0x4321, 0xF140, 0xF320, 0xFFFF};
+        const unsigned char kEdgeV0[6] = {0, 1, 2, 0, 1, 2};
+        const unsigned char kEdgeV1[6] = {1, 2, 0, 3, 3, 3};
+        const unsigned entry = kEdgeTable[code];
+        n = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int edge = (entry >> (4 * k)) & 0xF;
+          if (edge != 0xF && n == k) {
+            const int e0 = kEdgeV0[edge], e1 = kEdgeV1[edge];
+            // dist[] is indexed dynamically; select to keep it in registers.
+            const double d0 = e0 == 0 ? dist[0] : (e0 == 1 ? dist[1] : dist[2]);
+            const double d1 = e1 == 1 ? dist[1] : (e1 == 2 ? dist[2] : (e1 == 0 ? dist[0] : dist[3]));
+            const D3 V0 = load3(tet0.v[e0]);
+            const D3 V1 = load3(tet0.v[e1]);
+            const double t = d0 / (d0 - d1);
+            P.set(0, n, V0 + t * (V1 - V0));
+            ++n;
+          }
+        }
+        n = remove_nearly_duplicate(P, 0, n);
+        if (n < 3) n = 0;
+        // Clip by the four faces of tet1 (field_intersection.cc:120-190).
+        if (n > 0) {
+          D3 p_MV[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) p_MV[k] = xform_point(X, load3(tet1.v[k]));
+          const TetNormals& tn = a.assets[pr.asset_b].normals[c.z];
+#pragma unroll
+          for (int face = 0; face < 4; ++face) {
+            if (n > 0) {
+              const D3 p_MA = p_MV[(face + 1) % 4];
+              const D3 outward = rot(X, -load3(tn.n[face]));
+              const double mag = norm(outward);
+              if (mag < 1e-10) {
+                raise_error(a.counters, 9, c.x);
+                n = 0;
+              } else {
+                const D3 nh = outward / mag;
+                const double d = dot(nh, p_MA);
+                // field_intersection.cc:146-182: same polygon as
+                // ClipPolygonByHalfSpace but walking edges (i, i+1) with
+                // wa = d_j / (d_j - d_i), p = wa P_i + wb P_j.
+                for (int k = 0; k < n; ++k) P.dist(k) = dot(nh, P.get(buf, k)) - d;
+                int m = 0;
+                for (int k = 0; k < n; ++k) {
+                  const int j = (k + 1 == n) ? 0 : k + 1;
+                  const double di = P.dist(k), dj = P.dist(j);
+                  if (di <= 0) {
+                    if (m < kMaxPolyVerts) P.set(1 - buf, m, P.get(buf, k));
+                    ++m;
+                    if (dj > 0) {
+                      const double wa = dj / (dj - di);
+                      const double wb = 1.0 - wa;
+                      if (m < kMaxPolyVerts) P.set(1 - buf, m, wa * P.get(buf, k) + wb * P.get(buf, j));
+                      ++m;
+                    }
+                  } else if (dj <= 0) {
+                    const double wa = dj / (dj - di);
+                    const double wb = 1.0 - wa;
+                    if (m < kMaxPolyVerts) P.set(1 - buf, m, wa * P.get(buf, k) + wb * P.get(buf, j));
+                    ++m;
+                  }
+                }
+                if (m > kMaxPolyVerts) {
+                  raise_error(a.counters, 5, 5);
+                  m = 0;
+                }
+                n = m;
+                buf = 1 - buf;
+              }
+            }
+          }
+          n = remove_nearly_duplicate(P, buf, n);
+          if (n < 3) n = 0;
+        }
+      }
+    }
+    emit_polygon(a, P, buf, n, c, grad0, f0_Mo, nhat_M);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Exclusive scans over the geometry-pair list (three kernels: per-block
+// partials, single-block scan of the partials, apply). Produces for every
+// pair the polygon offset, the polygon-vertex offset and the surface index.
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;  // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+struct ScanArgs {
+  const int* pair_polys;
+  const int* pair_verts;
+  int num_pairs;
+  long long* poly_off;   // [num_pairs + 1]
+  long long* vert_off;   // [num_pairs + 1]
+  int* surf_index;       // [num_pairs + 1]
+  long long* block_sums; // [3 * num_blocks]
+  int num_blocks;
+  int* surf_pair;        // [num_surfaces]
+  Counters* counters;
+};
+
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* total, long long* sh /*[kScanThreads/32]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) sh[w] = incl;
+  __syncthreads();
+  long long warp_base = 0, tot = 0;
+  for (int k = 0; k < kScanThreads / 32; ++k) {
+    if (k < w) warp_base += sh[k];
+    tot += sh[k];
+  }
+  __syncthreads();
+  *total = tot;
+  return warp_base + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_partials(ScanArgs a) {
+  __shared__ long long sh[kScanThreads / 32];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  long long s0 = 0, s1 = 0, s2 = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    const int p = base + k;
+    if (p < a.num_pairs) {
+      const int np = a.pair_polys[p];
+      s0 += np;
+      s1 += a.pair_verts[p];
+      s2 += np > 0;
+    }
+  }
+  long long t0, t1, t2;
+  block_exclusive_scan(s0, &t0, sh);
+  block_exclusive_scan(s1, &t1, sh);
+  block_exclusive_scan(s2, &t2, sh);
+  if (threadIdx.x == 0) {
+    a.block_sums[0 * a.num_blocks + blockIdx.x] = t0;
+    a.block_sums[1 * a.num_blocks + blockIdx.x] = t1;
+    a.block_sums[2 * a.num_blocks + blockIdx.x] = t2;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_blocks(ScanArgs a) {
+  // One block scans the per-block partials of the three sequences in turn.
+  __shared__ long long sh[kScanThreads / 32];
+  for (int seq = 0; seq < 3; ++seq) {
+    long long carry = 0;
+    for (int start = 0; start < a.num_blocks; start += kScanThreads) {
+      const int b = start + threadIdx.x;
+      const long long v = b < a.num_blocks ? a.block_sums[seq * a.num_blocks + b] : 0;
+      long long tot;
+      const long long ex = block_exclusive_scan(v, &tot, sh);
+      if (b < a.num_blocks) a.block_sums[seq * a.num_blocks + b] = carry + ex;
+      carry += tot;
+    }
+    if (threadIdx.x == 0) {
+      if (seq == 0) a.poly_off[a.num_pairs] = carry;
+      if (seq == 1) a.vert_off[a.num_pairs] = carry;
+      if (seq == 2) {
+        a.surf_index[a.num_pairs] = (int)carry;
+        a.counters->surfaces = (unsigned long long)carry;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(ScanArgs a) {
+  __shared__ long long sh[kScanThreads / 32];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int np[kScanItems], nv[kScanItems];
+  long long s0 = 0, s1 = 0, s2 = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    const int p = base + k;
+    np[k] = p < a.num_pairs ? a.pair_polys[p] : 0;
+    nv[k] = p < a.num_pairs ? a.pair_verts[p] : 0;
+    s0 += np[k];
+    s1 += nv[k];
+    s2 += np[k] > 0;
+  }
+  long long t;
+  long long e0 = block_exclusive_scan(s0, &t, sh) + a.block_sums[0 * a.num_blocks + blockIdx.x];
+  long long e1 = block_exclusive_scan(s1, &t, sh) + a.block_sums[1 * a.num_blocks + blockIdx.x];
+  long long e2 = block_exclusive_scan(s2, &t, sh) + a.block_sums[2 * a.num_blocks + blockIdx.x];
+  for (int k = 0; k < kScanItems; ++k) {
+    const int p = base + k;
+    if (p < a.num_pairs) {
+      a.poly_off[p] = e0;
+      a.vert_off[p] = e1;
+      a.surf_index[p] = (int)e2;
+      if (np[k] > 0) a.surf_pair[e2] = p;
+      e0 += np[k];
+      e1 += nv[k];
+      e2 += np[k] > 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_pack: one thread per staged polygon.
+struct PackArgs {
+  PolySoup soup;
+  const PairRec* pairs;
+  const AssetDev* assets;
+  const Xf* poses;
+  const long long* poly_off;
+  const long long* vert_off;
+  unsigned long long* pair_cursor;
+  int representation;  // DBH_TRIANGLE / DBH_POLYGON
+  // final arrays
+  double* face_f64;    // 14 planes, stride face_stride
+  int* face_i32;       // 6 planes
+  long long face_stride;
+  double* vert_f64;    // 4 planes, stride vert_stride
+  long long vert_stride;
+  Counters* counters;
+};
+
+enum FacePlane { kArea = 0, kNx, kNy, kNz, kCx, kCy, kCz, kEc, kGMx, kGMy, kGMz, kGNx, kGNy, kGNz, kNumFacePlanes };
+enum FaceIntPlane { kPair = 0, kElemA, kElemB, kI0, kI1, kI2, kNumFaceIntPlanes };
+
+__device__ __forceinline__ void store_face(const PackArgs& a, long long f, int pair, int ea, int eb, int i0, int i1,
+                                           int i2, double area, D3 n_W, D3 c_W, double e_c, D3 gA_W, D3 gB_W,
+                                           bool has_b, bool swapped) {
+  if (f >= a.face_stride) {
+    raise_error(a.counters, 5, 6);
+    return;
+  }
+  double* F = a.face_f64 + f;
+  const long long s = a.face_stride;
+  if (swapped) n_W = -n_W;  // ReverseFaceWinding negates normals (polygon_surface_mesh.cc:50-52)
+  F[kArea * s] = area;
+  F[kNx * s] = n_W.x;
+  F[kNy * s] = n_W.y;
+  F[kNz * s] = n_W.z;
+  F[kCx * s] = c_W.x;
+  F[kCy * s] = c_W.y;
+  F[kCz * s] = c_W.z;
+  F[kEc * s] = e_c;
+  const D3 zero = make_d3(0, 0, 0);
+  // swapped: grad_eM <-> grad_eN (contact_surface.cc:58).
+  const D3 gM = swapped ? (has_b ? gB_W : zero) : gA_W;
+  const D3 gN = swapped ? gA_W : (has_b ? gB_W : zero);
+  F[kGMx * s] = gM.x;
+  F[kGMy * s] = gM.y;
+  F[kGMz * s] = gM.z;
+  F[kGNx * s] = gN.x;
+  F[kGNy * s] = gN.y;
+  F[kGNz * s] = gN.z;
+  int* I = a.face_i32 + f;
+  I[kPair * s] = pair;
+  I[kElemA * s] = ea;
+  I[kElemB * s] = eb;
+  I[kI0 * s] = i0;
+  I[kI1 * s] = i1;
+  I[kI2 * s] = i2;
+}
+
+__global__ void __launch_bounds__(128) k_pack(PackArgs a) {
+  const unsigned long long count = a.counters->polys;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const int4 h = a.soup.hdr[i];
+    const int pair = h.x, n = h.w;
+    const PairRec pr = a.pairs[pair];
+    const bool soft_soft = pr.kind == kSoftSoft;
+    const bool swapped = pr.swapped != 0;
+    const Xf X_WM = a.poses[pr.geom_a];
+    D3 vM[kMaxPolyVerts];
+    double e[kMaxPolyVerts];
+    for (int k = 0; k < n; ++k) {
+      vM[k] = make_d3(a.soup.v[(k * 4 + 0) * a.soup.capacity + i], a.soup.v[(k * 4 + 1) * a.soup.capacity + i],
+                      a.soup.v[(k * 4 + 2) * a.soup.capacity + i]);
+      e[k] = a.soup.v[(k * 4 + 3) * a.soup.capacity + i];
+    }
+    const D3 gradA_M = load3(a.assets[pr.asset_a].tets[h.y].grad);
+    const D3 gA_W = rot(X_WM, gradA_M);
+    D3 gB_W = make_d3(0, 0, 0);
+    if (soft_soft) {
+      const Xf X_WN = a.poses[pr.geom_b];
+      gB_W = rot(X_WN, load3(a.assets[pr.asset_b].tets[h.z].grad));
+    }
+    // Slots inside the pair's ranges.
+    // One atomic claims both the polygon slot and the vertex range.
+    const unsigned long long cur = atomicAdd(&a.pair_cursor[pair], (1ull << 32) | (unsigned long long)n);
+    const int pj = (int)(cur >> 32);
+    const int vj = (int)(cur & 0xffffffffull);
+    if (a.representation == 1 /*DBH_POLYGON*/) {
+      const long long f = a.poly_off[pair] + pj;
+      const long long vb = a.vert_off[pair] + vj;
+      // PolygonSurfaceMesh::CalcAreaNormalAndCentroid (polygon_surface_mesh.cc:117-218).
+      const D3 r_MA = vM[0];
+      D3 p_scaled = make_d3(0, 0, 0), normal_M = make_d3(0, 0, 0);
+      double double_area = 0;
+      for (int k = 1; k < n - 1; ++k) {
+        const D3 cr = cross(vM[k] - r_MA, vM[k + 1] - r_MA);
+        normal_M = normal_M + cr;
+        const double mag = norm(cr);
+        double_area += mag;
+        p_scaled = p_scaled + mag * ((r_MA + vM[k]) + vM[k + 1]);
+      }
+      const double area = double_area / 2;
+      const D3 nM = normalized(normal_M);
+      const D3 p_as = p_scaled / 6;
+      D3 cM;
+      if (area != 0.0) {
+        cM = p_as / area;
+      } else {
+        D3 acc = r_MA;
+        for (int k = 1; k < n; ++k) acc = acc + vM[k];
+        cM = acc / (double)n;
+      }
+      // TransformVertices + field Transform (polygon_surface_mesh.cc:25-37,
+      // mesh_field_linear.h:377-383,502-509).
+      const D3 n_W = normalized(rot(X_WM, nM));
+      const D3 c_W = xform_point(X_WM, cM);
+      const double at_Mo = e[0] - dot(gradA_M, vM[0]);
+      const double at_Wo = at_Mo - dot(gA_W, make_d3(X_WM.m[9], X_WM.m[10], X_WM.m[11]));
+      const double e_c = dot(gA_W, c_W) + at_Wo;
+      if (vb + n > a.vert_stride) {
+        raise_error(a.counters, 5, 7);
+        continue;
+      }
+      for (int k = 0; k < n; ++k) {
+        const D3 w = xform_point(X_WM, vM[k]);
+        a.vert_f64[0 * a.vert_stride + vb + k] = w.x;
+        a.vert_f64[1 * a.vert_stride + vb + k] = w.y;
+        a.vert_f64[2 * a.vert_stride + vb + k] = w.z;
+        a.vert_f64[3 * a.vert_stride + vb + k] = e[k];
+      }
+      store_face(a, f, pair, h.y, h.z, n, (int)(vb - a.vert_off[pair]), 0, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft,
+                 swapped);
+    } else {
+      // Triangle representation: n fan triangles about the polygon centroid
+      // (contact_surface_utility.cc:137-164,218-316). Faces are counted by
+      // polygon vertices, vertices by n + 1 per polygon.
+      const long long fb = a.vert_off[pair] + vj;
+      const long long vb = a.vert_off[pair] + a.poly_off[pair] + vj + pj;
+      const D3 nhat = make_d3(a.soup.nhat[0 * a.soup.capacity + i], a.soup.nhat[1 * a.soup.capacity + i],
+                              a.soup.nhat[2 * a.soup.capacity + i]);
+      // CalcPolygonCentroid.
+      D3 p_c;
+      if (n == 3) {
+        p_c = ((vM[0] + vM[1]) + vM[2]) / 3.0;
+      } else {
+        D3 accum = make_d3(0, 0, 0);
+        double total_weight = 0;
+        for (int k = 2; k < n; ++k) {
+          const double weight = dot(cross(vM[k - 1] - vM[0], vM[k] - vM[0]), nhat);
+          accum = accum + weight * (((vM[0] + vM[k - 1]) + vM[k]) / 3.0);
+          total_weight += weight;
+        }
+        if (total_weight == 0) {
+          accum = make_d3(0, 0, 0);
+          for (int k = 0; k < n; ++k) accum = accum + vM[k];
+          total_weight = n;
+        }
+        p_c = accum / total_weight;
+      }
+      const double e_cv = dot(gradA_M, p_c - vM[0]) + e[0];
+      if (vb + n + 1 > a.vert_stride) {
+        raise_error(a.counters, 5, 7);
+        continue;
+      }
+      const long long vloc = vb - (a.vert_off[pair] + a.poly_off[pair]);  // local to the surface
+      D3 vW[kMaxPolyVerts];
+      for (int k = 0; k < n; ++k) {
+        vW[k] = xform_point(X_WM, vM[k]);
+        a.vert_f64[0 * a.vert_stride + vb + k] = vW[k].x;
+        a.vert_f64[1 * a.vert_stride + vb + k] = vW[k].y;
+        a.vert_f64[2 * a.vert_stride + vb + k] = vW[k].z;
+        a.vert_f64[3 * a.vert_stride + vb + k] = e[k];
+      }
+      const D3 cW = xform_point(X_WM, p_c);
+      a.vert_f64[0 * a.vert_stride + vb + n] = cW.x;
+      a.vert_f64[1 * a.vert_stride + vb + n] = cW.y;
+      a.vert_f64[2 * a.vert_stride + vb + n] = cW.z;
+      a.vert_f64[3 * a.vert_stride + vb + n] = e_cv;
+      const double third = 1.0 / 3.0;
+      int k1 = n - 1;
+      for (int k = 0; k < n; ++k) {
+        // Triangle (v_{k-1}, v_k, centroid): TriangleSurfaceMesh derived
+        // quantities in M (triangle_surface_mesh.h:452-487), then rotated.
+        const D3 cr = cross(vM[k] - vM[k1], p_c - vM[k1]);
+        const double nm = norm(cr);
+        const double area = 0.5 * nm;
+        const D3 nM = (nm != 0.0) ? cr / nm : cr;
+        const D3 n_W = rot(X_WM, nM);
+        const D3 c_W = ((vW[k1] + vW[k]) + cW) / 3.0;
+        double e_c = third * e[k1];
+        e_c += third * e[k];
+        e_c += third * e_cv;
+        int i0 = (int)vloc + k1, i1 = (int)vloc + k;
+        if (swapped) {  // SurfaceTriangle::ReverseWinding swaps vertices 0 and 1
+          const int tmp = i0;
+          i0 = i1;
+          i1 = tmp;
+        }
+        store_face(a, fb + k, pair, h.y, h.z, i0, i1, (int)vloc + n, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft,
+                   swapped);
+        k1 = k;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_surface: one warp per non-null surface: total area, area-weighted centroid
+// (polygon_surface_mesh.cc:208-217, triangle_surface_mesh.h:476-486), and the
+// per-scene statistics record.
+struct SurfaceArgs {
+  const int* surf_pair;
+  const PairRec* pairs;
+  const long long* poly_off;
+  const long long* vert_off;
+  int representation;
+  const double* face_f64;
+  long long face_stride;
+  long long* surf_face_off;  // [num_surfaces + 1]
+  long long* surf_vert_off;
+  double* surf_f64;          // 4 planes: area, cx, cy, cz; stride surf_stride
+  long long surf_stride;
+  long long* scene_stats;    // optional [num_scenes * 6]
+  Counters* counters;
+};
+
+__global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long num_surfaces = (long long)a.counters->surfaces;
+  for (long long s = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < num_surfaces;
+       s += (long long)gridDim.x * warps_per_block) {
+    const int p = a.surf_pair[s];
+    long long f0, f1, v0;
+    if (a.representation == 1) {
+      f0 = a.poly_off[p];
+      f1 = a.poly_off[p + 1];
+      v0 = a.vert_off[p];
+    } else {
+      f0 = a.vert_off[p];
+      f1 = a.vert_off[p + 1];
+      v0 = a.vert_off[p] + a.poly_off[p];
+    }
+    double area = 0, cx = 0, cy = 0, cz = 0;
+    for (long long f = f0 + lane; f < f1; f += 32) {
+      const double w = a.face_f64[kArea * a.face_stride + f];
+      area += w;
+      cx += w * a.face_f64[kCx * a.face_stride + f];
+      cy += w * a.face_f64[kCy * a.face_stride + f];
+      cz += w * a.face_f64[kCz * a.face_stride + f];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      area += __shfl_xor_sync(0xffffffffu, area, d);
+      cx += __shfl_xor_sync(0xffffffffu, cx, d);
+      cy += __shfl_xor_sync(0xffffffffu, cy, d);
+      cz += __shfl_xor_sync(0xffffffffu, cz, d);
+    }
+    if (lane == 0) {
+      if (area != 0.0) {
+        cx /= area;
+        cy /= area;
+        cz /= area;
+      } else {
+        // All faces have zero area: the reference keeps the centroid of the
+        // last polygon; we report the first face's.
+        cx = a.face_f64[kCx * a.face_stride + f0];
+        cy = a.face_f64[kCy * a.face_stride + f0];
+        cz = a.face_f64[kCz * a.face_stride + f0];
+      }
+      a.surf_face_off[s] = f0;
+      a.surf_vert_off[s] = v0;
+      a.surf_f64[0 * a.surf_stride + s] = area;
+      a.surf_f64[1 * a.surf_stride + s] = cx;
+      a.surf_f64[2 * a.surf_stride + s] = cy;
+      a.surf_f64[3 * a.surf_stride + s] = cz;
+      atomicAdd(&a.counters->total_area, area);
+      if (a.scene_stats) {
+        unsigned long long* st = (unsigned long long*)(a.scene_stats + 6ll * a.pairs[p].scene);
+        atomicAdd(st + 3, (unsigned long long)(f1 - f0));
+        atomicAdd(st + 4, 1ull);
+      }
+    }
+  }
+}
+
+// Writes the sentinel offsets and the face / vertex totals.
+__global__ void k_finalize(SurfaceArgs a, int num_pairs) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long polys = a.poly_off[num_pairs], pverts = a.vert_off[num_pairs];
+  const long long faces = a.representation == 1 ? polys : pverts;
+  const long long verts = a.representation == 1 ? pverts : pverts + polys;
+  const long long ns = (long long)a.counters->surfaces;
+  a.surf_face_off[ns] = faces;
+  a.surf_vert_off[ns] = verts;
+  a.counters->faces = (unsigned long long)faces;
+  a.counters->vertices = (unsigned long long)verts;
+  a.counters->poly_verts = (unsigned long long)pverts;
+}
+
+// Per-scene statistics that depend only on the static pair list and the
+// per-pair counters: geometry pairs tested and element pairs (approximated by
+// the pair's polygon count when per-pair candidate counting is off).
+__global__ void k_scene_stats(const PairRec* pairs, int num_pairs, const int* pair_polys, long long* scene_stats) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= num_pairs) return;
+  const PairRec& pr = pairs[p];
+  if (pr.kind > kSoftSoft) return;
+  unsigned long long* st = (unsigned long long*)(scene_stats + 6ll * pr.scene);
+  atomicAdd(st + 0, 1ull);
+}
+
+}  // namespace dbh

@@ -1,0 +1,450 @@
+"""Python host mirror of the C-ABI in include/drake_b200_hydro.h.
+
+Everything here is plumbing over libdrake_b200_hydro.so (ctypes): there is no
+Python or CPU implementation of the contact query. Importing works anywhere
+the shared library loads; creating a Context requires an sm_100 CUDA device and
+raises HydroError otherwise.
+
+Names follow the reference's domain: geometries, scenes, poses X_WG, contact
+surfaces with ids (id_M, id_N), polygon / triangle representation
+(geometry/proximity_engine.h:309-326, query_results/contact_surface.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import build as _build
+
+TRIANGLE, POLYGON = 0, 1
+UNDEFINED, RIGID, COMPLIANT = 0, 1, 2
+STRICT, WITH_FALLBACK = 0, 1
+
+OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_DEGENERATE_FIELD, ERR_CAPACITY = 1, 2, 3, 4, 5
+ERR_RIGID_RIGID, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_PLANE_NORMAL = 6, 7, 8, 9
+
+
+class HydroError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"dbh status {status}: {message}")
+        self.status = status
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_bp = C.POINTER(C.c_uint8)
+
+
+class AssetInfo(C.Structure):
+    _fields_ = [("type", C.c_int32), ("num_vertices", C.c_int32), ("num_elements", C.c_int32),
+                ("num_bvh_nodes", C.c_int32), ("bvh_height", C.c_int32), ("reserved", C.c_int32 * 3),
+                ("root_center", C.c_double * 3), ("root_half_width", C.c_double * 3)]
+
+
+class BatchInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("num_scenes", "num_geometries", "num_geometry_pairs", "num_soft_rigid_pairs", "num_soft_soft_pairs",
+                 "num_rigid_rigid_pairs", "num_unsupported_pairs", "max_traversal_levels")]
+
+
+class ResultSizes(C.Structure):
+    _fields_ = [("num_surfaces", C.c_int64), ("num_faces", C.c_int64), ("num_vertices", C.c_int64),
+                ("num_polygons", C.c_int64), ("face_data_ints", C.c_int64), ("representation", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class ResultBuffers(C.Structure):
+    _fields_ = [("surf_scene", _ip), ("surf_id_M", _lp), ("surf_id_N", _lp), ("surf_face_offset", _lp),
+                ("surf_vertex_offset", _lp), ("surf_total_area", _dp), ("surf_centroid", _dp), ("surf_flags", _bp),
+                ("vertices", _dp), ("pressures", _dp), ("face_data", _ip), ("areas", _dp), ("normals", _dp),
+                ("centroids", _dp), ("pressure_at_centroid", _dp), ("grad_eM", _dp), ("grad_eN", _dp),
+                ("elem_M", _ip), ("elem_N", _ip)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in
+                ("geometry_pairs_tested", "geometry_pairs_overlapping", "bv_pair_tests", "tet_tri_pairs",
+                 "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "algorithmic_bytes")] + \
+               [("total_area", C.c_double), ("reserved", C.c_double * 3)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads (building in-tree if stale) libdrake_b200_hydro.so. Fails loudly if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.is_stale():
+        try:
+            path = _build.build()
+        except Exception as e:  # no nvcc on this box and no prebuilt library
+            if not os.path.exists(_build.LIB_PATH):
+                raise HydroError(ERR_NO_DEVICE, f"libdrake_b200_hydro.so is missing and cannot be built: {e}")
+            path = _build.LIB_PATH
+    L = C.CDLL(path)
+    L.dbh_last_error.restype = C.c_char_p
+    L.dbh_batch_stream.restype = C.c_void_p
+    vp = C.c_void_p
+    L.dbh_context_create.argtypes = [C.c_int32, C.POINTER(vp)]
+    L.dbh_context_destroy.argtypes = [vp]
+    L.dbh_register_compliant_mesh.argtypes = [vp, C.c_int32, _dp, C.c_int32, _ip, _dp, _ip]
+    L.dbh_register_rigid_mesh.argtypes = [vp, C.c_int32, _dp, C.c_int32, _ip, _ip]
+    L.dbh_asset_get_info.argtypes = [vp, C.c_int32, C.POINTER(AssetInfo)]
+    L.dbh_asset_get_derived.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
+    L.dbh_batch_create.argtypes = [vp, C.c_int32, _ip, _ip, _lp, _bp, C.c_int32, _ip, C.POINTER(vp)]
+    L.dbh_batch_destroy.argtypes = [vp]
+    L.dbh_batch_set_capacity.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
+    L.dbh_batch_get_info.argtypes = [vp, C.POINTER(BatchInfo)]
+    L.dbh_batch_set_poses_host.argtypes = [vp, _dp]
+    L.dbh_batch_set_poses_device.argtypes = [vp, vp]
+    L.dbh_batch_query.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.dbh_batch_sync.argtypes = [vp]
+    L.dbh_batch_stream.argtypes = [vp]
+    L.dbh_batch_result_sizes.argtypes = [vp, C.POINTER(ResultSizes)]
+    L.dbh_batch_copy_results.argtypes = [vp, C.POINTER(ResultBuffers)]
+    L.dbh_batch_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.dbh_batch_copy_candidates.argtypes = [vp, C.c_int32, _ip, _lp]
+    L.dbh_batch_copy_geometry_pairs.argtypes = [vp, _ip]
+    L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
+    L.dbh_batch_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def _check(status: int):
+    if status != OK:
+        raise HydroError(status, lib().dbh_last_error().decode())
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+class Context:
+    """One per device (one process per GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().dbh_context_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().dbh_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def register_compliant_mesh(self, vertices, tets, pressure) -> int:
+        """VolumeMesh + VolumeMeshFieldLinear -> asset handle (hydroelastic_internal.cc:94-108)."""
+        v, t, p = _d(vertices).reshape(-1, 3), _i(tets).reshape(-1, 4), _d(pressure).reshape(-1)
+        if len(p) != len(v):
+            raise ValueError("one pressure value per vertex")
+        out = C.c_int32()
+        _check(lib().dbh_register_compliant_mesh(self._h, len(v), _ptr(v, _dp), len(t), _ptr(t, _ip), _ptr(p, _dp),
+                                                 C.byref(out)))
+        return out.value
+
+    def register_rigid_mesh(self, vertices, tris) -> int:
+        v, t = _d(vertices).reshape(-1, 3), _i(tris).reshape(-1, 3)
+        out = C.c_int32()
+        _check(lib().dbh_register_rigid_mesh(self._h, len(v), _ptr(v, _dp), len(t), _ptr(t, _ip), C.byref(out)))
+        return out.value
+
+    def asset_info(self, asset: int) -> AssetInfo:
+        info = AssetInfo()
+        _check(lib().dbh_asset_get_info(self._h, asset, C.byref(info)))
+        return info
+
+    def asset_derived(self, asset: int):
+        """Compliant: (gradients [T,3], values_at_Mo [T], inward_normals [T,4,3]); rigid: normals [T,3]."""
+        info = self.asset_info(asset)
+        n = info.num_elements
+        if info.type == COMPLIANT:
+            g, m, nn = np.zeros((n, 3)), np.zeros(n), np.zeros((n, 4, 3))
+            _check(lib().dbh_asset_get_derived(self._h, asset, _ptr(g, _dp), _ptr(m, _dp), _ptr(nn, _dp)))
+            return g, m, nn
+        g = np.zeros((n, 3))
+        _check(lib().dbh_asset_get_derived(self._h, asset, _ptr(g, _dp), None, None))
+        return g
+
+
+@dataclass
+class ContactSurface:
+    """Host copy of one ContactSurface<double> (query_results/contact_surface.h:160-415)."""
+    scene: int
+    id_M: int
+    id_N: int
+    representation: int
+    vertices: np.ndarray            # [V,3] p_WV
+    pressures: np.ndarray           # [V]
+    face_data: np.ndarray           # polygon: |n|v..|...; triangle: [F,3]; indices local to the surface
+    areas: np.ndarray
+    normals: np.ndarray
+    centroids: np.ndarray
+    pressure_at_centroid: np.ndarray
+    grad_eM: Optional[np.ndarray]
+    grad_eN: Optional[np.ndarray]
+    total_area: float
+    centroid: np.ndarray
+    elem_M: np.ndarray              # emitting element of the first-constructed body
+    elem_N: np.ndarray
+    swapped: bool
+
+    @property
+    def num_faces(self) -> int:
+        return len(self.areas)
+
+    def polygons(self) -> List[np.ndarray]:
+        if self.representation == TRIANGLE:
+            return [t for t in self.face_data]
+        out, i, fd = [], 0, self.face_data
+        while i < len(fd):
+            n = fd[i]
+            out.append(fd[i + 1:i + 1 + n])
+            i += n + 1
+        return out
+
+
+class PackedResults:
+    """The packed host buffers of one query (all surfaces of all scenes)."""
+
+    def __init__(self, sizes: ResultSizes):
+        ns, nf, nv = sizes.num_surfaces, sizes.num_faces, sizes.num_vertices
+        self.representation = sizes.representation
+        self.surf_scene = np.zeros(ns, np.int32)
+        self.surf_id_M = np.zeros(ns, np.int64)
+        self.surf_id_N = np.zeros(ns, np.int64)
+        self.surf_face_offset = np.zeros(ns + 1, np.int64)
+        self.surf_vertex_offset = np.zeros(ns + 1, np.int64)
+        self.surf_total_area = np.zeros(ns)
+        self.surf_centroid = np.zeros((ns, 3))
+        self.surf_flags = np.zeros(ns, np.uint8)
+        self.vertices = np.zeros((nv, 3))
+        self.pressures = np.zeros(nv)
+        self.face_data = np.zeros(sizes.face_data_ints, np.int32)
+        self.areas = np.zeros(nf)
+        self.normals = np.zeros((nf, 3))
+        self.centroids = np.zeros((nf, 3))
+        self.pressure_at_centroid = np.zeros(nf)
+        self.grad_eM = np.zeros((nf, 3))
+        self.grad_eN = np.zeros((nf, 3))
+        self.elem_M = np.zeros(nf, np.int32)
+        self.elem_N = np.zeros(nf, np.int32)
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, k).nbytes for k in vars(self) if isinstance(getattr(self, k), np.ndarray))
+
+    def c_struct(self) -> ResultBuffers:
+        b = ResultBuffers()
+        for name, t in ResultBuffers._fields_:
+            setattr(b, name, _ptr(getattr(self, name), t))
+        return b
+
+    @property
+    def num_surfaces(self) -> int:
+        return len(self.surf_scene)
+
+    def surfaces(self) -> List[ContactSurface]:
+        out = []
+        poly = self.representation == POLYGON
+        # face_data offsets for the polygon representation.
+        if poly:
+            nverts = []
+            i = 0
+            fd = self.face_data
+            starts = []
+            while i < len(fd):
+                starts.append(i)
+                i += fd[i] + 1
+            starts.append(len(fd))
+            starts = np.asarray(starts, np.int64)
+        for s in range(self.num_surfaces):
+            f0, f1 = self.surf_face_offset[s], self.surf_face_offset[s + 1]
+            v0, v1 = self.surf_vertex_offset[s], self.surf_vertex_offset[s + 1]
+            flags = int(self.surf_flags[s])
+            if poly:
+                fd = self.face_data[starts[f0]:starts[f1]]
+            else:
+                fd = self.face_data[3 * f0:3 * f1].reshape(-1, 3)
+            out.append(ContactSurface(
+                int(self.surf_scene[s]), int(self.surf_id_M[s]), int(self.surf_id_N[s]), self.representation,
+                self.vertices[v0:v1], self.pressures[v0:v1], fd, self.areas[f0:f1], self.normals[f0:f1],
+                self.centroids[f0:f1], self.pressure_at_centroid[f0:f1],
+                self.grad_eM[f0:f1] if flags & 1 else None, self.grad_eN[f0:f1] if flags & 2 else None,
+                float(self.surf_total_area[s]), self.surf_centroid[s], self.elem_M[f0:f1], self.elem_N[f0:f1],
+                bool(flags & 4)))
+        return out
+
+
+class SceneBatch:
+    """Registration state of many independent scenes + the batched query.
+
+    Mirrors the ProximityEngine calls on this path: geometries are added with
+    an asset (their hydroelastic representation), a GeometryId and an anchored
+    flag (AddDynamicGeometry / AddAnchoredGeometry, proximity_engine.h:122-133);
+    `excluded` lists filtered pairs (collision_filter.h:158).
+    """
+
+    def __init__(self, ctx: Context, scene_offsets, geom_asset, geom_id, geom_anchored=None, excluded=None):
+        self.ctx = ctx
+        so, ga, gi = _i(scene_offsets), _i(geom_asset), np.ascontiguousarray(geom_id, np.int64)
+        anch = np.ascontiguousarray(geom_anchored if geom_anchored is not None else np.zeros(len(ga)), np.uint8)
+        ex = _i(excluded if excluded is not None else np.zeros((0, 2))).reshape(-1, 2)
+        self._h = C.c_void_p()
+        _check(lib().dbh_batch_create(ctx._h, len(so) - 1, _ptr(so, _ip), _ptr(ga, _ip), _ptr(gi, _lp),
+                                      _ptr(anch, _bp), len(ex), _ptr(ex, _ip), C.byref(self._h)))
+        self.num_scenes = len(so) - 1
+        self.num_geometries = len(ga)
+        self.scene_offsets, self.geom_asset, self.geom_id = so, ga, gi
+        self._keep = None
+        self._grow = 0
+
+    @staticmethod
+    def replicated(ctx: Context, num_scenes: int, assets: Sequence[int], ids: Sequence[int], anchored=None,
+                   excluded_local=None) -> "SceneBatch":
+        """num_scenes instances of one scene template (geometries listed once)."""
+        g = len(assets)
+        so = np.arange(num_scenes + 1, dtype=np.int32) * g
+        ga = np.tile(_i(assets), num_scenes)
+        gi = np.tile(np.asarray(ids, np.int64), num_scenes)
+        an = np.tile(np.asarray(anchored if anchored is not None else np.zeros(g), np.uint8), num_scenes)
+        ex = None
+        if excluded_local is not None and len(excluded_local):
+            e = _i(excluded_local).reshape(-1, 2)
+            ex = (e[None, :, :] + (np.arange(num_scenes, dtype=np.int32) * g)[:, None, None]).reshape(-1, 2)
+        return SceneBatch(ctx, so, ga, gi, an, ex)
+
+    def close(self):
+        if self._h:
+            lib().dbh_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> BatchInfo:
+        out = BatchInfo()
+        _check(lib().dbh_batch_get_info(self._h, C.byref(out)))
+        return out
+
+    def set_capacity(self, bv_pairs: int = 0, element_pairs: int = 0, faces: int = 0):
+        _check(lib().dbh_batch_set_capacity(self._h, bv_pairs, element_pairs, faces))
+
+    def enable_timing(self, on: bool = True):
+        _check(lib().dbh_batch_enable_timing(self._h, int(on)))
+
+    def set_poses(self, X_WGs):
+        """UpdateWorldPoses: [G,12] host array (R column-major, then p)."""
+        P = _d(X_WGs).reshape(-1, 12)
+        if len(P) != self.num_geometries:
+            raise ValueError(f"expected {self.num_geometries} poses, got {len(P)}")
+        self._keep = P  # the H2D copy is asynchronous
+        _check(lib().dbh_batch_set_poses_host(self._h, _ptr(P, _dp)))
+
+    def set_poses_device(self, device_ptr: int):
+        _check(lib().dbh_batch_set_poses_device(self._h, C.c_void_p(device_ptr)))
+
+    def query(self, representation: int = POLYGON, kind: int = STRICT, scene_stats_device_ptr: int = 0):
+        _check(lib().dbh_batch_query(self._h, representation, kind,
+                                     C.c_void_p(scene_stats_device_ptr) if scene_stats_device_ptr else None))
+
+    def sync(self):
+        _check(lib().dbh_batch_sync(self._h))
+
+    def run(self, representation: int = POLYGON, kind: int = STRICT, scene_stats_device_ptr: int = 0,
+            max_grow: int = 8):
+        """query + sync, doubling device work-list capacities on DBH_ERR_CAPACITY."""
+        cap = None
+        for _ in range(max_grow + 1):
+            self.query(representation, kind, scene_stats_device_ptr)
+            try:
+                self.sync()
+                return
+            except HydroError as e:
+                if e.status != ERR_CAPACITY:
+                    raise
+                if cap is None:
+                    cap = self._default_caps()
+                cap = [2 * c for c in cap]
+                self.set_capacity(*cap)
+        raise HydroError(ERR_CAPACITY, "device work lists still overflow after growing")
+
+    def _default_caps(self):
+        inf = self.info()
+        est = max(1 << 16, 4 * inf.num_geometry_pairs * 1024)
+        return [est, est, est // 2]
+
+    def sizes(self) -> ResultSizes:
+        out = ResultSizes()
+        _check(lib().dbh_batch_result_sizes(self._h, C.byref(out)))
+        return out
+
+    def stats(self) -> Dict[str, float]:
+        s = Stats()
+        _check(lib().dbh_batch_stats(self._h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in Stats._fields_ if n != "reserved"}
+
+    def copy_results(self, into: Optional[PackedResults] = None) -> PackedResults:
+        res = into if into is not None else PackedResults(self.sizes())
+        bufs = res.c_struct()
+        _check(lib().dbh_batch_copy_results(self._h, C.byref(bufs)))
+        return res
+
+    def compute_contact_surfaces(self, X_WGs, representation: int = POLYGON) -> List[List[ContactSurface]]:
+        """ComputeContactSurfaces for every scene: per scene a list sorted by (id_M, id_N)."""
+        self.set_poses(X_WGs)
+        self.run(representation, STRICT)
+        out: List[List[ContactSurface]] = [[] for _ in range(self.num_scenes)]
+        for s in self.copy_results().surfaces():
+            out[s.scene].append(s)
+        return out
+
+    def candidates(self, kind: int) -> np.ndarray:
+        """(geometry pair, element of first body, element of second body) triples; kind 0 tet-tri, 1 tet-tet."""
+        n = C.c_int64()
+        _check(lib().dbh_batch_copy_candidates(self._h, kind, None, C.byref(n)))
+        out = np.zeros((n.value, 3), np.int32)
+        if n.value:
+            _check(lib().dbh_batch_copy_candidates(self._h, kind, _ptr(out, _ip), C.byref(n)))
+        return out
+
+    def geometry_pairs(self) -> np.ndarray:
+        """[P,4] = (scene, flat geom of first body, flat geom of second body, kind)."""
+        out = np.zeros((self.info().num_geometry_pairs, 4), np.int32)
+        if len(out):
+            _check(lib().dbh_batch_copy_geometry_pairs(self._h, _ptr(out, _ip)))
+        return out
+
+    def kernel_times_ms(self) -> Dict[str, float]:
+        t = (C.c_float * 8)()
+        _check(lib().dbh_batch_kernel_times_ms(self._h, t))
+        keys = ["pose_root", "traverse", "clip_tet_tri", "clip_tet_tet", "scan", "pack", "surface", "total"]
+        return dict(zip(keys, [float(x) for x in t]))
+
+    def stream(self) -> int:
+        return int(lib().dbh_batch_stream(self._h) or 0)

@@ -1,0 +1,240 @@
+/* drake_b200_hydro.h — C-ABI of the B200 hydroelastic contact-surface back end.
+ *
+ * This is the drop-in boundary for the hot path behind
+ *   geometry::internal::ProximityEngine<double>::ComputeContactSurfaces{,WithFallback}
+ *   (reference: geometry/proximity_engine.h:309-326, proximity_engine.cc:905-977)
+ * batched over many independent scenes. Plain pointers and sizes only; every
+ * function returns a dbh_status (0 = ok) and no exception crosses the boundary
+ * (the reference reports errors by throwing: proximity_engine.cc:1347-1397).
+ *
+ * Conventions
+ *  - RigidTransform = 12 doubles: rotation column-major (9) then translation
+ *    (3) — the memory layout of math::RigidTransform<double>
+ *    (math/rigid_transform.h:1004-1007, math/rotation_matrix.h:1185).
+ *  - Geometry ids are int64 (GeometryId::get_value()).
+ *  - All meshes are expressed in their geometry frame; all results in World.
+ *  - Representation: 0 = triangles, 1 = polygons
+ *    (HydroelasticContactRepresentation, query_results/contact_surface.h:24).
+ */
+#ifndef DRAKE_B200_HYDRO_H_
+#define DRAKE_B200_HYDRO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t dbh_status;
+enum {
+  DBH_OK = 0,
+  DBH_ERR_INVALID_ARGUMENT = 1,
+  DBH_ERR_CUDA = 2,               /* a CUDA runtime call failed; see dbh_last_error() */
+  DBH_ERR_NO_DEVICE = 3,          /* no usable sm_100 device: there is no CPU fallback */
+  DBH_ERR_DEGENERATE_FIELD = 4,   /* MeshFieldLinear kOkOrThrow: a tetrahedron has |volume| <= eps
+                                     (volume_mesh.h:430-434) */
+  DBH_ERR_CAPACITY = 5,           /* a work list overflowed its device buffer; enlarge with
+                                     dbh_batch_set_capacity() and re-run */
+  DBH_ERR_RIGID_RIGID = 6,        /* ContactSurfaceResult::kRigidRigid (hydroelastic_calculator.h:39-57)
+                                     in ComputeContactSurfaces (not raised by the WithFallback query) */
+  DBH_ERR_UNSUPPORTED = 7,        /* ContactSurfaceResult::kUnsupported: geometry without a
+                                     hydroelastic representation */
+  DBH_ERR_NOT_READY = 8,          /* results requested before a query completed */
+  DBH_ERR_PLANE_NORMAL = 9        /* Plane ctor: |normal| < 1e-10 (plane.cc:16-29) */
+};
+
+enum { DBH_TRIANGLE = 0, DBH_POLYGON = 1 };
+/* HydroelasticType (geometry/proximity_properties.h:84-88). */
+enum { DBH_UNDEFINED = 0, DBH_RIGID = 1, DBH_COMPLIANT = 2 };
+/* Query flavour. */
+enum { DBH_QUERY_STRICT = 0 /* ComputeContactSurfaces */, DBH_QUERY_WITH_FALLBACK = 1 };
+
+typedef struct dbh_context dbh_context;
+typedef struct dbh_batch dbh_batch;
+
+/* -- (1) context: one per device (one process per GPU). ---------------------- */
+dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out);
+void dbh_context_destroy(dbh_context* ctx);
+/* Thread-local message of the last failing call. */
+const char* dbh_last_error(void);
+/* ABI version of this library (major * 1000 + minor). */
+int32_t dbh_abi_version(void);
+
+/* -- (2) mesh assets (replaces hydroelastic::Geometries::MaybeAddGeometry,
+ *        hydroelastic_internal.cc:94-108,145-153): uploads the mesh, derives the
+ *        per-tetrahedron field gradient / value-at-origin / inward normals
+ *        (mesh_field_linear.h:440-509, volume_mesh.cc:91-138) or per-triangle
+ *        normals (triangle_surface_mesh.h:452-487), and builds the BVH. -------- */
+typedef struct dbh_asset_info {
+  int32_t type;          /* DBH_RIGID or DBH_COMPLIANT */
+  int32_t num_vertices;
+  int32_t num_elements;
+  int32_t num_bvh_nodes;
+  int32_t bvh_height;
+  int32_t reserved[3];
+  double root_center[3];
+  double root_half_width[3];
+} dbh_asset_info;
+
+/* VolumeMesh<double> + VolumeMeshFieldLinear<double,double>: verts [nv*3],
+ * tets [nt*4], pressure [nv]. */
+dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t num_vertices, const double* vertices,
+                                       int32_t num_tets, const int32_t* tets, const double* pressure,
+                                       int32_t* asset_out);
+/* TriangleSurfaceMesh<double>: verts [nv*3], tris [nt*3]. */
+dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t num_vertices, const double* vertices,
+                                   int32_t num_tris, const int32_t* tris, int32_t* asset_out);
+dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out);
+/* Copies the derived per-element data back (for tests): compliant: gradients
+ * [nt*3], values_at_Mo [nt], inward_normals [nt*12]; rigid: normals [nt*3].
+ * Any pointer may be NULL. */
+dbh_status dbh_asset_get_derived(dbh_context* ctx, int32_t asset, double* gradients_or_normals,
+                                 double* values_at_Mo, double* inward_normals);
+
+/* -- (3) scene batch (the SceneGraph / ProximityEngine registration state for
+ *        many independent scenes: AddDynamicGeometry / AddAnchoredGeometry /
+ *        collision_filter(), proximity_engine.h:87,122-133). ------------------- */
+/* scene_offsets [num_scenes+1] is a CSR over the flat geometry arrays (length
+ * G = scene_offsets[num_scenes]). geom_asset: asset handle or -1 for a geometry
+ * with no hydroelastic representation (DBH_UNDEFINED). geom_anchored: 0/1.
+ * excluded_pairs [num_excluded*2]: flat geometry indices filtered by the
+ * CollisionFilter (collision_filter.h:158). */
+dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t* scene_offsets,
+                            const int32_t* geom_asset, const int64_t* geom_id, const uint8_t* geom_anchored,
+                            int32_t num_excluded, const int32_t* excluded_pairs, dbh_batch** out);
+void dbh_batch_destroy(dbh_batch* batch);
+/* Device work-list capacities (entries). 0 keeps the current value. */
+dbh_status dbh_batch_set_capacity(dbh_batch* batch, int64_t max_bv_pairs_per_level, int64_t max_element_pairs,
+                                  int64_t max_faces);
+
+typedef struct dbh_batch_info {
+  int32_t num_scenes;
+  int32_t num_geometries;
+  int32_t num_geometry_pairs;      /* pairs that survive the filter / anchored rule (static) */
+  int32_t num_soft_rigid_pairs;
+  int32_t num_soft_soft_pairs;
+  int32_t num_rigid_rigid_pairs;
+  int32_t num_unsupported_pairs;
+  int32_t max_traversal_levels;
+} dbh_batch_info;
+dbh_status dbh_batch_get_info(dbh_batch* batch, dbh_batch_info* out);
+
+/* -- (4) poses (UpdateWorldPoses, proximity_engine.h:226-227): X_WG for every
+ *        geometry, [G*12]. The host variant copies H2D on the batch stream;
+ *        the device variant adopts a caller-owned device pointer (no copy). --- */
+dbh_status dbh_batch_set_poses_host(dbh_batch* batch, const double* X_WGs);
+dbh_status dbh_batch_set_poses_device(dbh_batch* batch, const double* X_WGs_device);
+
+/* -- (5) the query: ComputeContactSurfaces(representation, X_WGs) for every
+ *        scene of the batch. Asynchronous on the batch stream;
+ *        dbh_batch_sync() waits and reports device-side failures. per_scene_stats_device
+ *        (optional, may be NULL): caller-owned device buffer [num_scenes * 6]
+ *        int64 = {geometry pairs tested, BV-pair tests, element pairs, faces,
+ *        surfaces, reserved}, written by the pack kernel (the NCCL-gathered
+ *        payload of the multi-GPU path). -------------------------------------- */
+dbh_status dbh_batch_query(dbh_batch* batch, int32_t representation, int32_t query_kind,
+                           int64_t* per_scene_stats_device);
+dbh_status dbh_batch_sync(dbh_batch* batch);
+/* The CUDA stream (cudaStream_t) the batch launches on. */
+void* dbh_batch_stream(dbh_batch* batch);
+
+/* -- (6) sizes of the last completed query. --------------------------------- */
+typedef struct dbh_result_sizes {
+  int64_t num_surfaces;
+  int64_t num_faces;       /* polygons (DBH_POLYGON) or triangles (DBH_TRIANGLE) */
+  int64_t num_vertices;
+  int64_t num_polygons;    /* contact polygons (== num_faces for DBH_POLYGON) */
+  int64_t face_data_ints;  /* polygon rep: length of the concatenated face_data
+                              (polygon_surface_mesh.h:141-185); triangle rep: 3 * num_faces */
+  int32_t representation;
+  int32_t reserved;
+} dbh_result_sizes;
+dbh_status dbh_batch_result_sizes(dbh_batch* batch, dbh_result_sizes* out);
+
+/* -- (7) copy-out of packed results into caller buffers (host). Everything a
+ *        ContactSurface<double> exposes (query_results/contact_surface.h:160-415).
+ *        Surfaces are ordered by (scene, id_M, id_N) with id_M < id_N
+ *        (proximity_engine.cc:157-162,932; contact_surface.cc:39-41). Faces and
+ *        vertices of a surface are contiguous. Any pointer may be NULL. -------- */
+typedef struct dbh_result_buffers {
+  /* per surface [num_surfaces] */
+  int32_t* surf_scene;
+  int64_t* surf_id_M;
+  int64_t* surf_id_N;
+  int64_t* surf_face_offset;    /* [num_surfaces+1] into the face arrays */
+  int64_t* surf_vertex_offset;  /* [num_surfaces+1] into the vertex arrays */
+  double* surf_total_area;      /* mesh.total_area() */
+  double* surf_centroid;        /* [num_surfaces*3] mesh.centroid() in World */
+  uint8_t* surf_flags;          /* bit0: HasGradE_M, bit1: HasGradE_N, bit2: M/N swapped */
+  /* per vertex [num_vertices] */
+  double* vertices;             /* [num_vertices*3] p_WV */
+  double* pressures;            /* e_MN at each vertex */
+  /* per face [num_faces] */
+  int32_t* face_data;           /* polygon: |n|v0..vn-1| per face, indices local to the surface;
+                                   triangle: 3 local vertex indices per face */
+  double* areas;
+  double* normals;              /* [num_faces*3], unit, out of N into M */
+  double* centroids;            /* [num_faces*3] */
+  double* pressure_at_centroid; /* poly_e_MN().EvaluateCartesian(f, centroid) or
+                                   tri_e_MN().Evaluate(f, (1/3,1/3,1/3)) */
+  double* grad_eM;              /* [num_faces*3] EvaluateGradE_M_W; zeros where !HasGradE_M */
+  double* grad_eN;              /* [num_faces*3] */
+  int32_t* elem_M;              /* emitting element of the first-constructed body (tet of S / tet0) */
+  int32_t* elem_N;              /* emitting element of the second (triangle of R / tet1) */
+} dbh_result_buffers;
+dbh_status dbh_batch_copy_results(dbh_batch* batch, const dbh_result_buffers* buffers);
+
+/* Device-resident views of the same arrays for GPU consumers (valid until the
+ * next query). Vector quantities are structure-of-arrays on the device:
+ * component c of item i lives at base[c * stride + i]. */
+typedef struct dbh_device_results {
+  const int32_t* surf_pair;        /* index into the static geometry-pair list */
+  const int64_t* surf_face_offset;
+  const int64_t* surf_vertex_offset;
+  const double* surf_total_area;
+  const double* surf_centroid;     /* SoA, stride = surf_stride */
+  int64_t surf_stride;
+  const double* vertices;          /* SoA x|y|z|pressure, stride = vertex_stride */
+  int64_t vertex_stride;
+  const double* face_f64;          /* SoA planes: area, nx,ny,nz, cx,cy,cz, e_c, gMx..gMz, gNx..gNz */
+  int64_t face_stride;
+  const int32_t* face_i32;         /* SoA planes: pair, elem_M, elem_N, nverts, vertex_begin */
+} dbh_device_results;
+dbh_status dbh_batch_device_results(dbh_batch* batch, dbh_device_results* out);
+
+/* -- (8) statistics of the last completed query. ---------------------------- */
+typedef struct dbh_stats {
+  int64_t geometry_pairs_tested;   /* potential pairs whose poses were composed */
+  int64_t geometry_pairs_overlapping; /* root boxes overlap */
+  int64_t bv_pair_tests;
+  int64_t tet_tri_pairs;           /* candidate element pairs narrow-phased */
+  int64_t tet_tet_pairs;
+  int64_t polygons;
+  int64_t faces;
+  int64_t vertices;
+  int64_t surfaces;
+  int64_t algorithmic_bytes;       /* SURVEY.md §8(d) accounting */
+  double total_area;
+  double reserved[3];
+} dbh_stats;
+dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
+
+/* Candidate element pairs of the last query (for parity tests): triples
+ * (geometry pair index, element of first body, element of second body).
+ * kind 0 = tet-tri list, 1 = tet-tet list. Pass out == NULL to get the count. */
+dbh_status dbh_batch_copy_candidates(dbh_batch* batch, int32_t kind, int32_t* out_triples, int64_t* count);
+/* Static geometry-pair list: per pair {scene, flat geom index of first body
+ * (S or M), flat geom index of second body (R or N), kind (0 soft-rigid, 1
+ * soft-soft, 2 rigid-rigid, 3 unsupported)}. out [num_geometry_pairs*4]. */
+dbh_status dbh_batch_copy_geometry_pairs(dbh_batch* batch, int32_t* out);
+
+/* Per-kernel device time of the last query in milliseconds (CUDA events on
+ * the batch stream): {pose+root, traversal, clip tet-tri, clip tet-tet, scan,
+ * pack, reduce, total}. Only recorded when enabled (adds event records). */
+dbh_status dbh_batch_enable_timing(dbh_batch* batch, int32_t enabled);
+dbh_status dbh_batch_kernel_times_ms(dbh_batch* batch, float* out8);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* DRAKE_B200_HYDRO_H_ */

@@ -1,0 +1,80 @@
+"""Shared helpers for the GPU-vs-oracle parity tests (test infrastructure)."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import ho
+
+REL_TOL = 1e-10  # north_star: centroids, areas, normals, pressures within 1e-10 relative (fp64)
+
+
+def register_compliant(ctx, mesh: "ho.VolumeMesh", fld: "ho.VolumeField") -> int:
+    return ctx.register_compliant_mesh(mesh.verts, mesh.tets, fld.values)
+
+
+def register_rigid(ctx, mesh: "ho.TriMesh") -> int:
+    return ctx.register_rigid_mesh(mesh.verts, mesh.tris)
+
+
+def face_keys(elem_a, elem_b):
+    return np.asarray(elem_a, np.int64) * (1 << 32) + np.asarray(elem_b, np.int64)
+
+
+def assert_close(name, got, want, scale=None, tol=REL_TOL):
+    got, want = np.asarray(got, float), np.asarray(want, float)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} vs {want.shape}"
+    if got.size == 0:
+        return
+    s = np.max(np.abs(want)) if scale is None else scale
+    s = max(s, 1e-300)
+    err = np.max(np.abs(got - want)) / s
+    assert err <= tol, f"{name}: relative error {err:.3e} > {tol:.1e}"
+
+
+def polygon_vertex_lists(surface):
+    """Per-face vertex arrays in winding order."""
+    return [surface.vertices[idx] for idx in surface.polygons()]
+
+
+def compare_surface(gpu, ora, check_bitwise_keys=True):
+    """gpu: drake_b200.ContactSurface; ora: oracle ho.Surface. Faces are matched by their emitting
+    element pair (the reference's own notion of surface equality, field_intersection_test.cc:397-421);
+    within a polygon's triangle fan the order is the builder's."""
+    assert (gpu.id_M, gpu.id_N) == (ora.id_M, ora.id_N)
+    assert gpu.representation == ora.rep
+    assert gpu.num_faces == ora.num_faces, f"face count {gpu.num_faces} vs {ora.num_faces}"
+    assert len(gpu.vertices) == len(ora.vertices)
+    gk, ok = face_keys(gpu.elem_M, gpu.elem_N), face_keys(ora.elem_first, ora.elem_second)
+    gorder, oorder = np.argsort(gk, kind="stable"), np.argsort(ok, kind="stable")
+    np.testing.assert_array_equal(gk[gorder], ok[oorder])  # bit-exact emitted element-pair multiset
+    L = max(np.max(np.abs(ora.vertices)), 1e-300)
+    assert_close("areas", gpu.areas[gorder], ora.areas[oorder], scale=max(ora.areas.max(), 1e-300))
+    assert_close("normals", gpu.normals[gorder], ora.normals[oorder], scale=1.0)
+    assert_close("centroids", gpu.centroids[gorder], ora.centroids[oorder], scale=L)
+    pscale = max(np.max(np.abs(ora.pressures)), 1e-300)
+    assert_close("pressure_at_centroid", gpu.pressure_at_centroid[gorder], ora.e_centroid[oorder], scale=pscale)
+    assert (gpu.grad_eM is None) == (ora.grad_eM is None)
+    assert (gpu.grad_eN is None) == (ora.grad_eN is None)
+    if ora.grad_eM is not None:
+        assert_close("grad_eM", gpu.grad_eM[gorder], ora.grad_eM[oorder])
+    if ora.grad_eN is not None:
+        assert_close("grad_eN", gpu.grad_eN[gorder], ora.grad_eN[oorder])
+    # Vertices and per-vertex pressures, polygon by polygon in winding order.
+    gp, op = gpu.polygons(), ora.polygons()
+    for a, b in zip(gorder, oorder):
+        ia, ib = np.asarray(gp[a]), np.asarray(op[b])
+        assert len(ia) == len(ib)
+        assert_close("vertices", gpu.vertices[ia], ora.vertices[ib], scale=L)
+        assert_close("pressures", gpu.pressures[ia], ora.pressures[ib], scale=pscale)
+    assert_close("total_area", gpu.total_area, ora.total_area)
+    assert_close("surface centroid", gpu.centroid, ora.centroid, scale=L)
+
+
+def random_pose(rng, translation_scale=1.0, center=(0, 0, 0)):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return ho.xform(R, np.asarray(center, float) + translation_scale * rng.uniform(-1, 1, size=3))

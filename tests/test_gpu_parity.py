@@ -1,0 +1,260 @@
+"""GPU-vs-oracle parity through the C-ABI (run on the B200 box with -m gpu)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ho
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import drake_b200 as db
+    return db.Context(0)
+
+
+def sphere_kat_scene():
+    R = 0.25
+    X_WA = ho.xform(ho.rpy_matrix(math.pi, 0, 0))
+    X_WB = ho.xform(None, [0, 0, -(R + R) + 0.125])
+    soft = ho.VolumeMesh.sphere(R, 0.25)
+    return R, X_WA, X_WB, soft, ho.VolumeField.sphere(soft, R, 1e8)
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+@pytest.mark.parametrize("ids", [(1, 2), (2, 1)])
+def test_calculator_kat_soft_rigid(ctx, rep, ids):
+    """hydroelastic_calculator_test.cc:320-355: 100 triangles / 28 polygons, both id orders."""
+    import drake_b200 as db
+    R, X_WA, X_WB, soft, fld = sphere_kat_scene()
+    rigid = ho.TriMesh.sphere(R, 0.1)
+    a_s, a_r = parity.register_compliant(ctx, soft, fld), parity.register_rigid(ctx, rigid)
+    batch = db.SceneBatch(ctx, [0, 2], [a_s, a_r], list(ids))
+    got = batch.compute_contact_surfaces(np.stack([X_WA, X_WB]), rep)[0]
+    assert len(got) == 1
+    assert got[0].num_faces == (100 if rep == ho.KTRIANGLE else 28)
+    want = ho.soft_rigid(soft, fld, rigid, X_WA, X_WB, ids[0], ids[1], rep)
+    parity.compare_surface(got[0], want)
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+def test_calculator_kat_soft_soft(ctx, rep):
+    """hydroelastic_calculator_test.cc:467-504: 12 triangles / 4 polygons."""
+    import drake_b200 as db
+    R, X_WA, X_WB, soft, fld = sphere_kat_scene()
+    a = parity.register_compliant(ctx, soft, fld)
+    batch = db.SceneBatch(ctx, [0, 2], [a, a], [1, 2])
+    got = batch.compute_contact_surfaces(np.stack([X_WA, X_WB]), rep)[0]
+    assert len(got) == 1
+    assert got[0].num_faces == (12 if rep == ho.KTRIANGLE else 4)
+    want = ho.soft_soft(soft, fld, soft, fld, X_WA, X_WB, 1, 2, rep)
+    parity.compare_surface(got[0], want)
+
+
+def test_octagon_and_heptagon_literals(ctx):
+    """field_intersection_test.cc:196-259 and mesh_intersection_test.cc:660-709 through the full GPU path."""
+    import drake_b200 as db
+    m0 = ho.VolumeMesh.from_arrays([[2, 0, 2], [-2, 0, 2], [0, 2, -2], [0, -2, -2]], [[0, 1, 2, 3]])
+    f0 = ho.VolumeField.from_values(m0, [8e4, 4e4, 4e4, 0])
+    m1 = ho.VolumeMesh.from_arrays([[1.5, 1.5, 2.5], [-1.5, -1.5, 2.5], [-1.5, 1.5, -2.5], [1.5, -1.5, -2.5]],
+                                   [[0, 1, 2, 3]])
+    f1 = ho.VolumeField.from_values(m1, [7e4, 1e4, 4e4, 4e4])
+    a0, a1 = parity.register_compliant(ctx, m0, f0), parity.register_compliant(ctx, m1, f1)
+    batch = db.SceneBatch(ctx, [0, 2], [a0, a1], [1, 2])
+    s = batch.compute_contact_surfaces(np.stack([ho.IDENTITY, ho.IDENTITY]), ho.KPOLYGON)[0][0]
+    assert s.num_faces == 1 and s.face_data[0] == 8
+    expect = np.array([[-0.5, -1, 0], [0.5, -1, 0], [1, -0.5, 0], [1, 0.5, 0], [0.5, 1, 0], [-0.5, 1, 0], [-1, 0.5, 0],
+                       [-1, -0.5, 0]])
+    np.testing.assert_allclose(s.vertices[s.polygons()[0]], expect, rtol=0, atol=1e-14)
+    assert abs(s.total_area - 3.5) < 1e-14
+    # Heptagon: a rigid triangle through a tet whose pressure grows with z... use a field with
+    # gradient along +z so the face normal (+z) passes the filter.
+    ft = ho.VolumeField.from_values(m0, [2.0, 2.0, -2.0, -2.0])  # p = z
+    tri = ho.TriMesh.from_arrays([[1.5, 1.5, 0], [-1.5, 0, 0], [0, -1.5, 0]], [[0, 1, 2]])
+    at, ar = parity.register_compliant(ctx, m0, ft), parity.register_rigid(ctx, tri)
+    batch = db.SceneBatch(ctx, [0, 2], [at, ar], [1, 2])
+    s = batch.compute_contact_surfaces(np.stack([ho.IDENTITY, ho.IDENTITY]), ho.KPOLYGON)[0][0]
+    assert s.num_faces == 1 and s.face_data[0] == 7
+    hept = np.array([[1, 1, 0], [0.5, 1, 0], [-1, 0.25, 0], [-1, -0.5, 0], [-0.5, -1, 0], [0.25, -1, 0], [1, 0.5, 0]])
+    got = s.vertices[s.polygons()[0]]
+    k = int(np.argmin(np.linalg.norm(got - hept[0], axis=1)))
+    np.testing.assert_allclose(np.roll(got, -k, axis=0), hept, rtol=0, atol=1e-14)
+
+
+def test_asset_derived_quantities_bitwise(ctx):
+    """Per-tet gradient / value-at-origin / inward normals and per-triangle normals are bit-identical
+    to the oracle's (mesh_field_linear.h:440-509, volume_mesh.cc:91-138)."""
+    mS = ho.VolumeMesh.ellipsoid(3.01, 3.5, 4.0, 2.0, dense=True)
+    fS = ho.VolumeField.ellipsoid(mS, 3.01, 3.5, 4.0, 1e5)
+    a = parity.register_compliant(ctx, mS, fS)
+    g, mo, nn = ctx.asset_derived(a)
+    _, og, omo, _ = fS.arrays()
+    np.testing.assert_array_equal(g, og)
+    np.testing.assert_array_equal(mo, omo)
+    np.testing.assert_array_equal(nn, mS.arrays()[2])
+    mR = ho.TriMesh.sphere(3.0, 2.0)
+    np.testing.assert_array_equal(ctx.asset_derived(parity.register_rigid(ctx, mR)), mR.arrays()[2])
+
+
+BENCH_ARGS = [(0, 4, 0), (1, 4, 0), (2, 4, 0), (3, 4, 0), (2, 0, 0), (2, 1, 0), (2, 2, 0), (2, 3, 0), (2, 4, 1),
+              (2, 4, 2), (2, 4, 3), (2, 3, 1), (2, 2, 2)]
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+def test_config1_mesh_intersection_benchmark(ctx, rep):
+    """BASELINE config 1 (mesh_intersection_benchmark.cc:153-271): all 13 argument triples in one
+    batch of 13 scenes; candidate sets bit-exact against the leaf predicate; surfaces to 1e-10."""
+    import drake_b200 as db
+    hints = [4.0, 3.0, 2.0, 1.0]
+    trans = [(7, 7, 7), (4, 4, 4), (3.5, 3.5, 3.5), (1.2, 1.2, 1.2), (0, 0, 0)]
+    assets, meshes = {}, {}
+    for res in range(4):
+        mS = ho.VolumeMesh.ellipsoid(3.01, 3.5, 4.0, hints[res], dense=True)
+        fS = ho.VolumeField.ellipsoid(mS, 3.01, 3.5, 4.0, 1e5)
+        mR = ho.TriMesh.sphere(3.0, hints[res])
+        meshes[res] = (mS, fS, mR)
+        assets[res] = (parity.register_compliant(ctx, mS, fS), parity.register_rigid(ctx, mR))
+    geom_asset, poses = [], []
+    for res, ov, rot in BENCH_ARGS:
+        geom_asset += list(assets[res])
+        poses += [ho.IDENTITY, ho.xform(ho.angle_axis_matrix(rot / 3.0 * math.pi / 4, [1, 1, 1]), trans[ov])]
+    n = len(BENCH_ARGS)
+    batch = db.SceneBatch(ctx, np.arange(n + 1) * 2, geom_asset, [1, 2] * n)
+    got = batch.compute_contact_surfaces(np.stack(poses), rep)
+    cand = batch.candidates(0)
+    for k, (res, ov, rot) in enumerate(BENCH_ARGS):
+        mS, fS, mR = meshes[res]
+        want = ho.soft_rigid(mS, fS, mR, poses[2 * k], poses[2 * k + 1], 1, 2, rep)
+        if want is None:
+            assert got[k] == []
+        else:
+            assert len(got[k]) == 1
+            parity.compare_surface(got[k][0], want)
+        want_c, _ = ho.candidates(mS, mR, poses[2 * k + 1], ho.MODE_BRUTE)
+        mine = cand[cand[:, 0] == k][:, 1:]
+        mine = mine[np.lexsort((mine[:, 1], mine[:, 0]))]
+        np.testing.assert_array_equal(mine, want_c)  # bit-exact candidate element-pair set
+
+
+def test_config2_compliant_compliant(ctx):
+    """BASELINE config 2 (compliant_mesh_intersection_benchmark.cc:112-202): ellipsoid x sphere,
+    dense, resolutions 0..2 x overlaps 0..3, plus two dense spheres at random poses."""
+    import drake_b200 as db
+    hints = [4.0, 3.0, 2.0]
+    trans = [(7, 7, 7), (4, 4, 4), (3.5, 3.5, 3.5), (1.2, 1.2, 1.2)]
+    geom_asset, poses, meshes = [], [], []
+    for h in hints:
+        mS = ho.VolumeMesh.ellipsoid(3.01, 3.5, 4.0, h, dense=True)
+        fS = ho.VolumeField.ellipsoid(mS, 3.01, 3.5, 4.0, 1e5)
+        mR = ho.VolumeMesh.sphere(3.0, h, dense=True)
+        fR = ho.VolumeField.sphere(mR, 3.0, 1e5)
+        aS, aR = parity.register_compliant(ctx, mS, fS), parity.register_compliant(ctx, mR, fR)
+        for t in trans:
+            geom_asset += [aS, aR]
+            poses += [ho.IDENTITY, ho.xform(None, t)]
+            meshes.append((mS, fS, mR, fR))
+    rng = np.random.default_rng(11)
+    mA = ho.VolumeMesh.sphere(3.0, 1.0, dense=True)
+    fA = ho.VolumeField.sphere(mA, 3.0, 1e5)
+    aA = parity.register_compliant(ctx, mA, fA)
+    for _ in range(3):
+        geom_asset += [aA, aA]
+        d = rng.normal(size=3)
+        poses += [parity.random_pose(rng, 0.5), parity.random_pose(rng, 0.2, center=4.5 * d / np.linalg.norm(d))]
+        meshes.append((mA, fA, mA, fA))
+    n = len(meshes)
+    batch = db.SceneBatch(ctx, np.arange(n + 1) * 2, geom_asset, [1, 2] * n)
+    got = batch.compute_contact_surfaces(np.stack(poses), ho.KPOLYGON)
+    cand = batch.candidates(1)
+    nonnull = 0
+    for k, (mS, fS, mR, fR) in enumerate(meshes):
+        want = ho.soft_soft(mS, fS, mR, fR, poses[2 * k], poses[2 * k + 1], 1, 2, ho.KPOLYGON, mode=ho.MODE_TREE)
+        if want is None:
+            assert got[k] == []
+        else:
+            nonnull += 1
+            parity.compare_surface(got[k][0], want)
+        X_MN = ho.invert_and_compose(poses[2 * k], poses[2 * k + 1])
+        want_c, _ = ho.candidates(mS, mR, X_MN, ho.MODE_TREE)
+        mine = cand[cand[:, 0] == k][:, 1:]
+        mine = mine[np.lexsort((mine[:, 1], mine[:, 0]))]
+        np.testing.assert_array_equal(mine, want_c)
+    assert nonnull >= 8
+
+
+def test_scene_engine_contract(ctx):
+    """geometry/test/proximity_engine_test.cc:1956-2249: ordering, filter, anchored x anchored,
+    rigid-rigid error in the strict query and not in WithFallback."""
+    import drake_b200 as db
+    R = 0.25
+    soft = ho.VolumeMesh.sphere(R, 0.25)
+    fld = ho.VolumeField.sphere(soft, R, 1e8)
+    rigid = ho.TriMesh.sphere(R, 0.1)
+    a_s, a_r = parity.register_compliant(ctx, soft, fld), parity.register_rigid(ctx, rigid)
+    ids = [30, 10, 20]
+    poses = np.stack([ho.xform(None, [0, 0.2, 0.2]), ho.xform(None, [0, 0, 0]), ho.xform(None, [0, 0, 0.375])])
+    batch = db.SceneBatch(ctx, [0, 3], [a_s, a_r, a_s], ids)
+    got = batch.compute_contact_surfaces(poses, db.POLYGON)[0]
+    assert [(s.id_M, s.id_N) for s in got] == [(10, 20), (10, 30), (20, 30)]
+    osc = ho.Scene()
+    osc.add_compliant(30, soft, fld)
+    osc.add_rigid(10, rigid)
+    osc.add_compliant(20, soft, fld)
+    want, _ = osc.compute(poses[[1, 2, 0]], ho.KPOLYGON)
+    for g, w in zip(got, want):
+        parity.compare_surface(g, w)
+    assert got[0].grad_eM is None and got[0].grad_eN is not None and got[0].swapped
+    batch = db.SceneBatch(ctx, [0, 3], [a_s, a_r, a_s], ids, excluded=[[0, 1]])
+    got = batch.compute_contact_surfaces(poses, db.POLYGON)[0]
+    assert [(s.id_M, s.id_N) for s in got] == [(10, 20), (20, 30)]
+    # Rigid-rigid.
+    near = np.stack([ho.xform(None, [0, 0, 0]), ho.xform(None, [0, 0, 0.3]), ho.xform(None, [0, 0, 10.0])])
+    batch = db.SceneBatch(ctx, [0, 3], [a_r, a_r, a_s], [1, 2, 3])
+    batch.set_poses(near)
+    with pytest.raises(db.HydroError) as ei:
+        batch.run(db.POLYGON, db.STRICT)
+    assert ei.value.status == 6 and "rigid-rigid" in str(ei.value)
+    batch.run(db.POLYGON, db.WITH_FALLBACK)
+    assert batch.sizes().num_surfaces == 0
+    apart = np.stack([ho.xform(None, [0, 0, 0]), ho.xform(None, [0, 0, 3.0]), ho.xform(None, [0, 0, 0.3])])
+    got = batch.compute_contact_surfaces(apart, db.POLYGON)[0]
+    assert [(s.id_M, s.id_N) for s in got] == [(1, 3)]
+    batch = db.SceneBatch(ctx, [0, 3], [a_r, a_r, a_s], [1, 2, 3], geom_anchored=[1, 1, 0])
+    both = np.stack([ho.xform(None, [0, 0, 0]), ho.xform(None, [0, 0, 0.6]), ho.xform(None, [0, 0, 0.3])])
+    got = batch.compute_contact_surfaces(both, db.POLYGON)[0]
+    assert [(s.id_M, s.id_N) for s in got] == [(1, 3), (2, 3)]
+    # Undefined geometry: strict query fails, fallback ignores it.
+    batch = db.SceneBatch(ctx, [0, 2], [a_s, -1], [1, 2])
+    batch.set_poses(near[:2])
+    with pytest.raises(db.HydroError) as ei:
+        batch.run(db.POLYGON, db.STRICT)
+    assert ei.value.status == 7
+    batch.run(db.POLYGON, db.WITH_FALLBACK)
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    import drake_b200 as db
+    R, X_WA, X_WB, soft, fld = sphere_kat_scene()
+    a = parity.register_compliant(ctx, soft, fld)
+    # A scene with a single geometry has no pairs.
+    batch = db.SceneBatch(ctx, [0, 1], [a], [1])
+    assert batch.compute_contact_surfaces(np.stack([X_WA]), db.POLYGON) == [[]]
+    # Ragged batch: scenes with 1, 2 and 0 geometries.
+    batch = db.SceneBatch(ctx, [0, 1, 3, 3], [a, a, a], [1, 1, 2])
+    got = batch.compute_contact_surfaces(np.stack([X_WA, X_WA, X_WB]), db.POLYGON)
+    assert [len(g) for g in got] == [0, 1, 0] and got[1][0].num_faces == 4
+    # Degenerate tetrahedron is rejected at registration (MeshGradientMode::kOkOrThrow).
+    with pytest.raises(db.HydroError) as ei:
+        ctx.register_compliant_mesh([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], [[0, 1, 2, 3]], [0, 0, 0, 1])
+    assert ei.value.status == 4
+    # A tetrahedron with zero pressure gradient passes both filters.
+    flat = ho.VolumeField.from_values(soft, np.zeros(soft.num_vertices))
+    rigid = ho.TriMesh.sphere(R, 0.1)
+    af, ar = parity.register_compliant(ctx, soft, flat), parity.register_rigid(ctx, rigid)
+    batch = db.SceneBatch(ctx, [0, 2], [af, ar], [1, 2])
+    got = batch.compute_contact_surfaces(np.stack([X_WA, X_WB]), db.POLYGON)[0]
+    want = ho.soft_rigid(soft, flat, rigid, X_WA, X_WB, 1, 2, ho.KPOLYGON)
+    parity.compare_surface(got[0], want)
