@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — batched hydroelastic ComputeContactSurfaces on N B200s (one process per GPU).
+
+A "step" is one batched query (all scenes of this rank's shard): poses in ->
+packed ContactSurface data out. Default workload: BASELINE config 3
+(ball_plate geometry batched, 16384 independent scenes per GPU, weak scaling).
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...     # the CPU port of the reference path on the host cores
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "contact_surfaces_per_sec"
+UNIT = "surfaces/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c2s", "c3", "c4", "c5"])
+    ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default: the config's)")
+    ap.add_argument("--rep", default="polygon", choices=["polygon", "triangle"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+DEFAULT_SCENES = {"c2s": 256, "c3": 16384, "c4": 4096, "c5": 16}
+
+
+def make_workload(name: str, scenes: int, scene0: int):
+    from drake_b200 import workloads as W
+    if name == "c3":
+        return W.config3(scenes, scene0)
+    if name == "c4":
+        return W.config4(scenes, scene0)
+    if name == "c5":
+        return W.config5(scenes, scene0)
+    return W.config2_spheres(scenes, 0.5, scene0)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, n in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_scene(workload):
+    """Builds the oracle's scene from the SAME arrays the GPU registered (cpu_baseline / reference arm)."""
+    from oracle import ho
+    sc = ho.Scene()
+    cache = {}
+    for g, mi in enumerate(workload.geom_mesh):
+        m = workload.meshes[mi]
+        if mi not in cache:
+            v, e, p = m.arrays()
+            if m.vertices_per_element == 4:
+                om = ho.VolumeMesh.from_arrays(v, e)
+                cache[mi] = (om, ho.VolumeField.from_values(om, p))
+            else:
+                cache[mi] = (ho.TriMesh.from_arrays(v, e), None)
+        om, of = cache[mi]
+        if of is None:
+            sc.add_rigid(workload.geom_id[g], om, bool(workload.geom_anchored[g]))
+        else:
+            sc.add_compliant(workload.geom_id[g], om, of, bool(workload.geom_anchored[g]))
+    order = np.argsort(np.asarray(workload.geom_id))  # the oracle wants poses by ascending id
+    return sc, order
+
+
+def time_cpu_port(workload, rep: int, budget_s: float, threads: int):
+    """Times the CPU port of the reference path (reference-shaped Bvh<Aabb> traversal + clipping +
+    mesh construction) on a bounded sample of the workload's scenes."""
+    from oracle import ho
+    sc, order = oracle_scene(workload)
+    poses = workload.poses[:, order, :]
+    probe = min(len(poses), max(threads, 8))
+    t, st = sc.batch_time(poses[:probe], rep, ho.MODE_REFERENCE_BVH, threads)
+    per_scene = max(t / probe, 1e-7)
+    n = int(min(len(poses), max(probe, budget_s / per_scene)))
+    t, st = sc.batch_time(poses[:n], rep, ho.MODE_REFERENCE_BVH, threads)
+    return {"seconds": t, "scenes": n, "stats": st, "surfaces_per_s": st["surfaces"] / t,
+            "element_pairs_per_s": st["element_pairs"] / t}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from drake_b200 import engine
+    rep = engine.POLYGON if args.rep == "polygon" else engine.TRIANGLE
+    scenes = args.scenes or DEFAULT_SCENES[args.config]
+    wl = make_workload(args.config, scenes, 0)
+    threads = os.cpu_count() or 1
+    # Each step is a bounded sample; K + W steps must finish within a few minutes.
+    per_step_budget = min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup))
+    for _ in range(args.warmup):
+        time_cpu_port(wl, rep, per_step_budget, threads)
+    vals, pairs, secs, nscenes = [], [], [], 0
+    for _ in range(args.steps):
+        r = time_cpu_port(wl, rep, per_step_budget, threads)
+        vals.append(r["surfaces_per_s"])
+        pairs.append(r["element_pairs_per_s"])
+        secs.append(r["seconds"])
+        nscenes = r["scenes"]
+    v = float(np.mean(vals))
+    sample = f"{nscenes} of {scenes} scenes of {wl.name} per step, all host threads"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl.name, "scenes_per_gpu": scenes, "representation": args.rep,
+                      "description": wl.description},
+           "element_pairs_per_sec": float(np.mean(pairs)),
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import drake_b200 as db
+    from drake_b200 import engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rep = engine.POLYGON if args.rep == "polygon" else engine.TRIANGLE
+    scenes = args.scenes or DEFAULT_SCENES[args.config]
+
+    # ---- set-up (untimed): meshes, assets, BVHs, scene batch, two pose sets resident in HBM.
+    wl = make_workload(args.config, scenes, rank * scenes)
+    wl_b = make_workload(args.config, scenes, (world + rank) * scenes)
+    ctx = db.Context(local)
+    batch = wl.register(ctx)
+    G = wl.geoms_per_scene
+    pose_sets = [torch.from_numpy(np.ascontiguousarray(w.poses.reshape(-1, 12))).to(dev) for w in (wl, wl_b)]
+    pinned_poses = [torch.from_numpy(np.ascontiguousarray(w.poses.reshape(-1, 12))).pin_memory() for w in (wl, wl_b)]
+    stats_local = torch.zeros((scenes, 6), dtype=torch.int64, device=dev)
+    stats_all = torch.zeros((world * scenes, 6), dtype=torch.int64, device=dev) if world > 1 else None
+    stream = torch.cuda.ExternalStream(batch.stream(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    batch.enable_timing(True)
+
+    def step(k: int, timed_events=None):
+        with torch.cuda.stream(stream):
+            flush.zero_()  # L2 flush between steps, outside the timed events
+            if timed_events is not None:
+                timed_events[0].record(stream)
+            batch.set_poses_device(pose_sets[k % 2].data_ptr())
+            batch.query(rep, engine.STRICT, stats_local.data_ptr())
+            if world > 1:
+                # The only collective of the path: per-scene statistics over NVLink.
+                dist.all_gather_into_tensor(stats_all, stats_local)
+            if timed_events is not None:
+                timed_events[1].record(stream)
+        batch.sync()
+
+    # Grow device work lists until the workload fits (untimed).
+    batch.set_poses_device(pose_sets[0].data_ptr())
+    batch.run(rep, engine.STRICT, stats_local.data_ptr())
+    batch.set_poses_device(pose_sets[1].data_ptr())
+    batch.run(rep, engine.STRICT, stats_local.data_ptr())
+    for k in range(args.warmup):
+        step(k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    kernel_ms = {}
+    step_stats = []
+    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        step(k, events[k])
+        step_stats.append(batch.stats())
+        for name, ms in batch.kernel_times_ms().items():
+            kernel_ms[name] = kernel_ms.get(name, 0.0) + ms
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in events)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([sum(s["surfaces"] for s in step_stats), sum(s["tet_tri_pairs"] + s["tet_tet_pairs"] for s in step_stats),
+                        sum(s["bv_pair_tests"] for s in step_stats), sum(s["faces"] for s in step_stats)],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    max_ms = float(t.item())
+    surfaces, pairs, bvtests, faces = [float(x) for x in tot.tolist()]
+    sec = max_ms / 1e3
+    value = surfaces / sec
+
+    # ---- end-to-end through the C-ABI with HOST buffers (H2D poses, D2H packed surfaces).
+    e2e = None
+    if not args.no_e2e:
+        sizes = batch.sizes()
+        cap = engine.ResultSizes()
+        for f, _ in engine.ResultSizes._fields_:
+            setattr(cap, f, getattr(sizes, f))
+        for f in ("num_surfaces", "num_faces", "num_vertices", "num_polygons", "face_data_ints"):
+            setattr(cap, f, int(getattr(sizes, f) * 1.25) + 1024)
+
+        def pinned(shape, dtype):
+            n = int(np.prod(shape))
+            tt = torch.empty(max(n, 1), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+            return tt.numpy()[:n].reshape(shape)
+
+        host = engine.PackedResults(sizes, allocator=pinned, capacity=cap)
+
+        def e2e_step(k: int):
+            batch.set_poses_host_ptr(pinned_poses[k % 2].data_ptr())
+            batch.query(rep, engine.STRICT, 0)
+            batch.sync()
+            return batch.copy_results(host)
+
+        for k in range(min(3, args.warmup)):
+            e2e_step(k)
+        barrier()
+        e0 = time.perf_counter()
+        e_surf, d2h = 0, 0
+        for k in range(args.steps):
+            r = e2e_step(k)
+            e_surf += r.num_surfaces
+            d2h += r.nbytes()
+        barrier()
+        e_sec = time.perf_counter() - e0
+        et = torch.tensor([e_sec], dtype=torch.float64, device=dev)
+        es = torch.tensor([float(e_surf)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            dist.all_reduce(es, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(es.item()) / float(et.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(pinned_poses[0].numel() * 8), "d2h_bytes_per_step": int(d2h / args.steps),
+               "ms_per_step": 1e3 * float(et.item()) / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (algorithmic bytes, SURVEY.md §8d / DESIGN.md).
+    K = args.steps
+    avg = {k: v / K for k, v in kernel_ms.items()}
+    s_mean = {k: float(np.mean([s[k] for s in step_stats])) for k in step_stats[0]}
+    alg = {"traverse": s_mean["bv_pair_tests"] * 128.0,
+           "clip_tet_tri": s_mean["tet_tri_pairs"] * 260.0,
+           "clip_tet_tet": s_mean["tet_tet_pairs"] * 392.0}
+    # Polygon output bytes (32 n + 96 / + 120) are attributed to the clip kernels in proportion
+    # to their candidate counts.
+    out_bytes = (s_mean["vertices"] if rep == engine.POLYGON else s_mean["vertices"] - s_mean["polygons"]) * 32.0 + \
+        s_mean["polygons"] * 108.0
+    cand = max(1.0, s_mean["tet_tri_pairs"] + s_mean["tet_tet_pairs"])
+    alg["clip_tet_tri"] += out_bytes * s_mean["tet_tri_pairs"] / cand
+    alg["clip_tet_tet"] += out_bytes * s_mean["tet_tet_pairs"] / cand
+    dominant = max(alg, key=lambda k: avg.get(k, 0.0))
+    peak, peak_kind = measured_peaks()
+    achieved = alg[dominant] / (avg[dominant] * 1e-3) / 1e9 if avg[dominant] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": {"traverse": "k_traverse", "clip_tet_tri": "k_clip_tri",
+                                           "clip_tet_tet": "k_clip_tet"}[dominant],
+                "achieved": achieved, "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": avg[dominant],
+                "kernel_ms_breakdown": avg,
+                "whole_step_frac": (s_mean["algorithmic_bytes"] / (max_ms / K * 1e-3) / 1e9) / peak}
+
+    info = batch.info()
+    launches_per_step = 1 + info.max_traversal_levels + (1 if info.num_soft_rigid_pairs else 0) + \
+        (1 if info.num_soft_soft_pairs else 0) + 3 + 1 + 2 + 1
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r = time_cpu_port(wl, rep, args.cpu_seconds, threads)
+        r1 = time_cpu_port(wl, rep, min(5.0, args.cpu_seconds), 1)
+        cpu_baseline = {"value": r["surfaces_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{r['scenes']} of {scenes} scenes of {wl.name}, {r['seconds']:.1f} s",
+                        "element_pairs_per_sec": r["element_pairs_per_s"],
+                        "single_thread": {"value": r1["surfaces_per_s"], "scenes": r1["scenes"],
+                                          "element_pairs_per_sec": r1["element_pairs_per_s"]}}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+           "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl.name, "description": wl.description, "scenes_per_gpu": scenes,
+                      "geometries_per_scene": G, "representation": args.rep,
+                      "l2": "256 MB L2 flush between steps; work lists and outputs stream through HBM, the "
+                            "instanced mesh assets are L2-resident by design"},
+           "element_pairs_per_sec": pairs / sec, "bv_pair_tests_per_sec": bvtests / sec, "faces_per_sec": faces / sec,
+           "surfaces_per_step": surfaces / K, "element_pairs_per_step": pairs / K,
+           "wall_ms_per_step_incl_flush_and_sync": 1e3 * wall / K,
+           "e2e": e2e, "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roofline,
+           "cpu_baseline": cpu_baseline}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -5,4 +5,4 @@ include/drake_b200_hydro.h); `engine` is its thin ctypes host mirror.
 """
 from . import build  # noqa: F401
 from .engine import (COMPLIANT, POLYGON, RIGID, STRICT, TRIANGLE, WITH_FALLBACK, ContactSurface, Context,  # noqa: F401
-                     HydroError, PackedResults, SceneBatch)
+                     HydroError, Mesh, PackedResults, SceneBatch)

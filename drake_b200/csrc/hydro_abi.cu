@@ -211,8 +211,14 @@ struct dbh_batch {
   DevBuf<long long> d_poly_off, d_vert_off, d_block_sums, d_surf_face_off, d_surf_vert_off;
   DevBuf<int4> d_soup_hdr;
   DevBuf<double> d_soup_v, d_soup_nhat;
-  DevBuf<double> d_face_f64, d_vert_f64, d_surf_f64;
-  DevBuf<int> d_face_i32;
+  // Final results in the caller's layout.
+  DevBuf<double> r_vertices, r_pressures, r_areas, r_normals, r_centroids, r_e_centroid, r_grad_eM, r_grad_eN;
+  DevBuf<int> r_face_data, r_elem_a, r_elem_b, r_face_pair;
+  DevBuf<double> r_surf_total_area, r_surf_centroid;
+  DevBuf<int> r_surf_scene;
+  DevBuf<long long> r_surf_id_m, r_surf_id_n;
+  DevBuf<unsigned char> r_surf_flags;
+  long long cap_face_data{0};
   Counters* h_counters{nullptr};  // pinned
 
   int representation{DBH_POLYGON};
@@ -236,9 +242,19 @@ struct dbh_batch {
     CUDA_OK(d_soup_hdr.ensure(cap_polys));
     CUDA_OK(d_soup_v.ensure(static_cast<size_t>(cap_polys) * kMaxPolyVerts * 4));
     CUDA_OK(d_soup_nhat.ensure(static_cast<size_t>(cap_polys) * 3));
-    CUDA_OK(d_face_f64.ensure(static_cast<size_t>(cap_faces) * kNumFacePlanes));
-    CUDA_OK(d_face_i32.ensure(static_cast<size_t>(cap_faces) * kNumFaceIntPlanes));
-    CUDA_OK(d_vert_f64.ensure(static_cast<size_t>(cap_verts) * 4));
+    cap_face_data = std::max(cap_faces + cap_verts, 3 * cap_faces);
+    CUDA_OK(r_vertices.ensure(static_cast<size_t>(cap_verts) * 3));
+    CUDA_OK(r_pressures.ensure(cap_verts));
+    CUDA_OK(r_face_data.ensure(cap_face_data));
+    CUDA_OK(r_areas.ensure(cap_faces));
+    CUDA_OK(r_normals.ensure(static_cast<size_t>(cap_faces) * 3));
+    CUDA_OK(r_centroids.ensure(static_cast<size_t>(cap_faces) * 3));
+    CUDA_OK(r_e_centroid.ensure(cap_faces));
+    CUDA_OK(r_grad_eM.ensure(static_cast<size_t>(cap_faces) * 3));
+    CUDA_OK(r_grad_eN.ensure(static_cast<size_t>(cap_faces) * 3));
+    CUDA_OK(r_elem_a.ensure(cap_faces));
+    CUDA_OK(r_elem_b.ensure(cap_faces));
+    CUDA_OK(r_face_pair.ensure(cap_faces));
     return DBH_OK;
   }
 };
@@ -532,7 +548,12 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   CUDA_OK(b->d_vert_off.alloc(np + 1));
   CUDA_OK(b->d_surf_face_off.alloc(np + 1));
   CUDA_OK(b->d_surf_vert_off.alloc(np + 1));
-  CUDA_OK(b->d_surf_f64.alloc(np * 4));
+  CUDA_OK(b->r_surf_total_area.alloc(np));
+  CUDA_OK(b->r_surf_centroid.alloc(np * 3));
+  CUDA_OK(b->r_surf_scene.alloc(np));
+  CUDA_OK(b->r_surf_id_m.alloc(np));
+  CUDA_OK(b->r_surf_id_n.alloc(np));
+  CUDA_OK(b->r_surf_flags.alloc(np));
   const int scan_blocks = (b->num_pairs + kScanTile - 1) / kScanTile;
   CUDA_OK(b->d_block_sums.alloc(3 * std::max(1, scan_blocks)));
   *out = b.release();
@@ -679,11 +700,21 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pk.vert_off = b->d_vert_off.p;
     pk.pair_cursor = b->d_pair_cursor.p;
     pk.representation = representation;
-    pk.face_f64 = b->d_face_f64.p;
-    pk.face_i32 = b->d_face_i32.p;
-    pk.face_stride = b->cap_faces;
-    pk.vert_f64 = b->d_vert_f64.p;
-    pk.vert_stride = b->cap_verts;
+    pk.out.vertices = b->r_vertices.p;
+    pk.out.pressures = b->r_pressures.p;
+    pk.out.face_data = b->r_face_data.p;
+    pk.out.areas = b->r_areas.p;
+    pk.out.normals = b->r_normals.p;
+    pk.out.centroids = b->r_centroids.p;
+    pk.out.e_centroid = b->r_e_centroid.p;
+    pk.out.grad_eM = b->r_grad_eM.p;
+    pk.out.grad_eN = b->r_grad_eN.p;
+    pk.out.elem_a = b->r_elem_a.p;
+    pk.out.elem_b = b->r_elem_b.p;
+    pk.out.face_pair = b->r_face_pair.p;
+    pk.out.face_capacity = b->cap_faces;
+    pk.out.vert_capacity = b->cap_verts;
+    pk.out.face_data_capacity = b->cap_face_data;
     pk.counters = b->d_counters.p;
     k_pack<<<sms * 8, 128, 0, st>>>(pk);
     mark(6);
@@ -693,18 +724,22 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     su.poly_off = b->d_poly_off.p;
     su.vert_off = b->d_vert_off.p;
     su.representation = representation;
-    su.face_f64 = b->d_face_f64.p;
-    su.face_stride = b->cap_faces;
+    su.areas = b->r_areas.p;
+    su.centroids = b->r_centroids.p;
     su.surf_face_off = b->d_surf_face_off.p;
     su.surf_vert_off = b->d_surf_vert_off.p;
-    su.surf_f64 = b->d_surf_f64.p;
-    su.surf_stride = std::max(1, b->num_pairs);
+    su.surf_total_area = b->r_surf_total_area.p;
+    su.surf_centroid = b->r_surf_centroid.p;
+    su.surf_scene = b->r_surf_scene.p;
+    su.surf_id_m = b->r_surf_id_m.p;
+    su.surf_id_n = b->r_surf_id_n.p;
+    su.surf_flags = b->r_surf_flags.p;
     su.scene_stats = reinterpret_cast<long long*>(scene_stats_dev);
     su.counters = b->d_counters.p;
     k_surface<<<sms * 4, 128, 0, st>>>(su);
     k_finalize<<<1, 32, 0, st>>>(su, b->num_pairs);
     if (scene_stats_dev)
-      k_scene_stats<<<(b->num_pairs + 255) / 256, 256, 0, st>>>(b->d_pairs.p, b->num_pairs, b->d_pair_polys.p,
+      k_scene_stats<<<(b->num_pairs + 255) / 256, 256, 0, st>>>(b->d_pairs.p, b->num_pairs,
                                                                reinterpret_cast<long long*>(scene_stats_dev));
     mark(7);
   }
@@ -826,17 +861,28 @@ dbh_status dbh_batch_copy_geometry_pairs(dbh_batch* b, int32_t* out) {
 dbh_status dbh_batch_device_results(dbh_batch* b, dbh_device_results* out) {
   if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "device_results: bad argument");
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
+  std::memset(out, 0, sizeof(*out));
   out->surf_pair = b->d_surf_pair.p;
+  out->surf_scene = b->r_surf_scene.p;
+  out->surf_id_M = reinterpret_cast<const int64_t*>(b->r_surf_id_m.p);
+  out->surf_id_N = reinterpret_cast<const int64_t*>(b->r_surf_id_n.p);
   out->surf_face_offset = reinterpret_cast<const int64_t*>(b->d_surf_face_off.p);
   out->surf_vertex_offset = reinterpret_cast<const int64_t*>(b->d_surf_vert_off.p);
-  out->surf_total_area = b->d_surf_f64.p;
-  out->surf_centroid = b->d_surf_f64.p + std::max(1, b->num_pairs);
-  out->surf_stride = std::max(1, b->num_pairs);
-  out->vertices = b->d_vert_f64.p;
-  out->vertex_stride = b->cap_verts;
-  out->face_f64 = b->d_face_f64.p;
-  out->face_stride = b->cap_faces;
-  out->face_i32 = b->d_face_i32.p;
+  out->surf_total_area = b->r_surf_total_area.p;
+  out->surf_centroid = b->r_surf_centroid.p;
+  out->surf_flags = b->r_surf_flags.p;
+  out->vertices = b->r_vertices.p;
+  out->pressures = b->r_pressures.p;
+  out->face_data = b->r_face_data.p;
+  out->areas = b->r_areas.p;
+  out->normals = b->r_normals.p;
+  out->centroids = b->r_centroids.p;
+  out->pressure_at_centroid = b->r_e_centroid.p;
+  out->grad_eM = b->r_grad_eM.p;
+  out->grad_eN = b->r_grad_eN.p;
+  out->elem_M = b->r_elem_a.p;
+  out->elem_N = b->r_elem_b.p;
+  out->face_pair = b->r_face_pair.p;
   return DBH_OK;
 }
 
@@ -845,128 +891,35 @@ dbh_status dbh_batch_copy_results(dbh_batch* b, const dbh_result_buffers* buf) {
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   CUDA_OK(cudaSetDevice(b->ctx->device));
   const Counters& c = *b->h_counters;
-  const int64_t ns = static_cast<int64_t>(c.surfaces), nf = static_cast<int64_t>(c.faces),
-                nv = static_cast<int64_t>(c.vertices);
-  const bool poly = b->representation == DBH_POLYGON;
-  // Surfaces.
-  std::vector<int> surf_pair(ns);
-  std::vector<long long> foff(ns + 1), voff(ns + 1);
-  std::vector<double> sf(4 * ns);
-  if (ns) {
-    CUDA_OK(cudaMemcpy(surf_pair.data(), b->d_surf_pair.p, ns * sizeof(int), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 4; ++k)
-      CUDA_OK(cudaMemcpy(sf.data() + k * ns, b->d_surf_f64.p + static_cast<size_t>(k) * std::max(1, b->num_pairs),
-                         ns * sizeof(double), cudaMemcpyDeviceToHost));
-  }
-  CUDA_OK(cudaMemcpy(foff.data(), b->d_surf_face_off.p, (ns + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
-  CUDA_OK(cudaMemcpy(voff.data(), b->d_surf_vert_off.p, (ns + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
-  for (int64_t s = 0; s < ns; ++s) {
-    const PairRec& pr = b->pairs[surf_pair[s]];
-    if (buf->surf_scene) buf->surf_scene[s] = pr.scene;
-    if (buf->surf_id_M) buf->surf_id_M[s] = pr.id_m;
-    if (buf->surf_id_N) buf->surf_id_N[s] = pr.id_n;
-    if (buf->surf_total_area) buf->surf_total_area[s] = sf[s];
-    if (buf->surf_centroid)
-      for (int k = 0; k < 3; ++k) buf->surf_centroid[3 * s + k] = sf[(k + 1) * ns + s];
-    if (buf->surf_flags) {
-      uint8_t f = 0;
-      if (pr.kind == kSoftSoft) {
-        f = 3;
-      } else {
-        f = pr.swapped ? (2 | 4) : 1;
-      }
-      buf->surf_flags[s] = f;
-    }
-  }
-  if (buf->surf_face_offset)
-    for (int64_t s = 0; s <= ns; ++s) buf->surf_face_offset[s] = foff[s];
-  if (buf->surf_vertex_offset)
-    for (int64_t s = 0; s <= ns; ++s) buf->surf_vertex_offset[s] = voff[s];
-  // Vertices.
-  if (nv && (buf->vertices || buf->pressures)) {
-    std::vector<double> tmp(nv);
-    for (int k = 0; k < 4; ++k) {
-      if (k < 3 && !buf->vertices) continue;
-      if (k == 3 && !buf->pressures) continue;
-      CUDA_OK(cudaMemcpy(tmp.data(), b->d_vert_f64.p + static_cast<size_t>(k) * b->cap_verts, nv * sizeof(double),
-                         cudaMemcpyDeviceToHost));
-      if (k < 3) {
-        for (int64_t i = 0; i < nv; ++i) buf->vertices[3 * i + k] = tmp[i];
-      } else {
-        std::memcpy(buf->pressures, tmp.data(), nv * sizeof(double));
-      }
-    }
-  }
-  // Faces.
-  if (nf) {
-    std::vector<double> tmp(nf);
-    auto plane = [&](int k) -> dbh_status {
-      CUDA_OK(cudaMemcpy(tmp.data(), b->d_face_f64.p + static_cast<size_t>(k) * b->cap_faces, nf * sizeof(double),
-                         cudaMemcpyDeviceToHost));
-      return DBH_OK;
-    };
-    auto vec3 = [&](double* dst, int k0) -> dbh_status {
-      if (!dst) return DBH_OK;
-      for (int k = 0; k < 3; ++k) {
-        if (dbh_status s = plane(k0 + k)) return s;
-        for (int64_t i = 0; i < nf; ++i) dst[3 * i + k] = tmp[i];
-      }
-      return DBH_OK;
-    };
-    if (buf->areas) {
-      if (dbh_status s = plane(kArea)) return s;
-      std::memcpy(buf->areas, tmp.data(), nf * sizeof(double));
-    }
-    if (buf->pressure_at_centroid) {
-      if (dbh_status s = plane(kEc)) return s;
-      std::memcpy(buf->pressure_at_centroid, tmp.data(), nf * sizeof(double));
-    }
-    if (dbh_status s = vec3(buf->normals, kNx)) return s;
-    if (dbh_status s = vec3(buf->centroids, kCx)) return s;
-    if (dbh_status s = vec3(buf->grad_eM, kGMx)) return s;
-    if (dbh_status s = vec3(buf->grad_eN, kGNx)) return s;
-    std::vector<int> itmp[kNumFaceIntPlanes];
-    auto iplane = [&](int k) -> dbh_status {
-      itmp[k].resize(nf);
-      CUDA_OK(cudaMemcpy(itmp[k].data(), b->d_face_i32.p + static_cast<size_t>(k) * b->cap_faces, nf * sizeof(int),
-                         cudaMemcpyDeviceToHost));
-      return DBH_OK;
-    };
-    if (buf->elem_M) {
-      if (dbh_status s = iplane(kElemA)) return s;
-      std::memcpy(buf->elem_M, itmp[kElemA].data(), nf * sizeof(int));
-    }
-    if (buf->elem_N) {
-      if (dbh_status s = iplane(kElemB)) return s;
-      std::memcpy(buf->elem_N, itmp[kElemB].data(), nf * sizeof(int));
-    }
-    if (buf->face_data) {
-      for (int k : {kI0, kI1, kI2})
-        if (dbh_status s = iplane(k)) return s;
-      if (poly) {
-        // |n|v0..vn-1| with surface-local indices; reversed when M and N were
-        // swapped (PolygonSurfaceMesh::ReverseFaceWinding, polygon_surface_mesh.cc:39-49).
-        if (dbh_status s = iplane(kPair)) return s;
-        int64_t w = 0;
-        for (int64_t f = 0; f < nf; ++f) {
-          const int n = itmp[kI0][f], vb = itmp[kI1][f];
-          const bool swapped = b->pairs[itmp[kPair][f]].swapped != 0;
-          buf->face_data[w++] = n;
-          if (!swapped) {
-            for (int k = 0; k < n; ++k) buf->face_data[w++] = vb + k;
-          } else {
-            for (int k = n - 1; k >= 0; --k) buf->face_data[w++] = vb + k;
-          }
-        }
-      } else {
-        for (int64_t f = 0; f < nf; ++f) {
-          buf->face_data[3 * f] = itmp[kI0][f];
-          buf->face_data[3 * f + 1] = itmp[kI1][f];
-          buf->face_data[3 * f + 2] = itmp[kI2][f];
-        }
-      }
-    }
-  }
+  const size_t ns = c.surfaces, nf = c.faces, nv = c.vertices;
+  const size_t nfd = b->representation == DBH_POLYGON ? static_cast<size_t>(c.polys + c.poly_verts) : 3 * nf;
+  cudaStream_t st = b->stream;
+  // The device arrays already have the caller's layout: straight D2H copies
+  // (asynchronous when the destination is pinned), one synchronisation.
+#define DBH_COPY(dst, src, count, T)                                                                  \
+  if ((dst) && (count))                                                                               \
+    CUDA_OK(cudaMemcpyAsync((dst), (src), (count) * sizeof(T), cudaMemcpyDeviceToHost, st))
+  DBH_COPY(buf->surf_scene, b->r_surf_scene.p, ns, int32_t);
+  DBH_COPY(buf->surf_id_M, b->r_surf_id_m.p, ns, int64_t);
+  DBH_COPY(buf->surf_id_N, b->r_surf_id_n.p, ns, int64_t);
+  DBH_COPY(buf->surf_face_offset, b->d_surf_face_off.p, ns + 1, int64_t);
+  DBH_COPY(buf->surf_vertex_offset, b->d_surf_vert_off.p, ns + 1, int64_t);
+  DBH_COPY(buf->surf_total_area, b->r_surf_total_area.p, ns, double);
+  DBH_COPY(buf->surf_centroid, b->r_surf_centroid.p, 3 * ns, double);
+  DBH_COPY(buf->surf_flags, b->r_surf_flags.p, ns, uint8_t);
+  DBH_COPY(buf->vertices, b->r_vertices.p, 3 * nv, double);
+  DBH_COPY(buf->pressures, b->r_pressures.p, nv, double);
+  DBH_COPY(buf->face_data, b->r_face_data.p, nfd, int32_t);
+  DBH_COPY(buf->areas, b->r_areas.p, nf, double);
+  DBH_COPY(buf->normals, b->r_normals.p, 3 * nf, double);
+  DBH_COPY(buf->centroids, b->r_centroids.p, 3 * nf, double);
+  DBH_COPY(buf->pressure_at_centroid, b->r_e_centroid.p, nf, double);
+  DBH_COPY(buf->grad_eM, b->r_grad_eM.p, 3 * nf, double);
+  DBH_COPY(buf->grad_eN, b->r_grad_eN.p, 3 * nf, double);
+  DBH_COPY(buf->elem_M, b->r_elem_a.p, nf, int32_t);
+  DBH_COPY(buf->elem_N, b->r_elem_b.p, nf, int32_t);
+#undef DBH_COPY
+  CUDA_OK(cudaStreamSynchronize(st));
   return DBH_OK;
 }
 

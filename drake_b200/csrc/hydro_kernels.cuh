@@ -644,6 +644,27 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(ScanArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// Final packed results, in the caller's layout (include/drake_b200_hydro.h
+// dbh_result_buffers): 3-vectors are xyz-interleaved, faces and vertices of a
+// surface are contiguous, surfaces ordered like the static pair list.
+struct ResultArrays {
+  double* vertices;      // [V*3]
+  double* pressures;     // [V]
+  int* face_data;        // polygon: |n|v..|; triangle: [F*3]; indices local to the surface
+  double* areas;         // [F]
+  double* normals;       // [F*3]
+  double* centroids;     // [F*3]
+  double* e_centroid;    // [F]
+  double* grad_eM;       // [F*3]
+  double* grad_eN;       // [F*3]
+  int* elem_a;           // [F]
+  int* elem_b;           // [F]
+  int* face_pair;        // [F]
+  long long face_capacity;
+  long long vert_capacity;
+  long long face_data_capacity;
+};
+
 // k_pack: one thread per staged polygon.
 struct PackArgs {
   PolySoup soup;
@@ -654,53 +675,30 @@ struct PackArgs {
   const long long* vert_off;
   unsigned long long* pair_cursor;
   int representation;  // DBH_TRIANGLE / DBH_POLYGON
-  // final arrays
-  double* face_f64;    // 14 planes, stride face_stride
-  int* face_i32;       // 6 planes
-  long long face_stride;
-  double* vert_f64;    // 4 planes, stride vert_stride
-  long long vert_stride;
+  ResultArrays out;
   Counters* counters;
 };
 
-enum FacePlane { kArea = 0, kNx, kNy, kNz, kCx, kCy, kCz, kEc, kGMx, kGMy, kGMz, kGNx, kGNy, kGNz, kNumFacePlanes };
-enum FaceIntPlane { kPair = 0, kElemA, kElemB, kI0, kI1, kI2, kNumFaceIntPlanes };
+__device__ __forceinline__ void store3(double* base, long long i, D3 v) {
+  base[3 * i] = v.x;
+  base[3 * i + 1] = v.y;
+  base[3 * i + 2] = v.z;
+}
 
-__device__ __forceinline__ void store_face(const PackArgs& a, long long f, int pair, int ea, int eb, int i0, int i1,
-                                           int i2, double area, D3 n_W, D3 c_W, double e_c, D3 gA_W, D3 gB_W,
-                                           bool has_b, bool swapped) {
-  if (f >= a.face_stride) {
-    raise_error(a.counters, 5, 6);
-    return;
-  }
-  double* F = a.face_f64 + f;
-  const long long s = a.face_stride;
+__device__ __forceinline__ void store_face(const PackArgs& a, long long f, int pair, int ea, int eb, double area,
+                                           D3 n_W, D3 c_W, double e_c, D3 gA_W, D3 gB_W, bool has_b, bool swapped) {
   if (swapped) n_W = -n_W;  // ReverseFaceWinding negates normals (polygon_surface_mesh.cc:50-52)
-  F[kArea * s] = area;
-  F[kNx * s] = n_W.x;
-  F[kNy * s] = n_W.y;
-  F[kNz * s] = n_W.z;
-  F[kCx * s] = c_W.x;
-  F[kCy * s] = c_W.y;
-  F[kCz * s] = c_W.z;
-  F[kEc * s] = e_c;
+  a.out.areas[f] = area;
+  store3(a.out.normals, f, n_W);
+  store3(a.out.centroids, f, c_W);
+  a.out.e_centroid[f] = e_c;
   const D3 zero = make_d3(0, 0, 0);
   // swapped: grad_eM <-> grad_eN (contact_surface.cc:58).
-  const D3 gM = swapped ? (has_b ? gB_W : zero) : gA_W;
-  const D3 gN = swapped ? gA_W : (has_b ? gB_W : zero);
-  F[kGMx * s] = gM.x;
-  F[kGMy * s] = gM.y;
-  F[kGMz * s] = gM.z;
-  F[kGNx * s] = gN.x;
-  F[kGNy * s] = gN.y;
-  F[kGNz * s] = gN.z;
-  int* I = a.face_i32 + f;
-  I[kPair * s] = pair;
-  I[kElemA * s] = ea;
-  I[kElemB * s] = eb;
-  I[kI0 * s] = i0;
-  I[kI1 * s] = i1;
-  I[kI2 * s] = i2;
+  store3(a.out.grad_eM, f, swapped ? (has_b ? gB_W : zero) : gA_W);
+  store3(a.out.grad_eN, f, swapped ? gA_W : (has_b ? gB_W : zero));
+  a.out.elem_a[f] = ea;
+  a.out.elem_b[f] = eb;
+  a.out.face_pair[f] = pair;
 }
 
 __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
@@ -727,14 +725,18 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
       const Xf X_WN = a.poses[pr.geom_b];
       gB_W = rot(X_WN, load3(a.assets[pr.asset_b].tets[h.z].grad));
     }
-    // Slots inside the pair's ranges.
-    // One atomic claims both the polygon slot and the vertex range.
+    // One atomic claims both the polygon slot and the vertex range, so within
+    // a pair polygon order and vertex order agree.
     const unsigned long long cur = atomicAdd(&a.pair_cursor[pair], (1ull << 32) | (unsigned long long)n);
     const int pj = (int)(cur >> 32);
     const int vj = (int)(cur & 0xffffffffull);
     if (a.representation == 1 /*DBH_POLYGON*/) {
       const long long f = a.poly_off[pair] + pj;
       const long long vb = a.vert_off[pair] + vj;
+      if (f >= a.out.face_capacity || vb + n > a.out.vert_capacity || f + vb + n + 1 > a.out.face_data_capacity) {
+        raise_error(a.counters, 5, 6);
+        continue;
+      }
       // PolygonSurfaceMesh::CalcAreaNormalAndCentroid (polygon_surface_mesh.cc:117-218).
       const D3 r_MA = vM[0];
       D3 p_scaled = make_d3(0, 0, 0), normal_M = make_d3(0, 0, 0);
@@ -764,25 +766,28 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
       const double at_Mo = e[0] - dot(gradA_M, vM[0]);
       const double at_Wo = at_Mo - dot(gA_W, make_d3(X_WM.m[9], X_WM.m[10], X_WM.m[11]));
       const double e_c = dot(gA_W, c_W) + at_Wo;
-      if (vb + n > a.vert_stride) {
-        raise_error(a.counters, 5, 7);
-        continue;
-      }
+      // face_data: |n|v0..vn-1| with surface-local indices, reversed when M and
+      // N are swapped (PolygonSurfaceMesh::ReverseFaceWinding, polygon_surface_mesh.cc:39-49).
+      int* fd = a.out.face_data + (f + vb);
+      fd[0] = n;
       for (int k = 0; k < n; ++k) {
-        const D3 w = xform_point(X_WM, vM[k]);
-        a.vert_f64[0 * a.vert_stride + vb + k] = w.x;
-        a.vert_f64[1 * a.vert_stride + vb + k] = w.y;
-        a.vert_f64[2 * a.vert_stride + vb + k] = w.z;
-        a.vert_f64[3 * a.vert_stride + vb + k] = e[k];
+        store3(a.out.vertices, vb + k, xform_point(X_WM, vM[k]));
+        a.out.pressures[vb + k] = e[k];
+        fd[1 + k] = vj + (swapped ? (n - 1 - k) : k);
       }
-      store_face(a, f, pair, h.y, h.z, n, (int)(vb - a.vert_off[pair]), 0, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft,
-                 swapped);
+      store_face(a, f, pair, h.y, h.z, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft, swapped);
     } else {
       // Triangle representation: n fan triangles about the polygon centroid
       // (contact_surface_utility.cc:137-164,218-316). Faces are counted by
       // polygon vertices, vertices by n + 1 per polygon.
       const long long fb = a.vert_off[pair] + vj;
-      const long long vb = a.vert_off[pair] + a.poly_off[pair] + vj + pj;
+      const int vloc = vj + pj;  // local to the surface
+      const long long vb = a.vert_off[pair] + a.poly_off[pair] + vloc;
+      if (fb + n > a.out.face_capacity || vb + n + 1 > a.out.vert_capacity ||
+          3 * (fb + n) > a.out.face_data_capacity) {
+        raise_error(a.counters, 5, 6);
+        continue;
+      }
       const D3 nhat = make_d3(a.soup.nhat[0 * a.soup.capacity + i], a.soup.nhat[1 * a.soup.capacity + i],
                               a.soup.nhat[2 * a.soup.capacity + i]);
       // CalcPolygonCentroid.
@@ -805,24 +810,15 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
         p_c = accum / total_weight;
       }
       const double e_cv = dot(gradA_M, p_c - vM[0]) + e[0];
-      if (vb + n + 1 > a.vert_stride) {
-        raise_error(a.counters, 5, 7);
-        continue;
-      }
-      const long long vloc = vb - (a.vert_off[pair] + a.poly_off[pair]);  // local to the surface
       D3 vW[kMaxPolyVerts];
       for (int k = 0; k < n; ++k) {
         vW[k] = xform_point(X_WM, vM[k]);
-        a.vert_f64[0 * a.vert_stride + vb + k] = vW[k].x;
-        a.vert_f64[1 * a.vert_stride + vb + k] = vW[k].y;
-        a.vert_f64[2 * a.vert_stride + vb + k] = vW[k].z;
-        a.vert_f64[3 * a.vert_stride + vb + k] = e[k];
+        store3(a.out.vertices, vb + k, vW[k]);
+        a.out.pressures[vb + k] = e[k];
       }
       const D3 cW = xform_point(X_WM, p_c);
-      a.vert_f64[0 * a.vert_stride + vb + n] = cW.x;
-      a.vert_f64[1 * a.vert_stride + vb + n] = cW.y;
-      a.vert_f64[2 * a.vert_stride + vb + n] = cW.z;
-      a.vert_f64[3 * a.vert_stride + vb + n] = e_cv;
+      store3(a.out.vertices, vb + n, cW);
+      a.out.pressures[vb + n] = e_cv;
       const double third = 1.0 / 3.0;
       int k1 = n - 1;
       for (int k = 0; k < n; ++k) {
@@ -837,14 +833,17 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
         double e_c = third * e[k1];
         e_c += third * e[k];
         e_c += third * e_cv;
-        int i0 = (int)vloc + k1, i1 = (int)vloc + k;
+        int i0 = vloc + k1, i1 = vloc + k;
         if (swapped) {  // SurfaceTriangle::ReverseWinding swaps vertices 0 and 1
           const int tmp = i0;
           i0 = i1;
           i1 = tmp;
         }
-        store_face(a, fb + k, pair, h.y, h.z, i0, i1, (int)vloc + n, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft,
-                   swapped);
+        int* fd = a.out.face_data + 3 * (fb + k);
+        fd[0] = i0;
+        fd[1] = i1;
+        fd[2] = vloc + n;
+        store_face(a, fb + k, pair, h.y, h.z, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft, swapped);
         k1 = k;
       }
     }
@@ -853,20 +852,24 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
 
 // ---------------------------------------------------------------------------
 // k_surface: one warp per non-null surface: total area, area-weighted centroid
-// (polygon_surface_mesh.cc:208-217, triangle_surface_mesh.h:476-486), and the
-// per-scene statistics record.
+// (polygon_surface_mesh.cc:208-217, triangle_surface_mesh.h:476-486), offsets,
+// ids, and the per-scene statistics record.
 struct SurfaceArgs {
   const int* surf_pair;
   const PairRec* pairs;
   const long long* poly_off;
   const long long* vert_off;
   int representation;
-  const double* face_f64;
-  long long face_stride;
+  const double* areas;
+  const double* centroids;
   long long* surf_face_off;  // [num_surfaces + 1]
   long long* surf_vert_off;
-  double* surf_f64;          // 4 planes: area, cx, cy, cz; stride surf_stride
-  long long surf_stride;
+  double* surf_total_area;   // [num_surfaces]
+  double* surf_centroid;     // [num_surfaces*3]
+  int* surf_scene;
+  long long* surf_id_m;
+  long long* surf_id_n;
+  unsigned char* surf_flags;
   long long* scene_stats;    // optional [num_scenes * 6]
   Counters* counters;
 };
@@ -890,11 +893,11 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
     }
     double area = 0, cx = 0, cy = 0, cz = 0;
     for (long long f = f0 + lane; f < f1; f += 32) {
-      const double w = a.face_f64[kArea * a.face_stride + f];
+      const double w = a.areas[f];
       area += w;
-      cx += w * a.face_f64[kCx * a.face_stride + f];
-      cy += w * a.face_f64[kCy * a.face_stride + f];
-      cz += w * a.face_f64[kCz * a.face_stride + f];
+      cx += w * a.centroids[3 * f];
+      cy += w * a.centroids[3 * f + 1];
+      cz += w * a.centroids[3 * f + 2];
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -911,19 +914,25 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
       } else {
         // All faces have zero area: the reference keeps the centroid of the
         // last polygon; we report the first face's.
-        cx = a.face_f64[kCx * a.face_stride + f0];
-        cy = a.face_f64[kCy * a.face_stride + f0];
-        cz = a.face_f64[kCz * a.face_stride + f0];
+        cx = a.centroids[3 * f0];
+        cy = a.centroids[3 * f0 + 1];
+        cz = a.centroids[3 * f0 + 2];
       }
+      const PairRec& pr = a.pairs[p];
       a.surf_face_off[s] = f0;
       a.surf_vert_off[s] = v0;
-      a.surf_f64[0 * a.surf_stride + s] = area;
-      a.surf_f64[1 * a.surf_stride + s] = cx;
-      a.surf_f64[2 * a.surf_stride + s] = cy;
-      a.surf_f64[3 * a.surf_stride + s] = cz;
+      a.surf_total_area[s] = area;
+      a.surf_centroid[3 * s] = cx;
+      a.surf_centroid[3 * s + 1] = cy;
+      a.surf_centroid[3 * s + 2] = cz;
+      a.surf_scene[s] = pr.scene;
+      a.surf_id_m[s] = pr.id_m;
+      a.surf_id_n[s] = pr.id_n;
+      // bit0 HasGradE_M, bit1 HasGradE_N, bit2 swapped.
+      a.surf_flags[s] = pr.kind == kSoftSoft ? 3 : (pr.swapped ? (2 | 4) : 1);
       atomicAdd(&a.counters->total_area, area);
       if (a.scene_stats) {
-        unsigned long long* st = (unsigned long long*)(a.scene_stats + 6ll * a.pairs[p].scene);
+        unsigned long long* st = (unsigned long long*)(a.scene_stats + 6ll * pr.scene);
         atomicAdd(st + 3, (unsigned long long)(f1 - f0));
         atomicAdd(st + 4, 1ull);
       }
@@ -945,10 +954,8 @@ __global__ void k_finalize(SurfaceArgs a, int num_pairs) {
   a.counters->poly_verts = (unsigned long long)pverts;
 }
 
-// Per-scene statistics that depend only on the static pair list and the
-// per-pair counters: geometry pairs tested and element pairs (approximated by
-// the pair's polygon count when per-pair candidate counting is off).
-__global__ void k_scene_stats(const PairRec* pairs, int num_pairs, const int* pair_polys, long long* scene_stats) {
+// Per-scene statistics that depend only on the static pair list.
+__global__ void k_scene_stats(const PairRec* pairs, int num_pairs, long long* scene_stats) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= num_pairs) return;
   const PairRec& pr = pairs[p];

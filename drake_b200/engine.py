@@ -116,6 +116,20 @@ def lib():
     L.dbh_batch_copy_geometry_pairs.argtypes = [vp, _ip]
     L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
     L.dbh_batch_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.dbh_mesh_last_error.restype = C.c_char_p
+    dbl = C.c_double
+    L.dbh_mesh_make_sphere_volume.argtypes = [dbl, dbl, C.c_int32, C.POINTER(vp)]
+    L.dbh_mesh_make_ellipsoid_volume.argtypes = [dbl, dbl, dbl, dbl, C.c_int32, C.POINTER(vp)]
+    L.dbh_mesh_make_box_volume_with_ma.argtypes = [dbl, dbl, dbl, C.POINTER(vp)]
+    L.dbh_mesh_make_box_volume.argtypes = [dbl, dbl, dbl, dbl, C.POINTER(vp)]
+    L.dbh_mesh_convert_volume_to_surface.argtypes = [vp, C.POINTER(vp)]
+    L.dbh_mesh_set_sphere_pressure.argtypes = [vp, dbl, dbl, dbl]
+    L.dbh_mesh_set_ellipsoid_pressure.argtypes = [vp, dbl, dbl, dbl, dbl, dbl]
+    L.dbh_mesh_set_box_pressure.argtypes = [vp, dbl, dbl, dbl, dbl, dbl]
+    L.dbh_mesh_get_sizes.argtypes = [vp, _ip, _ip, _ip, _ip]
+    L.dbh_mesh_copy.argtypes = [vp, _dp, _ip, _dp]
+    L.dbh_mesh_destroy.argtypes = [vp]
+    L.dbh_register_mesh.argtypes = [vp, vp, _ip]
     _lib = L
     return L
 
@@ -135,6 +149,109 @@ def _i(a):
 
 def _ptr(a, t):
     return a.ctypes.data_as(t) if a is not None else None
+
+
+SINGLE_INTERIOR_VERTEX, DENSE_INTERIOR_VERTICES = 0, 1
+
+
+class Mesh:
+    """A generated primitive-shape mesh (host memory, set-up time): VolumeMesh (+ pressure field) or
+    TriangleSurfaceMesh. Static constructors mirror the reference generators."""
+
+    def __init__(self, handle):
+        self._h = handle
+        nv, ne, k, hp = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check_mesh(lib().dbh_mesh_get_sizes(self._h, C.byref(nv), C.byref(ne), C.byref(k), C.byref(hp)))
+        self.num_vertices, self.num_elements, self.vertices_per_element = nv.value, ne.value, k.value
+        self._cache = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().dbh_mesh_destroy(self._h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _make(fn, *args) -> "Mesh":
+        h = C.c_void_p()
+        _check_mesh(fn(*args, C.byref(h)))
+        return Mesh(h)
+
+    @staticmethod
+    def sphere_volume(radius, resolution_hint, strategy=SINGLE_INTERIOR_VERTEX) -> "Mesh":
+        return Mesh._make(lib().dbh_mesh_make_sphere_volume, radius, resolution_hint, strategy)
+
+    @staticmethod
+    def ellipsoid_volume(a, b, c, resolution_hint, strategy=SINGLE_INTERIOR_VERTEX) -> "Mesh":
+        return Mesh._make(lib().dbh_mesh_make_ellipsoid_volume, a, b, c, resolution_hint, strategy)
+
+    @staticmethod
+    def box_volume_with_ma(x, y, z) -> "Mesh":
+        return Mesh._make(lib().dbh_mesh_make_box_volume_with_ma, x, y, z)
+
+    @staticmethod
+    def box_volume(x, y, z, resolution_hint) -> "Mesh":
+        return Mesh._make(lib().dbh_mesh_make_box_volume, x, y, z, resolution_hint)
+
+    def to_surface(self) -> "Mesh":
+        return Mesh._make(lib().dbh_mesh_convert_volume_to_surface, self._h)
+
+    @staticmethod
+    def sphere_surface(radius, resolution_hint) -> "Mesh":
+        return Mesh.sphere_volume(radius, resolution_hint, SINGLE_INTERIOR_VERTEX).to_surface()
+
+    @staticmethod
+    def ellipsoid_surface(a, b, c, resolution_hint) -> "Mesh":
+        return Mesh.ellipsoid_volume(a, b, c, resolution_hint, SINGLE_INTERIOR_VERTEX).to_surface()
+
+    @staticmethod
+    def box_surface(x, y, z) -> "Mesh":
+        return Mesh.box_volume_with_ma(x, y, z).to_surface()
+
+    def set_sphere_pressure(self, radius, modulus, margin=0.0) -> "Mesh":
+        _check_mesh(lib().dbh_mesh_set_sphere_pressure(self._h, radius, modulus, margin))
+        self._cache = None
+        return self
+
+    def set_ellipsoid_pressure(self, a, b, c, modulus, margin=0.0) -> "Mesh":
+        _check_mesh(lib().dbh_mesh_set_ellipsoid_pressure(self._h, a, b, c, modulus, margin))
+        self._cache = None
+        return self
+
+    def set_box_pressure(self, x, y, z, modulus, margin=0.0) -> "Mesh":
+        _check_mesh(lib().dbh_mesh_set_box_pressure(self._h, x, y, z, modulus, margin))
+        self._cache = None
+        return self
+
+    def arrays(self):
+        """(vertices [V,3], elements [E,k], pressure [V] or None)."""
+        if self._cache is None:
+            hp = C.c_int32()
+            _check_mesh(lib().dbh_mesh_get_sizes(self._h, None, None, None, C.byref(hp)))
+            v = np.zeros((self.num_vertices, 3))
+            e = np.zeros((self.num_elements, self.vertices_per_element), np.int32)
+            p = np.zeros(self.num_vertices) if hp.value else None
+            _check_mesh(lib().dbh_mesh_copy(self._h, _ptr(v, _dp), _ptr(e, _ip), _ptr(p, _dp)))
+            self._cache = (v, e, p)
+        return self._cache
+
+    @property
+    def vertices(self):
+        return self.arrays()[0]
+
+    @property
+    def elements(self):
+        return self.arrays()[1]
+
+    @property
+    def pressure(self):
+        return self.arrays()[2]
+
+
+def _check_mesh(status: int):
+    if status != OK:
+        raise HydroError(status, lib().dbh_mesh_last_error().decode())
 
 
 class Context:
@@ -170,6 +287,12 @@ class Context:
         v, t = _d(vertices).reshape(-1, 3), _i(tris).reshape(-1, 3)
         out = C.c_int32()
         _check(lib().dbh_register_rigid_mesh(self._h, len(v), _ptr(v, _dp), len(t), _ptr(t, _ip), C.byref(out)))
+        return out.value
+
+    def register_mesh(self, mesh: "Mesh") -> int:
+        """Volume mesh with pressure -> compliant asset; surface mesh -> rigid asset."""
+        out = C.c_int32()
+        _check(lib().dbh_register_mesh(self._h, mesh._h, C.byref(out)))
         return out.value
 
     def asset_info(self, asset: int) -> AssetInfo:
@@ -230,31 +353,44 @@ class ContactSurface:
 class PackedResults:
     """The packed host buffers of one query (all surfaces of all scenes)."""
 
-    def __init__(self, sizes: ResultSizes):
-        ns, nf, nv = sizes.num_surfaces, sizes.num_faces, sizes.num_vertices
+    _LAYOUT = [("surf_scene", np.int32, "s", 1), ("surf_id_M", np.int64, "s", 1), ("surf_id_N", np.int64, "s", 1),
+               ("surf_face_offset", np.int64, "s+1", 1), ("surf_vertex_offset", np.int64, "s+1", 1),
+               ("surf_total_area", np.float64, "s", 1), ("surf_centroid", np.float64, "s", 3),
+               ("surf_flags", np.uint8, "s", 1), ("vertices", np.float64, "v", 3), ("pressures", np.float64, "v", 1),
+               ("face_data", np.int32, "d", 1), ("areas", np.float64, "f", 1), ("normals", np.float64, "f", 3),
+               ("centroids", np.float64, "f", 3), ("pressure_at_centroid", np.float64, "f", 1),
+               ("grad_eM", np.float64, "f", 3), ("grad_eN", np.float64, "f", 3), ("elem_M", np.int32, "f", 1),
+               ("elem_N", np.int32, "f", 1)]
+
+    def __init__(self, sizes: ResultSizes, allocator=None, capacity: Optional[ResultSizes] = None):
+        """allocator(shape, dtype) -> ndarray lets callers supply pinned host memory; `capacity`
+        (>= sizes) allocates larger buffers once so they can be reused across queries."""
         self.representation = sizes.representation
-        self.surf_scene = np.zeros(ns, np.int32)
-        self.surf_id_M = np.zeros(ns, np.int64)
-        self.surf_id_N = np.zeros(ns, np.int64)
-        self.surf_face_offset = np.zeros(ns + 1, np.int64)
-        self.surf_vertex_offset = np.zeros(ns + 1, np.int64)
-        self.surf_total_area = np.zeros(ns)
-        self.surf_centroid = np.zeros((ns, 3))
-        self.surf_flags = np.zeros(ns, np.uint8)
-        self.vertices = np.zeros((nv, 3))
-        self.pressures = np.zeros(nv)
-        self.face_data = np.zeros(sizes.face_data_ints, np.int32)
-        self.areas = np.zeros(nf)
-        self.normals = np.zeros((nf, 3))
-        self.centroids = np.zeros((nf, 3))
-        self.pressure_at_centroid = np.zeros(nf)
-        self.grad_eM = np.zeros((nf, 3))
-        self.grad_eN = np.zeros((nf, 3))
-        self.elem_M = np.zeros(nf, np.int32)
-        self.elem_N = np.zeros(nf, np.int32)
+        self._alloc = allocator or (lambda shape, dtype: np.zeros(shape, dtype))
+        cap = capacity or sizes
+        self._full = {}
+        counts = {"s": cap.num_surfaces, "s+1": cap.num_surfaces + 1, "v": cap.num_vertices, "f": cap.num_faces,
+                  "d": cap.face_data_ints}
+        for name, dtype, kind, width in self._LAYOUT:
+            shape = (counts[kind],) if width == 1 else (counts[kind], width)
+            self._full[name] = self._alloc(shape, dtype)
+        self.resize(sizes)
+
+    def fits(self, sizes: ResultSizes) -> bool:
+        f = self._full
+        return (len(f["surf_scene"]) >= sizes.num_surfaces and len(f["vertices"]) >= sizes.num_vertices and
+                len(f["areas"]) >= sizes.num_faces and len(f["face_data"]) >= sizes.face_data_ints)
+
+    def resize(self, sizes: ResultSizes):
+        """Re-slices the views to the sizes of the latest query (no reallocation)."""
+        self.representation = sizes.representation
+        counts = {"s": sizes.num_surfaces, "s+1": sizes.num_surfaces + 1, "v": sizes.num_vertices,
+                  "f": sizes.num_faces, "d": sizes.face_data_ints}
+        for name, _, kind, _ in self._LAYOUT:
+            setattr(self, name, self._full[name][:counts[kind]])
 
     def nbytes(self) -> int:
-        return sum(getattr(self, k).nbytes for k in vars(self) if isinstance(getattr(self, k), np.ndarray))
+        return sum(getattr(self, name).nbytes for name, _, _, _ in self._LAYOUT)
 
     def c_struct(self) -> ResultBuffers:
         b = ResultBuffers()
@@ -366,6 +502,10 @@ class SceneBatch:
         self._keep = P  # the H2D copy is asynchronous
         _check(lib().dbh_batch_set_poses_host(self._h, _ptr(P, _dp)))
 
+    def set_poses_host_ptr(self, host_ptr: int):
+        """Same as set_poses for a caller-owned (ideally pinned) host buffer of G*12 doubles."""
+        _check(lib().dbh_batch_set_poses_host(self._h, C.cast(C.c_void_p(host_ptr), _dp)))
+
     def set_poses_device(self, device_ptr: int):
         _check(lib().dbh_batch_set_poses_device(self._h, C.c_void_p(device_ptr)))
 
@@ -410,7 +550,12 @@ class SceneBatch:
         return {n: getattr(s, n) for n, _ in Stats._fields_ if n != "reserved"}
 
     def copy_results(self, into: Optional[PackedResults] = None) -> PackedResults:
-        res = into if into is not None else PackedResults(self.sizes())
+        sizes = self.sizes()
+        if into is not None and into.fits(sizes):
+            res = into
+            res.resize(sizes)
+        else:
+            res = PackedResults(sizes)
         bufs = res.c_struct()
         _check(lib().dbh_batch_copy_results(self._h, C.byref(bufs)))
         return res

@@ -91,6 +91,35 @@ dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* o
 dbh_status dbh_asset_get_derived(dbh_context* ctx, int32_t asset, double* gradients_or_normals,
                                  double* values_at_Mo, double* inward_normals);
 
+/* -- (2b) primitive-shape mesh + pressure-field generators (host, set-up time).
+ *        Same topology, element order and vertex order as the reference's
+ *        MakeSphereVolumeMesh (make_sphere_mesh.h:543-598), MakeEllipsoidVolumeMesh
+ *        (make_ellipsoid_mesh.h:50-73), MakeBoxVolumeMeshWithMaAndSymmetricTriangles
+ *        (make_box_mesh.cc:475-504), MakeBoxVolumeMesh (make_box_mesh.cc:870-890),
+ *        ConvertVolumeToSurfaceMesh (volume_to_surface_mesh.cc:152-187) and
+ *        Make{Sphere,Ellipsoid,Box}PressureField. strategy: 0 = kSingleInteriorVertex,
+ *        1 = kDenseInteriorVertices (tessellation_strategy.h). ------------------- */
+typedef struct dbh_mesh dbh_mesh;
+const char* dbh_mesh_last_error(void);
+dbh_status dbh_mesh_make_sphere_volume(double radius, double resolution_hint, int32_t strategy, dbh_mesh** out);
+dbh_status dbh_mesh_make_ellipsoid_volume(double a, double b, double c, double resolution_hint, int32_t strategy,
+                                          dbh_mesh** out);
+dbh_status dbh_mesh_make_box_volume_with_ma(double x, double y, double z, dbh_mesh** out);
+dbh_status dbh_mesh_make_box_volume(double x, double y, double z, double resolution_hint, dbh_mesh** out);
+dbh_status dbh_mesh_convert_volume_to_surface(const dbh_mesh* volume, dbh_mesh** out);
+dbh_status dbh_mesh_set_sphere_pressure(dbh_mesh* mesh, double radius, double hydroelastic_modulus, double margin);
+dbh_status dbh_mesh_set_ellipsoid_pressure(dbh_mesh* mesh, double a, double b, double c, double hydroelastic_modulus,
+                                           double margin);
+dbh_status dbh_mesh_set_box_pressure(dbh_mesh* mesh, double x, double y, double z, double hydroelastic_modulus,
+                                     double margin);
+dbh_status dbh_mesh_get_sizes(const dbh_mesh* mesh, int32_t* num_vertices, int32_t* num_elements,
+                              int32_t* vertices_per_element, int32_t* has_pressure);
+/* vertices [nv*3], elements [ne*vertices_per_element], pressure [nv]; any may be NULL. */
+dbh_status dbh_mesh_copy(const dbh_mesh* mesh, double* vertices, int32_t* elements, double* pressure);
+void dbh_mesh_destroy(dbh_mesh* mesh);
+/* Registers a generated mesh: volume mesh with pressure -> compliant asset, surface mesh -> rigid asset. */
+dbh_status dbh_register_mesh(dbh_context* ctx, const dbh_mesh* mesh, int32_t* asset_out);
+
 /* -- (3) scene batch (the SceneGraph / ProximityEngine registration state for
  *        many independent scenes: AddDynamicGeometry / AddAnchoredGeometry /
  *        collision_filter(), proximity_engine.h:87,122-133). ------------------- */
@@ -184,21 +213,30 @@ typedef struct dbh_result_buffers {
 } dbh_result_buffers;
 dbh_status dbh_batch_copy_results(dbh_batch* batch, const dbh_result_buffers* buffers);
 
-/* Device-resident views of the same arrays for GPU consumers (valid until the
- * next query). Vector quantities are structure-of-arrays on the device:
- * component c of item i lives at base[c * stride + i]. */
+/* Device-resident views of the same arrays, in the same layout, for GPU
+ * consumers (valid until the next query on this batch). */
 typedef struct dbh_device_results {
   const int32_t* surf_pair;        /* index into the static geometry-pair list */
+  const int32_t* surf_scene;
+  const int64_t* surf_id_M;
+  const int64_t* surf_id_N;
   const int64_t* surf_face_offset;
   const int64_t* surf_vertex_offset;
   const double* surf_total_area;
-  const double* surf_centroid;     /* SoA, stride = surf_stride */
-  int64_t surf_stride;
-  const double* vertices;          /* SoA x|y|z|pressure, stride = vertex_stride */
-  int64_t vertex_stride;
-  const double* face_f64;          /* SoA planes: area, nx,ny,nz, cx,cy,cz, e_c, gMx..gMz, gNx..gNz */
-  int64_t face_stride;
-  const int32_t* face_i32;         /* SoA planes: pair, elem_M, elem_N, nverts, vertex_begin */
+  const double* surf_centroid;
+  const uint8_t* surf_flags;
+  const double* vertices;
+  const double* pressures;
+  const int32_t* face_data;
+  const double* areas;
+  const double* normals;
+  const double* centroids;
+  const double* pressure_at_centroid;
+  const double* grad_eM;
+  const double* grad_eN;
+  const int32_t* elem_M;
+  const int32_t* elem_N;
+  const int32_t* face_pair;        /* per face: index into the static geometry-pair list */
 } dbh_device_results;
 dbh_status dbh_batch_device_results(dbh_batch* batch, dbh_device_results* out);
 
