@@ -120,25 +120,8 @@ class ClockSampler:
 
 def oracle_scene(workload):
     """Builds the oracle's scene from the SAME arrays the GPU registered (cpu_baseline / reference arm)."""
-    from oracle import ho
-    sc = ho.Scene()
-    cache = {}
-    for g, mi in enumerate(workload.geom_mesh):
-        m = workload.meshes[mi]
-        if mi not in cache:
-            v, e, p = m.arrays()
-            if m.vertices_per_element == 4:
-                om = ho.VolumeMesh.from_arrays(v, e)
-                cache[mi] = (om, ho.VolumeField.from_values(om, p))
-            else:
-                cache[mi] = (ho.TriMesh.from_arrays(v, e), None)
-        om, of = cache[mi]
-        if of is None:
-            sc.add_rigid(workload.geom_id[g], om, bool(workload.geom_anchored[g]))
-        else:
-            sc.add_compliant(workload.geom_id[g], om, of, bool(workload.geom_anchored[g]))
-    order = np.argsort(np.asarray(workload.geom_id))  # the oracle wants poses by ascending id
-    return sc, order
+    from tests import parity
+    return parity.oracle_scene_for(workload)
 
 
 def time_cpu_port(workload, rep: int, budget_s: float, threads: int):
@@ -348,8 +331,8 @@ def main():
     dominant = max(alg, key=lambda k: avg.get(k, 0.0))
     peak, peak_kind = measured_peaks()
     achieved = alg[dominant] / (avg[dominant] * 1e-3) / 1e9 if avg[dominant] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": {"traverse": "k_traverse", "clip_tet_tri": "k_clip_tri",
-                                           "clip_tet_tet": "k_clip_tet"}[dominant],
+    roofline = {"bound": "hbm", "kernel": {"traverse": "k_traverse", "clip_tet_tri": "k_clip<false>",
+                                           "clip_tet_tet": "k_clip<true>"}[dominant],
                 "achieved": achieved, "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": avg[dominant],
@@ -358,7 +341,7 @@ def main():
 
     info = batch.info()
     launches_per_step = 1 + info.max_traversal_levels + (1 if info.num_soft_rigid_pairs else 0) + \
-        (1 if info.num_soft_soft_pairs else 0) + 3 + 1 + 2 + 1
+        (1 if info.num_soft_soft_pairs else 0) + 1 + 3 + 1 + 2 + 1
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

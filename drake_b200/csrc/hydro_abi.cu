@@ -61,13 +61,12 @@ struct HostAsset {
   int num_elements{0};
   int height{0};
   std::vector<TetRec> tets;
-  std::vector<TetNormals> normals;
+  std::vector<TetAux> aux;
   std::vector<TriRec> tris;
-  std::vector<BvhNode> nodes;
-  DevBuf<TetRec> d_tets;
-  DevBuf<TetNormals> d_normals;
-  DevBuf<TriRec> d_tris;
-  DevBuf<BvhNode> d_nodes;
+  std::vector<BvhNode> nodes;   // links local to this asset; rebased into the pool on upload
+  // First pool index of this asset's elements (tet pool or tri pool) and nodes.
+  int elem_base{0};
+  int node_base{0};
 };
 
 struct Box {
@@ -162,26 +161,69 @@ struct dbh_context {
   int device{0};
   cudaDeviceProp prop{};
   std::vector<std::unique_ptr<HostAsset>> assets;
-  DevBuf<AssetDev> d_assets;
-  bool assets_dirty{true};
+  // Pools: every asset's records concatenated in registration order, so pool
+  // indices handed out at registration stay valid when later assets are added.
+  long long num_tets{0}, num_tris{0}, num_nodes{0};
+  DevBuf<TetRec> d_tets;
+  DevBuf<TetAux> d_aux;
+  DevBuf<TriRec> d_tris;
+  DevBuf<BvhNode> d_nodes;
+  size_t uploaded_assets{0};
+  long long up_tets{0}, up_tris{0}, up_nodes{0};
 
-  dbh_status UploadAssetTable() {
-    if (!assets_dirty) return DBH_OK;
-    std::vector<AssetDev> tab(assets.size());
-    for (size_t i = 0; i < assets.size(); ++i) {
-      const HostAsset& a = *assets[i];
-      tab[i].tets = a.d_tets.p;
-      tab[i].normals = a.d_normals.p;
-      tab[i].tris = a.d_tris.p;
-      tab[i].nodes = a.d_nodes.p;
-      tab[i].num_elements = a.num_elements;
-      tab[i].num_nodes = static_cast<int>(a.nodes.size());
-      tab[i].type = a.type;
-      tab[i].height = a.height;
+  Pools pools() const { return Pools{d_tets.p, d_aux.p, d_tris.p, d_nodes.p}; }
+
+  void Place(HostAsset* a) {
+    a->node_base = static_cast<int>(num_nodes);
+    num_nodes += static_cast<long long>(a->nodes.size());
+    if (a->type == DBH_COMPLIANT) {
+      a->elem_base = static_cast<int>(num_tets);
+      num_tets += a->num_elements;
+    } else {
+      a->elem_base = static_cast<int>(num_tris);
+      num_tris += a->num_elements;
     }
-    CUDA_OK(d_assets.alloc(tab.size()));
-    CUDA_OK(cudaMemcpy(d_assets.p, tab.data(), tab.size() * sizeof(AssetDev), cudaMemcpyHostToDevice));
-    assets_dirty = false;
+  }
+
+  // Uploads assets registered since the last call. Pools grow geometrically;
+  // growing re-uploads everything (set-up path).
+  dbh_status UploadPools() {
+    if (uploaded_assets == assets.size()) return DBH_OK;
+    auto grow = [](auto& buf, long long need, bool* regrown) -> cudaError_t {
+      if (static_cast<long long>(buf.n) >= need && buf.p) return cudaSuccess;
+      *regrown = true;
+      return buf.alloc(static_cast<size_t>(std::max<long long>(need + need / 2, 1024)));
+    };
+    bool regrown = false;
+    CUDA_OK(grow(d_tets, num_tets, &regrown));
+    CUDA_OK(grow(d_aux, num_tets, &regrown));
+    CUDA_OK(grow(d_tris, num_tris, &regrown));
+    CUDA_OK(grow(d_nodes, num_nodes, &regrown));
+    const size_t first = regrown ? 0 : uploaded_assets;
+    std::vector<BvhNode> rebased;
+    for (size_t i = first; i < assets.size(); ++i) {
+      const HostAsset& a = *assets[i];
+      if (a.type == DBH_COMPLIANT) {
+        CUDA_OK(cudaMemcpy(d_tets.p + a.elem_base, a.tets.data(), a.tets.size() * sizeof(TetRec),
+                           cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_aux.p + a.elem_base, a.aux.data(), a.aux.size() * sizeof(TetAux), cudaMemcpyHostToDevice));
+      } else {
+        CUDA_OK(cudaMemcpy(d_tris.p + a.elem_base, a.tris.data(), a.tris.size() * sizeof(TriRec),
+                           cudaMemcpyHostToDevice));
+      }
+      rebased = a.nodes;
+      for (BvhNode& n : rebased) {
+        if (n.left < 0) {
+          n.left = ~(~n.left + a.elem_base);
+        } else {
+          n.left += a.node_base;
+          n.right += a.node_base;
+        }
+      }
+      CUDA_OK(cudaMemcpy(d_nodes.p + a.node_base, rebased.data(), rebased.size() * sizeof(BvhNode),
+                         cudaMemcpyHostToDevice));
+    }
+    uploaded_assets = assets.size();
     return DBH_OK;
   }
 };
@@ -204,7 +246,8 @@ struct dbh_batch {
   const Xf* d_poses{nullptr};
   DevBuf<Xf> d_pair_X;
   DevBuf<int4> d_frontier[2];
-  DevBuf<int4> d_cand_tri, d_cand_tet;
+  DevBuf<int4> d_cand_tri, d_cand_tet, d_slow;
+  long long cap_slow{1 << 16};
   DevBuf<Counters> d_counters;
   DevBuf<int> d_pair_polys, d_pair_verts, d_surf_index, d_surf_pair;
   DevBuf<unsigned long long> d_pair_cursor;
@@ -239,6 +282,7 @@ struct dbh_batch {
     CUDA_OK(d_frontier[1].ensure(cap_frontier));
     CUDA_OK(d_cand_tri.ensure(info.num_soft_rigid_pairs ? cap_cand : 1));
     CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_cand : 1));
+    CUDA_OK(d_slow.ensure(cap_slow));
     CUDA_OK(d_soup_hdr.ensure(cap_polys));
     CUDA_OK(d_soup_v.ensure(static_cast<size_t>(cap_polys) * kMaxPolyVerts * 4));
     CUDA_OK(d_soup_nhat.ensure(static_cast<size_t>(cap_polys) * 3));
@@ -279,8 +323,8 @@ dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out) {
   CUDA_OK(cudaGetDeviceProperties(&ctx->prop, device_ordinal));
   if (ctx->prop.major < 10)
     return Fail(DBH_ERR_NO_DEVICE, "device is not sm_100 class; kernels are built for sm_100a only");
-  CUDA_OK(cudaFuncSetAttribute(k_clip_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
-  CUDA_OK(cudaFuncSetAttribute(k_clip_tet, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_clip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_clip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
   *out = ctx.release();
   return DBH_OK;
 }
@@ -299,7 +343,7 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
   a->num_vertices = nv;
   a->num_elements = nt;
   a->tets.resize(nt);
-  a->normals.resize(nt);
+  a->aux.resize(nt);
   constexpr double kEps = std::numeric_limits<double>::epsilon();
   for (int e = 0; e < nt; ++e) {
     TetRec& r = a->tets[e];
@@ -332,21 +376,48 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
     const D3 ab = v[1] - v[0], ac = v[2] - v[0], ad = v[3] - v[0], bc = v[2] - v[1], bd = v[3] - v[1];
     const D3 n[4] = {normalized(cross(bd, bc)), normalized(cross(ac, ad)), normalized(cross(ad, ab)),
                      normalized(cross(ab, ac))};
+    TetAux& x = a->aux[e];
     for (int f = 0; f < 4; ++f) {
-      a->normals[e].n[f][0] = n[f].x;
-      a->normals[e].n[f][1] = n[f].y;
-      a->normals[e].n[f][2] = n[f].z;
+      x.inward[f][0] = n[f].x;
+      x.inward[f][1] = n[f].y;
+      x.inward[f][2] = n[f].z;
+    }
+    // Face half spaces of ClipTriangleByTetrahedron (mesh_intersection.cc:225-238 + plane.cc:16-29).
+    static const int kFaces[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+    for (int f = 0; f < 4; ++f) {
+      const D3 A = v[kFaces[f][0]], B = v[kFaces[f][1]], C = v[kFaces[f][2]];
+      const D3 normal = cross(B - A, C - A);
+      const double mag = norm(normal);
+      if (mag < 1e-10) {
+        x.plane_nh[f][0] = x.plane_nh[f][1] = x.plane_nh[f][2] = 0.0;
+        x.plane_d[f] = std::numeric_limits<double>::quiet_NaN();  // the Plane ctor throws when reached
+      } else {
+        const D3 nh = normal / mag;
+        x.plane_nh[f][0] = nh.x;
+        x.plane_nh[f][1] = nh.y;
+        x.plane_nh[f][2] = nh.z;
+        x.plane_d[f] = dot(nh, A);
+      }
+    }
+    const D3 ng = normalized(g);
+    x.ngrad[0] = ng.x;
+    x.ngrad[1] = ng.y;
+    x.ngrad[2] = ng.z;
+    // Shape factor for the cull margins: the tetrahedron bounded by the four face planes offset
+    // outward by e is this one scaled about its incentre by (1 + e / inradius).
+    {
+      const D3 cd = v[3] - v[2];
+      const double diam2 = std::max({dot(ab, ab), dot(ac, ac), dot(ad, ad), dot(bc, bc), dot(bd, bd), dot(cd, cd)});
+      const double vol6 = std::fabs(dot(cross(ab, ac), ad));
+      const double area2 = norm(cross(bd, bc)) + norm(cross(ac, ad)) + norm(cross(ad, ab)) + norm(cross(ab, ac));
+      const double inradius = area2 > 0 ? vol6 / area2 : 0.0;  // 3V / sum(A) = (vol6 / 2) / (area2 / 2)
+      x.amp = inradius > 0 ? std::sqrt(diam2) / inradius : 1e300;
+      if (!(x.amp < 1e300)) x.amp = 1e300;
     }
   }
   BuildAssetBvh<4>(verts, tets, nt, a.get());
-  CUDA_OK(a->d_tets.alloc(nt));
-  CUDA_OK(a->d_normals.alloc(nt));
-  CUDA_OK(a->d_nodes.alloc(a->nodes.size()));
-  CUDA_OK(cudaMemcpy(a->d_tets.p, a->tets.data(), nt * sizeof(TetRec), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(a->d_normals.p, a->normals.data(), nt * sizeof(TetNormals), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(a->d_nodes.p, a->nodes.data(), a->nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+  ctx->Place(a.get());
   ctx->assets.push_back(std::move(a));
-  ctx->assets_dirty = true;
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
   return DBH_OK;
 }
@@ -381,12 +452,8 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* v
     r.n[2] = n.z;
   }
   BuildAssetBvh<3>(verts, tris, nt, a.get());
-  CUDA_OK(a->d_tris.alloc(nt));
-  CUDA_OK(a->d_nodes.alloc(a->nodes.size()));
-  CUDA_OK(cudaMemcpy(a->d_tris.p, a->tris.data(), nt * sizeof(TriRec), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(a->d_nodes.p, a->nodes.data(), a->nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+  ctx->Place(a.get());
   ctx->assets.push_back(std::move(a));
-  ctx->assets_dirty = true;
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
   return DBH_OK;
 }
@@ -413,20 +480,21 @@ dbh_status dbh_asset_get_derived(dbh_context* ctx, int32_t asset, double* g_or_n
     return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_get_derived: bad argument");
   CUDA_OK(cudaSetDevice(ctx->device));
   HostAsset& a = *ctx->assets[asset];
-  // Read back from the device copies so tests see what the kernels see.
+  if (dbh_status st = ctx->UploadPools()) return st;
+  // Read back from the device pools so tests see what the kernels see.
   if (a.type == DBH_COMPLIANT) {
     std::vector<TetRec> t(a.num_elements);
-    std::vector<TetNormals> n(a.num_elements);
-    CUDA_OK(cudaMemcpy(t.data(), a.d_tets.p, t.size() * sizeof(TetRec), cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(n.data(), a.d_normals.p, n.size() * sizeof(TetNormals), cudaMemcpyDeviceToHost));
+    std::vector<TetAux> n(a.num_elements);
+    CUDA_OK(cudaMemcpy(t.data(), ctx->d_tets.p + a.elem_base, t.size() * sizeof(TetRec), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(n.data(), ctx->d_aux.p + a.elem_base, n.size() * sizeof(TetAux), cudaMemcpyDeviceToHost));
     for (int e = 0; e < a.num_elements; ++e) {
       if (g_or_n) std::memcpy(g_or_n + 3 * e, t[e].grad, 24);
       if (at_Mo) at_Mo[e] = t[e].p_mo;
-      if (inward) std::memcpy(inward + 12 * e, n[e].n, 96);
+      if (inward) std::memcpy(inward + 12 * e, n[e].inward, 96);
     }
   } else {
     std::vector<TriRec> t(a.num_elements);
-    CUDA_OK(cudaMemcpy(t.data(), a.d_tris.p, t.size() * sizeof(TriRec), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(t.data(), ctx->d_tris.p + a.elem_base, t.size() * sizeof(TriRec), cudaMemcpyDeviceToHost));
     for (int e = 0; e < a.num_elements; ++e)
       if (g_or_n) std::memcpy(g_or_n + 3 * e, t[e].n, 24);
   }
@@ -461,6 +529,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   std::sort(excl.begin(), excl.end());
   // Static geometry-pair list in (scene, id_M, id_N) order.
   int max_levels = 1;
+  long long est = 0;
   for (int s = 0; s < num_scenes; ++s) {
     const int g0 = scene_offsets[s], g1 = scene_offsets[s + 1];
     std::vector<int> order(g1 - g0);
@@ -498,10 +567,19 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
           }
           ++b->info.num_soft_rigid_pairs;
         }
-        pr.asset_a = geom_asset[pr.geom_a];
-        pr.asset_b = geom_asset[pr.geom_b];
-        if (pr.kind <= kSoftSoft) {
-          max_levels = std::max(max_levels, std::max(ctx->assets[pr.asset_a]->height, ctx->assets[pr.asset_b]->height) + 1);
+        pr.root_a = pr.root_b = -1;
+        if (pr.kind != kUnsupported) {
+          const HostAsset& A = *ctx->assets[geom_asset[pr.geom_a]];
+          const HostAsset& B = *ctx->assets[geom_asset[pr.geom_b]];
+          pr.root_a = A.node_base;
+          pr.root_b = B.node_base;
+          pr.elem_base_a = A.elem_base;
+          pr.elem_base_b = B.elem_base;
+          pr.root_leaf = (A.nodes[0].left < 0 ? 1 : 0) | (B.nodes[0].left < 0 ? 2 : 0);
+          if (pr.kind <= kSoftSoft) {
+            max_levels = std::max(max_levels, std::max(A.height, B.height) + 1);
+            est += 2ll * (A.num_elements + B.num_elements);
+          }
         }
         b->pairs.push_back(pr);
       }
@@ -514,18 +592,16 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   b->info.max_traversal_levels = max_levels;
   if (max_levels > 62) return Fail(DBH_ERR_INVALID_ARGUMENT, "BVH too deep");
 
-  // Default capacities: a few entries per element of every pair; grown by
-  // the caller on DBH_ERR_CAPACITY.
-  long long est = 0;
-  for (const PairRec& pr : b->pairs)
-    if (pr.kind <= kSoftSoft)
-      est += 2ll * (ctx->assets[pr.asset_a]->num_elements + ctx->assets[pr.asset_b]->num_elements);
-  est = std::max(est, 1ll << 16);
-  b->cap_frontier = est;
+  // Default capacities: a few entries per element of every pair, bounded (a
+  // scene with many geometries has mostly non-overlapping pairs); the first
+  // queries of a batch grow exactly the lists that overflow
+  // (dbh_batch_grow_capacity) and steady state never reallocates.
+  est = std::min(std::max(est, 1ll << 16), 1ll << 23);
+  b->cap_frontier = std::max<long long>(est, b->pairs.size());
   b->cap_cand = est;
-  b->cap_polys = est / 2;
-  b->cap_faces = est * 2;
-  b->cap_verts = est * 3;
+  b->cap_polys = est / 4;
+  b->cap_faces = est / 2;
+  b->cap_verts = est;
 
   CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaMallocHost(&b->h_counters, sizeof(Counters)));
@@ -574,6 +650,29 @@ dbh_status dbh_batch_set_capacity(dbh_batch* b, int64_t max_bv_pairs, int64_t ma
   return DBH_OK;
 }
 
+dbh_status dbh_batch_grow_capacity(dbh_batch* b) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  // The device counters keep counting past a full list, so after a failed
+  // query they say how many entries the failing stage wanted. Later stages did
+  // not run; the caller re-runs until the query fits (a handful of set-up
+  // iterations at most, each at least doubling what overflowed).
+  const Counters& c = *b->h_counters;
+  auto want = [](unsigned long long needed, long long cap) {
+    return static_cast<long long>(needed) > cap ? static_cast<long long>(needed) * 2 : cap;
+  };
+  unsigned long long fr = 0;
+  for (int l = 0; l < 64; ++l) fr = std::max(fr, c.frontier[l]);
+  b->cap_frontier = want(fr, b->cap_frontier);
+  b->cap_cand = want(std::max(c.cand_tri, c.cand_tet), b->cap_cand);
+  b->cap_polys = want(c.polys, b->cap_polys);
+  b->cap_slow = want(c.slow, b->cap_slow);
+  // Faces / vertices of either representation (triangle: one face per polygon vertex, one extra
+  // vertex per polygon), so switching representation does not overflow again.
+  b->cap_faces = want(std::max(c.faces, c.poly_verts), b->cap_faces);
+  b->cap_verts = want(std::max(c.vertices, c.poly_verts + c.polys), b->cap_verts);
+  return DBH_OK;
+}
+
 dbh_status dbh_batch_get_info(dbh_batch* b, dbh_batch_info* out) {
   if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_get_info: bad argument");
   *out = b->info;
@@ -608,7 +707,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_query: bad argument");
   dbh_context* ctx = b->ctx;
   CUDA_OK(cudaSetDevice(ctx->device));
-  if (dbh_status s = ctx->UploadAssetTable()) return s;
+  if (dbh_status s = ctx->UploadPools()) return s;
   if (dbh_status s = b->AllocWorkBuffers()) return s;
   b->representation = representation;
   b->query_done = false;
@@ -625,7 +724,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     PairsArgs pa{};
     pa.pairs = b->d_pairs.p;
     pa.num_pairs = b->num_pairs;
-    pa.assets = ctx->d_assets.p;
+    pa.pools = ctx->pools();
     pa.poses = b->d_poses;
     pa.pair_X = b->d_pair_X.p;
     pa.frontier0 = b->d_frontier[0].p;
@@ -639,9 +738,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     mark(1);
     // Dual-BVH traversal, one launch per level; counts stay on the device.
     TraverseArgs ta{};
-    ta.pairs = b->d_pairs.p;
     ta.pair_X = b->d_pair_X.p;
-    ta.assets = ctx->d_assets.p;
+    ta.pools = ctx->pools();
     ta.cand_tri = b->d_cand_tri.p;
     ta.cand_tet = b->d_cand_tet.p;
     ta.cand_capacity = static_cast<unsigned long long>(b->cap_cand);
@@ -655,9 +753,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     }
     mark(2);
     ClipArgs ca{};
-    ca.pairs = b->d_pairs.p;
     ca.pair_X = b->d_pair_X.p;
-    ca.assets = ctx->d_assets.p;
+    ca.cand_capacity = static_cast<unsigned long long>(b->cap_cand);
+    ca.pools = ctx->pools();
     ca.soup.hdr = b->d_soup_hdr.p;
     ca.soup.v = b->d_soup_v.p;
     ca.soup.nhat = b->d_soup_nhat.p;
@@ -665,16 +763,20 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     ca.pair_polys = b->d_pair_polys.p;
     ca.pair_verts = b->d_pair_verts.p;
     ca.counters = b->d_counters.p;
-    const int clip_blocks = sms * 3;
+    ca.slow = b->d_slow.p;
+    ca.slow_capacity = static_cast<unsigned int>(b->cap_slow);
+    const int clip_blocks = sms * 4;
     if (b->info.num_soft_rigid_pairs) {
       ca.cand = b->d_cand_tri.p;
-      k_clip_tri<<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+      k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
     }
     mark(3);
     if (b->info.num_soft_soft_pairs) {
       ca.cand = b->d_cand_tet.p;
-      k_clip_tet<<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+      k_clip<true><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
     }
+    // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
+    k_clip_slow<<<sms, 64, 0, st>>>(ca);
     mark(4);
     ScanArgs sa{};
     sa.pair_polys = b->d_pair_polys.p;
@@ -694,7 +796,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     PackArgs pk{};
     pk.soup = ca.soup;
     pk.pairs = b->d_pairs.p;
-    pk.assets = ctx->d_assets.p;
+    pk.pools = ctx->pools();
     pk.poses = b->d_poses;
     pk.poly_off = b->d_poly_off.p;
     pk.vert_off = b->d_vert_off.p;
@@ -764,9 +866,9 @@ dbh_status dbh_batch_sync(dbh_batch* b) {
   if (c.error != 0) {
     static const char* kWhere[] = {"",          "BV-pair frontier", "element-pair list", "polygon staging",
                                    "tet-tri polygon > 8 vertices", "tet-tet polygon > 8 vertices", "face arrays",
-                                   "vertex arrays"};
+                                   "vertex arrays", "exceptional-candidate list"};
     if (c.error == DBH_ERR_CAPACITY) {
-      const int d = (c.error_detail >= 1 && c.error_detail <= 7) ? c.error_detail : 0;
+      const int d = (c.error_detail >= 1 && c.error_detail <= 8) ? c.error_detail : 0;
       return Fail(DBH_ERR_CAPACITY, std::string("device work list overflow: ") + kWhere[d]);
     }
     if (c.error == DBH_ERR_RIGID_RIGID)
@@ -819,6 +921,8 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->vertices = static_cast<int64_t>(c.vertices);
   out->surfaces = static_cast<int64_t>(c.surfaces);
   out->total_area = c.total_area;
+  out->tet_tri_full_clips = static_cast<int64_t>(c.full_clips_tri);
+  out->tet_tet_full_clips = static_cast<int64_t>(c.full_clips_tet);
   // BV test 128 B; tet-tri pair 260 B in; tet-tet pair 392 B in;
   // emitted n-gon 32 n + 96 (soft-rigid) / + 120 (soft-soft) out; pose 96 B per geometry.
   // Triangle representation adds 32 B centroid vertex + n (12 + 24 + 8) B per polygon.
@@ -840,9 +944,10 @@ dbh_status dbh_batch_copy_candidates(dbh_batch* b, int32_t kind, int32_t* out_tr
   CUDA_OK(cudaMemcpy(tmp.data(), kind == 0 ? b->d_cand_tri.p : b->d_cand_tet.p, n * sizeof(int4),
                      cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n; ++i) {
+    const PairRec& pr = b->pairs[tmp[i].x];
     out_triples[3 * i] = tmp[i].x;
-    out_triples[3 * i + 1] = tmp[i].y;
-    out_triples[3 * i + 2] = tmp[i].z;
+    out_triples[3 * i + 1] = tmp[i].y - pr.elem_base_a;
+    out_triples[3 * i + 2] = tmp[i].z - pr.elem_base_b;
   }
   return DBH_OK;
 }

@@ -2,9 +2,9 @@
 //
 //   k_pairs      pose composition X_MN = X_WM^-1 X_WN per geometry pair, level-0 frontier
 //   k_traverse   one level of the dual-BVH traversal (replaces Bvh::Collide, bvh.h:220-262)
-//   k_clip_tri   tet-triangle clipping (SurfaceVolumeIntersector::CalcContactPolygon,
+//   k_clip<0>    tet-triangle clipping (SurfaceVolumeIntersector::CalcContactPolygon,
 //                mesh_intersection.cc:321-382)
-//   k_clip_tet   tet-tet equilibrium-plane clipping (VolumeIntersector::CalcContactPolygon,
+//   k_clip<1>    tet-tet equilibrium-plane clipping (VolumeIntersector::CalcContactPolygon,
 //                field_intersection.cc:377-428)
 //   k_scan_*     per-pair face/vertex offsets (CSR) and surface compaction
 //   k_pack       per-polygon area / normal / centroid / pressure, world transform, id-order
@@ -30,23 +30,31 @@ constexpr double kCosAlphaDevice = -0.38268343236508973;  // cos(5*pi/8) as std:
 __device__ __forceinline__ unsigned long long warp_append(unsigned long long* counter, int n) {
   const unsigned mask = __activemask();
   const int lane = threadIdx.x & 31;
+  if (mask != 0xffffffffu) {
+    // Partial warps only occur on exceptional paths: plain per-lane atomics.
+    return n ? atomicAdd(counter, (unsigned long long)n) : 0ull;
+  }
   int incl = n;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const int y = __shfl_up_sync(mask, incl, d);
+    const int y = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += y;
   }
-  // `mask` may be partial only at loop tails where whole trailing lanes are
-  // missing, so shfl_up from a missing lane never happens for active lanes
-  // below it... to stay safe we fall back to per-lane atomics on partial warps.
-  if (mask != 0xffffffffu) {
-    return n ? atomicAdd(counter, (unsigned long long)n) : 0ull;
-  }
-  const int total = __shfl_sync(mask, incl, 31);
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
   unsigned long long base = 0;
   if (lane == 31 && total) base = atomicAdd(counter, (unsigned long long)total);
-  base = __shfl_sync(mask, base, 31);
+  base = __shfl_sync(0xffffffffu, base, 31);
   return base + (unsigned long long)(incl - n);
+}
+
+// Same for lists where every lane contributes 0 or 1 entries (ballot + popc).
+__device__ __forceinline__ unsigned long long warp_append_flag(unsigned long long* counter, bool flag) {
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0 && m) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
 }
 
 __device__ __forceinline__ void raise_error(Counters* c, int status, int detail) {
@@ -58,10 +66,10 @@ __device__ __forceinline__ void raise_error(Counters* c, int status, int detail)
 struct PairsArgs {
   const PairRec* pairs;
   int num_pairs;
-  const AssetDev* assets;
+  Pools pools;
   const Xf* poses;       // X_WG per flat geometry index
   Xf* pair_X;            // out: X_MN per pair
-  int4* frontier0;       // out: level-0 frontier
+  int4* frontier0;       // out: level-0 frontier {pair, node a, node b, kind}
   Counters* counters;
   int strict;            // DBH_QUERY_STRICT
   int* pair_polys;       // zeroed here
@@ -73,11 +81,13 @@ __global__ void k_pairs(PairsArgs a) {
   // Launched with whole warps covering num_pairs rounded up to 32.
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   bool push = false;
+  PairRec pr;
+  pr.root_a = pr.root_b = pr.kind = 0;
   if (p < a.num_pairs) {
     a.pair_polys[p] = 0;
     a.pair_verts[p] = 0;
     a.pair_cursor[p] = 0ull;
-    const PairRec pr = a.pairs[p];
+    pr = a.pairs[p];
     if (pr.kind == kUnsupported) {
       if (a.strict) raise_error(a.counters, 7 /*DBH_ERR_UNSUPPORTED*/, p);
     } else {
@@ -89,8 +99,8 @@ __global__ void k_pairs(PairsArgs a) {
         // Stand-in for the geometry-level broad phase (FCL tree,
         // proximity_engine.cc:867-883): the pair only fails if the root boxes overlap.
         if (a.strict) {
-          const BvhNode& na = a.assets[pr.asset_a].nodes[0];
-          const BvhNode& nb = a.assets[pr.asset_b].nodes[0];
+          const BvhNode& na = a.pools.nodes[pr.root_a];
+          const BvhNode& nb = a.pools.nodes[pr.root_b];
           const D3 t = xform_point(X_AB, load3(nb.c)) - load3(na.c);
           if (boxes_overlap(na.h, nb.h, X_AB, t)) raise_error(a.counters, 6 /*DBH_ERR_RIGID_RIGID*/, p);
         }
@@ -99,20 +109,21 @@ __global__ void k_pairs(PairsArgs a) {
       }
     }
   }
-  const unsigned long long slot = warp_append(&a.counters->frontier[0], push ? 1 : 0);
-  if (push) a.frontier0[slot] = make_int4(p, 0, 0, 0);
+  const unsigned long long slot = warp_append_flag(&a.counters->frontier[0], push);
+  if (push) a.frontier0[slot] = make_int4(p, pr.root_a, pr.root_b, pr.kind);
 }
 
 // ---------------------------------------------------------------------------
-// k_traverse: one thread per BV pair of the current level.
+// k_traverse: one thread per BV pair of the current level. Frontier entries
+// carry pool node indices and the pair kind, so a test needs exactly three
+// independent loads (two nodes, the pair transform).
 struct TraverseArgs {
   const int4* in;
   int4* out;
   int level;
   unsigned long long out_capacity;
-  const PairRec* pairs;
   const Xf* pair_X;
-  const AssetDev* assets;
+  Pools pools;
   int4* cand_tri;
   int4* cand_tet;
   unsigned long long cand_capacity;
@@ -120,23 +131,23 @@ struct TraverseArgs {
 };
 
 __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
-  const unsigned long long count = a.counters->frontier[a.level];
+  if (a.counters->error != 0) return;  // the query already failed; the host re-runs it
+  // After an overflow the counter exceeds what was stored (the query fails
+  // with DBH_ERR_CAPACITY); never read past the stored entries.
+  const unsigned long long count = min(a.counters->frontier[a.level], a.out_capacity);
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  // Keep whole warps in the loop so warp_append sees full masks.
+  // Keep whole warps in the loop so the warp-aggregated appends see full masks.
   const unsigned long long rounded = (count + 31ull) & ~31ull;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
     int n_children = 0;
     bool emit = false;
     int4 e = make_int4(0, 0, 0, 0);
-    int kind = 0;
     int la = 0, ra = 0, lb = 0, rb = 0;
     bool leaf_a = false, leaf_b = false, root_hit = false;
     if (i < count) {
       e = a.in[i];
-      const PairRec& pr = a.pairs[e.x];
-      kind = pr.kind;
-      const BvhNode* na = a.assets[pr.asset_a].nodes + e.y;
-      const BvhNode* nb = a.assets[pr.asset_b].nodes + e.z;
+      const BvhNode* na = a.pools.nodes + e.y;
+      const BvhNode* nb = a.pools.nodes + e.z;
       const Xf X = a.pair_X[e.x];
       double ha[3] = {na->h[0], na->h[1], na->h[2]};
       double hb[3] = {nb->h[0], nb->h[1], nb->h[2]};
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
       }
       const bool overlap = boxes_overlap(ha, hb, X, t);
       if (overlap) {
-        root_hit = (e.y == 0 && e.z == 0);
+        root_hit = a.level == 0;
         if (leaf_a && leaf_b) {
           emit = true;
         } else if (leaf_b) {
@@ -182,43 +193,52 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
       if (slot + n_children > a.out_capacity) {
         raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
       } else if (leaf_b) {
-        a.out[slot] = make_int4(e.x, la, e.z, 0);
-        a.out[slot + 1] = make_int4(e.x, ra, e.z, 0);
+        a.out[slot] = make_int4(e.x, la, e.z, e.w);
+        a.out[slot + 1] = make_int4(e.x, ra, e.z, e.w);
       } else if (leaf_a) {
-        a.out[slot] = make_int4(e.x, e.y, lb, 0);
-        a.out[slot + 1] = make_int4(e.x, e.y, rb, 0);
+        a.out[slot] = make_int4(e.x, e.y, lb, e.w);
+        a.out[slot + 1] = make_int4(e.x, e.y, rb, e.w);
       } else {
-        a.out[slot] = make_int4(e.x, la, lb, 0);
-        a.out[slot + 1] = make_int4(e.x, ra, lb, 0);
-        a.out[slot + 2] = make_int4(e.x, la, rb, 0);
-        a.out[slot + 3] = make_int4(e.x, ra, rb, 0);
+        a.out[slot] = make_int4(e.x, la, lb, e.w);
+        a.out[slot + 1] = make_int4(e.x, ra, lb, e.w);
+        a.out[slot + 2] = make_int4(e.x, la, rb, e.w);
+        a.out[slot + 3] = make_int4(e.x, ra, rb, e.w);
       }
     }
-    const unsigned long long cslot_tri = warp_append(&a.counters->cand_tri, (emit && kind == kSoftRigid) ? 1 : 0);
-    const unsigned long long cslot_tet = warp_append(&a.counters->cand_tet, (emit && kind == kSoftSoft) ? 1 : 0);
+    const unsigned long long cslot_tri = warp_append_flag(&a.counters->cand_tri, emit && e.w == kSoftRigid);
+    const unsigned long long cslot_tet = warp_append_flag(&a.counters->cand_tet, emit && e.w == kSoftSoft);
     if (emit) {
-      const unsigned long long cs = (kind == kSoftRigid) ? cslot_tri : cslot_tet;
+      const unsigned long long cs = (e.w == kSoftRigid) ? cslot_tri : cslot_tet;
       if (cs >= a.cand_capacity) {
         raise_error(a.counters, 5, 2);
       } else {
-        int4* list = (kind == kSoftRigid) ? a.cand_tri : a.cand_tet;
-        list[cs] = make_int4(e.x, ~la, ~lb, 0);
+        int4* list = (e.w == kSoftRigid) ? a.cand_tri : a.cand_tet;
+        list[cs] = make_int4(e.x, ~la, ~lb, 0);   // pool element indices
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------
+// Narrow phase. Each clip kernel runs in two stages inside one persistent
+// block loop:
+//   stage A (every candidate, one per lane, branch-free): conservative culls
+//     that can only say "certainly no polygon" -- the gradient filters with a
+//     safety band and separating face planes with a 1e-9 relative margin.
+//     Anything uncertain survives.
+//   stage B (survivors only, re-packed into dense warps through a shared-memory
+//     queue): the reference's exact operation sequence.
+// So the emitted polygons are exactly those of running stage B on every
+// candidate, but divergent lanes no longer idle through another lane's clip.
+//
 // Per-thread polygon scratch in shared memory: [buffer][slot][coord][thread],
 // so a warp's access to one (slot, coord) is a single conflict-free 256 B row
-// whatever slot each lane is on (the slot stride is a multiple of 128 B).
+// whatever slot each lane is on.
 struct PolyScratch {
+  static constexpr int kCap = kMaxPolyVerts;
   double* base;  // &smem[threadIdx.x]
   __device__ __forceinline__ double& at(int buf, int slot, int c) const {
     return base[((buf * kMaxPolyVerts + slot) * 3 + c) * kClipThreads];
-  }
-  __device__ __forceinline__ double& dist(int slot) const {
-    return base[(2 * kMaxPolyVerts * 3 + slot) * kClipThreads];
   }
   __device__ __forceinline__ D3 get(int buf, int slot) const {
     return D3{at(buf, slot, 0), at(buf, slot, 1), at(buf, slot, 2)};
@@ -229,15 +249,27 @@ struct PolyScratch {
     at(buf, slot, 2) = v.z;
   }
 };
-constexpr int kClipSmemDoublesPerThread = 2 * kMaxPolyVerts * 3 + kMaxPolyVerts;
+// The exceptional path's scratch: twice the capacity, in local memory. Only
+// candidates whose intermediate polygon outgrows 8 vertices get here (a clip
+// plane coplanar with the polygon makes the inside/outside pattern of its
+// vertices arbitrary, so a clip can add more than one vertex).
+struct LocalPoly {
+  static constexpr int kCap = 2 * kMaxPolyVerts;
+  D3 v[2][kCap];
+  __device__ __forceinline__ D3 get(int buf, int slot) const { return v[buf][slot]; }
+  __device__ __forceinline__ void set(int buf, int slot, D3 p) { v[buf][slot] = p; }
+};
+constexpr int kClipSmemDoublesPerThread = 2 * kMaxPolyVerts * 3;
 constexpr int kClipSmemBytes = kClipSmemDoublesPerThread * kClipThreads * 8;
 
 // RemoveNearlyDuplicateVertices (mesh_intersection.cc:121-170), in place.
-__device__ __forceinline__ int remove_nearly_duplicate(const PolyScratch& P, int buf, int n) {
+template <class Poly>
+__device__ __forceinline__ int remove_nearly_duplicate(Poly& P, int buf, int n) {
   if (n <= 1) return n;
   const double kEpsSquared = 1e-14 * 1e-14;
   int result = 0;
   D3 kept = P.get(buf, 0);
+  const D3 first_v = kept;
   for (int first = 1; first < n; ++first) {
     const D3 q = P.get(buf, first);
     const D3 d = kept - q;
@@ -249,7 +281,7 @@ __device__ __forceinline__ int remove_nearly_duplicate(const PolyScratch& P, int
   }
   n = result + 1;
   if (n >= 3) {
-    const D3 d = P.get(buf, 0) - P.get(buf, n - 1);
+    const D3 d = first_v - kept;  // polygon[0] - polygon.back()
     if (dot(d, d) < kEpsSquared) --n;
   }
   return n;
@@ -257,53 +289,107 @@ __device__ __forceinline__ int remove_nearly_duplicate(const PolyScratch& P, int
 
 // ClipPolygonByHalfSpace (mesh_intersection.cc:76-119) from `buf` into `1-buf`.
 // Half space: unit normal nh, displacement d (height = nh.p - d, inside <= 0).
-__device__ __forceinline__ int clip_by_half_space(const PolyScratch& P, int buf, int n, D3 nh, double d) {
-  for (int i = 0; i < n; ++i) P.dist(i) = dot(nh, P.get(buf, i)) - d;
+// n >= 1.
+template <class Poly>
+__device__ __forceinline__ int clip_by_half_space(Poly& P, int buf, int n, D3 nh, double d) {
   int m = 0;
-  int prev = n - 1;
+  D3 prev = P.get(buf, n - 1);
+  double dp = dot(nh, prev) - d;
   for (int i = 0; i < n; ++i) {
-    const double dc = P.dist(i), dp = P.dist(prev);
+    const D3 cur = P.get(buf, i);
+    const double dc = dot(nh, cur) - d;
     const bool cur_in = dc <= 0, prev_in = dp <= 0;
     if (cur_in != prev_in) {
-      // CalcIntersection(current, previous, H): a = dist(current), b = dist(previous).
+      // CalcIntersection(current, previous, H): a = height(current), b = height(previous).
       const double wa = dp / (dp - dc);
       const double wb = 1.0 - wa;
-      const D3 cur = P.get(buf, i), pv = P.get(buf, prev);
-      if (m < kMaxPolyVerts) P.set(1 - buf, m, wa * cur + wb * pv);
+      if (m < Poly::kCap) P.set(1 - buf, m, wa * cur + wb * prev);
       ++m;
     }
     if (cur_in) {
-      if (m < kMaxPolyVerts) P.set(1 - buf, m, P.get(buf, i));
+      if (m < Poly::kCap) P.set(1 - buf, m, cur);
       ++m;
     }
-    prev = i;
+    prev = cur;
+    dp = dc;
+  }
+  return m;
+}
+
+// The same polygon clipped the way IntersectTetrahedra walks it
+// (field_intersection.cc:146-182): edges (i, i+1), wa = d_j / (d_j - d_i),
+// p = wa P_i + wb P_j. n >= 1.
+template <class Poly>
+__device__ __forceinline__ int clip_by_half_space_edges(Poly& P, int buf, int n, D3 nh, double d) {
+  int m = 0;
+  const D3 first = P.get(buf, 0);
+  const double d_first = dot(nh, first) - d;
+  D3 cur = first;
+  double di = d_first;
+  for (int k = 0; k < n; ++k) {
+    D3 nxt = first;
+    double dj = d_first;
+    if (k + 1 < n) {
+      nxt = P.get(buf, k + 1);
+      dj = dot(nh, nxt) - d;
+    }
+    if (di <= 0) {
+      if (m < Poly::kCap) P.set(1 - buf, m, cur);
+      ++m;
+      if (dj > 0) {
+        const double wa = dj / (dj - di);
+        const double wb = 1.0 - wa;
+        if (m < Poly::kCap) P.set(1 - buf, m, wa * cur + wb * nxt);
+        ++m;
+      }
+    } else if (dj <= 0) {
+      const double wa = dj / (dj - di);
+      const double wb = 1.0 - wa;
+      if (m < Poly::kCap) P.set(1 - buf, m, wa * cur + wb * nxt);
+      ++m;
+    }
+    cur = nxt;
+    di = dj;
   }
   return m;
 }
 
 // The staging soup of contact polygons (frame M of the first body).
 struct PolySoup {
-  int4* hdr;            // {pair, elem_a, elem_b, n}
+  int4* hdr;            // {pair, pool elem a, pool elem b, n}
   double* v;            // [(slot*4 + c) * capacity + i], c = x, y, z, pressure
   double* nhat;         // [c * capacity + i]: polygon normal in M (triangle rep needs it)
   unsigned long long capacity;
 };
 
 struct ClipArgs {
-  const int4* cand;
-  const PairRec* pairs;
+  const int4* cand;     // {pair, pool tet, pool tri | pool tet, 0}
+  unsigned long long cand_capacity;
   const Xf* pair_X;
-  const AssetDev* assets;
+  Pools pools;
   PolySoup soup;
   int* pair_polys;
   int* pair_verts;
   Counters* counters;
+  int4* slow;           // exceptional candidates {pair, elem, elem, 0 tri | 1 tet}
+  unsigned int slow_capacity;
 };
 
-__device__ __forceinline__ void emit_polygon(const ClipArgs& a, const PolyScratch& P, int buf, int n, int4 c, D3 grad,
-                                             double p_mo, D3 nhat) {
-  // One warp-aggregated atomic for the soup slot; per-pair counts by plain atomics.
-  const unsigned long long slot = warp_append(&a.counters->polys, n > 0 ? 1 : 0);
+// A candidate whose intermediate polygon does not fit the fast path's 8 slots.
+__device__ __forceinline__ void defer_to_slow_path(const ClipArgs& a, int4 c, int kind) {
+  const unsigned long long slot = atomicAdd(&a.counters->slow, 1ull);
+  if (slot < a.slow_capacity) {
+    a.slow[slot] = make_int4(c.x, c.y, c.z, kind);
+  } else {
+    raise_error(a.counters, 5, 8);
+  }
+}
+
+// Called by all 32 lanes of a warp (n == 0: nothing to emit for this lane).
+template <class Poly>
+__device__ __forceinline__ void emit_polygon(const ClipArgs& a, Poly& P, int buf, int n, int4 c, D3 grad, double p_mo,
+                                             D3 nhat) {
+  const unsigned long long slot = warp_append_flag(&a.counters->polys, n > 0);
   if (n <= 0) return;
   if (slot >= a.soup.capacity) {
     raise_error(a.counters, 5, 3);
@@ -325,201 +411,401 @@ __device__ __forceinline__ void emit_polygon(const ClipArgs& a, const PolyScratc
   atomicAdd(&a.pair_verts[c.x], n);
 }
 
-// ---------------------------------------------------------------------------
-// k_clip_tri: one thread per (tet, triangle) candidate.
-__global__ void __launch_bounds__(kClipThreads) k_clip_tri(ClipArgs a) {
-  extern __shared__ double smem[];
-  const PolyScratch P{smem + threadIdx.x};
-  const unsigned long long count = a.counters->cand_tri;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  const unsigned long long rounded = (count + 31ull) & ~31ull;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-    int n = 0;
-    int buf = 0;
-    int4 c = make_int4(0, 0, 0, 0);
-    D3 grad = make_d3(0, 0, 0), nhat_M = make_d3(0, 0, 0);
-    double p_mo = 0;
-    if (i < count) {
-      c = a.cand[i];
-      const PairRec& pr = a.pairs[c.x];
-      const TetRec& tet = a.assets[pr.asset_a].tets[c.y];
-      const TriRec& tri = a.assets[pr.asset_b].tris[c.z];
-      const Xf X = a.pair_X[c.x];
-      grad = load3(tet.grad);
-      p_mo = tet.p_mo;
-      // IsFaceNormalAlongPressureGradient (mesh_intersection.cc:266-288,
-      // contact_surface_utility.cc:336-354).
-      nhat_M = rot(X, load3(tri.n));
-      const double cos_theta = dot(normalized(grad), normalized(nhat_M));
-      if (cos_theta > kCosAlphaDevice) {
-        // ClipTriangleByTetrahedron (mesh_intersection.cc:176-264).
-        n = 3;
+// cos(theta) > cos(5 pi / 8) for cos(theta) = ngrad . normalized(v), with ngrad
+// already normalised (contact_surface_utility.cc:336-354). When |v| is 1 to
+// within 1e-12 the normalisation cannot move the dot product by more than
+// 1e-12, so outside an 1e-11 band around the threshold the comparison is
+// decided without the sqrt and the three divisions; inside the band (and for
+// any other |v|) the exact expression is evaluated.
+__device__ __forceinline__ bool face_normal_along_gradient(D3 ngrad, D3 v) {
+  const double s = dot(v, v);
+  const double c0 = dot(ngrad, v);
+  if (fabs(s - 1.0) < 1e-12) {
+    if (c0 > kCosAlphaDevice + 1e-11) return true;
+    if (c0 < kCosAlphaDevice - 1e-11) return false;
+  }
+  return dot(ngrad, normalized(v)) > kCosAlphaDevice;
+}
+
+__device__ __forceinline__ double abs_sum(D3 v) { return fabs(v.x) + fabs(v.y) + fabs(v.z); }
+// sum_i |a_i| |b_i|: the scale of the rounding error of dot(a, b).
+__device__ __forceinline__ double abs_dot(D3 a, D3 b) { return (fabs(a.x * b.x) + fabs(a.y * b.y)) + fabs(a.z * b.z); }
+constexpr double kCullMargin = 1e-9;  // relative; rounding is ~1e-15 of the same scale
+
+// ---- tet-triangle ---------------------------------------------------------
+// Why the culls below cannot change the result. Every vertex the reference's
+// clipper creates is a convex combination (weights in [0,1]) of the three
+// transformed triangle vertices, so it lies in hull(tri) up to rounding e ~
+// 1e-15 L; every vertex that survives all four half spaces has height <= e in
+// each of them, i.e. lies in the tetrahedron bounded by the face planes offset
+// by e, which is the tetrahedron scaled about its incentre by (1 + e/inradius)
+// and reaches at most e * amp beyond it (amp = longest edge / inradius, stored
+// in TetAux). Hence
+//  (R) three triangle vertices outside one face plane by 1e-9 L: empty;
+//  (N) tetrahedron separated from hull(tri) -- by the triangle's plane or by
+//      one of its three edge planes -- by more than 1e-11 (1 + amp) L: empty.
+// Slivers get a huge amp and are simply never culled by (N).
+constexpr double kHullMargin = 1e-11;
+
+// Stage A. false = certainly no polygon.
+__device__ __forceinline__ bool tri_stage_a(const ClipArgs& a, int4 c) {
+  const Xf X = a.pair_X[c.x];
+  const TetRec& tet = a.pools.tets[c.y];
+  const TetAux& aux = a.pools.aux[c.y];
+  const TriRec& tri = a.pools.tris[c.z];
+  // Gradient filter (certain rejections only).
+  const D3 nhat_M = rot(X, load3(tri.n));
+  const double s = dot(nhat_M, nhat_M);
+  const double c0 = dot(load3(aux.ngrad), nhat_M);
+  const bool unit = fabs(s - 1.0) < 1e-12;
+  if (unit && c0 < kCosAlphaDevice - 1e-11) return false;
+  const D3 q0 = xform_point(X, load3(tri.v[0]));
+  const D3 q1 = xform_point(X, load3(tri.v[1]));
+  const D3 q2 = xform_point(X, load3(tri.v[2]));
+  const double L = fmax(fmax(abs_sum(q0), abs_sum(q1)), abs_sum(q2));
+  bool keep = true;
+  // (R) tet face planes against the triangle's vertices.
 #pragma unroll
-        for (int k = 0; k < 3; ++k) P.set(0, k, xform_point(X, load3(tri.v[k])));
-        const int faces[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+  for (int f = 0; f < 4; ++f) {
+    const D3 nh = load3(aux.plane_nh[f]);
+    const double d = aux.plane_d[f];
+    const double h0 = dot(nh, q0) - d, h1 = dot(nh, q1) - d, h2 = dot(nh, q2) - d;
+    // A NaN displacement (degenerate face) never culls: stage B raises the error.
+    if (fmin(fmin(h0, h1), h2) > kCullMargin * (L + fabs(d))) keep = false;
+  }
+  // (N) the triangle's plane and edge planes against the tet's vertices.
+  if (unit) {
+    D3 v[4];
+    double Lv = L;
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          if (n > 0) {
-            const D3 A = load3(tet.v[faces[f][0]]);
-            const D3 B = load3(tet.v[faces[f][1]]);
-            const D3 C = load3(tet.v[faces[f][2]]);
-            const D3 normal = cross(B - A, C - A);
-            const double mag = norm(normal);
-            if (mag < 1e-10) {  // Plane ctor throws (plane.cc:16-29)
-              raise_error(a.counters, 9 /*DBH_ERR_PLANE_NORMAL*/, c.x);
+    for (int k = 0; k < 4; ++k) {
+      v[k] = load3(tet.v[k]);
+      Lv = fmax(Lv, abs_sum(v[k]));
+    }
+    const double m = kHullMargin * (1.0 + aux.amp) * Lv;  // inf / NaN for slivers: never culls
+    const double w = dot(nhat_M, q0);
+    int above = 0, below = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double h = dot(nhat_M, v[k]) - w;
+      above += h > m;
+      below += h < -m;
+    }
+    if (above == 4 || below == 4) keep = false;
+    // Edge e from qa to qb; u = nhat x (qb - qa) points into the triangle.
+    const D3 qa[3] = {q0, q1, q2};
+    const D3 qb[3] = {q1, q2, q0};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const D3 edge = qb[e] - qa[e];
+      const D3 u = cross(nhat_M, edge);
+      const double thr = -(m * abs_sum(edge));
+      int outside = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) outside += dot(u, v[k] - qa[e]) < thr;
+      if (outside == 4) keep = false;
+    }
+  }
+  return keep;
+}
+
+// Stage B: SurfaceVolumeIntersector::CalcContactPolygon (mesh_intersection.cc:321-382).
+template <class Poly>
+__device__ __forceinline__ void tri_stage_b(const ClipArgs& a, Poly& P, int4 c, bool active) {
+  constexpr bool kSlow = Poly::kCap > kMaxPolyVerts;
+  int n = 0;
+  int buf = 0;
+  D3 grad = make_d3(0, 0, 0), nhat_M = make_d3(0, 0, 0);
+  double p_mo = 0;
+  if (active) {
+    const Xf X = a.pair_X[c.x];
+    const TetRec& tet = a.pools.tets[c.y];
+    const TetAux& aux = a.pools.aux[c.y];
+    const TriRec& tri = a.pools.tris[c.z];
+    grad = load3(tet.grad);
+    p_mo = tet.p_mo;
+    // IsFaceNormalAlongPressureGradient (mesh_intersection.cc:266-288).
+    nhat_M = rot(X, load3(tri.n));
+    if (face_normal_along_gradient(load3(aux.ngrad), nhat_M)) {
+      // ClipTriangleByTetrahedron (mesh_intersection.cc:176-264) with the face
+      // half spaces precomputed at registration (TetAux).
+      n = 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) P.set(0, k, xform_point(X, load3(tri.v[k])));
+#pragma unroll 1
+      for (int f = 0; f < 4; ++f) {
+        if (n > 0) {
+          const double d = aux.plane_d[f];
+          if (d != d) {  // Plane ctor throws (plane.cc:16-29)
+            raise_error(a.counters, 9 /*DBH_ERR_PLANE_NORMAL*/, c.x);
+            n = 0;
+          } else {
+            n = clip_by_half_space(P, buf, n, load3(aux.plane_nh[f]), d);
+            if (n > Poly::kCap) {
+              if (kSlow) raise_error(a.counters, 5, 4); else defer_to_slow_path(a, c, 0);
               n = 0;
-            } else {
-              const D3 nh = normal / mag;
-              const double d = dot(nh, A);
-              n = clip_by_half_space(P, buf, n, nh, d);
-              if (n > kMaxPolyVerts) {
-                raise_error(a.counters, 5, 4);
-                n = 0;
-              }
-              buf = 1 - buf;
             }
+            buf = 1 - buf;
           }
         }
-        n = remove_nearly_duplicate(P, buf, n);
-        if (n < 3) n = 0;
+      }
+      n = remove_nearly_duplicate(P, buf, n);
+      if (n < 3) n = 0;
+      if (n > kMaxPolyVerts) {  // only reachable on the exceptional path
+        raise_error(a.counters, 5, 4);
+        n = 0;
       }
     }
-    emit_polygon(a, P, buf, n, c, grad, p_mo, nhat_M);
+  }
+  emit_polygon(a, P, buf, n, c, grad, p_mo, nhat_M);
+}
+
+// ---- tet-tet --------------------------------------------------------------
+// Same argument: the sliced polygon's vertices lie on edges of tet0 (in
+// hull(tet0) up to e) and within e of the equilibrium plane; vertices that
+// survive tet1's four half spaces lie in tet1 inflated by e * amp1.
+//  (R) tet0 entirely on one side of the equilibrium plane (marching-tets code
+//      0 or 15), or entirely outside one face of tet1, by 1e-9: empty;
+//  (N) tet1 entirely on one side of the equilibrium plane, or entirely outside
+//      one face of tet0, by more than 1e-11 (1 + amp1) L: empty.
+// Stage A. false = certainly no polygon.
+__device__ __forceinline__ bool tet_stage_a(const ClipArgs& a, int4 c) {
+  const Xf X = a.pair_X[c.x];
+  const TetRec& t0 = a.pools.tets[c.y];
+  const TetRec& t1 = a.pools.tets[c.z];
+  const TetAux& x0 = a.pools.aux[c.y];
+  const TetAux& x1 = a.pools.aux[c.z];
+  const D3 grad1_N = load3(t1.grad);
+  const D3 p_NMo = -rot_t(X, make_d3(X.m[9], X.m[10], X.m[11]));
+  const double f1_Mo = dot(grad1_N, p_NMo) + t1.p_mo;
+  const D3 n_M = load3(t0.grad) - rot(X, grad1_N);
+  const double s = dot(n_M, n_M);
+  if (s == 0.0) return false;  // magnitude <= 0 (field_intersection.cc:66)
+  // Both gradient filters on the un-normalised normal: cos <= cos(5pi/8) < 0
+  // is certain when c < 0 and c^2 > cos^2 |n|^2 (1 + 1e-9).
+  const double kCos2 = kCosAlphaDevice * kCosAlphaDevice * (1.0 + 1e-9);
+  const double c_0 = dot(n_M, load3(x0.ngrad));
+  if (c_0 < 0 && c_0 * c_0 > kCos2 * s) return false;
+  const double c_1 = dot(rot_t(X, -n_M), load3(x1.ngrad));
+  if (c_1 < 0 && c_1 * c_1 > kCos2 * s) return false;
+  // Equilibrium plane: |n| * height(p) = n.p - (f1(Mo) - f0(Mo)).
+  const double g = f1_Mo - t0.p_mo;
+  D3 v0[4], v1[4];
+  double L1 = 0;
+  int above = 0, below = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v0[k] = load3(t0.v[k]);
+    v1[k] = xform_point(X, load3(t1.v[k]));
+    L1 = fmax(L1, fmax(abs_sum(v0[k]), abs_sum(v1[k])));
+    const double h = dot(n_M, v0[k]) - g;
+    const double tol = kCullMargin * (abs_dot(n_M, v0[k]) + fabs(g));
+    above += h > tol;
+    below += h < -tol;
+  }
+  if (above == 4 || below == 4) return false;  // (R)
+  const double hull1 = kHullMargin * (1.0 + x1.amp);  // relative margin for tet1 as the clipped body
+  {
+    const double tol = hull1 * (abs_sum(n_M) * L1 + fabs(g));
+    above = below = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double h = dot(n_M, v1[k]) - g;
+      above += h > tol;
+      below += h < -tol;
+    }
+    if (above == 4 || below == 4) return false;  // (N)
+  }
+  bool keep = true;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    // (R) a face of tet1 with all of tet0 outside.
+    const D3 o = rot(X, -load3(x1.inward[f]));
+    const D3 A = v1[(f + 1) % 4];
+    const double dA = dot(o, A);
+    const double sA = abs_dot(o, A);
+    int out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out += (dot(o, v0[k]) - dA) > kCullMargin * (abs_dot(o, v0[k]) + sA);
+    if (out == 4) keep = false;
+    // (N) a face of tet0 with all of tet1 outside.
+    const D3 nh = load3(x0.plane_nh[f]);
+    const double d = x0.plane_d[f];
+    const double m = hull1 * (L1 + fabs(d));
+    out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out += (dot(nh, v1[k]) - d) > m;
+    if (out == 4) keep = false;
+  }
+  return keep;
+}
+
+// Stage B: VolumeIntersector::CalcContactPolygon (field_intersection.cc:377-428).
+template <class Poly>
+__device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, bool active) {
+  constexpr bool kSlow = Poly::kCap > kMaxPolyVerts;
+  int n = 0;
+  int buf = 0;
+  D3 grad0 = make_d3(0, 0, 0), nhat_M = make_d3(0, 0, 0);
+  double f0_Mo = 0;
+  if (active) {
+    const Xf X = a.pair_X[c.x];
+    const TetRec& tet0 = a.pools.tets[c.y];
+    const TetRec& tet1 = a.pools.tets[c.z];
+    const TetAux& aux0 = a.pools.aux[c.y];
+    const TetAux& aux1 = a.pools.aux[c.z];
+    // CalcEquilibriumPlane (field_intersection.cc:30-83).
+    grad0 = load3(tet0.grad);
+    f0_Mo = tet0.p_mo;
+    const D3 grad1_N = load3(tet1.grad);
+    const D3 grad1_M = rot(X, grad1_N);
+    const D3 p_NMo = -rot_t(X, make_d3(X.m[9], X.m[10], X.m[11]));
+    const double f1_Mo = dot(grad1_N, p_NMo) + tet1.p_mo;
+    const D3 n_M = grad0 - grad1_M;
+    const double magnitude = norm(n_M);
+    bool ok = magnitude > 0.0;
+    double displacement = 0;
+    if (ok) {
+      nhat_M = n_M / magnitude;
+      const D3 p_MQ = ((f1_Mo - f0_Mo) / magnitude) * nhat_M;
+      displacement = dot(nhat_M, p_MQ);
+      // IsPlaneNormalAlongPressureGradient x2 (field_intersection.cc:200-216,393-400).
+      ok = dot(nhat_M, load3(aux0.ngrad)) > kCosAlphaDevice;
+      if (ok) {
+        const D3 rev_N = rot_t(X, -nhat_M);
+        ok = dot(rev_N, load3(aux1.ngrad)) > kCosAlphaDevice;
+      }
+    }
+    if (ok) {
+      // SliceTetrahedronWithPlane (mesh_plane_intersection.cc:121-180).
+      double dist[4];
+      int code = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dist[k] = dot(nhat_M, load3(tet0.v[k])) - displacement;
+        if (dist[k] > 0) code |= 1 << k;
+      }
+      // kMarchingTetsEdgeTable packed 4 bits per entry (0xF = none), edges kTetEdges.
+      const unsigned short kEdgeTable[16] = {0xFFFF, 0xF230, 0xF410, 0x1234, 0xF521, 0x1530, 0x4520, 0xF453,
+                                             0xF543, 0x0254, 0x0351, 0xF251, 0x4321, 0xF140, 0xF320, 0xFFFF};
+      const unsigned entry = kEdgeTable[code];
+      n = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int edge = (entry >> (4 * k)) & 0xF;
+        if (edge != 0xF && n == k) {
+          // kTetEdges = {0,1},{1,2},{2,0},{0,3},{1,3},{2,3}.
+          const int e0 = edge < 3 ? edge : edge - 3;
+          const int e1 = edge < 3 ? (edge == 2 ? 0 : edge + 1) : 3;
+          // dist[] is indexed dynamically; select to keep it in registers.
+          const double d0 = e0 == 0 ? dist[0] : (e0 == 1 ? dist[1] : dist[2]);
+          const double d1 = e1 == 1 ? dist[1] : (e1 == 2 ? dist[2] : (e1 == 0 ? dist[0] : dist[3]));
+          const D3 V0 = load3(tet0.v[e0]);
+          const D3 V1 = load3(tet0.v[e1]);
+          const double t = d0 / (d0 - d1);
+          P.set(0, n, V0 + t * (V1 - V0));
+          ++n;
+        }
+      }
+      n = remove_nearly_duplicate(P, 0, n);
+      if (n < 3) n = 0;
+      // Clip by the four faces of tet1 (field_intersection.cc:120-190).
+#pragma unroll 1
+      for (int face = 0; face < 4; ++face) {
+        if (n > 0) {
+          const D3 p_MA = xform_point(X, load3(tet1.v[(face + 1) % 4]));
+          const D3 outward = rot(X, -load3(aux1.inward[face]));
+          const double mag = norm(outward);
+          if (mag < 1e-10) {
+            raise_error(a.counters, 9, c.x);
+            n = 0;
+          } else {
+            const D3 nh = outward / mag;
+            const double d = dot(nh, p_MA);
+            n = clip_by_half_space_edges(P, buf, n, nh, d);
+            if (n > Poly::kCap) {
+              if (kSlow) raise_error(a.counters, 5, 5); else defer_to_slow_path(a, c, 1);
+              n = 0;
+            }
+            buf = 1 - buf;
+          }
+        }
+      }
+      if (n > 0) {
+        n = remove_nearly_duplicate(P, buf, n);
+        if (n < 3) n = 0;
+        if (n > kMaxPolyVerts) {  // only reachable on the exceptional path
+          raise_error(a.counters, 5, 5);
+          n = 0;
+        }
+      }
+    }
+  }
+  emit_polygon(a, P, buf, n, c, grad0, f0_Mo, nhat_M);
+}
+
+// ---- the block loop ---------------------------------------------------------
+template <bool kTet>
+__global__ void __launch_bounds__(kClipThreads) k_clip(ClipArgs a) {
+  extern __shared__ double smem[];
+  __shared__ int4 queue[2 * kClipThreads];
+  __shared__ int q_count;
+  if (a.counters->error != 0) return;
+  PolyScratch P{smem + threadIdx.x};
+  const unsigned long long count = min(kTet ? a.counters->cand_tet : a.counters->cand_tri, a.cand_capacity);
+  if (threadIdx.x == 0) q_count = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  unsigned long long full = 0;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * kClipThreads; base < count;
+       base += (unsigned long long)gridDim.x * kClipThreads) {
+    const unsigned long long i = base + threadIdx.x;
+    bool keep = false;
+    int4 c = make_int4(0, 0, 0, 0);
+    if (i < count) {
+      c = a.cand[i];
+      keep = kTet ? tet_stage_a(a, c) : tri_stage_a(a, c);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    int wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&q_count, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (keep) queue[wbase + __popc(m & ((1u << lane) - 1u))] = c;
+    __syncthreads();
+    const int qn = q_count;  // block-uniform
+    __syncthreads();
+    if (qn >= kClipThreads) {
+      const int4 w = queue[qn - kClipThreads + threadIdx.x];
+      if (threadIdx.x == 0) q_count = qn - kClipThreads;
+      if (kTet) tet_stage_b(a, P, w, true); else tri_stage_b(a, P, w, true);
+      full += kClipThreads;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  const int qn = q_count;
+  const bool active = threadIdx.x < qn;
+  const int4 w = active ? queue[threadIdx.x] : make_int4(0, 0, 0, 0);
+  if (kTet) tet_stage_b(a, P, w, active); else tri_stage_b(a, P, w, active);
+  if (threadIdx.x == 0) {
+    full += qn;
+    if (full) atomicAdd(kTet ? &a.counters->full_clips_tet : &a.counters->full_clips_tri, full);
   }
 }
 
-// ---------------------------------------------------------------------------
-// k_clip_tet: one thread per (tet0, tet1) candidate.
-__global__ void __launch_bounds__(kClipThreads) k_clip_tet(ClipArgs a) {
-  extern __shared__ double smem[];
-  const PolyScratch P{smem + threadIdx.x};
-  const unsigned long long count = a.counters->cand_tet;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+// The exceptional path: the same stage B with 16-slot local-memory scratch.
+__global__ void __launch_bounds__(64) k_clip_slow(ClipArgs a) {
+  if (a.counters->error != 0) return;
+  const unsigned long long count = min(a.counters->slow, (unsigned long long)a.slow_capacity);
   const unsigned long long rounded = (count + 31ull) & ~31ull;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-    int n = 0;
-    int buf = 0;
-    int4 c = make_int4(0, 0, 0, 0);
-    D3 grad0 = make_d3(0, 0, 0), nhat_M = make_d3(0, 0, 0);
-    double f0_Mo = 0;
-    if (i < count) {
-      c = a.cand[i];
-      const PairRec& pr = a.pairs[c.x];
-      const TetRec& tet0 = a.assets[pr.asset_a].tets[c.y];
-      const TetRec& tet1 = a.assets[pr.asset_b].tets[c.z];
-      const Xf X = a.pair_X[c.x];
-      // CalcEquilibriumPlane (field_intersection.cc:30-83).
-      grad0 = load3(tet0.grad);
-      f0_Mo = tet0.p_mo;
-      const D3 grad1_N = load3(tet1.grad);
-      const D3 grad1_M = rot(X, grad1_N);
-      const D3 p_NMo = -rot_t(X, make_d3(X.m[9], X.m[10], X.m[11]));
-      const double f1_Mo = dot(grad1_N, p_NMo) + tet1.p_mo;
-      const D3 n_M = grad0 - grad1_M;
-      const double magnitude = norm(n_M);
-      bool ok = magnitude > 0.0;
-      double displacement = 0;
-      if (ok) {
-        nhat_M = n_M / magnitude;
-        const D3 p_MQ = ((f1_Mo - f0_Mo) / magnitude) * nhat_M;
-        displacement = dot(nhat_M, p_MQ);
-        // IsPlaneNormalAlongPressureGradient x2 (field_intersection.cc:200-216,393-400).
-        ok = dot(nhat_M, normalized(grad0)) > kCosAlphaDevice;
-        if (ok) {
-          const D3 rev_N = rot_t(X, -nhat_M);
-          ok = dot(rev_N, normalized(grad1_N)) > kCosAlphaDevice;
-        }
-      }
-      if (ok) {
-        // SliceTetrahedronWithPlane (mesh_plane_intersection.cc:121-180).
-        double dist[4];
-        int code = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          dist[k] = dot(nhat_M, load3(tet0.v[k])) - displacement;
-          if (dist[k] > 0) code |= 1 << k;
-        }
-        // kMarchingTetsEdgeTable packed 4 bits per entry (0xF = none), edges kTetEdges.
-        const unsigned short kEdgeTable[16] = {0xFFFF, 0xF230, 0xF410, 0x1234, 0xF521, 0x1530, 0x4520, 0xF453,
-                                               0xF543, 0x0254, 0x0351, 0xF251, 0x4321, 0xF140, 0xF320, 0xFFFF};
-        const unsigned char kEdgeV0[6] = {0, 1, 2, 0, 1, 2};
-        const unsigned char kEdgeV1[6] = {1, 2, 0, 3, 3, 3};
-        const unsigned entry = kEdgeTable[code];
-        n = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int edge = (entry >> (4 * k)) & 0xF;
-          if (edge != 0xF && n == k) {
-            const int e0 = kEdgeV0[edge], e1 = kEdgeV1[edge];
-            // dist[] is indexed dynamically; select to keep it in registers.
-            const double d0 = e0 == 0 ? dist[0] : (e0 == 1 ? dist[1] : dist[2]);
-            const double d1 = e1 == 1 ? dist[1] : (e1 == 2 ? dist[2] : (e1 == 0 ? dist[0] : dist[3]));
-            const D3 V0 = load3(tet0.v[e0]);
-            const D3 V1 = load3(tet0.v[e1]);
-            const double t = d0 / (d0 - d1);
-            P.set(0, n, V0 + t * (V1 - V0));
-            ++n;
-          }
-        }
-        n = remove_nearly_duplicate(P, 0, n);
-        if (n < 3) n = 0;
-        // Clip by the four faces of tet1 (field_intersection.cc:120-190).
-        if (n > 0) {
-          D3 p_MV[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) p_MV[k] = xform_point(X, load3(tet1.v[k]));
-          const TetNormals& tn = a.assets[pr.asset_b].normals[c.z];
-#pragma unroll
-          for (int face = 0; face < 4; ++face) {
-            if (n > 0) {
-              const D3 p_MA = p_MV[(face + 1) % 4];
-              const D3 outward = rot(X, -load3(tn.n[face]));
-              const double mag = norm(outward);
-              if (mag < 1e-10) {
-                raise_error(a.counters, 9, c.x);
-                n = 0;
-              } else {
-                const D3 nh = outward / mag;
-                const double d = dot(nh, p_MA);
-                // field_intersection.cc:146-182: same polygon as
-                // ClipPolygonByHalfSpace but walking edges (i, i+1) with
-                // wa = d_j / (d_j - d_i), p = wa P_i + wb P_j.
-                for (int k = 0; k < n; ++k) P.dist(k) = dot(nh, P.get(buf, k)) - d;
-                int m = 0;
-                for (int k = 0; k < n; ++k) {
-                  const int j = (k + 1 == n) ? 0 : k + 1;
-                  const double di = P.dist(k), dj = P.dist(j);
-                  if (di <= 0) {
-                    if (m < kMaxPolyVerts) P.set(1 - buf, m, P.get(buf, k));
-                    ++m;
-                    if (dj > 0) {
-                      const double wa = dj / (dj - di);
-                      const double wb = 1.0 - wa;
-                      if (m < kMaxPolyVerts) P.set(1 - buf, m, wa * P.get(buf, k) + wb * P.get(buf, j));
-                      ++m;
-                    }
-                  } else if (dj <= 0) {
-                    const double wa = dj / (dj - di);
-                    const double wb = 1.0 - wa;
-                    if (m < kMaxPolyVerts) P.set(1 - buf, m, wa * P.get(buf, k) + wb * P.get(buf, j));
-                    ++m;
-                  }
-                }
-                if (m > kMaxPolyVerts) {
-                  raise_error(a.counters, 5, 5);
-                  m = 0;
-                }
-                n = m;
-                buf = 1 - buf;
-              }
-            }
-          }
-          n = remove_nearly_duplicate(P, buf, n);
-          if (n < 3) n = 0;
-        }
-      }
-    }
-    emit_polygon(a, P, buf, n, c, grad0, f0_Mo, nhat_M);
+  LocalPoly P;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const bool active = i < count;
+    const int4 c = active ? a.slow[i] : make_int4(0, 0, 0, 0);
+    // Both flavours run so that every lane reaches both warp-wide appends.
+    tri_stage_b(a, P, c, active && c.w == 0);
+    tet_stage_b(a, P, c, active && c.w == 1);
   }
 }
 
@@ -669,7 +955,7 @@ struct ResultArrays {
 struct PackArgs {
   PolySoup soup;
   const PairRec* pairs;
-  const AssetDev* assets;
+  Pools pools;
   const Xf* poses;
   const long long* poly_off;
   const long long* vert_off;
@@ -702,7 +988,8 @@ __device__ __forceinline__ void store_face(const PackArgs& a, long long f, int p
 }
 
 __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
-  const unsigned long long count = a.counters->polys;
+  if (a.counters->error != 0) return;
+  const unsigned long long count = min(a.counters->polys, a.soup.capacity);
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
     const int4 h = a.soup.hdr[i];
@@ -718,12 +1005,12 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
                       a.soup.v[(k * 4 + 2) * a.soup.capacity + i]);
       e[k] = a.soup.v[(k * 4 + 3) * a.soup.capacity + i];
     }
-    const D3 gradA_M = load3(a.assets[pr.asset_a].tets[h.y].grad);
+    const D3 gradA_M = load3(a.pools.tets[h.y].grad);
     const D3 gA_W = rot(X_WM, gradA_M);
     D3 gB_W = make_d3(0, 0, 0);
     if (soft_soft) {
       const Xf X_WN = a.poses[pr.geom_b];
-      gB_W = rot(X_WN, load3(a.assets[pr.asset_b].tets[h.z].grad));
+      gB_W = rot(X_WN, load3(a.pools.tets[h.z].grad));
     }
     // One atomic claims both the polygon slot and the vertex range, so within
     // a pair polygon order and vertex order agree.
@@ -775,7 +1062,7 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
         a.out.pressures[vb + k] = e[k];
         fd[1 + k] = vj + (swapped ? (n - 1 - k) : k);
       }
-      store_face(a, f, pair, h.y, h.z, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft, swapped);
+      store_face(a, f, pair, h.y - pr.elem_base_a, h.z - pr.elem_base_b, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft, swapped);
     } else {
       // Triangle representation: n fan triangles about the polygon centroid
       // (contact_surface_utility.cc:137-164,218-316). Faces are counted by
@@ -843,7 +1130,7 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
         fd[0] = i0;
         fd[1] = i1;
         fd[2] = vloc + n;
-        store_face(a, fb + k, pair, h.y, h.z, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft, swapped);
+        store_face(a, fb + k, pair, h.y - pr.elem_base_a, h.z - pr.elem_base_b, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft, swapped);
         k1 = k;
       }
     }
@@ -875,6 +1162,7 @@ struct SurfaceArgs {
 };
 
 __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
+  if (a.counters->error != 0) return;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long num_surfaces = (long long)a.counters->surfaces;

@@ -17,13 +17,29 @@ struct alignas(128) TetRec {
 };
 static_assert(sizeof(TetRec) == 128, "TetRec must be one 128 B line");
 
-// Unit inward normals of the 4 faces (face f is opposite vertex f):
-// VolumeMesh::inward_normals_M_ (volume_mesh.cc:113-136). Only the second
-// tetrahedron of a tet-tet pair reads these.
-struct alignas(32) TetNormals {
-  double n[4][3];
+// Pose-independent derived data of one tetrahedron, computed once at
+// registration with the reference's own expressions so the per-query kernels
+// reuse the bits the reference would recompute for every element pair:
+//  - plane_nh/plane_d: the four face half spaces of ClipTriangleByTetrahedron
+//    (mesh_intersection.cc:225-238: n = (B-A)x(C-A) over the face table
+//    {1,2,3},{0,3,2},{0,1,3},{0,2,1}; Plane ctor normalises, plane.cc:16-29;
+//    d = nhat.A). plane_d[f] is NaN when |n| < 1e-10 (the Plane ctor throws).
+//  - inward: unit inward normals, face f opposite vertex f
+//    (VolumeMesh::inward_normals_M_, volume_mesh.cc:113-136); only the second
+//    tetrahedron of a tet-tet pair reads these.
+//  - ngrad: normalized(grad) used by both gradient filters
+//    (mesh_intersection.cc:286, field_intersection.cc:204-205).
+//  - amp: shape factor that scales the safety margin of the conservative culls
+//    (not part of the arithmetic contract).
+struct alignas(128) TetAux {
+  double plane_nh[4][3];
+  double plane_d[4];
+  double inward[4][3];
+  double ngrad[3];
+  double amp;   // longest edge / inradius (>= ~4.9; huge for slivers): how far, in units of a plane
+                // offset, the tetrahedron bounded by offset planes can reach beyond this one
 };
-static_assert(sizeof(TetNormals) == 96, "TetNormals is 96 B");
+static_assert(sizeof(TetAux) == 256, "TetAux is two 128 B lines");
 
 // One triangle of a rigid surface mesh: vertices + unit face normal
 // (triangle_surface_mesh.h:452-487).
@@ -34,9 +50,9 @@ struct alignas(32) TriRec {
 static_assert(sizeof(TriRec) == 96, "TriRec is 96 B");
 
 // BVH node: axis-aligned box in the mesh frame (center + half width, the
-// reference's Aabb, aabb.h:59-65) and two links. For an internal node
-// left/right are node indices; for a leaf left = ~element index (negative) and
-// right = -1.
+// reference's Aabb, aabb.h:59-65) and two links. All assets' nodes live in one
+// device pool; for an internal node left/right are POOL node indices; for a
+// leaf left = ~(pool element index) (negative) and right = -1.
 struct alignas(64) BvhNode {
   double c[3];
   double h[3];
@@ -46,16 +62,14 @@ struct alignas(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode is 64 B");
 
-// Device-side view of a registered mesh asset.
-struct AssetDev {
-  const TetRec* tets;          // compliant only
-  const TetNormals* normals;   // compliant only
-  const TriRec* tris;          // rigid only
+// The element / node pools of a context: every registered asset occupies a
+// contiguous range of each, so work-list entries carry pool indices and the
+// kernels never chase pair -> asset -> array pointers.
+struct Pools {
+  const TetRec* tets;
+  const TetAux* aux;
+  const TriRec* tris;
   const BvhNode* nodes;
-  int32_t num_elements;
-  int32_t num_nodes;
-  int32_t type;                // DBH_RIGID / DBH_COMPLIANT
-  int32_t height;
 };
 
 enum PairKind : int32_t { kSoftRigid = 0, kSoftSoft = 1, kRigidRigid = 2, kUnsupported = 3 };
@@ -63,19 +77,22 @@ enum PairKind : int32_t { kSoftRigid = 0, kSoftSoft = 1, kRigidRigid = 2, kUnsup
 // Static description of one potential geometry pair (one entry of
 // FindCollisionCandidates() after filtering, proximity_engine.cc:867-883, in
 // the canonical order of MaybeMakeContactSurface, hydroelastic_calculator.cc:77-156).
-struct PairRec {
+struct alignas(64) PairRec {
   int32_t scene;
   int32_t geom_a;    // flat geometry index of the first-constructed body (S or M)
   int32_t geom_b;    // second body (R or N)
-  int32_t asset_a;
-  int32_t asset_b;
   int32_t kind;      // PairKind
   int32_t swapped;   // soft-rigid with id_R < id_S: ContactSurface swaps M and N (contact_surface.cc:39-41)
-  int32_t pad;
+  int32_t root_a;    // pool index of the BVH root of the first body (-1 when unsupported)
+  int32_t root_b;
+  int32_t elem_base_a;  // pool index of element 0 of the first body (tet pool)
+  int32_t elem_base_b;  // second body (tri pool for soft-rigid, tet pool for soft-soft)
+  int32_t root_leaf;    // bit0: root_a is a leaf, bit1: root_b is a leaf
+  int32_t pad[2];
   int64_t id_m;      // final ids, id_m < id_n
   int64_t id_n;
 };
-static_assert(sizeof(PairRec) == 48, "PairRec is 48 B");
+static_assert(sizeof(PairRec) == 64, "PairRec is 64 B");
 
 // Rigid transform as 12 doubles: R column-major then p (math/rigid_transform.h:1004-1007).
 struct Xf {
@@ -93,6 +110,9 @@ struct Counters {
   unsigned long long surfaces;
   unsigned long long faces;
   unsigned long long vertices;
+  unsigned long long full_clips_tri; // tet-tri candidates that survived the conservative culls
+  unsigned long long full_clips_tet; // tet-tet candidates that survived the conservative culls
+  unsigned long long slow;           // candidates deferred to the exceptional (16-vertex) path
   int32_t error;                    // first device-side dbh_status raised
   int32_t error_detail;
   double total_area;

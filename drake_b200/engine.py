@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -71,7 +72,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("geometry_pairs_tested", "geometry_pairs_overlapping", "bv_pair_tests", "tet_tri_pairs",
                  "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "algorithmic_bytes")] + \
-               [("total_area", C.c_double), ("reserved", C.c_double * 3)]
+               [("total_area", C.c_double), ("tet_tri_full_clips", C.c_int64), ("tet_tet_full_clips", C.c_int64),
+                ("reserved", C.c_double)]
 
 
 _lib = None
@@ -103,6 +105,7 @@ def lib():
     L.dbh_batch_create.argtypes = [vp, C.c_int32, _ip, _ip, _lp, _bp, C.c_int32, _ip, C.POINTER(vp)]
     L.dbh_batch_destroy.argtypes = [vp]
     L.dbh_batch_set_capacity.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
+    L.dbh_batch_grow_capacity.argtypes = [vp]
     L.dbh_batch_get_info.argtypes = [vp, C.POINTER(BatchInfo)]
     L.dbh_batch_set_poses_host.argtypes = [vp, _dp]
     L.dbh_batch_set_poses_device.argtypes = [vp, vp]
@@ -517,9 +520,8 @@ class SceneBatch:
         _check(lib().dbh_batch_sync(self._h))
 
     def run(self, representation: int = POLYGON, kind: int = STRICT, scene_stats_device_ptr: int = 0,
-            max_grow: int = 8):
+            max_grow: int = 48):
         """query + sync, doubling device work-list capacities on DBH_ERR_CAPACITY."""
-        cap = None
         for _ in range(max_grow + 1):
             self.query(representation, kind, scene_stats_device_ptr)
             try:
@@ -528,16 +530,10 @@ class SceneBatch:
             except HydroError as e:
                 if e.status != ERR_CAPACITY:
                     raise
-                if cap is None:
-                    cap = self._default_caps()
-                cap = [2 * c for c in cap]
-                self.set_capacity(*cap)
+                if os.environ.get("DBH_DEBUG"):
+                    print("[drake_b200] growing work lists:", e, file=sys.stderr, flush=True)
+                _check(lib().dbh_batch_grow_capacity(self._h))
         raise HydroError(ERR_CAPACITY, "device work lists still overflow after growing")
-
-    def _default_caps(self):
-        inf = self.info()
-        est = max(1 << 16, 4 * inf.num_geometry_pairs * 1024)
-        return [est, est, est // 2]
 
     def sizes(self) -> ResultSizes:
         out = ResultSizes()

@@ -136,6 +136,11 @@ void dbh_batch_destroy(dbh_batch* batch);
 dbh_status dbh_batch_set_capacity(dbh_batch* batch, int64_t max_bv_pairs_per_level, int64_t max_element_pairs,
                                   int64_t max_faces);
 
+/* After dbh_batch_sync() returned DBH_ERR_CAPACITY: enlarges exactly the lists that overflowed, from
+ * the device counters of the failed query (they keep counting past a full list). Re-run the query;
+ * repeat while it still reports DBH_ERR_CAPACITY (later stages only run once earlier ones fit). */
+dbh_status dbh_batch_grow_capacity(dbh_batch* batch);
+
 typedef struct dbh_batch_info {
   int32_t num_scenes;
   int32_t num_geometries;
@@ -253,7 +258,9 @@ typedef struct dbh_stats {
   int64_t surfaces;
   int64_t algorithmic_bytes;       /* SURVEY.md §8(d) accounting */
   double total_area;
-  double reserved[3];
+  int64_t tet_tri_full_clips;      /* candidates that survived the conservative culls and ran */
+  int64_t tet_tet_full_clips;      /* the reference's full clipping sequence */
+  double reserved;
 } dbh_stats;
 dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
 

@@ -78,3 +78,26 @@ def random_pose(rng, translation_scale=1.0, center=(0, 0, 0)):
                   [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                   [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
     return ho.xform(R, np.asarray(center, float) + translation_scale * rng.uniform(-1, 1, size=3))
+
+
+def oracle_scene_for(workload):
+    """Oracle scene built from the SAME arrays the GPU registers for a drake_b200.workloads.Workload
+    (one template scene; poses differ per scene). Returns (scene, order) where `order` sorts the
+    template geometries by ascending id, the order in which the oracle wants poses."""
+    sc = ho.Scene()
+    cache = {}
+    for g, mi in enumerate(workload.geom_mesh):
+        m = workload.meshes[mi]
+        if mi not in cache:
+            v, e, p = m.arrays()
+            if m.vertices_per_element == 4:
+                om = ho.VolumeMesh.from_arrays(v, e)
+                cache[mi] = (om, ho.VolumeField.from_values(om, p))
+            else:
+                cache[mi] = (ho.TriMesh.from_arrays(v, e), None)
+        om, of = cache[mi]
+        if of is None:
+            sc.add_rigid(workload.geom_id[g], om, bool(workload.geom_anchored[g]))
+        else:
+            sc.add_compliant(workload.geom_id[g], om, of, bool(workload.geom_anchored[g]))
+    return sc, np.argsort(np.asarray(workload.geom_id))

@@ -258,3 +258,40 @@ def test_empty_and_degenerate_inputs(ctx):
     got = batch.compute_contact_surfaces(np.stack([X_WA, X_WB]), db.POLYGON)[0]
     want = ho.soft_rigid(soft, flat, rigid, X_WA, X_WB, 1, 2, ho.KPOLYGON)
     parity.compare_surface(got[0], want)
+
+
+@pytest.mark.parametrize("rep", [ho.KPOLYGON, ho.KTRIANGLE])
+def test_config3_ball_plate_scenes(ctx, rep):
+    """BASELINE config 3: 24 of the batched ball / plate / floor scenes against the scene-level oracle
+    (ids, ordering, every surface); soft-rigid and soft-soft pairs in one batch, anchored floor."""
+    from drake_b200 import workloads as W
+    wl = W.config3(24)
+    batch = wl.register(ctx)
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), rep)
+    osc, order = parity.oracle_scene_for(wl)
+    total = 0
+    for s in range(wl.num_scenes):
+        want, _ = osc.compute(wl.poses[s][order], rep)
+        assert [(x.id_M, x.id_N) for x in got[s]] == [(x.id_M, x.id_N) for x in want]
+        for g, w in zip(got[s], want):
+            parity.compare_surface(g, w)
+        total += len(want)
+    assert total >= 40
+
+
+def test_config4_clutter_scenes_including_coplanar_clips(ctx):
+    """BASELINE config 4: 3 scenes of 32 soft boxes / ellipsoids in a rigid bin. The grid box meshes
+    have boundary tetrahedra with zero pressure gradient, whose equilibrium plane against another
+    body is coplanar with that body's boundary faces: intermediate polygons outgrow 8 vertices and
+    take the exceptional path; results must still match the oracle face for face."""
+    from drake_b200 import workloads as W
+    wl = W.config4(3)
+    batch = wl.register(ctx)
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KPOLYGON)
+    osc, order = parity.oracle_scene_for(wl)
+    for s in range(wl.num_scenes):
+        want, _ = osc.compute(wl.poses[s][order], ho.KPOLYGON)
+        assert [(x.id_M, x.id_N) for x in got[s]] == [(x.id_M, x.id_N) for x in want]
+        for g, w in zip(got[s], want):
+            parity.compare_surface(g, w)
+        assert len(want) >= 20
