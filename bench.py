@@ -318,7 +318,7 @@ def main():
     K = args.steps
     avg = {k: v / K for k, v in kernel_ms.items()}
     s_mean = {k: float(np.mean([s[k] for s in step_stats])) for k in step_stats[0]}
-    alg = {"traverse": s_mean["bv_pair_tests"] * 128.0,
+    alg = {"traverse": s_mean["bv_pair_tests"] * 64.0,
            "clip_tet_tri": s_mean["tet_tri_pairs"] * 260.0,
            "clip_tet_tet": s_mean["tet_tet_pairs"] * 392.0}
     # Polygon output bytes (32 n + 96 / + 120) are attributed to the clip kernels in proportion

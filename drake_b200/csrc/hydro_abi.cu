@@ -87,11 +87,11 @@ struct BuildItem {
 };
 
 // Top-down median split on the longest box axis (the reference's strategy,
-// bvh.cc:32-104), one element per leaf, nodes in DFS pre-order.
-int BuildBvh(const std::vector<Box>& elem_boxes, std::vector<BuildItem>& items, int start, int end,
-             std::vector<BvhNode>* nodes, int depth, int* height) {
-  const int me = static_cast<int>(nodes->size());
-  nodes->emplace_back();
+// bvh.cc:32-104), one element per leaf. Node 0 is unused, node 1 the root, the
+// two children of a node are adjacent (so a descent step fetches both with one
+// 64 B line of the fp32 copy).
+void BuildBvh(const std::vector<Box>& elem_boxes, std::vector<BuildItem>& items, int start, int end,
+              std::vector<BvhNode>* nodes, int me, int depth, int* height) {
   *height = std::max(*height, depth);
   Box b = elem_boxes[items[start].elem];
   for (int i = start + 1; i < end; ++i) {
@@ -107,7 +107,7 @@ int BuildBvh(const std::vector<Box>& elem_boxes, std::vector<BuildItem>& items, 
     node.left = ~items[start].elem;
     node.right = -1;
     (*nodes)[me] = node;
-    return me;
+    return;
   }
   int axis = 0;
   if (node.h[1] > node.h[axis]) axis = 1;
@@ -118,12 +118,13 @@ int BuildBvh(const std::vector<Box>& elem_boxes, std::vector<BuildItem>& items, 
                      if (x.centroid[axis] != y.centroid[axis]) return x.centroid[axis] < y.centroid[axis];
                      return x.elem < y.elem;
                    });
-  const int l = BuildBvh(elem_boxes, items, start, mid, nodes, depth + 1, height);
-  const int r = BuildBvh(elem_boxes, items, mid, end, nodes, depth + 1, height);
-  node.left = l;
-  node.right = r;
+  const int base = static_cast<int>(nodes->size());
+  nodes->resize(base + 2);
+  node.left = base;
+  node.right = base + 1;
   (*nodes)[me] = node;
-  return me;
+  BuildBvh(elem_boxes, items, start, mid, nodes, base, depth + 1, height);
+  BuildBvh(elem_boxes, items, mid, end, nodes, base + 1, depth + 1, height);
 }
 
 template <int kVerts>
@@ -151,8 +152,9 @@ void BuildAssetBvh(const double* verts, const int32_t* elems, int num_elems, Hos
   }
   a->nodes.clear();
   a->nodes.reserve(2 * static_cast<size_t>(num_elems));
+  a->nodes.resize(2);  // [0] unused, [1] root
   a->height = 0;
-  BuildBvh(boxes, items, 0, num_elems, &a->nodes, 0, &a->height);
+  BuildBvh(boxes, items, 0, num_elems, &a->nodes, 1, 0, &a->height);
 }
 
 }  // namespace
@@ -168,10 +170,11 @@ struct dbh_context {
   DevBuf<TetAux> d_aux;
   DevBuf<TriRec> d_tris;
   DevBuf<BvhNode> d_nodes;
+  DevBuf<Node32> d_nodes32;
   size_t uploaded_assets{0};
   long long up_tets{0}, up_tris{0}, up_nodes{0};
 
-  Pools pools() const { return Pools{d_tets.p, d_aux.p, d_tris.p, d_nodes.p}; }
+  Pools pools() const { return Pools{d_tets.p, d_aux.p, d_tris.p, d_nodes.p, d_nodes32.p}; }
 
   void Place(HostAsset* a) {
     a->node_base = static_cast<int>(num_nodes);
@@ -199,8 +202,10 @@ struct dbh_context {
     CUDA_OK(grow(d_aux, num_tets, &regrown));
     CUDA_OK(grow(d_tris, num_tris, &regrown));
     CUDA_OK(grow(d_nodes, num_nodes, &regrown));
+    CUDA_OK(grow(d_nodes32, num_nodes, &regrown));
     const size_t first = regrown ? 0 : uploaded_assets;
     std::vector<BvhNode> rebased;
+    std::vector<Node32> rebased32;
     for (size_t i = first; i < assets.size(); ++i) {
       const HostAsset& a = *assets[i];
       if (a.type == DBH_COMPLIANT) {
@@ -221,6 +226,23 @@ struct dbh_context {
         }
       }
       CUDA_OK(cudaMemcpy(d_nodes.p + a.node_base, rebased.data(), rebased.size() * sizeof(BvhNode),
+                         cudaMemcpyHostToDevice));
+      // Outward-rounded fp32 copy: |c - c32| is added to the half width, then both roundings go up.
+      rebased32.resize(rebased.size());
+      for (size_t k = 0; k < rebased.size(); ++k) {
+        const BvhNode& n = rebased[k];
+        Node32& m = rebased32[k];
+        for (int d = 0; d < 3; ++d) {
+          m.c[d] = static_cast<float>(n.c[d]);
+          const double need = n.h[d] + std::fabs(n.c[d] - static_cast<double>(m.c[d]));
+          float h = static_cast<float>(need);
+          if (static_cast<double>(h) < need) h = std::nextafterf(h, std::numeric_limits<float>::infinity());
+          m.h[d] = std::nextafterf(h, std::numeric_limits<float>::infinity());
+        }
+        m.child = n.left;
+        m.pad = 0;
+      }
+      CUDA_OK(cudaMemcpy(d_nodes32.p + a.node_base, rebased32.data(), rebased32.size() * sizeof(Node32),
                          cudaMemcpyHostToDevice));
     }
     uploaded_assets = assets.size();
@@ -245,6 +267,7 @@ struct dbh_batch {
   DevBuf<Xf> d_poses_own;
   const Xf* d_poses{nullptr};
   DevBuf<Xf> d_pair_X;
+  DevBuf<PairF32> d_pair_f32;
   DevBuf<int4> d_frontier[2];
   DevBuf<int4> d_cand_tri, d_cand_tet, d_slow;
   long long cap_slow{1 << 16};
@@ -466,11 +489,11 @@ dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* o
   out->type = a.type;
   out->num_vertices = a.num_vertices;
   out->num_elements = a.num_elements;
-  out->num_bvh_nodes = static_cast<int>(a.nodes.size());
+  out->num_bvh_nodes = static_cast<int>(a.nodes.size()) - 1;
   out->bvh_height = a.height;
   for (int k = 0; k < 3; ++k) {
-    out->root_center[k] = a.nodes[0].c[k];
-    out->root_half_width[k] = a.nodes[0].h[k];
+    out->root_center[k] = a.nodes[1].c[k];
+    out->root_half_width[k] = a.nodes[1].h[k];
   }
   return DBH_OK;
 }
@@ -571,11 +594,11 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
         if (pr.kind != kUnsupported) {
           const HostAsset& A = *ctx->assets[geom_asset[pr.geom_a]];
           const HostAsset& B = *ctx->assets[geom_asset[pr.geom_b]];
-          pr.root_a = A.node_base;
-          pr.root_b = B.node_base;
+          pr.root_a = A.node_base + 1;
+          pr.root_b = B.node_base + 1;
           pr.elem_base_a = A.elem_base;
           pr.elem_base_b = B.elem_base;
-          pr.root_leaf = (A.nodes[0].left < 0 ? 1 : 0) | (B.nodes[0].left < 0 ? 2 : 0);
+          pr.root_leaf = (A.nodes[1].left < 0 ? 1 : 0) | (B.nodes[1].left < 0 ? 2 : 0);
           if (pr.kind <= kSoftSoft) {
             max_levels = std::max(max_levels, std::max(A.height, B.height) + 1);
             est += 2ll * (A.num_elements + B.num_elements);
@@ -614,6 +637,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   CUDA_OK(b->d_poses_own.alloc(std::max(1, b->num_geoms)));
   b->d_poses = b->d_poses_own.p;
   CUDA_OK(b->d_pair_X.alloc(np));
+  CUDA_OK(b->d_pair_f32.alloc(np));
   CUDA_OK(b->d_counters.alloc(1));
   CUDA_OK(b->d_pair_polys.alloc(np));
   CUDA_OK(b->d_pair_verts.alloc(np));
@@ -663,7 +687,7 @@ dbh_status dbh_batch_grow_capacity(dbh_batch* b) {
   unsigned long long fr = 0;
   for (int l = 0; l < 64; ++l) fr = std::max(fr, c.frontier[l]);
   b->cap_frontier = want(fr, b->cap_frontier);
-  b->cap_cand = want(std::max(c.cand_tri, c.cand_tet), b->cap_cand);
+  b->cap_cand = want(std::max(c.leaf_tri, c.leaf_tet), b->cap_cand);
   b->cap_polys = want(c.polys, b->cap_polys);
   b->cap_slow = want(c.slow, b->cap_slow);
   // Faces / vertices of either representation (triangle: one face per polygon vertex, one extra
@@ -727,22 +751,26 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pa.pools = ctx->pools();
     pa.poses = b->d_poses;
     pa.pair_X = b->d_pair_X.p;
+    pa.pair_f32 = b->d_pair_f32.p;
     pa.frontier0 = b->d_frontier[0].p;
+    pa.leaf_tri = b->d_cand_tri.p;
+    pa.leaf_tet = b->d_cand_tet.p;
     pa.counters = b->d_counters.p;
     pa.strict = query_kind == DBH_QUERY_STRICT;
     pa.pair_polys = b->d_pair_polys.p;
     pa.pair_verts = b->d_pair_verts.p;
     pa.pair_cursor = b->d_pair_cursor.p;
-    if (b->num_pairs > b->cap_frontier) return Fail(DBH_ERR_CAPACITY, "frontier capacity below the pair count");
+    if (b->num_pairs > b->cap_frontier || b->num_pairs > b->cap_cand)
+      return Fail(DBH_ERR_CAPACITY, "work-list capacity below the geometry-pair count");
     k_pairs<<<(b->num_pairs + 127) / 128, 128, 0, st>>>(pa);
     mark(1);
     // Dual-BVH traversal, one launch per level; counts stay on the device.
     TraverseArgs ta{};
-    ta.pair_X = b->d_pair_X.p;
+    ta.pair_f32 = b->d_pair_f32.p;
     ta.pools = ctx->pools();
-    ta.cand_tri = b->d_cand_tri.p;
-    ta.cand_tet = b->d_cand_tet.p;
-    ta.cand_capacity = static_cast<unsigned long long>(b->cap_cand);
+    ta.leaf_tri = b->d_cand_tri.p;
+    ta.leaf_tet = b->d_cand_tet.p;
+    ta.leaf_capacity = static_cast<unsigned long long>(b->cap_cand);
     ta.out_capacity = static_cast<unsigned long long>(b->cap_frontier);
     ta.counters = b->d_counters.p;
     for (int level = 0; level < b->info.max_traversal_levels; ++level) {
@@ -911,9 +939,10 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   const Counters& c = *b->h_counters;
   std::memset(out, 0, sizeof(*out));
-  out->geometry_pairs_tested = static_cast<int64_t>(c.frontier[0]);
+  out->geometry_pairs_tested = static_cast<int64_t>(b->info.num_soft_rigid_pairs + b->info.num_soft_soft_pairs);
   out->geometry_pairs_overlapping = static_cast<int64_t>(c.root_overlaps);
-  for (int l = 0; l < 64; ++l) out->bv_pair_tests += static_cast<int64_t>(c.frontier[l]);
+  out->bv_pair_tests = static_cast<int64_t>(c.bv_tests);
+  out->leaf_pairs = static_cast<int64_t>(c.leaf_tri + c.leaf_tet);
   out->tet_tri_pairs = static_cast<int64_t>(c.cand_tri);
   out->tet_tet_pairs = static_cast<int64_t>(c.cand_tet);
   out->polygons = static_cast<int64_t>(c.polys);
@@ -923,10 +952,11 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->total_area = c.total_area;
   out->tet_tri_full_clips = static_cast<int64_t>(c.full_clips_tri);
   out->tet_tet_full_clips = static_cast<int64_t>(c.full_clips_tet);
-  // BV test 128 B; tet-tri pair 260 B in; tet-tet pair 392 B in;
+  // BV test 64 B (two 32 B fp32 nodes; SURVEY.md §8(d) counts 128 B for the
+  // reference-shaped fp64 node); tet-tri pair 260 B in; tet-tet pair 392 B in;
   // emitted n-gon 32 n + 96 (soft-rigid) / + 120 (soft-soft) out; pose 96 B per geometry.
   // Triangle representation adds 32 B centroid vertex + n (12 + 24 + 8) B per polygon.
-  long long bytes = out->bv_pair_tests * 128 + out->tet_tri_pairs * 260 + out->tet_tet_pairs * 392 +
+  long long bytes = out->bv_pair_tests * 64 + out->tet_tri_pairs * 260 + out->tet_tet_pairs * 392 +
                     static_cast<long long>(c.poly_verts) * 32 + out->polygons * 108 + 96ll * b->num_geoms;
   if (b->representation == DBH_TRIANGLE) bytes += out->polygons * 32 + static_cast<long long>(c.poly_verts) * 44;
   out->algorithmic_bytes = bytes;
@@ -940,15 +970,22 @@ dbh_status dbh_batch_copy_candidates(dbh_batch* b, int32_t kind, int32_t* out_tr
   const int64_t n = static_cast<int64_t>(kind == 0 ? b->h_counters->cand_tri : b->h_counters->cand_tet);
   *count = n;
   if (!out_triples || n == 0) return DBH_OK;
-  std::vector<int4> tmp(n);
-  CUDA_OK(cudaMemcpy(tmp.data(), kind == 0 ? b->d_cand_tri.p : b->d_cand_tet.p, n * sizeof(int4),
+  // The narrow phase left the leaf list as {pair, pool elem a, pool elem b, flag}; the candidates
+  // are the flagged entries.
+  const int64_t listed = static_cast<int64_t>(kind == 0 ? b->h_counters->leaf_tri : b->h_counters->leaf_tet);
+  std::vector<int4> tmp(listed);
+  CUDA_OK(cudaMemcpy(tmp.data(), kind == 0 ? b->d_cand_tri.p : b->d_cand_tet.p, listed * sizeof(int4),
                      cudaMemcpyDeviceToHost));
-  for (int64_t i = 0; i < n; ++i) {
+  int64_t k = 0;
+  for (int64_t i = 0; i < listed && k < n; ++i) {
+    if (tmp[i].w != 1) continue;
     const PairRec& pr = b->pairs[tmp[i].x];
-    out_triples[3 * i] = tmp[i].x;
-    out_triples[3 * i + 1] = tmp[i].y - pr.elem_base_a;
-    out_triples[3 * i + 2] = tmp[i].z - pr.elem_base_b;
+    out_triples[3 * k] = tmp[i].x;
+    out_triples[3 * k + 1] = tmp[i].y - pr.elem_base_a;
+    out_triples[3 * k + 2] = tmp[i].z - pr.elem_base_b;
+    ++k;
   }
+  if (k != n) return Fail(DBH_ERR_CUDA, "candidate flags disagree with the candidate counter");
   return DBH_OK;
 }
 

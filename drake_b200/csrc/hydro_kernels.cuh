@@ -62,14 +62,27 @@ __device__ __forceinline__ void raise_error(Counters* c, int status, int detail)
 }
 
 // ---------------------------------------------------------------------------
-// k_pairs: one thread per potential geometry pair.
+// Work-list entries.
+//  frontier: {pair, a, b, kind}: an overlapping node pair still to be
+//    expanded. a >= 0: pool index of the first of two adjacent children to
+//    expand; a < 0: ~(pool index) of a leaf node that is kept as is. Same for b.
+//  leaf list: {pair, leaf node a, leaf node b, 0}: leaf pairs that passed the
+//    conservative fp32 box test; the narrow phase applies the exact predicate.
+__device__ __forceinline__ int frontier_code(int node_index, int child) { return child < 0 ? ~node_index : child; }
+
+// ---------------------------------------------------------------------------
+// k_pairs: one thread per potential geometry pair: X_MN, its fp32 copy, the
+// root box test, level-0 frontier.
 struct PairsArgs {
   const PairRec* pairs;
   int num_pairs;
   Pools pools;
   const Xf* poses;       // X_WG per flat geometry index
   Xf* pair_X;            // out: X_MN per pair
-  int4* frontier0;       // out: level-0 frontier {pair, node a, node b, kind}
+  PairF32* pair_f32;     // out
+  int4* frontier0;       // out: level-0 frontier
+  int4* leaf_tri;        // out: single-element meshes go straight to the leaf lists
+  int4* leaf_tet;
   Counters* counters;
   int strict;            // DBH_QUERY_STRICT
   int* pair_polys;       // zeroed here
@@ -80,9 +93,10 @@ struct PairsArgs {
 __global__ void k_pairs(PairsArgs a) {
   // Launched with whole warps covering num_pairs rounded up to 32.
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  bool push = false;
+  bool push = false, tested = false;
   PairRec pr;
-  pr.root_a = pr.root_b = pr.kind = 0;
+  pr.root_a = pr.root_b = pr.kind = pr.root_leaf = 0;
+  int child_a = 0, child_b = 0;
   if (p < a.num_pairs) {
     a.pair_polys[p] = 0;
     a.pair_verts[p] = 0;
@@ -95,40 +109,116 @@ __global__ void k_pairs(PairsArgs a) {
       const Xf X_WB = a.poses[pr.geom_b];
       const Xf X_AB = invert_and_compose(X_WA, X_WB);
       a.pair_X[p] = X_AB;
-      if (pr.kind == kRigidRigid) {
-        // Stand-in for the geometry-level broad phase (FCL tree,
-        // proximity_engine.cc:867-883): the pair only fails if the root boxes overlap.
-        if (a.strict) {
-          const BvhNode& na = a.pools.nodes[pr.root_a];
-          const BvhNode& nb = a.pools.nodes[pr.root_b];
-          const D3 t = xform_point(X_AB, load3(nb.c)) - load3(na.c);
-          if (boxes_overlap(na.h, nb.h, X_AB, t)) raise_error(a.counters, 6 /*DBH_ERR_RIGID_RIGID*/, p);
+      PairF32 f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f.R[k] = (float)X_AB.m[k];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) f.AR[i * 3 + j] = fabsf(f.R[j * 3 + i]) + 1e-6f;
+        f.p[i] = (float)X_AB.m[9 + i];
+      }
+      f.S = fabsf(f.p[0]) + fabsf(f.p[1]) + fabsf(f.p[2]);
+      f.pad[0] = f.pad[1] = 0.f;
+      a.pair_f32[p] = f;
+      // Root boxes: the exact 15-axis test on boxes padded by 1e-12 (an ancestor
+      // must never hide a passing leaf pair). For rigid-rigid pairs this stands in
+      // for the geometry-level broad phase (FCL tree, proximity_engine.cc:867-883):
+      // the strict query only fails if the root boxes overlap.
+      if (pr.kind != kRigidRigid || a.strict) {
+        const BvhNode& na = a.pools.nodes[pr.root_a];
+        const BvhNode& nb = a.pools.nodes[pr.root_b];
+        child_a = na.left;
+        child_b = nb.left;
+        double ha[3] = {na.h[0], na.h[1], na.h[2]};
+        double hb[3] = {nb.h[0], nb.h[1], nb.h[2]};
+        const D3 t = xform_point(X_AB, load3(nb.c)) - load3(na.c);
+        const double s =
+            1e-12 * (fabs(t.x) + fabs(t.y) + fabs(t.z) + ha[0] + ha[1] + ha[2] + hb[0] + hb[1] + hb[2]) + 1e-300;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          ha[k] += s;
+          hb[k] += s;
         }
-      } else {
-        push = true;
+        const bool overlap = boxes_overlap(ha, hb, X_AB, t);
+        if (pr.kind == kRigidRigid) {
+          if (overlap) raise_error(a.counters, 6 /*DBH_ERR_RIGID_RIGID*/, p);
+        } else {
+          tested = true;
+          push = overlap;
+        }
       }
     }
   }
-  const unsigned long long slot = warp_append_flag(&a.counters->frontier[0], push);
-  if (push) a.frontier0[slot] = make_int4(p, pr.root_a, pr.root_b, pr.kind);
+  const unsigned tests = __ballot_sync(0xffffffffu, tested);
+  const unsigned hits = __ballot_sync(0xffffffffu, push);
+  if ((threadIdx.x & 31) == 0) {
+    if (tests) atomicAdd(&a.counters->bv_tests, (unsigned long long)__popc(tests));
+    if (hits) atomicAdd(&a.counters->root_overlaps, (unsigned long long)__popc(hits));
+  }
+  const bool both_leaves = child_a < 0 && child_b < 0;
+  const unsigned long long slot = warp_append_flag(&a.counters->frontier[0], push && !both_leaves);
+  if (push && !both_leaves)
+    a.frontier0[slot] = make_int4(p, frontier_code(pr.root_a, child_a), frontier_code(pr.root_b, child_b), pr.kind);
+  const unsigned long long lt = warp_append_flag(&a.counters->leaf_tri, push && both_leaves && pr.kind == kSoftRigid);
+  const unsigned long long lq = warp_append_flag(&a.counters->leaf_tet, push && both_leaves && pr.kind == kSoftSoft);
+  if (push && both_leaves) {
+    // Lists are at least num_pairs long (host guarantees).
+    if (pr.kind == kSoftRigid) a.leaf_tri[lt] = make_int4(p, pr.root_a, pr.root_b, 0);
+    else a.leaf_tet[lq] = make_int4(p, pr.root_a, pr.root_b, 0);
+  }
 }
 
 // ---------------------------------------------------------------------------
-// k_traverse: one thread per BV pair of the current level. Frontier entries
-// carry pool node indices and the pair kind, so a test needs exactly three
-// independent loads (two nodes, the pair transform).
+// k_traverse: one level of the dual-tree descent (replaces Bvh::Collide,
+// bvh.h:220-262). One thread per overlapping node pair: it fetches the two
+// children of each internal side (one 64 B line per side) and tests the up to
+// four child pairs with a conservative fp32 6-axis box test (the face axes of
+// Gottschalk's SAT; outward-rounded boxes plus a 4e-6 relative pad cover every
+// fp32 rounding, so a pair that the exact fp64 predicate accepts at the leaves
+// is never dropped on the way down). Overlapping child pairs go to the next
+// level's frontier, overlapping leaf pairs to the leaf lists.
 struct TraverseArgs {
   const int4* in;
   int4* out;
   int level;
   unsigned long long out_capacity;
-  const Xf* pair_X;
+  const PairF32* pair_f32;
   Pools pools;
-  int4* cand_tri;
-  int4* cand_tet;
-  unsigned long long cand_capacity;
+  int4* leaf_tri;
+  int4* leaf_tet;
+  unsigned long long leaf_capacity;
   Counters* counters;
 };
+
+struct Box32 {
+  float cx, cy, cz, hx, hy, hz;
+};
+
+// Conservative: false only if the boxes are certainly disjoint under the
+// exact predicate. tb = R cb + p (b's centre in a's frame).
+__device__ __forceinline__ bool overlap6_f32(const Box32& A, const Box32& B, float tbx, float tby, float tbz, float sb,
+                                             const PairF32& f) {
+  const float tx = tbx - A.cx, ty = tby - A.cy, tz = tbz - A.cz;
+  const float S = ((fabsf(A.cx) + fabsf(A.cy)) + fabsf(A.cz)) + sb + ((A.hx + A.hy) + A.hz);
+  const float delta = 4e-6f * S;
+  const float ax = A.hx + delta, ay = A.hy + delta, az = A.hz + delta;
+  const float bx = B.hx + delta, by = B.hy + delta, bz = B.hz + delta;
+  // a's face axes.
+  if (fabsf(tx) > ax + fmaf(bx, f.AR[0], fmaf(by, f.AR[1], bz * f.AR[2]))) return false;
+  if (fabsf(ty) > ay + fmaf(bx, f.AR[3], fmaf(by, f.AR[4], bz * f.AR[5]))) return false;
+  if (fabsf(tz) > az + fmaf(bx, f.AR[6], fmaf(by, f.AR[7], bz * f.AR[8]))) return false;
+  // b's face axes: t . R(:, i).
+  if (fabsf(fmaf(tx, f.R[0], fmaf(ty, f.R[1], tz * f.R[2]))) > bx + fmaf(ax, f.AR[0], fmaf(ay, f.AR[3], az * f.AR[6])))
+    return false;
+  if (fabsf(fmaf(tx, f.R[3], fmaf(ty, f.R[4], tz * f.R[5]))) > by + fmaf(ax, f.AR[1], fmaf(ay, f.AR[4], az * f.AR[7])))
+    return false;
+  if (fabsf(fmaf(tx, f.R[6], fmaf(ty, f.R[7], tz * f.R[8]))) > bz + fmaf(ax, f.AR[2], fmaf(ay, f.AR[5], az * f.AR[8])))
+    return false;
+  return true;
+}
+
+__device__ __forceinline__ Box32 load_box32(const Node32& n) { return Box32{n.c[0], n.c[1], n.c[2], n.h[0], n.h[1], n.h[2]}; }
 
 __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
   if (a.counters->error != 0) return;  // the query already failed; the host re-runs it
@@ -138,85 +228,78 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   // Keep whole warps in the loop so the warp-aggregated appends see full masks.
   const unsigned long long rounded = (count + 31ull) & ~31ull;
+  unsigned int tests = 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-    int n_children = 0;
-    bool emit = false;
     int4 e = make_int4(0, 0, 0, 0);
-    int la = 0, ra = 0, lb = 0, rb = 0;
-    bool leaf_a = false, leaf_b = false, root_hit = false;
+    int n_next = 0, n_leaf = 0;
+    int next_a[4], next_b[4], leaf_a[4], leaf_b[4];
     if (i < count) {
       e = a.in[i];
-      const BvhNode* na = a.pools.nodes + e.y;
-      const BvhNode* nb = a.pools.nodes + e.z;
-      const Xf X = a.pair_X[e.x];
-      double ha[3] = {na->h[0], na->h[1], na->h[2]};
-      double hb[3] = {nb->h[0], nb->h[1], nb->h[2]};
-      la = na->left;
-      ra = na->right;
-      lb = nb->left;
-      rb = nb->right;
-      leaf_a = la < 0;
-      leaf_b = lb < 0;
-      // Aabb::HasOverlap (aabb.cc:16-33): t = X_GH * b.center - a.center.
-      const D3 t = xform_point(X, load3(nb->c)) - load3(na->c);
-      if (!(leaf_a && leaf_b)) {
-        // Internal tests are made strictly more permissive than the exact leaf
-        // predicate so rounding at an ancestor can never hide a passing leaf pair.
-        const double s =
-            1e-12 * (fabs(t.x) + fabs(t.y) + fabs(t.z) + ha[0] + ha[1] + ha[2] + hb[0] + hb[1] + hb[2]) + 1e-300;
+      const int na = e.y >= 0 ? 2 : 1, nb = e.z >= 0 ? 2 : 1;
+      const int ia = e.y >= 0 ? e.y : ~e.y, ib = e.z >= 0 ? e.z : ~e.z;
+      const PairF32 f = a.pair_f32[e.x];
+      Node32 A[2], B[2];
+      A[0] = a.pools.nodes32[ia];
+      B[0] = a.pools.nodes32[ib];
+      A[1] = na == 2 ? a.pools.nodes32[ia + 1] : A[0];
+      B[1] = nb == 2 ? a.pools.nodes32[ib + 1] : B[0];
+      tests = tests + na * nb;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          ha[k] += s;
-          hb[k] += s;
-        }
-      }
-      const bool overlap = boxes_overlap(ha, hb, X, t);
-      if (overlap) {
-        root_hit = a.level == 0;
-        if (leaf_a && leaf_b) {
-          emit = true;
-        } else if (leaf_b) {
-          n_children = 2;
-        } else if (leaf_a) {
-          n_children = 2;
-        } else {
-          n_children = 4;
+      for (int jb = 0; jb < 2; ++jb) {
+        if (jb < nb) {
+          const Box32 bb = load_box32(B[jb]);
+          const float tbx = fmaf(f.R[0], bb.cx, fmaf(f.R[3], bb.cy, fmaf(f.R[6], bb.cz, f.p[0])));
+          const float tby = fmaf(f.R[1], bb.cx, fmaf(f.R[4], bb.cy, fmaf(f.R[7], bb.cz, f.p[1])));
+          const float tbz = fmaf(f.R[2], bb.cx, fmaf(f.R[5], bb.cy, fmaf(f.R[8], bb.cz, f.p[2])));
+          const float sb = ((fabsf(bb.cx) + fabsf(bb.cy)) + fabsf(bb.cz)) + f.S + ((bb.hx + bb.hy) + bb.hz);
+#pragma unroll
+          for (int ja = 0; ja < 2; ++ja) {
+            if (ja < na) {
+              if (overlap6_f32(load_box32(A[ja]), bb, tbx, tby, tbz, sb, f)) {
+                const int ca = A[ja].child, cb = B[jb].child;
+                if (ca < 0 && cb < 0) {
+                  leaf_a[n_leaf] = ia + ja;
+                  leaf_b[n_leaf] = ib + jb;
+                  ++n_leaf;
+                } else {
+                  next_a[n_next] = frontier_code(ia + ja, ca);
+                  next_b[n_next] = frontier_code(ib + jb, cb);
+                  ++n_next;
+                }
+              }
+            }
+          }
         }
       }
     }
-    if (a.level == 0) {
-      const unsigned hits = __ballot_sync(0xffffffffu, root_hit);
-      if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&a.counters->root_overlaps, (unsigned long long)__popc(hits));
-    }
-    const unsigned long long slot = warp_append(&a.counters->frontier[a.level + 1], n_children);
-    if (n_children) {
-      if (slot + n_children > a.out_capacity) {
+    const unsigned long long slot = warp_append(&a.counters->frontier[a.level + 1], n_next);
+    if (n_next) {
+      if (slot + n_next > a.out_capacity) {
         raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
-      } else if (leaf_b) {
-        a.out[slot] = make_int4(e.x, la, e.z, e.w);
-        a.out[slot + 1] = make_int4(e.x, ra, e.z, e.w);
-      } else if (leaf_a) {
-        a.out[slot] = make_int4(e.x, e.y, lb, e.w);
-        a.out[slot + 1] = make_int4(e.x, e.y, rb, e.w);
       } else {
-        a.out[slot] = make_int4(e.x, la, lb, e.w);
-        a.out[slot + 1] = make_int4(e.x, ra, lb, e.w);
-        a.out[slot + 2] = make_int4(e.x, la, rb, e.w);
-        a.out[slot + 3] = make_int4(e.x, ra, rb, e.w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < n_next) a.out[slot + k] = make_int4(e.x, next_a[k], next_b[k], e.w);
       }
     }
-    const unsigned long long cslot_tri = warp_append_flag(&a.counters->cand_tri, emit && e.w == kSoftRigid);
-    const unsigned long long cslot_tet = warp_append_flag(&a.counters->cand_tet, emit && e.w == kSoftSoft);
-    if (emit) {
-      const unsigned long long cs = (e.w == kSoftRigid) ? cslot_tri : cslot_tet;
-      if (cs >= a.cand_capacity) {
+    const unsigned long long ls_tri = warp_append(&a.counters->leaf_tri, e.w == kSoftRigid ? n_leaf : 0);
+    const unsigned long long ls_tet = warp_append(&a.counters->leaf_tet, e.w == kSoftSoft ? n_leaf : 0);
+    if (n_leaf) {
+      const unsigned long long ls = (e.w == kSoftRigid) ? ls_tri : ls_tet;
+      if (ls + n_leaf > a.leaf_capacity) {
         raise_error(a.counters, 5, 2);
       } else {
-        int4* list = (e.w == kSoftRigid) ? a.cand_tri : a.cand_tet;
-        list[cs] = make_int4(e.x, ~la, ~lb, 0);   // pool element indices
+        int4* list = (e.w == kSoftRigid) ? a.leaf_tri : a.leaf_tet;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < n_leaf) list[ls + k] = make_int4(e.x, leaf_a[k], leaf_b[k], 0);
       }
     }
   }
+  // One atomic per warp for the test count.
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, d);
+  if ((threadIdx.x & 31) == 0 && tests) atomicAdd(&a.counters->bv_tests, (unsigned long long)tests);
 }
 
 // ---------------------------------------------------------------------------
@@ -363,7 +446,11 @@ struct PolySoup {
 };
 
 struct ClipArgs {
-  const int4* cand;     // {pair, pool tet, pool tri | pool tet, 0}
+  // In: leaf pairs {pair, leaf node a, leaf node b, 0} from the descent. The
+  // kernel rewrites every entry as {pair, pool tet, pool tri | pool tet, flag},
+  // flag = 1 iff the pair passes the exact leaf predicate, i.e. is a candidate
+  // element pair (dbh_batch_copy_candidates reads the flagged entries).
+  int4* cand;
   unsigned long long cand_capacity;
   const Xf* pair_X;
   Pools pools;
@@ -752,20 +839,31 @@ __global__ void __launch_bounds__(kClipThreads) k_clip(ClipArgs a) {
   __shared__ int q_count;
   if (a.counters->error != 0) return;
   PolyScratch P{smem + threadIdx.x};
-  const unsigned long long count = min(kTet ? a.counters->cand_tet : a.counters->cand_tri, a.cand_capacity);
+  const unsigned long long count = min(kTet ? a.counters->leaf_tet : a.counters->leaf_tri, a.cand_capacity);
   if (threadIdx.x == 0) q_count = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   unsigned long long full = 0;
+  unsigned int n_cand = 0;  // per warp (every lane holds the warp's count)
   for (unsigned long long base = (unsigned long long)blockIdx.x * kClipThreads; base < count;
        base += (unsigned long long)gridDim.x * kClipThreads) {
     const unsigned long long i = base + threadIdx.x;
-    bool keep = false;
+    bool keep = false, is_cand = false;
     int4 c = make_int4(0, 0, 0, 0);
     if (i < count) {
       c = a.cand[i];
-      keep = kTet ? tet_stage_a(a, c) : tri_stage_a(a, c);
+      // The exact leaf predicate: Aabb::HasOverlap on the two elements' own
+      // boxes (aabb.cc:16-33 -> scalar BoxesOverlap, boxes_overlap.cc:197-255).
+      const BvhNode& na = a.pools.nodes[c.y];
+      const BvhNode& nb = a.pools.nodes[c.z];
+      const Xf X = a.pair_X[c.x];
+      const D3 t = xform_point(X, load3(nb.c)) - load3(na.c);
+      is_cand = boxes_overlap(na.h, nb.h, X, t);
+      c = make_int4(c.x, ~na.left, ~nb.left, is_cand ? 1 : 0);
+      a.cand[i] = c;
+      if (is_cand) keep = kTet ? tet_stage_a(a, c) : tri_stage_a(a, c);
     }
+    n_cand += __popc(__ballot_sync(0xffffffffu, is_cand));
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     int wbase = 0;
     if (lane == 0 && m) wbase = atomicAdd(&q_count, __popc(m));
@@ -787,6 +885,7 @@ __global__ void __launch_bounds__(kClipThreads) k_clip(ClipArgs a) {
   const bool active = threadIdx.x < qn;
   const int4 w = active ? queue[threadIdx.x] : make_int4(0, 0, 0, 0);
   if (kTet) tet_stage_b(a, P, w, active); else tri_stage_b(a, P, w, active);
+  if (lane == 0 && n_cand) atomicAdd(kTet ? &a.counters->cand_tet : &a.counters->cand_tri, (unsigned long long)n_cand);
   if (threadIdx.x == 0) {
     full += qn;
     if (full) atomicAdd(kTet ? &a.counters->full_clips_tet : &a.counters->full_clips_tri, full);

@@ -49,10 +49,12 @@ struct alignas(32) TriRec {
 };
 static_assert(sizeof(TriRec) == 96, "TriRec is 96 B");
 
-// BVH node: axis-aligned box in the mesh frame (center + half width, the
-// reference's Aabb, aabb.h:59-65) and two links. All assets' nodes live in one
-// device pool; for an internal node left/right are POOL node indices; for a
-// leaf left = ~(pool element index) (negative) and right = -1.
+// BVH node, exact copy: axis-aligned box in the mesh frame (center + half
+// width, the reference's Aabb, aabb.h:59-65). All assets' nodes live in one
+// device pool. Node 0 of an asset is unused, node 1 is the root, and the two
+// children of an internal node are adjacent (left = first child, right =
+// left + 1, both POOL indices); for a leaf left = ~(pool element index) and
+// right = -1. Only the exact leaf predicate and the root test read these.
 struct alignas(64) BvhNode {
   double c[3];
   double h[3];
@@ -62,6 +64,27 @@ struct alignas(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode is 64 B");
 
+// The same node for the conservative fp32 descent: the box is rounded outward
+// (h32 >= h + |c - c32|, so it contains the exact box), 32 B, siblings share one
+// 64 B line. child >= 0: pool index of the first child; child < 0: ~(pool element).
+struct alignas(32) Node32 {
+  float c[3];
+  float h[3];
+  int32_t child;
+  int32_t pad;
+};
+static_assert(sizeof(Node32) == 32, "Node32 is 32 B");
+
+// Per geometry pair, fp32 copy of X_MN for the conservative descent.
+struct alignas(32) PairF32 {
+  float R[9];    // column-major
+  float AR[9];   // |R| + 1e-6 (row-major: AR[i*3+j] = |R(i,j)| + eps, as in boxes_overlap.cc)
+  float p[3];
+  float S;       // |p|_1
+  float pad[2];
+};
+static_assert(sizeof(PairF32) == 96, "PairF32 is 96 B");
+
 // The element / node pools of a context: every registered asset occupies a
 // contiguous range of each, so work-list entries carry pool indices and the
 // kernels never chase pair -> asset -> array pointers.
@@ -70,6 +93,7 @@ struct Pools {
   const TetAux* aux;
   const TriRec* tris;
   const BvhNode* nodes;
+  const Node32* nodes32;
 };
 
 enum PairKind : int32_t { kSoftRigid = 0, kSoftSoft = 1, kRigidRigid = 2, kUnsupported = 3 };
@@ -101,8 +125,11 @@ struct Xf {
 
 // Device counters of one query (zeroed by the first kernel).
 struct Counters {
-  unsigned long long frontier[64];  // entries per traversal level (== BV-pair tests per level)
-  unsigned long long cand_tri;      // tet-tri candidate pairs
+  unsigned long long frontier[64];  // overlapping node pairs to expand, per traversal level
+  unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
+  unsigned long long leaf_tri;      // leaf pairs that passed the conservative fp32 test (tet-tri)
+  unsigned long long leaf_tet;      // same, tet-tet
+  unsigned long long cand_tri;      // tet-tri candidate pairs: leaf pairs that pass the exact predicate
   unsigned long long cand_tet;      // tet-tet candidate pairs
   unsigned long long polys;         // contact polygons in the staging soup
   unsigned long long poly_verts;    // sum of polygon vertex counts

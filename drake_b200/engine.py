@@ -73,7 +73,7 @@ class Stats(C.Structure):
                 ("geometry_pairs_tested", "geometry_pairs_overlapping", "bv_pair_tests", "tet_tri_pairs",
                  "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "algorithmic_bytes")] + \
                [("total_area", C.c_double), ("tet_tri_full_clips", C.c_int64), ("tet_tet_full_clips", C.c_int64),
-                ("reserved", C.c_double)]
+                ("leaf_pairs", C.c_int64)]
 
 
 _lib = None

@@ -247,7 +247,7 @@ dbh_status dbh_batch_device_results(dbh_batch* batch, dbh_device_results* out);
 
 /* -- (8) statistics of the last completed query. ---------------------------- */
 typedef struct dbh_stats {
-  int64_t geometry_pairs_tested;   /* potential pairs whose poses were composed */
+  int64_t geometry_pairs_tested;   /* soft-rigid + soft-soft pairs whose root boxes were tested */
   int64_t geometry_pairs_overlapping; /* root boxes overlap */
   int64_t bv_pair_tests;
   int64_t tet_tri_pairs;           /* candidate element pairs narrow-phased */
@@ -260,7 +260,7 @@ typedef struct dbh_stats {
   double total_area;
   int64_t tet_tri_full_clips;      /* candidates that survived the conservative culls and ran */
   int64_t tet_tet_full_clips;      /* the reference's full clipping sequence */
-  double reserved;
+  int64_t leaf_pairs;              /* leaf pairs passed by the conservative descent (>= candidates) */
 } dbh_stats;
 dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
 
