@@ -57,7 +57,7 @@ def make_workload(name: str, scenes: int, scene0: int):
         return W.config4(scenes, scene0)
     if name == "c5":
         return W.config5(scenes, scene0)
-    return W.config2_spheres(scenes, 0.5, scene0)
+    return W.config2_spheres(scenes, scene0, 0.5)
 
 
 def measured_peaks():

@@ -171,10 +171,15 @@ struct dbh_context {
   DevBuf<TriRec> d_tris;
   DevBuf<BvhNode> d_nodes;
   DevBuf<Node32> d_nodes32;
+  DevBuf<TetCullA> d_cull_a;
+  DevBuf<TetCullB> d_cull_b;
+  DevBuf<TriCull> d_cull_tri;
   size_t uploaded_assets{0};
   long long up_tets{0}, up_tris{0}, up_nodes{0};
 
-  Pools pools() const { return Pools{d_tets.p, d_aux.p, d_tris.p, d_nodes.p, d_nodes32.p}; }
+  Pools pools() const {
+    return Pools{d_tets.p, d_aux.p, d_tris.p, d_nodes.p, d_nodes32.p, d_cull_a.p, d_cull_b.p, d_cull_tri.p};
+  }
 
   void Place(HostAsset* a) {
     a->node_base = static_cast<int>(num_nodes);
@@ -201,6 +206,9 @@ struct dbh_context {
     CUDA_OK(grow(d_tets, num_tets, &regrown));
     CUDA_OK(grow(d_aux, num_tets, &regrown));
     CUDA_OK(grow(d_tris, num_tris, &regrown));
+    CUDA_OK(grow(d_cull_a, num_tets, &regrown));
+    CUDA_OK(grow(d_cull_b, num_tets, &regrown));
+    CUDA_OK(grow(d_cull_tri, num_tris, &regrown));
     CUDA_OK(grow(d_nodes, num_nodes, &regrown));
     CUDA_OK(grow(d_nodes32, num_nodes, &regrown));
     const size_t first = regrown ? 0 : uploaded_assets;
@@ -212,9 +220,38 @@ struct dbh_context {
         CUDA_OK(cudaMemcpy(d_tets.p + a.elem_base, a.tets.data(), a.tets.size() * sizeof(TetRec),
                            cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpy(d_aux.p + a.elem_base, a.aux.data(), a.aux.size() * sizeof(TetAux), cudaMemcpyHostToDevice));
+        // fp32 copies for the cull stage.
+        std::vector<TetCullA> ca(a.tets.size());
+        std::vector<TetCullB> cb(a.tets.size());
+        for (size_t e = 0; e < a.tets.size(); ++e) {
+          const TetRec& t = a.tets[e];
+          const TetAux& x = a.aux[e];
+          for (int k = 0; k < 4; ++k)
+            for (int d = 0; d < 3; ++d) {
+              ca[e].v[k][d] = static_cast<float>(t.v[k][d]);
+              // Outward normal of the face opposite vertex k (a degenerate face gives 0: never culls).
+              cb[e].nh[k][d] = static_cast<float>(-x.inward[k][d]);
+            }
+          for (int d = 0; d < 3; ++d) ca[e].grad[d] = static_cast<float>(t.grad[d]);
+          ca[e].p_mo = static_cast<float>(t.p_mo);
+          const double len = std::sqrt(t.grad[0] * t.grad[0] + t.grad[1] * t.grad[1] + t.grad[2] * t.grad[2]);
+          cb[e].inv_grad_len = len > 0 ? static_cast<float>(1.0 / len) : 0.f;
+          const double m = std::max(2e-5, 1e-11 * (1.0 + x.amp));
+          cb[e].margin = m < 1e30 ? static_cast<float>(m) : std::numeric_limits<float>::infinity();
+          cb[e].pad[0] = cb[e].pad[1] = 0.f;
+        }
+        CUDA_OK(cudaMemcpy(d_cull_a.p + a.elem_base, ca.data(), ca.size() * sizeof(TetCullA), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_cull_b.p + a.elem_base, cb.data(), cb.size() * sizeof(TetCullB), cudaMemcpyHostToDevice));
       } else {
         CUDA_OK(cudaMemcpy(d_tris.p + a.elem_base, a.tris.data(), a.tris.size() * sizeof(TriRec),
                            cudaMemcpyHostToDevice));
+        std::vector<TriCull> ct(a.tris.size());
+        for (size_t e = 0; e < a.tris.size(); ++e)
+          for (int d = 0; d < 3; ++d) {
+            for (int k = 0; k < 3; ++k) ct[e].v[k][d] = static_cast<float>(a.tris[e].v[k][d]);
+            ct[e].n[d] = static_cast<float>(a.tris[e].n[d]);
+          }
+        CUDA_OK(cudaMemcpy(d_cull_tri.p + a.elem_base, ct.data(), ct.size() * sizeof(TriCull), cudaMemcpyHostToDevice));
       }
       rebased = a.nodes;
       for (BvhNode& n : rebased) {
@@ -782,6 +819,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     mark(2);
     ClipArgs ca{};
     ca.pair_X = b->d_pair_X.p;
+    ca.pair_f32 = b->d_pair_f32.p;
     ca.cand_capacity = static_cast<unsigned long long>(b->cap_cand);
     ca.pools = ctx->pools();
     ca.soup.hdr = b->d_soup_hdr.p;

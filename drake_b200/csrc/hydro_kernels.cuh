@@ -453,6 +453,7 @@ struct ClipArgs {
   int4* cand;
   unsigned long long cand_capacity;
   const Xf* pair_X;
+  const PairF32* pair_f32;
   Pools pools;
   PolySoup soup;
   int* pair_polys;
@@ -534,62 +535,85 @@ constexpr double kCullMargin = 1e-9;  // relative; rounding is ~1e-15 of the sam
 // Slivers get a huge amp and are simply never culled by (N).
 constexpr double kHullMargin = 1e-11;
 
+// The culls run in fp32 on fp32 copies of the records (TetCullA/B, TriCull,
+// PairF32): a cull never produces a value, it only has to be certain, so its
+// margins are simply widened to 2e-5 relative (fp32 rounding through these
+// short expressions stays below ~2e-6 of the same scale).
+struct F3 {
+  float x, y, z;
+};
+__device__ __forceinline__ F3 f3(const float* p) { return F3{p[0], p[1], p[2]}; }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return F3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float dotf(F3 a, F3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ F3 crossf(F3 a, F3 b) {
+  return F3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ float abs_sumf(F3 a) { return fabsf(a.x) + fabsf(a.y) + fabsf(a.z); }
+__device__ __forceinline__ F3 rotf(const PairF32& f, F3 v) {
+  return F3{fmaf(f.R[0], v.x, fmaf(f.R[3], v.y, f.R[6] * v.z)), fmaf(f.R[1], v.x, fmaf(f.R[4], v.y, f.R[7] * v.z)),
+            fmaf(f.R[2], v.x, fmaf(f.R[5], v.y, f.R[8] * v.z))};
+}
+__device__ __forceinline__ F3 rot_tf(const PairF32& f, F3 v) {
+  return F3{fmaf(f.R[0], v.x, fmaf(f.R[1], v.y, f.R[2] * v.z)), fmaf(f.R[3], v.x, fmaf(f.R[4], v.y, f.R[5] * v.z)),
+            fmaf(f.R[6], v.x, fmaf(f.R[7], v.y, f.R[8] * v.z))};
+}
+__device__ __forceinline__ F3 xformf(const PairF32& f, F3 v) {
+  const F3 r = rotf(f, v);
+  return F3{r.x + f.p[0], r.y + f.p[1], r.z + f.p[2]};
+}
+constexpr float kCullMarginF = 2e-5f;
+constexpr float kCosAlphaF = -0.38268343f;
+
 // Stage A. false = certainly no polygon.
 __device__ __forceinline__ bool tri_stage_a(const ClipArgs& a, int4 c) {
-  const Xf X = a.pair_X[c.x];
-  const TetRec& tet = a.pools.tets[c.y];
-  const TetAux& aux = a.pools.aux[c.y];
-  const TriRec& tri = a.pools.tris[c.z];
+  const PairF32 X = a.pair_f32[c.x];
+  const TetCullA& ta = a.pools.cull_a[c.y];
+  const TetCullB& tb = a.pools.cull_b[c.y];
+  const TriCull& tri = a.pools.cull_tri[c.z];
   // Gradient filter (certain rejections only).
-  const D3 nhat_M = rot(X, load3(tri.n));
-  const double s = dot(nhat_M, nhat_M);
-  const double c0 = dot(load3(aux.ngrad), nhat_M);
-  const bool unit = fabs(s - 1.0) < 1e-12;
-  if (unit && c0 < kCosAlphaDevice - 1e-11) return false;
-  const D3 q0 = xform_point(X, load3(tri.v[0]));
-  const D3 q1 = xform_point(X, load3(tri.v[1]));
-  const D3 q2 = xform_point(X, load3(tri.v[2]));
-  const double L = fmax(fmax(abs_sum(q0), abs_sum(q1)), abs_sum(q2));
+  const F3 nhat = rotf(X, f3(tri.n));
+  const bool unit = fabsf(dotf(nhat, nhat) - 1.0f) < 1e-4f;
+  if (unit && dotf(f3(ta.grad), nhat) * tb.inv_grad_len < kCosAlphaF - 1e-3f) return false;
+  const F3 q0 = xformf(X, f3(tri.v[0])), q1 = xformf(X, f3(tri.v[1])), q2 = xformf(X, f3(tri.v[2]));
+  F3 v[4];
+  float L = fmaxf(fmaxf(abs_sumf(q0), abs_sumf(q1)), abs_sumf(q2));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = f3(ta.v[k]);
+    L = fmaxf(L, abs_sumf(v[k]));
+  }
   bool keep = true;
   // (R) tet face planes against the triangle's vertices.
+  const float mr = kCullMarginF * L;
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
-    const D3 nh = load3(aux.plane_nh[f]);
-    const double d = aux.plane_d[f];
-    const double h0 = dot(nh, q0) - d, h1 = dot(nh, q1) - d, h2 = dot(nh, q2) - d;
-    // A NaN displacement (degenerate face) never culls: stage B raises the error.
-    if (fmin(fmin(h0, h1), h2) > kCullMargin * (L + fabs(d))) keep = false;
+    const F3 nh = f3(tb.nh[f]);
+    const float d = dotf(nh, v[(f + 1) % 4]);
+    if (fminf(fminf(dotf(nh, q0) - d, dotf(nh, q1) - d), dotf(nh, q2) - d) > mr) keep = false;
   }
   // (N) the triangle's plane and edge planes against the tet's vertices.
   if (unit) {
-    D3 v[4];
-    double Lv = L;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = load3(tet.v[k]);
-      Lv = fmax(Lv, abs_sum(v[k]));
-    }
-    const double m = kHullMargin * (1.0 + aux.amp) * Lv;  // inf / NaN for slivers: never culls
-    const double w = dot(nhat_M, q0);
+    const float m = tb.margin * L;  // inf for slivers: never culls
+    const float w = dotf(nhat, q0);
     int above = 0, below = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const double h = dot(nhat_M, v[k]) - w;
+      const float h = dotf(nhat, v[k]) - w;
       above += h > m;
       below += h < -m;
     }
     if (above == 4 || below == 4) keep = false;
     // Edge e from qa to qb; u = nhat x (qb - qa) points into the triangle.
-    const D3 qa[3] = {q0, q1, q2};
-    const D3 qb[3] = {q1, q2, q0};
+    const F3 qa[3] = {q0, q1, q2};
+    const F3 qb[3] = {q1, q2, q0};
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-      const D3 edge = qb[e] - qa[e];
-      const D3 u = cross(nhat_M, edge);
-      const double thr = -(m * abs_sum(edge));
+      const F3 edge = qb[e] - qa[e];
+      const F3 u = crossf(nhat, edge);
+      const float thr = -(m * abs_sumf(edge));
       int outside = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) outside += dot(u, v[k] - qa[e]) < thr;
+      for (int k = 0; k < 4; ++k) outside += dotf(u, v[k] - qa[e]) < thr;
       if (outside == 4) keep = false;
     }
   }
@@ -657,71 +681,69 @@ __device__ __forceinline__ void tri_stage_b(const ClipArgs& a, Poly& P, int4 c, 
 //      one face of tet0, by more than 1e-11 (1 + amp1) L: empty.
 // Stage A. false = certainly no polygon.
 __device__ __forceinline__ bool tet_stage_a(const ClipArgs& a, int4 c) {
-  const Xf X = a.pair_X[c.x];
-  const TetRec& t0 = a.pools.tets[c.y];
-  const TetRec& t1 = a.pools.tets[c.z];
-  const TetAux& x0 = a.pools.aux[c.y];
-  const TetAux& x1 = a.pools.aux[c.z];
-  const D3 grad1_N = load3(t1.grad);
-  const D3 p_NMo = -rot_t(X, make_d3(X.m[9], X.m[10], X.m[11]));
-  const double f1_Mo = dot(grad1_N, p_NMo) + t1.p_mo;
-  const D3 n_M = load3(t0.grad) - rot(X, grad1_N);
-  const double s = dot(n_M, n_M);
-  if (s == 0.0) return false;  // magnitude <= 0 (field_intersection.cc:66)
-  // Both gradient filters on the un-normalised normal: cos <= cos(5pi/8) < 0
-  // is certain when c < 0 and c^2 > cos^2 |n|^2 (1 + 1e-9).
-  const double kCos2 = kCosAlphaDevice * kCosAlphaDevice * (1.0 + 1e-9);
-  const double c_0 = dot(n_M, load3(x0.ngrad));
+  const PairF32 X = a.pair_f32[c.x];
+  const TetCullA& a0 = a.pools.cull_a[c.y];
+  const TetCullA& a1 = a.pools.cull_a[c.z];
+  const TetCullB& b0 = a.pools.cull_b[c.y];
+  const TetCullB& b1 = a.pools.cull_b[c.z];
+  const F3 g0 = f3(a0.grad), g1 = f3(a1.grad);
+  const F3 p_NMo = rot_tf(X, F3{-X.p[0], -X.p[1], -X.p[2]});
+  const float f1_Mo = dotf(g1, p_NMo) + a1.p_mo;
+  const F3 n = g0 - rotf(X, g1);
+  const float s = dotf(n, n);
+  const float gsum = abs_sumf(g0) + abs_sumf(g1);
+  // n is a difference of gradients: when it nearly cancels fp32 cannot say
+  // anything about the plane; leave the pair to the exact stage.
+  if (!(s > 1e-6f * gsum * gsum)) return true;
+  // Both gradient filters on the un-normalised normal: cos <= cos(5pi/8) < 0 is
+  // certain when c < 0 and c^2 > cos^2 |n|^2 (1 + 2 %).
+  const float kCos2 = kCosAlphaF * kCosAlphaF * 1.02f;
+  const float c_0 = dotf(n, g0) * b0.inv_grad_len;
   if (c_0 < 0 && c_0 * c_0 > kCos2 * s) return false;
-  const double c_1 = dot(rot_t(X, -n_M), load3(x1.ngrad));
+  const float c_1 = -dotf(rot_tf(X, n), g1) * b1.inv_grad_len;
   if (c_1 < 0 && c_1 * c_1 > kCos2 * s) return false;
   // Equilibrium plane: |n| * height(p) = n.p - (f1(Mo) - f0(Mo)).
-  const double g = f1_Mo - t0.p_mo;
-  D3 v0[4], v1[4];
-  double L1 = 0;
-  int above = 0, below = 0;
+  const float g = f1_Mo - a0.p_mo;
+  F3 v0[4], v1[4];
+  float L = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    v0[k] = load3(t0.v[k]);
-    v1[k] = xform_point(X, load3(t1.v[k]));
-    L1 = fmax(L1, fmax(abs_sum(v0[k]), abs_sum(v1[k])));
-    const double h = dot(n_M, v0[k]) - g;
-    const double tol = kCullMargin * (abs_dot(n_M, v0[k]) + fabs(g));
-    above += h > tol;
-    below += h < -tol;
+    v0[k] = f3(a0.v[k]);
+    v1[k] = xformf(X, f3(a1.v[k]));
+    L = fmaxf(L, fmaxf(abs_sumf(v0[k]), abs_sumf(v1[k])));
   }
-  if (above == 4 || below == 4) return false;  // (R)
-  const double hull1 = kHullMargin * (1.0 + x1.amp);  // relative margin for tet1 as the clipped body
-  {
-    const double tol = hull1 * (abs_sum(n_M) * L1 + fabs(g));
-    above = below = 0;
+  // Scale of every term that enters a height, times the margin.
+  const float scale = gsum * L + (fabsf(a0.p_mo) + fabsf(a1.p_mo) + abs_sumf(g1) * X.S);
+  const float tol0 = kCullMarginF * scale;   // (R) tet0 against the plane
+  const float tol1 = b1.margin * scale;      // (N) tet1 against the plane (margin >= 2e-5)
+  int above0 = 0, below0 = 0, above1 = 0, below1 = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double h = dot(n_M, v1[k]) - g;
-      above += h > tol;
-      below += h < -tol;
-    }
-    if (above == 4 || below == 4) return false;  // (N)
+  for (int k = 0; k < 4; ++k) {
+    const float h0 = dotf(n, v0[k]) - g;
+    const float h1 = dotf(n, v1[k]) - g;
+    above0 += h0 > tol0;
+    below0 += h0 < -tol0;
+    above1 += h1 > tol1;
+    below1 += h1 < -tol1;
   }
+  if (above0 == 4 || below0 == 4 || above1 == 4 || below1 == 4) return false;
   bool keep = true;
+  const float mr = kCullMarginF * L, mn = b1.margin * L;
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
-    // (R) a face of tet1 with all of tet0 outside.
-    const D3 o = rot(X, -load3(x1.inward[f]));
-    const D3 A = v1[(f + 1) % 4];
-    const double dA = dot(o, A);
-    const double sA = abs_dot(o, A);
+    // (R) a face of tet1 (outward normal rotated into M) with all of tet0 outside.
+    const F3 o = rotf(X, f3(b1.nh[f]));
+    const F3 A = v1[(f + 1) % 4];
     int out = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out += (dot(o, v0[k]) - dA) > kCullMargin * (abs_dot(o, v0[k]) + sA);
+    for (int k = 0; k < 4; ++k) out += dotf(o, v0[k] - A) > mr;
     if (out == 4) keep = false;
     // (N) a face of tet0 with all of tet1 outside.
-    const D3 nh = load3(x0.plane_nh[f]);
-    const double d = x0.plane_d[f];
-    const double m = hull1 * (L1 + fabs(d));
+    const F3 nh = f3(b0.nh[f]);
+    const F3 B = v0[(f + 1) % 4];
     out = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out += (dot(nh, v1[k]) - d) > m;
+    for (int k = 0; k < 4; ++k) out += dotf(nh, v1[k] - B) > mn;
     if (out == 4) keep = false;
   }
   return keep;

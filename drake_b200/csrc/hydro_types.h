@@ -41,6 +41,26 @@ struct alignas(128) TetAux {
 };
 static_assert(sizeof(TetAux) == 256, "TetAux is two 128 B lines");
 
+// fp32 copies for the conservative cull stage of the narrow phase (never used
+// for results): one 64 B line of vertices + field, one of outward unit face
+// normals (face f opposite vertex f; its plane passes through vertex (f+1)%4).
+struct alignas(64) TetCullA {
+  float v[4][3];
+  float grad[3];
+  float p_mo;
+};
+struct alignas(64) TetCullB {
+  float nh[4][3];
+  float inv_grad_len;  // 1 / |grad| (0 for a zero gradient)
+  float margin;        // relative safety margin of the hull culls: max(2e-5, 1e-11 (1 + amp))
+  float pad[2];
+};
+struct alignas(16) TriCull {
+  float v[3][3];
+  float n[3];
+};
+static_assert(sizeof(TetCullA) == 64 && sizeof(TetCullB) == 64 && sizeof(TriCull) == 48, "cull records");
+
 // One triangle of a rigid surface mesh: vertices + unit face normal
 // (triangle_surface_mesh.h:452-487).
 struct alignas(32) TriRec {
@@ -94,6 +114,9 @@ struct Pools {
   const TriRec* tris;
   const BvhNode* nodes;
   const Node32* nodes32;
+  const TetCullA* cull_a;
+  const TetCullB* cull_b;
+  const TriCull* cull_tri;
 };
 
 enum PairKind : int32_t { kSoftRigid = 0, kSoftSoft = 1, kRigidRigid = 2, kUnsupported = 3 };

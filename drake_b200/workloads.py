@@ -2,8 +2,8 @@
 
 Meshes come from the library's own generators (drake_b200.Mesh, the product
 side of MakeSphereVolumeMesh / MakeEllipsoidVolumeMesh / MakeBoxVolumeMesh*),
-poses from a counter-based RNG (Philox keyed by seed ^ config id; one draw
-stream per scene index) so any rank can generate any scene range.
+poses from a counter-based RNG (SceneDraws: draw k of scene i is a pure
+function of (config, i, k)) so any rank can generate any scene range.
 
   C1  mesh_intersection_benchmark: soft ellipsoid x rigid sphere, 13 argument triples
   C2  compliant_mesh_intersection_benchmark: soft ellipsoid x soft sphere (+ two dense spheres)
@@ -58,17 +58,50 @@ def angle_axis_matrix(angle: float, axis: Sequence[float]) -> np.ndarray:
     return np.eye(3) + math.sin(angle) * K + (1 - math.cos(angle)) * (K @ K)
 
 
-def scene_rng(config_id: int, scene0: int) -> np.random.Generator:
-    """Counter-based generator positioned at scene `scene0` (1024 draws reserved per scene)."""
-    bit = np.random.Philox(key=SEED ^ config_id)
-    bit.advance(scene0 * 1024)
-    return np.random.Generator(bit)
+class SceneDraws:
+    """Counter-based random draws: draw k of scene i of config c is a pure function of (c, i, k)
+    (SplitMix64 of the packed counter), so any rank generates any scene range and gets exactly the
+    poses a single process would (tests/test_sharding_cpu.py)."""
 
+    def __init__(self, config_id: int, scene0: int, num_scenes: int):
+        self.scenes = np.arange(scene0, scene0 + num_scenes, dtype=np.uint64)
+        self.key = np.uint64((SEED ^ (config_id * 0x9E3779B1)) & 0xFFFFFFFF)
+        self.next = 0
 
-def random_rotations(rng: np.random.Generator, n: int) -> np.ndarray:
-    q = rng.normal(size=(n, 4))
-    q /= np.linalg.norm(q, axis=1, keepdims=True)
-    return quat_to_matrix(q)
+    def _bits(self, n: int) -> np.ndarray:
+        """[S, n] uint64, draws next .. next + n of every scene."""
+        k = np.arange(self.next, self.next + n, dtype=np.uint64)
+        self.next += n
+        with np.errstate(over="ignore"):
+            z = (self.scenes[:, None] << np.uint64(20)) + k[None, :] + (self.key << np.uint64(44))
+            z = z + np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        return z
+
+    def uniform(self, n: int) -> np.ndarray:
+        """[S, n] doubles in [0, 1)."""
+        return (self._bits(n) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+    def normal(self, n: int) -> np.ndarray:
+        """[S, n] standard normals (Box-Muller)."""
+        m = (n + 1) // 2
+        u1 = 1.0 - self.uniform(m)
+        u2 = self.uniform(m)
+        r = np.sqrt(-2.0 * np.log(u1))
+        out = np.concatenate([r * np.cos(2 * np.pi * u2), r * np.sin(2 * np.pi * u2)], axis=1)
+        return out[:, :n]
+
+    def rotations(self, n: int = 1) -> np.ndarray:
+        """[S, n, 3, 3] uniform random rotations (normalised 4-vectors of normals)."""
+        q = self.normal(4 * n).reshape(len(self.scenes) * n, 4)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        return quat_to_matrix(q).reshape(len(self.scenes), n, 3, 3)
+
+    def directions(self) -> np.ndarray:
+        d = self.normal(3)
+        return d / np.linalg.norm(d, axis=1, keepdims=True)
 
 
 @dataclass
@@ -148,15 +181,14 @@ def config2(resolutions=(0, 1, 2, 3), overlaps=(0, 1, 2, 3)) -> Workload:
                     [0, 1], [1, 2], [0, 0], poses, POLYGON, None, per_scene)
 
 
-def config2_spheres(num_scenes: int, hint: float = 0.5, scene0: int = 0) -> Workload:
+def config2_spheres(num_scenes: int, scene0: int = 0, hint: float = 0.5) -> Workload:
     """Two soft spheres r=3 (dense, fine resolution_hint) at random relative poses."""
     m = Mesh.sphere_volume(3.0, hint, DENSE_INTERIOR_VERTICES).set_sphere_pressure(3.0, 1e5)
-    rng = scene_rng(2, scene0)
-    RA, RB = random_rotations(rng, num_scenes), random_rotations(rng, num_scenes)
-    d = rng.normal(size=(num_scenes, 3))
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    dist = rng.uniform(3.6, 5.85, size=(num_scenes, 1))
-    poses = np.stack([xforms(RA, np.zeros((num_scenes, 3))), xforms(RB, dist * d)], axis=1)
+    rng = SceneDraws(2, scene0, num_scenes)
+    R = rng.rotations(2)
+    d = rng.directions()
+    dist = 3.6 + (5.85 - 3.6) * rng.uniform(1)
+    poses = np.stack([xforms(R[:, 0], np.zeros((num_scenes, 3))), xforms(R[:, 1], dist * d)], axis=1)
     return Workload(f"c2_two_dense_spheres_hint{hint}", f"two soft spheres r=3 dense ({m.num_elements} tets each)",
                     [m], [0, 0], [1, 2], [0, 0], poses, POLYGON)
 
@@ -174,10 +206,10 @@ def config3(num_scenes: int = 16384, scene0: int = 0) -> Workload:
     plate = Mesh.box_surface(0.2, 0.2, 0.01)
     r = 0.05
     ball = Mesh.sphere_volume(r, 0.015, SINGLE_INTERIOR_VERTEX).set_sphere_pressure(r, 3e4)
-    rng = scene_rng(3, scene0)
+    rng = SceneDraws(3, scene0, num_scenes)
     S = num_scenes
-    draws = rng.uniform(size=(S, 3))
-    R = random_rotations(rng, S)
+    draws = rng.uniform(3)
+    R = rng.rotations(1)[:, 0]
     plate_top = 0.005 - 0.0005 + 0.005
     x = -0.05 + 0.2 * draws[:, 0]
     y = -0.1 + 0.2 * draws[:, 1]
@@ -215,9 +247,9 @@ def config4(num_scenes: int = 4096, scene0: int = 0, bodies: int = 32) -> Worklo
         wall_mesh.append(len(meshes))
         meshes.append(Mesh.box_surface(*size))
     S = num_scenes
-    rng = scene_rng(4, scene0)
-    c = rng.uniform(size=(S, bodies, 3)) * np.array([0.36, 0.36, 0.16]) - np.array([0.18, 0.18, 0.08])
-    R = random_rotations(rng, S * bodies)
+    rng = SceneDraws(4, scene0, num_scenes)
+    c = rng.uniform(3 * bodies).reshape(S, bodies, 3) * np.array([0.36, 0.36, 0.16]) - np.array([0.18, 0.18, 0.08])
+    R = rng.rotations(bodies).reshape(S * bodies, 3, 3)
     body_poses = xforms(R, c.reshape(-1, 3)).reshape(S, bodies, 12)
     wall_poses = np.tile(np.stack([xform(None, p) for _, p in walls])[None], (S, 1, 1))
     poses = np.concatenate([wall_poses, body_poses], axis=1)
@@ -235,13 +267,12 @@ def config5(num_scenes: int = 1024, scene0: int = 0, hint: float = 0.03) -> Work
     each ("~1M tets" is not reachable: level 5 gives 262 144); one shared asset instanced twice per
     scene; centre distance ~U(1.2, 1.95), uniform relative orientation."""
     m = Mesh.sphere_volume(1.0, hint, DENSE_INTERIOR_VERTICES).set_sphere_pressure(1.0, 1e5)
-    rng = scene_rng(5, scene0)
+    rng = SceneDraws(5, scene0, num_scenes)
     S = num_scenes
-    RA, RB = random_rotations(rng, S), random_rotations(rng, S)
-    d = rng.normal(size=(S, 3))
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    dist = rng.uniform(1.2, 1.95, size=(S, 1))
-    poses = np.stack([xforms(RA, np.zeros((S, 3))), xforms(RB, dist * d)], axis=1)
+    R = rng.rotations(2)
+    d = rng.directions()
+    dist = 1.2 + (1.95 - 1.2) * rng.uniform(1)
+    poses = np.stack([xforms(R[:, 0], np.zeros((S, 3))), xforms(R[:, 1], dist * d)], axis=1)
     return Workload("c5_high_resolution_stress", f"two soft spheres r=1 dense ({m.num_elements} tets each)", [m],
                     [0, 0], [1, 2], [0, 0], poses, POLYGON)
 

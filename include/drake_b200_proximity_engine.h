@@ -1,0 +1,417 @@
+// drake_b200_proximity_engine.h — host-side C++ mirror of the reference interface for the
+// hydroelastic contact-surface path, over the C-ABI in drake_b200_hydro.h.
+//
+// Header-only C++17, no Eigen. Mirrors, name for name and with the same argument meaning and
+// error behaviour, the part of geometry::internal::ProximityEngine<double> that sits on the path
+// (reference: geometry/proximity_engine.h:60-395):
+//   AddDynamicGeometry / AddAnchoredGeometry      proximity_engine.h:122-133
+//   UpdateWorldPoses                              proximity_engine.h:226-227
+//   ComputeContactSurfaces                        proximity_engine.h:309-315
+//   ComputeContactSurfacesWithFallback            proximity_engine.h:320-326
+//   collision_filter().  (as ExcludeCollisionsBetween)   proximity_engine.h:87
+// and geometry::ContactSurface<double> (query_results/contact_surface.h:160-415).
+// Results are returned by value; WithFallback appends to caller vectors and never clears them
+// (query_object.h:439-447); failures are std::logic_error / std::runtime_error as in
+// proximity_engine.cc:1347-1397.
+//
+// One engine = one scene template. `set_num_scenes(S)` instances the registered scene S times so a
+// single ComputeContactSurfacesBatched() call evaluates S pose sets on the GPU (the batched,
+// scene-sharded use the north star asks for); the unbatched calls are the S = 1 case.
+#ifndef DRAKE_B200_PROXIMITY_ENGINE_H_
+#define DRAKE_B200_PROXIMITY_ENGINE_H_
+
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <variant>
+#include <vector>
+
+#include "drake_b200_hydro.h"
+
+namespace drake_b200 {
+
+using GeometryId = int64_t;
+
+// math::RigidTransform<double>: rotation column-major then translation (math/rigid_transform.h:1004-1007).
+struct RigidTransformd {
+  std::array<double, 12> m{1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  static RigidTransformd Identity() { return {}; }
+  static RigidTransformd FromTranslation(double x, double y, double z) {
+    RigidTransformd X;
+    X.m[9] = x;
+    X.m[10] = y;
+    X.m[11] = z;
+    return X;
+  }
+};
+
+// geometry/shape_specification.h (the primitives the path's mesh generators cover) plus explicit meshes.
+struct Sphere {
+  double radius;
+};
+struct Box {
+  double width, depth, height;
+};
+struct Ellipsoid {
+  double a, b, c;
+};
+struct VolumeMeshShape {  // VolumeMesh<double> + per-vertex pressure
+  std::vector<double> vertices;  // [nv*3]
+  std::vector<int32_t> tetrahedra;  // [nt*4]
+  std::vector<double> pressure;  // [nv]
+};
+struct SurfaceMeshShape {  // TriangleSurfaceMesh<double>
+  std::vector<double> vertices;
+  std::vector<int32_t> triangles;
+};
+using Shape = std::variant<Sphere, Box, Ellipsoid, VolumeMeshShape, SurfaceMeshShape>;
+
+enum class HydroelasticType { kUndefined = DBH_UNDEFINED, kRigid = DBH_RIGID, kCompliant = DBH_COMPLIANT };
+enum class HydroelasticContactRepresentation { kTriangle = DBH_TRIANGLE, kPolygon = DBH_POLYGON };
+enum class TessellationStrategy { kSingleInteriorVertex = 0, kDenseInteriorVertices = 1 };
+
+// The "hydroelastic" property group (geometry/proximity_properties.cc:16-21).
+struct ProximityProperties {
+  HydroelasticType compliance_type{HydroelasticType::kUndefined};
+  double hydroelastic_modulus{1e7};
+  double resolution_hint{0.02};
+  double margin{0.0};
+  TessellationStrategy tessellation_strategy{TessellationStrategy::kSingleInteriorVertex};
+};
+
+// geometry::PenetrationAsPointPair<double> (the fallback result; produced by the reference's FCL
+// narrow phase, which is outside this path: the vector is left untouched).
+struct PenetrationAsPointPair {
+  GeometryId id_A, id_B;
+  std::array<double, 3> p_WCa, p_WCb, nhat_BA_W;
+  double depth;
+};
+
+// geometry::ContactSurface<double>. Faces and vertices are owned by value; all quantities in World.
+class ContactSurface {
+ public:
+  GeometryId id_M() const { return id_M_; }
+  GeometryId id_N() const { return id_N_; }
+  HydroelasticContactRepresentation representation() const { return rep_; }
+  bool is_triangle() const { return rep_ == HydroelasticContactRepresentation::kTriangle; }
+  int num_faces() const { return static_cast<int>(areas_.size()); }
+  int num_vertices() const { return static_cast<int>(pressures_.size()); }
+  double area(int f) const { return areas_[f]; }
+  double total_area() const { return total_area_; }
+  const double* face_normal(int f) const { return &normals_[3 * f]; }   // out of N into M
+  const double* centroid(int f) const { return &centroids_[3 * f]; }
+  const double* centroid() const { return centroid_.data(); }
+  const double* vertex(int v) const { return &vertices_[3 * v]; }
+  double vertex_pressure(int v) const { return pressures_[v]; }          // e_MN at vertex v
+  // poly_e_MN().EvaluateCartesian(f, centroid(f)) / tri_e_MN().Evaluate(f, (1/3,1/3,1/3)).
+  double pressure_at_centroid(int f) const { return e_centroid_[f]; }
+  bool HasGradE_M() const { return has_grad_M_; }
+  bool HasGradE_N() const { return has_grad_N_; }
+  const double* EvaluateGradE_M_W(int f) const {
+    if (!has_grad_M_) throw std::runtime_error("ContactSurface::EvaluateGradE_M_W() invalid; no gradient values stored");
+    return &grad_eM_[3 * f];
+  }
+  const double* EvaluateGradE_N_W(int f) const {
+    if (!has_grad_N_) throw std::runtime_error("ContactSurface::EvaluateGradE_N_W() invalid; no gradient values stored");
+    return &grad_eN_[3 * f];
+  }
+  // PolygonSurfaceMesh::face_data_ encoding |n|v0..vn-1| (polygon_surface_mesh.h:141-185) or 3
+  // vertex indices per triangle.
+  const std::vector<int32_t>& face_data() const { return face_data_; }
+  const std::vector<double>& vertices() const { return vertices_; }
+  const std::vector<double>& pressures() const { return pressures_; }
+
+ private:
+  friend class ProximityEngine;
+  GeometryId id_M_{}, id_N_{};
+  HydroelasticContactRepresentation rep_{HydroelasticContactRepresentation::kPolygon};
+  std::vector<double> vertices_, pressures_, areas_, normals_, centroids_, e_centroid_, grad_eM_, grad_eN_;
+  std::vector<int32_t> face_data_;
+  double total_area_{0};
+  std::array<double, 3> centroid_{};
+  bool has_grad_M_{false}, has_grad_N_{false};
+};
+
+class ProximityEngine {
+ public:
+  explicit ProximityEngine(int device_ordinal = 0) {
+    Check(dbh_context_create(device_ordinal, &ctx_), "ProximityEngine");
+  }
+  ~ProximityEngine() {
+    if (batch_) dbh_batch_destroy(batch_);
+    if (ctx_) dbh_context_destroy(ctx_);
+  }
+  ProximityEngine(const ProximityEngine&) = delete;
+  ProximityEngine& operator=(const ProximityEngine&) = delete;
+
+  void AddDynamicGeometry(const Shape& shape, const RigidTransformd& X_WG, GeometryId id,
+                          const ProximityProperties& props = {}) {
+    AddGeometry(shape, X_WG, id, props, /*anchored=*/false);
+  }
+  void AddAnchoredGeometry(const Shape& shape, const RigidTransformd& X_WG, GeometryId id,
+                           const ProximityProperties& props = {}) {
+    AddGeometry(shape, X_WG, id, props, /*anchored=*/true);
+  }
+  int num_geometries() const { return static_cast<int>(ids_.size()); }
+
+  // CollisionFilter declaration ExcludeBetween for one pair (collision_filter.h:158 CanCollideWith).
+  void ExcludeCollisionsBetween(GeometryId a, GeometryId b) {
+    excluded_.emplace_back(IndexOf(a), IndexOf(b));
+    Invalidate();
+  }
+
+  // Number of scene instances evaluated per batched call (default 1).
+  void set_num_scenes(int num_scenes) {
+    if (num_scenes < 1) throw std::logic_error("set_num_scenes: need at least one scene");
+    num_scenes_ = num_scenes;
+    Invalidate();
+  }
+  int num_scenes() const { return num_scenes_; }
+
+  // UpdateWorldPoses: only ids present in the map are updated (proximity_engine.cc:551-576).
+  void UpdateWorldPoses(const std::unordered_map<GeometryId, RigidTransformd>& X_WGs) {
+    for (const auto& [id, X] : X_WGs) {
+      auto it = index_.find(id);
+      if (it != index_.end()) poses_[it->second] = X;
+    }
+  }
+
+  std::vector<ContactSurface> ComputeContactSurfaces(
+      HydroelasticContactRepresentation representation,
+      const std::unordered_map<GeometryId, RigidTransformd>& X_WGs) {
+    UpdateWorldPoses(X_WGs);
+    auto all = Run(representation, DBH_QUERY_STRICT, PosesOfOneScene());
+    return std::move(all[0]);
+  }
+
+  void ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation representation,
+                                          const std::unordered_map<GeometryId, RigidTransformd>& X_WGs,
+                                          std::vector<ContactSurface>* surfaces,
+                                          std::vector<PenetrationAsPointPair>* point_pairs) {
+    if (surfaces == nullptr || point_pairs == nullptr)  // DRAKE_DEMAND (query_object.cc:174-175)
+      throw std::logic_error("ComputeContactSurfacesWithFallback: null output");
+    UpdateWorldPoses(X_WGs);
+    auto all = Run(representation, DBH_QUERY_WITH_FALLBACK, PosesOfOneScene());
+    for (auto& s : all[0]) surfaces->push_back(std::move(s));
+  }
+
+  // Batched form: X_WGs is [num_scenes * num_geometries * 12] doubles, scene-major, geometries in
+  // registration order. Returns the surfaces of every scene, each list sorted by (id_M, id_N).
+  std::vector<std::vector<ContactSurface>> ComputeContactSurfacesBatched(
+      HydroelasticContactRepresentation representation, const std::vector<double>& X_WGs) {
+    if (X_WGs.size() != static_cast<size_t>(num_scenes_) * ids_.size() * 12)
+      throw std::logic_error("ComputeContactSurfacesBatched: expected num_scenes * num_geometries poses");
+    return Run(representation, DBH_QUERY_STRICT, X_WGs);
+  }
+
+  dbh_stats stats() const {
+    dbh_stats s{};
+    if (batch_) dbh_batch_stats(batch_, &s);
+    return s;
+  }
+
+ private:
+  static void Check(dbh_status s, const char* where) {
+    if (s == DBH_OK) return;
+    const std::string msg = std::string(where) + ": " + dbh_last_error();
+    // The reference throws std::logic_error for unsupported / rigid-rigid pairs
+    // (proximity_engine.cc:1361-1390); everything else is a runtime failure.
+    if (s == DBH_ERR_RIGID_RIGID || s == DBH_ERR_UNSUPPORTED || s == DBH_ERR_INVALID_ARGUMENT) throw std::logic_error(msg);
+    throw std::runtime_error(msg);
+  }
+  static void CheckMesh(dbh_status s, const char* where) {
+    if (s != DBH_OK) throw std::logic_error(std::string(where) + ": " + dbh_mesh_last_error());
+  }
+  int IndexOf(GeometryId id) const {
+    auto it = index_.find(id);
+    if (it == index_.end()) throw std::logic_error("unknown GeometryId " + std::to_string(id));
+    return it->second;
+  }
+  void Invalidate() {
+    if (batch_) dbh_batch_destroy(batch_);
+    batch_ = nullptr;
+  }
+
+  // hydroelastic::Geometries::MaybeAddGeometry (hydroelastic_internal.cc:145-153, 328-343, 412-536).
+  int32_t MakeAsset(const Shape& shape, const ProximityProperties& p) {
+    if (p.compliance_type == HydroelasticType::kUndefined) return -1;
+    const bool soft = p.compliance_type == HydroelasticType::kCompliant;
+    int32_t asset = -1;
+    struct MeshHandle {
+      dbh_mesh* h{nullptr};
+      ~MeshHandle() {
+        if (h) dbh_mesh_destroy(h);
+      }
+    } vol, surf;
+    if (const auto* s = std::get_if<Sphere>(&shape)) {
+      CheckMesh(dbh_mesh_make_sphere_volume(s->radius, p.resolution_hint,
+                                            soft ? static_cast<int>(p.tessellation_strategy) : 0, &vol.h),
+                "MakeSphereVolumeMesh");
+      if (soft) CheckMesh(dbh_mesh_set_sphere_pressure(vol.h, s->radius, p.hydroelastic_modulus, p.margin), "MakeSpherePressureField");
+    } else if (const auto* b = std::get_if<Box>(&shape)) {
+      CheckMesh(dbh_mesh_make_box_volume_with_ma(b->width, b->depth, b->height, &vol.h), "MakeBoxVolumeMeshWithMa");
+      if (soft)
+        CheckMesh(dbh_mesh_set_box_pressure(vol.h, b->width, b->depth, b->height, p.hydroelastic_modulus, p.margin),
+                  "MakeBoxPressureField");
+    } else if (const auto* e = std::get_if<Ellipsoid>(&shape)) {
+      CheckMesh(dbh_mesh_make_ellipsoid_volume(e->a, e->b, e->c, p.resolution_hint,
+                                               soft ? static_cast<int>(p.tessellation_strategy) : 0, &vol.h),
+                "MakeEllipsoidVolumeMesh");
+      if (soft)
+        CheckMesh(dbh_mesh_set_ellipsoid_pressure(vol.h, e->a, e->b, e->c, p.hydroelastic_modulus, p.margin),
+                  "MakeEllipsoidPressureField");
+    } else if (const auto* v = std::get_if<VolumeMeshShape>(&shape)) {
+      if (!soft) throw std::logic_error("a volume mesh can only be registered as a compliant geometry");
+      Check(dbh_register_compliant_mesh(ctx_, static_cast<int32_t>(v->vertices.size() / 3), v->vertices.data(),
+                                        static_cast<int32_t>(v->tetrahedra.size() / 4), v->tetrahedra.data(),
+                                        v->pressure.data(), &asset),
+            "register_compliant_mesh");
+      return asset;
+    } else if (const auto* t = std::get_if<SurfaceMeshShape>(&shape)) {
+      if (soft) throw std::logic_error("a surface mesh can only be registered as a rigid geometry");
+      Check(dbh_register_rigid_mesh(ctx_, static_cast<int32_t>(t->vertices.size() / 3), t->vertices.data(),
+                                    static_cast<int32_t>(t->triangles.size() / 3), t->triangles.data(), &asset),
+            "register_rigid_mesh");
+      return asset;
+    }
+    if (soft) {
+      Check(dbh_register_mesh(ctx_, vol.h, &asset), "register_mesh");
+    } else {
+      CheckMesh(dbh_mesh_convert_volume_to_surface(vol.h, &surf.h), "ConvertVolumeToSurfaceMesh");
+      Check(dbh_register_mesh(ctx_, surf.h, &asset), "register_mesh");
+    }
+    return asset;
+  }
+
+  void AddGeometry(const Shape& shape, const RigidTransformd& X_WG, GeometryId id, const ProximityProperties& props,
+                   bool anchored) {
+    if (index_.count(id)) throw std::logic_error("GeometryId " + std::to_string(id) + " already registered");
+    const int32_t asset = MakeAsset(shape, props);
+    index_[id] = static_cast<int>(ids_.size());
+    ids_.push_back(id);
+    assets_.push_back(asset);
+    anchored_.push_back(anchored ? 1 : 0);
+    poses_.push_back(X_WG);
+    Invalidate();
+  }
+
+  std::vector<double> PosesOfOneScene() const {
+    if (num_scenes_ != 1) throw std::logic_error("use ComputeContactSurfacesBatched when num_scenes > 1");
+    std::vector<double> out(ids_.size() * 12);
+    for (size_t g = 0; g < ids_.size(); ++g) std::copy(poses_[g].m.begin(), poses_[g].m.end(), out.begin() + 12 * g);
+    return out;
+  }
+
+  void EnsureBatch() {
+    if (batch_) return;
+    const int G = static_cast<int>(ids_.size());
+    std::vector<int32_t> offsets(num_scenes_ + 1), assets;
+    std::vector<int64_t> ids;
+    std::vector<uint8_t> anchored;
+    std::vector<int32_t> excluded;
+    for (int s = 0; s <= num_scenes_; ++s) offsets[s] = s * G;
+    for (int s = 0; s < num_scenes_; ++s) {
+      assets.insert(assets.end(), assets_.begin(), assets_.end());
+      ids.insert(ids.end(), ids_.begin(), ids_.end());
+      anchored.insert(anchored.end(), anchored_.begin(), anchored_.end());
+      for (const auto& [a, b] : excluded_) {
+        excluded.push_back(s * G + a);
+        excluded.push_back(s * G + b);
+      }
+    }
+    Check(dbh_batch_create(ctx_, num_scenes_, offsets.data(), assets.data(), ids.data(), anchored.data(),
+                           static_cast<int32_t>(excluded.size() / 2), excluded.data(), &batch_),
+          "batch_create");
+  }
+
+  std::vector<std::vector<ContactSurface>> Run(HydroelasticContactRepresentation rep, int query_kind,
+                                               const std::vector<double>& X_WGs) {
+    std::vector<std::vector<ContactSurface>> out(num_scenes_);
+    if (ids_.empty()) return out;
+    EnsureBatch();
+    for (int attempt = 0;; ++attempt) {
+      Check(dbh_batch_set_poses_host(batch_, X_WGs.data()), "set_poses");
+      Check(dbh_batch_query(batch_, static_cast<int32_t>(rep), query_kind, nullptr), "query");
+      const dbh_status s = dbh_batch_sync(batch_);
+      if (s == DBH_ERR_CAPACITY && attempt < 64) {  // first queries size the device work lists
+        Check(dbh_batch_grow_capacity(batch_), "grow_capacity");
+        continue;
+      }
+      Check(s, "ComputeContactSurfaces");
+      break;
+    }
+    dbh_result_sizes sz{};
+    Check(dbh_batch_result_sizes(batch_, &sz), "result_sizes");
+    const size_t ns = sz.num_surfaces, nf = sz.num_faces, nv = sz.num_vertices, nfd = sz.face_data_ints;
+    std::vector<int32_t> scene(ns), face_data(nfd);
+    std::vector<int64_t> id_M(ns), id_N(ns), foff(ns + 1), voff(ns + 1);
+    std::vector<double> tarea(ns), scent(3 * ns), verts(3 * nv), pres(nv), areas(nf), normals(3 * nf), cents(3 * nf),
+        ecent(nf), gM(3 * nf), gN(3 * nf);
+    std::vector<uint8_t> flags(ns);
+    dbh_result_buffers buf{};
+    buf.surf_scene = scene.data();
+    buf.surf_id_M = id_M.data();
+    buf.surf_id_N = id_N.data();
+    buf.surf_face_offset = foff.data();
+    buf.surf_vertex_offset = voff.data();
+    buf.surf_total_area = tarea.data();
+    buf.surf_centroid = scent.data();
+    buf.surf_flags = flags.data();
+    buf.vertices = verts.data();
+    buf.pressures = pres.data();
+    buf.face_data = face_data.data();
+    buf.areas = areas.data();
+    buf.normals = normals.data();
+    buf.centroids = cents.data();
+    buf.pressure_at_centroid = ecent.data();
+    buf.grad_eM = gM.data();
+    buf.grad_eN = gN.data();
+    Check(dbh_batch_copy_results(batch_, &buf), "copy_results");
+    const bool poly = rep == HydroelasticContactRepresentation::kPolygon;
+    for (size_t k = 0; k < ns; ++k) {
+      ContactSurface cs;
+      cs.id_M_ = id_M[k];
+      cs.id_N_ = id_N[k];
+      cs.rep_ = rep;
+      const size_t f0 = foff[k], f1 = foff[k + 1], v0 = voff[k], v1 = voff[k + 1];
+      // The concatenated face_data of a surface starts at f0 + v0 (polygon: one count per face plus
+      // one index per vertex) or 3 * f0 (triangles).
+      const size_t d0 = poly ? f0 + v0 : 3 * f0, d1 = poly ? f1 + v1 : 3 * f1;
+      cs.vertices_.assign(verts.begin() + 3 * v0, verts.begin() + 3 * v1);
+      cs.pressures_.assign(pres.begin() + v0, pres.begin() + v1);
+      cs.face_data_.assign(face_data.begin() + d0, face_data.begin() + d1);
+      cs.areas_.assign(areas.begin() + f0, areas.begin() + f1);
+      cs.normals_.assign(normals.begin() + 3 * f0, normals.begin() + 3 * f1);
+      cs.centroids_.assign(cents.begin() + 3 * f0, cents.begin() + 3 * f1);
+      cs.e_centroid_.assign(ecent.begin() + f0, ecent.begin() + f1);
+      cs.has_grad_M_ = flags[k] & 1;
+      cs.has_grad_N_ = flags[k] & 2;
+      if (cs.has_grad_M_) cs.grad_eM_.assign(gM.begin() + 3 * f0, gM.begin() + 3 * f1);
+      if (cs.has_grad_N_) cs.grad_eN_.assign(gN.begin() + 3 * f0, gN.begin() + 3 * f1);
+      cs.total_area_ = tarea[k];
+      cs.centroid_ = {scent[3 * k], scent[3 * k + 1], scent[3 * k + 2]};
+      out[scene[k]].push_back(std::move(cs));
+    }
+    return out;
+  }
+
+  dbh_context* ctx_{nullptr};
+  dbh_batch* batch_{nullptr};
+  int num_scenes_{1};
+  std::vector<GeometryId> ids_;
+  std::vector<int32_t> assets_;
+  std::vector<uint8_t> anchored_;
+  std::vector<RigidTransformd> poses_;
+  std::vector<std::pair<int, int>> excluded_;
+  std::unordered_map<GeometryId, int> index_;
+};
+
+}  // namespace drake_b200
+
+#endif  // DRAKE_B200_PROXIMITY_ENGINE_H_

@@ -1,0 +1,127 @@
+// Exercises the C++ mirror of the reference interface (include/drake_b200_proximity_engine.h) the way
+// the reference's own tests exercise ProximityEngine / ContactCalculator:
+//   hydroelastic_calculator_test.cc:320-355  compliant sphere x rigid sphere  -> 100 triangles / 28 polygons
+//   hydroelastic_calculator_test.cc:467-504  compliant x compliant            ->  12 triangles /  4 polygons
+//   proximity_engine_test.cc:1956-2249       ordering, rigid-rigid throws, WithFallback appends
+// Exit code 0 = all checks passed; 3 = no CUDA device (the library has no CPU fallback).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "drake_b200_proximity_engine.h"
+
+using namespace drake_b200;
+
+#define EXPECT(cond)                                                        \
+  do {                                                                      \
+    if (!(cond)) {                                                          \
+      std::fprintf(stderr, "%s:%d: EXPECT failed: %s\n", __FILE__, __LINE__, #cond); \
+      std::exit(1);                                                         \
+    }                                                                       \
+  } while (0)
+
+static RigidTransformd RotX(double angle, double x, double y, double z) {
+  RigidTransformd X;
+  const double c = std::cos(angle), s = std::sin(angle);
+  // column-major: columns (1,0,0), (0,c,s), (0,-s,c)
+  X.m = {1, 0, 0, 0, c, s, 0, -s, c, x, y, z};
+  return X;
+}
+
+int main() {
+  std::unique_ptr<ProximityEngine> engine;
+  try {
+    engine = std::make_unique<ProximityEngine>(0);
+  } catch (const std::runtime_error& e) {
+    std::printf("no device: %s\n", e.what());
+    return 3;
+  }
+  const double R = 0.25;
+  ProximityProperties soft;
+  soft.compliance_type = HydroelasticType::kCompliant;
+  soft.hydroelastic_modulus = 1e8;
+  soft.resolution_hint = 0.25;
+  ProximityProperties rigid;
+  rigid.compliance_type = HydroelasticType::kRigid;
+  rigid.resolution_hint = 0.1;
+  const RigidTransformd X_WA = RotX(M_PI, 0, 0, 0);
+  const RigidTransformd X_WB = RigidTransformd::FromTranslation(0, 0, -(R + R) + 0.125);
+
+  {  // compliant (id 1) x rigid (id 2)
+    ProximityEngine e(0);
+    e.AddDynamicGeometry(Sphere{R}, X_WA, 1, soft);
+    e.AddDynamicGeometry(Sphere{R}, X_WB, 2, rigid);
+    auto tri = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kTriangle, {});
+    EXPECT(tri.size() == 1 && tri[0].num_faces() == 100 && tri[0].is_triangle());
+    auto poly = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
+    EXPECT(poly.size() == 1 && poly[0].num_faces() == 28);
+    EXPECT(poly[0].id_M() == 1 && poly[0].id_N() == 2);
+    EXPECT(poly[0].HasGradE_M() && !poly[0].HasGradE_N());
+    EXPECT(std::fabs(poly[0].total_area() - tri[0].total_area()) < 1e-12 * poly[0].total_area());
+    double sum = 0;
+    for (int f = 0; f < poly[0].num_faces(); ++f) sum += poly[0].area(f);
+    EXPECT(std::fabs(sum - poly[0].total_area()) < 1e-12);
+    bool threw = false;
+    try {
+      poly[0].EvaluateGradE_N_W(0);
+    } catch (const std::runtime_error&) {
+      threw = true;
+    }
+    EXPECT(threw);
+    // Pose updates through the map, as QueryObject::FullPoseUpdate would deliver them.
+    auto none = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon,
+                                         {{2, RigidTransformd::FromTranslation(0, 0, -5.0)}});
+    EXPECT(none.empty());
+  }
+  {  // compliant x compliant
+    ProximityEngine e(0);
+    e.AddDynamicGeometry(Sphere{R}, X_WA, 1, soft);
+    e.AddDynamicGeometry(Sphere{R}, X_WB, 2, soft);
+    EXPECT(e.ComputeContactSurfaces(HydroelasticContactRepresentation::kTriangle, {})[0].num_faces() == 12);
+    auto poly = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
+    EXPECT(poly[0].num_faces() == 4 && poly[0].HasGradE_M() && poly[0].HasGradE_N());
+  }
+  {  // ordering, rigid-rigid, fallback, filter, batching
+    ProximityEngine e(0);
+    e.AddDynamicGeometry(Sphere{R}, RigidTransformd::FromTranslation(0, 0.2, 0.2), 30, soft);
+    e.AddDynamicGeometry(Sphere{R}, RigidTransformd::Identity(), 10, rigid);
+    e.AddDynamicGeometry(Sphere{R}, RigidTransformd::FromTranslation(0, 0, 0.375), 20, soft);
+    auto s = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
+    EXPECT(s.size() == 3);
+    EXPECT(s[0].id_M() == 10 && s[0].id_N() == 20 && s[1].id_M() == 10 && s[1].id_N() == 30 && s[2].id_M() == 20 &&
+           s[2].id_N() == 30);
+    EXPECT(!s[0].HasGradE_M() && s[0].HasGradE_N());  // rigid id < compliant id: M and N swapped
+    e.ExcludeCollisionsBetween(10, 30);
+    EXPECT(e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {}).size() == 2);
+    // Batched: 4 scenes, the ball pair separated in scenes 1 and 3.
+    e.set_num_scenes(4);
+    std::vector<double> poses;
+    for (int sc = 0; sc < 4; ++sc) {
+      const RigidTransformd X[3] = {RigidTransformd::FromTranslation(0, 0.2, 0.2), RigidTransformd::Identity(),
+                                    RigidTransformd::FromTranslation(0, 0, (sc % 2) ? 3.0 : 0.375)};
+      for (const auto& x : X) poses.insert(poses.end(), x.m.begin(), x.m.end());
+    }
+    auto batched = e.ComputeContactSurfacesBatched(HydroelasticContactRepresentation::kPolygon, poses);
+    EXPECT(batched.size() == 4 && batched[0].size() == 2 && batched[1].size() == 0 && batched[2].size() == 2);
+    EXPECT(batched[0][0].num_faces() == batched[2][0].num_faces());
+  }
+  {
+    ProximityEngine e(0);
+    e.AddDynamicGeometry(Sphere{R}, RigidTransformd::Identity(), 1, rigid);
+    e.AddDynamicGeometry(Sphere{R}, RigidTransformd::FromTranslation(0, 0, 0.3), 2, rigid);
+    bool threw = false;
+    try {
+      e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
+    } catch (const std::logic_error& err) {
+      threw = std::string(err.what()).find("rigid-rigid") != std::string::npos;
+    }
+    EXPECT(threw);
+    std::vector<ContactSurface> surfaces(1);  // WithFallback appends, never clears
+    std::vector<PenetrationAsPointPair> pairs;
+    e.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    EXPECT(surfaces.size() == 1);
+  }
+  std::printf("ok\n");
+  return 0;
+}
