@@ -49,7 +49,9 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build libdrake_b200_hydro.so")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB_PATH] + sources()
+    # DBH_EXTRA_NVCC_FLAGS: debug builds only (e.g. -DDBH_TRACE).
+    extra_env = os.environ.get("DBH_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + extra_env + ["-o", LIB_PATH] + sources()
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -327,6 +328,7 @@ struct dbh_batch {
   int representation{DBH_POLYGON};
   bool query_done{false};
   bool timing{false};
+  bool verify{false};
   cudaEvent_t ev[9]{};
   float times_ms[8]{};
 
@@ -763,6 +765,12 @@ dbh_status dbh_batch_enable_timing(dbh_batch* b, int32_t enabled) {
   return DBH_OK;
 }
 
+dbh_status dbh_batch_set_verify(dbh_batch* b, int32_t enabled) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  b->verify = enabled != 0;
+  return DBH_OK;
+}
+
 dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_kind, int64_t* scene_stats_dev) {
   if (!b || (representation != DBH_TRIANGLE && representation != DBH_POLYGON))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_query: bad argument");
@@ -831,6 +839,15 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     ca.counters = b->d_counters.p;
     ca.slow = b->d_slow.p;
     ca.slow_capacity = static_cast<unsigned int>(b->cap_slow);
+    ca.verify = b->verify ? 1 : 0;
+    ca.trace = make_int4(-1, -1, -1, 0);
+#ifdef DBH_TRACE
+    if (const char* t = std::getenv("DBH_TRACE_PAIR")) {
+      int p = -1, e0 = -1, e1 = -1;
+      if (std::sscanf(t, "%d,%d,%d", &p, &e0, &e1) == 3 && p >= 0 && p < b->num_pairs)
+        ca.trace = make_int4(p, e0 + b->pairs[p].elem_base_a, e1 + b->pairs[p].elem_base_b, 0);
+    }
+#endif
     const int clip_blocks = sms * 4;
     if (b->info.num_soft_rigid_pairs) {
       ca.cand = b->d_cand_tri.p;
@@ -981,6 +998,8 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->geometry_pairs_overlapping = static_cast<int64_t>(c.root_overlaps);
   out->bv_pair_tests = static_cast<int64_t>(c.bv_tests);
   out->leaf_pairs = static_cast<int64_t>(c.leaf_tri + c.leaf_tet);
+  out->cull_violations = static_cast<int64_t>(c.cull_violations);
+  out->exceptional_clips = static_cast<int64_t>(c.slow);
   out->tet_tri_pairs = static_cast<int64_t>(c.cand_tri);
   out->tet_tet_pairs = static_cast<int64_t>(c.cand_tet);
   out->polygons = static_cast<int64_t>(c.polys);
@@ -1002,21 +1021,22 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
 }
 
 dbh_status dbh_batch_copy_candidates(dbh_batch* b, int32_t kind, int32_t* out_triples, int64_t* count) {
-  if (!b || !count || (kind != 0 && kind != 1)) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_candidates: bad argument");
+  if (!b || !count || kind < 0 || kind > 3) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_candidates: bad argument");
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   CUDA_OK(cudaSetDevice(b->ctx->device));
-  const int64_t n = static_cast<int64_t>(kind == 0 ? b->h_counters->cand_tri : b->h_counters->cand_tet);
+  const bool tet = (kind & 1) != 0, raw = (kind & 2) != 0;
+  // The narrow phase left the leaf list as {pair, pool elem a, pool elem b, flag}; the candidates
+  // are the flagged entries (kind | 2: every leaf pair the conservative descent passed).
+  const int64_t listed = static_cast<int64_t>(tet ? b->h_counters->leaf_tet : b->h_counters->leaf_tri);
+  const int64_t n = raw ? listed : static_cast<int64_t>(tet ? b->h_counters->cand_tet : b->h_counters->cand_tri);
   *count = n;
   if (!out_triples || n == 0) return DBH_OK;
-  // The narrow phase left the leaf list as {pair, pool elem a, pool elem b, flag}; the candidates
-  // are the flagged entries.
-  const int64_t listed = static_cast<int64_t>(kind == 0 ? b->h_counters->leaf_tri : b->h_counters->leaf_tet);
   std::vector<int4> tmp(listed);
-  CUDA_OK(cudaMemcpy(tmp.data(), kind == 0 ? b->d_cand_tri.p : b->d_cand_tet.p, listed * sizeof(int4),
+  CUDA_OK(cudaMemcpy(tmp.data(), tet ? b->d_cand_tet.p : b->d_cand_tri.p, listed * sizeof(int4),
                      cudaMemcpyDeviceToHost));
   int64_t k = 0;
   for (int64_t i = 0; i < listed && k < n; ++i) {
-    if (tmp[i].w != 1) continue;
+    if (!raw && tmp[i].w != 1) continue;
     const PairRec& pr = b->pairs[tmp[i].x];
     out_triples[3 * k] = tmp[i].x;
     out_triples[3 * k + 1] = tmp[i].y - pr.elem_base_a;

@@ -19,6 +19,15 @@
 #include "hydro_math.cuh"
 #include "hydro_types.h"
 
+#ifdef DBH_TRACE
+#include <cstdio>
+// Debug build only (-DDBH_TRACE): prints the exact stage's intermediate values for one tet-tet
+// candidate {pair, pool tet0, pool tet1} chosen by DBH_TRACE_PAIR="pair,tet0,tet1".
+#define DBH_TR(...) do { if (c.x == a.trace.x && c.y == a.trace.y && c.z == a.trace.z) printf(__VA_ARGS__); } while (0)
+#else
+#define DBH_TR(...) do { } while (0)
+#endif
+
 namespace dbh {
 
 constexpr int kClipThreads = 128;
@@ -350,19 +359,20 @@ template <class Poly>
 __device__ __forceinline__ int remove_nearly_duplicate(Poly& P, int buf, int n) {
   if (n <= 1) return n;
   const double kEpsSquared = 1e-14 * 1e-14;
-  int result = 0;
+  // std::unique: keep the first of each run, comparing against the last kept vertex.
+  int kept_count = 1;
   D3 kept = P.get(buf, 0);
   const D3 first_v = kept;
-  for (int first = 1; first < n; ++first) {
-    const D3 q = P.get(buf, first);
+  for (int i = 1; i < n; ++i) {
+    const D3 q = P.get(buf, i);
     const D3 d = kept - q;
     if (!(dot(d, d) < kEpsSquared)) {
-      ++result;
-      if (result != first) P.set(buf, result, q);
+      P.set(buf, kept_count, q);
+      ++kept_count;
       kept = q;
     }
   }
-  n = result + 1;
+  n = kept_count;
   if (n >= 3) {
     const D3 d = first_v - kept;  // polygon[0] - polygon.back()
     if (dot(d, d) < kEpsSquared) --n;
@@ -459,15 +469,19 @@ struct ClipArgs {
   int* pair_polys;
   int* pair_verts;
   Counters* counters;
-  int4* slow;           // exceptional candidates {pair, elem, elem, 0 tri | 1 tet}
+  int4* slow;           // exceptional candidates {pair, elem, elem, 0 tri | 1 tet (| 2: culled, verify mode)}
   unsigned int slow_capacity;
+  // Self-check mode (dbh_batch_set_verify): the exact stage runs for EVERY candidate and
+  // Counters::cull_violations_* count polygons emitted by candidates stage A had rejected.
+  int verify;
+  int4 trace;           // debug builds only
 };
 
 // A candidate whose intermediate polygon does not fit the fast path's 8 slots.
 __device__ __forceinline__ void defer_to_slow_path(const ClipArgs& a, int4 c, int kind) {
   const unsigned long long slot = atomicAdd(&a.counters->slow, 1ull);
   if (slot < a.slow_capacity) {
-    a.slow[slot] = make_int4(c.x, c.y, c.z, kind);
+    a.slow[slot] = make_int4(c.x, c.y, c.z, kind | (c.w & 2));
   } else {
     raise_error(a.counters, 5, 8);
   }
@@ -483,6 +497,7 @@ __device__ __forceinline__ void emit_polygon(const ClipArgs& a, Poly& P, int buf
     raise_error(a.counters, 5, 3);
     return;
   }
+  if (c.w & 2) atomicAdd(&a.counters->cull_violations, 1ull);  // verify mode only
   a.soup.hdr[slot] = make_int4(c.x, c.y, c.z, n);
   for (int k = 0; k < n; ++k) {
     const D3 p = P.get(buf, k);
@@ -785,6 +800,7 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
         ok = dot(rev_N, load3(aux1.ngrad)) > kCosAlphaDevice;
       }
     }
+    DBH_TR("[trace] filters ok %d magnitude %.17g f1_Mo %.17g f0_Mo %.17g\n", (int)ok, magnitude, f1_Mo, f0_Mo);
     if (ok) {
       // SliceTetrahedronWithPlane (mesh_plane_intersection.cc:121-180).
       double dist[4];
@@ -798,6 +814,8 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
       const unsigned short kEdgeTable[16] = {0xFFFF, 0xF230, 0xF410, 0x1234, 0xF521, 0x1530, 0x4520, 0xF453,
                                              0xF543, 0x0254, 0x0351, 0xF251, 0x4321, 0xF140, 0xF320, 0xFFFF};
       const unsigned entry = kEdgeTable[code];
+      DBH_TR("[trace] mag %.17g nhat %.17g %.17g %.17g disp %.17g dist %.17g %.17g %.17g %.17g code %d\n", magnitude,
+             nhat_M.x, nhat_M.y, nhat_M.z, displacement, dist[0], dist[1], dist[2], dist[3], code);
       n = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -816,7 +834,21 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
           ++n;
         }
       }
+      DBH_TR("[trace] sliced n %d\n", n);
+#ifdef DBH_TRACE
+      for (int q = 0; q < 4; ++q) {
+        const D3 pv = P.get(0, q);
+        DBH_TR("[trace]   sliced slot%d %.17g %.17g %.17g\n", q, pv.x, pv.y, pv.z);
+      }
+#endif
       n = remove_nearly_duplicate(P, 0, n);
+#ifdef DBH_TRACE
+      for (int q = 0; q < 4; ++q) {
+        const D3 pv = P.get(0, q);
+        DBH_TR("[trace]   deduped slot%d %.17g %.17g %.17g\n", q, pv.x, pv.y, pv.z);
+      }
+#endif
+      DBH_TR("[trace] deduped n %d\n", n);
       if (n < 3) n = 0;
       // Clip by the four faces of tet1 (field_intersection.cc:120-190).
 #pragma unroll 1
@@ -831,7 +863,14 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
           } else {
             const D3 nh = outward / mag;
             const double d = dot(nh, p_MA);
+#ifdef DBH_TRACE
+            for (int q = 0; q < n; ++q) {
+              const D3 pv = P.get(buf, q);
+              DBH_TR("[trace]   in v%d %.17g %.17g %.17g h %.17g\n", q, pv.x, pv.y, pv.z, dot(nh, pv) - d);
+            }
+#endif
             n = clip_by_half_space_edges(P, buf, n, nh, d);
+            DBH_TR("[trace] face %d nh %.17g %.17g %.17g d %.17g -> n %d\n", face, nh.x, nh.y, nh.z, d, n);
             if (n > Poly::kCap) {
               if (kSlow) raise_error(a.counters, 5, 5); else defer_to_slow_path(a, c, 1);
               n = 0;
@@ -883,7 +922,13 @@ __global__ void __launch_bounds__(kClipThreads) k_clip(ClipArgs a) {
       is_cand = boxes_overlap(na.h, nb.h, X, t);
       c = make_int4(c.x, ~na.left, ~nb.left, is_cand ? 1 : 0);
       a.cand[i] = c;
-      if (is_cand) keep = kTet ? tet_stage_a(a, c) : tri_stage_a(a, c);
+      if (is_cand) {
+        keep = kTet ? tet_stage_a(a, c) : tri_stage_a(a, c);
+        if (!keep && a.verify) {
+          keep = true;
+          c.w |= 2;
+        }
+      }
     }
     n_cand += __popc(__ballot_sync(0xffffffffu, is_cand));
     const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -925,8 +970,8 @@ __global__ void __launch_bounds__(64) k_clip_slow(ClipArgs a) {
     const bool active = i < count;
     const int4 c = active ? a.slow[i] : make_int4(0, 0, 0, 0);
     // Both flavours run so that every lane reaches both warp-wide appends.
-    tri_stage_b(a, P, c, active && c.w == 0);
-    tet_stage_b(a, P, c, active && c.w == 1);
+    tri_stage_b(a, P, c, active && (c.w & 1) == 0);
+    tet_stage_b(a, P, c, active && (c.w & 1) == 1);
   }
 }
 

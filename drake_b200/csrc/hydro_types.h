@@ -163,6 +163,7 @@ struct Counters {
   unsigned long long full_clips_tri; // tet-tri candidates that survived the conservative culls
   unsigned long long full_clips_tet; // tet-tet candidates that survived the conservative culls
   unsigned long long slow;           // candidates deferred to the exceptional (16-vertex) path
+  unsigned long long cull_violations; // verify mode: polygons from candidates the conservative cull rejected
   int32_t error;                    // first device-side dbh_status raised
   int32_t error_detail;
   double total_area;

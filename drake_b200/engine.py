@@ -73,7 +73,7 @@ class Stats(C.Structure):
                 ("geometry_pairs_tested", "geometry_pairs_overlapping", "bv_pair_tests", "tet_tri_pairs",
                  "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "algorithmic_bytes")] + \
                [("total_area", C.c_double), ("tet_tri_full_clips", C.c_int64), ("tet_tet_full_clips", C.c_int64),
-                ("leaf_pairs", C.c_int64)]
+                ("leaf_pairs", C.c_int64), ("cull_violations", C.c_int64), ("exceptional_clips", C.c_int64)]
 
 
 _lib = None
@@ -118,6 +118,7 @@ def lib():
     L.dbh_batch_copy_candidates.argtypes = [vp, C.c_int32, _ip, _lp]
     L.dbh_batch_copy_geometry_pairs.argtypes = [vp, _ip]
     L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
+    L.dbh_batch_set_verify.argtypes = [vp, C.c_int32]
     L.dbh_batch_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.dbh_mesh_last_error.restype = C.c_char_p
     dbl = C.c_double
@@ -493,6 +494,10 @@ class SceneBatch:
 
     def set_capacity(self, bv_pairs: int = 0, element_pairs: int = 0, faces: int = 0):
         _check(lib().dbh_batch_set_capacity(self._h, bv_pairs, element_pairs, faces))
+
+    def set_verify(self, on: bool = True):
+        """Self-check mode: exact clipping for every candidate; stats()['cull_violations'] must stay 0."""
+        _check(lib().dbh_batch_set_verify(self._h, int(on)))
 
     def enable_timing(self, on: bool = True):
         _check(lib().dbh_batch_enable_timing(self._h, int(on)))

@@ -261,12 +261,16 @@ typedef struct dbh_stats {
   int64_t tet_tri_full_clips;      /* candidates that survived the conservative culls and ran */
   int64_t tet_tet_full_clips;      /* the reference's full clipping sequence */
   int64_t leaf_pairs;              /* leaf pairs passed by the conservative descent (>= candidates) */
+  int64_t cull_violations;         /* self-check mode only (dbh_batch_set_verify): polygons emitted by
+                                      candidates the conservative cull stage had rejected; must be 0 */
+  int64_t exceptional_clips;       /* candidates whose intermediate polygon outgrew 8 vertices */
 } dbh_stats;
 dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
 
 /* Candidate element pairs of the last query (for parity tests): triples
  * (geometry pair index, element of first body, element of second body).
- * kind 0 = tet-tri list, 1 = tet-tet list. Pass out == NULL to get the count. */
+ * kind 0 = tet-tri list, 1 = tet-tet list; kind | 2 = every leaf pair the conservative
+ * descent passed (a superset). Pass out == NULL to get the count. */
 dbh_status dbh_batch_copy_candidates(dbh_batch* batch, int32_t kind, int32_t* out_triples, int64_t* count);
 /* Static geometry-pair list: per pair {scene, flat geom index of first body
  * (S or M), flat geom index of second body (R or N), kind (0 soft-rigid, 1
@@ -277,6 +281,11 @@ dbh_status dbh_batch_copy_geometry_pairs(dbh_batch* batch, int32_t* out);
  * the batch stream): {pose+root, traversal, clip tet-tri, clip tet-tet, scan,
  * pack, reduce, total}. Only recorded when enabled (adds event records). */
 dbh_status dbh_batch_enable_timing(dbh_batch* batch, int32_t enabled);
+/* Self-check mode: the reference's exact clipping sequence runs for EVERY
+ * candidate element pair (the conservative cull stage only flags), and
+ * dbh_stats::cull_violations counts flagged candidates that emitted a polygon.
+ * Results are those of the un-culled pipeline. Slower; for tests. */
+dbh_status dbh_batch_set_verify(dbh_batch* batch, int32_t enabled);
 dbh_status dbh_batch_kernel_times_ms(dbh_batch* batch, float* out8);
 
 #ifdef __cplusplus

@@ -295,3 +295,27 @@ def test_config4_clutter_scenes_including_coplanar_clips(ctx):
         for g, w in zip(got[s], want):
             parity.compare_surface(g, w)
         assert len(want) >= 20
+
+
+@pytest.mark.parametrize("config,scenes", [("c3", 64), ("c4", 4), ("c2s", 4)])
+def test_conservative_culls_never_reject_an_emitting_candidate(ctx, config, scenes):
+    """Self-check mode (dbh_batch_set_verify): the reference's exact clipping sequence runs for every
+    candidate element pair; no candidate the fp32 cull stage rejects may emit a polygon, and the
+    polygon / face / vertex totals must equal those of the normal (culled) pipeline."""
+    from drake_b200 import engine, workloads as W
+    wl = W.CONFIGS[config](scenes)
+    batch = wl.register(ctx)
+    batch.set_poses(wl.poses.reshape(-1, 12))
+    batch.run(ho.KPOLYGON, engine.STRICT)
+    normal = batch.stats()
+    batch.set_verify(True)
+    batch.run(ho.KPOLYGON, engine.STRICT)
+    checked = batch.stats()
+    assert checked["cull_violations"] == 0
+    assert checked["tet_tri_full_clips"] == checked["tet_tri_pairs"]
+    assert checked["tet_tet_full_clips"] == checked["tet_tet_pairs"]
+    for k in ("polygons", "faces", "vertices", "surfaces", "tet_tri_pairs", "tet_tet_pairs"):
+        assert normal[k] == checked[k], k
+    assert normal["polygons"] > 0
+    # The cull stage must actually cull (otherwise this test checks nothing).
+    assert normal["tet_tri_full_clips"] + normal["tet_tet_full_clips"] < normal["tet_tri_pairs"] + normal["tet_tet_pairs"]
