@@ -175,11 +175,13 @@ struct dbh_context {
   DevBuf<TetCullA> d_cull_a;
   DevBuf<TetCullB> d_cull_b;
   DevBuf<TriCull> d_cull_tri;
+  DevBuf<ElemBox> d_ebox_tet, d_ebox_tri;
   size_t uploaded_assets{0};
   long long up_tets{0}, up_tris{0}, up_nodes{0};
 
   Pools pools() const {
-    return Pools{d_tets.p, d_aux.p, d_tris.p, d_nodes.p, d_nodes32.p, d_cull_a.p, d_cull_b.p, d_cull_tri.p};
+    return Pools{d_tets.p,   d_aux.p,      d_tris.p,     d_nodes.p,    d_nodes32.p,
+                 d_cull_a.p, d_cull_b.p,   d_cull_tri.p, d_ebox_tet.p, d_ebox_tri.p};
   }
 
   void Place(HostAsset* a) {
@@ -210,6 +212,8 @@ struct dbh_context {
     CUDA_OK(grow(d_cull_a, num_tets, &regrown));
     CUDA_OK(grow(d_cull_b, num_tets, &regrown));
     CUDA_OK(grow(d_cull_tri, num_tris, &regrown));
+    CUDA_OK(grow(d_ebox_tet, num_tets, &regrown));
+    CUDA_OK(grow(d_ebox_tri, num_tris, &regrown));
     CUDA_OK(grow(d_nodes, num_nodes, &regrown));
     CUDA_OK(grow(d_nodes32, num_nodes, &regrown));
     const size_t first = regrown ? 0 : uploaded_assets;
@@ -253,6 +257,20 @@ struct dbh_context {
             ct[e].n[d] = static_cast<float>(a.tris[e].n[d]);
           }
         CUDA_OK(cudaMemcpy(d_cull_tri.p + a.elem_base, ct.data(), ct.size() * sizeof(TriCull), cudaMemcpyHostToDevice));
+      }
+      // Per-element exact boxes = the leaves' boxes.
+      {
+        std::vector<ElemBox> eb(a.num_elements);
+        for (const BvhNode& n : a.nodes)
+          if (n.left < 0 && n.right == -1 && &n != &a.nodes[0]) {
+            ElemBox& x = eb[~n.left];
+            for (int d = 0; d < 3; ++d) {
+              x.c[d] = n.c[d];
+              x.h[d] = n.h[d];
+            }
+          }
+        ElemBox* dst = (a.type == DBH_COMPLIANT ? d_ebox_tet.p : d_ebox_tri.p) + a.elem_base;
+        CUDA_OK(cudaMemcpy(dst, eb.data(), eb.size() * sizeof(ElemBox), cudaMemcpyHostToDevice));
       }
       rebased = a.nodes;
       for (BvhNode& n : rebased) {
@@ -298,8 +316,15 @@ struct dbh_batch {
   std::vector<PairRec> pairs;
   dbh_batch_info info{};
 
-  // capacities (entries)
-  long long cap_frontier{0}, cap_cand{0}, cap_faces{0}, cap_verts{0}, cap_polys{0};
+  // Work-list capacities (entries) of ONE chunk of scenes; result-array capacities of the whole query.
+  long long cap_frontier{0}, cap_tri{0}, cap_tet{0}, cap_polys{0};
+  long long cap_faces{0}, cap_verts{0};
+  // A query processes the scenes in num_chunks contiguous chunks that reuse the work lists, so their
+  // size is bounded by work_budget_bytes whatever the batch size (chunk c = scenes
+  // [c S / C, (c + 1) S / C)). scene_first_pair[s] = index of the first pair of scene s.
+  int num_chunks{1};
+  size_t work_budget_bytes{0};
+  std::vector<int> scene_first_pair;
 
   DevBuf<PairRec> d_pairs;
   DevBuf<Xf> d_poses_own;
@@ -329,21 +354,40 @@ struct dbh_batch {
   bool query_done{false};
   bool timing{false};
   bool verify{false};
-  cudaEvent_t ev[9]{};
+  // Timing (optional): two events around the whole query, eight per chunk around its stages.
+  cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
+  std::vector<cudaEvent_t> ev_chunk;   // 8 per chunk that ran in the last query
+  int timed_chunks{0};
   float times_ms[8]{};
 
   ~dbh_batch() {
     if (h_counters) cudaFreeHost(h_counters);
-    for (auto& e : ev)
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    for (auto& e : ev_chunk)
       if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+  }
+
+  size_t WorkBytes(long long fr, long long tri, long long tet, long long polys) const {
+    return static_cast<size_t>(fr) * 32 + static_cast<size_t>(tri + tet) * 16 +
+           static_cast<size_t>(polys) * (16 + kMaxPolyVerts * 32 + 24);
+  }
+  int MaxPairsPerChunk() const {
+    int m = 0;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int s0 = static_cast<int>(static_cast<long long>(num_scenes) * c / num_chunks);
+      const int s1 = static_cast<int>(static_cast<long long>(num_scenes) * (c + 1) / num_chunks);
+      m = std::max(m, scene_first_pair[s1] - scene_first_pair[s0]);
+    }
+    return m;
   }
 
   dbh_status AllocWorkBuffers() {
     CUDA_OK(d_frontier[0].ensure(cap_frontier));
     CUDA_OK(d_frontier[1].ensure(cap_frontier));
-    CUDA_OK(d_cand_tri.ensure(info.num_soft_rigid_pairs ? cap_cand : 1));
-    CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_cand : 1));
+    CUDA_OK(d_cand_tri.ensure(info.num_soft_rigid_pairs ? cap_tri : 1));
+    CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_tet : 1));
     CUDA_OK(d_slow.ensure(cap_slow));
     CUDA_OK(d_soup_hdr.ensure(cap_polys));
     CUDA_OK(d_soup_v.ensure(static_cast<size_t>(cap_polys) * kMaxPolyVerts * 4));
@@ -591,8 +635,10 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   std::sort(excl.begin(), excl.end());
   // Static geometry-pair list in (scene, id_M, id_N) order.
   int max_levels = 1;
-  long long est = 0;
+  long long est_tri = 0, est_tet = 0;
+  b->scene_first_pair.assign(num_scenes + 1, 0);
   for (int s = 0; s < num_scenes; ++s) {
+    b->scene_first_pair[s] = static_cast<int>(b->pairs.size());
     const int g0 = scene_offsets[s], g1 = scene_offsets[s + 1];
     std::vector<int> order(g1 - g0);
     for (int i = 0; i < g1 - g0; ++i) order[i] = g0 + i;
@@ -640,7 +686,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
           pr.root_leaf = (A.nodes[1].left < 0 ? 1 : 0) | (B.nodes[1].left < 0 ? 2 : 0);
           if (pr.kind <= kSoftSoft) {
             max_levels = std::max(max_levels, std::max(A.height, B.height) + 1);
-            est += 2ll * (A.num_elements + B.num_elements);
+            (pr.kind == kSoftRigid ? est_tri : est_tet) += 2ll * (A.num_elements + B.num_elements);
           }
         }
         b->pairs.push_back(pr);
@@ -648,6 +694,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
     }
   }
   b->num_pairs = static_cast<int>(b->pairs.size());
+  b->scene_first_pair[num_scenes] = b->num_pairs;
   b->info.num_scenes = num_scenes;
   b->info.num_geometries = b->num_geoms;
   b->info.num_geometry_pairs = b->num_pairs;
@@ -656,19 +703,39 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
 
   // Default capacities: a few entries per element of every pair, bounded (a
   // scene with many geometries has mostly non-overlapping pairs); the first
-  // queries of a batch grow exactly the lists that overflow
-  // (dbh_batch_grow_capacity) and steady state never reallocates.
-  est = std::min(std::max(est, 1ll << 16), 1ll << 23);
-  b->cap_frontier = std::max<long long>(est, b->pairs.size());
-  b->cap_cand = est;
-  b->cap_polys = est / 4;
-  b->cap_faces = est / 2;
-  b->cap_verts = est;
+  // queries of a batch grow exactly the lists that overflow, or split the batch
+  // into more chunks of scenes when the lists would outgrow the memory budget
+  // (dbh_batch_grow_capacity); steady state never reallocates.
+  {
+    size_t free_b = 0, total_b = 0;
+    CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    b->work_budget_bytes = static_cast<size_t>(0.35 * static_cast<double>(total_b));
+    if (const char* e = std::getenv("DBH_WORK_BUDGET_MB")) b->work_budget_bytes = static_cast<size_t>(std::atoll(e)) << 20;
+  }
+  auto clampest = [](long long e) { return std::min(std::max(e, 1ll << 16), 1ll << 23); };
+  for (;;) {
+    const long long est = clampest((est_tri + est_tet) / b->num_chunks);
+    const long long min_list = b->MaxPairsPerChunk();
+    b->cap_frontier = std::max<long long>(est, min_list);
+    b->cap_tri = std::max<long long>(clampest(est_tri / b->num_chunks), min_list);
+    b->cap_tet = std::max<long long>(clampest(est_tet / b->num_chunks), min_list);
+    b->cap_polys = est / 4;
+    if (b->WorkBytes(b->cap_frontier, b->cap_tri, b->cap_tet, b->cap_polys) <= b->work_budget_bytes ||
+        b->num_chunks >= num_scenes)
+      break;
+    b->num_chunks = std::min(num_scenes, b->num_chunks * 2);
+  }
+  {
+    const long long est = clampest(est_tri + est_tet);
+    b->cap_faces = est / 2;
+    b->cap_verts = est;
+  }
 
   CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaMallocHost(&b->h_counters, sizeof(Counters)));
   std::memset(b->h_counters, 0, sizeof(Counters));
-  for (auto& e : b->ev) CUDA_OK(cudaEventCreate(&e));
+  CUDA_OK(cudaEventCreate(&b->ev_begin));
+  CUDA_OK(cudaEventCreate(&b->ev_end));
   const size_t np = std::max(1, b->num_pairs);
   CUDA_OK(b->d_pairs.alloc(np));
   if (b->num_pairs)
@@ -704,7 +771,7 @@ void dbh_batch_destroy(dbh_batch* batch) { delete batch; }
 dbh_status dbh_batch_set_capacity(dbh_batch* b, int64_t max_bv_pairs, int64_t max_element_pairs, int64_t max_faces) {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   if (max_bv_pairs > 0) b->cap_frontier = max_bv_pairs;
-  if (max_element_pairs > 0) b->cap_cand = max_element_pairs;
+  if (max_element_pairs > 0) b->cap_tri = b->cap_tet = max_element_pairs;
   if (max_faces > 0) {
     b->cap_polys = max_faces;
     b->cap_faces = max_faces * 4;   // triangle rep: up to ~5 triangles per polygon on average
@@ -713,26 +780,44 @@ dbh_status dbh_batch_set_capacity(dbh_batch* b, int64_t max_bv_pairs, int64_t ma
   return DBH_OK;
 }
 
+dbh_status dbh_batch_set_chunks(dbh_batch* b, int32_t num_chunks) {
+  if (!b || num_chunks < 1) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_chunks: bad argument");
+  b->num_chunks = std::min<int>(num_chunks, b->num_scenes);
+  return DBH_OK;
+}
+
+int32_t dbh_batch_get_chunks(dbh_batch* b) { return b ? b->num_chunks : 0; }
+
 dbh_status dbh_batch_grow_capacity(dbh_batch* b) {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   // The device counters keep counting past a full list, so after a failed
-  // query they say how many entries the failing stage wanted. Later stages did
-  // not run; the caller re-runs until the query fits (a handful of set-up
-  // iterations at most, each at least doubling what overflowed).
+  // query they say how many entries the failing stage wanted (the maximum over
+  // the chunks that ran). Later stages did not run; the caller re-runs until
+  // the query fits (a handful of set-up iterations, each at least doubling
+  // what overflowed -- or halving the chunks when the lists would outgrow the
+  // memory budget).
   const Counters& c = *b->h_counters;
   auto want = [](unsigned long long needed, long long cap) {
     return static_cast<long long>(needed) > cap ? static_cast<long long>(needed) * 2 : cap;
   };
-  unsigned long long fr = 0;
-  for (int l = 0; l < 64; ++l) fr = std::max(fr, c.frontier[l]);
-  b->cap_frontier = want(fr, b->cap_frontier);
-  b->cap_cand = want(std::max(c.leaf_tri, c.leaf_tet), b->cap_cand);
-  b->cap_polys = want(c.polys, b->cap_polys);
-  b->cap_slow = want(c.slow, b->cap_slow);
+  const long long fr = want(c.frontier_max, b->cap_frontier);
+  const long long tri = want(c.leaf_tri_max, b->cap_tri);
+  const long long tet = want(c.leaf_tet_max, b->cap_tet);
+  const long long polys = want(c.polys_max, b->cap_polys);
+  const bool lists_grow = fr != b->cap_frontier || tri != b->cap_tri || tet != b->cap_tet || polys != b->cap_polys;
+  if (lists_grow && b->WorkBytes(fr, tri, tet, polys) > b->work_budget_bytes && b->num_chunks < b->num_scenes) {
+    b->num_chunks = std::min(b->num_scenes, b->num_chunks * 2);
+  } else {
+    b->cap_frontier = fr;
+    b->cap_tri = tri;
+    b->cap_tet = tet;
+    b->cap_polys = polys;
+  }
+  b->cap_slow = want(c.slow_max, b->cap_slow);
   // Faces / vertices of either representation (triangle: one face per polygon vertex, one extra
   // vertex per polygon), so switching representation does not overflow again.
   b->cap_faces = want(std::max(c.faces, c.poly_verts), b->cap_faces);
-  b->cap_verts = want(std::max(c.vertices, c.poly_verts + c.polys), b->cap_verts);
+  b->cap_verts = want(std::max(c.vertices, c.poly_verts + c.polygons), b->cap_verts);
   return DBH_OK;
 }
 
@@ -782,17 +867,26 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   b->query_done = false;
   cudaStream_t st = b->stream;
   const int sms = ctx->prop.multiProcessorCount;
+  if (b->timing) {
+    while (b->ev_chunk.size() < 8u * static_cast<size_t>(b->num_chunks)) {
+      cudaEvent_t e = nullptr;
+      CUDA_OK(cudaEventCreate(&e));
+      b->ev_chunk.push_back(e);
+    }
+    cudaEventRecord(b->ev_begin, st);
+  }
+  b->timed_chunks = 0;
   auto mark = [&](int i) {
-    if (b->timing) cudaEventRecord(b->ev[i], st);
+    if (b->timing) cudaEventRecord(b->ev_chunk[8 * b->timed_chunks + i], st);
   };
-  mark(0);
   CUDA_OK(cudaMemsetAsync(b->d_counters.p, 0, sizeof(Counters), st));
   if (scene_stats_dev)
     CUDA_OK(cudaMemsetAsync(scene_stats_dev, 0, static_cast<size_t>(b->num_scenes) * 6 * sizeof(int64_t), st));
   if (b->num_pairs > 0) {
+    if (b->MaxPairsPerChunk() > std::min(b->cap_frontier, std::min(b->cap_tri, b->cap_tet)))
+      return Fail(DBH_ERR_CAPACITY, "work-list capacity below the geometry-pair count of a chunk");
     PairsArgs pa{};
     pa.pairs = b->d_pairs.p;
-    pa.num_pairs = b->num_pairs;
     pa.pools = ctx->pools();
     pa.poses = b->d_poses;
     pa.pair_X = b->d_pair_X.p;
@@ -805,30 +899,18 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pa.pair_polys = b->d_pair_polys.p;
     pa.pair_verts = b->d_pair_verts.p;
     pa.pair_cursor = b->d_pair_cursor.p;
-    if (b->num_pairs > b->cap_frontier || b->num_pairs > b->cap_cand)
-      return Fail(DBH_ERR_CAPACITY, "work-list capacity below the geometry-pair count");
-    k_pairs<<<(b->num_pairs + 127) / 128, 128, 0, st>>>(pa);
-    mark(1);
-    // Dual-BVH traversal, one launch per level; counts stay on the device.
     TraverseArgs ta{};
     ta.pair_f32 = b->d_pair_f32.p;
     ta.pools = ctx->pools();
     ta.leaf_tri = b->d_cand_tri.p;
     ta.leaf_tet = b->d_cand_tet.p;
-    ta.leaf_capacity = static_cast<unsigned long long>(b->cap_cand);
+    ta.leaf_capacity_tri = static_cast<unsigned long long>(b->cap_tri);
+    ta.leaf_capacity_tet = static_cast<unsigned long long>(b->cap_tet);
     ta.out_capacity = static_cast<unsigned long long>(b->cap_frontier);
     ta.counters = b->d_counters.p;
-    for (int level = 0; level < b->info.max_traversal_levels; ++level) {
-      ta.in = b->d_frontier[level & 1].p;
-      ta.out = b->d_frontier[(level + 1) & 1].p;
-      ta.level = level;
-      k_traverse<<<sms * 8, 256, 0, st>>>(ta);
-    }
-    mark(2);
     ClipArgs ca{};
     ca.pair_X = b->d_pair_X.p;
     ca.pair_f32 = b->d_pair_f32.p;
-    ca.cand_capacity = static_cast<unsigned long long>(b->cap_cand);
     ca.pools = ctx->pools();
     ca.soup.hdr = b->d_soup_hdr.p;
     ca.soup.v = b->d_soup_v.p;
@@ -848,34 +930,15 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ca.trace = make_int4(p, e0 + b->pairs[p].elem_base_a, e1 + b->pairs[p].elem_base_b, 0);
     }
 #endif
-    const int clip_blocks = sms * 4;
-    if (b->info.num_soft_rigid_pairs) {
-      ca.cand = b->d_cand_tri.p;
-      k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
-    }
-    mark(3);
-    if (b->info.num_soft_soft_pairs) {
-      ca.cand = b->d_cand_tet.p;
-      k_clip<true><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
-    }
-    // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
-    k_clip_slow<<<sms, 64, 0, st>>>(ca);
-    mark(4);
     ScanArgs sa{};
     sa.pair_polys = b->d_pair_polys.p;
     sa.pair_verts = b->d_pair_verts.p;
-    sa.num_pairs = b->num_pairs;
     sa.poly_off = b->d_poly_off.p;
     sa.vert_off = b->d_vert_off.p;
     sa.surf_index = b->d_surf_index.p;
     sa.block_sums = b->d_block_sums.p;
-    sa.num_blocks = (b->num_pairs + kScanTile - 1) / kScanTile;
     sa.surf_pair = b->d_surf_pair.p;
     sa.counters = b->d_counters.p;
-    k_scan_partials<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
-    k_scan_blocks<<<1, kScanThreads, 0, st>>>(sa);
-    k_scan_apply<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
-    mark(5);
     PackArgs pk{};
     pk.soup = ca.soup;
     pk.pairs = b->d_pairs.p;
@@ -901,9 +964,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pk.out.vert_capacity = b->cap_verts;
     pk.out.face_data_capacity = b->cap_face_data;
     pk.counters = b->d_counters.p;
-    k_pack<<<sms * 8, 128, 0, st>>>(pk);
-    mark(6);
     SurfaceArgs su{};
+    su.surf_index = b->d_surf_index.p;
     su.surf_pair = b->d_surf_pair.p;
     su.pairs = b->d_pairs.p;
     su.poly_off = b->d_poly_off.p;
@@ -921,15 +983,70 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     su.surf_flags = b->r_surf_flags.p;
     su.scene_stats = reinterpret_cast<long long*>(scene_stats_dev);
     su.counters = b->d_counters.p;
-    k_surface<<<sms * 4, 128, 0, st>>>(su);
+    const int clip_blocks = sms * 4;
+    for (int chunk = 0; chunk < b->num_chunks; ++chunk) {
+      const int s0 = static_cast<int>(static_cast<long long>(b->num_scenes) * chunk / b->num_chunks);
+      const int s1 = static_cast<int>(static_cast<long long>(b->num_scenes) * (chunk + 1) / b->num_chunks);
+      const int p0 = b->scene_first_pair[s0], p1 = b->scene_first_pair[s1];
+      if (p1 == p0) continue;
+      pa.pair_begin = p0;
+      pa.pair_end = p1;
+      mark(0);
+      k_pairs<<<(p1 - p0 + 127) / 128, 128, 0, st>>>(pa);
+      mark(1);
+      // Dual-BVH traversal, one launch per level; counts stay on the device.
+      for (int level = 0; level < b->info.max_traversal_levels; ++level) {
+        ta.in = b->d_frontier[level & 1].p;
+        ta.out = b->d_frontier[(level + 1) & 1].p;
+        ta.level = level;
+        k_traverse<<<sms * 8, 256, 0, st>>>(ta);
+      }
+      mark(2);
+      // Filter (leaf predicate + conservative culls) then the exact stage, per element kind. The
+      // survivor lists reuse the two frontier buffers.
+      ca.surv_capacity = static_cast<unsigned long long>(b->cap_frontier);
+      if (b->info.num_soft_rigid_pairs) {
+        ca.cand = b->d_cand_tri.p;
+        ca.cand_capacity = static_cast<unsigned long long>(b->cap_tri);
+        ca.surv = b->d_frontier[0].p;
+        k_filter<false><<<sms * 6, kFilterThreads, 0, st>>>(ca);
+        k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+      }
+      mark(3);
+      if (b->info.num_soft_soft_pairs) {
+        ca.cand = b->d_cand_tet.p;
+        ca.cand_capacity = static_cast<unsigned long long>(b->cap_tet);
+        ca.surv = b->d_frontier[1].p;
+        k_filter<true><<<sms * 6, kFilterThreads, 0, st>>>(ca);
+        k_clip<true><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+      }
+      // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
+      k_clip_slow<<<sms, 64, 0, st>>>(ca);
+      mark(4);
+      sa.pair_begin = p0;
+      sa.num_pairs = p1;
+      sa.first_chunk = p0 == 0;
+      sa.num_blocks = (p1 - p0 + kScanTile - 1) / kScanTile;
+      k_scan_partials<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
+      k_scan_blocks<<<1, kScanThreads, 0, st>>>(sa);
+      k_scan_apply<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
+      mark(5);
+      k_pack<<<sms * 8, 128, 0, st>>>(pk);
+      mark(6);
+      su.pair_begin = p0;
+      su.pair_end = p1;
+      k_surface<<<sms * 4, 128, 0, st>>>(su);
+      k_next_chunk<<<1, 64, 0, st>>>(b->d_counters.p);
+      mark(7);
+      if (b->timing) ++b->timed_chunks;
+    }
     k_finalize<<<1, 32, 0, st>>>(su, b->num_pairs);
     if (scene_stats_dev)
       k_scene_stats<<<(b->num_pairs + 255) / 256, 256, 0, st>>>(b->d_pairs.p, b->num_pairs,
                                                                reinterpret_cast<long long*>(scene_stats_dev));
-    mark(7);
   }
   CUDA_OK(cudaMemcpyAsync(b->h_counters, b->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  mark(8);
+  if (b->timing) cudaEventRecord(b->ev_end, st);
   CUDA_OK(cudaGetLastError());
   return DBH_OK;
 }
@@ -940,20 +1057,30 @@ dbh_status dbh_batch_sync(dbh_batch* b) {
   CUDA_OK(cudaStreamSynchronize(b->stream));
   if (b->timing) {
     // {pose+root, traversal, clip tri, clip tet, scan, pack, surface+finalize, total}
-    float t[8];
-    for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&t[i], b->ev[i], b->ev[i + 1]);
-    cudaEventElapsedTime(&t[7], b->ev[0], b->ev[8]);
+    float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < b->timed_chunks; ++c)
+      for (int i = 0; i < 7; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, b->ev_chunk[8 * c + i], b->ev_chunk[8 * c + i + 1]);
+        t[i] += ms;
+      }
+    cudaEventElapsedTime(&t[7], b->ev_begin, b->ev_end);
     std::memcpy(b->times_ms, t, sizeof(t));
   }
   const Counters& c = *b->h_counters;
   if (c.error != 0) {
     static const char* kWhere[] = {"",          "BV-pair frontier", "element-pair list", "polygon staging",
-                                   "tet-tri polygon > 8 vertices", "tet-tet polygon > 8 vertices", "face arrays",
+                                   "(unused)", "(unused)", "face arrays",
                                    "vertex arrays", "exceptional-candidate list"};
     if (c.error == DBH_ERR_CAPACITY) {
       const int d = (c.error_detail >= 1 && c.error_detail <= 8) ? c.error_detail : 0;
       return Fail(DBH_ERR_CAPACITY, std::string("device work list overflow: ") + kWhere[d]);
     }
+    if (c.error == DBH_ERR_POLYGON_SIZE)
+      return Fail(DBH_ERR_POLYGON_SIZE, "geometry pair " + std::to_string(c.error_detail) +
+                                            ": a contact polygon outgrew what the reference defines (tet-triangle: more "
+                                            "than 7 vertices, mesh_intersection.cc:261-262; tet-tet: more than 16 "
+                                            "intermediate vertices)");
     if (c.error == DBH_ERR_RIGID_RIGID)
       return Fail(DBH_ERR_RIGID_RIGID, "rigid-rigid contact between geometries " +
                                            std::to_string(b->pairs[c.error_detail].id_m) + " and " +
@@ -982,9 +1109,9 @@ dbh_status dbh_batch_result_sizes(dbh_batch* b, dbh_result_sizes* out) {
   out->num_surfaces = static_cast<int64_t>(c.surfaces);
   out->num_faces = static_cast<int64_t>(c.faces);
   out->num_vertices = static_cast<int64_t>(c.vertices);
-  out->num_polygons = static_cast<int64_t>(c.polys);
+  out->num_polygons = static_cast<int64_t>(c.polygons);
   out->representation = b->representation;
-  out->face_data_ints = b->representation == DBH_POLYGON ? static_cast<int64_t>(c.polys + c.poly_verts)
+  out->face_data_ints = b->representation == DBH_POLYGON ? static_cast<int64_t>(c.polygons + c.poly_verts)
                                                          : 3 * static_cast<int64_t>(c.faces);
   return DBH_OK;
 }
@@ -997,12 +1124,13 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->geometry_pairs_tested = static_cast<int64_t>(b->info.num_soft_rigid_pairs + b->info.num_soft_soft_pairs);
   out->geometry_pairs_overlapping = static_cast<int64_t>(c.root_overlaps);
   out->bv_pair_tests = static_cast<int64_t>(c.bv_tests);
-  out->leaf_pairs = static_cast<int64_t>(c.leaf_tri + c.leaf_tet);
+  out->leaf_pairs = static_cast<int64_t>(c.leaf_tri_total + c.leaf_tet_total);
   out->cull_violations = static_cast<int64_t>(c.cull_violations);
-  out->exceptional_clips = static_cast<int64_t>(c.slow);
+  out->exceptional_clips = static_cast<int64_t>(c.slow_total);
+  out->leaf_exact_tests = static_cast<int64_t>(c.leaf_exact);
   out->tet_tri_pairs = static_cast<int64_t>(c.cand_tri);
   out->tet_tet_pairs = static_cast<int64_t>(c.cand_tet);
-  out->polygons = static_cast<int64_t>(c.polys);
+  out->polygons = static_cast<int64_t>(c.polygons);
   out->faces = static_cast<int64_t>(c.faces);
   out->vertices = static_cast<int64_t>(c.vertices);
   out->surfaces = static_cast<int64_t>(c.surfaces);
@@ -1027,7 +1155,9 @@ dbh_status dbh_batch_copy_candidates(dbh_batch* b, int32_t kind, int32_t* out_tr
   const bool tet = (kind & 1) != 0, raw = (kind & 2) != 0;
   // The narrow phase left the leaf list as {pair, pool elem a, pool elem b, flag}; the candidates
   // are the flagged entries (kind | 2: every leaf pair the conservative descent passed).
-  const int64_t listed = static_cast<int64_t>(tet ? b->h_counters->leaf_tet : b->h_counters->leaf_tri);
+  if (b->num_chunks != 1)
+    return Fail(DBH_ERR_NOT_READY, "candidate lists are only kept for single-chunk queries (dbh_batch_set_chunks(batch, 1))");
+  const int64_t listed = static_cast<int64_t>(tet ? b->h_counters->leaf_tet_total : b->h_counters->leaf_tri_total);
   const int64_t n = raw ? listed : static_cast<int64_t>(tet ? b->h_counters->cand_tet : b->h_counters->cand_tri);
   *count = n;
   if (!out_triples || n == 0) return DBH_OK;
@@ -1087,12 +1217,18 @@ dbh_status dbh_batch_device_results(dbh_batch* b, dbh_device_results* out) {
 }
 
 dbh_status dbh_batch_copy_results(dbh_batch* b, const dbh_result_buffers* buf) {
+  if (dbh_status s = dbh_batch_copy_results_async(b, buf)) return s;
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_copy_results_async(dbh_batch* b, const dbh_result_buffers* buf) {
   if (!b || !buf) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_results: bad argument");
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   CUDA_OK(cudaSetDevice(b->ctx->device));
   const Counters& c = *b->h_counters;
   const size_t ns = c.surfaces, nf = c.faces, nv = c.vertices;
-  const size_t nfd = b->representation == DBH_POLYGON ? static_cast<size_t>(c.polys + c.poly_verts) : 3 * nf;
+  const size_t nfd = b->representation == DBH_POLYGON ? static_cast<size_t>(c.polygons + c.poly_verts) : 3 * nf;
   cudaStream_t st = b->stream;
   // The device arrays already have the caller's layout: straight D2H copies
   // (asynchronous when the destination is pinned), one synchronisation.
@@ -1119,7 +1255,6 @@ dbh_status dbh_batch_copy_results(dbh_batch* b, const dbh_result_buffers* buf) {
   DBH_COPY(buf->elem_M, b->r_elem_a.p, nf, int32_t);
   DBH_COPY(buf->elem_N, b->r_elem_b.p, nf, int32_t);
 #undef DBH_COPY
-  CUDA_OK(cudaStreamSynchronize(st));
   return DBH_OK;
 }
 

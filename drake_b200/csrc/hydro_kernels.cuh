@@ -75,8 +75,8 @@ __device__ __forceinline__ void raise_error(Counters* c, int status, int detail)
 //  frontier: {pair, a, b, kind}: an overlapping node pair still to be
 //    expanded. a >= 0: pool index of the first of two adjacent children to
 //    expand; a < 0: ~(pool index) of a leaf node that is kept as is. Same for b.
-//  leaf list: {pair, leaf node a, leaf node b, 0}: leaf pairs that passed the
-//    conservative fp32 box test; the narrow phase applies the exact predicate.
+//  leaf list: {pair, pool element a, pool element b, 0}: leaf pairs that passed
+//    the conservative fp32 box test; the narrow phase applies the exact predicate.
 __device__ __forceinline__ int frontier_code(int node_index, int child) { return child < 0 ? ~node_index : child; }
 
 // ---------------------------------------------------------------------------
@@ -84,7 +84,8 @@ __device__ __forceinline__ int frontier_code(int node_index, int child) { return
 // root box test, level-0 frontier.
 struct PairsArgs {
   const PairRec* pairs;
-  int num_pairs;
+  int pair_begin;        // this chunk's range of the static pair list
+  int pair_end;
   Pools pools;
   const Xf* poses;       // X_WG per flat geometry index
   Xf* pair_X;            // out: X_MN per pair
@@ -100,13 +101,13 @@ struct PairsArgs {
 };
 
 __global__ void k_pairs(PairsArgs a) {
-  // Launched with whole warps covering num_pairs rounded up to 32.
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  // Launched with whole warps covering the chunk's pair range rounded up to 32.
+  const int p = a.pair_begin + blockIdx.x * blockDim.x + threadIdx.x;
   bool push = false, tested = false;
   PairRec pr;
   pr.root_a = pr.root_b = pr.kind = pr.root_leaf = 0;
   int child_a = 0, child_b = 0;
-  if (p < a.num_pairs) {
+  if (p < a.pair_end) {
     a.pair_polys[p] = 0;
     a.pair_verts[p] = 0;
     a.pair_cursor[p] = 0ull;
@@ -172,9 +173,9 @@ __global__ void k_pairs(PairsArgs a) {
   const unsigned long long lt = warp_append_flag(&a.counters->leaf_tri, push && both_leaves && pr.kind == kSoftRigid);
   const unsigned long long lq = warp_append_flag(&a.counters->leaf_tet, push && both_leaves && pr.kind == kSoftSoft);
   if (push && both_leaves) {
-    // Lists are at least num_pairs long (host guarantees).
-    if (pr.kind == kSoftRigid) a.leaf_tri[lt] = make_int4(p, pr.root_a, pr.root_b, 0);
-    else a.leaf_tet[lq] = make_int4(p, pr.root_a, pr.root_b, 0);
+    // Lists are at least as long as a chunk's pair range (host guarantees).
+    if (pr.kind == kSoftRigid) a.leaf_tri[lt] = make_int4(p, ~child_a, ~child_b, 0);
+    else a.leaf_tet[lq] = make_int4(p, ~child_a, ~child_b, 0);
   }
 }
 
@@ -196,7 +197,8 @@ struct TraverseArgs {
   Pools pools;
   int4* leaf_tri;
   int4* leaf_tet;
-  unsigned long long leaf_capacity;
+  unsigned long long leaf_capacity_tri;
+  unsigned long long leaf_capacity_tet;
   Counters* counters;
 };
 
@@ -267,8 +269,8 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
               if (overlap6_f32(load_box32(A[ja]), bb, tbx, tby, tbz, sb, f)) {
                 const int ca = A[ja].child, cb = B[jb].child;
                 if (ca < 0 && cb < 0) {
-                  leaf_a[n_leaf] = ia + ja;
-                  leaf_b[n_leaf] = ib + jb;
+                  leaf_a[n_leaf] = ~ca;  // pool element indices
+                  leaf_b[n_leaf] = ~cb;
                   ++n_leaf;
                 } else {
                   next_a[n_next] = frontier_code(ia + ja, ca);
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
     const unsigned long long ls_tet = warp_append(&a.counters->leaf_tet, e.w == kSoftSoft ? n_leaf : 0);
     if (n_leaf) {
       const unsigned long long ls = (e.w == kSoftRigid) ? ls_tri : ls_tet;
-      if (ls + n_leaf > a.leaf_capacity) {
+      if (ls + n_leaf > ((e.w == kSoftRigid) ? a.leaf_capacity_tri : a.leaf_capacity_tet)) {
         raise_error(a.counters, 5, 2);
       } else {
         int4* list = (e.w == kSoftRigid) ? a.leaf_tri : a.leaf_tet;
@@ -312,16 +314,17 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// Narrow phase. Each clip kernel runs in two stages inside one persistent
-// block loop:
-//   stage A (every candidate, one per lane, branch-free): conservative culls
-//     that can only say "certainly no polygon" -- the gradient filters with a
-//     safety band and separating face planes with a 1e-9 relative margin.
-//     Anything uncertain survives.
-//   stage B (survivors only, re-packed into dense warps through a shared-memory
-//     queue): the reference's exact operation sequence.
+// Narrow phase, two kernels per element kind:
+//   k_filter (every leaf pair, one per thread): the leaf predicate, then stage
+//     A: conservative fp32 culls that can only say "certainly no polygon" --
+//     the gradient filters with a safety band and separating face / hull
+//     planes with a relative margin. Anything uncertain survives and is
+//     compacted into a dense survivor list.
+//   k_clip (survivors only, dense warps): stage B, the reference's exact
+//     operation sequence in fp64.
 // So the emitted polygons are exactly those of running stage B on every
-// candidate, but divergent lanes no longer idle through another lane's clip.
+// candidate, but divergent lanes no longer idle through another lane's clip and
+// the filter runs without the clip's shared-memory footprint.
 //
 // Per-thread polygon scratch in shared memory: [buffer][slot][coord][thread],
 // so a warp's access to one (slot, coord) is a single conflict-free 256 B row
@@ -456,12 +459,16 @@ struct PolySoup {
 };
 
 struct ClipArgs {
-  // In: leaf pairs {pair, leaf node a, leaf node b, 0} from the descent. The
-  // kernel rewrites every entry as {pair, pool tet, pool tri | pool tet, flag},
-  // flag = 1 iff the pair passes the exact leaf predicate, i.e. is a candidate
-  // element pair (dbh_batch_copy_candidates reads the flagged entries).
+  // In: leaf pairs {pair, pool tet, pool tri | pool tet, 0} from the descent. The
+  // kernel sets the flag of every entry: 1 iff the pair passes the exact leaf
+  // predicate, i.e. is a candidate element pair (dbh_batch_copy_candidates
+  // reads the flagged entries).
   int4* cand;
   unsigned long long cand_capacity;
+  // The survivors of the filter stage {pair, pool tet, pool tri | pool tet, 1 (| 2 culled, verify
+  // mode)}: the traversal's frontier buffers, free once the descent is done.
+  int4* surv;
+  unsigned long long surv_capacity;
   const Xf* pair_X;
   const PairF32* pair_f32;
   Pools pools;
@@ -506,6 +513,38 @@ __device__ __forceinline__ void emit_polygon(const ClipArgs& a, Poly& P, int buf
     a.soup.v[(k * 4 + 2) * a.soup.capacity + slot] = p.z;
     // MeshFieldLinear::EvaluateCartesian (mesh_field_linear.h:349).
     a.soup.v[(k * 4 + 3) * a.soup.capacity + slot] = dot(grad, p) + p_mo;
+  }
+  a.soup.nhat[0 * a.soup.capacity + slot] = nhat.x;
+  a.soup.nhat[1 * a.soup.capacity + slot] = nhat.y;
+  a.soup.nhat[2 * a.soup.capacity + slot] = nhat.z;
+  atomicAdd(&a.pair_polys[c.x], 1);
+  atomicAdd(&a.pair_verts[c.x], n);
+}
+
+// The exceptional path's emit: per-lane atomics. A polygon with more than 8 vertices (only a clip
+// plane coplanar with the polygon can produce one; the reference's vectors have no bound) takes two
+// consecutive staging slots: vertices 8.. live in the second, whose header has n = 0.
+template <class Poly>
+__device__ __forceinline__ void emit_polygon_slow(const ClipArgs& a, Poly& P, int buf, int n, int4 c, D3 grad,
+                                                  double p_mo, D3 nhat) {
+  if (n <= 0) return;
+  const int slots = n > kMaxPolyVerts ? 2 : 1;
+  const unsigned long long slot = atomicAdd(&a.counters->polys, (unsigned long long)slots);
+  if (slot + slots > a.soup.capacity) {
+    raise_error(a.counters, 5, 3);
+    return;
+  }
+  if (c.w & 2) atomicAdd(&a.counters->cull_violations, 1ull);  // verify mode only
+  a.soup.hdr[slot] = make_int4(c.x, c.y, c.z, n);
+  if (slots == 2) a.soup.hdr[slot + 1] = make_int4(c.x, c.y, c.z, 0);
+  for (int k = 0; k < n; ++k) {
+    const D3 p = P.get(buf, k);
+    const unsigned long long s = slot + (k >> 3);
+    const int kk = k & 7;
+    a.soup.v[(kk * 4 + 0) * a.soup.capacity + s] = p.x;
+    a.soup.v[(kk * 4 + 1) * a.soup.capacity + s] = p.y;
+    a.soup.v[(kk * 4 + 2) * a.soup.capacity + s] = p.z;
+    a.soup.v[(kk * 4 + 3) * a.soup.capacity + s] = dot(grad, p) + p_mo;
   }
   a.soup.nhat[0 * a.soup.capacity + slot] = nhat.x;
   a.soup.nhat[1 * a.soup.capacity + slot] = nhat.y;
@@ -579,12 +618,82 @@ __device__ __forceinline__ F3 xformf(const PairF32& f, F3 v) {
 constexpr float kCullMarginF = 2e-5f;
 constexpr float kCosAlphaF = -0.38268343f;
 
+// ---- the leaf predicate ------------------------------------------------------
+// A leaf pair is a candidate iff the two elements' own boxes pass the scalar
+// 15-axis BoxesOverlap in fp64 (aabb.cc:16-33, boxes_overlap.cc:197-255). The
+// fp32 pass below evaluates the same 15 inequalities on boxes rebuilt from the
+// fp32 vertex copies and answers only when every axis is decided by more than
+// 1e-5 of the scale of the operands (fp32 rounding through these expressions
+// stays below ~1e-6 of it); anything closer is settled by the exact predicate.
+struct BoxF {
+  float c[3], h[3];
+  float l1;  // |c|_1 + |h|_1
+};
+template <int N>
+__device__ __forceinline__ BoxF box_of(const float (*v)[3]) {
+  BoxF b;
+  b.l1 = 0.f;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float mn = v[0][d], mx = v[0][d];
+#pragma unroll
+    for (int k = 1; k < N; ++k) {
+      mn = fminf(mn, v[k][d]);
+      mx = fmaxf(mx, v[k][d]);
+    }
+    b.c[d] = 0.5f * (mn + mx);
+    b.h[d] = mx - b.c[d];
+    b.l1 += fabsf(b.c[d]) + b.h[d];
+  }
+  return b;
+}
+// +1: certainly overlapping, -1: certainly separated, 0: too close to call in fp32.
+__device__ __forceinline__ int boxes_overlap_f32(const BoxF& A, const BoxF& B, const PairF32& f) {
+  const float delta = 1e-5f * (A.l1 + B.l1 + f.S);
+  float t[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    t[i] = fmaf(f.R[i], B.c[0], fmaf(f.R[3 + i], B.c[1], fmaf(f.R[6 + i], B.c[2], f.p[i]))) - A.c[i];
+  bool separated = false, unsure = false;
+  auto axis = [&](float lhs, float rhs) {
+    const float g = lhs - rhs;
+    separated |= g > delta;
+    unsure |= g > -delta;
+  };
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    axis(fabsf(t[i]), A.h[i] + fmaf(B.h[0], f.AR[i * 3 + 0], fmaf(B.h[1], f.AR[i * 3 + 1], B.h[2] * f.AR[i * 3 + 2])));
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    axis(fabsf(fmaf(t[0], f.R[i * 3 + 0], fmaf(t[1], f.R[i * 3 + 1], t[2] * f.R[i * 3 + 2]))),
+         B.h[i] + fmaf(A.h[0], f.AR[0 * 3 + i], fmaf(A.h[1], f.AR[1 * 3 + i], A.h[2] * f.AR[2 * 3 + i])));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      axis(fabsf(t[i2] * f.R[j * 3 + i1] - t[i1] * f.R[j * 3 + i2]),
+           fmaf(A.h[i1], f.AR[i2 * 3 + j], A.h[i2] * f.AR[i1 * 3 + j]) +
+               fmaf(B.h[j1], f.AR[i * 3 + j2], B.h[j2] * f.AR[i * 3 + j1]));
+    }
+  }
+  return separated ? -1 : (unsure ? 0 : 1);
+}
+// The exact predicate (rare: only when fp32 cannot decide).
+template <bool kTet>
+__device__ __noinline__ bool leaf_predicate_exact(const ClipArgs& a, int4 c) {
+  const ElemBox& ba = a.pools.ebox_tet[c.y];
+  const ElemBox& bb = kTet ? a.pools.ebox_tet[c.z] : a.pools.ebox_tri[c.z];
+  const Xf X = a.pair_X[c.x];
+  const D3 t = xform_point(X, load3(bb.c)) - load3(ba.c);
+  return boxes_overlap(ba.h, bb.h, X, t);
+}
+
 // Stage A. false = certainly no polygon.
-__device__ __forceinline__ bool tri_stage_a(const ClipArgs& a, int4 c) {
-  const PairF32 X = a.pair_f32[c.x];
-  const TetCullA& ta = a.pools.cull_a[c.y];
+__device__ __forceinline__ bool tri_stage_a(const ClipArgs& a, int4 c, const PairF32& X, const TetCullA& ta,
+                                            const TriCull& tri) {
   const TetCullB& tb = a.pools.cull_b[c.y];
-  const TriCull& tri = a.pools.cull_tri[c.z];
   // Gradient filter (certain rejections only).
   const F3 nhat = rotf(X, f3(tri.n));
   const bool unit = fabsf(dotf(nhat, nhat) - 1.0f) < 1e-4f;
@@ -668,7 +777,7 @@ __device__ __forceinline__ void tri_stage_b(const ClipArgs& a, Poly& P, int4 c, 
           } else {
             n = clip_by_half_space(P, buf, n, load3(aux.plane_nh[f]), d);
             if (n > Poly::kCap) {
-              if (kSlow) raise_error(a.counters, 5, 4); else defer_to_slow_path(a, c, 0);
+              if (kSlow) raise_error(a.counters, 10 /*DBH_ERR_POLYGON_SIZE*/, c.x); else defer_to_slow_path(a, c, 0);
               n = 0;
             }
             buf = 1 - buf;
@@ -677,13 +786,14 @@ __device__ __forceinline__ void tri_stage_b(const ClipArgs& a, Poly& P, int4 c, 
       }
       n = remove_nearly_duplicate(P, buf, n);
       if (n < 3) n = 0;
-      if (n > kMaxPolyVerts) {  // only reachable on the exceptional path
-        raise_error(a.counters, 5, 4);
+      if (n > 7) {  // DRAKE_DEMAND(polygon_M->size() <= 7), mesh_intersection.cc:261-262
+        raise_error(a.counters, 10, c.x);
         n = 0;
       }
     }
   }
-  emit_polygon(a, P, buf, n, c, grad, p_mo, nhat_M);
+  if constexpr (kSlow) emit_polygon_slow(a, P, buf, n, c, grad, p_mo, nhat_M);
+  else emit_polygon(a, P, buf, n, c, grad, p_mo, nhat_M);
 }
 
 // ---- tet-tet --------------------------------------------------------------
@@ -695,10 +805,8 @@ __device__ __forceinline__ void tri_stage_b(const ClipArgs& a, Poly& P, int4 c, 
 //  (N) tet1 entirely on one side of the equilibrium plane, or entirely outside
 //      one face of tet0, by more than 1e-11 (1 + amp1) L: empty.
 // Stage A. false = certainly no polygon.
-__device__ __forceinline__ bool tet_stage_a(const ClipArgs& a, int4 c) {
-  const PairF32 X = a.pair_f32[c.x];
-  const TetCullA& a0 = a.pools.cull_a[c.y];
-  const TetCullA& a1 = a.pools.cull_a[c.z];
+__device__ __forceinline__ bool tet_stage_a(const ClipArgs& a, int4 c, const PairF32& X, const TetCullA& a0,
+                                            const TetCullA& a1) {
   const TetCullB& b0 = a.pools.cull_b[c.y];
   const TetCullB& b1 = a.pools.cull_b[c.z];
   const F3 g0 = f3(a0.grad), g1 = f3(a1.grad);
@@ -872,7 +980,9 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
             n = clip_by_half_space_edges(P, buf, n, nh, d);
             DBH_TR("[trace] face %d nh %.17g %.17g %.17g d %.17g -> n %d\n", face, nh.x, nh.y, nh.z, d, n);
             if (n > Poly::kCap) {
-              if (kSlow) raise_error(a.counters, 5, 5); else defer_to_slow_path(a, c, 1);
+              // More than 16 intermediate vertices: far outside the reference's defined behaviour
+              // (its distances array holds 8, field_intersection.cc:98).
+              if (kSlow) raise_error(a.counters, 10 /*DBH_ERR_POLYGON_SIZE*/, c.x); else defer_to_slow_path(a, c, 1);
               n = 0;
             }
             buf = 1 - buf;
@@ -882,81 +992,87 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
       if (n > 0) {
         n = remove_nearly_duplicate(P, buf, n);
         if (n < 3) n = 0;
-        if (n > kMaxPolyVerts) {  // only reachable on the exceptional path
-          raise_error(a.counters, 5, 5);
+        if (!kSlow && n > kMaxPolyVerts) {  // cannot happen: the fast path's scratch holds 8
+          raise_error(a.counters, 10, c.x);
           n = 0;
         }
       }
     }
   }
-  emit_polygon(a, P, buf, n, c, grad0, f0_Mo, nhat_M);
+  if constexpr (kSlow) emit_polygon_slow(a, P, buf, n, c, grad0, f0_Mo, nhat_M);
+  else emit_polygon(a, P, buf, n, c, grad0, f0_Mo, nhat_M);
 }
 
-// ---- the block loop ---------------------------------------------------------
+// ---- k_filter: the leaf predicate + stage A over every leaf pair ------------
+// One thread per leaf pair, no shared memory, light enough on registers to keep
+// the SM full. Survivors are compacted (warp ballot + one atomic per warp) into
+// a dense list for the exact stage; every entry's candidate flag is written
+// back to the leaf list.
+constexpr int kFilterThreads = 256;
 template <bool kTet>
-__global__ void __launch_bounds__(kClipThreads) k_clip(ClipArgs a) {
-  extern __shared__ double smem[];
-  __shared__ int4 queue[2 * kClipThreads];
-  __shared__ int q_count;
+__global__ void __launch_bounds__(kFilterThreads, 3) k_filter(ClipArgs a) {
   if (a.counters->error != 0) return;
-  PolyScratch P{smem + threadIdx.x};
   const unsigned long long count = min(kTet ? a.counters->leaf_tet : a.counters->leaf_tri, a.cand_capacity);
-  if (threadIdx.x == 0) q_count = 0;
-  __syncthreads();
+  const unsigned long long rounded = (count + 31ull) & ~31ull;  // whole warps reach the ballots
+  const unsigned long long stride = (unsigned long long)gridDim.x * kFilterThreads;
   const int lane = threadIdx.x & 31;
-  unsigned long long full = 0;
-  unsigned int n_cand = 0;  // per warp (every lane holds the warp's count)
-  for (unsigned long long base = (unsigned long long)blockIdx.x * kClipThreads; base < count;
-       base += (unsigned long long)gridDim.x * kClipThreads) {
-    const unsigned long long i = base + threadIdx.x;
-    bool keep = false, is_cand = false;
+  unsigned int n_cand = 0, n_exact = 0;  // per warp (every lane holds the warp's count)
+  unsigned long long* cursor = kTet ? &a.counters->surv_tet : &a.counters->surv_tri;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * kFilterThreads + threadIdx.x; i < rounded; i += stride) {
+    bool keep = false, is_cand = false, undecided = false;
     int4 c = make_int4(0, 0, 0, 0);
     if (i < count) {
       c = a.cand[i];
-      // The exact leaf predicate: Aabb::HasOverlap on the two elements' own
-      // boxes (aabb.cc:16-33 -> scalar BoxesOverlap, boxes_overlap.cc:197-255).
-      const BvhNode& na = a.pools.nodes[c.y];
-      const BvhNode& nb = a.pools.nodes[c.z];
-      const Xf X = a.pair_X[c.x];
-      const D3 t = xform_point(X, load3(nb.c)) - load3(na.c);
-      is_cand = boxes_overlap(na.h, nb.h, X, t);
-      c = make_int4(c.x, ~na.left, ~nb.left, is_cand ? 1 : 0);
-      a.cand[i] = c;
-      if (is_cand) {
-        keep = kTet ? tet_stage_a(a, c) : tri_stage_a(a, c);
-        if (!keep && a.verify) {
-          keep = true;
-          c.w |= 2;
-        }
+      const PairF32 X = a.pair_f32[c.x];
+      const TetCullA ta = a.pools.cull_a[c.y];
+      int decided;
+      if (kTet) {
+        const TetCullA t1 = a.pools.cull_a[c.z];
+        decided = boxes_overlap_f32(box_of<4>(ta.v), box_of<4>(t1.v), X);
+        is_cand = decided > 0 || (decided == 0 && leaf_predicate_exact<true>(a, c));
+        if (is_cand) keep = tet_stage_a(a, c, X, ta, t1);
+      } else {
+        const TriCull tri = a.pools.cull_tri[c.z];
+        decided = boxes_overlap_f32(box_of<4>(ta.v), box_of<3>(tri.v), X);
+        is_cand = decided > 0 || (decided == 0 && leaf_predicate_exact<false>(a, c));
+        if (is_cand) keep = tri_stage_a(a, c, X, ta, tri);
+      }
+      undecided = decided == 0;
+      c.w = is_cand ? 1 : 0;
+      a.cand[i].w = c.w;
+      if (is_cand && !keep && a.verify) {
+        keep = true;
+        c.w |= 2;
       }
     }
     n_cand += __popc(__ballot_sync(0xffffffffu, is_cand));
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    int wbase = 0;
-    if (lane == 0 && m) wbase = atomicAdd(&q_count, __popc(m));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (keep) queue[wbase + __popc(m & ((1u << lane) - 1u))] = c;
-    __syncthreads();
-    const int qn = q_count;  // block-uniform
-    __syncthreads();
-    if (qn >= kClipThreads) {
-      const int4 w = queue[qn - kClipThreads + threadIdx.x];
-      if (threadIdx.x == 0) q_count = qn - kClipThreads;
-      if (kTet) tet_stage_b(a, P, w, true); else tri_stage_b(a, P, w, true);
-      full += kClipThreads;
-      __syncthreads();
+    n_exact += __popc(__ballot_sync(0xffffffffu, undecided));
+    const unsigned long long slot = warp_append_flag(cursor, keep);
+    if (keep) {
+      if (slot < a.surv_capacity) a.surv[slot] = c;
+      else raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
     }
   }
-  __syncthreads();
-  const int qn = q_count;
-  const bool active = threadIdx.x < qn;
-  const int4 w = active ? queue[threadIdx.x] : make_int4(0, 0, 0, 0);
-  if (kTet) tet_stage_b(a, P, w, active); else tri_stage_b(a, P, w, active);
   if (lane == 0 && n_cand) atomicAdd(kTet ? &a.counters->cand_tet : &a.counters->cand_tri, (unsigned long long)n_cand);
-  if (threadIdx.x == 0) {
-    full += qn;
-    if (full) atomicAdd(kTet ? &a.counters->full_clips_tet : &a.counters->full_clips_tri, full);
+  if (lane == 0 && n_exact) atomicAdd(&a.counters->leaf_exact, (unsigned long long)n_exact);
+}
+
+// ---- k_clip: the exact stage over the survivors, one per thread, dense warps --
+template <bool kTet>
+__global__ void __launch_bounds__(kClipThreads) k_clip(ClipArgs a) {
+  extern __shared__ double smem[];
+  if (a.counters->error != 0) return;
+  PolyScratch P{smem + threadIdx.x};
+  const unsigned long long count = min(kTet ? a.counters->surv_tet : a.counters->surv_tri, a.surv_capacity);
+  for (unsigned long long base = (unsigned long long)blockIdx.x * kClipThreads; base < count;
+       base += (unsigned long long)gridDim.x * kClipThreads) {
+    const unsigned long long i = base + threadIdx.x;
+    const bool active = i < count;
+    const int4 w = active ? a.surv[i] : make_int4(0, 0, 0, 0);
+    if (kTet) tet_stage_b(a, P, w, active); else tri_stage_b(a, P, w, active);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && count)
+    atomicAdd(kTet ? &a.counters->full_clips_tet : &a.counters->full_clips_tri, count);
 }
 
 // The exceptional path: the same stage B with 16-slot local-memory scratch.
@@ -969,7 +1085,6 @@ __global__ void __launch_bounds__(64) k_clip_slow(ClipArgs a) {
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const bool active = i < count;
     const int4 c = active ? a.slow[i] : make_int4(0, 0, 0, 0);
-    // Both flavours run so that every lane reaches both warp-wide appends.
     tri_stage_b(a, P, c, active && (c.w & 1) == 0);
     tet_stage_b(a, P, c, active && (c.w & 1) == 1);
   }
@@ -986,7 +1101,9 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 struct ScanArgs {
   const int* pair_polys;
   const int* pair_verts;
-  int num_pairs;
+  int pair_begin;        // this chunk's pair range; offsets continue from the previous chunk's
+  int num_pairs;         // end of the range (exclusive)
+  int first_chunk;       // the running offsets start at 0
   long long* poly_off;   // [num_pairs + 1]
   long long* vert_off;   // [num_pairs + 1]
   int* surf_index;       // [num_pairs + 1]
@@ -1018,7 +1135,7 @@ __device__ __forceinline__ long long block_exclusive_scan(long long v, long long
 
 __global__ void __launch_bounds__(kScanThreads) k_scan_partials(ScanArgs a) {
   __shared__ long long sh[kScanThreads / 32];
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  const int base = a.pair_begin + blockIdx.x * kScanTile + threadIdx.x * kScanItems;
   long long s0 = 0, s1 = 0, s2 = 0;
   for (int k = 0; k < kScanItems; ++k) {
     const int p = base + k;
@@ -1044,7 +1161,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_blocks(ScanArgs a) {
   // One block scans the per-block partials of the three sequences in turn.
   __shared__ long long sh[kScanThreads / 32];
   for (int seq = 0; seq < 3; ++seq) {
+    // The previous chunk left its totals in the sentinel slot, which is this chunk's first.
     long long carry = 0;
+    if (!a.first_chunk)
+      carry = seq == 0 ? a.poly_off[a.pair_begin] : (seq == 1 ? a.vert_off[a.pair_begin] : a.surf_index[a.pair_begin]);
     for (int start = 0; start < a.num_blocks; start += kScanThreads) {
       const int b = start + threadIdx.x;
       const long long v = b < a.num_blocks ? a.block_sums[seq * a.num_blocks + b] : 0;
@@ -1066,7 +1186,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_blocks(ScanArgs a) {
 
 __global__ void __launch_bounds__(kScanThreads) k_scan_apply(ScanArgs a) {
   __shared__ long long sh[kScanThreads / 32];
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  const int base = a.pair_begin + blockIdx.x * kScanTile + threadIdx.x * kScanItems;
   int np[kScanItems], nv[kScanItems];
   long long s0 = 0, s1 = 0, s2 = 0;
   for (int k = 0; k < kScanItems; ++k) {
@@ -1117,7 +1237,8 @@ struct ResultArrays {
   long long face_data_capacity;
 };
 
-// k_pack: one thread per staged polygon.
+// k_pack: one thread per staged polygon (up to 16 vertices: the exceptional path's capacity).
+constexpr int kPackMaxVerts = 2 * kMaxPolyVerts;
 struct PackArgs {
   PolySoup soup;
   const PairRec* pairs;
@@ -1160,16 +1281,19 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
     const int4 h = a.soup.hdr[i];
     const int pair = h.x, n = h.w;
+    if (n == 0) continue;  // second staging slot of a polygon with more than 8 vertices
     const PairRec pr = a.pairs[pair];
     const bool soft_soft = pr.kind == kSoftSoft;
     const bool swapped = pr.swapped != 0;
     const Xf X_WM = a.poses[pr.geom_a];
-    D3 vM[kMaxPolyVerts];
-    double e[kMaxPolyVerts];
+    D3 vM[kPackMaxVerts];
+    double e[kPackMaxVerts];
     for (int k = 0; k < n; ++k) {
-      vM[k] = make_d3(a.soup.v[(k * 4 + 0) * a.soup.capacity + i], a.soup.v[(k * 4 + 1) * a.soup.capacity + i],
-                      a.soup.v[(k * 4 + 2) * a.soup.capacity + i]);
-      e[k] = a.soup.v[(k * 4 + 3) * a.soup.capacity + i];
+      const unsigned long long s = i + (k >> 3);  // vertices 8.. are in the next slot
+      const int kk = k & 7;
+      vM[k] = make_d3(a.soup.v[(kk * 4 + 0) * a.soup.capacity + s], a.soup.v[(kk * 4 + 1) * a.soup.capacity + s],
+                      a.soup.v[(kk * 4 + 2) * a.soup.capacity + s]);
+      e[k] = a.soup.v[(kk * 4 + 3) * a.soup.capacity + s];
     }
     const D3 gradA_M = load3(a.pools.tets[h.y].grad);
     const D3 gA_W = rot(X_WM, gradA_M);
@@ -1263,7 +1387,7 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
         p_c = accum / total_weight;
       }
       const double e_cv = dot(gradA_M, p_c - vM[0]) + e[0];
-      D3 vW[kMaxPolyVerts];
+      D3 vW[kPackMaxVerts];
       for (int k = 0; k < n; ++k) {
         vW[k] = xform_point(X_WM, vM[k]);
         store3(a.out.vertices, vb + k, vW[k]);
@@ -1308,6 +1432,9 @@ __global__ void __launch_bounds__(128) k_pack(PackArgs a) {
 // (polygon_surface_mesh.cc:208-217, triangle_surface_mesh.h:476-486), offsets,
 // ids, and the per-scene statistics record.
 struct SurfaceArgs {
+  const int* surf_index;     // [num_pairs + 1]: surfaces before each pair
+  int pair_begin;            // this chunk's pair range
+  int pair_end;
   const int* surf_pair;
   const PairRec* pairs;
   const long long* poly_off;
@@ -1331,8 +1458,9 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
   if (a.counters->error != 0) return;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long num_surfaces = (long long)a.counters->surfaces;
-  for (long long s = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < num_surfaces;
+  const long long first_surface = a.pair_begin == 0 ? 0 : a.surf_index[a.pair_begin];
+  const long long num_surfaces = a.surf_index[a.pair_end];
+  for (long long s = first_surface + (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < num_surfaces;
        s += (long long)gridDim.x * warps_per_block) {
     const int p = a.surf_pair[s];
     long long f0, f1, v0;
@@ -1394,6 +1522,28 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
   }
 }
 
+// Between chunks: folds the chunk-local list cursors into totals / maxima and zeroes them.
+__global__ void k_next_chunk(Counters* c) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long fr = c->frontier_max;
+    for (int l = 0; l < 64; ++l) fr = max(fr, c->frontier[l]);
+    c->frontier_max = max(fr, max(c->surv_tri, c->surv_tet));  // the survivor lists live in the frontier buffers
+    c->leaf_tri_total += c->leaf_tri;
+    c->leaf_tet_total += c->leaf_tet;
+    c->polys_total += c->polys;
+    c->slow_total += c->slow;
+    c->leaf_tri_max = max(c->leaf_tri_max, c->leaf_tri);
+    c->leaf_tet_max = max(c->leaf_tet_max, c->leaf_tet);
+    c->polys_max = max(c->polys_max, c->polys);
+    c->slow_max = max(c->slow_max, c->slow);
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < 64) c->frontier[threadIdx.x] = 0;
+    if (threadIdx.x == 0) c->leaf_tri = c->leaf_tet = c->polys = c->slow = c->surv_tri = c->surv_tet = 0;
+  }
+}
+
 // Writes the sentinel offsets and the face / vertex totals.
 __global__ void k_finalize(SurfaceArgs a, int num_pairs) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -1406,6 +1556,7 @@ __global__ void k_finalize(SurfaceArgs a, int num_pairs) {
   a.counters->faces = (unsigned long long)faces;
   a.counters->vertices = (unsigned long long)verts;
   a.counters->poly_verts = (unsigned long long)pverts;
+  a.counters->polygons = (unsigned long long)polys;
 }
 
 // Per-scene statistics that depend only on the static pair list.

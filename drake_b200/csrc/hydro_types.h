@@ -84,6 +84,14 @@ struct alignas(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode is 64 B");
 
+// Exact axis-aligned box of ONE element in its mesh frame (the leaf's Aabb, aabb.cc:102-117),
+// indexed by pool element: the exact leaf predicate reads these when fp32 cannot decide.
+struct alignas(16) ElemBox {
+  double c[3];
+  double h[3];
+};
+static_assert(sizeof(ElemBox) == 48, "ElemBox is 48 B");
+
 // The same node for the conservative fp32 descent: the box is rounded outward
 // (h32 >= h + |c - c32|, so it contains the exact box), 32 B, siblings share one
 // 64 B line. child >= 0: pool index of the first child; child < 0: ~(pool element).
@@ -117,6 +125,8 @@ struct Pools {
   const TetCullA* cull_a;
   const TetCullB* cull_b;
   const TriCull* cull_tri;
+  const ElemBox* ebox_tet;   // per pool tetrahedron
+  const ElemBox* ebox_tri;   // per pool triangle
 };
 
 enum PairKind : int32_t { kSoftRigid = 0, kSoftSoft = 1, kRigidRigid = 2, kUnsupported = 3 };
@@ -146,24 +156,38 @@ struct Xf {
   double m[12];
 };
 
-// Device counters of one query (zeroed by the first kernel).
+// Device counters of one query (zeroed when the query starts). A query runs
+// over one or more chunks of scenes that reuse the same work lists; the list
+// cursors are chunk-local (k_next_chunk folds them into totals / maxima and
+// zeroes them), everything else accumulates over the whole query.
 struct Counters {
+  // -- chunk-local list cursors (they keep counting past a full list, so after
+  //    an overflow they say how many entries the failing stage wanted)
   unsigned long long frontier[64];  // overlapping node pairs to expand, per traversal level
-  unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
   unsigned long long leaf_tri;      // leaf pairs that passed the conservative fp32 test (tet-tri)
   unsigned long long leaf_tet;      // same, tet-tet
+  unsigned long long polys;         // contact polygons in the staging soup
+  unsigned long long slow;          // candidates deferred to the exceptional (16-vertex) path
+  unsigned long long surv_tri;      // tet-tri candidates that survived the conservative culls
+  unsigned long long surv_tet;      // same, tet-tet
+  // -- whole query
+  unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
   unsigned long long cand_tri;      // tet-tri candidate pairs: leaf pairs that pass the exact predicate
   unsigned long long cand_tet;      // tet-tet candidate pairs
-  unsigned long long polys;         // contact polygons in the staging soup
   unsigned long long poly_verts;    // sum of polygon vertex counts
+  unsigned long long polygons;      // contact polygons (polys_total counts staging slots: a polygon with
+                                    // more than 8 vertices takes two)
   unsigned long long root_overlaps; // geometry pairs whose root boxes overlap
   unsigned long long surfaces;
   unsigned long long faces;
   unsigned long long vertices;
   unsigned long long full_clips_tri; // tet-tri candidates that survived the conservative culls
   unsigned long long full_clips_tet; // tet-tet candidates that survived the conservative culls
-  unsigned long long slow;           // candidates deferred to the exceptional (16-vertex) path
+  unsigned long long leaf_exact;     // leaf pairs the fp32 predicate could not decide (exact fp64 test ran)
   unsigned long long cull_violations; // verify mode: polygons from candidates the conservative cull rejected
+  // -- totals and per-chunk maxima of the chunk-local cursors
+  unsigned long long leaf_tri_total, leaf_tet_total, polys_total, slow_total;
+  unsigned long long frontier_max, leaf_tri_max, leaf_tet_max, polys_max, slow_max;
   int32_t error;                    // first device-side dbh_status raised
   int32_t error_detail;
   double total_area;

@@ -27,7 +27,7 @@ STRICT, WITH_FALLBACK = 0, 1
 
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_DEGENERATE_FIELD, ERR_CAPACITY = 1, 2, 3, 4, 5
-ERR_RIGID_RIGID, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_PLANE_NORMAL = 6, 7, 8, 9
+ERR_RIGID_RIGID, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_PLANE_NORMAL, ERR_POLYGON_SIZE = 6, 7, 8, 9, 10
 
 
 class HydroError(RuntimeError):
@@ -73,7 +73,8 @@ class Stats(C.Structure):
                 ("geometry_pairs_tested", "geometry_pairs_overlapping", "bv_pair_tests", "tet_tri_pairs",
                  "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "algorithmic_bytes")] + \
                [("total_area", C.c_double), ("tet_tri_full_clips", C.c_int64), ("tet_tet_full_clips", C.c_int64),
-                ("leaf_pairs", C.c_int64), ("cull_violations", C.c_int64), ("exceptional_clips", C.c_int64)]
+                ("leaf_pairs", C.c_int64), ("cull_violations", C.c_int64), ("exceptional_clips", C.c_int64),
+                ("leaf_exact_tests", C.c_int64)]
 
 
 _lib = None
@@ -106,6 +107,8 @@ def lib():
     L.dbh_batch_destroy.argtypes = [vp]
     L.dbh_batch_set_capacity.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.dbh_batch_grow_capacity.argtypes = [vp]
+    L.dbh_batch_set_chunks.argtypes = [vp, C.c_int32]
+    L.dbh_batch_get_chunks.argtypes = [vp]
     L.dbh_batch_get_info.argtypes = [vp, C.POINTER(BatchInfo)]
     L.dbh_batch_set_poses_host.argtypes = [vp, _dp]
     L.dbh_batch_set_poses_device.argtypes = [vp, vp]
@@ -114,6 +117,7 @@ def lib():
     L.dbh_batch_stream.argtypes = [vp]
     L.dbh_batch_result_sizes.argtypes = [vp, C.POINTER(ResultSizes)]
     L.dbh_batch_copy_results.argtypes = [vp, C.POINTER(ResultBuffers)]
+    L.dbh_batch_copy_results_async.argtypes = [vp, C.POINTER(ResultBuffers)]
     L.dbh_batch_stats.argtypes = [vp, C.POINTER(Stats)]
     L.dbh_batch_copy_candidates.argtypes = [vp, C.c_int32, _ip, _lp]
     L.dbh_batch_copy_geometry_pairs.argtypes = [vp, _ip]
@@ -495,6 +499,14 @@ class SceneBatch:
     def set_capacity(self, bv_pairs: int = 0, element_pairs: int = 0, faces: int = 0):
         _check(lib().dbh_batch_set_capacity(self._h, bv_pairs, element_pairs, faces))
 
+    def set_chunks(self, num_chunks: int):
+        """Process the batch in `num_chunks` chunks of scenes that reuse the device work lists."""
+        _check(lib().dbh_batch_set_chunks(self._h, num_chunks))
+
+    @property
+    def num_chunks(self) -> int:
+        return int(lib().dbh_batch_get_chunks(self._h))
+
     def set_verify(self, on: bool = True):
         """Self-check mode: exact clipping for every candidate; stats()['cull_violations'] must stay 0."""
         _check(lib().dbh_batch_set_verify(self._h, int(on)))
@@ -550,7 +562,9 @@ class SceneBatch:
         _check(lib().dbh_batch_stats(self._h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in Stats._fields_ if n != "reserved"}
 
-    def copy_results(self, into: Optional[PackedResults] = None) -> PackedResults:
+    def copy_results(self, into: Optional[PackedResults] = None, wait: bool = True) -> PackedResults:
+        """D2H of the packed results. wait=False only enqueues the copies on the batch stream (use pinned
+        destination buffers); sync() completes them."""
         sizes = self.sizes()
         if into is not None and into.fits(sizes):
             res = into
@@ -558,7 +572,10 @@ class SceneBatch:
         else:
             res = PackedResults(sizes)
         bufs = res.c_struct()
-        _check(lib().dbh_batch_copy_results(self._h, C.byref(bufs)))
+        if wait:
+            _check(lib().dbh_batch_copy_results(self._h, C.byref(bufs)))
+        else:
+            _check(lib().dbh_batch_copy_results_async(self._h, C.byref(bufs)))
         return res
 
     def compute_contact_surfaces(self, X_WGs, representation: int = POLYGON) -> List[List[ContactSurface]]:

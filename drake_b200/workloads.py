@@ -126,10 +126,13 @@ class Workload:
     def geoms_per_scene(self) -> int:
         return len(self.geom_id)
 
-    def register(self, ctx):
-        """Registers the assets and returns a SceneBatch for all scenes."""
+    def register(self, ctx, assets=None):
+        """Registers the assets (unless the handles of an earlier registration in the same context are
+        passed) and returns a SceneBatch for all scenes. The handles used are kept in self.assets."""
         from .engine import SceneBatch
-        assets = [ctx.register_mesh(m) for m in self.meshes]
+        if assets is None:
+            assets = [ctx.register_mesh(m) for m in self.meshes]
+        self.assets = list(assets)
         S, G = self.num_scenes, self.geoms_per_scene
         if self.per_scene_mesh is None:
             return SceneBatch.replicated(ctx, S, [assets[i] for i in self.geom_mesh], self.geom_id,

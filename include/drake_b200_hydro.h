@@ -40,7 +40,11 @@ enum {
   DBH_ERR_UNSUPPORTED = 7,        /* ContactSurfaceResult::kUnsupported: geometry without a
                                      hydroelastic representation */
   DBH_ERR_NOT_READY = 8,          /* results requested before a query completed */
-  DBH_ERR_PLANE_NORMAL = 9        /* Plane ctor: |normal| < 1e-10 (plane.cc:16-29) */
+  DBH_ERR_PLANE_NORMAL = 9,       /* Plane ctor: |normal| < 1e-10 (plane.cc:16-29) */
+  DBH_ERR_POLYGON_SIZE = 10       /* tet-triangle polygon with more than 7 vertices (DRAKE_DEMAND,
+                                     mesh_intersection.cc:261-262), or a tet-tet clip whose intermediate
+                                     polygon outgrew 16 vertices (the reference's own buffer holds 8,
+                                     field_intersection.cc:98: beyond that its behaviour is undefined) */
 };
 
 enum { DBH_TRIANGLE = 0, DBH_POLYGON = 1 };
@@ -140,6 +144,13 @@ dbh_status dbh_batch_set_capacity(dbh_batch* batch, int64_t max_bv_pairs_per_lev
  * the device counters of the failed query (they keep counting past a full list). Re-run the query;
  * repeat while it still reports DBH_ERR_CAPACITY (later stages only run once earlier ones fit). */
 dbh_status dbh_batch_grow_capacity(dbh_batch* batch);
+/* A query walks the batch in `num_chunks` contiguous chunks of scenes that reuse the same device
+ * work lists (BV-pair frontier, element-pair lists, polygon staging), so their footprint does not
+ * grow with the batch: results are identical for any chunking. dbh_batch_grow_capacity raises the
+ * chunk count by itself when the lists would outgrow the memory budget (35 % of device memory, or
+ * DBH_WORK_BUDGET_MB). Default 1. */
+dbh_status dbh_batch_set_chunks(dbh_batch* batch, int32_t num_chunks);
+int32_t dbh_batch_get_chunks(dbh_batch* batch);
 
 typedef struct dbh_batch_info {
   int32_t num_scenes;
@@ -217,6 +228,10 @@ typedef struct dbh_result_buffers {
   int32_t* elem_N;              /* emitting element of the second (triangle of R / tet1) */
 } dbh_result_buffers;
 dbh_status dbh_batch_copy_results(dbh_batch* batch, const dbh_result_buffers* buffers);
+/* Same copies enqueued on the batch stream without waiting (destinations should be pinned host
+ * memory); dbh_batch_sync() completes them. Lets a caller that alternates two batches overlap
+ * one batch's copy-out with the other's query. */
+dbh_status dbh_batch_copy_results_async(dbh_batch* batch, const dbh_result_buffers* buffers);
 
 /* Device-resident views of the same arrays, in the same layout, for GPU
  * consumers (valid until the next query on this batch). */
@@ -264,6 +279,7 @@ typedef struct dbh_stats {
   int64_t cull_violations;         /* self-check mode only (dbh_batch_set_verify): polygons emitted by
                                       candidates the conservative cull stage had rejected; must be 0 */
   int64_t exceptional_clips;       /* candidates whose intermediate polygon outgrew 8 vertices */
+  int64_t leaf_exact_tests;        /* leaf pairs whose box predicate fp32 could not decide (fp64 test ran) */
 } dbh_stats;
 dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
 

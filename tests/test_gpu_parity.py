@@ -319,3 +319,79 @@ def test_conservative_culls_never_reject_an_emitting_candidate(ctx, config, scen
     assert normal["polygons"] > 0
     # The cull stage must actually cull (otherwise this test checks nothing).
     assert normal["tet_tri_full_clips"] + normal["tet_tet_full_clips"] < normal["tet_tri_pairs"] + normal["tet_tet_pairs"]
+
+
+def _surface_digest(surfaces):
+    """Order-independent digest of a scene's surfaces (faces inside a surface come in atomic order)."""
+    out = []
+    for s in surfaces:
+        keys = np.sort(parity.face_keys(s.elem_M, s.elem_N))
+        out.append((s.id_M, s.id_N, s.num_faces, len(s.vertices), keys.tobytes(), float(s.total_area),
+                    float(np.sort(s.areas).sum()), float(np.sort(s.pressures).sum())))
+    return out
+
+
+@pytest.mark.parametrize("rep", [ho.KPOLYGON, ho.KTRIANGLE])
+def test_chunked_query_equals_single_chunk(ctx, rep):
+    """A query that walks the batch in several chunks of scenes (work lists reused) returns the same
+    surfaces, face for face, as the single-chunk query; explicit chunk counts incl. more chunks than scenes."""
+    from drake_b200 import workloads as W
+    wl = W.config3(37)
+    batch = wl.register(ctx)
+    poses = wl.poses.reshape(-1, 12)
+    want = [_surface_digest(s) for s in batch.compute_contact_surfaces(poses, rep)]
+    base = batch.stats()
+    for chunks in (2, 5, 37, 1000):
+        batch.set_chunks(chunks)
+        assert batch.num_chunks == min(chunks, 37)
+        got = [_surface_digest(s) for s in batch.compute_contact_surfaces(poses, rep)]
+        st = batch.stats()
+        for k in ("bv_pair_tests", "tet_tri_pairs", "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "leaf_pairs"):
+            assert st[k] == base[k], (chunks, k)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert len(g) == len(w)
+            for a, b in zip(g, w):
+                assert a[:5] == b[:5]
+                assert a[5] == pytest.approx(b[5], rel=1e-12)
+                assert a[6] == pytest.approx(b[6], rel=1e-12)
+                assert a[7] == pytest.approx(b[7], rel=1e-12)
+
+
+def test_work_lists_stay_within_the_memory_budget_by_chunking(ctx, monkeypatch):
+    """With a tiny work-list budget the batch splits itself into chunks of scenes instead of growing
+    the lists; results still match the oracle."""
+    from drake_b200 import workloads as W
+    monkeypatch.setenv("DBH_WORK_BUDGET_MB", "16")
+    wl = W.config3(512)
+    batch = wl.register(ctx)
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KPOLYGON)
+    assert batch.num_chunks > 1
+    osc, order = parity.oracle_scene_for(wl)
+    for s in (0, 100, 255, 256, 511):
+        want, _ = osc.compute(wl.poses[s][order], ho.KPOLYGON)
+        assert [(x.id_M, x.id_N) for x in got[s]] == [(x.id_M, x.id_N) for x in want]
+        for g, w in zip(got[s], want):
+            parity.compare_surface(g, w)
+
+
+def test_polygon_with_more_than_eight_vertices(ctx):
+    """C4 scene 7280: a clip plane coplanar with the polygon makes the tet-tet clip return a 9-gon
+    (the reference's vectors have no bound; its "at most 8" comment assumes general position). The
+    exceptional path stages it in two slots; the surface must match the oracle face for face."""
+    from drake_b200 import workloads as W
+    wl = W.config4(1, 7280)
+    batch = wl.register(ctx)
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KPOLYGON)[0]
+    assert batch.stats()["exceptional_clips"] >= 1
+    osc, order = parity.oracle_scene_for(wl)
+    want, _ = osc.compute(wl.poses[0][order], ho.KPOLYGON)
+    assert max(len(p) for s in want for p in s.polygons()) == 9
+    assert [(x.id_M, x.id_N) for x in got] == [(x.id_M, x.id_N) for x in want]
+    for g, w in zip(got, want):
+        parity.compare_surface(g, w)
+    # Same scene in the triangle representation (a 9-fan).
+    got_t = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KTRIANGLE)[0]
+    want_t, _ = osc.compute(wl.poses[0][order], ho.KTRIANGLE)
+    for g, w in zip(got_t, want_t):
+        parity.compare_surface(g, w)
