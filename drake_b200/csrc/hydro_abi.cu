@@ -984,6 +984,19 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     su.scene_stats = reinterpret_cast<long long*>(scene_stats_dev);
     su.counters = b->d_counters.p;
     const int clip_blocks = sms * 4;
+    // Launch-bound variants (occupancy against registers), chosen by measurement; DBH_TUNE="traverse=4,filter=3,pack=4"
+    // overrides for experiments.
+    struct Tune { int traverse = 3, filter = 3, pack = 3; } tune;
+    if (const char* t = std::getenv("DBH_TUNE")) {
+      const std::string str(t);
+      auto get = [&](const char* key, int* v) {
+        const size_t p = str.find(std::string(key) + "=");
+        if (p != std::string::npos) *v = std::atoi(str.c_str() + p + std::strlen(key) + 1);
+      };
+      get("traverse", &tune.traverse);
+      get("filter", &tune.filter);
+      get("pack", &tune.pack);
+    }
     for (int chunk = 0; chunk < b->num_chunks; ++chunk) {
       const int s0 = static_cast<int>(static_cast<long long>(b->num_scenes) * chunk / b->num_chunks);
       const int s1 = static_cast<int>(static_cast<long long>(b->num_scenes) * (chunk + 1) / b->num_chunks);
@@ -999,7 +1012,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ta.in = b->d_frontier[level & 1].p;
         ta.out = b->d_frontier[(level + 1) & 1].p;
         ta.level = level;
-        k_traverse<<<sms * 8, 256, 0, st>>>(ta);
+        if (tune.traverse == 4) k_traverse<4><<<sms * 8, 256, 0, st>>>(ta);
+        else k_traverse<3><<<sms * 8, 256, 0, st>>>(ta);
       }
       mark(2);
       // Filter (leaf predicate + conservative culls) then the exact stage, per element kind. The
@@ -1009,7 +1023,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ca.cand = b->d_cand_tri.p;
         ca.cand_capacity = static_cast<unsigned long long>(b->cap_tri);
         ca.surv = b->d_frontier[0].p;
-        k_filter<false><<<sms * 6, kFilterThreads, 0, st>>>(ca);
+        if (tune.filter == 4) k_filter<false, 4><<<sms * 8, kFilterThreads, 0, st>>>(ca);
+        else if (tune.filter == 2) k_filter<false, 2><<<sms * 4, kFilterThreads, 0, st>>>(ca);
+        else k_filter<false, 3><<<sms * 6, kFilterThreads, 0, st>>>(ca);
         k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
       }
       mark(3);
@@ -1017,7 +1033,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ca.cand = b->d_cand_tet.p;
         ca.cand_capacity = static_cast<unsigned long long>(b->cap_tet);
         ca.surv = b->d_frontier[1].p;
-        k_filter<true><<<sms * 6, kFilterThreads, 0, st>>>(ca);
+        if (tune.filter == 4) k_filter<true, 4><<<sms * 8, kFilterThreads, 0, st>>>(ca);
+        else if (tune.filter == 2) k_filter<true, 2><<<sms * 4, kFilterThreads, 0, st>>>(ca);
+        else k_filter<true, 3><<<sms * 6, kFilterThreads, 0, st>>>(ca);
         k_clip<true><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
       }
       // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
@@ -1031,7 +1049,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       k_scan_blocks<<<1, kScanThreads, 0, st>>>(sa);
       k_scan_apply<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
       mark(5);
-      k_pack<<<sms * 8, 128, 0, st>>>(pk);
+      if (tune.pack == 4) k_pack<4><<<sms * 8, 128, 0, st>>>(pk);
+      else if (tune.pack == 6) k_pack<6><<<sms * 12, 128, 0, st>>>(pk);
+      else k_pack<3><<<sms * 6, 128, 0, st>>>(pk);
       mark(6);
       su.pair_begin = p0;
       su.pair_end = p1;

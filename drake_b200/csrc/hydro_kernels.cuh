@@ -66,6 +66,77 @@ __device__ __forceinline__ unsigned long long warp_append_flag(unsigned long lon
   return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
 }
 
+// Block-aggregated appends: ONE atomic per list per block iteration. The list cursors are single
+// addresses hit by every block of the grid, and same-address atomics serialise in L2 (about one per
+// nanosecond): per-warp appends ran the traversal and filter kernels at that limit. Every thread of
+// the block must call these (two barriers inside).
+template <int kWarps>
+struct BlockAppendSmem {
+  unsigned int tot[kWarps][2];
+  unsigned long long base[3];
+};
+struct Slots3 {
+  unsigned long long s0, s1, s2;
+};
+// Three lists at once; n0, n1, n2 <= 63 per thread, block totals < 65536.
+template <int kWarps>
+__device__ __forceinline__ Slots3 block_append3(unsigned long long* c0, unsigned long long* c1, unsigned long long* c2,
+                                                int n0, int n1, int n2, BlockAppendSmem<kWarps>& sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int a = (unsigned int)n0 | ((unsigned int)n1 << 16), b = (unsigned int)n2;
+  unsigned int ia = a, ib = b;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int ya = __shfl_up_sync(0xffffffffu, ia, d);
+    const unsigned int yb = __shfl_up_sync(0xffffffffu, ib, d);
+    if (lane >= d) {
+      ia += ya;
+      ib += yb;
+    }
+  }
+  if (lane == 31) {
+    sh.tot[warp][0] = ia;
+    sh.tot[warp][1] = ib;
+  }
+  __syncthreads();
+  unsigned int pa = 0, pb = 0, ta = 0, tb = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    const unsigned int x = sh.tot[w][0], y = sh.tot[w][1];
+    if (w < warp) {
+      pa += x;
+      pb += y;
+    }
+    ta += x;
+    tb += y;
+  }
+  if (threadIdx.x == 0 && (ta & 0xffffu)) sh.base[0] = atomicAdd(c0, (unsigned long long)(ta & 0xffffu));
+  if (threadIdx.x == 32 && (ta >> 16)) sh.base[1] = atomicAdd(c1, (unsigned long long)(ta >> 16));
+  if (threadIdx.x == 64 && tb) sh.base[2] = atomicAdd(c2, (unsigned long long)tb);
+  __syncthreads();
+  const unsigned int ea = pa + ia - a, eb = pb + ib - b;
+  return Slots3{sh.base[0] + (ea & 0xffffu), sh.base[1] + (ea >> 16), sh.base[2] + eb};
+}
+// One list, 0 or 1 entries per thread.
+template <int kWarps>
+__device__ __forceinline__ unsigned long long block_append_flag(unsigned long long* counter, bool flag,
+                                                                BlockAppendSmem<kWarps>& sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) sh.tot[warp][0] = __popc(m);
+  __syncthreads();
+  unsigned int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    const unsigned int x = sh.tot[w][0];
+    if (w < warp) before += x;
+    total += x;
+  }
+  if (threadIdx.x == 0 && total) sh.base[0] = atomicAdd(counter, (unsigned long long)total);
+  __syncthreads();
+  return sh.base[0] + before + __popc(m & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void raise_error(Counters* c, int status, int detail) {
   if (atomicCAS(&c->error, 0, status) == 0) c->error_detail = detail;
 }
@@ -231,16 +302,18 @@ __device__ __forceinline__ bool overlap6_f32(const Box32& A, const Box32& B, flo
 
 __device__ __forceinline__ Box32 load_box32(const Node32& n) { return Box32{n.c[0], n.c[1], n.c[2], n.h[0], n.h[1], n.h[2]}; }
 
-__global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_traverse(TraverseArgs a) {
   if (a.counters->error != 0) return;  // the query already failed; the host re-runs it
   // After an overflow the counter exceeds what was stored (the query fails
   // with DBH_ERR_CAPACITY); never read past the stored entries.
+  __shared__ BlockAppendSmem<8> sh;
   const unsigned long long count = min(a.counters->frontier[a.level], a.out_capacity);
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  // Keep whole warps in the loop so the warp-aggregated appends see full masks.
-  const unsigned long long rounded = (count + 31ull) & ~31ull;
+  const unsigned long long stride = (unsigned long long)gridDim.x * 256;
   unsigned int tests = 0;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+  // Whole blocks stay in the loop: the appends are block-wide.
+  for (unsigned long long base = (unsigned long long)blockIdx.x * 256; base < count; base += stride) {
+    const unsigned long long i = base + threadIdx.x;
     int4 e = make_int4(0, 0, 0, 0);
     int n_next = 0, n_leaf = 0;
     int next_a[4], next_b[4], leaf_a[4], leaf_b[4];
@@ -283,24 +356,24 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
         }
       }
     }
-    const unsigned long long slot = warp_append(&a.counters->frontier[a.level + 1], n_next);
+    const bool tri = e.w == kSoftRigid;
+    const Slots3 slots = block_append3<8>(&a.counters->frontier[a.level + 1], &a.counters->leaf_tri, &a.counters->leaf_tet,
+                                          n_next, tri ? n_leaf : 0, tri ? 0 : n_leaf, sh);
     if (n_next) {
-      if (slot + n_next > a.out_capacity) {
+      if (slots.s0 + n_next > a.out_capacity) {
         raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (k < n_next) a.out[slot + k] = make_int4(e.x, next_a[k], next_b[k], e.w);
+          if (k < n_next) a.out[slots.s0 + k] = make_int4(e.x, next_a[k], next_b[k], e.w);
       }
     }
-    const unsigned long long ls_tri = warp_append(&a.counters->leaf_tri, e.w == kSoftRigid ? n_leaf : 0);
-    const unsigned long long ls_tet = warp_append(&a.counters->leaf_tet, e.w == kSoftSoft ? n_leaf : 0);
     if (n_leaf) {
-      const unsigned long long ls = (e.w == kSoftRigid) ? ls_tri : ls_tet;
-      if (ls + n_leaf > ((e.w == kSoftRigid) ? a.leaf_capacity_tri : a.leaf_capacity_tet)) {
+      const unsigned long long ls = tri ? slots.s1 : slots.s2;
+      if (ls + n_leaf > (tri ? a.leaf_capacity_tri : a.leaf_capacity_tet)) {
         raise_error(a.counters, 5, 2);
       } else {
-        int4* list = (e.w == kSoftRigid) ? a.leaf_tri : a.leaf_tet;
+        int4* list = tri ? a.leaf_tri : a.leaf_tet;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (k < n_leaf) list[ls + k] = make_int4(e.x, leaf_a[k], leaf_b[k], 0);
@@ -648,34 +721,43 @@ __device__ __forceinline__ BoxF box_of(const float (*v)[3]) {
   return b;
 }
 // +1: certainly overlapping, -1: certainly separated, 0: too close to call in fp32.
+// Error budget per axis (relative 1e-5, fp32 rounding stays below ~1e-6): the translation t carries an
+// absolute error proportional to S = |ca|_1 + |ha|_1 + |cb|_1 + |hb|_1 + |p|_1, so face axes get
+// 1e-5 S. An edge axis multiplies t by two entries of R, so its error scales with |R(i1,j)| + |R(i2,j)|
+// -- which is what keeps the parallel-axes case decidable: with R(i1,j) = R(i2,j) = 0 both sides
+// vanish except for the 1e-6 term of the right-hand side, and the margin shrinks with them.
 __device__ __forceinline__ int boxes_overlap_f32(const BoxF& A, const BoxF& B, const PairF32& f) {
-  const float delta = 1e-5f * (A.l1 + B.l1 + f.S);
+  const float S = A.l1 + B.l1 + f.S;
+  const float delta = 1e-5f * S;
   float t[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
     t[i] = fmaf(f.R[i], B.c[0], fmaf(f.R[3 + i], B.c[1], fmaf(f.R[6 + i], B.c[2], f.p[i]))) - A.c[i];
   bool separated = false, unsure = false;
-  auto axis = [&](float lhs, float rhs) {
+  auto axis = [&](float lhs, float rhs, float d) {
     const float g = lhs - rhs;
-    separated |= g > delta;
-    unsure |= g > -delta;
+    separated |= g > d;
+    unsure |= g > -d;
   };
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    axis(fabsf(t[i]), A.h[i] + fmaf(B.h[0], f.AR[i * 3 + 0], fmaf(B.h[1], f.AR[i * 3 + 1], B.h[2] * f.AR[i * 3 + 2])));
+    axis(fabsf(t[i]), A.h[i] + fmaf(B.h[0], f.AR[i * 3 + 0], fmaf(B.h[1], f.AR[i * 3 + 1], B.h[2] * f.AR[i * 3 + 2])),
+         delta);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
     axis(fabsf(fmaf(t[0], f.R[i * 3 + 0], fmaf(t[1], f.R[i * 3 + 1], t[2] * f.R[i * 3 + 2]))),
-         B.h[i] + fmaf(A.h[0], f.AR[0 * 3 + i], fmaf(A.h[1], f.AR[1 * 3 + i], A.h[2] * f.AR[2 * 3 + i])));
+         B.h[i] + fmaf(A.h[0], f.AR[0 * 3 + i], fmaf(A.h[1], f.AR[1 * 3 + i], A.h[2] * f.AR[2 * 3 + i])), delta);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-      axis(fabsf(t[i2] * f.R[j * 3 + i1] - t[i1] * f.R[j * 3 + i2]),
-           fmaf(A.h[i1], f.AR[i2 * 3 + j], A.h[i2] * f.AR[i1 * 3 + j]) +
-               fmaf(B.h[j1], f.AR[i * 3 + j2], B.h[j2] * f.AR[i * 3 + j1]));
+      const float rhs = fmaf(A.h[i1], f.AR[i2 * 3 + j], A.h[i2] * f.AR[i1 * 3 + j]) +
+                        fmaf(B.h[j1], f.AR[i * 3 + j2], B.h[j2] * f.AR[i * 3 + j1]);
+      // AR = |R| + 1e-6: a slight over-estimate of |R(i1,j)| + |R(i2,j)|.
+      axis(fabsf(t[i2] * f.R[j * 3 + i1] - t[i1] * f.R[j * 3 + i2]), rhs,
+           1e-5f * fmaf(S, f.AR[i1 * 3 + j] + f.AR[i2 * 3 + j], rhs));
     }
   }
   return separated ? -1 : (unsure ? 0 : 1);
@@ -1009,16 +1091,18 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
 // a dense list for the exact stage; every entry's candidate flag is written
 // back to the leaf list.
 constexpr int kFilterThreads = 256;
-template <bool kTet>
-__global__ void __launch_bounds__(kFilterThreads, 3) k_filter(ClipArgs a) {
+template <bool kTet, int kMinBlocks>
+__global__ void __launch_bounds__(kFilterThreads, kMinBlocks) k_filter(ClipArgs a) {
   if (a.counters->error != 0) return;
   const unsigned long long count = min(kTet ? a.counters->leaf_tet : a.counters->leaf_tri, a.cand_capacity);
-  const unsigned long long rounded = (count + 31ull) & ~31ull;  // whole warps reach the ballots
+  __shared__ BlockAppendSmem<kFilterThreads / 32> sh;
   const unsigned long long stride = (unsigned long long)gridDim.x * kFilterThreads;
   const int lane = threadIdx.x & 31;
   unsigned int n_cand = 0, n_exact = 0;  // per warp (every lane holds the warp's count)
   unsigned long long* cursor = kTet ? &a.counters->surv_tet : &a.counters->surv_tri;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * kFilterThreads + threadIdx.x; i < rounded; i += stride) {
+  // Whole blocks stay in the loop: the append is block-wide.
+  for (unsigned long long base = (unsigned long long)blockIdx.x * kFilterThreads; base < count; base += stride) {
+    const unsigned long long i = base + threadIdx.x;
     bool keep = false, is_cand = false, undecided = false;
     int4 c = make_int4(0, 0, 0, 0);
     if (i < count) {
@@ -1047,7 +1131,7 @@ __global__ void __launch_bounds__(kFilterThreads, 3) k_filter(ClipArgs a) {
     }
     n_cand += __popc(__ballot_sync(0xffffffffu, is_cand));
     n_exact += __popc(__ballot_sync(0xffffffffu, undecided));
-    const unsigned long long slot = warp_append_flag(cursor, keep);
+    const unsigned long long slot = block_append_flag<kFilterThreads / 32>(cursor, keep, sh);
     if (keep) {
       if (slot < a.surv_capacity) a.surv[slot] = c;
       else raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
@@ -1274,7 +1358,8 @@ __device__ __forceinline__ void store_face(const PackArgs& a, long long f, int p
   a.out.face_pair[f] = pair;
 }
 
-__global__ void __launch_bounds__(128) k_pack(PackArgs a) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
   if (a.counters->error != 0) return;
   const unsigned long long count = min(a.counters->polys, a.soup.capacity);
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
