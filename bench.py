@@ -375,9 +375,7 @@ def main():
                 "kernel_ms_breakdown": avg,
                 "whole_step_frac": (s_mean["algorithmic_bytes"] / (max_ms / K * 1e-3) / 1e9) / peak}
 
-    info = batch.info()
-    launches_per_step = 1 + info.max_traversal_levels + (1 if info.num_soft_rigid_pairs else 0) + \
-        (1 if info.num_soft_soft_pairs else 0) + 1 + 3 + 1 + 2 + 1
+    launches_per_step = batch.last_launch_count  # counted by the library at every kernel launch of a query
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -15,6 +15,7 @@
 
 #include "../../include/drake_b200_hydro.h"
 #include "hydro_kernels.cuh"
+#include "hydro_lbvh.h"
 
 using namespace dbh;
 
@@ -130,6 +131,7 @@ void BuildBvh(const std::vector<Box>& elem_boxes, std::vector<BuildItem>& items,
 
 template <int kVerts>
 void BuildAssetBvh(const double* verts, const int32_t* elems, int num_elems, HostAsset* a) {
+  // Host builder (default): top-down median split, the reference's strategy.
   std::vector<Box> boxes(num_elems);
   std::vector<BuildItem> items(num_elems);
   for (int e = 0; e < num_elems; ++e) {
@@ -162,6 +164,7 @@ void BuildAssetBvh(const double* verts, const int32_t* elems, int num_elems, Hos
 
 struct dbh_context {
   int device{0};
+  int bvh_builder{DBH_BVH_HOST_MEDIAN_SPLIT};
   cudaDeviceProp prop{};
   std::vector<std::unique_ptr<HostAsset>> assets;
   // Pools: every asset's records concatenated in registration order, so pool
@@ -335,7 +338,7 @@ struct dbh_batch {
   DevBuf<int4> d_cand_tri, d_cand_tet, d_slow;
   long long cap_slow{1 << 16};
   DevBuf<Counters> d_counters;
-  DevBuf<int> d_pair_polys, d_pair_verts, d_surf_index, d_surf_pair;
+  DevBuf<int> d_pair_polys, d_pair_verts, d_surf_index, d_surf_pair, d_big_list;
   DevBuf<unsigned long long> d_pair_cursor;
   DevBuf<long long> d_poly_off, d_vert_off, d_block_sums, d_surf_face_off, d_surf_vert_off;
   DevBuf<int4> d_soup_hdr;
@@ -354,6 +357,7 @@ struct dbh_batch {
   bool query_done{false};
   bool timing{false};
   bool verify{false};
+  int last_launches{0};   // kernels launched by the last query
   // Timing (optional): two events around the whole query, eight per chunk around its stages.
   cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
   std::vector<cudaEvent_t> ev_chunk;   // 8 per chunk that ran in the last query
@@ -409,9 +413,46 @@ struct dbh_batch {
   }
 };
 
+namespace {
+// Builds the asset's BVH with the context's builder (the GPU LBVH needs at least two elements).
+template <int kVerts>
+dbh_status BuildBvhFor(dbh_context* ctx, const double* verts, int nv, const int32_t* elems, int ne, HostAsset* a) {
+  if (ctx->bvh_builder == DBH_BVH_GPU_LBVH && ne >= 2) {
+    std::string err;
+    if (!BuildLbvhOnDevice(verts, nv, elems, ne, kVerts, &a->nodes, &a->height, &err)) return Fail(DBH_ERR_CUDA, err);
+    return DBH_OK;
+  }
+  BuildAssetBvh<kVerts>(verts, elems, ne, a);
+  return DBH_OK;
+}
+}  // namespace
+
 extern "C" {
 
 const char* dbh_last_error(void) { return g_error.c_str(); }
+
+dbh_status dbh_context_set_bvh_builder(dbh_context* ctx, int32_t builder) {
+  if (!ctx || (builder != DBH_BVH_HOST_MEDIAN_SPLIT && builder != DBH_BVH_GPU_LBVH))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "set_bvh_builder: bad argument");
+  ctx->bvh_builder = builder;
+  return DBH_OK;
+}
+
+dbh_status dbh_asset_copy_bvh(dbh_context* ctx, int32_t asset, double* boxes, int32_t* left) {
+  if (!ctx || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_copy_bvh: bad argument");
+  const HostAsset& a = *ctx->assets[asset];
+  for (size_t k = 0; k < a.nodes.size(); ++k) {
+    if (boxes) {
+      for (int d = 0; d < 3; ++d) {
+        boxes[6 * k + d] = a.nodes[k].c[d];
+        boxes[6 * k + 3 + d] = a.nodes[k].h[d];
+      }
+    }
+    if (left) left[k] = a.nodes[k].left;
+  }
+  return DBH_OK;
+}
 int32_t dbh_abi_version(void) { return 1000; }
 
 dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out) {
@@ -521,7 +562,7 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
       if (!(x.amp < 1e300)) x.amp = 1e300;
     }
   }
-  BuildAssetBvh<4>(verts, tets, nt, a.get());
+  if (dbh_status st = BuildBvhFor<4>(ctx, verts, nv, tets, nt, a.get())) return st;
   ctx->Place(a.get());
   ctx->assets.push_back(std::move(a));
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
@@ -557,7 +598,7 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* v
     r.n[1] = n.y;
     r.n[2] = n.z;
   }
-  BuildAssetBvh<3>(verts, tris, nt, a.get());
+  if (dbh_status st = BuildBvhFor<3>(ctx, verts, nv, tris, nt, a.get())) return st;
   ctx->Place(a.get());
   ctx->assets.push_back(std::move(a));
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
@@ -750,6 +791,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   CUDA_OK(b->d_pair_cursor.alloc(np));
   CUDA_OK(b->d_surf_index.alloc(np + 1));
   CUDA_OK(b->d_surf_pair.alloc(np));
+  CUDA_OK(b->d_big_list.alloc(np));
   CUDA_OK(b->d_poly_off.alloc(np + 1));
   CUDA_OK(b->d_vert_off.alloc(np + 1));
   CUDA_OK(b->d_surf_face_off.alloc(np + 1));
@@ -787,6 +829,7 @@ dbh_status dbh_batch_set_chunks(dbh_batch* b, int32_t num_chunks) {
 }
 
 int32_t dbh_batch_get_chunks(dbh_batch* b) { return b ? b->num_chunks : 0; }
+int32_t dbh_batch_last_launch_count(dbh_batch* b) { return b ? b->last_launches : 0; }
 
 dbh_status dbh_batch_grow_capacity(dbh_batch* b) {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
@@ -865,6 +908,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   if (dbh_status s = b->AllocWorkBuffers()) return s;
   b->representation = representation;
   b->query_done = false;
+  b->last_launches = 0;
   cudaStream_t st = b->stream;
   const int sms = ctx->prop.multiProcessorCount;
   if (b->timing) {
@@ -982,11 +1026,12 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     su.surf_id_n = b->r_surf_id_n.p;
     su.surf_flags = b->r_surf_flags.p;
     su.scene_stats = reinterpret_cast<long long*>(scene_stats_dev);
+    su.big_list = b->d_big_list.p;
     su.counters = b->d_counters.p;
     const int clip_blocks = sms * 4;
     // Launch-bound variants (occupancy against registers), chosen by measurement; DBH_TUNE="traverse=4,filter=3,pack=4"
     // overrides for experiments.
-    struct Tune { int traverse = 3, filter = 3, pack = 3; } tune;
+    struct Tune { int traverse = 3, filter = 2, pack = 4; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1005,6 +1050,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       pa.pair_begin = p0;
       pa.pair_end = p1;
       mark(0);
+      ++b->last_launches;
       k_pairs<<<(p1 - p0 + 127) / 128, 128, 0, st>>>(pa);
       mark(1);
       // Dual-BVH traversal, one launch per level; counts stay on the device.
@@ -1012,8 +1058,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ta.in = b->d_frontier[level & 1].p;
         ta.out = b->d_frontier[(level + 1) & 1].p;
         ta.level = level;
-        if (tune.traverse == 4) k_traverse<4><<<sms * 8, 256, 0, st>>>(ta);
-        else k_traverse<3><<<sms * 8, 256, 0, st>>>(ta);
+        if (tune.traverse == 4) { ++b->last_launches; k_traverse<4><<<sms * 8, 256, 0, st>>>(ta); }
+        else { ++b->last_launches; k_traverse<3><<<sms * 8, 256, 0, st>>>(ta); }
       }
       mark(2);
       // Filter (leaf predicate + conservative culls) then the exact stage, per element kind. The
@@ -1023,9 +1069,10 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ca.cand = b->d_cand_tri.p;
         ca.cand_capacity = static_cast<unsigned long long>(b->cap_tri);
         ca.surv = b->d_frontier[0].p;
-        if (tune.filter == 4) k_filter<false, 4><<<sms * 8, kFilterThreads, 0, st>>>(ca);
-        else if (tune.filter == 2) k_filter<false, 2><<<sms * 4, kFilterThreads, 0, st>>>(ca);
-        else k_filter<false, 3><<<sms * 6, kFilterThreads, 0, st>>>(ca);
+        if (tune.filter == 4) { ++b->last_launches; k_filter<false, 4><<<sms * 8, kFilterThreads, 0, st>>>(ca); }
+        else if (tune.filter == 2) { ++b->last_launches; k_filter<false, 2><<<sms * 4, kFilterThreads, 0, st>>>(ca); }
+        else { ++b->last_launches; k_filter<false, 3><<<sms * 6, kFilterThreads, 0, st>>>(ca); }
+        ++b->last_launches;
         k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
       }
       mark(3);
@@ -1033,37 +1080,49 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ca.cand = b->d_cand_tet.p;
         ca.cand_capacity = static_cast<unsigned long long>(b->cap_tet);
         ca.surv = b->d_frontier[1].p;
-        if (tune.filter == 4) k_filter<true, 4><<<sms * 8, kFilterThreads, 0, st>>>(ca);
-        else if (tune.filter == 2) k_filter<true, 2><<<sms * 4, kFilterThreads, 0, st>>>(ca);
-        else k_filter<true, 3><<<sms * 6, kFilterThreads, 0, st>>>(ca);
+        if (tune.filter == 4) { ++b->last_launches; k_filter<true, 4><<<sms * 8, kFilterThreads, 0, st>>>(ca); }
+        else if (tune.filter == 2) { ++b->last_launches; k_filter<true, 2><<<sms * 4, kFilterThreads, 0, st>>>(ca); }
+        else { ++b->last_launches; k_filter<true, 3><<<sms * 6, kFilterThreads, 0, st>>>(ca); }
+        ++b->last_launches;
         k_clip<true><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
       }
       // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
+      ++b->last_launches;
       k_clip_slow<<<sms, 64, 0, st>>>(ca);
       mark(4);
       sa.pair_begin = p0;
       sa.num_pairs = p1;
       sa.first_chunk = p0 == 0;
       sa.num_blocks = (p1 - p0 + kScanTile - 1) / kScanTile;
+      ++b->last_launches;
       k_scan_partials<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
+      ++b->last_launches;
       k_scan_blocks<<<1, kScanThreads, 0, st>>>(sa);
+      ++b->last_launches;
       k_scan_apply<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
       mark(5);
-      if (tune.pack == 4) k_pack<4><<<sms * 8, 128, 0, st>>>(pk);
-      else if (tune.pack == 6) k_pack<6><<<sms * 12, 128, 0, st>>>(pk);
-      else k_pack<3><<<sms * 6, 128, 0, st>>>(pk);
+      if (tune.pack == 4) { ++b->last_launches; k_pack<4><<<sms * 8, 128, 0, st>>>(pk); }
+      else if (tune.pack == 6) { ++b->last_launches; k_pack<6><<<sms * 12, 128, 0, st>>>(pk); }
+      else { ++b->last_launches; k_pack<3><<<sms * 6, 128, 0, st>>>(pk); }
       mark(6);
       su.pair_begin = p0;
       su.pair_end = p1;
+      b->last_launches += 3;
       k_surface<<<sms * 4, 128, 0, st>>>(su);
+      k_surface_big_sum<<<sms * 4, 128, 0, st>>>(su);
+      k_surface_big_finish<<<1, 128, 0, st>>>(su);
+      ++b->last_launches;
       k_next_chunk<<<1, 64, 0, st>>>(b->d_counters.p);
       mark(7);
       if (b->timing) ++b->timed_chunks;
     }
+    ++b->last_launches;
     k_finalize<<<1, 32, 0, st>>>(su, b->num_pairs);
-    if (scene_stats_dev)
+    if (scene_stats_dev) {
+      ++b->last_launches;
       k_scene_stats<<<(b->num_pairs + 255) / 256, 256, 0, st>>>(b->d_pairs.p, b->num_pairs,
                                                                reinterpret_cast<long long*>(scene_stats_dev));
+    }
   }
   CUDA_OK(cudaMemcpyAsync(b->h_counters, b->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   if (b->timing) cudaEventRecord(b->ev_end, st);

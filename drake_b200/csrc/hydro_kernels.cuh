@@ -1086,27 +1086,68 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
 }
 
 // ---- k_filter: the leaf predicate + stage A over every leaf pair ------------
-// One thread per leaf pair, no shared memory, light enough on registers to keep
-// the SM full. Survivors are compacted (warp ballot + one atomic per warp) into
-// a dense list for the exact stage; every entry's candidate flag is written
-// back to the leaf list.
+// One thread per leaf pair, light enough on registers to keep the SM full. The
+// kernel is bound by the latency of its gathers (leaf entry -> per-element
+// records), so the loop is software-pipelined two deep: the entry of iteration
+// k + 2 is loaded and the records of iteration k + 1 are prefetched into L1 while
+// iteration k computes. Survivors are staged per warp in shared memory (ballot +
+// popc, no atomics) and flushed 32 at a time: one global atomic and one coalesced
+// 512 B store per 32 survivors, no block-wide barrier. Every entry's candidate
+// flag is written back to the leaf list.
 constexpr int kFilterThreads = 256;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <bool kTet>
+__device__ __forceinline__ void prefetch_records(const ClipArgs& a, int4 c) {
+  prefetch_l1(a.pair_f32 + c.x);
+  prefetch_l1(a.pools.cull_a + c.y);
+  prefetch_l1(a.pools.cull_b + c.y);
+  if (kTet) {
+    prefetch_l1(a.pools.cull_a + c.z);
+    prefetch_l1(a.pools.cull_b + c.z);
+  } else {
+    prefetch_l1(a.pools.cull_tri + c.z);
+  }
+}
 template <bool kTet, int kMinBlocks>
 __global__ void __launch_bounds__(kFilterThreads, kMinBlocks) k_filter(ClipArgs a) {
+  __shared__ int4 stage[kFilterThreads / 32][64];
   if (a.counters->error != 0) return;
   const unsigned long long count = min(kTet ? a.counters->leaf_tet : a.counters->leaf_tri, a.cand_capacity);
-  __shared__ BlockAppendSmem<kFilterThreads / 32> sh;
-  const unsigned long long stride = (unsigned long long)gridDim.x * kFilterThreads;
+  const unsigned long long rounded = (count + 31ull) & ~31ull;  // whole warps reach the ballots
+  // Every warp walks its own contiguous range of the leaf list, 32 entries at a time, so the
+  // survivors it stages (and later the polygons they emit) stay in leaf-list order: long runs of
+  // the same geometry pair, which is what keeps the pack kernel's writes contiguous.
+  const unsigned long long num_warps = (unsigned long long)gridDim.x * (kFilterThreads / 32);
+  const unsigned long long per_warp = (((count + num_warps - 1) / num_warps) + 31ull) & ~31ull;
+  const unsigned long long warp_begin = ((unsigned long long)blockIdx.x * (kFilterThreads / 32) + (threadIdx.x >> 5)) * per_warp;
+  const unsigned long long warp_end = min(warp_begin + per_warp, rounded);
+  const unsigned long long stride = 32;
   const int lane = threadIdx.x & 31;
+  int4* const my_stage = stage[threadIdx.x >> 5];
+  int fill = 0;  // staged survivors of this warp (warp-uniform)
   unsigned int n_cand = 0, n_exact = 0;  // per warp (every lane holds the warp's count)
   unsigned long long* cursor = kTet ? &a.counters->surv_tet : &a.counters->surv_tri;
-  // Whole blocks stay in the loop: the append is block-wide.
-  for (unsigned long long base = (unsigned long long)blockIdx.x * kFilterThreads; base < count; base += stride) {
-    const unsigned long long i = base + threadIdx.x;
+  auto flush = [&](int n) {  // the first n staged entries (n <= 32) go to the survivor list
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < n) {
+      if (base + lane < a.surv_capacity) a.surv[base + lane] = my_stage[lane];
+      else raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
+    }
+  };
+  const int4 kNone = make_int4(0, 0, 0, 0);
+  unsigned long long i = warp_begin + lane;
+  const unsigned long long last = min(warp_end, count);  // entries at or past `last` do not exist / are not ours
+  int4 c_cur = i < last ? a.cand[i] : kNone;
+  int4 c_next = i + stride < last ? a.cand[i + stride] : kNone;
+  if (i < last) prefetch_records<kTet>(a, c_cur);
+  for (; i < warp_end; i += stride) {
+    const int4 c_next2 = i + 2 * stride < last ? a.cand[i + 2 * stride] : kNone;
+    if (i + stride < last) prefetch_records<kTet>(a, c_next);
     bool keep = false, is_cand = false, undecided = false;
-    int4 c = make_int4(0, 0, 0, 0);
+    int4 c = c_cur;
     if (i < count) {
-      c = a.cand[i];
       const PairF32 X = a.pair_f32[c.x];
       const TetCullA ta = a.pools.cull_a[c.y];
       int decided;
@@ -1131,12 +1172,24 @@ __global__ void __launch_bounds__(kFilterThreads, kMinBlocks) k_filter(ClipArgs 
     }
     n_cand += __popc(__ballot_sync(0xffffffffu, is_cand));
     n_exact += __popc(__ballot_sync(0xffffffffu, undecided));
-    const unsigned long long slot = block_append_flag<kFilterThreads / 32>(cursor, keep, sh);
-    if (keep) {
-      if (slot < a.surv_capacity) a.surv[slot] = c;
-      else raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) my_stage[fill + __popc(m & ((1u << lane) - 1u))] = c;
+    fill += __popc(m);
+    __syncwarp();
+    if (fill >= 32) {
+      flush(32);
+      __syncwarp();
+      int4 moved = kNone;
+      if (lane < fill - 32) moved = my_stage[32 + lane];
+      __syncwarp();
+      if (lane < fill - 32) my_stage[lane] = moved;
+      fill -= 32;
+      __syncwarp();
     }
+    c_cur = c_next;
+    c_next = c_next2;
   }
+  if (fill > 0) flush(fill);
   if (lane == 0 && n_cand) atomicAdd(kTet ? &a.counters->cand_tet : &a.counters->cand_tri, (unsigned long long)n_cand);
   if (lane == 0 && n_exact) atomicAdd(&a.counters->leaf_exact, (unsigned long long)n_exact);
 }
@@ -1362,11 +1415,42 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
   if (a.counters->error != 0) return;
   const unsigned long long count = min(a.counters->polys, a.soup.capacity);
+  const unsigned long long rounded = (count + 31ull) & ~31ull;  // whole warps reach the collectives
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    const int4 h = a.soup.hdr[i];
+  const int lane = threadIdx.x & 31;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+    int4 h = make_int4(-1, 0, 0, 0);
+    if (i < count) h = a.soup.hdr[i];
     const int pair = h.x, n = h.w;
-    if (n == 0) continue;  // second staging slot of a polygon with more than 8 vertices
+    // n == 0: the second staging slot of a polygon with more than 8 vertices.
+    const bool valid = i < count && n != 0;
+    // One atomic claims both the polygon slot and the vertex range, so within a pair polygon order
+    // and vertex order agree. When the whole warp works on one geometry pair (large meshes: tens of
+    // thousands of polygons per pair) a single atomic serves the warp; same-address atomics serialise.
+    unsigned long long cur = 0;
+    {
+      const unsigned validmask = __ballot_sync(0xffffffffu, valid);
+      const int lead = validmask ? __ffs(validmask) - 1 : 0;
+      const int pair0 = __shfl_sync(0xffffffffu, pair, lead);
+      const bool uniform = __all_sync(0xffffffffu, !valid || pair == pair0);
+      const unsigned long long v = valid ? ((1ull << 32) | (unsigned long long)n) : 0ull;
+      if (uniform) {
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += y;
+        }
+        const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == lead && total) base = atomicAdd(&a.pair_cursor[pair], total);
+        base = __shfl_sync(0xffffffffu, base, lead);
+        cur = base + incl - v;
+      } else if (valid) {
+        cur = atomicAdd(&a.pair_cursor[pair], v);
+      }
+    }
+    if (!valid) continue;
     const PairRec pr = a.pairs[pair];
     const bool soft_soft = pr.kind == kSoftSoft;
     const bool swapped = pr.swapped != 0;
@@ -1387,9 +1471,6 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
       const Xf X_WN = a.poses[pr.geom_b];
       gB_W = rot(X_WN, load3(a.pools.tets[h.z].grad));
     }
-    // One atomic claims both the polygon slot and the vertex range, so within
-    // a pair polygon order and vertex order agree.
-    const unsigned long long cur = atomicAdd(&a.pair_cursor[pair], (1ull << 32) | (unsigned long long)n);
     const int pj = (int)(cur >> 32);
     const int vj = (int)(cur & 0xffffffffull);
     if (a.representation == 1 /*DBH_POLYGON*/) {
@@ -1536,8 +1617,25 @@ struct SurfaceArgs {
   long long* surf_id_n;
   unsigned char* surf_flags;
   long long* scene_stats;    // optional [num_scenes * 6]
+  int* big_list;             // surfaces with more than kBigSurfaceFaces faces (this chunk)
   Counters* counters;
 };
+
+// Surfaces with more faces than this are summed by the whole grid (k_surface_big_*), not by one warp.
+constexpr long long kBigSurfaceFaces = 4096;
+constexpr long long kBigSegment = 2048;
+
+__device__ __forceinline__ void surface_face_range(const SurfaceArgs& a, int p, long long* f0, long long* f1, long long* v0) {
+  if (a.representation == 1) {
+    *f0 = a.poly_off[p];
+    *f1 = a.poly_off[p + 1];
+    *v0 = a.vert_off[p];
+  } else {
+    *f0 = a.vert_off[p];
+    *f1 = a.vert_off[p + 1];
+    *v0 = a.vert_off[p] + a.poly_off[p];
+  }
+}
 
 __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
   if (a.counters->error != 0) return;
@@ -1549,17 +1647,10 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
        s += (long long)gridDim.x * warps_per_block) {
     const int p = a.surf_pair[s];
     long long f0, f1, v0;
-    if (a.representation == 1) {
-      f0 = a.poly_off[p];
-      f1 = a.poly_off[p + 1];
-      v0 = a.vert_off[p];
-    } else {
-      f0 = a.vert_off[p];
-      f1 = a.vert_off[p + 1];
-      v0 = a.vert_off[p] + a.poly_off[p];
-    }
+    surface_face_range(a, p, &f0, &f1, &v0);
+    const bool big = f1 - f0 > kBigSurfaceFaces;  // summed by k_surface_big_sum / _finish
     double area = 0, cx = 0, cy = 0, cz = 0;
-    for (long long f = f0 + lane; f < f1; f += 32) {
+    for (long long f = f0 + lane; f < f1 && !big; f += 32) {
       const double w = a.areas[f];
       area += w;
       cx += w * a.centroids[3 * f];
@@ -1574,7 +1665,9 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
       cz += __shfl_xor_sync(0xffffffffu, cz, d);
     }
     if (lane == 0) {
-      if (area != 0.0) {
+      if (big) {
+        a.big_list[atomicAdd(&a.counters->big_surfaces, 1ull)] = (int)s;  // accumulators start at 0 below
+      } else if (area != 0.0) {
         cx /= area;
         cy /= area;
         cz /= area;
@@ -1597,13 +1690,76 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
       a.surf_id_n[s] = pr.id_n;
       // bit0 HasGradE_M, bit1 HasGradE_N, bit2 swapped.
       a.surf_flags[s] = pr.kind == kSoftSoft ? 3 : (pr.swapped ? (2 | 4) : 1);
-      atomicAdd(&a.counters->total_area, area);
+      if (!big) atomicAdd(&a.counters->total_area, area);
       if (a.scene_stats) {
         unsigned long long* st = (unsigned long long*)(a.scene_stats + 6ll * pr.scene);
         atomicAdd(st + 3, (unsigned long long)(f1 - f0));
         atomicAdd(st + 4, 1ull);
       }
     }
+  }
+}
+
+// Large surfaces (tens of thousands of faces: one warp would take milliseconds): every warp of the
+// grid sums segments of 2048 faces and adds its partial sums to the surface's accumulators.
+__global__ void __launch_bounds__(128) k_surface_big_sum(SurfaceArgs a) {
+  if (a.counters->error != 0) return;
+  const int lane = threadIdx.x & 31;
+  const long long num_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nbig = (long long)a.counters->big_surfaces;
+  long long unit0 = 0;  // units (segments) before the current surface, to spread the warps evenly
+  for (long long k = 0; k < nbig; ++k) {
+    const int s = a.big_list[k];
+    long long f0, f1, v0;
+    surface_face_range(a, a.surf_pair[s], &f0, &f1, &v0);
+    const long long nseg = (f1 - f0 + kBigSegment - 1) / kBigSegment;
+    // First segment of this surface that falls to this warp.
+    long long j = (gwarp - unit0 % num_warps + num_warps) % num_warps;
+    for (; j < nseg; j += num_warps) {
+      const long long b = f0 + j * kBigSegment, e = min(b + kBigSegment, f1);
+      double area = 0, cx = 0, cy = 0, cz = 0;
+      for (long long f = b + lane; f < e; f += 32) {
+        const double w = a.areas[f];
+        area += w;
+        cx += w * a.centroids[3 * f];
+        cy += w * a.centroids[3 * f + 1];
+        cz += w * a.centroids[3 * f + 2];
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        area += __shfl_xor_sync(0xffffffffu, area, d);
+        cx += __shfl_xor_sync(0xffffffffu, cx, d);
+        cy += __shfl_xor_sync(0xffffffffu, cy, d);
+        cz += __shfl_xor_sync(0xffffffffu, cz, d);
+      }
+      if (lane == 0) {
+        atomicAdd(&a.surf_total_area[s], area);
+        atomicAdd(&a.surf_centroid[3 * s], cx);
+        atomicAdd(&a.surf_centroid[3 * s + 1], cy);
+        atomicAdd(&a.surf_centroid[3 * s + 2], cz);
+      }
+    }
+    unit0 += nseg;
+  }
+}
+
+__global__ void k_surface_big_finish(SurfaceArgs a) {
+  if (a.counters->error != 0) return;
+  const long long nbig = (long long)a.counters->big_surfaces;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nbig; k += (long long)gridDim.x * blockDim.x) {
+    const int s = a.big_list[k];
+    const double area = a.surf_total_area[s];
+    if (area != 0.0) {
+      a.surf_centroid[3 * s] /= area;
+      a.surf_centroid[3 * s + 1] /= area;
+      a.surf_centroid[3 * s + 2] /= area;
+    } else {
+      long long f0, f1, v0;
+      surface_face_range(a, a.surf_pair[s], &f0, &f1, &v0);
+      for (int d = 0; d < 3; ++d) a.surf_centroid[3 * s + d] = a.centroids[3 * f0 + d];
+    }
+    atomicAdd(&a.counters->total_area, area);
   }
 }
 
@@ -1625,7 +1781,7 @@ __global__ void k_next_chunk(Counters* c) {
   __syncthreads();
   if (blockIdx.x == 0) {
     if (threadIdx.x < 64) c->frontier[threadIdx.x] = 0;
-    if (threadIdx.x == 0) c->leaf_tri = c->leaf_tet = c->polys = c->slow = c->surv_tri = c->surv_tet = 0;
+    if (threadIdx.x == 0) c->leaf_tri = c->leaf_tet = c->polys = c->slow = c->surv_tri = c->surv_tet = c->big_surfaces = 0;
   }
 }
 

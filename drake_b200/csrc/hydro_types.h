@@ -170,6 +170,7 @@ struct Counters {
   unsigned long long slow;          // candidates deferred to the exceptional (16-vertex) path
   unsigned long long surv_tri;      // tet-tri candidates that survived the conservative culls
   unsigned long long surv_tet;      // same, tet-tet
+  unsigned long long big_surfaces;  // surfaces of this chunk summed by the whole grid
   // -- whole query
   unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
   unsigned long long cand_tri;      // tet-tri candidate pairs: leaf pairs that pass the exact predicate

@@ -27,6 +27,7 @@ STRICT, WITH_FALLBACK = 0, 1
 
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_DEGENERATE_FIELD, ERR_CAPACITY = 1, 2, 3, 4, 5
+BVH_HOST_MEDIAN_SPLIT, BVH_GPU_LBVH = 0, 1
 ERR_RIGID_RIGID, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_PLANE_NORMAL, ERR_POLYGON_SIZE = 6, 7, 8, 9, 10
 
 
@@ -103,12 +104,15 @@ def lib():
     L.dbh_register_rigid_mesh.argtypes = [vp, C.c_int32, _dp, C.c_int32, _ip, _ip]
     L.dbh_asset_get_info.argtypes = [vp, C.c_int32, C.POINTER(AssetInfo)]
     L.dbh_asset_get_derived.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
+    L.dbh_asset_copy_bvh.argtypes = [vp, C.c_int32, _dp, _ip]
+    L.dbh_context_set_bvh_builder.argtypes = [vp, C.c_int32]
     L.dbh_batch_create.argtypes = [vp, C.c_int32, _ip, _ip, _lp, _bp, C.c_int32, _ip, C.POINTER(vp)]
     L.dbh_batch_destroy.argtypes = [vp]
     L.dbh_batch_set_capacity.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.dbh_batch_grow_capacity.argtypes = [vp]
     L.dbh_batch_set_chunks.argtypes = [vp, C.c_int32]
     L.dbh_batch_get_chunks.argtypes = [vp]
+    L.dbh_batch_last_launch_count.argtypes = [vp]
     L.dbh_batch_get_info.argtypes = [vp, C.POINTER(BatchInfo)]
     L.dbh_batch_set_poses_host.argtypes = [vp, _dp]
     L.dbh_batch_set_poses_device.argtypes = [vp, vp]
@@ -308,6 +312,17 @@ class Context:
         _check(lib().dbh_asset_get_info(self._h, asset, C.byref(info)))
         return info
 
+    def set_bvh_builder(self, builder: int):
+        """BVH_HOST_MEDIAN_SPLIT (default) or BVH_GPU_LBVH, for the registrations that follow."""
+        _check(lib().dbh_context_set_bvh_builder(self._h, builder))
+
+    def asset_bvh(self, asset: int):
+        """(boxes [n,6] = centre, half width; left [n]) with n = num_bvh_nodes + 1 (node 0 unused, 1 = root)."""
+        n = self.asset_info(asset).num_bvh_nodes + 1
+        boxes, left = np.zeros((n, 6)), np.zeros(n, np.int32)
+        _check(lib().dbh_asset_copy_bvh(self._h, asset, _ptr(boxes, _dp), _ptr(left, _ip)))
+        return boxes, left
+
     def asset_derived(self, asset: int):
         """Compliant: (gradients [T,3], values_at_Mo [T], inward_normals [T,4,3]); rigid: normals [T,3]."""
         info = self.asset_info(asset)
@@ -506,6 +521,10 @@ class SceneBatch:
     @property
     def num_chunks(self) -> int:
         return int(lib().dbh_batch_get_chunks(self._h))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(lib().dbh_batch_last_launch_count(self._h))
 
     def set_verify(self, on: bool = True):
         """Self-check mode: exact clipping for every candidate; stats()['cull_violations'] must stay 0."""

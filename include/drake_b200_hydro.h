@@ -59,6 +59,12 @@ typedef struct dbh_batch dbh_batch;
 /* -- (1) context: one per device (one process per GPU). ---------------------- */
 dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out);
 void dbh_context_destroy(dbh_context* ctx);
+/* BVH builder used by the registrations that follow. DBH_BVH_HOST_MEDIAN_SPLIT (default): top-down
+ * median split on the host, the reference's strategy (bvh.cc:18-122). DBH_BVH_GPU_LBVH: linear BVH
+ * built on the device (Morton codes + radix sort + Karras' parallel construction + bottom-up fit).
+ * Query results do not depend on the builder: one element per leaf, leaf boxes bit-identical. */
+enum { DBH_BVH_HOST_MEDIAN_SPLIT = 0, DBH_BVH_GPU_LBVH = 1 };
+dbh_status dbh_context_set_bvh_builder(dbh_context* ctx, int32_t builder);
 /* Thread-local message of the last failing call. */
 const char* dbh_last_error(void);
 /* ABI version of this library (major * 1000 + minor). */
@@ -89,6 +95,10 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t num_vertices, c
 dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t num_vertices, const double* vertices,
                                    int32_t num_tris, const int32_t* tris, int32_t* asset_out);
 dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out);
+/* The asset's BVH for inspection: boxes [(num_bvh_nodes + 1) * 6] = centre, half width per node
+ * (node 0 unused, node 1 root), left [(num_bvh_nodes + 1)] = index of the first of the two adjacent
+ * children, or ~element for a leaf. Either may be NULL. */
+dbh_status dbh_asset_copy_bvh(dbh_context* ctx, int32_t asset, double* boxes, int32_t* left);
 /* Copies the derived per-element data back (for tests): compliant: gradients
  * [nt*3], values_at_Mo [nt], inward_normals [nt*12]; rigid: normals [nt*3].
  * Any pointer may be NULL. */
@@ -151,6 +161,8 @@ dbh_status dbh_batch_grow_capacity(dbh_batch* batch);
  * DBH_WORK_BUDGET_MB). Default 1. */
 dbh_status dbh_batch_set_chunks(dbh_batch* batch, int32_t num_chunks);
 int32_t dbh_batch_get_chunks(dbh_batch* batch);
+/* Number of kernels the last dbh_batch_query launched. */
+int32_t dbh_batch_last_launch_count(dbh_batch* batch);
 
 typedef struct dbh_batch_info {
   int32_t num_scenes;

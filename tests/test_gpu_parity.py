@@ -395,3 +395,91 @@ def test_polygon_with_more_than_eight_vertices(ctx):
     want_t, _ = osc.compute(wl.poses[0][order], ho.KTRIANGLE)
     for g, w in zip(got_t, want_t):
         parity.compare_surface(g, w)
+
+
+def _check_bvh(boxes, left, num_elements):
+    """Structure + containment of a BVH in the library's layout."""
+    seen = np.zeros(num_elements, int)
+    stack = [1]
+    depth = {1: 0}
+    height = 0
+    while stack:
+        k = stack.pop()
+        if left[k] < 0:
+            seen[~left[k]] += 1
+            height = max(height, depth[k])
+            continue
+        for c in (left[k], left[k] + 1):
+            lo_p, hi_p = boxes[k, :3] - boxes[k, 3:], boxes[k, :3] + boxes[k, 3:]
+            lo_c, hi_c = boxes[c, :3] - boxes[c, 3:], boxes[c, :3] + boxes[c, 3:]
+            tol = 1e-12 * (1 + np.abs(boxes[k]).max())
+            assert np.all(lo_c >= lo_p - tol) and np.all(hi_c <= hi_p + tol), (k, c)
+            depth[c] = depth[k] + 1
+            stack.append(c)
+    assert np.all(seen == 1)
+    return height
+
+
+def test_gpu_lbvh_builder_gives_the_same_query_results():
+    """The device-built linear BVH (Morton sort + Karras + bottom-up fit): a valid tree over every
+    element with leaf boxes bit-identical to the host builder's, and -- the candidate set being
+    tree-independent -- bit-identical candidate sets and matching surfaces."""
+    import drake_b200 as db
+    from drake_b200 import engine
+    R = 3.0
+    soft = ho.VolumeMesh.sphere(R, 1.0)                 # 4096 tets, dense
+    fld = ho.VolumeField.sphere(soft, R, 1e5)
+    rigid = ho.TriMesh.sphere(R, 1.0)
+    poses = np.stack([ho.xform(ho.rpy_matrix(0.3, -0.2, 0.9), [0.1, 0.2, 0.3]), ho.xform(ho.rpy_matrix(1.0, 0.4, 0.2), [2.5, 1.0, 0.5]),
+                      ho.xform(None, [-1.5, 2.0, 0.5])])
+    out = []
+    for builder in (engine.BVH_HOST_MEDIAN_SPLIT, engine.BVH_GPU_LBVH):
+        c = db.Context(0)
+        c.set_bvh_builder(builder)
+        a_s = parity.register_compliant(c, soft, fld)
+        a_r = parity.register_rigid(c, rigid)
+        for a, ne in ((a_s, len(soft.tets)), (a_r, len(rigid.tris))):
+            boxes, left = c.asset_bvh(a)
+            assert len(left) == 2 * ne
+            h = _check_bvh(boxes, left, ne)
+            assert h == c.asset_info(a).bvh_height
+        boxes, left = c.asset_bvh(a_s)
+        leaf = left < 0
+        leaf[0] = False
+        order = np.argsort(~left[leaf])
+        out_boxes = boxes[leaf][order]
+        batch = db.SceneBatch(c, [0, 3], [a_s, a_s, a_r], [1, 2, 3])
+        got = batch.compute_contact_surfaces(poses, db.POLYGON)[0]
+        cands = [batch.candidates(k) for k in (0, 1)]
+        cands = [x[np.lexsort(x.T[::-1])] for x in cands]
+        out.append((out_boxes, got, cands, batch.stats()))
+    (b0, s0, c0, st0), (b1, s1, c1, st1) = out
+    np.testing.assert_array_equal(b0, b1)               # leaf boxes bit-identical
+    for x, y in zip(c0, c1):
+        np.testing.assert_array_equal(x, y)             # candidate sets bit-identical
+    assert len(c0[0]) > 1000 and len(c0[1]) > 1000
+    assert [(s.id_M, s.id_N) for s in s0] == [(s.id_M, s.id_N) for s in s1] == [(1, 2), (1, 3), (2, 3)]
+    for g, w in zip(_surface_digest(s0), _surface_digest(s1)):
+        assert g[:5] == w[:5]
+        assert g[5] == pytest.approx(w[5], rel=1e-12)
+    for k in ("polygons", "faces", "vertices", "tet_tri_pairs", "tet_tet_pairs"):
+        assert st0[k] == st1[k]
+
+
+@pytest.mark.parametrize("rep", [ho.KPOLYGON, ho.KTRIANGLE])
+def test_large_surfaces_reduced_by_the_whole_grid(ctx, rep):
+    """Two dense spheres of 32768 tets: one surface of thousands of faces per scene; above 4096 faces
+    the per-surface area / centroid reduction is spread over the grid. Totals must match the oracle."""
+    from drake_b200 import workloads as W
+    wl = W.config2_spheres(2, 0, 0.5)
+    batch = wl.register(ctx)
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), rep)
+    osc, order = parity.oracle_scene_for(wl)
+    biggest = 0
+    for s in range(wl.num_scenes):
+        want, _ = osc.compute(wl.poses[s][order], rep)
+        assert len(got[s]) == len(want) == 1
+        parity.compare_surface(got[s][0], want[0])
+        biggest = max(biggest, want[0].num_faces)
+    if rep == ho.KTRIANGLE:
+        assert biggest > 4096
