@@ -483,3 +483,80 @@ def test_large_surfaces_reduced_by_the_whole_grid(ctx, rep):
         biggest = max(biggest, want[0].num_faces)
     if rep == ho.KTRIANGLE:
         assert biggest > 4096
+
+
+@pytest.mark.parametrize("name", ["c3_16_scenes", "c3_16_scenes_tri", "c4_2_scenes", "c2s_2_scenes"])
+def test_against_committed_golden_fixtures(ctx, name):
+    """GPU results against tests/golden/*.json (no oracle call): ids, face / vertex counts, the checksum of the
+    emitting element-pair keys (bit-exact), total area, centroid and summed face pressure (1e-10)."""
+    import json
+    import os
+    from tests.golden import make_golden as G
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(G.__file__)), name + ".json")))
+    make, rep = G.CASES[name]
+    wl = make()
+    batch = wl.register(ctx)
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), rep)
+    assert len(got) == len(want["scenes"])
+    for gs, ws in zip(got, want["scenes"]):
+        assert [(g.id_M, g.id_N, g.num_faces, len(g.vertices)) for g in gs] == \
+               [(w["id_M"], w["id_N"], w["faces"], w["vertices"]) for w in ws]
+        for g, w in zip(gs, ws):
+            keys = parity.face_keys(g.elem_M, g.elem_N) * np.int64(2654435761) % np.int64(1 << 61)
+            assert int(np.bitwise_xor.reduce(keys)) == w["key_checksum"]
+            assert g.total_area == pytest.approx(w["total_area"], rel=1e-10)
+            assert float(np.sum(g.pressure_at_centroid)) == pytest.approx(w["sum_face_pressure"], rel=1e-10)
+            assert np.allclose(g.centroid, w["centroid"], rtol=1e-10, atol=1e-13)
+
+
+def test_full_size_config3_properties(ctx):
+    """BASELINE config 3 at its full size (16 384 scenes, 49 152 geometry pairs, ~13.6 M candidate element pairs):
+    size-independent properties instead of an oracle run. (1) idempotence: the same query twice gives the same
+    counters; (2) the per-scene statistics sum to the batch totals; (3) a chunked query gives the same counters and
+    total area; (4) moving every geometry of every scene by one rigid transform leaves the number of surfaces
+    unchanged and the total contact area within 1e-9; (5) the self-check mode finds no cull violation."""
+    import torch
+    from drake_b200 import engine, workloads as W
+    wl = W.config3(16384)
+    batch = wl.register(ctx)
+    poses = wl.poses.reshape(-1, 12)
+    stats_dev = torch.zeros((wl.num_scenes, 6), dtype=torch.int64, device="cuda")
+    batch.set_poses(poses)
+    batch.run(ho.KPOLYGON, engine.STRICT, stats_dev.data_ptr())
+    a = batch.stats()
+    per_scene = stats_dev.cpu().numpy()
+    batch.run(ho.KPOLYGON, engine.STRICT)
+    b = batch.stats()
+    counters = ("bv_pair_tests", "leaf_pairs", "tet_tri_pairs", "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces")
+    for k in counters:
+        assert a[k] == b[k], k
+    assert a["total_area"] == pytest.approx(b["total_area"], rel=1e-12)
+    assert a["surfaces"] > 40000 and a["tet_tri_pairs"] + a["tet_tet_pairs"] > 13_000_000
+    assert per_scene[:, 3].sum() == a["faces"] and per_scene[:, 4].sum() == a["surfaces"]
+    assert per_scene[:, 0].sum() == a["geometry_pairs_tested"]
+    batch.set_chunks(5)
+    batch.run(ho.KPOLYGON, engine.STRICT)
+    c = batch.stats()
+    for k in counters:
+        assert a[k] == c[k], k
+    assert a["total_area"] == pytest.approx(c["total_area"], rel=1e-12)
+    batch.set_chunks(1)
+    # (4) one rigid transform applied to the whole world.
+    X = parity.random_pose(np.random.default_rng(7), 0.3)
+    R, p = X[:9].reshape(3, 3).T, X[9:]
+    Rg = poses[:, :9].reshape(-1, 3, 3).transpose(0, 2, 1)
+    moved = np.concatenate([(R @ Rg).transpose(0, 2, 1).reshape(-1, 9), poses[:, 9:] @ R.T + p], axis=1)
+    batch.set_poses(moved)
+    batch.run(ho.KPOLYGON, engine.STRICT)
+    d = batch.stats()
+    assert d["surfaces"] == a["surfaces"]
+    assert abs(d["faces"] - a["faces"]) <= 1e-4 * a["faces"]          # ulp-level classifications may flip
+    assert d["total_area"] == pytest.approx(a["total_area"], rel=1e-9)
+    # (5)
+    batch.set_poses(poses)
+    batch.set_verify(True)
+    batch.run(ho.KPOLYGON, engine.STRICT)
+    v = batch.stats()
+    assert v["cull_violations"] == 0
+    for k in ("polygons", "faces", "vertices", "surfaces"):
+        assert v[k] == a[k], k
