@@ -137,6 +137,8 @@ __device__ __forceinline__ unsigned long long block_append_flag(unsigned long lo
   return sh.base[0] + before + __popc(m & ((1u << lane) - 1u));
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void raise_error(Counters* c, int status, int detail) {
   if (atomicCAS(&c->error, 0, status) == 0) c->error_detail = detail;
 }
@@ -311,7 +313,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_traverse(TraverseArgs a) {
   const unsigned long long count = min(a.counters->frontier[a.level], a.out_capacity);
   const unsigned long long stride = (unsigned long long)gridDim.x * 256;
   unsigned int tests = 0;
-  // Whole blocks stay in the loop: the appends are block-wide.
+  // Whole blocks stay in the loop: the appends are block-wide. (A two-deep software pipeline with L1
+  // prefetches, which pays in the filter kernel, was measured here and does not: the nodes of the batched
+  // configs are L1-resident and the extra registers spill.)
   for (unsigned long long base = (unsigned long long)blockIdx.x * 256; base < count; base += stride) {
     const unsigned long long i = base + threadIdx.x;
     int4 e = make_int4(0, 0, 0, 0);
@@ -1095,7 +1099,6 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
 // 512 B store per 32 survivors, no block-wide barrier. Every entry's candidate
 // flag is written back to the leaf list.
 constexpr int kFilterThreads = 256;
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <bool kTet>
 __device__ __forceinline__ void prefetch_records(const ClipArgs& a, int4 c) {
   prefetch_l1(a.pair_f32 + c.x);
@@ -1455,15 +1458,15 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
     const bool soft_soft = pr.kind == kSoftSoft;
     const bool swapped = pr.swapped != 0;
     const Xf X_WM = a.poses[pr.geom_a];
-    D3 vM[kPackMaxVerts];
-    double e[kPackMaxVerts];
-    for (int k = 0; k < n; ++k) {
-      const unsigned long long s = i + (k >> 3);  // vertices 8.. are in the next slot
+    // The polygon is streamed from the staging soup (coalesced SoA reads; a second pass hits L1 / L2):
+    // no per-thread vertex arrays, so no local memory. Vertices 8.. of a large polygon are in the next slot.
+    auto vert = [&](int k, double* e_k) {
+      const unsigned long long s = i + (k >> 3);
       const int kk = k & 7;
-      vM[k] = make_d3(a.soup.v[(kk * 4 + 0) * a.soup.capacity + s], a.soup.v[(kk * 4 + 1) * a.soup.capacity + s],
-                      a.soup.v[(kk * 4 + 2) * a.soup.capacity + s]);
-      e[k] = a.soup.v[(kk * 4 + 3) * a.soup.capacity + s];
-    }
+      *e_k = a.soup.v[(kk * 4 + 3) * a.soup.capacity + s];
+      return make_d3(a.soup.v[(kk * 4 + 0) * a.soup.capacity + s], a.soup.v[(kk * 4 + 1) * a.soup.capacity + s],
+                     a.soup.v[(kk * 4 + 2) * a.soup.capacity + s]);
+    };
     const D3 gradA_M = load3(a.pools.tets[h.y].grad);
     const D3 gA_W = rot(X_WM, gradA_M);
     D3 gB_W = make_d3(0, 0, 0);
@@ -1473,6 +1476,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
     }
     const int pj = (int)(cur >> 32);
     const int vj = (int)(cur & 0xffffffffull);
+    double e0;
+    const D3 v0 = vert(0, &e0);
     if (a.representation == 1 /*DBH_POLYGON*/) {
       const long long f = a.poly_off[pair] + pj;
       const long long vb = a.vert_off[pair] + vj;
@@ -1480,44 +1485,45 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
         raise_error(a.counters, 5, 6);
         continue;
       }
-      // PolygonSurfaceMesh::CalcAreaNormalAndCentroid (polygon_surface_mesh.cc:117-218).
-      const D3 r_MA = vM[0];
-      D3 p_scaled = make_d3(0, 0, 0), normal_M = make_d3(0, 0, 0);
+      // PolygonSurfaceMesh::CalcAreaNormalAndCentroid (polygon_surface_mesh.cc:117-218): fan about vertex 0,
+      // accumulated while the vertices stream by; vertices, pressures and face_data are written on the way
+      // (TransformVertices, polygon_surface_mesh.cc:25-37; face_data |n|v0..vn-1| with surface-local indices,
+      // reversed when M and N are swapped, ReverseFaceWinding :39-49).
+      int* fd = a.out.face_data + (f + vb);
+      fd[0] = n;
+      const D3 r_MA = v0;
+      D3 p_scaled = make_d3(0, 0, 0), normal_M = make_d3(0, 0, 0), vsum = v0;
       double double_area = 0;
-      for (int k = 1; k < n - 1; ++k) {
-        const D3 cr = cross(vM[k] - r_MA, vM[k + 1] - r_MA);
-        normal_M = normal_M + cr;
-        const double mag = norm(cr);
-        double_area += mag;
-        p_scaled = p_scaled + mag * ((r_MA + vM[k]) + vM[k + 1]);
+      store3(a.out.vertices, vb, xform_point(X_WM, v0));
+      a.out.pressures[vb] = e0;
+      fd[1] = vj + (swapped ? (n - 1) : 0);
+      D3 prev = v0;  // vertex k - 1
+      for (int k = 1; k < n; ++k) {
+        double ek;
+        const D3 vk = vert(k, &ek);
+        store3(a.out.vertices, vb + k, xform_point(X_WM, vk));
+        a.out.pressures[vb + k] = ek;
+        fd[1 + k] = vj + (swapped ? (n - 1 - k) : k);
+        vsum = vsum + vk;
+        if (k >= 2) {  // triangle (0, k-1, k)
+          const D3 cr = cross(prev - r_MA, vk - r_MA);
+          normal_M = normal_M + cr;
+          const double mag = norm(cr);
+          double_area += mag;
+          p_scaled = p_scaled + mag * ((r_MA + prev) + vk);
+        }
+        prev = vk;
       }
       const double area = double_area / 2;
       const D3 nM = normalized(normal_M);
       const D3 p_as = p_scaled / 6;
-      D3 cM;
-      if (area != 0.0) {
-        cM = p_as / area;
-      } else {
-        D3 acc = r_MA;
-        for (int k = 1; k < n; ++k) acc = acc + vM[k];
-        cM = acc / (double)n;
-      }
-      // TransformVertices + field Transform (polygon_surface_mesh.cc:25-37,
-      // mesh_field_linear.h:377-383,502-509).
+      const D3 cM = area != 0.0 ? p_as / area : vsum / (double)n;
+      // field Transform (mesh_field_linear.h:377-383,502-509).
       const D3 n_W = normalized(rot(X_WM, nM));
       const D3 c_W = xform_point(X_WM, cM);
-      const double at_Mo = e[0] - dot(gradA_M, vM[0]);
+      const double at_Mo = e0 - dot(gradA_M, v0);
       const double at_Wo = at_Mo - dot(gA_W, make_d3(X_WM.m[9], X_WM.m[10], X_WM.m[11]));
       const double e_c = dot(gA_W, c_W) + at_Wo;
-      // face_data: |n|v0..vn-1| with surface-local indices, reversed when M and
-      // N are swapped (PolygonSurfaceMesh::ReverseFaceWinding, polygon_surface_mesh.cc:39-49).
-      int* fd = a.out.face_data + (f + vb);
-      fd[0] = n;
-      for (int k = 0; k < n; ++k) {
-        store3(a.out.vertices, vb + k, xform_point(X_WM, vM[k]));
-        a.out.pressures[vb + k] = e[k];
-        fd[1 + k] = vj + (swapped ? (n - 1 - k) : k);
-      }
       store_face(a, f, pair, h.y - pr.elem_base_a, h.z - pr.elem_base_b, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft, swapped);
     } else {
       // Triangle representation: n fan triangles about the polygon centroid
@@ -1533,48 +1539,56 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
       }
       const D3 nhat = make_d3(a.soup.nhat[0 * a.soup.capacity + i], a.soup.nhat[1 * a.soup.capacity + i],
                               a.soup.nhat[2 * a.soup.capacity + i]);
-      // CalcPolygonCentroid.
-      D3 p_c;
-      if (n == 3) {
-        p_c = ((vM[0] + vM[1]) + vM[2]) / 3.0;
-      } else {
-        D3 accum = make_d3(0, 0, 0);
-        double total_weight = 0;
-        for (int k = 2; k < n; ++k) {
-          const double weight = dot(cross(vM[k - 1] - vM[0], vM[k] - vM[0]), nhat);
-          accum = accum + weight * (((vM[0] + vM[k - 1]) + vM[k]) / 3.0);
+      // Pass 1: vertices + pressures out, CalcPolygonCentroid.
+      D3 accum = make_d3(0, 0, 0), vsum = v0;
+      double total_weight = 0;
+      store3(a.out.vertices, vb, xform_point(X_WM, v0));
+      a.out.pressures[vb] = e0;
+      D3 prev = v0;
+      double e_prev = e0;
+      for (int k = 1; k < n; ++k) {
+        double ek;
+        const D3 vk = vert(k, &ek);
+        store3(a.out.vertices, vb + k, xform_point(X_WM, vk));
+        a.out.pressures[vb + k] = ek;
+        vsum = vsum + vk;
+        if (k >= 2) {
+          const double weight = dot(cross(prev - v0, vk - v0), nhat);
+          accum = accum + weight * (((v0 + prev) + vk) / 3.0);
           total_weight += weight;
         }
+        prev = vk;
+        e_prev = ek;
+      }
+      D3 p_c;
+      if (n == 3) {
+        p_c = vsum / 3.0;  // ((v0 + v1) + v2) / 3
+      } else {
         if (total_weight == 0) {
-          accum = make_d3(0, 0, 0);
-          for (int k = 0; k < n; ++k) accum = accum + vM[k];
+          accum = vsum;  // ((0 + v0) + v1) + ... : adding to zero first is exact
           total_weight = n;
         }
         p_c = accum / total_weight;
       }
-      const double e_cv = dot(gradA_M, p_c - vM[0]) + e[0];
-      D3 vW[kPackMaxVerts];
-      for (int k = 0; k < n; ++k) {
-        vW[k] = xform_point(X_WM, vM[k]);
-        store3(a.out.vertices, vb + k, vW[k]);
-        a.out.pressures[vb + k] = e[k];
-      }
+      const double e_cv = dot(gradA_M, p_c - v0) + e0;
       const D3 cW = xform_point(X_WM, p_c);
       store3(a.out.vertices, vb + n, cW);
       a.out.pressures[vb + n] = e_cv;
       const double third = 1.0 / 3.0;
+      // Pass 2: triangle (v_{k-1}, v_k, centroid), k = 0 pairs the last vertex (still in prev) with vertex 0.
       int k1 = n - 1;
       for (int k = 0; k < n; ++k) {
-        // Triangle (v_{k-1}, v_k, centroid): TriangleSurfaceMesh derived
-        // quantities in M (triangle_surface_mesh.h:452-487), then rotated.
-        const D3 cr = cross(vM[k] - vM[k1], p_c - vM[k1]);
+        double ek = e0;
+        const D3 vk = k == 0 ? v0 : vert(k, &ek);
+        // TriangleSurfaceMesh derived quantities in M (triangle_surface_mesh.h:452-487), then rotated.
+        const D3 cr = cross(vk - prev, p_c - prev);
         const double nm = norm(cr);
         const double area = 0.5 * nm;
         const D3 nM = (nm != 0.0) ? cr / nm : cr;
         const D3 n_W = rot(X_WM, nM);
-        const D3 c_W = ((vW[k1] + vW[k]) + cW) / 3.0;
-        double e_c = third * e[k1];
-        e_c += third * e[k];
+        const D3 c_W = ((xform_point(X_WM, prev) + xform_point(X_WM, vk)) + cW) / 3.0;
+        double e_c = third * e_prev;
+        e_c += third * ek;
         e_c += third * e_cv;
         int i0 = vloc + k1, i1 = vloc + k;
         if (swapped) {  // SurfaceTriangle::ReverseWinding swaps vertices 0 and 1
@@ -1588,6 +1602,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
         fd[2] = vloc + n;
         store_face(a, fb + k, pair, h.y - pr.elem_base_a, h.z - pr.elem_base_b, area, n_W, c_W, e_c, gA_W, gB_W, soft_soft, swapped);
         k1 = k;
+        prev = vk;
+        e_prev = ek;
       }
     }
   }
