@@ -576,6 +576,29 @@ template <class Poly>
 __device__ __forceinline__ void emit_polygon(const ClipArgs& a, Poly& P, int buf, int n, int4 c, D3 grad, double p_mo,
                                              D3 nhat) {
   const unsigned long long slot = warp_append_flag(&a.counters->polys, n > 0);
+  // Per-pair polygon / vertex counts (the scan's input). The polygons of a warp mostly belong to one
+  // geometry pair: then one lane adds the warp's totals instead of 32 lanes hitting the same address.
+  {
+    const unsigned emitting = __ballot_sync(0xffffffffu, n > 0);
+    if (emitting) {
+      const int lane = threadIdx.x & 31;
+      const int lead = __ffs(emitting) - 1;
+      const int pair0 = __shfl_sync(0xffffffffu, c.x, lead);
+      const bool uniform = __all_sync(0xffffffffu, n <= 0 || c.x == pair0);
+      if (uniform) {
+        int total = n > 0 ? n : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+        if (lane == lead) {
+          atomicAdd(&a.pair_polys[pair0], __popc(emitting));
+          atomicAdd(&a.pair_verts[pair0], total);
+        }
+      } else if (n > 0) {
+        atomicAdd(&a.pair_polys[c.x], 1);
+        atomicAdd(&a.pair_verts[c.x], n);
+      }
+    }
+  }
   if (n <= 0) return;
   if (slot >= a.soup.capacity) {
     raise_error(a.counters, 5, 3);
@@ -594,8 +617,6 @@ __device__ __forceinline__ void emit_polygon(const ClipArgs& a, Poly& P, int buf
   a.soup.nhat[0 * a.soup.capacity + slot] = nhat.x;
   a.soup.nhat[1 * a.soup.capacity + slot] = nhat.y;
   a.soup.nhat[2 * a.soup.capacity + slot] = nhat.z;
-  atomicAdd(&a.pair_polys[c.x], 1);
-  atomicAdd(&a.pair_verts[c.x], n);
 }
 
 // The exceptional path's emit: per-lane atomics. A polygon with more than 8 vertices (only a clip
@@ -1659,6 +1680,7 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
   const int lane = threadIdx.x & 31;
   const long long first_surface = a.pair_begin == 0 ? 0 : a.surf_index[a.pair_begin];
   const long long num_surfaces = a.surf_index[a.pair_end];
+  double warp_area = 0;  // lane 0: total area of this warp's surfaces (one atomic per warp at the end)
   for (long long s = first_surface + (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < num_surfaces;
        s += (long long)gridDim.x * warps_per_block) {
     const int p = a.surf_pair[s];
@@ -1706,7 +1728,7 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
       a.surf_id_n[s] = pr.id_n;
       // bit0 HasGradE_M, bit1 HasGradE_N, bit2 swapped.
       a.surf_flags[s] = pr.kind == kSoftSoft ? 3 : (pr.swapped ? (2 | 4) : 1);
-      if (!big) atomicAdd(&a.counters->total_area, area);
+      if (!big) warp_area += area;
       if (a.scene_stats) {
         unsigned long long* st = (unsigned long long*)(a.scene_stats + 6ll * pr.scene);
         atomicAdd(st + 3, (unsigned long long)(f1 - f0));
@@ -1714,6 +1736,7 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
       }
     }
   }
+  if (lane == 0 && warp_area != 0.0) atomicAdd(&a.counters->total_area, warp_area);
 }
 
 // Large surfaces (tens of thousands of faces: one warp would take milliseconds): every warp of the
