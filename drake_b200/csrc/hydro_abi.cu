@@ -299,7 +299,7 @@ struct dbh_context {
           m.h[d] = std::nextafterf(h, std::numeric_limits<float>::infinity());
         }
         m.child = n.left;
-        m.pad = 0;
+        m.l1 = ((std::fabs(m.c[0]) + std::fabs(m.c[1])) + std::fabs(m.c[2])) + ((m.h[0] + m.h[1]) + m.h[2]);
       }
       CUDA_OK(cudaMemcpy(d_nodes32.p + a.node_base, rebased32.data(), rebased32.size() * sizeof(Node32),
                          cudaMemcpyHostToDevice));

@@ -276,15 +276,17 @@ struct TraverseArgs {
 };
 
 struct Box32 {
-  float cx, cy, cz, hx, hy, hz;
+  float cx, cy, cz, hx, hy, hz, l1;
 };
 
 // Conservative: false only if the boxes are certainly disjoint under the
-// exact predicate. tb = R cb + p (b's centre in a's frame).
+// exact predicate. tb = R cb + p (b's centre in a's frame). (Hoisting the one-box parts of the right-hand
+// sides out of the four child tests saves a sixth of the instructions on paper and was measured 8 % slower:
+// the extra live values spill.)
 __device__ __forceinline__ bool overlap6_f32(const Box32& A, const Box32& B, float tbx, float tby, float tbz, float sb,
                                              const PairF32& f) {
   const float tx = tbx - A.cx, ty = tby - A.cy, tz = tbz - A.cz;
-  const float S = ((fabsf(A.cx) + fabsf(A.cy)) + fabsf(A.cz)) + sb + ((A.hx + A.hy) + A.hz);
+  const float S = A.l1 + sb;
   const float delta = 4e-6f * S;
   const float ax = A.hx + delta, ay = A.hy + delta, az = A.hz + delta;
   const float bx = B.hx + delta, by = B.hy + delta, bz = B.hz + delta;
@@ -302,7 +304,9 @@ __device__ __forceinline__ bool overlap6_f32(const Box32& A, const Box32& B, flo
   return true;
 }
 
-__device__ __forceinline__ Box32 load_box32(const Node32& n) { return Box32{n.c[0], n.c[1], n.c[2], n.h[0], n.h[1], n.h[2]}; }
+__device__ __forceinline__ Box32 load_box32(const Node32& n) {
+  return Box32{n.c[0], n.c[1], n.c[2], n.h[0], n.h[1], n.h[2], n.l1};
+}
 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) k_traverse(TraverseArgs a) {
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_traverse(TraverseArgs a) {
           const float tbx = fmaf(f.R[0], bb.cx, fmaf(f.R[3], bb.cy, fmaf(f.R[6], bb.cz, f.p[0])));
           const float tby = fmaf(f.R[1], bb.cx, fmaf(f.R[4], bb.cy, fmaf(f.R[7], bb.cz, f.p[1])));
           const float tbz = fmaf(f.R[2], bb.cx, fmaf(f.R[5], bb.cy, fmaf(f.R[8], bb.cz, f.p[2])));
-          const float sb = ((fabsf(bb.cx) + fabsf(bb.cy)) + fabsf(bb.cz)) + f.S + ((bb.hx + bb.hy) + bb.hz);
+          const float sb = bb.l1 + f.S;
 #pragma unroll
           for (int ja = 0; ja < 2; ++ja) {
             if (ja < na) {
@@ -841,10 +845,11 @@ __device__ __forceinline__ bool tri_stage_a(const ClipArgs& a, int4 c, const Pai
     for (int e = 0; e < 3; ++e) {
       const F3 edge = qb[e] - qa[e];
       const F3 u = crossf(nhat, edge);
-      const float thr = -(m * abs_sumf(edge));
+      // u.(v - qa) < thr as u.v < thr + u.qa: the cancellation error (~1e-7 |u| L) is far inside the margin.
+      const float thr = dotf(u, qa[e]) - m * abs_sumf(edge);
       int outside = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) outside += dotf(u, v[k] - qa[e]) < thr;
+      for (int k = 0; k < 4; ++k) outside += dotf(u, v[k]) < thr;
       if (outside == 4) keep = false;
     }
   }
@@ -962,18 +967,19 @@ __device__ __forceinline__ bool tet_stage_a(const ClipArgs& a, int4 c, const Pai
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
     // (R) a face of tet1 (outward normal rotated into M) with all of tet0 outside.
+    // (n.(v - A) > m evaluated as n.v > m + n.A: the cancellation error, ~1e-7 L, is far inside the margins.)
     const F3 o = rotf(X, f3(b1.nh[f]));
-    const F3 A = v1[(f + 1) % 4];
+    const float da = dotf(o, v1[(f + 1) % 4]) + mr;
     int out = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out += dotf(o, v0[k] - A) > mr;
+    for (int k = 0; k < 4; ++k) out += dotf(o, v0[k]) > da;
     if (out == 4) keep = false;
     // (N) a face of tet0 with all of tet1 outside.
     const F3 nh = f3(b0.nh[f]);
-    const F3 B = v0[(f + 1) % 4];
+    const float db = dotf(nh, v0[(f + 1) % 4]) + mn;
     out = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out += dotf(nh, v1[k] - B) > mn;
+    for (int k = 0; k < 4; ++k) out += dotf(nh, v1[k]) > db;
     if (out == 4) keep = false;
   }
   return keep;

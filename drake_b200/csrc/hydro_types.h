@@ -99,7 +99,7 @@ struct alignas(32) Node32 {
   float c[3];
   float h[3];
   int32_t child;
-  int32_t pad;
+  float l1;   // |c|_1 + |h|_1: the scale of this box's contribution to the descent's safety pad
 };
 static_assert(sizeof(Node32) == 32, "Node32 is 32 B");
 
