@@ -323,18 +323,25 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_traverse(TraverseArgs a) {
   for (unsigned long long base = (unsigned long long)blockIdx.x * 256; base < count; base += stride) {
     const unsigned long long i = base + threadIdx.x;
     int4 e = make_int4(0, 0, 0, 0);
-    int n_next = 0, n_leaf = 0;
-    int next_a[4], next_b[4], leaf_a[4], leaf_b[4];
+    // Results of the up to four child tests as bit masks (bit q = jb * 2 + ja), so nothing is indexed
+    // dynamically and everything stays in registers; the entries are rebuilt from the masks when stored.
+    unsigned pass = 0, leafm = 0;
+    int ia = 0, ib = 0, child_a0 = 0, child_a1 = 0, child_b0 = 0, child_b1 = 0;
     if (i < count) {
       e = a.in[i];
       const int na = e.y >= 0 ? 2 : 1, nb = e.z >= 0 ? 2 : 1;
-      const int ia = e.y >= 0 ? e.y : ~e.y, ib = e.z >= 0 ? e.z : ~e.z;
+      ia = e.y >= 0 ? e.y : ~e.y;
+      ib = e.z >= 0 ? e.z : ~e.z;
       const PairF32 f = a.pair_f32[e.x];
       Node32 A[2], B[2];
       A[0] = a.pools.nodes32[ia];
       B[0] = a.pools.nodes32[ib];
       A[1] = na == 2 ? a.pools.nodes32[ia + 1] : A[0];
       B[1] = nb == 2 ? a.pools.nodes32[ib + 1] : B[0];
+      child_a0 = A[0].child;
+      child_a1 = A[1].child;
+      child_b0 = B[0].child;
+      child_b1 = B[1].child;
       tests = tests + na * nb;
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb) {
@@ -348,43 +355,41 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_traverse(TraverseArgs a) {
           for (int ja = 0; ja < 2; ++ja) {
             if (ja < na) {
               if (overlap6_f32(load_box32(A[ja]), bb, tbx, tby, tbz, sb, f)) {
-                const int ca = A[ja].child, cb = B[jb].child;
-                if (ca < 0 && cb < 0) {
-                  leaf_a[n_leaf] = ~ca;  // pool element indices
-                  leaf_b[n_leaf] = ~cb;
-                  ++n_leaf;
-                } else {
-                  next_a[n_next] = frontier_code(ia + ja, ca);
-                  next_b[n_next] = frontier_code(ib + jb, cb);
-                  ++n_next;
-                }
+                pass |= 1u << (jb * 2 + ja);
+                if (A[ja].child < 0 && B[jb].child < 0) leafm |= 1u << (jb * 2 + ja);
               }
             }
           }
         }
       }
     }
+    const int n_leaf = __popc(leafm), n_next = __popc(pass) - n_leaf;
     const bool tri = e.w == kSoftRigid;
     const Slots3 slots = block_append3<8>(&a.counters->frontier[a.level + 1], &a.counters->leaf_tri, &a.counters->leaf_tet,
                                           n_next, tri ? n_leaf : 0, tri ? 0 : n_leaf, sh);
-    if (n_next) {
-      if (slots.s0 + n_next > a.out_capacity) {
-        raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < n_next) a.out[slots.s0 + k] = make_int4(e.x, next_a[k], next_b[k], e.w);
-      }
+    unsigned long long s_next = slots.s0, s_leaf = tri ? slots.s1 : slots.s2;
+    bool ok_next = true, ok_leaf = true;
+    if (n_next && s_next + n_next > a.out_capacity) {
+      raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 1);
+      ok_next = false;
     }
-    if (n_leaf) {
-      const unsigned long long ls = tri ? slots.s1 : slots.s2;
-      if (ls + n_leaf > (tri ? a.leaf_capacity_tri : a.leaf_capacity_tet)) {
-        raise_error(a.counters, 5, 2);
-      } else {
-        int4* list = tri ? a.leaf_tri : a.leaf_tet;
+    if (n_leaf && s_leaf + n_leaf > (tri ? a.leaf_capacity_tri : a.leaf_capacity_tet)) {
+      raise_error(a.counters, 5, 2);
+      ok_leaf = false;
+    }
+    int4* const leaf_list = tri ? a.leaf_tri : a.leaf_tet;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < n_leaf) list[ls + k] = make_int4(e.x, leaf_a[k], leaf_b[k], 0);
+    for (int q = 0; q < 4; ++q) {
+      if ((pass >> q) & 1u) {
+        const int ja = q & 1, jb = q >> 1;
+        const int ca = ja ? child_a1 : child_a0, cb = jb ? child_b1 : child_b0;
+        if ((leafm >> q) & 1u) {
+          if (ok_leaf) leaf_list[s_leaf] = make_int4(e.x, ~ca, ~cb, 0);  // pool element indices
+          ++s_leaf;
+        } else {
+          if (ok_next) a.out[s_next] = make_int4(e.x, frontier_code(ia + ja, ca), frontier_code(ib + jb, cb), e.w);
+          ++s_next;
+        }
       }
     }
   }
