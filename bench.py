@@ -189,11 +189,31 @@ def run_reference(args):
            "element_pairs_per_sec": float(np.mean(pairs)),
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(json.dumps(out))
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """The ONE JSON line goes to the process's real stdout; everything else any library prints while the bench runs
+    (e.g. NCCL's version banner) was sent to stderr by quiet_stdout()."""
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -207,6 +227,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # Rank 0 prints ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off stdout.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -215,6 +238,18 @@ def main():
     dev = torch.device("cuda", local)
     rep = engine.POLYGON if args.rep == "polygon" else engine.TRIANGLE
     scenes = args.scenes or DEFAULT_SCENES[args.config]
+    # Bind this rank to the CPUs (NUMA node) next to its GPU before any pinned host buffer is allocated: the
+    # end-to-end leg moves ~0.6 GB per step per GPU over PCIe, and with N ranks the copies otherwise cross sockets.
+    numa = "unbound"
+    all_cpus = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        numa = f"{len(os.sched_getaffinity(0))} cpus near gpu {local}"
+    except Exception as ex:  # affinity is an optimisation only
+        numa = f"unbound ({type(ex).__name__})"
 
     # ---- set-up (untimed): meshes, assets, BVHs, scene batch, two pose sets resident in HBM.
     wl = make_workload(args.config, scenes, rank * scenes)
@@ -335,6 +370,29 @@ def main():
         e_surf, d2h = e2e_run(args.steps)
         barrier()
         e_sec = time.perf_counter() - e0
+        # The same loop copying out only what MultibodyPlant's discrete update reads from a ContactSurface
+        # (per-face area / normal / centroid / pressure / gradients, per-surface totals): reported
+        # beside the complete copy-out, never instead of it.
+        full_hosts = hosts
+        hosts = [engine.PackedResults(sizes, allocator=pinned, capacity=cap, fields=engine.PackedResults.FACE_FIELDS)
+                 for _ in batches]
+        e2e_run(2)
+        barrier()
+        f0 = time.perf_counter()
+        f_surf, f_d2h = e2e_run(args.steps)
+        barrier()
+        f_sec = time.perf_counter() - f0
+        hosts = full_hosts
+        ft = torch.tensor([f_sec, float(f_surf)], dtype=torch.float64, device=dev)
+        if world > 1:
+            fmax = ft.clone()
+            dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ft, op=dist.ReduceOp.SUM)
+            ft[0] = fmax[0]
+        faces_only = {"value": float(ft[1].item()) / float(ft[0].item()), "unit": UNIT,
+                      "d2h_bytes_per_step": int(f_d2h / args.steps), "ms_per_step": 1e3 * float(ft[0].item()) / args.steps,
+                      "arrays": "per-face area, normal, centroid, pressure at centroid, grad_eM, grad_eN; per-surface ids, "
+                                "offsets, total area, centroid"}
         et = torch.tensor([e_sec], dtype=torch.float64, device=dev)
         es = torch.tensor([float(e_surf)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -343,7 +401,8 @@ def main():
         e2e = {"value": float(es.item()) / float(et.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(pinned_poses[0].numel() * 8), "d2h_bytes_per_step": int(d2h / args.steps),
                "ms_per_step": 1e3 * float(et.item()) / args.steps,
-               "pipelining": "two batches alternated: D2H of step k overlaps H2D + query of step k+1"}
+               "pipelining": "two batches alternated: D2H of step k overlaps H2D + query of step k+1",
+               "host_affinity": numa, "faces_only": faces_only}
 
     if rank != 0:
         if world > 1:
@@ -395,6 +454,7 @@ def main():
     launches_per_step = batch.last_launch_count  # counted by the library at every kernel launch of a query
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core again
         threads = os.cpu_count() or 1
         r = time_cpu_port(wl, rep, args.cpu_seconds, threads)
         r1 = time_cpu_port(wl, rep, min(5.0, args.cpu_seconds), 1)
@@ -415,7 +475,7 @@ def main():
            "wall_ms_per_step_incl_flush_and_sync": 1e3 * wall / K,
            "e2e": e2e, "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roofline,
            "cpu_baseline": cpu_baseline}
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

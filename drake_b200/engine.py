@@ -385,24 +385,37 @@ class PackedResults:
                ("grad_eM", np.float64, "f", 3), ("grad_eN", np.float64, "f", 3), ("elem_M", np.int32, "f", 1),
                ("elem_N", np.int32, "f", 1)]
 
-    def __init__(self, sizes: ResultSizes, allocator=None, capacity: Optional[ResultSizes] = None):
+    # What MultibodyPlant's discrete update reads from a ContactSurface: per-face area, normal,
+    # centroid, pressure at centroid, both gradients; per-surface ids, offsets, total area and centroid.
+    FACE_FIELDS = ("surf_scene", "surf_id_M", "surf_id_N", "surf_face_offset", "surf_vertex_offset", "surf_total_area",
+                   "surf_centroid", "surf_flags", "areas", "normals", "centroids", "pressure_at_centroid", "grad_eM",
+                   "grad_eN")
+
+    def __init__(self, sizes: ResultSizes, allocator=None, capacity: Optional[ResultSizes] = None, fields=None):
         """allocator(shape, dtype) -> ndarray lets callers supply pinned host memory; `capacity`
-        (>= sizes) allocates larger buffers once so they can be reused across queries."""
+        (>= sizes) allocates larger buffers once so they can be reused across queries; `fields` (names of
+        dbh_result_buffers members) restricts the copy-out to those arrays (the others stay NULL / empty)."""
         self.representation = sizes.representation
         self._alloc = allocator or (lambda shape, dtype: np.zeros(shape, dtype))
+        self._fields = None if fields is None else set(fields)
         cap = capacity or sizes
         self._full = {}
         counts = {"s": cap.num_surfaces, "s+1": cap.num_surfaces + 1, "v": cap.num_vertices, "f": cap.num_faces,
                   "d": cap.face_data_ints}
         for name, dtype, kind, width in self._LAYOUT:
-            shape = (counts[kind],) if width == 1 else (counts[kind], width)
-            self._full[name] = self._alloc(shape, dtype)
+            n = counts[kind] if self._wanted(name) else 0
+            shape = (n,) if width == 1 else (n, width)
+            self._full[name] = self._alloc(shape, dtype) if n else np.zeros(shape, dtype)
+        self._cap = {k: int(v) for k, v in counts.items()}
         self.resize(sizes)
 
+    def _wanted(self, name: str) -> bool:
+        return self._fields is None or name in self._fields
+
     def fits(self, sizes: ResultSizes) -> bool:
-        f = self._full
-        return (len(f["surf_scene"]) >= sizes.num_surfaces and len(f["vertices"]) >= sizes.num_vertices and
-                len(f["areas"]) >= sizes.num_faces and len(f["face_data"]) >= sizes.face_data_ints)
+        c = self._cap
+        return (c["s"] >= sizes.num_surfaces and c["v"] >= sizes.num_vertices and c["f"] >= sizes.num_faces and
+                c["d"] >= sizes.face_data_ints)
 
     def resize(self, sizes: ResultSizes):
         """Re-slices the views to the sizes of the latest query (no reallocation)."""
@@ -410,7 +423,7 @@ class PackedResults:
         counts = {"s": sizes.num_surfaces, "s+1": sizes.num_surfaces + 1, "v": sizes.num_vertices,
                   "f": sizes.num_faces, "d": sizes.face_data_ints}
         for name, _, kind, _ in self._LAYOUT:
-            setattr(self, name, self._full[name][:counts[kind]])
+            setattr(self, name, self._full[name][:counts[kind] if self._wanted(name) else 0])
 
     def nbytes(self) -> int:
         return sum(getattr(self, name).nbytes for name, _, _, _ in self._LAYOUT)
@@ -418,12 +431,13 @@ class PackedResults:
     def c_struct(self) -> ResultBuffers:
         b = ResultBuffers()
         for name, t in ResultBuffers._fields_:
-            setattr(b, name, _ptr(getattr(self, name), t))
+            if self._wanted(name):
+                setattr(b, name, _ptr(getattr(self, name), t))
         return b
 
     @property
     def num_surfaces(self) -> int:
-        return len(self.surf_scene)
+        return len(self.surf_face_offset) - 1 if self._wanted("surf_face_offset") else len(self.surf_scene)
 
     def surfaces(self) -> List[ContactSurface]:
         out = []
