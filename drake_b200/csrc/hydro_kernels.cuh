@@ -34,29 +34,7 @@ constexpr int kClipThreads = 128;
 constexpr double kCosAlphaDevice = -0.38268343236508973;  // cos(5*pi/8) as std::cos returns it
 
 // ---------------------------------------------------------------------------
-// Warp-aggregated append: every lane asks for `n` slots of a global list; one
-// atomic per warp. Returns the lane's first slot.
-__device__ __forceinline__ unsigned long long warp_append(unsigned long long* counter, int n) {
-  const unsigned mask = __activemask();
-  const int lane = threadIdx.x & 31;
-  if (mask != 0xffffffffu) {
-    // Partial warps only occur on exceptional paths: plain per-lane atomics.
-    return n ? atomicAdd(counter, (unsigned long long)n) : 0ull;
-  }
-  int incl = n;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int y = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += y;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned long long base = 0;
-  if (lane == 31 && total) base = atomicAdd(counter, (unsigned long long)total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  return base + (unsigned long long)(incl - n);
-}
-
-// Same for lists where every lane contributes 0 or 1 entries (ballot + popc).
+// Warp-aggregated append for lists where every lane contributes 0 or 1 entries (ballot + popc; one atomic per warp).
 __device__ __forceinline__ unsigned long long warp_append_flag(unsigned long long* counter, bool flag) {
   const unsigned m = __ballot_sync(0xffffffffu, flag);
   const int lane = threadIdx.x & 31;
@@ -676,10 +654,6 @@ __device__ __forceinline__ bool face_normal_along_gradient(D3 ngrad, D3 v) {
   return dot(ngrad, normalized(v)) > kCosAlphaDevice;
 }
 
-__device__ __forceinline__ double abs_sum(D3 v) { return fabs(v.x) + fabs(v.y) + fabs(v.z); }
-// sum_i |a_i| |b_i|: the scale of the rounding error of dot(a, b).
-__device__ __forceinline__ double abs_dot(D3 a, D3 b) { return (fabs(a.x * b.x) + fabs(a.y * b.y)) + fabs(a.z * b.z); }
-constexpr double kCullMargin = 1e-9;  // relative; rounding is ~1e-15 of the same scale
 
 // ---- tet-triangle ---------------------------------------------------------
 // Why the culls below cannot change the result. Every vertex the reference's
@@ -690,11 +664,10 @@ constexpr double kCullMargin = 1e-9;  // relative; rounding is ~1e-15 of the sam
 // by e, which is the tetrahedron scaled about its incentre by (1 + e/inradius)
 // and reaches at most e * amp beyond it (amp = longest edge / inradius, stored
 // in TetAux). Hence
-//  (R) three triangle vertices outside one face plane by 1e-9 L: empty;
+//  (R) three triangle vertices outside one face plane by a margin: empty;
 //  (N) tetrahedron separated from hull(tri) -- by the triangle's plane or by
 //      one of its three edge planes -- by more than 1e-11 (1 + amp) L: empty.
 // Slivers get a huge amp and are simply never culled by (N).
-constexpr double kHullMargin = 1e-11;
 
 // The culls run in fp32 on fp32 copies of the records (TetCullA/B, TriCull,
 // PairF32): a cull never produces a value, it only has to be certain, so its
@@ -918,7 +891,7 @@ __device__ __forceinline__ void tri_stage_b(const ClipArgs& a, Poly& P, int4 c, 
 // hull(tet0) up to e) and within e of the equilibrium plane; vertices that
 // survive tet1's four half spaces lie in tet1 inflated by e * amp1.
 //  (R) tet0 entirely on one side of the equilibrium plane (marching-tets code
-//      0 or 15), or entirely outside one face of tet1, by 1e-9: empty;
+//      0 or 15), or entirely outside one face of tet1, by a margin: empty;
 //  (N) tet1 entirely on one side of the equilibrium plane, or entirely outside
 //      one face of tet0, by more than 1e-11 (1 + amp1) L: empty.
 // Stage A. false = certainly no polygon.
@@ -1410,7 +1383,6 @@ struct ResultArrays {
 };
 
 // k_pack: one thread per staged polygon (up to 16 vertices: the exceptional path's capacity).
-constexpr int kPackMaxVerts = 2 * kMaxPolyVerts;
 struct PackArgs {
   PolySoup soup;
   const PairRec* pairs;
