@@ -154,9 +154,16 @@ def time_cpu_port(workload, rep: int, budget_s: float, threads: int):
     t, st = sc.batch_time(poses[:probe], rep, ho.MODE_REFERENCE_BVH, threads)
     per_scene = max(t / probe, 1e-7)
     n = int(min(len(poses), max(probe, budget_s / per_scene)))
-    t, st = sc.batch_time(poses[:n], rep, ho.MODE_REFERENCE_BVH, threads)
-    return {"seconds": t, "scenes": n, "stats": st, "surfaces_per_s": st["surfaces"] / t,
-            "element_pairs_per_s": st["element_pairs"] / t}
+    # When the whole workload takes less than the budget, repeat it (bounded) so the sample is seconds, not a blink.
+    passes = int(min(32, max(1, budget_s / max(per_scene * n, 1e-9)))) if n == len(poses) else 1
+    t, surfaces, pairs = 0.0, 0, 0
+    for _ in range(passes):
+        tp, st = sc.batch_time(poses[:n], rep, ho.MODE_REFERENCE_BVH, threads)
+        t += tp
+        surfaces += st["surfaces"]
+        pairs += st["element_pairs"]
+    return {"seconds": t, "scenes": n, "passes": passes, "stats": st, "surfaces_per_s": surfaces / t,
+            "element_pairs_per_s": pairs / t}
 
 
 def run_reference(args):
@@ -172,15 +179,16 @@ def run_reference(args):
     per_step_budget = min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup))
     for _ in range(args.warmup):
         time_cpu_port(wl, rep, per_step_budget, threads)
-    vals, pairs, secs, nscenes = [], [], [], 0
+    vals, pairs, secs, nscenes, npasses = [], [], [], 0, 1
     for _ in range(args.steps):
         r = time_cpu_port(wl, rep, per_step_budget, threads)
         vals.append(r["surfaces_per_s"])
         pairs.append(r["element_pairs_per_s"])
         secs.append(r["seconds"])
         nscenes = r["scenes"]
+        npasses = r["passes"]
     v = float(np.mean(vals))
-    sample = f"{nscenes} of {scenes} scenes of {wl.name} per step, all host threads"
+    sample = f"{npasses} x {nscenes} of {scenes} scenes of {wl.name} per step, all host threads"
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -459,7 +467,7 @@ def main():
         r = time_cpu_port(wl, rep, args.cpu_seconds, threads)
         r1 = time_cpu_port(wl, rep, min(5.0, args.cpu_seconds), 1)
         cpu_baseline = {"value": r["surfaces_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{r['scenes']} of {scenes} scenes of {wl.name}, {r['seconds']:.1f} s",
+                        "sample": f"{r['passes']} x {r['scenes']} of {scenes} scenes of {wl.name}, {r['seconds']:.1f} s",
                         "element_pairs_per_sec": r["element_pairs_per_s"],
                         "single_thread": {"value": r1["surfaces_per_s"], "scenes": r1["scenes"],
                                           "element_pairs_per_sec": r1["element_pairs_per_s"]}}
