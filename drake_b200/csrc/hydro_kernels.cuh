@@ -286,19 +286,19 @@ __device__ __forceinline__ Box32 load_box32(const Node32& n) {
   return Box32{n.c[0], n.c[1], n.c[2], n.h[0], n.h[1], n.h[2], n.l1};
 }
 
-template <int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks) k_traverse(TraverseArgs a) {
+template <int kMinBlocks, int kThreads>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_traverse(TraverseArgs a) {
   if (a.counters->error != 0) return;  // the query already failed; the host re-runs it
   // After an overflow the counter exceeds what was stored (the query fails
   // with DBH_ERR_CAPACITY); never read past the stored entries.
-  __shared__ BlockAppendSmem<8> sh;
+  __shared__ BlockAppendSmem<kThreads / 32> sh;
   const unsigned long long count = min(a.counters->frontier[a.level], a.out_capacity);
-  const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
   unsigned int tests = 0;
   // Whole blocks stay in the loop: the appends are block-wide. (A two-deep software pipeline with L1
   // prefetches, which pays in the filter kernel, was measured here and does not: the nodes of the batched
   // configs are L1-resident and the extra registers spill.)
-  for (unsigned long long base = (unsigned long long)blockIdx.x * 256; base < count; base += stride) {
+  for (unsigned long long base = (unsigned long long)blockIdx.x * kThreads; base < count; base += stride) {
     const unsigned long long i = base + threadIdx.x;
     int4 e = make_int4(0, 0, 0, 0);
     // Results of the up to four child tests as bit masks (bit q = jb * 2 + ja), so nothing is indexed
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_traverse(TraverseArgs a) {
     }
     const int n_leaf = __popc(leafm), n_next = __popc(pass) - n_leaf;
     const bool tri = e.w == kSoftRigid;
-    const Slots3 slots = block_append3<8>(&a.counters->frontier[a.level + 1], &a.counters->leaf_tri, &a.counters->leaf_tet,
+    const Slots3 slots = block_append3<kThreads / 32>(&a.counters->frontier[a.level + 1], &a.counters->leaf_tri, &a.counters->leaf_tet,
                                           n_next, tri ? n_leaf : 0, tri ? 0 : n_leaf, sh);
     unsigned long long s_next = slots.s0, s_leaf = tri ? slots.s1 : slots.s2;
     bool ok_next = true, ok_leaf = true;
