@@ -825,6 +825,11 @@ dbh_status dbh_batch_set_capacity(dbh_batch* b, int64_t max_bv_pairs, int64_t ma
 dbh_status dbh_batch_set_chunks(dbh_batch* b, int32_t num_chunks) {
   if (!b || num_chunks < 1) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_chunks: bad argument");
   b->num_chunks = std::min<int>(num_chunks, b->num_scenes);
+  // The lists must hold at least one entry per geometry pair of a chunk (k_pairs writes them unchecked).
+  const long long min_list = b->MaxPairsPerChunk();
+  b->cap_frontier = std::max(b->cap_frontier, min_list);
+  b->cap_tri = std::max(b->cap_tri, min_list);
+  b->cap_tet = std::max(b->cap_tet, min_list);
   return DBH_OK;
 }
 
