@@ -373,10 +373,11 @@ def test_work_lists_stay_within_the_memory_budget_by_chunking(ctx, monkeypatch):
         assert [(x.id_M, x.id_N) for x in got[s]] == [(x.id_M, x.id_N) for x in want]
         for g, w in zip(got[s], want):
             parity.compare_surface(g, w)
-    # Back to a single chunk by hand: the lists grow again (run() handles the capacity errors) and nothing changes.
+    # Asking for a single chunk by hand: the lists overflow, and since the budget still holds the batch splits
+    # itself again (run() handles the capacity errors); nothing changes in the results.
     batch.set_chunks(1)
     again = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KPOLYGON)
-    assert batch.num_chunks == 1
+    assert batch.num_chunks > 1
     for s in (0, 255, 511):
         for g, w in zip(_surface_digest(again[s]), _surface_digest(got[s])):
             assert g[:5] == w[:5]
