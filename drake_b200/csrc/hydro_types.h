@@ -171,6 +171,8 @@ struct Counters {
   unsigned long long surv_tri;      // tet-tri candidates that survived the conservative culls
   unsigned long long surv_tet;      // same, tet-tet
   unsigned long long big_surfaces;  // surfaces of this chunk summed by the whole grid
+  unsigned long long work_tri;      // next unclaimed 1024-entry chunk of the tet-tri leaf list (filter kernel)
+  unsigned long long work_tet;      // same, tet-tet
   // -- whole query
   unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
   unsigned long long cand_tri;      // tet-tri candidate pairs: leaf pairs that pass the exact predicate
