@@ -61,6 +61,10 @@ def lib():
                                        _ip, C.c_int, C.c_int]
         _lib.ho_soft_soft.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int64, C.c_int64, C.c_int,
                                       C.c_int, _ip, C.c_int]
+        _lib.ho_soft_mesh_rigid_half_space.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int64, C.c_int64, C.c_int]
+        _lib.ho_soft_half_space_rigid_mesh.argtypes = [C.c_int, _dp, C.c_double, C.c_double, _dp, C.c_int64, C.c_int64,
+                                                       C.c_int]
+        _lib.ho_scene_add_half_space.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int]
         _lib.ho_scene_add_geometry.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib.ho_scene_exclude_pair.argtypes = [C.c_int, C.c_int64, C.c_int64]
     return _lib
@@ -382,6 +386,27 @@ def soft_soft(mesh_M: VolumeMesh, field_M: VolumeField, mesh_N: VolumeMesh, fiel
     return _fetch_result(_check(h, "soft_soft"))
 
 
+def soft_mesh_rigid_half_space(mesh_S: VolumeMesh, field_S: VolumeField, X_WS, X_WR, id_S: int = 1, id_R: int = 2,
+                               rep: int = KPOLYGON) -> Optional[Surface]:
+    """ComputeContactSurfaceFromCompliantVolumeRigidHalfSpace (mesh_plane_intersection.cc:251-342): the half
+    space is z <= 0 of frame R. Faces carry (tet, -1) as their emitting element pair."""
+    h = lib().ho_soft_mesh_rigid_half_space(mesh_S.h, field_S.h, _pd(_d(X_WS)), _pd(_d(X_WR)), id_S, id_R, rep)
+    if h == -1:
+        return None
+    return _fetch_result(_check(h, "soft_mesh_rigid_half_space"))
+
+
+def soft_half_space_rigid_mesh(mesh_R: TriMesh, X_WS, pressure_scale: float, X_WR, id_S: int = 1, id_R: int = 2,
+                               rep: int = KPOLYGON, margin: float = 0.0) -> Optional[Surface]:
+    """ComputeContactSurfaceFromCompliantHalfSpaceRigidMesh (mesh_half_space_intersection.cc:338-418): the
+    compliant half space is z <= 0 of frame S. Faces carry (-1, triangle) as their emitting element pair."""
+    h = lib().ho_soft_half_space_rigid_mesh(mesh_R.h, _pd(_d(X_WS)), pressure_scale, margin, _pd(_d(X_WR)), id_S, id_R,
+                                            rep)
+    if h == -1:
+        return None
+    return _fetch_result(_check(h, "soft_half_space_rigid_mesh"))
+
+
 def candidates(mesh_A: VolumeMesh, mesh_B, X_AB, mode: int = MODE_BRUTE) -> Tuple[np.ndarray, int]:
     """Candidate element pairs [(a, b)] and the number of BV tests (mode 2 only)."""
     kind = 0 if isinstance(mesh_B, VolumeMesh) else 1
@@ -412,6 +437,12 @@ class Scene:
         self._keep += [mesh, fld]
         lib().ho_scene_add_geometry(self.h, gid, COMPLIANT, mesh.h, fld.h, -1, int(anchored))
 
+    def add_half_space(self, gid: int, compliant: bool = False, pressure_scale: float = 0.0, margin: float = 0.0,
+                       anchored: bool = False):
+        """HalfSpace shape (z <= 0 of its frame); compliant: pressure_scale = modulus / slab thickness."""
+        lib().ho_scene_add_half_space(self.h, gid, COMPLIANT if compliant else RIGID, pressure_scale, margin,
+                                      int(anchored))
+
     def exclude(self, a: int, b: int):
         lib().ho_scene_exclude_pair(self.h, a, b)
 
@@ -433,6 +464,10 @@ class Scene:
             raise RuntimeError("rigid-rigid contact is not supported by the hydroelastic model")
         if n == -2:
             raise RuntimeError("geometry without a hydroelastic representation")
+        if n == -4:
+            raise RuntimeError("contact between two half spaces is not allowed")
+        if n == -5:
+            raise RuntimeError("contact between two compliant geometries, one of which is a half space, is not allowed")
         _check(n, "scene_compute")
         surfaces = [_fetch_result(handles[k]) for k in range(n)]
         keys = ["geometry_pairs", "bv_tests", "element_pairs", "faces", "surfaces"]

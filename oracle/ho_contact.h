@@ -248,7 +248,11 @@ struct SurfaceResult {
 // (polygon_surface_mesh.cc:25-37,97-236), MeshFieldLinear ctor + Transform
 // (mesh_field_linear.h:218-229,377-383,502-509), TriangleSurfaceMesh
 // (triangle_surface_mesh.h:190-198,452-487).
-inline void MakeMeshAndFieldInWorld(MeshBuilder&& b, const Xform& X_WM, SurfaceResult* out) {
+// `already_in_world`: the builder's frame B is World (the half-space paths build their mesh in
+// World directly, mesh_plane_intersection.cc:236-249, mesh_half_space_intersection.cc:84-86): no
+// TransformVertices / field Transform step, so normals are not re-normalised either.
+inline void MakeMeshAndFieldInWorld(MeshBuilder&& b, const Xform& X_WM, SurfaceResult* out,
+                                    bool already_in_world = false) {
   out->rep = b.rep;
   std::vector<Vec3>& verts = b.vertices_B;
   if (b.rep == Representation::kPolygon) {
@@ -303,19 +307,21 @@ inline void MakeMeshAndFieldInWorld(MeshBuilder&& b, const Xform& X_WM, SurfaceR
       values_at_Mo[f] = b.pressures[v0] - dot(b.grad_e_per_face[f], verts[v0]);
     }
     // --- TransformVertices(X_WM) + field.Transform(X_WM).
-    for (Vec3& v : verts) v = X_WM * v;
-    for (Vec3& n : out->normals_W) n = normalized(X_WM.R * n);
+    if (!already_in_world) {
+      for (Vec3& v : verts) v = X_WM * v;
+      for (Vec3& n : out->normals_W) n = normalized(X_WM.R * n);
+    }
     out->centroids_W.reserve(nf);
-    for (const Vec3& c : centroids_M) out->centroids_W.push_back(X_WM * c);
-    out->centroid_W = X_WM * p_MSc;
+    for (const Vec3& c : centroids_M) out->centroids_W.push_back(already_in_world ? c : X_WM * c);
+    out->centroid_W = already_in_world ? p_MSc : X_WM * p_MSc;
     out->total_area = total_area;
     out->field_grad_W.resize(nf);
     out->field_at_Wo.resize(nf);
     out->e_centroid.resize(nf);
     for (int f = 0; f < nf; ++f) {
-      const Vec3 g = X_WM.R * b.grad_e_per_face[f];
+      const Vec3 g = already_in_world ? b.grad_e_per_face[f] : X_WM.R * b.grad_e_per_face[f];
       out->field_grad_W[f] = g;
-      out->field_at_Wo[f] = values_at_Mo[f] - dot(g, X_WM.p);
+      out->field_at_Wo[f] = already_in_world ? values_at_Mo[f] : values_at_Mo[f] - dot(g, X_WM.p);
       out->e_centroid[f] = dot(g, out->centroids_W[f]) + out->field_at_Wo[f];  // EvaluateCartesian(f, p_WC)
     }
     out->face_data = std::move(b.face_data);
@@ -340,9 +346,11 @@ inline void MakeMeshAndFieldInWorld(MeshBuilder&& b, const Xform& X_WM, SurfaceR
     }
     if (total_area != 0.) p_MSc = p_MSc / (3. * total_area);
     // --- TransformVertices(X_WM): normals are NOT renormalised for triangles.
-    for (Vec3& v : verts) v = X_WM * v;
-    for (Vec3& n : out->normals_W) n = X_WM.R * n;
-    out->centroid_W = X_WM * p_MSc;
+    if (!already_in_world) {
+      for (Vec3& v : verts) v = X_WM * v;
+      for (Vec3& n : out->normals_W) n = X_WM.R * n;
+    }
+    out->centroid_W = already_in_world ? p_MSc : X_WM * p_MSc;
     out->total_area = total_area;
     out->centroids_W.resize(nf);
     out->e_centroid.resize(nf);

@@ -18,6 +18,7 @@
 
 #include "ho_bvh.h"
 #include "ho_contact.h"
+#include "ho_halfspace.h"
 
 using namespace ho;
 
@@ -111,6 +112,11 @@ struct SceneGeom {
   int type;  // 0 undefined, 1 rigid, 2 compliant (proximity_properties.h:84-88)
   int vol, field, tri;
   bool anchored;
+  // Half space (shape_specification.h HalfSpace): no mesh; a compliant one has
+  // pressure_scale = hydroelastic_modulus / slab_thickness and a margin
+  // (hydroelastic_internal.h SoftHalfSpace).
+  bool half_space{false};
+  double pressure_scale{0}, margin{0};
 };
 struct Scene {
   std::vector<SceneGeom> geoms;  // kept sorted by id
@@ -124,7 +130,8 @@ struct SceneStats {
 };
 
 // Error codes mirror hydroelastic_calculator.h:39-57 failures.
-enum { kOk = 0, kErrUnsupported = -2, kErrRigidRigid = -3 };
+enum { kOk = 0, kErrUnsupported = -2, kErrRigidRigid = -3, kErrHalfSpaceHalfSpace = -4,
+       kErrCompliantHalfSpaceCompliantMesh = -5 };
 
 // Restates the engine loop for one scene. `poses` is indexed like scene.geoms.
 int ComputeScene(const Scene& scene, const double* poses, Representation rep, int mode, bool with_fallback,
@@ -144,7 +151,12 @@ int ComputeScene(const Scene& scene, const double* poses, Representation rep, in
       }
       if (A.type == 1 && B.type == 1) {
         // Rigid-rigid only matters when the geometry-level broad phase reports
-        // the pair; stand-in for FCL's tree: root boxes under the relative pose.
+        // the pair; stand-in for FCL's tree: root boxes under the relative pose
+        // (a half space's box is unbounded: always reported).
+        if (A.half_space || B.half_space) {
+          if (with_fallback) continue;
+          return kErrRigidRigid;
+        }
         TriAsset& ta = *g_tris[A.tri];
         TriAsset& tb = *g_tris[B.tri];
         const Xform X_AB = InvertAndCompose(X_WA, X_WB);
@@ -155,7 +167,33 @@ int ComputeScene(const Scene& scene, const double* poses, Representation rep, in
       if (stats) ++stats->geometry_pairs;
       SurfaceResult res;
       bool non_null = false;
-      if (A.type == 2 && B.type == 2) {
+      if (A.half_space || B.half_space) {
+        // hydroelastic_calculator.cc:113-123,145-147 (failures) and :25-41 (the two supported cases).
+        int failure = 0;
+        if (A.half_space && B.half_space) failure = kErrHalfSpaceHalfSpace;
+        else if (A.type == 2 && B.type == 2) failure = kErrCompliantHalfSpaceCompliantMesh;
+        if (failure) {
+          if (stats) --stats->geometry_pairs;
+          if (with_fallback) continue;
+          return failure;
+        }
+        const bool A_is_rigid = A.type == 1;
+        const SceneGeom& S = A_is_rigid ? B : A;
+        const SceneGeom& R = A_is_rigid ? A : B;
+        const Xform& X_WS = A_is_rigid ? X_WB : X_WA;
+        const Xform& X_WR = A_is_rigid ? X_WA : X_WB;
+        if (S.half_space) {
+          TriAsset& tr = *g_tris[R.tri];
+          if (stats) stats->element_pairs += tr.mesh.num_elements();
+          non_null = ContactSurfaceFromCompliantHalfSpaceRigidMesh(S.id, X_WS, S.pressure_scale, R.id, tr.mesh, X_WR, rep,
+                                                                   S.margin, &res);
+        } else {
+          VolAsset& vs = *g_vols[S.vol];
+          if (stats) stats->element_pairs += vs.mesh.num_elements();
+          non_null = ContactSurfaceFromCompliantVolumeRigidHalfSpace(S.id, vs.mesh, *g_fields[S.field], X_WS, R.id, X_WR,
+                                                                     rep, &res);
+        }
+      } else if (A.type == 2 && B.type == 2) {
         VolAsset& va = *g_vols[A.vol];
         VolAsset& vb = *g_vols[B.vol];
         const Xform X_MN = InvertAndCompose(X_WA, X_WB);
@@ -497,6 +535,30 @@ int ho_soft_soft(int volM, int fieldM, int volN, int fieldN, const double* X_WM,
   HO_CATCH(-2)
 }
 
+// The half-space special cases of CalcRigidCompliant (hydroelastic_calculator.cc:25-41).
+int ho_soft_mesh_rigid_half_space(int vol, int field, const double* X_WS, const double* X_WR, int64_t id_S, int64_t id_R,
+                                  int rep) {
+  HO_TRY
+  SurfaceResult res;
+  if (!ContactSurfaceFromCompliantVolumeRigidHalfSpace(id_S, g_vols[vol]->mesh, *g_fields[field], Xform::FromArray(X_WS),
+                                                       id_R, Xform::FromArray(X_WR), static_cast<Representation>(rep),
+                                                       &res))
+    return -1;
+  return AddResult(std::move(res));
+  HO_CATCH(-2)
+}
+int ho_soft_half_space_rigid_mesh(int tri, const double* X_WS, double pressure_scale, double margin, const double* X_WR,
+                                  int64_t id_S, int64_t id_R, int rep) {
+  HO_TRY
+  SurfaceResult res;
+  if (!ContactSurfaceFromCompliantHalfSpaceRigidMesh(id_S, Xform::FromArray(X_WS), pressure_scale, id_R,
+                                                     g_tris[tri]->mesh, Xform::FromArray(X_WR),
+                                                     static_cast<Representation>(rep), margin, &res))
+    return -1;
+  return AddResult(std::move(res));
+  HO_CATCH(-2)
+}
+
 // info[0..7] = rep, nfaces, nverts, nfacedata (poly) or 3*ntris, has_grad_eM, has_grad_eN, -, -
 int ho_result_info(int h, int64_t* ids2, int* info8) {
   const SurfaceResult& r = *g_results[h];
@@ -565,6 +627,18 @@ int ho_scene_add_geometry(int scene, int64_t id, int type, int vol, int field, i
   s.geoms.insert(it, g);
   return pos;
 }
+// A half space: type 1 rigid or 2 compliant (pressure_scale, margin).
+int ho_scene_add_half_space(int scene, int64_t id, int type, double pressure_scale, double margin, int anchored) {
+  Scene& s = *g_scenes[scene];
+  SceneGeom g{id, type, -1, -1, -1, anchored != 0};
+  g.half_space = true;
+  g.pressure_scale = pressure_scale;
+  g.margin = margin;
+  auto it = std::lower_bound(s.geoms.begin(), s.geoms.end(), g, [](const SceneGeom& a, const SceneGeom& b) { return a.id < b.id; });
+  const int pos = static_cast<int>(it - s.geoms.begin());
+  s.geoms.insert(it, g);
+  return pos;
+}
 int ho_scene_num_geometries(int scene) { return static_cast<int>(g_scenes[scene]->geoms.size()); }
 void ho_scene_geometry_ids(int scene, int64_t* ids) {
   const Scene& s = *g_scenes[scene];
@@ -611,6 +685,7 @@ int ho_scene_batch_time(int scene, int nscenes, const double* poses, int rep, in
   const int G = static_cast<int>(sc.geoms.size());
   // Warm the lazily built per-asset structures outside the timed region.
   for (const SceneGeom& g : sc.geoms) {
+    if (g.half_space) continue;
     if (g.type == 2) { Boxes(*g_vols[g.vol]); RefBvh(*g_vols[g.vol]); }
     if (g.type == 1) { Boxes(*g_tris[g.tri]); RefBvh(*g_tris[g.tri]); Leaf1Bvh(*g_tris[g.tri]); }
   }

@@ -1,0 +1,205 @@
+"""Known-answer tests that pin the oracle's half-space special cases to the reference's
+own tests: geometry/proximity/test/mesh_plane_intersection_test.cc and mesh_half_space_intersection_test.cc.
+CPU only."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ho
+
+EPS = np.finfo(float).eps
+
+
+def trivial_volume_mesh():
+    # mesh_plane_intersection_test.cc:44-65 (minimum_vertices)
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, -1]], float)
+    return ho.VolumeMesh.from_arrays(v, [[0, 1, 2, 3], [0, 2, 1, 4]])
+
+
+def box_mesh(X_FB):
+    # mesh_half_space_intersection_test.cc:44-92 (CreateBoxMesh)
+    R, p = ho.xform_parts(X_FB)
+    v = np.array([[-1, -1, -1], [-1, -1, 1], [-1, 1, -1], [-1, 1, 1], [1, -1, -1], [1, -1, 1], [1, 1, -1], [1, 1, 1]], float)
+    v = v @ R.T + p
+    faces = [[4, 6, 7], [7, 5, 4], [1, 3, 2], [2, 0, 1], [2, 3, 7], [7, 6, 2], [4, 5, 1], [1, 0, 4], [7, 3, 1], [1, 5, 7],
+             [4, 0, 2], [2, 6, 4]]
+    return ho.TriMesh.from_arrays(v, faces)
+
+
+def test_compliant_volume_rigid_half_space():
+    # mesh_plane_intersection_test.cc:1217-1316 (CompliantVolumeRigidHalfSpace)
+    mesh = trivial_volume_mesh()
+    fld = ho.VolumeField.from_values(mesh, [0.25, 0.5, 0.75, 1, -1])
+    X_WS = ho.xform(ho.angle_axis_matrix(math.pi / 3, np.array([-1, 1, 1]) / math.sqrt(3)), [1.25, 2.5, -3.75])
+    X_SR = ho.xform(ho.angle_axis_matrix(math.pi / 2, [0, 1, 0]), [0.5, 2.25, -1.25])
+    X_WR = ho.compose(X_WS, X_SR)
+    k_eps = 16 * EPS
+    R_WS, _ = ho.xform_parts(X_WS)
+    Sx_W = R_WS[:, 0]
+    # Case 1: six triangles, normals along Sx, vertices at x = 0.5 in S.
+    s = ho.soft_mesh_rigid_half_space(mesh, fld, X_WS, X_WR, 1, 2, ho.KTRIANGLE)
+    assert s is not None and s.grad_eM is not None and s.grad_eN is None
+    assert (s.id_M, s.id_N) == (1, 2)
+    assert s.num_faces == 6
+    np.testing.assert_allclose(s.normals[0], Sx_W, atol=k_eps)
+    X_SW = ho.invert_and_compose(X_WS, ho.IDENTITY)
+    R_SW, p_SW = ho.xform_parts(X_SW)
+    p_SV = s.vertices @ R_SW.T + p_SW
+    np.testing.assert_allclose(p_SV[:, 0], 0.5, atol=k_eps)
+    # Case 2: mesh moved out of intersection.
+    assert ho.soft_mesh_rigid_half_space(mesh, fld, ho.compose(X_WS, ho.xform(None, [-0.51, 0, 0])), X_WR, 1, 2,
+                                         ho.KTRIANGLE) is None
+    # Case 3: plane moved out of intersection.
+    R_SR, _ = ho.xform_parts(X_SR)
+    assert ho.soft_mesh_rigid_half_space(mesh, fld, X_WS, ho.compose(X_WS, ho.xform(R_SR, [1.01, 0, 0])), 1, 2,
+                                         ho.KTRIANGLE) is None
+    # Case 4: reversed ids flip the normals.
+    s = ho.soft_mesh_rigid_half_space(mesh, fld, X_WS, X_WR, 2, 1, ho.KTRIANGLE)
+    assert (s.id_M, s.id_N) == (1, 2)
+    np.testing.assert_allclose(s.normals[0], -Sx_W, atol=k_eps)
+    assert s.grad_eM is None and s.grad_eN is not None
+    # Case 5: polygons: one triangle per tetrahedron, vertices welded along the shared face.
+    s = ho.soft_mesh_rigid_half_space(mesh, fld, X_WS, X_WR, 1, 2, ho.KPOLYGON)
+    assert s.rep == ho.KPOLYGON and s.num_faces == 2
+    assert len(s.vertices) == 4  # 2 x 3 cut edges, two of them shared (cut_edges, mesh_plane_intersection.cc:205-231)
+    # Pressure is interpolated along the cut edges (mesh_plane_intersection.cc:224-227): all cuts are at t = 0.5
+    # on edges out of vertices 1 / from x = 0 to x = 1.
+    want = sorted([(0.25 + 0.5) / 2, (0.75 + 0.5) / 2, (1 + 0.5) / 2, (-1 + 0.5) / 2])
+    np.testing.assert_allclose(sorted(s.pressures), want, atol=k_eps)
+
+
+def test_slice_normals_follow_the_plane_normal():
+    # mesh_plane_intersection_test.cc:565-731 (Triangle / QuadIntersections): whatever the sign pattern, the
+    # polygon's winding gives a normal along the plane normal (and the surface's faces point out of the half
+    # space into the mesh, contact_surface.h:182).
+    mesh = ho.VolumeMesh.from_arrays([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], [[0, 1, 2, 3]])
+    fld = ho.VolumeField.from_values(mesh, [0.0, 1.0, 2.0, 3.0])
+    rng = np.random.default_rng(7)
+    seen = set()
+    for _ in range(200):
+        n = rng.normal(size=3)
+        n /= np.linalg.norm(n)
+        # Frame R with z = n through a random point inside the tetrahedron.
+        a = np.cross(n, [1, 0, 0]) if abs(n[0]) < 0.9 else np.cross(n, [0, 1, 0])
+        a /= np.linalg.norm(a)
+        R = np.column_stack([a, np.cross(n, a), n])
+        w = rng.dirichlet(np.ones(4))
+        p = w @ mesh.verts
+        s = ho.soft_mesh_rigid_half_space(mesh, fld, ho.IDENTITY, ho.xform(R, p), 1, 2, ho.KPOLYGON)
+        assert s is not None and s.num_faces == 1
+        seen.add(len(s.polygons()[0]))
+        np.testing.assert_allclose(s.normals[0], n, atol=1e-12)
+        # The field on the surface is the tetrahedron's linear field.
+        g = np.array([1.0, 2.0, 3.0])
+        np.testing.assert_allclose(s.pressures, s.vertices @ g, atol=1e-12)
+        np.testing.assert_allclose(s.grad_eM[0], g, atol=1e-12)
+    assert seen == {3, 4}
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+def test_half_space_against_box_mesh_counts(rep):
+    # mesh_half_space_intersection_test.cc:886-1007 (ComputeContactSurfaceInvocation): the half space's boundary
+    # passes through the box centre: 10 polygons over 12 welded vertices; triangles: +24 faces, +10 vertices.
+    X_WF = ho.xform(ho.angle_axis_matrix(math.pi / 7, np.array([1, 2, 3]) / math.sqrt(14)), [-0.25, 0.5, 0.75])
+    X_FB = ho.xform(ho.rpy_matrix(math.pi / 4, math.pi / 4, math.pi / 4), [1.0, 2.0, 3.0])
+    mesh_F = box_mesh(X_FB)
+    X_WH = ho.compose(X_WF, X_FB)  # the half space is z <= 0 of B
+    s = ho.soft_half_space_rigid_mesh(mesh_F, X_WH, 17.0, X_WF, id_S=2, id_R=1, rep=rep)
+    assert s is not None
+    if rep == ho.KPOLYGON:
+        assert (len(s.vertices), s.num_faces) == (12, 10)
+        assert sorted(len(p) for p in s.polygons()) == [3] * 6 + [4] * 4
+    else:
+        assert (len(s.vertices), s.num_faces) == (22, 34)
+    # M = mesh (id 1), N = half space (id 2): the half space's gradient is grad_eN.
+    assert (s.id_M, s.id_N) == (1, 2) and s.grad_eM is None
+    R_WH, p_WH = ho.xform_parts(X_WH)
+    grad_p_W = -17.0 * R_WH[:, 2]
+    np.testing.assert_allclose(s.grad_eN, np.tile(grad_p_W, (s.num_faces, 1)), atol=1e-13)
+    # Pressure = -17 * signed distance; the deepest vertices are one unit below the boundary.
+    depth = -(s.vertices - p_WH) @ R_WH[:, 2]
+    np.testing.assert_allclose(s.pressures, 17.0 * depth, atol=1e-12)
+    assert abs(s.pressures.max() - 17.0) < 1e-12 and s.pressures.min() > -1e-12
+    # Area: four side faces of height 1 and the bottom: 4 * 2 + 4.
+    np.testing.assert_allclose(s.total_area, 12.0, atol=1e-12)
+
+
+def test_compliant_half_space_rigid_mesh_double_valued():
+    # mesh_half_space_intersection_test.cc:1030-1104
+    X_WF = ho.xform(ho.angle_axis_matrix(math.pi / 7, np.array([1, 2, 3]) / math.sqrt(14)), [-0.25, 0.5, 0.75])
+    X_FB = ho.xform(ho.rpy_matrix(math.pi / 4, math.pi / 4, math.pi / 4), [1.0, 2.0, 3.0])
+    mesh_F = box_mesh(X_FB)
+    for rep in (ho.KTRIANGLE, ho.KPOLYGON):
+        assert ho.soft_half_space_rigid_mesh(mesh_F, ho.xform(None, [0, 0, -5]), 1.5, X_WF, rep=rep) is None
+    X_BH = ho.xform(ho.angle_axis_matrix(math.pi * 0.027, np.array([1, 1, 0]) / math.sqrt(2)), [0.1, -0.05, 0.075])
+    X_WH = ho.compose(ho.compose(X_WF, X_FB), X_BH)
+    for rep in (ho.KTRIANGLE, ho.KPOLYGON):
+        s = ho.soft_half_space_rigid_mesh(mesh_F, X_WH, 1.5, X_WF, rep=rep)
+        assert s is not None and s.rep == rep
+
+
+def test_compliant_half_space_margin():
+    # mesh_half_space_intersection_test.cc:1107-1186 (Margin): the box only reaches into the margin layer.
+    X_WF = ho.xform(ho.angle_axis_matrix(math.pi / 7, np.array([1, 2, 3]) / math.sqrt(14)), [-0.25, 0.5, 0.75])
+    R_WF, p_WF = ho.xform_parts(X_WF)
+    mesh_F = box_mesh(ho.xform(None, [0, 0, 1.0]))
+    pressure_scale, margin = 1.5, 0.012
+    X_WH = ho.xform(R_WF, p_WF + (-margin / 2.0) * R_WF[:, 2])
+    for rep in (ho.KTRIANGLE, ho.KPOLYGON):
+        s = ho.soft_half_space_rigid_mesh(mesh_F, X_WH, pressure_scale, X_WF, rep=rep, margin=margin)
+        assert s is not None and s.rep == rep
+        assert abs(s.pressures.min() - (-margin * pressure_scale)) <= 4 * EPS
+        assert abs(s.pressures.max() - (-margin * pressure_scale / 2.0)) <= 4 * EPS
+
+
+def test_compliant_half_space_culls_back_faces():
+    # mesh_half_space_intersection_test.cc:1192-1290 (BackfaceCulling): a box fully inside the half space
+    # contributes only the faces whose normals are within 5 pi / 8 of the pressure gradient (-Sz).
+    mesh = box_mesh(ho.IDENTITY)
+    X_WS = ho.xform(None, [0, 0, 5.0])  # boundary at z = 5: the whole box is inside
+    s = ho.soft_half_space_rigid_mesh(mesh, X_WS, 2.0, ho.IDENTITY, rep=ho.KPOLYGON)
+    assert s is not None
+    # -Z face (cos 1) and the four side faces (cos 0) pass; the +Z face (cos -1) is culled.
+    assert s.num_faces == 10
+    assert sorted(set(s.elem_second)) == [0, 1, 2, 3, 4, 5, 6, 7, 10, 11]
+    assert set(s.elem_first) == {-1}
+
+
+def test_scene_dispatch_with_half_spaces():
+    # hydroelastic_calculator_test.cc:373-460 (dispatch), :576-631 (failures), proximity_engine.cc:1361-1390.
+    ball = ho.VolumeMesh.sphere(0.5, 0.25)
+    fld = ho.VolumeField.sphere(ball, 0.5, 1e8)
+    rigid_ball = ball.to_surface()
+    pose_ball = ho.xform(None, [0, 0, 0.3])
+    sc = ho.Scene()
+    sc.add_compliant(1, ball, fld)
+    sc.add_half_space(2)  # rigid
+    surfaces, stats = sc.compute([pose_ball, ho.IDENTITY])
+    assert len(surfaces) == 1 and (surfaces[0].id_M, surfaces[0].id_N) == (1, 2)
+    assert stats["element_pairs"] == len(ball.tets)
+    assert sc.compute([ho.xform(None, [0, 0, 0.6]), ho.IDENTITY])[0] == []
+    sc = ho.Scene()
+    sc.add_rigid(1, rigid_ball)
+    sc.add_half_space(2, compliant=True, pressure_scale=1e8 / 0.25)
+    surfaces, _ = sc.compute([pose_ball, ho.IDENTITY], rep=ho.KTRIANGLE)
+    assert len(surfaces) == 1 and surfaces[0].grad_eN is not None and surfaces[0].grad_eM is None
+    # Failures: two half spaces; compliant half space x compliant mesh; rigid half space x rigid mesh.
+    sc = ho.Scene()
+    sc.add_half_space(1)
+    sc.add_half_space(2, compliant=True, pressure_scale=1.0)
+    with pytest.raises(RuntimeError, match="two half spaces"):
+        sc.compute([ho.IDENTITY, ho.IDENTITY])
+    assert sc.compute([ho.IDENTITY, ho.IDENTITY], with_fallback=True)[0] == []
+    sc = ho.Scene()
+    sc.add_compliant(1, ball, fld)
+    sc.add_half_space(2, compliant=True, pressure_scale=1.0)
+    with pytest.raises(RuntimeError, match="one of which is a half space"):
+        sc.compute([pose_ball, ho.IDENTITY])
+    sc = ho.Scene()
+    sc.add_rigid(1, rigid_ball)
+    sc.add_half_space(2)
+    with pytest.raises(RuntimeError, match="rigid-rigid"):
+        sc.compute([pose_ball, ho.IDENTITY])
