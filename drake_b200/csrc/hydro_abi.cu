@@ -65,7 +65,11 @@ struct HostAsset {
   std::vector<TetRec> tets;
   std::vector<TetAux> aux;
   std::vector<TriRec> tris;
+  std::vector<double> tet_vp;   // compliant meshes: the four vertex pressures of every tetrahedron
   std::vector<BvhNode> nodes;   // links local to this asset; rebased into the pool on upload
+  // HalfSpace shape (dbh_register_half_space): no elements, no nodes.
+  bool half_space{false};
+  double pressure_scale{0}, margin{0};
   // First pool index of this asset's elements (tet pool or tri pool) and nodes.
   int elem_base{0};
   int node_base{0};
@@ -179,6 +183,7 @@ struct dbh_context {
   DevBuf<TetCullB> d_cull_b;
   DevBuf<TriCull> d_cull_tri;
   DevBuf<ElemBox> d_ebox_tet, d_ebox_tri;
+  DevBuf<double> d_tet_vp;   // [4 * pool tet] vertex pressures (the half-space slicer interpolates them)
   size_t uploaded_assets{0};
   long long up_tets{0}, up_tris{0}, up_nodes{0};
 
@@ -211,6 +216,7 @@ struct dbh_context {
     bool regrown = false;
     CUDA_OK(grow(d_tets, num_tets, &regrown));
     CUDA_OK(grow(d_aux, num_tets, &regrown));
+    CUDA_OK(grow(d_tet_vp, 4 * num_tets, &regrown));
     CUDA_OK(grow(d_tris, num_tris, &regrown));
     CUDA_OK(grow(d_cull_a, num_tets, &regrown));
     CUDA_OK(grow(d_cull_b, num_tets, &regrown));
@@ -224,8 +230,11 @@ struct dbh_context {
     std::vector<Node32> rebased32;
     for (size_t i = first; i < assets.size(); ++i) {
       const HostAsset& a = *assets[i];
+      if (a.half_space) continue;
       if (a.type == DBH_COMPLIANT) {
         CUDA_OK(cudaMemcpy(d_tets.p + a.elem_base, a.tets.data(), a.tets.size() * sizeof(TetRec),
+                           cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_tet_vp.p + 4ll * a.elem_base, a.tet_vp.data(), a.tet_vp.size() * sizeof(double),
                            cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpy(d_aux.p + a.elem_base, a.aux.data(), a.aux.size() * sizeof(TetAux), cudaMemcpyHostToDevice));
         // fp32 copies for the cull stage.
@@ -328,6 +337,14 @@ struct dbh_batch {
   int num_chunks{1};
   size_t work_budget_bytes{0};
   std::vector<int> scene_first_pair;
+
+  // Half-space pairs (kSoftMeshRigidPlane / kSoftPlaneRigidMesh): their indices in the pair list (ascending) and
+  // the exclusive prefix of the element counts of their one mesh; per geometry, the parameters of a compliant half space.
+  std::vector<int> plane_pairs;
+  std::vector<long long> plane_elem_off;
+  DevBuf<int> d_plane_pairs;
+  DevBuf<long long> d_plane_elem_off;
+  DevBuf<double> d_geom_hs;
 
   DevBuf<PairRec> d_pairs;
   DevBuf<Xf> d_poses_own;
@@ -491,6 +508,7 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
   a->num_elements = nt;
   a->tets.resize(nt);
   a->aux.resize(nt);
+  a->tet_vp.resize(4 * static_cast<size_t>(nt));
   constexpr double kEps = std::numeric_limits<double>::epsilon();
   for (int e = 0; e < nt; ++e) {
     TetRec& r = a->tets[e];
@@ -500,6 +518,7 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
       const int vi = tets[4 * e + i];
       v[i] = load3(verts + 3 * vi);
       u[i] = pressure[vi];
+      a->tet_vp[4 * static_cast<size_t>(e) + i] = u[i];
       r.v[i][0] = v[i].x;
       r.v[i][1] = v[i].y;
       r.v[i][2] = v[i].z;
@@ -605,6 +624,23 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* v
   return DBH_OK;
 }
 
+dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressure_scale, double margin,
+                                   int32_t* asset_out) {
+  if (!ctx || !asset_out || (type != DBH_RIGID && type != DBH_COMPLIANT))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "register_half_space: bad argument");
+  if (type == DBH_COMPLIANT && !(pressure_scale > 0))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "register_half_space: a compliant half space needs pressure_scale > 0");
+  auto a = std::make_unique<HostAsset>();
+  a->type = type;
+  a->half_space = true;
+  a->pressure_scale = type == DBH_COMPLIANT ? pressure_scale : 0.0;
+  a->margin = type == DBH_COMPLIANT ? margin : 0.0;
+  ctx->Place(a.get());
+  ctx->assets.push_back(std::move(a));
+  *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
+  return DBH_OK;
+}
+
 dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out) {
   if (!ctx || !out || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_get_info: bad argument");
@@ -613,6 +649,10 @@ dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* o
   out->type = a.type;
   out->num_vertices = a.num_vertices;
   out->num_elements = a.num_elements;
+  if (a.half_space) {
+    out->is_half_space = 1;
+    return DBH_OK;
+  }
   out->num_bvh_nodes = static_cast<int>(a.nodes.size()) - 1;
   out->bvh_height = a.height;
   for (int k = 0; k < 3; ++k) {
@@ -676,7 +716,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   std::sort(excl.begin(), excl.end());
   // Static geometry-pair list in (scene, id_M, id_N) order.
   int max_levels = 1;
-  long long est_tri = 0, est_tet = 0;
+  long long est_tri = 0, est_tet = 0, est_plane = 0;
   b->scene_first_pair.assign(num_scenes + 1, 0);
   for (int s = 0; s < num_scenes; ++s) {
     b->scene_first_pair[s] = static_cast<int>(b->pairs.size());
@@ -698,26 +738,45 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
         const int tb = geom_asset[gb] < 0 ? DBH_UNDEFINED : ctx->assets[geom_asset[gb]]->type;
         pr.geom_a = ga;
         pr.geom_b = gb;
+        const bool ha = ta != DBH_UNDEFINED && ctx->assets[geom_asset[ga]]->half_space;
+        const bool hb = tb != DBH_UNDEFINED && ctx->assets[geom_asset[gb]]->half_space;
         if (ta == DBH_UNDEFINED || tb == DBH_UNDEFINED) {
           pr.kind = kUnsupported;
           ++b->info.num_unsupported_pairs;
         } else if (ta == DBH_RIGID && tb == DBH_RIGID) {
-          pr.kind = kRigidRigid;
+          pr.kind = (ha || hb) ? kRigidRigidPlane : kRigidRigid;
           ++b->info.num_rigid_rigid_pairs;
+        } else if (ha && hb) {
+          pr.kind = kHalfSpaceHalfSpace;  // hydroelastic_calculator.cc:113-118,145-147
+          ++b->info.num_rejected_half_space_pairs;
         } else if (ta == DBH_COMPLIANT && tb == DBH_COMPLIANT) {
-          pr.kind = kSoftSoft;  // smaller id is M / field0 (hydroelastic_calculator.cc:109-111)
-          ++b->info.num_soft_soft_pairs;
+          if (ha || hb) {
+            pr.kind = kSoftPlaneSoftMesh;  // kCompliantHalfSpaceCompliantMesh (:120-123)
+            ++b->info.num_rejected_half_space_pairs;
+          } else {
+            pr.kind = kSoftSoft;  // smaller id is M / field0 (hydroelastic_calculator.cc:109-111)
+            ++b->info.num_soft_soft_pairs;
+          }
         } else {
-          pr.kind = kSoftRigid;  // built as (S, R), swapped when id_R < id_S
+          // Rigid-compliant, built as (S, R), swapped when id_R < id_S; CalcRigidCompliant picks the
+          // half-space special cases by shape (hydroelastic_calculator.cc:25-41).
           if (ta == DBH_RIGID) {
             pr.geom_a = gb;
             pr.geom_b = ga;
             pr.swapped = 1;
           }
-          ++b->info.num_soft_rigid_pairs;
+          const bool soft_is_half_space = ta == DBH_RIGID ? hb : ha;
+          if (ha || hb) {
+            pr.kind = soft_is_half_space ? kSoftPlaneRigidMesh : kSoftMeshRigidPlane;
+            ++b->info.num_half_space_pairs;
+          } else {
+            pr.kind = kSoftRigid;
+            ++b->info.num_soft_rigid_pairs;
+          }
         }
         pr.root_a = pr.root_b = -1;
-        if (pr.kind != kUnsupported) {
+        pr.elem_base_a = pr.elem_base_b = -1;
+        if (pr.kind <= kRigidRigid) {
           const HostAsset& A = *ctx->assets[geom_asset[pr.geom_a]];
           const HostAsset& B = *ctx->assets[geom_asset[pr.geom_b]];
           pr.root_a = A.node_base + 1;
@@ -729,6 +788,14 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
             max_levels = std::max(max_levels, std::max(A.height, B.height) + 1);
             (pr.kind == kSoftRigid ? est_tri : est_tet) += 2ll * (A.num_elements + B.num_elements);
           }
+        } else if (pr.kind == kSoftMeshRigidPlane || pr.kind == kSoftPlaneRigidMesh) {
+          // The one mesh of the pair: the compliant volume (a) or the rigid surface (b).
+          const HostAsset& M = *ctx->assets[geom_asset[pr.kind == kSoftMeshRigidPlane ? pr.geom_a : pr.geom_b]];
+          (pr.kind == kSoftMeshRigidPlane ? pr.root_a : pr.root_b) = M.node_base + 1;
+          (pr.kind == kSoftMeshRigidPlane ? pr.elem_base_a : pr.elem_base_b) = M.elem_base;
+          b->plane_pairs.push_back(static_cast<int>(b->pairs.size()));
+          b->plane_elem_off.push_back(est_plane);
+          est_plane += M.num_elements;
         }
         b->pairs.push_back(pr);
       }
@@ -736,6 +803,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   }
   b->num_pairs = static_cast<int>(b->pairs.size());
   b->scene_first_pair[num_scenes] = b->num_pairs;
+  b->plane_elem_off.push_back(est_plane);
   b->info.num_scenes = num_scenes;
   b->info.num_geometries = b->num_geoms;
   b->info.num_geometry_pairs = b->num_pairs;
@@ -767,7 +835,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
     b->num_chunks = std::min(num_scenes, b->num_chunks * 2);
   }
   {
-    const long long est = clampest(est_tri + est_tet);
+    const long long est = clampest(est_tri + est_tet + est_plane);
     b->cap_faces = est / 2;
     b->cap_verts = est;
   }
@@ -804,6 +872,22 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   CUDA_OK(b->r_surf_flags.alloc(np));
   const int scan_blocks = (b->num_pairs + kScanTile - 1) / kScanTile;
   CUDA_OK(b->d_block_sums.alloc(3 * std::max(1, scan_blocks)));
+  if (!b->plane_pairs.empty()) {
+    CUDA_OK(b->d_plane_pairs.alloc(b->plane_pairs.size()));
+    CUDA_OK(cudaMemcpy(b->d_plane_pairs.p, b->plane_pairs.data(), b->plane_pairs.size() * sizeof(int),
+                       cudaMemcpyHostToDevice));
+    CUDA_OK(b->d_plane_elem_off.alloc(b->plane_elem_off.size()));
+    CUDA_OK(cudaMemcpy(b->d_plane_elem_off.p, b->plane_elem_off.data(), b->plane_elem_off.size() * sizeof(long long),
+                       cudaMemcpyHostToDevice));
+    std::vector<double> hs(2 * static_cast<size_t>(b->num_geoms), 0.0);
+    for (int g = 0; g < b->num_geoms; ++g)
+      if (geom_asset[g] >= 0) {
+        hs[2 * g] = ctx->assets[geom_asset[g]]->pressure_scale;
+        hs[2 * g + 1] = ctx->assets[geom_asset[g]]->margin;
+      }
+    CUDA_OK(b->d_geom_hs.alloc(hs.size()));
+    CUDA_OK(cudaMemcpy(b->d_geom_hs.p, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   *out = b.release();
   return DBH_OK;
 }
@@ -1033,6 +1117,23 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     su.scene_stats = reinterpret_cast<long long*>(scene_stats_dev);
     su.big_list = b->d_big_list.p;
     su.counters = b->d_counters.p;
+    PlaneArgs pl{};
+    pl.pairs = b->d_pairs.p;
+    pl.poses = b->d_poses;
+    pl.pair_X = b->d_pair_X.p;
+    pl.pools = ctx->pools();
+    pl.tet_vp = ctx->d_tet_vp.p;
+    pl.plane_pairs = b->d_plane_pairs.p;
+    pl.plane_elem_off = b->d_plane_elem_off.p;
+    pl.geom_hs = b->d_geom_hs.p;
+    pl.pair_polys = b->d_pair_polys.p;
+    pl.pair_verts = b->d_pair_verts.p;
+    pl.pair_cursor = b->d_pair_cursor.p;
+    pl.poly_off = b->d_poly_off.p;
+    pl.vert_off = b->d_vert_off.p;
+    pl.representation = representation;
+    pl.out = pk.out;
+    pl.counters = b->d_counters.p;
     const int clip_blocks = sms * 4;
     // Launch configurations chosen by measurement (tools/tune.py; DBH_TUNE="traverse=3,tgrid=8,..." overrides for
     // experiments). traverse: 6 = 128-thread blocks, 6 per SM (3 = 256 x 3, 1 = 512 x 1): smaller blocks mean cheaper
@@ -1104,6 +1205,17 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
       ++b->last_launches;
       k_clip_slow<<<sms, 64, 0, st>>>(ca);
+      // Half-space pairs of this chunk: pose + root test per pair, then one thread per element (count pass).
+      pl.q_begin = static_cast<int>(std::lower_bound(b->plane_pairs.begin(), b->plane_pairs.end(), p0) - b->plane_pairs.begin());
+      pl.q_end = static_cast<int>(std::lower_bound(b->plane_pairs.begin(), b->plane_pairs.end(), p1) - b->plane_pairs.begin());
+      int plane_blocks = 0;
+      if (pl.q_end > pl.q_begin) {
+        const long long elems = b->plane_elem_off[pl.q_end] - b->plane_elem_off[pl.q_begin];
+        plane_blocks = static_cast<int>(std::min<long long>((elems + 127) / 128, static_cast<long long>(sms) * 16));
+        b->last_launches += 2;
+        k_plane_setup<<<(pl.q_end - pl.q_begin + 127) / 128, 128, 0, st>>>(pl);
+        k_plane<false><<<plane_blocks, 128, 0, st>>>(pl);
+      }
       mark(4);
       sa.pair_begin = p0;
       sa.num_pairs = p1;
@@ -1119,6 +1231,10 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       ++b->last_launches;
       if (tune.pack == 4) k_pack<4><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
       else k_pack<3><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
+      if (plane_blocks) {  // pack pass of the half-space pairs: straight into the final layout
+        ++b->last_launches;
+        k_plane<true><<<plane_blocks, 128, 0, st>>>(pl);
+      }
       mark(6);
       su.pair_begin = p0;
       su.pair_end = p1;
@@ -1180,6 +1296,22 @@ dbh_status dbh_batch_sync(dbh_batch* b) {
                                            std::to_string(b->pairs[c.error_detail].id_m) + " and " +
                                            std::to_string(b->pairs[c.error_detail].id_n) +
                                            " is not supported by the hydroelastic contact model");
+    if (c.error == DBH_ERR_HALF_SPACE_HALF_SPACE)
+      return Fail(DBH_ERR_HALF_SPACE_HALF_SPACE, "contact between two half spaces with ids " +
+                                                     std::to_string(b->pairs[c.error_detail].id_m) + " and " +
+                                                     std::to_string(b->pairs[c.error_detail].id_n) + " is not allowed");
+    if (c.error == DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH)
+      return Fail(DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH,
+                  "hydroelastic contact between two compliant geometries, one of which is a half space (ids " +
+                      std::to_string(b->pairs[c.error_detail].id_m) + " and " +
+                      std::to_string(b->pairs[c.error_detail].id_n) + "), is not allowed");
+    if (c.error == DBH_ERR_PLANE_NORMAL || c.error == DBH_ERR_REFERENCE_DEMAND)
+      return Fail(static_cast<dbh_status>(c.error),
+                  "geometry pair " + std::to_string(c.error_detail) +
+                      (c.error == DBH_ERR_PLANE_NORMAL
+                           ? ": half-space normal too small to normalise (plane.cc:16-29)"
+                           : ": a triangle edge does not cross the half-space boundary it was asked to be split by "
+                             "(DRAKE_DEMAND, mesh_half_space_intersection.cc:43,66)"));
     if (c.error == DBH_ERR_UNSUPPORTED)
       return Fail(DBH_ERR_UNSUPPORTED, "geometry pair " + std::to_string(c.error_detail) +
                                            " has a geometry without a hydroelastic representation");

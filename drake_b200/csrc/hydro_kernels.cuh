@@ -11,12 +11,15 @@
 //                swap, final packed layout (PolyMeshBuilder/TriMeshBuilder + PolygonSurfaceMesh /
 //                TriangleSurfaceMesh derived quantities + TransformVertices + SwapMAndN)
 //   k_surface    per-surface total area and centroid
+//   k_plane_*    the half-space special cases (mesh_plane_intersection.cc:182-342,
+//                mesh_half_space_intersection.cc:17-430): one thread per element of the one mesh
 //
 // All arithmetic is fp64 with the reference's operation order (hydro_math.cuh).
 #pragma once
 #include <cuda_runtime.h>
 
 #include "hydro_math.cuh"
+#include "hydro_plane.cuh"
 #include "hydro_types.h"
 
 #ifdef DBH_TRACE
@@ -163,7 +166,13 @@ __global__ void k_pairs(PairsArgs a) {
     a.pair_verts[p] = 0;
     a.pair_cursor[p] = 0ull;
     pr = a.pairs[p];
-    if (pr.kind == kUnsupported) {
+    if (pr.kind >= kSoftMeshRigidPlane) {
+      // Pairs with a half space have no BVH pair to descend: k_plane_setup / k_plane handle the two
+      // supported cases; the rest fail the strict query (proximity_engine.cc:1361-1390).
+      if (a.strict && pr.kind == kHalfSpaceHalfSpace) raise_error(a.counters, 11 /*DBH_ERR_HALF_SPACE_HALF_SPACE*/, p);
+      if (a.strict && pr.kind == kSoftPlaneSoftMesh) raise_error(a.counters, 12 /*DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH*/, p);
+      if (a.strict && pr.kind == kRigidRigidPlane) raise_error(a.counters, 6 /*DBH_ERR_RIGID_RIGID*/, p);
+    } else if (pr.kind == kUnsupported) {
       if (a.strict) raise_error(a.counters, 7 /*DBH_ERR_UNSUPPORTED*/, p);
     } else {
       const Xf X_WA = a.poses[pr.geom_a];
@@ -1838,9 +1847,219 @@ __global__ void k_scene_stats(const PairRec* pairs, int num_pairs, long long* sc
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= num_pairs) return;
   const PairRec& pr = pairs[p];
-  if (pr.kind > kSoftSoft) return;
+  if (pr.kind > kSoftSoft && pr.kind != kSoftMeshRigidPlane && pr.kind != kSoftPlaneRigidMesh) return;
   unsigned long long* st = (unsigned long long*)(scene_stats + 6ll * pr.scene);
   atomicAdd(st + 0, 1ull);
+}
+
+// ---------------------------------------------------------------------------
+// Half-space pairs (CalcRigidCompliant's special cases, hydroelastic_calculator.cc:25-41). There is
+// one mesh per pair, so no dual-tree descent: k_plane_setup poses the half space in the mesh's frame
+// and tests the mesh's root box against it; k_plane<false> runs one thread per element of every pair
+// whose root box straddles the boundary and counts its polygon; after the scan k_plane<true> runs the
+// same arithmetic again and writes the polygon straight into its final slot (the polygons are at most
+// quadrilaterals out of one record each: recomputing is cheaper than staging them). Vertices are per
+// polygon; the reference welds the ones cut from the same mesh edge (cut_edges,
+// mesh_plane_intersection.cc:205-231): face quantities do not depend on that.
+struct PlaneArgs {
+  const PairRec* pairs;
+  const Xf* poses;
+  Xf* pair_X;                       // per pair: m[0..2] unit normal, m[3] displacement (mesh frame), m[4] active,
+                                    // m[5] pressure scale, m[6] margin
+  Pools pools;
+  const double* tet_vp;             // [4 * pool tet]: pressure at the tetrahedron's vertices
+  const int* plane_pairs;           // static list of the half-space pairs (pair indices, ascending)
+  const long long* plane_elem_off;  // [num_plane_pairs + 1]: elements before each of them
+  const double* geom_hs;            // [2 * flat geometry]: pressure scale, margin of a compliant half space
+  int q_begin, q_end;               // this chunk's range of the list
+  int* pair_polys;
+  int* pair_verts;
+  unsigned long long* pair_cursor;
+  const long long* poly_off;
+  const long long* vert_off;
+  int representation;
+  ResultArrays out;
+  Counters* counters;
+};
+
+__global__ void k_plane_setup(PlaneArgs a) {
+  const int q = a.q_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.q_end) return;
+  const int p = a.plane_pairs[q];
+  const PairRec pr = a.pairs[p];
+  const Xf X_WS = a.poses[pr.geom_a], X_WR = a.poses[pr.geom_b];
+  Xf rec;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) rec.m[k] = 0.0;
+  D3 nhat = make_d3(0, 0, 1);
+  double disp = 0;
+  bool active = true;
+  const bool mesh_is_soft = pr.kind == kSoftMeshRigidPlane;
+  if (mesh_is_soft) {
+    rigid_half_space_in_mesh_frame(X_WS, X_WR, &nhat, &disp);
+  } else {
+    rec.m[5] = a.geom_hs[2 * pr.geom_a];
+    rec.m[6] = a.geom_hs[2 * pr.geom_a + 1];
+    const int st = compliant_half_space_in_mesh_frame(X_WR, X_WS, rec.m[6], &nhat, &disp);
+    if (st) {
+      raise_error(a.counters, st, p);
+      active = false;
+    }
+  }
+  // The mesh's root box against the boundary plane: every vertex strictly outside (both cases), or
+  // every vertex strictly inside (slicing only): no polygon. Exact fp64 box, padded against rounding.
+  const BvhNode& root = a.pools.nodes[mesh_is_soft ? pr.root_a : pr.root_b];
+  const double s = dot(nhat, load3(root.c)) - disp;
+  const double r = (fabs(nhat.x) * root.h[0] + fabs(nhat.y) * root.h[1]) + fabs(nhat.z) * root.h[2];
+  const double pad = 1e-12 * (fabs(s) + r + fabs(disp)) + 1e-300;
+  if (s - r > pad) active = false;
+  if (mesh_is_soft && s + r < -pad) active = false;
+  rec.m[0] = nhat.x;
+  rec.m[1] = nhat.y;
+  rec.m[2] = nhat.z;
+  rec.m[3] = disp;
+  rec.m[4] = active ? 1.0 : 0.0;
+  a.pair_X[p] = rec;
+  atomicAdd(&a.counters->bv_tests, 1ull);
+  if (active) atomicAdd(&a.counters->root_overlaps, 1ull);
+}
+
+template <bool kPack>
+__global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
+  if (kPack && a.counters->error != 0) return;
+  const long long w0 = a.plane_elem_off[a.q_begin];
+  const long long count = a.plane_elem_off[a.q_end] - w0;
+  const long long rounded = (count + 31ll) & ~31ll;  // whole warps reach the collectives
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+    WorldPoly P;
+    P.n = 0;
+    P.status = 0;
+    int pair = -1, elem = 0;
+    bool mesh_is_soft = false, swapped = false, worked = false;
+    if (i < count) {
+      const long long w = w0 + i;
+      int lo = a.q_begin, hi = a.q_end;  // plane_elem_off[lo] <= w < plane_elem_off[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a.plane_elem_off[mid] <= w) lo = mid;
+        else hi = mid;
+      }
+      pair = a.plane_pairs[lo];
+      const Xf rec = a.pair_X[pair];
+      if (rec.m[4] != 0.0) {
+        const PairRec pr = a.pairs[pair];
+        elem = (int)(w - a.plane_elem_off[lo]);
+        mesh_is_soft = pr.kind == kSoftMeshRigidPlane;
+        swapped = pr.swapped != 0;
+        const D3 nhat = make_d3(rec.m[0], rec.m[1], rec.m[2]);
+        if (mesh_is_soft) {
+          const int t = pr.elem_base_a + elem;
+          slice_tet_with_plane(a.pools.tets[t], a.tet_vp + 4ll * t, nhat, rec.m[3], a.poses[pr.geom_a], &P);
+        } else {
+          clip_tri_by_half_space(a.pools.tris[pr.elem_base_b + elem], nhat, rec.m[3], rec.m[5], rec.m[6],
+                                 a.poses[pr.geom_b], a.poses[pr.geom_a], &P);
+        }
+        worked = true;
+        if (!kPack && P.status) raise_error(a.counters, P.status, pair);
+      }
+    }
+    if (!kPack) {
+      const unsigned workmask = __ballot_sync(0xffffffffu, worked);
+      if (lane == 0 && workmask) atomicAdd(&a.counters->plane_elems, (unsigned long long)__popc(workmask));
+    }
+    const int n = P.status ? 0 : P.n;
+    const bool valid = n > 0;
+    // The polygons of a warp mostly belong to one geometry pair: one lane updates the pair's counters
+    // (or claims the warp's slots) for all of them.
+    const unsigned validmask = __ballot_sync(0xffffffffu, valid);
+    if (!validmask) continue;
+    const int lead = __ffs(validmask) - 1;
+    const int pair0 = __shfl_sync(0xffffffffu, pair, lead);
+    const bool uniform = __all_sync(0xffffffffu, !valid || pair == pair0);
+    if (!kPack) {
+      if (uniform) {
+        int total = valid ? n : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+        if (lane == lead) {
+          atomicAdd(&a.pair_polys[pair0], __popc(validmask));
+          atomicAdd(&a.pair_verts[pair0], total);
+        }
+      } else if (valid) {
+        atomicAdd(&a.pair_polys[pair], 1);
+        atomicAdd(&a.pair_verts[pair], n);
+      }
+      continue;
+    }
+    // hi 32 bits: polygons placed, lo 32: polygon vertices placed (as in k_pack).
+    unsigned long long cur = 0;
+    {
+      const unsigned long long v = valid ? ((1ull << 32) | (unsigned long long)n) : 0ull;
+      if (uniform) {
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += y;
+        }
+        const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == lead) base = atomicAdd(&a.pair_cursor[pair0], total);
+        base = __shfl_sync(0xffffffffu, base, lead);
+        cur = base + incl - v;
+      } else if (valid) {
+        cur = atomicAdd(&a.pair_cursor[pair], v);
+      }
+    }
+    if (!valid) continue;
+    const int pj = (int)(cur >> 32);
+    const int vj = (int)(cur & 0xffffffffull);
+    const bool polygons = a.representation == 1 /*DBH_POLYGON*/;
+    long long f0, vb, fd0;
+    int vloc;
+    if (polygons) {
+      f0 = a.poly_off[pair] + pj;
+      vb = a.vert_off[pair] + vj;
+      fd0 = f0 + vb;
+      vloc = vj;
+      if (f0 >= a.out.face_capacity || vb + n > a.out.vert_capacity || fd0 + n + 1 > a.out.face_data_capacity) {
+        raise_error(a.counters, 5, 6);
+        continue;
+      }
+    } else {
+      f0 = a.vert_off[pair] + vj;
+      vloc = vj + pj;
+      vb = a.vert_off[pair] + a.poly_off[pair] + vloc;
+      fd0 = 3 * f0;
+      if (f0 + n > a.out.face_capacity || vb + n + 1 > a.out.vert_capacity || 3 * (f0 + n) > a.out.face_data_capacity) {
+        raise_error(a.counters, 5, 6);
+        continue;
+      }
+    }
+    PackedPoly K;
+    pack_world_polygon(P, a.representation, swapped, vloc, &K);
+    for (int k = 0; k < K.nv; ++k) {
+      store3(a.out.vertices, vb + k, K.v[k]);
+      a.out.pressures[vb + k] = K.e[k];
+    }
+    for (int k = 0; k < K.nfd; ++k) a.out.face_data[fd0 + k] = K.fd[k];
+    const D3 zero = make_d3(0, 0, 0);
+    for (int k = 0; k < K.nf; ++k) {
+      const long long f = f0 + k;
+      a.out.areas[f] = K.area[k];
+      store3(a.out.normals, f, swapped ? -K.normal[k] : K.normal[k]);  // ReverseFaceWinding negates normals
+      store3(a.out.centroids, f, K.centroid[k]);
+      a.out.e_centroid[f] = K.e_c[k];
+      // The compliant body is the first-constructed M; swapped: grad_eM <-> grad_eN (contact_surface.cc:58).
+      store3(a.out.grad_eM, f, swapped ? zero : P.grad_W);
+      store3(a.out.grad_eN, f, swapped ? P.grad_W : zero);
+      a.out.elem_a[f] = mesh_is_soft ? elem : -1;
+      a.out.elem_b[f] = mesh_is_soft ? -1 : elem;
+      a.out.face_pair[f] = pair;
+    }
+  }
 }
 
 }  // namespace dbh

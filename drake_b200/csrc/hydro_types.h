@@ -129,7 +129,21 @@ struct Pools {
   const ElemBox* ebox_tri;   // per pool triangle
 };
 
-enum PairKind : int32_t { kSoftRigid = 0, kSoftSoft = 1, kRigidRigid = 2, kUnsupported = 3 };
+// 0-3: mesh pairs and the failures of MaybeMakeContactSurface that need no shape knowledge. 4-8: pairs
+// with a HalfSpace (hydroelastic_calculator.cc:25-41,113-123,145-147): the two supported special cases
+// (k_plane_*), and the combinations the reference rejects (ContactSurfaceResult::kHalfSpaceHalfSpace,
+// kCompliantHalfSpaceCompliantMesh, kRigidRigid with a half space: no root boxes to test).
+enum PairKind : int32_t {
+  kSoftRigid = 0,
+  kSoftSoft = 1,
+  kRigidRigid = 2,
+  kUnsupported = 3,
+  kSoftMeshRigidPlane = 4,   // compliant volume mesh (a) x rigid half space (b)
+  kSoftPlaneRigidMesh = 5,   // compliant half space (a) x rigid surface mesh (b)
+  kHalfSpaceHalfSpace = 6,
+  kSoftPlaneSoftMesh = 7,
+  kRigidRigidPlane = 8
+};
 
 // Static description of one potential geometry pair (one entry of
 // FindCollisionCandidates() after filtering, proximity_engine.cc:867-883, in
@@ -145,7 +159,7 @@ struct alignas(64) PairRec {
   int32_t elem_base_a;  // pool index of element 0 of the first body (tet pool)
   int32_t elem_base_b;  // second body (tri pool for soft-rigid, tet pool for soft-soft)
   int32_t root_leaf;    // bit0: root_a is a leaf, bit1: root_b is a leaf
-  int32_t pad[2];
+  int32_t pad[2];       // half-space pairs: root_* / elem_base_* describe the one mesh, the other side's are -1
   int64_t id_m;      // final ids, id_m < id_n
   int64_t id_n;
 };
@@ -188,6 +202,7 @@ struct Counters {
   unsigned long long full_clips_tet; // tet-tet candidates that survived the conservative culls
   unsigned long long leaf_exact;     // leaf pairs the fp32 predicate could not decide (exact fp64 test ran)
   unsigned long long cull_violations; // verify mode: polygons from candidates the conservative cull rejected
+  unsigned long long plane_elems;     // elements sliced / clipped against a half space (k_plane, active pairs only)
   // -- totals and per-chunk maxima of the chunk-local cursors
   unsigned long long leaf_tri_total, leaf_tet_total, polys_total, slow_total;
   unsigned long long frontier_max, leaf_tri_max, leaf_tet_max, polys_max, slow_max;

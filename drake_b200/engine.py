@@ -29,6 +29,7 @@ OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_DEGENERATE_FIELD, ERR_CAPACITY = 1, 2, 3, 4, 5
 BVH_HOST_MEDIAN_SPLIT, BVH_GPU_LBVH = 0, 1
 ERR_RIGID_RIGID, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_PLANE_NORMAL, ERR_POLYGON_SIZE = 6, 7, 8, 9, 10
+ERR_HALF_SPACE_HALF_SPACE, ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH, ERR_REFERENCE_DEMAND = 11, 12, 13
 
 
 class HydroError(RuntimeError):
@@ -45,14 +46,16 @@ _bp = C.POINTER(C.c_uint8)
 
 class AssetInfo(C.Structure):
     _fields_ = [("type", C.c_int32), ("num_vertices", C.c_int32), ("num_elements", C.c_int32),
-                ("num_bvh_nodes", C.c_int32), ("bvh_height", C.c_int32), ("reserved", C.c_int32 * 3),
+                ("num_bvh_nodes", C.c_int32), ("bvh_height", C.c_int32), ("is_half_space", C.c_int32),
+                ("reserved", C.c_int32 * 2),
                 ("root_center", C.c_double * 3), ("root_half_width", C.c_double * 3)]
 
 
 class BatchInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("num_scenes", "num_geometries", "num_geometry_pairs", "num_soft_rigid_pairs", "num_soft_soft_pairs",
-                 "num_rigid_rigid_pairs", "num_unsupported_pairs", "max_traversal_levels")]
+                 "num_rigid_rigid_pairs", "num_unsupported_pairs", "max_traversal_levels", "num_half_space_pairs",
+                 "num_rejected_half_space_pairs")]
 
 
 class ResultSizes(C.Structure):
@@ -102,6 +105,7 @@ def lib():
     L.dbh_context_destroy.argtypes = [vp]
     L.dbh_register_compliant_mesh.argtypes = [vp, C.c_int32, _dp, C.c_int32, _ip, _dp, _ip]
     L.dbh_register_rigid_mesh.argtypes = [vp, C.c_int32, _dp, C.c_int32, _ip, _ip]
+    L.dbh_register_half_space.argtypes = [vp, C.c_int32, C.c_double, C.c_double, _ip]
     L.dbh_asset_get_info.argtypes = [vp, C.c_int32, C.POINTER(AssetInfo)]
     L.dbh_asset_get_derived.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     L.dbh_asset_copy_bvh.argtypes = [vp, C.c_int32, _dp, _ip]
@@ -299,6 +303,15 @@ class Context:
         v, t = _d(vertices).reshape(-1, 3), _i(tris).reshape(-1, 3)
         out = C.c_int32()
         _check(lib().dbh_register_rigid_mesh(self._h, len(v), _ptr(v, _dp), len(t), _ptr(t, _ip), C.byref(out)))
+        return out.value
+
+    def register_half_space(self, compliant: bool = False, pressure_scale: float = 0.0, margin: float = 0.0) -> int:
+        """HalfSpace shape (z <= 0 of its frame). compliant: pressure_scale = hydroelastic modulus / slab thickness
+        (hydroelastic_internal.h SoftHalfSpace). Pairs with it are CalcRigidCompliant's special cases
+        (hydroelastic_calculator.cc:25-41)."""
+        out = C.c_int32()
+        _check(lib().dbh_register_half_space(self._h, COMPLIANT if compliant else RIGID, float(pressure_scale),
+                                             float(margin), C.byref(out)))
         return out.value
 
     def register_mesh(self, mesh: "Mesh") -> int:

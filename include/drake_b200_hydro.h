@@ -41,10 +41,16 @@ enum {
                                      hydroelastic representation */
   DBH_ERR_NOT_READY = 8,          /* results requested before a query completed */
   DBH_ERR_PLANE_NORMAL = 9,       /* Plane ctor: |normal| < 1e-10 (plane.cc:16-29) */
-  DBH_ERR_POLYGON_SIZE = 10       /* tet-triangle polygon with more than 7 vertices (DRAKE_DEMAND,
+  DBH_ERR_POLYGON_SIZE = 10,      /* tet-triangle polygon with more than 7 vertices (DRAKE_DEMAND,
                                      mesh_intersection.cc:261-262), or a tet-tet clip whose intermediate
                                      polygon outgrew 16 vertices (the reference's own buffer holds 8,
                                      field_intersection.cc:98: beyond that its behaviour is undefined) */
+  DBH_ERR_HALF_SPACE_HALF_SPACE = 11,  /* ContactSurfaceResult::kHalfSpaceHalfSpace (hydroelastic_calculator.cc:113-118,
+                                          145-147), strict query only */
+  DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH = 12, /* kCompliantHalfSpaceCompliantMesh (:120-123), strict query only */
+  DBH_ERR_REFERENCE_DEMAND = 13   /* a DRAKE_DEMAND of the reference would have fired: a triangle edge whose end
+                                     points do not lie on different sides of the half-space boundary
+                                     (mesh_half_space_intersection.cc:43,66) */
 };
 
 enum { DBH_TRIANGLE = 0, DBH_POLYGON = 1 };
@@ -81,7 +87,8 @@ typedef struct dbh_asset_info {
   int32_t num_elements;
   int32_t num_bvh_nodes;
   int32_t bvh_height;
-  int32_t reserved[3];
+  int32_t is_half_space; /* 1 for dbh_register_half_space assets (no elements, no BVH) */
+  int32_t reserved[2];
   double root_center[3];
   double root_half_width[3];
 } dbh_asset_info;
@@ -94,6 +101,17 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t num_vertices, c
 /* TriangleSurfaceMesh<double>: verts [nv*3], tris [nt*3]. */
 dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t num_vertices, const double* vertices,
                                    int32_t num_tris, const int32_t* tris, int32_t* asset_out);
+/* HalfSpace shape (z <= 0 of its geometry frame; shape_specification.h): no mesh. type DBH_RIGID, or
+ * DBH_COMPLIANT with pressure_scale = hydroelastic_modulus / slab_thickness and margin
+ * (hydroelastic_internal.h SoftHalfSpace; hydroelastic_internal.cc MakeSoftRepresentation(HalfSpace)).
+ * Pairs with a half space are the special cases of CalcRigidCompliant (hydroelastic_calculator.cc:25-41):
+ * compliant mesh x rigid half space (mesh_plane_intersection.cc:251-342) and compliant half space x
+ * rigid mesh (mesh_half_space_intersection.cc:338-418); the other combinations fail the strict query
+ * like the reference's (DBH_ERR_HALF_SPACE_HALF_SPACE, DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH,
+ * DBH_ERR_RIGID_RIGID). Faces of such surfaces carry -1 as the half space's emitting element, and each
+ * polygon keeps its own vertices (the reference welds vertices cut from the same mesh edge). */
+dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressure_scale, double margin,
+                                   int32_t* asset_out);
 dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out);
 /* The asset's BVH for inspection: boxes [(num_bvh_nodes + 1) * 6] = centre, half width per node
  * (node 0 unused, node 1 root), left [(num_bvh_nodes + 1)] = index of the first of the two adjacent
@@ -173,6 +191,8 @@ typedef struct dbh_batch_info {
   int32_t num_rigid_rigid_pairs;
   int32_t num_unsupported_pairs;
   int32_t max_traversal_levels;
+  int32_t num_half_space_pairs;    /* compliant mesh x rigid half space + compliant half space x rigid mesh */
+  int32_t num_rejected_half_space_pairs; /* combinations with a half space that the reference rejects */
 } dbh_batch_info;
 dbh_status dbh_batch_get_info(dbh_batch* batch, dbh_batch_info* out);
 

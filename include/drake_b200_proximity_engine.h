@@ -61,6 +61,7 @@ struct Box {
 struct Ellipsoid {
   double a, b, c;
 };
+struct HalfSpace {};  // z <= 0 of the geometry frame (shape_specification.h)
 struct VolumeMeshShape {  // VolumeMesh<double> + per-vertex pressure
   std::vector<double> vertices;  // [nv*3]
   std::vector<int32_t> tetrahedra;  // [nt*4]
@@ -70,7 +71,7 @@ struct SurfaceMeshShape {  // TriangleSurfaceMesh<double>
   std::vector<double> vertices;
   std::vector<int32_t> triangles;
 };
-using Shape = std::variant<Sphere, Box, Ellipsoid, VolumeMeshShape, SurfaceMeshShape>;
+using Shape = std::variant<Sphere, Box, Ellipsoid, VolumeMeshShape, SurfaceMeshShape, HalfSpace>;
 
 enum class HydroelasticType { kUndefined = DBH_UNDEFINED, kRigid = DBH_RIGID, kCompliant = DBH_COMPLIANT };
 enum class HydroelasticContactRepresentation { kTriangle = DBH_TRIANGLE, kPolygon = DBH_POLYGON };
@@ -82,6 +83,7 @@ struct ProximityProperties {
   double hydroelastic_modulus{1e7};
   double resolution_hint{0.02};
   double margin{0.0};
+  double slab_thickness{0.0};  // kSlabThickness: compliant half spaces only (hydroelastic_internal.cc:539-553)
   TessellationStrategy tessellation_strategy{TessellationStrategy::kSingleInteriorVertex};
 };
 
@@ -222,7 +224,9 @@ class ProximityEngine {
     const std::string msg = std::string(where) + ": " + dbh_last_error();
     // The reference throws std::logic_error for unsupported / rigid-rigid pairs
     // (proximity_engine.cc:1361-1390); everything else is a runtime failure.
-    if (s == DBH_ERR_RIGID_RIGID || s == DBH_ERR_UNSUPPORTED || s == DBH_ERR_INVALID_ARGUMENT) throw std::logic_error(msg);
+    if (s == DBH_ERR_RIGID_RIGID || s == DBH_ERR_UNSUPPORTED || s == DBH_ERR_INVALID_ARGUMENT ||
+        s == DBH_ERR_HALF_SPACE_HALF_SPACE || s == DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH)
+      throw std::logic_error(msg);
     throw std::runtime_error(msg);
   }
   static void CheckMesh(dbh_status s, const char* where) {
@@ -249,6 +253,14 @@ class ProximityEngine {
         if (h) dbh_mesh_destroy(h);
       }
     } vol, surf;
+    if (std::get_if<HalfSpace>(&shape)) {
+      // Rigid: hydroelastic_internal.cc:323-326; compliant: pressure scale = modulus / slab thickness (:539-553).
+      if (soft && !(p.slab_thickness > 0)) throw std::logic_error("a compliant HalfSpace needs a positive slab_thickness");
+      Check(dbh_register_half_space(ctx_, soft ? DBH_COMPLIANT : DBH_RIGID,
+                                    soft ? p.hydroelastic_modulus / p.slab_thickness : 0.0, soft ? p.margin : 0.0, &asset),
+            "register_half_space");
+      return asset;
+    }
     if (const auto* s = std::get_if<Sphere>(&shape)) {
       CheckMesh(dbh_mesh_make_sphere_volume(s->radius, p.resolution_hint,
                                             soft ? static_cast<int>(p.tessellation_strategy) : 0, &vol.h),

@@ -51,7 +51,7 @@ def test_product_does_not_touch_the_oracle():
 def test_struct_layouts_match_header():
     from drake_b200 import engine
     assert ctypes.sizeof(engine.AssetInfo) == 8 * 4 + 6 * 8
-    assert ctypes.sizeof(engine.BatchInfo) == 8 * 4
+    assert ctypes.sizeof(engine.BatchInfo) == 10 * 4
     assert ctypes.sizeof(engine.ResultSizes) == 5 * 8 + 2 * 4
     assert ctypes.sizeof(engine.ResultBuffers) == 19 * 8
     assert ctypes.sizeof(engine.Stats) == 10 * 8 + 7 * 8

@@ -1,0 +1,190 @@
+"""The per-element arithmetic of the half-space kernels (drake_b200/csrc/hydro_plane.cuh, __host__ __device__)
+compiled with g++ (tests/cpp/plane_host_check.cc) and compared with the oracle on this CPU-only machine. The GPU
+tests (test_zz_gpu_halfspace.py) run the same expressions through k_plane and the C-ABI; this file is what
+lets them be checked before a GPU is available. Test infrastructure only: not a CPU path of the product."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ho
+from tests.parity import REL_TOL, assert_close, face_keys, random_pose
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "plane_host_check.cc")
+HDRS = [os.path.join(ROOT, "drake_b200", "csrc", n) for n in ("hydro_plane.cuh", "hydro_math.cuh", "hydro_types.h")]
+LIB = os.path.join(ROOT, "tests", "cpp", "_build", "libplane_host_check.so")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def harness():
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    newest = max(os.path.getmtime(p) for p in [SRC] + HDRS)
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        # -ffp-contract=off: the device code is compiled with -fmad=false.
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra",
+                        "-Wno-unknown-pragmas", "-o", LIB, SRC], check=True)
+    return C.CDLL(LIB)
+
+
+class HostSurface:
+    """What k_plane would pack for one geometry pair (faces in element order)."""
+
+    def __init__(self, rep, cap_f, cap_v):
+        self.rep = rep
+        self.elem = np.zeros(cap_f, np.int32)
+        self.face_n = np.zeros(cap_f, np.int32)
+        self.areas = np.zeros(cap_f)
+        self.normals = np.zeros((cap_f, 3))
+        self.centroids = np.zeros((cap_f, 3))
+        self.e_c = np.zeros(cap_f)
+        self.grad = np.zeros((cap_f, 3))
+        self.vertices = np.zeros((cap_v, 3))
+        self.pressures = np.zeros(cap_v)
+        self.face_data = np.zeros(4 * cap_f + cap_v, np.int32)
+        self.counts = np.zeros(4, np.int32)
+
+    def args(self):
+        d = lambda a: a.ctypes.data_as(_dp)
+        i = lambda a: a.ctypes.data_as(_ip)
+        return [i(self.elem), i(self.face_n), d(self.areas), d(self.normals), d(self.centroids), d(self.e_c),
+                d(self.grad), d(self.vertices), d(self.pressures), i(self.face_data), i(self.counts)]
+
+    def trim(self):
+        nf, nv, nfd, _ = (int(c) for c in self.counts)
+        for name in ("elem", "face_n", "areas", "normals", "centroids", "e_c", "grad"):
+            setattr(self, name, getattr(self, name)[:nf])
+        self.vertices, self.pressures, self.face_data = self.vertices[:nv], self.pressures[:nv], self.face_data[:nfd]
+        return self
+
+    def polygons(self):
+        if self.rep == ho.KTRIANGLE:
+            return list(self.face_data.reshape(-1, 3))
+        out, i = [], 0
+        while i < len(self.face_data):
+            n = self.face_data[i]
+            out.append(self.face_data[i + 1:i + 1 + n])
+            i += n + 1
+        return out
+
+
+def host_mesh_vs_half_space(mesh, fld, X_WS, X_WR, rep, swapped):
+    verts, tets = mesh.arrays()[:2]
+    values, grads = fld.arrays()[:2]
+    tet_v = np.ascontiguousarray(verts[tets].reshape(-1, 12))
+    tet_vp = np.ascontiguousarray(values[tets])
+    hs = HostSurface(rep, 4 * len(tets), 5 * len(tets))
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+    rc = harness().phc_mesh_vs_rigid_half_space(len(tets), d(tet_v), d(grads), d(tet_vp), d(X_WS), d(X_WR), rep,
+                                                int(swapped), *hs.args())
+    assert rc == 0
+    return hs.trim()
+
+
+def host_half_space_vs_mesh(mesh, X_WS, pressure_scale, margin, X_WR, rep, swapped):
+    verts, tris, normals = mesh.arrays()[:3]
+    tri_v = np.ascontiguousarray(verts[tris].reshape(-1, 9))
+    hs = HostSurface(rep, 4 * len(tris), 5 * len(tris))
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+    lib = harness()
+    lib.phc_half_space_vs_rigid_mesh.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp, C.c_int, C.c_int,
+                                                 _ip, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+    rc = lib.phc_half_space_vs_rigid_mesh(len(tris), d(tri_v), d(normals), d(X_WS), pressure_scale, margin, d(X_WR),
+                                          rep, int(swapped), *hs.args())
+    assert rc == 0
+    return hs.trim()
+
+
+def compare_with_oracle(host, ora, elem_of_oracle, grad_of_oracle):
+    """Faces matched by emitting element (stable: a polygon's fan triangles keep the builder's order)."""
+    assert host.counts[0] == ora.num_faces
+    go, oo = np.argsort(host.elem, kind="stable"), np.argsort(elem_of_oracle, kind="stable")
+    np.testing.assert_array_equal(host.elem[go], np.asarray(elem_of_oracle)[oo])  # bit-exact emitted set
+    L = max(np.max(np.abs(ora.vertices)), 1e-300)
+    pscale = max(np.max(np.abs(ora.pressures)), 1e-300)
+    assert_close("areas", host.areas[go], ora.areas[oo], scale=max(ora.areas.max(), 1e-300))
+    assert_close("normals", host.normals[go], ora.normals[oo], scale=1.0)
+    assert_close("centroids", host.centroids[go], ora.centroids[oo], scale=L)
+    assert_close("pressure_at_centroid", host.e_c[go], ora.e_centroid[oo], scale=pscale)
+    assert_close("grad", host.grad[go], grad_of_oracle[oo])
+    hp, op = host.polygons(), ora.polygons()
+    for a, b in zip(go, oo):
+        ia, ib = np.asarray(hp[a]), np.asarray(op[b])
+        assert len(ia) == len(ib)
+        # The oracle welds vertices (as the reference does), the kernel keeps them per polygon.
+        assert_close("vertices", host.vertices[ia], ora.vertices[ib], scale=L)
+        assert_close("pressures", host.pressures[ia], ora.pressures[ib], scale=pscale)
+    assert_close("total_area", host.areas.sum(), ora.total_area)
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+@pytest.mark.parametrize("swapped", [False, True])
+def test_mesh_vs_rigid_half_space_matches_the_oracle(rep, swapped):
+    rng = np.random.default_rng(11)
+    mesh = ho.VolumeMesh.ellipsoid(0.3, 0.4, 0.5, 0.2, dense=True)
+    fld = ho.VolumeField.ellipsoid(mesh, 0.3, 0.4, 0.5, 1e5)
+    id_S, id_R = (2, 1) if swapped else (1, 2)
+    hits = 0
+    for _ in range(12):
+        X_WS = random_pose(rng, 0.5)
+        X_WR = random_pose(rng, 0.5)
+        ora = ho.soft_mesh_rigid_half_space(mesh, fld, X_WS, X_WR, id_S, id_R, rep)
+        host = host_mesh_vs_half_space(mesh, fld, X_WS, X_WR, rep, swapped)
+        if ora is None:
+            assert host.counts[0] == 0
+            continue
+        hits += 1
+        compare_with_oracle(host, ora, ora.elem_first, ora.grad_eN if swapped else ora.grad_eM)
+    assert hits >= 4
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+@pytest.mark.parametrize("swapped", [False, True])
+def test_half_space_vs_rigid_mesh_matches_the_oracle(rep, swapped):
+    rng = np.random.default_rng(12)
+    mesh = ho.VolumeMesh.ellipsoid(0.3, 0.4, 0.5, 0.2, dense=True).to_surface()
+    id_S, id_R = (2, 1) if swapped else (1, 2)
+    hits = 0
+    for k in range(12):
+        X_WS = random_pose(rng, 0.5)
+        X_WR = random_pose(rng, 0.5)
+        margin = 0.0 if k % 2 else 0.01
+        ora = ho.soft_half_space_rigid_mesh(mesh, X_WS, 4e5, X_WR, id_S, id_R, rep, margin=margin)
+        host = host_half_space_vs_mesh(mesh, X_WS, 4e5, margin, X_WR, rep, swapped)
+        if ora is None:
+            assert host.counts[0] == 0
+            continue
+        hits += 1
+        compare_with_oracle(host, ora, ora.elem_second, ora.grad_eN if swapped else ora.grad_eM)
+    assert hits >= 4
+
+
+def test_reference_fixtures_through_the_kernel_arithmetic():
+    # mesh_plane_intersection_test.cc:1217-1262 (six triangles, x = 0.5 in S) and
+    # mesh_half_space_intersection_test.cc:886-1007 (10 polygons / 34 triangles).
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, -1]], float)
+    mesh = ho.VolumeMesh.from_arrays(v, [[0, 1, 2, 3], [0, 2, 1, 4]])
+    fld = ho.VolumeField.from_values(mesh, [0.25, 0.5, 0.75, 1, -1])
+    X_WS = ho.xform(ho.angle_axis_matrix(math.pi / 3, np.array([-1, 1, 1]) / math.sqrt(3)), [1.25, 2.5, -3.75])
+    X_WR = ho.compose(X_WS, ho.xform(ho.angle_axis_matrix(math.pi / 2, [0, 1, 0]), [0.5, 2.25, -1.25]))
+    host = host_mesh_vs_half_space(mesh, fld, X_WS, X_WR, ho.KTRIANGLE, False)
+    assert list(host.counts) == [6, 8, 18, 2]
+    R_WS, p_WS = ho.xform_parts(X_WS)
+    np.testing.assert_allclose(host.normals, np.tile(R_WS[:, 0], (6, 1)), atol=16 * np.finfo(float).eps)
+    np.testing.assert_allclose(((host.vertices - p_WS) @ R_WS)[:, 0], 0.5, atol=16 * np.finfo(float).eps)
+    from tests.test_oracle_halfspace import box_mesh
+    X_WF = ho.xform(ho.angle_axis_matrix(math.pi / 7, np.array([1, 2, 3]) / math.sqrt(14)), [-0.25, 0.5, 0.75])
+    X_FB = ho.xform(ho.rpy_matrix(math.pi / 4, math.pi / 4, math.pi / 4), [1.0, 2.0, 3.0])
+    box = box_mesh(X_FB)
+    X_WH = ho.compose(X_WF, X_FB)
+    host = host_half_space_vs_mesh(box, X_WH, 17.0, 0.0, X_WF, ho.KPOLYGON, False)
+    assert list(host.counts) == [10, 6 * 3 + 4 * 4, 10 + 6 * 3 + 4 * 4, 10]
+    np.testing.assert_allclose(host.areas.sum(), 12.0, atol=1e-12)
+    host = host_half_space_vs_mesh(box, X_WH, 17.0, 0.0, X_WF, ho.KTRIANGLE, False)
+    assert list(host.counts) == [34, 34 + 10, 3 * 34, 10]
