@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c2s", "c3", "c4", "c5"])
+    ap.add_argument("--config", default="c3", choices=["c2s", "c3", "c3h", "c4", "c5"])
     ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default: the config's)")
     ap.add_argument("--rep", default="polygon", choices=["polygon", "triangle"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -46,13 +46,15 @@ def parse_args():
     return ap.parse_args()
 
 
-DEFAULT_SCENES = {"c2s": 256, "c3": 16384, "c4": 4096, "c5": 16}
+DEFAULT_SCENES = {"c2s": 256, "c3": 16384, "c3h": 16384, "c4": 4096, "c5": 16}
 
 
 def make_workload(name: str, scenes: int, scene0: int):
     from drake_b200 import workloads as W
     if name == "c3":
         return W.config3(scenes, scene0)
+    if name == "c3h":
+        return W.config3_half_space(scenes, scene0)
     if name == "c4":
         return W.config4(scenes, scene0)
     if name == "c5":
@@ -318,7 +320,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in events)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([sum(s["surfaces"] for s in step_stats), sum(s["tet_tri_pairs"] + s["tet_tet_pairs"] for s in step_stats),
+    tot = torch.tensor([sum(s["surfaces"] for s in step_stats), sum(s["tet_tri_pairs"] + s["tet_tet_pairs"] + s["half_space_elements"] for s in step_stats),
                         sum(s["bv_pair_tests"] for s in step_stats), sum(s["faces"] for s in step_stats)],
                        dtype=torch.float64, device=dev)
     if world > 1:

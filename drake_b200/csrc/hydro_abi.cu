@@ -1347,7 +1347,9 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   const Counters& c = *b->h_counters;
   std::memset(out, 0, sizeof(*out));
-  out->geometry_pairs_tested = static_cast<int64_t>(b->info.num_soft_rigid_pairs + b->info.num_soft_soft_pairs);
+  out->geometry_pairs_tested =
+      static_cast<int64_t>(b->info.num_soft_rigid_pairs + b->info.num_soft_soft_pairs + b->info.num_half_space_pairs);
+  out->half_space_elements = static_cast<int64_t>(c.plane_tets + c.plane_tris);
   out->geometry_pairs_overlapping = static_cast<int64_t>(c.root_overlaps);
   out->bv_pair_tests = static_cast<int64_t>(c.bv_tests);
   out->leaf_pairs = static_cast<int64_t>(c.leaf_tri_total + c.leaf_tet_total);
@@ -1369,6 +1371,9 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   // Triangle representation adds 32 B centroid vertex + n (12 + 24 + 8) B per polygon.
   long long bytes = out->bv_pair_tests * 64 + out->tet_tri_pairs * 260 + out->tet_tet_pairs * 392 +
                     static_cast<long long>(c.poly_verts) * 32 + out->polygons * 108 + 96ll * b->num_geoms;
+  // Half-space pairs: one record per element (tetrahedron: 16 B indices + 96 B vertices + 32 B vertex pressures +
+  // 24 B gradient = 168 B; triangle: 12 + 72 + 24 = 108 B).
+  bytes += static_cast<long long>(c.plane_tets) * 168 + static_cast<long long>(c.plane_tris) * 108;
   if (b->representation == DBH_TRIANGLE) bytes += out->polygons * 32 + static_cast<long long>(c.poly_verts) * 44;
   out->algorithmic_bytes = bytes;
   return DBH_OK;

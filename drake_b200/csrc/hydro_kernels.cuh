@@ -1966,8 +1966,10 @@ __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
       }
     }
     if (!kPack) {
-      const unsigned workmask = __ballot_sync(0xffffffffu, worked);
-      if (lane == 0 && workmask) atomicAdd(&a.counters->plane_elems, (unsigned long long)__popc(workmask));
+      const unsigned tets = __ballot_sync(0xffffffffu, worked && mesh_is_soft);
+      const unsigned tris = __ballot_sync(0xffffffffu, worked && !mesh_is_soft);
+      if (lane == 0 && tets) atomicAdd(&a.counters->plane_tets, (unsigned long long)__popc(tets));
+      if (lane == 0 && tris) atomicAdd(&a.counters->plane_tris, (unsigned long long)__popc(tris));
     }
     const int n = P.status ? 0 : P.n;
     const bool valid = n > 0;

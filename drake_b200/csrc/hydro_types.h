@@ -202,7 +202,8 @@ struct Counters {
   unsigned long long full_clips_tet; // tet-tet candidates that survived the conservative culls
   unsigned long long leaf_exact;     // leaf pairs the fp32 predicate could not decide (exact fp64 test ran)
   unsigned long long cull_violations; // verify mode: polygons from candidates the conservative cull rejected
-  unsigned long long plane_elems;     // elements sliced / clipped against a half space (k_plane, active pairs only)
+  unsigned long long plane_tets;      // tetrahedra sliced by a rigid half space (k_plane, active pairs only)
+  unsigned long long plane_tris;      // triangles clipped by a compliant half space
   // -- totals and per-chunk maxima of the chunk-local cursors
   unsigned long long leaf_tri_total, leaf_tet_total, polys_total, slow_total;
   unsigned long long frontier_max, leaf_tri_max, leaf_tet_max, polys_max, slow_max;

@@ -78,7 +78,7 @@ class Stats(C.Structure):
                  "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "algorithmic_bytes")] + \
                [("total_area", C.c_double), ("tet_tri_full_clips", C.c_int64), ("tet_tet_full_clips", C.c_int64),
                 ("leaf_pairs", C.c_int64), ("cull_violations", C.c_int64), ("exceptional_clips", C.c_int64),
-                ("leaf_exact_tests", C.c_int64)]
+                ("leaf_exact_tests", C.c_int64), ("half_space_elements", C.c_int64)]
 
 
 _lib = None

@@ -105,6 +105,15 @@ class SceneDraws:
 
 
 @dataclass
+class HalfSpaceShape:
+    """HalfSpace (z <= 0 of its frame) in a workload's asset list; compliant: pressure_scale = E / slab thickness."""
+    compliant: bool = False
+    pressure_scale: float = 0.0
+    margin: float = 0.0
+    vertices_per_element: int = 0
+
+
+@dataclass
 class Workload:
     """A batch of scenes instancing one scene template."""
     name: str
@@ -131,7 +140,8 @@ class Workload:
         passed) and returns a SceneBatch for all scenes. The handles used are kept in self.assets."""
         from .engine import SceneBatch
         if assets is None:
-            assets = [ctx.register_mesh(m) for m in self.meshes]
+            assets = [ctx.register_half_space(m.compliant, m.pressure_scale, m.margin) if isinstance(m, HalfSpaceShape)
+                      else ctx.register_mesh(m) for m in self.meshes]
         self.assets = list(assets)
         S, G = self.num_scenes, self.geoms_per_scene
         if self.per_scene_mesh is None:
@@ -225,6 +235,32 @@ def config3(num_scenes: int = 16384, scene0: int = 0) -> Workload:
                     [floor, plate, ball], [0, 1, 2], [1, 2, 3], [1, 0, 0], poses, POLYGON)
 
 
+def config3_half_space(num_scenes: int = 16384, scene0: int = 0) -> Workload:
+    """The ball_plate scene on a rigid HalfSpace ground (the most common rigid geometry):
+    rigid half space z <= 0 (anchored), the same soft ball (512 tets, E = 3e4) resting on it with penetration
+    ~U(0, r/2) under a uniform random orientation, and the rigid plate (24 triangles) pressed ~U(0, r/4) into
+    the top of the ball. Per scene: one compliant-mesh x rigid-half-space pair (k_plane) and one soft-rigid
+    mesh pair; plate x ground is rigid-rigid and filtered, as MultibodyPlant's default filters would."""
+    r = 0.05
+    ball = Mesh.sphere_volume(r, 0.015, SINGLE_INTERIOR_VERTEX).set_sphere_pressure(r, 3e4)
+    plate = Mesh.box_surface(0.2, 0.2, 0.01)
+    rng = SceneDraws(6, scene0, num_scenes)
+    S = num_scenes
+    draws = rng.uniform(4)
+    R = rng.rotations(1)[:, 0]
+    x = -0.05 + 0.1 * draws[:, 0]
+    y = -0.05 + 0.1 * draws[:, 1]
+    zb = r - 0.5 * r * draws[:, 2]
+    zp = zb + r - 0.25 * r * draws[:, 3] + 0.005
+    I = np.tile(np.eye(3), (S, 1, 1))
+    poses = np.stack([xforms(I, np.zeros((S, 3))), xforms(I, np.stack([np.zeros(S), np.zeros(S), zp], axis=1)),
+                      xforms(R, np.stack([x, y, zb], axis=1))], axis=1)
+    return Workload("c3h_ball_plate_half_space_ground",
+                    "soft ball (512 tets) on a rigid half space, rigid plate (24 tris) on the ball",
+                    [HalfSpaceShape(), plate, ball], [0, 1, 2], [1, 2, 3], [1, 0, 0], poses, POLYGON,
+                    excluded_local=np.array([[0, 1]], np.int32))
+
+
 # ----------------------------------------------------------------------- C4 ---
 
 def config4(num_scenes: int = 4096, scene0: int = 0, bodies: int = 32) -> Workload:
@@ -280,4 +316,5 @@ def config5(num_scenes: int = 1024, scene0: int = 0, hint: float = 0.03) -> Work
                     [0, 0], [1, 2], [0, 0], poses, POLYGON)
 
 
-CONFIGS = {"c1": config1, "c2": config2, "c2s": config2_spheres, "c3": config3, "c4": config4, "c5": config5}
+CONFIGS = {"c1": config1, "c2": config2, "c2s": config2_spheres, "c3": config3, "c3h": config3_half_space, "c4": config4,
+           "c5": config5}

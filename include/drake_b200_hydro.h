@@ -294,7 +294,7 @@ dbh_status dbh_batch_device_results(dbh_batch* batch, dbh_device_results* out);
 
 /* -- (8) statistics of the last completed query. ---------------------------- */
 typedef struct dbh_stats {
-  int64_t geometry_pairs_tested;   /* soft-rigid + soft-soft pairs whose root boxes were tested */
+  int64_t geometry_pairs_tested;   /* soft-rigid + soft-soft + half-space pairs whose root boxes were tested */
   int64_t geometry_pairs_overlapping; /* root boxes overlap */
   int64_t bv_pair_tests;
   int64_t tet_tri_pairs;           /* candidate element pairs narrow-phased */
@@ -312,6 +312,9 @@ typedef struct dbh_stats {
                                       candidates the conservative cull stage had rejected; must be 0 */
   int64_t exceptional_clips;       /* candidates whose intermediate polygon outgrew 8 vertices */
   int64_t leaf_exact_tests;        /* leaf pairs whose box predicate fp32 could not decide (fp64 test ran) */
+  int64_t half_space_elements;     /* tetrahedra sliced by a rigid half space + triangles clipped by a compliant
+                                      one (pairs whose root box reaches the boundary); 168 B / 108 B of
+                                      algorithmic bytes each */
 } dbh_stats;
 dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
 

@@ -93,6 +93,9 @@ def oracle_scene_for(workload):
     cache = {}
     for g, mi in enumerate(workload.geom_mesh):
         m = workload.meshes[mi]
+        if m.vertices_per_element == 0:  # drake_b200.workloads.HalfSpaceShape
+            sc.add_half_space(workload.geom_id[g], m.compliant, m.pressure_scale, m.margin, bool(workload.geom_anchored[g]))
+            continue
         if mi not in cache:
             v, e, p = m.arrays()
             if m.vertices_per_element == 4:
@@ -105,4 +108,7 @@ def oracle_scene_for(workload):
             sc.add_rigid(workload.geom_id[g], om, bool(workload.geom_anchored[g]))
         else:
             sc.add_compliant(workload.geom_id[g], om, of, bool(workload.geom_anchored[g]))
+    if workload.excluded_local is not None:
+        for a, b in np.asarray(workload.excluded_local).reshape(-1, 2):
+            sc.exclude(int(workload.geom_id[a]), int(workload.geom_id[b]))
     return sc, np.argsort(np.asarray(workload.geom_id))

@@ -233,3 +233,23 @@ def test_cpp_adapter_half_space():
     res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
     assert res.stdout.strip().endswith("ok")
+
+
+def test_config3_on_a_half_space_ground(ctx):
+    """The bench workload c3h (ball on a rigid HalfSpace ground, plate on the ball): 32 scenes against the
+    scene-level oracle, and the half-space element counter of the stats call."""
+    from drake_b200 import workloads as W
+    wl = W.config3_half_space(32)
+    batch = wl.register(ctx)
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KPOLYGON)
+    osc, order = parity.oracle_scene_for(wl)
+    total = 0
+    for s in range(wl.num_scenes):
+        want, _ = osc.compute(wl.poses[s][order], ho.KPOLYGON)
+        assert [(x.id_M, x.id_N) for x in got[s]] == [(x.id_M, x.id_N) for x in want]
+        for g, w in zip(got[s], want):
+            parity.compare_surface(g, w, welded=is_welded(w))
+        total += len(want)
+    assert total == 64  # ball x ground and ball x plate in every scene
+    st = batch.stats()
+    assert st["half_space_elements"] == 32 * 512 and st["geometry_pairs_tested"] == 64
