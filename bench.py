@@ -430,9 +430,13 @@ def main():
     # to their candidate counts.
     out_bytes = (s_mean["vertices"] if rep == engine.POLYGON else s_mean["vertices"] - s_mean["polygons"]) * 32.0 + \
         s_mean["polygons"] * 108.0
-    cand = max(1.0, s_mean["tet_tri_pairs"] + s_mean["tet_tet_pairs"])
+    # Half-space pairs (k_plane count pass, timed in the same slot as the tet-tet clip): 168 B per sliced
+    # tetrahedron (the bench workloads have no compliant half space, whose triangles would count 108 B).
+    plane_bytes = s_mean["half_space_elements"] * 168.0
+    alg["clip_tet_tet"] += plane_bytes
+    cand = max(1.0, s_mean["tet_tri_pairs"] + s_mean["tet_tet_pairs"] + s_mean["half_space_elements"])
     alg["clip_tet_tri"] += out_bytes * s_mean["tet_tri_pairs"] / cand
-    alg["clip_tet_tet"] += out_bytes * s_mean["tet_tet_pairs"] / cand
+    alg["clip_tet_tet"] += out_bytes * (s_mean["tet_tet_pairs"] + s_mean["half_space_elements"]) / cand
     dominant = max(alg, key=lambda k: avg.get(k, 0.0))
     peak, peak_kind = measured_peaks()
     achieved = alg[dominant] / (avg[dominant] * 1e-3) / 1e9 if avg[dominant] > 0 else 0.0
@@ -451,7 +455,8 @@ def main():
                 traffic = None
     roofline = {"bound": "hbm", "kernel": {"traverse": "k_traverse (all levels of one query)",
                                            "clip_tet_tri": "k_filter<false> + k_clip<false>",
-                                           "clip_tet_tet": "k_filter<true> + k_clip<true>"}[dominant],
+                                           "clip_tet_tet": "k_filter<true> + k_clip<true>" if not plane_bytes else
+                                           "k_filter<true> + k_clip<true> + k_plane_setup + k_plane<count>"}[dominant],
                 "achieved": achieved, "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": avg[dominant],

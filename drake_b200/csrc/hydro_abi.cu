@@ -344,6 +344,7 @@ struct dbh_batch {
   std::vector<long long> plane_elem_off;
   DevBuf<int> d_plane_pairs;
   DevBuf<long long> d_plane_elem_off;
+  DevBuf<unsigned char> d_plane_n;   // polygon size per element of the current chunk's half-space pairs
   DevBuf<double> d_geom_hs;
 
   DevBuf<PairRec> d_pairs;
@@ -410,6 +411,17 @@ struct dbh_batch {
     CUDA_OK(d_cand_tri.ensure(info.num_soft_rigid_pairs ? cap_tri : 1));
     CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_tet : 1));
     CUDA_OK(d_slow.ensure(cap_slow));
+    if (!plane_pairs.empty()) {
+      long long most = 1;
+      for (int c = 0; c < num_chunks; ++c) {
+        const int s0 = static_cast<int>(static_cast<long long>(num_scenes) * c / num_chunks);
+        const int s1 = static_cast<int>(static_cast<long long>(num_scenes) * (c + 1) / num_chunks);
+        const auto q0 = std::lower_bound(plane_pairs.begin(), plane_pairs.end(), scene_first_pair[s0]) - plane_pairs.begin();
+        const auto q1 = std::lower_bound(plane_pairs.begin(), plane_pairs.end(), scene_first_pair[s1]) - plane_pairs.begin();
+        most = std::max(most, plane_elem_off[q1] - plane_elem_off[q0]);
+      }
+      CUDA_OK(d_plane_n.ensure(static_cast<size_t>(most)));
+    }
     CUDA_OK(d_soup_hdr.ensure(cap_polys));
     CUDA_OK(d_soup_v.ensure(static_cast<size_t>(cap_polys) * kMaxPolyVerts * 4));
     CUDA_OK(d_soup_nhat.ensure(static_cast<size_t>(cap_polys) * 3));
@@ -1126,6 +1138,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pl.plane_pairs = b->d_plane_pairs.p;
     pl.plane_elem_off = b->d_plane_elem_off.p;
     pl.geom_hs = b->d_geom_hs.p;
+    pl.elem_n = b->d_plane_n.p;
     pl.pair_polys = b->d_pair_polys.p;
     pl.pair_verts = b->d_pair_verts.p;
     pl.pair_cursor = b->d_pair_cursor.p;

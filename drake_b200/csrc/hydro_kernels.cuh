@@ -1856,9 +1856,10 @@ __global__ void k_scene_stats(const PairRec* pairs, int num_pairs, long long* sc
 // Half-space pairs (CalcRigidCompliant's special cases, hydroelastic_calculator.cc:25-41). There is
 // one mesh per pair, so no dual-tree descent: k_plane_setup poses the half space in the mesh's frame
 // and tests the mesh's root box against it; k_plane<false> runs one thread per element of every pair
-// whose root box straddles the boundary and counts its polygon; after the scan k_plane<true> runs the
-// same arithmetic again and writes the polygon straight into its final slot (the polygons are at most
-// quadrilaterals out of one record each: recomputing is cheaper than staging them). Vertices are per
+// whose root box straddles the boundary, counts its polygon and notes its size in a byte per element;
+// after the scan k_plane<true> runs the same arithmetic again for the elements that emit and writes
+// the polygon straight into its final slot (the polygons are at most quadrilaterals out of one record
+// each: recomputing is cheaper than staging them). Vertices are per
 // polygon; the reference welds the ones cut from the same mesh edge (cut_edges,
 // mesh_plane_intersection.cc:205-231): face quantities do not depend on that.
 struct PlaneArgs {
@@ -1872,6 +1873,7 @@ struct PlaneArgs {
   const long long* plane_elem_off;  // [num_plane_pairs + 1]: elements before each of them
   const double* geom_hs;            // [2 * flat geometry]: pressure scale, margin of a compliant half space
   int q_begin, q_end;               // this chunk's range of the list
+  unsigned char* elem_n;            // [elements of the chunk's half-space pairs]: polygon size found by the count pass
   int* pair_polys;
   int* pair_verts;
   unsigned long long* pair_cursor;
@@ -1938,7 +1940,7 @@ __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
     P.status = 0;
     int pair = -1, elem = 0;
     bool mesh_is_soft = false, swapped = false, worked = false;
-    if (i < count) {
+    if (i < count && (!kPack || a.elem_n[i] != 0)) {
       const long long w = w0 + i;
       int lo = a.q_begin, hi = a.q_end;  // plane_elem_off[lo] <= w < plane_elem_off[hi]
       while (hi - lo > 1) {
@@ -1973,6 +1975,7 @@ __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
     }
     const int n = P.status ? 0 : P.n;
     const bool valid = n > 0;
+    if (!kPack && i < count) a.elem_n[i] = (unsigned char)n;
     // The polygons of a warp mostly belong to one geometry pair: one lane updates the pair's counters
     // (or claims the warp's slots) for all of them.
     const unsigned validmask = __ballot_sync(0xffffffffu, valid);
