@@ -344,7 +344,7 @@ struct dbh_batch {
   std::vector<long long> plane_elem_off;
   DevBuf<int> d_plane_pairs;
   DevBuf<long long> d_plane_elem_off;
-  DevBuf<unsigned char> d_plane_n;   // polygon size per element of the current chunk's half-space pairs
+  DevBuf<unsigned int> d_plane_emit;  // the current chunk's emitting half-space elements (chunk-local indices)
   DevBuf<double> d_geom_hs;
 
   DevBuf<PairRec> d_pairs;
@@ -420,7 +420,9 @@ struct dbh_batch {
         const auto q1 = std::lower_bound(plane_pairs.begin(), plane_pairs.end(), scene_first_pair[s1]) - plane_pairs.begin();
         most = std::max(most, plane_elem_off[q1] - plane_elem_off[q0]);
       }
-      CUDA_OK(d_plane_n.ensure(static_cast<size_t>(most)));
+      if (most >= (1ll << 32))
+        return Fail(DBH_ERR_CAPACITY, "more than 2^32 half-space elements in one chunk of scenes: raise dbh_batch_set_chunks");
+      CUDA_OK(d_plane_emit.ensure(static_cast<size_t>(most)));
     }
     CUDA_OK(d_soup_hdr.ensure(cap_polys));
     CUDA_OK(d_soup_v.ensure(static_cast<size_t>(cap_polys) * kMaxPolyVerts * 4));
@@ -1138,7 +1140,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pl.plane_pairs = b->d_plane_pairs.p;
     pl.plane_elem_off = b->d_plane_elem_off.p;
     pl.geom_hs = b->d_geom_hs.p;
-    pl.elem_n = b->d_plane_n.p;
+    pl.emit_list = b->d_plane_emit.p;
     pl.pair_polys = b->d_pair_polys.p;
     pl.pair_verts = b->d_pair_verts.p;
     pl.pair_cursor = b->d_pair_cursor.p;

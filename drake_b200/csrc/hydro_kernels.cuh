@@ -1823,7 +1823,8 @@ __global__ void k_next_chunk(Counters* c) {
   if (blockIdx.x == 0) {
     if (threadIdx.x < 64) c->frontier[threadIdx.x] = 0;
     if (threadIdx.x == 0)
-      c->leaf_tri = c->leaf_tet = c->polys = c->slow = c->surv_tri = c->surv_tet = c->big_surfaces = c->work_tri = c->work_tet = 0;
+      c->leaf_tri = c->leaf_tet = c->polys = c->slow = c->surv_tri = c->surv_tet = c->big_surfaces = c->work_tri = c->work_tet =
+          c->plane_emit = 0;
   }
 }
 
@@ -1856,8 +1857,8 @@ __global__ void k_scene_stats(const PairRec* pairs, int num_pairs, long long* sc
 // Half-space pairs (CalcRigidCompliant's special cases, hydroelastic_calculator.cc:25-41). There is
 // one mesh per pair, so no dual-tree descent: k_plane_setup poses the half space in the mesh's frame
 // and tests the mesh's root box against it; k_plane<false> runs one thread per element of every pair
-// whose root box straddles the boundary, counts its polygon and notes its size in a byte per element;
-// after the scan k_plane<true> runs the same arithmetic again for the elements that emit and writes
+// whose root box straddles the boundary, counts its polygon and lists the elements that emit one;
+// after the scan k_plane<true> runs the same arithmetic again for the listed elements and writes
 // the polygon straight into its final slot (the polygons are at most quadrilaterals out of one record
 // each: recomputing is cheaper than staging them). Vertices are per
 // polygon; the reference welds the ones cut from the same mesh edge (cut_edges,
@@ -1873,7 +1874,8 @@ struct PlaneArgs {
   const long long* plane_elem_off;  // [num_plane_pairs + 1]: elements before each of them
   const double* geom_hs;            // [2 * flat geometry]: pressure scale, margin of a compliant half space
   int q_begin, q_end;               // this chunk's range of the list
-  unsigned char* elem_n;            // [elements of the chunk's half-space pairs]: polygon size found by the count pass
+  unsigned int* emit_list;          // [elements of the chunk's half-space pairs]: the ones that emit a polygon
+                                    // (count pass -> pack pass; Counters::plane_emit entries)
   int* pair_polys;
   int* pair_verts;
   unsigned long long* pair_cursor;
@@ -1926,11 +1928,39 @@ __global__ void k_plane_setup(PlaneArgs a) {
   if (active) atomicAdd(&a.counters->root_overlaps, 1ull);
 }
 
+// Which half-space pair owns work item w (plane_elem_off[q] <= w < plane_elem_off[q + 1])? The pairs of a
+// batch mostly have meshes of similar size, so an interpolated guess plus a short walk finds it in O(1)
+// loads; a binary search (a chain of ~log2(pairs) dependent loads) is only the fallback.
+__device__ __forceinline__ int find_plane_pair(const long long* off, int q_begin, int q_end, long long w, long long w0,
+                                               long long count) {
+  int q = q_begin + (int)(((w - w0) * (long long)(q_end - q_begin)) / count);  // in [q_begin, q_end - 1]
+  int steps = 0;
+  while (steps < 4 && off[q] > w) {
+    --q;
+    ++steps;
+  }
+  while (steps < 4 && off[q + 1] <= w) {
+    ++q;
+    ++steps;
+  }
+  if (off[q] <= w && w < off[q + 1]) return q;
+  int lo = q_begin, hi = q_end;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= w) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
 template <bool kPack>
 __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
   if (kPack && a.counters->error != 0) return;
   const long long w0 = a.plane_elem_off[a.q_begin];
-  const long long count = a.plane_elem_off[a.q_end] - w0;
+  const long long num_elems = a.plane_elem_off[a.q_end] - w0;
+  // Count pass: every element of the chunk's half-space pairs. Pack pass: the emitting elements only,
+  // from the list the count pass wrote.
+  const long long count = kPack ? (long long)a.counters->plane_emit : num_elems;
   const long long rounded = (count + 31ll) & ~31ll;  // whole warps reach the collectives
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -1939,20 +1969,17 @@ __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
     P.n = 0;
     P.status = 0;
     int pair = -1, elem = 0;
+    long long item = 0;
     bool mesh_is_soft = false, swapped = false, worked = false;
-    if (i < count && (!kPack || a.elem_n[i] != 0)) {
-      const long long w = w0 + i;
-      int lo = a.q_begin, hi = a.q_end;  // plane_elem_off[lo] <= w < plane_elem_off[hi]
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (a.plane_elem_off[mid] <= w) lo = mid;
-        else hi = mid;
-      }
-      pair = a.plane_pairs[lo];
+    if (i < count) {
+      item = kPack ? (long long)a.emit_list[i] : i;
+      const long long w = w0 + item;
+      const int q = find_plane_pair(a.plane_elem_off, a.q_begin, a.q_end, w, w0, num_elems);
+      pair = a.plane_pairs[q];
       const Xf rec = a.pair_X[pair];
       if (rec.m[4] != 0.0) {
         const PairRec pr = a.pairs[pair];
-        elem = (int)(w - a.plane_elem_off[lo]);
+        elem = (int)(w - a.plane_elem_off[q]);
         mesh_is_soft = pr.kind == kSoftMeshRigidPlane;
         swapped = pr.swapped != 0;
         const D3 nhat = make_d3(rec.m[0], rec.m[1], rec.m[2]);
@@ -1975,7 +2002,10 @@ __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
     }
     const int n = P.status ? 0 : P.n;
     const bool valid = n > 0;
-    if (!kPack && i < count) a.elem_n[i] = (unsigned char)n;
+    if (!kPack) {  // the emitting elements, for the pack pass (the list holds every element: it cannot overflow)
+      const unsigned long long slot = warp_append_flag(&a.counters->plane_emit, valid);
+      if (valid) a.emit_list[slot] = (unsigned int)item;
+    }
     // The polygons of a warp mostly belong to one geometry pair: one lane updates the pair's counters
     // (or claims the warp's slots) for all of them.
     const unsigned validmask = __ballot_sync(0xffffffffu, valid);

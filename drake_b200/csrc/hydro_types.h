@@ -187,6 +187,7 @@ struct Counters {
   unsigned long long big_surfaces;  // surfaces of this chunk summed by the whole grid
   unsigned long long work_tri;      // next unclaimed 1024-entry chunk of the tet-tri leaf list (filter kernel)
   unsigned long long work_tet;      // same, tet-tet
+  unsigned long long plane_emit;    // half-space pairs: elements that emit a polygon (entries of the pack pass's list)
   // -- whole query
   unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
   unsigned long long cand_tri;      // tet-tri candidate pairs: leaf pairs that pass the exact predicate
