@@ -1985,7 +1985,8 @@ __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
         const D3 nhat = make_d3(rec.m[0], rec.m[1], rec.m[2]);
         if (mesh_is_soft) {
           const int t = pr.elem_base_a + elem;
-          slice_tet_with_plane(a.pools.tets[t], a.tet_vp + 4ll * t, nhat, rec.m[3], a.poses[pr.geom_a], &P);
+          if (kPack) slice_tet_with_plane(a.pools.tets[t], a.tet_vp + 4ll * t, nhat, rec.m[3], a.poses[pr.geom_a], &P);
+          else P.n = count_tet_slice(a.pools.tets[t], nhat, rec.m[3]);  // same heights, same sign code
         } else {
           clip_tri_by_half_space(a.pools.tris[pr.elem_base_b + elem], nhat, rec.m[3], rec.m[5], rec.m[6],
                                  a.poses[pr.geom_b], a.poses[pr.geom_a], &P);

@@ -39,14 +39,33 @@ __host__ __device__ __forceinline__ void rigid_half_space_in_mesh_frame(const Xf
   *displacement = dot(Rz_S, p_SRo);
 }
 
+// kMarchingTetsEdgeTable (mesh_plane_intersection.cc:47-64): the up to four tetrahedron edges cut by the
+// plane for a sign code (bit i set: vertex i strictly above), one edge index per nibble, 0xF = none.
+__host__ __device__ __forceinline__ unsigned int marching_tets_row(int code) {
+  const unsigned short kEdgeTable[16] = {0xFFFF, 0xF230, 0xF410, 0x1234, 0xF521, 0x1530, 0x4520, 0xF453,
+                                         0xF543, 0x0254, 0x0351, 0xF251, 0x4321, 0xF140, 0xF320, 0xFFFF};
+  return kEdgeTable[code];
+}
+
+// Only the size (0, 3 or 4) of the polygon slice_tet_with_plane would produce: the same heights and
+// sign code, nothing else (the count pass needs no pose, pressure or gradient).
+__host__ __device__ __forceinline__ int count_tet_slice(const TetRec& tet, D3 nhat_S, double displacement) {
+  int code = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (dot(nhat_S, load3(tet.v[i])) - displacement > 0) code |= 1 << i;
+  }
+  const unsigned int row = marching_tets_row(code);
+  if ((row & 0xFu) == 0xFu) return 0;
+  return ((row >> 12) & 0xFu) == 0xFu ? 3 : 4;
+}
+
 // SliceTetWithPlane (mesh_plane_intersection.cc:182-249) for one tetrahedron: marching-tetrahedra
 // tables (:20-117, four edge indices per sign code, packed one per nibble, 0xF = none), cut point
 // p_MV0 + t (p_MV1 - p_MV0) with t = d0 / (d0 - d1), pressure e0 + t (e1 - e0) from the VERTEX values,
 // vertices re-expressed in World before they reach the builder. vp: the four vertex pressures.
 __host__ __device__ __forceinline__ void slice_tet_with_plane(const TetRec& tet, const double* vp, D3 nhat_S,
                                                               double displacement, const Xf& X_WS, WorldPoly* out) {
-  const unsigned short kEdgeTable[16] = {0xFFFF, 0xF230, 0xF410, 0x1234, 0xF521, 0x1530, 0x4520, 0xF453,
-                                         0xF543, 0x0254, 0x0351, 0xF251, 0x4321, 0xF140, 0xF320, 0xFFFF};
   const unsigned int kEdgeFirst = 0x210210u;   // kTetEdges[k].first, one per nibble
   const unsigned int kEdgeSecond = 0x333021u;  // kTetEdges[k].second
   out->n = 0;
@@ -58,7 +77,7 @@ __host__ __device__ __forceinline__ void slice_tet_with_plane(const TetRec& tet,
     distance[i] = dot(nhat_S, load3(tet.v[i])) - displacement;  // Plane::CalcHeight (plane.h:69-71)
     if (distance[i] > 0) code |= 1 << i;
   }
-  const unsigned int row = kEdgeTable[code];
+  const unsigned int row = marching_tets_row(code);
   if ((row & 0xFu) == 0xFu) return;
   int n = 0;
 #pragma unroll

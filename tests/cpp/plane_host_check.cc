@@ -84,6 +84,7 @@ int phc_mesh_vs_rigid_half_space(int nt, const double* tet_v, const double* tet_
     WorldPoly P;
     slice_tet_with_plane(rec, tet_vp + 4 * t, nhat_S, disp, XS, &P);
     if (P.status) return P.status;
+    if (count_tet_slice(rec, nhat_S, disp) != P.n) return -1;  // the count pass's shortcut must agree
     if (P.n) Append(P, rep, swapped != 0, t, &o);
   }
   counts4[0] = o.nf, counts4[1] = o.nv, counts4[2] = o.nfd, counts4[3] = o.npoly;
