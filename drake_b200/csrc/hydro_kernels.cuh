@@ -1928,31 +1928,6 @@ __global__ void k_plane_setup(PlaneArgs a) {
   if (active) atomicAdd(&a.counters->root_overlaps, 1ull);
 }
 
-// Which half-space pair owns work item w (plane_elem_off[q] <= w < plane_elem_off[q + 1])? The pairs of a
-// batch mostly have meshes of similar size, so an interpolated guess plus a short walk finds it in O(1)
-// loads; a binary search (a chain of ~log2(pairs) dependent loads) is only the fallback.
-__device__ __forceinline__ int find_plane_pair(const long long* off, int q_begin, int q_end, long long w, long long w0,
-                                               long long count) {
-  int q = q_begin + (int)(((w - w0) * (long long)(q_end - q_begin)) / count);  // in [q_begin, q_end - 1]
-  int steps = 0;
-  while (steps < 4 && off[q] > w) {
-    --q;
-    ++steps;
-  }
-  while (steps < 4 && off[q + 1] <= w) {
-    ++q;
-    ++steps;
-  }
-  if (off[q] <= w && w < off[q + 1]) return q;
-  int lo = q_begin, hi = q_end;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (off[mid] <= w) lo = mid;
-    else hi = mid;
-  }
-  return lo;
-}
-
 template <bool kPack>
 __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
   if (kPack && a.counters->error != 0) return;

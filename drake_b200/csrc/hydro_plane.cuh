@@ -175,6 +175,31 @@ __host__ __device__ __forceinline__ void clip_tri_by_half_space(const TriRec& tr
   out->grad_W = (-pressure_scale) * Sz_W;  // grad_p_W (:398)
 }
 
+// Which half-space pair owns work item w (plane_elem_off[q] <= w < plane_elem_off[q + 1])? The pairs of a
+// batch mostly have meshes of similar size, so an interpolated guess plus a short walk finds it in O(1)
+// loads; a binary search (a chain of ~log2(pairs) dependent loads) is only the fallback.
+__host__ __device__ __forceinline__ int find_plane_pair(const long long* off, int q_begin, int q_end, long long w, long long w0,
+                                               long long count) {
+  int q = q_begin + (int)(((w - w0) * (long long)(q_end - q_begin)) / count);  // in [q_begin, q_end - 1]
+  int steps = 0;
+  while (steps < 4 && off[q] > w) {
+    --q;
+    ++steps;
+  }
+  while (steps < 4 && off[q + 1] <= w) {
+    ++q;
+    ++steps;
+  }
+  if (off[q] <= w && w < off[q + 1]) return q;
+  int lo = q_begin, hi = q_end;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= w) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
 // What one polygon contributes to the packed results.
 struct PackedPoly {
   int nv;           // vertices: n (polygons) or n + 1 (triangle fan about the centroid)

@@ -116,4 +116,17 @@ int phc_half_space_vs_rigid_mesh(int nt, const double* tri_v, const double* tri_
   return 0;
 }
 
+// The work item -> pair map of k_plane (interpolated guess + short walk + binary-search fallback) against a
+// plain linear scan, for every work item of the range [q_begin, q_end). Returns the number of mismatches.
+int phc_check_find_plane_pair(int num_pairs, const long long* off, int q_begin, int q_end) {
+  (void)num_pairs;
+  const long long w0 = off[q_begin], count = off[q_end] - w0;
+  int bad = 0, q_lin = q_begin;
+  for (long long w = w0; w < w0 + count; ++w) {
+    while (off[q_lin + 1] <= w) ++q_lin;
+    if (find_plane_pair(off, q_begin, q_end, w, w0, count) != q_lin) ++bad;
+  }
+  return bad;
+}
+
 }  // extern "C"

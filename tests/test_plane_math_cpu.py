@@ -188,3 +188,18 @@ def test_reference_fixtures_through_the_kernel_arithmetic():
     np.testing.assert_allclose(host.areas.sum(), 12.0, atol=1e-12)
     host = host_half_space_vs_mesh(box, X_WH, 17.0, 0.0, X_WF, ho.KTRIANGLE, False)
     assert list(host.counts) == [34, 34 + 10, 3 * 34, 10]
+
+
+def test_work_item_to_pair_lookup():
+    """find_plane_pair (interpolated guess, <= 4-step walk, binary-search fallback) for equal, mixed and wildly
+    different mesh sizes, on whole lists and on chunk sub-ranges."""
+    lib = harness()
+    lp = C.POINTER(C.c_longlong)
+    lib.phc_check_find_plane_pair.argtypes = [C.c_int, lp, C.c_int, C.c_int]
+    rng = np.random.default_rng(2)
+    for sizes in ([512] * 200, [24, 512, 116] * 50, list(rng.integers(1, 40, size=300)),
+                  [1] * 100 + [5000] + [1] * 100, [3000, 1, 1, 1, 1, 1, 1, 1, 2000], [7]):
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        n = len(sizes)
+        for qb, qe in [(0, n), (n // 3, n), (0, max(1, n // 2)), (n // 4, max(n // 4 + 1, 3 * n // 4))]:
+            assert lib.phc_check_find_plane_pair(n, off.ctypes.data_as(lp), qb, qe) == 0, (sizes[:5], qb, qe)
