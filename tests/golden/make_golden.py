@@ -17,7 +17,11 @@ from oracle import ho  # noqa: E402
 from tests import parity  # noqa: E402
 
 CASES = {"c3_16_scenes": (lambda: W.config3(16), ho.KPOLYGON), "c3_16_scenes_tri": (lambda: W.config3(16), ho.KTRIANGLE),
-         "c4_2_scenes": (lambda: W.config4(2), ho.KPOLYGON), "c2s_2_scenes": (lambda: W.config2_spheres(2, 0, 1.0), ho.KPOLYGON)}
+         "c4_2_scenes": (lambda: W.config4(2), ho.KPOLYGON), "c2s_2_scenes": (lambda: W.config2_spheres(2, 0, 1.0), ho.KPOLYGON),
+         # Half-space ground. "vertices" is the oracle's WELDED count (the reference welds vertices cut
+         # from the same mesh edge); the kernels keep vertices per polygon, so GPU tests do not compare it for these surfaces.
+         "c3h_16_scenes": (lambda: W.config3_half_space(16), ho.KPOLYGON),
+         "c3h_16_scenes_tri": (lambda: W.config3_half_space(16), ho.KTRIANGLE)}
 
 
 def digest(workload, rep):
