@@ -1155,7 +1155,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     // block-wide appends; filter / pack: resident blocks per SM the launch bound asks for (registers against
     // occupancy); tgrid / fgrid / pgrid: grid size in units of the resident blocks -- persistent grids (1x for the
     // traversal and the pack) beat over-subscribed ones by 5-15 % (no tail wave).
-    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1; } tune;
+    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, plane = 1; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1168,6 +1168,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       get("tgrid", &tune.tgrid);
       get("fgrid", &tune.fgrid);
       get("pgrid", &tune.pgrid);
+      get("plane", &tune.plane);  // 2: experimental count pass of the half-space pairs (k_plane_count2)
     }
     for (int chunk = 0; chunk < b->num_chunks; ++chunk) {
       const int s0 = static_cast<int>(static_cast<long long>(b->num_scenes) * chunk / b->num_chunks);
@@ -1229,7 +1230,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         plane_blocks = static_cast<int>(std::min<long long>((elems + 127) / 128, static_cast<long long>(sms) * 16));
         b->last_launches += 2;
         k_plane_setup<<<(pl.q_end - pl.q_begin + 127) / 128, 128, 0, st>>>(pl);
-        k_plane<false><<<plane_blocks, 128, 0, st>>>(pl);
+        if (tune.plane == 2) k_plane_count2<<<plane_blocks, 128, 0, st>>>(pl);
+        else k_plane<false><<<plane_blocks, 128, 0, st>>>(pl);
       }
       mark(4);
       sa.pair_begin = p0;

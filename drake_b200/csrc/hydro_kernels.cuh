@@ -2073,4 +2073,73 @@ __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
   }
 }
 
+// EXPERIMENTAL count pass (DBH_TUNE="plane=2"; NOT the default and not yet run on a GPU: the round's GPU
+// time ended with the measurement that motivates it, profiles/README.md "Half-space kernels"). Same
+// arithmetic and the same outputs as k_plane<false>; what changes is where the same-address atomics go:
+// the statistics are accumulated in registers and added once per warp at the end, and the emit list is
+// appended with one atomic per block iteration (block_append_flag) instead of one per warp iteration.
+__global__ void __launch_bounds__(128) k_plane_count2(PlaneArgs a) {
+  __shared__ BlockAppendSmem<4> sh;
+  const long long w0 = a.plane_elem_off[a.q_begin];
+  const long long num_elems = a.plane_elem_off[a.q_end] - w0;
+  const long long rounded = (num_elems + 127ll) & ~127ll;  // whole blocks reach the barriers of the append
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  unsigned int my_tets = 0, my_tris = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+    WorldPoly P;
+    P.n = 0;
+    P.status = 0;
+    int pair = -1;
+    if (i < num_elems) {
+      const long long w = w0 + i;
+      const int q = find_plane_pair(a.plane_elem_off, a.q_begin, a.q_end, w, w0, num_elems);
+      pair = a.plane_pairs[q];
+      const Xf rec = a.pair_X[pair];
+      if (rec.m[4] != 0.0) {
+        const PairRec pr = a.pairs[pair];
+        const int elem = (int)(w - a.plane_elem_off[q]);
+        const D3 nhat = make_d3(rec.m[0], rec.m[1], rec.m[2]);
+        if (pr.kind == kSoftMeshRigidPlane) {
+          P.n = count_tet_slice(a.pools.tets[pr.elem_base_a + elem], nhat, rec.m[3]);
+          ++my_tets;
+        } else {
+          clip_tri_by_half_space(a.pools.tris[pr.elem_base_b + elem], nhat, rec.m[3], rec.m[5], rec.m[6],
+                                 a.poses[pr.geom_b], a.poses[pr.geom_a], &P);
+          ++my_tris;
+          if (P.status) raise_error(a.counters, P.status, pair);
+        }
+      }
+    }
+    const int n = P.status ? 0 : P.n;
+    const bool valid = n > 0;
+    const unsigned long long slot = block_append_flag<4>(&a.counters->plane_emit, valid, sh);
+    if (valid) a.emit_list[slot] = (unsigned int)i;
+    const unsigned validmask = __ballot_sync(0xffffffffu, valid);
+    if (!validmask) continue;
+    const int lead = __ffs(validmask) - 1;
+    const int pair0 = __shfl_sync(0xffffffffu, pair, lead);
+    const bool uniform = __all_sync(0xffffffffu, !valid || pair == pair0);
+    if (uniform) {
+      int total = valid ? n : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+      if (lane == lead) {
+        atomicAdd(&a.pair_polys[pair0], __popc(validmask));
+        atomicAdd(&a.pair_verts[pair0], total);
+      }
+    } else if (valid) {
+      atomicAdd(&a.pair_polys[pair], 1);
+      atomicAdd(&a.pair_verts[pair], n);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    my_tets += __shfl_xor_sync(0xffffffffu, my_tets, d);
+    my_tris += __shfl_xor_sync(0xffffffffu, my_tris, d);
+  }
+  if (lane == 0 && my_tets) atomicAdd(&a.counters->plane_tets, (unsigned long long)my_tets);
+  if (lane == 0 && my_tris) atomicAdd(&a.counters->plane_tris, (unsigned long long)my_tris);
+}
+
 }  // namespace dbh
