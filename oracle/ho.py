@@ -64,6 +64,12 @@ def lib():
         _lib.ho_soft_mesh_rigid_half_space.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int64, C.c_int64, C.c_int]
         _lib.ho_soft_half_space_rigid_mesh.argtypes = [C.c_int, _dp, C.c_double, C.c_double, _dp, C.c_int64, C.c_int64,
                                                        C.c_int]
+        _lib.ho_result_from_arrays.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, _ip, _dp, C.c_int64, C.c_int64]
+        _lib.ho_traction.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, _dp]
+        for name, n in (("ho_atan_x_over_x_from_x_squared", 1), ("ho_combined_dissipation", 4),
+                        ("ho_combined_friction", 2)):
+            getattr(_lib, name).argtypes = [C.c_double] * n
+            getattr(_lib, name).restype = C.c_double
         _lib.ho_scene_add_half_space.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int]
         _lib.ho_scene_add_geometry.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib.ho_scene_exclude_pair.argtypes = [C.c_int, C.c_int64, C.c_int64]
@@ -314,6 +320,7 @@ class Surface:
     centroid: np.ndarray
     elem_first: np.ndarray
     elem_second: np.ndarray
+    handle: Optional[int] = None  # oracle-side result kept alive (inside `with keep_handles():`) for traction()
 
     @property
     def num_faces(self) -> int:
@@ -330,6 +337,29 @@ class Surface:
             out.append(fd[i + 1:i + 1 + n])
             i += n + 1
         return out
+
+
+_KEEP_HANDLES = False
+
+
+class keep_handles:
+    """Context manager: surfaces fetched inside keep their oracle-side result (Surface.handle) so that
+    traction() can run on exactly the arrays the oracle computed."""
+
+    def __enter__(self):
+        global _KEEP_HANDLES
+        self._old, _KEEP_HANDLES = _KEEP_HANDLES, True
+        return self
+
+    def __exit__(self, *exc):
+        global _KEEP_HANDLES
+        _KEEP_HANDLES = self._old
+        return False
+
+
+def _fetch_result_keep(h: int) -> "Surface":
+    with keep_handles():
+        return _fetch_result(h)
 
 
 def _fetch_result(h: int) -> Surface:
@@ -353,11 +383,12 @@ def _fetch_result(h: int) -> Surface:
     e1 = np.zeros(nf, dtype=np.int32)
     L.ho_result_get(h, _pd(verts), _pd(pres), _pi(fd), _pd(areas), _pd(normals), _pd(cents), _pd(ec), _pd(fg), _pd(fo),
                     _pd(gm), _pd(gn), _pd(tot), _pi(e0), _pi(e1))
-    L.ho_result_free(h)
+    if not _KEEP_HANDLES:
+        L.ho_result_free(h)
     if rep == KTRIANGLE:
         fd = fd.reshape(-1, 3)
     return Surface(ids[0], ids[1], rep, verts, pres, fd, areas, normals, cents, ec, fg, fo, gm, gn, float(tot[0]),
-                   tot[1:4].copy(), e0, e1)
+                   tot[1:4].copy(), e0, e1, h if _KEEP_HANDLES else None)
 
 
 def soft_rigid(mesh_S: VolumeMesh, field_S: VolumeField, mesh_R: TriMesh, X_WS, X_WR, id_S: int = 1, id_R: int = 2,
@@ -405,6 +436,42 @@ def soft_half_space_rigid_mesh(mesh_R: TriMesh, X_WS, pressure_scale: float, X_W
     if h == -1:
         return None
     return _fetch_result(_check(h, "soft_half_space_rigid_mesh"))
+
+
+# ---- the contact-surface consumer of SURVEY 8(f) rank 3 (hydroelastic_traction_calculator.cc) -------------
+
+def surface_from_arrays(rep: int, verts, pressures, face_data, grads=None, id_M: int = 1, id_N: int = 2):
+    """A ContactSurface from explicit World-frame arrays (polygon: face_data |n|v..| + one gradient per face;
+    triangle: [F,3] indices). The returned Surface keeps its handle for traction()."""
+    v, p, fd = _d(verts).reshape(-1, 3), _d(pressures).reshape(-1), _i(face_data).reshape(-1)
+    g = _d(grads).reshape(-1, 3) if grads is not None else None
+    h = _check(lib().ho_result_from_arrays(rep, len(v), _pd(v), _pd(p), len(fd), _pi(fd), _pd(g), id_M, id_N),
+               "result_from_arrays")
+    return _fetch_result_keep(h)
+
+
+def traction(surface: Surface, p_WAo, p_WBo, V_WA, V_WB, dissipation: float, mu_coulomb: float,
+             vslip_regularizer: float = 1e-6):
+    """HydroelasticTractionCalculator: (F_Ac_W, F_Ao_W, F_Bo_W), each [6] = (tau, f); V = (w, v); A / B are the
+    bodies of geometries M / N. `surface` must have been fetched inside `with keep_handles():`."""
+    assert surface.handle is not None, "fetch the surface inside `with ho.keep_handles():`"
+    out = np.zeros(18)
+    rc = lib().ho_traction(surface.handle, _pd(_d(p_WAo)), _pd(_d(p_WBo)), _pd(_d(V_WA)), _pd(_d(V_WB)), dissipation,
+                           mu_coulomb, vslip_regularizer, _pd(out))
+    _check(rc, "traction")
+    return out[0:6], out[6:12], out[12:18]
+
+
+def atan_x_over_x_from_x_squared(x2: float) -> float:
+    return lib().ho_atan_x_over_x_from_x_squared(x2)
+
+
+def combined_dissipation(stiffness_A, stiffness_B, dA, dB) -> float:
+    return lib().ho_combined_dissipation(stiffness_A, stiffness_B, dA, dB)
+
+
+def combined_friction(mu_A, mu_B) -> float:
+    return lib().ho_combined_friction(mu_A, mu_B)
 
 
 def candidates(mesh_A: VolumeMesh, mesh_B, X_AB, mode: int = MODE_BRUTE) -> Tuple[np.ndarray, int]:

@@ -19,6 +19,7 @@
 #include "ho_bvh.h"
 #include "ho_contact.h"
 #include "ho_halfspace.h"
+#include "ho_traction.h"
 
 using namespace ho;
 
@@ -558,6 +559,62 @@ int ho_soft_half_space_rigid_mesh(int tri, const double* X_WS, double pressure_s
   return AddResult(std::move(res));
   HO_CATCH(-2)
 }
+
+// A ContactSurface built from explicit arrays already in World (what the reference's traction tests do,
+// hydroelastic_traction_calculator_test.cc:149-187): polygon rep: face_data |n|v..|, one gradient per face;
+// triangle rep: face_data = 3 indices per face, grads ignored.
+int ho_result_from_arrays(int rep, int nv, const double* verts, const double* pressures, int nfd, const int* face_data,
+                          const double* grads, int64_t id_M, int64_t id_N) {
+  HO_TRY
+  MeshBuilder b(static_cast<Representation>(rep));
+  b.vertices_B = ToVec3(nv, verts);
+  b.pressures.assign(pressures, pressures + nv);
+  if (b.rep == Representation::kPolygon) {
+    b.face_data.assign(face_data, face_data + nfd);
+    int f = 0;
+    for (int i = 0; i < nfd; i += face_data[i] + 1, ++f)
+      b.grad_e_per_face.push_back(Vec3{grads[3 * f], grads[3 * f + 1], grads[3 * f + 2]});
+  } else {
+    for (int i = 0; i + 2 < nfd; i += 3) b.faces.push_back({face_data[i], face_data[i + 1], face_data[i + 2]});
+  }
+  SurfaceResult res;
+  MakeMeshAndFieldInWorld(std::move(b), Xform{}, &res, /*already_in_world=*/true);
+  res.id_M = id_M;
+  res.id_N = id_N;
+  res.elem_first.assign(res.num_faces(), 0);
+  res.elem_second.assign(res.num_faces(), 0);
+  return AddResult(std::move(res));
+  HO_CATCH(-2)
+}
+
+// HydroelasticTractionCalculator (hydroelastic_traction_calculator.cc:24-83) on a result handle: A / B are
+// the bodies of geometries M / N. V = (w, v). out18 = F_Ac_W, F_Ao_W, F_Bo_W, each (tau, f).
+int ho_traction(int h, const double* p_WAo, const double* p_WBo, const double* V_WA, const double* V_WB,
+                double dissipation, double mu_coulomb, double vslip_regularizer, double* out18) {
+  HO_TRY
+  const SurfaceResult& r = *g_results[h];
+  TractionData d;
+  d.p_WAo = {p_WAo[0], p_WAo[1], p_WAo[2]};
+  d.p_WBo = {p_WBo[0], p_WBo[1], p_WBo[2]};
+  d.V_WA = {Vec3{V_WA[0], V_WA[1], V_WA[2]}, Vec3{V_WA[3], V_WA[4], V_WA[5]}};
+  d.V_WB = {Vec3{V_WB[0], V_WB[1], V_WB[2]}, Vec3{V_WB[3], V_WB[4], V_WB[5]}};
+  d.p_WC = r.centroid_W;
+  const Spatial F_Ac_W = SpatialForceAtCentroid(r, d, dissipation, mu_coulomb, vslip_regularizer);
+  Spatial F_Ao_W, F_Bo_W;
+  ShiftToBodyOrigins(d, F_Ac_W, &F_Ao_W, &F_Bo_W);
+  const Spatial* all[3] = {&F_Ac_W, &F_Ao_W, &F_Bo_W};
+  for (int k = 0; k < 3; ++k) {
+    out18[6 * k + 0] = all[k]->rot.x, out18[6 * k + 1] = all[k]->rot.y, out18[6 * k + 2] = all[k]->rot.z;
+    out18[6 * k + 3] = all[k]->trans.x, out18[6 * k + 4] = all[k]->trans.y, out18[6 * k + 5] = all[k]->trans.z;
+  }
+  return 0;
+  HO_CATCH(-2)
+}
+double ho_atan_x_over_x_from_x_squared(double x2) { return CalcAtanXOverXFromXSquared(x2); }
+double ho_combined_dissipation(double kA, double kB, double dA, double dB) {
+  return CombinedHuntCrossleyDissipation(kA, kB, dA, dB);
+}
+double ho_combined_friction(double mu_A, double mu_B) { return CombinedDynamicFriction(mu_A, mu_B); }
 
 // info[0..7] = rep, nfaces, nverts, nfacedata (poly) or 3*ntris, has_grad_eM, has_grad_eN, -, -
 int ho_result_info(int h, int64_t* ids2, int* info8) {
