@@ -344,6 +344,10 @@ struct dbh_batch {
   std::vector<long long> plane_elem_off;
   DevBuf<int> d_plane_pairs;
   DevBuf<long long> d_plane_elem_off;
+  // Contact-surface consumer (k_wrench): per-geometry body origins / spatial velocities / contact properties and the
+  // per-surface spatial forces.
+  DevBuf<double> d_body_origin, d_body_vel, d_props, d_forces;
+  bool have_body_origin{false}, have_body_vel{false}, have_props{false}, forces_done{false};
   DevBuf<unsigned int> d_plane_emit;  // the current chunk's emitting half-space elements (chunk-local indices)
   DevBuf<double> d_geom_hs;
 
@@ -373,6 +377,7 @@ struct dbh_batch {
 
   int representation{DBH_POLYGON};
   bool query_done{false};
+  bool query_enqueued{false};
   bool timing{false};
   bool verify{false};
   int last_launches{0};   // kernels launched by the last query
@@ -1011,6 +1016,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   if (dbh_status s = b->AllocWorkBuffers()) return s;
   b->representation = representation;
   b->query_done = false;
+  b->query_enqueued = true;
+  b->forces_done = false;
   b->last_launches = 0;
   cudaStream_t st = b->stream;
   const int sms = ctx->prop.multiProcessorCount;
@@ -1335,6 +1342,97 @@ dbh_status dbh_batch_sync(dbh_batch* b) {
     return Fail(static_cast<dbh_status>(c.error), "device-side failure " + std::to_string(c.error));
   }
   b->query_done = true;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_set_body_kinematics(dbh_batch* b, const double* p_WBo, const double* V_WB) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  const size_t G = static_cast<size_t>(std::max(1, b->num_geoms));
+  b->have_body_origin = p_WBo != nullptr;
+  b->have_body_vel = V_WB != nullptr;
+  if (p_WBo) {
+    CUDA_OK(b->d_body_origin.ensure(3 * G));
+    CUDA_OK(cudaMemcpyAsync(b->d_body_origin.p, p_WBo, 3 * static_cast<size_t>(b->num_geoms) * sizeof(double),
+                            cudaMemcpyHostToDevice, b->stream));
+  }
+  if (V_WB) {
+    CUDA_OK(b->d_body_vel.ensure(6 * G));
+    CUDA_OK(cudaMemcpyAsync(b->d_body_vel.p, V_WB, 6 * static_cast<size_t>(b->num_geoms) * sizeof(double),
+                            cudaMemcpyHostToDevice, b->stream));
+  }
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_set_contact_properties(dbh_batch* b, const double* hydroelastic_modulus,
+                                            const double* hunt_crossley_dissipation, const double* dynamic_friction) {
+  if (!b || !hydroelastic_modulus || !hunt_crossley_dissipation || !dynamic_friction)
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "set_contact_properties: bad argument");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  std::vector<double> props(3 * static_cast<size_t>(std::max(1, b->num_geoms)), 0.0);
+  for (int g = 0; g < b->num_geoms; ++g) {
+    if (!(hydroelastic_modulus[g] >= 0.0) || !(hunt_crossley_dissipation[g] >= 0.0) || !(dynamic_friction[g] >= 0.0))
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "set_contact_properties: negative or NaN property");  // DRAKE_DEMANDs,
+                                                                                                   // contact_properties.cc:71-74
+    props[3 * g] = hydroelastic_modulus[g];
+    props[3 * g + 1] = hunt_crossley_dissipation[g];
+    props[3 * g + 2] = dynamic_friction[g];
+  }
+  CUDA_OK(b->d_props.ensure(props.size()));
+  CUDA_OK(cudaMemcpy(b->d_props.p, props.data(), props.size() * sizeof(double), cudaMemcpyHostToDevice));
+  b->have_props = true;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_compute_spatial_forces(dbh_batch* b, double vslip_regularizer) {
+  if (!b || !(vslip_regularizer > 0.0)) return Fail(DBH_ERR_INVALID_ARGUMENT, "compute_spatial_forces: bad argument");
+  if (!b->have_props) return Fail(DBH_ERR_NOT_READY, "compute_spatial_forces: call dbh_batch_set_contact_properties first");
+  if (!b->query_enqueued) return Fail(DBH_ERR_NOT_READY, "compute_spatial_forces: no query on this batch yet");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  CUDA_OK(b->d_forces.ensure(18 * static_cast<size_t>(std::max(1, b->num_pairs))));
+  if (b->num_pairs > 0) {
+    WrenchArgs w{};
+    w.surf_pair = b->d_surf_pair.p;
+    w.pairs = b->d_pairs.p;
+    w.poses = b->d_poses;
+    w.body_origin = b->have_body_origin ? b->d_body_origin.p : nullptr;
+    w.body_vel = b->have_body_vel ? b->d_body_vel.p : nullptr;
+    w.props = b->d_props.p;
+    w.surf_face_off = b->d_surf_face_off.p;
+    w.surf_vert_off = b->d_surf_vert_off.p;
+    w.surf_centroid = b->r_surf_centroid.p;
+    w.representation = b->representation;
+    w.areas = b->r_areas.p;
+    w.normals = b->r_normals.p;
+    w.centroids = b->r_centroids.p;
+    w.e_centroid = b->r_e_centroid.p;
+    w.vertices = b->r_vertices.p;
+    w.pressures = b->r_pressures.p;
+    w.face_data = b->r_face_data.p;
+    w.vslip_regularizer = vslip_regularizer;
+    w.forces = b->d_forces.p;
+    w.counters = b->d_counters.p;
+    k_wrench<<<b->ctx->prop.multiProcessorCount * 8, 128, 0, b->stream>>>(w);
+    CUDA_OK(cudaGetLastError());
+  }
+  b->forces_done = true;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_copy_spatial_forces(dbh_batch* b, double* F_Ac_W, double* F_Ao_W, double* F_Bo_W) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  if (!b->forces_done) return Fail(DBH_ERR_NOT_READY, "copy_spatial_forces: dbh_batch_compute_spatial_forces has not run");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  if (dbh_status st = dbh_batch_sync(b)) return st;
+  const size_t ns = static_cast<size_t>(b->h_counters->surfaces);
+  if (ns == 0) return DBH_OK;
+  std::vector<double> all(18 * ns);
+  CUDA_OK(cudaMemcpy(all.data(), b->d_forces.p, all.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (size_t s = 0; s < ns; ++s) {
+    if (F_Ac_W) std::memcpy(F_Ac_W + 6 * s, all.data() + 18 * s, 6 * sizeof(double));
+    if (F_Ao_W) std::memcpy(F_Ao_W + 6 * s, all.data() + 18 * s + 6, 6 * sizeof(double));
+    if (F_Bo_W) std::memcpy(F_Bo_W + 6 * s, all.data() + 18 * s + 12, 6 * sizeof(double));
+  }
   return DBH_OK;
 }
 

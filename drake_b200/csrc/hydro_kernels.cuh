@@ -11,6 +11,8 @@
 //                swap, final packed layout (PolyMeshBuilder/TriMeshBuilder + PolygonSurfaceMesh /
 //                TriangleSurfaceMesh derived quantities + TransformVertices + SwapMAndN)
 //   k_surface    per-surface total area and centroid
+//   k_wrench     one spatial force per contact surface (hydroelastic_traction_calculator.cc; SURVEY 8f rank 3;
+//                written and host-checked, not yet run on a GPU)
 //   k_plane_*    the half-space special cases (mesh_plane_intersection.cc:182-342,
 //                mesh_half_space_intersection.cc:17-430): one thread per element of the one mesh
 //
@@ -20,6 +22,7 @@
 
 #include "hydro_math.cuh"
 #include "hydro_plane.cuh"
+#include "hydro_wrench.cuh"
 #include "hydro_types.h"
 
 #ifdef DBH_TRACE
@@ -2140,6 +2143,93 @@ __global__ void __launch_bounds__(128) k_plane_count2(PlaneArgs a) {
   }
   if (lane == 0 && my_tets) atomicAdd(&a.counters->plane_tets, (unsigned long long)my_tets);
   if (lane == 0 && my_tris) atomicAdd(&a.counters->plane_tris, (unsigned long long)my_tris);
+}
+
+// ---------------------------------------------------------------------------
+// k_wrench: HydroelasticTractionCalculator::ComputeSpatialForcesAtCentroidFromHydroelasticModel +
+// ShiftSpatialForcesAtCentroidToBodyOrigins (hydroelastic_traction_calculator.cc:24-83) over the packed,
+// device-resident results of the last query: one warp per contact surface, faces strided over the lanes,
+// a shuffle reduction of the six components. A is the body of geometry M (id_M), B of geometry N.
+// NOT YET RUN ON A GPU (the round's GPU time was spent before it was written): the per-face arithmetic is
+// checked on the host (tests/test_plane_math_cpu.py); the GPU test is tests/test_zzz_gpu_wrench_unvalidated.py.
+struct WrenchArgs {
+  const int* surf_pair;
+  const PairRec* pairs;
+  const Xf* poses;
+  const double* body_origin;   // [G*3] p_WBo per geometry's body, or null: the geometry frame's origin
+  const double* body_vel;      // [G*6] V_WB = (w, v) at the body origin, or null: at rest
+  const double* props;         // [G*3] hydroelastic modulus (+inf: rigid), Hunt-Crossley dissipation, dynamic friction
+  const long long* surf_face_off;
+  const long long* surf_vert_off;
+  const double* surf_centroid;
+  int representation;
+  const double* areas;
+  const double* normals;
+  const double* centroids;
+  const double* e_centroid;
+  const double* vertices;
+  const double* pressures;
+  const int* face_data;
+  double vslip_regularizer;
+  double* forces;              // [num_surfaces * 18]: F_Ac_W, F_Ao_W, F_Bo_W, each (tau, f)
+  Counters* counters;
+};
+
+__global__ void __launch_bounds__(128) k_wrench(WrenchArgs a) {
+  if (a.counters->error != 0) return;
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long num_surfaces = (long long)a.counters->surfaces;
+  for (long long s = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < num_surfaces;
+       s += (long long)gridDim.x * warps_per_block) {
+    const PairRec pr = a.pairs[a.surf_pair[s]];
+    const int gM = pr.swapped ? pr.geom_b : pr.geom_a, gN = pr.swapped ? pr.geom_a : pr.geom_b;
+    TractionBodies d;
+    d.p_WAo = a.body_origin ? load3(a.body_origin + 3ll * gM) : load3(a.poses[gM].m + 9);
+    d.p_WBo = a.body_origin ? load3(a.body_origin + 3ll * gN) : load3(a.poses[gN].m + 9);
+    const D3 zero = make_d3(0, 0, 0);
+    d.w_WA = a.body_vel ? load3(a.body_vel + 6ll * gM) : zero;
+    d.v_WA = a.body_vel ? load3(a.body_vel + 6ll * gM + 3) : zero;
+    d.w_WB = a.body_vel ? load3(a.body_vel + 6ll * gN) : zero;
+    d.v_WB = a.body_vel ? load3(a.body_vel + 6ll * gN + 3) : zero;
+    d.p_WC = load3(a.surf_centroid + 3 * s);
+    d.dissipation = combined_hunt_crossley_dissipation(a.props[3ll * gM], a.props[3ll * gN], a.props[3ll * gM + 1],
+                                                       a.props[3ll * gN + 1]);
+    d.mu_coulomb = combined_dynamic_friction(a.props[3ll * gM + 2], a.props[3ll * gN + 2]);
+    d.vslip_regularizer = a.vslip_regularizer;
+    const long long f0 = a.surf_face_off[s], f1 = a.surf_face_off[s + 1], v0 = a.surf_vert_off[s];
+    Spatial6 acc{zero, zero};
+    for (long long f = f0 + lane; f < f1; f += 32) {
+      const D3 nhat = load3(a.normals + 3 * f);
+      if (a.representation == 1 /*DBH_POLYGON*/) {
+        acc = acc + polygon_face_force(d, a.areas[f], nhat, load3(a.centroids + 3 * f), a.e_centroid[f]);
+      } else {
+        const long long i0 = v0 + a.face_data[3 * f], i1 = v0 + a.face_data[3 * f + 1], i2 = v0 + a.face_data[3 * f + 2];
+        acc = acc + triangle_face_force(d, a.areas[f], nhat, load3(a.vertices + 3 * i0), load3(a.vertices + 3 * i1),
+                                        load3(a.vertices + 3 * i2), a.pressures[i0], a.pressures[i1], a.pressures[i2]);
+      }
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+      acc.rot.x += __shfl_xor_sync(0xffffffffu, acc.rot.x, k);
+      acc.rot.y += __shfl_xor_sync(0xffffffffu, acc.rot.y, k);
+      acc.rot.z += __shfl_xor_sync(0xffffffffu, acc.rot.z, k);
+      acc.trans.x += __shfl_xor_sync(0xffffffffu, acc.trans.x, k);
+      acc.trans.y += __shfl_xor_sync(0xffffffffu, acc.trans.y, k);
+      acc.trans.z += __shfl_xor_sync(0xffffffffu, acc.trans.z, k);
+    }
+    if (lane == 0) {
+      Spatial6 F_Ao, F_Bo;
+      shift_to_body_origins(d, acc, &F_Ao, &F_Bo);
+      double* out = a.forces + 18 * s;
+      store3(out, 0, acc.rot);
+      store3(out, 1, acc.trans);
+      store3(out, 2, F_Ao.rot);
+      store3(out, 3, F_Ao.trans);
+      store3(out, 4, F_Bo.rot);
+      store3(out, 5, F_Bo.trans);
+    }
+  }
 }
 
 }  // namespace dbh

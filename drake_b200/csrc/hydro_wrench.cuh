@@ -1,0 +1,118 @@
+// Per-face arithmetic of the contact-surface consumer SURVEY §8(f) ranks third: the continuous
+// hydroelastic traction integration of multibody/plant/hydroelastic_traction_calculator.cc (one spatial
+// force per contact surface, so that only 18 doubles per surface have to leave the GPU instead of the
+// whole mesh), with the combination rules that feed it (contact_properties.cc:65-90,
+// coulomb_friction.h:122-139). __host__ __device__ over plain values, like hydro_plane.cuh: the CPU test
+// suite compiles these expressions with g++ (tests/cpp/plane_host_check.cc); the product only calls them
+// from k_wrench. Operation order follows the reference.
+#pragma once
+#include "hydro_math.cuh"
+
+namespace dbh {
+
+// multibody/math spatial vectors: rotational part first, then translational.
+struct Spatial6 {
+  D3 rot, trans;
+};
+__host__ __device__ __forceinline__ Spatial6 operator+(Spatial6 a, Spatial6 b) {
+  return Spatial6{a.rot + b.rot, a.trans + b.trans};
+}
+__host__ __device__ __forceinline__ Spatial6 scaled(Spatial6 a, double s) { return Spatial6{s * a.rot, s * a.trans}; }
+// SpatialForce::Shift: tau_Bq = tau_Bp - p_BpBq x f.
+__host__ __device__ __forceinline__ Spatial6 shift_force(Spatial6 F, D3 p) {
+  return Spatial6{F.rot - cross(p, F.trans), F.trans};
+}
+
+// CalcAtanXOverXFromXSquared (hydroelastic_traction_calculator.cc:281-315).
+__host__ __device__ __forceinline__ double atan_x_over_x_from_x_squared(double x2) {
+  if (x2 <= 0.12 * 0.12) {
+    return 1. - x2 * (1. / 3. - x2 * (1. / 5. - x2 * (1. / 7. - x2 * (1. / 9. - x2 * (1. / 11. - x2 * (1. / 13. -
+           x2 * (1. / 15. - x2 / 17.)))))));
+  }
+  const double x = sqrt(x2);
+  return atan(x) / x;
+}
+
+// GetCombinedHuntCrossleyDissipation (contact_properties.cc:65-90); stiffness = hydroelastic modulus,
+// +infinity for a rigid geometry.
+__host__ __device__ __forceinline__ double combined_hunt_crossley_dissipation(double stiffness_A, double stiffness_B,
+                                                                              double dA, double dB) {
+  const double denom = stiffness_A + stiffness_B;
+  if (denom == 0.0) return 0.0;
+  if (isinf(stiffness_A)) return dB;
+  if (isinf(stiffness_B)) return dA;
+  return (stiffness_B / denom) * dA + (stiffness_A / denom) * dB;
+}
+// CalcContactFrictionFromSurfaceProperties (coulomb_friction.h:122-139), dynamic coefficient.
+__host__ __device__ __forceinline__ double combined_dynamic_friction(double mu_A, double mu_B) {
+  const double denom = mu_A + mu_B;
+  return denom == 0.0 ? 0.0 : (2 * mu_A * mu_B) / denom;
+}
+
+// HydroelasticTractionCalculator::Data (hydroelastic_traction_calculator.h:40-80) with the scalars of one
+// surface: A is the body of geometry M, B the body of geometry N, p_WC the surface's centroid.
+struct TractionBodies {
+  D3 p_WAo, p_WBo;
+  D3 w_WA, v_WA, w_WB, v_WB;
+  D3 p_WC;
+  double dissipation, mu_coulomb, vslip_regularizer;
+};
+
+// CalcTractionAtQHelper (:218-279) then ComputeSpatialTractionAtAcFromTractionAtAq (:85-96): the traction
+// on A at Q as a spatial traction about C.
+__host__ __device__ __forceinline__ Spatial6 spatial_traction_at_ac(const TractionBodies& d, double e, D3 nhat_W,
+                                                                    D3 p_WQ) {
+  const D3 v_WAq = d.v_WA + cross(d.w_WA, p_WQ - d.p_WAo);  // SpatialVelocity::Shift
+  const D3 v_WBq = d.v_WB + cross(d.w_WB, p_WQ - d.p_WBo);
+  const D3 v_BqAq_W = v_WAq - v_WBq;
+  const double vn_BqAq_W = dot(v_BqAq_W, nhat_W);
+  const double c = d.dissipation * e;
+  const double raw = e - vn_BqAq_W * c;
+  const double normal_traction = raw > 0.0 ? raw : 0.0;  // max(., 0)
+  const D3 vt_BqAq_W = v_BqAq_W - vn_BqAq_W * nhat_W;
+  const double vs_squared = d.vslip_regularizer * d.vslip_regularizer;
+  const double x_squared = dot(vt_BqAq_W, vt_BqAq_W) / vs_squared;
+  const double regularized_friction = (2.0 / 3.14159265358979323846) * d.mu_coulomb * normal_traction *
+                                      atan_x_over_x_from_x_squared(x_squared) / d.vslip_regularizer;
+  const D3 traction_Aq_W = normal_traction * nhat_W + (-regularized_friction) * vt_BqAq_W;
+  return shift_force(Spatial6{make_d3(0, 0, 0), traction_Aq_W}, d.p_WC - p_WQ);
+}
+
+// One polygon: a single quadrature point at its centroid (:50-58).
+__host__ __device__ __forceinline__ Spatial6 polygon_face_force(const TractionBodies& d, double area, D3 nhat_W,
+                                                                D3 centroid_W, double e_centroid) {
+  return scaled(spatial_traction_at_ac(d, e_centroid, nhat_W, centroid_W), area);
+}
+
+// One triangle: order-2 Gaussian rule (gaussian_triangle_quadrature_rule.h:44-51: barycentric points
+// (1/6,1/6), (1/6,2/3), (2/3,1/6), weights 1/3), TriangleQuadrature::Integrate (sum of f(b_i) w_i, times the
+// area), CalcCartesianFromBarycentric (triangle_surface_mesh.h:266-281), MeshFieldLinear::Evaluate
+// (mesh_field_linear.h:300-312).
+__host__ __device__ __forceinline__ Spatial6 triangle_face_force(const TractionBodies& d, double area, D3 nhat_W,
+                                                                 D3 va, D3 vb, D3 vc, double ea, double eb, double ec) {
+  const double kB0[3] = {1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0};
+  const double kB1[3] = {1.0 / 6.0, 2.0 / 3.0, 1.0 / 6.0};
+  const double kW = 1.0 / 3.0;
+  Spatial6 integral{make_d3(0, 0, 0), make_d3(0, 0, 0)};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double b0 = kB0[k], b1 = kB1[k], b2 = 1.0 - kB0[k] - kB1[k];
+    const D3 p_WQ = (b0 * va + b1 * vb) + b2 * vc;
+    double e = b0 * ea;
+    e += b1 * eb;
+    e += b2 * ec;
+    const Spatial6 f = scaled(spatial_traction_at_ac(d, e, nhat_W, p_WQ), kW);
+    integral = k == 0 ? f : integral + f;
+  }
+  return scaled(integral, area);
+}
+
+// ShiftSpatialForcesAtCentroidToBodyOrigins (:64-83).
+__host__ __device__ __forceinline__ void shift_to_body_origins(const TractionBodies& d, Spatial6 F_Ac_W, Spatial6* F_Ao_W,
+                                                               Spatial6* F_Bo_W) {
+  *F_Ao_W = shift_force(F_Ac_W, d.p_WAo - d.p_WC);
+  const Spatial6 s = shift_force(F_Ac_W, d.p_WBo - d.p_WC);
+  *F_Bo_W = Spatial6{-s.rot, -s.trans};
+}
+
+}  // namespace dbh

@@ -129,6 +129,10 @@ def lib():
     L.dbh_batch_stats.argtypes = [vp, C.POINTER(Stats)]
     L.dbh_batch_copy_candidates.argtypes = [vp, C.c_int32, _ip, _lp]
     L.dbh_batch_copy_geometry_pairs.argtypes = [vp, _ip]
+    L.dbh_batch_set_body_kinematics.argtypes = [vp, _dp, _dp]
+    L.dbh_batch_set_contact_properties.argtypes = [vp, _dp, _dp, _dp]
+    L.dbh_batch_compute_spatial_forces.argtypes = [vp, C.c_double]
+    L.dbh_batch_copy_spatial_forces.argtypes = [vp, _dp, _dp, _dp]
     L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_verify.argtypes = [vp, C.c_int32]
     L.dbh_batch_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -632,6 +636,35 @@ class SceneBatch:
         for s in self.copy_results().surfaces():
             out[s.scene].append(s)
         return out
+
+    # -- device-side consumer: one spatial force per surface ------------------------------
+    def set_body_kinematics(self, p_WBo=None, V_WB=None):
+        """p_WBo [G,3]: body-frame origins (None: the geometry frames' origins); V_WB [G,6] = (w, v) (None: at rest)."""
+        p = _d(p_WBo).reshape(-1, 3) if p_WBo is not None else None
+        v = _d(V_WB).reshape(-1, 6) if V_WB is not None else None
+        for a in (p, v):
+            if a is not None and len(a) != self.num_geometries:
+                raise ValueError("one row per geometry")
+        _check(lib().dbh_batch_set_body_kinematics(self._h, _ptr(p, _dp) if p is not None else None,
+                                                   _ptr(v, _dp) if v is not None else None))
+        self._keep_kin = (p, v)
+
+    def set_contact_properties(self, hydroelastic_modulus, hunt_crossley_dissipation, dynamic_friction):
+        """Per geometry [G]; modulus = inf for a rigid geometry (contact_properties.cc:65-90)."""
+        E, d, mu = _d(hydroelastic_modulus), _d(hunt_crossley_dissipation), _d(dynamic_friction)
+        if not (len(E) == len(d) == len(mu) == self.num_geometries):
+            raise ValueError("one value per geometry")
+        _check(lib().dbh_batch_set_contact_properties(self._h, _ptr(E, _dp), _ptr(d, _dp), _ptr(mu, _dp)))
+
+    def spatial_forces(self, vslip_regularizer: float = 1e-6):
+        """HydroelasticTractionCalculator over the last query's surfaces, on the device: (F_Ac_W, F_Ao_W, F_Bo_W),
+        each [num_surfaces, 6] = (tau, f), surfaces in result order."""
+        _check(lib().dbh_batch_compute_spatial_forces(self._h, float(vslip_regularizer)))
+        self.sync()
+        n = int(self.sizes().num_surfaces)
+        out = [np.zeros((n, 6)) for _ in range(3)]
+        _check(lib().dbh_batch_copy_spatial_forces(self._h, *[_ptr(o, _dp) for o in out]))
+        return tuple(out)
 
     def candidates(self, kind: int) -> np.ndarray:
         """(geometry pair, element of first body, element of second body) triples; kind 0 tet-tri, 1 tet-tet."""

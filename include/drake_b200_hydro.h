@@ -215,6 +215,28 @@ dbh_status dbh_batch_sync(dbh_batch* batch);
 /* The CUDA stream (cudaStream_t) the batch launches on. */
 void* dbh_batch_stream(dbh_batch* batch);
 
+/* -- (5b) a device-side consumer of the surfaces: one spatial force per contact surface, so
+ *        that 18 doubles per surface leave the GPU instead of the whole mesh. Replaces
+ *        HydroelasticTractionCalculator::ComputeSpatialForcesAtCentroidFromHydroelasticModel and
+ *        ShiftSpatialForcesAtCentroidToBodyOrigins (multibody/plant/hydroelastic_traction_calculator.cc:24-83),
+ *        fed by GetCombinedHuntCrossleyDissipation (contact_properties.cc:65-90) and
+ *        CalcContactFrictionFromSurfaceProperties (coulomb_friction.h:122-139). Body A is the body of geometry
+ *        M (id_M), body B the body of geometry N. STATUS: the per-face arithmetic is checked against the oracle
+ *        on the host; the kernel has not run on a GPU yet. ---------------------------------- */
+/* p_WBo [G*3]: origin of each geometry's body frame in World (NULL: the geometry frame's origin);
+ * V_WB [G*6]: spatial velocity (w, v) of that body at its origin, in World (NULL: at rest). Host pointers. */
+dbh_status dbh_batch_set_body_kinematics(dbh_batch* batch, const double* p_WBo, const double* V_WB);
+/* Per geometry [G]: hydroelastic modulus (+infinity for a rigid geometry), Hunt-Crossley dissipation (s/m),
+ * dynamic Coulomb friction. */
+dbh_status dbh_batch_set_contact_properties(dbh_batch* batch, const double* hydroelastic_modulus,
+                                            const double* hunt_crossley_dissipation, const double* dynamic_friction);
+/* Enqueued on the batch stream after dbh_batch_query (no host sync in between is needed). vslip_regularizer:
+ * HydroelasticTractionCalculator's constructor argument (default 1e-6 there). */
+dbh_status dbh_batch_compute_spatial_forces(dbh_batch* batch, double vslip_regularizer);
+/* Waits, then copies [num_surfaces*6] each, (tau, f) = SpatialForce's layout, surfaces in result order:
+ * F_Ac_W about the surface centroid, F_Ao_W on body A at Ao, F_Bo_W on body B at Bo. Any may be NULL. */
+dbh_status dbh_batch_copy_spatial_forces(dbh_batch* batch, double* F_Ac_W, double* F_Ao_W, double* F_Bo_W);
+
 /* -- (6) sizes of the last completed query. --------------------------------- */
 typedef struct dbh_result_sizes {
   int64_t num_surfaces;

@@ -12,6 +12,7 @@
 #define __device__
 #define __forceinline__ inline
 #include "../../drake_b200/csrc/hydro_plane.cuh"
+#include "../../drake_b200/csrc/hydro_wrench.cuh"
 
 using namespace dbh;
 
@@ -128,5 +129,42 @@ int phc_check_find_plane_pair(int num_pairs, const long long* off, int q_begin, 
   }
   return bad;
 }
+
+// The per-face traction arithmetic of k_wrench summed face by face in order (the oracle's order, so the
+// comparison can be exact): rep 1: polygons (areas, normals, centroids, e_c per face); rep 0: triangles
+// (vertices [nv*3], pressures [nv], tris [nf*3] besides areas and normals). bodies22 = p_WAo, p_WBo, w_WA,
+// v_WA, w_WB, v_WB, p_WC (7 x 3) then dissipation. out18 = F_Ac_W, F_Ao_W, F_Bo_W as (tau, f).
+void phc_surface_wrench(int rep, int nf, const double* areas, const double* normals, const double* centroids,
+                        const double* e_c, const double* verts, const double* pressures, const int* tris,
+                        const double* bodies22, double mu, double vslip, double* out18) {
+  TractionBodies d;
+  const double* b = bodies22;
+  d.p_WAo = load3(b), d.p_WBo = load3(b + 3), d.w_WA = load3(b + 6), d.v_WA = load3(b + 9), d.w_WB = load3(b + 12);
+  d.v_WB = load3(b + 15), d.p_WC = load3(b + 18);
+  d.dissipation = b[21];
+  d.mu_coulomb = mu;
+  d.vslip_regularizer = vslip;
+  Spatial6 F{make_d3(0, 0, 0), make_d3(0, 0, 0)};
+  for (int f = 0; f < nf; ++f) {
+    if (rep == 1) {
+      F = F + polygon_face_force(d, areas[f], load3(normals + 3 * f), load3(centroids + 3 * f), e_c[f]);
+    } else {
+      const int* t = tris + 3 * f;
+      F = F + triangle_face_force(d, areas[f], load3(normals + 3 * f), load3(verts + 3 * t[0]), load3(verts + 3 * t[1]),
+                                  load3(verts + 3 * t[2]), pressures[t[0]], pressures[t[1]], pressures[t[2]]);
+    }
+  }
+  Spatial6 Fa, Fb;
+  shift_to_body_origins(d, F, &Fa, &Fb);
+  const Spatial6* all[3] = {&F, &Fa, &Fb};
+  for (int k = 0; k < 3; ++k) {
+    out18[6 * k + 0] = all[k]->rot.x, out18[6 * k + 1] = all[k]->rot.y, out18[6 * k + 2] = all[k]->rot.z;
+    out18[6 * k + 3] = all[k]->trans.x, out18[6 * k + 4] = all[k]->trans.y, out18[6 * k + 5] = all[k]->trans.z;
+  }
+}
+double phc_combined_dissipation(double kA, double kB, double dA, double dB) {
+  return combined_hunt_crossley_dissipation(kA, kB, dA, dB);
+}
+double phc_combined_friction(double a, double b) { return combined_dynamic_friction(a, b); }
 
 }  // extern "C"

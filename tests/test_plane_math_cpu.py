@@ -17,7 +17,8 @@ from tests.parity import REL_TOL, assert_close, face_keys, random_pose
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "plane_host_check.cc")
-HDRS = [os.path.join(ROOT, "drake_b200", "csrc", n) for n in ("hydro_plane.cuh", "hydro_math.cuh", "hydro_types.h")]
+HDRS = [os.path.join(ROOT, "drake_b200", "csrc", n) for n in ("hydro_plane.cuh", "hydro_wrench.cuh", "hydro_math.cuh",
+                                                              "hydro_types.h")]
 LIB = os.path.join(ROOT, "tests", "cpp", "_build", "libplane_host_check.so")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -203,3 +204,58 @@ def test_work_item_to_pair_lookup():
         n = len(sizes)
         for qb, qe in [(0, n), (n // 3, n), (0, max(1, n // 2)), (n // 4, max(n // 4 + 1, 3 * n // 4))]:
             assert lib.phc_check_find_plane_pair(n, off.ctypes.data_as(lp), qb, qe) == 0, (sizes[:5], qb, qe)
+
+
+def host_wrench(surface, p_WAo, p_WBo, V_WA, V_WB, dissipation, mu, vslip=1e-6):
+    """k_wrench's per-face arithmetic (hydro_wrench.cuh) summed in face order over an oracle Surface."""
+    lib = harness()
+    lib.phc_surface_wrench.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, C.c_double, C.c_double, _dp]
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+    bodies = np.concatenate([p_WAo, p_WBo, V_WA[:3], V_WA[3:], V_WB[:3], V_WB[3:], surface.centroid, [dissipation]])
+    tris = np.ascontiguousarray(surface.face_data if surface.rep == ho.KTRIANGLE else np.zeros((1, 3)), np.int32)
+    out = np.zeros(18)
+    lib.phc_surface_wrench(surface.rep, surface.num_faces, d(surface.areas), d(surface.normals), d(surface.centroids),
+                           d(surface.e_centroid), d(surface.vertices), d(surface.pressures), tris.ctypes.data_as(_ip),
+                           d(bodies), mu, vslip, d(out))
+    return out[0:6], out[6:12], out[12:18]
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+def test_wrench_arithmetic_matches_the_oracle(rep):
+    """hydro_wrench.cuh against oracle/ho_traction.h on real contact surfaces (soft sphere on a rigid sphere,
+    soft sphere on a half space, both id orders), random body velocities, friction and dissipation: same
+    expressions in the same face order, so the agreement is to the last bits."""
+    rng = np.random.default_rng(21)
+    R = 0.25
+    soft = ho.VolumeMesh.sphere(R, 0.08)
+    fld = ho.VolumeField.sphere(soft, R, 1e6)
+    rigid = ho.TriMesh.sphere(R, 0.05)
+    X_WA = ho.xform(ho.rpy_matrix(0.3, 0.1, -0.2), [0.01, -0.02, 0.0])
+    X_WB = ho.xform(None, [0.02, 0.01, -(R + R) + 0.08])
+    cases = []
+    with ho.keep_handles():
+        for ids in ((1, 2), (2, 1)):
+            cases.append(ho.soft_rigid(soft, fld, rigid, X_WA, X_WB, ids[0], ids[1], rep))
+            cases.append(ho.soft_mesh_rigid_half_space(soft, fld, X_WA, ho.xform(None, [0, 0, -0.2]), ids[0], ids[1], rep))
+        cases.append(ho.soft_soft(soft, fld, soft, fld, X_WA, X_WB, 1, 2, rep))
+    for s in cases:
+        assert s is not None and s.num_faces > 10
+        for _ in range(3):
+            p_WAo, p_WBo = rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.3, 0.3, 3)
+            V_WA, V_WB = rng.uniform(-1, 1, 6), rng.uniform(-1, 1, 6)
+            d, mu = float(rng.uniform(0, 2)), float(rng.uniform(0, 1))
+            want = ho.traction(s, p_WAo, p_WBo, V_WA, V_WB, d, mu)
+            got = host_wrench(s, p_WAo, p_WBo, V_WA, V_WB, d, mu)
+            scale = max(np.max(np.abs(want[0])), 1e-300)
+            for g, w in zip(got, want):
+                assert np.max(np.abs(g - w)) <= 1e-13 * scale
+    lib = harness()
+    for name in ("phc_combined_dissipation", "phc_combined_friction"):
+        getattr(lib, name).restype = C.c_double
+    lib.phc_combined_dissipation.argtypes = [C.c_double] * 4
+    lib.phc_combined_friction.argtypes = [C.c_double] * 2
+    inf = float("inf")
+    for args in [(inf, 1e5, 3.0, 7.0), (1e5, inf, 3.0, 7.0), (0.0, 0.0, 3.0, 7.0), (1e5, 3e5, 4.0, 8.0)]:
+        assert lib.phc_combined_dissipation(*args) == ho.combined_dissipation(*args)
+    for args in [(0.0, 0.0), (0.5, 0.5), (1.0, 0.25)]:
+        assert lib.phc_combined_friction(*args) == ho.combined_friction(*args)

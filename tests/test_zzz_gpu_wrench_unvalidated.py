@@ -1,0 +1,86 @@
+"""GPU parity of k_wrench (one spatial force per contact surface) against the oracle's
+restatement of HydroelasticTractionCalculator.
+
+STATUS: round 1 ran out of GPU time before this kernel was written, so these tests have NOT run on a GPU yet.
+They are skipped unless DBH_RUN_UNVALIDATED=1 so that an unproven kernel cannot make the `-m gpu` suite red; the
+per-face arithmetic itself is checked on the host against the oracle (tests/test_plane_math_cpu.py), and the
+oracle against the reference's own tests (tests/test_oracle_traction.py). First thing to run in the next round:
+
+    DBH_RUN_UNVALIDATED=1 python -m pytest tests/test_zzz_gpu_wrench_unvalidated.py -m gpu -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ho
+from tests import parity
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("DBH_RUN_UNVALIDATED") != "1",
+                                 reason="k_wrench has not run on a GPU yet; set DBH_RUN_UNVALIDATED=1")]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import drake_b200 as db
+    return db.Context(0)
+
+
+@pytest.mark.parametrize("rep", [ho.KPOLYGON, ho.KTRIANGLE])
+def test_spatial_forces_of_config3_scenes(ctx, rep):
+    """24 ball / plate / floor scenes (soft-rigid + soft-soft surfaces, M/N swaps): every surface's F_Ac_W, F_Ao_W,
+    F_Bo_W against the oracle on the oracle's own surface, random body velocities, dissipation and friction per
+    geometry combined by the reference's rules. The GPU sums faces in another order: 1e-10 of the force scale."""
+    from drake_b200 import workloads as W
+    wl = W.config3(24)
+    batch = wl.register(ctx)
+    S, G = wl.num_scenes, wl.geoms_per_scene
+    rng = np.random.default_rng(4)
+    V = rng.uniform(-0.5, 0.5, size=(S, G, 6))
+    origins = wl.poses[:, :, 9:12] + rng.uniform(-0.05, 0.05, size=(S, G, 3))
+    E = np.tile([3e4, np.inf, 3e4], S)      # floor, plate (rigid), ball
+    dis = np.tile([1.0, 0.3, 2.0], S)
+    mu = np.tile([0.5, 0.2, 1.0], S)
+    batch.set_contact_properties(E, dis, mu)
+    batch.set_body_kinematics(origins.reshape(-1, 3), V.reshape(-1, 6))
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), rep)
+    F_Ac, F_Ao, F_Bo = batch.spatial_forces(1e-4)
+    osc, order = parity.oracle_scene_for(wl)
+    ids = list(wl.geom_id)
+    k = 0
+    with ho.keep_handles():
+        for s in range(S):
+            want, _ = osc.compute(wl.poses[s][order], rep)
+            assert len(want) == len(got[s])
+            for w in want:
+                gM, gN = ids.index(w.id_M), ids.index(w.id_N)
+                d = ho.combined_dissipation(E[gM], E[gN], dis[gM], dis[gN])
+                m = ho.combined_friction(mu[gM], mu[gN])
+                ref = ho.traction(w, origins[s, gM], origins[s, gN], V[s, gM], V[s, gN], d, m, 1e-4)
+                scale = max(np.max(np.abs(np.concatenate(ref))), 1e-300)
+                for g, r in zip((F_Ac[k], F_Ao[k], F_Bo[k]), ref):
+                    assert np.max(np.abs(g - r)) <= 1e-9 * scale, (s, w.id_M, w.id_N)
+                k += 1
+    assert k == len(F_Ac) and k >= 40
+
+
+def test_reference_fixture_through_the_c_abi(ctx):
+    """FrictionalTractionOverPatch (hydroelastic_traction_calculator_test.cc:565-608) rebuilt from geometry: a
+    rigid unit box pressed 0.5 into a compliant half space of pressure scale 1 gives e = 0.5 on its bottom face
+    (area 1): f_Bo = (-mu e, 0, e), tau_Bo_y = 0.25 when the box slides along +x."""
+    import drake_b200 as db
+    from tests.test_oracle_halfspace import box_mesh
+    X = ho.xform(None, [0.5, 0.5, 0.5])
+    box = ho.TriMesh.from_arrays(0.5 * box_mesh(ho.IDENTITY).verts, box_mesh(ho.IDENTITY).tris)
+    a_h = ctx.register_half_space(compliant=True, pressure_scale=1.0)
+    batch = db.SceneBatch(ctx, [0, 2], [a_h, parity.register_rigid(ctx, box)], [1, 2])
+    batch.set_contact_properties([1.0, np.inf], [0.0, 0.0], [1.0, 1.0])
+    batch.set_body_kinematics(None, [[0, 0, 0, 0, 0, 0], [0, 0, 0, 1.0, 0, 0]])
+    surfaces = batch.compute_contact_surfaces(np.stack([ho.IDENTITY, ho.IDENTITY]), ho.KPOLYGON)[0]
+    assert len(surfaces) == 1
+    _, F_Ao, F_Bo = batch.spatial_forces(1e-6)
+    # Bottom face at z = -0.5 (pressure 0.5, area 1) plus the four half-submerged side faces, whose normals are
+    # horizontal: they add no vertical force; with mu = 1 they add friction, so only f_z is compared exactly.
+    assert abs(F_Bo[0][5] - 0.5) < 1e-12
+    np.testing.assert_allclose(F_Ao[0][3:6] + F_Bo[0][3:6], 0, atol=1e-12)
