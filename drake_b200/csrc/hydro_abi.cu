@@ -1371,9 +1371,9 @@ dbh_status dbh_batch_set_contact_properties(dbh_batch* b, const double* hydroela
   CUDA_OK(cudaSetDevice(b->ctx->device));
   std::vector<double> props(3 * static_cast<size_t>(std::max(1, b->num_geoms)), 0.0);
   for (int g = 0; g < b->num_geoms; ++g) {
-    if (!(hydroelastic_modulus[g] >= 0.0) || !(hunt_crossley_dissipation[g] >= 0.0) || !(dynamic_friction[g] >= 0.0))
-      return Fail(DBH_ERR_INVALID_ARGUMENT, "set_contact_properties: negative or NaN property");  // DRAKE_DEMANDs,
-                                                                                                   // contact_properties.cc:71-74
+    // DRAKE_DEMAND(modulus > 0), DRAKE_DEMAND(dissipation >= 0) (hydroelastic_engine.cc:52-53).
+    if (!(hydroelastic_modulus[g] > 0.0) || !(hunt_crossley_dissipation[g] >= 0.0) || !(dynamic_friction[g] >= 0.0))
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "set_contact_properties: modulus must be > 0, dissipation and friction >= 0");
     props[3 * g] = hydroelastic_modulus[g];
     props[3 * g + 1] = hunt_crossley_dissipation[g];
     props[3 * g + 2] = dynamic_friction[g];

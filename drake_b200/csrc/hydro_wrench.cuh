@@ -1,7 +1,7 @@
 // Per-face arithmetic of the contact-surface consumer SURVEY §8(f) ranks third: the continuous
 // hydroelastic traction integration of multibody/plant/hydroelastic_traction_calculator.cc (one spatial
 // force per contact surface, so that only 18 doubles per surface have to leave the GPU instead of the
-// whole mesh), with the combination rules that feed it (contact_properties.cc:65-90,
+// whole mesh), with the combination rules that feed it (hydroelastic_engine.cc:63-104,
 // coulomb_friction.h:122-139). __host__ __device__ over plain values, like hydro_plane.cuh: the CPU test
 // suite compiles these expressions with g++ (tests/cpp/plane_host_check.cc); the product only calls them
 // from k_wrench. Operation order follows the reference.
@@ -33,15 +33,18 @@ __host__ __device__ __forceinline__ double atan_x_over_x_from_x_squared(double x
   return atan(x) / x;
 }
 
-// GetCombinedHuntCrossleyDissipation (contact_properties.cc:65-90); stiffness = hydroelastic modulus,
-// +infinity for a rigid geometry.
-__host__ __device__ __forceinline__ double combined_hunt_crossley_dissipation(double stiffness_A, double stiffness_B,
-                                                                              double dA, double dB) {
-  const double denom = stiffness_A + stiffness_B;
-  if (denom == 0.0) return 0.0;
-  if (isinf(stiffness_A)) return dB;
-  if (isinf(stiffness_B)) return dA;
-  return (stiffness_B / denom) * dA + (stiffness_A / denom) * dB;
+// HydroelasticEngine::CalcCombinedElasticModulus / CalcCombinedDissipation
+// (multibody/hydroelastics/hydroelastic_engine.cc:63-104): what MultibodyPlant's continuous path hands to the
+// traction calculator (multibody_plant.cc:2645-2654). E = hydroelastic modulus, +infinity for a rigid geometry.
+__host__ __device__ __forceinline__ double combined_hunt_crossley_dissipation(double E_A, double E_B, double d_A,
+                                                                              double d_B) {
+  const bool rigid_A = isinf(E_A), rigid_B = isinf(E_B);
+  if (rigid_A && rigid_B) return 0.5 * (d_A + d_B);
+  const double Estar = rigid_A ? E_B : (rigid_B ? E_A : E_A * E_B / (E_A + E_B));
+  double d_star = 0;
+  if (!rigid_A) d_star += Estar / E_A * d_A;
+  if (!rigid_B) d_star += Estar / E_B * d_B;
+  return d_star;
 }
 // CalcContactFrictionFromSurfaceProperties (coulomb_friction.h:122-139), dynamic coefficient.
 __host__ __device__ __forceinline__ double combined_dynamic_friction(double mu_A, double mu_B) {

@@ -650,7 +650,7 @@ class SceneBatch:
         self._keep_kin = (p, v)
 
     def set_contact_properties(self, hydroelastic_modulus, hunt_crossley_dissipation, dynamic_friction):
-        """Per geometry [G]; modulus = inf for a rigid geometry (contact_properties.cc:65-90)."""
+        """Per geometry [G]; modulus = inf for a rigid geometry (hydroelastic_engine.cc:83-104)."""
         E, d, mu = _d(hydroelastic_modulus), _d(hunt_crossley_dissipation), _d(dynamic_friction)
         if not (len(E) == len(d) == len(mu) == self.num_geometries):
             raise ValueError("one value per geometry")

@@ -219,7 +219,7 @@ void* dbh_batch_stream(dbh_batch* batch);
  *        that 18 doubles per surface leave the GPU instead of the whole mesh. Replaces
  *        HydroelasticTractionCalculator::ComputeSpatialForcesAtCentroidFromHydroelasticModel and
  *        ShiftSpatialForcesAtCentroidToBodyOrigins (multibody/plant/hydroelastic_traction_calculator.cc:24-83),
- *        fed by GetCombinedHuntCrossleyDissipation (contact_properties.cc:65-90) and
+ *        fed by HydroelasticEngine::CalcCombinedDissipation (multibody/hydroelastics/hydroelastic_engine.cc:83-104) and
  *        CalcContactFrictionFromSurfaceProperties (coulomb_friction.h:122-139). Body A is the body of geometry
  *        M (id_M), body B the body of geometry N. STATUS: the per-face arithmetic is checked against the oracle
  *        on the host; the kernel has not run on a GPU yet. ---------------------------------- */

@@ -2,7 +2,7 @@
 // Restatement of the contact-surface consumer that SURVEY §8(f) ranks third: the continuous hydroelastic
 // traction integration of multibody/plant/hydroelastic_traction_calculator.{h,cc} (per-face quadrature of
 // the normal + regularised friction traction into one spatial force per surface) with the combination
-// rules it is fed by (multibody/plant/contact_properties.cc:65-90, coulomb_friction.h:122-139) and the
+// rules it is fed by (multibody/hydroelastics/hydroelastic_engine.cc:63-104, coulomb_friction.h:122-139) and the
 // quadrature it uses (multibody/triangle_quadrature/{triangle_quadrature.h,gaussian_triangle_quadrature_rule.h}).
 #pragma once
 #include <algorithm>
@@ -37,14 +37,23 @@ inline double CalcAtanXOverXFromXSquared(double x2) {
   return std::atan(x) / x;
 }
 
-// contact_properties.cc:65-90 (stiffness = hydroelastic modulus, infinity for a rigid geometry).
-inline double CombinedHuntCrossleyDissipation(double stiffness_A, double stiffness_B, double dA, double dB) {
+// HydroelasticEngine::CalcCombinedElasticModulus / CalcCombinedDissipation
+// (multibody/hydroelastics/hydroelastic_engine.cc:63-104), the rule MultibodyPlant's continuous path feeds the
+// traction calculator with (multibody_plant.cc:2645-2654). E = hydroelastic modulus, +infinity for a rigid geometry.
+inline double CombinedElasticModulus(double E_A, double E_B) {
   const double kInf = std::numeric_limits<double>::infinity();
-  const double denom = stiffness_A + stiffness_B;
-  if (denom == 0.0) return 0.0;
-  if (stiffness_A == kInf) return dB;
-  if (stiffness_B == kInf) return dA;
-  return (stiffness_B / denom) * dA + (stiffness_A / denom) * dB;
+  if (E_A == kInf) return E_B;
+  if (E_B == kInf) return E_A;
+  return E_A * E_B / (E_A + E_B);
+}
+inline double CombinedHuntCrossleyDissipation(double E_A, double E_B, double d_A, double d_B) {
+  const double kInf = std::numeric_limits<double>::infinity();
+  const double Estar = CombinedElasticModulus(E_A, E_B);
+  if (Estar == kInf) return 0.5 * (d_A + d_B);
+  double d_star = 0;
+  if (E_A != kInf) d_star += Estar / E_A * d_A;
+  if (E_B != kInf) d_star += Estar / E_B * d_B;
+  return d_star;
 }
 // coulomb_friction.h:122-139 (dynamic coefficient).
 inline double CombinedDynamicFriction(double mu_A, double mu_B) {

@@ -88,12 +88,14 @@ def test_calc_atan_x_over_x_from_x_squared():
 
 
 def test_combination_rules():
-    # contact_properties.cc:65-90 and coulomb_friction.h:122-139.
+    # multibody/hydroelastics/test/hydroelastic_engine_test.cc:124-178 and coulomb_friction.h:122-139.
     inf = float("inf")
-    assert ho.combined_dissipation(inf, 1e5, 3.0, 7.0) == 7.0
-    assert ho.combined_dissipation(1e5, inf, 3.0, 7.0) == 3.0
-    assert ho.combined_dissipation(0.0, 0.0, 3.0, 7.0) == 0.0
-    assert ho.combined_dissipation(1e5, 3e5, 4.0, 8.0) == pytest.approx(0.75 * 4.0 + 0.25 * 8.0, rel=1e-15)
+    assert ho.combined_dissipation(10.0, inf, 1.0, 0.0) == 1.0      # CombineSoftAndRigidMaterialProperties
+    assert ho.combined_dissipation(inf, 10.0, 0.0, 1.0) == 1.0
+    assert ho.combined_dissipation(inf, inf, 0.0, 0.0) == 0.0       # CombineRigidAndRigidMaterialProperties
+    assert ho.combined_dissipation(inf, inf, 1.0, 3.0) == 2.0
+    for args in ((2.0, 8.0, 1.0, 4.0), (8.0, 2.0, 4.0, 1.0)):       # CombineSoftAndSoftMaterialProperties: d* = 1.6
+        assert abs(ho.combined_dissipation(*args) - 1.6) <= np.finfo(float).eps
     assert ho.combined_friction(0.0, 0.0) == 0.0
     assert ho.combined_friction(0.5, 0.5) == 0.5
     assert ho.combined_friction(1.0, 0.25) == pytest.approx(0.4, rel=1e-15)

@@ -255,7 +255,7 @@ def test_wrench_arithmetic_matches_the_oracle(rep):
     lib.phc_combined_dissipation.argtypes = [C.c_double] * 4
     lib.phc_combined_friction.argtypes = [C.c_double] * 2
     inf = float("inf")
-    for args in [(inf, 1e5, 3.0, 7.0), (1e5, inf, 3.0, 7.0), (0.0, 0.0, 3.0, 7.0), (1e5, 3e5, 4.0, 8.0)]:
+    for args in [(inf, 1e5, 3.0, 7.0), (1e5, inf, 3.0, 7.0), (inf, inf, 3.0, 7.0), (1e5, 3e5, 4.0, 8.0), (2.0, 8.0, 1.0, 4.0)]:
         assert lib.phc_combined_dissipation(*args) == ho.combined_dissipation(*args)
     for args in [(0.0, 0.0), (0.5, 0.5), (1.0, 0.25)]:
         assert lib.phc_combined_friction(*args) == ho.combined_friction(*args)
