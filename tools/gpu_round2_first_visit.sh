@@ -1,0 +1,25 @@
+#!/bin/bash
+# First GPU visit of round 2: everything round 1 wrote after its GPU minutes ran out, in the order that
+# decides what to keep.   usage: tools/gpu_round2_first_visit.sh <tag>      (≈ 6 GPU-minutes)
+#  1. the `-m gpu` suite as the driver runs it (must stay green);
+#  2. k_wrench (never run on a GPU): its skipped tests, explicitly enabled;
+#  3. k_plane_count2 (DBH_TUNE plane=2, never run): the half-space tests under it, then c3h bench lines with
+#     the default and the experimental count pass side by side;
+#  4. launch list + one `--set full` capture of the half-space kernels on c3h (none exists yet).
+tag=${1:-r2a}
+mkdir -p gpurun_out
+(timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) > gpurun_out/${tag}_tests.log
+(DBH_RUN_UNVALIDATED=1 timeout 200 python -m pytest tests/test_zzz_gpu_wrench_unvalidated.py -m gpu -q 2>&1 | tail -40) \
+  > gpurun_out/${tag}_tests_wrench.log
+(DBH_TUNE=plane=2 timeout 200 python -m pytest tests/test_zz_gpu_halfspace.py -m gpu -q 2>&1 | tail -40) \
+  > gpurun_out/${tag}_tests_plane2.log
+timeout 120 python bench.py --config c3h --no-cpu-baseline --steps 20 --warmup 5 \
+  > gpurun_out/${tag}_bench_c3h.json 2> gpurun_out/${tag}_bench_c3h.err
+DBH_TUNE=plane=2 timeout 120 python bench.py --config c3h --no-cpu-baseline --steps 20 --warmup 5 \
+  > gpurun_out/${tag}_bench_c3h_plane2.json 2> gpurun_out/${tag}_bench_c3h_plane2.err
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+  --log-file gpurun_out/${tag}_launches_c3h.csv python tools/profile_one.py c3h:16384 2 > gpurun_out/${tag}_launches.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'k_plane' \
+  -o gpurun_out/${tag}_full_c3h -f python tools/profile_one.py c3h:16384 1 > gpurun_out/${tag}_full_c3h.log 2>&1
+for f in tests tests_wrench tests_plane2; do echo "== $f"; tail -3 gpurun_out/${tag}_$f.log; done
+for f in bench_c3h bench_c3h_plane2; do echo "== $f"; cut -c1-260 gpurun_out/${tag}_$f.json; done
