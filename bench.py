@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--forces", action="store_true",
+                    help="also time the device-side consumer (k_wrench: one spatial force per surface, 18 doubles out "
+                         "per surface). Off by default: the kernel has not been validated on a GPU yet (DESIGN.md 4b)")
     return ap.parse_args()
 
 
@@ -393,6 +396,37 @@ def main():
         barrier()
         f_sec = time.perf_counter() - f0
         hosts = full_hosts
+        forces_e2e = None
+        if args.forces:
+            # Same loop, but what leaves the GPU is HydroelasticTractionCalculator's output: synthetic
+            # contact properties (compliant E = 3e4 Pa, rigid = inf; dissipation 1 s/m; friction 0.5) and body velocities.
+            G = wl.geoms_per_scene
+            compliant = np.array([getattr(wl.meshes[m], "vertices_per_element", 0) == 4 or getattr(wl.meshes[m], "compliant", False)
+                                  for m in wl.geom_mesh])
+            E = np.tile(np.where(compliant, 3e4, np.inf), scenes)
+            vel = np.random.default_rng(1234 + rank).uniform(-0.1, 0.1, size=(scenes * G, 6))
+            for b in batches:
+                b.set_contact_properties(E, np.ones(scenes * G), np.full(scenes * G, 0.5))
+                b.set_body_kinematics(None, vel)
+
+            def forces_run(n_steps: int):
+                surf = 0
+                for k in range(n_steps):
+                    b = batches[k % 2]
+                    b.set_poses_host_ptr(pinned_poses[k % 2].data_ptr())
+                    b.query(rep, engine.STRICT, 0)
+                    surf += len(b.spatial_forces(1e-4)[0])   # waits, then copies 3 x [num_surfaces, 6] doubles
+                return surf
+
+            forces_run(2)
+            barrier()
+            g0 = time.perf_counter()
+            g_surf = forces_run(args.steps)
+            barrier()
+            g_sec = time.perf_counter() - g0
+            forces_e2e = {"value": g_surf / g_sec, "unit": UNIT, "ms_per_step": 1e3 * g_sec / args.steps,
+                          "d2h_bytes_per_step": int(g_surf / args.steps) * 18 * 8,
+                          "what": "host poses in, one spatial force per surface (F_Ac_W, F_Ao_W, F_Bo_W) out; this rank only"}
         ft = torch.tensor([f_sec, float(f_surf)], dtype=torch.float64, device=dev)
         if world > 1:
             fmax = ft.clone()
@@ -413,6 +447,8 @@ def main():
                "ms_per_step": 1e3 * float(et.item()) / args.steps,
                "pipelining": "two batches alternated: D2H of step k overlaps H2D + query of step k+1",
                "host_affinity": numa, "faces_only": faces_only}
+        if forces_e2e is not None:
+            e2e["spatial_forces"] = forces_e2e
 
     if rank != 0:
         if world > 1:
