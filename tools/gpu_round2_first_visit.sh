@@ -21,5 +21,11 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
   --log-file gpurun_out/${tag}_launches_c3h.csv python tools/profile_one.py c3h:16384 2 > gpurun_out/${tag}_launches.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'k_plane' \
   -o gpurun_out/${tag}_full_c3h -f python tools/profile_one.py c3h:16384 1 > gpurun_out/${tag}_full_c3h.log 2>&1
+# 5. only if step 2 is green: the e2e figure through the consumer (18 doubles per surface out instead of the mesh).
+if tail -1 gpurun_out/${tag}_tests_wrench.log | grep -q "passed" && ! tail -1 gpurun_out/${tag}_tests_wrench.log | grep -q "failed"; then
+  timeout 200 python bench.py --no-cpu-baseline --forces --steps 20 --warmup 5 \
+    > gpurun_out/${tag}_bench_c3_forces.json 2> gpurun_out/${tag}_bench_c3_forces.err
+  echo "== bench c3 --forces"; cut -c1-260 gpurun_out/${tag}_bench_c3_forces.json
+fi
 for f in tests tests_wrench tests_plane2; do echo "== $f"; tail -3 gpurun_out/${tag}_$f.log; done
 for f in bench_c3h bench_c3h_plane2; do echo "== $f"; cut -c1-260 gpurun_out/${tag}_$f.json; done
