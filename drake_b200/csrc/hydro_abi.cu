@@ -349,6 +349,7 @@ struct dbh_batch {
   DevBuf<double> d_body_origin, d_body_vel, d_props, d_forces;
   bool have_body_origin{false}, have_body_vel{false}, have_props{false}, forces_done{false};
   DevBuf<unsigned int> d_plane_emit;  // the current chunk's emitting half-space elements (chunk-local indices)
+  int plane_emit_sized_for{0};        // the chunk count d_plane_emit was last sized for
   DevBuf<double> d_geom_hs;
 
   DevBuf<PairRec> d_pairs;
@@ -416,7 +417,7 @@ struct dbh_batch {
     CUDA_OK(d_cand_tri.ensure(info.num_soft_rigid_pairs ? cap_tri : 1));
     CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_tet : 1));
     CUDA_OK(d_slow.ensure(cap_slow));
-    if (!plane_pairs.empty()) {
+    if (!plane_pairs.empty() && plane_emit_sized_for != num_chunks) {  // depends on the chunking only
       long long most = 1;
       for (int c = 0; c < num_chunks; ++c) {
         const int s0 = static_cast<int>(static_cast<long long>(num_scenes) * c / num_chunks);
@@ -428,6 +429,7 @@ struct dbh_batch {
       if (most >= (1ll << 32))
         return Fail(DBH_ERR_CAPACITY, "more than 2^32 half-space elements in one chunk of scenes: raise dbh_batch_set_chunks");
       CUDA_OK(d_plane_emit.ensure(static_cast<size_t>(most)));
+      plane_emit_sized_for = num_chunks;
     }
     CUDA_OK(d_soup_hdr.ensure(cap_polys));
     CUDA_OK(d_soup_v.ensure(static_cast<size_t>(cap_polys) * kMaxPolyVerts * 4));
