@@ -120,12 +120,15 @@ __host__ __device__ __forceinline__ int sgn_of(double x) { return x > 0 ? 1 : (x
 // evaluated at the mesh-frame point, positions X_WR * p (:84-86).
 __host__ __device__ __forceinline__ void clip_tri_by_half_space(const TriRec& tri, D3 nhat_R, double displacement,
                                                                 double pressure_scale, double margin, const Xf& X_WR,
-                                                                const Xf& X_WS, WorldPoly* out) {
+                                                                const Xf& X_WS, WorldPoly* out,
+                                                                bool filter_normals = true) {
   out->n = 0;
   out->status = 0;
   const D3 Sz_W = make_d3(X_WS.m[6], X_WS.m[7], X_WS.m[8]);
   const D3 face_normal_W = rot(X_WR, load3(tri.n));
-  if (!(dot(-Sz_W, normalized(face_normal_W)) > kCosAlphaPlane)) return;
+  // filter_normals is only ever false in the host check of the reference's single-triangle cases, which call
+  // ConstructTriangleHalfspaceIntersectionPolygon without the BVH callback.
+  if (filter_normals && !(dot(-Sz_W, normalized(face_normal_W)) > kCosAlphaPlane)) return;
   D3 p[3];
   double s[3];
   int num_positive = 0;

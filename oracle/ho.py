@@ -63,7 +63,7 @@ def lib():
                                       C.c_int, _ip, C.c_int]
         _lib.ho_soft_mesh_rigid_half_space.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int64, C.c_int64, C.c_int]
         _lib.ho_soft_half_space_rigid_mesh.argtypes = [C.c_int, _dp, C.c_double, C.c_double, _dp, C.c_int64, C.c_int64,
-                                                       C.c_int]
+                                                       C.c_int, C.c_int]
         _lib.ho_result_from_arrays.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, _ip, _dp, C.c_int64, C.c_int64]
         _lib.ho_traction.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, _dp]
         for name, n in (("ho_atan_x_over_x_from_x_squared", 1), ("ho_combined_dissipation", 4),
@@ -428,11 +428,13 @@ def soft_mesh_rigid_half_space(mesh_S: VolumeMesh, field_S: VolumeField, X_WS, X
 
 
 def soft_half_space_rigid_mesh(mesh_R: TriMesh, X_WS, pressure_scale: float, X_WR, id_S: int = 1, id_R: int = 2,
-                               rep: int = KPOLYGON, margin: float = 0.0) -> Optional[Surface]:
+                               rep: int = KPOLYGON, margin: float = 0.0, filter_normals: bool = True) -> Optional[Surface]:
     """ComputeContactSurfaceFromCompliantHalfSpaceRigidMesh (mesh_half_space_intersection.cc:338-418): the
-    compliant half space is z <= 0 of frame S. Faces carry (-1, triangle) as their emitting element pair."""
+    compliant half space is z <= 0 of frame S. Faces carry (-1, triangle) as their emitting element pair.
+    filter_normals=False skips the BVH callback's face-normal filter (ComputeContactSurface over every triangle,
+    :264-336, which is what the reference's MeshHalfSpaceValueTest cases exercise)."""
     h = lib().ho_soft_half_space_rigid_mesh(mesh_R.h, _pd(_d(X_WS)), pressure_scale, margin, _pd(_d(X_WR)), id_S, id_R,
-                                            rep)
+                                            rep, int(filter_normals))
     if h == -1:
         return None
     return _fetch_result(_check(h, "soft_half_space_rigid_mesh"))

@@ -184,7 +184,8 @@ struct HalfSpaceClipper {
 // Returns false when the surface is null.
 inline bool ContactSurfaceFromCompliantHalfSpaceRigidMesh(int64_t id_S, const Xform& X_WS, double pressure_scale,
                                                           int64_t id_R, const TriMesh& mesh_R, const Xform& X_WR,
-                                                          Representation rep, double margin, SurfaceResult* out) {
+                                                          Representation rep, double margin, SurfaceResult* out,
+                                                          bool filter_normals = true) {
   const Vec3 unit_grad_p_W = -Vec3{X_WS.R(0, 2), X_WS.R(1, 2), X_WS.R(2, 2)};
   Xform X_RS = InvertAndCompose(X_WR, X_WS);
   const Vec3 Sz_R{X_RS.R(0, 2), X_RS.R(1, 2), X_RS.R(2, 2)};
@@ -196,7 +197,9 @@ inline bool ContactSurfaceFromCompliantHalfSpaceRigidMesh(int64_t id_S, const Xf
   std::vector<int> e1;
   for (int tri = 0; tri < mesh_R.num_elements(); ++tri) {
     // The BVH callback's filter (:349-358); the BVH itself only drops triangles with no vertex inside.
-    if (!IsFaceNormalInNormalDirection(unit_grad_p_W, mesh_R, tri, X_WR.R)) continue;
+    // filter_normals = false: ComputeContactSurface (:264-336) over every triangle, as the reference's
+    // MeshHalfSpaceValueTest cases call it.
+    if (filter_normals && !IsFaceNormalInNormalDirection(unit_grad_p_W, mesh_R, tri, X_WR.R)) continue;
     const int n = clipper.Clip(tri, grad_p_W);
     for (int i = 0; i < n; ++i) e1.push_back(tri);
   }

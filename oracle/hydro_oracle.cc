@@ -549,12 +549,12 @@ int ho_soft_mesh_rigid_half_space(int vol, int field, const double* X_WS, const 
   HO_CATCH(-2)
 }
 int ho_soft_half_space_rigid_mesh(int tri, const double* X_WS, double pressure_scale, double margin, const double* X_WR,
-                                  int64_t id_S, int64_t id_R, int rep) {
+                                  int64_t id_S, int64_t id_R, int rep, int filter_normals) {
   HO_TRY
   SurfaceResult res;
   if (!ContactSurfaceFromCompliantHalfSpaceRigidMesh(id_S, Xform::FromArray(X_WS), pressure_scale, id_R,
                                                      g_tris[tri]->mesh, Xform::FromArray(X_WR),
-                                                     static_cast<Representation>(rep), margin, &res))
+                                                     static_cast<Representation>(rep), margin, &res, filter_normals != 0))
     return -1;
   return AddResult(std::move(res));
   HO_CATCH(-2)

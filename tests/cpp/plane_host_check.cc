@@ -95,7 +95,7 @@ int phc_mesh_vs_rigid_half_space(int nt, const double* tet_v, const double* tet_
 // Compliant half space x rigid mesh over a whole mesh. tri_v [nt*9], tri_n [nt*3].
 int phc_half_space_vs_rigid_mesh(int nt, const double* tri_v, const double* tri_n, const double* X_WS,
                                  double pressure_scale, double margin, const double* X_WR, int rep, int swapped,
-                                 int* elem, int* face_n, double* areas, double* normals, double* centroids, double* e_c,
+                                 int filter_normals, int* elem, int* face_n, double* areas, double* normals, double* centroids, double* e_c,
                                  double* grad, double* verts, double* pressures, int* face_data, int* counts4) {
   Xf XS, XR;
   std::memcpy(XS.m, X_WS, sizeof(XS.m));
@@ -109,7 +109,7 @@ int phc_half_space_vs_rigid_mesh(int nt, const double* tri_v, const double* tri_
     std::memcpy(rec.v, tri_v + 9 * t, sizeof(rec.v));
     std::memcpy(rec.n, tri_n + 3 * t, sizeof(rec.n));
     WorldPoly P;
-    clip_tri_by_half_space(rec, nhat_R, disp, pressure_scale, margin, XR, XS, &P);
+    clip_tri_by_half_space(rec, nhat_R, disp, pressure_scale, margin, XR, XS, &P, filter_normals != 0);
     if (P.status) return P.status;
     if (P.n) Append(P, rep, swapped != 0, t, &o);
   }

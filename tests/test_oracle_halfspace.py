@@ -203,3 +203,79 @@ def test_scene_dispatch_with_half_spaces():
     sc.add_half_space(2)
     with pytest.raises(RuntimeError, match="rigid-rigid"):
         sc.compute([pose_ball, ho.IDENTITY])
+
+
+# ---- ConstructTriangleHalfspaceIntersectionPolygon, one triangle at a time --------------------------------
+# mesh_half_space_intersection_test.cc:405-885 (MeshHalfSpaceValueTest): half space z <= 2 in the mesh frame F,
+# pressure 17 (2 - z), F posed arbitrarily in World; the BVH callback's normal filter is not part of these.
+
+X_WF_VALUE = ho.xform(ho.angle_axis_matrix(math.pi / 7, np.array([1, 2, 3]) / math.sqrt(14)), [-0.25, 0.5, 0.75])
+
+
+def clip_one(tri_vertices, tris=((0, 1, 2),), rep=ho.KPOLYGON, clip=None):
+    """`clip(mesh_F, X_WS, pressure_scale, X_WF, rep)` defaults to the oracle; tests/test_plane_math_cpu.py passes
+    the kernel arithmetic instead."""
+    mesh_F = ho.TriMesh.from_arrays(np.asarray(tri_vertices, float), list(tris))
+    X_WS = ho.compose(X_WF_VALUE, ho.xform(None, [0, 0, 2.0]))
+    if clip is None:
+        clip = lambda m, X_WS, scale, X_WF, rep: ho.soft_half_space_rigid_mesh(m, X_WS, scale, X_WF, 1, 2, rep,
+                                                                                 filter_normals=False)
+    return clip(mesh_F, X_WS, 17.0, X_WF_VALUE, rep)
+
+
+def in_F(points_W):
+    R, p = ho.xform_parts(X_WF_VALUE)
+    return (np.asarray(points_W) - p) @ R
+
+
+SINGLE_TRIANGLE_CASES = [
+    # name, triangle, expected polygon in F (None: no face), expected number of distinct vertices
+    ("NoIntersection", [(0, 0, 3), (1, 0, 3), (0, 1, 3)], None),
+    ("Inside", [(3, 5, 1), (4, 5, 1), (3, 6, 1)], [(3, 5, 1), (4, 5, 1), (3, 6, 1)]),
+    ("OnBoundary", [(3, 5, 2), (4, 5, 2), (3, 6, 2)], [(3, 5, 2), (4, 5, 2), (3, 6, 2)]),
+    ("VertexOnRestOutside", [(3, 5, 2), (4, 5, 3), (3, 6, 3)], [(3, 5, 2)] * 3),          # degenerate: zero area
+    ("VertexOnRestInside", [(3, 5, 2), (4, 5, 1), (3, 6, 1)], [(3, 5, 2), (4, 5, 1), (3, 6, 1)]),
+    ("EdgeOnRestOutside", [(3, 5, 3), (2, 5, 2), (4, 5, 2)], [(2, 5, 2), (4, 5, 2), (4, 5, 2), (2, 5, 2)]),
+    ("EdgeOnRestInside", [(3, 5, 1), (4, 5, 2), (3, 6, 2)], [(3, 5, 1), (4, 5, 2), (3, 6, 2)]),
+    ("QuadrilateralResults", [(3, 5, 3), (2, 5, 1), (4, 5, 1)], [(2, 5, 1), (4, 5, 1), (3.5, 5, 2), (2.5, 5, 2)]),
+    ("OutsideInsideOn", [(3, 5, 3), (2, 5, 1), (3.5, 5, 2)], [(2, 5, 1), (3.5, 5, 2), (3.5, 5, 2), (2.5, 5, 2)]),
+    ("OneInsideTwoOutside", [(3, 5, 3), (4, 5, 3), (3, 6, 1)], [(3, 6, 1), (3, 5.5, 2), (3.5, 5.5, 2)]),
+]
+
+
+def check_single_triangle_case(tri, expected, clip=None):
+    for rep in (ho.KPOLYGON, ho.KTRIANGLE):
+        s = clip_one(tri, rep=rep, clip=clip)
+        if expected is None:
+            assert s is None or s.num_faces == 0
+            continue
+        n = len(expected)
+        assert s.num_faces == (1 if rep == ho.KPOLYGON else n)
+        if rep == ho.KPOLYGON:
+            poly = s.polygons()[0]
+            assert len(poly) == n
+            np.testing.assert_allclose(in_F(s.vertices[np.asarray(poly)]), np.asarray(expected, float), atol=1e-14)
+            # FieldConsistent (:293-356): vertex pressures = 17 (2 - z); gradient = R_WF (0, 0, -17).
+            np.testing.assert_allclose(s.pressures[np.asarray(poly)], 17.0 * (2.0 - np.asarray(expected, float)[:, 2]),
+                                       atol=3e-14)
+        else:
+            # The fan: triangles (v_{k-1}, v_k, centroid); the centroid vertex is last (:288-316 of
+            # contact_surface_utility.cc); areas add up to the polygon's.
+            P = np.asarray(expected, float)
+            area = 0.5 * np.linalg.norm(sum(np.cross(P[k] - P[0], P[k + 1] - P[0]) for k in range(1, n - 1)))
+            np.testing.assert_allclose(s.areas.sum(), area, atol=1e-14)
+            fans = s.polygons()
+            for k in range(n):
+                np.testing.assert_allclose(in_F(s.vertices[fans[k][0]]), P[k - 1], atol=1e-14)
+                np.testing.assert_allclose(in_F(s.vertices[fans[k][1]]), P[k], atol=1e-14)
+
+
+@pytest.mark.parametrize("name,tri,expected", SINGLE_TRIANGLE_CASES, ids=[c[0] for c in SINGLE_TRIANGLE_CASES])
+def test_single_triangle_cases(name, tri, expected):
+    check_single_triangle_case(tri, expected)
+
+
+def test_two_triangle_fan_on_the_boundary():
+    # InsideOrOnIntersection, third block (:470-486): a fan of two triangles, welded along the shared edge.
+    s = clip_one([(4, 5, 2), (3, 5, 2), (3, 5, 1), (2, 5, 2)], tris=[(0, 1, 2), (2, 1, 3)])
+    assert s.num_faces == 2 and len(s.vertices) == 4

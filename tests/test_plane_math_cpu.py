@@ -88,16 +88,16 @@ def host_mesh_vs_half_space(mesh, fld, X_WS, X_WR, rep, swapped):
     return hs.trim()
 
 
-def host_half_space_vs_mesh(mesh, X_WS, pressure_scale, margin, X_WR, rep, swapped):
+def host_half_space_vs_mesh(mesh, X_WS, pressure_scale, margin, X_WR, rep, swapped, filter_normals=True):
     verts, tris, normals = mesh.arrays()[:3]
     tri_v = np.ascontiguousarray(verts[tris].reshape(-1, 9))
     hs = HostSurface(rep, 4 * len(tris), 5 * len(tris))
     d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
     lib = harness()
     lib.phc_half_space_vs_rigid_mesh.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp, C.c_int, C.c_int,
-                                                 _ip, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+                                                 C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
     rc = lib.phc_half_space_vs_rigid_mesh(len(tris), d(tri_v), d(normals), d(X_WS), pressure_scale, margin, d(X_WR),
-                                          rep, int(swapped), *hs.args())
+                                          rep, int(swapped), int(filter_normals), *hs.args())
     assert rc == 0
     return hs.trim()
 
@@ -259,3 +259,25 @@ def test_wrench_arithmetic_matches_the_oracle(rep):
         assert lib.phc_combined_dissipation(*args) == ho.combined_dissipation(*args)
     for args in [(0.0, 0.0), (0.5, 0.5), (1.0, 0.25)]:
         assert lib.phc_combined_friction(*args) == ho.combined_friction(*args)
+
+
+@pytest.mark.parametrize("name,tri,expected", __import__("tests.test_oracle_halfspace", fromlist=["x"]).SINGLE_TRIANGLE_CASES,
+                         ids=[c[0] for c in __import__("tests.test_oracle_halfspace", fromlist=["x"]).SINGLE_TRIANGLE_CASES])
+def test_single_triangle_cases_through_the_kernel_arithmetic(name, tri, expected):
+    """The reference's MeshHalfSpaceValueTest cases (vertices and edges exactly on the boundary, the >= 0 / <= 0
+    vertex choices, zero-area results) through clip_tri_by_half_space + pack_world_polygon."""
+    from tests.test_oracle_halfspace import check_single_triangle_case
+
+    class AsSurface:
+        def __init__(self, h):
+            self.h = h
+            self.num_faces = int(h.counts[0])
+            self.vertices, self.pressures, self.areas = h.vertices, h.pressures, h.areas
+
+        def polygons(self):
+            return self.h.polygons()
+
+    def clip(mesh_F, X_WS, scale, X_WF, rep):
+        return AsSurface(host_half_space_vs_mesh(mesh_F, X_WS, scale, 0.0, X_WF, rep, False, filter_normals=False))
+
+    check_single_triangle_case(tri, expected, clip=clip)
