@@ -279,3 +279,35 @@ def test_two_triangle_fan_on_the_boundary():
     # InsideOrOnIntersection, third block (:470-486): a fan of two triangles, welded along the shared edge.
     s = clip_one([(4, 5, 2), (3, 5, 2), (3, 5, 1), (2, 5, 2)], tris=[(0, 1, 2), (2, 1, 3)])
     assert s.num_faces == 2 and len(s.vertices) == 4
+
+
+def test_no_double_counting_on_a_shared_face():
+    # mesh_plane_intersection_test.cc:810-850 (NoDoubleCounting): the plane z = 0 is coplanar with the face the
+    # two tetrahedra share; `distance > 0` (:139) makes exactly one of them (the one above) emit, and its
+    # polygon is the shared face itself.
+    mesh = trivial_volume_mesh()
+    fld = ho.VolumeField.from_values(mesh, [0.25, 0.5, 0.75, 1, -1])
+    s = ho.soft_mesh_rigid_half_space(mesh, fld, ho.IDENTITY, ho.IDENTITY, 1, 2, ho.KPOLYGON)
+    assert s.num_faces == 1 and list(s.elem_first) == [0]
+    got = {tuple(v) for v in np.round(s.vertices[s.polygons()[0]], 15) + 0.0}
+    assert got == {(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)}
+    np.testing.assert_allclose(sorted(s.pressures), [0.25, 0.5, 0.75], atol=0)
+
+
+def test_duplicate_output_from_duplicate_input():
+    # mesh_plane_intersection_test.cc:732-805: welding follows the input's vertex sharing: the 5-vertex mesh gives
+    # 6 triangles over 6 vertices (4 cut edges + 2 centroids), the 8-vertex copy (no shared vertices) 6 over 8.
+    X_WF = ho.xform(ho.rpy_matrix(0.2, -0.4, 0.9), [0.5, -1.0, 2.0])
+    X_FR = ho.xform(ho.angle_axis_matrix(math.pi / 2, [0, 1, 0]), [0.5, 0, 0])  # plane x = 0.5, normal +x, in F
+    X_WR = ho.compose(X_WF, X_FR)
+    mini = trivial_volume_mesh()
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, 0], [0, 1, 0], [1, 0, 0], [0, 0, -1]], float)
+    dupe = ho.VolumeMesh.from_arrays(v, [[0, 1, 2, 3], [4, 5, 6, 7]])
+    s_min = ho.soft_mesh_rigid_half_space(mini, ho.VolumeField.from_values(mini, [0, 0, 0, 1, -1]), X_WF, X_WR, 1, 2,
+                                          ho.KTRIANGLE)
+    s_dup = ho.soft_mesh_rigid_half_space(dupe, ho.VolumeField.from_values(dupe, [0, 0, 0, 1, 0, 0, 0, -1]), X_WF,
+                                          X_WR, 1, 2, ho.KTRIANGLE)
+    assert (s_min.num_faces, len(s_min.vertices)) == (6, 6)
+    assert (s_dup.num_faces, len(s_dup.vertices)) == (6, 8)
+    for a, b in zip(s_min.polygons(), s_dup.polygons()):
+        np.testing.assert_allclose(s_min.vertices[a], s_dup.vertices[b], atol=4 * EPS)

@@ -281,3 +281,15 @@ def test_single_triangle_cases_through_the_kernel_arithmetic(name, tri, expected
         return AsSurface(host_half_space_vs_mesh(mesh_F, X_WS, scale, 0.0, X_WF, rep, False, filter_normals=False))
 
     check_single_triangle_case(tri, expected, clip=clip)
+
+
+def test_no_double_counting_through_the_kernel_arithmetic():
+    """mesh_plane_intersection_test.cc:810-850 through slice_tet_with_plane / count_tet_slice: a plane coplanar with
+    the face two tetrahedra share makes exactly one of them emit (`distance > 0` is strict)."""
+    from tests.test_oracle_halfspace import trivial_volume_mesh
+    mesh = trivial_volume_mesh()
+    fld = ho.VolumeField.from_values(mesh, [0.25, 0.5, 0.75, 1, -1])
+    host = host_mesh_vs_half_space(mesh, fld, ho.IDENTITY, ho.IDENTITY, ho.KPOLYGON, False)
+    assert list(host.counts) == [1, 3, 4, 1] and list(host.elem) == [0]
+    assert {tuple(v) for v in host.vertices + 0.0} == {(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)}
+    assert sorted(host.pressures) == [0.25, 0.5, 0.75]
