@@ -25,6 +25,53 @@ def shard_bounds(total_scenes: int, world_size: int) -> np.ndarray:
     return np.concatenate([[0], np.cumsum(sizes)])
 
 
+def cost_balanced_bounds(scene_costs, world_size: int) -> np.ndarray:
+    """[world_size + 1] boundaries of contiguous scene ranges whose largest total cost is minimal (SURVEY.md §8e:
+    "balanced further by a precomputed cost" when scenes differ a lot, e.g. the clutter config). scene_costs: a
+    non-negative cost per scene, typically the element_pairs column of a dry run's gathered statistics
+    (gather_scene_stats). Exact: binary search on the bottleneck over the prefix sums, then a greedy fill that also
+    leaves no rank without a scene while scenes remain."""
+    c = np.asarray(scene_costs, dtype=np.float64)
+    if c.ndim != 1 or world_size < 1 or np.any(c < 0) or not np.all(np.isfinite(c)):
+        raise ValueError("cost_balanced_bounds: bad arguments")
+    n = len(c)
+    prefix = np.concatenate([[0.0], np.cumsum(c)])
+
+    def parts_needed(limit: float) -> int:
+        parts, start = 0, 0
+        while start < n:
+            # Furthest end with prefix[end] - prefix[start] <= limit (at least one scene per part).
+            end = int(np.searchsorted(prefix, prefix[start] + limit, side="right")) - 1
+            end = max(end, start + 1)
+            parts += 1
+            start = end
+        return parts
+
+    lo, hi = (float(c.max()) if n else 0.0), float(prefix[-1])
+    for _ in range(100):
+        if hi - lo <= 1e-12 * max(hi, 1.0):
+            break
+        mid = 0.5 * (lo + hi)
+        if parts_needed(mid) <= world_size:
+            hi = mid
+        else:
+            lo = mid
+    bounds, start = [0], 0
+    for r in range(world_size):
+        remaining_ranks = world_size - r - 1
+        if start >= n:
+            bounds.append(n)
+            continue
+        end = int(np.searchsorted(prefix, prefix[start] + hi * (1 + 1e-12), side="right")) - 1
+        end = max(end, start + 1)
+        end = min(end, n - min(remaining_ranks, n - start - 1))  # keep a scene for each later rank while any remain
+        if remaining_ranks == 0:
+            end = n
+        bounds.append(end)
+        start = end
+    return np.asarray(bounds, dtype=np.int64)
+
+
 def shard_of(total_scenes: int, rank: int, world_size: int) -> Tuple[int, int]:
     """[lo, hi) scene range of `rank`."""
     if not 0 <= rank < world_size:

@@ -86,3 +86,32 @@ def test_stats_all_gather_world_size_2(total, ragged):
     want = _oracle_scene_stats(0, total)
     np.testing.assert_array_equal(got, want)
     assert want[:, 4].sum() > 0   # the scenes do produce surfaces
+
+
+def test_cost_balanced_bounds():
+    """Contiguous cost-balanced scene ranges: cover every scene once, never worse than the equal-count split, optimal
+    on small cases (checked against brute force), and equal to the equal-count split for uniform costs."""
+    import itertools
+    from drake_b200 import sharding
+    rng = np.random.default_rng(0)
+
+    def bottleneck(costs, b):
+        return max(costs[b[r]:b[r + 1]].sum() for r in range(len(b) - 1))
+
+    for n, w in [(1, 1), (1, 4), (7, 3), (12, 4), (10, 8), (64, 8)]:
+        for _ in range(5):
+            costs = rng.integers(0, 50, size=n).astype(float)
+            b = sharding.cost_balanced_bounds(costs, w)
+            assert b[0] == 0 and b[-1] == n and len(b) == w + 1 and np.all(np.diff(b) >= 0)
+            assert np.count_nonzero(np.diff(b)) == min(n, w)     # no idle rank while scenes remain
+            equal = sharding.shard_bounds(n, w)
+            if n <= 12:   # brute force over all contiguous partitions into at most w non-empty parts
+                best = min(bottleneck(costs, np.array((0,) + cut + (n,)))
+                           for k in range(0, min(w, n)) for cut in itertools.combinations(range(1, n), k))
+                best_full = min(bottleneck(costs, np.array((0,) + cut + (n,)))
+                                for cut in itertools.combinations(range(1, n), min(w, n) - 1))
+                assert best <= bottleneck(costs, b) <= best_full + 1e-9
+            assert bottleneck(costs, b) <= bottleneck(costs, equal) + 1e-9 or n <= w
+    np.testing.assert_array_equal(sharding.cost_balanced_bounds(np.ones(16), 4), sharding.shard_bounds(16, 4))
+    with pytest.raises(ValueError):
+        sharding.cost_balanced_bounds([1.0, -1.0], 2)
