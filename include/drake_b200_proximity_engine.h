@@ -4,7 +4,9 @@
 // Header-only C++17, no Eigen. Mirrors, name for name and with the same argument meaning and
 // error behaviour, the part of geometry::internal::ProximityEngine<double> that sits on the path
 // (reference: geometry/proximity_engine.h:60-395):
-//   AddDynamicGeometry / AddAnchoredGeometry      proximity_engine.h:122-133
+//   AddDynamicGeometry / AddAnchoredGeometry      proximity_engine.h:122-133 (shapes incl. HalfSpace)
+//   RemoveGeometry                                proximity_engine.h:186
+//   num_geometries / num_dynamic / num_anchored   proximity_engine.h:196-202
 //   UpdateWorldPoses                              proximity_engine.h:226-227
 //   ComputeContactSurfaces                        proximity_engine.h:309-315
 //   ComputeContactSurfacesWithFallback            proximity_engine.h:320-326
@@ -161,6 +163,36 @@ class ProximityEngine {
     AddGeometry(shape, X_WG, id, props, /*anchored=*/true);
   }
   int num_geometries() const { return static_cast<int>(ids_.size()); }
+  // proximity_engine.h:196-202.
+  int num_anchored() const {
+    int n = 0;
+    for (uint8_t a : anchored_) n += a;
+    return n;
+  }
+  int num_dynamic() const { return num_geometries() - num_anchored(); }
+
+  // RemoveGeometry (proximity_engine.h:186, proximity_engine.cc:483-520): the geometry leaves its tree, the
+  // hydroelastic representations and the collision filter. `is_dynamic` must match how it was added
+  // (the reference looks it up in the tree that flag names and .at() throws otherwise).
+  void RemoveGeometry(GeometryId id, bool is_dynamic) {
+    const int g = IndexOf(id);
+    if ((anchored_[g] == 0) != is_dynamic)
+      throw std::out_of_range("RemoveGeometry: GeometryId " + std::to_string(id) + " is not " +
+                              (is_dynamic ? "dynamic" : "anchored"));
+    ids_.erase(ids_.begin() + g);
+    assets_.erase(assets_.begin() + g);
+    anchored_.erase(anchored_.begin() + g);
+    poses_.erase(poses_.begin() + g);
+    index_.clear();
+    for (size_t k = 0; k < ids_.size(); ++k) index_[ids_[k]] = static_cast<int>(k);
+    std::vector<std::pair<int, int>> kept;  // CollisionFilter::RemoveGeometry: declarations naming it go away
+    for (const auto& [a, b] : excluded_) {
+      if (a == g || b == g) continue;
+      kept.emplace_back(a > g ? a - 1 : a, b > g ? b - 1 : b);
+    }
+    excluded_ = std::move(kept);
+    Invalidate();  // the mesh asset stays registered in the context (assets are shared by handle)
+  }
 
   // CollisionFilter declaration ExcludeBetween for one pair (collision_filter.h:158 CanCollideWith).
   void ExcludeCollisionsBetween(GeometryId a, GeometryId b) {
