@@ -311,3 +311,34 @@ def test_duplicate_output_from_duplicate_input():
     assert (s_dup.num_faces, len(s_dup.vertices)) == (6, 8)
     for a, b in zip(s_min.polygons(), s_dup.polygons()):
         np.testing.assert_allclose(s_min.vertices[a], s_dup.vertices[b], atol=4 * EPS)
+
+
+def test_compute_contact_surface_responsibilities():
+    # mesh_plane_intersection_test.cc:955-1000,1102-1192 (AllTetsAreConsidered, NormalsInPlaneDirection,
+    # GradientConstituentPressure) in the reference's non-trivial frames.
+    X_WF = ho.xform(ho.angle_axis_matrix(math.pi / 2, [1, 0, 0]), [1.25, 2.5, -3.75])
+    X_FM = ho.xform(ho.angle_axis_matrix(9 * math.pi / 7, np.array([1, 2, 3]) / math.sqrt(14)), [-2.3, -4.2, 3.7])
+    X_WM = ho.compose(X_WF, X_FM)
+    mesh = trivial_volume_mesh()
+    fld = ho.VolumeField.from_values(mesh, [0, 0, 0, 1, -1])
+    R_WM, _ = ho.xform_parts(X_WM)
+    # Plane with normal Mx through 0.5 Mx: cuts both tetrahedra.
+    X_WR = ho.compose(X_WM, ho.xform(ho.angle_axis_matrix(math.pi / 2, [0, 1, 0]), [0.5, 0, 0]))
+    s = ho.soft_mesh_rigid_half_space(mesh, fld, X_WM, X_WR, 1, 2, ho.KTRIANGLE)
+    assert (s.num_faces, len(s.vertices)) == (6, 6)
+    grads = fld.arrays()[1]
+    np.testing.assert_allclose(s.grad_eM[:3], np.tile(R_WM @ grads[0], (3, 1)), atol=4 * EPS)
+    np.testing.assert_allclose(s.grad_eM[3:], np.tile(R_WM @ grads[1], (3, 1)), atol=4 * EPS)
+    assert s.grad_eN is None
+    s = ho.soft_mesh_rigid_half_space(mesh, fld, X_WM, X_WR, 2, 1, ho.KTRIANGLE)
+    assert s.grad_eM is None
+    np.testing.assert_allclose(s.grad_eN[:3], np.tile(R_WM @ grads[0], (3, 1)), atol=4 * EPS)
+    np.testing.assert_allclose(s.grad_eN[3:], np.tile(R_WM @ grads[1], (3, 1)), atol=4 * EPS)
+    # Plane with normal Mz through 0.5 Mz: only the upper tetrahedron; normals along the plane normal, reversed
+    # when the half space has the smaller id.
+    X_WR = ho.compose(X_WM, ho.xform(None, [0, 0, 0.5]))
+    for ids, sign in (((1, 2), 1.0), ((2, 1), -1.0)):
+        s = ho.soft_mesh_rigid_half_space(mesh, fld, X_WM, X_WR, ids[0], ids[1], ho.KTRIANGLE)
+        assert s.num_faces == 3 and set(s.elem_first) == {0}
+        np.testing.assert_allclose(s.normals, np.tile(sign * R_WM[:, 2], (3, 1)), atol=64 * EPS)
+    assert ho.soft_mesh_rigid_half_space(mesh, fld, X_WM, X_WR, 1, 2, ho.KPOLYGON).rep == ho.KPOLYGON
