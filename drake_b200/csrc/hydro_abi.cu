@@ -1164,7 +1164,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     // block-wide appends; filter / pack: resident blocks per SM the launch bound asks for (registers against
     // occupancy); tgrid / fgrid / pgrid: grid size in units of the resident blocks -- persistent grids (1x for the
     // traversal and the pack) beat over-subscribed ones by 5-15 % (no tail wave).
-    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, plane = 1; } tune;
+    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, plane = 1, ppack = 1; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1178,6 +1178,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       get("fgrid", &tune.fgrid);
       get("pgrid", &tune.pgrid);
       get("plane", &tune.plane);  // 2: experimental count pass of the half-space pairs (k_plane_count2)
+      get("ppack", &tune.ppack);  // 4: half-space pack pass capped at 128 registers (4 blocks / SM); experimental
     }
     for (int chunk = 0; chunk < b->num_chunks; ++chunk) {
       const int s0 = static_cast<int>(static_cast<long long>(b->num_scenes) * chunk / b->num_chunks);
@@ -1259,7 +1260,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       else k_pack<3><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
       if (plane_blocks) {  // pack pass of the half-space pairs: straight into the final layout
         ++b->last_launches;
-        k_plane<true><<<plane_blocks, 128, 0, st>>>(pl);
+        if (tune.ppack == 4) k_plane_pack_capped<4><<<plane_blocks, 128, 0, st>>>(pl);
+        else k_plane<true><<<plane_blocks, 128, 0, st>>>(pl);
       }
       mark(6);
       su.pair_begin = p0;

@@ -1932,7 +1932,7 @@ __global__ void k_plane_setup(PlaneArgs a) {
 }
 
 template <bool kPack>
-__global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
+__device__ __forceinline__ void plane_pass(const PlaneArgs& a) {
   if (kPack && a.counters->error != 0) return;
   const long long w0 = a.plane_elem_off[a.q_begin];
   const long long num_elems = a.plane_elem_off[a.q_end] - w0;
@@ -2074,6 +2074,17 @@ __global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
       a.out.face_pair[f] = pair;
     }
   }
+}
+
+template <bool kPack>
+__global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
+  plane_pass<kPack>(a);
+}
+// The pack pass under a register cap (kMinBlocks resident blocks of 128 threads per SM; DBH_TUNE="ppack=4"): an
+// occupancy experiment that has NOT run on a GPU yet. The default above is the validated build.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) k_plane_pack_capped(PlaneArgs a) {
+  plane_pass<true>(a);
 }
 
 // EXPERIMENTAL count pass (DBH_TUNE="plane=2"; NOT the default and not yet run on a GPU: the round's GPU
