@@ -17,6 +17,10 @@ timeout 120 python bench.py --config c3h --no-cpu-baseline --steps 20 --warmup 5
   > gpurun_out/${tag}_bench_c3h.json 2> gpurun_out/${tag}_bench_c3h.err
 DBH_TUNE=plane=2 timeout 120 python bench.py --config c3h --no-cpu-baseline --steps 20 --warmup 5 \
   > gpurun_out/${tag}_bench_c3h_plane2.json 2> gpurun_out/${tag}_bench_c3h_plane2.err
+(DBH_TUNE=ppack=4 timeout 100 python -m pytest tests/test_zz_gpu_halfspace.py -m gpu -q 2>&1 | tail -5) \
+  > gpurun_out/${tag}_tests_ppack4.log
+DBH_TUNE=plane=2,ppack=4 timeout 120 python bench.py --config c3h --no-cpu-baseline --steps 20 --warmup 5 \
+  > gpurun_out/${tag}_bench_c3h_plane2_ppack4.json 2> gpurun_out/${tag}_bench_c3h_plane2_ppack4.err
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
   --log-file gpurun_out/${tag}_launches_c3h.csv python tools/profile_one.py c3h:16384 2 > gpurun_out/${tag}_launches.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'k_plane' \
@@ -27,5 +31,5 @@ if tail -1 gpurun_out/${tag}_tests_wrench.log | grep -q "passed" && ! tail -1 gp
     > gpurun_out/${tag}_bench_c3_forces.json 2> gpurun_out/${tag}_bench_c3_forces.err
   echo "== bench c3 --forces"; cut -c1-260 gpurun_out/${tag}_bench_c3_forces.json
 fi
-for f in tests tests_wrench tests_plane2; do echo "== $f"; tail -3 gpurun_out/${tag}_$f.log; done
-for f in bench_c3h bench_c3h_plane2; do echo "== $f"; cut -c1-260 gpurun_out/${tag}_$f.json; done
+for f in tests tests_wrench tests_plane2 tests_ppack4; do echo "== $f"; tail -3 gpurun_out/${tag}_$f.log; done
+for f in bench_c3h bench_c3h_plane2 bench_c3h_plane2_ppack4; do echo "== $f"; cut -c1-260 gpurun_out/${tag}_$f.json; done
