@@ -11,6 +11,7 @@
 #define __host__
 #define __device__
 #define __forceinline__ inline
+#include "../../drake_b200/csrc/hydro_clip.cuh"
 #include "../../drake_b200/csrc/hydro_plane.cuh"
 #include "../../drake_b200/csrc/hydro_wrench.cuh"
 
@@ -166,5 +167,118 @@ double phc_combined_dissipation(double kA, double kB, double dA, double dB) {
   return combined_hunt_crossley_dissipation(kA, kB, dA, dB);
 }
 double phc_combined_friction(double a, double b) { return combined_dynamic_friction(a, b); }
+
+// ---- the exact stage's polygon primitives (hydro_clip.cuh) on the exceptional path's storage ------------------
+// PosedHalfSpace(normal, point) = Plane ctor (plane.cc:16-29): normalise, displacement = nhat . point.
+static bool MakeHalfSpace(D3 normal, D3 point, D3* nh, double* d) {
+  const double mag = norm(normal);
+  if (mag < 1e-10) return false;
+  *nh = normal / mag;
+  *d = dot(*nh, point);
+  return true;
+}
+// ClipPolygonByHalfSpace (mesh_intersection.cc:76-119). Returns the vertex count, -1 for a bad normal.
+int phc_clip_polygon_by_half_space(int n, const double* verts, const double* normal, const double* point, double* out) {
+  LocalPoly P;
+  for (int i = 0; i < n; ++i) P.set(0, i, load3(verts + 3 * i));
+  D3 nh;
+  double d;
+  if (!MakeHalfSpace(load3(normal), load3(point), &nh, &d)) return -1;
+  const int m = n > 0 ? clip_by_half_space(P, 0, n, nh, d) : 0;
+  for (int i = 0; i < m && i < LocalPoly::kCap; ++i) {
+    const D3 v = P.get(1, i);
+    out[3 * i] = v.x, out[3 * i + 1] = v.y, out[3 * i + 2] = v.z;
+  }
+  return m;
+}
+// RemoveNearlyDuplicateVertices (mesh_intersection.cc:121-170).
+int phc_remove_nearly_duplicate(int n, const double* verts, double* out) {
+  LocalPoly P;
+  for (int i = 0; i < n; ++i) P.set(0, i, load3(verts + 3 * i));
+  const int m = remove_nearly_duplicate(P, 0, n);
+  for (int i = 0; i < m; ++i) {
+    const D3 v = P.get(0, i);
+    out[3 * i] = v.x, out[3 * i + 1] = v.y, out[3 * i + 2] = v.z;
+  }
+  return m;
+}
+// IntersectTetrahedra (field_intersection.cc:85-198) for a given equilibrium plane, with the sequence
+// tet_stage_b runs: slice tet0 (marching tetrahedra), dedupe, clip by the four faces of tet1 (outward normal =
+// R_MN * -inward, through vertex (face + 1) % 4; PosedHalfSpace normalises), dedupe. tet1_inward: 4 x 3 unit
+// inward normals (VolumeMesh::inward_normal). Returns the vertex count (0: no polygon).
+int phc_intersect_tetrahedra(const double* tet0_v, const double* tet1_v, const double* tet1_inward, const double* X_MN,
+                             const double* nhat3, double displacement, double* out) {
+  Xf X;
+  std::memcpy(X.m, X_MN, sizeof(X.m));
+  const D3 nhat_M = load3(nhat3);
+  LocalPoly P;
+  double dist[4];
+  int code = 0;
+  for (int k = 0; k < 4; ++k) {
+    dist[k] = dot(nhat_M, load3(tet0_v + 3 * k)) - displacement;
+    if (dist[k] > 0) code |= 1 << k;
+  }
+  const unsigned row = marching_tets_row(code);
+  int n = 0;
+  for (int k = 0; k < 4; ++k) {
+    const unsigned edge = (row >> (4 * k)) & 0xFu;
+    if (edge == 0xFu) break;
+    const int e0 = (0x210210u >> (4 * edge)) & 0xF, e1 = (0x333021u >> (4 * edge)) & 0xF;
+    const D3 V0 = load3(tet0_v + 3 * e0), V1 = load3(tet0_v + 3 * e1);
+    const double t = dist[e0] / (dist[e0] - dist[e1]);
+    P.set(0, n++, V0 + t * (V1 - V0));
+  }
+  n = remove_nearly_duplicate(P, 0, n);
+  if (n < 3) return 0;
+  int buf = 0;
+  for (int face = 0; face < 4; ++face) {
+    const D3 p_MA = xform_point(X, load3(tet1_v + 3 * ((face + 1) % 4)));
+    D3 nh;
+    double d;
+    if (!MakeHalfSpace(rot(X, -load3(tet1_inward + 3 * face)), p_MA, &nh, &d)) return -1;
+    n = clip_by_half_space_edges(P, buf, n, nh, d);
+    if (n > LocalPoly::kCap) return -2;
+    buf = 1 - buf;
+    if (n == 0) return 0;
+  }
+  n = remove_nearly_duplicate(P, buf, n);
+  if (n < 3) return 0;
+  for (int i = 0; i < n; ++i) {
+    const D3 v = P.get(buf, i);
+    out[3 * i] = v.x, out[3 * i + 1] = v.y, out[3 * i + 2] = v.z;
+  }
+  return n;
+}
+// ClipTriangleByTetrahedron (mesh_intersection.cc:176-264) with the sequence tri_stage_b runs: the triangle's
+// vertices into frame M, four clips by the tetrahedron's face half spaces (built the way registration builds
+// TetAux::plane_nh / plane_d: n = (B-A)x(C-A) over the face table {1,2,3},{0,3,2},{0,1,3},{0,2,1}, Plane ctor,
+// d = nhat . A), dedupe. Returns the vertex count.
+int phc_clip_triangle_by_tetrahedron(const double* tet_v, const double* tri_v, const double* X_MN, double* out) {
+  Xf X;
+  std::memcpy(X.m, X_MN, sizeof(X.m));
+  LocalPoly P;
+  for (int k = 0; k < 3; ++k) P.set(0, k, xform_point(X, load3(tri_v + 3 * k)));
+  static const int kFaces[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+  int n = 3, buf = 0;
+  for (int f = 0; f < 4 && n > 0; ++f) {
+    const D3 A = load3(tet_v + 3 * kFaces[f][0]), B = load3(tet_v + 3 * kFaces[f][1]), Cc = load3(tet_v + 3 * kFaces[f][2]);
+    D3 nh;
+    double d;
+    if (!MakeHalfSpace(cross(B - A, Cc - A), A, &nh, &d)) return -1;
+    n = clip_by_half_space(P, buf, n, nh, d);
+    if (n > LocalPoly::kCap) return -2;
+    buf = 1 - buf;
+  }
+  n = remove_nearly_duplicate(P, buf, n);
+  if (n < 3) return 0;
+  for (int i = 0; i < n; ++i) {
+    const D3 v = P.get(buf, i);
+    out[3 * i] = v.x, out[3 * i + 1] = v.y, out[3 * i + 2] = v.z;
+  }
+  return n;
+}
+int phc_face_normal_along_gradient(const double* ngrad, const double* v) {
+  return face_normal_along_gradient(load3(ngrad), load3(v)) ? 1 : 0;
+}
 
 }  // extern "C"

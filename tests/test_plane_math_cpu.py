@@ -17,8 +17,8 @@ from tests.parity import REL_TOL, assert_close, face_keys, random_pose
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "plane_host_check.cc")
-HDRS = [os.path.join(ROOT, "drake_b200", "csrc", n) for n in ("hydro_plane.cuh", "hydro_wrench.cuh", "hydro_math.cuh",
-                                                              "hydro_types.h")]
+HDRS = [os.path.join(ROOT, "drake_b200", "csrc", n) for n in ("hydro_plane.cuh", "hydro_wrench.cuh", "hydro_clip.cuh",
+                                                              "hydro_math.cuh", "hydro_types.h")]
 LIB = os.path.join(ROOT, "tests", "cpp", "_build", "libplane_host_check.so")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -293,3 +293,162 @@ def test_no_double_counting_through_the_kernel_arithmetic():
     assert list(host.counts) == [1, 3, 4, 1] and list(host.elem) == [0]
     assert {tuple(v) for v in host.vertices + 0.0} == {(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)}
     assert sorted(host.pressures) == [0.25, 0.5, 0.75]
+
+
+# ---- the exact stage's polygon primitives (hydro_clip.cuh): bit-exact against the oracle ----------------------
+
+def host_clip(verts, normal, point):
+    lib = harness()
+    v = np.ascontiguousarray(verts, float).reshape(-1, 3)
+    out = np.zeros((16, 3))
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+    m = lib.phc_clip_polygon_by_half_space(len(v), d(v), d(normal), d(point), d(out))
+    assert 0 <= m <= 16
+    return out[:m]
+
+
+def host_dedupe(verts):
+    v = np.ascontiguousarray(verts, float).reshape(-1, 3)
+    out = np.zeros((max(len(v), 1), 3))
+    d = lambda a: a.ctypes.data_as(_dp)
+    m = harness().phc_remove_nearly_duplicate(len(v), d(v), d(out))
+    return out[:m]
+
+
+def test_clip_polygon_by_half_space_is_bit_exact():
+    """clip_by_half_space (the tet-triangle clipper's inner routine) against the oracle's ClipPolygonByHalfSpace:
+    the reference's literal cases (mesh_intersection_test.cc:142-281, through the oracle KAT list) and random convex
+    polygons with vertices on, inside and outside the boundary: identical bits, vertex for vertex."""
+    n, p = [1.0, 0.0, 0.0], [2.0, 0.0, 0.0]
+    square = lambda x0, x1: [[x0, 0, 0], [x1, 0, 0], [x1, 1, 0], [x0, 1, 0]]
+    for poly in (square(0, 1), square(1, 2), square(3, 4), square(2, 3), square(1.5, 2.5),
+                 [[1, 0, 0], [3, 0, 0], [3, 2, 0]], [[1, 0, 0], [2, 1, 0], [2, 3, 0]], [[2, 0, 0], [2, 1, 0], [2, 3, 0]]):
+        want, got = ho.clip_polygon_by_half_space(poly, n, p), host_clip(poly, n, p)
+        assert got.shape == want.shape and np.array_equal(got, want), poly
+    rng = np.random.default_rng(31)
+    for _ in range(300):
+        k = int(rng.integers(3, 9))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        poly = np.stack([np.cos(ang), np.sin(ang), np.zeros(k)], axis=1) * rng.uniform(0.1, 3)
+        R = parity_rotation(rng)
+        poly = poly @ R.T + rng.uniform(-1, 1, 3)
+        normal = rng.normal(size=3) * rng.uniform(0.1, 10)
+        point = poly[int(rng.integers(k))] if rng.uniform() < 0.3 else rng.uniform(-1, 1, 3)   # a vertex on the boundary
+        want, got = ho.clip_polygon_by_half_space(poly, normal, point), host_clip(poly, normal, point)
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def parity_rotation(rng):
+    R, _ = ho.xform_parts(random_pose(rng, 0.0))
+    return R
+
+
+def test_remove_nearly_duplicate_vertices_is_bit_exact():
+    """mesh_intersection_test.cc:285-360 and random runs of near-duplicates (|p - q|^2 < 1e-28, first vs last)."""
+    eps = np.finfo(float).eps
+    cases = [[[0, 0, 0], [0, 1, 0], [0, 1, 1], [0, 0, 1]], [[2, 0, 0]] * 3, [[2, 0, 0], [2, 0, 0], [2, 2, 0], [2, 2, 0]],
+             [[2, 0, 0], [2, 0, 1], [2, 1, 0], [2, 0, 2 * eps]], [[1, 2, 3]], []]
+    rng = np.random.default_rng(32)
+    for _ in range(200):
+        k = int(rng.integers(1, 9))
+        base = rng.uniform(-2, 2, size=(k, 3))
+        reps = rng.integers(1, 4, size=k)
+        v = np.repeat(base, reps, axis=0) + rng.choice([0.0, 1e-15, 3e-14], size=(int(reps.sum()), 1))
+        if rng.uniform() < 0.5:
+            v = np.concatenate([v, v[:1] + 1e-16])
+        cases.append(v[:16])
+    for v in cases:
+        want = ho.remove_nearly_duplicate_vertices(v) if len(v) else np.zeros((0, 3))
+        got = host_dedupe(v) if len(v) else np.zeros((0, 3))
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_intersect_tetrahedra_is_bit_exact():
+    """The tet-tet exact stage's sequence (slice by the equilibrium plane, dedupe, clip by the four faces with
+    clip_by_half_space_edges, dedupe) on the candidate pairs of two overlapping soft spheres, against the oracle's
+    IntersectTetrahedra (field_intersection.cc:85-198): the same polygon, bit for bit, for every candidate; and the
+    reference's octagon (field_intersection_test.cc:196-259)."""
+    lib = harness()
+    lib.phc_intersect_tetrahedra.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_double, _dp]
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+
+    def host(m0, e0, m1, e1, X_MN, nhat, disp):
+        v0, t0, _ = m0.arrays()
+        v1, t1, inward1 = m1.arrays()
+        out = np.zeros((16, 3))
+        n = lib.phc_intersect_tetrahedra(d(v0[t0[e0]]), d(v1[t1[e1]]), d(inward1[e1]), d(X_MN), d(nhat), disp, d(out))
+        assert n >= 0
+        return out[:n]
+
+    m0 = ho.VolumeMesh.from_arrays([[2, 0, 2], [-2, 0, 2], [0, 2, -2], [0, -2, -2]], [[0, 1, 2, 3]])
+    m1 = ho.VolumeMesh.from_arrays([[1.5, 1.5, 2.5], [-1.5, -1.5, 2.5], [-1.5, 1.5, -2.5], [1.5, -1.5, -2.5]],
+                                   [[0, 1, 2, 3]])
+    got = host(m0, 0, m1, 0, ho.IDENTITY, [0, 0, 1.0], 0.0)
+    want, _ = ho.intersect_tetrahedra(m0, 0, m1, 0, ho.IDENTITY, [0, 0, 1.0], 0.0)
+    assert len(got) == 8 and np.array_equal(got, want)
+    R = 0.25
+    soft = ho.VolumeMesh.sphere(R, 0.1)
+    fld = ho.VolumeField.sphere(soft, R, 1e6)
+    rng = np.random.default_rng(33)
+    polygons = 0
+    for _ in range(3):
+        X_MN = ho.invert_and_compose(random_pose(rng, 0.02), random_pose(rng, 0.02, center=(0, 0, 0.3)))
+        pairs, _ = ho.candidates(soft, soft, X_MN)
+        for e0, e1 in pairs[::7]:
+            plane = ho.calc_equilibrium_plane(fld, int(e0), fld, int(e1), X_MN)
+            if plane is None:
+                continue
+            nhat, disp = plane
+            want, _ = ho.intersect_tetrahedra(soft, int(e0), soft, int(e1), X_MN, nhat, disp)
+            got = host(soft, int(e0), soft, int(e1), X_MN, nhat, disp)
+            assert got.shape == want.shape and np.array_equal(got, want), (e0, e1)
+            polygons += len(want) > 0
+    assert polygons >= 50
+
+
+def test_clip_triangle_by_tetrahedron_is_bit_exact():
+    """The tet-triangle exact stage's sequence against the oracle's ClipTriangleByTetrahedron
+    (mesh_intersection.cc:176-264): the reference's heptagon (mesh_intersection_test.cc:660-709) and every candidate
+    pair of a soft sphere on a rigid sphere, bit for bit; plus the band-limited cos filter against the plain one."""
+    lib = harness()
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+
+    def host(vol, tet, surf, tri, X_MN):
+        v, t, _ = vol.arrays()
+        sv, st = surf.arrays()[:2]
+        out = np.zeros((16, 3))
+        n = lib.phc_clip_triangle_by_tetrahedron(d(v[t[tet]]), d(sv[st[tri]]), d(X_MN), d(out))
+        assert n >= 0
+        return out[:n]
+
+    vol = ho.VolumeMesh.from_arrays([[2, 0, 2], [-2, 0, 2], [0, 2, -2], [0, -2, -2]], [[0, 1, 2, 3]])
+    surf = ho.TriMesh.from_arrays([[1.5, 1.5, 0], [-1.5, 0, 0], [0, -1.5, 0]], [[0, 1, 2]])
+    got, want = host(vol, 0, surf, 0, ho.IDENTITY), ho.clip_triangle_by_tetrahedron(vol, 0, surf, 0, ho.IDENTITY)
+    assert len(got) == 7 and np.array_equal(got, want)
+    R = 0.25
+    soft, rigid = ho.VolumeMesh.sphere(R, 0.1), ho.TriMesh.sphere(R, 0.05)
+    fld = ho.VolumeField.sphere(soft, R, 1e6)
+    rng = np.random.default_rng(34)
+    polygons = 0
+    for _ in range(3):
+        X_MN = ho.invert_and_compose(random_pose(rng, 0.02), random_pose(rng, 0.02, center=(0, 0, 0.4)))
+        pairs, _ = ho.candidates(soft, rigid, X_MN)
+        for tet, tri in pairs[::5]:
+            want = ho.clip_triangle_by_tetrahedron(soft, int(tet), rigid, int(tri), X_MN)
+            got = host(soft, int(tet), rigid, int(tri), X_MN)
+            assert got.shape == want.shape and np.array_equal(got, want), (tet, tri)
+            polygons += len(want) > 0
+    assert polygons >= 50
+    # face_normal_along_gradient: the shortcut band around cos(5 pi / 8) never changes the decision.
+    lib.phc_face_normal_along_gradient.argtypes = [_dp, _dp]
+    grads = fld.arrays()[1]
+    R_MN, _ = ho.xform_parts(X_MN)
+    normals = rigid.arrays()[2]
+    for tet, tri in pairs[::3]:
+        g = grads[tet] / np.linalg.norm(grads[tet])
+        want = ho.is_face_normal_along_pressure_gradient(fld, rigid, X_MN, int(tet), int(tri))
+        # The kernel's ngrad is normalized(grad) computed at registration with the oracle's expression; numpy's
+        # normalisation can differ in the last bit, which only matters inside 1e-15 of the threshold.
+        got = bool(lib.phc_face_normal_along_gradient(d(g), d(R_MN @ normals[tri])))
+        cos = float(g @ (R_MN @ normals[tri]))
+        assert got == want or abs(cos - math.cos(5 * math.pi / 8)) < 1e-12
