@@ -649,8 +649,10 @@ dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressu
                                    int32_t* asset_out) {
   if (!ctx || !asset_out || (type != DBH_RIGID && type != DBH_COMPLIANT))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "register_half_space: bad argument");
-  if (type == DBH_COMPLIANT && !(pressure_scale > 0))
-    return Fail(DBH_ERR_INVALID_ARGUMENT, "register_half_space: a compliant half space needs pressure_scale > 0");
+  // PositiveDouble / NonNegativeDouble validators of MakeSoftRepresentation(HalfSpace) (hydroelastic_internal.cc:539-553).
+  if (type == DBH_COMPLIANT && (!(pressure_scale > 0) || !(margin >= 0) || std::isinf(pressure_scale) || std::isinf(margin)))
+    return Fail(DBH_ERR_INVALID_ARGUMENT,
+                "register_half_space: a compliant half space needs a finite pressure_scale > 0 and a finite margin >= 0");
   auto a = std::make_unique<HostAsset>();
   a->type = type;
   a->half_space = true;
