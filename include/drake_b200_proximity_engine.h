@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <array>
 #include <cstdint>
+#include <limits>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -95,6 +96,30 @@ struct PenetrationAsPointPair {
   GeometryId id_A, id_B;
   std::array<double, 3> p_WCa, p_WCb, nhat_BA_W;
   double depth;
+};
+
+// multibody::SpatialForce<double> / SpatialVelocity<double>: rotational part first, then translational.
+struct SpatialVector {
+  std::array<double, 3> rotational{}, translational{};
+};
+// What MultibodyPlant::CalcHydroelasticContactForcesContinuous (multibody_plant.cc:2559-2670) keeps of one contact
+// surface: the spatial force about the surface centroid and the same force shifted to the two body origins
+// (A = body of geometry M, B = body of geometry N).
+struct HydroelasticContactForce {
+  GeometryId id_M, id_N;
+  SpatialVector F_Ac_W, F_Ao_W, F_Bo_W;
+};
+// Per geometry: where its body is and how it moves (EvalPoseInWorld / EvalSpatialVelocityInWorld of the body the
+// geometry is attached to), and the material properties the continuous model reads (hydroelastic modulus, +infinity
+// for a rigid geometry; Hunt-Crossley dissipation; dynamic Coulomb friction).
+struct BodyKinematics {
+  std::array<double, 3> p_WBo{};
+  SpatialVector V_WB;
+};
+struct ContactMaterial {
+  double hydroelastic_modulus{std::numeric_limits<double>::infinity()};
+  double hunt_crossley_dissipation{0.0};
+  double dynamic_friction{0.0};
 };
 
 // geometry::ContactSurface<double>. Faces and vertices are owned by value; all quantities in World.
@@ -248,6 +273,67 @@ class ProximityEngine {
     dbh_stats s{};
     if (batch_) dbh_batch_stats(batch_, &s);
     return s;
+  }
+
+  // The consumer of the surfaces in the continuous hydroelastic model, on the device:
+  // HydroelasticTractionCalculator::ComputeSpatialForcesAtCentroidFromHydroelasticModel +
+  // ShiftSpatialForcesAtCentroidToBodyOrigins (multibody/plant/hydroelastic_traction_calculator.cc:24-83) for every
+  // surface of the last ComputeContactSurfaces* call of a one-scene engine, in result order. vslip_regularizer is the
+  // calculator's constructor argument (the plant passes its stiction tolerance). Geometries without an entry in
+  // `bodies` sit at rest with their body origin at the geometry frame's origin as last posed; every geometry needs a
+  // ContactMaterial. NOTE: the kernel behind this (k_wrench) has not run on a GPU yet.
+  std::vector<HydroelasticContactForce> ComputeHydroelasticContactForces(
+      const std::unordered_map<GeometryId, ContactMaterial>& materials,
+      const std::unordered_map<GeometryId, BodyKinematics>& bodies, double vslip_regularizer = 1e-6) {
+    if (!batch_ || num_scenes_ != 1)
+      throw std::logic_error("ComputeHydroelasticContactForces: run ComputeContactSurfaces on a one-scene engine first");
+    const size_t G = ids_.size();
+    std::vector<double> E(G), d(G), mu(G), origin(3 * G), vel(6 * G, 0.0);
+    for (size_t g = 0; g < G; ++g) {
+      const auto m = materials.find(ids_[g]);
+      if (m == materials.end())
+        throw std::logic_error("ComputeHydroelasticContactForces: no ContactMaterial for GeometryId " + std::to_string(ids_[g]));
+      E[g] = m->second.hydroelastic_modulus;
+      d[g] = m->second.hunt_crossley_dissipation;
+      mu[g] = m->second.dynamic_friction;
+      const auto b = bodies.find(ids_[g]);
+      for (int k = 0; k < 3; ++k) {
+        origin[3 * g + k] = b != bodies.end() ? b->second.p_WBo[k] : poses_[g].m[9 + k];
+        if (b != bodies.end()) {
+          vel[6 * g + k] = b->second.V_WB.rotational[k];
+          vel[6 * g + 3 + k] = b->second.V_WB.translational[k];
+        }
+      }
+    }
+    Check(dbh_batch_set_contact_properties(batch_, E.data(), d.data(), mu.data()), "set_contact_properties");
+    Check(dbh_batch_set_body_kinematics(batch_, origin.data(), vel.data()), "set_body_kinematics");
+    Check(dbh_batch_compute_spatial_forces(batch_, vslip_regularizer), "compute_spatial_forces");
+    Check(dbh_batch_sync(batch_), "ComputeHydroelasticContactForces");
+    dbh_result_sizes sz{};
+    Check(dbh_batch_result_sizes(batch_, &sz), "result_sizes");
+    const size_t ns = sz.num_surfaces;
+    std::vector<double> F_Ac(6 * ns), F_Ao(6 * ns), F_Bo(6 * ns);
+    std::vector<int64_t> id_M(ns), id_N(ns);
+    Check(dbh_batch_copy_spatial_forces(batch_, F_Ac.data(), F_Ao.data(), F_Bo.data()), "copy_spatial_forces");
+    dbh_result_buffers buf{};
+    buf.surf_id_M = id_M.data();
+    buf.surf_id_N = id_N.data();
+    Check(dbh_batch_copy_results(batch_, &buf), "copy_results");
+    std::vector<HydroelasticContactForce> out(ns);
+    auto fill = [](const std::vector<double>& src, size_t s, SpatialVector* v) {
+      for (int k = 0; k < 3; ++k) {
+        v->rotational[k] = src[6 * s + k];
+        v->translational[k] = src[6 * s + 3 + k];
+      }
+    };
+    for (size_t s = 0; s < ns; ++s) {
+      out[s].id_M = id_M[s];
+      out[s].id_N = id_N[s];
+      fill(F_Ac, s, &out[s].F_Ac_W);
+      fill(F_Ao, s, &out[s].F_Ao_W);
+      fill(F_Bo, s, &out[s].F_Bo_W);
+    }
+    return out;
   }
 
  private:

@@ -37,3 +37,20 @@ def test_cpp_adapter_known_answers():
     res = subprocess.run([build_exe()], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
     assert res.stdout.strip().endswith("ok")
+
+
+def test_traction_mirror_compiles():
+    """tests/cpp/test_traction_engine.cc (ComputeHydroelasticContactForces of the C++ mirror) compiles against the
+    C-ABI with -Werror; without a GPU it must stop at context creation like every other entry point."""
+    import torch
+    from drake_b200 import build
+    lib = build.build()
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_traction_engine")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "test_traction_engine.cc"), "-o", exe, "-L", os.path.dirname(lib),
+                    "-ldrake_b200_hydro", "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: executed by tests/test_zzz_gpu_wrench_unvalidated.py once enabled")
+    res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 3 and "no CPU fallback" in res.stdout

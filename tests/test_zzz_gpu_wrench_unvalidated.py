@@ -84,3 +84,19 @@ def test_reference_fixture_through_the_c_abi(ctx):
     # horizontal: they add no vertical force; with mu = 1 they add friction, so only f_z is compared exactly.
     assert abs(F_Bo[0][5] - 0.5) < 1e-12
     np.testing.assert_allclose(F_Ao[0][3:6] + F_Bo[0][3:6], 0, atol=1e-12)
+
+
+def test_cpp_adapter_contact_forces():
+    """ComputeHydroelasticContactForces of the C++ mirror (tests/cpp/test_traction_engine.cc)."""
+    import subprocess
+    from drake_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = build.build()
+    exe = os.path.join(root, "tests", "cpp", "_build", "test_traction_engine")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "test_traction_engine.cc"), "-o", exe, "-L", os.path.dirname(lib),
+                    "-ldrake_b200_hydro", "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    assert res.stdout.strip().endswith("ok")
