@@ -342,3 +342,25 @@ def test_compute_contact_surface_responsibilities():
         assert s.num_faces == 3 and set(s.elem_first) == {0}
         np.testing.assert_allclose(s.normals, np.tile(sign * R_WM[:, 2], (3, 1)), atol=64 * EPS)
     assert ho.soft_mesh_rigid_half_space(mesh, fld, X_WM, X_WR, 1, 2, ho.KPOLYGON).rep == ho.KPOLYGON
+
+
+def on_boundary_quirk(clip=None):
+    """Not in the reference's tests. Its `s[i0] >= 0` choice (mesh_half_space_intersection.cc:188-189) with a vertex
+    EXACTLY on the boundary listed before the outside one treats the boundary vertex as "the" outside vertex and keeps
+    the truly outside one in the polygon. Needs exact zeros, hence identity frames. Reproduced bit-compatibly
+     and pinned here against accidental "fixes"."""
+    mesh = ho.TriMesh.from_arrays([[0, 0, 0], [1, 0, 1], [0, 1, -1]], [[0, 1, 2]])   # s = (0, +1, -1)
+    if clip is None:
+        return ho.soft_half_space_rigid_mesh(mesh, ho.IDENTITY, 17.0, ho.IDENTITY, 1, 2, ho.KPOLYGON, filter_normals=False)
+    return clip(mesh, ho.IDENTITY, 17.0, ho.IDENTITY, ho.KPOLYGON)
+
+
+def check_on_boundary_quirk(s):
+    assert s.num_faces == 1
+    poly = np.asarray(s.polygons()[0])
+    np.testing.assert_array_equal(s.vertices[poly] + 0.0, [[1, 0, 1], [0, 1, -1], [0, 0, 0], [0, 0, 0]])
+    np.testing.assert_array_equal(s.pressures[poly] + 0.0, [-17.0, 17.0, 0.0, 0.0])   # negative pressure outside
+
+
+def test_vertex_on_the_boundary_before_the_outside_vertex():
+    check_on_boundary_quirk(on_boundary_quirk())

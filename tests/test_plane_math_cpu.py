@@ -452,3 +452,21 @@ def test_clip_triangle_by_tetrahedron_is_bit_exact():
         got = bool(lib.phc_face_normal_along_gradient(d(g), d(R_MN @ normals[tri])))
         cos = float(g @ (R_MN @ normals[tri]))
         assert got == want or abs(cos - math.cos(5 * math.pi / 8)) < 1e-12
+
+
+def test_on_boundary_quirk_through_the_kernel_arithmetic():
+    """The reference's on-boundary vertex choice (see tests/test_oracle_halfspace.py::on_boundary_quirk) is reproduced
+    by clip_tri_by_half_space, not corrected."""
+    from tests.test_oracle_halfspace import check_on_boundary_quirk, on_boundary_quirk
+
+    class AsSurface:
+        def __init__(self, h):
+            self.h, self.num_faces = h, int(h.counts[0])
+            self.vertices, self.pressures = h.vertices, h.pressures
+
+        def polygons(self):
+            return self.h.polygons()
+
+    check_on_boundary_quirk(on_boundary_quirk(
+        lambda m, X_WS, scale, X_WF, rep: AsSurface(host_half_space_vs_mesh(m, X_WS, scale, 0.0, X_WF, rep, False,
+                                                                             filter_normals=False))))
