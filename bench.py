@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--forces", action="store_true",
                     help="also time the device-side consumer (k_wrench: one spatial force per surface, 18 doubles out "
-                         "per surface). Off by default: the kernel has not been validated on a GPU yet (DESIGN.md 4b)")
+                         "per surface). Off by default: parity-green on the B200 but not yet timed there (DESIGN.md 4b)")
     return ap.parse_args()
 
 

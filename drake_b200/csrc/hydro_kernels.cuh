@@ -12,7 +12,7 @@
 //                TriangleSurfaceMesh derived quantities + TransformVertices + SwapMAndN)
 //   k_surface    per-surface total area and centroid
 //   k_wrench     one spatial force per contact surface (hydroelastic_traction_calculator.cc; SURVEY 8f rank 3;
-//                written and host-checked, not yet run on a GPU)
+//                parity-green on the B200, not yet timed)
 //   k_plane_*    the half-space special cases (mesh_plane_intersection.cc:182-342,
 //                mesh_half_space_intersection.cc:17-430): one thread per element of the one mesh
 //
@@ -2041,8 +2041,9 @@ __global__ void __launch_bounds__(128) k_plane_count2(PlaneArgs a) {
 // ShiftSpatialForcesAtCentroidToBodyOrigins (hydroelastic_traction_calculator.cc:24-83) over the packed,
 // device-resident results of the last query: one warp per contact surface, faces strided over the lanes,
 // a shuffle reduction of the six components. A is the body of geometry M (id_M), B of geometry N.
-// NOT YET RUN ON A GPU (the round's GPU time was spent before it was written): the per-face arithmetic is
-// checked on the host (tests/test_plane_math_cpu.py); the GPU test is tests/test_zzz_gpu_wrench_unvalidated.py.
+// Parity-green on the B200 (tests/test_zz_gpu_wrench.py, profiles/r1h_gpu_tests_wrench.log) with the round's last
+// GPU seconds; not yet timed or profiled. The per-face arithmetic is also checked on the host
+// (tests/test_plane_math_cpu.py).
 struct WrenchArgs {
   const int* surf_pair;
   const PairRec* pairs;

@@ -221,8 +221,8 @@ void* dbh_batch_stream(dbh_batch* batch);
  *        ShiftSpatialForcesAtCentroidToBodyOrigins (multibody/plant/hydroelastic_traction_calculator.cc:24-83),
  *        fed by HydroelasticEngine::CalcCombinedDissipation (multibody/hydroelastics/hydroelastic_engine.cc:83-104) and
  *        CalcContactFrictionFromSurfaceProperties (coulomb_friction.h:122-139). Body A is the body of geometry
- *        M (id_M), body B the body of geometry N. STATUS: the per-face arithmetic is checked against the oracle
- *        on the host; the kernel has not run on a GPU yet. ---------------------------------- */
+ *        M (id_M), body B the body of geometry N. Parity-green on the B200 (tests/test_zz_gpu_wrench.py); not yet
+ *        timed. ---------------------------------- */
 /* p_WBo [G*3]: origin of each geometry's body frame in World (NULL: the geometry frame's origin);
  * V_WB [G*6]: spatial velocity (w, v) of that body at its origin, in World (NULL: at rest). Host pointers. */
 dbh_status dbh_batch_set_body_kinematics(dbh_batch* batch, const double* p_WBo, const double* V_WB);

@@ -281,7 +281,7 @@ class ProximityEngine {
   // surface of the last ComputeContactSurfaces* call of a one-scene engine, in result order. vslip_regularizer is the
   // calculator's constructor argument (the plant passes its stiction tolerance). Geometries without an entry in
   // `bodies` sit at rest with their body origin at the geometry frame's origin as last posed; every geometry needs a
-  // ContactMaterial. NOTE: the kernel behind this (k_wrench) has not run on a GPU yet.
+  // ContactMaterial.
   std::vector<HydroelasticContactForce> ComputeHydroelasticContactForces(
       const std::unordered_map<GeometryId, ContactMaterial>& materials,
       const std::unordered_map<GeometryId, BodyKinematics>& bodies, double vslip_regularizer = 1e-6) {

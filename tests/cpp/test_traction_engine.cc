@@ -1,7 +1,7 @@
 // ComputeHydroelasticContactForces through the C++ mirror, against the reference's own fixture
 // (multibody/plant/test/hydroelastic_traction_calculator_test.cc:536-650): a rigid unit box pressed 0.5 into a
-// compliant half space of pressure scale 1 (e = 0.5 on its bottom face, area 1). NOT YET RUN ON A GPU: compiled
-// by the CPU suite, executed only by tests/test_zzz_gpu_wrench_unvalidated.py (DBH_RUN_UNVALIDATED=1).
+// compliant half space of pressure scale 1 (e = 0.5 on its bottom face, area 1). Compiled by the CPU suite
+// (tests/test_cpp_adapter.py), executed on the GPU box by tests/test_zz_gpu_wrench.py.
 // Exit code 0 = all checks passed; 3 = no CUDA device.
 #include <cmath>
 #include <cstdio>

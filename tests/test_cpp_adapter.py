@@ -51,6 +51,6 @@ def test_traction_mirror_compiles():
                     os.path.join(ROOT, "tests", "cpp", "test_traction_engine.cc"), "-o", exe, "-L", os.path.dirname(lib),
                     "-ldrake_b200_hydro", "-Wl,-rpath," + os.path.dirname(lib)], check=True)
     if torch.cuda.is_available():
-        pytest.skip("GPU present: executed by tests/test_zzz_gpu_wrench_unvalidated.py once enabled")
+        pytest.skip("GPU present: executed by tests/test_zz_gpu_wrench.py")
     res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 3 and "no CPU fallback" in res.stdout

@@ -1,12 +1,9 @@
 """GPU parity of k_wrench (one spatial force per contact surface) against the oracle's
 restatement of HydroelasticTractionCalculator.
 
-STATUS: round 1 ran out of GPU time before this kernel was written, so these tests have NOT run on a GPU yet.
-They are skipped unless DBH_RUN_UNVALIDATED=1 so that an unproven kernel cannot make the `-m gpu` suite red; the
-per-face arithmetic itself is checked on the host against the oracle (tests/test_plane_math_cpu.py), and the
-oracle against the reference's own tests (tests/test_oracle_traction.py). First thing to run in the next round:
-
-    DBH_RUN_UNVALIDATED=1 python -m pytest tests/test_zzz_gpu_wrench_unvalidated.py -m gpu -q
+All four cases passed on the B200 with the last GPU seconds of round 1 (profiles/r1h_gpu_tests_wrench.log); the kernel
+has not been timed yet. The per-face arithmetic is also checked on the host against the oracle
+(tests/test_plane_math_cpu.py), and the oracle against the reference's own tests (tests/test_oracle_traction.py).
 """
 import os
 
@@ -16,9 +13,7 @@ import pytest
 from oracle import ho
 from tests import parity
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DBH_RUN_UNVALIDATED") != "1",
-                                 reason="k_wrench has not run on a GPU yet; set DBH_RUN_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

@@ -2,14 +2,14 @@
 # First GPU visit of round 2: everything round 1 wrote after its GPU minutes ran out, in the order that
 # decides what to keep.   usage: tools/gpu_round2_first_visit.sh <tag>      (≈ 6 GPU-minutes)
 #  1. the `-m gpu` suite as the driver runs it (must stay green);
-#  2. k_wrench (never run on a GPU): its skipped tests, explicitly enabled;
+#  2. k_wrench (parity-green at the very end of round 1, never timed): its tests again, then (step 5) its bench;
 #  3. k_plane_count2 (DBH_TUNE plane=2, never run): the half-space tests under it, then c3h bench lines with
 #     the default and the experimental count pass side by side;
 #  4. launch list + one `--set full` capture of the half-space kernels on c3h (none exists yet).
 tag=${1:-r2a}
 mkdir -p gpurun_out
 (timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) > gpurun_out/${tag}_tests.log
-(DBH_RUN_UNVALIDATED=1 timeout 200 python -m pytest tests/test_zzz_gpu_wrench_unvalidated.py -m gpu -q 2>&1 | tail -40) \
+(timeout 200 python -m pytest tests/test_zz_gpu_wrench.py -m gpu -q 2>&1 | tail -40) \
   > gpurun_out/${tag}_tests_wrench.log
 (DBH_TUNE=plane=2 timeout 200 python -m pytest tests/test_zz_gpu_halfspace.py -m gpu -q 2>&1 | tail -40) \
   > gpurun_out/${tag}_tests_plane2.log
