@@ -9,7 +9,7 @@
 tag=${1:-r2a}
 mkdir -p gpurun_out
 (timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) > gpurun_out/${tag}_tests.log
-(timeout 200 python -m pytest tests/test_zz_gpu_wrench.py -m gpu -q 2>&1 | tail -40) \
+(DBH_RUN_NEW=1 timeout 200 python -m pytest tests/test_zz_gpu_wrench.py -m gpu -q 2>&1 | tail -40) \
   > gpurun_out/${tag}_tests_wrench.log
 (DBH_TUNE=plane=2 timeout 200 python -m pytest tests/test_zz_gpu_halfspace.py -m gpu -q 2>&1 | tail -40) \
   > gpurun_out/${tag}_tests_plane2.log
