@@ -54,10 +54,14 @@ def compare_surface(gpu, ora, check_bitwise_keys=True, welded=False):
     np.testing.assert_array_equal(gk[gorder], ok[oorder])  # bit-exact emitted element-pair multiset
     L = max(np.max(np.abs(ora.vertices)), 1e-300)
     assert_close("areas", gpu.areas[gorder], ora.areas[oorder], scale=max(ora.areas.max(), 1e-300))
-    assert_close("normals", gpu.normals[gorder], ora.normals[oorder], scale=1.0)
-    assert_close("centroids", gpu.centroids[gorder], ora.centroids[oorder], scale=L)
+    # Degenerate polygons of a half-space surface (a vertex or an edge exactly on the boundary: area ~ 0) have no
+    # meaningful normal or centroid: quotients of rounding noise (polygon_surface_mesh.cc:189-207), which differs
+    # between welded and per-polygon vertices. Mesh-mesh surfaces are compared in full.
+    solid = (ora.areas[oorder] > 1e-12 * max(ora.areas.max(), 1e-300)) if welded else np.ones(len(oorder), bool)
+    assert_close("normals", gpu.normals[gorder][solid], ora.normals[oorder][solid], scale=1.0)
+    assert_close("centroids", gpu.centroids[gorder][solid], ora.centroids[oorder][solid], scale=L)
     pscale = max(np.max(np.abs(ora.pressures)), 1e-300)
-    assert_close("pressure_at_centroid", gpu.pressure_at_centroid[gorder], ora.e_centroid[oorder], scale=pscale)
+    assert_close("pressure_at_centroid", gpu.pressure_at_centroid[gorder][solid], ora.e_centroid[oorder][solid], scale=pscale)
     assert (gpu.grad_eM is None) == (ora.grad_eM is None)
     assert (gpu.grad_eN is None) == (ora.grad_eN is None)
     if ora.grad_eM is not None:
@@ -66,9 +70,11 @@ def compare_surface(gpu, ora, check_bitwise_keys=True, welded=False):
         assert_close("grad_eN", gpu.grad_eN[gorder], ora.grad_eN[oorder])
     # Vertices and per-vertex pressures, polygon by polygon in winding order.
     gp, op = gpu.polygons(), ora.polygons()
-    for a, b in zip(gorder, oorder):
+    for a, b, is_solid in zip(gorder, oorder, solid):
         ia, ib = np.asarray(gp[a]), np.asarray(op[b])
         assert len(ia) == len(ib)
+        if not is_solid and ora.rep == ho.KTRIANGLE:
+            ia, ib = ia[:2], ib[:2]   # the fan's third vertex is the degenerate polygon's (meaningless) centroid
         assert_close("vertices", gpu.vertices[ia], ora.vertices[ib], scale=L)
         assert_close("pressures", gpu.pressures[ia], ora.pressures[ib], scale=pscale)
     assert_close("total_area", gpu.total_area, ora.total_area)
