@@ -574,3 +574,21 @@ def test_parity_compare_surface_on_cpu():
             bad.normals[0] = -bad.normals[0]
             with pytest.raises(AssertionError):
                 parity.compare_surface(bad, s, welded=welded)
+
+
+def test_reference_demand_is_reported_not_hidden():
+    """Two vertices exactly on the boundary and the third outside, listed so that GetVertexAddIfNeeded's
+    DRAKE_DEMAND(sgn(s_a) != sgn(s_b)) (mesh_half_space_intersection.cc:66) fires in the reference: the oracle throws,
+    the kernel arithmetic raises DBH_ERR_REFERENCE_DEMAND (13) instead of emitting a polygon with a 0 / 0 vertex."""
+    mesh = ho.TriMesh.from_arrays([[0, 0, 0], [1, 0, 0], [0, 1, 1]], [[0, 1, 2]])   # s = (0, 0, +1)
+    with pytest.raises(RuntimeError, match="DRAKE_DEMAND"):
+        ho.soft_half_space_rigid_mesh(mesh, ho.IDENTITY, 1.0, ho.IDENTITY, 1, 2, ho.KPOLYGON, filter_normals=False)
+    verts, tris, normals = mesh.arrays()[:3]
+    hs = HostSurface(ho.KPOLYGON, 4, 5)
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+    lib = harness()
+    lib.phc_half_space_vs_rigid_mesh.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp, C.c_int, C.c_int,
+                                                 C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+    rc = lib.phc_half_space_vs_rigid_mesh(1, d(verts[tris].reshape(-1, 9)), d(normals), d(ho.IDENTITY), 1.0, 0.0,
+                                          d(ho.IDENTITY), ho.KPOLYGON, 0, 0, *hs.args())
+    assert rc == 13
