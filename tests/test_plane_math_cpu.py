@@ -592,3 +592,41 @@ def test_reference_demand_is_reported_not_hidden():
     rc = lib.phc_half_space_vs_rigid_mesh(1, d(verts[tris].reshape(-1, 9)), d(normals), d(ho.IDENTITY), 1.0, 0.0,
                                           d(ho.IDENTITY), ho.KPOLYGON, 0, 0, *hs.args())
     assert rc == 13
+
+
+def test_nine_gon_of_config4_is_bit_exact_on_the_exceptional_storage():
+    """BASELINE config 4, scene 7280: a clip plane coplanar with the polygon makes IntersectTetrahedra return a 9-gon
+    (the reference's "at most 8" comment assumes general position). The kernel's primitives on the exceptional path's
+    16-slot storage (LocalPoly) reproduce the oracle's polygons of that body pair bit for bit, the 9-gon included."""
+    from drake_b200 import workloads as W
+    from tests import parity
+    lib = harness()
+    lib.phc_intersect_tetrahedra.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_double, _dp]
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+    wl = W.config4(1, 7280)
+    osc, order = parity.oracle_scene_for(wl)
+    surfaces, _ = osc.compute(wl.poses[0][order], ho.KPOLYGON)
+    big = [s for s in surfaces if max(len(p) for p in s.polygons()) == 9]
+    assert len(big) == 1
+    s = big[0]
+    ids = list(wl.geom_id)
+    gM, gN = ids.index(s.id_M), ids.index(s.id_N)
+
+    def oracle_mesh(g):
+        v, e, p = wl.meshes[wl.geom_mesh[g]].arrays()
+        m = ho.VolumeMesh.from_arrays(v, e)
+        return m, ho.VolumeField.from_values(m, p)
+
+    (m0, f0), (m1, f1) = oracle_mesh(gM), oracle_mesh(gN)
+    X_MN = ho.invert_and_compose(wl.poses[0][gM], wl.poses[0][gN])
+    v0, t0, _ = m0.arrays()
+    v1, t1, in1 = m1.arrays()
+    sizes = []
+    for e0, e1 in sorted(set(zip(s.elem_first.tolist(), s.elem_second.tolist()))):
+        nhat, disp = ho.calc_equilibrium_plane(f0, e0, f1, e1, X_MN)
+        want, _ = ho.intersect_tetrahedra(m0, e0, m1, e1, X_MN, nhat, disp)
+        out = np.zeros((16, 3))
+        n = lib.phc_intersect_tetrahedra(d(v0[t0[e0]]), d(v1[t1[e1]]), d(in1[e1]), d(X_MN), d(nhat), disp, d(out))
+        assert n == len(want) and np.array_equal(out[:n], want)
+        sizes.append(n)
+    assert max(sizes) == 9
