@@ -15,6 +15,7 @@
 
 #include "../../include/drake_b200_hydro.h"
 #include "hydro_kernels.cuh"
+#include "hydro_small.cuh"
 #include "hydro_lbvh.h"
 
 using namespace dbh;
@@ -337,6 +338,8 @@ struct dbh_batch {
   int num_chunks{1};
   size_t work_budget_bytes{0};
   std::vector<int> scene_first_pair;
+  std::vector<int> scene_small_before;   // [num_scenes + 1]: small pairs before each scene
+  std::vector<int> scene_mesh_before;    // [num_scenes + 1]: mesh pairs (soft-rigid + soft-soft) before each scene
 
   // Half-space pairs (kSoftMeshRigidPlane / kSoftPlaneRigidMesh): their indices in the pair list (ascending) and
   // the exclusive prefix of the element counts of their one mesh; per geometry, the parameters of a compliant half space.
@@ -348,6 +351,16 @@ struct dbh_batch {
   // per-surface spatial forces.
   DevBuf<double> d_body_origin, d_body_vel, d_props, d_forces;
   bool have_body_origin{false}, have_body_vel{false}, have_props{false}, forces_done{false};
+  // Small pairs (both trees at most kSmallMaxNodes nodes): k_small_pairs descends and culls them on chip, one warp
+  // per pair. small_mode: 0 never, 1 whenever a pair is eligible, 2 (default) when a chunk holds enough eligible
+  // pairs to fill the machine (a handful of pairs is faster through the generic pipeline, which spreads ONE pair
+  // over the whole grid). record_candidates: keep the candidate lists of the last query (dbh_batch_copy_candidates).
+  int small_mode{2};
+  int small_stack_cap{2048};
+  int num_small_pairs{0};
+  bool record_candidates{false};
+  bool small_used{false};           // the last query ran k_small_pairs
+  DevBuf<int> d_small_list;
   DevBuf<unsigned int> d_plane_emit;  // the current chunk's emitting half-space elements (chunk-local indices)
   int plane_emit_sized_for{0};        // the chunk count d_plane_emit was last sized for
   DevBuf<double> d_geom_hs;
@@ -417,6 +430,7 @@ struct dbh_batch {
     CUDA_OK(d_cand_tri.ensure(info.num_soft_rigid_pairs ? cap_tri : 1));
     CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_tet : 1));
     CUDA_OK(d_slow.ensure(cap_slow));
+    if (num_small_pairs) CUDA_OK(d_small_list.ensure(2 * static_cast<size_t>(MaxPairsPerChunk())));
     if (!plane_pairs.empty() && plane_emit_sized_for != num_chunks) {  // depends on the chunking only
       long long most = 1;
       for (int c = 0; c < num_chunks; ++c) {
@@ -741,8 +755,12 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   int max_levels = 1;
   long long est_tri = 0, est_tet = 0, est_plane = 0;
   b->scene_first_pair.assign(num_scenes + 1, 0);
+  b->scene_small_before.assign(num_scenes + 1, 0);
+  b->scene_mesh_before.assign(num_scenes + 1, 0);
   for (int s = 0; s < num_scenes; ++s) {
     b->scene_first_pair[s] = static_cast<int>(b->pairs.size());
+    b->scene_small_before[s] = b->num_small_pairs;
+    b->scene_mesh_before[s] = b->info.num_soft_rigid_pairs + b->info.num_soft_soft_pairs;
     const int g0 = scene_offsets[s], g1 = scene_offsets[s + 1];
     std::vector<int> order(g1 - g0);
     for (int i = 0; i < g1 - g0; ++i) order[i] = g0 + i;
@@ -807,6 +825,11 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
           pr.elem_base_a = A.elem_base;
           pr.elem_base_b = B.elem_base;
           pr.root_leaf = (A.nodes[1].left < 0 ? 1 : 0) | (B.nodes[1].left < 0 ? 2 : 0);
+          if (pr.kind <= kSoftSoft && static_cast<int>(A.nodes.size()) <= kSmallMaxNodes &&
+              static_cast<int>(B.nodes.size()) <= kSmallMaxNodes) {
+            pr.small = 1;
+            ++b->num_small_pairs;
+          }
           if (pr.kind <= kSoftSoft) {
             max_levels = std::max(max_levels, std::max(A.height, B.height) + 1);
             (pr.kind == kSoftRigid ? est_tri : est_tet) += 2ll * (A.num_elements + B.num_elements);
@@ -826,6 +849,8 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   }
   b->num_pairs = static_cast<int>(b->pairs.size());
   b->scene_first_pair[num_scenes] = b->num_pairs;
+  b->scene_small_before[num_scenes] = b->num_small_pairs;
+  b->scene_mesh_before[num_scenes] = b->info.num_soft_rigid_pairs + b->info.num_soft_soft_pairs;
   b->plane_elem_off.push_back(est_plane);
   b->info.num_scenes = num_scenes;
   b->info.num_geometries = b->num_geoms;
@@ -952,6 +977,12 @@ dbh_status dbh_batch_grow_capacity(dbh_batch* b) {
   // what overflowed -- or halving the chunks when the lists would outgrow the
   // memory budget).
   const Counters& c = *b->h_counters;
+  if (c.error == DBH_ERR_CAPACITY && c.error_detail == 9) {
+    // A small pair's node-pair stack outgrew its shared-memory slot: double it while four warps still fit a
+    // block's shared memory, else hand the batch's pairs to the generic pipeline.
+    if (b->small_stack_cap < 8192) b->small_stack_cap *= 2;
+    else b->small_mode = 0;
+  }
   auto want = [](unsigned long long needed, long long cap) {
     return static_cast<long long>(needed) > cap ? static_cast<long long>(needed) * 2 : cap;
   };
@@ -1002,6 +1033,18 @@ void* dbh_batch_stream(dbh_batch* b) { return b ? b->stream : nullptr; }
 dbh_status dbh_batch_enable_timing(dbh_batch* b, int32_t enabled) {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   b->timing = enabled != 0;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_set_small_pair_path(dbh_batch* b, int32_t mode) {
+  if (!b || mode < 0 || mode > 2) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_small_pair_path: bad argument");
+  b->small_mode = mode;
+  return DBH_OK;
+}
+
+dbh_status dbh_batch_set_record_candidates(dbh_batch* b, int32_t enabled) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  b->record_candidates = enabled != 0;
   return DBH_OK;
 }
 
@@ -1057,6 +1100,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pa.pair_polys = b->d_pair_polys.p;
     pa.pair_verts = b->d_pair_verts.p;
     pa.pair_cursor = b->d_pair_cursor.p;
+    pa.small_list = nullptr;
     TraverseArgs ta{};
     ta.pair_f32 = b->d_pair_f32.p;
     ta.pools = ctx->pools();
@@ -1088,6 +1132,13 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ca.trace = make_int4(p, e0 + b->pairs[p].elem_base_a, e1 + b->pairs[p].elem_base_b, 0);
     }
 #endif
+    SmallArgs sm{};
+    sm.c = ca;
+    sm.pairs = b->d_pairs.p;
+    sm.surv_capacity = static_cast<unsigned long long>(b->cap_frontier);
+    sm.record = b->record_candidates ? 1 : 0;
+    sm.stack_cap = b->small_stack_cap;
+    b->small_used = false;
     ScanArgs sa{};
     sa.pair_polys = b->d_pair_polys.p;
     sa.pair_verts = b->d_pair_verts.p;
@@ -1166,7 +1217,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     // block-wide appends; filter / pack: resident blocks per SM the launch bound asks for (registers against
     // occupancy); tgrid / fgrid / pgrid: grid size in units of the resident blocks -- persistent grids (1x for the
     // traversal and the pack) beat over-subscribed ones by 5-15 % (no tail wave).
-    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, plane = 1, ppack = 1; } tune;
+    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, plane = 1, ppack = 1,
+                  small = -1, sblocks = 4; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1181,6 +1233,16 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       get("pgrid", &tune.pgrid);
       get("plane", &tune.plane);  // 2: experimental count pass of the half-space pairs (k_plane_count2)
       get("ppack", &tune.ppack);  // 4: half-space pack pass capped at 128 registers (4 blocks / SM); experimental
+      get("small", &tune.small);  // overrides dbh_batch_set_small_pair_path: 0 never, 1 always, 2 auto
+      get("sblocks", &tune.sblocks);  // k_small_pairs: resident 128-thread blocks per SM asked of the launch bound
+    }
+    const int small_mode = tune.small >= 0 ? tune.small : b->small_mode;
+    const int small_smem = kSmallWarps * small_smem_bytes_per_warp(b->small_stack_cap);
+    if (b->num_small_pairs && small_mode != 0 && small_smem > 48 * 1024) {
+      CUDA_OK(cudaFuncSetAttribute(k_small_pairs<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_small_pairs<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_small_pairs<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_small_pairs<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
     }
     for (int chunk = 0; chunk < b->num_chunks; ++chunk) {
       const int s0 = static_cast<int>(static_cast<long long>(b->num_scenes) * chunk / b->num_chunks);
@@ -1189,12 +1251,20 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       if (p1 == p0) continue;
       pa.pair_begin = p0;
       pa.pair_end = p1;
+      // Small pairs take the on-chip path when the chunk has enough of them to fill the machine (one warp per pair).
+      const int n_small = b->scene_small_before[s1] - b->scene_small_before[s0];
+      const int n_mesh = b->scene_mesh_before[s1] - b->scene_mesh_before[s0];
+      const bool use_small =
+          n_small > 0 && (small_mode == 1 || (small_mode == 2 && n_small >= 2 * sms * tune.sblocks * kSmallWarps));
+      const bool generic = n_mesh - (use_small ? n_small : 0) > 0;   // pairs left to the per-level pipeline
+      pa.small_list = use_small ? b->d_small_list.p : nullptr;
+      pa.small_list_tet = use_small ? b->d_small_list.p + b->MaxPairsPerChunk() : nullptr;
       mark(0);
       ++b->last_launches;
       k_pairs<<<(p1 - p0 + 127) / 128, 128, 0, st>>>(pa);
       mark(1);
       // Dual-BVH traversal, one launch per level; counts stay on the device.
-      for (int level = 0; level < b->info.max_traversal_levels; ++level) {
+      for (int level = 0; generic && level < b->info.max_traversal_levels; ++level) {
         ta.in = b->d_frontier[level & 1].p;
         ta.out = b->d_frontier[(level + 1) & 1].p;
         ta.level = level;
@@ -1207,7 +1277,10 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       // Filter (leaf predicate + conservative culls) then the exact stage, per element kind. The
       // survivor lists reuse the two frontier buffers.
       ca.surv_capacity = static_cast<unsigned long long>(b->cap_frontier);
-      if (b->info.num_soft_rigid_pairs) {
+      // The generic pairs' leaf lists go through the filter first (the survivor lists reuse the frontier buffers,
+      // which the descent has released); then the small pairs are descended and culled on chip and append their
+      // survivors to the same lists; then the exact stage runs over both.
+      if (generic && b->info.num_soft_rigid_pairs) {
         ca.cand = b->d_cand_tri.p;
         ca.cand_capacity = static_cast<unsigned long long>(b->cap_tri);
         ca.surv = b->d_frontier[0].p;
@@ -1215,11 +1288,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         if (tune.filter == 4) k_filter<false, 4><<<sms * 4 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
         else if (tune.filter == 2) k_filter<false, 2><<<sms * 2 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
         else k_filter<false, 3><<<sms * 3 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-        ++b->last_launches;
-        k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
       }
-      mark(3);
-      if (b->info.num_soft_soft_pairs) {
+      if (generic && b->info.num_soft_soft_pairs) {
         ca.cand = b->d_cand_tet.p;
         ca.cand_capacity = static_cast<unsigned long long>(b->cap_tet);
         ca.surv = b->d_frontier[1].p;
@@ -1227,6 +1297,37 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         if (tune.filter == 4) k_filter<true, 4><<<sms * 4 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
         else if (tune.filter == 2) k_filter<true, 2><<<sms * 2 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
         else k_filter<true, 3><<<sms * 3 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+      }
+      if (use_small) {
+        b->small_used = true;
+        const int blocks = std::min(sms * tune.sblocks, (n_small + kSmallWarps - 1) / kSmallWarps);
+        if (b->info.num_soft_rigid_pairs) {
+          sm.small_list = pa.small_list;
+          sm.surv = b->d_frontier[0].p;
+          sm.cand = b->d_cand_tri.p;
+          sm.cand_capacity = static_cast<unsigned long long>(b->cap_tri);
+          ++b->last_launches;
+          if (tune.sblocks >= 4) k_small_pairs<false, 4><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          else k_small_pairs<false, 3><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+        }
+        if (b->info.num_soft_soft_pairs) {
+          sm.small_list = pa.small_list_tet;
+          sm.surv = b->d_frontier[1].p;
+          sm.cand = b->d_cand_tet.p;
+          sm.cand_capacity = static_cast<unsigned long long>(b->cap_tet);
+          ++b->last_launches;
+          if (tune.sblocks >= 4) k_small_pairs<true, 4><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          else k_small_pairs<true, 3><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+        }
+      }
+      mark(3);
+      if (b->info.num_soft_rigid_pairs) {
+        ca.surv = b->d_frontier[0].p;
+        ++b->last_launches;
+        k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+      }
+      if (b->info.num_soft_soft_pairs) {
+        ca.surv = b->d_frontier[1].p;
         ++b->last_launches;
         k_clip<true><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
       }
@@ -1311,9 +1412,9 @@ dbh_status dbh_batch_sync(dbh_batch* b) {
   if (c.error != 0) {
     static const char* kWhere[] = {"",          "BV-pair frontier", "element-pair list", "polygon staging",
                                    "(unused)", "(unused)", "face arrays",
-                                   "vertex arrays", "exceptional-candidate list"};
+                                   "vertex arrays", "exceptional-candidate list", "node-pair stack of a small pair"};
     if (c.error == DBH_ERR_CAPACITY) {
-      const int d = (c.error_detail >= 1 && c.error_detail <= 8) ? c.error_detail : 0;
+      const int d = (c.error_detail >= 1 && c.error_detail <= 9) ? c.error_detail : 0;
       return Fail(DBH_ERR_CAPACITY, std::string("device work list overflow: ") + kWhere[d]);
     }
     if (c.error == DBH_ERR_POLYGON_SIZE)
@@ -1473,7 +1574,7 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->half_space_elements = static_cast<int64_t>(c.plane_tets + c.plane_tris);
   out->geometry_pairs_overlapping = static_cast<int64_t>(c.root_overlaps);
   out->bv_pair_tests = static_cast<int64_t>(c.bv_tests);
-  out->leaf_pairs = static_cast<int64_t>(c.leaf_tri_total + c.leaf_tet_total);
+  out->leaf_pairs = static_cast<int64_t>(c.leaf_tri_total + c.leaf_tet_total + c.small_leaf_tri + c.small_leaf_tet);
   out->cull_violations = static_cast<int64_t>(c.cull_violations);
   out->exceptional_clips = static_cast<int64_t>(c.slow_total);
   out->leaf_exact_tests = static_cast<int64_t>(c.leaf_exact);
@@ -1509,6 +1610,10 @@ dbh_status dbh_batch_copy_candidates(dbh_batch* b, int32_t kind, int32_t* out_tr
   // are the flagged entries (kind | 2: every leaf pair the conservative descent passed).
   if (b->num_chunks != 1)
     return Fail(DBH_ERR_NOT_READY, "candidate lists are only kept for single-chunk queries (dbh_batch_set_chunks(batch, 1))");
+  if (b->small_used && !b->record_candidates)
+    return Fail(DBH_ERR_NOT_READY,
+                "the last query culled its small pairs on chip without keeping their candidate lists: call "
+                "dbh_batch_set_record_candidates(batch, 1) before the query");
   const int64_t listed = static_cast<int64_t>(tet ? b->h_counters->leaf_tet_total : b->h_counters->leaf_tri_total);
   const int64_t n = raw ? listed : static_cast<int64_t>(tet ? b->h_counters->cand_tet : b->h_counters->cand_tri);
   *count = n;

@@ -155,6 +155,9 @@ struct PairsArgs {
   int* pair_polys;       // zeroed here
   int* pair_verts;
   unsigned long long* pair_cursor;  // hi 32: polygons placed, lo 32: polygon vertices placed
+  int* small_list;       // out: overlapping tet-tri pairs that k_small_pairs descends on chip (null: every pair
+                         // takes the generic path)
+  int* small_list_tet;   // same, tet-tet pairs
 };
 
 __global__ void k_pairs(PairsArgs a) {
@@ -162,7 +165,7 @@ __global__ void k_pairs(PairsArgs a) {
   const int p = a.pair_begin + blockIdx.x * blockDim.x + threadIdx.x;
   bool push = false, tested = false;
   PairRec pr;
-  pr.root_a = pr.root_b = pr.kind = pr.root_leaf = 0;
+  pr.root_a = pr.root_b = pr.kind = pr.root_leaf = pr.small = 0;
   int child_a = 0, child_b = 0;
   if (p < a.pair_end) {
     a.pair_polys[p] = 0;
@@ -229,6 +232,12 @@ __global__ void k_pairs(PairsArgs a) {
     if (tests) atomicAdd(&a.counters->bv_tests, (unsigned long long)__popc(tests));
     if (hits) atomicAdd(&a.counters->root_overlaps, (unsigned long long)__popc(hits));
   }
+  // Small pairs (both trees fit 15-bit node indices) are descended by one warp each in k_small_pairs.
+  const bool small = a.small_list != nullptr && pr.small != 0;
+  const unsigned long long s0 = warp_append_flag(&a.counters->small_pairs[0], push && small && pr.kind == kSoftRigid);
+  const unsigned long long s1 = warp_append_flag(&a.counters->small_pairs[1], push && small && pr.kind == kSoftSoft);
+  if (push && small) (pr.kind == kSoftRigid ? a.small_list : a.small_list_tet)[pr.kind == kSoftRigid ? s0 : s1] = p;
+  push = push && !small;
   const bool both_leaves = child_a < 0 && child_b < 0;
   const unsigned long long slot = warp_append_flag(&a.counters->frontier[0], push && !both_leaves);
   if (push && !both_leaves)
@@ -1707,7 +1716,7 @@ __global__ void k_next_chunk(Counters* c) {
     if (threadIdx.x < 64) c->frontier[threadIdx.x] = 0;
     if (threadIdx.x == 0)
       c->leaf_tri = c->leaf_tet = c->polys = c->slow = c->surv_tri = c->surv_tet = c->big_surfaces = c->work_tri = c->work_tet =
-          c->plane_emit = 0;
+          c->plane_emit = c->small_pairs[0] = c->small_pairs[1] = c->small_work[0] = c->small_work[1] = 0;
   }
 }
 

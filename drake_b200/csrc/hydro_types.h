@@ -159,7 +159,8 @@ struct alignas(64) PairRec {
   int32_t elem_base_a;  // pool index of element 0 of the first body (tet pool)
   int32_t elem_base_b;  // second body (tri pool for soft-rigid, tet pool for soft-soft)
   int32_t root_leaf;    // bit0: root_a is a leaf, bit1: root_b is a leaf
-  int32_t pad[2];       // half-space pairs: root_* / elem_base_* describe the one mesh, the other side's are -1
+  int32_t small;        // mesh pair whose two trees have at most 32767 nodes: eligible for k_small_pairs
+  int32_t pad;          // half-space pairs: root_* / elem_base_* describe the one mesh, the other side's are -1
   int64_t id_m;      // final ids, id_m < id_n
   int64_t id_n;
 };
@@ -188,6 +189,9 @@ struct Counters {
   unsigned long long work_tri;      // next unclaimed 1024-entry chunk of the tet-tri leaf list (filter kernel)
   unsigned long long work_tet;      // same, tet-tet
   unsigned long long plane_emit;    // half-space pairs: elements that emit a polygon (entries of the pack pass's list)
+  unsigned long long small_pairs[2]; // overlapping small pairs of the chunk, [0] tet-tri, [1] tet-tet (entries of
+                                     // k_small_pairs' work lists)
+  unsigned long long small_work[2];  // next unclaimed entry of each list
   // -- whole query
   unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
   unsigned long long cand_tri;      // tet-tri candidate pairs: leaf pairs that pass the exact predicate
@@ -205,6 +209,8 @@ struct Counters {
   unsigned long long cull_violations; // verify mode: polygons from candidates the conservative cull rejected
   unsigned long long plane_tets;      // tetrahedra sliced by a rigid half space (k_plane, active pairs only)
   unsigned long long plane_tris;      // triangles clipped by a compliant half space
+  unsigned long long small_leaf_tri;  // leaf pairs k_small_pairs filtered on chip (not recording: they never reach a list)
+  unsigned long long small_leaf_tet;
   // -- totals and per-chunk maxima of the chunk-local cursors
   unsigned long long leaf_tri_total, leaf_tet_total, polys_total, slow_total;
   unsigned long long frontier_max, leaf_tri_max, leaf_tet_max, polys_max, slow_max;

@@ -135,6 +135,8 @@ def lib():
     L.dbh_batch_copy_spatial_forces.argtypes = [vp, _dp, _dp, _dp]
     L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_verify.argtypes = [vp, C.c_int32]
+    L.dbh_batch_set_small_pair_path.argtypes = [vp, C.c_int32]
+    L.dbh_batch_set_record_candidates.argtypes = [vp, C.c_int32]
     L.dbh_batch_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.dbh_mesh_last_error.restype = C.c_char_p
     dbl = C.c_double
@@ -497,6 +499,10 @@ class SceneBatch:
     `excluded` lists filtered pairs (collision_filter.h:158).
     """
 
+    # Test hook: (small-pair path mode, record candidates) applied to every batch created while it is set
+    # (tests/test_gpu_parity.py runs its cases through both mid-phase implementations).
+    test_defaults = None
+
     def __init__(self, ctx: Context, scene_offsets, geom_asset, geom_id, geom_anchored=None, excluded=None):
         self.ctx = ctx
         so, ga, gi = _i(scene_offsets), _i(geom_asset), np.ascontiguousarray(geom_id, np.int64)
@@ -510,6 +516,9 @@ class SceneBatch:
         self.scene_offsets, self.geom_asset, self.geom_id = so, ga, gi
         self._keep = None
         self._grow = 0
+        if SceneBatch.test_defaults is not None:
+            self.set_small_pair_path(SceneBatch.test_defaults[0])
+            self.set_record_candidates(SceneBatch.test_defaults[1])
 
     @staticmethod
     def replicated(ctx: Context, num_scenes: int, assets: Sequence[int], ids: Sequence[int], anchored=None,
@@ -560,6 +569,15 @@ class SceneBatch:
     def set_verify(self, on: bool = True):
         """Self-check mode: exact clipping for every candidate; stats()['cull_violations'] must stay 0."""
         _check(lib().dbh_batch_set_verify(self._h, int(on)))
+
+    def set_small_pair_path(self, mode: int):
+        """Mid phase of small geometry pairs on chip, one warp per pair (k_small_pairs): 0 never, 1 every eligible
+        pair, 2 (default) when a chunk holds enough of them to fill the device."""
+        _check(lib().dbh_batch_set_small_pair_path(self._h, int(mode)))
+
+    def set_record_candidates(self, on: bool = True):
+        """Keep the candidate element-pair lists of the following queries for candidates()."""
+        _check(lib().dbh_batch_set_record_candidates(self._h, int(on)))
 
     def enable_timing(self, on: bool = True):
         _check(lib().dbh_batch_enable_timing(self._h, int(on)))

@@ -360,6 +360,17 @@ dbh_status dbh_batch_enable_timing(dbh_batch* batch, int32_t enabled);
  * dbh_stats::cull_violations counts flagged candidates that emitted a polygon.
  * Results are those of the un-culled pipeline. Slower; for tests. */
 dbh_status dbh_batch_set_verify(dbh_batch* batch, int32_t enabled);
+/* Mid phase of SMALL geometry pairs (both BVHs at most 32767 nodes): one warp per pair descends the dual
+ * tree on a node-pair stack in shared memory and runs the leaf predicate and the conservative culls on chip
+ * (k_small_pairs), instead of one launch per tree level through global frontier lists. mode 0: never; 1: every
+ * eligible pair; 2 (default): when a chunk of scenes holds enough eligible pairs to fill the device (a handful
+ * of pairs is faster through the per-level pipeline, which spreads one pair over the whole grid). Results
+ * do not depend on the mode. */
+dbh_status dbh_batch_set_small_pair_path(dbh_batch* batch, int32_t mode);
+/* Keep the candidate element-pair lists of the following queries for dbh_batch_copy_candidates (parity
+ * tests). The per-level pipeline always has them (they are its work lists); the on-chip path only writes
+ * them out when asked. Off by default. */
+dbh_status dbh_batch_set_record_candidates(dbh_batch* batch, int32_t enabled);
 dbh_status dbh_batch_kernel_times_ms(dbh_batch* batch, float* out8);
 
 #ifdef __cplusplus

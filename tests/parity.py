@@ -7,6 +7,15 @@ from oracle import ho
 
 REL_TOL = 1e-10  # north_star: centroids, areas, normals, pressures within 1e-10 relative (fp64)
 
+_MEMO = {}
+
+
+def memo(key, fn):
+    """Oracle results shared by the runs of one test through both mid-phase implementations."""
+    if key not in _MEMO:
+        _MEMO[key] = fn()
+    return _MEMO[key]
+
 
 def register_compliant(ctx, mesh: "ho.VolumeMesh", fld: "ho.VolumeField") -> int:
     return ctx.register_compliant_mesh(mesh.verts, mesh.tets, fld.values)
