@@ -29,6 +29,21 @@ dbh_status Fail(dbh_status s, const std::string& msg) {
   return s;
 }
 
+// No C++ exception crosses the C boundary: host allocations (std::bad_alloc, std::length_error) and anything else a
+// body throws become a status.
+template <class F>
+dbh_status Guarded(F&& body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    return Fail(DBH_ERR_HOST, "out of host memory");
+  } catch (const std::exception& e) {
+    return Fail(DBH_ERR_HOST, std::string("host-side failure: ") + e.what());
+  } catch (...) {
+    return Fail(DBH_ERR_HOST, "host-side failure");
+  }
+}
+
 #define CUDA_OK(expr)                                                                              \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \
@@ -356,11 +371,19 @@ struct dbh_batch {
   // pairs to fill the machine (a handful of pairs is faster through the generic pipeline, which spreads ONE pair
   // over the whole grid). record_candidates: keep the candidate lists of the last query (dbh_batch_copy_candidates).
   int small_mode{2};
-  int small_stack_cap{2048};
+  int small_stack_cap{1024};
   int num_small_pairs{0};
   bool record_candidates{false};
   bool small_used{false};           // the last query ran k_small_pairs
   DevBuf<int> d_small_list;
+  // Geometry-level broad phase of the no-surface pairs (rejected combinations, rigid-rigid, undefined): per-geometry
+  // bounds in the geometry frame, and the list of such pairs whose world boxes overlapped in the last WithFallback
+  // query (the pairs the reference hands to MaybeMakePointPair, proximity_engine.cc:958-970).
+  std::vector<GeomBound> geom_bounds;
+  DevBuf<GeomBound> d_geom_bounds;
+  DevBuf<int> d_fallback;
+  int num_no_surface_pairs{0};
+  int last_query_kind{DBH_QUERY_STRICT};
   DevBuf<unsigned int> d_plane_emit;  // the current chunk's emitting half-space elements (chunk-local indices)
   int plane_emit_sized_for{0};        // the chunk count d_plane_emit was last sized for
   DevBuf<double> d_geom_hs;
@@ -484,13 +507,16 @@ extern "C" {
 const char* dbh_last_error(void) { return g_error.c_str(); }
 
 dbh_status dbh_context_set_bvh_builder(dbh_context* ctx, int32_t builder) {
+  return Guarded([&]() -> dbh_status {
   if (!ctx || (builder != DBH_BVH_HOST_MEDIAN_SPLIT && builder != DBH_BVH_GPU_LBVH))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "set_bvh_builder: bad argument");
   ctx->bvh_builder = builder;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_asset_copy_bvh(dbh_context* ctx, int32_t asset, double* boxes, int32_t* left) {
+  return Guarded([&]() -> dbh_status {
   if (!ctx || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_copy_bvh: bad argument");
   const HostAsset& a = *ctx->assets[asset];
@@ -504,10 +530,12 @@ dbh_status dbh_asset_copy_bvh(dbh_context* ctx, int32_t asset, double* boxes, in
     if (left) left[k] = a.nodes[k].left;
   }
   return DBH_OK;
+  });
 }
 int32_t dbh_abi_version(void) { return 1000; }
 
 dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out) {
+  return Guarded([&]() -> dbh_status {
   if (!out) return Fail(DBH_ERR_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   int count = 0;
@@ -526,12 +554,14 @@ dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out) {
   CUDA_OK(cudaFuncSetAttribute(k_clip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
   *out = ctx.release();
   return DBH_OK;
+  });
 }
 
 void dbh_context_destroy(dbh_context* ctx) { delete ctx; }
 
 dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const double* verts, int32_t nt,
                                        const int32_t* tets, const double* pressure, int32_t* asset_out) {
+  return Guarded([&]() -> dbh_status {
   if (!ctx || !verts || !tets || !pressure || !asset_out || nv <= 0 || nt <= 0)
     return Fail(DBH_ERR_INVALID_ARGUMENT, "register_compliant_mesh: bad argument");
   CUDA_OK(cudaSetDevice(ctx->device));
@@ -621,10 +651,12 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
   ctx->assets.push_back(std::move(a));
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* verts, int32_t nt,
                                    const int32_t* tris, int32_t* asset_out) {
+  return Guarded([&]() -> dbh_status {
   if (!ctx || !verts || !tris || !asset_out || nv <= 0 || nt <= 0)
     return Fail(DBH_ERR_INVALID_ARGUMENT, "register_rigid_mesh: bad argument");
   CUDA_OK(cudaSetDevice(ctx->device));
@@ -657,10 +689,12 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* v
   ctx->assets.push_back(std::move(a));
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressure_scale, double margin,
                                    int32_t* asset_out) {
+  return Guarded([&]() -> dbh_status {
   if (!ctx || !asset_out || (type != DBH_RIGID && type != DBH_COMPLIANT))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "register_half_space: bad argument");
   // PositiveDouble / NonNegativeDouble validators of MakeSoftRepresentation(HalfSpace) (hydroelastic_internal.cc:539-553).
@@ -676,9 +710,11 @@ dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressu
   ctx->assets.push_back(std::move(a));
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out) {
+  return Guarded([&]() -> dbh_status {
   if (!ctx || !out || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_get_info: bad argument");
   const HostAsset& a = *ctx->assets[asset];
@@ -697,9 +733,11 @@ dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* o
     out->root_half_width[k] = a.nodes[1].h[k];
   }
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_asset_get_derived(dbh_context* ctx, int32_t asset, double* g_or_n, double* at_Mo, double* inward) {
+  return Guarded([&]() -> dbh_status {
   if (!ctx || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_get_derived: bad argument");
   CUDA_OK(cudaSetDevice(ctx->device));
@@ -723,14 +761,25 @@ dbh_status dbh_asset_get_derived(dbh_context* ctx, int32_t asset, double* g_or_n
       if (g_or_n) std::memcpy(g_or_n + 3 * e, t[e].n, 24);
   }
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t* scene_offsets,
                             const int32_t* geom_asset, const int64_t* geom_id, const uint8_t* geom_anchored,
                             int32_t num_excluded, const int32_t* excluded_pairs, dbh_batch** out) {
+  return Guarded([&]() -> dbh_status {
   if (!ctx || !out || num_scenes <= 0 || !scene_offsets || !geom_asset || !geom_id)
     return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_create: bad argument");
   *out = nullptr;
+  if (scene_offsets[0] != 0) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_create: scene_offsets[0] must be 0");
+  for (int s = 0; s < num_scenes; ++s)
+    if (scene_offsets[s + 1] < scene_offsets[s])
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_create: scene_offsets must be non-decreasing");
+  if (num_excluded < 0 || (num_excluded > 0 && !excluded_pairs))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_create: excluded_pairs is null but num_excluded > 0");
+  for (int i = 0; i < 2 * num_excluded; ++i)
+    if (excluded_pairs[i] < 0 || excluded_pairs[i] >= scene_offsets[num_scenes])
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_create: excluded pair index out of range");
   CUDA_OK(cudaSetDevice(ctx->device));
   auto b = std::make_unique<dbh_batch>();
   b->ctx = ctx;
@@ -815,6 +864,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
             ++b->info.num_soft_rigid_pairs;
           }
         }
+        if (pr.kind == kUnsupported || pr.kind == kRigidRigid || pr.kind >= kHalfSpaceHalfSpace) ++b->num_no_surface_pairs;
         pr.root_a = pr.root_b = -1;
         pr.elem_base_a = pr.elem_base_b = -1;
         if (pr.kind <= kRigidRigid) {
@@ -897,6 +947,28 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   CUDA_OK(b->d_pairs.alloc(np));
   if (b->num_pairs)
     CUDA_OK(cudaMemcpy(b->d_pairs.p, b->pairs.data(), b->num_pairs * sizeof(PairRec), cudaMemcpyHostToDevice));
+  // Bounds: a mesh's root box, a half space, or "everywhere" for a geometry with no hydroelastic representation
+  // (until dbh_batch_set_geometry_bounds says otherwise).
+  b->geom_bounds.assign(std::max(1, b->num_geoms), GeomBound{});
+  for (int g = 0; g < b->num_geoms; ++g) {
+    GeomBound& gb = b->geom_bounds[g];
+    gb.kind = kBoundEverywhere;
+    if (geom_asset[g] < 0) continue;
+    const HostAsset& A = *ctx->assets[geom_asset[g]];
+    if (A.half_space) {
+      gb.kind = kBoundHalfSpace;
+    } else {
+      gb.kind = kBoundBox;
+      for (int k = 0; k < 3; ++k) {
+        gb.c[k] = A.nodes[1].c[k];
+        gb.h[k] = A.nodes[1].h[k];
+      }
+    }
+  }
+  CUDA_OK(b->d_geom_bounds.alloc(b->geom_bounds.size()));
+  CUDA_OK(cudaMemcpy(b->d_geom_bounds.p, b->geom_bounds.data(), b->geom_bounds.size() * sizeof(GeomBound),
+                     cudaMemcpyHostToDevice));
+  CUDA_OK(b->d_fallback.alloc(std::max(1, b->num_no_surface_pairs)));
   CUDA_OK(b->d_poses_own.alloc(std::max(1, b->num_geoms)));
   b->d_poses = b->d_poses_own.p;
   CUDA_OK(b->d_pair_X.alloc(np));
@@ -938,11 +1010,13 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   }
   *out = b.release();
   return DBH_OK;
+  });
 }
 
 void dbh_batch_destroy(dbh_batch* batch) { delete batch; }
 
 dbh_status dbh_batch_set_capacity(dbh_batch* b, int64_t max_bv_pairs, int64_t max_element_pairs, int64_t max_faces) {
+  return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   if (max_bv_pairs > 0) b->cap_frontier = max_bv_pairs;
   if (max_element_pairs > 0) b->cap_tri = b->cap_tet = max_element_pairs;
@@ -952,9 +1026,11 @@ dbh_status dbh_batch_set_capacity(dbh_batch* b, int64_t max_bv_pairs, int64_t ma
     b->cap_verts = max_faces * 6;
   }
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_set_chunks(dbh_batch* b, int32_t num_chunks) {
+  return Guarded([&]() -> dbh_status {
   if (!b || num_chunks < 1) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_chunks: bad argument");
   b->num_chunks = std::min<int>(num_chunks, b->num_scenes);
   // The lists must hold at least one entry per geometry pair of a chunk (k_pairs writes them unchecked).
@@ -963,12 +1039,14 @@ dbh_status dbh_batch_set_chunks(dbh_batch* b, int32_t num_chunks) {
   b->cap_tri = std::max(b->cap_tri, min_list);
   b->cap_tet = std::max(b->cap_tet, min_list);
   return DBH_OK;
+  });
 }
 
 int32_t dbh_batch_get_chunks(dbh_batch* b) { return b ? b->num_chunks : 0; }
 int32_t dbh_batch_last_launch_count(dbh_batch* b) { return b ? b->last_launches : 0; }
 
 dbh_status dbh_batch_grow_capacity(dbh_batch* b) {
+  return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   // The device counters keep counting past a full list, so after a failed
   // query they say how many entries the failing stage wanted (the maximum over
@@ -1005,56 +1083,72 @@ dbh_status dbh_batch_grow_capacity(dbh_batch* b) {
   b->cap_faces = want(std::max(c.faces, c.poly_verts), b->cap_faces);
   b->cap_verts = want(std::max(c.vertices, c.poly_verts + c.polygons), b->cap_verts);
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_get_info(dbh_batch* b, dbh_batch_info* out) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_get_info: bad argument");
   *out = b->info;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_set_poses_host(dbh_batch* b, const double* X_WGs) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !X_WGs) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_poses_host: bad argument");
   CUDA_OK(cudaSetDevice(b->ctx->device));
   b->d_poses = b->d_poses_own.p;
   CUDA_OK(cudaMemcpyAsync(b->d_poses_own.p, X_WGs, static_cast<size_t>(b->num_geoms) * sizeof(Xf),
                           cudaMemcpyHostToDevice, b->stream));
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_set_poses_device(dbh_batch* b, const double* X_WGs_device) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !X_WGs_device) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_poses_device: bad argument");
   b->d_poses = reinterpret_cast<const Xf*>(X_WGs_device);
   return DBH_OK;
+  });
 }
 
 void* dbh_batch_stream(dbh_batch* b) { return b ? b->stream : nullptr; }
 
 dbh_status dbh_batch_enable_timing(dbh_batch* b, int32_t enabled) {
+  return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   b->timing = enabled != 0;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_set_small_pair_path(dbh_batch* b, int32_t mode) {
+  return Guarded([&]() -> dbh_status {
   if (!b || mode < 0 || mode > 2) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_small_pair_path: bad argument");
   b->small_mode = mode;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_set_record_candidates(dbh_batch* b, int32_t enabled) {
+  return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   b->record_candidates = enabled != 0;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_set_verify(dbh_batch* b, int32_t enabled) {
+  return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   b->verify = enabled != 0;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_kind, int64_t* scene_stats_dev) {
+  return Guarded([&]() -> dbh_status {
   if (!b || (representation != DBH_TRIANGLE && representation != DBH_POLYGON))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_query: bad argument");
   dbh_context* ctx = b->ctx;
@@ -1066,6 +1160,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   b->query_enqueued = true;
   b->forces_done = false;
   b->last_launches = 0;
+  b->last_query_kind = query_kind;
   cudaStream_t st = b->stream;
   const int sms = ctx->prop.multiProcessorCount;
   if (b->timing) {
@@ -1101,6 +1196,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pa.pair_verts = b->d_pair_verts.p;
     pa.pair_cursor = b->d_pair_cursor.p;
     pa.small_list = nullptr;
+    pa.geom_bounds = b->d_geom_bounds.p;
+    pa.fallback_list = b->d_fallback.p;
+    pa.fallback_capacity = static_cast<unsigned long long>(b->num_no_surface_pairs);
     TraverseArgs ta{};
     ta.pair_f32 = b->d_pair_f32.p;
     ta.pools = ctx->pools();
@@ -1217,8 +1315,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     // block-wide appends; filter / pack: resident blocks per SM the launch bound asks for (registers against
     // occupancy); tgrid / fgrid / pgrid: grid size in units of the resident blocks -- persistent grids (1x for the
     // traversal and the pack) beat over-subscribed ones by 5-15 % (no tail wave).
-    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, plane = 1, ppack = 1,
-                  small = -1, sblocks = 4; } tune;
+    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, small = -1, sblocks = 4; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1231,8 +1328,6 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       get("tgrid", &tune.tgrid);
       get("fgrid", &tune.fgrid);
       get("pgrid", &tune.pgrid);
-      get("plane", &tune.plane);  // 2: experimental count pass of the half-space pairs (k_plane_count2)
-      get("ppack", &tune.ppack);  // 4: half-space pack pass capped at 128 registers (4 blocks / SM); experimental
       get("small", &tune.small);  // overrides dbh_batch_set_small_pair_path: 0 never, 1 always, 2 auto
       get("sblocks", &tune.sblocks);  // k_small_pairs: resident 128-thread blocks per SM asked of the launch bound
     }
@@ -1307,7 +1402,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
           sm.cand = b->d_cand_tri.p;
           sm.cand_capacity = static_cast<unsigned long long>(b->cap_tri);
           ++b->last_launches;
-          if (tune.sblocks >= 4) k_small_pairs<false, 4><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          if (tune.sblocks >= 6) k_small_pairs<false, 6><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          else if (tune.sblocks == 5) k_small_pairs<false, 5><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          else if (tune.sblocks == 4) k_small_pairs<false, 4><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
           else k_small_pairs<false, 3><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
         }
         if (b->info.num_soft_soft_pairs) {
@@ -1316,7 +1413,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
           sm.cand = b->d_cand_tet.p;
           sm.cand_capacity = static_cast<unsigned long long>(b->cap_tet);
           ++b->last_launches;
-          if (tune.sblocks >= 4) k_small_pairs<true, 4><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          if (tune.sblocks >= 6) k_small_pairs<true, 6><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          else if (tune.sblocks == 5) k_small_pairs<true, 5><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          else if (tune.sblocks == 4) k_small_pairs<true, 4><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
           else k_small_pairs<true, 3><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
         }
       }
@@ -1343,8 +1442,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         plane_blocks = static_cast<int>(std::min<long long>((elems + 127) / 128, static_cast<long long>(sms) * 16));
         b->last_launches += 2;
         k_plane_setup<<<(pl.q_end - pl.q_begin + 127) / 128, 128, 0, st>>>(pl);
-        if (tune.plane == 2) k_plane_count2<<<plane_blocks, 128, 0, st>>>(pl);
-        else k_plane<false><<<plane_blocks, 128, 0, st>>>(pl);
+        k_plane<false><<<plane_blocks, 128, 0, st>>>(pl);
       }
       mark(4);
       sa.pair_begin = p0;
@@ -1363,8 +1461,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       else k_pack<3><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
       if (plane_blocks) {  // pack pass of the half-space pairs: straight into the final layout
         ++b->last_launches;
-        if (tune.ppack == 4) k_plane_pack_capped<4><<<plane_blocks, 128, 0, st>>>(pl);
-        else k_plane<true><<<plane_blocks, 128, 0, st>>>(pl);
+        k_plane<true><<<plane_blocks, 128, 0, st>>>(pl);
       }
       mark(6);
       su.pair_begin = p0;
@@ -1390,9 +1487,11 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   if (b->timing) cudaEventRecord(b->ev_end, st);
   CUDA_OK(cudaGetLastError());
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_sync(dbh_batch* b) {
+  return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   CUDA_OK(cudaSetDevice(b->ctx->device));
   CUDA_OK(cudaStreamSynchronize(b->stream));
@@ -1450,9 +1549,11 @@ dbh_status dbh_batch_sync(dbh_batch* b) {
   }
   b->query_done = true;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_set_body_kinematics(dbh_batch* b, const double* p_WBo, const double* V_WB) {
+  return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   CUDA_OK(cudaSetDevice(b->ctx->device));
   const size_t G = static_cast<size_t>(std::max(1, b->num_geoms));
@@ -1469,10 +1570,12 @@ dbh_status dbh_batch_set_body_kinematics(dbh_batch* b, const double* p_WBo, cons
                             cudaMemcpyHostToDevice, b->stream));
   }
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_set_contact_properties(dbh_batch* b, const double* hydroelastic_modulus,
                                             const double* hunt_crossley_dissipation, const double* dynamic_friction) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !hydroelastic_modulus || !hunt_crossley_dissipation || !dynamic_friction)
     return Fail(DBH_ERR_INVALID_ARGUMENT, "set_contact_properties: bad argument");
   CUDA_OK(cudaSetDevice(b->ctx->device));
@@ -1489,9 +1592,11 @@ dbh_status dbh_batch_set_contact_properties(dbh_batch* b, const double* hydroela
   CUDA_OK(cudaMemcpy(b->d_props.p, props.data(), props.size() * sizeof(double), cudaMemcpyHostToDevice));
   b->have_props = true;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_compute_spatial_forces(dbh_batch* b, double vslip_regularizer) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !(vslip_regularizer > 0.0)) return Fail(DBH_ERR_INVALID_ARGUMENT, "compute_spatial_forces: bad argument");
   if (!b->have_props) return Fail(DBH_ERR_NOT_READY, "compute_spatial_forces: call dbh_batch_set_contact_properties first");
   if (!b->query_enqueued) return Fail(DBH_ERR_NOT_READY, "compute_spatial_forces: no query on this batch yet");
@@ -1524,9 +1629,11 @@ dbh_status dbh_batch_compute_spatial_forces(dbh_batch* b, double vslip_regulariz
   }
   b->forces_done = true;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_copy_spatial_forces(dbh_batch* b, double* F_Ac_W, double* F_Ao_W, double* F_Bo_W) {
+  return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
   if (!b->forces_done) return Fail(DBH_ERR_NOT_READY, "copy_spatial_forces: dbh_batch_compute_spatial_forces has not run");
   CUDA_OK(cudaSetDevice(b->ctx->device));
@@ -1541,15 +1648,19 @@ dbh_status dbh_batch_copy_spatial_forces(dbh_batch* b, double* F_Ac_W, double* F
     if (F_Bo_W) std::memcpy(F_Bo_W + 6 * s, all.data() + 18 * s + 12, 6 * sizeof(double));
   }
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_kernel_times_ms(dbh_batch* b, float* out8) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !out8) return Fail(DBH_ERR_INVALID_ARGUMENT, "kernel_times: bad argument");
   std::memcpy(out8, b->times_ms, sizeof(b->times_ms));
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_result_sizes(dbh_batch* b, dbh_result_sizes* out) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "result_sizes: bad argument");
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   const Counters& c = *b->h_counters;
@@ -1562,9 +1673,11 @@ dbh_status dbh_batch_result_sizes(dbh_batch* b, dbh_result_sizes* out) {
   out->face_data_ints = b->representation == DBH_POLYGON ? static_cast<int64_t>(c.polygons + c.poly_verts)
                                                          : 3 * static_cast<int64_t>(c.faces);
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "stats: bad argument");
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   const Counters& c = *b->h_counters;
@@ -1587,6 +1700,7 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->total_area = c.total_area;
   out->tet_tri_full_clips = static_cast<int64_t>(c.full_clips_tri);
   out->tet_tet_full_clips = static_cast<int64_t>(c.full_clips_tet);
+  out->fallback_pairs = b->last_query_kind == DBH_QUERY_WITH_FALLBACK ? static_cast<int64_t>(c.fallback) : 0;
   // BV test 64 B (two 32 B fp32 nodes; SURVEY.md §8(d) counts 128 B for the
   // reference-shaped fp64 node); tet-tri pair 260 B in; tet-tet pair 392 B in;
   // emitted n-gon 32 n + 96 (soft-rigid) / + 120 (soft-soft) out; pose 96 B per geometry.
@@ -1599,9 +1713,11 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   if (b->representation == DBH_TRIANGLE) bytes += out->polygons * 32 + static_cast<long long>(c.poly_verts) * 44;
   out->algorithmic_bytes = bytes;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_copy_candidates(dbh_batch* b, int32_t kind, int32_t* out_triples, int64_t* count) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !count || kind < 0 || kind > 3) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_candidates: bad argument");
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   CUDA_OK(cudaSetDevice(b->ctx->device));
@@ -1632,9 +1748,54 @@ dbh_status dbh_batch_copy_candidates(dbh_batch* b, int32_t kind, int32_t* out_tr
   }
   if (k != n) return Fail(DBH_ERR_CUDA, "candidate flags disagree with the candidate counter");
   return DBH_OK;
+  });
+}
+
+dbh_status dbh_batch_set_geometry_bounds(dbh_batch* b, const double* boxes) {
+  return Guarded([&]() -> dbh_status {
+  if (!b || !boxes) return Fail(DBH_ERR_INVALID_ARGUMENT, "set_geometry_bounds: bad argument");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  for (int g = 0; g < b->num_geoms; ++g) {
+    if (b->geom_asset[g] >= 0) continue;   // meshes and half spaces carry their own bound
+    GeomBound& gb = b->geom_bounds[g];
+    bool finite = true;
+    for (int k = 0; k < 6; ++k) finite = finite && std::isfinite(boxes[6 * g + k]);
+    gb.kind = finite ? kBoundBox : kBoundEverywhere;
+    for (int k = 0; k < 3; ++k) {
+      gb.c[k] = finite ? boxes[6 * g + k] : 0.0;
+      gb.h[k] = finite ? std::fabs(boxes[6 * g + 3 + k]) : 0.0;
+    }
+  }
+  CUDA_OK(cudaMemcpy(b->d_geom_bounds.p, b->geom_bounds.data(), b->geom_bounds.size() * sizeof(GeomBound),
+                     cudaMemcpyHostToDevice));
+  return DBH_OK;
+  });
+}
+
+dbh_status dbh_batch_copy_fallback_pairs(dbh_batch* b, int32_t* out_quads, int64_t* count) {
+  return Guarded([&]() -> dbh_status {
+  if (!b || !count) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_fallback_pairs: bad argument");
+  if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  const int64_t n = b->last_query_kind == DBH_QUERY_WITH_FALLBACK ? static_cast<int64_t>(b->h_counters->fallback) : 0;
+  *count = n;
+  if (!out_quads || n == 0) return DBH_OK;
+  std::vector<int> idx(n);
+  CUDA_OK(cudaMemcpy(idx.data(), b->d_fallback.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  std::sort(idx.begin(), idx.end());   // the static pair list is in (scene, id_M, id_N) order
+  for (int64_t k = 0; k < n; ++k) {
+    const PairRec& pr = b->pairs[idx[k]];
+    out_quads[4 * k] = pr.scene;
+    out_quads[4 * k + 1] = pr.geom_a;
+    out_quads[4 * k + 2] = pr.geom_b;
+    out_quads[4 * k + 3] = pr.kind;
+  }
+  return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_copy_geometry_pairs(dbh_batch* b, int32_t* out) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_geometry_pairs: bad argument");
   for (int i = 0; i < b->num_pairs; ++i) {
     out[4 * i] = b->pairs[i].scene;
@@ -1643,9 +1804,11 @@ dbh_status dbh_batch_copy_geometry_pairs(dbh_batch* b, int32_t* out) {
     out[4 * i + 3] = b->pairs[i].kind;
   }
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_device_results(dbh_batch* b, dbh_device_results* out) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !out) return Fail(DBH_ERR_INVALID_ARGUMENT, "device_results: bad argument");
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   std::memset(out, 0, sizeof(*out));
@@ -1671,15 +1834,19 @@ dbh_status dbh_batch_device_results(dbh_batch* b, dbh_device_results* out) {
   out->elem_N = b->r_elem_b.p;
   out->face_pair = b->r_face_pair.p;
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_copy_results(dbh_batch* b, const dbh_result_buffers* buf) {
+  return Guarded([&]() -> dbh_status {
   if (dbh_status s = dbh_batch_copy_results_async(b, buf)) return s;
   CUDA_OK(cudaStreamSynchronize(b->stream));
   return DBH_OK;
+  });
 }
 
 dbh_status dbh_batch_copy_results_async(dbh_batch* b, const dbh_result_buffers* buf) {
+  return Guarded([&]() -> dbh_status {
   if (!b || !buf) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_results: bad argument");
   if (!b->query_done) return Fail(DBH_ERR_NOT_READY, "no completed query");
   CUDA_OK(cudaSetDevice(b->ctx->device));
@@ -1713,6 +1880,7 @@ dbh_status dbh_batch_copy_results_async(dbh_batch* b, const dbh_result_buffers* 
   DBH_COPY(buf->elem_N, b->r_elem_b.p, nf, int32_t);
 #undef DBH_COPY
   return DBH_OK;
+  });
 }
 
 }  // extern "C"

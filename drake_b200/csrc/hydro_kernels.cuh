@@ -11,8 +11,7 @@
 //                swap, final packed layout (PolyMeshBuilder/TriMeshBuilder + PolygonSurfaceMesh /
 //                TriangleSurfaceMesh derived quantities + TransformVertices + SwapMAndN)
 //   k_surface    per-surface total area and centroid
-//   k_wrench     one spatial force per contact surface (hydroelastic_traction_calculator.cc; SURVEY 8f rank 3;
-//                parity-green on the B200, not yet timed)
+//   k_wrench     one spatial force per contact surface (hydroelastic_traction_calculator.cc)
 //   k_plane_*    the half-space special cases (mesh_plane_intersection.cc:182-342,
 //                mesh_half_space_intersection.cc:17-430): one thread per element of the one mesh
 //
@@ -158,6 +157,9 @@ struct PairsArgs {
   int* small_list;       // out: overlapping tet-tri pairs that k_small_pairs descends on chip (null: every pair
                          // takes the generic path)
   int* small_list_tet;   // same, tet-tet pairs
+  const GeomBound* geom_bounds;      // per flat geometry: its bound in its own frame (broad phase of the no-surface pairs)
+  int* fallback_list;                // out, WithFallback query: no-surface pairs whose world boxes overlap
+  unsigned long long fallback_capacity;
 };
 
 __global__ void k_pairs(PairsArgs a) {
@@ -172,15 +174,25 @@ __global__ void k_pairs(PairsArgs a) {
     a.pair_verts[p] = 0;
     a.pair_cursor[p] = 0ull;
     pr = a.pairs[p];
-    if (pr.kind >= kSoftMeshRigidPlane) {
-      // Pairs with a half space have no BVH pair to descend: k_plane_setup / k_plane handle the two
-      // supported cases; the rest fail the strict query (proximity_engine.cc:1361-1390).
-      if (a.strict && pr.kind == kHalfSpaceHalfSpace) raise_error(a.counters, 11 /*DBH_ERR_HALF_SPACE_HALF_SPACE*/, p);
-      if (a.strict && pr.kind == kSoftPlaneSoftMesh) raise_error(a.counters, 12 /*DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH*/, p);
-      if (a.strict && pr.kind == kRigidRigidPlane) raise_error(a.counters, 6 /*DBH_ERR_RIGID_RIGID*/, p);
-    } else if (pr.kind == kUnsupported) {
-      if (a.strict) raise_error(a.counters, 7 /*DBH_ERR_UNSUPPORTED*/, p);
-    } else {
+    // The pairs that produce no surface -- the combinations MaybeMakeContactSurface rejects (hydroelastic_calculator.cc:
+    // 77-156) -- only matter when the geometry-level broad phase reports them (proximity_engine.cc:867-883): the strict
+    // query then fails with the reference's result code (proximity_engine.cc:1361-1390), the WithFallback query hands
+    // them to the point-pair narrow phase (:958-970; here: lists them for the host, dbh_batch_copy_fallback_pairs).
+    const bool no_surface = pr.kind == kUnsupported || pr.kind == kRigidRigid || pr.kind >= kHalfSpaceHalfSpace;
+    if (no_surface) {
+      if (world_boxes_overlap(a.geom_bounds[pr.geom_a], a.poses[pr.geom_a], a.geom_bounds[pr.geom_b], a.poses[pr.geom_b])) {
+        if (a.strict) {
+          const int code = pr.kind == kUnsupported ? 7 /*DBH_ERR_UNSUPPORTED*/
+                           : pr.kind == kHalfSpaceHalfSpace ? 11 /*DBH_ERR_HALF_SPACE_HALF_SPACE*/
+                           : pr.kind == kSoftPlaneSoftMesh ? 12 /*DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH*/
+                                                           : 6 /*DBH_ERR_RIGID_RIGID*/;
+          raise_error(a.counters, code, p);
+        } else {
+          const unsigned long long slot = atomicAdd(&a.counters->fallback, 1ull);
+          if (slot < a.fallback_capacity) a.fallback_list[slot] = p;
+        }
+      }
+    } else if (pr.kind <= kSoftSoft) {
       const Xf X_WA = a.poses[pr.geom_a];
       const Xf X_WB = a.poses[pr.geom_b];
       const Xf X_AB = invert_and_compose(X_WA, X_WB);
@@ -197,34 +209,26 @@ __global__ void k_pairs(PairsArgs a) {
       f.S = fabsf(f.p[0]) + fabsf(f.p[1]) + fabsf(f.p[2]);
       f.pad[0] = f.pad[1] = 0.f;
       a.pair_f32[p] = f;
-      // Root boxes: the exact 15-axis test on boxes padded by 1e-12 (an ancestor
-      // must never hide a passing leaf pair). For rigid-rigid pairs this stands in
-      // for the geometry-level broad phase (FCL tree, proximity_engine.cc:867-883):
-      // the strict query only fails if the root boxes overlap.
-      if (pr.kind != kRigidRigid || a.strict) {
-        const BvhNode& na = a.pools.nodes[pr.root_a];
-        const BvhNode& nb = a.pools.nodes[pr.root_b];
-        child_a = na.left;
-        child_b = nb.left;
-        double ha[3] = {na.h[0], na.h[1], na.h[2]};
-        double hb[3] = {nb.h[0], nb.h[1], nb.h[2]};
-        const D3 t = xform_point(X_AB, load3(nb.c)) - load3(na.c);
-        const double s =
-            1e-12 * (fabs(t.x) + fabs(t.y) + fabs(t.z) + ha[0] + ha[1] + ha[2] + hb[0] + hb[1] + hb[2]) + 1e-300;
+      // Root boxes: the exact 15-axis test on boxes padded by 1e-12 (an ancestor must never hide a passing leaf
+      // pair).
+      const BvhNode& na = a.pools.nodes[pr.root_a];
+      const BvhNode& nb = a.pools.nodes[pr.root_b];
+      child_a = na.left;
+      child_b = nb.left;
+      double ha[3] = {na.h[0], na.h[1], na.h[2]};
+      double hb[3] = {nb.h[0], nb.h[1], nb.h[2]};
+      const D3 t = xform_point(X_AB, load3(nb.c)) - load3(na.c);
+      const double s =
+          1e-12 * (fabs(t.x) + fabs(t.y) + fabs(t.z) + ha[0] + ha[1] + ha[2] + hb[0] + hb[1] + hb[2]) + 1e-300;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          ha[k] += s;
-          hb[k] += s;
-        }
-        const bool overlap = boxes_overlap(ha, hb, X_AB, t);
-        if (pr.kind == kRigidRigid) {
-          if (overlap) raise_error(a.counters, 6 /*DBH_ERR_RIGID_RIGID*/, p);
-        } else {
-          tested = true;
-          push = overlap;
-        }
+      for (int k = 0; k < 3; ++k) {
+        ha[k] += s;
+        hb[k] += s;
       }
+      tested = true;
+      push = boxes_overlap(ha, hb, X_AB, t);
     }
+    // (kSoftMeshRigidPlane / kSoftPlaneRigidMesh: k_plane_setup poses the half space and tests the mesh's root box.)
   }
   const unsigned tests = __ballot_sync(0xffffffffu, tested);
   const unsigned hits = __ballot_sync(0xffffffffu, push);
@@ -309,10 +313,15 @@ __device__ __forceinline__ Box32 load_box32(const Node32& n) {
 
 template <int kMinBlocks, int kThreads>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_traverse(TraverseArgs a) {
-  if (a.counters->error != 0) return;  // the query already failed; the host re-runs it
+  // The query already failed (the host re-runs it): one block-uniform decision, because the appends below are
+  // block-wide collectives and another block may raise the flag while this one starts.
+  __shared__ BlockAppendSmem<kThreads / 32> sh;
+  __shared__ int failed_already;
+  if (threadIdx.x == 0) failed_already = a.counters->error;
+  __syncthreads();
+  if (failed_already != 0) return;
   // After an overflow the counter exceeds what was stored (the query fails
   // with DBH_ERR_CAPACITY); never read past the stored entries.
-  __shared__ BlockAppendSmem<kThreads / 32> sh;
   const unsigned long long count = min(a.counters->frontier[a.level], a.out_capacity);
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
   unsigned int tests = 0;
@@ -1338,7 +1347,22 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
   const int lane = threadIdx.x & 31;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
     int4 h = make_int4(-1, 0, 0, 0);
-    if (i < count) h = a.soup.hdr[i];
+    // The first three vertices of the staged polygon (every polygon has at least three) are requested together with
+    // the header, before the dependent chain header -> pair record -> poses -> offsets starts: the kernel is bound by
+    // the latency of these DRAM round trips, not by their number.
+    D3 pv0 = make_d3(0, 0, 0), pv1 = pv0, pv2 = pv0;
+    double pe0 = 0, pe1 = 0, pe2 = 0;
+    if (i < count) {
+      h = a.soup.hdr[i];
+      const double* sv = a.soup.v + i;
+      const unsigned long long cap = a.soup.capacity;
+      pv0 = make_d3(sv[0 * cap], sv[1 * cap], sv[2 * cap]);
+      pe0 = sv[3 * cap];
+      pv1 = make_d3(sv[4 * cap], sv[5 * cap], sv[6 * cap]);
+      pe1 = sv[7 * cap];
+      pv2 = make_d3(sv[8 * cap], sv[9 * cap], sv[10 * cap]);
+      pe2 = sv[11 * cap];
+    }
     const int pair = h.x, n = h.w;
     // n == 0: the second staging slot of a polygon with more than 8 vertices.
     const bool valid = i < count && n != 0;
@@ -1376,6 +1400,10 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
     // The polygon is streamed from the staging soup (coalesced SoA reads; a second pass hits L1 / L2):
     // no per-thread vertex arrays, so no local memory. Vertices 8.. of a large polygon are in the next slot.
     auto vert = [&](int k, double* e_k) {
+      if (k < 3) {
+        *e_k = k == 0 ? pe0 : (k == 1 ? pe1 : pe2);
+        return k == 0 ? pv0 : (k == 1 ? pv1 : pv2);
+      }
       const unsigned long long s = i + (k >> 3);
       const int kk = k & 7;
       *e_k = a.soup.v[(kk * 4 + 3) * a.soup.capacity + s];
@@ -1413,9 +1441,13 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
       a.out.pressures[vb] = e0;
       fd[1] = vj + (swapped ? (n - 1) : 0);
       D3 prev = v0;  // vertex k - 1
+      // The loads of vertex k + 1 are issued before vertex k is consumed (the loop is bound by load latency).
+      double e_nx = 0;
+      D3 v_nx = n > 1 ? vert(1, &e_nx) : v0;
       for (int k = 1; k < n; ++k) {
-        double ek;
-        const D3 vk = vert(k, &ek);
+        const double ek = e_nx;
+        const D3 vk = v_nx;
+        if (k + 1 < n) v_nx = vert(k + 1, &e_nx);
         store3(a.out.vertices, vb + k, xform_point(X_WM, vk));
         a.out.pressures[vb + k] = ek;
         fd[1 + k] = vj + (swapped ? (n - 1 - k) : k);
@@ -1965,86 +1997,13 @@ __device__ __forceinline__ void plane_pass(const PlaneArgs& a) {
   }
 }
 
+// The pack pass runs under a 128-register cap (4 resident blocks per SM): measured 1.5 % faster on the ball / plate /
+// half-space workload than the uncapped build (140 registers); a count pass with register-accumulated statistics and
+// block-aggregated list appends measured no different from this one and was dropped (profiles/README.md, r2a).
 template <bool kPack>
-__global__ void __launch_bounds__(128) k_plane(PlaneArgs a) {
+__global__ void __launch_bounds__(128, kPack ? 4 : 1) k_plane(PlaneArgs a) {
   plane_pass<kPack>(a);
 }
-// The pack pass under a register cap (kMinBlocks resident blocks of 128 threads per SM; DBH_TUNE="ppack=4"): an
-// occupancy experiment that has NOT run on a GPU yet. The default above is the validated build.
-template <int kMinBlocks>
-__global__ void __launch_bounds__(128, kMinBlocks) k_plane_pack_capped(PlaneArgs a) {
-  plane_pass<true>(a);
-}
-
-// EXPERIMENTAL count pass (DBH_TUNE="plane=2"; NOT the default and not yet run on a GPU: the round's GPU
-// time ended with the measurement that motivates it, profiles/README.md "Half-space kernels"). Same
-// arithmetic and the same outputs as k_plane<false>; what changes is where the same-address atomics go:
-// the statistics are accumulated in registers and added once per warp at the end, and the emit list is
-// appended with one atomic per block iteration (block_append_flag) instead of one per warp iteration.
-__global__ void __launch_bounds__(128) k_plane_count2(PlaneArgs a) {
-  __shared__ BlockAppendSmem<4> sh;
-  const long long w0 = a.plane_elem_off[a.q_begin];
-  const long long num_elems = a.plane_elem_off[a.q_end] - w0;
-  const long long rounded = (num_elems + 127ll) & ~127ll;  // whole blocks reach the barriers of the append
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31;
-  unsigned int my_tets = 0, my_tris = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-    WorldPoly P;
-    P.n = 0;
-    P.status = 0;
-    int pair = -1;
-    if (i < num_elems) {
-      const long long w = w0 + i;
-      const int q = find_plane_pair(a.plane_elem_off, a.q_begin, a.q_end, w, w0, num_elems);
-      pair = a.plane_pairs[q];
-      const Xf rec = a.pair_X[pair];
-      if (rec.m[4] != 0.0) {
-        const PairRec pr = a.pairs[pair];
-        const int elem = (int)(w - a.plane_elem_off[q]);
-        const D3 nhat = make_d3(rec.m[0], rec.m[1], rec.m[2]);
-        if (pr.kind == kSoftMeshRigidPlane) {
-          P.n = count_tet_slice(a.pools.tets[pr.elem_base_a + elem], nhat, rec.m[3]);
-          ++my_tets;
-        } else {
-          clip_tri_by_half_space(a.pools.tris[pr.elem_base_b + elem], nhat, rec.m[3], rec.m[5], rec.m[6],
-                                 a.poses[pr.geom_b], a.poses[pr.geom_a], &P);
-          ++my_tris;
-          if (P.status) raise_error(a.counters, P.status, pair);
-        }
-      }
-    }
-    const int n = P.status ? 0 : P.n;
-    const bool valid = n > 0;
-    const unsigned long long slot = block_append_flag<4>(&a.counters->plane_emit, valid, sh);
-    if (valid) a.emit_list[slot] = (unsigned int)i;
-    const unsigned validmask = __ballot_sync(0xffffffffu, valid);
-    if (!validmask) continue;
-    const int lead = __ffs(validmask) - 1;
-    const int pair0 = __shfl_sync(0xffffffffu, pair, lead);
-    const bool uniform = __all_sync(0xffffffffu, !valid || pair == pair0);
-    if (uniform) {
-      int total = valid ? n : 0;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
-      if (lane == lead) {
-        atomicAdd(&a.pair_polys[pair0], __popc(validmask));
-        atomicAdd(&a.pair_verts[pair0], total);
-      }
-    } else if (valid) {
-      atomicAdd(&a.pair_polys[pair], 1);
-      atomicAdd(&a.pair_verts[pair], n);
-    }
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    my_tets += __shfl_xor_sync(0xffffffffu, my_tets, d);
-    my_tris += __shfl_xor_sync(0xffffffffu, my_tris, d);
-  }
-  if (lane == 0 && my_tets) atomicAdd(&a.counters->plane_tets, (unsigned long long)my_tets);
-  if (lane == 0 && my_tris) atomicAdd(&a.counters->plane_tris, (unsigned long long)my_tris);
-}
-
 // ---------------------------------------------------------------------------
 // k_wrench: HydroelasticTractionCalculator::ComputeSpatialForcesAtCentroidFromHydroelasticModel +
 // ShiftSpatialForcesAtCentroidToBodyOrigins (hydroelastic_traction_calculator.cc:24-83) over the packed,

@@ -66,6 +66,48 @@ __host__ __device__ __forceinline__ Xf invert_and_compose(const Xf& X_BA, const 
   return X_AC;
 }
 
+// World box of a geometry the way FCL's CollisionObject::computeAABB builds the boxes of its broad phase: the local
+// box translated when the rotation is the identity, else the cube around the transformed box centre that holds the
+// box's bounding sphere. A half space (z <= 0) is bounded -- from above, in z -- only under the identity rotation.
+__host__ __device__ __forceinline__ void world_box(const GeomBound& g, const Xf& X, double mn[3], double mx[3]) {
+  const double kInf = 1.0 / 0.0;
+  bool identity = true;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) identity = identity && fabs(X.m[k] - ((k % 4 == 0) ? 1.0 : 0.0)) <= 1e-12;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    mn[k] = -kInf;
+    mx[k] = kInf;
+  }
+  if (g.kind == kBoundHalfSpace) {
+    if (identity) mx[2] = X.m[11];
+  } else if (g.kind == kBoundBox) {
+    if (identity) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        mn[k] = X.m[9 + k] + (g.c[k] - g.h[k]);
+        mx[k] = X.m[9 + k] + (g.c[k] + g.h[k]);
+      }
+    } else {
+      const D3 c = xform_point(X, make_d3(g.c[0], g.c[1], g.c[2]));
+      const double r = norm(make_d3(g.h[0], g.h[1], g.h[2]));
+      mn[0] = c.x - r; mx[0] = c.x + r;
+      mn[1] = c.y - r; mx[1] = c.y + r;
+      mn[2] = c.z - r; mx[2] = c.z + r;
+    }
+  }
+}
+__host__ __device__ __forceinline__ bool world_boxes_overlap(const GeomBound& ga, const Xf& Xa, const GeomBound& gb,
+                                                             const Xf& Xb) {
+  double amn[3], amx[3], bmn[3], bmx[3];
+  world_box(ga, Xa, amn, amx);
+  world_box(gb, Xb, bmn, bmx);
+  bool overlap = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) overlap = overlap && amn[k] <= bmx[k] && bmn[k] <= amx[k];
+  return overlap;
+}
+
 // Gottschalk 15-axis SAT between boxes with half widths a, b under (R, t) =
 // pose of b's frame in a's frame: the scalar BoxesOverlap
 // (boxes_overlap.cc:197-255). X.m[0..8] = R column-major, t given separately.

@@ -171,6 +171,20 @@ struct Xf {
   double m[12];
 };
 
+// Bound of one geometry in its own frame, for the geometry-level broad phase of the pairs that only matter when
+// they touch (the combinations MaybeMakeContactSurface rejects and the point-pair fallback pairs): the reference
+// calls the calculator only for FindCollisionCandidates() results (proximity_engine.cc:867-883,905-934), i.e. for
+// pairs whose FCL world boxes overlap. kBox: the mesh's root box, or the box the caller gave for a geometry with no
+// hydroelastic representation; kEverywhere: no bound known; kHalfSpace: z <= 0.
+enum GeomBoundKind : int32_t { kBoundBox = 0, kBoundEverywhere = 1, kBoundHalfSpace = 2 };
+struct alignas(64) GeomBound {
+  double c[3];
+  double h[3];
+  int32_t kind;
+  int32_t pad[3];
+};
+static_assert(sizeof(GeomBound) == 64, "GeomBound is 64 B");
+
 // Device counters of one query (zeroed when the query starts). A query runs
 // over one or more chunks of scenes that reuse the same work lists; the list
 // cursors are chunk-local (k_next_chunk folds them into totals / maxima and
@@ -189,6 +203,7 @@ struct Counters {
   unsigned long long work_tri;      // next unclaimed 1024-entry chunk of the tet-tri leaf list (filter kernel)
   unsigned long long work_tet;      // same, tet-tet
   unsigned long long plane_emit;    // half-space pairs: elements that emit a polygon (entries of the pack pass's list)
+  unsigned long long fallback;      // WithFallback query: pairs handed to the point-pair narrow phase (whole query)
   unsigned long long small_pairs[2]; // overlapping small pairs of the chunk, [0] tet-tri, [1] tet-tet (entries of
                                      // k_small_pairs' work lists)
   unsigned long long small_work[2];  // next unclaimed entry of each list

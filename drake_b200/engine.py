@@ -29,7 +29,7 @@ OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_DEGENERATE_FIELD, ERR_CAPACITY = 1, 2, 3, 4, 5
 BVH_HOST_MEDIAN_SPLIT, BVH_GPU_LBVH = 0, 1
 ERR_RIGID_RIGID, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_PLANE_NORMAL, ERR_POLYGON_SIZE = 6, 7, 8, 9, 10
-ERR_HALF_SPACE_HALF_SPACE, ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH, ERR_REFERENCE_DEMAND = 11, 12, 13
+ERR_HALF_SPACE_HALF_SPACE, ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH, ERR_REFERENCE_DEMAND, ERR_HOST = 11, 12, 13, 14
 
 
 class HydroError(RuntimeError):
@@ -78,7 +78,7 @@ class Stats(C.Structure):
                  "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "algorithmic_bytes")] + \
                [("total_area", C.c_double), ("tet_tri_full_clips", C.c_int64), ("tet_tet_full_clips", C.c_int64),
                 ("leaf_pairs", C.c_int64), ("cull_violations", C.c_int64), ("exceptional_clips", C.c_int64),
-                ("leaf_exact_tests", C.c_int64), ("half_space_elements", C.c_int64)]
+                ("leaf_exact_tests", C.c_int64), ("half_space_elements", C.c_int64), ("fallback_pairs", C.c_int64)]
 
 
 _lib = None
@@ -136,6 +136,8 @@ def lib():
     L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_verify.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_small_pair_path.argtypes = [vp, C.c_int32]
+    L.dbh_batch_set_geometry_bounds.argtypes = [vp, _dp]
+    L.dbh_batch_copy_fallback_pairs.argtypes = [vp, _ip, _lp]
     L.dbh_batch_set_record_candidates.argtypes = [vp, C.c_int32]
     L.dbh_batch_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.dbh_mesh_last_error.restype = C.c_char_p
@@ -570,6 +572,25 @@ class SceneBatch:
         """Self-check mode: exact clipping for every candidate; stats()['cull_violations'] must stay 0."""
         _check(lib().dbh_batch_set_verify(self._h, int(on)))
 
+    def set_geometry_bounds(self, boxes):
+        """[G,6] centre + half widths, in the geometry frame, of the geometries registered with asset -1 (no
+        hydroelastic representation); NaN rows = no bound. Pairs that produce no surface only count when the world boxes
+        overlap (the reference's FindCollisionCandidates)."""
+        B = _d(boxes).reshape(-1, 6)
+        if len(B) != self.num_geometries:
+            raise ValueError("one box per geometry")
+        _check(lib().dbh_batch_set_geometry_bounds(self._h, _ptr(B, _dp)))
+
+    def fallback_pairs(self) -> np.ndarray:
+        """After a WITH_FALLBACK query: [n,4] = scene, flat geometry index (smaller id), flat geometry index (larger id),
+        kind, of the pairs the reference hands to the point-pair narrow phase."""
+        n = C.c_int64(0)
+        _check(lib().dbh_batch_copy_fallback_pairs(self._h, None, C.byref(n)))
+        out = np.zeros((n.value, 4), np.int32)
+        if n.value:
+            _check(lib().dbh_batch_copy_fallback_pairs(self._h, _ptr(out, _ip), C.byref(n)))
+        return out
+
     def set_small_pair_path(self, mode: int):
         """Mid phase of small geometry pairs on chip, one warp per pair (k_small_pairs): 0 never, 1 every eligible
         pair, 2 (default) when a chunk holds enough of them to fill the device."""
@@ -646,10 +667,12 @@ class SceneBatch:
             _check(lib().dbh_batch_copy_results_async(self._h, C.byref(bufs)))
         return res
 
-    def compute_contact_surfaces(self, X_WGs, representation: int = POLYGON) -> List[List[ContactSurface]]:
-        """ComputeContactSurfaces for every scene: per scene a list sorted by (id_M, id_N)."""
+    def compute_contact_surfaces(self, X_WGs, representation: int = POLYGON,
+                                 query_kind: int = STRICT) -> List[List[ContactSurface]]:
+        """ComputeContactSurfaces (or, with WITH_FALLBACK, the surfaces of ComputeContactSurfacesWithFallback) for
+        every scene: per scene a list sorted by (id_M, id_N)."""
         self.set_poses(X_WGs)
-        self.run(representation, STRICT)
+        self.run(representation, query_kind)
         out: List[List[ContactSurface]] = [[] for _ in range(self.num_scenes)]
         for s in self.copy_results().surfaces():
             out[s.scene].append(s)

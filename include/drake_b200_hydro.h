@@ -48,9 +48,11 @@ enum {
   DBH_ERR_HALF_SPACE_HALF_SPACE = 11,  /* ContactSurfaceResult::kHalfSpaceHalfSpace (hydroelastic_calculator.cc:113-118,
                                           145-147), strict query only */
   DBH_ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH = 12, /* kCompliantHalfSpaceCompliantMesh (:120-123), strict query only */
-  DBH_ERR_REFERENCE_DEMAND = 13   /* a DRAKE_DEMAND of the reference would have fired: a triangle edge whose end
+  DBH_ERR_REFERENCE_DEMAND = 13,  /* a DRAKE_DEMAND of the reference would have fired: a triangle edge whose end
                                      points do not lie on different sides of the half-space boundary
                                      (mesh_half_space_intersection.cc:43,66) */
+  DBH_ERR_HOST = 14               /* a host-side failure inside the library (out of host memory, ...): no C++
+                                     exception crosses this boundary */
 };
 
 enum { DBH_TRIANGLE = 0, DBH_POLYGON = 1 };
@@ -338,6 +340,8 @@ typedef struct dbh_stats {
   int64_t half_space_elements;     /* tetrahedra sliced by a rigid half space + triangles clipped by a compliant
                                       one (pairs whose root box reaches the boundary); 168 B / 108 B of
                                       algorithmic bytes each */
+  int64_t fallback_pairs;          /* WithFallback query: pairs handed to the point-pair narrow phase
+                                      (dbh_batch_copy_fallback_pairs) */
 } dbh_stats;
 dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
 
@@ -346,6 +350,25 @@ dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
  * kind 0 = tet-tri list, 1 = tet-tet list; kind | 2 = every leaf pair the conservative
  * descent passed (a superset). Pass out == NULL to get the count. */
 dbh_status dbh_batch_copy_candidates(dbh_batch* batch, int32_t kind, int32_t* out_triples, int64_t* count);
+/* Geometry-level broad phase of the pairs that produce no contact surface. The reference calls
+ * MaybeMakeContactSurface only for the pairs FindCollisionCandidates() reports (proximity_engine.cc:867-883,
+ * 905-934: FCL world boxes overlap), so a far-away rigid-rigid pair, a geometry with no hydroelastic
+ * representation, or a rejected half-space combination neither fails ComputeContactSurfaces nor reaches the
+ * point-pair fallback. Here such a pair counts when the two world boxes overlap, built the way FCL builds
+ * them (CollisionObject::computeAABB: the local box translated under an identity rotation, else the cube around
+ * the box's bounding sphere; a half space is bounded only under the identity rotation): a mesh's box is its root
+ * box; for geometries registered with asset -1 the caller provides the box of the shape in the geometry frame,
+ * boxes [G*6] = centre, half widths (entries of geometries that have an asset are ignored; a non-finite entry
+ * means "no bound": the pair always counts, the default). */
+dbh_status dbh_batch_set_geometry_bounds(dbh_batch* batch, const double* boxes);
+/* After a DBH_QUERY_WITH_FALLBACK query: the pairs the reference hands to penetration_as_point_pair::
+ * MaybeMakePointPair (proximity_engine.cc:958-970) -- rigid-rigid, undefined-type and rejected half-space
+ * combinations whose world boxes overlap -- as quads {scene, flat geometry index of the smaller id, flat geometry
+ * index of the larger id, kind (2 rigid-rigid, 3 unsupported, 6 half space x half space, 7 compliant half space x
+ * compliant mesh, 8 rigid half space x rigid)}, in (scene, id_M, id_N) order. The point-pair arithmetic itself is
+ * host-side (include/drake_b200_proximity_engine.h): it needs the primitive shapes, which this library never
+ * sees. Pass out == NULL to get the count. */
+dbh_status dbh_batch_copy_fallback_pairs(dbh_batch* batch, int32_t* out_quads, int64_t* count);
 /* Static geometry-pair list: per pair {scene, flat geom index of first body
  * (S or M), flat geom index of second body (R or N), kind (0 soft-rigid, 1
  * soft-soft, 2 rigid-rigid, 3 unsupported)}. out [num_geometry_pairs*4]. */

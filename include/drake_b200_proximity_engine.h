@@ -379,23 +379,29 @@ class ProximityEngine {
             "register_half_space");
       return asset;
     }
+    // A compliant primitive is meshed, and its pressure field built, on the shape INFLATED by the margin (every
+    // face moved `margin` along its outward normal): Sphere(radius + margin), Box(size + 2 margin),
+    // Ellipsoid(a + margin, ...); Make*PressureField is then given the inflated shape and the margin, so the
+    // zero-pressure level set stays on the nominal surface (hydroelastic_internal.cc:412-465,514-536). Rigid
+    // representations ignore the margin.
+    const double m = soft ? p.margin : 0.0;
     if (const auto* s = std::get_if<Sphere>(&shape)) {
-      CheckMesh(dbh_mesh_make_sphere_volume(s->radius, p.resolution_hint,
-                                            soft ? static_cast<int>(p.tessellation_strategy) : 0, &vol.h),
+      const double r = s->radius + m;
+      CheckMesh(dbh_mesh_make_sphere_volume(r, p.resolution_hint, soft ? static_cast<int>(p.tessellation_strategy) : 0,
+                                            &vol.h),
                 "MakeSphereVolumeMesh");
-      if (soft) CheckMesh(dbh_mesh_set_sphere_pressure(vol.h, s->radius, p.hydroelastic_modulus, p.margin), "MakeSpherePressureField");
+      if (soft) CheckMesh(dbh_mesh_set_sphere_pressure(vol.h, r, p.hydroelastic_modulus, m), "MakeSpherePressureField");
     } else if (const auto* b = std::get_if<Box>(&shape)) {
-      CheckMesh(dbh_mesh_make_box_volume_with_ma(b->width, b->depth, b->height, &vol.h), "MakeBoxVolumeMeshWithMa");
-      if (soft)
-        CheckMesh(dbh_mesh_set_box_pressure(vol.h, b->width, b->depth, b->height, p.hydroelastic_modulus, p.margin),
-                  "MakeBoxPressureField");
+      const double w = b->width + 2.0 * m, d = b->depth + 2.0 * m, h = b->height + 2.0 * m;
+      CheckMesh(dbh_mesh_make_box_volume_with_ma(w, d, h, &vol.h), "MakeBoxVolumeMeshWithMa");
+      if (soft) CheckMesh(dbh_mesh_set_box_pressure(vol.h, w, d, h, p.hydroelastic_modulus, m), "MakeBoxPressureField");
     } else if (const auto* e = std::get_if<Ellipsoid>(&shape)) {
-      CheckMesh(dbh_mesh_make_ellipsoid_volume(e->a, e->b, e->c, p.resolution_hint,
+      const double ea = e->a + m, eb = e->b + m, ec = e->c + m;
+      CheckMesh(dbh_mesh_make_ellipsoid_volume(ea, eb, ec, p.resolution_hint,
                                                soft ? static_cast<int>(p.tessellation_strategy) : 0, &vol.h),
                 "MakeEllipsoidVolumeMesh");
       if (soft)
-        CheckMesh(dbh_mesh_set_ellipsoid_pressure(vol.h, e->a, e->b, e->c, p.hydroelastic_modulus, p.margin),
-                  "MakeEllipsoidPressureField");
+        CheckMesh(dbh_mesh_set_ellipsoid_pressure(vol.h, ea, eb, ec, p.hydroelastic_modulus, m), "MakeEllipsoidPressureField");
     } else if (const auto* v = std::get_if<VolumeMeshShape>(&shape)) {
       if (!soft) throw std::logic_error("a volume mesh can only be registered as a compliant geometry");
       Check(dbh_register_compliant_mesh(ctx_, static_cast<int32_t>(v->vertices.size() / 3), v->vertices.data(),

@@ -72,6 +72,8 @@ def lib():
             getattr(_lib, name).restype = C.c_double
         _lib.ho_scene_add_half_space.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int]
         _lib.ho_scene_add_geometry.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.ho_scene_add_undefined.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int]
+        _lib.ho_scene_fallback_pairs.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]
         _lib.ho_scene_exclude_pair.argtypes = [C.c_int, C.c_int64, C.c_int64]
     return _lib
 
@@ -511,6 +513,22 @@ class Scene:
         """HalfSpace shape (z <= 0 of its frame); compliant: pressure_scale = modulus / slab thickness."""
         lib().ho_scene_add_half_space(self.h, gid, COMPLIANT if compliant else RIGID, pressure_scale, margin,
                                       int(anchored))
+
+    def add_undefined(self, gid: int, box=None, anchored: bool = False):
+        """A geometry with no hydroelastic representation; box = (centre, half widths) of its shape in its frame, or
+        None when unknown (then the geometry-level broad phase reports every pair with it)."""
+        b = None if box is None else _pd(_d(box).reshape(6))
+        lib().ho_scene_add_undefined(self.h, gid, b, int(anchored))
+
+    def fallback_pairs(self, poses) -> np.ndarray:
+        """[n,2] id pairs a WithFallback query hands to the point-pair narrow phase (proximity_engine.cc:958-970)."""
+        P = _d(poses).reshape(-1, 12)
+        assert len(P) == lib().ho_scene_num_geometries(self.h)
+        cap = len(P) * (len(P) - 1) // 2 + 1
+        out = np.zeros((cap, 2), np.int64)
+        n = lib().ho_scene_fallback_pairs(self.h, _pd(P), out.ctypes.data_as(_lp), cap)
+        _check(n, "scene_fallback_pairs")
+        return out[:n]
 
     def exclude(self, a: int, b: int):
         lib().ho_scene_exclude_pair(self.h, a, b)

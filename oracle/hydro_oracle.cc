@@ -118,6 +118,10 @@ struct SceneGeom {
   // (hydroelastic_internal.h SoftHalfSpace).
   bool half_space{false};
   double pressure_scale{0}, margin{0};
+  // Geometry with no hydroelastic representation: the box of its shape in its own frame (centre, half widths) when
+  // the caller knows one; otherwise it is everywhere as far as the geometry-level broad phase is concerned.
+  bool has_box{false};
+  Aabb box{};
 };
 struct Scene {
   std::vector<SceneGeom> geoms;  // kept sorted by id
@@ -134,9 +138,62 @@ struct SceneStats {
 enum { kOk = 0, kErrUnsupported = -2, kErrRigidRigid = -3, kErrHalfSpaceHalfSpace = -4,
        kErrCompliantHalfSpaceCompliantMesh = -5 };
 
-// Restates the engine loop for one scene. `poses` is indexed like scene.geoms.
+// The geometry-level broad phase (FindCollisionCandidates, proximity_engine.cc:867-883) as far as it matters for the
+// pairs that produce no surface: the two world boxes overlap, each built the way FCL's CollisionObject::computeAABB
+// builds them (FCL is an external dependency of the reference, pinned in tools/workspace/fcl_internal; restated from
+// its published behaviour): the local box translated when the rotation is the identity, otherwise the cube about the
+// transformed box centre that holds the box's bounding sphere. A half space (z <= 0) has an unbounded local box; only
+// under the identity rotation does the translation leave it bounded (in z, from above).
+struct WorldBox {
+  double mn[3], mx[3];
+};
+WorldBox WorldBoxOf(const SceneGeom& g, const Xform& X) {
+  const double inf = std::numeric_limits<double>::infinity();
+  WorldBox w{{-inf, -inf, -inf}, {inf, inf, inf}};
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double m[12];
+  X.ToArray(m);
+  bool identity = true;
+  for (int k = 0; k < 9; ++k) identity = identity && std::fabs(m[k] - I[k]) <= 1e-12;
+  if (g.half_space) {
+    if (identity) w.mx[2] = m[11];
+    return w;
+  }
+  Aabb box;
+  if (g.type == 2) box = RefBvh(*g_vols[g.vol]).nodes[0].bv;
+  else if (g.type == 1) box = RefBvh(*g_tris[g.tri]).nodes[0].bv;
+  else if (g.has_box) box = g.box;
+  else return w;
+  const double c[3] = {box.center.x, box.center.y, box.center.z};
+  const double h[3] = {box.half_width.x, box.half_width.y, box.half_width.z};
+  if (identity) {
+    for (int k = 0; k < 3; ++k) {
+      w.mn[k] = m[9 + k] + (c[k] - h[k]);
+      w.mx[k] = m[9 + k] + (c[k] + h[k]);
+    }
+  } else {
+    const Vec3 cw = X * box.center;
+    const double r = std::sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+    const double cc[3] = {cw.x, cw.y, cw.z};
+    for (int k = 0; k < 3; ++k) {
+      w.mn[k] = cc[k] - r;
+      w.mx[k] = cc[k] + r;
+    }
+  }
+  return w;
+}
+bool BroadPhaseReports(const SceneGeom& A, const Xform& X_WA, const SceneGeom& B, const Xform& X_WB) {
+  const WorldBox a = WorldBoxOf(A, X_WA), b = WorldBoxOf(B, X_WB);
+  for (int k = 0; k < 3; ++k)
+    if (!(a.mn[k] <= b.mx[k] && b.mn[k] <= a.mx[k])) return false;
+  return true;
+}
+
+// Restates the engine loop for one scene. `poses` is indexed like scene.geoms. fallback_pairs (optional): the id pairs
+// the WithFallback query hands to MaybeMakePointPair (proximity_engine.cc:958-970).
 int ComputeScene(const Scene& scene, const double* poses, Representation rep, int mode, bool with_fallback,
-                 std::vector<SurfaceResult>* out, SceneStats* stats) {
+                 std::vector<SurfaceResult>* out, SceneStats* stats,
+                 std::vector<std::pair<int64_t, int64_t>>* fallback_pairs = nullptr) {
   const int n = static_cast<int>(scene.geoms.size());
   for (int i = 0; i < n; ++i) {
     for (int j = i + 1; j < n; ++j) {
@@ -146,38 +203,25 @@ int ComputeScene(const Scene& scene, const double* poses, Representation rep, in
       if (scene.filtered.count({A.id, B.id})) continue;
       const Xform X_WA = Xform::FromArray(poses + 12 * i);
       const Xform X_WB = Xform::FromArray(poses + 12 * j);
-      if (A.type == 0 || B.type == 0) {
-        if (with_fallback) continue;
-        return kErrUnsupported;
-      }
-      if (A.type == 1 && B.type == 1) {
-        // Rigid-rigid only matters when the geometry-level broad phase reports
-        // the pair; stand-in for FCL's tree: root boxes under the relative pose
-        // (a half space's box is unbounded: always reported).
-        if (A.half_space || B.half_space) {
-          if (with_fallback) continue;
-          return kErrRigidRigid;
-        }
-        TriAsset& ta = *g_tris[A.tri];
-        TriAsset& tb = *g_tris[B.tri];
-        const Xform X_AB = InvertAndCompose(X_WA, X_WB);
-        if (!AabbHasOverlap(RefBvh(ta).nodes[0].bv, RefBvh(tb).nodes[0].bv, X_AB)) continue;
-        if (with_fallback) continue;  // point-pair fallback is out of scope
-        return kErrRigidRigid;
+      // The combinations MaybeMakeContactSurface rejects (hydroelastic_calculator.cc:77-156) only matter for the pairs
+      // the geometry-level broad phase reports: the strict query throws (proximity_engine.cc:1361-1390), the
+      // WithFallback query hands the pair to the point-pair narrow phase (:958-970).
+      int failure = 0;
+      if (A.type == 0 || B.type == 0) failure = kErrUnsupported;
+      else if (A.type == 1 && B.type == 1) failure = kErrRigidRigid;
+      else if (A.half_space && B.half_space) failure = kErrHalfSpaceHalfSpace;
+      else if ((A.half_space || B.half_space) && A.type == 2 && B.type == 2) failure = kErrCompliantHalfSpaceCompliantMesh;
+      if (failure) {
+        if (!BroadPhaseReports(A, X_WA, B, X_WB)) continue;
+        if (!with_fallback) return failure;
+        if (fallback_pairs) fallback_pairs->emplace_back(A.id, B.id);
+        continue;
       }
       if (stats) ++stats->geometry_pairs;
       SurfaceResult res;
       bool non_null = false;
       if (A.half_space || B.half_space) {
-        // hydroelastic_calculator.cc:113-123,145-147 (failures) and :25-41 (the two supported cases).
-        int failure = 0;
-        if (A.half_space && B.half_space) failure = kErrHalfSpaceHalfSpace;
-        else if (A.type == 2 && B.type == 2) failure = kErrCompliantHalfSpaceCompliantMesh;
-        if (failure) {
-          if (stats) --stats->geometry_pairs;
-          if (with_fallback) continue;
-          return failure;
-        }
+        // hydroelastic_calculator.cc:25-41 (the two supported cases).
         const bool A_is_rigid = A.type == 1;
         const SceneGeom& S = A_is_rigid ? B : A;
         const SceneGeom& R = A_is_rigid ? A : B;
@@ -695,6 +739,33 @@ int ho_scene_add_half_space(int scene, int64_t id, int type, double pressure_sca
   const int pos = static_cast<int>(it - s.geoms.begin());
   s.geoms.insert(it, g);
   return pos;
+}
+// A geometry with no hydroelastic representation; box6 (centre, half widths in its frame) may be null.
+int ho_scene_add_undefined(int scene, int64_t id, const double* box6, int anchored) {
+  Scene& s = *g_scenes[scene];
+  SceneGeom g{id, 0, -1, -1, -1, anchored != 0};
+  if (box6) {
+    g.has_box = true;
+    g.box.center = {box6[0], box6[1], box6[2]};
+    g.box.half_width = {box6[3], box6[4], box6[5]};
+  }
+  auto it = std::lower_bound(s.geoms.begin(), s.geoms.end(), g, [](const SceneGeom& a, const SceneGeom& b) { return a.id < b.id; });
+  const int pos = static_cast<int>(it - s.geoms.begin());
+  s.geoms.insert(it, g);
+  return pos;
+}
+// The id pairs a WithFallback query of the scene hands to the point-pair narrow phase: out_ids [max_pairs*2].
+int ho_scene_fallback_pairs(int scene, const double* poses, int64_t* out_ids, int max_pairs) {
+  HO_TRY
+  std::vector<std::pair<int64_t, int64_t>> pairs;
+  const int rc = ComputeScene(*g_scenes[scene], poses, Representation::kPolygon, 1, true, nullptr, nullptr, &pairs);
+  if (rc != kOk) return rc;
+  for (size_t k = 0; k < pairs.size() && static_cast<int>(k) < max_pairs; ++k) {
+    out_ids[2 * k] = pairs[k].first;
+    out_ids[2 * k + 1] = pairs[k].second;
+  }
+  return static_cast<int>(pairs.size());
+  HO_CATCH(-100)
 }
 int ho_scene_num_geometries(int scene) { return static_cast<int>(g_scenes[scene]->geoms.size()); }
 void ho_scene_geometry_ids(int scene, int64_t* ids) {

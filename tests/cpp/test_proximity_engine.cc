@@ -29,7 +29,43 @@ static RigidTransformd RotX(double angle, double x, double y, double z) {
   return X;
 }
 
-int main() {
+// `margin <faces> <total area> <sum of face pressures> <faces> <area> <pressures>`: a compliant Sphere and a compliant Box
+// registered with margin > 0 against a rigid sphere; the expected values come from the oracle's construction on the
+// INFLATED shapes (hydroelastic_internal.cc:412-465), computed by tests/test_cpp_adapter.py.
+static int MarginCase(char** argv) {
+  const double R = 0.25, margin = 0.01;
+  ProximityProperties soft;
+  soft.compliance_type = HydroelasticType::kCompliant;
+  soft.hydroelastic_modulus = 1e8;
+  soft.resolution_hint = 0.25;
+  soft.margin = margin;
+  ProximityProperties rigid;
+  rigid.compliance_type = HydroelasticType::kRigid;
+  rigid.resolution_hint = 0.1;
+  const RigidTransformd X_WA = RotX(M_PI, 0, 0, 0);
+  const RigidTransformd X_WB = RigidTransformd::FromTranslation(0, 0, -(R + R) + 0.125);
+  for (int k = 0; k < 2; ++k) {
+    ProximityEngine e(0);
+    if (k == 0) e.AddDynamicGeometry(Sphere{R}, X_WA, 1, soft);
+    else e.AddDynamicGeometry(Box{0.5, 0.4, 0.5}, X_WA, 1, soft);
+    e.AddDynamicGeometry(Sphere{R}, X_WB, 2, rigid);
+    auto poly = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
+    EXPECT(poly.size() == 1);
+    const int faces = std::atoi(argv[2 + 3 * k]);
+    const double area = std::atof(argv[3 + 3 * k]), psum = std::atof(argv[4 + 3 * k]);
+    double got_p = 0;
+    for (int f = 0; f < poly[0].num_faces(); ++f) got_p += poly[0].pressure_at_centroid(f);
+    std::printf("case %d: faces %d (want %d) area %.17g (want %.17g) pressure sum %.17g (want %.17g)\n", k,
+                poly[0].num_faces(), faces, poly[0].total_area(), area, got_p, psum);
+    EXPECT(poly[0].num_faces() == faces);
+    EXPECT(std::fabs(poly[0].total_area() - area) <= 1e-10 * area);
+    EXPECT(std::fabs(got_p - psum) <= 1e-10 * std::fabs(psum));
+  }
+  std::printf("ok\n");
+  return 0;
+}
+
+int main(int argc, char** argv) {
   std::unique_ptr<ProximityEngine> engine;
   try {
     engine = std::make_unique<ProximityEngine>(0);
@@ -37,6 +73,7 @@ int main() {
     std::printf("no device: %s\n", e.what());
     return 3;
   }
+  if (argc == 8 && std::string(argv[1]) == "margin") return MarginCase(argv);
   const double R = 0.25;
   ProximityProperties soft;
   soft.compliance_type = HydroelasticType::kCompliant;

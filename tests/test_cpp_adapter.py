@@ -39,6 +39,37 @@ def test_cpp_adapter_known_answers():
     assert res.stdout.strip().endswith("ok")
 
 
+@pytest.mark.gpu
+def test_cpp_adapter_inflates_compliant_primitives_by_the_margin():
+    """A compliant Sphere / Box with margin > 0 is meshed and given its pressure field on the shape inflated by the
+    margin (hydroelastic_internal.cc:412-465): the adapter's surfaces must match the oracle's inflated construction."""
+    import math
+
+    import numpy as np
+
+    from oracle import ho
+    R, margin, E = 0.25, 0.01, 1e8
+    X_WA = ho.xform(ho.rpy_matrix(math.pi, 0, 0))
+    X_WB = ho.xform(None, [0, 0, -(R + R) + 0.125])
+    rigid = ho.TriMesh.sphere(R, 0.1)
+    args = []
+    ms = ho.VolumeMesh.sphere(R + margin, 0.25)
+    fs = ho.VolumeField.sphere(ms, R + margin, E, margin)
+    mb = ho.VolumeMesh.box_ma(0.5 + 2 * margin, 0.4 + 2 * margin, 0.5 + 2 * margin)
+    fb = ho.VolumeField.box(mb, 0.5 + 2 * margin, 0.4 + 2 * margin, 0.5 + 2 * margin, E, margin)
+    for m, f in ((ms, fs), (mb, fb)):
+        want = ho.soft_rigid(m, f, rigid, X_WA, X_WB, 1, 2, ho.KPOLYGON)
+        assert want is not None and want.num_faces > 4
+        args += [str(want.num_faces), repr(float(want.total_area)), repr(float(np.sum(want.e_centroid)))]
+    # The nominal (un-inflated) construction gives a different surface: the test can tell the two apart.
+    nominal = ho.soft_rigid(ho.VolumeMesh.sphere(R, 0.25), ho.VolumeField.sphere(ho.VolumeMesh.sphere(R, 0.25), R, E, margin),
+                            rigid, X_WA, X_WB, 1, 2, ho.KPOLYGON)
+    assert abs(nominal.total_area - float(args[1])) > 1e-6 * float(args[1])
+    res = subprocess.run([build_exe(), "margin"] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    assert res.stdout.strip().endswith("ok")
+
+
 def test_traction_mirror_compiles():
     """tests/cpp/test_traction_engine.cc (ComputeHydroelasticContactForces of the C++ mirror) compiles against the
     C-ABI with -Werror; without a GPU it must stop at context creation like every other entry point."""
