@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py — batched hydroelastic ComputeContactSurfaces on N B200s (one process per GPU).
 
-A "step" is one batched query (all scenes of this rank's shard): poses in ->
-packed ContactSurface data out. Default workload: BASELINE config 3
-(ball_plate geometry batched, 16384 independent scenes per GPU, weak scaling).
+A "step" is one batched query (all scenes of this rank's shard): poses in -> packed ContactSurface data out.
+Headline workload: BASELINE config 3 (ball_plate geometry batched, 16384 independent scenes per GPU, weak scaling;
+at N > 1 the strong split -- 16384 scenes over all GPUs -- is measured as well). At N = 1 the other BASELINE configs
+(C1 mesh_intersection_benchmark, C2 compliant_mesh_intersection_benchmark, C4 dense clutter, C5 high-resolution
+stress) are measured in the same run and reported under "other_configs".
 
   python bench.py --gpus 1 --steps 20 --warmup 5
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-  python bench.py --impl reference ...     # the CPU port of the reference path on the host cores
+  python bench.py --impl reference ...     # the CPU port of the reference path on the host cores (never maps
+                                           # the product library)
 
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -29,6 +33,12 @@ if ROOT not in sys.path:
 
 METRIC = "contact_surfaces_per_sec"
 UNIT = "surfaces/s"
+CONFIGS = ["c1", "c2", "c2s", "c3", "c3h", "c4", "c5"]
+DEFAULT_SCENES = {"c1": 1, "c2": 1, "c2s": 256, "c3": 16384, "c3h": 16384, "c4": 4096, "c5": 1024}
+# The reference's own printed numbers for the two configs it can run (single thread, unnamed workstation: context,
+# not a target): mesh_intersection_benchmark.cc:79 (args 3/4/0) and compliant_mesh_intersection_benchmark.cc:76 (3/3).
+REFERENCE_PRINTED_MS = {"c1": (14.3, "geometry/benchmarking/mesh_intersection_benchmark.cc:79"),
+                        "c2": (59.971, "geometry/benchmarking/compliant_mesh_intersection_benchmark.cc:76")}
 
 
 def parse_args():
@@ -37,32 +47,35 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c2s", "c3", "c3h", "c4", "c5"])
+    ap.add_argument("--config", default="c3", choices=CONFIGS)
     ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default: the config's)")
-    ap.add_argument("--rep", default="polygon", choices=["polygon", "triangle"])
+    ap.add_argument("--rep", default="", choices=["", "polygon", "triangle"], help="default: the config's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--forces", action="store_true",
-                    help="also time the device-side consumer (k_wrench: one spatial force per surface, 18 doubles out "
-                         "per surface). Off by default: parity-green on the B200 but not yet timed there (DESIGN.md 4b)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip C1 / C2 / C4 / C5 (they run at N = 1 only)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1 only)")
     return ap.parse_args()
 
 
-DEFAULT_SCENES = {"c2s": 256, "c3": 16384, "c3h": 16384, "c4": 4096, "c5": 16}
-
-
-def make_workload(name: str, scenes: int, scene0: int):
+def make_workload(name: str, scenes: int, scene0: int, Mesh=None):
     from drake_b200 import workloads as W
+    kw = {} if Mesh is None else {"Mesh": Mesh}
+    if name == "c1":
+        wl = W.config1(args=[(3, 4, 0)] * scenes, **kw)   # the finest case of the reference's table ...
+        wl.normal_filter = False                          # ... run the way its benchmark runs it (no normal filter)
+        return wl
+    if name == "c2":
+        return W.config2(resolutions=(3,), overlaps=(3,) * scenes, **kw)
     if name == "c3":
-        return W.config3(scenes, scene0)
+        return W.config3(scenes, scene0, **kw)
     if name == "c3h":
-        return W.config3_half_space(scenes, scene0)
+        return W.config3_half_space(scenes, scene0, **kw)
     if name == "c4":
-        return W.config4(scenes, scene0)
+        return W.config4(scenes, scene0, **kw)
     if name == "c5":
-        return W.config5(scenes, scene0)
-    return W.config2_spheres(scenes, scene0, 0.5)
+        return W.config5(scenes, scene0, **kw)
+    return W.config2_spheres(scenes, scene0, 0.5, **kw)
 
 
 def measured_peaks():
@@ -143,24 +156,22 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
 
 
-def oracle_scene(workload):
-    """Builds the oracle's scene from the SAME arrays the GPU registered (cpu_baseline / reference arm)."""
-    from tests import parity
-    return parity.oracle_scene_for(workload)
+# ------------------------------------------------------------------------------------------ the CPU port ---
 
-
-def time_cpu_port(workload, rep: int, budget_s: float, threads: int):
-    """Times the CPU port of the reference path (reference-shaped Bvh<Aabb> traversal + clipping +
-    mesh construction) on a bounded sample of the workload's scenes."""
-    from oracle import ho
-    sc, order = oracle_scene(workload)
-    poses = workload.poses[:, order, :]
+def time_cpu_port(config: str, scenes: int, rep: int, budget_s: float, threads: int):
+    """Times the CPU port of the reference path (reference-shaped BVH traversal + clipping + mesh construction) on a
+    bounded sample of the config's scenes. Everything here is built by the oracle's own generators
+    (oracle/ref_workloads.py): this leg never touches the product library."""
+    from oracle import ho, ref_workloads as RW
+    wl = make_workload(config, min(scenes, 4096) if config in ("c4", "c5") else scenes, 0, Mesh=RW.RefMesh)
+    sc, order = RW.scene_for(wl)
+    poses = wl.poses[:, order, :]
     probe = min(len(poses), max(threads, 8))
     t, st = sc.batch_time(poses[:probe], rep, ho.MODE_REFERENCE_BVH, threads)
     per_scene = max(t / probe, 1e-7)
     n = int(min(len(poses), max(probe, budget_s / per_scene)))
     # When the whole workload takes less than the budget, repeat it (bounded) so the sample is seconds, not a blink.
-    passes = int(min(32, max(1, budget_s / max(per_scene * n, 1e-9)))) if n == len(poses) else 1
+    passes = int(min(64, max(1, budget_s / max(per_scene * n, 1e-9)))) if n == len(poses) else 1
     t, surfaces, pairs = 0.0, 0, 0
     for _ in range(passes):
         tp, st = sc.batch_time(poses[:n], rep, ho.MODE_REFERENCE_BVH, threads)
@@ -168,41 +179,53 @@ def time_cpu_port(workload, rep: int, budget_s: float, threads: int):
         surfaces += st["surfaces"]
         pairs += st["element_pairs"]
     return {"seconds": t, "scenes": n, "passes": passes, "stats": st, "surfaces_per_s": surfaces / t,
-            "element_pairs_per_s": pairs / t}
+            "element_pairs_per_s": pairs / t, "ms_per_scene": 1e3 * t / (n * passes), "workload": wl}
+
+
+def config_record(wl, scenes: int, rep_name: str, geoms: int):
+    """The `config` object: identical keys in both arms (the driver compares them)."""
+    return {"workload": wl.name, "description": wl.description, "scenes_per_gpu": scenes, "geometries_per_scene": geoms,
+            "representation": rep_name,
+            "l2": "256 MB L2 flush between steps; work lists and outputs stream through HBM, the instanced mesh assets "
+                  "are L2-resident by design"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from drake_b200 import engine
-    rep = engine.POLYGON if args.rep == "polygon" else engine.TRIANGLE
     scenes = args.scenes or DEFAULT_SCENES[args.config]
-    wl = make_workload(args.config, scenes, 0)
+    rep_name = args.rep or default_rep(args.config)
+    rep = 1 if rep_name == "polygon" else 0
     threads = os.cpu_count() or 1
     # Each step is a bounded sample; K + W steps must finish within a few minutes.
     per_step_budget = min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup))
     for _ in range(args.warmup):
-        time_cpu_port(wl, rep, per_step_budget, threads)
-    vals, pairs, secs, nscenes, npasses = [], [], [], 0, 1
+        time_cpu_port(args.config, scenes, rep, per_step_budget, threads)
+    vals, pairs, secs, r = [], [], [], None
     for _ in range(args.steps):
-        r = time_cpu_port(wl, rep, per_step_budget, threads)
+        r = time_cpu_port(args.config, scenes, rep, per_step_budget, threads)
         vals.append(r["surfaces_per_s"])
         pairs.append(r["element_pairs_per_s"])
         secs.append(r["seconds"])
-        nscenes = r["scenes"]
-        npasses = r["passes"]
+    wl = r["workload"]
     v = float(np.mean(vals))
-    sample = f"{npasses} x {nscenes} of {scenes} scenes of {wl.name} per step, all host threads"
+    sample = f"{r['passes']} x {r['scenes']} of {scenes} scenes of {wl.name} per step, all host threads"
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": wl.name, "scenes_per_gpu": scenes, "representation": args.rep,
-                      "description": wl.description},
+           "config": config_record(wl, scenes, rep_name, wl.geoms_per_scene),
            "element_pairs_per_sec": float(np.mean(pairs)),
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                            "bvh": "reference-shaped Bvh<Aabb> (median split, <= 1 tet / 3 tris per leaf), scalar BoxesOverlap",
+                            "native": "oracle/_build/libhydro_oracle.so only: meshes, fields and BVHs come from the oracle's "
+                                      "own generators (oracle/ref_workloads.py)"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(json.dumps(out))
+
+
+def default_rep(config: str) -> str:
+    return "triangle" if config == "c1" else "polygon"
 
 
 _REAL_STDOUT = None
@@ -224,119 +247,123 @@ def quiet_stdout():
     os.dup2(2, 1)
 
 
-def main():
-    args = parse_args()
-    quiet_stdout()
-    if args.impl == "reference":
-        run_reference(args)
-        return
-    import torch
-    import torch.distributed as dist
+# ---------------------------------------------------------------------------------------- the GPU legs ---
 
-    import drake_b200 as db
-    from drake_b200 import engine
+class Dist:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            # Rank 0 prints ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off stdout.
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        # Rank 0 prints ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off stdout.
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    rep = engine.POLYGON if args.rep == "polygon" else engine.TRIANGLE
-    scenes = args.scenes or DEFAULT_SCENES[args.config]
-    # Bind this rank to the CPUs (NUMA node) next to its GPU before any pinned host buffer is allocated: the
-    # end-to-end leg moves ~0.6 GB per step per GPU over PCIe, and with N ranks the copies otherwise cross sockets.
-    numa = "unbound"
-    all_cpus = os.sched_getaffinity(0)
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local)
-        pynvml.nvmlDeviceSetCpuAffinity(h)
-        numa = f"{len(os.sched_getaffinity(0))} cpus near gpu {local}"
-    except Exception as ex:  # affinity is an optimisation only
-        numa = f"unbound ({type(ex).__name__})"
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    # ---- set-up (untimed): meshes, assets, BVHs, scene batch, two pose sets resident in HBM.
-    wl = make_workload(args.config, scenes, rank * scenes)
-    wl_b = make_workload(args.config, scenes, (world + rank) * scenes)
-    ctx = db.Context(local)
-    batch = wl.register(ctx)
-    G = wl.geoms_per_scene
-    pose_sets = [torch.from_numpy(np.ascontiguousarray(w.poses.reshape(-1, 12))).to(dev) for w in (wl, wl_b)]
-    pinned_poses = [torch.from_numpy(np.ascontiguousarray(w.poses.reshape(-1, 12))).pin_memory() for w in (wl, wl_b)]
-    stats_local = torch.zeros((scenes, 6), dtype=torch.int64, device=dev)
-    stats_all = torch.zeros((world * scenes, 6), dtype=torch.int64, device=dev) if world > 1 else None
-    stream = torch.cuda.ExternalStream(batch.stream(), device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    batch.enable_timing(True)
+    def max_sum(self, max_vals, sum_vals):
+        """(max over ranks of each of max_vals, sum over ranks of each of sum_vals)."""
+        torch = self.torch
+        a = torch.tensor(list(max_vals), dtype=torch.float64, device=self.dev)
+        b = torch.tensor(list(sum_vals), dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(a, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(b, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in a.tolist()], [float(x) for x in b.tolist()]
 
-    def step(k: int, timed_events=None):
-        with torch.cuda.stream(stream):
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+class Leg:
+    """One workload registered on this rank's GPU: set-up (untimed), the device-timed loop, the end-to-end loops."""
+
+    def __init__(self, D: Dist, config: str, scenes: int, scene0: int, scene0_b: int, rep_name: str):
+        import drake_b200 as db
+        from drake_b200 import engine
+        torch = D.torch
+        self.D, self.config, self.scenes, self.engine = D, config, scenes, engine
+        self.rep_name = rep_name
+        self.rep = engine.POLYGON if rep_name == "polygon" else engine.TRIANGLE
+        self.wl = make_workload(config, scenes, scene0)
+        wl_b = make_workload(config, scenes, scene0_b) if config in ("c3", "c3h", "c4", "c5", "c2s") else self.wl
+        self.ctx = db.Context(D.local)
+        self.batch = self.wl.register(self.ctx)
+        poses = [np.ascontiguousarray(w.poses.reshape(-1, 12)) for w in (self.wl, wl_b)]
+        self.pose_sets = [torch.from_numpy(p).to(D.dev) for p in poses]
+        self.pinned_poses = [torch.from_numpy(p).pin_memory() for p in poses]
+        self.stats_local = torch.zeros((scenes, 6), dtype=torch.int64, device=D.dev)
+        self.stats_all = torch.zeros((D.world * scenes, 6), dtype=torch.int64, device=D.dev) if D.world > 1 else None
+        self.stream = torch.cuda.ExternalStream(self.batch.stream(), device=D.dev)
+        self.batch.enable_timing(True)
+        # Grow the device work lists until the workload fits (untimed).
+        for k in (0, 1):
+            self.batch.set_poses_device(self.pose_sets[k].data_ptr())
+            self.batch.run(self.rep, engine.STRICT, self.stats_local.data_ptr())
+
+    def step(self, k: int, flush, timed_events=None):
+        torch, D = self.D.torch, self.D
+        with torch.cuda.stream(self.stream):
             flush.zero_()  # L2 flush between steps, outside the timed events
             if timed_events is not None:
-                timed_events[0].record(stream)
-            batch.set_poses_device(pose_sets[k % 2].data_ptr())
-            batch.query(rep, engine.STRICT, stats_local.data_ptr())
-            if world > 1:
+                timed_events[0].record(self.stream)
+            self.batch.set_poses_device(self.pose_sets[k % 2].data_ptr())
+            self.batch.query(self.rep, self.engine.STRICT, self.stats_local.data_ptr())
+            if D.world > 1:
                 # The only collective of the path: per-scene statistics over NVLink.
-                dist.all_gather_into_tensor(stats_all, stats_local)
+                D.dist.all_gather_into_tensor(self.stats_all, self.stats_local)
             if timed_events is not None:
-                timed_events[1].record(stream)
-        batch.sync()
+                timed_events[1].record(self.stream)
+        self.batch.sync()
 
-    # Grow device work lists until the workload fits (untimed).
-    batch.set_poses_device(pose_sets[0].data_ptr())
-    batch.run(rep, engine.STRICT, stats_local.data_ptr())
-    batch.set_poses_device(pose_sets[1].data_ptr())
-    batch.run(rep, engine.STRICT, stats_local.data_ptr())
-    for k in range(args.warmup):
-        step(k)
+    def device_timed(self, steps: int, warmup: int, flush, sampler=None):
+        torch, D = self.D.torch, self.D
+        for k in range(warmup):
+            self.step(k, flush)
+        stage_ms, step_stats = {}, []
+        events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        D.barrier()
+        if sampler is not None:
+            sampler.start()
+        wall0 = time.perf_counter()
+        for k in range(steps):
+            self.step(k, flush, events[k])
+            step_stats.append(self.batch.stats())
+            for name, ms in self.batch.stage_times_ms().items():
+                stage_ms[name] = stage_ms.get(name, 0.0) + ms
+        D.barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler is not None else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in events)
+        tot = [sum(s[k] for s in step_stats) for k in ("surfaces", "bv_pair_tests", "faces")]
+        tot.append(sum(s["tet_tri_pairs"] + s["tet_tet_pairs"] + s["half_space_elements"] for s in step_stats))
+        (max_ms,), (surfaces, bvtests, faces, pairs) = D.max_sum([dev_ms], tot)
+        sec = max_ms / 1e3
+        return {"ms_per_step": max_ms / steps, "value": surfaces / sec, "element_pairs_per_sec": pairs / sec,
+                "bv_pair_tests_per_sec": bvtests / sec, "faces_per_sec": faces / sec,
+                "surfaces_per_step": surfaces / steps, "element_pairs_per_step": pairs / steps,
+                "wall_ms_per_step_incl_flush_and_sync": 1e3 * wall / steps,
+                "stage_ms": {k: v / steps for k, v in stage_ms.items()},
+                "stats_mean": {k: float(np.mean([s[k] for s in step_stats])) for k in step_stats[0]},
+                "launches_per_step": self.batch.last_launch_count, "clocks": clocks}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    kernel_ms = {}
-    step_stats = []
-    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    if rank == 0:
-        sampler.start()
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        step(k, events[k])
-        step_stats.append(batch.stats())
-        for name, ms in batch.kernel_times_ms().items():
-            kernel_ms[name] = kernel_ms.get(name, 0.0) + ms
-    barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in events)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([sum(s["surfaces"] for s in step_stats), sum(s["tet_tri_pairs"] + s["tet_tet_pairs"] + s["half_space_elements"] for s in step_stats),
-                        sum(s["bv_pair_tests"] for s in step_stats), sum(s["faces"] for s in step_stats)],
-                       dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    max_ms = float(t.item())
-    surfaces, pairs, bvtests, faces = [float(x) for x in tot.tolist()]
-    sec = max_ms / 1e3
-    value = surfaces / sec
-
-    # ---- end-to-end through the C-ABI with HOST buffers (H2D poses, D2H packed surfaces).
-    e2e = None
-    if not args.no_e2e:
+    # -- end to end through the C-ABI with HOST buffers: H2D poses + D2H of what the variant returns, every step.
+    def e2e(self, steps: int, warmup: int, variants=("full", "faces_only", "spatial_forces", "discrete_pairs")):
+        engine, torch, D = self.engine, self.D.torch, self.D
+        batch, rep = self.batch, self.rep
         sizes = batch.sizes()
         cap = engine.ResultSizes()
         for f, _ in engine.ResultSizes._fields_:
@@ -349,186 +376,302 @@ def main():
             tt = torch.empty(max(n, 1), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
             return tt.numpy()[:n].reshape(shape)
 
-        # Two batches over the same assets, alternated: while one batch's packed results travel D2H
-        # (asynchronous copies into pinned buffers on its own stream), the other batch's poses travel
-        # H2D and its query runs. Every step still includes the H2D copy of its poses and the D2H
-        # read of its complete result.
-        batches = [batch, wl.register(ctx, assets=wl.assets)]
-        hosts = [engine.PackedResults(sizes, allocator=pinned, capacity=cap) for _ in batches]
-        batches[1].set_poses_host_ptr(pinned_poses[1].data_ptr())
-        batches[1].run(rep, engine.STRICT, 0)   # grows the second batch's work lists (untimed)
-        batches[1].set_poses_host_ptr(pinned_poses[0].data_ptr())
-        batches[1].run(rep, engine.STRICT, 0)
+        # Two batches over the same assets, alternated: while one batch's results travel D2H (asynchronous copies into
+        # pinned buffers on its own stream), the other batch's poses travel H2D and its query runs. Every step still
+        # includes the H2D copy of its poses and the D2H read of its complete result.
+        batches = [batch, self.wl.register(self.ctx, assets=self.wl.assets)]
+        for k in (1, 0):
+            batches[1].set_poses_host_ptr(self.pinned_poses[k].data_ptr())
+            batches[1].run(rep, engine.STRICT, 0)   # grows the second batch's work lists (untimed)
+        G = self.wl.geoms_per_scene
+        out = {}
+        for variant in variants:
+            if variant in ("full", "faces_only"):
+                fields = None if variant == "full" else engine.PackedResults.FACE_FIELDS
+                hosts = [engine.PackedResults(sizes, allocator=pinned, capacity=cap, fields=fields) for _ in batches]
+            elif variant == "spatial_forces":
+                compliant = np.array([getattr(self.wl.meshes[m], "vertices_per_element", 0) == 4 or
+                                      getattr(self.wl.meshes[m], "compliant", False) for m in self.wl.geom_mesh])
+                E = np.tile(np.where(compliant, 3e4, np.inf), self.scenes)
+                vel = np.random.default_rng(1234 + D.rank).uniform(-0.1, 0.1, size=(self.scenes * G, 6))
+                for b in batches:
+                    b.set_contact_properties(E, np.ones(self.scenes * G), np.full(self.scenes * G, 0.5))
+                    b.set_body_kinematics(None, vel)
+                hosts = [pinned((cap.num_surfaces, 18), np.float64) for _ in batches]
+            else:
+                hosts = [pinned((cap.num_faces, 9), np.float64) for _ in batches]
 
-        def e2e_run(n_steps: int):
-            surf, nbytes, pending = 0, 0, None
-            for k in range(n_steps):
-                b, h = batches[k % 2], hosts[k % 2]
-                b.set_poses_host_ptr(pinned_poses[k % 2].data_ptr())
-                b.query(rep, engine.STRICT, 0)
-                if pending is not None:
-                    pending.sync()          # the previous step's D2H copies
-                b.sync()                    # this step's query: result sizes are now known
-                r = b.copy_results(h, wait=False)
-                surf += r.num_surfaces
-                nbytes += r.nbytes()
-                pending = b
-            if pending is not None:
-                pending.sync()
-            return surf, nbytes
-
-        e2e_run(max(2, min(4, args.warmup)))
-        barrier()
-        e0 = time.perf_counter()
-        e_surf, d2h = e2e_run(args.steps)
-        barrier()
-        e_sec = time.perf_counter() - e0
-        # The same loop copying out only what MultibodyPlant's discrete update reads from a ContactSurface
-        # (per-face area / normal / centroid / pressure / gradients, per-surface totals): reported
-        # beside the complete copy-out, never instead of it.
-        full_hosts = hosts
-        hosts = [engine.PackedResults(sizes, allocator=pinned, capacity=cap, fields=engine.PackedResults.FACE_FIELDS)
-                 for _ in batches]
-        e2e_run(2)
-        barrier()
-        f0 = time.perf_counter()
-        f_surf, f_d2h = e2e_run(args.steps)
-        barrier()
-        f_sec = time.perf_counter() - f0
-        hosts = full_hosts
-        forces_e2e = None
-        if args.forces:
-            # Same loop, but what leaves the GPU is HydroelasticTractionCalculator's output: synthetic
-            # contact properties (compliant E = 3e4 Pa, rigid = inf; dissipation 1 s/m; friction 0.5) and body velocities.
-            G = wl.geoms_per_scene
-            compliant = np.array([getattr(wl.meshes[m], "vertices_per_element", 0) == 4 or getattr(wl.meshes[m], "compliant", False)
-                                  for m in wl.geom_mesh])
-            E = np.tile(np.where(compliant, 3e4, np.inf), scenes)
-            vel = np.random.default_rng(1234 + rank).uniform(-0.1, 0.1, size=(scenes * G, 6))
-            for b in batches:
-                b.set_contact_properties(E, np.ones(scenes * G), np.full(scenes * G, 0.5))
-                b.set_body_kinematics(None, vel)
-
-            def forces_run(n_steps: int):
-                surf = 0
+            def run(n_steps: int):
+                surf, nbytes, pending = 0, 0, None
                 for k in range(n_steps):
-                    b = batches[k % 2]
-                    b.set_poses_host_ptr(pinned_poses[k % 2].data_ptr())
+                    b, h = batches[k % 2], hosts[k % 2]
+                    b.set_poses_host_ptr(self.pinned_poses[k % 2].data_ptr())
                     b.query(rep, engine.STRICT, 0)
-                    surf += len(b.spatial_forces(1e-4)[0])   # waits, then copies 3 x [num_surfaces, 6] doubles
-                return surf
+                    if variant == "spatial_forces":
+                        b.compute_spatial_forces(1e-4)
+                    elif variant == "discrete_pairs":
+                        b.compute_discrete_pairs()
+                    if pending is not None:
+                        pending.sync()          # the previous step's D2H copies
+                    b.sync()                    # this step's query: result sizes are now known
+                    if variant in ("full", "faces_only"):
+                        r = b.copy_results(h, wait=False)
+                        surf += r.num_surfaces
+                        nbytes += r.nbytes()
+                    elif variant == "spatial_forces":
+                        ns = b.copy_spatial_forces(h, wait=False)
+                        surf += ns
+                        nbytes += ns * 18 * 8
+                    else:
+                        view = b.copy_discrete_pairs(h, wait=False)
+                        surf += int(b.sizes().num_surfaces)
+                        nbytes += view.size * 8
+                    pending = b
+                if pending is not None:
+                    pending.sync()
+                return surf, nbytes
 
-            forces_run(2)
-            barrier()
-            g0 = time.perf_counter()
-            g_surf = forces_run(args.steps)
-            barrier()
-            g_sec = time.perf_counter() - g0
-            forces_e2e = {"value": g_surf / g_sec, "unit": UNIT, "ms_per_step": 1e3 * g_sec / args.steps,
-                          "d2h_bytes_per_step": int(g_surf / args.steps) * 18 * 8,
-                          "what": "host poses in, one spatial force per surface (F_Ac_W, F_Ao_W, F_Bo_W) out; this rank only"}
-        ft = torch.tensor([f_sec, float(f_surf)], dtype=torch.float64, device=dev)
-        if world > 1:
-            fmax = ft.clone()
-            dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ft, op=dist.ReduceOp.SUM)
-            ft[0] = fmax[0]
-        faces_only = {"value": float(ft[1].item()) / float(ft[0].item()), "unit": UNIT,
-                      "d2h_bytes_per_step": int(f_d2h / args.steps), "ms_per_step": 1e3 * float(ft[0].item()) / args.steps,
-                      "arrays": "per-face area, normal, centroid, pressure at centroid, grad_eM, grad_eN; per-surface ids, "
-                                "offsets, total area, centroid"}
-        et = torch.tensor([e_sec], dtype=torch.float64, device=dev)
-        es = torch.tensor([float(e_surf)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(et, op=dist.ReduceOp.MAX)
-            dist.all_reduce(es, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(es.item()) / float(et.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(pinned_poses[0].numel() * 8), "d2h_bytes_per_step": int(d2h / args.steps),
-               "ms_per_step": 1e3 * float(et.item()) / args.steps,
-               "pipelining": "two batches alternated: D2H of step k overlaps H2D + query of step k+1",
-               "host_affinity": numa, "faces_only": faces_only}
-        if forces_e2e is not None:
-            e2e["spatial_forces"] = forces_e2e
+            run(max(2, min(4, warmup)))
+            D.barrier()
+            t0 = time.perf_counter()
+            surf, nbytes = run(steps)
+            D.barrier()
+            sec = time.perf_counter() - t0
+            (sec_max,), (surf_all,) = D.max_sum([sec], [float(surf)])
+            out[variant] = {"value": surf_all / sec_max, "unit": UNIT, "ms_per_step": 1e3 * sec_max / steps,
+                            "d2h_bytes_per_step": int(nbytes / steps)}
+            del hosts
+        return out, int(self.pinned_poses[0].numel() * 8)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+
+E2E_WHAT = {
+    "full": "the complete packed ContactSurface data of every surface (vertices, pressures, face data, per-face area / "
+            "normal / centroid / pressure / gradients, per-surface totals)",
+    "faces_only": "per-face area, normal, centroid, pressure at centroid, grad_eM, grad_eN; per-surface ids, offsets, "
+                  "total area, centroid (what MultibodyPlant's discrete update reads, SURVEY 3.6)",
+    "spatial_forces": "one spatial force per surface computed on the device (k_wrench = HydroelasticTractionCalculator, "
+                      "hydroelastic_traction_calculator.cc:24-83): F_Ac_W, F_Ao_W, F_Bo_W, 18 doubles per surface",
+    "discrete_pairs": "the per-face data of DiscreteUpdateManager::AppendDiscreteContactPairsForHydroelasticContact computed "
+                      "on the device (k_discrete, discrete_update_manager.cc:896-1036): p_WC, nhat_BA_W, phi0, fn0, stiffness, "
+                      "9 doubles per face"}
+
+
+def ncu_profile(config: str):
+    """Per-kernel DRAM bytes / instructions of the committed `ncu --set full` capture of this config at its default size
+    (profiles/*_kernels_<config>.json, written by tools/ncu_traffic.py), or None."""
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_kernels_{config}.json")))
+    if not cands:
+        return None, None
+    try:
+        return json.load(open(cands[-1])), os.path.relpath(cands[-1], ROOT)
+    except Exception:
+        return None, None
+
+
+def roofline_for(leg: Leg, res: dict, config: str, default_size: bool):
+    """The dominant kernel group by event time, its algorithmic bytes, and beside it what the
+    committed ncu capture says really bounds it: DRAM bytes moved and issue slots used."""
+    st, ms = res["stats_mean"], res["stage_ms"]
+    n_poly, n_vert = st["polygons"], st["vertices"] if leg.rep == 1 else st["vertices"] - st["polygons"]
+    cand_tri, cand_tet = st["tet_tri_pairs"], st["tet_tet_pairs"]
+    leaf_tet = st["leaf_pairs_tet_tet"]
+    leaf_tri = st["leaf_pairs"] - leaf_tet
+    bv_tet = st["bv_pair_tests_tet_tet"]
+    bv_tri = st["bv_pair_tests"] - bv_tet
+    surv_tri, surv_tet = st["tet_tri_full_clips"], st["tet_tet_full_clips"]
+    share_tri = cand_tri / max(1.0, cand_tri + cand_tet + st["half_space_elements"])
+    soup = n_poly * 40.0 + n_vert * 32.0          # staged polygons: header 16 + normal 24 + 32 B per vertex
+    out_bytes = n_vert * 32.0 + n_poly * 108.0    # final layout (SURVEY 8d: 32 n + 96 / 120, + face_data)
+    # Per kernel group: name -> (event ms, algorithmic bytes, kernels)
+    groups = {
+        "mid_phase_tet_tri": (ms["cull_tet_tri"] + ms["traverse"] * (bv_tri / max(1.0, bv_tri + bv_tet)),
+                              bv_tri * 64.0 + leaf_tri * 176.0 + surv_tri * 16.0,
+                              "k_small_pairs<tri> (or k_traverse + k_filter<tri>): 64 B per box test, 176 B of fp32 cull "
+                              "records per leaf pair, 16 B per survivor"),
+        "mid_phase_tet_tet": (ms["cull_tet_tet"] + ms["traverse"] * (bv_tet / max(1.0, bv_tri + bv_tet)),
+                              bv_tet * 64.0 + leaf_tet * 256.0 + surv_tet * 16.0,
+                              "k_small_pairs<tet> (or k_traverse + k_filter<tet>): 64 B per box test, 256 B per leaf pair, "
+                              "16 B per survivor"),
+        "exact_clip_tet_tri": (ms["clip_tet_tri"], surv_tri * (16.0 + 128 + 256 + 96) + soup * share_tri,
+                               "k_clip<tri>: survivor entry + TetRec + TetAux + TriRec in, staged polygon out"),
+        "exact_clip_tet_tet": (ms["clip_tet_tet"], surv_tet * (16.0 + 2 * (128 + 256)) + soup * (1 - share_tri),
+                               "k_clip<tet>: survivor entry + 2 x (TetRec + TetAux) in, staged polygon out"),
+        "pack": (ms["pack"], soup + out_bytes, "k_pack: staged polygon in, final layout out"),
+    }
+    if st["half_space_elements"]:
+        groups["half_space"] = (ms["half_space"], st["half_space_elements"] * 168.0, "k_plane_setup + k_plane<count>")
+    dominant = max(groups, key=lambda k: groups[k][0])
+    d_ms, d_bytes, d_kernels = groups[dominant]
+    peak, peak_kind = measured_peaks()
+    achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+    prof, prof_src = ncu_profile(config) if default_size else (None, None)
+    traffic, issue = None, None
+    if prof and dominant in prof.get("groups", {}):
+        g = prof["groups"][dominant]
+        traffic = g.get("dram_bytes")
+        if g.get("warp_instructions") and d_ms > 0:
+            # Issue-slot roofline: warp instructions of the capture / live event time, against 4 schedulers x SMs x clock.
+            sm_clock = (res.get("clocks") or {}).get("sm_mhz") or 1965.0
+            sms = prof.get("sms", 148)
+            peak_issue = 4.0 * sms * sm_clock * 1e6
+            rate = g["warp_instructions"] / (d_ms * 1e-3)
+            issue = {"warp_instructions_per_launch": g["warp_instructions"], "achieved_ginst_s": rate / 1e9,
+                     "peak_ginst_s": peak_issue / 1e9, "frac": rate / peak_issue,
+                     "ncu_issue_active_pct": g.get("issue_active_pct"), "ncu_active_lanes": g.get("active_lanes"),
+                     "ncu_warps_active_pct": g.get("warps_active_pct")}
+    whole_alg = st["algorithmic_bytes"]
+    compulsory = None
+    if prof and prof.get("compulsory_dram_bytes"):
+        compulsory = {"bytes": prof["compulsory_dram_bytes"], "measured_dram_bytes_whole_query": prof.get("dram_bytes_whole_query"),
+                      "what": "every asset byte once + poses + work lists written and read once + the packed result once"}
+    return {"bound": "hbm", "kernel": d_kernels, "group": dominant, "achieved": achieved, "peak": peak,
+            "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+            "traffic_source": prof_src, "algorithmic_bytes_per_launch": d_bytes, "kernel_ms": d_ms,
+            "kernel_ms_breakdown": res["stage_ms"],
+            "groups": {k: {"ms": v[0], "algorithmic_bytes": v[1], "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None}
+                       for k, v in groups.items()},
+            "issue_slots": issue, "compulsory_dram": compulsory,
+            "note": "achieved = algorithmic bytes of the group (DESIGN.md 4) / its CUDA-event time. The instanced mesh assets "
+                    "are cache-resident, so DRAM traffic is far below the algorithmic bytes: the group is bound by "
+                    "instruction issue, which `issue_slots` measures (profiles/README.md)",
+            "whole_step_frac": (whole_alg / (res["ms_per_step"] * 1e-3) / 1e9) / peak if peak else None}
+
+
+def cpu_baseline_record(config: str, scenes: int, rep: int, seconds: float):
+    threads = os.cpu_count() or 1
+    r = time_cpu_port(config, scenes, rep, seconds, threads)
+    r1 = time_cpu_port(config, scenes, rep, min(5.0, seconds), 1)
+    return {"value": r["surfaces_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{r['passes']} x {r['scenes']} of {scenes} scenes of {r['workload'].name}, {r['seconds']:.1f} s",
+            "element_pairs_per_sec": r["element_pairs_per_s"], "ms_per_scene_all_cores": r["ms_per_scene"],
+            "single_thread": {"value": r1["surfaces_per_s"], "scenes": r1["scenes"], "ms_per_scene": r1["ms_per_scene"],
+                              "element_pairs_per_sec": r1["element_pairs_per_s"]}}
+
+
+def other_config_line(D: Dist, config: str, flush, cpu_seconds: float, with_cpu: bool):
+    """One BASELINE config measured the same way as the headline, with fewer steps."""
+    scenes = DEFAULT_SCENES[config]
+    rep_name = default_rep(config)
+    t0 = time.perf_counter()
+    leg = Leg(D, config, scenes, 0, scenes, rep_name)
+    steps, warmup = (5, 3) if config in ("c4", "c5") else (20, 5)
+    res = leg.device_timed(steps, warmup, flush)
+    line = {"workload": leg.wl.name, "description": leg.wl.description, "scenes": scenes, "representation": rep_name,
+            "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "value": res["value"], "unit": UNIT,
+            "element_pairs_per_sec": res["element_pairs_per_sec"], "bv_pair_tests_per_sec": res["bv_pair_tests_per_sec"],
+            "faces_per_sec": res["faces_per_sec"], "surfaces_per_step": res["surfaces_per_step"],
+            "element_pairs_per_step": res["element_pairs_per_step"], "gpu_launches_per_step": res["launches_per_step"],
+            "chunks": leg.batch.num_chunks, "roofline": roofline_for(leg, res, config, True)}
+    sizes = leg.batch.sizes()
+    result_bytes = int(sizes.num_faces) * 150 + int(sizes.num_vertices) * 36
+    if result_bytes < (3 << 30):
+        e2e, h2d = leg.e2e(steps, 2, variants=("full",))
+        line["e2e"] = dict(e2e["full"], h2d_bytes_per_step=h2d, what=E2E_WHAT["full"])
+    else:
+        line["e2e"] = None
+        line["e2e_skipped"] = f"the complete result of one query is ~{result_bytes / 2**30:.1f} GiB: not staged on the host here"
+    if config in REFERENCE_PRINTED_MS:
+        ms, src = REFERENCE_PRINTED_MS[config]
+        line["reference_printed"] = {"ms": ms, "source": src,
+                                     "note": "the reference's own example output (single thread, unnamed workstation, timed "
+                                             "region = its narrow phase only): context, not a measurement of this run"}
+    del leg
+    if with_cpu:
+        line["cpu_baseline"] = cpu_baseline_record(config, scenes, 1 if rep_name == "polygon" else 0, cpu_seconds)
+    line["bench_seconds"] = time.perf_counter() - t0
+    return line
+
+
+def main():
+    args = parse_args()
+    quiet_stdout()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    D = Dist()
+    torch = D.torch
+    rep_name = args.rep or default_rep(args.config)
+    scenes = args.scenes or DEFAULT_SCENES[args.config]
+    # Bind this rank to the CPUs (NUMA node) next to its GPU before any pinned host buffer is allocated: the
+    # end-to-end leg moves ~0.6 GB per step per GPU over PCIe, and with N ranks the copies otherwise cross sockets.
+    numa = "unbound"
+    all_cpus = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(D.local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        numa = f"{len(os.sched_getaffinity(0))} cpus near gpu {D.local}"
+    except Exception as ex:  # affinity is an optimisation only
+        numa = f"unbound ({type(ex).__name__})"
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=D.dev)  # > 126 MB L2
+    # ---- headline: weak scaling, `scenes` per GPU.
+    leg = Leg(D, args.config, scenes, D.rank * scenes, (D.world + D.rank) * scenes, rep_name)
+    res = leg.device_timed(args.steps, args.warmup, flush, ClockSampler(D.local) if D.rank == 0 else None)
+    e2e = None
+    if not args.no_e2e:
+        variants, h2d = leg.e2e(args.steps, args.warmup)
+        e2e = dict(variants["full"], h2d_bytes_per_step=h2d, what=E2E_WHAT["full"],
+                   pipelining="two batches alternated: D2H of step k overlaps H2D + query of step k+1", host_affinity=numa)
+        for k in ("faces_only", "spatial_forces", "discrete_pairs"):
+            e2e[k] = dict(variants[k], what=E2E_WHAT[k])
+        if D.world > 1:
+            e2e["note"] = ("all ranks copy out concurrently: the box's host side sustains a fixed aggregate D2H rate "
+                           "(profiles/README.md, tools/d2h_ceiling.py), so the complete copy-out does not scale with N; "
+                           "the device-side consumers (spatial_forces, discrete_pairs) do")
+    G = leg.wl.geoms_per_scene
+    config = config_record(leg.wl, scenes, rep_name, G)
+    roofline = roofline_for(leg, res, args.config, scenes == DEFAULT_SCENES[args.config] and rep_name == default_rep(args.config)) \
+        if D.rank == 0 else None
+    del leg
+
+    # ---- strong scaling: the config's scene count split over all GPUs (BASELINE config 3: "16384 independent scenes,
+    # sharded 1/2/4/8 GPUs").
+    strong = None
+    if D.world > 1 and not args.no_strong:
+        from drake_b200 import sharding
+        total = DEFAULT_SCENES[args.config]
+        bounds = sharding.shard_bounds(total, D.world)
+        mine = int(bounds[D.rank + 1] - bounds[D.rank])
+        sleg = Leg(D, args.config, mine, int(bounds[D.rank]), total + int(bounds[D.rank]), rep_name)
+        sres = sleg.device_timed(args.steps, args.warmup, flush)
+        strong = {"scenes_total": total, "scenes_per_gpu": mine, "ms_per_step": sres["ms_per_step"], "value": sres["value"],
+                  "unit": UNIT, "element_pairs_per_sec": sres["element_pairs_per_sec"],
+                  "gpu_launches_per_step": sres["launches_per_step"], "stage_ms": sres["stage_ms"]}
+        if not args.no_e2e:
+            sv, _ = sleg.e2e(args.steps, args.warmup, variants=("full", "discrete_pairs"))
+            strong["e2e"] = {k: v for k, v in sv.items()}
+        del sleg
+
+    if D.rank != 0:
+        D.close()
         return
 
-    # ---- roofline of the dominant kernel (algorithmic bytes, SURVEY.md §8d / DESIGN.md).
-    K = args.steps
-    avg = {k: v / K for k, v in kernel_ms.items()}
-    s_mean = {k: float(np.mean([s[k] for s in step_stats])) for k in step_stats[0]}
-    alg = {"traverse": s_mean["bv_pair_tests"] * 64.0,
-           "clip_tet_tri": s_mean["tet_tri_pairs"] * 260.0,
-           "clip_tet_tet": s_mean["tet_tet_pairs"] * 392.0}
-    # Polygon output bytes (32 n + 96 / + 120) are attributed to the clip kernels in proportion
-    # to their candidate counts.
-    out_bytes = (s_mean["vertices"] if rep == engine.POLYGON else s_mean["vertices"] - s_mean["polygons"]) * 32.0 + \
-        s_mean["polygons"] * 108.0
-    # Half-space pairs (k_plane count pass, timed in the same slot as the tet-tet clip): 168 B per sliced
-    # tetrahedron (the bench workloads have no compliant half space, whose triangles would count 108 B).
-    plane_bytes = s_mean["half_space_elements"] * 168.0
-    alg["clip_tet_tet"] += plane_bytes
-    cand = max(1.0, s_mean["tet_tri_pairs"] + s_mean["tet_tet_pairs"] + s_mean["half_space_elements"])
-    alg["clip_tet_tri"] += out_bytes * s_mean["tet_tri_pairs"] / cand
-    alg["clip_tet_tet"] += out_bytes * (s_mean["tet_tet_pairs"] + s_mean["half_space_elements"]) / cand
-    dominant = max(alg, key=lambda k: avg.get(k, 0.0))
-    peak, peak_kind = measured_peaks()
-    achieved = alg[dominant] / (avg[dominant] * 1e-3) / 1e9 if avg[dominant] > 0 else 0.0
-    # DRAM traffic of the same stage from the committed ncu --set full capture of this workload at this size
-    # (profiles/*_traffic_<config>.json, written by tools/ncu_traffic.py); null when no capture matches.
-    traffic, traffic_src = None, None
-    if scenes == DEFAULT_SCENES[args.config] and args.rep == "polygon":
-        import glob
-        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_traffic_{args.config}.json")))
-        if cands:
-            try:
-                tj = json.load(open(cands[-1]))
-                traffic = tj["stages"][dominant]["dram_bytes"]
-                traffic_src = os.path.relpath(cands[-1], ROOT)
-            except Exception:
-                traffic = None
-    roofline = {"bound": "hbm", "kernel": {"traverse": "k_traverse (all levels of one query)",
-                                           "clip_tet_tri": "k_filter<false> + k_clip<false>",
-                                           "clip_tet_tet": "k_filter<true> + k_clip<true>" if not plane_bytes else
-                                           "k_filter<true> + k_clip<true> + k_plane_setup + k_plane<count>"}[dominant],
-                "achieved": achieved, "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": avg[dominant],
-                "kernel_ms_breakdown": avg,
-                "note": "achieved = SURVEY 8(d) algorithmic bytes of the stage / its CUDA-event time; the instanced mesh "
-                        "assets are cache-resident, so DRAM traffic is far below the algorithmic bytes and the stage is "
-                        "bound by issue / latency, not HBM (profiles/README.md)",
-                "whole_step_frac": (s_mean["algorithmic_bytes"] / (max_ms / K * 1e-3) / 1e9) / peak}
-
-    launches_per_step = batch.last_launch_count  # counted by the library at every kernel launch of a query
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core again
-        threads = os.cpu_count() or 1
-        r = time_cpu_port(wl, rep, args.cpu_seconds, threads)
-        r1 = time_cpu_port(wl, rep, min(5.0, args.cpu_seconds), 1)
-        cpu_baseline = {"value": r["surfaces_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{r['passes']} x {r['scenes']} of {scenes} scenes of {wl.name}, {r['seconds']:.1f} s",
-                        "element_pairs_per_sec": r["element_pairs_per_s"],
-                        "single_thread": {"value": r1["surfaces_per_s"], "scenes": r1["scenes"],
-                                          "element_pairs_per_sec": r1["element_pairs_per_s"]}}
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-           "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic",
-           "config": {"workload": wl.name, "description": wl.description, "scenes_per_gpu": scenes,
-                      "geometries_per_scene": G, "representation": args.rep,
-                      "l2": "256 MB L2 flush between steps; work lists and outputs stream through HBM, the "
-                            "instanced mesh assets are L2-resident by design"},
-           "element_pairs_per_sec": pairs / sec, "bv_pair_tests_per_sec": bvtests / sec, "faces_per_sec": faces / sec,
-           "surfaces_per_step": surfaces / K, "element_pairs_per_step": pairs / K,
-           "wall_ms_per_step_incl_flush_and_sync": 1e3 * wall / K,
-           "e2e": e2e, "gpu_launches": launches_per_step * K, "clocks": clocks, "roofline": roofline,
-           "cpu_baseline": cpu_baseline}
+    other = None
+    if D.world == 1:
+        os.sched_setaffinity(0, all_cpus)   # the CPU legs get every host core again
+        if not args.no_cpu_baseline:
+            cpu_baseline = cpu_baseline_record(args.config, scenes, 1 if rep_name == "polygon" else 0, args.cpu_seconds)
+        if not args.no_other_configs and args.config == "c3" and not args.scenes:
+            other = {}
+            for cfg in ("c1", "c2", "c4", "c5"):
+                try:
+                    other[cfg] = other_config_line(D, cfg, flush, min(6.0, args.cpu_seconds), not args.no_cpu_baseline)
+                except Exception as ex:  # a failing side config must not take the headline with it
+                    other[cfg] = {"error": f"{type(ex).__name__}: {ex}"}
+    out = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+           "element_pairs_per_sec": res["element_pairs_per_sec"], "bv_pair_tests_per_sec": res["bv_pair_tests_per_sec"],
+           "faces_per_sec": res["faces_per_sec"], "surfaces_per_step": res["surfaces_per_step"],
+           "element_pairs_per_step": res["element_pairs_per_step"],
+           "wall_ms_per_step_incl_flush_and_sync": res["wall_ms_per_step_incl_flush_and_sync"],
+           "e2e": e2e, "gpu_launches": res["launches_per_step"] * args.steps, "clocks": res["clocks"], "roofline": roofline,
+           "cpu_baseline": cpu_baseline, "strong_scaling": strong, "other_configs": other}
     emit(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

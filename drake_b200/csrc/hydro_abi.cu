@@ -334,6 +334,10 @@ struct dbh_context {
   }
 };
 
+// Timing marks per chunk of scenes: pose + root | per-level descent | cull tet-tri (k_filter + k_small_pairs) | cull
+// tet-tet | exact clip tet-tri | exact clip tet-tet (+ exceptional) | half-space setup + count | scan | pack | surface.
+constexpr int kStageEvents = 11;
+
 struct dbh_batch {
   dbh_context* ctx{nullptr};
   cudaStream_t stream{nullptr};
@@ -364,7 +368,9 @@ struct dbh_batch {
   DevBuf<long long> d_plane_elem_off;
   // Contact-surface consumer (k_wrench): per-geometry body origins / spatial velocities / contact properties and the
   // per-surface spatial forces.
-  DevBuf<double> d_body_origin, d_body_vel, d_props, d_forces;
+  DevBuf<double> d_body_origin, d_body_vel, d_props, d_forces, d_discrete;
+  bool discrete_done{false};
+  long long discrete_pairs{0};
   bool have_body_origin{false}, have_body_vel{false}, have_props{false}, forces_done{false};
   // Small pairs (both trees at most kSmallMaxNodes nodes): k_small_pairs descends and culls them on chip, one warp
   // per pair. small_mode: 0 never, 1 whenever a pair is eligible, 2 (default) when a chunk holds enough eligible
@@ -417,12 +423,14 @@ struct dbh_batch {
   bool query_enqueued{false};
   bool timing{false};
   bool verify{false};
+  bool normal_filter{true};
   int last_launches{0};   // kernels launched by the last query
   // Timing (optional): two events around the whole query, eight per chunk around its stages.
   cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
-  std::vector<cudaEvent_t> ev_chunk;   // 8 per chunk that ran in the last query
+  std::vector<cudaEvent_t> ev_chunk;   // kStageEvents per chunk that ran in the last query
   int timed_chunks{0};
   float times_ms[8]{};
+  float stage_ms[kStageEvents]{};      // kStageEvents - 1 stages, then the whole query
 
   ~dbh_batch() {
     if (h_counters) cudaFreeHost(h_counters);
@@ -1139,6 +1147,12 @@ dbh_status dbh_batch_set_record_candidates(dbh_batch* b, int32_t enabled) {
   });
 }
 
+dbh_status dbh_batch_set_normal_filter(dbh_batch* b, int32_t enabled) {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  b->normal_filter = enabled != 0;
+  return DBH_OK;
+}
+
 dbh_status dbh_batch_set_verify(dbh_batch* b, int32_t enabled) {
   return Guarded([&]() -> dbh_status {
   if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
@@ -1159,12 +1173,13 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   b->query_done = false;
   b->query_enqueued = true;
   b->forces_done = false;
+  b->discrete_done = false;
   b->last_launches = 0;
   b->last_query_kind = query_kind;
   cudaStream_t st = b->stream;
   const int sms = ctx->prop.multiProcessorCount;
   if (b->timing) {
-    while (b->ev_chunk.size() < 8u * static_cast<size_t>(b->num_chunks)) {
+    while (b->ev_chunk.size() < static_cast<size_t>(kStageEvents) * static_cast<size_t>(b->num_chunks)) {
       cudaEvent_t e = nullptr;
       CUDA_OK(cudaEventCreate(&e));
       b->ev_chunk.push_back(e);
@@ -1173,7 +1188,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   }
   b->timed_chunks = 0;
   auto mark = [&](int i) {
-    if (b->timing) cudaEventRecord(b->ev_chunk[8 * b->timed_chunks + i], st);
+    if (b->timing) cudaEventRecord(b->ev_chunk[kStageEvents * b->timed_chunks + i], st);
   };
   CUDA_OK(cudaMemsetAsync(b->d_counters.p, 0, sizeof(Counters), st));
   if (scene_stats_dev)
@@ -1222,6 +1237,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     ca.slow = b->d_slow.p;
     ca.slow_capacity = static_cast<unsigned int>(b->cap_slow);
     ca.verify = b->verify ? 1 : 0;
+    ca.no_normal_filter = b->normal_filter ? 0 : 1;
     ca.trace = make_int4(-1, -1, -1, 0);
 #ifdef DBH_TRACE
     if (const char* t = std::getenv("DBH_TRACE_PAIR")) {
@@ -1375,56 +1391,54 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       // The generic pairs' leaf lists go through the filter first (the survivor lists reuse the frontier buffers,
       // which the descent has released); then the small pairs are descended and culled on chip and append their
       // survivors to the same lists; then the exact stage runs over both.
-      if (generic && b->info.num_soft_rigid_pairs) {
-        ca.cand = b->d_cand_tri.p;
-        ca.cand_capacity = static_cast<unsigned long long>(b->cap_tri);
-        ca.surv = b->d_frontier[0].p;
-        ++b->last_launches;
-        if (tune.filter == 4) k_filter<false, 4><<<sms * 4 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-        else if (tune.filter == 2) k_filter<false, 2><<<sms * 2 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-        else k_filter<false, 3><<<sms * 3 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-      }
-      if (generic && b->info.num_soft_soft_pairs) {
-        ca.cand = b->d_cand_tet.p;
-        ca.cand_capacity = static_cast<unsigned long long>(b->cap_tet);
-        ca.surv = b->d_frontier[1].p;
-        ++b->last_launches;
-        if (tune.filter == 4) k_filter<true, 4><<<sms * 4 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-        else if (tune.filter == 2) k_filter<true, 2><<<sms * 2 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-        else k_filter<true, 3><<<sms * 3 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-      }
-      if (use_small) {
-        b->small_used = true;
-        const int blocks = std::min(sms * tune.sblocks, (n_small + kSmallWarps - 1) / kSmallWarps);
-        if (b->info.num_soft_rigid_pairs) {
-          sm.small_list = pa.small_list;
-          sm.surv = b->d_frontier[0].p;
-          sm.cand = b->d_cand_tri.p;
-          sm.cand_capacity = static_cast<unsigned long long>(b->cap_tri);
-          ++b->last_launches;
-          if (tune.sblocks >= 6) k_small_pairs<false, 6><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-          else if (tune.sblocks == 5) k_small_pairs<false, 5><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-          else if (tune.sblocks == 4) k_small_pairs<false, 4><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-          else k_small_pairs<false, 3><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+      const int small_blocks = use_small ? std::min(sms * tune.sblocks, (n_small + kSmallWarps - 1) / kSmallWarps) : 0;
+      b->small_used = b->small_used || use_small;
+      for (int tet = 0; tet < 2; ++tet) {
+        if (!(tet ? b->info.num_soft_soft_pairs : b->info.num_soft_rigid_pairs)) {
+          mark(3 + tet);
+          continue;
         }
-        if (b->info.num_soft_soft_pairs) {
-          sm.small_list = pa.small_list_tet;
-          sm.surv = b->d_frontier[1].p;
-          sm.cand = b->d_cand_tet.p;
-          sm.cand_capacity = static_cast<unsigned long long>(b->cap_tet);
+        ca.cand = tet ? b->d_cand_tet.p : b->d_cand_tri.p;
+        ca.cand_capacity = static_cast<unsigned long long>(tet ? b->cap_tet : b->cap_tri);
+        ca.surv = b->d_frontier[tet].p;
+        if (generic) {
           ++b->last_launches;
-          if (tune.sblocks >= 6) k_small_pairs<true, 6><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-          else if (tune.sblocks == 5) k_small_pairs<true, 5><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-          else if (tune.sblocks == 4) k_small_pairs<true, 4><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-          else k_small_pairs<true, 3><<<blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          if (tet) {
+            if (tune.filter == 4) k_filter<true, 4><<<sms * 4 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+            else if (tune.filter == 2) k_filter<true, 2><<<sms * 2 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+            else k_filter<true, 3><<<sms * 3 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+          } else {
+            if (tune.filter == 4) k_filter<false, 4><<<sms * 4 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+            else if (tune.filter == 2) k_filter<false, 2><<<sms * 2 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+            else k_filter<false, 3><<<sms * 3 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+          }
         }
+        if (use_small) {
+          sm.small_list = tet ? pa.small_list_tet : pa.small_list;
+          sm.surv = ca.surv;
+          sm.cand = ca.cand;
+          sm.cand_capacity = ca.cand_capacity;
+          ++b->last_launches;
+          if (tet) {
+            if (tune.sblocks >= 6) k_small_pairs<true, 6><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+            else if (tune.sblocks == 5) k_small_pairs<true, 5><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+            else if (tune.sblocks == 4) k_small_pairs<true, 4><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+            else k_small_pairs<true, 3><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          } else {
+            if (tune.sblocks >= 6) k_small_pairs<false, 6><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+            else if (tune.sblocks == 5) k_small_pairs<false, 5><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+            else if (tune.sblocks == 4) k_small_pairs<false, 4><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+            else k_small_pairs<false, 3><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          }
+        }
+        mark(3 + tet);
       }
-      mark(3);
       if (b->info.num_soft_rigid_pairs) {
         ca.surv = b->d_frontier[0].p;
         ++b->last_launches;
         k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
       }
+      mark(5);
       if (b->info.num_soft_soft_pairs) {
         ca.surv = b->d_frontier[1].p;
         ++b->last_launches;
@@ -1433,6 +1447,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
       ++b->last_launches;
       k_clip_slow<<<sms, 64, 0, st>>>(ca);
+      mark(6);
       // Half-space pairs of this chunk: pose + root test per pair, then one thread per element (count pass).
       pl.q_begin = static_cast<int>(std::lower_bound(b->plane_pairs.begin(), b->plane_pairs.end(), p0) - b->plane_pairs.begin());
       pl.q_end = static_cast<int>(std::lower_bound(b->plane_pairs.begin(), b->plane_pairs.end(), p1) - b->plane_pairs.begin());
@@ -1444,7 +1459,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         k_plane_setup<<<(pl.q_end - pl.q_begin + 127) / 128, 128, 0, st>>>(pl);
         k_plane<false><<<plane_blocks, 128, 0, st>>>(pl);
       }
-      mark(4);
+      mark(7);
       sa.pair_begin = p0;
       sa.num_pairs = p1;
       sa.first_chunk = p0 == 0;
@@ -1455,7 +1470,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       k_scan_blocks<<<1, kScanThreads, 0, st>>>(sa);
       ++b->last_launches;
       k_scan_apply<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
-      mark(5);
+      mark(8);
       ++b->last_launches;
       if (tune.pack == 4) k_pack<4><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
       else k_pack<3><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
@@ -1463,7 +1478,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ++b->last_launches;
         k_plane<true><<<plane_blocks, 128, 0, st>>>(pl);
       }
-      mark(6);
+      mark(9);
       su.pair_begin = p0;
       su.pair_end = p1;
       b->last_launches += 3;
@@ -1472,7 +1487,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       k_surface_big_finish<<<1, 128, 0, st>>>(su);
       ++b->last_launches;
       k_next_chunk<<<1, 64, 0, st>>>(b->d_counters.p);
-      mark(7);
+      mark(10);
       if (b->timing) ++b->timed_chunks;
     }
     ++b->last_launches;
@@ -1496,15 +1511,18 @@ dbh_status dbh_batch_sync(dbh_batch* b) {
   CUDA_OK(cudaSetDevice(b->ctx->device));
   CUDA_OK(cudaStreamSynchronize(b->stream));
   if (b->timing) {
-    // {pose+root, traversal, clip tri, clip tet, scan, pack, surface+finalize, total}
-    float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float st[kStageEvents] = {};
     for (int c = 0; c < b->timed_chunks; ++c)
-      for (int i = 0; i < 7; ++i) {
+      for (int i = 0; i + 1 < kStageEvents; ++i) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, b->ev_chunk[8 * c + i], b->ev_chunk[8 * c + i + 1]);
-        t[i] += ms;
+        cudaEventElapsedTime(&ms, b->ev_chunk[kStageEvents * c + i], b->ev_chunk[kStageEvents * c + i + 1]);
+        st[i] += ms;
       }
-    cudaEventElapsedTime(&t[7], b->ev_begin, b->ev_end);
+    cudaEventElapsedTime(&st[kStageEvents - 1], b->ev_begin, b->ev_end);
+    std::memcpy(b->stage_ms, st, sizeof(st));
+    // The eight figures of dbh_batch_kernel_times_ms: {pose+root, per-level descent, narrow phase tet-tri (cull +
+    // exact clip), narrow phase tet-tet (cull + exact clip + half-space count), scan, pack, surface, total}.
+    const float t[8] = {st[0], st[1], st[2] + st[4], st[3] + st[5] + st[6], st[7], st[8], st[9], st[kStageEvents - 1]};
     std::memcpy(b->times_ms, t, sizeof(t));
   }
   const Counters& c = *b->h_counters;
@@ -1651,6 +1669,67 @@ dbh_status dbh_batch_copy_spatial_forces(dbh_batch* b, double* F_Ac_W, double* F
   });
 }
 
+dbh_status dbh_batch_copy_spatial_forces_async(dbh_batch* b, double* out18, int64_t* num_surfaces) {
+  return Guarded([&]() -> dbh_status {
+  if (!b || !num_surfaces) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_spatial_forces_async: bad argument");
+  if (!b->query_done || !b->forces_done)
+    return Fail(DBH_ERR_NOT_READY, "dbh_batch_compute_spatial_forces + dbh_batch_sync first");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  const size_t ns = static_cast<size_t>(b->h_counters->surfaces);
+  *num_surfaces = static_cast<int64_t>(ns);
+  if (out18 && ns)
+    CUDA_OK(cudaMemcpyAsync(out18, b->d_forces.p, ns * 18 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  return DBH_OK;
+  });
+}
+
+dbh_status dbh_batch_compute_discrete_pairs(dbh_batch* b) {
+  return Guarded([&]() -> dbh_status {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  if (!b->query_enqueued) return Fail(DBH_ERR_NOT_READY, "no query enqueued");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  // Sized for the face capacity: the face count of the query is still on the device.
+  CUDA_OK(b->d_discrete.ensure(static_cast<size_t>(std::max<long long>(b->cap_faces, 1)) * 9));
+  DiscreteArgs da{};
+  da.pairs = b->d_pairs.p;
+  da.face_pair = b->r_face_pair.p;
+  da.areas = b->r_areas.p;
+  da.normals = b->r_normals.p;
+  da.centroids = b->r_centroids.p;
+  da.e_centroid = b->r_e_centroid.p;
+  da.grad_eM = b->r_grad_eM.p;
+  da.grad_eN = b->r_grad_eN.p;
+  da.out = b->d_discrete.p;
+  da.counters = b->d_counters.p;
+  CUDA_OK(cudaMemsetAsync(&b->d_counters.p->discrete_pairs, 0, sizeof(unsigned long long), b->stream));
+  k_discrete<<<b->ctx->prop.multiProcessorCount * 8, 256, 0, b->stream>>>(da);
+  CUDA_OK(cudaMemcpyAsync(&b->h_counters->discrete_pairs, &b->d_counters.p->discrete_pairs, sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaGetLastError());
+  b->discrete_done = true;
+  return DBH_OK;
+  });
+}
+
+dbh_status dbh_batch_copy_discrete_pairs_async(dbh_batch* b, double* out, int64_t* num_faces) {
+  return Guarded([&]() -> dbh_status {
+  if (!b || !num_faces) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_discrete_pairs: bad argument");
+  if (!b->query_done || !b->discrete_done)
+    return Fail(DBH_ERR_NOT_READY, "dbh_batch_compute_discrete_pairs + dbh_batch_sync first");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  const size_t nf = b->h_counters->faces;
+  *num_faces = static_cast<int64_t>(nf);
+  if (out && nf) CUDA_OK(cudaMemcpyAsync(out, b->d_discrete.p, nf * 9 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  return DBH_OK;
+  });
+}
+
+dbh_status dbh_batch_stage_times_ms(dbh_batch* b, float* out, int32_t n) {
+  if (!b || !out || n < 0) return Fail(DBH_ERR_INVALID_ARGUMENT, "stage_times: bad argument");
+  for (int i = 0; i < n; ++i) out[i] = i < kStageEvents ? b->stage_ms[i] : 0.f;
+  return DBH_OK;
+}
+
 dbh_status dbh_batch_kernel_times_ms(dbh_batch* b, float* out8) {
   return Guarded([&]() -> dbh_status {
   if (!b || !out8) return Fail(DBH_ERR_INVALID_ARGUMENT, "kernel_times: bad argument");
@@ -1687,6 +1766,8 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->half_space_elements = static_cast<int64_t>(c.plane_tets + c.plane_tris);
   out->geometry_pairs_overlapping = static_cast<int64_t>(c.root_overlaps);
   out->bv_pair_tests = static_cast<int64_t>(c.bv_tests);
+  out->bv_pair_tests_tet_tet = static_cast<int64_t>(c.bv_tests_tet);
+  out->leaf_pairs_tet_tet = static_cast<int64_t>(c.leaf_tet_total + c.small_leaf_tet);
   out->leaf_pairs = static_cast<int64_t>(c.leaf_tri_total + c.leaf_tet_total + c.small_leaf_tri + c.small_leaf_tet);
   out->cull_violations = static_cast<int64_t>(c.cull_violations);
   out->exceptional_clips = static_cast<int64_t>(c.slow_total);
@@ -1700,6 +1781,7 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->total_area = c.total_area;
   out->tet_tri_full_clips = static_cast<int64_t>(c.full_clips_tri);
   out->tet_tet_full_clips = static_cast<int64_t>(c.full_clips_tet);
+  out->discrete_pairs = b->discrete_done ? static_cast<int64_t>(c.discrete_pairs) : 0;
   out->fallback_pairs = b->last_query_kind == DBH_QUERY_WITH_FALLBACK ? static_cast<int64_t>(c.fallback) : 0;
   // BV test 64 B (two 32 B fp32 nodes; SURVEY.md §8(d) counts 128 B for the
   // reference-shaped fp64 node); tet-tri pair 260 B in; tet-tet pair 392 B in;

@@ -231,9 +231,11 @@ __global__ void k_pairs(PairsArgs a) {
     // (kSoftMeshRigidPlane / kSoftPlaneRigidMesh: k_plane_setup poses the half space and tests the mesh's root box.)
   }
   const unsigned tests = __ballot_sync(0xffffffffu, tested);
+  const unsigned tests_tet = __ballot_sync(0xffffffffu, tested && pr.kind == kSoftSoft);
   const unsigned hits = __ballot_sync(0xffffffffu, push);
   if ((threadIdx.x & 31) == 0) {
     if (tests) atomicAdd(&a.counters->bv_tests, (unsigned long long)__popc(tests));
+    if (tests_tet) atomicAdd(&a.counters->bv_tests_tet, (unsigned long long)__popc(tests_tet));
     if (hits) atomicAdd(&a.counters->root_overlaps, (unsigned long long)__popc(hits));
   }
   // Small pairs (both trees fit 15-bit node indices) are descended by one warp each in k_small_pairs.
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_traverse(TraverseArgs 
   // with DBH_ERR_CAPACITY); never read past the stored entries.
   const unsigned long long count = min(a.counters->frontier[a.level], a.out_capacity);
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
-  unsigned int tests = 0;
+  unsigned int tests = 0, tests_tet = 0;
   // Whole blocks stay in the loop: the appends are block-wide. (A two-deep software pipeline with L1
   // prefetches, which pays in the filter kernel, was measured here and does not: the nodes of the batched
   // configs are L1-resident and the extra registers spill.)
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_traverse(TraverseArgs 
       child_b0 = B[0].child;
       child_b1 = B[1].child;
       tests = tests + na * nb;
+      if (e.w == kSoftSoft) tests_tet = tests_tet + na * nb;
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb) {
         if (jb < nb) {
@@ -403,8 +406,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_traverse(TraverseArgs 
   }
   // One atomic per warp for the test count.
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) tests += __shfl_xor_sync(0xffffffffu, tests, d);
+  for (int d = 16; d > 0; d >>= 1) {
+    tests += __shfl_xor_sync(0xffffffffu, tests, d);
+    tests_tet += __shfl_xor_sync(0xffffffffu, tests_tet, d);
+  }
   if ((threadIdx.x & 31) == 0 && tests) atomicAdd(&a.counters->bv_tests, (unsigned long long)tests);
+  if ((threadIdx.x & 31) == 0 && tests_tet) atomicAdd(&a.counters->bv_tests_tet, (unsigned long long)tests_tet);
 }
 
 // ---------------------------------------------------------------------------
@@ -472,6 +479,10 @@ struct ClipArgs {
   // Self-check mode (dbh_batch_set_verify): the exact stage runs for EVERY candidate and
   // Counters::cull_violations_* count polygons emitted by candidates stage A had rejected.
   int verify;
+  // Tet-triangle pairs without IsFaceNormalAlongPressureGradient: SurfaceVolumeIntersector::SampleVolumeFieldOnSurface's
+  // filter_face_normal_along_field_gradient = false (mesh_intersection.h), which is how the reference's own
+  // mesh_intersection_benchmark runs it. ComputeContactSurfaces always filters (the default).
+  int no_normal_filter;
   int4 trace;           // debug builds only
 };
 
@@ -696,7 +707,7 @@ __device__ __forceinline__ bool tri_stage_a(const ClipArgs& a, int4 c, const Pai
   // Gradient filter (certain rejections only).
   const F3 nhat = rotf(X, f3(tri.n));
   const bool unit = fabsf(dotf(nhat, nhat) - 1.0f) < 1e-4f;
-  if (unit && dotf(f3(ta.grad), nhat) * tb.inv_grad_len < kCosAlphaF - 1e-3f) return false;
+  if (unit && !a.no_normal_filter && dotf(f3(ta.grad), nhat) * tb.inv_grad_len < kCosAlphaF - 1e-3f) return false;
   const F3 q0 = xformf(X, f3(tri.v[0])), q1 = xformf(X, f3(tri.v[1])), q2 = xformf(X, f3(tri.v[2]));
   F3 v[4];
   float L = fmaxf(fmaxf(abs_sumf(q0), abs_sumf(q1)), abs_sumf(q2));
@@ -761,7 +772,7 @@ __device__ __forceinline__ void tri_stage_b(const ClipArgs& a, Poly& P, int4 c, 
     p_mo = tet.p_mo;
     // IsFaceNormalAlongPressureGradient (mesh_intersection.cc:266-288).
     nhat_M = rot(X, load3(tri.n));
-    if (face_normal_along_gradient(load3(aux.ngrad), nhat_M)) {
+    if (a.no_normal_filter || face_normal_along_gradient(load3(aux.ngrad), nhat_M)) {
       // ClipTriangleByTetrahedron (mesh_intersection.cc:176-264) with the face
       // half spaces precomputed at registration (TetAux).
       n = 3;
@@ -2090,6 +2101,50 @@ __global__ void __launch_bounds__(128) k_wrench(WrenchArgs a) {
       store3(out, 5, F_Bo.trans);
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// k_discrete: the geometry-only half of DiscreteUpdateManager::AppendDiscreteContactPairsForHydroelasticContact
+// (discrete_update_manager.cc:896-1036) over the packed, device-resident results of the last query: one thread per
+// face, 9 doubles out per face (p_WC, nhat_BA_W, phi0, fn0, stiffness; stiffness == 0 marks a face the reference
+// skips), in face order, so face f of surface s is record surf_face_offset[s] + f. 72 B per face leave the GPU
+// instead of the ~250 B of the complete ContactSurface.
+struct DiscreteArgs {
+  const PairRec* pairs;
+  const int* face_pair;
+  const double* areas;
+  const double* normals;
+  const double* centroids;
+  const double* e_centroid;
+  const double* grad_eM;
+  const double* grad_eN;
+  double* out;             // [num_faces * 9]
+  Counters* counters;
+};
+
+__global__ void __launch_bounds__(256) k_discrete(DiscreteArgs a) {
+  if (a.counters->error != 0) return;
+  const long long num_faces = (long long)a.counters->faces;
+  unsigned int kept = 0;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < num_faces; f += (long long)gridDim.x * blockDim.x) {
+    const PairRec& pr = a.pairs[a.face_pair[f]];
+    // bit0 HasGradE_M, bit1 HasGradE_N as k_surface reports them: both for two compliant bodies; else the compliant
+    // body is M unless the ids were swapped.
+    const bool both = pr.kind == kSoftSoft;
+    const bool has_M = both || !pr.swapped, has_N = both || pr.swapped;
+    DiscreteFacePair d;
+    kept += discrete_face_pair(a.areas[f], load3(a.normals + 3 * f), load3(a.centroids + 3 * f), a.e_centroid[f],
+                               load3(a.grad_eM + 3 * f), load3(a.grad_eN + 3 * f), has_M, has_N, &d);
+    double* o = a.out + 9 * f;
+    store3(o, 0, d.p_WC);
+    store3(o, 1, d.nhat_BA_W);
+    o[6] = d.phi0;
+    o[7] = d.fn0;
+    o[8] = d.stiffness;
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, k);
+  if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&a.counters->discrete_pairs, (unsigned long long)kept);
 }
 
 }  // namespace dbh

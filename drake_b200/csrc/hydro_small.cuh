@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
   if (fill > 0 && !failed) flush(fill);
   if (lane == 0) {
     if (n_tests) atomicAdd(&ctr->bv_tests, (unsigned long long)n_tests);
+    if (kTet && n_tests) atomicAdd(&ctr->bv_tests_tet, (unsigned long long)n_tests);
     if (n_cand) atomicAdd(kTet ? &ctr->cand_tet : &ctr->cand_tri, (unsigned long long)n_cand);
     if (n_exact) atomicAdd(&ctr->leaf_exact, (unsigned long long)n_exact);
     // (Recording mode counts the leaf pairs through the leaf-list cursors.)

@@ -209,6 +209,8 @@ struct Counters {
   unsigned long long small_work[2];  // next unclaimed entry of each list
   // -- whole query
   unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
+  unsigned long long bv_tests_tet;  // of which: between two tetrahedron trees (the rest: tetrahedron x triangle trees,
+                                    // plus one per half-space pair)
   unsigned long long cand_tri;      // tet-tri candidate pairs: leaf pairs that pass the exact predicate
   unsigned long long cand_tet;      // tet-tet candidate pairs
   unsigned long long poly_verts;    // sum of polygon vertex counts
@@ -224,6 +226,7 @@ struct Counters {
   unsigned long long cull_violations; // verify mode: polygons from candidates the conservative cull rejected
   unsigned long long plane_tets;      // tetrahedra sliced by a rigid half space (k_plane, active pairs only)
   unsigned long long plane_tris;      // triangles clipped by a compliant half space
+  unsigned long long discrete_pairs;  // k_discrete: faces that give a discrete contact pair (zeroed by its launch)
   unsigned long long small_leaf_tri;  // leaf pairs k_small_pairs filtered on chip (not recording: they never reach a list)
   unsigned long long small_leaf_tet;
   // -- totals and per-chunk maxima of the chunk-local cursors

@@ -118,4 +118,37 @@ __host__ __device__ __forceinline__ void shift_to_body_origins(const TractionBod
   *F_Bo_W = Spatial6{-s.rot, -s.trans};
 }
 
+// The geometry-only half of DiscreteUpdateManager::AppendDiscreteContactPairsForHydroelasticContact
+// (multibody/plant/discrete_update_manager.cc:896-1036): what the discrete solvers read from one face of a contact
+// surface -- first-order quadrature, one point per face at its centroid. The other half (Jacobians, vn0, friction
+// and dissipation look-ups) needs the plant's kinematic tree and stays on the host.
+struct DiscreteFacePair {
+  D3 p_WC;        // quadrature point = face centroid                                  (:965-967)
+  D3 nhat_BA_W;   // face normal, out of N into M                                      (:926-929)
+  double phi0;    // -p0 / g, negative in penetration                                  (:1028-1029)
+  double fn0;     // Ae * p0                                                           (:1017-1018)
+  double stiffness;  // k = Ae * g; 0 marks a face the reference skips                  (:1025)
+};
+// has_M / has_N: HasGradE_M / HasGradE_N of the surface. Returns false for the faces the reference skips:
+// Ae <= 1e-14 (:909-919) or a pressure gradient along the normal below 1e-14 on either side (:941-949).
+__host__ __device__ __forceinline__ bool discrete_face_pair(double Ae, D3 nhat_BA_W, D3 p_WC, double p0, D3 grad_eM_W,
+                                                            D3 grad_eN_W, bool has_M, bool has_N, DiscreteFacePair* out) {
+  out->p_WC = p_WC;
+  out->nhat_BA_W = nhat_BA_W;
+  out->phi0 = 0.0;
+  out->fn0 = 0.0;
+  out->stiffness = 0.0;
+  if (!(Ae > 1.0e-14)) return false;
+  const double kInf = 1.0 / 0.0;
+  const double gM = has_M ? dot(grad_eM_W, nhat_BA_W) : kInf;
+  const double gN = has_N ? -dot(grad_eN_W, nhat_BA_W) : kInf;
+  const double kGradientEpsilon = 1.0e-14;
+  if (gM < kGradientEpsilon || gN < kGradientEpsilon) return false;
+  const double g = 1.0 / (1.0 / gM + 1.0 / gN);
+  out->fn0 = Ae * p0;
+  out->stiffness = Ae * g;
+  out->phi0 = -p0 / g;
+  return true;
+}
+
 }  // namespace dbh

@@ -78,7 +78,9 @@ class Stats(C.Structure):
                  "tet_tet_pairs", "polygons", "faces", "vertices", "surfaces", "algorithmic_bytes")] + \
                [("total_area", C.c_double), ("tet_tri_full_clips", C.c_int64), ("tet_tet_full_clips", C.c_int64),
                 ("leaf_pairs", C.c_int64), ("cull_violations", C.c_int64), ("exceptional_clips", C.c_int64),
-                ("leaf_exact_tests", C.c_int64), ("half_space_elements", C.c_int64), ("fallback_pairs", C.c_int64)]
+                ("leaf_exact_tests", C.c_int64), ("half_space_elements", C.c_int64), ("bv_pair_tests_tet_tet", C.c_int64),
+                ("leaf_pairs_tet_tet", C.c_int64), ("discrete_pairs", C.c_int64),
+                ("fallback_pairs", C.c_int64)]
 
 
 _lib = None
@@ -133,13 +135,18 @@ def lib():
     L.dbh_batch_set_contact_properties.argtypes = [vp, _dp, _dp, _dp]
     L.dbh_batch_compute_spatial_forces.argtypes = [vp, C.c_double]
     L.dbh_batch_copy_spatial_forces.argtypes = [vp, _dp, _dp, _dp]
+    L.dbh_batch_copy_spatial_forces_async.argtypes = [vp, vp, _lp]
+    L.dbh_batch_compute_discrete_pairs.argtypes = [vp]
+    L.dbh_batch_copy_discrete_pairs_async.argtypes = [vp, vp, _lp]
     L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_verify.argtypes = [vp, C.c_int32]
+    L.dbh_batch_set_normal_filter.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_small_pair_path.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_geometry_bounds.argtypes = [vp, _dp]
     L.dbh_batch_copy_fallback_pairs.argtypes = [vp, _ip, _lp]
     L.dbh_batch_set_record_candidates.argtypes = [vp, C.c_int32]
     L.dbh_batch_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.dbh_batch_stage_times_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int32]
     L.dbh_mesh_last_error.restype = C.c_char_p
     dbl = C.c_double
     L.dbh_mesh_make_sphere_volume.argtypes = [dbl, dbl, C.c_int32, C.POINTER(vp)]
@@ -591,6 +598,11 @@ class SceneBatch:
             _check(lib().dbh_batch_copy_fallback_pairs(self._h, _ptr(out, _ip), C.byref(n)))
         return out
 
+    def set_normal_filter(self, on: bool = True):
+        """Rigid-compliant mesh pairs with (default, ComputeContactSurfaces) or without the face-normal filter (the
+        reference's mesh_intersection_benchmark)."""
+        _check(lib().dbh_batch_set_normal_filter(self._h, int(on)))
+
     def set_small_pair_path(self, mode: int):
         """Mid phase of small geometry pairs on chip, one warp per pair (k_small_pairs): 0 never, 1 every eligible
         pair, 2 (default) when a chunk holds enough of them to fill the device."""
@@ -707,6 +719,39 @@ class SceneBatch:
         _check(lib().dbh_batch_copy_spatial_forces(self._h, *[_ptr(o, _dp) for o in out]))
         return tuple(out)
 
+    def compute_discrete_pairs(self):
+        """Enqueues the per-face discrete contact data of the last query's surfaces (discrete_update_manager.cc:896-1036)."""
+        _check(lib().dbh_batch_compute_discrete_pairs(self._h))
+
+    def copy_discrete_pairs(self, out=None, wait: bool = True):
+        """[num_faces, 9] = p_WC, nhat_BA_W, phi0, fn0, stiffness (0: a face the reference skips). `out`: a (pinned)
+        buffer of at least that size; wait=False leaves the copy in flight (complete with sync())."""
+        n = C.c_int64(0)
+        _check(lib().dbh_batch_copy_discrete_pairs_async(self._h, None, C.byref(n)))
+        if out is None:
+            out = np.zeros((n.value, 9))
+        view = out.reshape(-1)[: n.value * 9].reshape(n.value, 9)
+        if n.value:
+            _check(lib().dbh_batch_copy_discrete_pairs_async(self._h, view.ctypes.data, C.byref(n)))
+        if wait:
+            self.sync()
+        return view
+
+    def compute_spatial_forces(self, vslip_regularizer: float = 1e-6):
+        """Enqueues k_wrench over the last query's surfaces (no host sync)."""
+        _check(lib().dbh_batch_compute_spatial_forces(self._h, float(vslip_regularizer)))
+
+    def copy_spatial_forces(self, out, wait: bool = True) -> int:
+        """After sync(): one D2H copy of [num_surfaces, 18] = F_Ac_W, F_Ao_W, F_Bo_W per surface into `out` (a pinned
+        buffer of at least that size); returns num_surfaces. wait=False leaves the copy in flight."""
+        n = C.c_int64(0)
+        _check(lib().dbh_batch_copy_spatial_forces_async(self._h, None, C.byref(n)))
+        if n.value:
+            _check(lib().dbh_batch_copy_spatial_forces_async(self._h, out.ctypes.data, C.byref(n)))
+        if wait:
+            self.sync()
+        return int(n.value)
+
     def candidates(self, kind: int) -> np.ndarray:
         """(geometry pair, element of first body, element of second body) triples; kind 0 tet-tri, 1 tet-tet."""
         n = C.c_int64()
@@ -728,6 +773,15 @@ class SceneBatch:
         _check(lib().dbh_batch_kernel_times_ms(self._h, t))
         keys = ["pose_root", "traverse", "clip_tet_tri", "clip_tet_tet", "scan", "pack", "surface", "total"]
         return dict(zip(keys, [float(x) for x in t]))
+
+    STAGES = ("pose_root", "traverse", "cull_tet_tri", "cull_tet_tet", "clip_tet_tri", "clip_tet_tet", "half_space",
+              "scan", "pack", "surface", "total")
+
+    def stage_times_ms(self) -> Dict[str, float]:
+        """Device time of the last query per stage (enable_timing): cull = k_filter + k_small_pairs, clip = k_clip."""
+        t = (C.c_float * len(self.STAGES))()
+        _check(lib().dbh_batch_stage_times_ms(self._h, t, len(self.STAGES)))
+        return dict(zip(self.STAGES, [float(x) for x in t]))
 
     def stream(self) -> int:
         return int(lib().dbh_batch_stream(self._h) or 0)

@@ -1,7 +1,10 @@
 """BASELINE.json configs as concrete synthetic inputs.
 
 Meshes come from the library's own generators (drake_b200.Mesh, the product
-side of MakeSphereVolumeMesh / MakeEllipsoidVolumeMesh / MakeBoxVolumeMesh*),
+side of MakeSphereVolumeMesh / MakeEllipsoidVolumeMesh / MakeBoxVolumeMesh*) --
+or, when a config is given another mesh factory with the same constructors
+(`Mesh=`; the reference arm of bench.py passes the CPU checker's, so that it never
+maps the product library), from that one --
 poses from a counter-based RNG (SceneDraws: draw k of scene i is a pure
 function of (config, i, k)) so any rank can generate any scene range.
 
@@ -126,6 +129,8 @@ class Workload:
     representation: int = POLYGON
     excluded_local: Optional[np.ndarray] = None
     per_scene_mesh: Optional[np.ndarray] = None  # [S, G] mesh index when scenes differ in assets
+    normal_filter: bool = True         # False: the reference's mesh_intersection_benchmark runs its intersector with
+                                       # filter_face_normal_along_field_gradient = false
 
     @property
     def num_scenes(self) -> int:
@@ -145,13 +150,19 @@ class Workload:
         self.assets = list(assets)
         S, G = self.num_scenes, self.geoms_per_scene
         if self.per_scene_mesh is None:
-            return SceneBatch.replicated(ctx, S, [assets[i] for i in self.geom_mesh], self.geom_id,
-                                         self.geom_anchored, self.excluded_local)
+            batch = SceneBatch.replicated(ctx, S, [assets[i] for i in self.geom_mesh], self.geom_id,
+                                          self.geom_anchored, self.excluded_local)
+            if not self.normal_filter:
+                batch.set_normal_filter(False)
+            return batch
         so = np.arange(S + 1, dtype=np.int32) * G
         ga = np.asarray(assets, np.int32)[self.per_scene_mesh.reshape(-1)]
         gi = np.tile(np.asarray(self.geom_id, np.int64), S)
         an = np.tile(np.asarray(self.geom_anchored, np.uint8), S)
-        return SceneBatch(ctx, so, ga, gi, an, None)
+        batch = SceneBatch(ctx, so, ga, gi, an, None)
+        if not self.normal_filter:
+            batch.set_normal_filter(False)
+        return batch
 
 
 # ------------------------------------------------------------------ C1 / C2 ---
@@ -162,7 +173,7 @@ _HINTS = [4.0, 3.0, 2.0, 1.0]
 _TRANS = [(7, 7, 7), (4, 4, 4), (3.5, 3.5, 3.5), (1.2, 1.2, 1.2), (0, 0, 0)]
 
 
-def config1(args=C1_ARGS) -> Workload:
+def config1(args=C1_ARGS, Mesh=Mesh) -> Workload:
     """geometry/benchmarking/mesh_intersection_benchmark.cc:153-271, one scene per argument triple."""
     meshes, index = [], {}
     for res in sorted({a[0] for a in args}):
@@ -178,7 +189,7 @@ def config1(args=C1_ARGS) -> Workload:
                     meshes, [0, 1], [1, 2], [0, 0], poses, TRIANGLE, None, per_scene)
 
 
-def config2(resolutions=(0, 1, 2, 3), overlaps=(0, 1, 2, 3)) -> Workload:
+def config2(resolutions=(0, 1, 2, 3), overlaps=(0, 1, 2, 3), Mesh=Mesh) -> Workload:
     """geometry/benchmarking/compliant_mesh_intersection_benchmark.cc:112-202."""
     meshes, index = [], {}
     for res in resolutions:
@@ -194,7 +205,7 @@ def config2(resolutions=(0, 1, 2, 3), overlaps=(0, 1, 2, 3)) -> Workload:
                     [0, 1], [1, 2], [0, 0], poses, POLYGON, None, per_scene)
 
 
-def config2_spheres(num_scenes: int, scene0: int = 0, hint: float = 0.5) -> Workload:
+def config2_spheres(num_scenes: int, scene0: int = 0, hint: float = 0.5, Mesh=Mesh) -> Workload:
     """Two soft spheres r=3 (dense, fine resolution_hint) at random relative poses."""
     m = Mesh.sphere_volume(3.0, hint, DENSE_INTERIOR_VERTICES).set_sphere_pressure(3.0, 1e5)
     rng = SceneDraws(2, scene0, num_scenes)
@@ -208,7 +219,7 @@ def config2_spheres(num_scenes: int, scene0: int = 0, hint: float = 0.5) -> Work
 
 # ----------------------------------------------------------------------- C3 ---
 
-def config3(num_scenes: int = 16384, scene0: int = 0) -> Workload:
+def config3(num_scenes: int = 16384, scene0: int = 0, Mesh=Mesh) -> Workload:
     """examples/hydroelastic/ball_plate geometry, batched. Per scene: soft floor box 0.3x0.3x0.05
     (floor.sdf, E = 3e4, medial-axis mesh, 44 tets, anchored), rigid plate stand-in = box
     0.2x0.2x0.01 surface (24 triangles; plate_8in.sdf is external to the reference tree), soft ball
@@ -235,7 +246,7 @@ def config3(num_scenes: int = 16384, scene0: int = 0) -> Workload:
                     [floor, plate, ball], [0, 1, 2], [1, 2, 3], [1, 0, 0], poses, POLYGON)
 
 
-def config3_half_space(num_scenes: int = 16384, scene0: int = 0) -> Workload:
+def config3_half_space(num_scenes: int = 16384, scene0: int = 0, Mesh=Mesh) -> Workload:
     """The ball_plate scene on a rigid HalfSpace ground (the most common rigid geometry):
     rigid half space z <= 0 (anchored), the same soft ball (512 tets, E = 3e4) resting on it with penetration
     ~U(0, r/2) under a uniform random orientation, and the rigid plate (24 triangles) pressed ~U(0, r/4) into
@@ -263,7 +274,7 @@ def config3_half_space(num_scenes: int = 16384, scene0: int = 0) -> Workload:
 
 # ----------------------------------------------------------------------- C4 ---
 
-def config4(num_scenes: int = 4096, scene0: int = 0, bodies: int = 32) -> Workload:
+def config4(num_scenes: int = 4096, scene0: int = 0, bodies: int = 32, Mesh=Mesh) -> Workload:
     """Dense clutter: `bodies` soft bodies (half boxes via MakeBoxVolumeMesh hint 0.02, sizes
     ~U(0.04,0.10)^3; half dense ellipsoids, semi-axes ~U(0.02,0.05), hint 0.01) in a rigid bin of
     5 anchored box walls (interior 0.4x0.4x0.2). The body palette is shared by all scenes; poses
@@ -301,7 +312,7 @@ def config4(num_scenes: int = 4096, scene0: int = 0, bodies: int = 32) -> Worklo
 
 # ----------------------------------------------------------------------- C5 ---
 
-def config5(num_scenes: int = 1024, scene0: int = 0, hint: float = 0.03) -> Workload:
+def config5(num_scenes: int = 1024, scene0: int = 0, hint: float = 0.03, Mesh=Mesh) -> Workload:
     """High-resolution stress: two soft spheres r = 1, dense, hint 0.03 -> level 6, 2 097 152 tets
     each ("~1M tets" is not reachable: level 5 gives 262 144); one shared asset instanced twice per
     scene; centre distance ~U(1.2, 1.95), uniform relative orientation."""

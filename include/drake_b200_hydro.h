@@ -239,6 +239,25 @@ dbh_status dbh_batch_compute_spatial_forces(dbh_batch* batch, double vslip_regul
 /* Waits, then copies [num_surfaces*6] each, (tau, f) = SpatialForce's layout, surfaces in result order:
  * F_Ac_W about the surface centroid, F_Ao_W on body A at Ao, F_Bo_W on body B at Bo. Any may be NULL. */
 dbh_status dbh_batch_copy_spatial_forces(dbh_batch* batch, double* F_Ac_W, double* F_Ao_W, double* F_Bo_W);
+/* The same without waiting and without splitting: after dbh_batch_sync, enqueues one copy of [num_surfaces*18] =
+ * per surface F_Ac_W, F_Ao_W, F_Bo_W (6 doubles each) into out18 (pinned host memory; may be NULL to get the
+ * count); another dbh_batch_sync completes it. */
+dbh_status dbh_batch_copy_spatial_forces_async(dbh_batch* batch, double* out18, int64_t* num_surfaces);
+
+/* -- (5c) a second device-side consumer: the geometry-only half of
+ *        DiscreteUpdateManager::AppendDiscreteContactPairsForHydroelasticContact (multibody/plant/
+ *        discrete_update_manager.cc:896-1036), the per-face data the discrete contact solvers (SAP, TAMSI, ...) read
+ *        from a ContactSurface with first-order quadrature: one record of 9 doubles per face, in face order (face f
+ *        of surface s is record surf_face_offset[s] + f):
+ *          p_WC[3] (face centroid), nhat_BA_W[3] (face normal), phi0 = -p0 / g, fn0 = Ae p0, stiffness k = Ae g,
+ *        with g = 1 / (1 / gM + 1 / gN), gM = grad_eM . nhat (infinity for a rigid M), gN = -grad_eN . nhat.
+ *        stiffness == 0 marks a face the reference skips (Ae <= 1e-14, or gM or gN below 1e-14). Jacobians,
+ *        vn0, friction and dissipation need the plant's kinematic tree and stay on the host. Enqueued on the batch
+ *        stream after dbh_batch_query; copy after dbh_batch_sync (asynchronous: complete with another
+ *        dbh_batch_sync). 72 B per face leave the GPU instead of the complete mesh. ------------------------- */
+dbh_status dbh_batch_compute_discrete_pairs(dbh_batch* batch);
+dbh_status dbh_batch_copy_discrete_pairs_async(dbh_batch* batch, double* out /* [num_faces*9], may be NULL */,
+                                               int64_t* num_faces);
 
 /* -- (6) sizes of the last completed query. --------------------------------- */
 typedef struct dbh_result_sizes {
@@ -340,6 +359,9 @@ typedef struct dbh_stats {
   int64_t half_space_elements;     /* tetrahedra sliced by a rigid half space + triangles clipped by a compliant
                                       one (pairs whose root box reaches the boundary); 168 B / 108 B of
                                       algorithmic bytes each */
+  int64_t bv_pair_tests_tet_tet;   /* of bv_pair_tests: tests between two tetrahedron trees */
+  int64_t leaf_pairs_tet_tet;      /* of leaf_pairs: tetrahedron x tetrahedron */
+  int64_t discrete_pairs;          /* faces kept by dbh_batch_compute_discrete_pairs (0 if it did not run) */
   int64_t fallback_pairs;          /* WithFallback query: pairs handed to the point-pair narrow phase
                                       (dbh_batch_copy_fallback_pairs) */
 } dbh_stats;
@@ -374,15 +396,20 @@ dbh_status dbh_batch_copy_fallback_pairs(dbh_batch* batch, int32_t* out_quads, i
  * soft-soft, 2 rigid-rigid, 3 unsupported)}. out [num_geometry_pairs*4]. */
 dbh_status dbh_batch_copy_geometry_pairs(dbh_batch* batch, int32_t* out);
 
-/* Per-kernel device time of the last query in milliseconds (CUDA events on
- * the batch stream): {pose+root, traversal, clip tet-tri, clip tet-tet, scan,
- * pack, reduce, total}. Only recorded when enabled (adds event records). */
+/* Device time of the last query in milliseconds (CUDA events on the batch stream): {pose+root, per-level
+ * descent, narrow phase tet-tri (cull + exact clip), narrow phase tet-tet (cull + exact clip + half-space
+ * count pass), scan, pack, reduce, total}. Only recorded when enabled (adds event records). */
 dbh_status dbh_batch_enable_timing(dbh_batch* batch, int32_t enabled);
 /* Self-check mode: the reference's exact clipping sequence runs for EVERY
  * candidate element pair (the conservative cull stage only flags), and
  * dbh_stats::cull_violations counts flagged candidates that emitted a polygon.
  * Results are those of the un-culled pipeline. Slower; for tests. */
 dbh_status dbh_batch_set_verify(dbh_batch* batch, int32_t enabled);
+/* Rigid-compliant mesh pairs with or without the face-normal filter: SurfaceVolumeIntersector::
+ * SampleVolumeFieldOnSurface(..., filter_face_normal_along_field_gradient) (mesh_intersection.h). On (the default)
+ * is what ComputeContactSurfaces does; off is how geometry/benchmarking/mesh_intersection_benchmark.cc runs the
+ * intersector (its rigid sphere sits inside the compliant ellipsoid, where the filter would reject every face). */
+dbh_status dbh_batch_set_normal_filter(dbh_batch* batch, int32_t enabled);
 /* Mid phase of SMALL geometry pairs (both BVHs at most 32767 nodes): one warp per pair descends the dual
  * tree on a node-pair stack in shared memory and runs the leaf predicate and the conservative culls on chip
  * (k_small_pairs), instead of one launch per tree level through global frontier lists. mode 0: never; 1: every
@@ -395,6 +422,11 @@ dbh_status dbh_batch_set_small_pair_path(dbh_batch* batch, int32_t mode);
  * them out when asked. Off by default. */
 dbh_status dbh_batch_set_record_candidates(dbh_batch* batch, int32_t enabled);
 dbh_status dbh_batch_kernel_times_ms(dbh_batch* batch, float* out8);
+/* The same at stage granularity (first n of 11 values): {pose + root test, per-level descent (k_traverse), cull
+ * tet-tri (k_filter + k_small_pairs), cull tet-tet, exact clip tet-tri (k_clip), exact clip tet-tet (+ exceptional
+ * candidates), half-space set-up + count pass, scan, pack (k_pack + half-space pack pass), surface totals, whole
+ * query}. */
+dbh_status dbh_batch_stage_times_ms(dbh_batch* batch, float* out, int32_t n);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -8,6 +8,7 @@ The product package (drake_b200/) never imports this module.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 from dataclasses import dataclass, field
@@ -466,6 +467,30 @@ def traction(surface: Surface, p_WAo, p_WBo, V_WA, V_WB, dissipation: float, mu_
     return out[0:6], out[6:12], out[12:18]
 
 
+def discrete_pairs(surface: Surface) -> np.ndarray:
+    """The geometry-only half of DiscreteUpdateManager::AppendDiscreteContactPairsForHydroelasticContact
+    (multibody/plant/discrete_update_manager.cc:896-1036), face by face (plain loops: test sizes only): [F,9] = p_WC,
+    nhat_BA_W, phi0, fn0, stiffness; a face the reference skips (:909-919, :941-949) keeps stiffness 0."""
+    out = np.zeros((surface.num_faces, 9))
+    for f in range(surface.num_faces):
+        Ae = float(surface.areas[f])
+        nhat = surface.normals[f]
+        out[f, 0:3] = surface.centroids[f]
+        out[f, 3:6] = nhat
+        if not Ae > 1.0e-14:
+            continue
+        gM = float(np.dot(surface.grad_eM[f], nhat)) if surface.grad_eM is not None else math.inf
+        gN = -float(np.dot(surface.grad_eN[f], nhat)) if surface.grad_eN is not None else math.inf
+        if gM < 1.0e-14 or gN < 1.0e-14:
+            continue
+        g = 1.0 / (1.0 / gM + 1.0 / gN)
+        p0 = float(surface.e_centroid[f])
+        out[f, 6] = -p0 / g
+        out[f, 7] = Ae * p0
+        out[f, 8] = Ae * g
+    return out
+
+
 def atan_x_over_x_from_x_squared(x2: float) -> float:
     return lib().ho_atan_x_over_x_from_x_squared(x2)
 
@@ -529,6 +554,11 @@ class Scene:
         n = lib().ho_scene_fallback_pairs(self.h, _pd(P), out.ctypes.data_as(_lp), cap)
         _check(n, "scene_fallback_pairs")
         return out[:n]
+
+    def set_normal_filter(self, on: bool = True):
+        """Rigid-compliant mesh pairs with (default) or without IsFaceNormalAlongPressureGradient
+        (SampleVolumeFieldOnSurface's filter_face_normal_along_field_gradient, mesh_intersection.h)."""
+        lib().ho_scene_set_normal_filter(self.h, int(on))
 
     def exclude(self, a: int, b: int):
         lib().ho_scene_exclude_pair(self.h, a, b)

@@ -124,6 +124,9 @@ struct SceneGeom {
   Aabb box{};
 };
 struct Scene {
+  // SampleVolumeFieldOnSurface's filter_face_normal_along_field_gradient (mesh_intersection.h): true in
+  // ComputeContactSurfaces, false in the reference's mesh_intersection_benchmark.
+  bool normal_filter{true};
   std::vector<SceneGeom> geoms;  // kept sorted by id
   std::set<std::pair<int64_t, int64_t>> filtered;
 };
@@ -258,7 +261,7 @@ int ComputeScene(const Scene& scene, const double* poses, Representation rep, in
         const auto cand = Candidates(vs, tr, X_SR, mode, stats ? &stats->bv_tests : nullptr);
         if (stats) stats->element_pairs += cand.size();
         non_null = ContactSurfaceFromCompliantVolumeRigidSurface(S.id, vs.mesh, *g_fields[S.field], X_WS, R.id,
-                                                                 tr.mesh, X_WR, cand, rep, &res);
+                                                                 tr.mesh, X_WR, cand, rep, &res, scene.normal_filter);
       }
       if (non_null) {
         if (stats) {
@@ -767,6 +770,7 @@ int ho_scene_fallback_pairs(int scene, const double* poses, int64_t* out_ids, in
   return static_cast<int>(pairs.size());
   HO_CATCH(-100)
 }
+void ho_scene_set_normal_filter(int scene, int enabled) { g_scenes[scene]->normal_filter = enabled != 0; }
 int ho_scene_num_geometries(int scene) { return static_cast<int>(g_scenes[scene]->geoms.size()); }
 void ho_scene_geometry_ids(int scene, int64_t* ids) {
   const Scene& s = *g_scenes[scene];

@@ -150,6 +150,33 @@ def test_config1_mesh_intersection_benchmark(ctx, rep):
         np.testing.assert_array_equal(mine, want_c)  # bit-exact candidate element-pair set
 
 
+def test_config1_without_the_normal_filter_reproduces_the_benchmark_output(ctx):
+    """mesh_intersection_benchmark.cc runs SampleVolumeFieldOnSurface with filter_face_normal_along_field_gradient = false
+    (its rigid sphere sits INSIDE the compliant ellipsoid, where the filter rejects every face). With the filter switched
+    off (dbh_batch_set_normal_filter) the four full-overlap cases give the areas the reference prints
+    (mesh_intersection_benchmark.cc:90-93: 93.76, 93.76, 107.59, 111.67 m^2) and match the oracle face for face; with it on
+    (ComputeContactSurfaces) they are empty."""
+    import drake_b200 as db
+    from drake_b200 import workloads as W
+    wl = W.config1(args=[(0, 4, 0), (1, 4, 0), (2, 4, 0), (3, 4, 0)])
+    poses = wl.poses.reshape(-1, 12)
+    batch = wl.register(ctx)
+    assert all(s == [] for s in batch.compute_contact_surfaces(poses, ho.KTRIANGLE))
+    wl.normal_filter = False
+    batch = wl.register(ctx, assets=wl.assets)
+    got = batch.compute_contact_surfaces(poses, ho.KTRIANGLE)
+    hints = [4.0, 3.0, 2.0, 1.0]
+    for k, printed in enumerate([93.76, 93.76, 107.59, 111.67]):
+        mS = ho.VolumeMesh.ellipsoid(3.01, 3.5, 4.0, hints[k], dense=True)
+        fS = ho.VolumeField.ellipsoid(mS, 3.01, 3.5, 4.0, 1e5)
+        mR = ho.TriMesh.sphere(3.0, hints[k])
+        want = parity.memo(("c1nf", k), lambda: ho.soft_rigid(mS, fS, mR, wl.poses[k][0], wl.poses[k][1], 1, 2, ho.KTRIANGLE,
+                                                              filter_face_normal=False))
+        assert len(got[k]) == 1
+        assert round(float(got[k][0].total_area), 2) == printed
+        parity.compare_surface(got[k][0], want)
+
+
 def test_config2_compliant_compliant(ctx):
     """BASELINE config 2 (compliant_mesh_intersection_benchmark.cc:112-202): ellipsoid x sphere,
     dense, resolutions 0..2 x overlaps 0..3, plus two dense spheres at random poses."""

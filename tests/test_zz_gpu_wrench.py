@@ -97,14 +97,10 @@ def test_cpp_adapter_contact_forces():
     assert res.stdout.strip().endswith("ok")
 
 
-@pytest.mark.skipif(os.environ.get("DBH_RUN_NEW") != "1",
-                    reason="written after the round's GPU time ended: k_wrench over a half-space surface has not run yet")
 @pytest.mark.parametrize("rep", [ho.KPOLYGON, ho.KTRIANGLE])
 def test_spatial_forces_with_a_half_space_surface(ctx, rep):
     """Mesh pairs and a half-space pair in one scene, forces of every surface against the oracle (the half-space
-    surface's vertices are per polygon here and welded in the oracle; its face quantities agree). Each piece has
-    passed on the B200 separately; this combination was written after the GPU budget was spent, so it is gated
-    (DBH_RUN_NEW=1) until it has run once."""
+    surface's vertices are per polygon here and welded in the oracle; its face quantities agree)."""
     import math
     import drake_b200 as db
     R = 0.25
@@ -139,3 +135,51 @@ def test_spatial_forces_with_a_half_space_surface(ctx, rep):
         scale = max(np.max(np.abs(np.concatenate(ref))), 1e-300)
         for f_gpu, f_ref in zip(forces, ref):
             assert np.max(np.abs(f_gpu[k] - f_ref)) <= 1e-9 * scale
+
+
+@pytest.mark.parametrize("rep", [ho.KPOLYGON, ho.KTRIANGLE])
+def test_discrete_contact_pairs_match_the_oracle(ctx, rep):
+    """k_discrete (the geometry-only half of AppendDiscreteContactPairsForHydroelasticContact,
+    discrete_update_manager.cc:896-1036) over every surface of 24 ball / plate / floor scenes -- soft-rigid in both
+    id orders and soft-soft -- against the oracle's restatement, face by face (faces matched by their emitting element
+    pair): p_WC, nhat, phi0, fn0, stiffness to 1e-10; the same faces skipped."""
+    from drake_b200 import engine, workloads as W
+    wl = W.config3(24)
+    batch = wl.register(ctx)
+    batch.set_poses(wl.poses.reshape(-1, 12))
+    batch.query(rep, engine.STRICT)
+    batch.compute_discrete_pairs()
+    batch.sync()
+    pairs = batch.copy_discrete_pairs()
+    res = batch.copy_results()
+    surfaces = res.surfaces()
+    assert len(pairs) == batch.sizes().num_faces
+    osc, order = parity.oracle_scene_for(wl)
+    by_scene = {}
+    for k, s in enumerate(surfaces):
+        by_scene.setdefault(s.scene, []).append((k, s))
+    kept = 0
+    for sc in range(wl.num_scenes):
+        want, _ = osc.compute(wl.poses[sc][order], rep)
+        got = by_scene.get(sc, [])
+        assert [(s.id_M, s.id_N) for _, s in got] == [(w.id_M, w.id_N) for w in want]
+        for (k, g), w in zip(got, want):
+            f0 = int(res.surf_face_offset[k])
+            mine = pairs[f0:f0 + g.num_faces]
+            ref = ho.discrete_pairs(w)
+            go = np.argsort(parity.face_keys(g.elem_M, g.elem_N), kind="stable")
+            wo = np.argsort(parity.face_keys(w.elem_first, w.elem_second), kind="stable")
+            if rep == ho.KTRIANGLE:   # several triangles per element pair: order them by centroid as well
+                go = np.lexsort((g.centroids[:, 2], g.centroids[:, 1], g.centroids[:, 0], parity.face_keys(g.elem_M, g.elem_N)))
+                wo = np.lexsort((w.centroids[:, 2], w.centroids[:, 1], w.centroids[:, 0], parity.face_keys(w.elem_first, w.elem_second)))
+            a, b = mine[go], ref[wo]
+            np.testing.assert_array_equal(a[:, 8] == 0, b[:, 8] == 0)
+            L = max(np.max(np.abs(b[:, 0:3])), 1e-300)
+            assert np.max(np.abs(a[:, 0:3] - b[:, 0:3])) <= 1e-10 * L
+            assert np.max(np.abs(a[:, 3:6] - b[:, 3:6])) <= 1e-10
+            for col in (6, 7, 8):
+                scale = max(np.max(np.abs(b[:, col])), 1e-300)
+                assert np.max(np.abs(a[:, col] - b[:, col])) <= 1e-10 * scale, col
+            kept += int(np.count_nonzero(b[:, 8]))
+    assert kept > 1000
+    assert batch.stats()["discrete_pairs"] == kept
