@@ -467,26 +467,21 @@ class PackedResults:
     def num_surfaces(self) -> int:
         return len(self.surf_face_offset) - 1 if self._wanted("surf_face_offset") else len(self.surf_scene)
 
-    def surfaces(self) -> List[ContactSurface]:
+    def surfaces(self, scenes=None) -> List[ContactSurface]:
+        """Per-surface views of the packed arrays, in result order; `scenes`: only the surfaces of these scenes."""
         out = []
         poly = self.representation == POLYGON
-        # face_data offsets for the polygon representation.
-        if poly:
-            nverts = []
-            i = 0
-            fd = self.face_data
-            starts = []
-            while i < len(fd):
-                starts.append(i)
-                i += fd[i] + 1
-            starts.append(len(fd))
-            starts = np.asarray(starts, np.int64)
-        for s in range(self.num_surfaces):
+        which = range(self.num_surfaces)
+        if scenes is not None:
+            which = np.nonzero(np.isin(self.surf_scene, np.asarray(list(scenes))))[0]
+        for s in which:
             f0, f1 = self.surf_face_offset[s], self.surf_face_offset[s + 1]
             v0, v1 = self.surf_vertex_offset[s], self.surf_vertex_offset[s + 1]
             flags = int(self.surf_flags[s])
             if poly:
-                fd = self.face_data[starts[f0]:starts[f1]]
+                # |n|v0..vn-1| per face, faces and vertices of a surface contiguous and every polygon with its own
+                # vertices: the surface's slice starts after f0 counts and v0 indices.
+                fd = self.face_data[f0 + v0:f1 + v1]
             else:
                 fd = self.face_data[3 * f0:3 * f1].reshape(-1, 3)
             out.append(ContactSurface(

@@ -1,0 +1,163 @@
+// drake_b200_point_pair.h — the point-pair half of ComputeContactSurfacesWithFallback, host-side C++17.
+//
+// The reference hands every pair whose hydroelastic surface cannot be made (rigid-rigid, a geometry with no
+// hydroelastic representation, the rejected half-space combinations) to penetration_as_point_pair::MaybeMakePointPair
+// (geometry/proximity_engine.cc:958-970). That narrow phase has two halves:
+//   * Drake's own closed forms, used whenever one of the two shapes is a sphere
+//     (penetration_as_point_pair_callback.cc:92-118,203-300: sphere x {sphere, box, half space, cylinder, capsule})
+//     through point_distance::DistanceToPoint (distance_to_point_callback.cc:15-77,160-178,406-482);
+//   * FCL's general GJK / EPA collide() for everything else (:145-195) -- an external dependency of the reference
+//     (tools/workspace/fcl_internal), not restated here.
+// This header restates the first half for the shapes the adapter registers (Sphere, Box, HalfSpace). The batched
+// query (dbh_batch_query, DBH_QUERY_WITH_FALLBACK) reports WHICH pairs need it (dbh_batch_copy_fallback_pairs): a
+// handful per scene, so the arithmetic stays on the host next to the shape descriptions the C-ABI never sees.
+// No Eigen: 3-vectors are std::array<double, 3>; operation order follows the reference.
+#ifndef DRAKE_B200_POINT_PAIR_H_
+#define DRAKE_B200_POINT_PAIR_H_
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <limits>
+#include <optional>
+
+namespace drake_b200 {
+namespace point_pair {
+
+using Vec3 = std::array<double, 3>;
+// RigidTransform<double> as the C-ABI lays it out: rotation column-major (9), then translation (3).
+using Pose = std::array<double, 12>;
+
+inline Vec3 Rotate(const Pose& X, const Vec3& v) {
+  return {(X[0] * v[0] + X[3] * v[1]) + X[6] * v[2], (X[1] * v[0] + X[4] * v[1]) + X[7] * v[2],
+          (X[2] * v[0] + X[5] * v[1]) + X[8] * v[2]};
+}
+inline Vec3 RotateT(const Pose& X, const Vec3& v) {
+  return {(X[0] * v[0] + X[1] * v[1]) + X[2] * v[2], (X[3] * v[0] + X[4] * v[1]) + X[5] * v[2],
+          (X[6] * v[0] + X[7] * v[1]) + X[8] * v[2]};
+}
+inline Vec3 Apply(const Pose& X, const Vec3& v) {  // X * v
+  const Vec3 r = Rotate(X, v);
+  return {X[9] + r[0], X[10] + r[1], X[11] + r[2]};
+}
+inline Vec3 ApplyInverse(const Pose& X, const Vec3& p) {  // X.inverse() * p = R^T (p - t)
+  return RotateT(X, {p[0] - X[9], p[1] - X[10], p[2] - X[11]});
+}
+inline double Dot(const Vec3& a, const Vec3& b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+inline double Norm(const Vec3& a) { return std::sqrt(Dot(a, a)); }
+
+// DistanceToPointRelativeTolerance (proximity_utilities.h:29-31).
+inline double RelativeTolerance(double size) { return 1e-14 * std::max(1.0, size); }
+// DistanceToPoint::Sign: Sign(0) = 1 (distance_to_point_callback.h:185-191).
+inline double Sign(double x) { return x < 0.0 ? -1.0 : 1.0; }
+
+// SignedDistanceToPoint<double> (query_results/signed_distance_to_point.h): nearest point N on the boundary of G in
+// G's frame, signed distance (negative inside), gradient in World.
+struct SignedDistanceToPoint {
+  Vec3 p_GN;
+  double distance;
+  Vec3 grad_W;
+};
+
+// DistanceToPoint::operator()(Sphere) (distance_to_point_callback.cc:15-58,361-369).
+inline SignedDistanceToPoint DistanceToSphere(double radius, const Pose& X_WG, const Vec3& p_WQ) {
+  const Vec3 p_GQ = ApplyInverse(X_WG, p_WQ);
+  const double dist = Norm(p_GQ);
+  const double tolerance = RelativeTolerance(radius);
+  const Vec3 grad_G = dist > tolerance ? Vec3{p_GQ[0] / dist, p_GQ[1] / dist, p_GQ[2] / dist} : Vec3{1.0, 0.0, 0.0};
+  const Vec3 p_GN{radius * grad_G[0], radius * grad_G[1], radius * grad_G[2]};
+  const double distance = Dot({p_GQ[0] - p_GN[0], p_GQ[1] - p_GN[1], p_GQ[2] - p_GN[2]}, grad_G);
+  return {p_GN, distance, Rotate(X_WG, grad_G)};
+}
+
+// DistanceToPoint::operator()(HalfSpace) (distance_to_point_callback.cc:60-77,350-359): the half space is z <= 0.
+inline SignedDistanceToPoint DistanceToHalfSpace(const Pose& X_WG, const Vec3& p_WQ) {
+  const Vec3 p_GQ = ApplyInverse(X_WG, p_WQ);
+  return {{p_GQ[0], p_GQ[1], 0.0}, p_GQ[2], Rotate(X_WG, {0.0, 0.0, 1.0})};
+}
+
+// DistanceToPoint::operator()(Box) = ComputeDistanceToBox (distance_to_point_callback.cc:160-178,384-482); size = full
+// side lengths.
+inline SignedDistanceToPoint DistanceToBox(const Vec3& size, const Pose& X_WG, const Vec3& p_WQ) {
+  const Vec3 p_GQ = ApplyInverse(X_WG, p_WQ);
+  const Vec3 h{size[0] / 2.0, size[1] / 2.0, size[2] / 2.0};
+  enum Location { kInside, kBoundary, kOutside };
+  Location location[3];
+  Vec3 p_GC;
+  for (int i = 0; i < 3; ++i) {
+    const double tolerance = RelativeTolerance(h[i]);
+    if (std::abs(p_GQ[i]) > h[i] + tolerance) {
+      location[i] = kOutside;
+      p_GC[i] = Sign(p_GQ[i]) * h[i];
+    } else if (std::abs(p_GQ[i]) >= h[i] - tolerance) {
+      location[i] = kBoundary;
+      p_GC[i] = Sign(p_GQ[i]) * h[i];
+    } else {
+      location[i] = kInside;
+      p_GC[i] = p_GQ[i];
+    }
+  }
+  Vec3 p_GN = p_GC;
+  Vec3 grad_G{0.0, 0.0, 0.0};
+  const bool any_outside = location[0] == kOutside || location[1] == kOutside || location[2] == kOutside;
+  const bool any_boundary = location[0] == kBoundary || location[1] == kBoundary || location[2] == kBoundary;
+  if (any_outside) {
+    const Vec3 p_NQ{p_GQ[0] - p_GN[0], p_GQ[1] - p_GN[1], p_GQ[2] - p_GN[2]};
+    const double distance = Norm(p_NQ);
+    grad_G = {p_NQ[0] / distance, p_NQ[1] / distance, p_NQ[2] / distance};
+  } else if (any_boundary) {
+    for (int i = 0; i < 3; ++i)
+      if (location[i] == kBoundary) grad_G[i] = Sign(p_GC[i]);
+    const double n = Norm(grad_G);
+    grad_G = {grad_G[0] / n, grad_G[1] / n, grad_G[2] / n};
+  } else {
+    // Inside: project onto the nearest face; ties go to +x, -x, +y, -y, +z, -z (ExtremalAxis, :384-400).
+    double min_dist = std::numeric_limits<double>::infinity();
+    int axis = -1;
+    for (int i = 0; i < 3; ++i)
+      for (const double bound : {h[i], -h[i]}) {
+        const double dist = std::abs(bound - p_GQ[i]);
+        if (dist < min_dist) {
+          min_dist = dist;
+          axis = i;
+        }
+      }
+    const double sign = Sign(p_GQ[axis]);
+    p_GN[axis] = sign * h[axis];
+    grad_G[axis] = sign;
+  }
+  const Vec3 grad_W = Rotate(X_WG, grad_G);
+  const Vec3 p_WN = Apply(X_WG, p_GN);
+  const double distance = Dot(grad_W, {p_WQ[0] - p_WN[0], p_WQ[1] - p_WN[1], p_WQ[2] - p_WN[2]});
+  return {p_GN, distance, grad_W};
+}
+
+struct Result {  // PenetrationAsPointPair<double> without the ids
+  Vec3 p_WCa, p_WCb, nhat_BA_W;
+  double depth;
+};
+
+// SphereShapePenetration (penetration_as_point_pair_callback.cc:92-118): sphere A of radius r at X_WA against the
+// signed distance of the other shape B to A's centre. Empty when depth < 0.
+inline std::optional<Result> SphereShapePenetration(double radius_A, const Pose& X_WA, const Pose& X_WB,
+                                                    const SignedDistanceToPoint& shape_B_to_point_Ao) {
+  const double depth = radius_A - shape_B_to_point_Ao.distance;
+  if (!(depth >= 0)) return std::nullopt;
+  Result r;
+  r.depth = depth;
+  r.p_WCb = Apply(X_WB, shape_B_to_point_Ao.p_GN);
+  r.nhat_BA_W = shape_B_to_point_Ao.grad_W;
+  r.p_WCa = {X_WA[9] - radius_A * r.nhat_BA_W[0], X_WA[10] - radius_A * r.nhat_BA_W[1],
+             X_WA[11] - radius_A * r.nhat_BA_W[2]};
+  return r;
+}
+
+// PenetrationAsPointPair::SwapAAndB (query_results/penetration_as_point_pair.h:26-31).
+inline void SwapAAndB(Result* r) {
+  std::swap(r->p_WCa, r->p_WCb);
+  r->nhat_BA_W = {-r->nhat_BA_W[0], -r->nhat_BA_W[1], -r->nhat_BA_W[2]};
+}
+
+}  // namespace point_pair
+}  // namespace drake_b200
+#endif  // DRAKE_B200_POINT_PAIR_H_

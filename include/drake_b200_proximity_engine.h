@@ -27,6 +27,7 @@
 #include <cstdint>
 #include <limits>
 #include <map>
+#include <optional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -36,6 +37,7 @@
 #include <vector>
 
 #include "drake_b200_hydro.h"
+#include "drake_b200_point_pair.h"
 
 namespace drake_b200 {
 
@@ -90,8 +92,8 @@ struct ProximityProperties {
   TessellationStrategy tessellation_strategy{TessellationStrategy::kSingleInteriorVertex};
 };
 
-// geometry::PenetrationAsPointPair<double> (the fallback result; produced by the reference's FCL
-// narrow phase, which is outside this path: the vector is left untouched).
+// geometry::PenetrationAsPointPair<double>, the fallback result (query_results/penetration_as_point_pair.h):
+// filled for the pairs one of whose shapes is a Sphere (Drake's own closed forms, drake_b200_point_pair.h).
 struct PenetrationAsPointPair {
   GeometryId id_A, id_B;
   std::array<double, 3> p_WCa, p_WCb, nhat_BA_W;
@@ -205,6 +207,7 @@ class ProximityEngine {
       throw std::out_of_range("RemoveGeometry: GeometryId " + std::to_string(id) + " is not " +
                               (is_dynamic ? "dynamic" : "anchored"));
     ids_.erase(ids_.begin() + g);
+    shapes_.erase(shapes_.begin() + g);
     assets_.erase(assets_.begin() + g);
     anchored_.erase(anchored_.begin() + g);
     poses_.erase(poses_.begin() + g);
@@ -258,7 +261,22 @@ class ProximityEngine {
     UpdateWorldPoses(X_WGs);
     auto all = Run(representation, DBH_QUERY_WITH_FALLBACK, PosesOfOneScene());
     for (auto& s : all[0]) surfaces->push_back(std::move(s));
+    // The pairs whose surface could not be made and whose world boxes overlap go to the point-pair narrow phase
+    // (proximity_engine.cc:958-970), in (id_A, id_B) order.
+    int64_t n = 0;
+    Check(dbh_batch_copy_fallback_pairs(batch_, nullptr, &n), "copy_fallback_pairs");
+    std::vector<int32_t> quads(static_cast<size_t>(4 * n));
+    if (n) Check(dbh_batch_copy_fallback_pairs(batch_, quads.data(), &n), "copy_fallback_pairs");
+    for (int64_t k = 0; k < n; ++k) {
+      auto pp = MaybeMakePointPair(quads[4 * k + 1], quads[4 * k + 2]);
+      if (pp) point_pairs->push_back(*pp);
+    }
   }
+
+  // What to do with a fallback pair neither of whose shapes is a Sphere: the reference calls FCL's general narrow
+  // phase there (penetration_as_point_pair_callback.cc:145-195), which this back end does not contain. false (the
+  // default): throw std::logic_error naming the pair, so that no contact is lost silently; true: skip such pairs.
+  void set_skip_unsupported_point_pairs(bool skip) { skip_unsupported_point_pairs_ = skip; }
 
   // Batched form: X_WGs is [num_scenes * num_geometries * 12] doubles, scene-major, geometries in
   // registration order. Returns the surfaces of every scene, each list sorted by (id_M, id_N).
@@ -361,6 +379,46 @@ class ProximityEngine {
   }
 
   // hydroelastic::Geometries::MaybeAddGeometry (hydroelastic_internal.cc:145-153, 328-343, 412-536).
+  // penetration_as_point_pair::ComputeNarrowPhasePenetration (penetration_as_point_pair_callback.cc:203-300) for the
+  // geometries at indices ga, gb (id(ga) < id(gb)) at their current poses.
+  std::optional<PenetrationAsPointPair> MaybeMakePointPair(int ga, int gb) const {
+    namespace pp = point_pair;
+    const Shape& a = shapes_[ga];
+    const Shape& b = shapes_[gb];
+    const bool a_is_sphere = std::holds_alternative<Sphere>(a), b_is_sphere = std::holds_alternative<Sphere>(b);
+    if (!a_is_sphere && !b_is_sphere) {
+      // The reference rejects half space x half space itself (:525-555 of its test; penetration_as_point_pair_callback.cc
+      // "@pre The pair should not be (Halfspace, X), unless X is Sphere") and hands the rest to FCL.
+      if (skip_unsupported_point_pairs_) return std::nullopt;
+      throw std::logic_error("ComputeContactSurfacesWithFallback: the point-pair fallback for geometries " +
+                             std::to_string(ids_[ga]) + " and " + std::to_string(ids_[gb]) +
+                             " needs FCL's general narrow phase (neither shape is a Sphere), which this back end does not "
+                             "provide; filter the pair or call set_skip_unsupported_point_pairs(true)");
+    }
+    const int gs = a_is_sphere ? ga : gb, go = a_is_sphere ? gb : ga;   // sphere, other
+    const pp::Pose& X_WS = poses_[gs].m;
+    const pp::Pose& X_WO = poses_[go].m;
+    const pp::Vec3 p_WSo{X_WS[9], X_WS[10], X_WS[11]};
+    const double r = std::get<Sphere>(shapes_[gs]).radius;
+    pp::SignedDistanceToPoint d;
+    if (const auto* s = std::get_if<Sphere>(&shapes_[go])) {
+      d = pp::DistanceToSphere(s->radius, X_WO, p_WSo);
+    } else if (const auto* bx = std::get_if<Box>(&shapes_[go])) {
+      d = pp::DistanceToBox({bx->width, bx->depth, bx->height}, X_WO, p_WSo);
+    } else if (std::holds_alternative<HalfSpace>(shapes_[go])) {
+      d = pp::DistanceToHalfSpace(X_WO, p_WSo);
+    } else {
+      if (skip_unsupported_point_pairs_) return std::nullopt;
+      throw std::logic_error("ComputeContactSurfacesWithFallback: the point-pair fallback between a Sphere and the shape of "
+                             "geometry " + std::to_string(ids_[go]) + " needs FCL (ellipsoids and meshes have no closed form, "
+                             "penetration_as_point_pair_callback.cc:273-278)");
+    }
+    auto res = pp::SphereShapePenetration(r, X_WS, X_WO, d);
+    if (!res) return std::nullopt;
+    if (!a_is_sphere) pp::SwapAAndB(&*res);
+    return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
+  }
+
   int32_t MakeAsset(const Shape& shape, const ProximityProperties& p) {
     if (p.compliance_type == HydroelasticType::kUndefined) return -1;
     const bool soft = p.compliance_type == HydroelasticType::kCompliant;
@@ -431,6 +489,7 @@ class ProximityEngine {
     const int32_t asset = MakeAsset(shape, props);
     index_[id] = static_cast<int>(ids_.size());
     ids_.push_back(id);
+    shapes_.push_back(shape);
     assets_.push_back(asset);
     anchored_.push_back(anchored ? 1 : 0);
     poses_.push_back(X_WG);
@@ -541,6 +600,8 @@ class ProximityEngine {
   dbh_batch* batch_{nullptr};
   int num_scenes_{1};
   std::vector<GeometryId> ids_;
+  std::vector<Shape> shapes_;
+  bool skip_unsupported_point_pairs_{false};
   std::vector<int32_t> assets_;
   std::vector<uint8_t> anchored_;
   std::vector<RigidTransformd> poses_;

@@ -1,0 +1,52 @@
+// Host check of include/drake_b200_point_pair.h (no GPU, no library): reads pairs from stdin, one per line
+//   <kindA> <paramsA...> <poseA x12> <kindB> <paramsB...> <poseB x12>       kind: s r | b x y z | h
+// and prints `none` or `depth p_WCa(3) p_WCb(3) nhat(3)` with 17 significant digits, the way
+// ComputeNarrowPhasePenetration (penetration_as_point_pair_callback.cc:203-300) orders its operands.
+#include <cstdio>
+#include <iostream>
+#include <string>
+
+#include "drake_b200_point_pair.h"
+
+using namespace drake_b200::point_pair;
+
+struct Geo {
+  char kind;
+  double r;
+  Vec3 size;
+  Pose X;
+};
+
+static bool Read(Geo* g) {
+  std::string k;
+  if (!(std::cin >> k)) return false;
+  g->kind = k[0];
+  if (g->kind == 's') std::cin >> g->r;
+  if (g->kind == 'b') std::cin >> g->size[0] >> g->size[1] >> g->size[2];
+  for (double& v : g->X) std::cin >> v;
+  return true;
+}
+
+int main() {
+  Geo a, b;
+  while (Read(&a) && Read(&b)) {
+    const bool a_is_sphere = a.kind == 's';
+    const Geo& s = a_is_sphere ? a : b;
+    const Geo& o = a_is_sphere ? b : a;
+    const Vec3 p_WSo{s.X[9], s.X[10], s.X[11]};
+    SignedDistanceToPoint d;
+    if (o.kind == 's') d = DistanceToSphere(o.r, o.X, p_WSo);
+    else if (o.kind == 'b') d = DistanceToBox(o.size, o.X, p_WSo);
+    else d = DistanceToHalfSpace(o.X, p_WSo);
+    auto res = SphereShapePenetration(s.r, s.X, o.X, d);
+    if (!res) {
+      std::printf("none\n");
+      continue;
+    }
+    if (!a_is_sphere) SwapAAndB(&*res);
+    std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", res->depth, res->p_WCa[0], res->p_WCa[1],
+                res->p_WCa[2], res->p_WCb[0], res->p_WCb[1], res->p_WCb[2], res->nhat_BA_W[0], res->nhat_BA_W[1],
+                res->nhat_BA_W[2]);
+  }
+  return 0;
+}

@@ -158,6 +158,49 @@ int main(int argc, char** argv) {
     std::vector<PenetrationAsPointPair> pairs;
     e.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
     EXPECT(surfaces.size() == 1);
+    // The rigid-rigid pair comes back as a point pair (proximity_engine.cc:958-970): two spheres of radius R whose
+    // centres are 0.3 apart along z penetrate by 2 R - 0.3, normal from B (the upper one) into A.
+    EXPECT(pairs.size() == 1 && pairs[0].id_A == 1 && pairs[0].id_B == 2);
+    EXPECT(std::fabs(pairs[0].depth - (2 * R - 0.3)) < 1e-15);
+    EXPECT(std::fabs(pairs[0].nhat_BA_W[2] + 1.0) < 1e-15 && pairs[0].nhat_BA_W[0] == 0 && pairs[0].nhat_BA_W[1] == 0);
+    EXPECT(std::fabs(pairs[0].p_WCa[2] - R) < 1e-15 && std::fabs(pairs[0].p_WCb[2] - (0.3 - R)) < 1e-15);
+    // Far apart: neither an exception from the strict query nor a point pair (the geometry-level broad phase).
+    auto none = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon,
+                                         {{2, RigidTransformd::FromTranslation(0, 0, 3.0)}});
+    EXPECT(none.empty());
+    pairs.clear();
+    e.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    EXPECT(pairs.empty());
+  }
+  {  // A compliant sphere on a rigid half space AND a rigid sphere on the same half space: one surface, one point pair.
+    ProximityEngine e(0);
+    e.AddAnchoredGeometry(HalfSpace{}, RigidTransformd::Identity(), 1, rigid);
+    e.AddDynamicGeometry(Sphere{R}, RigidTransformd::FromTranslation(0, 0, 0.2), 2, soft);
+    e.AddDynamicGeometry(Sphere{R}, RigidTransformd::FromTranslation(2.0, 0, 0.15), 3, rigid);
+    std::vector<ContactSurface> surfaces;
+    std::vector<PenetrationAsPointPair> pairs;
+    e.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    EXPECT(surfaces.size() == 1 && surfaces[0].id_M() == 1 && surfaces[0].id_N() == 2);
+    EXPECT(pairs.size() == 1 && pairs[0].id_A == 1 && pairs[0].id_B == 3);
+    EXPECT(std::fabs(pairs[0].depth - (R - 0.15)) < 1e-15);
+    // A is the half space, B the sphere: the normal points from the sphere into the half space, i.e. down.
+    EXPECT(std::fabs(pairs[0].nhat_BA_W[2] + 1.0) < 1e-15);
+    EXPECT(std::fabs(pairs[0].p_WCa[2]) < 1e-15 && std::fabs(pairs[0].p_WCb[2] - (0.15 - R)) < 1e-15);
+    // Two rigid boxes: FCL's general narrow phase is not part of this back end -- loud unless the caller opts out.
+    ProximityEngine b(0);
+    b.AddDynamicGeometry(Box{0.2, 0.2, 0.2}, RigidTransformd::Identity(), 1, rigid);
+    b.AddDynamicGeometry(Box{0.2, 0.2, 0.2}, RigidTransformd::FromTranslation(0, 0, 0.1), 2, rigid);
+    bool threw = false;
+    try {
+      b.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    } catch (const std::logic_error& err) {
+      threw = std::string(err.what()).find("FCL") != std::string::npos;
+    }
+    EXPECT(threw);
+    b.set_skip_unsupported_point_pairs(true);
+    pairs.clear();
+    b.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    EXPECT(pairs.empty());
   }
   std::printf("ok\n");
   return 0;
