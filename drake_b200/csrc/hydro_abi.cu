@@ -89,11 +89,54 @@ struct HostAsset {
   // First pool index of this asset's elements (tet pool or tri pool) and nodes.
   int elem_base{0};
   int node_base{0};
+  // Bvh::Collide(plane) for the half-space pairs (bvh.h:285-309), flattened to one cut of the tree: the elements in
+  // the tree's leaf order (depth first), and the box of every run of kPlaneBlock consecutive leaves.
+  std::vector<int> leaf_order;       // asset-local element indices
+  std::vector<ElemBox> block_boxes;  // ceil(num_elements / kPlaneBlock)
+  int block_base{0};                 // first pool index of this asset's block boxes
 };
 
 struct Box {
   double mn[3], mx[3];
 };
+
+// Leaf order + block boxes of a built tree (nodes[1] is the root, the two children of a node are adjacent).
+void BuildPlaneBlocks(HostAsset* a) {
+  a->leaf_order.clear();
+  a->block_boxes.clear();
+  if (a->half_space || a->num_elements == 0 || a->nodes.size() < 2) return;
+  a->leaf_order.reserve(a->num_elements);
+  std::vector<const BvhNode*> leaves;
+  leaves.reserve(a->num_elements);
+  std::vector<int> stack{1};
+  while (!stack.empty()) {
+    const int n = stack.back();
+    stack.pop_back();
+    const BvhNode& node = a->nodes[n];
+    if (node.left < 0) {
+      a->leaf_order.push_back(~node.left);
+      leaves.push_back(&node);
+    } else {
+      stack.push_back(node.right);
+      stack.push_back(node.left);
+    }
+  }
+  const int blocks = (a->num_elements + kPlaneBlock - 1) / kPlaneBlock;
+  a->block_boxes.assign(blocks, ElemBox{});
+  for (int b = 0; b < blocks; ++b) {
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int k = b * kPlaneBlock; k < std::min(a->num_elements, (b + 1) * kPlaneBlock); ++k)
+      for (int d = 0; d < 3; ++d) {
+        mn[d] = std::min(mn[d], leaves[k]->c[d] - leaves[k]->h[d]);
+        mx[d] = std::max(mx[d], leaves[k]->c[d] + leaves[k]->h[d]);
+      }
+    for (int d = 0; d < 3; ++d) {
+      a->block_boxes[b].c[d] = 0.5 * (mn[d] + mx[d]);
+      // Outward: the box must contain every leaf box whatever the rounding of the centre.
+      a->block_boxes[b].h[d] = std::max(mx[d] - a->block_boxes[b].c[d], a->block_boxes[b].c[d] - mn[d]) * (1 + 1e-15);
+    }
+  }
+}
 
 // Aabb from min/max exactly as AabbMaker::Compute (aabb.cc:102-117).
 void BoxToNode(const Box& b, BvhNode* n) {
@@ -200,6 +243,9 @@ struct dbh_context {
   DevBuf<TriCull> d_cull_tri;
   DevBuf<ElemBox> d_ebox_tet, d_ebox_tri;
   DevBuf<double> d_tet_vp;   // [4 * pool tet] vertex pressures (the half-space slicer interpolates them)
+  DevBuf<int> d_order_tet, d_order_tri;   // per pool element position: asset-local element index in BVH leaf order
+  DevBuf<ElemBox> d_plane_blocks;         // box of every run of kPlaneBlock consecutive leaves, all assets
+  long long num_blocks{0};
   size_t uploaded_assets{0};
   long long up_tets{0}, up_tris{0}, up_nodes{0};
 
@@ -218,6 +264,9 @@ struct dbh_context {
       a->elem_base = static_cast<int>(num_tris);
       num_tris += a->num_elements;
     }
+    BuildPlaneBlocks(a);
+    a->block_base = static_cast<int>(num_blocks);
+    num_blocks += static_cast<long long>(a->block_boxes.size());
   }
 
   // Uploads assets registered since the last call. Pools grow geometrically;
@@ -241,6 +290,9 @@ struct dbh_context {
     CUDA_OK(grow(d_ebox_tri, num_tris, &regrown));
     CUDA_OK(grow(d_nodes, num_nodes, &regrown));
     CUDA_OK(grow(d_nodes32, num_nodes, &regrown));
+    CUDA_OK(grow(d_order_tet, num_tets, &regrown));
+    CUDA_OK(grow(d_order_tri, num_tris, &regrown));
+    CUDA_OK(grow(d_plane_blocks, num_blocks, &regrown));
     const size_t first = regrown ? 0 : uploaded_assets;
     std::vector<BvhNode> rebased;
     std::vector<Node32> rebased32;
@@ -286,6 +338,11 @@ struct dbh_context {
           }
         CUDA_OK(cudaMemcpy(d_cull_tri.p + a.elem_base, ct.data(), ct.size() * sizeof(TriCull), cudaMemcpyHostToDevice));
       }
+      CUDA_OK(cudaMemcpy((a.type == DBH_COMPLIANT ? d_order_tet.p : d_order_tri.p) + a.elem_base, a.leaf_order.data(),
+                         a.leaf_order.size() * sizeof(int), cudaMemcpyHostToDevice));
+      if (!a.block_boxes.empty())
+        CUDA_OK(cudaMemcpy(d_plane_blocks.p + a.block_base, a.block_boxes.data(), a.block_boxes.size() * sizeof(ElemBox),
+                           cudaMemcpyHostToDevice));
       // Per-element exact boxes = the leaves' boxes.
       {
         std::vector<ElemBox> eb(a.num_elements);
@@ -364,7 +421,8 @@ struct dbh_batch {
   // the exclusive prefix of the element counts of their one mesh; per geometry, the parameters of a compliant half space.
   std::vector<int> plane_pairs;
   std::vector<long long> plane_elem_off;
-  DevBuf<int> d_plane_pairs;
+  std::vector<int> plane_nelem, plane_block_base;   // per half-space pair: elements of its mesh, first block box
+  DevBuf<int> d_plane_pairs, d_plane_nelem, d_plane_block_base;
   DevBuf<long long> d_plane_elem_off;
   // Contact-surface consumer (k_wrench): per-geometry body origins / spatial velocities / contact properties and the
   // per-surface spatial forces.
@@ -410,7 +468,7 @@ struct dbh_batch {
   DevBuf<double> d_soup_v, d_soup_nhat;
   // Final results in the caller's layout.
   DevBuf<double> r_vertices, r_pressures, r_areas, r_normals, r_centroids, r_e_centroid, r_grad_eM, r_grad_eN;
-  DevBuf<int> r_face_data, r_elem_a, r_elem_b, r_face_pair;
+  DevBuf<int> r_face_data, r_elem_a, r_elem_b, r_face_pair, r_vertex_origin;
   DevBuf<double> r_surf_total_area, r_surf_centroid;
   DevBuf<int> r_surf_scene;
   DevBuf<long long> r_surf_id_m, r_surf_id_n;
@@ -492,6 +550,7 @@ struct dbh_batch {
     CUDA_OK(r_elem_a.ensure(cap_faces));
     CUDA_OK(r_elem_b.ensure(cap_faces));
     CUDA_OK(r_face_pair.ensure(cap_faces));
+    if (!plane_pairs.empty()) CUDA_OK(r_vertex_origin.ensure(cap_verts));
     return DBH_OK;
   }
 };
@@ -897,9 +956,13 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
           const HostAsset& M = *ctx->assets[geom_asset[pr.kind == kSoftMeshRigidPlane ? pr.geom_a : pr.geom_b]];
           (pr.kind == kSoftMeshRigidPlane ? pr.root_a : pr.root_b) = M.node_base + 1;
           (pr.kind == kSoftMeshRigidPlane ? pr.elem_base_a : pr.elem_base_b) = M.elem_base;
+          // Work items are padded to whole blocks of kPlaneBlock leaves, so that one 128-thread block of the count
+          // pass is one (pair, leaf block) and can cull it as a whole.
           b->plane_pairs.push_back(static_cast<int>(b->pairs.size()));
           b->plane_elem_off.push_back(est_plane);
-          est_plane += M.num_elements;
+          b->plane_nelem.push_back(M.num_elements);
+          b->plane_block_base.push_back(M.block_base);
+          est_plane += static_cast<long long>((M.num_elements + kPlaneBlock - 1) / kPlaneBlock) * kPlaneBlock;
         }
         b->pairs.push_back(pr);
       }
@@ -1003,6 +1066,11 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   if (!b->plane_pairs.empty()) {
     CUDA_OK(b->d_plane_pairs.alloc(b->plane_pairs.size()));
     CUDA_OK(cudaMemcpy(b->d_plane_pairs.p, b->plane_pairs.data(), b->plane_pairs.size() * sizeof(int),
+                       cudaMemcpyHostToDevice));
+    CUDA_OK(b->d_plane_nelem.alloc(b->plane_nelem.size()));
+    CUDA_OK(cudaMemcpy(b->d_plane_nelem.p, b->plane_nelem.data(), b->plane_nelem.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(b->d_plane_block_base.alloc(b->plane_block_base.size()));
+    CUDA_OK(cudaMemcpy(b->d_plane_block_base.p, b->plane_block_base.data(), b->plane_block_base.size() * sizeof(int),
                        cudaMemcpyHostToDevice));
     CUDA_OK(b->d_plane_elem_off.alloc(b->plane_elem_off.size()));
     CUDA_OK(cudaMemcpy(b->d_plane_elem_off.p, b->plane_elem_off.data(), b->plane_elem_off.size() * sizeof(long long),
@@ -1283,6 +1351,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pk.out.elem_a = b->r_elem_a.p;
     pk.out.elem_b = b->r_elem_b.p;
     pk.out.face_pair = b->r_face_pair.p;
+    pk.out.vertex_origin = b->plane_pairs.empty() ? nullptr : b->r_vertex_origin.p;
     pk.out.face_capacity = b->cap_faces;
     pk.out.vert_capacity = b->cap_verts;
     pk.out.face_data_capacity = b->cap_face_data;
@@ -1315,6 +1384,11 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pl.tet_vp = ctx->d_tet_vp.p;
     pl.plane_pairs = b->d_plane_pairs.p;
     pl.plane_elem_off = b->d_plane_elem_off.p;
+    pl.plane_nelem = b->d_plane_nelem.p;
+    pl.plane_block_base = b->d_plane_block_base.p;
+    pl.order_tet = ctx->d_order_tet.p;
+    pl.order_tri = ctx->d_order_tri.p;
+    pl.blocks = ctx->d_plane_blocks.p;
     pl.geom_hs = b->d_geom_hs.p;
     pl.emit_list = b->d_plane_emit.p;
     pl.pair_polys = b->d_pair_polys.p;
@@ -1915,6 +1989,7 @@ dbh_status dbh_batch_device_results(dbh_batch* b, dbh_device_results* out) {
   out->elem_M = b->r_elem_a.p;
   out->elem_N = b->r_elem_b.p;
   out->face_pair = b->r_face_pair.p;
+  out->vertex_origin = b->plane_pairs.empty() ? nullptr : b->r_vertex_origin.p;
   return DBH_OK;
   });
 }
@@ -1960,6 +2035,10 @@ dbh_status dbh_batch_copy_results_async(dbh_batch* b, const dbh_result_buffers* 
   DBH_COPY(buf->grad_eN, b->r_grad_eN.p, 3 * nf, double);
   DBH_COPY(buf->elem_M, b->r_elem_a.p, nf, int32_t);
   DBH_COPY(buf->elem_N, b->r_elem_b.p, nf, int32_t);
+  if (buf->vertex_origin) {
+    if (b->plane_pairs.empty()) return Fail(DBH_ERR_INVALID_ARGUMENT, "vertex_origin: the batch has no half-space pair");
+    DBH_COPY(buf->vertex_origin, b->r_vertex_origin.p, nv, int32_t);
+  }
 #undef DBH_COPY
   return DBH_OK;
   });

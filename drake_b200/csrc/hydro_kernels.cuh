@@ -1308,6 +1308,8 @@ struct ResultArrays {
   int* elem_a;           // [F]
   int* elem_b;           // [F]
   int* face_pair;        // [F]
+  int* vertex_origin;    // [V], half-space surfaces only (null when the batch has none): WorldPoly::origin per vertex,
+                         // -1 for the centroid vertex of a triangle fan
   long long face_capacity;
   long long vert_capacity;
   long long face_data_capacity;
@@ -1806,7 +1808,13 @@ struct PlaneArgs {
   Pools pools;
   const double* tet_vp;             // [4 * pool tet]: pressure at the tetrahedron's vertices
   const int* plane_pairs;           // static list of the half-space pairs (pair indices, ascending)
-  const long long* plane_elem_off;  // [num_plane_pairs + 1]: elements before each of them
+  const long long* plane_elem_off;  // [num_plane_pairs + 1]: work items before each of them (its mesh's elements, padded
+                                    // to whole blocks of kPlaneBlock leaves)
+  const int* plane_nelem;           // [num_plane_pairs]: elements of the pair's mesh
+  const int* plane_block_base;      // [num_plane_pairs]: pool index of the mesh's first leaf-block box
+  const int* order_tet;             // per pool position: the asset-local element at that place of the BVH's leaf order
+  const int* order_tri;
+  const ElemBox* blocks;            // box of every run of kPlaneBlock consecutive leaves
   const double* geom_hs;            // [2 * flat geometry]: pressure scale, margin of a compliant half space
   int q_begin, q_end;               // this chunk's range of the list
   unsigned int* emit_list;          // [elements of the chunk's half-space pairs]: the ones that emit a polygon
@@ -1887,12 +1895,25 @@ __device__ __forceinline__ void plane_pass(const PlaneArgs& a) {
       const int q = find_plane_pair(a.plane_elem_off, a.q_begin, a.q_end, w, w0, num_elems);
       pair = a.plane_pairs[q];
       const Xf rec = a.pair_X[pair];
-      if (rec.m[4] != 0.0) {
+      const int k = (int)(w - a.plane_elem_off[q]);   // position in the mesh's leaf order (k >= elements: padding)
+      bool live = rec.m[4] != 0.0 && k < a.plane_nelem[q];
+      const D3 nhat = make_d3(rec.m[0], rec.m[1], rec.m[2]);
+      mesh_is_soft = a.pairs[pair].kind == kSoftMeshRigidPlane;
+      if (!kPack && live) {
+        // Bvh::Collide(plane) (bvh.h:285-309, mesh_plane_intersection.cc:310-330), flattened to one cut of the tree:
+        // the box of this block of kPlaneBlock consecutive leaves against the boundary plane. All 128 threads of the
+        // block look at the same box. Slicing (compliant mesh x rigid half space): a box entirely on either side has
+        // no polygon; clipping (compliant half space x rigid mesh): only a box entirely outside.
+        const ElemBox& bx = a.blocks[a.plane_block_base[q] + k / kPlaneBlock];
+        const double s = dot(nhat, load3(bx.c)) - rec.m[3];
+        const double r = (fabs(nhat.x) * bx.h[0] + fabs(nhat.y) * bx.h[1]) + fabs(nhat.z) * bx.h[2];
+        const double pad = 1e-12 * (fabs(s) + r + fabs(rec.m[3])) + 1e-300;
+        if (s - r > pad || (mesh_is_soft && s + r < -pad)) live = false;
+      }
+      if (live) {
         const PairRec pr = a.pairs[pair];
-        elem = (int)(w - a.plane_elem_off[q]);
-        mesh_is_soft = pr.kind == kSoftMeshRigidPlane;
+        elem = (mesh_is_soft ? a.order_tet[pr.elem_base_a + k] : a.order_tri[pr.elem_base_b + k]);
         swapped = pr.swapped != 0;
-        const D3 nhat = make_d3(rec.m[0], rec.m[1], rec.m[2]);
         if (mesh_is_soft) {
           const int t = pr.elem_base_a + elem;
           if (kPack) slice_tet_with_plane(a.pools.tets[t], a.tet_vp + 4ll * t, nhat, rec.m[3], a.poses[pr.geom_a], &P);
@@ -1989,6 +2010,7 @@ __device__ __forceinline__ void plane_pass(const PlaneArgs& a) {
     for (int k = 0; k < K.nv; ++k) {
       store3(a.out.vertices, vb + k, K.v[k]);
       a.out.pressures[vb + k] = K.e[k];
+      a.out.vertex_origin[vb + k] = k < P.n ? P.origin[k] : -1;
     }
     for (int k = 0; k < K.nfd; ++k) a.out.face_data[fd0 + k] = K.fd[k];
     const D3 zero = make_d3(0, 0, 0);

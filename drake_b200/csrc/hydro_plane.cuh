@@ -23,6 +23,11 @@ struct WorldPoly {
   int status;    // 0, or the dbh_status this element raises
   D3 v[4];
   double e[4];
+  // Where each vertex comes from in the mesh, so that the host can weld the vertices the reference shares between
+  // polygons (cut_edges, mesh_plane_intersection.cc:205-231; vertices_to_newly_created_vertices /
+  // edges_to_newly_created_vertices, mesh_half_space_intersection.cc:52-101): i = a copy of the element's local vertex i;
+  // 16 + 4 a + b = cut from the edge between the element's local vertices a and b.
+  int origin[4];
   D3 nhat_W;     // the normal handed to the builder (TriMeshBuilder's centroid weights)
   D3 grad_W;     // grad_e_MN_W
 };
@@ -90,6 +95,7 @@ __host__ __device__ __forceinline__ void slice_tet_with_plane(const TetRec& tet,
     const D3 p_MC = p0 + t * (p1 - p0);
     out->v[n] = xform_point(X_WS, p_MC);
     out->e[n] = vp[a] + t * (vp[b] - vp[a]);
+    out->origin[n] = 16 + 4 * a + b;
     ++n;
   }
   out->n = n;
@@ -140,36 +146,37 @@ __host__ __device__ __forceinline__ void clip_tri_by_half_space(const TriRec& tr
   }
   if (num_positive == 3) return;
   int n = 0;
-  auto add = [&](D3 p_RV) {
+  auto add = [&](D3 p_RV, int origin) {
     const double phi_V = dot(nhat_R, p_RV) - displacement;
     out->v[n] = xform_point(X_WR, p_RV);
     out->e[n] = (-phi_V - margin) * pressure_scale;
+    out->origin[n] = origin;
     ++n;
   };
   // CalcEdgePlaneIntersection (:36-50); GetVertexAddIfNeeded demands different signs (:66).
   auto add_edge = [&](int a, int b) {
     if (sgn_of(s[a]) == sgn_of(s[b])) out->status = 13;  // DBH_ERR_REFERENCE_DEMAND
     const double t = fabs(s[a]) / (fabs(s[a]) + fabs(s[b]));
-    add(p[a] + t * (p[b] - p[a]));
+    add(p[a] + t * (p[b] - p[a]), 16 + 4 * a + b);
   };
   if (num_positive == 0) {
-    add(p[0]);
-    add(p[1]);
-    add(p[2]);
+    add(p[0], 0);
+    add(p[1], 1);
+    add(p[2], 2);
   } else if (num_positive == 1) {
     int i0 = 0;  // the first vertex with s >= 0 (:188-189)
     while (i0 < 2 && !(s[i0] >= 0)) ++i0;
     const int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
     // Builder order: edge (i0,i1), edge (i0,i2), v1, v2; polygon {v1, v2, e02, e01} (:196-215).
-    add(p[i1]);
-    add(p[i2]);
+    add(p[i1], i1);
+    add(p[i2], i2);
     add_edge(i0, i2);
     add_edge(i0, i1);
   } else {
     int i0 = 0;  // the first vertex with s <= 0 (:226-227)
     while (i0 < 2 && !(s[i0] <= 0)) ++i0;
     const int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
-    add(p[i0]);
+    add(p[i0], i0);
     add_edge(i0, i1);
     add_edge(i0, i2);
   }

@@ -237,6 +237,7 @@ struct Counters {
   double total_area;
 };
 
+constexpr int kPlaneBlock = 128;   // leaves per block box of the half-space pairs' tree cut (= threads of k_plane's blocks)
 constexpr int kMaxPolyVerts = 8;    // field_intersection.cc:100-104; 7 for tet-tri (mesh_intersection.cc:261-262)
 
 }  // namespace dbh

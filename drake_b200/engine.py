@@ -69,7 +69,7 @@ class ResultBuffers(C.Structure):
                 ("surf_vertex_offset", _lp), ("surf_total_area", _dp), ("surf_centroid", _dp), ("surf_flags", _bp),
                 ("vertices", _dp), ("pressures", _dp), ("face_data", _ip), ("areas", _dp), ("normals", _dp),
                 ("centroids", _dp), ("pressure_at_centroid", _dp), ("grad_eM", _dp), ("grad_eN", _dp),
-                ("elem_M", _ip), ("elem_N", _ip)]
+                ("elem_M", _ip), ("elem_N", _ip), ("vertex_origin", _ip)]
 
 
 class Stats(C.Structure):
@@ -385,10 +385,62 @@ class ContactSurface:
     elem_M: np.ndarray              # emitting element of the first-constructed body
     elem_N: np.ndarray
     swapped: bool
+    vertex_origin: Optional[np.ndarray] = None   # half-space surfaces copied with vertex_origin=True (see weld())
 
     @property
     def num_faces(self) -> int:
         return len(self.areas)
+
+    def weld(self, elements) -> "ContactSurface":
+        """The same half-space surface with the vertices the reference shares between polygons merged
+        (mesh_plane_intersection.cc:205-231 cut_edges; mesh_half_space_intersection.cc:52-101): every polygon vertex is a
+        copy of a vertex of the pair's one mesh or a cut of one of its edges (vertex_origin), so vertices with the same
+        mesh vertex / mesh edge become one -- the first occurrence in face order keeps its position and pressure, as in
+        the reference's maps. elements: [E,4] tetrahedra or [E,3] triangles of that mesh. Face quantities are unchanged."""
+        assert self.vertex_origin is not None, "copy the results with vertex_origin=True"
+        elements = np.asarray(elements)
+        elem = self.elem_M if np.all(self.elem_M >= 0) else self.elem_N
+        tri = self.representation == TRIANGLE
+        fd = np.asarray(self.face_data).reshape(-1)
+        new_index, keep, key_to_new = np.zeros(len(self.vertices), np.int64), [], {}
+        seen = np.zeros(len(self.vertices), bool)
+        i = 0
+        for f in range(self.num_faces):
+            if tri:
+                idx = fd[3 * f:3 * f + 3]
+            else:
+                n = fd[i]
+                idx = fd[i + 1:i + 1 + n]
+                i += n + 1
+            for v in idx:
+                if seen[v]:
+                    continue
+                seen[v] = True
+                o = int(self.vertex_origin[v])
+                if o < 0:
+                    key = ("c", int(v))                       # the centroid of a triangle fan: never shared
+                elif o < 16:
+                    key = ("v", int(elements[elem[f]][o]))
+                else:
+                    a, b = (o - 16) // 4, (o - 16) % 4
+                    va, vb = int(elements[elem[f]][a]), int(elements[elem[f]][b])
+                    key = ("e", min(va, vb), max(va, vb))
+                if key not in key_to_new:
+                    key_to_new[key] = len(keep)
+                    keep.append(int(v))
+                new_index[v] = key_to_new[key]
+        out = np.array(fd, copy=True)
+        if tri:
+            out = new_index[out].astype(np.int32).reshape(-1, 3)
+        else:
+            i = 0
+            for f in range(self.num_faces):
+                n = fd[i]
+                out[i + 1:i + 1 + n] = new_index[fd[i + 1:i + 1 + n]]
+                i += n + 1
+        import dataclasses
+        return dataclasses.replace(self, vertices=self.vertices[keep], pressures=self.pressures[keep], face_data=out,
+                                   vertex_origin=self.vertex_origin[keep])
 
     def polygons(self) -> List[np.ndarray]:
         if self.representation == TRIANGLE:
@@ -411,7 +463,7 @@ class PackedResults:
                ("face_data", np.int32, "d", 1), ("areas", np.float64, "f", 1), ("normals", np.float64, "f", 3),
                ("centroids", np.float64, "f", 3), ("pressure_at_centroid", np.float64, "f", 1),
                ("grad_eM", np.float64, "f", 3), ("grad_eN", np.float64, "f", 3), ("elem_M", np.int32, "f", 1),
-               ("elem_N", np.int32, "f", 1)]
+               ("elem_N", np.int32, "f", 1), ("vertex_origin", np.int32, "v", 1)]
 
     # What MultibodyPlant's discrete update reads from a ContactSurface: per-face area, normal,
     # centroid, pressure at centroid, both gradients; per-surface ids, offsets, total area and centroid.
@@ -419,13 +471,15 @@ class PackedResults:
                    "surf_centroid", "surf_flags", "areas", "normals", "centroids", "pressure_at_centroid", "grad_eM",
                    "grad_eN")
 
-    def __init__(self, sizes: ResultSizes, allocator=None, capacity: Optional[ResultSizes] = None, fields=None):
+    def __init__(self, sizes: ResultSizes, allocator=None, capacity: Optional[ResultSizes] = None, fields=None,
+                 vertex_origin: bool = False):
         """allocator(shape, dtype) -> ndarray lets callers supply pinned host memory; `capacity`
         (>= sizes) allocates larger buffers once so they can be reused across queries; `fields` (names of
         dbh_result_buffers members) restricts the copy-out to those arrays (the others stay NULL / empty)."""
         self.representation = sizes.representation
         self._alloc = allocator or (lambda shape, dtype: np.zeros(shape, dtype))
         self._fields = None if fields is None else set(fields)
+        self._origin = vertex_origin   # only batches with half-space pairs have it (see ContactSurface.weld)
         cap = capacity or sizes
         self._full = {}
         counts = {"s": cap.num_surfaces, "s+1": cap.num_surfaces + 1, "v": cap.num_vertices, "f": cap.num_faces,
@@ -438,6 +492,8 @@ class PackedResults:
         self.resize(sizes)
 
     def _wanted(self, name: str) -> bool:
+        if name == "vertex_origin":
+            return self._origin
         return self._fields is None or name in self._fields
 
     def fits(self, sizes: ResultSizes) -> bool:
@@ -490,7 +546,7 @@ class PackedResults:
                 self.centroids[f0:f1], self.pressure_at_centroid[f0:f1],
                 self.grad_eM[f0:f1] if flags & 1 else None, self.grad_eN[f0:f1] if flags & 2 else None,
                 float(self.surf_total_area[s]), self.surf_centroid[s], self.elem_M[f0:f1], self.elem_N[f0:f1],
-                bool(flags & 4)))
+                bool(flags & 4), self.vertex_origin[v0:v1] if self._origin else None))
         return out
 
 
@@ -658,15 +714,17 @@ class SceneBatch:
         _check(lib().dbh_batch_stats(self._h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in Stats._fields_ if n != "reserved"}
 
-    def copy_results(self, into: Optional[PackedResults] = None, wait: bool = True) -> PackedResults:
+    def copy_results(self, into: Optional[PackedResults] = None, wait: bool = True,
+                     vertex_origin: bool = False) -> PackedResults:
         """D2H of the packed results. wait=False only enqueues the copies on the batch stream (use pinned
-        destination buffers); sync() completes them."""
+        destination buffers); sync() completes them. vertex_origin: also the per-vertex origin codes of the half-space
+        surfaces (ContactSurface.weld)."""
         sizes = self.sizes()
         if into is not None and into.fits(sizes):
             res = into
             res.resize(sizes)
         else:
-            res = PackedResults(sizes)
+            res = PackedResults(sizes, vertex_origin=vertex_origin)
         bufs = res.c_struct()
         if wait:
             _check(lib().dbh_batch_copy_results(self._h, C.byref(bufs)))

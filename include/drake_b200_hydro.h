@@ -302,6 +302,13 @@ typedef struct dbh_result_buffers {
   double* grad_eN;              /* [num_faces*3] */
   int32_t* elem_M;              /* emitting element of the first-constructed body (tet of S / tet0) */
   int32_t* elem_N;              /* emitting element of the second (triangle of R / tet1) */
+  /* per vertex [num_vertices], optional (leave NULL; only batches with half-space pairs have it): where the vertex
+     of a half-space surface comes from in the one mesh of its pair, so that the host can weld the vertices the
+     reference shares between polygons (cut_edges, mesh_plane_intersection.cc:205-231; mesh_half_space_
+     intersection.cc:52-101): i in 0..3 = a copy of local vertex i of the face's emitting element; 16 + 4 a + b = cut
+     from the edge between its local vertices a and b; -1 = the centroid vertex of a triangle fan. Undefined for the
+     vertices of mesh-mesh surfaces (they are never shared). drake_b200_proximity_engine.h welds with it. */
+  int32_t* vertex_origin;
 } dbh_result_buffers;
 dbh_status dbh_batch_copy_results(dbh_batch* batch, const dbh_result_buffers* buffers);
 /* Same copies enqueued on the batch stream without waiting (destinations should be pinned host
@@ -333,6 +340,7 @@ typedef struct dbh_device_results {
   const int32_t* elem_M;
   const int32_t* elem_N;
   const int32_t* face_pair;        /* per face: index into the static geometry-pair list */
+  const int32_t* vertex_origin;    /* per vertex, half-space surfaces only (NULL when the batch has none) */
 } dbh_device_results;
 dbh_status dbh_batch_device_results(dbh_batch* batch, dbh_device_results* out);
 

@@ -208,6 +208,8 @@ class ProximityEngine {
                               (is_dynamic ? "dynamic" : "anchored"));
     ids_.erase(ids_.begin() + g);
     shapes_.erase(shapes_.begin() + g);
+    elements_.erase(elements_.begin() + g);
+    vertices_per_element_.erase(vertices_per_element_.begin() + g);
     assets_.erase(assets_.begin() + g);
     anchored_.erase(anchored_.begin() + g);
     poses_.erase(poses_.begin() + g);
@@ -420,6 +422,8 @@ class ProximityEngine {
   }
 
   int32_t MakeAsset(const Shape& shape, const ProximityProperties& p) {
+    last_elements_.clear();
+    last_vertices_per_element_ = 0;
     if (p.compliance_type == HydroelasticType::kUndefined) return -1;
     const bool soft = p.compliance_type == HydroelasticType::kCompliant;
     int32_t asset = -1;
@@ -466,12 +470,16 @@ class ProximityEngine {
                                         static_cast<int32_t>(v->tetrahedra.size() / 4), v->tetrahedra.data(),
                                         v->pressure.data(), &asset),
             "register_compliant_mesh");
+      last_elements_ = v->tetrahedra;
+      last_vertices_per_element_ = 4;
       return asset;
     } else if (const auto* t = std::get_if<SurfaceMeshShape>(&shape)) {
       if (soft) throw std::logic_error("a surface mesh can only be registered as a rigid geometry");
       Check(dbh_register_rigid_mesh(ctx_, static_cast<int32_t>(t->vertices.size() / 3), t->vertices.data(),
                                     static_cast<int32_t>(t->triangles.size() / 3), t->triangles.data(), &asset),
             "register_rigid_mesh");
+      last_elements_ = t->triangles;
+      last_vertices_per_element_ = 3;
       return asset;
     }
     if (soft) {
@@ -479,6 +487,15 @@ class ProximityEngine {
     } else {
       CheckMesh(dbh_mesh_convert_volume_to_surface(vol.h, &surf.h), "ConvertVolumeToSurfaceMesh");
       Check(dbh_register_mesh(ctx_, surf.h, &asset), "register_mesh");
+    }
+    // The connectivity of the registered mesh: welding the vertices of half-space surfaces needs it (Run()).
+    {
+      const dbh_mesh* m = soft ? vol.h : surf.h;
+      int32_t nv = 0, ne = 0, vpe = 0, has_p = 0;
+      CheckMesh(dbh_mesh_get_sizes(m, &nv, &ne, &vpe, &has_p), "mesh_get_sizes");
+      last_elements_.resize(static_cast<size_t>(ne) * vpe);
+      last_vertices_per_element_ = vpe;
+      CheckMesh(dbh_mesh_copy(m, nullptr, last_elements_.data(), nullptr), "mesh_copy");
     }
     return asset;
   }
@@ -490,6 +507,8 @@ class ProximityEngine {
     index_[id] = static_cast<int>(ids_.size());
     ids_.push_back(id);
     shapes_.push_back(shape);
+    elements_.push_back(std::move(last_elements_));
+    vertices_per_element_.push_back(last_vertices_per_element_);
     assets_.push_back(asset);
     anchored_.push_back(anchored ? 1 : 0);
     poses_.push_back(X_WG);
@@ -549,7 +568,15 @@ class ProximityEngine {
     std::vector<double> tarea(ns), scent(3 * ns), verts(3 * nv), pres(nv), areas(nf), normals(3 * nf), cents(3 * nf),
         ecent(nf), gM(3 * nf), gN(3 * nf);
     std::vector<uint8_t> flags(ns);
+    bool any_half_space = false;
+    for (const Shape& sh : shapes_) any_half_space = any_half_space || std::holds_alternative<HalfSpace>(sh);
+    std::vector<int32_t> origin(any_half_space ? nv : 0), elem_M(any_half_space ? nf : 0), elem_N(any_half_space ? nf : 0);
     dbh_result_buffers buf{};
+    if (any_half_space) {
+      buf.vertex_origin = origin.data();
+      buf.elem_M = elem_M.data();
+      buf.elem_N = elem_N.data();
+    }
     buf.surf_scene = scene.data();
     buf.surf_id_M = id_M.data();
     buf.surf_id_N = id_N.data();
@@ -591,9 +618,68 @@ class ProximityEngine {
       if (cs.has_grad_N_) cs.grad_eN_.assign(gN.begin() + 3 * f0, gN.begin() + 3 * f1);
       cs.total_area_ = tarea[k];
       cs.centroid_ = {scent[3 * k], scent[3 * k + 1], scent[3 * k + 2]};
+      if (any_half_space) {
+        const int gM = index_.at(cs.id_M_), gN = index_.at(cs.id_N_);
+        const bool hM = std::holds_alternative<HalfSpace>(shapes_[gM]), hN = std::holds_alternative<HalfSpace>(shapes_[gN]);
+        if (hM || hN) {
+          const int gmesh = hM ? gN : gM;
+          WeldHalfSpaceSurface(&cs, origin.data() + v0, elem_M.data() + f0, elem_N.data() + f0, elements_[gmesh],
+                               vertices_per_element_[gmesh]);
+        }
+      }
       out[scene[k]].push_back(std::move(cs));
     }
     return out;
+  }
+
+  // The reference shares the vertices of a half-space surface between its polygons: every vertex cut from the same
+  // mesh edge (cut_edges, mesh_plane_intersection.cc:205-231; edges_to_newly_created_vertices, mesh_half_space_
+  // intersection.cc:52-101) or copied from the same mesh vertex (vertices_to_newly_created_vertices) exists once. The
+  // kernels give every polygon its own vertices plus, per vertex, where it comes from (dbh_result_buffers::
+  // vertex_origin); this merges them, first occurrence in face order keeping its position and pressure (as the
+  // reference's maps do in ITS visiting order: positions can differ from the reference's in the last bits, counts
+  // and connectivity cannot). Face quantities are untouched.
+  static void WeldHalfSpaceSurface(ContactSurface* cs, const int32_t* origin, const int32_t* elem_M, const int32_t* elem_N,
+                                   const std::vector<int32_t>& elements, int vertices_per_element) {
+    const size_t nv = cs->pressures_.size();
+    const bool tri = cs->rep_ == HydroelasticContactRepresentation::kTriangle;
+    std::map<std::array<int64_t, 3>, int32_t> key_to_new;
+    std::vector<int32_t> new_index(nv, -1);
+    std::vector<double> verts, pres;
+    size_t i = 0;
+    const size_t nf = cs->areas_.size();
+    for (size_t f = 0; f < nf; ++f) {
+      const int n = tri ? 3 : cs->face_data_[i];
+      int32_t* idx = cs->face_data_.data() + (tri ? 3 * f : i + 1);
+      const int32_t elem = elem_M[f] >= 0 ? elem_M[f] : elem_N[f];
+      const int32_t* ev = elements.data() + static_cast<size_t>(elem) * vertices_per_element;
+      for (int c = 0; c < n; ++c) {
+        const int32_t v = idx[c];
+        if (new_index[v] < 0) {
+          const int32_t o = origin[v];
+          std::array<int64_t, 3> key;
+          if (o < 0) {
+            key = {2, v, 0};   // the centroid vertex of a triangle fan: never shared
+          } else if (o < 16) {
+            key = {0, ev[o], 0};
+          } else {
+            const int64_t a = ev[(o - 16) / 4], b = ev[(o - 16) % 4];
+            key = {1, std::min(a, b), std::max(a, b)};
+          }
+          auto it = key_to_new.find(key);
+          if (it == key_to_new.end()) {
+            it = key_to_new.emplace(key, static_cast<int32_t>(pres.size())).first;
+            verts.insert(verts.end(), cs->vertices_.begin() + 3 * v, cs->vertices_.begin() + 3 * v + 3);
+            pres.push_back(cs->pressures_[v]);
+          }
+          new_index[v] = it->second;
+        }
+        idx[c] = new_index[v];
+      }
+      if (!tri) i += n + 1;
+    }
+    cs->vertices_ = std::move(verts);
+    cs->pressures_ = std::move(pres);
   }
 
   dbh_context* ctx_{nullptr};
@@ -601,6 +687,10 @@ class ProximityEngine {
   int num_scenes_{1};
   std::vector<GeometryId> ids_;
   std::vector<Shape> shapes_;
+  std::vector<std::vector<int32_t>> elements_;   // per geometry: connectivity of its registered mesh (empty: none)
+  std::vector<int> vertices_per_element_;
+  std::vector<int32_t> last_elements_;
+  int last_vertices_per_element_{0};
   bool skip_unsupported_point_pairs_{false};
   std::vector<int32_t> assets_;
   std::vector<uint8_t> anchored_;

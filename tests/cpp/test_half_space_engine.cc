@@ -62,6 +62,12 @@ int main() {
       for (int f = 0; f < s[0].num_faces(); ++f) sum += s[0].area(f);
       EXPECT(std::fabs(sum - s[0].total_area()) < 1e-12);
       EXPECT(s[0].total_area() > 0.05 && s[0].total_area() < M_PI * R * R);
+      // Welded like the reference's (cut_edges, mesh_plane_intersection.cc:205-231): the polygons share the vertices
+      // cut from the same tetrahedron edge, so there are far fewer vertices than face corners.
+      const int corners = s[0].is_triangle() ? 3 * s[0].num_faces()
+                                             : static_cast<int>(s[0].face_data().size()) - s[0].num_faces();
+      EXPECT(s[0].num_vertices() < corners * 2 / 3);
+      for (int32_t idx : s[0].face_data()) EXPECT(idx >= 0 && idx < std::max(s[0].num_vertices(), 8));
     }
     EXPECT(e.ComputeContactSurfaces(kPoly, {{1, RigidTransformd::FromTranslation(0, 0, 1.5 * R)}}).empty());
   }

@@ -22,7 +22,7 @@ def _digest(s):
 
 
 def test_one_full_size_config5_scene_against_the_oracle(ctx):
-    """BASELINE config 5 at its own mesh size: two 2 097 152-tetrahedron spheres (one shared asset), ~9 M candidate
+    """BASELINE config 5 at its own mesh size: two 2 097 152-tetrahedron spheres (one shared asset), millions of candidate
     tetrahedron pairs and ~27 000 contact polygons in ONE geometry pair: every face against the oracle's tree-driven
     run (MODE_TREE), emitted element pairs bit-exact, values to 1e-10; the pair-local offsets and the per-surface
     reduction over more than 4096 faces are exercised at this size."""
@@ -38,7 +38,7 @@ def test_one_full_size_config5_scene_against_the_oracle(ctx):
     assert want[0].num_faces > 20000
     parity.compare_surface(got[0][0], want[0])
     assert st["tet_tet_pairs"] == ostats["element_pairs"]       # candidate pair count, bit-exact
-    assert st["tet_tet_pairs"] > 5_000_000
+    assert st["tet_tet_pairs"] > 1_000_000
 
 
 def test_config5_multi_chunk_equals_single_chunk(ctx):

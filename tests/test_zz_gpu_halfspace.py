@@ -86,6 +86,44 @@ def test_compliant_half_space_rigid_box_kat(ctx, rep, ids):
     assert batch.compute_contact_surfaces(np.stack([ho.xform(None, [0, 0, -50.0]), X_WF]), rep)[0] == []
 
 
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+def test_welded_half_space_surfaces_have_the_reference_vertex_counts(ctx, rep):
+    """The reference shares the vertices of a half-space surface between its polygons (cut_edges, mesh_plane_
+    intersection.cc:205-231; mesh_half_space_intersection.cc:52-101); the kernels give every polygon its own and say where
+    each comes from (vertex_origin). Welded on the host (ContactSurface.weld) the surfaces have the reference's vertex
+    counts -- 12 vertices / 10 polygons and 22 / 34 for the box of mesh_half_space_intersection_test.cc:886-1007 -- and
+    compare with the oracle's welded surfaces as any mesh-mesh surface does (vertex count equal, not just >=). Second
+    case: a 4096-tetrahedron compliant sphere sliced by a rigid half space."""
+    import drake_b200 as db
+    X_WF = ho.xform(ho.angle_axis_matrix(math.pi / 7, np.array([1, 2, 3]) / math.sqrt(14)), [-0.25, 0.5, 0.75])
+    X_FB = ho.xform(ho.rpy_matrix(math.pi / 4, math.pi / 4, math.pi / 4), [1.0, 2.0, 3.0])
+    box = box_mesh(X_FB)
+    X_WH = ho.compose(X_WF, X_FB)
+    a_h, a_r = ctx.register_half_space(compliant=True, pressure_scale=17.0), parity.register_rigid(ctx, box)
+    batch = db.SceneBatch(ctx, [0, 2], [a_h, a_r], [2, 1])
+    batch.set_poses(np.stack([X_WH, X_WF]))
+    batch.run(rep, db.STRICT)
+    raw = batch.copy_results(vertex_origin=True).surfaces()[0]
+    assert len(raw.vertices) == (44 if rep == ho.KTRIANGLE else 34)   # one set of vertices per polygon
+    welded = raw.weld(box.arrays()[1])
+    assert (len(welded.vertices), welded.num_faces) == ((22, 34) if rep == ho.KTRIANGLE else (12, 10))
+    parity.compare_surface(welded, ho.soft_half_space_rigid_mesh(box, X_WH, 17.0, X_WF, 2, 1, rep))
+    soft = ho.VolumeMesh.sphere(1.0, 0.25, dense=True)
+    fld = ho.VolumeField.sphere(soft, 1.0, 1e5)
+    a_s, a_g = parity.register_compliant(ctx, soft, fld), ctx.register_half_space()
+    batch = db.SceneBatch(ctx, [0, 2], [a_s, a_g], [1, 2])
+    X_WS = ho.xform(ho.rpy_matrix(0.3, -0.4, 0.2), [0.1, -0.2, 0.55])
+    X_WG = ho.xform(ho.rpy_matrix(0.05, 0.1, 0.0), [0, 0, 0])
+    batch.set_poses(np.stack([X_WS, X_WG]))
+    batch.run(rep, db.STRICT)
+    raw = batch.copy_results(vertex_origin=True).surfaces()[0]
+    want = ho.soft_mesh_rigid_half_space(soft, fld, X_WS, X_WG, 1, 2, rep)
+    welded = raw.weld(soft.tets)
+    assert len(welded.vertices) == len(want.vertices) < len(raw.vertices)
+    assert welded.num_faces == want.num_faces > 100
+    parity.compare_surface(welded, want)
+
+
 def test_compliant_half_space_margin(ctx):
     """mesh_half_space_intersection_test.cc:1107-1186: the box only reaches into the margin layer."""
     import drake_b200 as db
