@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libhydro_oracle.so")
 
 KTRIANGLE, KPOLYGON = 0, 1
-MODE_BRUTE, MODE_TREE, MODE_REFERENCE_BVH = 0, 1, 2
+MODE_BRUTE, MODE_TREE, MODE_REFERENCE_BVH, MODE_REFERENCE_OBB = 0, 1, 2, 3
 
 
 def build(force: bool = False) -> str:

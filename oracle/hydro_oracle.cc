@@ -17,6 +17,7 @@
 #include <unordered_map>
 
 #include "ho_bvh.h"
+#include "ho_obb.h"
 #include "ho_contact.h"
 #include "ho_halfspace.h"
 #include "ho_traction.h"
@@ -29,12 +30,14 @@ struct VolAsset {
   VolumeMesh mesh;
   std::unique_ptr<std::vector<Aabb>> boxes;
   std::unique_ptr<Bvh> bvh_ref;    // reference-shaped (1 tet / leaf)
+  std::unique_ptr<ObbBvh> bvh_obb; // Bvh<Obb, VolumeMesh> (hydroelastic_internal.h:71-100)
 };
 struct TriAsset {
   TriMesh mesh;
   std::unique_ptr<std::vector<Aabb>> boxes;
   std::unique_ptr<Bvh> bvh_ref;    // reference-shaped (<= 3 tris / leaf)
   std::unique_ptr<Bvh> bvh_leaf1;  // one triangle per leaf
+  std::unique_ptr<ObbBvh> bvh_obb; // Bvh<Obb, TriangleSurfaceMesh> (hydroelastic_internal.h:268)
 };
 
 std::vector<std::unique_ptr<VolAsset>> g_vols;
@@ -91,6 +94,11 @@ const Bvh& RefBvh(TriAsset& a) {
   if (!a.bvh_ref) a.bvh_ref = std::make_unique<Bvh>(MakeBvh(a.mesh, 3));
   return *a.bvh_ref;
 }
+template <class Asset>
+const ObbBvh& RefObbBvh(Asset& a) {
+  if (!a.bvh_obb) a.bvh_obb = std::make_unique<ObbBvh>(MakeObbBvh(a.mesh));
+  return *a.bvh_obb;
+}
 const Bvh& Leaf1Bvh(VolAsset& a) { return RefBvh(a); }
 const Bvh& Leaf1Bvh(TriAsset& a) {
   if (!a.bvh_leaf1) a.bvh_leaf1 = std::make_unique<Bvh>(MakeBvh(a.mesh, 1));
@@ -98,13 +106,14 @@ const Bvh& Leaf1Bvh(TriAsset& a) {
 }
 
 // mode 0: leaf predicate by brute force; 1: leaf predicate through trees;
-// 2: reference-shaped Bvh<Aabb>::Collide (bvh.h:220-262).
+// 2: reference-shaped Bvh<Aabb>::Collide (bvh.h:220-262); 3: the reference's own Bvh<Obb>::Collide (ho_obb.h).
 template <class A, class B>
 std::vector<std::pair<int, int>> Candidates(A& a, B& b, const Xform& X_AB, int mode, int64_t* bv_tests = nullptr) {
   if (mode == 0) return LeafCandidatesBruteForce(Boxes(a), Boxes(b), X_AB);
   if (mode == 1) return LeafCandidatesTree(Leaf1Bvh(a), Leaf1Bvh(b), X_AB);
   std::vector<std::pair<int, int>> out;
-  Collide(RefBvh(a), RefBvh(b), X_AB, &out, bv_tests);
+  if (mode == 3) CollideObb(RefObbBvh(a), RefObbBvh(b), X_AB, &out, bv_tests);
+  else Collide(RefBvh(a), RefBvh(b), X_AB, &out, bv_tests);
   return out;
 }
 
@@ -818,8 +827,8 @@ int ho_scene_batch_time(int scene, int nscenes, const double* poses, int rep, in
   // Warm the lazily built per-asset structures outside the timed region.
   for (const SceneGeom& g : sc.geoms) {
     if (g.half_space) continue;
-    if (g.type == 2) { Boxes(*g_vols[g.vol]); RefBvh(*g_vols[g.vol]); }
-    if (g.type == 1) { Boxes(*g_tris[g.tri]); RefBvh(*g_tris[g.tri]); Leaf1Bvh(*g_tris[g.tri]); }
+    if (g.type == 2) { Boxes(*g_vols[g.vol]); RefBvh(*g_vols[g.vol]); if (mode == 3) RefObbBvh(*g_vols[g.vol]); }
+    if (g.type == 1) { Boxes(*g_tris[g.tri]); RefBvh(*g_tris[g.tri]); Leaf1Bvh(*g_tris[g.tri]); if (mode == 3) RefObbBvh(*g_tris[g.tri]); }
   }
   std::vector<SceneStats> per_thread(nthreads);
   std::atomic<int> next{0};
