@@ -158,23 +158,25 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ the CPU port ---
 
-def time_cpu_port(config: str, scenes: int, rep: int, budget_s: float, threads: int):
+def time_cpu_port(config: str, scenes: int, rep: int, budget_s: float, threads: int, obb: bool = True):
     """Times the CPU port of the reference path (reference-shaped BVH traversal + clipping + mesh construction) on a
-    bounded sample of the config's scenes. Everything here is built by the oracle's own generators
+    bounded sample of the config's scenes. obb: the reference's own hierarchy, Bvh<Obb> (oracle/ho_obb.h), else the
+    axis-aligned Bvh<Aabb> of the same shape. Everything here is built by the oracle's own generators
     (oracle/ref_workloads.py): this leg never touches the product library."""
     from oracle import ho, ref_workloads as RW
+    mode = ho.MODE_REFERENCE_OBB if obb else ho.MODE_REFERENCE_BVH
     wl = make_workload(config, min(scenes, 4096) if config in ("c4", "c5") else scenes, 0, Mesh=RW.RefMesh)
     sc, order = RW.scene_for(wl)
     poses = wl.poses[:, order, :]
     probe = min(len(poses), max(threads, 8))
-    t, st = sc.batch_time(poses[:probe], rep, ho.MODE_REFERENCE_BVH, threads)
+    t, st = sc.batch_time(poses[:probe], rep, mode, threads)
     per_scene = max(t / probe, 1e-7)
     n = int(min(len(poses), max(probe, budget_s / per_scene)))
     # When the whole workload takes less than the budget, repeat it (bounded) so the sample is seconds, not a blink.
     passes = int(min(64, max(1, budget_s / max(per_scene * n, 1e-9)))) if n == len(poses) else 1
     t, surfaces, pairs = 0.0, 0, 0
     for _ in range(passes):
-        tp, st = sc.batch_time(poses[:n], rep, ho.MODE_REFERENCE_BVH, threads)
+        tp, st = sc.batch_time(poses[:n], rep, mode, threads)
         t += tp
         surfaces += st["surfaces"]
         pairs += st["element_pairs"]
@@ -217,7 +219,8 @@ def run_reference(args):
            "config": config_record(wl, scenes, rep_name, wl.geoms_per_scene),
            "element_pairs_per_sec": float(np.mean(pairs)),
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                            "bvh": "reference-shaped Bvh<Aabb> (median split, <= 1 tet / 3 tris per leaf), scalar BoxesOverlap",
+                            "bvh": "the reference's Bvh<Obb> (PCA + volume line search, median split, <= 1 tet / 3 tris per leaf), "
+                                   "scalar BoxesOverlap",
                             "native": "oracle/_build/libhydro_oracle.so only: meshes, fields and BVHs come from the oracle's "
                                       "own generators (oracle/ref_workloads.py)"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -541,11 +544,19 @@ def cpu_baseline_record(config: str, scenes: int, rep: int, seconds: float):
     threads = os.cpu_count() or 1
     r = time_cpu_port(config, scenes, rep, seconds, threads)
     r1 = time_cpu_port(config, scenes, rep, min(5.0, seconds), 1)
+    ra = time_cpu_port(config, scenes, rep, min(5.0, seconds), threads, obb=False)
     return {"value": r["surfaces_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+            "bvh": "Bvh<Obb> as in the reference (oracle/ho_obb.h)",
             "sample": f"{r['passes']} x {r['scenes']} of {scenes} scenes of {r['workload'].name}, {r['seconds']:.1f} s",
             "element_pairs_per_sec": r["element_pairs_per_s"], "ms_per_scene_all_cores": r["ms_per_scene"],
+            "bv_tests_per_scene": r["stats"]["bv_tests"] / max(1, r["scenes"]),
+            "element_pairs_per_scene": r["stats"]["element_pairs"] / max(1, r["scenes"]),
             "single_thread": {"value": r1["surfaces_per_s"], "scenes": r1["scenes"], "ms_per_scene": r1["ms_per_scene"],
-                              "element_pairs_per_sec": r1["element_pairs_per_s"]}}
+                              "element_pairs_per_sec": r1["element_pairs_per_s"]},
+            "aabb_hierarchy": {"value": ra["surfaces_per_s"], "cores": threads, "ms_per_scene_all_cores": ra["ms_per_scene"],
+                               "bv_tests_per_scene": ra["stats"]["bv_tests"] / max(1, ra["scenes"]),
+                               "element_pairs_per_scene": ra["stats"]["element_pairs"] / max(1, ra["scenes"]),
+                               "what": "the same port over Bvh<Aabb> (looser boxes under rotation)"}}
 
 
 def other_config_line(D: Dist, config: str, flush, cpu_seconds: float, with_cpu: bool):

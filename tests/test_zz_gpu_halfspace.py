@@ -290,7 +290,10 @@ def test_config3_on_a_half_space_ground(ctx):
         total += len(want)
     assert total == 64  # ball x ground and ball x plate in every scene
     st = batch.stats()
-    assert st["half_space_elements"] == 32 * 512 and st["geometry_pairs_tested"] == 64
+    # Elements sliced = the leaf blocks of the ball's tree that reach the ground plane (Bvh::Collide(plane)), not the
+    # whole 512-tetrahedron mesh of every scene.
+    assert 0 < st["half_space_elements"] < 32 * 512 and st["half_space_elements"] % 128 == 0
+    assert st["geometry_pairs_tested"] == 64
 
 
 @pytest.mark.parametrize("name", ["c3h_16_scenes", "c3h_16_scenes_tri"])
