@@ -1405,7 +1405,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     // block-wide appends; filter / pack: resident blocks per SM the launch bound asks for (registers against
     // occupancy); tgrid / fgrid / pgrid: grid size in units of the resident blocks -- persistent grids (1x for the
     // traversal and the pack) beat over-subscribed ones by 5-15 % (no tail wave).
-    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, small = -1, sblocks = 4; } tune;
+    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, small = -1, sblocks = 4, stagea = 0; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1419,8 +1419,11 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       get("fgrid", &tune.fgrid);
       get("pgrid", &tune.pgrid);
       get("small", &tune.small);  // overrides dbh_batch_set_small_pair_path: 0 never, 1 always, 2 auto
+      get("stagea", &tune.stagea);    // experiments on the conservative culls (ClipArgs::tune)
       get("sblocks", &tune.sblocks);  // k_small_pairs: resident 128-thread blocks per SM asked of the launch bound
     }
+    ca.tune = tune.stagea;
+    sm.c.tune = tune.stagea;
     const int small_mode = tune.small >= 0 ? tune.small : b->small_mode;
     const int small_smem = kSmallWarps * small_smem_bytes_per_warp(b->small_stack_cap);
     if (b->num_small_pairs && small_mode != 0 && small_smem > 48 * 1024) {

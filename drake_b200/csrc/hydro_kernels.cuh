@@ -483,6 +483,8 @@ struct ClipArgs {
   // filter_face_normal_along_field_gradient = false (mesh_intersection.h), which is how the reference's own
   // mesh_intersection_benchmark runs it. ComputeContactSurfaces always filters (the default).
   int no_normal_filter;
+  int tune;             // experiments (DBH_TUNE "stagea="): bit0 no triangle-edge planes, bit1 no triangle plane, bit2 no
+                        // tet-tet face planes, bit3 no tet-tet equilibrium-plane cull (each only widens the survivor set)
   int4 trace;           // debug builds only
 };
 
@@ -736,7 +738,8 @@ __device__ __forceinline__ bool tri_stage_a(const ClipArgs& a, int4 c, const Pai
       above += h > m;
       below += h < -m;
     }
-    if (above == 4 || below == 4) keep = false;
+    if (!(a.tune & 2) && (above == 4 || below == 4)) keep = false;
+    if (a.tune & 1) return keep;
     // Edge e from qa to qb; u = nhat x (qb - qa) points into the triangle.
     const F3 qa[3] = {q0, q1, q2};
     const F3 qb[3] = {q1, q2, q0};
@@ -860,8 +863,9 @@ __device__ __forceinline__ bool tet_stage_a(const ClipArgs& a, int4 c, const Pai
     above1 += h1 > tol1;
     below1 += h1 < -tol1;
   }
-  if (above0 == 4 || below0 == 4 || above1 == 4 || below1 == 4) return false;
+  if (!(a.tune & 8) && (above0 == 4 || below0 == 4 || above1 == 4 || below1 == 4)) return false;
   bool keep = true;
+  if (a.tune & 4) return keep;
   const float mr = kCullMarginF * L, mn = b1.margin * L;
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
