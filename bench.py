@@ -304,6 +304,8 @@ class Leg:
         self.wl = make_workload(config, scenes, scene0)
         wl_b = make_workload(config, scenes, scene0_b) if config in ("c3", "c3h", "c4", "c5", "c2s") else self.wl
         self.ctx = db.Context(D.local)
+        if os.environ.get("DBH_BVH", "") == "host":   # A/B of the two BVH builders (default: the device-built LBVH)
+            self.ctx.set_bvh_builder(engine.BVH_HOST_MEDIAN_SPLIT)
         self.batch = self.wl.register(self.ctx)
         poses = [np.ascontiguousarray(w.poses.reshape(-1, 12)) for w in (self.wl, wl_b)]
         self.pose_sets = [torch.from_numpy(p).to(D.dev) for p in poses]
