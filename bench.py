@@ -511,8 +511,14 @@ def roofline_for(leg: Leg, res: dict, config: str, default_size: bool):
     achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
     prof, prof_src = ncu_profile(config) if default_size else (None, None)
     traffic, issue = None, None
+    # A capture taken on fewer scenes of the same config (ncu replays every launch ~40 times: the full-size clutter and
+    # stress configs are captured on a slice) is scaled by the scene ratio: per-scene work is statistically uniform.
+    k = (leg.scenes / prof["scenes"]) if prof and prof.get("scenes") else 1.0
     if prof and dominant in prof.get("groups", {}):
-        g = prof["groups"][dominant]
+        g = dict(prof["groups"][dominant])
+        for key in ("dram_bytes", "warp_instructions"):
+            if g.get(key) is not None:
+                g[key] = g[key] * k
         traffic = g.get("dram_bytes")
         if g.get("warp_instructions") and d_ms > 0:
             # Issue-slot roofline: warp instructions of the capture / live event time, against 4 schedulers x SMs x clock.
@@ -527,7 +533,9 @@ def roofline_for(leg: Leg, res: dict, config: str, default_size: bool):
     whole_alg = st["algorithmic_bytes"]
     compulsory = None
     if prof and prof.get("compulsory_dram_bytes"):
-        compulsory = {"bytes": prof["compulsory_dram_bytes"], "measured_dram_bytes_whole_query": prof.get("dram_bytes_whole_query"),
+        compulsory = {"bytes": prof["compulsory_dram_bytes"] * k,
+                      "measured_dram_bytes_whole_query": (prof.get("dram_bytes_whole_query") or 0) * k,
+                      "scaled_from_scenes": prof.get("scenes") if k != 1.0 else None,
                       "what": "every asset byte once + poses + work lists written and read once + the packed result once"}
     return {"bound": "hbm", "kernel": d_kernels, "group": dominant, "achieved": achieved, "peak": peak,
             "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,

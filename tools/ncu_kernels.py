@@ -2,7 +2,7 @@
 (tools/ncu_summary.py over an `ncu --set full --clock-control none` capture of tools/profile_one.py <config>:<scenes> 1),
 in the form bench.py reads for `roofline.traffic`, `roofline.issue_slots` and `roofline.compulsory_dram`.
 
-  python tools/ncu_kernels.py profiles/r2_ncu_full_c3_summary.csv gpurun_out/r2x_full.log c3 profiles/r2_kernels_c3.json
+  python tools/ncu_kernels.py profiles/r2_ncu_full_c3_summary.csv gpurun_out/r2x_full.log c3 profiles/r2_kernels_c3.json [scenes]
 
 The log is profile_one.py's stdout: its last line is the stats dict of the profiled query, from which the compulsory
 DRAM traffic is computed (every byte that must cross the HBM interface at least once however good the caches are):
@@ -15,6 +15,7 @@ import json
 import sys
 
 summary, log, config, out_path = sys.argv[1:5]
+scenes = int(sys.argv[5]) if len(sys.argv) > 5 else None   # scenes of the captured query (None: the config's default size)
 rows = list(csv.reader(open(summary)))
 hdr, units = rows[0], rows[1]
 col = {n: hdr.index(n) for n in hdr}
@@ -77,7 +78,7 @@ if stats:
     result = stats["vertices"] * 32 + stats["polygons"] * 108 + (stats["polygons"] + stats["vertices"]) * 4
     poses = stats["geometry_pairs_tested"] * 2 * 96
     compulsory = poses + 2 * 16 * surv + 2 * soup + result
-out = {"config": config, "source": summary, "sms": 148,
+out = {"config": config, "scenes": scenes, "source": summary, "sms": 148,
        "note": "one query under `ncu --set full --clock-control none` (cold caches, kernels serialised): shares and counters, "
                "not timings",
        "groups": groups, "dram_bytes_whole_query": total_dram, "ncu_ms_whole_query": total_ms,
