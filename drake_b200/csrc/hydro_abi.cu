@@ -16,6 +16,7 @@
 #include "../../include/drake_b200_hydro.h"
 #include "hydro_kernels.cuh"
 #include "hydro_small.cuh"
+#include "hydro_refit.cuh"
 #include "hydro_lbvh.h"
 
 using namespace dbh;
@@ -91,6 +92,10 @@ struct HostAsset {
   int node_base{0};
   // Bvh::Collide(plane) for the half-space pairs (bvh.h:285-309), flattened to one cut of the tree: the elements in
   // the tree's leaf order (depth first), and the box of every run of kPlaneBlock consecutive leaves.
+  // Triangle assets keep their vertices and connectivity: dbh_context_update_vertices re-poses them on the device.
+  std::vector<double> rverts;        // [num_vertices * 3]
+  std::vector<int> tri_idx;          // [num_elements * 3], asset-local vertex indices
+  int vert_base{0};                  // first pool index of this asset's vertices (triangle assets)
   std::vector<int> leaf_order;       // asset-local element indices
   std::vector<ElemBox> block_boxes;  // ceil(num_elements / kPlaneBlock)
   int block_base{0};                 // first pool index of this asset's block boxes
@@ -246,6 +251,12 @@ struct dbh_context {
   DevBuf<int> d_order_tet, d_order_tri;   // per pool element position: asset-local element index in BVH leaf order
   DevBuf<ElemBox> d_plane_blocks;         // box of every run of kPlaneBlock consecutive leaves, all assets
   long long num_blocks{0};
+  // Deformable reuse: the triangle assets' vertex pool and connectivity, parent links of every node, visit counters.
+  DevBuf<double> d_rverts;
+  DevBuf<int> d_tri_idx, d_node_parent, d_node_visit;
+  DevBuf<int4> d_block_desc;
+  long long num_rverts{0};
+  int bounds_version{0};   // bumped when an update moves root boxes: batches refresh their geometry bounds
   size_t uploaded_assets{0};
   long long up_tets{0}, up_tris{0}, up_nodes{0};
 
@@ -263,6 +274,10 @@ struct dbh_context {
     } else {
       a->elem_base = static_cast<int>(num_tris);
       num_tris += a->num_elements;
+    }
+    if (a->type == DBH_RIGID && !a->half_space) {
+      a->vert_base = static_cast<int>(num_rverts);
+      num_rverts += a->num_vertices;
     }
     BuildPlaneBlocks(a);
     a->block_base = static_cast<int>(num_blocks);
@@ -293,6 +308,10 @@ struct dbh_context {
     CUDA_OK(grow(d_order_tet, num_tets, &regrown));
     CUDA_OK(grow(d_order_tri, num_tris, &regrown));
     CUDA_OK(grow(d_plane_blocks, num_blocks, &regrown));
+    CUDA_OK(grow(d_rverts, 3 * num_rverts, &regrown));
+    CUDA_OK(grow(d_tri_idx, 3 * num_tris, &regrown));
+    CUDA_OK(grow(d_node_parent, num_nodes, &regrown));
+    CUDA_OK(grow(d_node_visit, num_nodes, &regrown));
     const size_t first = regrown ? 0 : uploaded_assets;
     std::vector<BvhNode> rebased;
     std::vector<Node32> rebased32;
@@ -337,6 +356,22 @@ struct dbh_context {
             ct[e].n[d] = static_cast<float>(a.tris[e].n[d]);
           }
         CUDA_OK(cudaMemcpy(d_cull_tri.p + a.elem_base, ct.data(), ct.size() * sizeof(TriCull), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_rverts.p + 3ll * a.vert_base, a.rverts.data(), a.rverts.size() * sizeof(double),
+                           cudaMemcpyHostToDevice));
+        std::vector<int> idx(a.tri_idx);
+        for (int& i : idx) i += a.vert_base;
+        CUDA_OK(cudaMemcpy(d_tri_idx.p + 3ll * a.elem_base, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+      }
+      {
+        // Parent links (pool indices): -1 for the root, -2 for the unused node 0.
+        std::vector<int> parent(a.nodes.size(), -1);
+        parent[0] = -2;
+        for (size_t k = 1; k < a.nodes.size(); ++k)
+          if (a.nodes[k].left >= 0) {
+            parent[a.nodes[k].left] = static_cast<int>(k) + a.node_base;
+            parent[a.nodes[k].right] = static_cast<int>(k) + a.node_base;
+          }
+        CUDA_OK(cudaMemcpy(d_node_parent.p + a.node_base, parent.data(), parent.size() * sizeof(int), cudaMemcpyHostToDevice));
       }
       CUDA_OK(cudaMemcpy((a.type == DBH_COMPLIANT ? d_order_tet.p : d_order_tri.p) + a.elem_base, a.leaf_order.data(),
                          a.leaf_order.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -448,6 +483,7 @@ struct dbh_batch {
   DevBuf<int> d_fallback;
   int num_no_surface_pairs{0};
   int last_query_kind{DBH_QUERY_STRICT};
+  int bounds_version{0};
   DevBuf<unsigned int> d_plane_emit;  // the current chunk's emitting half-space elements (chunk-local indices)
   int plane_emit_sized_for{0};        // the chunk count d_plane_emit was last sized for
   DevBuf<double> d_geom_hs;
@@ -733,6 +769,8 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* v
   a->type = DBH_RIGID;
   a->num_vertices = nv;
   a->num_elements = nt;
+  a->rverts.assign(verts, verts + 3ll * nv);
+  a->tri_idx.assign(tris, tris + 3ll * nt);
   a->tris.resize(nt);
   for (int e = 0; e < nt; ++e) {
     TriRec& r = a->tris[e];
@@ -755,6 +793,97 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* v
   ctx->Place(a.get());
   ctx->assets.push_back(std::move(a));
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
+  return DBH_OK;
+  });
+}
+
+dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices) {
+  return Guarded([&]() -> dbh_status {
+  if (!ctx || num_assets <= 0 || !assets || !vertices)
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: bad argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  for (int k = 0; k < num_assets; ++k) {
+    if (assets[k] < 0 || assets[k] >= static_cast<int>(ctx->assets.size()))
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: bad asset handle");
+    const HostAsset& a = *ctx->assets[assets[k]];
+    if (a.type != DBH_RIGID || a.half_space)
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: only triangle-mesh (rigid) assets can be re-posed");
+  }
+  if (dbh_status s = ctx->UploadPools()) return s;
+  // Group the list into runs of assets whose pool ranges follow one another (assets registered consecutively): one
+  // vertex upload and three launches per run.
+  const double* src = vertices;
+  int k = 0;
+  while (k < num_assets) {
+    const HostAsset& first = *ctx->assets[assets[k]];
+    int k1 = k + 1;
+    long long nverts = first.num_vertices;
+    while (k1 < num_assets) {
+      const HostAsset& prev = *ctx->assets[assets[k1 - 1]];
+      const HostAsset& next = *ctx->assets[assets[k1]];
+      if (next.vert_base != prev.vert_base + prev.num_vertices || next.elem_base != prev.elem_base + prev.num_elements ||
+          next.node_base != prev.node_base + static_cast<int>(prev.nodes.size()) ||
+          next.block_base != prev.block_base + static_cast<int>(prev.block_boxes.size()))
+        break;
+      nverts += next.num_vertices;
+      ++k1;
+    }
+    const HostAsset& last = *ctx->assets[assets[k1 - 1]];
+    CUDA_OK(cudaMemcpyAsync(ctx->d_rverts.p + 3ll * first.vert_base, src, 3ll * nverts * sizeof(double),
+                            cudaMemcpyHostToDevice, nullptr));
+    for (int j = k; j < k1; ++j) {   // the host copy stays current (a later pool regrowth re-uploads it)
+      HostAsset& a = *ctx->assets[assets[j]];
+      std::copy(src, src + 3ll * a.num_vertices, a.rverts.begin());
+      src += 3ll * a.num_vertices;
+    }
+    RefitArgs ra{};
+    ra.verts = ctx->d_rverts.p;
+    ra.tri_idx = ctx->d_tri_idx.p;
+    ra.tris = ctx->d_tris.p;
+    ra.cull_tri = ctx->d_cull_tri.p;
+    ra.ebox_tri = ctx->d_ebox_tri.p;
+    ra.nodes = ctx->d_nodes.p;
+    ra.nodes32 = ctx->d_nodes32.p;
+    ra.node_parent = ctx->d_node_parent.p;
+    ra.node_visit = ctx->d_node_visit.p;
+    ra.tri_begin = first.elem_base;
+    ra.tri_end = last.elem_base + last.num_elements;
+    ra.node_begin = first.node_base;
+    ra.node_end = last.node_base + static_cast<int>(last.nodes.size());
+    ra.order_tri = ctx->d_order_tri.p;
+    ra.blocks = ctx->d_plane_blocks.p;
+    std::vector<int4> desc;
+    for (int j = k; j < k1; ++j) {
+      const HostAsset& a = *ctx->assets[assets[j]];
+      for (int b = 0; b < static_cast<int>(a.block_boxes.size()); ++b)
+        desc.push_back(make_int4(a.elem_base + b * kPlaneBlock, std::min(kPlaneBlock, a.num_elements - b * kPlaneBlock),
+                                 a.elem_base, 0));
+    }
+    CUDA_OK(ctx->d_block_desc.ensure(std::max<size_t>(desc.size(), 1)));
+    CUDA_OK(cudaMemcpyAsync(ctx->d_block_desc.p, desc.data(), desc.size() * sizeof(int4), cudaMemcpyHostToDevice, nullptr));
+    ra.block_desc = ctx->d_block_desc.p;
+    ra.block_begin = first.block_base;
+    ra.block_end = first.block_base + static_cast<int>(desc.size());
+    CUDA_OK(cudaMemsetAsync(ctx->d_node_visit.p + ra.node_begin, 0, sizeof(int) * (ra.node_end - ra.node_begin), nullptr));
+    const int ntri = ra.tri_end - ra.tri_begin, nnode = ra.node_end - ra.node_begin;
+    k_refit_tris<<<(ntri + 255) / 256, 256>>>(ra);
+    k_refit_nodes<<<(nnode + 255) / 256, 256>>>(ra);
+    if (!desc.empty()) k_refit_blocks<<<(static_cast<int>(desc.size()) + 127) / 128, 128>>>(ra);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(nullptr));   // d_block_desc and `desc` are reused by the next run
+    k = k1;
+  }
+  // Root boxes feed the geometry-level broad phase of the no-surface pairs (batches refresh them lazily).
+  for (int j = 0; j < num_assets; ++j) {
+    HostAsset& a = *ctx->assets[assets[j]];
+    BvhNode root;
+    CUDA_OK(cudaMemcpy(&root, ctx->d_nodes.p + a.node_base + 1, sizeof(BvhNode), cudaMemcpyDeviceToHost));
+    for (int d = 0; d < 3; ++d) {
+      a.nodes[1].c[d] = root.c[d];
+      a.nodes[1].h[d] = root.h[d];
+    }
+  }
+  ++ctx->bounds_version;
   return DBH_OK;
   });
 }
@@ -1237,6 +1366,19 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   CUDA_OK(cudaSetDevice(ctx->device));
   if (dbh_status s = ctx->UploadPools()) return s;
   if (dbh_status s = b->AllocWorkBuffers()) return s;
+  if (b->bounds_version != ctx->bounds_version) {   // dbh_context_update_vertices moved root boxes
+    for (int g = 0; g < b->num_geoms; ++g) {
+      if (b->geom_asset[g] < 0 || b->geom_bounds[g].kind != kBoundBox) continue;
+      const HostAsset& A = *ctx->assets[b->geom_asset[g]];
+      for (int k = 0; k < 3; ++k) {
+        b->geom_bounds[g].c[k] = A.nodes[1].c[k];
+        b->geom_bounds[g].h[k] = A.nodes[1].h[k];
+      }
+    }
+    CUDA_OK(cudaMemcpyAsync(b->d_geom_bounds.p, b->geom_bounds.data(), b->geom_bounds.size() * sizeof(GeomBound),
+                            cudaMemcpyHostToDevice, b->stream));
+    b->bounds_version = ctx->bounds_version;
+  }
   b->representation = representation;
   b->query_done = false;
   b->query_enqueued = true;

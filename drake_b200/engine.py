@@ -109,6 +109,7 @@ def lib():
     L.dbh_register_rigid_mesh.argtypes = [vp, C.c_int32, _dp, C.c_int32, _ip, _ip]
     L.dbh_register_half_space.argtypes = [vp, C.c_int32, C.c_double, C.c_double, _ip]
     L.dbh_asset_get_info.argtypes = [vp, C.c_int32, C.POINTER(AssetInfo)]
+    L.dbh_context_update_vertices.argtypes = [vp, C.c_int32, _ip, _dp]
     L.dbh_asset_get_derived.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     L.dbh_asset_copy_bvh.argtypes = [vp, C.c_int32, _dp, _ip]
     L.dbh_context_set_bvh_builder.argtypes = [vp, C.c_int32]
@@ -319,6 +320,13 @@ class Context:
         out = C.c_int32()
         _check(lib().dbh_register_rigid_mesh(self._h, len(v), _ptr(v, _dp), len(t), _ptr(t, _ip), C.byref(out)))
         return out.value
+
+    def update_vertices(self, assets, vertices):
+        """Deformable reuse: new vertex positions for triangle-mesh assets (DeformableMeshWithBvh::UpdateVertexPositions):
+        per-triangle records recomputed and the BVHs refitted on the device. vertices: one [nv,3] array per asset."""
+        ids = _i(list(assets))
+        flat = np.ascontiguousarray(np.concatenate([_d(v).reshape(-1) for v in vertices]))
+        _check(lib().dbh_context_update_vertices(self._h, len(ids), _ptr(ids, _ip), _ptr(flat, _dp)))
 
     def register_half_space(self, compliant: bool = False, pressure_scale: float = 0.0, margin: float = 0.0) -> int:
         """HalfSpace shape (z <= 0 of its frame). compliant: pressure_scale = hydroelastic modulus / slab thickness

@@ -116,6 +116,16 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t num_vertices, const
  * polygon keeps its own vertices (the reference welds vertices cut from the same mesh edge). */
 dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressure_scale, double margin,
                                    int32_t* asset_out);
+/* Deformable reuse (first step): new vertex positions for registered triangle-mesh assets whose
+ * surface deforms from step to step -- the surface mesh of a deformable body in deformable-rigid contact, which the
+ * reference keeps in a DeformableSurfaceMeshWithBvh and intersects with the rigid body's pressure-field volume mesh
+ * through the same tetrahedron-triangle intersector as rigid-compliant contact (deformable_mesh_intersection.cc:83-110).
+ * One call = DeformableMeshWithBvh::UpdateVertexPositions for every listed asset (deformable_mesh_with_bvh.h:86-93):
+ * per-triangle vertices and normals recomputed (triangle_surface_mesh.h:452-487) and the BVH refitted bottom-up with its
+ * topology kept (BvhUpdater::Update, bvh_updater.h:45-103), all on the device. vertices: host, the assets' vertex
+ * arrays one after the other ([num_vertices * 3] each, in the order of `assets`). Synchronous; no query of a batch
+ * that uses these assets may be in flight. The next queries see the new surface. */
+dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices);
 dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out);
 /* The asset's BVH for inspection: boxes [(num_bvh_nodes + 1) * 6] = centre, half width per node
  * (node 0 unused, node 1 root), left [(num_bvh_nodes + 1)] = index of the first of the two adjacent

@@ -220,6 +220,18 @@ class TriMesh:
         v, t = _d(verts).reshape(-1, 3), _i(tris).reshape(-1, 3)
         return TriMesh(lib().ho_make_tri(len(v), _pd(v), len(t), _pi(t)))
 
+    def update_vertices(self, verts):
+        """DeformableMeshWithBvh::UpdateVertexPositions (deformable_mesh_with_bvh.h:86-93): new vertex positions, derived
+        quantities recomputed, BVHs refitted with their topology kept (BvhUpdater::Update, bvh_updater.h:45-103)."""
+        v = _d(verts).reshape(-1, 3)
+        assert len(v) == self.num_vertices
+        _check(lib().ho_tri_update_vertices(self.h, _pd(v)), "tri_update_vertices")
+        self._cache = None
+
+    def bvh_is_fitted(self) -> bool:
+        """Every box of the reference-shaped BVH contains its triangles and the root is the mesh's own box."""
+        return bool(lib().ho_tri_bvh_is_fitted(self.h))
+
     @staticmethod
     def sphere(r: float, hint: float) -> "TriMesh":
         return VolumeMesh.sphere(r, hint, dense=False).to_surface()

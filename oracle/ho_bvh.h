@@ -5,6 +5,7 @@
 //   geometry/proximity/aabb.{h,cc}, boxes_overlap.cc:197-255 (scalar variant),
 //   bvh.h:220-262, bvh.cc:18-136.
 #pragma once
+#include <limits>
 #include <algorithm>
 #include <memory>
 #include <set>
@@ -142,6 +143,35 @@ struct Bvh {
     return me;
   }
 };
+
+// BvhUpdater::Update (bvh_updater.h:45-103): the topology stays, every box is refitted bottom-up to the mesh's
+// current vertex positions; Aabb::set_bounds (aabb.h:188-191) puts the centre at (lower + upper) / 2 and the half width
+// at (upper - lower) / 2. Returns (lower, upper) of the node.
+template <class Mesh, int kVerts>
+inline std::pair<Vec3, Vec3> RefitBvh(Bvh* bvh, const Mesh& mesh, const std::vector<std::array<int, kVerts>>& elements,
+                                      int node = 0) {
+  const double inf = std::numeric_limits<double>::infinity();
+  BvhNode& n = bvh->nodes[node];
+  Vec3 lower{inf, inf, inf}, upper{-inf, -inf, -inf};
+  if (n.is_leaf()) {
+    for (int e = 0; e < n.num_index; ++e)
+      for (int v = 0; v < kVerts; ++v) {
+        const Vec3& p = mesh.verts[elements[n.indices[e]][v]];
+        lower = {std::min(lower.x, p.x), std::min(lower.y, p.y), std::min(lower.z, p.z)};
+        upper = {std::max(upper.x, p.x), std::max(upper.y, p.y), std::max(upper.z, p.z)};
+      }
+  } else {
+    const auto l = RefitBvh<Mesh, kVerts>(bvh, mesh, elements, n.left);
+    const auto r = RefitBvh<Mesh, kVerts>(bvh, mesh, elements, n.right);
+    lower = {std::min(l.first.x, r.first.x), std::min(l.first.y, r.first.y), std::min(l.first.z, r.first.z)};
+    upper = {std::max(l.second.x, r.second.x), std::max(l.second.y, r.second.y), std::max(l.second.z, r.second.z)};
+  }
+  bvh->nodes[node].bv.center = (lower + upper) / 2;
+  bvh->nodes[node].bv.half_width = (upper - lower) / 2;
+  // Aabb::lower() / upper() of the refitted box: what the parent reads.
+  const Aabb& b = bvh->nodes[node].bv;
+  return {b.center - b.half_width, b.center + b.half_width};
+}
 
 inline Bvh MakeBvh(const VolumeMesh& m) {
   Bvh b;

@@ -779,6 +779,55 @@ int ho_scene_fallback_pairs(int scene, const double* poses, int64_t* out_ids, in
   return static_cast<int>(pairs.size());
   HO_CATCH(-100)
 }
+// DeformableMeshWithBvh::UpdateVertexPositions for a triangle mesh (deformable_mesh_with_bvh.h:86-93): new vertex
+// positions, per-triangle normals / areas recomputed, the reference-shaped BVH(s) refitted with their topology kept.
+int ho_tri_update_vertices(int h, const double* verts) {
+  HO_TRY
+  TriAsset& a = *g_tris[h];
+  RefBvh(a);
+  Leaf1Bvh(a);
+  for (size_t i = 0; i < a.mesh.verts.size(); ++i) a.mesh.verts[i] = {verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]};
+  a.mesh.ComputePositionDependentQuantities();
+  RefitBvh<TriMesh, 3>(a.bvh_ref.get(), a.mesh, a.mesh.tris);
+  RefitBvh<TriMesh, 3>(a.bvh_leaf1.get(), a.mesh, a.mesh.tris);
+  a.boxes.reset();
+  a.bvh_obb.reset();
+  return 0;
+  HO_CATCH(-100)
+}
+// Checks the refitted reference-shaped BVH: every node's box contains the vertices of every triangle below it, and the
+// root is exactly the box of the mesh (bvh_updater_test.cc). Returns 1 when it holds.
+int ho_tri_bvh_is_fitted(int h) {
+  TriAsset& a = *g_tris[h];
+  const Bvh& b = RefBvh(a);
+  std::vector<std::pair<Vec3, Vec3>> ext(b.nodes.size());
+  const double inf = std::numeric_limits<double>::infinity();
+  for (int n = static_cast<int>(b.nodes.size()) - 1; n >= 0; --n) {   // children come after their parent
+    Vec3 lo{inf, inf, inf}, up{-inf, -inf, -inf};
+    auto grow = [&](const Vec3& p) {
+      lo = {std::min(lo.x, p.x), std::min(lo.y, p.y), std::min(lo.z, p.z)};
+      up = {std::max(up.x, p.x), std::max(up.y, p.y), std::max(up.z, p.z)};
+    };
+    if (b.nodes[n].is_leaf()) {
+      for (int e = 0; e < b.nodes[n].num_index; ++e)
+        for (int v = 0; v < 3; ++v) grow(a.mesh.verts[a.mesh.tris[b.nodes[n].indices[e]][v]]);
+    } else {
+      grow(ext[b.nodes[n].left].first);
+      grow(ext[b.nodes[n].left].second);
+      grow(ext[b.nodes[n].right].first);
+      grow(ext[b.nodes[n].right].second);
+    }
+    ext[n] = {lo, up};
+    const Aabb& bv = b.nodes[n].bv;
+    for (int d = 0; d < 3; ++d) {
+      const double tol = 4e-16 * (std::fabs(lo[d]) + std::fabs(up[d]) + 1e-300);
+      if (bv.center[d] - bv.half_width[d] > lo[d] + tol || bv.center[d] + bv.half_width[d] < up[d] - tol) return 0;
+      if (n == 0 && (std::fabs(bv.center[d] - (lo[d] + up[d]) / 2) > tol || std::fabs(bv.half_width[d] - (up[d] - lo[d]) / 2) > tol))
+        return 0;
+    }
+  }
+  return 1;
+}
 void ho_scene_set_normal_filter(int scene, int enabled) { g_scenes[scene]->normal_filter = enabled != 0; }
 int ho_scene_num_geometries(int scene) { return static_cast<int>(g_scenes[scene]->geoms.size()); }
 void ho_scene_geometry_ids(int scene, int64_t* ids) {

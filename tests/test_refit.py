@@ -1,0 +1,131 @@
+"""Deformable reuse, first step: triangle-mesh assets whose vertices move from step to step --
+DeformableMeshWithBvh::UpdateVertexPositions = new positions + derived quantities + BvhUpdater::Update (topology kept,
+boxes refitted bottom-up; bvh_updater.h:45-103). The oracle's restatement is checked against the updater's contract
+(bvh_updater_test.cc: every box bounds its contents, the root is the mesh's box; topology unchanged); the device path
+(dbh_context_update_vertices: k_refit_tris / k_refit_nodes / k_refit_blocks) must give, after an update, the surfaces
+the oracle computes on the deformed mesh."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ho
+
+
+def deform(verts, t):
+    """A smooth, clearly non-rigid deformation of a point set (stretch + twist + ripple), parameter t."""
+    v = np.asarray(verts, float).copy()
+    ang = 0.8 * t * v[:, 2] / max(np.abs(v[:, 2]).max(), 1e-9)
+    c, s = np.cos(ang), np.sin(ang)
+    x, y = v[:, 0] * c - v[:, 1] * s, v[:, 0] * s + v[:, 1] * c
+    v[:, 0], v[:, 1] = x * (1 + 0.3 * t), y * (1 - 0.2 * t)
+    v[:, 2] = v[:, 2] * (1 + 0.15 * t) + 0.02 * t * np.sin(7 * x)
+    return v
+
+
+def test_oracle_refit_keeps_topology_and_bounds_the_deformed_mesh():
+    m = ho.TriMesh.sphere(0.25, 0.05)
+    nodes0, leaves0, height0 = m.bvh_stats()
+    assert m.bvh_is_fitted()
+    v0 = m.verts.copy()
+    for t in (0.5, 1.0, -0.7):
+        m.update_vertices(deform(v0, t))
+        assert m.bvh_stats() == (nodes0, leaves0, height0)      # no change of topology
+        assert m.bvh_is_fitted()                                # every box bounds its contents, root = mesh box
+        np.testing.assert_array_equal(m.verts, deform(v0, t))
+    # Normals follow the vertices: recomputed, unit length.
+    n = m.arrays()[2]
+    np.testing.assert_allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-14)
+    # The traversal over the refitted tree still finds every overlapping element pair of the deformed mesh.
+    soft = ho.VolumeMesh.sphere(0.3, 0.1)
+    X = ho.xform(ho.rpy_matrix(0.2, 0.1, 0.4), [0.1, 0.05, 0.3])
+    brute = set(map(tuple, ho.candidates(soft, m, X, ho.MODE_BRUTE)[0]))
+    tree = set(map(tuple, ho.candidates(soft, m, X, ho.MODE_REFERENCE_BVH)[0]))
+    assert brute and brute <= tree
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rep", [ho.KPOLYGON, ho.KTRIANGLE])
+def test_device_refit_gives_the_surfaces_of_the_deformed_mesh(rep):
+    """Two deforming surfaces (one asset each) in contact with a static pressure-field volume (the rigid side of a
+    deformable-rigid pair), updated three times: after every update the
+    query equals the oracle on the deformed mesh face for face, and a freshly registered copy of the deformed mesh gives
+    the same surface as the refitted one."""
+    import drake_b200 as db
+    from tests import parity
+    ctx = db.Context(0)
+    vol = ho.VolumeMesh.sphere(0.3, 0.1, dense=True)
+    fld = ho.VolumeField.sphere(vol, 0.3, 1e6)
+    surf = [ho.TriMesh.sphere(0.25, 0.05), ho.TriMesh.ellipsoid(0.2, 0.3, 0.25, 0.06)]
+    v0 = [s.verts.copy() for s in surf]
+    a_v = parity.register_compliant(ctx, vol, fld)
+    a_s = [parity.register_rigid(ctx, s) for s in surf]
+    poses = np.stack([ho.xform(None, [0, 0, 0]), ho.xform(ho.rpy_matrix(0.2, 0.1, 0.4), [0.1, 0.05, 0.3]),
+                      ho.xform(ho.rpy_matrix(-0.3, 0.2, 0.1), [-0.15, 0.1, -0.32])])
+    batch = db.SceneBatch(ctx, [0, 3], [a_v, a_s[0], a_s[1]], [1, 2, 3], excluded=[[1, 2]])
+    batch.set_record_candidates(True)
+    for step, t in enumerate((0.0, 0.6, 1.0, -0.8)):
+        if step:
+            new = [deform(v, t) for v in v0]
+            ctx.update_vertices(a_s, new)
+            for s, v in zip(surf, new):
+                s.update_vertices(v)
+        got = batch.compute_contact_surfaces(poses, rep)[0]
+        assert [(g.id_M, g.id_N) for g in got] == [(1, 2), (1, 3)]
+        for k, g in enumerate(got):
+            want = ho.soft_rigid(vol, fld, surf[k], poses[0], poses[1 + k], 1, 2 + k, rep)
+            parity.compare_surface(g, want)
+        if step:
+            fresh = [parity.register_rigid(ctx, ho.TriMesh.from_arrays(s.verts, s.arrays()[1])) for s in surf]
+            b2 = db.SceneBatch(ctx, [0, 3], [a_v, fresh[0], fresh[1]], [1, 2, 3], excluded=[[1, 2]])
+            again = b2.compute_contact_surfaces(poses, rep)[0]
+            for g, h in zip(got, again):
+                np.testing.assert_array_equal(np.sort(parity.face_keys(g.elem_M, g.elem_N)),
+                                              np.sort(parity.face_keys(h.elem_M, h.elem_N)))
+                assert g.total_area == pytest.approx(h.total_area, rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_device_refit_of_many_assets_and_a_half_space_pair():
+    """64 scenes, each with its own deforming surface asset (registered one after the other: one upload and three
+    launches re-pose them all) over a compliant half space and against a static pressure-field volume; per-scene
+    deformations; every surface against the oracle after the update (the half-space pair exercises the refitted
+    leaf-block boxes)."""
+    import drake_b200 as db
+    from tests import parity
+    ctx = db.Context(0)
+    vol = ho.VolumeMesh.sphere(0.3, 0.1, dense=True)
+    fld = ho.VolumeField.sphere(vol, 0.3, 1e6)
+    base = ho.TriMesh.sphere(0.25, 0.06)
+    v0, tris = base.verts.copy(), base.arrays()[1]
+    S = 64
+    a_v = parity.register_compliant(ctx, vol, fld)
+    a_h = ctx.register_half_space(compliant=True, pressure_scale=2e5)
+    a_s = [parity.register_rigid(ctx, base) for _ in range(S)]
+    so = np.arange(S + 1) * 3
+    ga = np.array([[a_v, a_s[s], a_h] for s in range(S)]).reshape(-1)
+    gi = np.tile([1, 2, 3], S)
+    an = np.tile([0, 0, 1], S)
+    ex = np.array([[3 * s, 3 * s + 2] for s in range(S)])     # volume x half space: rejected combination, filtered
+    batch = db.SceneBatch(ctx, so, ga, gi, an, ex)
+    rng = np.random.default_rng(3)
+    poses = np.stack([np.stack([ho.xform(None, [0, 0, 0.4]), parity.random_pose(rng, 0.05, center=(0.1, 0.0, 0.15)),
+                                ho.xform(None, [0, 0, 0])]) for _ in range(S)])
+    ts = rng.uniform(-1, 1, S)
+    new = [deform(v0, t) for t in ts]
+    ctx.update_vertices(a_s, new)
+    got = batch.compute_contact_surfaces(poses.reshape(-1, 12), ho.KPOLYGON)
+    total = 0
+    for s in range(S):
+        mesh = ho.TriMesh.from_arrays(new[s], tris)
+        osc = ho.Scene()
+        osc.add_compliant(1, vol, fld)
+        osc.add_rigid(2, mesh)
+        osc.add_half_space(3, compliant=True, pressure_scale=2e5, anchored=True)
+        osc.exclude(1, 3)
+        want, _ = osc.compute(poses[s], ho.KPOLYGON)
+        assert [(x.id_M, x.id_N) for x in got[s]] == [(x.id_M, x.id_N) for x in want], s
+        for g, w in zip(got[s], want):
+            parity.compare_surface(g, w, welded=bool(np.any(np.asarray(w.elem_second) < 0) or np.any(np.asarray(w.elem_first) < 0)))
+        total += len(want)
+    assert total >= S
