@@ -533,10 +533,13 @@ def roofline_for(leg: Leg, res: dict, config: str, default_size: bool):
     whole_alg = st["algorithmic_bytes"]
     compulsory = None
     if prof and prof.get("compulsory_dram_bytes"):
-        compulsory = {"bytes": prof["compulsory_dram_bytes"] * k,
+        compulsory = {"bytes": prof["compulsory_dram_bytes"] * k, "staging_bytes": (prof.get("staging_dram_bytes") or 0) * k,
                       "measured_dram_bytes_whole_query": (prof.get("dram_bytes_whole_query") or 0) * k,
                       "scaled_from_scenes": prof.get("scenes") if k != 1.0 else None,
-                      "what": "every asset byte once + poses + work lists written and read once + the packed result once"}
+                      "what": "bytes: what any implementation must move per query (poses in + the packed result out); "
+                              "staging_bytes: this pipeline's own intermediate lists, each written once and read once "
+                              "(survivor entries, staged polygons, leaf lists of the per-level path); measured: "
+                              "dram__bytes_read + write over the query's kernels in the committed ncu capture"}
     return {"bound": "hbm", "kernel": d_kernels, "group": dominant, "achieved": achieved, "peak": peak,
             "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
             "traffic_source": prof_src, "algorithmic_bytes_per_launch": d_bytes, "kernel_ms": d_ms,
