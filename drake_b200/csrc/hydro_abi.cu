@@ -471,6 +471,9 @@ struct dbh_batch {
   // over the whole grid). record_candidates: keep the candidate lists of the last query (dbh_batch_copy_candidates).
   int small_mode{2};
   int small_stack_cap{1024};
+  int num_large_small_pairs{0};   // small pairs whose descent is split into work items (PairRec::small == 2)
+  DevBuf<int2> d_small_items;     // [2][cap_small_items]
+  long long cap_small_items{1 << 20};
   int num_small_pairs{0};
   bool record_candidates{false};
   bool small_used{false};           // the last query ran k_small_pairs
@@ -494,8 +497,9 @@ struct dbh_batch {
   DevBuf<Xf> d_pair_X;
   DevBuf<PairF32> d_pair_f32;
   DevBuf<int4> d_frontier[2];
-  DevBuf<int4> d_cand_tri, d_cand_tet, d_slow;
+  DevBuf<int4> d_cand_tri, d_cand_tet, d_slow, d_undecided;
   long long cap_slow{1 << 16};
+  long long cap_undecided{1 << 19};   // leaf pairs left to the fp64 leaf predicate, per chunk
   DevBuf<Counters> d_counters;
   DevBuf<int> d_pair_polys, d_pair_verts, d_surf_index, d_surf_pair, d_big_list;
   DevBuf<unsigned long long> d_pair_cursor;
@@ -556,6 +560,8 @@ struct dbh_batch {
     CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_tet : 1));
     CUDA_OK(d_slow.ensure(cap_slow));
     if (num_small_pairs) CUDA_OK(d_small_list.ensure(2 * static_cast<size_t>(MaxPairsPerChunk())));
+    CUDA_OK(d_undecided.ensure(cap_undecided));
+    if (num_large_small_pairs) CUDA_OK(d_small_items.ensure(2 * static_cast<size_t>(cap_small_items)));
     if (!plane_pairs.empty() && plane_emit_sized_for != num_chunks) {  // depends on the chunking only
       long long most = 1;
       for (int c = 0; c < num_chunks; ++c) {
@@ -603,6 +609,25 @@ dbh_status BuildBvhFor(dbh_context* ctx, const double* verts, int nv, const int3
   BuildAssetBvh<kVerts>(verts, elems, ne, a);
   return DBH_OK;
 }
+}  // namespace
+
+namespace {
+// k_small_pairs by element kind, resident blocks per SM (4, 5, 6) and pass (hydro_small.cuh).
+using SmallKernelFn = void (*)(SmallArgs);
+int SmallBlocksPerSm(int per_sm) { return per_sm >= 6 ? 6 : (per_sm == 5 ? 5 : 4); }
+template <bool kTet>
+SmallKernelFn SmallKernelOf(int per_sm, int pass) {
+  static const SmallKernelFn k[3][3] = {
+      {k_small_pairs<kTet, 4, 0>, k_small_pairs<kTet, 4, 1>, k_small_pairs<kTet, 4, 2>},
+      {k_small_pairs<kTet, 5, 0>, k_small_pairs<kTet, 5, 1>, k_small_pairs<kTet, 5, 2>},
+      {k_small_pairs<kTet, 6, 0>, k_small_pairs<kTet, 6, 1>, k_small_pairs<kTet, 6, 2>}};
+  return k[SmallBlocksPerSm(per_sm) - 4][pass];
+}
+SmallKernelFn SmallKernel(bool tet, int per_sm, int pass) {
+  return tet ? SmallKernelOf<true>(per_sm, pass) : SmallKernelOf<false>(per_sm, pass);
+}
+constexpr int kSmallSplitNodes = 2048;
+
 }  // namespace
 
 extern "C" {
@@ -1075,6 +1100,10 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
               static_cast<int>(B.nodes.size()) <= kSmallMaxNodes) {
             pr.small = 1;
             ++b->num_small_pairs;
+            if (static_cast<int>(A.nodes.size() + B.nodes.size()) > kSmallSplitNodes) {
+              pr.small = 2;
+              ++b->num_large_small_pairs;
+            }
           }
           if (pr.kind <= kSoftSoft) {
             max_levels = std::max(max_levels, std::max(A.height, B.height) + 1);
@@ -1283,6 +1312,8 @@ dbh_status dbh_batch_grow_capacity(dbh_batch* b) {
     b->cap_polys = polys;
   }
   b->cap_slow = want(c.slow_max, b->cap_slow);
+  b->cap_undecided = want(c.undecided_max, b->cap_undecided);
+  b->cap_small_items = want(c.small_items_max, b->cap_small_items);
   // Faces / vertices of either representation (triangle: one face per polygon vertex, one extra
   // vertex per polygon), so switching representation does not overflow again.
   b->cap_faces = want(std::max(c.faces, c.poly_verts), b->cap_faces);
@@ -1446,6 +1477,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     ca.counters = b->d_counters.p;
     ca.slow = b->d_slow.p;
     ca.slow_capacity = static_cast<unsigned int>(b->cap_slow);
+    ca.undecided = b->d_undecided.p;
+    ca.undecided_capacity = static_cast<unsigned long long>(b->cap_undecided);
     ca.verify = b->verify ? 1 : 0;
     ca.no_normal_filter = b->normal_filter ? 0 : 1;
     ca.trace = make_int4(-1, -1, -1, 0);
@@ -1462,6 +1495,14 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     sm.surv_capacity = static_cast<unsigned long long>(b->cap_frontier);
     sm.record = b->record_candidates ? 1 : 0;
     sm.stack_cap = b->small_stack_cap;
+    UndecidedArgs ua{};
+    ua.c = ca;
+    ua.pairs = b->d_pairs.p;
+    ua.surv[0] = b->d_frontier[0].p;
+    ua.surv[1] = b->d_frontier[1].p;
+    ua.surv_capacity = static_cast<unsigned long long>(b->cap_frontier);
+    ua.cand[0] = b->d_cand_tri.p;
+    ua.cand[1] = b->d_cand_tet.p;
     b->small_used = false;
     ScanArgs sa{};
     sa.pair_polys = b->d_pair_polys.p;
@@ -1547,7 +1588,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     // block-wide appends; filter / pack: resident blocks per SM the launch bound asks for (registers against
     // occupancy); tgrid / fgrid / pgrid: grid size in units of the resident blocks -- persistent grids (1x for the
     // traversal and the pack) beat over-subscribed ones by 5-15 % (no tail wave).
-    struct Tune { int traverse = 6, filter = 2, pack = 4, tgrid = 3, fgrid = 2, pgrid = 1, small = -1, sblocks = 4, stagea = 0; } tune;
+    struct Tune { int traverse = 6, filter = 5, pack = 4, tgrid = 3, fgrid = 1, pgrid = 1, small = -1, sblocks = 6, sblocks_tet = 5, stagea = 0, split = 1; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1562,17 +1603,20 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       get("pgrid", &tune.pgrid);
       get("small", &tune.small);  // overrides dbh_batch_set_small_pair_path: 0 never, 1 always, 2 auto
       get("stagea", &tune.stagea);    // experiments on the conservative culls (ClipArgs::tune)
-      get("sblocks", &tune.sblocks);  // k_small_pairs: resident 128-thread blocks per SM asked of the launch bound
+      get("sblocks", &tune.sblocks);  // (tet-triangle pairs; "sblocks_tet": tet-tet pairs)
+      get("split", &tune.split);      // 0: large small pairs are not split into work items
+      get("sblocks_tet", &tune.sblocks_tet);  // k_small_pairs: resident 128-thread blocks per SM asked of the launch bound
     }
     ca.tune = tune.stagea;
     sm.c.tune = tune.stagea;
+    ua.c.tune = tune.stagea;
     const int small_mode = tune.small >= 0 ? tune.small : b->small_mode;
     const int small_smem = kSmallWarps * small_smem_bytes_per_warp(b->small_stack_cap);
     if (b->num_small_pairs && small_mode != 0 && small_smem > 48 * 1024) {
-      CUDA_OK(cudaFuncSetAttribute(k_small_pairs<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
-      CUDA_OK(cudaFuncSetAttribute(k_small_pairs<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
-      CUDA_OK(cudaFuncSetAttribute(k_small_pairs<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
-      CUDA_OK(cudaFuncSetAttribute(k_small_pairs<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
+      for (int tet = 0; tet < 2; ++tet)
+        for (int per_sm = 4; per_sm <= 6; ++per_sm)
+          for (int pass = 0; pass < 3; ++pass)
+            CUDA_OK(cudaFuncSetAttribute(SmallKernel(tet != 0, per_sm, pass), cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
     }
     for (int chunk = 0; chunk < b->num_chunks; ++chunk) {
       const int s0 = static_cast<int>(static_cast<long long>(b->num_scenes) * chunk / b->num_chunks);
@@ -1585,7 +1629,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       const int n_small = b->scene_small_before[s1] - b->scene_small_before[s0];
       const int n_mesh = b->scene_mesh_before[s1] - b->scene_mesh_before[s0];
       const bool use_small =
-          n_small > 0 && (small_mode == 1 || (small_mode == 2 && n_small >= 2 * sms * tune.sblocks * kSmallWarps));
+          n_small > 0 && (small_mode == 1 || (small_mode == 2 && n_small >= 2 * sms * 4 * kSmallWarps));
       const bool generic = n_mesh - (use_small ? n_small : 0) > 0;   // pairs left to the per-level pipeline
       pa.small_list = use_small ? b->d_small_list.p : nullptr;
       pa.small_list_tet = use_small ? b->d_small_list.p + b->MaxPairsPerChunk() : nullptr;
@@ -1610,10 +1654,15 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       // The generic pairs' leaf lists go through the filter first (the survivor lists reuse the frontier buffers,
       // which the descent has released); then the small pairs are descended and culled on chip and append their
       // survivors to the same lists; then the exact stage runs over both.
-      const int small_blocks = use_small ? std::min(sms * tune.sblocks, (n_small + kSmallWarps - 1) / kSmallWarps) : 0;
       b->small_used = b->small_used || use_small;
+      // After both kinds' small pairs: the leaf pairs their fp32 leaf predicate left undecided (one short launch).
+      auto settle_undecided = [&]() {
+        ++b->last_launches;
+        k_leaf_undecided<<<sms * 8, 128, 0, st>>>(ua);
+      };
       for (int tet = 0; tet < 2; ++tet) {
         if (!(tet ? b->info.num_soft_soft_pairs : b->info.num_soft_rigid_pairs)) {
+          if (tet) settle_undecided();
           mark(3 + tet);
           continue;
         }
@@ -1622,14 +1671,18 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ca.surv = b->d_frontier[tet].p;
         if (generic) {
           ++b->last_launches;
+          // tune.filter: resident warps per SM / 8 asked of the launch bound (2, 3, 4: 256-thread blocks; 5: 20 warps in
+          // 128-thread blocks).
           if (tet) {
-            if (tune.filter == 4) k_filter<true, 4><<<sms * 4 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-            else if (tune.filter == 2) k_filter<true, 2><<<sms * 2 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-            else k_filter<true, 3><<<sms * 3 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+            if (tune.filter == 5) k_filter<true, 128, 5><<<sms * 5 * tune.fgrid, 128, 0, st>>>(ca);
+            else if (tune.filter == 4) k_filter<true, 256, 4><<<sms * 4 * tune.fgrid, 256, 0, st>>>(ca);
+            else if (tune.filter == 2) k_filter<true, 256, 2><<<sms * 2 * tune.fgrid, 256, 0, st>>>(ca);
+            else k_filter<true, 256, 3><<<sms * 3 * tune.fgrid, 256, 0, st>>>(ca);
           } else {
-            if (tune.filter == 4) k_filter<false, 4><<<sms * 4 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-            else if (tune.filter == 2) k_filter<false, 2><<<sms * 2 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
-            else k_filter<false, 3><<<sms * 3 * tune.fgrid, kFilterThreads, 0, st>>>(ca);
+            if (tune.filter == 5) k_filter<false, 128, 5><<<sms * 5 * tune.fgrid, 128, 0, st>>>(ca);
+            else if (tune.filter == 4) k_filter<false, 256, 4><<<sms * 4 * tune.fgrid, 256, 0, st>>>(ca);
+            else if (tune.filter == 2) k_filter<false, 256, 2><<<sms * 2 * tune.fgrid, 256, 0, st>>>(ca);
+            else k_filter<false, 256, 3><<<sms * 3 * tune.fgrid, 256, 0, st>>>(ca);
           }
         }
         if (use_small) {
@@ -1638,18 +1691,20 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
           sm.cand = ca.cand;
           sm.cand_capacity = ca.cand_capacity;
           ++b->last_launches;
-          if (tet) {
-            if (tune.sblocks >= 6) k_small_pairs<true, 6><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-            else if (tune.sblocks == 5) k_small_pairs<true, 5><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-            else if (tune.sblocks == 4) k_small_pairs<true, 4><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-            else k_small_pairs<true, 3><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-          } else {
-            if (tune.sblocks >= 6) k_small_pairs<false, 6><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-            else if (tune.sblocks == 5) k_small_pairs<false, 5><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-            else if (tune.sblocks == 4) k_small_pairs<false, 4><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
-            else k_small_pairs<false, 3><<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          // Resident 128-thread blocks per SM (measured: 6 for tet-triangle pairs, 5 for tet-tet, whose stage A needs
+          // 96 registers; profiles/README.md).
+          const int per_sm = tet ? tune.sblocks_tet : tune.sblocks;
+          const int small_blocks = std::min(sms * SmallBlocksPerSm(per_sm), (n_small + kSmallWarps - 1) / kSmallWarps);
+          sm.items = b->d_small_items.p + (tet ? b->cap_small_items : 0);
+          sm.items_capacity = static_cast<unsigned long long>(b->cap_small_items);
+          const bool split = b->num_large_small_pairs > 0 && tune.split != 0;
+          SmallKernel(tet != 0, per_sm, split ? 1 : 0)<<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          if (split) {   // the work items of the large pairs
+            ++b->last_launches;
+            SmallKernel(tet != 0, per_sm, 2)<<<sms * SmallBlocksPerSm(per_sm), kSmallWarps * 32, small_smem, st>>>(sm);
           }
         }
+        if (tet) settle_undecided();
         mark(3 + tet);
       }
       if (b->info.num_soft_rigid_pairs) {
@@ -1691,8 +1746,13 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       k_scan_apply<<<sa.num_blocks, kScanThreads, 0, st>>>(sa);
       mark(8);
       ++b->last_launches;
-      if (tune.pack == 4) k_pack<4><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
-      else k_pack<3><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
+      if (pk.representation == DBH_POLYGON) {
+        if (tune.pack == 4) k_pack<4, 1><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
+        else k_pack<3, 1><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
+      } else {
+        if (tune.pack == 4) k_pack<4, 0><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
+        else k_pack<3, 0><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
+      }
       if (plane_blocks) {  // pack pass of the half-space pairs: straight into the final layout
         ++b->last_launches;
         k_plane<true><<<plane_blocks, 128, 0, st>>>(pl);

@@ -476,6 +476,9 @@ struct ClipArgs {
   Counters* counters;
   int4* slow;           // exceptional candidates {pair, elem, elem, 0 tri | 1 tet (| 2: culled, verify mode)}
   unsigned int slow_capacity;
+  int4* undecided;      // leaf pairs the fp32 leaf predicate cannot decide {pair, pool elem a, pool elem b, index + 1 of the
+                        // entry in the leaf list | 0}: settled in fp64 by k_leaf_undecided (hydro_small.cuh)
+  unsigned long long undecided_capacity;
   // Self-check mode (dbh_batch_set_verify): the exact stage runs for EVERY candidate and
   // Counters::cull_violations_* count polygons emitted by candidates stage A had rejected.
   int verify;
@@ -781,15 +784,24 @@ __device__ __forceinline__ void tri_stage_b(const ClipArgs& a, Poly& P, int4 c, 
       n = 3;
 #pragma unroll
       for (int k = 0; k < 3; ++k) P.set(0, k, xform_point(X, load3(tri.v[k])));
+      // The next face's half space is requested while the current one clips (the loop is bound by the latency of
+      // these loads: 4 % of the kernel, profiles/README.md).
+      D3 nh_next = load3(aux.plane_nh[0]);
+      double d_next = aux.plane_d[0];
 #pragma unroll 1
       for (int f = 0; f < 4; ++f) {
+        const D3 nh = nh_next;
+        const double d = d_next;
+        if (f < 3 && n > 0) {
+          nh_next = load3(aux.plane_nh[f + 1]);
+          d_next = aux.plane_d[f + 1];
+        }
         if (n > 0) {
-          const double d = aux.plane_d[f];
           if (d != d) {  // Plane ctor throws (plane.cc:16-29)
             raise_error(a.counters, 9 /*DBH_ERR_PLANE_NORMAL*/, c.x);
             n = 0;
           } else {
-            n = clip_by_half_space(P, buf, n, load3(aux.plane_nh[f]), d);
+            n = clip_by_half_space(P, buf, n, nh, d);
             if (n > Poly::kCap) {
               if (kSlow) raise_error(a.counters, 10 /*DBH_ERR_POLYGON_SIZE*/, c.x); else defer_to_slow_path(a, c, 0);
               n = 0;
@@ -1029,7 +1041,6 @@ __device__ __forceinline__ void tet_stage_b(const ClipArgs& a, Poly& P, int4 c, 
 // 512 B store per 32 survivors, no block-wide barrier. Warps claim contiguous
 // chunks of the leaf list dynamically (the cost per pair varies with the survivor
 // density). Every entry's candidate flag is written back to the leaf list.
-constexpr int kFilterThreads = 256;
 template <bool kTet>
 __device__ __forceinline__ void prefetch_records(const ClipArgs& a, int4 c) {
   prefetch_l1(a.pair_f32 + c.x);
@@ -1042,7 +1053,7 @@ __device__ __forceinline__ void prefetch_records(const ClipArgs& a, int4 c) {
     prefetch_l1(a.pools.cull_tri + c.z);
   }
 }
-template <bool kTet, int kMinBlocks>
+template <bool kTet, int kFilterThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kFilterThreads, kMinBlocks) k_filter(ClipArgs a) {
   __shared__ int4 stage[kFilterThreads / 32][64];
   if (a.counters->error != 0) return;
@@ -1095,12 +1106,12 @@ __global__ void __launch_bounds__(kFilterThreads, kMinBlocks) k_filter(ClipArgs 
         if (kTet) {
           const TetCullA t1 = a.pools.cull_a[c.z];
           decided = boxes_overlap_f32(box_of<4>(ta.v), box_of<4>(t1.v), X);
-          is_cand = decided > 0 || (decided == 0 && leaf_predicate_exact<true>(a, c));
+          is_cand = decided > 0;
           if (is_cand) keep = tet_stage_a(a, c, X, ta, t1);
         } else {
           const TriCull tri = a.pools.cull_tri[c.z];
           decided = boxes_overlap_f32(box_of<4>(ta.v), box_of<3>(tri.v), X);
-          is_cand = decided > 0 || (decided == 0 && leaf_predicate_exact<false>(a, c));
+          is_cand = decided > 0;
           if (is_cand) keep = tri_stage_a(a, c, X, ta, tri);
         }
         undecided = decided == 0;
@@ -1112,7 +1123,20 @@ __global__ void __launch_bounds__(kFilterThreads, kMinBlocks) k_filter(ClipArgs 
         }
       }
       n_cand += __popc(__ballot_sync(0xffffffffu, is_cand));
-      n_exact += __popc(__ballot_sync(0xffffffffu, undecided));
+      // Undecided in fp32 (0.1 - 3 % of the leaf pairs): left to k_leaf_undecided, whose fp64 predicate would cost this
+      // kernel a third of its resident warps in registers and stack.
+      const unsigned um = __ballot_sync(0xffffffffu, undecided);
+      if (um) {
+        n_exact += __popc(um);
+        unsigned long long ubase = 0;
+        if (lane == 0) ubase = atomicAdd(&a.counters->undecided, (unsigned long long)__popc(um));
+        ubase = __shfl_sync(0xffffffffu, ubase, 0);
+        if (undecided) {
+          const unsigned long long slot = ubase + __popc(um & ((1u << lane) - 1u));
+          if (slot < a.undecided_capacity) a.undecided[slot] = make_int4(c.x, c.y, c.z, (int)i + 1);   // (a leaf list holds far fewer than 2^31 entries: 16 B each)
+          else raise_error(a.counters, 5 /*DBH_ERR_CAPACITY*/, 10);
+        }
+      }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       if (keep) my_stage[fill + __popc(m & ((1u << lane) - 1u))] = c;
       fill += __popc(m);
@@ -1355,7 +1379,10 @@ __device__ __forceinline__ void store_face(const PackArgs& a, long long f, int p
   a.out.face_pair[f] = pair;
 }
 
-template <int kMinBlocks>
+// kRep: the representation (DBH_POLYGON = 1 / DBH_TRIANGLE = 0) as a template parameter: the two branches share
+// little, and a kernel holding both is allocated the registers of the larger (polygon alone: 16 B of spills
+// under the 128-register bound instead of 124 B).
+template <int kMinBlocks, int kRep>
 __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
   if (a.counters->error != 0) return;
   const unsigned long long count = min(a.counters->polys, a.soup.capacity);
@@ -1438,7 +1465,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_pack(PackArgs a) {
     const int vj = (int)(cur & 0xffffffffull);
     double e0;
     const D3 v0 = vert(0, &e0);
-    if (a.representation == 1 /*DBH_POLYGON*/) {
+    if constexpr (kRep == 1 /*DBH_POLYGON*/) {
       const long long f = a.poly_off[pair] + pj;
       const long long vb = a.vert_off[pair] + vj;
       if (f >= a.out.face_capacity || vb + n > a.out.vert_capacity || f + vb + n + 1 > a.out.face_data_capacity) {
@@ -1759,13 +1786,17 @@ __global__ void k_next_chunk(Counters* c) {
     c->leaf_tet_max = max(c->leaf_tet_max, c->leaf_tet);
     c->polys_max = max(c->polys_max, c->polys);
     c->slow_max = max(c->slow_max, c->slow);
+    c->undecided_max = max(c->undecided_max, c->undecided);
+    c->small_items_max = max(c->small_items_max, max(c->small_items[0], c->small_items[1]));
   }
   __syncthreads();
   if (blockIdx.x == 0) {
     if (threadIdx.x < 64) c->frontier[threadIdx.x] = 0;
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
       c->leaf_tri = c->leaf_tet = c->polys = c->slow = c->surv_tri = c->surv_tet = c->big_surfaces = c->work_tri = c->work_tet =
-          c->plane_emit = c->small_pairs[0] = c->small_pairs[1] = c->small_work[0] = c->small_work[1] = 0;
+          c->plane_emit = c->small_pairs[0] = c->small_pairs[1] = c->small_work[0] = c->small_work[1] = c->undecided = 0;
+      c->small_items[0] = c->small_items[1] = c->small_items_work[0] = c->small_items_work[1] = 0;
+    }
   }
 }
 

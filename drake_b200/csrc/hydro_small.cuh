@@ -16,7 +16,8 @@
 //     once the smaller tree had bottomed out; profiles/README.md);
 //   * whenever 32 leaf pairs are waiting, the lanes run the leaf predicate (BoxesOverlap on the elements'
 //     own boxes, boxes_overlap.cc:197-255: fp32 on the leaves' node boxes with a two-sided margin, exact
-//     fp64 on the exact boxes when undecided) and the
+//     fp64 on the exact boxes when undecided -- those few go to a list that k_leaf_undecided settles: the fp64
+//     predicate's registers and stack frame would cost every warp of this kernel a fifth of its occupancy) and the
 //     conservative stage-A culls of the narrow phase (the same tri_stage_a / tet_stage_a as k_filter) on
 //     them, and stage the survivors in shared memory;
 //   * full groups of 32 survivors go to the global survivor list (one atomic + one coalesced 512 B store),
@@ -51,6 +52,8 @@ struct SmallArgs {
   unsigned long long cand_capacity;
   int record;
   int stack_cap;              // node-pair stack entries per warp
+  int2* items;                // kPass 1 writes, kPass 2 reads: {pair, node pair} work items of the large small pairs
+  unsigned long long items_capacity;
 };
 
 __host__ __device__ constexpr int small_smem_bytes_per_warp(int stack_cap) {
@@ -90,7 +93,14 @@ __device__ __forceinline__ BoxF small_leaf_box(const Node32& n) {
   return b;
 }
 
-template <bool kTet, int kMinBlocks>
+// kPass: 0 the whole descent of every pair of the work list (ball_plate);
+//        1 the same, except that a LARGE small pair (PairRec::small == 2: thousands of nodes, up to 10^5 box tests -- one
+//          warp would work on it long after the others have run out of pairs: dense clutter ran at half its occupancy)
+//          is only descended until kSmallSplitAt node pairs are waiting, which then go to the item list
+//          {pair, node pair};
+//        2 the items: the same descent started from the item's node pair instead of the root pair.
+constexpr int kSmallSplitAt = 64;
+template <bool kTet, int kMinBlocks, int kPass>
 __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(SmallArgs a) {
   extern __shared__ __align__(16) unsigned char small_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -102,7 +112,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
   Counters* const ctr = a.c.counters;
   // The query already failed: every warp takes the same decision for itself (no block-wide collectives here).
   if (__shfl_sync(0xffffffffu, lane == 0 ? ctr->error : 0, 0) != 0) return;
-  const int count = (int)min(ctr->small_pairs[kTet], (unsigned long long)0x7fffffff);
+  const int count = (int)min(kPass == 2 ? min(ctr->small_items[kTet], a.items_capacity) : ctr->small_pairs[kTet],
+                             (unsigned long long)0x7fffffff);
   unsigned n_tests = 0, n_cand = 0, n_exact = 0, n_leaf = 0;   // warp-uniform
   const Node32* const nodes = a.c.pools.nodes32;
   int4* const surv_list = a.surv;
@@ -120,20 +131,43 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
   bool failed = false;
   for (;;) {
     int t = 0;
-    if (lane == 0) t = (int)atomicAdd(&ctr->small_work[kTet], 1ull);
+    if (lane == 0) t = (int)atomicAdd(kPass == 2 ? &ctr->small_items_work[kTet] : &ctr->small_work[kTet], 1ull);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= count) break;
-    const int p = a.small_list[t];
+    int p;
+    unsigned start = 1u | (1u << 16);   // the root pair
+    if constexpr (kPass == 2) {
+      const int2 item = a.items[t];
+      p = item.x;
+      start = (unsigned)item.y;
+    } else {
+      p = a.small_list[t];
+    }
     const PairRec pr = a.pairs[p];
     const PairF32 f = a.c.pair_f32[p];
     const Node32* const nodes_a = nodes + (pr.root_a - 1);   // node 0 of each asset (1 is the root)
     const Node32* const nodes_b = nodes + (pr.root_b - 1);
     // A stack entry is a node pair still to be TESTED: asset-local node indices (15 bits each). The root pair
     // passed the exact test in k_pairs; it is simply tested again in fp32 (which cannot reject it).
-    if (lane == 0) stack[0] = 1u | (1u << 16);
+    if (lane == 0) stack[0] = start;
     int top = 1, nleaf = 0;
+    bool split = kPass == 1 && pr.small == 2;   // warp-uniform
     __syncwarp();
     while (top > 0 || nleaf > 0) {
+      if (kPass == 1 && split && top >= kSmallSplitAt) {
+        // Hand the waiting node pairs to the item list (the leaf pairs found so far are finished here).
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->small_items[kTet], (unsigned long long)top);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int k = lane; k < top; k += 32) {
+          if (base + k < a.items_capacity) a.items[base + k] = make_int2(p, (int)stack[k]);
+          else raise_error(ctr, 5 /*DBH_ERR_CAPACITY*/, 11);
+        }
+        __syncwarp();
+        top = 0;
+        split = false;
+        continue;
+      }
       if (nleaf >= 32 || top == 0) {
         // ---- leaf predicate + stage A on up to 32 waiting leaf pairs -------------------------------
         const int cnt = min(32, nleaf);
@@ -146,8 +180,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
           c.y = ~la.child;   // pool elements
           c.z = ~lb.child;
           const int decided = boxes_overlap_f32(small_leaf_box(la), small_leaf_box(lb), f);
-          undecided = decided == 0;
-          is_cand = decided > 0 || (undecided && leaf_predicate_exact<kTet>(a.c, c));
+          undecided = decided == 0;   // 2.6 % of ball_plate's leaf pairs: handed to k_leaf_undecided (fp64)
+          is_cand = decided > 0;
           if (is_cand) {
             const TetCullA ta = a.c.pools.cull_a[c.y];
             if (kTet) keep = tet_stage_a(a.c, c, f, ta, a.c.pools.cull_a[c.z]);
@@ -160,15 +194,31 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
           }
         }
         n_cand += __popc(__ballot_sync(0xffffffffu, is_cand));
-        n_exact += __popc(__ballot_sync(0xffffffffu, undecided));
+        const unsigned um = __ballot_sync(0xffffffffu, undecided);
+        n_exact += __popc(um);
         n_leaf += cnt;
+        int cand_index = 0;   // + 1; 0: not recording
         if (a.record) {   // the candidate list of the parity tests (dbh_batch_copy_candidates)
           unsigned long long base = 0;
           if (lane == 0) base = atomicAdd(kTet ? &ctr->leaf_tet : &ctr->leaf_tri, (unsigned long long)cnt);
           base = __shfl_sync(0xffffffffu, base, 0);
           if (lane < cnt) {
-            if (base + lane < a.cand_capacity) a.cand[base + lane] = make_int4(c.x, c.y, c.z, c.w & 1);
-            else raise_error(ctr, 5, 2);
+            if (base + lane < a.cand_capacity) {
+              a.cand[base + lane] = make_int4(c.x, c.y, c.z, c.w & 1);
+              cand_index = (int)(base + lane) + 1;
+            } else {
+              raise_error(ctr, 5, 2);
+            }
+          }
+        }
+        if (um) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(&ctr->undecided, (unsigned long long)__popc(um));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (undecided) {
+            const unsigned long long slot = base + __popc(um & lt);
+            if (slot < a.c.undecided_capacity) a.c.undecided[slot] = make_int4(c.x, c.y, c.z, cand_index);
+            else raise_error(ctr, 5 /*DBH_ERR_CAPACITY*/, 10);
           }
         }
         const unsigned km = __ballot_sync(0xffffffffu, keep);
@@ -200,7 +250,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
             const bool la = A.child < 0, lb = B.child < 0;
             leaf_hit = la && lb;
             // Children are adjacent: (ca, cb), (ca + 1, cb), (ca, cb + 1), (ca + 1, cb + 1); a leaf stays as it is
-            // while the other side descends.
+            // while the other side descends. (Descending only the larger of two inner boxes -- 2 child pairs instead
+            // of 4 -- runs as many box tests on ball_plate in more iterations: 4 % slower, profiles/README.md.)
             const unsigned ca = la ? (e & 0xffffu) : (unsigned)(A.child - (pr.root_a - 1));
             const unsigned cb = lb ? (e >> 16) : (unsigned)(B.child - (pr.root_b - 1));
             first = ca | (cb << 16);
@@ -247,6 +298,61 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
     if (n_exact) atomicAdd(&ctr->leaf_exact, (unsigned long long)n_exact);
     // (Recording mode counts the leaf pairs through the leaf-list cursors.)
     if (!a.record && n_leaf) atomicAdd(kTet ? &ctr->small_leaf_tet : &ctr->small_leaf_tri, (unsigned long long)n_leaf);
+  }
+}
+
+// ---- k_leaf_undecided: the leaf pairs k_small_pairs / k_filter could not decide in fp32 ----------------------
+// One thread per entry: the exact fp64 leaf predicate (BoxesOverlap on the elements' exact boxes), then -- for a
+// candidate -- the same stage-A culls, and the survivor joins the same survivor list (order within the list is free).
+struct UndecidedArgs {
+  ClipArgs c;                 // pools, pair_X, pair_f32, counters, verify
+  const PairRec* pairs;
+  int4* surv[2];              // [0] tet-tri, [1] tet-tet
+  unsigned long long surv_capacity;
+  int4* cand[2];              // recording mode: the entries' flags are set here
+};
+
+__global__ void __launch_bounds__(128) k_leaf_undecided(UndecidedArgs a) {
+  Counters* const ctr = a.c.counters;
+  if (ctr->error != 0) return;
+  const unsigned long long count = min(ctr->undecided, a.c.undecided_capacity);
+  const unsigned long long rounded = (count + 31ull) & ~31ull;
+  unsigned n_cand[2] = {0, 0};
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rounded;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    bool keep = false, is_cand = false, tet = false;
+    int4 c = make_int4(0, 0, 0, 0);
+    if (i < count) {
+      const int4 e = a.c.undecided[i];
+      c = make_int4(e.x, e.y, e.z, 0);
+      tet = a.pairs[e.x].kind == kSoftSoft;
+      is_cand = tet ? leaf_predicate_exact<true>(a.c, c) : leaf_predicate_exact<false>(a.c, c);
+      if (is_cand) {
+        const PairF32 f = a.c.pair_f32[c.x];
+        const TetCullA ta = a.c.pools.cull_a[c.y];
+        if (tet) keep = tet_stage_a(a.c, c, f, ta, a.c.pools.cull_a[c.z]);
+        else keep = tri_stage_a(a.c, c, f, ta, a.c.pools.cull_tri[c.z]);
+        c.w = 1;
+        if (!keep && a.c.verify) {
+          keep = true;
+          c.w |= 2;
+        }
+        if (e.w) a.cand[tet][e.w - 1].w = 1;
+      }
+    }
+    n_cand[0] += __popc(__ballot_sync(0xffffffffu, is_cand && !tet));
+    n_cand[1] += __popc(__ballot_sync(0xffffffffu, is_cand && tet));
+    const unsigned long long s0 = warp_append_flag(&ctr->surv_tri, keep && !tet);
+    const unsigned long long s1 = warp_append_flag(&ctr->surv_tet, keep && tet);
+    if (keep) {
+      const unsigned long long slot = tet ? s1 : s0;
+      if (slot < a.surv_capacity) a.surv[tet][slot] = c;
+      else raise_error(ctr, 5 /*DBH_ERR_CAPACITY*/, 1);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_cand[0]) atomicAdd(&ctr->cand_tri, (unsigned long long)n_cand[0]);
+    if (n_cand[1]) atomicAdd(&ctr->cand_tet, (unsigned long long)n_cand[1]);
   }
 }
 

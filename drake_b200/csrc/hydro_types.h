@@ -159,7 +159,8 @@ struct alignas(64) PairRec {
   int32_t elem_base_a;  // pool index of element 0 of the first body (tet pool)
   int32_t elem_base_b;  // second body (tri pool for soft-rigid, tet pool for soft-soft)
   int32_t root_leaf;    // bit0: root_a is a leaf, bit1: root_b is a leaf
-  int32_t small;        // mesh pair whose two trees have at most 32767 nodes: eligible for k_small_pairs
+  int32_t small;        // mesh pair whose two trees have at most 32767 nodes: eligible for k_small_pairs (2: a large one,
+                        // more than kSmallSplitNodes nodes in the two trees together: its descent is split into work items)
   int32_t pad;          // half-space pairs: root_* / elem_base_* describe the one mesh, the other side's are -1
   int64_t id_m;      // final ids, id_m < id_n
   int64_t id_n;
@@ -207,6 +208,10 @@ struct Counters {
   unsigned long long small_pairs[2]; // overlapping small pairs of the chunk, [0] tet-tri, [1] tet-tet (entries of
                                      // k_small_pairs' work lists)
   unsigned long long small_work[2];  // next unclaimed entry of each list
+  unsigned long long small_items[2];      // work items of the large small pairs (k_small_pairs, pass 1 -> pass 2)
+  unsigned long long small_items_work[2]; // next unclaimed item
+  unsigned long long undecided;      // leaf pairs of small geometry pairs whose fp32 leaf predicate could not decide: entries of
+                                     // the list k_leaf_undecided settles in fp64
   // -- whole query
   unsigned long long bv_tests;      // node-pair box tests (root + every child pair tested)
   unsigned long long bv_tests_tet;  // of which: between two tetrahedron trees (the rest: tetrahedron x triangle trees,
@@ -231,7 +236,7 @@ struct Counters {
   unsigned long long small_leaf_tet;
   // -- totals and per-chunk maxima of the chunk-local cursors
   unsigned long long leaf_tri_total, leaf_tet_total, polys_total, slow_total;
-  unsigned long long frontier_max, leaf_tri_max, leaf_tet_max, polys_max, slow_max;
+  unsigned long long frontier_max, leaf_tri_max, leaf_tet_max, polys_max, slow_max, undecided_max, small_items_max;
   int32_t error;                    // first device-side dbh_status raised
   int32_t error_detail;
   double total_area;
