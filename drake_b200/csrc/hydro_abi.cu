@@ -612,6 +612,19 @@ dbh_status BuildBvhFor(dbh_context* ctx, const double* verts, int nv, const int3
 }  // namespace
 
 namespace {
+// k_clip's launch shapes: threads per block x resident blocks per SM, bounded by the polygon scratch in shared memory
+// (2 x 8 x 24 B per tet-tet thread, 2 x 7 x 24 B per tet-triangle thread).
+struct ClipLaunch {
+  void (*fn)(ClipArgs);
+  int threads, blocks_per_sm, smem;
+};
+ClipLaunch ClipConfig(bool tet, int cfg) {
+  // Measured (profiles/r2v_clip_launch_shapes.txt): tet-triangle 64 x 10 (20 warps, 94 registers, no spills) is 5 % faster
+  // than 128 x 4; tet-tet needs 120 registers and loses more to spills under a 96-register bound than 18-20 warps give.
+  if (cfg == 1) return tet ? ClipLaunch{k_clip<true, 96, 6>, 96, 6, clip_smem_bytes(96, 8)} : ClipLaunch{k_clip<false, 128, 4>, 128, 4, clip_smem_bytes(128, 7)};
+  return tet ? ClipLaunch{k_clip<true, 128, 4>, 128, 4, clip_smem_bytes(128, 8)} : ClipLaunch{k_clip<false, 64, 10>, 64, 10, clip_smem_bytes(64, 7)};
+}
+
 // k_small_pairs by element kind, resident blocks per SM (4, 5, 6) and pass (hydro_small.cuh).
 using SmallKernelFn = void (*)(SmallArgs);
 int SmallBlocksPerSm(int per_sm) { return per_sm >= 6 ? 6 : (per_sm == 5 ? 5 : 4); }
@@ -678,8 +691,12 @@ dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out) {
   CUDA_OK(cudaGetDeviceProperties(&ctx->prop, device_ordinal));
   if (ctx->prop.major < 10)
     return Fail(DBH_ERR_NO_DEVICE, "device is not sm_100 class; kernels are built for sm_100a only");
-  CUDA_OK(cudaFuncSetAttribute(k_clip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
-  CUDA_OK(cudaFuncSetAttribute(k_clip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
+  for (int cfg = 0; cfg < 2; ++cfg) {
+    for (int tet = 0; tet < 2; ++tet) {
+      const ClipLaunch cl = ClipConfig(tet != 0, cfg);
+      CUDA_OK(cudaFuncSetAttribute(cl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cl.smem));
+    }
+  }
   *out = ctx.release();
   return DBH_OK;
   });
@@ -1582,13 +1599,12 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pl.representation = representation;
     pl.out = pk.out;
     pl.counters = b->d_counters.p;
-    const int clip_blocks = sms * 4;
     // Launch configurations chosen by measurement (tools/tune.py; DBH_TUNE="traverse=3,tgrid=8,..." overrides for
     // experiments). traverse: 6 = 128-thread blocks, 6 per SM (3 = 256 x 3, 1 = 512 x 1): smaller blocks mean cheaper
     // block-wide appends; filter / pack: resident blocks per SM the launch bound asks for (registers against
     // occupancy); tgrid / fgrid / pgrid: grid size in units of the resident blocks -- persistent grids (1x for the
     // traversal and the pack) beat over-subscribed ones by 5-15 % (no tail wave).
-    struct Tune { int traverse = 6, filter = 5, pack = 4, tgrid = 3, fgrid = 1, pgrid = 1, small = -1, sblocks = 6, sblocks_tet = 5, stagea = 0, split = 1; } tune;
+    struct Tune { int traverse = 6, filter = 5, pack = 4, tgrid = 3, fgrid = 1, pgrid = 1, small = -1, sblocks = 6, sblocks_tet = 5, stagea = 0, split = 1, split_at = 32, clip = 0; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1604,6 +1620,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       get("small", &tune.small);  // overrides dbh_batch_set_small_pair_path: 0 never, 1 always, 2 auto
       get("stagea", &tune.stagea);    // experiments on the conservative culls (ClipArgs::tune)
       get("sblocks", &tune.sblocks);  // (tet-triangle pairs; "sblocks_tet": tet-tet pairs)
+      get("clip", &tune.clip);        // k_clip launch shape: 0 the measured default, 1 the alternative (ClipConfig)
+      get("split_at", &tune.split_at);
       get("split", &tune.split);      // 0: large small pairs are not split into work items
       get("sblocks_tet", &tune.sblocks_tet);  // k_small_pairs: resident 128-thread blocks per SM asked of the launch bound
     }
@@ -1697,6 +1715,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
           const int small_blocks = std::min(sms * SmallBlocksPerSm(per_sm), (n_small + kSmallWarps - 1) / kSmallWarps);
           sm.items = b->d_small_items.p + (tet ? b->cap_small_items : 0);
           sm.items_capacity = static_cast<unsigned long long>(b->cap_small_items);
+          sm.split_at = std::min(tune.split_at, b->small_stack_cap / 2);
           const bool split = b->num_large_small_pairs > 0 && tune.split != 0;
           SmallKernel(tet != 0, per_sm, split ? 1 : 0)<<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
           if (split) {   // the work items of the large pairs
@@ -1710,13 +1729,15 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       if (b->info.num_soft_rigid_pairs) {
         ca.surv = b->d_frontier[0].p;
         ++b->last_launches;
-        k_clip<false><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+        const ClipLaunch cl = ClipConfig(false, tune.clip);
+        cl.fn<<<sms * cl.blocks_per_sm, cl.threads, cl.smem, st>>>(ca);
       }
       mark(5);
       if (b->info.num_soft_soft_pairs) {
         ca.surv = b->d_frontier[1].p;
         ++b->last_launches;
-        k_clip<true><<<clip_blocks, kClipThreads, kClipSmemBytes, st>>>(ca);
+        const ClipLaunch cl = ClipConfig(true, tune.clip);
+        cl.fn<<<sms * cl.blocks_per_sm, cl.threads, cl.smem, st>>>(ca);
       }
       // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
       ++b->last_launches;

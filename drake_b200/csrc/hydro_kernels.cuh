@@ -36,7 +36,6 @@
 
 namespace dbh {
 
-constexpr int kClipThreads = 128;
 
 // ---------------------------------------------------------------------------
 // Warp-aggregated append for lists where every lane contributes 0 or 1 entries (ballot + popc; one atomic per warp).
@@ -430,11 +429,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_traverse(TraverseArgs 
 // Per-thread polygon scratch in shared memory: [buffer][slot][coord][thread],
 // so a warp's access to one (slot, coord) is a single conflict-free 256 B row
 // whatever slot each lane is on.
-struct PolyScratch {
-  static constexpr int kCap = kMaxPolyVerts;
+// kThreads: the block size; kSlots: vertices per buffer (8: IntersectTetrahedra's bound; a triangle clipped by four
+// half spaces has at most 7).
+template <int kThreads, int kSlots>
+struct PolyScratchT {
+  static constexpr int kCap = kSlots;
   double* base;  // &smem[threadIdx.x]
   __device__ __forceinline__ double& at(int buf, int slot, int c) const {
-    return base[((buf * kMaxPolyVerts + slot) * 3 + c) * kClipThreads];
+    return base[((buf * kSlots + slot) * 3 + c) * kThreads];
   }
   __device__ __forceinline__ D3 get(int buf, int slot) const {
     return D3{at(buf, slot, 0), at(buf, slot, 1), at(buf, slot, 2)};
@@ -445,8 +447,7 @@ struct PolyScratch {
     at(buf, slot, 2) = v.z;
   }
 };
-constexpr int kClipSmemDoublesPerThread = 2 * kMaxPolyVerts * 3;
-constexpr int kClipSmemBytes = kClipSmemDoublesPerThread * kClipThreads * 8;
+constexpr int clip_smem_bytes(int threads, int slots) { return 2 * slots * 3 * threads * 8; }
 
 // The staging soup of contact polygons (frame M of the first body).
 struct PolySoup {
@@ -1161,15 +1162,15 @@ __global__ void __launch_bounds__(kFilterThreads, kMinBlocks) k_filter(ClipArgs 
 }
 
 // ---- k_clip: the exact stage over the survivors, one per thread, dense warps --
-template <bool kTet>
-__global__ void __launch_bounds__(kClipThreads) k_clip(ClipArgs a) {
+template <bool kTet, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_clip(ClipArgs a) {
   extern __shared__ double smem[];
   if (a.counters->error != 0) return;
-  PolyScratch P{smem + threadIdx.x};
+  PolyScratchT<kThreads, kTet ? 8 : 7> P{smem + threadIdx.x};
   const unsigned long long count = min(kTet ? a.counters->surv_tet : a.counters->surv_tri, a.surv_capacity);
   // (Claiming blocks of survivors dynamically, which pays in the filter kernel, was measured 3 % slower here.)
-  for (unsigned long long base = (unsigned long long)blockIdx.x * kClipThreads; base < count;
-       base += (unsigned long long)gridDim.x * kClipThreads) {
+  for (unsigned long long base = (unsigned long long)blockIdx.x * kThreads; base < count;
+       base += (unsigned long long)gridDim.x * kThreads) {
     const unsigned long long i = base + threadIdx.x;
     const bool active = i < count;
     const int4 w = active ? a.surv[i] : make_int4(0, 0, 0, 0);

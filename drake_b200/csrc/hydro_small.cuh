@@ -54,6 +54,7 @@ struct SmallArgs {
   int stack_cap;              // node-pair stack entries per warp
   int2* items;                // kPass 1 writes, kPass 2 reads: {pair, node pair} work items of the large small pairs
   unsigned long long items_capacity;
+  int split_at;               // pass 1: a large pair's descent stops when this many node pairs wait
 };
 
 __host__ __device__ constexpr int small_smem_bytes_per_warp(int stack_cap) {
@@ -96,10 +97,9 @@ __device__ __forceinline__ BoxF small_leaf_box(const Node32& n) {
 // kPass: 0 the whole descent of every pair of the work list (ball_plate);
 //        1 the same, except that a LARGE small pair (PairRec::small == 2: thousands of nodes, up to 10^5 box tests -- one
 //          warp would work on it long after the others have run out of pairs: dense clutter ran at half its occupancy)
-//          is only descended until kSmallSplitAt node pairs are waiting, which then go to the item list
+//          is only descended until SmallArgs::split_at node pairs are waiting, which then go to the item list
 //          {pair, node pair};
 //        2 the items: the same descent started from the item's node pair instead of the root pair.
-constexpr int kSmallSplitAt = 64;
 template <bool kTet, int kMinBlocks, int kPass>
 __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(SmallArgs a) {
   extern __shared__ __align__(16) unsigned char small_smem[];
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
     bool split = kPass == 1 && pr.small == 2;   // warp-uniform
     __syncwarp();
     while (top > 0 || nleaf > 0) {
-      if (kPass == 1 && split && top >= kSmallSplitAt) {
+      if (kPass == 1 && split && top >= a.split_at) {
         // Hand the waiting node pairs to the item list (the leaf pairs found so far are finished here).
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&ctr->small_items[kTet], (unsigned long long)top);
