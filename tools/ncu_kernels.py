@@ -26,6 +26,7 @@ tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 def group(name):
     if "k_small_pairs<0" in name or "k_filter<0" in name: return "mid_phase_tet_tri"
     if "k_small_pairs<1" in name or "k_filter<1" in name: return "mid_phase_tet_tet"
+    if "k_leaf_undecided" in name: return "mid_phase_tet_tet"   # both kinds; timed with the tet-tet stage (bench.py marks)
     if "k_traverse" in name: return "traverse"
     if "k_clip<0" in name: return "exact_clip_tet_tri"
     if "k_clip<1" in name or "k_clip_slow" in name: return "exact_clip_tet_tet"
