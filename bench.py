@@ -34,6 +34,8 @@ if ROOT not in sys.path:
 METRIC = "contact_surfaces_per_sec"
 UNIT = "surfaces/s"
 CONFIGS = ["c1", "c2", "c2s", "c3", "c3h", "c4", "c5"]
+# Aggregate device-to-host rate the GPU box's host side sustains with N GPUs copying at once (measured, GB/s).
+D2H_CEILING_GBS = {1: 56.0, 8: 91.0}
 DEFAULT_SCENES = {"c1": 1, "c2": 1, "c2s": 256, "c3": 16384, "c3h": 16384, "c4": 4096, "c5": 1024}
 # The reference's own printed numbers for the two configs it can run (single thread, unnamed workstation: context,
 # not a target): mesh_intersection_benchmark.cc:79 (args 3/4/0) and compliant_mesh_intersection_benchmark.cc:76 (3/3).
@@ -463,7 +465,7 @@ E2E_WHAT = {
 
 def ncu_profile(config: str):
     """Per-kernel DRAM bytes / instructions of the committed `ncu --set full` capture of this config at its default size
-    (profiles/*_kernels_<config>.json, written by tools/ncu_traffic.py), or None."""
+    (profiles/*_kernels_<config>.json, written by tools/ncu_kernels.py), or None."""
     cands = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_kernels_{config}.json")))
     if not cands:
         return None, None
@@ -640,6 +642,13 @@ def main():
                    pipelining="two batches alternated: D2H of step k overlaps H2D + query of step k+1", host_affinity=numa)
         for k in ("faces_only", "spatial_forces", "discrete_pairs"):
             e2e[k] = dict(variants[k], what=E2E_WHAT[k])
+        # How close the complete copy-out runs to what the box's host side can take (plain pinned cudaMemcpyAsync from
+        # every GPU at once, nothing of this repository on the path: tools/d2h_ceiling.py, profiles/r2y_d2h_ceiling_8gpu.json).
+        ceiling = D2H_CEILING_GBS.get(D.world)
+        agg = D.world * e2e["d2h_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9
+        e2e["d2h_aggregate_gbs"] = agg
+        e2e["d2h_ceiling_gbs"] = ceiling
+        e2e["d2h_frac_of_ceiling"] = agg / ceiling if ceiling else None
         if D.world > 1:
             e2e["note"] = ("all ranks copy out concurrently: the box's host side sustains a fixed aggregate D2H rate "
                            "(profiles/README.md, tools/d2h_ceiling.py), so the complete copy-out does not scale with N; "

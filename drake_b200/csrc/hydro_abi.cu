@@ -618,26 +618,23 @@ struct ClipLaunch {
   void (*fn)(ClipArgs);
   int threads, blocks_per_sm, smem;
 };
-ClipLaunch ClipConfig(bool tet, int cfg) {
+ClipLaunch ClipConfig(bool tet) {
   // Measured (profiles/r2v_clip_launch_shapes.txt): tet-triangle 64 x 10 (20 warps, 94 registers, no spills) is 5 % faster
   // than 128 x 4; tet-tet needs 120 registers and loses more to spills under a 96-register bound than 18-20 warps give.
-  if (cfg == 1) return tet ? ClipLaunch{k_clip<true, 96, 6>, 96, 6, clip_smem_bytes(96, 8)} : ClipLaunch{k_clip<false, 128, 4>, 128, 4, clip_smem_bytes(128, 7)};
   return tet ? ClipLaunch{k_clip<true, 128, 4>, 128, 4, clip_smem_bytes(128, 8)} : ClipLaunch{k_clip<false, 64, 10>, 64, 10, clip_smem_bytes(64, 7)};
 }
 
-// k_small_pairs by element kind, resident blocks per SM (4, 5, 6) and pass (hydro_small.cuh).
+// k_small_pairs by element kind and pass (hydro_small.cuh). Resident 128-thread blocks per SM, by measurement
+// (profiles/r2s_small_pairs_blocks_per_sm.txt): 6 for tet-triangle pairs (80 registers, no spills), 5 for tet-tet pairs
+// (96 registers; 6 spills and is 8 % slower).
+constexpr int kSmallBlocksTri = 6, kSmallBlocksTet = 5;
 using SmallKernelFn = void (*)(SmallArgs);
-int SmallBlocksPerSm(int per_sm) { return per_sm >= 6 ? 6 : (per_sm == 5 ? 5 : 4); }
-template <bool kTet>
-SmallKernelFn SmallKernelOf(int per_sm, int pass) {
-  static const SmallKernelFn k[3][3] = {
-      {k_small_pairs<kTet, 4, 0>, k_small_pairs<kTet, 4, 1>, k_small_pairs<kTet, 4, 2>},
-      {k_small_pairs<kTet, 5, 0>, k_small_pairs<kTet, 5, 1>, k_small_pairs<kTet, 5, 2>},
-      {k_small_pairs<kTet, 6, 0>, k_small_pairs<kTet, 6, 1>, k_small_pairs<kTet, 6, 2>}};
-  return k[SmallBlocksPerSm(per_sm) - 4][pass];
-}
-SmallKernelFn SmallKernel(bool tet, int per_sm, int pass) {
-  return tet ? SmallKernelOf<true>(per_sm, pass) : SmallKernelOf<false>(per_sm, pass);
+SmallKernelFn SmallKernel(bool tet, int pass) {
+  static const SmallKernelFn kTri[3] = {k_small_pairs<false, kSmallBlocksTri, 0>, k_small_pairs<false, kSmallBlocksTri, 1>,
+                                        k_small_pairs<false, kSmallBlocksTri, 2>};
+  static const SmallKernelFn kTetK[3] = {k_small_pairs<true, kSmallBlocksTet, 0>, k_small_pairs<true, kSmallBlocksTet, 1>,
+                                         k_small_pairs<true, kSmallBlocksTet, 2>};
+  return (tet ? kTetK : kTri)[pass];
 }
 constexpr int kSmallSplitNodes = 2048;
 
@@ -691,11 +688,9 @@ dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out) {
   CUDA_OK(cudaGetDeviceProperties(&ctx->prop, device_ordinal));
   if (ctx->prop.major < 10)
     return Fail(DBH_ERR_NO_DEVICE, "device is not sm_100 class; kernels are built for sm_100a only");
-  for (int cfg = 0; cfg < 2; ++cfg) {
-    for (int tet = 0; tet < 2; ++tet) {
-      const ClipLaunch cl = ClipConfig(tet != 0, cfg);
-      CUDA_OK(cudaFuncSetAttribute(cl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cl.smem));
-    }
+  for (int tet = 0; tet < 2; ++tet) {
+    const ClipLaunch cl = ClipConfig(tet != 0);
+    CUDA_OK(cudaFuncSetAttribute(cl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cl.smem));
   }
   *out = ctx.release();
   return DBH_OK;
@@ -1599,31 +1594,24 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     pl.representation = representation;
     pl.out = pk.out;
     pl.counters = b->d_counters.p;
-    // Launch configurations chosen by measurement (tools/tune.py; DBH_TUNE="traverse=3,tgrid=8,..." overrides for
-    // experiments). traverse: 6 = 128-thread blocks, 6 per SM (3 = 256 x 3, 1 = 512 x 1): smaller blocks mean cheaper
-    // block-wide appends; filter / pack: resident blocks per SM the launch bound asks for (registers against
-    // occupancy); tgrid / fgrid / pgrid: grid size in units of the resident blocks -- persistent grids (1x for the
-    // traversal and the pack) beat over-subscribed ones by 5-15 % (no tail wave).
-    struct Tune { int traverse = 6, filter = 5, pack = 4, tgrid = 3, fgrid = 1, pgrid = 1, small = -1, sblocks = 6, sblocks_tet = 5, stagea = 0, split = 1, split_at = 32, clip = 0; } tune;
+    // Launch shapes are fixed by measurement (profiles/README.md): block sizes and resident blocks per SM are template
+    // arguments of the kernels. What stays adjustable for experiments (DBH_TUNE="tgrid=2,small=0,..."): grid sizes in units
+    // of the resident blocks (persistent grids beat over-subscribed ones by 5-15 %: no tail wave), the mid-phase path,
+    // the stage-A ablation bits and the work-item split of the large small pairs.
+    struct Tune { int tgrid = 3, fgrid = 1, pgrid = 1, small = -1, stagea = 0, split = 1, split_at = 32; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
         const size_t p = str.find(std::string(key) + "=");
         if (p != std::string::npos) *v = std::atoi(str.c_str() + p + std::strlen(key) + 1);
       };
-      get("traverse", &tune.traverse);
-      get("filter", &tune.filter);
-      get("pack", &tune.pack);
       get("tgrid", &tune.tgrid);
       get("fgrid", &tune.fgrid);
       get("pgrid", &tune.pgrid);
       get("small", &tune.small);  // overrides dbh_batch_set_small_pair_path: 0 never, 1 always, 2 auto
       get("stagea", &tune.stagea);    // experiments on the conservative culls (ClipArgs::tune)
-      get("sblocks", &tune.sblocks);  // (tet-triangle pairs; "sblocks_tet": tet-tet pairs)
-      get("clip", &tune.clip);        // k_clip launch shape: 0 the measured default, 1 the alternative (ClipConfig)
       get("split_at", &tune.split_at);
       get("split", &tune.split);      // 0: large small pairs are not split into work items
-      get("sblocks_tet", &tune.sblocks_tet);  // k_small_pairs: resident 128-thread blocks per SM asked of the launch bound
     }
     ca.tune = tune.stagea;
     sm.c.tune = tune.stagea;
@@ -1632,9 +1620,8 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     const int small_smem = kSmallWarps * small_smem_bytes_per_warp(b->small_stack_cap);
     if (b->num_small_pairs && small_mode != 0 && small_smem > 48 * 1024) {
       for (int tet = 0; tet < 2; ++tet)
-        for (int per_sm = 4; per_sm <= 6; ++per_sm)
-          for (int pass = 0; pass < 3; ++pass)
-            CUDA_OK(cudaFuncSetAttribute(SmallKernel(tet != 0, per_sm, pass), cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
+        for (int pass = 0; pass < 3; ++pass)
+          CUDA_OK(cudaFuncSetAttribute(SmallKernel(tet != 0, pass), cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem));
     }
     for (int chunk = 0; chunk < b->num_chunks; ++chunk) {
       const int s0 = static_cast<int>(static_cast<long long>(b->num_scenes) * chunk / b->num_chunks);
@@ -1661,9 +1648,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ta.out = b->d_frontier[(level + 1) & 1].p;
         ta.level = level;
         ++b->last_launches;
-        if (tune.traverse == 6) k_traverse<6, 128><<<sms * tune.tgrid * 2, 128, 0, st>>>(ta);
-        else if (tune.traverse == 1) k_traverse<1, 512><<<sms * ((tune.tgrid + 1) / 2), 512, 0, st>>>(ta);
-        else k_traverse<3, 256><<<sms * tune.tgrid, 256, 0, st>>>(ta);
+        k_traverse<6, 128><<<sms * tune.tgrid * 2, 128, 0, st>>>(ta);
       }
       mark(2);
       // Filter (leaf predicate + conservative culls) then the exact stage, per element kind. The
@@ -1689,19 +1674,10 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         ca.surv = b->d_frontier[tet].p;
         if (generic) {
           ++b->last_launches;
-          // tune.filter: resident warps per SM / 8 asked of the launch bound (2, 3, 4: 256-thread blocks; 5: 20 warps in
-          // 128-thread blocks).
-          if (tet) {
-            if (tune.filter == 5) k_filter<true, 128, 5><<<sms * 5 * tune.fgrid, 128, 0, st>>>(ca);
-            else if (tune.filter == 4) k_filter<true, 256, 4><<<sms * 4 * tune.fgrid, 256, 0, st>>>(ca);
-            else if (tune.filter == 2) k_filter<true, 256, 2><<<sms * 2 * tune.fgrid, 256, 0, st>>>(ca);
-            else k_filter<true, 256, 3><<<sms * 3 * tune.fgrid, 256, 0, st>>>(ca);
-          } else {
-            if (tune.filter == 5) k_filter<false, 128, 5><<<sms * 5 * tune.fgrid, 128, 0, st>>>(ca);
-            else if (tune.filter == 4) k_filter<false, 256, 4><<<sms * 4 * tune.fgrid, 256, 0, st>>>(ca);
-            else if (tune.filter == 2) k_filter<false, 256, 2><<<sms * 2 * tune.fgrid, 256, 0, st>>>(ca);
-            else k_filter<false, 256, 3><<<sms * 3 * tune.fgrid, 256, 0, st>>>(ca);
-          }
+          // 20 resident warps per SM in 128-thread blocks (95 registers, no spills, now that the fp64 leaf predicate lives
+          // in k_leaf_undecided; 16 warps at 127 registers: 6 % slower, 24 at 80: spills, profiles/r2u_split_and_filter.txt).
+          if (tet) k_filter<true, 128, 5><<<sms * 5 * tune.fgrid, 128, 0, st>>>(ca);
+          else k_filter<false, 128, 5><<<sms * 5 * tune.fgrid, 128, 0, st>>>(ca);
         }
         if (use_small) {
           sm.small_list = tet ? pa.small_list_tet : pa.small_list;
@@ -1711,16 +1687,16 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
           ++b->last_launches;
           // Resident 128-thread blocks per SM (measured: 6 for tet-triangle pairs, 5 for tet-tet, whose stage A needs
           // 96 registers; profiles/README.md).
-          const int per_sm = tet ? tune.sblocks_tet : tune.sblocks;
-          const int small_blocks = std::min(sms * SmallBlocksPerSm(per_sm), (n_small + kSmallWarps - 1) / kSmallWarps);
+          const int per_sm = tet ? kSmallBlocksTet : kSmallBlocksTri;
+          const int small_blocks = std::min(sms * per_sm, (n_small + kSmallWarps - 1) / kSmallWarps);
           sm.items = b->d_small_items.p + (tet ? b->cap_small_items : 0);
           sm.items_capacity = static_cast<unsigned long long>(b->cap_small_items);
           sm.split_at = std::min(tune.split_at, b->small_stack_cap / 2);
           const bool split = b->num_large_small_pairs > 0 && tune.split != 0;
-          SmallKernel(tet != 0, per_sm, split ? 1 : 0)<<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
+          SmallKernel(tet != 0, split ? 1 : 0)<<<small_blocks, kSmallWarps * 32, small_smem, st>>>(sm);
           if (split) {   // the work items of the large pairs
             ++b->last_launches;
-            SmallKernel(tet != 0, per_sm, 2)<<<sms * SmallBlocksPerSm(per_sm), kSmallWarps * 32, small_smem, st>>>(sm);
+            SmallKernel(tet != 0, 2)<<<sms * per_sm, kSmallWarps * 32, small_smem, st>>>(sm);
           }
         }
         if (tet) settle_undecided();
@@ -1729,14 +1705,14 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       if (b->info.num_soft_rigid_pairs) {
         ca.surv = b->d_frontier[0].p;
         ++b->last_launches;
-        const ClipLaunch cl = ClipConfig(false, tune.clip);
+        const ClipLaunch cl = ClipConfig(false);
         cl.fn<<<sms * cl.blocks_per_sm, cl.threads, cl.smem, st>>>(ca);
       }
       mark(5);
       if (b->info.num_soft_soft_pairs) {
         ca.surv = b->d_frontier[1].p;
         ++b->last_launches;
-        const ClipLaunch cl = ClipConfig(true, tune.clip);
+        const ClipLaunch cl = ClipConfig(true);
         cl.fn<<<sms * cl.blocks_per_sm, cl.threads, cl.smem, st>>>(ca);
       }
       // Exceptional candidates (normally none): a tiny launch that returns at once when the list is empty.
@@ -1768,11 +1744,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       mark(8);
       ++b->last_launches;
       if (pk.representation == DBH_POLYGON) {
-        if (tune.pack == 4) k_pack<4, 1><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
-        else k_pack<3, 1><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
+        k_pack<4, 1><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
       } else {
-        if (tune.pack == 4) k_pack<4, 0><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
-        else k_pack<3, 0><<<sms * 3 * tune.pgrid, 128, 0, st>>>(pk);
+        k_pack<4, 0><<<sms * 4 * tune.pgrid, 128, 0, st>>>(pk);
       }
       if (plane_blocks) {  // pack pass of the half-space pairs: straight into the final layout
         ++b->last_launches;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/gpu_r2p.sh <tag> "<config:scenes ...>": ncu captures of the final build: C3 (whole query), c3h (half-space kernels), C4 on 256 scenes, C5 on 16 scenes.
+# tools/gpu_ncu_capture.sh <tag> "<config:scenes ...>": ncu captures of the final build: C3 (whole query), c3h (half-space kernels), C4 on 256 scenes, C5 on 16 scenes.
 # The .ncu-rep files stay on the box (/tmp): only the summaries come back (gpurun_out is capped at 64 MiB).
 tag=${1:-r2p}; specs=${2:-c3:16384 c3h:16384 c4:256 c5:16}
 mkdir -p gpurun_out

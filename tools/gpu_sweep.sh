@@ -1,5 +1,5 @@
 #!/bin/bash
-# Variant sweep of one visit: tools/gpu_r2r.sh <tag> "<DBH_TUNE variants separated by ;>" [config]   (bench only, no tests)
+# Variant sweep of one visit: tools/gpu_sweep.sh <tag> "<DBH_TUNE variants separated by ;>" [config]   (bench only, no tests)
 tag=$1; variants=$2; cfg=${3:-c3}
 mkdir -p gpurun_out
 IFS=';' read -ra VS <<< "$variants"
