@@ -461,8 +461,9 @@ struct dbh_batch {
   DevBuf<long long> d_plane_elem_off;
   // Contact-surface consumer (k_wrench): per-geometry body origins / spatial velocities / contact properties and the
   // per-surface spatial forces.
-  DevBuf<double> d_body_origin, d_body_vel, d_props, d_forces, d_discrete;
+  DevBuf<double> d_body_origin, d_body_vel, d_props, d_forces, d_discrete, d_deformable;
   bool discrete_done{false};
+  bool deformable_done{false};
   long long discrete_pairs{0};
   bool have_body_origin{false}, have_body_vel{false}, have_props{false}, forces_done{false};
   // Small pairs (both trees at most kSmallMaxNodes nodes): k_small_pairs descends and culls them on chip, one warp
@@ -1427,6 +1428,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
   b->query_enqueued = true;
   b->forces_done = false;
   b->discrete_done = false;
+  b->deformable_done = false;
   b->last_launches = 0;
   b->last_query_kind = query_kind;
   cudaStream_t st = b->stream;
@@ -1994,6 +1996,50 @@ dbh_status dbh_batch_copy_discrete_pairs_async(dbh_batch* b, double* out, int64_
   const size_t nf = b->h_counters->faces;
   *num_faces = static_cast<int64_t>(nf);
   if (out && nf) CUDA_OK(cudaMemcpyAsync(out, b->d_discrete.p, nf * 9 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  return DBH_OK;
+  });
+}
+
+dbh_status dbh_batch_compute_deformable_contact(dbh_batch* b) {
+  return Guarded([&]() -> dbh_status {
+  if (!b) return Fail(DBH_ERR_INVALID_ARGUMENT, "batch is null");
+  if (!b->query_enqueued) return Fail(DBH_ERR_NOT_READY, "no query enqueued");
+  if (b->representation != DBH_POLYGON)
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "deformable contact data is defined on polygon surfaces (DeformableContactSurface holds "
+                                          "a PolygonSurfaceMesh): query with DBH_POLYGON");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  CUDA_OK(b->d_deformable.ensure(static_cast<size_t>(std::max<long long>(b->cap_faces, 1)) * 22));
+  DeformableArgs da{};
+  da.pairs = b->d_pairs.p;
+  da.poses = b->d_poses;
+  da.tris = b->ctx->d_tris.p;
+  da.face_pair = b->r_face_pair.p;
+  da.elem_b = b->r_elem_b.p;
+  da.normals = b->r_normals.p;
+  da.centroids = b->r_centroids.p;
+  da.e_centroid = b->r_e_centroid.p;
+  da.grad_eM = b->r_grad_eM.p;
+  da.grad_eN = b->r_grad_eN.p;
+  da.out = b->d_deformable.p;
+  da.counters = b->d_counters.p;
+  k_deformable<<<b->ctx->prop.multiProcessorCount * 8, 256, 0, b->stream>>>(da);
+  CUDA_OK(cudaGetLastError());
+  b->deformable_done = true;
+  return DBH_OK;
+  });
+}
+
+dbh_status dbh_batch_copy_deformable_contact_async(dbh_batch* b, double* out, int32_t* triangle_index, int64_t* num_faces) {
+  return Guarded([&]() -> dbh_status {
+  if (!b || !num_faces) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_deformable_contact: bad argument");
+  if (!b->query_done || !b->deformable_done)
+    return Fail(DBH_ERR_NOT_READY, "dbh_batch_compute_deformable_contact + dbh_batch_sync first");
+  CUDA_OK(cudaSetDevice(b->ctx->device));
+  const size_t nf = b->h_counters->faces;
+  *num_faces = static_cast<int64_t>(nf);
+  if (out && nf) CUDA_OK(cudaMemcpyAsync(out, b->d_deformable.p, nf * 22 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (triangle_index && nf)
+    CUDA_OK(cudaMemcpyAsync(triangle_index, b->r_elem_b.p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
   return DBH_OK;
   });
 }

@@ -2205,4 +2205,51 @@ __global__ void __launch_bounds__(256) k_discrete(DiscreteArgs a) {
   if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&a.counters->discrete_pairs, (unsigned long long)kept);
 }
 
+// ---- k_deformable: the deformable x rigid contact data of every face of the last query (hydro_wrench.cuh) ----------
+// One thread per face, 22 doubles out: p_WC[3], nhat_W[3], R_WC[9] (column-major), pressure, grad_W[3], barycentric[3].
+// Faces of surfaces that are not tet-triangle surfaces get NaN records. The deformable body is the pair's triangle
+// side, whatever the order of the two ids (a swapped surface's normals and gradients are swapped back here).
+struct DeformableArgs {
+  const PairRec* pairs;
+  const Xf* poses;
+  const TriRec* tris;
+  const int* face_pair;
+  const int* elem_b;
+  const double* normals;
+  const double* centroids;
+  const double* e_centroid;
+  const double* grad_eM;
+  const double* grad_eN;
+  double* out;             // [num_faces * 22]
+  Counters* counters;
+};
+
+__global__ void __launch_bounds__(256) k_deformable(DeformableArgs a) {
+  if (a.counters->error != 0) return;
+  const long long num_faces = (long long)a.counters->faces;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < num_faces; f += (long long)gridDim.x * blockDim.x) {
+    const PairRec& pr = a.pairs[a.face_pair[f]];
+    double* o = a.out + 22 * f;
+    if (pr.kind != kSoftRigid) {
+      const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+      for (int k = 0; k < 22; ++k) o[k] = kNaN;
+      continue;
+    }
+    const bool swapped = pr.swapped != 0;
+    D3 n = load3(a.normals + 3 * f);
+    if (swapped) n = -n;
+    const D3 grad = load3((swapped ? a.grad_eN : a.grad_eM) + 3 * f);
+    const TriRec& t = a.tris[pr.elem_base_b + a.elem_b[f]];
+    const DeformableFaceContact c =
+        deformable_face_contact(n, load3(a.centroids + 3 * f), a.e_centroid[f], grad, a.poses[pr.geom_a], a.poses[pr.geom_b],
+                                load3(t.v[0]), load3(t.v[1]), load3(t.v[2]));
+    store3(o, 0, c.p_WC);
+    store3(o, 1, c.nhat_W);
+    for (int k = 0; k < 9; ++k) o[6 + k] = c.R_WC[k];
+    o[15] = c.pressure;
+    store3(o + 16, 0, c.grad_W);
+    store3(o + 19, 0, c.barycentric);
+  }
+}
+
 }  // namespace dbh

@@ -151,4 +151,73 @@ __host__ __device__ __forceinline__ bool discrete_face_pair(double Ae, D3 nhat_B
   return true;
 }
 
+// ---- deformable x rigid contact data ------------------------------------------------------------
+// What the reference derives per polygon of a tet-triangle contact surface whose triangle mesh is a DEFORMABLE body's
+// surface and whose volume mesh + pressure field belong to a rigid geometry (AddDeformableRigidContactSurface,
+// geometry/proximity/deformable_mesh_intersection.cc:85-183; DeformableContactSurface ctor,
+// geometry/query_results/deformable_contact.cc:35-66):
+struct DeformableFaceContact {
+  D3 p_WC;          // contact point = polygon centroid                                   (deformable_contact.cc:59)
+  D3 nhat_W;        // from the rigid body into the deformable one: -face normal          (:58)
+  double R_WC[9];   // MakeFromOneUnitVector(-nhat_W, z), column-major                    (:60-61)
+  double pressure;  // rigid pressure field at the centroid                               (deformable_mesh_intersection.cc:112-121)
+  D3 grad_W;        // X_WR * grad_R: the POINT transform, as the reference writes it     (:172-174)
+  D3 barycentric;   // of the centroid in the deformable triangle                         (:69-79)
+};
+
+// RotationMatrix::MakeFromOneUnitVector (math/rotation_matrix.cc:133-242), column-major into R.
+__host__ __device__ __forceinline__ void make_from_one_unit_vector(D3 u, int axis_index, double* R) {
+  const double uu[3] = {u.x, u.y, u.z};
+  int i = 0;   // minCoeff of |u|: the first of equal minima
+  if (fabs(uu[1]) < fabs(uu[i])) i = 1;
+  if (fabs(uu[2]) < fabs(uu[i])) i = 2;
+  const int j = (i + 1) % 3, k = (j + 1) % 3;
+  const double mag_a_x_u = sqrt(1 - uu[i] * uu[i]);
+  const double r = 1 / mag_a_x_u;
+  const double s = -r * uu[i];
+  double v[3], w[3];
+  v[i] = 0;
+  v[j] = -r * uu[k];
+  v[k] = r * uu[j];
+  w[i] = mag_a_x_u;
+  w[j] = s * uu[j];
+  w[k] = s * uu[k];
+  const int cv = (axis_index + 1) % 3, cw = (axis_index + 2) % 3;
+  for (int q = 0; q < 3; ++q) {
+    R[axis_index * 3 + q] = uu[q];
+    R[cv * 3 + q] = v[q];
+    R[cw * 3 + q] = w[q];
+  }
+}
+
+// TriangleSurfaceMesh::CalcBarycentric (triangle_surface_mesh.cc:53-87): the least-squares solution of
+// [v1 - v0, v2 - v0] b = p - v0 -- there through Eigen's colPivHouseholderQr, here through the 2 x 2 normal equations
+// (the same solution up to rounding: the parity tests compare it with a tolerance).
+__host__ __device__ __forceinline__ D3 calc_barycentric(D3 p, D3 v0, D3 v1, D3 v2) {
+  const D3 u1 = v1 - v0, u2 = v2 - v0, r = p - v0;
+  const double a11 = dot(u1, u1), a12 = dot(u1, u2), a22 = dot(u2, u2);
+  const double c1 = dot(u1, r), c2 = dot(u2, r);
+  const double det = a11 * a22 - a12 * a12;
+  const double b1 = (a22 * c1 - a12 * c2) / det;
+  const double b2 = (a11 * c2 - a12 * c1) / det;
+  return D3{1.0 - b1 - b2, b1, b2};
+}
+
+// mesh_normal_W: the contact mesh's face normal as the intersector built it (out of the triangle's front side: the
+// deformable surface's outward normal); grad_W: the rigid field's gradient rotated into World; X_WR / X_WD: poses of the
+// rigid geometry and of the deformable surface mesh (identity in the reference); tri: the triangle's vertices in D.
+__host__ __device__ __forceinline__ DeformableFaceContact deformable_face_contact(D3 mesh_normal_W, D3 centroid_W,
+                                                                                  double pressure, D3 grad_W, const Xf& X_WR,
+                                                                                  const Xf& X_WD, D3 t0, D3 t1, D3 t2) {
+  DeformableFaceContact c;
+  c.p_WC = centroid_W;
+  c.nhat_W = -mesh_normal_W;
+  make_from_one_unit_vector(mesh_normal_W, 2, c.R_WC);
+  c.pressure = pressure;
+  c.grad_W = D3{X_WR.m[9] + grad_W.x, X_WR.m[10] + grad_W.y, X_WR.m[11] + grad_W.z};
+  const D3 p_DC = rot_t(X_WD, centroid_W - make_d3(X_WD.m[9], X_WD.m[10], X_WD.m[11]));
+  c.barycentric = calc_barycentric(p_DC, t0, t1, t2);
+  return c;
+}
+
 }  // namespace dbh

@@ -139,6 +139,8 @@ def lib():
     L.dbh_batch_copy_spatial_forces_async.argtypes = [vp, vp, _lp]
     L.dbh_batch_compute_discrete_pairs.argtypes = [vp]
     L.dbh_batch_copy_discrete_pairs_async.argtypes = [vp, vp, _lp]
+    L.dbh_batch_compute_deformable_contact.argtypes = [vp]
+    L.dbh_batch_copy_deformable_contact_async.argtypes = [vp, vp, vp, _lp]
     L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_verify.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_normal_filter.argtypes = [vp, C.c_int32]
@@ -797,6 +799,23 @@ class SceneBatch:
         if wait:
             self.sync()
         return view
+
+    def compute_deformable_contact(self):
+        """Enqueues the deformable x rigid contact data of the last query's faces (deformable_mesh_intersection.cc:85-183)."""
+        _check(lib().dbh_batch_compute_deformable_contact(self._h))
+
+    def copy_deformable_contact(self, wait: bool = True):
+        """([num_faces, 22], triangle_index [num_faces]): p_WC, nhat_W, R_WC (column-major), pressure, grad_W (the
+        reference's point-transformed gradient), barycentric centroid; NaN rows for faces of other surface kinds."""
+        n = C.c_int64(0)
+        _check(lib().dbh_batch_copy_deformable_contact_async(self._h, None, None, C.byref(n)))
+        out = np.zeros((n.value, 22))
+        tri = np.zeros(n.value, dtype=np.int32)
+        if n.value:
+            _check(lib().dbh_batch_copy_deformable_contact_async(self._h, out.ctypes.data, tri.ctypes.data, C.byref(n)))
+        if wait:
+            self.sync()
+        return out, tri
 
     def compute_spatial_forces(self, vslip_regularizer: float = 1e-6):
         """Enqueues k_wrench over the last query's surfaces (no host sync)."""

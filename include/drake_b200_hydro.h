@@ -271,6 +271,33 @@ dbh_status dbh_batch_compute_discrete_pairs(dbh_batch* batch);
 dbh_status dbh_batch_copy_discrete_pairs_async(dbh_batch* batch, double* out /* [num_faces*9], may be NULL */,
                                                int64_t* num_faces);
 
+/* -- (5d) a third device-side consumer: the per-contact-point data of a DEFORMABLE x rigid pair
+ *        (AddDeformableRigidContactSurface, geometry/proximity/deformable_mesh_intersection.cc:85-183, and the
+ *        DeformableContactSurface constructor, geometry/query_results/deformable_contact.cc:35-66). The reference runs
+ *        such a pair through the same tet-triangle intersector as a hydroelastic soft-rigid pair: the volume mesh +
+ *        pressure field are the RIGID geometry's (dbh_register_compliant_mesh), the triangle mesh is the deformable
+ *        body's surface (dbh_register_rigid_mesh; its vertices move every step: dbh_context_update_vertices, the
+ *        device-side BvhUpdater). One record of 22 doubles per face of the last query, in face order:
+ *          p_WC[3]   contact point = polygon centroid
+ *          nhat_W[3] from the rigid body into the deformable one (-face normal of the contact mesh as the
+ *                    intersector builds it, whatever the order of the two ids)
+ *          R_WC[9]   RotationMatrix::MakeFromOneUnitVector(-nhat_W, z) (math/rotation_matrix.cc:133-242), column-major
+ *          pressure  the rigid pressure field at the centroid
+ *          grad_W[3] "pressure_gradient_W" as the reference computes it (:172-174): X_WR * grad_R with the POINT
+ *                    transform, i.e. the rotated gradient PLUS p_WR (reproduced, not corrected; subtract p_WR for the
+ *                    gradient itself, or read grad_eM)
+ *          barycentric[3] of the centroid in the deformable triangle (TriangleSurfaceMesh::CalcBarycentric: least
+ *                    squares; agrees with the reference's QR solve to rounding, not bitwise)
+ *        plus, per face, the index of that triangle in the deformable surface mesh. Faces of other kinds of surfaces
+ *        get NaN records. The index bookkeeping that needs the deformable VOLUME mesh (contact_vertex_indexes,
+ *        participating vertices, is_element_inverted; :127-170) is a host-side gather over triangle_index
+ *        (INTEGRATION.md). Polygon representation only. Enqueued after dbh_batch_query; copy after dbh_batch_sync
+ *        (asynchronous: complete with another dbh_batch_sync). ---------------------------------------------- */
+dbh_status dbh_batch_compute_deformable_contact(dbh_batch* batch);
+dbh_status dbh_batch_copy_deformable_contact_async(dbh_batch* batch, double* out /* [num_faces*22], may be NULL */,
+                                                   int32_t* triangle_index /* [num_faces], may be NULL */,
+                                                   int64_t* num_faces);
+
 /* -- (6) sizes of the last completed query. --------------------------------- */
 typedef struct dbh_result_sizes {
   int64_t num_surfaces;

@@ -163,6 +163,26 @@ void phc_surface_wrench(int rep, int nf, const double* areas, const double* norm
     out18[6 * k + 3] = all[k]->trans.x, out18[6 * k + 4] = all[k]->trans.y, out18[6 * k + 5] = all[k]->trans.z;
   }
 }
+// deformable_face_contact (hydro_wrench.cuh) for nf faces: per face normal, centroid, pressure, rotated gradient and the
+// deformable triangle's three vertices (9 doubles); 22 doubles out per face, the layout of k_deformable.
+void phc_deformable_contact(int nf, const double* mesh_normals, const double* centroids, const double* pressures,
+                            const double* grads, const double* X_WR, const double* X_WD, const double* tri_verts, double* out) {
+  Xf XR, XD;
+  std::memcpy(XR.m, X_WR, sizeof(XR.m));
+  std::memcpy(XD.m, X_WD, sizeof(XD.m));
+  for (int f = 0; f < nf; ++f) {
+    const DeformableFaceContact c =
+        deformable_face_contact(load3(mesh_normals + 3 * f), load3(centroids + 3 * f), pressures[f], load3(grads + 3 * f), XR, XD,
+                                load3(tri_verts + 9 * f), load3(tri_verts + 9 * f + 3), load3(tri_verts + 9 * f + 6));
+    double* o = out + 22 * f;
+    o[0] = c.p_WC.x, o[1] = c.p_WC.y, o[2] = c.p_WC.z;
+    o[3] = c.nhat_W.x, o[4] = c.nhat_W.y, o[5] = c.nhat_W.z;
+    for (int k = 0; k < 9; ++k) o[6 + k] = c.R_WC[k];
+    o[15] = c.pressure;
+    o[16] = c.grad_W.x, o[17] = c.grad_W.y, o[18] = c.grad_W.z;
+    o[19] = c.barycentric.x, o[20] = c.barycentric.y, o[21] = c.barycentric.z;
+  }
+}
 double phc_combined_dissipation(double kA, double kB, double dA, double dB) {
   return combined_hunt_crossley_dissipation(kA, kB, dA, dB);
 }

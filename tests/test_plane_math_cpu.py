@@ -306,6 +306,63 @@ def test_wrench_arithmetic_matches_the_oracle(rep):
         assert lib.phc_combined_friction(*args) == ho.combined_friction(*args)
 
 
+def check_deformable_rows(rows, tri_index, want, atol_scale=1.0):
+    """Rows of k_deformable's layout (p_WC, nhat_W, R_WC column-major, pressure, grad_W, barycentric) against
+    oracle/ho_deformable.py's DeformableRigidContact, faces matched by the caller."""
+    assert rows.shape == (len(want.pressures), 22) and np.array_equal(tri_index, want.triangle_index)
+    L = max(np.max(np.abs(want.contact_points_W)), 1e-300)
+    assert np.max(np.abs(rows[:, 0:3] - want.contact_points_W)) <= 1e-12 * L * atol_scale
+    assert np.max(np.abs(rows[:, 3:6] - want.nhats_W)) <= 1e-12 * atol_scale
+    R = rows[:, 6:15].reshape(-1, 3, 3).transpose(0, 2, 1)          # column-major -> [row, col]
+    assert np.max(np.abs(R - want.R_WCs)) <= 1e-11 * atol_scale
+    P = max(np.max(np.abs(want.pressures)), 1e-300)
+    assert np.max(np.abs(rows[:, 15] - want.pressures)) <= 1e-10 * P
+    G = max(np.max(np.abs(want.pressure_gradients_W)), 1e-300)
+    assert np.max(np.abs(rows[:, 16:19] - want.pressure_gradients_W)) <= 1e-10 * G
+    assert np.max(np.abs(rows[:, 19:22] - want.barycentric_centroids)) <= 1e-9 * atol_scale
+    assert np.max(np.abs(rows[:, 19:22].sum(axis=1) - 1.0)) <= 1e-12
+
+
+def test_deformable_contact_arithmetic_matches_the_oracle():
+    """hydro_wrench.cuh's deformable_face_contact (MakeFromOneUnitVector, CalcBarycentric through the normal equations,
+    the reference's point-transformed gradient) on the faces of real tet-triangle surfaces against
+    oracle/ho_deformable.py, incl. the reference's one-polygon fixture (deformable_mesh_intersection_test.cc:106-178)."""
+    from oracle import ho_deformable as hd
+    lib = harness()
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+
+    def host_rows(want, surface_mesh, X_WR, X_WD):
+        s = want.surface
+        verts, tris = surface_mesh.arrays()[:2]
+        tv = verts[tris[want.triangle_index]].reshape(-1, 9)
+        out = np.zeros((s.num_faces, 22))
+        lib.phc_deformable_contact(s.num_faces, d(s.normals), d(s.centroids), d(s.e_centroid), d(s.grad_eM), d(X_WR), d(X_WD),
+                                   d(tv), d(out))
+        return out
+
+    single = ho.VolumeMesh.from_arrays([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], [[0, 1, 2, 3]])
+    X_WR = ho.xform(None, [1.0 / 6.0, 1.0 / 6.0, -0.5])
+    surface = single.to_surface()
+    want = hd.deformable_rigid_contact(single, ho.VolumeField.from_values(single, [123.0] * 4), surface, X_WR)
+    rows = host_rows(want, surface, X_WR, ho.IDENTITY)
+    check_deformable_rows(rows, want.triangle_index, want)
+    assert np.allclose(rows[0, 19:22], 1.0 / 3, atol=1e-14) and np.allclose(rows[0, 0:3], [1.0 / 3, 1.0 / 3, 0], atol=1e-14)
+
+    vol = ho.VolumeMesh.sphere(0.3, 0.1, dense=True)
+    fld = ho.VolumeField.sphere(vol, 0.3, 1e6)
+    surface = ho.TriMesh.sphere(0.25, 0.05)
+    rng = np.random.default_rng(41)
+    faces = 0
+    for _ in range(4):
+        X_WR = random_pose(rng, 0.05)
+        X_WD = ho.compose(X_WR, ho.xform(ho.rpy_matrix(*rng.uniform(-1, 1, 3)), [0.1, 0.05, 0.3]))
+        want = hd.deformable_rigid_contact(vol, fld, surface, X_WR, X_WD)
+        assert want is not None
+        check_deformable_rows(host_rows(want, surface, X_WR, X_WD), want.triangle_index, want)
+        faces += len(want.pressures)
+    assert faces > 200
+
+
 @pytest.mark.parametrize("name,tri,expected", __import__("tests.test_oracle_halfspace", fromlist=["x"]).SINGLE_TRIANGLE_CASES,
                          ids=[c[0] for c in __import__("tests.test_oracle_halfspace", fromlist=["x"]).SINGLE_TRIANGLE_CASES])
 def test_single_triangle_cases_through_the_kernel_arithmetic(name, tri, expected):

@@ -4,6 +4,7 @@ boxes refitted bottom-up; bvh_updater.h:45-103). The oracle's restatement is che
 (bvh_updater_test.cc: every box bounds its contents, the root is the mesh's box; topology unchanged); the device path
 (dbh_context_update_vertices: k_refit_tris / k_refit_nodes / k_refit_blocks) must give, after an update, the surfaces
 the oracle computes on the deformed mesh."""
+import copy
 import math
 
 import numpy as np
@@ -129,3 +130,69 @@ def test_device_refit_of_many_assets_and_a_half_space_pair():
             parity.compare_surface(g, w, welded=bool(np.any(np.asarray(w.elem_second) < 0) or np.any(np.asarray(w.elem_first) < 0)))
         total += len(want)
     assert total >= S
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ids", [(1, 2, 3), (7, 2, 3)])
+def test_deformable_rigid_contact_data_after_device_refit(ids):
+    """SURVEY 8f rank 4, deformable x rigid: k_deformable over the faces of two deforming surfaces against a rigid
+    geometry's pressure-field volume, after every device-side vertex update, against oracle/ho_deformable.py
+    (AddDeformableRigidContactSurface + the DeformableContactSurface constructor): contact points, normals into the
+    deformable body, R_WC, pressures, the reference's point-transformed gradients, triangle indices and barycentric
+    centroids, faces matched by their emitting element pair. ids (7, 2, 3): the rigid geometry has the larger id, so the
+    ContactSurface is stored swapped and the consumer has to undo it."""
+    import drake_b200 as db
+    from drake_b200 import engine
+    from oracle import ho_deformable as hd
+    from tests import parity
+    from tests.test_plane_math_cpu import check_deformable_rows
+    ctx = db.Context(0)
+    vol = ho.VolumeMesh.sphere(0.3, 0.1, dense=True)
+    fld = ho.VolumeField.sphere(vol, 0.3, 1e6)
+    surf = [ho.TriMesh.sphere(0.25, 0.05), ho.TriMesh.ellipsoid(0.2, 0.3, 0.25, 0.06)]
+    v0 = [s.verts.copy() for s in surf]
+    a_v = parity.register_compliant(ctx, vol, fld)
+    a_s = [parity.register_rigid(ctx, s) for s in surf]
+    # The rigid geometry is posed; the deformable surfaces live in World (identity), as in the reference.
+    X_WR = ho.xform(ho.rpy_matrix(0.2, 0.1, 0.4), [0.1, 0.05, 0.3])
+    offsets = [np.array([0.0, 0.0, 0.0]), np.array([0.3, -0.1, 0.75])]
+    poses = np.stack([X_WR, ho.IDENTITY, ho.IDENTITY])
+    batch = db.SceneBatch(ctx, [0, 3], [a_v, a_s[0], a_s[1]], list(ids), excluded=[[1, 2]])
+    checked = 0
+    for t in (0.0, 0.6, -0.8):
+        new = [deform(v, t) + o for v, o in zip(v0, offsets)]
+        ctx.update_vertices(a_s, new)
+        for s, v in zip(surf, new):
+            s.update_vertices(v)
+        batch.set_poses(poses)
+        batch.query(ho.KPOLYGON, engine.STRICT)
+        batch.compute_deformable_contact()
+        batch.sync()
+        rows, tri = batch.copy_deformable_contact()
+        res = batch.copy_results()
+        got = res.surfaces()
+        want = [hd.deformable_rigid_contact(vol, fld, s, X_WR) for s in surf]
+        assert len(got) == sum(w is not None for w in want) >= 1
+        k = 0
+        for which, w in enumerate(want):
+            if w is None:
+                continue
+            g = got[k]
+            assert {g.id_M, g.id_N} == {ids[0], ids[1 + which]}
+            f0 = int(res.surf_face_offset[k])
+            mine, mine_tri = rows[f0:f0 + g.num_faces], tri[f0:f0 + g.num_faces]
+            tet, tr = g.elem_M, g.elem_N      # elements of the first-constructed body (the volume) / the triangle mesh
+            np.testing.assert_array_equal(mine_tri, tr)
+            go = np.argsort(parity.face_keys(tet, tr), kind="stable")
+            wo = np.argsort(parity.face_keys(w.surface.elem_first, w.surface.elem_second), kind="stable")
+            w2 = copy.copy(w)
+            for name in ("contact_points_W", "nhats_W", "R_WCs", "pressures", "pressure_gradients_W", "triangle_index",
+                         "barycentric_centroids"):
+                setattr(w2, name, getattr(w, name)[wo])
+            check_deformable_rows(mine[go], mine_tri[go], w2, atol_scale=10.0)
+            checked += g.num_faces
+            k += 1
+    assert checked > 300
+    with pytest.raises(engine.HydroError):
+        batch.query(ho.KTRIANGLE, engine.STRICT)
+        batch.compute_deformable_contact()
