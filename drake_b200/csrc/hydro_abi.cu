@@ -16,6 +16,7 @@
 #include "../../include/drake_b200_hydro.h"
 #include "hydro_kernels.cuh"
 #include "hydro_small.cuh"
+#include "hydro_derive.cuh"
 #include "hydro_refit.cuh"
 #include "hydro_lbvh.h"
 
@@ -92,10 +93,11 @@ struct HostAsset {
   int node_base{0};
   // Bvh::Collide(plane) for the half-space pairs (bvh.h:285-309), flattened to one cut of the tree: the elements in
   // the tree's leaf order (depth first), and the box of every run of kPlaneBlock consecutive leaves.
-  // Triangle assets keep their vertices and connectivity: dbh_context_update_vertices re-poses them on the device.
-  std::vector<double> rverts;        // [num_vertices * 3]
-  std::vector<int> tri_idx;          // [num_elements * 3], asset-local vertex indices
-  int vert_base{0};                  // first pool index of this asset's vertices (triangle assets)
+  // Mesh assets keep their vertices and connectivity: dbh_context_update_vertices re-poses them on the device.
+  std::vector<double> rverts;        // [num_vertices * 3], the current positions
+  std::vector<int> tri_idx;          // [num_elements * 3 (triangles) or 4 (tetrahedra)], asset-local vertex indices
+  int vert_base{0};                  // first pool index of this asset's vertices
+  bool deformed{false};              // re-posed since registration: the per-element host records are stale
   std::vector<int> leaf_order;       // asset-local element indices
   std::vector<ElemBox> block_boxes;  // ceil(num_elements / kPlaneBlock)
   int block_base{0};                 // first pool index of this asset's block boxes
@@ -253,7 +255,7 @@ struct dbh_context {
   long long num_blocks{0};
   // Deformable reuse: the triangle assets' vertex pool and connectivity, parent links of every node, visit counters.
   DevBuf<double> d_rverts;
-  DevBuf<int> d_tri_idx, d_node_parent, d_node_visit;
+  DevBuf<int> d_tri_idx, d_tet_idx, d_node_parent, d_node_visit, d_refit_error;
   DevBuf<int4> d_block_desc;
   long long num_rverts{0};
   int bounds_version{0};   // bumped when an update moves root boxes: batches refresh their geometry bounds
@@ -275,7 +277,7 @@ struct dbh_context {
       a->elem_base = static_cast<int>(num_tris);
       num_tris += a->num_elements;
     }
-    if (a->type == DBH_RIGID && !a->half_space) {
+    if (!a->half_space) {
       a->vert_base = static_cast<int>(num_rverts);
       num_rverts += a->num_vertices;
     }
@@ -310,6 +312,7 @@ struct dbh_context {
     CUDA_OK(grow(d_plane_blocks, num_blocks, &regrown));
     CUDA_OK(grow(d_rverts, 3 * num_rverts, &regrown));
     CUDA_OK(grow(d_tri_idx, 3 * num_tris, &regrown));
+    CUDA_OK(grow(d_tet_idx, 4 * num_tets, &regrown));
     CUDA_OK(grow(d_node_parent, num_nodes, &regrown));
     CUDA_OK(grow(d_node_visit, num_nodes, &regrown));
     const size_t first = regrown ? 0 : uploaded_assets;
@@ -327,25 +330,14 @@ struct dbh_context {
         // fp32 copies for the cull stage.
         std::vector<TetCullA> ca(a.tets.size());
         std::vector<TetCullB> cb(a.tets.size());
-        for (size_t e = 0; e < a.tets.size(); ++e) {
-          const TetRec& t = a.tets[e];
-          const TetAux& x = a.aux[e];
-          for (int k = 0; k < 4; ++k)
-            for (int d = 0; d < 3; ++d) {
-              ca[e].v[k][d] = static_cast<float>(t.v[k][d]);
-              // Outward normal of the face opposite vertex k (a degenerate face gives 0: never culls).
-              cb[e].nh[k][d] = static_cast<float>(-x.inward[k][d]);
-            }
-          for (int d = 0; d < 3; ++d) ca[e].grad[d] = static_cast<float>(t.grad[d]);
-          ca[e].p_mo = static_cast<float>(t.p_mo);
-          const double len = std::sqrt(t.grad[0] * t.grad[0] + t.grad[1] * t.grad[1] + t.grad[2] * t.grad[2]);
-          cb[e].inv_grad_len = len > 0 ? static_cast<float>(1.0 / len) : 0.f;
-          const double m = std::max(2e-5, 1e-11 * (1.0 + x.amp));
-          cb[e].margin = m < 1e30 ? static_cast<float>(m) : std::numeric_limits<float>::infinity();
-          cb[e].pad[0] = cb[e].pad[1] = 0.f;
-        }
+        for (size_t e = 0; e < a.tets.size(); ++e) derive_tet_cull(a.tets[e], a.aux[e], &ca[e], &cb[e]);
         CUDA_OK(cudaMemcpy(d_cull_a.p + a.elem_base, ca.data(), ca.size() * sizeof(TetCullA), cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpy(d_cull_b.p + a.elem_base, cb.data(), cb.size() * sizeof(TetCullB), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_rverts.p + 3ll * a.vert_base, a.rverts.data(), a.rverts.size() * sizeof(double),
+                           cudaMemcpyHostToDevice));
+        std::vector<int> idx(a.tri_idx);
+        for (int& i : idx) i += a.vert_base;
+        CUDA_OK(cudaMemcpy(d_tet_idx.p + 4ll * a.elem_base, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
       } else {
         CUDA_OK(cudaMemcpy(d_tris.p + a.elem_base, a.tris.data(), a.tris.size() * sizeof(TriRec),
                            cudaMemcpyHostToDevice));
@@ -422,8 +414,15 @@ struct dbh_context {
                          cudaMemcpyHostToDevice));
     }
     uploaded_assets = assets.size();
+    // The per-element records and boxes just uploaded are the registration-time ones: assets re-posed since then are
+    // derived again from their current vertices (set-up path: only after a pool regrowth).
+    if (regrown) {
+      for (size_t i = 0; i < assets.size(); ++i)
+        if (assets[i]->deformed) regrown_deformed.push_back(static_cast<int>(i));
+    }
     return DBH_OK;
   }
+  std::vector<int> regrown_deformed;   // consumed by Upload()
 };
 
 // Timing marks per chunk of scenes: pose + root | per-level descent | cull tet-tri (k_filter + k_small_pairs) | cull
@@ -715,9 +714,9 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
   a->tets.resize(nt);
   a->aux.resize(nt);
   a->tet_vp.resize(4 * static_cast<size_t>(nt));
-  constexpr double kEps = std::numeric_limits<double>::epsilon();
+  a->rverts.assign(verts, verts + 3ll * nv);     // kept: dbh_context_update_vertices re-poses deforming volume meshes
+  a->tri_idx.assign(tets, tets + 4ll * nt);
   for (int e = 0; e < nt; ++e) {
-    TetRec& r = a->tets[e];
     D3 v[4];
     double u[4];
     for (int i = 0; i < 4; ++i) {
@@ -725,67 +724,9 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
       v[i] = load3(verts + 3 * vi);
       u[i] = pressure[vi];
       a->tet_vp[4 * static_cast<size_t>(e) + i] = u[i];
-      r.v[i][0] = v[i].x;
-      r.v[i][1] = v[i].y;
-      r.v[i][2] = v[i].z;
     }
-    // MeshFieldLinear::CalcGradientField / VolumeMesh::MaybeCalcGradBarycentric
-    // (mesh_field_linear.h:440-478, volume_mesh.h:275-289,361-448).
-    D3 g = make_d3(0, 0, 0);
-    for (int i = 0; i < 4; ++i) {
-      const D3 V = v[i], A = v[(i + 1) % 4], B = v[(i + 2) % 4], C = v[(i + 3) % 4];
-      const D3 area_vector = cross(B - A, C - A);
-      const double signed_volume = dot(area_vector, V - A);
-      if (std::fabs(signed_volume) <= kEps)
-        return Fail(DBH_ERR_DEGENERATE_FIELD, "tetrahedron " + std::to_string(e) + " is degenerate");
-      g = g + u[i] * (area_vector / signed_volume);
-    }
-    r.grad[0] = g.x;
-    r.grad[1] = g.y;
-    r.grad[2] = g.z;
-    r.p_mo = u[0] - dot(g, v[0]);  // CalcValueAtMeshOrigin (mesh_field_linear.h:502-509)
-    // Inward normals (volume_mesh.cc:91-138).
-    const D3 ab = v[1] - v[0], ac = v[2] - v[0], ad = v[3] - v[0], bc = v[2] - v[1], bd = v[3] - v[1];
-    const D3 n[4] = {normalized(cross(bd, bc)), normalized(cross(ac, ad)), normalized(cross(ad, ab)),
-                     normalized(cross(ab, ac))};
-    TetAux& x = a->aux[e];
-    for (int f = 0; f < 4; ++f) {
-      x.inward[f][0] = n[f].x;
-      x.inward[f][1] = n[f].y;
-      x.inward[f][2] = n[f].z;
-    }
-    // Face half spaces of ClipTriangleByTetrahedron (mesh_intersection.cc:225-238 + plane.cc:16-29).
-    static const int kFaces[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
-    for (int f = 0; f < 4; ++f) {
-      const D3 A = v[kFaces[f][0]], B = v[kFaces[f][1]], C = v[kFaces[f][2]];
-      const D3 normal = cross(B - A, C - A);
-      const double mag = norm(normal);
-      if (mag < 1e-10) {
-        x.plane_nh[f][0] = x.plane_nh[f][1] = x.plane_nh[f][2] = 0.0;
-        x.plane_d[f] = std::numeric_limits<double>::quiet_NaN();  // the Plane ctor throws when reached
-      } else {
-        const D3 nh = normal / mag;
-        x.plane_nh[f][0] = nh.x;
-        x.plane_nh[f][1] = nh.y;
-        x.plane_nh[f][2] = nh.z;
-        x.plane_d[f] = dot(nh, A);
-      }
-    }
-    const D3 ng = normalized(g);
-    x.ngrad[0] = ng.x;
-    x.ngrad[1] = ng.y;
-    x.ngrad[2] = ng.z;
-    // Shape factor for the cull margins: the tetrahedron bounded by the four face planes offset
-    // outward by e is this one scaled about its incentre by (1 + e / inradius).
-    {
-      const D3 cd = v[3] - v[2];
-      const double diam2 = std::max({dot(ab, ab), dot(ac, ac), dot(ad, ad), dot(bc, bc), dot(bd, bd), dot(cd, cd)});
-      const double vol6 = std::fabs(dot(cross(ab, ac), ad));
-      const double area2 = norm(cross(bd, bc)) + norm(cross(ac, ad)) + norm(cross(ad, ab)) + norm(cross(ab, ac));
-      const double inradius = area2 > 0 ? vol6 / area2 : 0.0;  // 3V / sum(A) = (vol6 / 2) / (area2 / 2)
-      x.amp = inradius > 0 ? std::sqrt(diam2) / inradius : 1e300;
-      if (!(x.amp < 1e300)) x.amp = 1e300;
-    }
+    if (!derive_tet(v, u, &a->tets[e], &a->aux[e]))
+      return Fail(DBH_ERR_DEGENERATE_FIELD, "tetrahedron " + std::to_string(e) + " is degenerate");
   }
   if (dbh_status st = BuildBvhFor<4>(ctx, verts, nv, tets, nt, a.get())) return st;
   ctx->Place(a.get());
@@ -835,45 +776,28 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t nv, const double* v
   });
 }
 
-dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices) {
-  return Guarded([&]() -> dbh_status {
-  if (!ctx || num_assets <= 0 || !assets || !vertices)
-    return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: bad argument");
-  CUDA_OK(cudaSetDevice(ctx->device));
-  for (int k = 0; k < num_assets; ++k) {
-    if (assets[k] < 0 || assets[k] >= static_cast<int>(ctx->assets.size()))
-      return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: bad asset handle");
-    const HostAsset& a = *ctx->assets[assets[k]];
-    if (a.type != DBH_RIGID || a.half_space)
-      return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: only triangle-mesh (rigid) assets can be re-posed");
-  }
-  if (dbh_status s = ctx->UploadPools()) return s;
-  // Group the list into runs of assets whose pool ranges follow one another (assets registered consecutively): one
-  // vertex upload and three launches per run.
-  const double* src = vertices;
-  int k = 0;
-  while (k < num_assets) {
-    const HostAsset& first = *ctx->assets[assets[k]];
-    int k1 = k + 1;
-    long long nverts = first.num_vertices;
-    while (k1 < num_assets) {
-      const HostAsset& prev = *ctx->assets[assets[k1 - 1]];
-      const HostAsset& next = *ctx->assets[assets[k1]];
-      if (next.vert_base != prev.vert_base + prev.num_vertices || next.elem_base != prev.elem_base + prev.num_elements ||
+// Re-derives everything that depends on the vertex positions for the listed mesh assets, whose current positions are in
+// the device vertex pool (and in HostAsset::rverts): per-element records, leaf boxes, the trees' boxes bottom-up, the
+// half-space pairs' leaf-block boxes. The list is grouped into runs of assets of one kind whose pool ranges follow one
+// another (assets registered consecutively): three launches per run.
+static dbh_status RefitAssets(dbh_context* ctx, const std::vector<int>& ids) {
+  CUDA_OK(ctx->d_refit_error.ensure(1));
+  CUDA_OK(cudaMemsetAsync(ctx->d_refit_error.p, 0, sizeof(int), nullptr));
+  size_t k = 0;
+  while (k < ids.size()) {
+    const HostAsset& first = *ctx->assets[ids[k]];
+    size_t k1 = k + 1;
+    while (k1 < ids.size()) {
+      const HostAsset& prev = *ctx->assets[ids[k1 - 1]];
+      const HostAsset& next = *ctx->assets[ids[k1]];
+      if (next.type != prev.type || next.elem_base != prev.elem_base + prev.num_elements ||
           next.node_base != prev.node_base + static_cast<int>(prev.nodes.size()) ||
           next.block_base != prev.block_base + static_cast<int>(prev.block_boxes.size()))
         break;
-      nverts += next.num_vertices;
       ++k1;
     }
-    const HostAsset& last = *ctx->assets[assets[k1 - 1]];
-    CUDA_OK(cudaMemcpyAsync(ctx->d_rverts.p + 3ll * first.vert_base, src, 3ll * nverts * sizeof(double),
-                            cudaMemcpyHostToDevice, nullptr));
-    for (int j = k; j < k1; ++j) {   // the host copy stays current (a later pool regrowth re-uploads it)
-      HostAsset& a = *ctx->assets[assets[j]];
-      std::copy(src, src + 3ll * a.num_vertices, a.rverts.begin());
-      src += 3ll * a.num_vertices;
-    }
+    const HostAsset& last = *ctx->assets[ids[k1 - 1]];
+    const bool tets = first.type == DBH_COMPLIANT;
     RefitArgs ra{};
     ra.verts = ctx->d_rverts.p;
     ra.tri_idx = ctx->d_tri_idx.p;
@@ -884,15 +808,25 @@ dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, con
     ra.nodes32 = ctx->d_nodes32.p;
     ra.node_parent = ctx->d_node_parent.p;
     ra.node_visit = ctx->d_node_visit.p;
-    ra.tri_begin = first.elem_base;
-    ra.tri_end = last.elem_base + last.num_elements;
+    ra.order_tri = ctx->d_order_tri.p;
+    ra.tet_idx = ctx->d_tet_idx.p;
+    ra.tet_vp = ctx->d_tet_vp.p;
+    ra.tets = ctx->d_tets.p;
+    ra.aux = ctx->d_aux.p;
+    ra.cull_a = ctx->d_cull_a.p;
+    ra.cull_b = ctx->d_cull_b.p;
+    ra.ebox_tet = ctx->d_ebox_tet.p;
+    ra.error = ctx->d_refit_error.p;
+    ra.ebox_leaf = tets ? ctx->d_ebox_tet.p : ctx->d_ebox_tri.p;
+    ra.order_leaf = tets ? ctx->d_order_tet.p : ctx->d_order_tri.p;
+    (tets ? ra.tet_begin : ra.tri_begin) = first.elem_base;
+    (tets ? ra.tet_end : ra.tri_end) = last.elem_base + last.num_elements;
     ra.node_begin = first.node_base;
     ra.node_end = last.node_base + static_cast<int>(last.nodes.size());
-    ra.order_tri = ctx->d_order_tri.p;
     ra.blocks = ctx->d_plane_blocks.p;
     std::vector<int4> desc;
-    for (int j = k; j < k1; ++j) {
-      const HostAsset& a = *ctx->assets[assets[j]];
+    for (size_t j = k; j < k1; ++j) {
+      const HostAsset& a = *ctx->assets[ids[j]];
       for (int b = 0; b < static_cast<int>(a.block_boxes.size()); ++b)
         desc.push_back(make_int4(a.elem_base + b * kPlaneBlock, std::min(kPlaneBlock, a.num_elements - b * kPlaneBlock),
                                  a.elem_base, 0));
@@ -903,17 +837,23 @@ dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, con
     ra.block_begin = first.block_base;
     ra.block_end = first.block_base + static_cast<int>(desc.size());
     CUDA_OK(cudaMemsetAsync(ctx->d_node_visit.p + ra.node_begin, 0, sizeof(int) * (ra.node_end - ra.node_begin), nullptr));
-    const int ntri = ra.tri_end - ra.tri_begin, nnode = ra.node_end - ra.node_begin;
-    k_refit_tris<<<(ntri + 255) / 256, 256>>>(ra);
+    const int nelem = last.elem_base + last.num_elements - first.elem_base, nnode = ra.node_end - ra.node_begin;
+    if (tets) k_refit_tets<<<(nelem + 127) / 128, 128>>>(ra);
+    else k_refit_tris<<<(nelem + 255) / 256, 256>>>(ra);
     k_refit_nodes<<<(nnode + 255) / 256, 256>>>(ra);
     if (!desc.empty()) k_refit_blocks<<<(static_cast<int>(desc.size()) + 127) / 128, 128>>>(ra);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(nullptr));   // d_block_desc and `desc` are reused by the next run
     k = k1;
   }
+  int bad = 0;
+  CUDA_OK(cudaMemcpy(&bad, ctx->d_refit_error.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (bad)
+    return Fail(DBH_ERR_DEGENERATE_FIELD, "update_vertices: tetrahedron " + std::to_string(bad - 1) +
+                                              " (pool index) became degenerate: its field has no gradient");
   // Root boxes feed the geometry-level broad phase of the no-surface pairs (batches refresh them lazily).
-  for (int j = 0; j < num_assets; ++j) {
-    HostAsset& a = *ctx->assets[assets[j]];
+  for (int id : ids) {
+    HostAsset& a = *ctx->assets[id];
     BvhNode root;
     CUDA_OK(cudaMemcpy(&root, ctx->d_nodes.p + a.node_base + 1, sizeof(BvhNode), cudaMemcpyDeviceToHost));
     for (int d = 0; d < 3; ++d) {
@@ -923,6 +863,52 @@ dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, con
   }
   ++ctx->bounds_version;
   return DBH_OK;
+}
+
+// UploadPools + the re-derivation a pool regrowth owes to the assets re-posed since their registration.
+static dbh_status Upload(dbh_context* ctx) {
+  if (dbh_status s = ctx->UploadPools()) return s;
+  if (ctx->regrown_deformed.empty()) return DBH_OK;
+  const std::vector<int> ids = std::move(ctx->regrown_deformed);
+  ctx->regrown_deformed.clear();
+  return RefitAssets(ctx, ids);
+}
+
+dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices) {
+  return Guarded([&]() -> dbh_status {
+  if (!ctx || num_assets <= 0 || !assets || !vertices)
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: bad argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  for (int k = 0; k < num_assets; ++k) {
+    if (assets[k] < 0 || assets[k] >= static_cast<int>(ctx->assets.size()))
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: bad asset handle");
+    if (ctx->assets[assets[k]]->half_space)
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: a half space has no vertices");
+  }
+  if (dbh_status s = Upload(ctx)) return s;
+  // The host copy stays current (a later pool regrowth re-uploads it and re-derives the rest); runs of assets whose
+  // vertex ranges follow one another go up in one copy.
+  const double* src = vertices;
+  int k = 0;
+  while (k < num_assets) {
+    const HostAsset& first = *ctx->assets[assets[k]];
+    const double* run_src = src;
+    long long nverts = 0;
+    int k1 = k;
+    while (k1 < num_assets) {
+      HostAsset& a = *ctx->assets[assets[k1]];
+      if (k1 > k && a.vert_base != first.vert_base + nverts) break;
+      std::copy(src, src + 3ll * a.num_vertices, a.rverts.begin());
+      a.deformed = true;
+      src += 3ll * a.num_vertices;
+      nverts += a.num_vertices;
+      ++k1;
+    }
+    CUDA_OK(cudaMemcpyAsync(ctx->d_rverts.p + 3ll * first.vert_base, run_src, 3ll * nverts * sizeof(double),
+                            cudaMemcpyHostToDevice, nullptr));
+    k = k1;
+  }
+  return RefitAssets(ctx, std::vector<int>(assets, assets + num_assets));
   });
 }
 
@@ -976,7 +962,7 @@ dbh_status dbh_asset_get_derived(dbh_context* ctx, int32_t asset, double* g_or_n
     return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_get_derived: bad argument");
   CUDA_OK(cudaSetDevice(ctx->device));
   HostAsset& a = *ctx->assets[asset];
-  if (dbh_status st = ctx->UploadPools()) return st;
+  if (dbh_status st = Upload(ctx)) return st;
   // Read back from the device pools so tests see what the kernels see.
   if (a.type == DBH_COMPLIANT) {
     std::vector<TetRec> t(a.num_elements);
@@ -1408,7 +1394,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     return Fail(DBH_ERR_INVALID_ARGUMENT, "batch_query: bad argument");
   dbh_context* ctx = b->ctx;
   CUDA_OK(cudaSetDevice(ctx->device));
-  if (dbh_status s = ctx->UploadPools()) return s;
+  if (dbh_status s = Upload(ctx)) return s;
   if (dbh_status s = b->AllocWorkBuffers()) return s;
   if (b->bounds_version != ctx->bounds_version) {   // dbh_context_update_vertices moved root boxes
     for (int g = 0; g < b->num_geoms; ++g) {
@@ -2008,12 +1994,14 @@ dbh_status dbh_batch_compute_deformable_contact(dbh_batch* b) {
     return Fail(DBH_ERR_INVALID_ARGUMENT, "deformable contact data is defined on polygon surfaces (DeformableContactSurface holds "
                                           "a PolygonSurfaceMesh): query with DBH_POLYGON");
   CUDA_OK(cudaSetDevice(b->ctx->device));
-  CUDA_OK(b->d_deformable.ensure(static_cast<size_t>(std::max<long long>(b->cap_faces, 1)) * 22));
+  CUDA_OK(b->d_deformable.ensure(static_cast<size_t>(std::max<long long>(b->cap_faces, 1)) * kDeformableRecord));
   DeformableArgs da{};
   da.pairs = b->d_pairs.p;
   da.poses = b->d_poses;
   da.tris = b->ctx->d_tris.p;
+  da.tets = b->ctx->d_tets.p;
   da.face_pair = b->r_face_pair.p;
+  da.elem_a = b->r_elem_a.p;
   da.elem_b = b->r_elem_b.p;
   da.normals = b->r_normals.p;
   da.centroids = b->r_centroids.p;
@@ -2029,7 +2017,8 @@ dbh_status dbh_batch_compute_deformable_contact(dbh_batch* b) {
   });
 }
 
-dbh_status dbh_batch_copy_deformable_contact_async(dbh_batch* b, double* out, int32_t* triangle_index, int64_t* num_faces) {
+dbh_status dbh_batch_copy_deformable_contact_async(dbh_batch* b, double* out, int32_t* element_a, int32_t* element_b,
+                                                   int64_t* num_faces) {
   return Guarded([&]() -> dbh_status {
   if (!b || !num_faces) return Fail(DBH_ERR_INVALID_ARGUMENT, "copy_deformable_contact: bad argument");
   if (!b->query_done || !b->deformable_done)
@@ -2037,9 +2026,12 @@ dbh_status dbh_batch_copy_deformable_contact_async(dbh_batch* b, double* out, in
   CUDA_OK(cudaSetDevice(b->ctx->device));
   const size_t nf = b->h_counters->faces;
   *num_faces = static_cast<int64_t>(nf);
-  if (out && nf) CUDA_OK(cudaMemcpyAsync(out, b->d_deformable.p, nf * 22 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-  if (triangle_index && nf)
-    CUDA_OK(cudaMemcpyAsync(triangle_index, b->r_elem_b.p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+  if (out && nf)
+    CUDA_OK(cudaMemcpyAsync(out, b->d_deformable.p, nf * kDeformableRecord * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (element_a && nf)
+    CUDA_OK(cudaMemcpyAsync(element_a, b->r_elem_a.p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+  if (element_b && nf)
+    CUDA_OK(cudaMemcpyAsync(element_b, b->r_elem_b.p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
   return DBH_OK;
   });
 }

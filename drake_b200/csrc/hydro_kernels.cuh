@@ -2205,22 +2205,30 @@ __global__ void __launch_bounds__(256) k_discrete(DiscreteArgs a) {
   if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&a.counters->discrete_pairs, (unsigned long long)kept);
 }
 
-// ---- k_deformable: the deformable x rigid contact data of every face of the last query (hydro_wrench.cuh) ----------
-// One thread per face, 22 doubles out: p_WC[3], nhat_W[3], R_WC[9] (column-major), pressure, grad_W[3], barycentric[3].
-// Faces of surfaces that are not tet-triangle surfaces get NaN records. The deformable body is the pair's triangle
-// side, whatever the order of the two ids (a swapped surface's normals and gradients are swapped back here).
+// ---- k_deformable: the deformable contact data of every face of the last query (hydro_wrench.cuh) -------------------
+// One thread per face, kDeformableRecord = 24 doubles out.
+//   tet-triangle surface (deformable surface x rigid pressure field):
+//     p_WC[3], nhat_W[3], R_WC[9] (column-major), pressure, grad_W[3], barycentric[3] in the deformable triangle, 0, 0.
+//     The deformable body is the pair's triangle side, whatever the order of the two ids (a swapped surface's normals
+//     and gradients are swapped back here).
+//   tet-tet surface (two deformable volumes, signed-distance fields):
+//     p_WC[3], nhat_W[3], R_WC[9], signed distance, barycentric[4] in M's tetrahedron, barycentric[4] in N's.
+//   Faces of half-space surfaces get NaN records.
+constexpr int kDeformableRecord = 24;
 struct DeformableArgs {
   const PairRec* pairs;
   const Xf* poses;
   const TriRec* tris;
+  const TetRec* tets;
   const int* face_pair;
+  const int* elem_a;
   const int* elem_b;
   const double* normals;
   const double* centroids;
   const double* e_centroid;
   const double* grad_eM;
   const double* grad_eN;
-  double* out;             // [num_faces * 22]
+  double* out;             // [num_faces * kDeformableRecord]
   Counters* counters;
 };
 
@@ -2229,26 +2237,40 @@ __global__ void __launch_bounds__(256) k_deformable(DeformableArgs a) {
   const long long num_faces = (long long)a.counters->faces;
   for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < num_faces; f += (long long)gridDim.x * blockDim.x) {
     const PairRec& pr = a.pairs[a.face_pair[f]];
-    double* o = a.out + 22 * f;
-    if (pr.kind != kSoftRigid) {
+    double* o = a.out + kDeformableRecord * f;
+    if (pr.kind == kSoftRigid) {
+      const bool swapped = pr.swapped != 0;
+      D3 n = load3(a.normals + 3 * f);
+      if (swapped) n = -n;
+      const D3 grad = load3((swapped ? a.grad_eN : a.grad_eM) + 3 * f);
+      const TriRec& t = a.tris[pr.elem_base_b + a.elem_b[f]];
+      const DeformableFaceContact c =
+          deformable_face_contact(n, load3(a.centroids + 3 * f), a.e_centroid[f], grad, a.poses[pr.geom_a], a.poses[pr.geom_b],
+                                  load3(t.v[0]), load3(t.v[1]), load3(t.v[2]));
+      store3(o, 0, c.p_WC);
+      store3(o, 1, c.nhat_W);
+      for (int k = 0; k < 9; ++k) o[6 + k] = c.R_WC[k];
+      o[15] = c.pressure;
+      store3(o + 16, 0, c.grad_W);
+      store3(o + 19, 0, c.barycentric);
+      o[22] = o[23] = 0.0;
+    } else if (pr.kind == kSoftSoft) {
+      const TetRec& t0 = a.tets[pr.elem_base_a + a.elem_a[f]];
+      const TetRec& t1 = a.tets[pr.elem_base_b + a.elem_b[f]];
+      const DeformablePairContact c = deformable_pair_contact(load3(a.normals + 3 * f), load3(a.centroids + 3 * f), a.e_centroid[f],
+                                                              a.poses[pr.geom_a], a.poses[pr.geom_b], t0.v, t1.v);
+      store3(o, 0, c.p_WC);
+      store3(o, 1, c.nhat_W);
+      for (int k = 0; k < 9; ++k) o[6 + k] = c.R_WC[k];
+      o[15] = c.signed_distance;
+      for (int k = 0; k < 4; ++k) {
+        o[16 + k] = c.bary0[k];
+        o[20 + k] = c.bary1[k];
+      }
+    } else {
       const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
-      for (int k = 0; k < 22; ++k) o[k] = kNaN;
-      continue;
+      for (int k = 0; k < kDeformableRecord; ++k) o[k] = kNaN;
     }
-    const bool swapped = pr.swapped != 0;
-    D3 n = load3(a.normals + 3 * f);
-    if (swapped) n = -n;
-    const D3 grad = load3((swapped ? a.grad_eN : a.grad_eM) + 3 * f);
-    const TriRec& t = a.tris[pr.elem_base_b + a.elem_b[f]];
-    const DeformableFaceContact c =
-        deformable_face_contact(n, load3(a.centroids + 3 * f), a.e_centroid[f], grad, a.poses[pr.geom_a], a.poses[pr.geom_b],
-                                load3(t.v[0]), load3(t.v[1]), load3(t.v[2]));
-    store3(o, 0, c.p_WC);
-    store3(o, 1, c.nhat_W);
-    for (int k = 0; k < 9; ++k) o[6 + k] = c.R_WC[k];
-    o[15] = c.pressure;
-    store3(o + 16, 0, c.grad_W);
-    store3(o + 19, 0, c.barycentric);
   }
 }
 

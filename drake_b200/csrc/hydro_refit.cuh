@@ -10,11 +10,16 @@
 //                   leaf walks towards the root; the second child to arrive at a node (atomic counter) merges the two
 //                   child boxes and continues. Also the outward-rounded fp32 node the descent reads;
 //   k_refit_blocks  the leaf-block boxes of the half-space pairs' tree cut.
+// Deforming VOLUME meshes (both bodies of a deformable x deformable pair carry their signed-distance field on one,
+// deformable_field_intersection.cc) take the same path with k_refit_tets in place of k_refit_tris: the vertex field
+// values stay, everything that depends on the positions -- gradient, value at the origin, inward normals, face half
+// spaces, cull copies, leaf box -- is derived again by the function registration uses (hydro_derive.cuh).
 // All on the device, for any number of assets per launch (their pool ranges are contiguous when they were registered
 // one after the other; the host groups an update into such runs).
 #pragma once
 #include <cuda_runtime.h>
 
+#include "hydro_derive.cuh"
 #include "hydro_math.cuh"
 #include "hydro_types.h"
 
@@ -33,6 +38,19 @@ struct RefitArgs {
   int tri_begin, tri_end;   // pool ranges of this run of assets
   int node_begin, node_end;
   const int* order_tri;     // leaf order (asset-local element per pool position)
+  // Tetrahedron assets (k_refit_tets): pool tetrahedra [tet_begin, tet_end).
+  const int* tet_idx;       // [pool tetrahedron][4]: pool vertex indices
+  const double* tet_vp;     // [pool tetrahedron][4]: the vertex field values
+  TetRec* tets;
+  TetAux* aux;
+  TetCullA* cull_a;
+  TetCullB* cull_b;
+  ElemBox* ebox_tet;
+  int tet_begin, tet_end;
+  int* error;               // set to 1 + pool index of a tetrahedron that became degenerate
+  // What the node / block passes read: the element boxes and leaf order of this run's kind.
+  const ElemBox* ebox_leaf;
+  const int* order_leaf;
   ElemBox* blocks;
   // Per block of this run: pool position of its first leaf, number of leaves, pool index of element 0 of its asset.
   const int4* block_desc;
@@ -94,13 +112,48 @@ __global__ void __launch_bounds__(256) k_refit_tris(RefitArgs a) {
   a.ebox_tri[t] = b;
 }
 
+__global__ void __launch_bounds__(128) k_refit_tets(RefitArgs a) {
+  const int t = a.tet_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.tet_end) return;
+  D3 v[4];
+  double u[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = load3(a.verts + 3ll * a.tet_idx[4ll * t + i]);
+    u[i] = a.tet_vp[4ll * t + i];
+  }
+  TetRec r;
+  TetAux x;
+  if (!derive_tet(v, u, &r, &x)) {
+    atomicCAS(a.error, 0, t + 1);
+    return;
+  }
+  TetCullA ca;
+  TetCullB cb;
+  derive_tet_cull(r, x, &ca, &cb);
+  a.tets[t] = r;
+  a.aux[t] = x;
+  a.cull_a[t] = ca;
+  a.cull_b[t] = cb;
+  // The leaf's box as BvhUpdater sets it (Aabb::set_bounds).
+  ElemBox b;
+  const double p[4][3] = {{v[0].x, v[0].y, v[0].z}, {v[1].x, v[1].y, v[1].z}, {v[2].x, v[2].y, v[2].z}, {v[3].x, v[3].y, v[3].z}};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double lo = fmin(fmin(p[0][d], p[1][d]), fmin(p[2][d], p[3][d])), up = fmax(fmax(p[0][d], p[1][d]), fmax(p[2][d], p[3][d]));
+    b.c[d] = (lo + up) / 2;
+    b.h[d] = (up - lo) / 2;
+  }
+  a.ebox_tet[t] = b;
+}
+
 __global__ void __launch_bounds__(256) k_refit_nodes(RefitArgs a) {
   int n = a.node_begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= a.node_end) return;
   BvhNode node = a.nodes[n];
   if (!(node.left < 0 && node.right == -1) || a.node_parent[n] == -2) return;   // leaves only start a walk (-2: unused node 0)
   {
-    const ElemBox b = a.ebox_tri[~node.left];
+    const ElemBox b = a.ebox_leaf[~node.left];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       node.c[d] = b.c[d];
@@ -138,7 +191,7 @@ __global__ void __launch_bounds__(128) k_refit_blocks(RefitArgs a) {
   const int4 d = a.block_desc[b - a.block_begin];
   double lo[3] = {1e300, 1e300, 1e300}, up[3] = {-1e300, -1e300, -1e300};
   for (int k = 0; k < d.y; ++k) {
-    const ElemBox e = a.ebox_tri[d.z + a.order_tri[d.x + k]];
+    const ElemBox e = a.ebox_leaf[d.z + a.order_leaf[d.x + k]];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       lo[c] = fmin(lo[c], e.c[c] - e.h[c]);

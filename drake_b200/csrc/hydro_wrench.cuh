@@ -203,6 +203,43 @@ __host__ __device__ __forceinline__ D3 calc_barycentric(D3 p, D3 v0, D3 v1, D3 v
   return D3{1.0 - b1 - b2, b1, b2};
 }
 
+// VolumeMesh::CalcBarycentric (volume_mesh.cc:24-52) solves the 4 x 4 system [1 ... ; v0 v1 v2 v3] b = [1; p] by LU;
+// here Cramer's rule on signed volumes (the same solution up to rounding: compared with a tolerance).
+__host__ __device__ __forceinline__ void calc_barycentric_tet(D3 p, D3 v0, D3 v1, D3 v2, D3 v3, double b[4]) {
+  const double vol = dot(cross(v1 - v0, v2 - v0), v3 - v0);
+  b[0] = dot(cross(v1 - p, v2 - p), v3 - p) / vol;
+  b[1] = dot(cross(p - v0, v2 - v0), v3 - v0) / vol;
+  b[2] = dot(cross(v1 - v0, p - v0), v3 - v0) / vol;
+  b[3] = dot(cross(v1 - v0, v2 - v0), p - v0) / vol;
+}
+
+// Deformable x deformable (AddDeformableDeformableContactSurface, deformable_field_intersection.cc:46-124, and the second
+// DeformableContactSurface constructor, deformable_contact.cc:68-100): the contact mesh is the equilibrium surface of the
+// two signed-distance fields; per polygon the contact point (centroid), the mesh's face normal, R_WC, the signed
+// distance there and the barycentric coordinates of the point in the two tetrahedra that made the polygon.
+struct DeformablePairContact {
+  D3 p_WC;
+  D3 nhat_W;        // contact_mesh_W.face_normal(i)                                     (deformable_contact.cc:96)
+  double R_WC[9];   // MakeFromOneUnitVector(-nhat_W, z), column-major                   (:98-99)
+  double signed_distance;
+  double bary0[4];  // in the tetrahedron of the intersector's first field (field0, its mesh M)
+  double bary1[4];  // in the tetrahedron of the second field
+};
+__host__ __device__ __forceinline__ DeformablePairContact deformable_pair_contact(D3 normal_W, D3 centroid_W, double value,
+                                                                                  const Xf& X_WM, const Xf& X_WN,
+                                                                                  const double tet0[4][3], const double tet1[4][3]) {
+  DeformablePairContact c;
+  c.p_WC = centroid_W;
+  c.nhat_W = normal_W;
+  make_from_one_unit_vector(-normal_W, 2, c.R_WC);
+  c.signed_distance = value;
+  const D3 p_M = rot_t(X_WM, centroid_W - make_d3(X_WM.m[9], X_WM.m[10], X_WM.m[11]));
+  const D3 p_N = rot_t(X_WN, centroid_W - make_d3(X_WN.m[9], X_WN.m[10], X_WN.m[11]));
+  calc_barycentric_tet(p_M, load3(tet0[0]), load3(tet0[1]), load3(tet0[2]), load3(tet0[3]), c.bary0);
+  calc_barycentric_tet(p_N, load3(tet1[0]), load3(tet1[1]), load3(tet1[2]), load3(tet1[3]), c.bary1);
+  return c;
+}
+
 // mesh_normal_W: the contact mesh's face normal as the intersector built it (out of the triangle's front side: the
 // deformable surface's outward normal); grad_W: the rigid field's gradient rotated into World; X_WR / X_WD: poses of the
 // rigid geometry and of the deformable surface mesh (identity in the reference); tri: the triangle's vertices in D.

@@ -140,7 +140,7 @@ def lib():
     L.dbh_batch_compute_discrete_pairs.argtypes = [vp]
     L.dbh_batch_copy_discrete_pairs_async.argtypes = [vp, vp, _lp]
     L.dbh_batch_compute_deformable_contact.argtypes = [vp]
-    L.dbh_batch_copy_deformable_contact_async.argtypes = [vp, vp, vp, _lp]
+    L.dbh_batch_copy_deformable_contact_async.argtypes = [vp, vp, vp, vp, _lp]
     L.dbh_batch_enable_timing.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_verify.argtypes = [vp, C.c_int32]
     L.dbh_batch_set_normal_filter.argtypes = [vp, C.c_int32]
@@ -324,8 +324,9 @@ class Context:
         return out.value
 
     def update_vertices(self, assets, vertices):
-        """Deformable reuse: new vertex positions for triangle-mesh assets (DeformableMeshWithBvh::UpdateVertexPositions):
-        per-triangle records recomputed and the BVHs refitted on the device. vertices: one [nv,3] array per asset."""
+        """Deformable reuse: new vertex positions for mesh assets (DeformableMeshWithBvh::UpdateVertexPositions): triangle
+        meshes (deforming surfaces) or volume meshes (deformable bodies carrying a signed-distance field): per-element
+        records derived again and the BVHs refitted on the device. vertices: one [nv,3] array per asset."""
         ids = _i(list(assets))
         flat = np.ascontiguousarray(np.concatenate([_d(v).reshape(-1) for v in vertices]))
         _check(lib().dbh_context_update_vertices(self._h, len(ids), _ptr(ids, _ip), _ptr(flat, _dp)))
@@ -805,17 +806,22 @@ class SceneBatch:
         _check(lib().dbh_batch_compute_deformable_contact(self._h))
 
     def copy_deformable_contact(self, wait: bool = True):
-        """([num_faces, 22], triangle_index [num_faces]): p_WC, nhat_W, R_WC (column-major), pressure, grad_W (the
-        reference's point-transformed gradient), barycentric centroid; NaN rows for faces of other surface kinds."""
+        """([num_faces, 24], element_a [num_faces], element_b [num_faces]). Tet-triangle faces (deformable surface x
+        rigid pressure field): p_WC, nhat_W, R_WC (column-major), pressure, grad_W (the reference's point-transformed
+        gradient), barycentric centroid in the triangle element_b, 0, 0. Tet-tet faces (two deformable volumes): p_WC,
+        nhat_W, R_WC, signed distance, barycentric[4] in tetrahedron element_a of M, barycentric[4] in element_b of N.
+        NaN rows for half-space faces."""
         n = C.c_int64(0)
-        _check(lib().dbh_batch_copy_deformable_contact_async(self._h, None, None, C.byref(n)))
-        out = np.zeros((n.value, 22))
-        tri = np.zeros(n.value, dtype=np.int32)
+        _check(lib().dbh_batch_copy_deformable_contact_async(self._h, None, None, None, C.byref(n)))
+        out = np.zeros((n.value, 24))
+        ea = np.zeros(n.value, dtype=np.int32)
+        eb = np.zeros(n.value, dtype=np.int32)
         if n.value:
-            _check(lib().dbh_batch_copy_deformable_contact_async(self._h, out.ctypes.data, tri.ctypes.data, C.byref(n)))
+            _check(lib().dbh_batch_copy_deformable_contact_async(self._h, out.ctypes.data, ea.ctypes.data, eb.ctypes.data,
+                                                                 C.byref(n)))
         if wait:
             self.sync()
-        return out, tri
+        return out, ea, eb
 
     def compute_spatial_forces(self, vslip_regularizer: float = 1e-6):
         """Enqueues k_wrench over the last query's surfaces (no host sync)."""

@@ -116,15 +116,20 @@ dbh_status dbh_register_rigid_mesh(dbh_context* ctx, int32_t num_vertices, const
  * polygon keeps its own vertices (the reference welds vertices cut from the same mesh edge). */
 dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressure_scale, double margin,
                                    int32_t* asset_out);
-/* Deformable reuse (first step): new vertex positions for registered triangle-mesh assets whose
- * surface deforms from step to step -- the surface mesh of a deformable body in deformable-rigid contact, which the
- * reference keeps in a DeformableSurfaceMeshWithBvh and intersects with the rigid body's pressure-field volume mesh
- * through the same tetrahedron-triangle intersector as rigid-compliant contact (deformable_mesh_intersection.cc:83-110).
- * One call = DeformableMeshWithBvh::UpdateVertexPositions for every listed asset (deformable_mesh_with_bvh.h:86-93):
- * per-triangle vertices and normals recomputed (triangle_surface_mesh.h:452-487) and the BVH refitted bottom-up with its
- * topology kept (BvhUpdater::Update, bvh_updater.h:45-103), all on the device. vertices: host, the assets' vertex
- * arrays one after the other ([num_vertices * 3] each, in the order of `assets`). Synchronous; no query of a batch
- * that uses these assets may be in flight. The next queries see the new surface. */
+/* Deformable reuse: new vertex positions for registered mesh assets that deform from step to step.
+ *  - Triangle-mesh assets: the surface mesh of a deformable body in deformable-rigid contact, which the reference keeps
+ *    in a DeformableSurfaceMeshWithBvh and intersects with the rigid body's pressure-field volume mesh through the same
+ *    tetrahedron-triangle intersector as rigid-compliant contact (deformable_mesh_intersection.cc:85-110): per-triangle
+ *    vertices and normals recomputed (triangle_surface_mesh.h:452-487).
+ *  - Volume-mesh assets: the deformable bodies of deformable-deformable contact (DeformableVolumeMeshWithBvh +
+ *    DeformableGeometry::CalcSignedDistanceField, deformable_contact_geometries.cc:87-92: the vertex values stay, the
+ *    field's gradients and values at the origin are rebuilt on the moved mesh): every per-tetrahedron record derived
+ *    again with the expressions of registration. A tetrahedron that became degenerate fails the call with
+ *    DBH_ERR_DEGENERATE_FIELD, as the reference's field constructor throws.
+ * One call = DeformableMeshWithBvh::UpdateVertexPositions for every listed asset (deformable_mesh_with_bvh.h:86-93): the
+ * BVH is refitted bottom-up with its topology kept (BvhUpdater::Update, bvh_updater.h:45-103), all on the device.
+ * vertices: host, the assets' vertex arrays one after the other ([num_vertices * 3] each, in the order of `assets`).
+ * Synchronous; no query of a batch that uses these assets may be in flight. The next queries see the new meshes. */
 dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices);
 dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out);
 /* The asset's BVH for inspection: boxes [(num_bvh_nodes + 1) * 6] = centre, half width per node
@@ -271,31 +276,42 @@ dbh_status dbh_batch_compute_discrete_pairs(dbh_batch* batch);
 dbh_status dbh_batch_copy_discrete_pairs_async(dbh_batch* batch, double* out /* [num_faces*9], may be NULL */,
                                                int64_t* num_faces);
 
-/* -- (5d) a third device-side consumer: the per-contact-point data of a DEFORMABLE x rigid pair
- *        (AddDeformableRigidContactSurface, geometry/proximity/deformable_mesh_intersection.cc:85-183, and the
- *        DeformableContactSurface constructor, geometry/query_results/deformable_contact.cc:35-66). The reference runs
- *        such a pair through the same tet-triangle intersector as a hydroelastic soft-rigid pair: the volume mesh +
- *        pressure field are the RIGID geometry's (dbh_register_compliant_mesh), the triangle mesh is the deformable
- *        body's surface (dbh_register_rigid_mesh; its vertices move every step: dbh_context_update_vertices, the
- *        device-side BvhUpdater). One record of 22 doubles per face of the last query, in face order:
+/* -- (5d) a third device-side consumer: the per-contact-point data of DEFORMABLE contact
+ *        (geometry/query_results/deformable_contact.{h,cc}). The reference runs deformable pairs through the same
+ *        intersectors as hydroelastic pairs:
+ *          deformable x rigid       AddDeformableRigidContactSurface, geometry/proximity/deformable_mesh_intersection.cc
+ *            :85-183: the volume mesh + pressure field are the RIGID geometry's (dbh_register_compliant_mesh), the
+ *            triangle mesh is the deformable body's surface (dbh_register_rigid_mesh);
+ *          deformable x deformable  AddDeformableDeformableContactSurface, deformable_field_intersection.cc:46-124: two
+ *            volume meshes carrying their signed-distance fields (dbh_register_compliant_mesh with the signed distances
+ *            as vertex values). The reference passes the geometry with the LARGER id as the intersector's first field
+ *            (:53, :120-124); this library orders a pair by id, smaller first: hand the batch ids in reversed order
+ *            (e.g. INT64_MAX - id) for such pairs and map them back.
+ *        Deforming meshes move every step: dbh_context_update_vertices, the device-side BvhUpdater.
+ *        One record of 24 doubles per face of the last query, in face order:
  *          p_WC[3]   contact point = polygon centroid
- *          nhat_W[3] from the rigid body into the deformable one (-face normal of the contact mesh as the
- *                    intersector builds it, whatever the order of the two ids)
+ *          nhat_W[3] deformable x rigid: from the rigid body into the deformable one (-face normal of the contact mesh as
+ *                    the intersector builds it, whatever the order of the two ids); deformable x deformable: the contact
+ *                    mesh's face normal (deformable_contact.cc:58, :96)
  *          R_WC[9]   RotationMatrix::MakeFromOneUnitVector(-nhat_W, z) (math/rotation_matrix.cc:133-242), column-major
- *          pressure  the rigid pressure field at the centroid
- *          grad_W[3] "pressure_gradient_W" as the reference computes it (:172-174): X_WR * grad_R with the POINT
- *                    transform, i.e. the rotated gradient PLUS p_WR (reproduced, not corrected; subtract p_WR for the
- *                    gradient itself, or read grad_eM)
- *          barycentric[3] of the centroid in the deformable triangle (TriangleSurfaceMesh::CalcBarycentric: least
- *                    squares; agrees with the reference's QR solve to rounding, not bitwise)
- *        plus, per face, the index of that triangle in the deformable surface mesh. Faces of other kinds of surfaces
- *        get NaN records. The index bookkeeping that needs the deformable VOLUME mesh (contact_vertex_indexes,
- *        participating vertices, is_element_inverted; :127-170) is a host-side gather over triangle_index
- *        (INTEGRATION.md). Polygon representation only. Enqueued after dbh_batch_query; copy after dbh_batch_sync
- *        (asynchronous: complete with another dbh_batch_sync). ---------------------------------------------- */
+ *          deformable x rigid:
+ *            pressure     the rigid pressure field at the centroid
+ *            grad_W[3]    "pressure_gradient_W" as the reference computes it (:172-174): X_WR * grad_R with the POINT
+ *                         transform, i.e. the rotated gradient PLUS p_WR (reproduced, not corrected)
+ *            barycentric[3] of the centroid in the deformable triangle (TriangleSurfaceMesh::CalcBarycentric), 0, 0
+ *          deformable x deformable:
+ *            signed distance at the centroid (the contact field's value there)
+ *            barycentric[4] of the centroid in M's tetrahedron, barycentric[4] in N's (VolumeMesh::CalcBarycentric)
+ *        (barycentric coordinates through normal equations / Cramer's rule: equal to the reference's QR / LU solves to
+ *        rounding, not bitwise) plus, per face, the indices of the two elements that made the polygon (tetrahedron of M;
+ *        triangle or tetrahedron of N). Faces of half-space surfaces get NaN records. The index bookkeeping that needs
+ *        the deformable meshes' connectivity (contact_vertex_indexes, participating vertices, is_element_inverted) is a
+ *        host-side gather over the element indices. Polygon representation only. Enqueued after
+ *        dbh_batch_query; copy after dbh_batch_sync (asynchronous: complete with another dbh_batch_sync). ------------ */
 dbh_status dbh_batch_compute_deformable_contact(dbh_batch* batch);
-dbh_status dbh_batch_copy_deformable_contact_async(dbh_batch* batch, double* out /* [num_faces*22], may be NULL */,
-                                                   int32_t* triangle_index /* [num_faces], may be NULL */,
+dbh_status dbh_batch_copy_deformable_contact_async(dbh_batch* batch, double* out /* [num_faces*24], may be NULL */,
+                                                   int32_t* element_a /* [num_faces], may be NULL */,
+                                                   int32_t* element_b /* [num_faces], may be NULL */,
                                                    int64_t* num_faces);
 
 /* -- (6) sizes of the last completed query. --------------------------------- */

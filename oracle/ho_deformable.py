@@ -6,6 +6,9 @@ In the reference a deformable body meets a rigid one through the SAME intersecto
 belong to the RIGID geometry (frame R) and the triangle mesh is the DEFORMABLE body's surface (frame D = World, its
 vertices move every step and its Bvh<Aabb> is refit, bvh_updater.h):
 
+  AddDeformableDeformableContactSurface       geometry/proximity/deformable_field_intersection.cc:46-124 (two deforming
+                                              volume meshes with signed-distance fields through VolumeIntersector)
+  VolumeMesh::CalcBarycentric                 geometry/proximity/volume_mesh.cc:24-52
   AddDeformableRigidContactSurface           geometry/proximity/deformable_mesh_intersection.cc:85-183
   DeformableSurfaceVolumeIntersector          :18-83 (triangle index + barycentric centroid per polygon)
   DeformableContactSurface ctor (rigid)       geometry/query_results/deformable_contact.cc:35-66
@@ -14,8 +17,10 @@ vertices move every step and its Bvh<Aabb> is refit, bvh_updater.h):
 
 Pinned by the reference's own fixture (geometry/proximity/test/deformable_mesh_intersection_test.cc:106-178: one polygon,
 pressure 123, contact point (1/3, 1/3, 0), barycentric (1/3, 1/3, 1/3), vertices {2, 1, 0}; :33-104: BVHs collide, no
-contact; :180-262: only the relative pose matters) and math/test/rotation_matrix_test.cc's properties of
-MakeFromOneUnitVector -- tests/test_oracle_deformable.py.
+contact; :180-262: only the relative pose matters), geometry/proximity/test/deformable_field_intersection_test.cc
+(:99-112 no contact; :114-173 one contact point, normal +z, signed distance and barycentric coordinates as the mesh and
+field compute them) and math/test/rotation_matrix_test.cc's properties of MakeFromOneUnitVector --
+tests/test_oracle_deformable.py.
 
 CalcBarycentric solves its 3 x 2 least-squares system with Eigen's colPivHouseholderQr; here numpy's lstsq. The two
 agree to rounding, not bit for bit: values from this file are compared with a tolerance (1e-10 of the triangle's scale),
@@ -109,3 +114,48 @@ def participating_vertices(triangle_index, surface_tris, surface_index_to_volume
     index mapping, one Vector3<int> of VOLUME mesh vertex indices per polygon."""
     tri_vol = np.asarray(surface_index_to_volume_index)[np.asarray(surface_tris)[np.asarray(triangle_index)]]
     return [tri_vol, np.unique(tri_vol)]
+
+
+def calc_barycentric_tet(p, v) -> np.ndarray:
+    """VolumeMesh::CalcBarycentric (volume_mesh.cc:24-52): [1 1 1 1; v0 v1 v2 v3] b = [1; p] (there by partial-pivot LU)."""
+    A = np.ones((4, 4))
+    A[1:, :] = np.asarray(v, float).T
+    return np.linalg.solve(A, np.concatenate([[1.0], np.asarray(p, float)]))
+
+
+@dataclass
+class DeformableDeformableContact:
+    """The second DeformableContactSurface constructor's data (deformable_contact.cc:68-100), per polygon. Index 0 is
+    the intersector's FIRST field (the reference passes the geometry with the larger id there and stores it as B), index
+    1 the second (stored as A)."""
+    contact_points_W: np.ndarray        # [F,3]
+    nhats_W: np.ndarray                 # [F,3] contact_mesh_W.face_normal: out of field 0's body, into field 1's
+    R_WCs: np.ndarray                   # [F,3,3] MakeFromOneUnitVector(-nhat, z)
+    signed_distances: np.ndarray        # [F]
+    tet0: np.ndarray                    # [F] tet0_of_polygon
+    tet1: np.ndarray
+    barycentric0: np.ndarray            # [F,4] of the contact point in tet0 of mesh 0
+    barycentric1: np.ndarray
+    surface: ho.Surface
+
+
+def deformable_deformable_contact(mesh0: ho.VolumeMesh, sdf0, mesh1: ho.VolumeMesh, sdf1) -> Optional[DeformableDeformableContact]:
+    """AddDeformableDeformableContactSurface (deformable_field_intersection.cc:46-124) on the meshes' CURRENT vertices:
+    (mesh0, sdf0) is the first argument pair of the reference's function (its geometry has the larger id). sdf*: the
+    per-vertex signed distances; the fields are rebuilt on the current meshes as CalcSignedDistanceField does
+    (deformable_contact_geometries.cc:87-92)."""
+    f0 = ho.VolumeField.from_values(mesh0, sdf0)
+    f1 = ho.VolumeField.from_values(mesh1, sdf1)
+    surf = ho.soft_soft(mesh0, f0, mesh1, f1, ho.IDENTITY, ho.IDENTITY, 1, 2, ho.KPOLYGON)
+    if surf is None or surf.num_faces == 0:
+        return None
+    F = surf.num_faces
+    v0, t0 = mesh0.arrays()[:2]
+    v1, t1 = mesh1.arrays()[:2]
+    out = DeformableDeformableContact(surf.centroids.copy(), surf.normals.copy(), np.zeros((F, 3, 3)), surf.e_centroid.copy(),
+                                      surf.elem_first.copy(), surf.elem_second.copy(), np.zeros((F, 4)), np.zeros((F, 4)), surf)
+    for f in range(F):
+        out.R_WCs[f] = make_from_one_unit_vector(-surf.normals[f], 2)
+        out.barycentric0[f] = calc_barycentric_tet(surf.centroids[f], v0[t0[int(surf.elem_first[f])]])
+        out.barycentric1[f] = calc_barycentric_tet(surf.centroids[f], v1[t1[int(surf.elem_second[f])]])
+    return out

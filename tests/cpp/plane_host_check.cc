@@ -183,6 +183,27 @@ void phc_deformable_contact(int nf, const double* mesh_normals, const double* ce
     o[19] = c.barycentric.x, o[20] = c.barycentric.y, o[21] = c.barycentric.z;
   }
 }
+// deformable_pair_contact (hydro_wrench.cuh) for nf faces of a tet-tet surface: per face normal, centroid, field value
+// and the two tetrahedra's vertices (12 doubles each); 24 doubles out per face, the layout of k_deformable.
+void phc_deformable_pair_contact(int nf, const double* normals, const double* centroids, const double* values,
+                                 const double* X_WM, const double* X_WN, const double* tet0_verts, const double* tet1_verts,
+                                 double* out) {
+  Xf XM, XN;
+  std::memcpy(XM.m, X_WM, sizeof(XM.m));
+  std::memcpy(XN.m, X_WN, sizeof(XN.m));
+  for (int f = 0; f < nf; ++f) {
+    double t0[4][3], t1[4][3];
+    std::memcpy(t0, tet0_verts + 12 * f, sizeof(t0));
+    std::memcpy(t1, tet1_verts + 12 * f, sizeof(t1));
+    const DeformablePairContact c = deformable_pair_contact(load3(normals + 3 * f), load3(centroids + 3 * f), values[f], XM, XN, t0, t1);
+    double* o = out + 24 * f;
+    o[0] = c.p_WC.x, o[1] = c.p_WC.y, o[2] = c.p_WC.z;
+    o[3] = c.nhat_W.x, o[4] = c.nhat_W.y, o[5] = c.nhat_W.z;
+    for (int k = 0; k < 9; ++k) o[6 + k] = c.R_WC[k];
+    o[15] = c.signed_distance;
+    for (int k = 0; k < 4; ++k) o[16 + k] = c.bary0[k], o[20 + k] = c.bary1[k];
+  }
+}
 double phc_combined_dissipation(double kA, double kB, double dA, double dB) {
   return combined_hunt_crossley_dissipation(kA, kB, dA, dB);
 }

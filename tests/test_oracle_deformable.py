@@ -101,3 +101,37 @@ def test_calc_barycentric():
         assert np.allclose(hd.calc_barycentric(p, v0, v1, v2), b, atol=1e-13)
         # A point off the plane gets the coordinates of its projection (least squares).
         assert np.allclose(hd.calc_barycentric(p + 0.7 * n, v0, v1, v2), b, atol=1e-12)
+
+
+def _two_tets(shift_z):
+    """deformable_field_intersection_test.cc:27-87: deform0 above the X-Y plane (signed distance 0 on the base, -1 at the
+    apex), deform1 below it with the element written {1, 0, 2, 3}, translated along z."""
+    d0 = ho.VolumeMesh.from_arrays([O, EX, EY, EZ], [[0, 1, 2, 3]])
+    v1 = np.array([O, EX, EY, [0, 0, -1.0]]) + [0, 0, shift_z]
+    d1 = ho.VolumeMesh.from_arrays(v1, [[1, 0, 2, 3]])
+    return d0, d1
+
+
+def test_deformable_deformable_fixture():
+    """:99-112 (translated out of contact: nothing) and :114-173: translated 0.2 into contact, the call
+    AddDeformableDeformableContactSurface(sdf1, deform1, id1, sdf0, deform0, id0) gives one contact point whose normal
+    is +z exactly, whose signed distance is sdf1 evaluated there and whose barycentric coordinates are what the two
+    meshes compute for the point."""
+    sdf = [0.0, 0.0, 0.0, -1.0]
+    d0, d1 = _two_tets(-0.2)
+    assert hd.deformable_deformable_contact(d1, sdf, d0, sdf) is None
+    d0, d1 = _two_tets(0.2)
+    c = hd.deformable_deformable_contact(d1, sdf, d0, sdf)
+    assert c is not None and len(c.signed_distances) == 1
+    assert np.array_equal(c.nhats_W[0], [0.0, 0.0, 1.0])
+    p = c.contact_points_W[0]
+    assert np.array_equal(p, c.surface.centroids[0]) and abs(p[2] - 0.1) < 1e-15
+    # sdf1 = z - 0.2 on deform1 (0 on its base at z = 0.2, -1 at its apex at z = -0.8).
+    assert abs(c.signed_distances[0] - (p[2] - 0.2)) < 1e-15
+    v0, t0 = d0.arrays()[:2]
+    v1, t1 = d1.arrays()[:2]
+    b_A, b_B = c.barycentric1[0], c.barycentric0[0]      # A = deform0 (smaller id) is the call's SECOND mesh
+    assert np.allclose(b_A @ v0[t0[0]], p, atol=1e-15) and abs(b_A.sum() - 1) < 1e-15
+    assert np.allclose(b_B @ v1[t1[0]], p, atol=1e-15) and abs(b_B.sum() - 1) < 1e-15
+    assert list(t0[0]) == [0, 1, 2, 3] and list(t1[0]) == [1, 0, 2, 3]      # contact vertex indexes A / B (:162-170)
+    assert np.allclose(c.R_WCs[0][:, 2], [0, 0, -1.0])

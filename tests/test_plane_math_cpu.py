@@ -309,7 +309,7 @@ def test_wrench_arithmetic_matches_the_oracle(rep):
 def check_deformable_rows(rows, tri_index, want, atol_scale=1.0):
     """Rows of k_deformable's layout (p_WC, nhat_W, R_WC column-major, pressure, grad_W, barycentric) against
     oracle/ho_deformable.py's DeformableRigidContact, faces matched by the caller."""
-    assert rows.shape == (len(want.pressures), 22) and np.array_equal(tri_index, want.triangle_index)
+    assert rows.shape[0] == len(want.pressures) and rows.shape[1] in (22, 24) and np.array_equal(tri_index, want.triangle_index)
     L = max(np.max(np.abs(want.contact_points_W)), 1e-300)
     assert np.max(np.abs(rows[:, 0:3] - want.contact_points_W)) <= 1e-12 * L * atol_scale
     assert np.max(np.abs(rows[:, 3:6] - want.nhats_W)) <= 1e-12 * atol_scale
@@ -321,6 +321,64 @@ def check_deformable_rows(rows, tri_index, want, atol_scale=1.0):
     assert np.max(np.abs(rows[:, 16:19] - want.pressure_gradients_W)) <= 1e-10 * G
     assert np.max(np.abs(rows[:, 19:22] - want.barycentric_centroids)) <= 1e-9 * atol_scale
     assert np.max(np.abs(rows[:, 19:22].sum(axis=1) - 1.0)) <= 1e-12
+
+
+def check_deformable_pair_rows(rows, want, atol_scale=1.0):
+    """Rows of k_deformable's tet-tet layout (p_WC, nhat_W, R_WC column-major, signed distance, barycentric[4] x 2) against
+    oracle/ho_deformable.py's DeformableDeformableContact, faces matched by the caller."""
+    assert rows.shape == (len(want.signed_distances), 24)
+    L = max(np.max(np.abs(want.contact_points_W)), 1e-300)
+    assert np.max(np.abs(rows[:, 0:3] - want.contact_points_W)) <= 1e-12 * L * atol_scale
+    assert np.max(np.abs(rows[:, 3:6] - want.nhats_W)) <= 1e-12 * atol_scale
+    R = rows[:, 6:15].reshape(-1, 3, 3).transpose(0, 2, 1)
+    assert np.max(np.abs(R - want.R_WCs)) <= 1e-11 * atol_scale
+    D = max(np.max(np.abs(want.signed_distances)), 1e-300)
+    assert np.max(np.abs(rows[:, 15] - want.signed_distances)) <= 1e-10 * D
+    # Barycentric coordinates of a point in a thin tetrahedron amplify rounding by its aspect ratio: compare the points
+    # they reproduce as well as the coordinates.
+    assert np.max(np.abs(rows[:, 16:20] - want.barycentric0)) <= 1e-8 * atol_scale
+    assert np.max(np.abs(rows[:, 20:24] - want.barycentric1)) <= 1e-8 * atol_scale
+    assert np.max(np.abs(rows[:, 16:20].sum(axis=1) - 1.0)) <= 1e-10 and np.max(np.abs(rows[:, 20:24].sum(axis=1) - 1.0)) <= 1e-10
+
+
+def sphere_sdf(mesh, r):
+    """Signed distances of a sphere mesh's vertices at rest (negative inside, 0 on the surface)."""
+    return np.linalg.norm(mesh.verts, axis=1) - r
+
+
+def test_deformable_pair_arithmetic_matches_the_oracle():
+    """hydro_wrench.cuh's deformable_pair_contact (Cramer's rule for VolumeMesh::CalcBarycentric) on the faces of the
+    equilibrium surface of two signed-distance fields against oracle/ho_deformable.py, incl. the reference's two-tetrahedra
+    fixture (deformable_field_intersection_test.cc:114-173)."""
+    from oracle import ho_deformable as hd
+    lib = harness()
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+
+    def host_rows(want, m0, m1):
+        s = want.surface
+        v0, t0 = m0.arrays()[:2]
+        v1, t1 = m1.arrays()[:2]
+        out = np.zeros((s.num_faces, 24))
+        lib.phc_deformable_pair_contact(s.num_faces, d(s.normals), d(s.centroids), d(s.e_centroid), d(ho.IDENTITY), d(ho.IDENTITY),
+                                        d(v0[t0[want.tet0]].reshape(-1, 12)), d(v1[t1[want.tet1]].reshape(-1, 12)), d(out))
+        return out
+
+    d0 = ho.VolumeMesh.from_arrays([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], [[0, 1, 2, 3]])
+    d1 = ho.VolumeMesh.from_arrays(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, -1.0]]) + [0, 0, 0.2], [[1, 0, 2, 3]])
+    sdf = [0.0, 0.0, 0.0, -1.0]
+    want = hd.deformable_deformable_contact(d1, sdf, d0, sdf)
+    rows = host_rows(want, d1, d0)
+    check_deformable_pair_rows(rows, want)
+    assert np.array_equal(rows[0, 3:6], [0, 0, 1.0]) and abs(rows[0, 15] + 0.1) < 1e-15
+
+    a = ho.VolumeMesh.sphere(0.25, 0.08)
+    b = ho.VolumeMesh.sphere(0.2, 0.07)
+    sa, sb = sphere_sdf(a, 0.25), sphere_sdf(b, 0.2)
+    b = ho.VolumeMesh.from_arrays(b.verts + [0.1, 0.05, 0.38], b.tets)
+    want = hd.deformable_deformable_contact(a, sa, b, sb)
+    assert want is not None and len(want.signed_distances) > 30
+    check_deformable_pair_rows(host_rows(want, a, b), want)
+    assert want.signed_distances.max() <= 1e-12       # the equilibrium surface lies inside both bodies
 
 
 def test_deformable_contact_arithmetic_matches_the_oracle():

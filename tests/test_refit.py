@@ -168,7 +168,7 @@ def test_deformable_rigid_contact_data_after_device_refit(ids):
         batch.query(ho.KPOLYGON, engine.STRICT)
         batch.compute_deformable_contact()
         batch.sync()
-        rows, tri = batch.copy_deformable_contact()
+        rows, _, tri = batch.copy_deformable_contact()
         res = batch.copy_results()
         got = res.surfaces()
         want = [hd.deformable_rigid_contact(vol, fld, s, X_WR) for s in surf]
@@ -196,3 +196,99 @@ def test_deformable_rigid_contact_data_after_device_refit(ids):
     with pytest.raises(engine.HydroError):
         batch.query(ho.KTRIANGLE, engine.STRICT)
         batch.compute_deformable_contact()
+
+
+def _sdf_spheres():
+    a = ho.VolumeMesh.sphere(0.25, 0.08)
+    b = ho.VolumeMesh.sphere(0.2, 0.07)
+    sa = np.linalg.norm(a.verts, axis=1) - 0.25      # signed distances at rest: negative inside, 0 on the surface
+    sb = np.linalg.norm(b.verts, axis=1) - 0.2
+    return a, sa, b, sb, np.array([0.1, 0.05, 0.36])
+
+
+@pytest.mark.gpu
+def test_volume_mesh_updated_to_its_own_vertices_keeps_every_bit():
+    """hydro_derive.cuh is one function for the host (registration) and the device (k_refit_tets): a volume mesh
+    re-posed on the device to the positions it was registered with gives the packed result it gave before, bit for bit
+    (per-tetrahedron records, cull copies, leaf boxes and tree boxes all derived again on the device)."""
+    import drake_b200 as db
+    from drake_b200 import engine
+    ctx = db.Context(0)
+    a, sa, b, sb, off = _sdf_spheres()
+    soft = ho.VolumeMesh.sphere(0.3, 0.1, dense=True)
+    fld = ho.VolumeField.sphere(soft, 0.3, 1e6)
+    h = [ctx.register_compliant_mesh(a.verts, a.tets, sa), ctx.register_compliant_mesh(b.verts + off, b.tets, sb),
+         ctx.register_compliant_mesh(soft.verts, soft.tets, fld.values)]
+    poses = np.stack([ho.IDENTITY, ho.IDENTITY, ho.xform(ho.rpy_matrix(0.3, -0.2, 0.1), [-0.2, 0.1, -0.25])])
+    batch = db.SceneBatch(ctx, [0, 3], h, [1, 2, 3])
+
+    def run():
+        batch.set_poses(poses)
+        batch.query(ho.KPOLYGON, engine.STRICT)
+        batch.sync()
+        res = batch.copy_results()
+        surf_of_face = np.repeat(np.arange(res.num_surfaces), np.diff(res.surf_face_offset))
+        order = np.lexsort((res.elem_N, res.elem_M, surf_of_face))
+        return res, order
+
+    r0, o0 = run()
+    nf = len(r0.areas)
+    assert nf > 100 and r0.num_surfaces >= 2
+    ctx.update_vertices(h, [a.verts, b.verts + off, soft.verts])
+    r1, o1 = run()
+    assert len(r1.areas) == nf
+    for name in ("areas", "normals", "centroids", "pressure_at_centroid", "grad_eM", "grad_eN", "elem_M", "elem_N"):
+        x0, x1 = getattr(r0, name), getattr(r1, name)
+        np.testing.assert_array_equal(x0.reshape(nf, -1)[o0], x1.reshape(nf, -1)[o1], err_msg=name)
+    # (Totals are sums in face order, which is the order of the atomics: equal to rounding only.)
+    np.testing.assert_allclose(r0.surf_total_area, r1.surf_total_area, rtol=1e-13)
+
+
+@pytest.mark.gpu
+def test_deformable_deformable_contact_data_after_device_refit():
+    """SURVEY 8f rank 4, deformable x deformable: two deforming volume meshes carrying signed-distance fields, updated on
+    the device every step (k_refit_tets: gradients, planes, cull copies, boxes), then the tet-tet pipeline and k_deformable
+    against oracle/ho_deformable.py (AddDeformableDeformableContactSurface): the contact mesh face for face, contact
+    points, normals, R_WC, signed distances and the barycentric coordinates in both tetrahedra."""
+    import drake_b200 as db
+    from drake_b200 import engine
+    from oracle import ho_deformable as hd
+    from tests import parity
+    from tests.test_plane_math_cpu import check_deformable_pair_rows
+    ctx = db.Context(0)
+    a, sa, b, sb, off = _sdf_spheres()
+    va0, vb0 = a.verts.copy(), b.verts.copy()
+    ha = ctx.register_compliant_mesh(va0, a.tets, sa)
+    hb = ctx.register_compliant_mesh(vb0 + off, b.tets, sb)
+    # M = the first mesh: the adapter gives the reference's `deformable0` (its larger id) the smaller batch id.
+    batch = db.SceneBatch(ctx, [0, 2], [ha, hb], [1, 2])
+    poses = np.stack([ho.IDENTITY, ho.IDENTITY])
+    checked = 0
+    for t in (0.0, 0.5, -0.6):
+        va, vb = deform(va0, t), deform(vb0, -t) + off
+        ctx.update_vertices([ha, hb], [va, vb])
+        ma, mb = ho.VolumeMesh.from_arrays(va, a.tets), ho.VolumeMesh.from_arrays(vb, b.tets)
+        want = hd.deformable_deformable_contact(ma, sa, mb, sb)
+        assert want is not None
+        batch.set_poses(poses)
+        batch.query(ho.KPOLYGON, engine.STRICT)
+        batch.compute_deformable_contact()
+        batch.sync()
+        rows, ea, eb = batch.copy_deformable_contact()
+        got = batch.copy_results().surfaces()
+        assert len(got) == 1 and (got[0].id_M, got[0].id_N) == (1, 2)
+        parity.compare_surface(got[0], want.surface)
+        go = np.argsort(parity.face_keys(ea, eb), kind="stable")
+        wo = np.argsort(parity.face_keys(want.tet0, want.tet1), kind="stable")
+        np.testing.assert_array_equal(np.stack([ea, eb], 1)[go], np.stack([want.tet0, want.tet1], 1)[wo])
+        w2 = copy.copy(want)
+        for name in ("contact_points_W", "nhats_W", "R_WCs", "signed_distances", "tet0", "tet1", "barycentric0", "barycentric1"):
+            setattr(w2, name, getattr(want, name)[wo])
+        check_deformable_pair_rows(rows[go], w2, atol_scale=10.0)
+        checked += len(rows)
+    assert checked > 100
+    # A volume mesh squashed flat has no field gradient: the update fails like the reference's field constructor.
+    flat = va0.copy()
+    flat[:, 2] = 0.0
+    with pytest.raises(engine.HydroError):
+        ctx.update_vertices([ha], [flat])
