@@ -255,7 +255,8 @@ struct dbh_context {
   long long num_blocks{0};
   // Deformable reuse: the triangle assets' vertex pool and connectivity, parent links of every node, visit counters.
   DevBuf<double> d_rverts;
-  DevBuf<int> d_tri_idx, d_tet_idx, d_node_parent, d_node_visit, d_refit_error;
+  DevBuf<int> d_tri_idx, d_tet_idx, d_node_parent, d_node_visit, d_refit_error, d_root_index;
+  DevBuf<double> d_root_box;
   DevBuf<int4> d_block_desc;
   long long num_rverts{0};
   int bounds_version{0};   // bumped when an update moves root boxes: batches refresh their geometry bounds
@@ -851,14 +852,25 @@ static dbh_status RefitAssets(dbh_context* ctx, const std::vector<int>& ids) {
   if (bad)
     return Fail(DBH_ERR_DEGENERATE_FIELD, "update_vertices: tetrahedron " + std::to_string(bad - 1) +
                                               " (pool index) became degenerate: its field has no gradient");
-  // Root boxes feed the geometry-level broad phase of the no-surface pairs (batches refresh them lazily).
-  for (int id : ids) {
-    HostAsset& a = *ctx->assets[id];
-    BvhNode root;
-    CUDA_OK(cudaMemcpy(&root, ctx->d_nodes.p + a.node_base + 1, sizeof(BvhNode), cudaMemcpyDeviceToHost));
-    for (int d = 0; d < 3; ++d) {
-      a.nodes[1].c[d] = root.c[d];
-      a.nodes[1].h[d] = root.h[d];
+  // Root boxes feed the geometry-level broad phase of the no-surface pairs (batches refresh them lazily): gathered on
+  // the device, one copy for all assets.
+  {
+    const int n = static_cast<int>(ids.size());
+    std::vector<int> roots(n);
+    for (int i = 0; i < n; ++i) roots[i] = ctx->assets[ids[i]]->node_base + 1;
+    CUDA_OK(ctx->d_root_index.ensure(n));
+    CUDA_OK(ctx->d_root_box.ensure(6 * static_cast<size_t>(n)));
+    CUDA_OK(cudaMemcpyAsync(ctx->d_root_index.p, roots.data(), n * sizeof(int), cudaMemcpyHostToDevice, nullptr));
+    k_gather_roots<<<(n + 255) / 256, 256>>>(ctx->d_nodes.p, ctx->d_root_index.p, n, ctx->d_root_box.p);
+    CUDA_OK(cudaGetLastError());
+    std::vector<double> boxes(6 * static_cast<size_t>(n));
+    CUDA_OK(cudaMemcpy(boxes.data(), ctx->d_root_box.p, boxes.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+      HostAsset& a = *ctx->assets[ids[i]];
+      for (int d = 0; d < 3; ++d) {
+        a.nodes[1].c[d] = boxes[6 * i + d];
+        a.nodes[1].h[d] = boxes[6 * i + 3 + d];
+      }
     }
   }
   ++ctx->bounds_version;

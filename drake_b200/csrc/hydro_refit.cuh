@@ -207,4 +207,17 @@ __global__ void __launch_bounds__(128) k_refit_blocks(RefitArgs a) {
   a.blocks[b] = out;
 }
 
+// The root boxes of the re-posed assets, gathered for one device-to-host copy (the geometry-level broad phase of the
+// no-surface pairs reads them on the host).
+__global__ void __launch_bounds__(256) k_gather_roots(const BvhNode* nodes, const int* root_index, int n, double* out /* [n][6] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const BvhNode& r = nodes[root_index[i]];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    out[6 * i + d] = r.c[d];
+    out[6 * i + 3 + d] = r.h[d];
+  }
+}
+
 }  // namespace dbh
