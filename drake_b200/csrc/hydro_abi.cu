@@ -98,6 +98,7 @@ struct HostAsset {
   std::vector<int> tri_idx;          // [num_elements * 3 (triangles) or 4 (tetrahedra)], asset-local vertex indices
   int vert_base{0};                  // first pool index of this asset's vertices
   bool deformed{false};              // re-posed since registration: the per-element host records are stale
+  bool host_verts_stale{false};      // re-posed from device memory: rverts is refreshed from the pool before it is regrown
   std::vector<int> leaf_order;       // asset-local element indices
   std::vector<ElemBox> block_boxes;  // ceil(num_elements / kPlaneBlock)
   int block_base{0};                 // first pool index of this asset's block boxes
@@ -291,6 +292,14 @@ struct dbh_context {
   // growing re-uploads everything (set-up path).
   dbh_status UploadPools() {
     if (uploaded_assets == assets.size()) return DBH_OK;
+    // Assets re-posed from device memory (dbh_context_update_vertices_device): the only current copy of their vertices
+    // is in the pool about to be regrown.
+    for (size_t i = 0; i < uploaded_assets; ++i) {
+      HostAsset& a = *assets[i];
+      if (!a.host_verts_stale) continue;
+      CUDA_OK(cudaMemcpy(a.rverts.data(), d_rverts.p + 3ll * a.vert_base, a.rverts.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      a.host_verts_stale = false;
+    }
     auto grow = [](auto& buf, long long need, bool* regrown) -> cudaError_t {
       if (static_cast<long long>(buf.n) >= need && buf.p) return cudaSuccess;
       *regrown = true;
@@ -886,8 +895,10 @@ static dbh_status Upload(dbh_context* ctx) {
   return RefitAssets(ctx, ids);
 }
 
-dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices) {
-  return Guarded([&]() -> dbh_status {
+// The two entry points differ in where the new positions are: host memory (the host copies follow) or this device (the
+// host copies are refreshed lazily, before a pool regrowth).
+static dbh_status UpdateVertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices,
+                                 bool on_device) {
   if (!ctx || num_assets <= 0 || !assets || !vertices)
     return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: bad argument");
   CUDA_OK(cudaSetDevice(ctx->device));
@@ -898,8 +909,7 @@ dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, con
       return Fail(DBH_ERR_INVALID_ARGUMENT, "update_vertices: a half space has no vertices");
   }
   if (dbh_status s = Upload(ctx)) return s;
-  // The host copy stays current (a later pool regrowth re-uploads it and re-derives the rest); runs of assets whose
-  // vertex ranges follow one another go up in one copy.
+  // Runs of assets whose vertex ranges follow one another go into the pool in one copy.
   const double* src = vertices;
   int k = 0;
   while (k < num_assets) {
@@ -910,18 +920,27 @@ dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, con
     while (k1 < num_assets) {
       HostAsset& a = *ctx->assets[assets[k1]];
       if (k1 > k && a.vert_base != first.vert_base + nverts) break;
-      std::copy(src, src + 3ll * a.num_vertices, a.rverts.begin());
+      if (!on_device) std::copy(src, src + 3ll * a.num_vertices, a.rverts.begin());
       a.deformed = true;
+      a.host_verts_stale = on_device;
       src += 3ll * a.num_vertices;
       nverts += a.num_vertices;
       ++k1;
     }
     CUDA_OK(cudaMemcpyAsync(ctx->d_rverts.p + 3ll * first.vert_base, run_src, 3ll * nverts * sizeof(double),
-                            cudaMemcpyHostToDevice, nullptr));
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, nullptr));
     k = k1;
   }
   return RefitAssets(ctx, std::vector<int>(assets, assets + num_assets));
-  });
+}
+
+dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices) {
+  return Guarded([&]() -> dbh_status { return UpdateVertices(ctx, num_assets, assets, vertices, false); });
+}
+
+dbh_status dbh_context_update_vertices_device(dbh_context* ctx, int32_t num_assets, const int32_t* assets,
+                                              const double* device_vertices) {
+  return Guarded([&]() -> dbh_status { return UpdateVertices(ctx, num_assets, assets, device_vertices, true); });
 }
 
 dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressure_scale, double margin,

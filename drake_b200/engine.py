@@ -110,6 +110,7 @@ def lib():
     L.dbh_register_half_space.argtypes = [vp, C.c_int32, C.c_double, C.c_double, _ip]
     L.dbh_asset_get_info.argtypes = [vp, C.c_int32, C.POINTER(AssetInfo)]
     L.dbh_context_update_vertices.argtypes = [vp, C.c_int32, _ip, _dp]
+    L.dbh_context_update_vertices_device.argtypes = [vp, C.c_int32, _ip, vp]
     L.dbh_asset_get_derived.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     L.dbh_asset_copy_bvh.argtypes = [vp, C.c_int32, _dp, _ip]
     L.dbh_context_set_bvh_builder.argtypes = [vp, C.c_int32]
@@ -330,6 +331,12 @@ class Context:
         ids = _i(list(assets))
         flat = np.ascontiguousarray(np.concatenate([_d(v).reshape(-1) for v in vertices]))
         _check(lib().dbh_context_update_vertices(self._h, len(ids), _ptr(ids, _ip), _ptr(flat, _dp)))
+
+    def update_vertices_device(self, assets, device_pointer: int):
+        """update_vertices with the new positions already on this device: the address of one float64 device buffer that
+        holds the listed assets' [num_vertices, 3] arrays one after the other (e.g. torch_tensor.data_ptr())."""
+        ids = _i(list(assets))
+        _check(lib().dbh_context_update_vertices_device(self._h, len(ids), _ptr(ids, _ip), C.c_void_p(int(device_pointer))))
 
     def register_half_space(self, compliant: bool = False, pressure_scale: float = 0.0, margin: float = 0.0) -> int:
         """HalfSpace shape (z <= 0 of its frame). compliant: pressure_scale = hydroelastic modulus / slab thickness

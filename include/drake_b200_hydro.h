@@ -131,6 +131,11 @@ dbh_status dbh_register_half_space(dbh_context* ctx, int32_t type, double pressu
  * vertices: host, the assets' vertex arrays one after the other ([num_vertices * 3] each, in the order of `assets`).
  * Synchronous; no query of a batch that uses these assets may be in flight. The next queries see the new meshes. */
 dbh_status dbh_context_update_vertices(dbh_context* ctx, int32_t num_assets, const int32_t* assets, const double* vertices);
+/* The same with the new positions already on this context's device (a GPU-resident deformable solver): one device
+ * buffer, the assets' vertex arrays one after the other like `vertices` above. No vertex crosses PCIe; the host's copy of
+ * the positions is refreshed lazily, only if the vertex pool has to be regrown by a later registration. */
+dbh_status dbh_context_update_vertices_device(dbh_context* ctx, int32_t num_assets, const int32_t* assets,
+                                              const double* device_vertices);
 dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* out);
 /* The asset's BVH for inspection: boxes [(num_bvh_nodes + 1) * 6] = centre, half width per node
  * (node 0 unused, node 1 root), left [(num_bvh_nodes + 1)] = index of the first of the two adjacent

@@ -292,3 +292,50 @@ def test_deformable_deformable_contact_data_after_device_refit():
     flat[:, 2] = 0.0
     with pytest.raises(engine.HydroError):
         ctx.update_vertices([ha], [flat])
+
+
+@pytest.mark.gpu
+def test_update_from_device_memory_and_pool_regrowth():
+    """dbh_context_update_vertices_device: the new positions come from device memory (torch tensors here); the query
+    equals the one after the host-pointer update. Then a registration that regrows the pools: the re-posed meshes are
+    re-uploaded from the refreshed host copy and derived again -- same surfaces as before the regrowth."""
+    import torch
+    import drake_b200 as db
+    from tests import parity
+    ctx = db.Context(0)
+    vol = ho.VolumeMesh.sphere(0.3, 0.1, dense=True)
+    fld = ho.VolumeField.sphere(vol, 0.3, 1e6)
+    surf = ho.TriMesh.sphere(0.25, 0.05)
+    soft2 = ho.VolumeMesh.sphere(0.25, 0.08)
+    sdf2 = np.linalg.norm(soft2.verts, axis=1) - 0.25
+    a_v = parity.register_compliant(ctx, vol, fld)
+    a_s = parity.register_rigid(ctx, surf)
+    a_d = ctx.register_compliant_mesh(soft2.verts, soft2.tets, 0.25 - np.linalg.norm(soft2.verts, axis=1))
+    poses = np.stack([ho.xform(None, [0, 0, 0]), ho.xform(ho.rpy_matrix(0.2, 0.1, 0.4), [0.1, 0.05, 0.3]),
+                      ho.xform(None, [-0.2, 0.1, -0.3])])
+    batch = db.SceneBatch(ctx, [0, 3], [a_v, a_s, a_d], [1, 2, 3])
+    new_s, new_d = deform(surf.verts, 0.7), deform(soft2.verts, -0.5)
+    ctx.update_vertices([a_s, a_d], [new_s, new_d])
+    want = batch.compute_contact_surfaces(poses, ho.KPOLYGON)[0]
+    assert len(want) >= 2
+    # Back to the registered shapes, then the same deformation from device memory.
+    ctx.update_vertices([a_s, a_d], [surf.verts, soft2.verts])
+    t = torch.from_numpy(np.concatenate([new_s.reshape(-1), new_d.reshape(-1)])).cuda()
+    torch.cuda.synchronize()
+    ctx.update_vertices_device([a_s, a_d], t.data_ptr())
+    got = batch.compute_contact_surfaces(poses, ho.KPOLYGON)[0]
+
+    def same(xs, ys):
+        assert [(x.id_M, x.id_N) for x in xs] == [(y.id_M, y.id_N) for y in ys]
+        for x, y in zip(xs, ys):
+            np.testing.assert_array_equal(np.sort(parity.face_keys(x.elem_M, x.elem_N)), np.sort(parity.face_keys(y.elem_M, y.elem_N)))
+            ox, oy = np.argsort(parity.face_keys(x.elem_M, x.elem_N), kind="stable"), np.argsort(parity.face_keys(y.elem_M, y.elem_N), kind="stable")
+            np.testing.assert_array_equal(x.areas[ox], y.areas[oy])
+            np.testing.assert_array_equal(x.centroids[ox], y.centroids[oy])
+
+    same(got, want)
+    # A large registration regrows every pool; the deformed assets must survive it.
+    big = ho.VolumeMesh.sphere(0.3, 0.03, dense=True)
+    ctx.register_compliant_mesh(big.verts, big.tets, ho.VolumeField.sphere(big, 0.3, 1e6).values)
+    b2 = db.SceneBatch(ctx, [0, 3], [a_v, a_s, a_d], [1, 2, 3])
+    same(b2.compute_contact_surfaces(poses, ho.KPOLYGON)[0], want)

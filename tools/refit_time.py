@@ -39,6 +39,10 @@ batch = db.SceneBatch(ctx, np.arange(S + 1) * 2, ga, np.tile([1, 2], S))
 new = [sv * (1 + 0.05 * np.sin(s)) for s in range(S)]
 flat = [np.ascontiguousarray(v) for v in new]
 t_update = timed(lambda: ctx.update_vertices(a_s, flat))
+import torch
+dev = torch.from_numpy(np.concatenate([v.reshape(-1) for v in flat])).cuda()
+torch.cuda.synchronize()
+t_update_dev = timed(lambda: ctx.update_vertices_device(a_s, dev.data_ptr()))
 
 
 def step():
@@ -52,7 +56,7 @@ t_query = timed(step)
 rows, _, _ = batch.copy_deformable_contact()
 print(json.dumps({"case": "deformable surfaces x rigid volume", "scenes": S, "triangles_per_surface": int(len(st)),
                   "tets_of_rigid_volume": int(len(vol.elements)), "update_vertices_ms": t_update,
-                  "update_vertices_us_per_asset": t_update * 1e3 / S, "query_plus_contact_data_ms": t_query,
+                  "update_vertices_us_per_asset": t_update * 1e3 / S, "update_vertices_device_ms": t_update_dev, "query_plus_contact_data_ms": t_query,
                   "contact_points": int(len(rows))}))
 
 # Deforming VOLUMES (deformable x deformable): two per scene.
@@ -64,6 +68,9 @@ b2 = db.SceneBatch(ctx, np.arange(S + 1) * 2, h, np.tile([1, 2], S))
 I = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], float), (2 * S, 1))
 newv = [np.ascontiguousarray((av * (1 + 0.04 * np.sin(k))) + ([0, 0, 0] if k % 2 == 0 else [0.1, 0.05, 0.42])) for k in range(2 * S)]
 t_update2 = timed(lambda: ctx.update_vertices(h, newv))
+dev2 = torch.from_numpy(np.concatenate([v.reshape(-1) for v in newv])).cuda()
+torch.cuda.synchronize()
+t_update2_dev = timed(lambda: ctx.update_vertices_device(h, dev2.data_ptr()))
 
 
 def step2():
@@ -76,5 +83,5 @@ def step2():
 t_query2 = timed(step2)
 rows2, _, _ = b2.copy_deformable_contact()
 print(json.dumps({"case": "deformable volumes x deformable volumes", "scenes": S, "tets_per_volume": int(len(at)),
-                  "update_vertices_ms": t_update2, "update_vertices_us_per_asset": t_update2 * 1e3 / (2 * S),
+                  "update_vertices_ms": t_update2, "update_vertices_us_per_asset": t_update2 * 1e3 / (2 * S), "update_vertices_device_ms": t_update2_dev,
                   "query_plus_contact_data_ms": t_query2, "contact_points": int(len(rows2))}))
