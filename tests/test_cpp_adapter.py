@@ -85,3 +85,38 @@ def test_traction_mirror_compiles():
         pytest.skip("GPU present: executed by tests/test_zz_gpu_wrench.py")
     res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 3 and "no CPU fallback" in res.stdout
+
+
+def build_deformable_exe():
+    from drake_b200 import build
+    lib = build.build()
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_deformable_contact")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "cpp", "test_deformable_contact.cc")
+    hdr = os.path.join(ROOT, "include", "drake_b200_deformable_contact.h")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(lib)):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src,
+                        "-o", exe, "-L", os.path.dirname(lib), "-ldrake_b200_hydro",
+                        "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    return exe
+
+
+def test_deformable_mirror_compiles_and_has_no_cpu_fallback():
+    """include/drake_b200_deformable_contact.h (deformable::Geometries, DeformableContact, DeformableContactSurface,
+    ContactParticipation) compiles warning-free against the C-ABI; without a GPU it fails loudly."""
+    import torch
+    exe = build_deformable_exe()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 3, res.stdout
+    assert "no CPU fallback" in res.stdout
+
+
+@pytest.mark.gpu
+def test_deformable_mirror_reference_fixtures():
+    """tests/cpp/test_deformable_contact.cc: the reference's OnePolygon / NoContact / InvertedElements fixtures
+    (deformable_mesh_intersection_test.cc) and the invariants of deformable x deformable surfaces through the mirror."""
+    res = subprocess.run([build_deformable_exe()], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    assert res.stdout.strip().endswith("ok")
