@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kMinBlocks) k_small_pairs(Sm
         if (leaf_hit) leaf[nleaf + __popc(ml & lt)] = e;
         nleaf += __popc(ml);
         const int pushed = 2 * __popc(m2) + 4 * __popc(m4);
+        __syncwarp();   // every lane has read its entry before the slots are written again (the ballots do not order memory)
         if (top + pushed > a.stack_cap) {
           failed = true;   // warp-uniform
         } else {
