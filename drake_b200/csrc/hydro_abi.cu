@@ -1574,6 +1574,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     su.surf_index = b->d_surf_index.p;
     su.surf_pair = b->d_surf_pair.p;
     su.pairs = b->d_pairs.p;
+    su.poses = b->d_poses;
     su.poly_off = b->d_poly_off.p;
     su.vert_off = b->d_vert_off.p;
     su.representation = representation;

@@ -1611,6 +1611,7 @@ struct SurfaceArgs {
   int pair_end;
   const int* surf_pair;
   const PairRec* pairs;
+  const Xf* poses;           // world poses, one per geometry (the all-zero-area centroid of a triangle mesh)
   const long long* poly_off;
   const long long* vert_off;
   int representation;
@@ -1643,6 +1644,20 @@ __device__ __forceinline__ void surface_face_range(const SurfaceArgs& a, int p, 
     *f1 = a.vert_off[p + 1];
     *v0 = a.vert_off[p] + a.poly_off[p];
   }
+}
+
+// Centroid of a surface whose faces all have zero area. Polygons: the running centroid stays the LAST polygon's
+// (polygon_surface_mesh.cc:210-217). Triangles: the area-weighted sum stays the zero vector of the frame the mesh was
+// built in (triangle_surface_mesh.h:456-486) -- frame M of a mesh pair, carried to the world by TransformVertices
+// (p_WMo), the world frame itself for the half-space pairs.
+__device__ __forceinline__ void zero_area_centroid(const SurfaceArgs& a, int p, long long f1, double* c) {
+  if (a.representation == 1) {
+    for (int d = 0; d < 3; ++d) c[d] = a.centroids[3 * (f1 - 1) + d];
+    return;
+  }
+  const PairRec& pr = a.pairs[p];
+  const bool mesh_pair = pr.kind == kSoftRigid || pr.kind == kSoftSoft;
+  for (int d = 0; d < 3; ++d) c[d] = mesh_pair ? a.poses[pr.geom_a].m[9 + d] : 0.0;
 }
 
 __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
@@ -1681,11 +1696,11 @@ __global__ void __launch_bounds__(128) k_surface(SurfaceArgs a) {
         cy /= area;
         cz /= area;
       } else {
-        // All faces have zero area: the reference keeps the centroid of the
-        // last polygon; we report the first face's.
-        cx = a.centroids[3 * f0];
-        cy = a.centroids[3 * f0 + 1];
-        cz = a.centroids[3 * f0 + 2];
+        double c[3];
+        zero_area_centroid(a, p, f1, c);
+        cx = c[0];
+        cy = c[1];
+        cz = c[2];
       }
       const PairRec& pr = a.pairs[p];
       a.surf_face_off[s] = f0;
@@ -1767,7 +1782,7 @@ __global__ void k_surface_big_finish(SurfaceArgs a) {
     } else {
       long long f0, f1, v0;
       surface_face_range(a, a.surf_pair[s], &f0, &f1, &v0);
-      for (int d = 0; d < 3; ++d) a.surf_centroid[3 * s + d] = a.centroids[3 * f0 + d];
+      zero_area_centroid(a, a.surf_pair[s], f1, &a.surf_centroid[3 * s]);
     }
     atomicAdd(&a.counters->total_area, area);
   }
