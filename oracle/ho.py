@@ -62,6 +62,8 @@ def lib():
                                        _ip, C.c_int, C.c_int]
         _lib.ho_soft_soft.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int64, C.c_int64, C.c_int,
                                       C.c_int, _ip, C.c_int]
+        _lib.ho_surface_bfs_pairs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+        _lib.ho_volume_neighbors.argtypes = [C.c_int, _ip]
         _lib.ho_soft_mesh_rigid_half_space.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int64, C.c_int64, C.c_int]
         _lib.ho_soft_half_space_rigid_mesh.argtypes = [C.c_int, _dp, C.c_double, C.c_double, _dp, C.c_int64, C.c_int64,
                                                        C.c_int, C.c_int]
@@ -192,6 +194,12 @@ class VolumeMesh:
 
     def total_volume(self) -> float:
         return lib().ho_volume_total_volume(self.h)
+
+    def neighbors(self) -> np.ndarray:
+        """VolumeMeshTopology (volume_mesh_topology.cc:13-68): [e, f] = the tetrahedron across face f of e, -1 outside."""
+        out = np.zeros((len(self.tets), 4), dtype=np.int32)
+        _check(lib().ho_volume_neighbors(self.h, _pi(out)), "volume_neighbors")
+        return out
 
     def to_surface(self) -> "TriMesh":
         return TriMesh(lib().ho_volume_to_surface(self.h, None))
@@ -525,6 +533,18 @@ def candidates(mesh_A: VolumeMesh, mesh_B, X_AB, mode: int = MODE_BRUTE) -> Tupl
     lib().ho_pairs_get(h, _pi(out))
     lib().ho_pairs_free(h)
     return out, tests.value
+
+
+def surface_bfs_pairs(mesh_M: VolumeMesh, field_M: VolumeField, mesh_N: VolumeMesh, field_N: VolumeField,
+                      X_MN) -> np.ndarray:
+    """The (tet of M, tet of N) pairs the surface-BVH + BFS overload of VolumeIntersector::IntersectFields hands to
+    CalcContactPolygon, in visit order (field_intersection.cc:254-375). soft_soft(..., pairs=these) is its surface."""
+    h = _check(lib().ho_surface_bfs_pairs(mesh_M.h, field_M.h, mesh_N.h, field_N.h, _pd(_d(X_MN))), "surface_bfs_pairs")
+    n = lib().ho_pairs_count(h)
+    out = np.zeros((n, 2), dtype=np.int32)
+    lib().ho_pairs_get(h, _pi(out))
+    lib().ho_pairs_free(h)
+    return out
 
 
 RIGID, COMPLIANT = 1, 2

@@ -10,6 +10,8 @@
 #include <cmath>
 #include <stdexcept>
 #include <utility>
+#include <set>
+#include <map>
 #include <vector>
 
 #include "ho_mesh.h"
@@ -616,6 +618,98 @@ inline bool ContactSurfaceFromCompliantVolumes(int64_t id_M, const VolumeMesh& m
   out->elem_second = std::move(tet1_of_face);
   EnforceIdOrder(out);
   return true;
+}
+
+// ---------------------------------------------------------------------------
+// Soft-soft through the surfaces: the second IntersectFields overload (field_intersection.cc:254-375), which the
+// reference builds and tests (field_intersection_test.cc:305-344,423-476) but does not call from
+// ComputeContactSurfaceFromCompliantVolumes (use_surfaces = false, :511-517).
+
+// VolumeMeshTopology::Initialize (volume_mesh_topology.cc:13-68): neighbor(e, f) = the tetrahedron sharing face f of e
+// (face f is the one opposite vertex f), -1 on the boundary.
+inline std::vector<std::array<int, 4>> VolumeMeshNeighbors(const VolumeMesh& mesh) {
+  std::vector<std::array<int, 4>> neighbors(mesh.num_elements(), std::array<int, 4>{-1, -1, -1, -1});
+  auto get_face = [&mesh](int e, int f) {
+    std::array<int, 3> t{mesh.tets[e][(f + 1) % 4], mesh.tets[e][(f + 2) % 4], mesh.tets[e][(f + 3) % 4]};
+    std::sort(t.begin(), t.end());
+    return t;
+  };
+  std::map<std::array<int, 3>, int> face_to_tet;
+  for (int tet = 0; tet < mesh.num_elements(); ++tet) {
+    for (int f = 0; f < 4; ++f) {
+      const std::array<int, 3> face = get_face(tet, f);
+      auto it = face_to_tet.find(face);
+      if (it == face_to_tet.end()) {
+        face_to_tet.emplace(face, tet);
+        continue;
+      }
+      const int other = it->second;
+      neighbors[tet][f] = other;
+      for (int g = 0; g < 4; ++g)
+        if (get_face(other, g) == face) {
+          neighbors[other][g] = tet;
+          break;
+        }
+    }
+  }
+  return neighbors;
+}
+
+// CalcContactPolygon as the BFS sees it (field_intersection.cc:377-428): the intersected faces of the two tetrahedra
+// (0-3: faces of tet0, 4-7: faces of tet1; one entry per vertex of the polygon BEFORE the last
+// RemoveNearlyDuplicateVertices), empty when no polygon was added.
+inline std::vector<int> CalcContactPolygonTetTetFaces(const VolumeMesh& mesh0_M, const VolumeField& field0_M,
+                                                      const VolumeMesh& mesh1_N, const VolumeField& field1_N,
+                                                      const Xform& X_MN, const Mat3& R_NM, int tet0, int tet1) {
+  Plane equilibrium_plane_M;
+  if (!CalcEquilibriumPlane(tet0, field0_M, tet1, field1_N, X_MN, &equilibrium_plane_M)) return {};
+  const Vec3 polygon_nhat_M = equilibrium_plane_M.nhat;
+  if (!IsPlaneNormalAlongPressureGradient(polygon_nhat_M, tet0, field0_M)) return {};
+  const Vec3 reverse_polygon_nhat_N = R_NM * (-polygon_nhat_M);
+  if (!IsPlaneNormalAlongPressureGradient(reverse_polygon_nhat_N, tet1, field1_N)) return {};
+  const auto [polygon_vertices_M, faces] = IntersectTetrahedra(tet0, mesh0_M, tet1, mesh1_N, X_MN, equilibrium_plane_M);
+  if (polygon_vertices_M.size() < 3) return {};
+  return faces;
+}
+
+// The tetrahedron pairs the BFS hands to CalcContactPolygon, in queue order (field_intersection.cc:254-375):
+// seeds = the tetrahedra behind every pair of surface triangles in overlapping leaves of the two surface BVHs,
+// then the face neighbours of every pair that produced a polygon. `surface_pairs` = Bvh::Collide of the two surface
+// hierarchies, (triangle of M's surface, triangle of N's surface) in traversal order.
+inline std::vector<std::pair<int, int>> SurfaceBfsTetPairs(const VolumeMesh& mesh0_M, const VolumeField& field0_M,
+                                                           const std::vector<int>& tri_to_tet_M,
+                                                           const std::vector<std::array<int, 4>>& neighbors_M,
+                                                           const VolumeMesh& mesh1_N, const VolumeField& field1_N,
+                                                           const std::vector<int>& tri_to_tet_N,
+                                                           const std::vector<std::array<int, 4>>& neighbors_N,
+                                                           const Xform& X_MN,
+                                                           const std::vector<std::pair<int, int>>& surface_pairs) {
+  std::set<std::pair<int, int>> visited;
+  std::vector<std::pair<int, int>> queue;  // never popped: `head` walks it, so it doubles as the visit order
+  for (const auto& [tri0, tri1] : surface_pairs) {
+    const std::pair<int, int> tet_pair(tri_to_tet_M[tri0], tri_to_tet_N[tri1]);
+    if (visited.insert(tet_pair).second) queue.push_back(tet_pair);
+  }
+  const Mat3 R_NM = transpose(X_MN.R);
+  for (size_t head = 0; head < queue.size(); ++head) {
+    const auto [tetM, tetN] = queue[head];
+    const std::vector<int> faces =
+        CalcContactPolygonTetTetFaces(mesh0_M, field0_M, mesh1_N, field1_N, X_MN, R_NM, tetM, tetN);
+    for (int face : faces) {
+      std::pair<int, int> next;
+      if (face < 4) {
+        const int neighborM = neighbors_M[tetM][face];
+        if (neighborM < 0) continue;
+        next = {neighborM, tetN};
+      } else {
+        const int neighborN = neighbors_N[tetN][face - 4];
+        if (neighborN < 0) continue;
+        next = {tetM, neighborN};
+      }
+      if (visited.insert(next).second) queue.push_back(next);
+    }
+  }
+  return queue;
 }
 
 }  // namespace ho

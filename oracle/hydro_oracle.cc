@@ -31,6 +31,11 @@ struct VolAsset {
   std::unique_ptr<std::vector<Aabb>> boxes;
   std::unique_ptr<Bvh> bvh_ref;    // reference-shaped (1 tet / leaf)
   std::unique_ptr<ObbBvh> bvh_obb; // Bvh<Obb, VolumeMesh> (hydroelastic_internal.h:71-100)
+  // CompliantMesh's surface side (hydroelastic_internal.h:71-100): surface mesh, tri_to_tet, its Bvh<Obb>, topology.
+  std::unique_ptr<TriMesh> surface;
+  std::vector<int> tri_to_tet;
+  std::unique_ptr<ObbBvh> surface_bvh;
+  std::unique_ptr<std::vector<std::array<int, 4>>> neighbors;
 };
 struct TriAsset {
   TriMesh mesh;
@@ -98,6 +103,12 @@ template <class Asset>
 const ObbBvh& RefObbBvh(Asset& a) {
   if (!a.bvh_obb) a.bvh_obb = std::make_unique<ObbBvh>(MakeObbBvh(a.mesh));
   return *a.bvh_obb;
+}
+void EnsureSurfaceSide(VolAsset& a) {
+  if (a.surface) return;
+  a.surface = std::make_unique<TriMesh>(ConvertVolumeToSurfaceMesh(a.mesh, &a.tri_to_tet));
+  a.surface_bvh = std::make_unique<ObbBvh>(MakeObbBvh(*a.surface));
+  a.neighbors = std::make_unique<std::vector<std::array<int, 4>>>(VolumeMeshNeighbors(a.mesh));
 }
 const Bvh& Leaf1Bvh(VolAsset& a) { return RefBvh(a); }
 const Bvh& Leaf1Bvh(TriAsset& a) {
@@ -537,6 +548,34 @@ int ho_candidates(int volA, int kindB, int hB, const double* X_AB, int mode, int
   auto c = kindB == 0 ? Candidates(*g_vols[volA], *g_vols[hB], X, mode, &tests)
                       : Candidates(*g_vols[volA], *g_tris[hB], X, mode, &tests);
   if (bv_tests) *bv_tests = tests;
+  std::lock_guard<std::mutex> l(g_mu);
+  g_pairlists.push_back(std::make_unique<std::vector<std::pair<int, int>>>(std::move(c)));
+  return static_cast<int>(g_pairlists.size()) - 1;
+  HO_CATCH(-1)
+}
+// VolumeMeshTopology (volume_mesh_topology.cc:13-68): out[4 * e + f] = neighbor(e, f).
+int ho_volume_neighbors(int vol, int* out) {
+  HO_TRY
+  EnsureSurfaceSide(*g_vols[vol]);
+  const auto& nb = *g_vols[vol]->neighbors;
+  for (size_t e = 0; e < nb.size(); ++e)
+    for (int f = 0; f < 4; ++f) out[4 * e + f] = nb[e][f];
+  return 0;
+  HO_CATCH(-1)
+}
+// The tetrahedron pairs of the surface-BVH + BFS intersector in visit order (field_intersection.cc:254-375); a
+// pair-list handle. ho_soft_soft over this list is the surface that overload builds.
+int ho_surface_bfs_pairs(int volM, int fieldM, int volN, int fieldN, const double* X_MN) {
+  HO_TRY
+  VolAsset& M = *g_vols[volM];
+  VolAsset& N = *g_vols[volN];
+  EnsureSurfaceSide(M);
+  EnsureSurfaceSide(N);
+  const Xform X = Xform::FromArray(X_MN);
+  std::vector<std::pair<int, int>> surface_pairs;
+  CollideObb(*M.surface_bvh, *N.surface_bvh, X, &surface_pairs);
+  auto c = SurfaceBfsTetPairs(M.mesh, *g_fields[fieldM], M.tri_to_tet, *M.neighbors, N.mesh, *g_fields[fieldN],
+                              N.tri_to_tet, *N.neighbors, X, surface_pairs);
   std::lock_guard<std::mutex> l(g_mu);
   g_pairlists.push_back(std::make_unique<std::vector<std::pair<int, int>>>(std::move(c)));
   return static_cast<int>(g_pairlists.size()) - 1;
