@@ -14,6 +14,8 @@
 #include "../../drake_b200/csrc/hydro_clip.cuh"
 #include "../../drake_b200/csrc/hydro_plane.cuh"
 #include "../../drake_b200/csrc/hydro_wrench.cuh"
+#include "../../drake_b200/csrc/hydro_derive.cuh"
+#include "../../drake_b200/csrc/hydro_bfs.cuh"
 
 using namespace dbh;
 
@@ -289,6 +291,35 @@ int phc_intersect_tetrahedra(const double* tet0_v, const double* tet1_v, const d
     out[3 * i] = v.x, out[3 * i + 1] = v.y, out[3 * i + 2] = v.z;
   }
   return n;
+}
+// CalcContactPolygon as the surface-seeded intersector's k_bfs_wave runs it (hydro_bfs.cuh): the records registration
+// derives (derive_tet), then tet_pair_polygon_with_faces on the exceptional path's storage. tet*_v: 4 x 3 vertices,
+// tet*_p: the 4 vertex field values. out_faces: IntersectTetrahedra's returned face codes (one per vertex before the last
+// dedupe); info2 = {number of codes, bit mask of the codes}. Returns the polygon size, or -status.
+int phc_tet_pair_polygon_faces(const double* tet0_v, const double* tet0_p, const double* tet1_v, const double* tet1_p,
+                               const double* X_MN, double* out_poly, int* out_faces, int* info2) {
+  Xf X;
+  std::memcpy(X.m, X_MN, sizeof(X.m));
+  TetRec r0, r1;
+  TetAux a0, a1;
+  D3 v0[4], v1[4];
+  for (int k = 0; k < 4; ++k) {
+    v0[k] = load3(tet0_v + 3 * k);
+    v1[k] = load3(tet1_v + 3 * k);
+  }
+  if (!derive_tet(v0, tet0_p, &r0, &a0) || !derive_tet(v1, tet1_p, &r1, &a1)) return -100;
+  LocalPoly P;
+  TetPairPolygon r;
+  tet_pair_polygon_with_faces(X, r0, r1, a0, a1, P, &r);
+  if (r.status) return -r.status;
+  for (int i = 0; i < r.n; ++i) {
+    const D3 v = P.get(r.buf, i);
+    out_poly[3 * i] = v.x, out_poly[3 * i + 1] = v.y, out_poly[3 * i + 2] = v.z;
+  }
+  for (int i = 0; i < r.codes_n; ++i) out_faces[i] = face_code_at(r.codes, i);
+  info2[0] = r.codes_n;
+  info2[1] = static_cast<int>(r.faces);
+  return r.n;
 }
 // ClipTriangleByTetrahedron (mesh_intersection.cc:176-264) with the sequence tri_stage_b runs: the triangle's
 // vertices into frame M, four clips by the tetrahedron's face half spaces (built the way registration builds

@@ -18,7 +18,8 @@ from tests.parity import REL_TOL, assert_close, face_keys, random_pose
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "plane_host_check.cc")
 HDRS = [os.path.join(ROOT, "drake_b200", "csrc", n) for n in ("hydro_plane.cuh", "hydro_wrench.cuh", "hydro_clip.cuh",
-                                                              "hydro_math.cuh", "hydro_types.h")]
+                                                              "hydro_math.cuh", "hydro_types.h", "hydro_bfs.cuh",
+                                                              "hydro_derive.cuh")]
 LIB = os.path.join(ROOT, "tests", "cpp", "_build", "libplane_host_check.so")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -745,3 +746,64 @@ def test_nine_gon_of_config4_is_bit_exact_on_the_exceptional_storage():
         assert n == len(want) and np.array_equal(out[:n], want)
         sizes.append(n)
     assert max(sizes) == 9
+
+
+def test_tet_pair_polygon_with_face_codes_is_bit_exact():
+    """The surface-seeded intersector's per-pair function (hydro_bfs.cuh: tet_pair_polygon_with_faces, what k_bfs_wave
+    runs) against the oracle's CalcContactPolygon pieces (field_intersection.cc:377-428): the same polygon bit for bit and
+    the same face codes in the same order (IntersectTetrahedra's second return value, :85-198) -- the reference's
+    octagon with its literal face list (field_intersection_test.cc:196-259) and the candidate pairs of two overlapping
+    soft spheres under random poses, filters included."""
+    lib = harness()
+    lib.phc_tet_pair_polygon_faces.argtypes = [_dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+    d = lambda a: np.ascontiguousarray(a, float).ctypes.data_as(_dp)
+
+    def host(m0, f0, e0, m1, f1, e1, X_MN):
+        v0, t0, _ = m0.arrays()
+        v1, t1, _ = m1.arrays()
+        poly, faces, info = np.zeros((16, 3)), np.zeros(16, np.int32), np.zeros(2, np.int32)
+        n = lib.phc_tet_pair_polygon_faces(d(v0[t0[e0]]), d(f0.values[t0[e0]]), d(v1[t1[e1]]), d(f1.values[t1[e1]]),
+                                           d(X_MN), d(poly), faces.ctypes.data_as(_ip), info.ctypes.data_as(_ip))
+        assert n >= 0, n
+        return poly[:n], faces[:info[0]], int(info[1])
+
+    def oracle(m0, f0, e0, m1, f1, e1, X_MN):
+        plane = ho.calc_equilibrium_plane(f0, e0, f1, e1, X_MN)
+        if plane is None:
+            return np.zeros((0, 3)), np.zeros(0, np.int32)
+        nhat, disp = plane
+        R_NM = np.asarray(X_MN[:9], float).reshape(3, 3)   # column-major R_MN read row-major = its transpose
+        if not ho.is_plane_normal_along_pressure_gradient(nhat, e0, f0):
+            return np.zeros((0, 3)), np.zeros(0, np.int32)
+        if not ho.is_plane_normal_along_pressure_gradient(R_NM @ (-nhat), e1, f1):
+            return np.zeros((0, 3)), np.zeros(0, np.int32)
+        return ho.intersect_tetrahedra(m0, e0, m1, e1, X_MN, nhat, disp)
+
+    # The reference's octagon: fields chosen so that the equilibrium plane is z = 0 (f0 = z, f1 = -z).
+    m0 = ho.VolumeMesh.from_arrays([[2, 0, 2], [-2, 0, 2], [0, 2, -2], [0, -2, -2]], [[0, 1, 2, 3]])
+    m1 = ho.VolumeMesh.from_arrays([[1.5, 1.5, 2.5], [-1.5, -1.5, 2.5], [-1.5, 1.5, -2.5], [1.5, -1.5, -2.5]],
+                                   [[0, 1, 2, 3]])
+    f0 = ho.VolumeField.from_values(m0, m0.verts[:, 2].copy())
+    f1 = ho.VolumeField.from_values(m1, -m1.verts[:, 2].copy())
+    want_poly, want_faces = oracle(m0, f0, 0, m1, f1, 0, ho.IDENTITY)
+    got_poly, got_faces, mask = host(m0, f0, 0, m1, f1, 0, ho.IDENTITY)
+    assert len(want_poly) == 8 and np.array_equal(got_poly, want_poly)
+    assert got_faces.tolist() == want_faces.tolist()
+    assert sorted(set(want_faces.tolist())) == list(range(8)) and mask == 0xFF   # every face of both tetrahedra
+    R = 0.25
+    soft = ho.VolumeMesh.sphere(R, 0.1)
+    fld = ho.VolumeField.sphere(soft, R, 1e6)
+    rng = np.random.default_rng(77)
+    polygons = rejected = 0
+    for _ in range(3):
+        X_MN = ho.invert_and_compose(random_pose(rng, 0.02), random_pose(rng, 0.02, center=(0, 0, 0.3)))
+        pairs, _ = ho.candidates(soft, soft, X_MN)
+        for e0, e1 in pairs[::5]:
+            want_poly, want_faces = oracle(soft, fld, int(e0), soft, fld, int(e1), X_MN)
+            got_poly, got_faces, mask = host(soft, fld, int(e0), soft, fld, int(e1), X_MN)
+            assert got_poly.shape == want_poly.shape and np.array_equal(got_poly, want_poly), (e0, e1)
+            assert got_faces.tolist() == want_faces.tolist(), (e0, e1)
+            assert mask == sum(1 << c for c in set(want_faces.tolist()))
+            polygons += len(want_poly) > 0
+            rejected += len(want_poly) == 0
+    assert polygons >= 50 and rejected >= 50
