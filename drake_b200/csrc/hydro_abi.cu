@@ -16,6 +16,7 @@
 #include "../../include/drake_b200_hydro.h"
 #include "hydro_kernels.cuh"
 #include "hydro_small.cuh"
+#include "hydro_bfs_kernels.cuh"
 #include "hydro_derive.cuh"
 #include "hydro_refit.cuh"
 #include "hydro_lbvh.h"
@@ -100,6 +101,14 @@ struct HostAsset {
   bool deformed{false};              // re-posed since registration: the per-element host records are stale
   bool host_verts_stale{false};      // re-posed from device memory: rverts is refreshed from the pool before it is regrown
   std::vector<int> leaf_order;       // asset-local element indices
+  // The surface-seeded soft-soft intersector (hydro_bfs.cuh), compliant meshes registered while the context's
+  // intersector is DBH_INTERSECTOR_SURFACE_BFS: the face neighbours of every tetrahedron (VolumeMeshTopology) and a
+  // second tree over the boundary triangles, appended to `nodes` (its node k lives at vol_nodes + k - 1, its leaves
+  // name the triangle's tetrahedron: tri_to_tet folded in).
+  int vol_nodes{0};                  // nodes of the element tree (= nodes.size() without a boundary tree)
+  int bfs_nodes{0};                  // nodes of the boundary tree incl. its unused node 0 (0: none)
+  int bfs_height{0};
+  std::vector<int> neighbors;        // [num_elements * 4], asset-local, -1 on the boundary
   std::vector<ElemBox> block_boxes;  // ceil(num_elements / kPlaneBlock)
   int block_base{0};                 // first pool index of this asset's block boxes
 };
@@ -236,6 +245,8 @@ void BuildAssetBvh(const double* verts, const int32_t* elems, int num_elems, Hos
 struct dbh_context {
   int device{0};
   int bvh_builder{DBH_BVH_GPU_LBVH};   // measured: 24-31 % fewer box tests than the median split (profiles/README.md)
+  int soft_soft_intersector{DBH_INTERSECTOR_VOLUME_BVH};
+  DevBuf<int4> d_tet_neighbors;        // per pool tetrahedron (surface intersector only; -2: the asset has no topology)
   cudaDeviceProp prop{};
   std::vector<std::unique_ptr<HostAsset>> assets;
   // Pools: every asset's records concatenated in registration order, so pool
@@ -270,6 +281,7 @@ struct dbh_context {
   }
 
   void Place(HostAsset* a) {
+    if (a->vol_nodes == 0) a->vol_nodes = static_cast<int>(a->nodes.size());
     a->node_base = static_cast<int>(num_nodes);
     num_nodes += static_cast<long long>(a->nodes.size());
     if (a->type == DBH_COMPLIANT) {
@@ -325,6 +337,9 @@ struct dbh_context {
     CUDA_OK(grow(d_tet_idx, 4 * num_tets, &regrown));
     CUDA_OK(grow(d_node_parent, num_nodes, &regrown));
     CUDA_OK(grow(d_node_visit, num_nodes, &regrown));
+    bool any_topology = false;
+    for (const auto& a : assets) any_topology = any_topology || !a->neighbors.empty();
+    if (any_topology) CUDA_OK(grow(d_tet_neighbors, num_tets, &regrown));
     const size_t first = regrown ? 0 : uploaded_assets;
     std::vector<BvhNode> rebased;
     std::vector<Node32> rebased32;
@@ -348,6 +363,11 @@ struct dbh_context {
         std::vector<int> idx(a.tri_idx);
         for (int& i : idx) i += a.vert_base;
         CUDA_OK(cudaMemcpy(d_tet_idx.p + 4ll * a.elem_base, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (d_tet_neighbors.p) {
+          std::vector<int> nb(a.neighbors);
+          if (nb.empty()) nb.assign(4 * static_cast<size_t>(a.num_elements), -2);
+          CUDA_OK(cudaMemcpy(d_tet_neighbors.p + a.elem_base, nb.data(), nb.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
       } else {
         CUDA_OK(cudaMemcpy(d_tris.p + a.elem_base, a.tris.data(), a.tris.size() * sizeof(TriRec),
                            cudaMemcpyHostToDevice));
@@ -383,14 +403,16 @@ struct dbh_context {
       // Per-element exact boxes = the leaves' boxes.
       {
         std::vector<ElemBox> eb(a.num_elements);
-        for (const BvhNode& n : a.nodes)
-          if (n.left < 0 && n.right == -1 && &n != &a.nodes[0]) {
+        for (int k = 1; k < a.vol_nodes; ++k) {   // the element tree's leaves (not the boundary tree's)
+          const BvhNode& n = a.nodes[k];
+          if (n.left < 0 && n.right == -1) {
             ElemBox& x = eb[~n.left];
             for (int d = 0; d < 3; ++d) {
               x.c[d] = n.c[d];
               x.h[d] = n.h[d];
             }
           }
+        }
         ElemBox* dst = (a.type == DBH_COMPLIANT ? d_ebox_tet.p : d_ebox_tri.p) + a.elem_base;
         CUDA_OK(cudaMemcpy(dst, eb.data(), eb.size() * sizeof(ElemBox), cudaMemcpyHostToDevice));
       }
@@ -442,6 +464,10 @@ constexpr int kStageEvents = 11;
 struct dbh_batch {
   dbh_context* ctx{nullptr};
   cudaStream_t stream{nullptr};
+  // The surface-seeded soft-soft intersector (hydro_bfs.cuh): chosen when the batch is created, from the context.
+  bool surface_bfs{false};
+  DevBuf<unsigned long long> d_bfs_table;   // visited set: open addressing, a power of two >= 2 x cap_frontier entries
+  unsigned long long last_bfs_pairs{0}, last_bfs_waves{0};
   int num_scenes{0}, num_geoms{0}, num_pairs{0};
   std::vector<int32_t> scene_offsets;
   std::vector<int32_t> geom_asset;
@@ -563,9 +589,17 @@ struct dbh_batch {
     return m;
   }
 
+  // The visited set of the surface intersector: a power of two, at least twice the queue (= tet-tet survivor list).
+  size_t BfsTableEntries() const {
+    size_t n = 1024;
+    while (n < 2 * static_cast<size_t>(cap_frontier)) n <<= 1;
+    return n;
+  }
+
   dbh_status AllocWorkBuffers() {
     CUDA_OK(d_frontier[0].ensure(cap_frontier));
     CUDA_OK(d_frontier[1].ensure(cap_frontier));
+    if (surface_bfs && info.num_soft_soft_pairs) CUDA_OK(d_bfs_table.ensure(BfsTableEntries()));
     CUDA_OK(d_cand_tri.ensure(info.num_soft_rigid_pairs ? cap_tri : 1));
     CUDA_OK(d_cand_tet.ensure(info.num_soft_soft_pairs ? cap_tet : 1));
     CUDA_OK(d_slow.ensure(cap_slow));
@@ -622,6 +656,74 @@ dbh_status BuildBvhFor(dbh_context* ctx, const double* verts, int nv, const int3
 }  // namespace
 
 namespace {
+// The surface side of a compliant mesh for the surface-seeded soft-soft intersector (hydro_bfs.cuh): the face
+// neighbours of every tetrahedron (VolumeMeshTopology::Initialize, volume_mesh_topology.cc:13-68; face f is the one
+// opposite vertex f) by sorting the faces instead of a std::map, the boundary triangles with their tetrahedron
+// (ConvertVolumeToSurfaceMeshWithBoundaryVertices' tri_to_tet, volume_to_surface_mesh.cc:152-187), and a tree over
+// the boundary triangles built by the context's builder, appended to the asset's nodes.
+dbh_status BuildSurfaceSide(dbh_context* ctx, const double* verts, int nv, const int32_t* tets, int nt, HostAsset* a) {
+  struct Face {
+    int v[3];
+    int tet, f;
+  };
+  std::vector<Face> faces(4 * static_cast<size_t>(nt));
+  for (int e = 0; e < nt; ++e)
+    for (int f = 0; f < 4; ++f) {
+      Face& x = faces[4 * static_cast<size_t>(e) + f];
+      x.v[0] = tets[4 * e + (f + 1) % 4];
+      x.v[1] = tets[4 * e + (f + 2) % 4];
+      x.v[2] = tets[4 * e + (f + 3) % 4];
+      std::sort(x.v, x.v + 3);
+      x.tet = e;
+      x.f = f;
+    }
+  std::sort(faces.begin(), faces.end(), [](const Face& p, const Face& q) {
+    if (p.v[0] != q.v[0]) return p.v[0] < q.v[0];
+    if (p.v[1] != q.v[1]) return p.v[1] < q.v[1];
+    if (p.v[2] != q.v[2]) return p.v[2] < q.v[2];
+    return p.tet < q.tet;
+  });
+  a->neighbors.assign(4 * static_cast<size_t>(nt), -1);
+  std::vector<int32_t> boundary;   // 3 vertex indices per boundary triangle
+  std::vector<int> tri_to_tet;
+  auto same = [](const Face& p, const Face& q) { return p.v[0] == q.v[0] && p.v[1] == q.v[1] && p.v[2] == q.v[2]; };
+  for (size_t i = 0; i < faces.size();) {
+    size_t j = i + 1;
+    while (j < faces.size() && same(faces[i], faces[j])) ++j;
+    if (j - i == 1) {
+      boundary.insert(boundary.end(), faces[i].v, faces[i].v + 3);
+      tri_to_tet.push_back(faces[i].tet);
+    } else if (j - i == 2) {
+      a->neighbors[4 * static_cast<size_t>(faces[i].tet) + faces[i].f] = faces[i + 1].tet;
+      a->neighbors[4 * static_cast<size_t>(faces[i + 1].tet) + faces[i + 1].f] = faces[i].tet;
+    } else {
+      return Fail(DBH_ERR_INVALID_ARGUMENT, "a face is shared by more than two tetrahedra: not a manifold volume mesh");
+    }
+    i = j;
+  }
+  const int ntri = static_cast<int>(tri_to_tet.size());
+  if (ntri < 2) return Fail(DBH_ERR_INVALID_ARGUMENT, "the volume mesh has no boundary");
+  HostAsset tree;
+  if (dbh_status st = BuildBvhFor<3>(ctx, verts, nv, boundary.data(), ntri, &tree)) return st;
+  a->vol_nodes = static_cast<int>(a->nodes.size());
+  a->bfs_nodes = static_cast<int>(tree.nodes.size());
+  a->bfs_height = tree.height;
+  const int shift = a->vol_nodes - 1;   // the boundary tree's node k lives at vol_nodes + k - 1 (its node 0 is unused)
+  for (size_t k = 1; k < tree.nodes.size(); ++k) {
+    BvhNode n = tree.nodes[k];
+    if (n.left < 0) {
+      n.left = ~tri_to_tet[~n.left];
+    } else {
+      n.left += shift;
+      n.right += shift;
+    }
+    a->nodes.push_back(n);
+  }
+  return DBH_OK;
+}
+}  // namespace
+
+namespace {
 // k_clip's launch shapes: threads per block x resident blocks per SM, bounded by the polygon scratch in shared memory
 // (2 x 8 x 24 B per tet-tet thread, 2 x 7 x 24 B per tet-triangle thread).
 struct ClipLaunch {
@@ -663,12 +765,21 @@ dbh_status dbh_context_set_bvh_builder(dbh_context* ctx, int32_t builder) {
   });
 }
 
+dbh_status dbh_context_set_soft_soft_intersector(dbh_context* ctx, int32_t intersector) {
+  return Guarded([&]() -> dbh_status {
+  if (!ctx || (intersector != DBH_INTERSECTOR_VOLUME_BVH && intersector != DBH_INTERSECTOR_SURFACE_BFS))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "set_soft_soft_intersector: bad argument");
+  ctx->soft_soft_intersector = intersector;
+  return DBH_OK;
+  });
+}
+
 dbh_status dbh_asset_copy_bvh(dbh_context* ctx, int32_t asset, double* boxes, int32_t* left) {
   return Guarded([&]() -> dbh_status {
   if (!ctx || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
     return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_copy_bvh: bad argument");
   const HostAsset& a = *ctx->assets[asset];
-  for (size_t k = 0; k < a.nodes.size(); ++k) {
+  for (size_t k = 0; k < static_cast<size_t>(a.vol_nodes); ++k) {
     if (boxes) {
       for (int d = 0; d < 3; ++d) {
         boxes[6 * k + d] = a.nodes[k].c[d];
@@ -739,6 +850,8 @@ dbh_status dbh_register_compliant_mesh(dbh_context* ctx, int32_t nv, const doubl
       return Fail(DBH_ERR_DEGENERATE_FIELD, "tetrahedron " + std::to_string(e) + " is degenerate");
   }
   if (dbh_status st = BuildBvhFor<4>(ctx, verts, nv, tets, nt, a.get())) return st;
+  if (ctx->soft_soft_intersector == DBH_INTERSECTOR_SURFACE_BFS)
+    if (dbh_status st = BuildSurfaceSide(ctx, verts, nv, tets, nt, a.get())) return st;
   ctx->Place(a.get());
   ctx->assets.push_back(std::move(a));
   *asset_out = static_cast<int32_t>(ctx->assets.size()) - 1;
@@ -977,7 +1090,7 @@ dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* o
     out->is_half_space = 1;
     return DBH_OK;
   }
-  out->num_bvh_nodes = static_cast<int>(a.nodes.size()) - 1;
+  out->num_bvh_nodes = a.vol_nodes - 1;
   out->bvh_height = a.height;
   for (int k = 0; k < 3; ++k) {
     out->root_center[k] = a.nodes[1].c[k];
@@ -1034,6 +1147,7 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
   CUDA_OK(cudaSetDevice(ctx->device));
   auto b = std::make_unique<dbh_batch>();
   b->ctx = ctx;
+  b->surface_bfs = ctx->soft_soft_intersector == DBH_INTERSECTOR_SURFACE_BFS;
   b->num_scenes = num_scenes;
   b->num_geoms = scene_offsets[num_scenes];
   b->scene_offsets.assign(scene_offsets, scene_offsets + num_scenes + 1);
@@ -1126,17 +1240,33 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
           pr.elem_base_a = A.elem_base;
           pr.elem_base_b = B.elem_base;
           pr.root_leaf = (A.nodes[1].left < 0 ? 1 : 0) | (B.nodes[1].left < 0 ? 2 : 0);
-          if (pr.kind <= kSoftSoft && static_cast<int>(A.nodes.size()) <= kSmallMaxNodes &&
-              static_cast<int>(B.nodes.size()) <= kSmallMaxNodes) {
+          int nodes_a = A.vol_nodes, nodes_b = B.vol_nodes, height = std::max(A.height, B.height);
+          if (pr.kind == kSoftSoft && b->surface_bfs) {
+            // The surface-seeded intersector: the mid phase descends the two BOUNDARY trees (hydro_bfs.cuh); node 0 of
+            // a boundary tree is the slot before its root.
+            if (!A.bfs_nodes || !B.bfs_nodes)
+              return Fail(DBH_ERR_INVALID_ARGUMENT,
+                          "the surface intersector needs compliant meshes registered after "
+                          "dbh_context_set_soft_soft_intersector(DBH_INTERSECTOR_SURFACE_BFS)");
+            if (A.num_elements > (1 << kBfsTetBits) || B.num_elements > (1 << kBfsTetBits))
+              return Fail(DBH_ERR_INVALID_ARGUMENT, "the surface intersector handles at most 2^21 tetrahedra per mesh");
+            pr.root_a = A.node_base + A.vol_nodes;
+            pr.root_b = B.node_base + B.vol_nodes;
+            pr.root_leaf = (A.nodes[A.vol_nodes].left < 0 ? 1 : 0) | (B.nodes[B.vol_nodes].left < 0 ? 2 : 0);
+            nodes_a = A.bfs_nodes;
+            nodes_b = B.bfs_nodes;
+            height = std::max(A.bfs_height, B.bfs_height);
+          }
+          if (pr.kind <= kSoftSoft && nodes_a <= kSmallMaxNodes && nodes_b <= kSmallMaxNodes) {
             pr.small = 1;
             ++b->num_small_pairs;
-            if (static_cast<int>(A.nodes.size() + B.nodes.size()) > kSmallSplitNodes) {
+            if (nodes_a + nodes_b > kSmallSplitNodes) {
               pr.small = 2;
               ++b->num_large_small_pairs;
             }
           }
           if (pr.kind <= kSoftSoft) {
-            max_levels = std::max(max_levels, std::max(A.height, B.height) + 1);
+            max_levels = std::max(max_levels, height + 1);
             (pr.kind == kSoftRigid ? est_tri : est_tet) += 2ll * (A.num_elements + B.num_elements);
           }
         } else if (pr.kind == kSoftMeshRigidPlane || pr.kind == kSoftPlaneRigidMesh) {
@@ -1157,6 +1287,8 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
     }
   }
   b->num_pairs = static_cast<int>(b->pairs.size());
+  if (b->surface_bfs && b->num_pairs > (1 << kBfsPairBits) - 2)
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "the surface intersector handles at most 2^22 - 2 geometry pairs per batch");
   b->scene_first_pair[num_scenes] = b->num_pairs;
   b->scene_small_before[num_scenes] = b->num_small_pairs;
   b->scene_mesh_before[num_scenes] = b->info.num_soft_rigid_pairs + b->info.num_soft_soft_pairs;
@@ -1729,7 +1861,40 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         cl.fn<<<sms * cl.blocks_per_sm, cl.threads, cl.smem, st>>>(ca);
       }
       mark(5);
-      if (b->info.num_soft_soft_pairs) {
+      if (b->info.num_soft_soft_pairs && b->surface_bfs) {
+        // The surface-seeded intersector (hydro_bfs_kernels.cuh): the survivors of the descent over the boundary trees
+        // are the seeds; breadth-first waves until one appends nothing. The wave bounds live on the device; the host
+        // looks at them once per kBfsWavesPerLook waves (a wave over an empty range returns at once).
+        constexpr int kBfsWavesPerLook = 8;
+        BfsArgs ba{};
+        ba.c = ca;
+        ba.pairs = b->d_pairs.p;
+        ba.queue = b->d_frontier[1].p;
+        ba.queue_capacity = static_cast<unsigned long long>(b->cap_frontier);
+        ba.table = b->d_bfs_table.p;
+        ba.table_mask = static_cast<unsigned long long>(b->BfsTableEntries()) - 1ull;
+        ba.neighbors = ctx->d_tet_neighbors.p;
+        CUDA_OK(cudaMemsetAsync(ba.table, 0xFF, b->BfsTableEntries() * sizeof(unsigned long long), st));
+        b->last_launches += 2;
+        k_bfs_seed<<<sms * 8, 128, 0, st>>>(ba);
+        ba.first = 1;
+        k_bfs_advance<<<1, 1, 0, st>>>(ba);
+        ba.first = 0;
+        for (int look = 0;; ++look) {
+          for (int w = 0; w < kBfsWavesPerLook; ++w) {
+            b->last_launches += 2;
+            k_bfs_wave<64><<<sms * 8, 64, clip_smem_bytes(64, 8), st>>>(ba);
+            k_bfs_advance<<<1, 1, 0, st>>>(ba);
+          }
+          unsigned long long bounds[2] = {0, 0};
+          int failed = 0;
+          CUDA_OK(cudaMemcpyAsync(bounds, &b->d_counters.p->bfs_begin, sizeof(bounds), cudaMemcpyDeviceToHost, st));
+          CUDA_OK(cudaMemcpyAsync(&failed, &b->d_counters.p->error, sizeof(failed), cudaMemcpyDeviceToHost, st));
+          CUDA_OK(cudaStreamSynchronize(st));
+          if (bounds[0] >= bounds[1] || failed != 0) break;
+          if (look > 100000) return Fail(DBH_ERR_CUDA, "surface intersector: the breadth-first search does not end");
+        }
+      } else if (b->info.num_soft_soft_pairs) {
         ca.surv = b->d_frontier[1].p;
         ++b->last_launches;
         const ClipLaunch cl = ClipConfig(true);
@@ -2127,6 +2292,8 @@ dbh_status dbh_batch_stats(dbh_batch* b, dbh_stats* out) {
   out->tet_tet_full_clips = static_cast<int64_t>(c.full_clips_tet);
   out->discrete_pairs = b->discrete_done ? static_cast<int64_t>(c.discrete_pairs) : 0;
   out->fallback_pairs = b->last_query_kind == DBH_QUERY_WITH_FALLBACK ? static_cast<int64_t>(c.fallback) : 0;
+  out->bfs_pairs = static_cast<int64_t>(c.bfs_pairs);
+  out->bfs_waves = static_cast<int64_t>(c.bfs_waves);
   // BV test 64 B (two 32 B fp32 nodes; SURVEY.md §8(d) counts 128 B for the
   // reference-shaped fp64 node); tet-tri pair 260 B in; tet-tet pair 392 B in;
   // emitted n-gon 32 n + 96 (soft-rigid) / + 120 (soft-soft) out; pose 96 B per geometry.

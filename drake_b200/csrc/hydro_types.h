@@ -234,6 +234,11 @@ struct Counters {
   unsigned long long discrete_pairs;  // k_discrete: faces that give a discrete contact pair (zeroed by its launch)
   unsigned long long small_leaf_tri;  // leaf pairs k_small_pairs filtered on chip (not recording: they never reach a list)
   unsigned long long small_leaf_tet;
+  // The surface-seeded soft-soft intersector (hydro_bfs.cuh): the wave being processed is queue[bfs_begin, bfs_end) of
+  // the tet-tet survivor list (chunk-local, set by k_bfs_advance); pairs handed to the exact stage and waves run (whole
+  // query).
+  unsigned long long bfs_begin, bfs_end;
+  unsigned long long bfs_pairs, bfs_waves;
   // -- totals and per-chunk maxima of the chunk-local cursors
   unsigned long long leaf_tri_total, leaf_tet_total, polys_total, slow_total;
   unsigned long long frontier_max, leaf_tri_max, leaf_tet_max, polys_max, slow_max, undecided_max, small_items_max;

@@ -28,6 +28,7 @@ STRICT, WITH_FALLBACK = 0, 1
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_DEGENERATE_FIELD, ERR_CAPACITY = 1, 2, 3, 4, 5
 BVH_HOST_MEDIAN_SPLIT, BVH_GPU_LBVH = 0, 1
+INTERSECTOR_VOLUME_BVH, INTERSECTOR_SURFACE_BFS = 0, 1
 ERR_RIGID_RIGID, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_PLANE_NORMAL, ERR_POLYGON_SIZE = 6, 7, 8, 9, 10
 ERR_HALF_SPACE_HALF_SPACE, ERR_COMPLIANT_HALF_SPACE_COMPLIANT_MESH, ERR_REFERENCE_DEMAND, ERR_HOST = 11, 12, 13, 14
 
@@ -80,7 +81,7 @@ class Stats(C.Structure):
                 ("leaf_pairs", C.c_int64), ("cull_violations", C.c_int64), ("exceptional_clips", C.c_int64),
                 ("leaf_exact_tests", C.c_int64), ("half_space_elements", C.c_int64), ("bv_pair_tests_tet_tet", C.c_int64),
                 ("leaf_pairs_tet_tet", C.c_int64), ("discrete_pairs", C.c_int64),
-                ("fallback_pairs", C.c_int64)]
+                ("fallback_pairs", C.c_int64), ("bfs_pairs", C.c_int64), ("bfs_waves", C.c_int64)]
 
 
 _lib = None
@@ -114,6 +115,7 @@ def lib():
     L.dbh_asset_get_derived.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     L.dbh_asset_copy_bvh.argtypes = [vp, C.c_int32, _dp, _ip]
     L.dbh_context_set_bvh_builder.argtypes = [vp, C.c_int32]
+    L.dbh_context_set_soft_soft_intersector.argtypes = [vp, C.c_int32]
     L.dbh_batch_create.argtypes = [vp, C.c_int32, _ip, _ip, _lp, _bp, C.c_int32, _ip, C.POINTER(vp)]
     L.dbh_batch_destroy.argtypes = [vp]
     L.dbh_batch_set_capacity.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
@@ -361,6 +363,12 @@ class Context:
     def set_bvh_builder(self, builder: int):
         """BVH_HOST_MEDIAN_SPLIT (default) or BVH_GPU_LBVH, for the registrations that follow."""
         _check(lib().dbh_context_set_bvh_builder(self._h, builder))
+
+    def set_soft_soft_intersector(self, intersector: int):
+        """INTERSECTOR_VOLUME_BVH (default: what ComputeContactSurfaceFromCompliantVolumes runs) or
+        INTERSECTOR_SURFACE_BFS (the reference's surface-BVH + BFS overload, field_intersection.cc:254-375), for the
+        compliant-mesh registrations and the batches created afterwards."""
+        _check(lib().dbh_context_set_soft_soft_intersector(self._h, intersector))
 
     def asset_bvh(self, asset: int):
         """(boxes [n,6] = centre, half width; left [n]) with n = num_bvh_nodes + 1 (node 0 unused, 1 = root)."""

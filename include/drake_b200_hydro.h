@@ -75,6 +75,19 @@ void dbh_context_destroy(dbh_context* ctx);
  * split and build a 2 M-tetrahedron asset in half the time. */
 enum { DBH_BVH_HOST_MEDIAN_SPLIT = 0, DBH_BVH_GPU_LBVH = 1 };
 dbh_status dbh_context_set_bvh_builder(dbh_context* ctx, int32_t builder);
+/* Soft-soft intersector used by the compliant-mesh registrations and the batches created afterwards.
+ * DBH_INTERSECTOR_VOLUME_BVH (default): the two volume hierarchies are descended against each other -- what
+ * ComputeContactSurfaceFromCompliantVolumes runs (field_intersection.cc:218-252,500-520, use_surfaces = false).
+ * DBH_INTERSECTOR_SURFACE_BFS: the reference's second IntersectFields overload (field_intersection.cc:254-375,
+ * volume_mesh_topology.h): tetrahedron pairs seeded where the two boundary surfaces meet, then a breadth-first walk
+ * over the face neighbours of every pair that produced a polygon. Its work is proportional to the contact surface,
+ * not to the overlap volume (two 2 M-tetrahedron spheres: ~10^5 instead of ~10^7 pairs per scene). Same polygons
+ * whenever every component of the contact surface reaches the boundary of both bodies (the reference's own caveat,
+ * field_intersection_test.cc:296-344: a body fully inside another yields no surface). Registration additionally
+ * builds the face-neighbour table and a tree over the boundary triangles. At most 2^21 tetrahedra per mesh and
+ * 2^22 - 2 geometry pairs per batch. */
+enum { DBH_INTERSECTOR_VOLUME_BVH = 0, DBH_INTERSECTOR_SURFACE_BFS = 1 };
+dbh_status dbh_context_set_soft_soft_intersector(dbh_context* ctx, int32_t intersector);
 /* Thread-local message of the last failing call. */
 const char* dbh_last_error(void);
 /* ABI version of this library (major * 1000 + minor). */
@@ -432,6 +445,8 @@ typedef struct dbh_stats {
   int64_t discrete_pairs;          /* faces kept by dbh_batch_compute_discrete_pairs (0 if it did not run) */
   int64_t fallback_pairs;          /* WithFallback query: pairs handed to the point-pair narrow phase
                                       (dbh_batch_copy_fallback_pairs) */
+  int64_t bfs_pairs;               /* surface intersector only: tetrahedron pairs handed to the exact stage */
+  int64_t bfs_waves;               /* and the breadth-first waves that took (summed over the chunks) */
 } dbh_stats;
 dbh_status dbh_batch_stats(dbh_batch* batch, dbh_stats* out);
 

@@ -54,4 +54,4 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(engine.BatchInfo) == 10 * 4
     assert ctypes.sizeof(engine.ResultSizes) == 5 * 8 + 2 * 4
     assert ctypes.sizeof(engine.ResultBuffers) == 20 * 8
-    assert ctypes.sizeof(engine.Stats) == 10 * 8 + 12 * 8
+    assert ctypes.sizeof(engine.Stats) == 10 * 8 + 14 * 8

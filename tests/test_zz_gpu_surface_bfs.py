@@ -1,0 +1,179 @@
+"""The surface-seeded soft-soft intersector on the B200 (dbh_context_set_soft_soft_intersector(DBH_INTERSECTOR_SURFACE_BFS);
+hydro_bfs.cuh / hydro_bfs_kernels.cuh: boundary trees for the seeds, breadth-first waves over the face neighbours) against
+the oracle, through the C-ABI. It is the reference's second VolumeIntersector::IntersectFields overload
+(field_intersection.cc:254-375); the reference's own tests for it compare the emitted tetrahedron pairs with the volume
+overload's (field_intersection_test.cc:397-476) and pin the one known difference (FullyPenetrated, :296-344) -- so do
+these. Every case runs through both mid-phase implementations (the seeds come from either)."""
+import numpy as np
+import pytest
+
+from oracle import ho
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import drake_b200 as db
+    from drake_b200 import engine
+    c = db.Context(0)
+    c.set_soft_soft_intersector(engine.INTERSECTOR_SURFACE_BFS)
+    return c
+
+
+@pytest.fixture(scope="module")
+def volume_ctx():
+    import drake_b200 as db
+    return db.Context(0)
+
+
+@pytest.fixture(scope="module", autouse=True, params=["per_level", "on_chip"])
+def mid_phase(request):
+    import drake_b200 as db
+    db.SceneBatch.test_defaults = (0 if request.param == "per_level" else 1, False)
+    yield request.param
+    db.SceneBatch.test_defaults = None
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+def test_dense_spheres_against_the_oracle(ctx, rep):
+    """Two dense spheres (4096 tetrahedra each) in six scenes of one batch, random relative poses from grazing to deep:
+    every face of every surface against the oracle's volume-hierarchy run, emitted element pairs bit-exact."""
+    import drake_b200 as db
+    s = ho.VolumeMesh.sphere(1.0, 0.25, dense=True)
+    f = ho.VolumeField.sphere(s, 1.0, 1e5)
+    a = parity.register_compliant(ctx, s, f)
+    rng = np.random.default_rng(21)
+    poses = []
+    for k in range(6):
+        d = rng.normal(size=3)
+        d *= (1.1 + 0.16 * k) / np.linalg.norm(d)
+        poses += [parity.random_pose(rng, 0.05), parity.random_pose(rng, 0.05, center=d)]
+    batch = db.SceneBatch(ctx, np.arange(7) * 2, [a, a] * 6, [1, 2] * 6)
+    got = batch.compute_contact_surfaces(np.stack(poses), rep)
+    st = batch.stats()
+    nonnull = 0
+    for k in range(6):
+        want = parity.memo(("bfs_spheres", k, rep), lambda: ho.soft_soft(s, f, s, f, poses[2 * k], poses[2 * k + 1], 1, 2,
+                                                                         rep, mode=ho.MODE_TREE))
+        if want is None:
+            assert got[k] == []
+            continue
+        nonnull += 1
+        assert len(got[k]) == 1
+        parity.compare_surface(got[k][0], want)
+    assert nonnull >= 5
+    assert st["bfs_waves"] > 0 and st["bfs_pairs"] >= st["polygons"]
+    # Work proportional to the surface: far fewer pairs reach the exact stage than the volume hierarchies would offer.
+    cand = sum(len(ho.candidates(s, s, ho.invert_and_compose(poses[2 * k], poses[2 * k + 1]), ho.MODE_TREE)[0])
+               for k in range(2))
+    assert st["bfs_pairs"] < 3 * cand
+
+
+@pytest.mark.parametrize("rep", [ho.KTRIANGLE, ho.KPOLYGON])
+def test_the_reference_fixture_pad_and_octahedron(ctx, rep):
+    """field_intersection_test.cc:346-476: Box(0.06, 0.10, 0.14) with medial axis x the octahedron of Sphere(0.03),
+    X_MN = 0.03 x (and the no-intersection pose 0.2 x, :532-560), both representations, both id orders."""
+    import drake_b200 as db
+    box = ho.VolumeMesh.box_ma(0.06, 0.10, 0.14)
+    bf = ho.VolumeField.box(box, 0.06, 0.10, 0.14, 1e5)
+    octa = ho.VolumeMesh.sphere(0.03, 0.3)
+    of = ho.VolumeField.sphere(octa, 0.03, 1e5)
+    a_box, a_octa = parity.register_compliant(ctx, box, bf), parity.register_compliant(ctx, octa, of)
+    X_WM, X_WN, X_far = ho.xform(), ho.xform(None, [0.03, 0, 0]), ho.xform(None, [0.2, 0, 0])
+    batch = db.SceneBatch(ctx, [0, 2, 4, 6], [a_box, a_octa, a_octa, a_box, a_box, a_octa], [1, 2, 1, 2, 1, 2])
+    got = batch.compute_contact_surfaces(np.stack([X_WM, X_WN, X_WN, X_WM, X_WM, X_far]), rep)
+    want = ho.soft_soft(box, bf, octa, of, X_WM, X_WN, 1, 2, rep, mode=ho.MODE_BRUTE)
+    assert want is not None and len(got[0]) == 1
+    parity.compare_surface(got[0][0], want)
+    want = ho.soft_soft(octa, of, box, bf, X_WN, X_WM, 1, 2, rep, mode=ho.MODE_BRUTE)
+    assert len(got[1]) == 1
+    parity.compare_surface(got[1][0], want)
+    assert got[2] == []
+
+
+def test_fully_penetrated_body_gives_no_surface_as_in_the_reference(ctx, volume_ctx):
+    """field_intersection_test.cc:296-344: a small sphere well inside a big one, surfaces apart. The volume overload
+    reports the surface, the surface overload none; both contexts reproduce their overload."""
+    import drake_b200 as db
+    big = ho.VolumeMesh.sphere(1.0, 1.0)
+    bigf = ho.VolumeField.sphere(big, 1.0, 1e5)
+    small = ho.VolumeMesh.sphere(0.125, 0.125)
+    smallf = ho.VolumeField.sphere(small, 0.125, 1e5)
+    poses = np.stack([ho.xform(), ho.xform(None, [0.5, 0, 0])])
+    results = []
+    for c in (ctx, volume_ctx):
+        a_big, a_small = parity.register_compliant(c, big, bigf), parity.register_compliant(c, small, smallf)
+        batch = db.SceneBatch(c, [0, 2], [a_big, a_small], [1, 2])
+        results.append(batch.compute_contact_surfaces(poses, ho.KPOLYGON)[0])
+    assert results[0] == []
+    assert len(results[1]) == 1
+    parity.compare_surface(results[1][0], ho.soft_soft(big, bigf, small, smallf, poses[0], poses[1], 1, 2, ho.KPOLYGON))
+
+
+def test_mixed_scene_batch_against_the_scene_oracle(ctx):
+    """The ball / plate / floor batch (soft-rigid and soft-soft pairs side by side, 96 scenes): every surface of every
+    scene against the scene-level oracle; only the soft-soft pairs go through the surface intersector."""
+    from drake_b200 import workloads as W
+    wl = W.config3(96)
+    batch = wl.register(ctx)
+    got = batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KPOLYGON)
+    st = batch.stats()
+    osc, order = parity.oracle_scene_for(wl)
+    compared = 0
+    for sc in range(wl.num_scenes):
+        want, _ = parity.memo(("bfs_c3", sc), lambda: osc.compute(wl.poses[sc][order], ho.KPOLYGON))
+        assert [(x.id_M, x.id_N) for x in got[sc]] == [(x.id_M, x.id_N) for x in want], sc
+        for g, w in zip(got[sc], want):
+            parity.compare_surface(g, w)
+        compared += len(want)
+    assert compared >= 150 and st["bfs_waves"] > 0
+
+
+def test_multi_chunk_equals_single_chunk(ctx):
+    """The queue and the visited set are chunk-local: the same batch walked in 1, 2 and 5 chunks of scenes."""
+    import drake_b200 as db
+    s = ho.VolumeMesh.sphere(1.0, 0.5, dense=True)
+    f = ho.VolumeField.sphere(s, 1.0, 1e5)
+    a = parity.register_compliant(ctx, s, f)
+    rng = np.random.default_rng(4)
+    n = 10
+    poses = []
+    for _ in range(n):
+        d = rng.normal(size=3)
+        d *= rng.uniform(1.2, 1.9) / np.linalg.norm(d)
+        poses += [parity.random_pose(rng, 0.05), parity.random_pose(rng, 0.05, center=d)]
+    batch = db.SceneBatch(ctx, np.arange(n + 1) * 2, [a, a] * n, [1, 2] * n)
+    base = None
+    for chunks in (1, 2, 5):
+        batch.set_chunks(chunks)
+        got = batch.compute_contact_surfaces(np.stack(poses), ho.KPOLYGON)
+        digest = [[(x.id_M, x.id_N, x.num_faces, np.sort(parity.face_keys(x.elem_M, x.elem_N)).tobytes()) for x in sc]
+                  for sc in got]
+        if base is None:
+            base = digest
+            assert sum(len(sc) for sc in got) >= 8
+        assert digest == base, chunks
+
+
+def test_one_full_size_config5_scene_equals_the_volume_intersector(ctx, volume_ctx):
+    """BASELINE config 5 at its own mesh size (two 2 097 152-tetrahedron spheres): the surface intersector's result --
+    boundary trees of 32 768 triangles, tens of waves -- equals the volume intersector's face for face (which
+    tests/test_zz_gpu_fullscale.py compares with the oracle), while a small fraction of its pairs reach the exact stage."""
+    from drake_b200 import workloads as W
+    wl = W.config5(1)
+    results, stats = [], []
+    for c in (ctx, volume_ctx):
+        batch = wl.register(c)
+        results.append(batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KPOLYGON)[0])
+        stats.append(batch.stats())
+    (got,), (want,) = results
+    assert want.num_faces > 20000 and got.num_faces == want.num_faces
+    gk, wk = parity.face_keys(got.elem_M, got.elem_N), parity.face_keys(want.elem_M, want.elem_N)
+    go, wo = np.argsort(gk, kind="stable"), np.argsort(wk, kind="stable")
+    np.testing.assert_array_equal(gk[go], wk[wo])
+    np.testing.assert_array_equal(got.areas[go], want.areas[wo])            # the same arithmetic: bit for bit
+    np.testing.assert_array_equal(got.centroids[go], want.centroids[wo])
+    assert got.total_area == pytest.approx(want.total_area, rel=1e-12)
+    assert stats[0]["bfs_pairs"] * 10 < stats[1]["tet_tet_pairs"]
