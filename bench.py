@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--soft-soft", default="", choices=["", "volume", "surface"],
+                    help="soft-soft intersector (default: volume, the reference's ComputeContactSurfaces path)")
+    ap.add_argument("--chunks", type=int, default=0, help="chunks of scenes per query (default: chosen by the library)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip C1 / C2 / C4 / C5 (they run at N = 1 only)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1 only)")
     return ap.parse_args()
@@ -296,7 +299,8 @@ class Dist:
 class Leg:
     """One workload registered on this rank's GPU: set-up (untimed), the device-timed loop, the end-to-end loops."""
 
-    def __init__(self, D: Dist, config: str, scenes: int, scene0: int, scene0_b: int, rep_name: str):
+    def __init__(self, D: Dist, config: str, scenes: int, scene0: int, scene0_b: int, rep_name: str,
+                 soft_soft: str = "", chunks: int = 0):
         import drake_b200 as db
         from drake_b200 import engine
         torch = D.torch
@@ -308,7 +312,14 @@ class Leg:
         self.ctx = db.Context(D.local)
         if os.environ.get("DBH_BVH", "") == "host":   # A/B of the two BVH builders (default: the device-built LBVH)
             self.ctx.set_bvh_builder(engine.BVH_HOST_MEDIAN_SPLIT)
+        # The soft-soft intersector: "volume" (default, what the reference's ComputeContactSurfaces runs) or "surface"
+        # (its surface-BVH + BFS overload, field_intersection.cc:254-375; hydro_bfs.cuh).
+        self.soft_soft = soft_soft or os.environ.get("DBH_SOFT_SOFT", "volume")
+        if self.soft_soft == "surface":
+            self.ctx.set_soft_soft_intersector(engine.INTERSECTOR_SURFACE_BFS)
         self.batch = self.wl.register(self.ctx)
+        if chunks:
+            self.batch.set_chunks(chunks)
         poses = [np.ascontiguousarray(w.poses.reshape(-1, 12)) for w in (self.wl, wl_b)]
         self.pose_sets = [torch.from_numpy(p).to(D.dev) for p in poses]
         self.pinned_poses = [torch.from_numpy(p).pin_memory() for p in poses]
@@ -574,12 +585,13 @@ def cpu_baseline_record(config: str, scenes: int, rep: int, seconds: float):
                                "what": "the same port over Bvh<Aabb> (looser boxes under rotation)"}}
 
 
-def other_config_line(D: Dist, config: str, flush, cpu_seconds: float, with_cpu: bool):
+def other_config_line(D: Dist, config: str, flush, cpu_seconds: float, with_cpu: bool, soft_soft: str = "",
+                      chunks: int = 0):
     """One BASELINE config measured the same way as the headline, with fewer steps."""
     scenes = DEFAULT_SCENES[config]
     rep_name = default_rep(config)
     t0 = time.perf_counter()
-    leg = Leg(D, config, scenes, 0, scenes, rep_name)
+    leg = Leg(D, config, scenes, 0, scenes, rep_name, soft_soft, chunks)
     steps, warmup = (5, 3) if config in ("c4", "c5") else (20, 5)
     res = leg.device_timed(steps, warmup, flush)
     line = {"workload": leg.wl.name, "description": leg.wl.description, "scenes": scenes, "representation": rep_name,
@@ -587,7 +599,11 @@ def other_config_line(D: Dist, config: str, flush, cpu_seconds: float, with_cpu:
             "element_pairs_per_sec": res["element_pairs_per_sec"], "bv_pair_tests_per_sec": res["bv_pair_tests_per_sec"],
             "faces_per_sec": res["faces_per_sec"], "surfaces_per_step": res["surfaces_per_step"],
             "element_pairs_per_step": res["element_pairs_per_step"], "gpu_launches_per_step": res["launches_per_step"],
-            "chunks": leg.batch.num_chunks, "roofline": roofline_for(leg, res, config, True)}
+            "chunks": leg.batch.num_chunks, "roofline": roofline_for(leg, res, config, True),
+            "soft_soft_intersector": leg.soft_soft}
+    if leg.soft_soft == "surface":
+        st = leg.batch.stats()
+        line["bfs_pairs_per_step"], line["bfs_waves_per_step"] = st["bfs_pairs"], st["bfs_waves"]
     sizes = leg.batch.sizes()
     result_bytes = int(sizes.num_faces) * 150 + int(sizes.num_vertices) * 36
     if result_bytes < (3 << 30):
@@ -633,7 +649,7 @@ def main():
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=D.dev)  # > 126 MB L2
     # ---- headline: weak scaling, `scenes` per GPU.
-    leg = Leg(D, args.config, scenes, D.rank * scenes, (D.world + D.rank) * scenes, rep_name)
+    leg = Leg(D, args.config, scenes, D.rank * scenes, (D.world + D.rank) * scenes, rep_name, args.soft_soft, args.chunks)
     res = leg.device_timed(args.steps, args.warmup, flush, ClockSampler(D.local) if D.rank == 0 else None)
     e2e = None
     if not args.no_e2e:
@@ -694,6 +710,13 @@ def main():
                     other[cfg] = other_config_line(D, cfg, flush, min(6.0, args.cpu_seconds), not args.no_cpu_baseline)
                 except Exception as ex:  # a failing side config must not take the headline with it
                     other[cfg] = {"error": f"{type(ex).__name__}: {ex}"}
+            # Config 5 again through the surface-seeded soft-soft intersector (the reference's second IntersectFields
+            # overload): work proportional to the contact surface instead of the overlap volume. Fewer, larger chunks:
+            # its lists are two orders of magnitude shorter.
+            try:
+                other["c5_surface_bfs"] = other_config_line(D, "c5", flush, 0.0, False, "surface", 8)
+            except Exception as ex:
+                other["c5_surface_bfs"] = {"error": f"{type(ex).__name__}: {ex}"}
     out = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,

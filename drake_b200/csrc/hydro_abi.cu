@@ -1267,7 +1267,11 @@ dbh_status dbh_batch_create(dbh_context* ctx, int32_t num_scenes, const int32_t*
           }
           if (pr.kind <= kSoftSoft) {
             max_levels = std::max(max_levels, height + 1);
-            (pr.kind == kSoftRigid ? est_tri : est_tet) += 2ll * (A.num_elements + B.num_elements);
+            // First guess of the list lengths (they grow on demand): proportional to the meshes' volume for the
+            // hierarchy descent, to their surface for the surface-seeded intersector.
+            const bool surface = pr.kind == kSoftSoft && b->surface_bfs;
+            (pr.kind == kSoftRigid ? est_tri : est_tet) +=
+                surface ? 2ll * (nodes_a + nodes_b) : 2ll * (A.num_elements + B.num_elements);
           }
         } else if (pr.kind == kSoftMeshRigidPlane || pr.kind == kSoftPlaneRigidMesh) {
           // The one mesh of the pair: the compliant volume (a) or the rigid surface (b).

@@ -83,7 +83,7 @@ dbh_status dbh_context_set_bvh_builder(dbh_context* ctx, int32_t builder);
  * over the face neighbours of every pair that produced a polygon. Its work is proportional to the contact surface,
  * not to the overlap volume (two 2 M-tetrahedron spheres: ~10^5 instead of ~10^7 pairs per scene). Same polygons
  * whenever every component of the contact surface reaches the boundary of both bodies (the reference's own caveat,
- * field_intersection_test.cc:296-344: a body fully inside another yields no surface). Registration additionally
+ * field_intersection_test.cc:296-344: a body fully inside another may yield no surface). Registration additionally
  * builds the face-neighbour table and a tree over the boundary triangles. At most 2^21 tetrahedra per mesh and
  * 2^22 - 2 geometry pairs per batch. */
 enum { DBH_INTERSECTOR_VOLUME_BVH = 0, DBH_INTERSECTOR_SURFACE_BFS = 1 };
