@@ -673,6 +673,11 @@ def main():
     config = config_record(leg.wl, scenes, rep_name, G)
     roofline = roofline_for(leg, res, args.config, scenes == DEFAULT_SCENES[args.config] and rep_name == default_rep(args.config)) \
         if D.rank == 0 else None
+    if leg.soft_soft == "surface":   # an experiment switch: the default line (volume intersector) keeps its keys
+        st = leg.batch.stats()
+        config["soft_soft_intersector"] = "surface"
+        config["chunks"] = leg.batch.num_chunks
+        config["bfs_pairs_per_step"], config["bfs_waves_per_step"] = st["bfs_pairs"], st["bfs_waves"]
     del leg
 
     # ---- strong scaling: the config's scene count split over all GPUs (BASELINE config 3: "16384 independent scenes,
