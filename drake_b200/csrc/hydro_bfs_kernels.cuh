@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(kThreads) k_bfs_wave(BfsArgs a) {
       }
     }
     emit_polygon(a.c, P, r.buf, r.n, q, r.grad0, r.f0_Mo, r.nhat_M);   // all 32 lanes
-    // The neighbours across the intersected faces (field_intersection.cc:327-369).
+    // The neighbours across the intersected faces (field_intersection.cc:327-369). The four hash inserts of one
+    // tetrahedron's faces are issued together (first probe; a collision continues alone), and the warp's new pairs
+    // are appended with ONE atomic on the queue cursor (a single address for the whole grid: one atomic per face and
+    // warp ran the first version of this kernel at the L2's same-address rate).
     int4 nb_a = make_int4(-1, -1, -1, -1), nb_b = nb_a;
     int base_a = 0, base_b = 0;
     if (active && r.faces) {
@@ -125,24 +128,74 @@ __global__ void __launch_bounds__(kThreads) k_bfs_wave(BfsArgs a) {
       if (r.faces & 0x0Fu) nb_a = a.neighbors[q.y];
       if (r.faces & 0xF0u) nb_b = a.neighbors[q.z];
     }
+    const int local_a = q.y - base_a, local_b = q.z - base_b;
+    unsigned new_mask = 0;   // bit f: the neighbour across face f joins the queue
 #pragma unroll
-    for (int f = 0; f < 8; ++f) {
-      bool is_new = false;
-      int4 next = q;
-      next.w = 1;
-      if (active && ((r.faces >> f) & 1u)) {
+    for (int half = 0; half < 2; ++half) {
+      const int4 nb = half ? nb_b : nb_a;
+      const int nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+      unsigned long long key[4], old[4], slot[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool valid = active && ((r.faces >> (4 * half + k)) & 1u) && nbv[k] >= 0;
+        key[k] = kBfsEmpty;
+        old[k] = 0;
+        slot[k] = 0;
+        if (valid) {
+          key[k] = half ? bfs_key(q.x, local_a, nbv[k]) : bfs_key(q.x, nbv[k], local_b);
+          unsigned long long h = key[k] * 0x9E3779B97F4A7C15ull;
+          h ^= h >> 29;
+          slot[k] = h & a.table_mask;
+          old[k] = atomicCAS(a.table + slot[k], kBfsEmpty, key[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (key[k] == kBfsEmpty) continue;
+        bool is_new = old[k] == kBfsEmpty;
+        if (!is_new && old[k] != key[k]) {   // the slot holds another key: linear probing from the next one
+          unsigned long long s = slot[k];
+          bool settled = false;
+          for (int probe = 0; probe < 100000 && !settled; ++probe) {
+            s = (s + 1) & a.table_mask;
+            const unsigned long long o = atomicCAS(a.table + s, kBfsEmpty, key[k]);
+            if (o == kBfsEmpty) {
+              is_new = true;
+              settled = true;
+            } else if (o == key[k]) {
+              settled = true;
+            }
+          }
+          if (!settled) raise_error(ctr, 5 /*DBH_ERR_CAPACITY*/, 12);   // cannot happen below 50 % load
+        }
+        if (is_new) new_mask |= 1u << (4 * half + k);
+      }
+    }
+    {
+      const int lane = threadIdx.x & 31;
+      const int mine = __popc(new_mask);
+      int incl = mine;   // inclusive prefix sum over the warp
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned long long slot0 = 0;
+      if (lane == 0 && total) slot0 = atomicAdd(&ctr->surv_tet, (unsigned long long)total);
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0) + (unsigned long long)(incl - mine);
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        if (!((new_mask >> f) & 1u)) continue;
+        int4 next = q;
+        next.w = 1;
         const int4 nb = f < 4 ? nb_a : nb_b;
         const int k = f & 3;
         const int neighbor = k == 0 ? nb.x : (k == 1 ? nb.y : (k == 2 ? nb.z : nb.w));
-        if (neighbor >= 0) {
-          if (f < 4) next.y = base_a + neighbor; else next.z = base_b + neighbor;
-          is_new = bfs_visit(a, bfs_key(q.x, next.y - base_a, next.z - base_b));
-        }
-      }
-      const unsigned long long slot = warp_append_flag(&ctr->surv_tet, is_new);
-      if (is_new) {
-        if (slot < a.queue_capacity) a.queue[slot] = next;
+        if (f < 4) next.y = base_a + neighbor; else next.z = base_b + neighbor;
+        if (slot0 < a.queue_capacity) a.queue[slot0] = next;
         else raise_error(ctr, 5 /*DBH_ERR_CAPACITY*/, 1);
+        ++slot0;
       }
     }
   }

@@ -13,8 +13,12 @@ from drake_b200 import engine, workloads as W  # noqa: E402
 name, n = sys.argv[1].split(":")
 queries = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 ctx = db.Context(0)
+if os.environ.get("DBH_SOFT_SOFT", "") == "surface":   # the surface-seeded soft-soft intersector (hydro_bfs.cuh)
+    ctx.set_soft_soft_intersector(engine.INTERSECTOR_SURFACE_BFS)
 wl = W.CONFIGS[name](int(n))
 b = wl.register(ctx)
+if os.environ.get("DBH_CHUNKS"):
+    b.set_chunks(int(os.environ["DBH_CHUNKS"]))
 b.set_poses(wl.poses.reshape(-1, 12))
 b.run(wl.representation, engine.STRICT)      # grows the work lists
 b.run(wl.representation, engine.STRICT)
