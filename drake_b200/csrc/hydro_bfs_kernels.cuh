@@ -9,7 +9,7 @@
 //                  pairs appended to the queue with one atomic per warp and face.
 // The queue is the tet-tet survivor list itself (the frontier buffer the descent has released): seeds at the front,
 // every wave appends behind; its cursor is Counters::surv_tet, so the capacity protocol of the lists (overflow ->
-// DBH_ERR_CAPACITY -> dbh_batch_grow_capacity) covers it. The visited set has at least twice the queue's capacity.
+// DBH_ERR_CAPACITY -> dbh_batch_grow_capacity) covers it. The visited set has at least four times the queue's capacity.
 #pragma once
 #include "hydro_bfs.cuh"
 #include "hydro_kernels.cuh"
@@ -27,11 +27,20 @@ struct BfsArgs {
   int first;                   // k_bfs_advance: 1 = the wave of the seeds
 };
 
+// The 64-bit finaliser of MurmurHash3: the keys of one batch differ in a few bit fields only (the scenes instance the
+// same meshes), every output bit must depend on all of them.
+__device__ __forceinline__ unsigned long long bfs_hash(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
 // true: the key was not in the set (and now is).
 __device__ __forceinline__ bool bfs_visit(const BfsArgs& a, unsigned long long key) {
-  unsigned long long h = key * 0x9E3779B97F4A7C15ull;
-  h ^= h >> 29;
-  unsigned long long slot = h & a.table_mask;
+  unsigned long long slot = bfs_hash(key) & a.table_mask;
   for (int probe = 0; probe < 100000; ++probe) {
     const unsigned long long old = atomicCAS(a.table + slot, kBfsEmpty, key);
     if (old == kBfsEmpty) return true;
@@ -66,8 +75,8 @@ __global__ void k_bfs_advance(BfsArgs a) {
   }
 }
 
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads) k_bfs_wave(BfsArgs a) {
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_bfs_wave(BfsArgs a) {
   extern __shared__ double smem[];
   Counters* const ctr = a.c.counters;
   // One decision per warp (the emit and the appends below are warp-wide collectives).
@@ -143,9 +152,7 @@ __global__ void __launch_bounds__(kThreads) k_bfs_wave(BfsArgs a) {
         slot[k] = 0;
         if (valid) {
           key[k] = half ? bfs_key(q.x, local_a, nbv[k]) : bfs_key(q.x, nbv[k], local_b);
-          unsigned long long h = key[k] * 0x9E3779B97F4A7C15ull;
-          h ^= h >> 29;
-          slot[k] = h & a.table_mask;
+          slot[k] = bfs_hash(key[k]) & a.table_mask;
           old[k] = atomicCAS(a.table + slot[k], kBfsEmpty, key[k]);
         }
       }
