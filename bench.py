@@ -513,7 +513,15 @@ def roofline_for(leg: Leg, res: dict, config: str, default_size: bool):
         "exact_clip_tet_tri": (ms["clip_tet_tri"], surv_tri * (16.0 + 128 + 256 + 96) + soup * share_tri,
                                "k_clip<tri>: survivor entry + TetRec + TetAux + TriRec in, staged polygon out"),
         "exact_clip_tet_tet": (ms["clip_tet_tet"], surv_tet * (16.0 + 2 * (128 + 256)) + soup * (1 - share_tri),
-                               "k_clip<tet>: survivor entry + 2 x (TetRec + TetAux) in, staged polygon out"),
+                               "k_clip<tet>: survivor entry + 2 x (TetRec + TetAux) in, staged polygon out")
+        if leg.soft_soft != "surface" else
+        # The surface-seeded intersector: every queued pair reads its entry, two TetRec lines and the second line of
+        # two TetAux records, two neighbour records, probes the visited set once per intersected face (<= 8 x 8 B) and
+        # writes on average one new queue entry; the staged polygon leaves as in k_clip.
+                              (ms["clip_tet_tet"], surv_tet * (16.0 + 2 * (128 + 128) + 2 * 16 + 8 * 8 + 16) + soup * (1 - share_tri),
+                               "k_bfs_seed + k_bfs_wave (surface-seeded soft-soft intersector, hydro_bfs_kernels.cuh): queue "
+                               "entry + 2 x (TetRec + half a TetAux) + neighbours + visited-set probes in, staged polygon + "
+                               "new queue entries out"),
         "pack": (ms["pack"], soup + out_bytes, "k_pack: staged polygon in, final layout out"),
     }
     if st["half_space_elements"]:
@@ -599,7 +607,7 @@ def other_config_line(D: Dist, config: str, flush, cpu_seconds: float, with_cpu:
             "element_pairs_per_sec": res["element_pairs_per_sec"], "bv_pair_tests_per_sec": res["bv_pair_tests_per_sec"],
             "faces_per_sec": res["faces_per_sec"], "surfaces_per_step": res["surfaces_per_step"],
             "element_pairs_per_step": res["element_pairs_per_step"], "gpu_launches_per_step": res["launches_per_step"],
-            "chunks": leg.batch.num_chunks, "roofline": roofline_for(leg, res, config, True),
+            "chunks": leg.batch.num_chunks, "roofline": roofline_for(leg, res, config, leg.soft_soft != "surface"),
             "soft_soft_intersector": leg.soft_soft}
     if leg.soft_soft == "surface":
         st = leg.batch.stats()
@@ -716,10 +724,10 @@ def main():
                 except Exception as ex:  # a failing side config must not take the headline with it
                     other[cfg] = {"error": f"{type(ex).__name__}: {ex}"}
             # Config 5 again through the surface-seeded soft-soft intersector (the reference's second IntersectFields
-            # overload): work proportional to the contact surface instead of the overlap volume. Fewer, larger chunks:
-            # its lists are two orders of magnitude shorter.
+            # overload): work proportional to the contact surface instead of the overlap volume. One chunk: its
+            # lists are two orders of magnitude shorter, and the waves of 1024 scenes together fill the machine.
             try:
-                other["c5_surface_bfs"] = other_config_line(D, "c5", flush, 0.0, False, "surface", 8)
+                other["c5_surface_bfs"] = other_config_line(D, "c5", flush, 0.0, False, "surface", 1)
             except Exception as ex:
                 other["c5_surface_bfs"] = {"error": f"{type(ex).__name__}: {ex}"}
     out = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps,

@@ -1754,7 +1754,7 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
     // arguments of the kernels. What stays adjustable for experiments (DBH_TUNE="tgrid=2,small=0,..."): grid sizes in units
     // of the resident blocks (persistent grids beat over-subscribed ones by 5-15 %: no tail wave), the mid-phase path,
     // the stage-A ablation bits and the work-item split of the large small pairs.
-    struct Tune { int tgrid = 3, fgrid = 1, pgrid = 1, small = -1, stagea = 0, split = 1, split_at = 32, bfsocc = 0; } tune;
+    struct Tune { int tgrid = 3, fgrid = 1, pgrid = 1, small = -1, stagea = 0, split = 1, split_at = 32; } tune;
     if (const char* t = std::getenv("DBH_TUNE")) {
       const std::string str(t);
       auto get = [&](const char* key, int* v) {
@@ -1768,7 +1768,6 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
       get("stagea", &tune.stagea);    // experiments on the conservative culls (ClipArgs::tune)
       get("split_at", &tune.split_at);
       get("split", &tune.split);      // 0: large small pairs are not split into work items
-      get("bfsocc", &tune.bfsocc);    // 1: k_bfs_wave bounded to 10 resident blocks per SM (20 warps) instead of 7
     }
     ca.tune = tune.stagea;
     sm.c.tune = tune.stagea;
@@ -1888,8 +1887,9 @@ dbh_status dbh_batch_query(dbh_batch* b, int32_t representation, int32_t query_k
         for (int look = 0;; ++look) {
           for (int w = 0; w < kBfsWavesPerLook; ++w) {
             b->last_launches += 2;
-            if (tune.bfsocc) k_bfs_wave<64, 10><<<sms * 10, 64, clip_smem_bytes(64, 8), st>>>(ba);
-            else k_bfs_wave<64, 1><<<sms * 7, 64, clip_smem_bytes(64, 8), st>>>(ba);
+            // 7 resident 64-thread blocks per SM at 142 registers; bounding the kernel to 96 registers for 10 blocks
+            // changed nothing (profiles/r4d_*: 77.2 / 77.0 ms on 1024 scenes of config 5).
+            k_bfs_wave<64, 1><<<sms * 7, 64, clip_smem_bytes(64, 8), st>>>(ba);
             k_bfs_advance<<<1, 1, 0, st>>>(ba);
           }
           unsigned long long bounds[2] = {0, 0};

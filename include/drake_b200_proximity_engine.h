@@ -171,8 +171,14 @@ class ContactSurface {
 
 class ProximityEngine {
  public:
-  explicit ProximityEngine(int device_ordinal = 0) {
+  // use_surfaces: HydroelasticVolumeIntersector::IntersectCompliantVolumes' switch (field_intersection.h:299-320).
+  // false (the default, and what the reference's ComputeContactSurfaceFromCompliantVolumes passes,
+  // field_intersection.cc:511-517): compliant x compliant pairs through the two volume hierarchies; true: through the
+  // surface-seeded breadth-first intersector (dbh_context_set_soft_soft_intersector, DBH_INTERSECTOR_SURFACE_BFS).
+  explicit ProximityEngine(int device_ordinal = 0, bool use_surfaces = false) {
     Check(dbh_context_create(device_ordinal, &ctx_), "ProximityEngine");
+    if (use_surfaces)
+      Check(dbh_context_set_soft_soft_intersector(ctx_, DBH_INTERSECTOR_SURFACE_BFS), "ProximityEngine");
   }
   ~ProximityEngine() {
     if (batch_) dbh_batch_destroy(batch_);

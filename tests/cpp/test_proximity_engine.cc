@@ -119,6 +119,23 @@ int main(int argc, char** argv) {
     auto poly = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
     EXPECT(poly[0].num_faces() == 4 && poly[0].HasGradE_M() && poly[0].HasGradE_N());
   }
+  {  // compliant x compliant through the surface-seeded intersector (use_surfaces = true, field_intersection.h:299-320):
+     // the same 12 triangles / 4 polygons, the same total area as the volume intersector.
+    ProximityEngine by_volume(0), by_surface(0, /*use_surfaces=*/true);
+    for (ProximityEngine* e : {&by_volume, &by_surface}) {
+      e->AddDynamicGeometry(Sphere{R}, X_WA, 1, soft);
+      e->AddDynamicGeometry(Sphere{R}, X_WB, 2, soft);
+      e->AddDynamicGeometry(Sphere{R}, RigidTransformd::FromTranslation(0, 0.3, -0.2), 3, soft);
+    }
+    EXPECT(by_surface.ComputeContactSurfaces(HydroelasticContactRepresentation::kTriangle, {})[0].num_faces() == 12);
+    auto a = by_volume.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
+    auto b = by_surface.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
+    EXPECT(a.size() == b.size() && a.size() >= 2 && b[0].num_faces() == 4);
+    for (size_t i = 0; i < a.size(); ++i) {
+      EXPECT(a[i].id_M() == b[i].id_M() && a[i].id_N() == b[i].id_N() && a[i].num_faces() == b[i].num_faces());
+      EXPECT(std::fabs(a[i].total_area() - b[i].total_area()) <= 1e-13 * a[i].total_area());
+    }
+  }
   {  // ordering, rigid-rigid, fallback, filter, batching
     ProximityEngine e(0);
     e.AddDynamicGeometry(Sphere{R}, RigidTransformd::FromTranslation(0, 0.2, 0.2), 30, soft);
