@@ -186,3 +186,34 @@ def test_one_full_size_config5_scene_equals_the_volume_intersector(ctx, volume_c
     np.testing.assert_array_equal(got.centroids[go], want.centroids[wo])
     assert got.total_area == pytest.approx(want.total_area, rel=1e-12)
     assert stats[0]["bfs_pairs"] * 10 < stats[1]["tet_tet_pairs"]
+
+
+def test_deforming_volume_meshes_through_the_surface_intersector(ctx):
+    """Deformable x deformable (deformable_field_intersection.cc:46-66) on the surface intersector: the device refit
+    re-derives the tetrahedra and refits BOTH trees of an asset (the boundary tree's leaves take their tetrahedron's box:
+    conservative), the face-neighbour table is topological and stays. After every update the surface equals the oracle's
+    on the deformed meshes face for face."""
+    import drake_b200 as db
+    from drake_b200 import engine
+    from oracle import ho_deformable as hd
+    from tests.test_refit import _sdf_spheres, deform
+    a, sa, b, sb, off = _sdf_spheres()
+    va0, vb0 = a.verts.copy(), b.verts.copy()
+    ha = ctx.register_compliant_mesh(va0, a.tets, sa)
+    hb = ctx.register_compliant_mesh(vb0 + off, b.tets, sb)
+    batch = db.SceneBatch(ctx, [0, 2], [ha, hb], [1, 2])
+    poses = np.stack([ho.IDENTITY, ho.IDENTITY])
+    faces = 0
+    for t in (0.0, 0.5, -0.6):
+        va, vb = deform(va0, t), deform(vb0, -t) + off
+        ctx.update_vertices([ha, hb], [va, vb])
+        ma, mb = ho.VolumeMesh.from_arrays(va, a.tets), ho.VolumeMesh.from_arrays(vb, b.tets)
+        want = hd.deformable_deformable_contact(ma, sa, mb, sb)
+        assert want is not None
+        batch.set_poses(poses)
+        batch.run(ho.KPOLYGON, engine.STRICT)
+        got = batch.copy_results().surfaces()
+        assert len(got) == 1
+        parity.compare_surface(got[0], want.surface)
+        faces += got[0].num_faces
+    assert faces > 100 and batch.stats()["bfs_waves"] > 0
