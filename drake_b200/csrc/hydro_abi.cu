@@ -791,6 +791,18 @@ dbh_status dbh_asset_copy_bvh(dbh_context* ctx, int32_t asset, double* boxes, in
   return DBH_OK;
   });
 }
+dbh_status dbh_asset_copy_topology(dbh_context* ctx, int32_t asset, int32_t* neighbors, int32_t* num_boundary_triangles) {
+  return Guarded([&]() -> dbh_status {
+  if (!ctx || asset < 0 || asset >= static_cast<int>(ctx->assets.size()))
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_copy_topology: bad argument");
+  const HostAsset& a = *ctx->assets[asset];
+  if (a.neighbors.empty())
+    return Fail(DBH_ERR_INVALID_ARGUMENT, "asset_copy_topology: the asset was not registered for the surface intersector");
+  if (neighbors) std::memcpy(neighbors, a.neighbors.data(), a.neighbors.size() * sizeof(int32_t));
+  if (num_boundary_triangles) *num_boundary_triangles = a.bfs_nodes / 2;   // 2 n nodes incl. the unused node 0
+  return DBH_OK;
+  });
+}
 int32_t dbh_abi_version(void) { return 1000; }
 
 dbh_status dbh_context_create(int32_t device_ordinal, dbh_context** out) {

@@ -114,6 +114,7 @@ def lib():
     L.dbh_context_update_vertices_device.argtypes = [vp, C.c_int32, _ip, vp]
     L.dbh_asset_get_derived.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     L.dbh_asset_copy_bvh.argtypes = [vp, C.c_int32, _dp, _ip]
+    L.dbh_asset_copy_topology.argtypes = [vp, C.c_int32, _ip, _ip]
     L.dbh_context_set_bvh_builder.argtypes = [vp, C.c_int32]
     L.dbh_context_set_soft_soft_intersector.argtypes = [vp, C.c_int32]
     L.dbh_batch_create.argtypes = [vp, C.c_int32, _ip, _ip, _lp, _bp, C.c_int32, _ip, C.POINTER(vp)]
@@ -369,6 +370,14 @@ class Context:
         INTERSECTOR_SURFACE_BFS (the reference's surface-BVH + BFS overload, field_intersection.cc:254-375), for the
         compliant-mesh registrations and the batches created afterwards."""
         _check(lib().dbh_context_set_soft_soft_intersector(self._h, intersector))
+
+    def asset_topology(self, asset: int):
+        """(neighbors [num_elements, 4], number of boundary triangles) of a compliant mesh registered for the surface
+        intersector (VolumeMeshTopology, volume_mesh_topology.h)."""
+        n = self.asset_info(asset).num_elements
+        nb, ntri = np.zeros((n, 4), np.int32), C.c_int32()
+        _check(lib().dbh_asset_copy_topology(self._h, asset, _ptr(nb, _ip), C.byref(ntri)))
+        return nb, ntri.value
 
     def asset_bvh(self, asset: int):
         """(boxes [n,6] = centre, half width; left [n]) with n = num_bvh_nodes + 1 (node 0 unused, 1 = root)."""

@@ -154,6 +154,11 @@ dbh_status dbh_asset_get_info(dbh_context* ctx, int32_t asset, dbh_asset_info* o
  * (node 0 unused, node 1 root), left [(num_bvh_nodes + 1)] = index of the first of the two adjacent
  * children, or ~element for a leaf. Either may be NULL. */
 dbh_status dbh_asset_copy_bvh(dbh_context* ctx, int32_t asset, double* boxes, int32_t* left);
+/* The surface side of a compliant mesh registered under DBH_INTERSECTOR_SURFACE_BFS, for inspection:
+ * neighbors [num_elements * 4] = VolumeMeshTopology::neighbor(e, f), -1 on the boundary (volume_mesh_topology.h);
+ * *num_boundary_triangles = triangles of its surface mesh = leaves of its boundary tree. Either may be NULL.
+ * DBH_ERR_INVALID_ARGUMENT when the asset has no surface side. */
+dbh_status dbh_asset_copy_topology(dbh_context* ctx, int32_t asset, int32_t* neighbors, int32_t* num_boundary_triangles);
 /* Copies the derived per-element data back (for tests): compliant: gradients
  * [nt*3], values_at_Mo [nt], inward_normals [nt*12]; rigid: normals [nt*3].
  * Any pointer may be NULL. */

@@ -217,3 +217,49 @@ def test_deforming_volume_meshes_through_the_surface_intersector(ctx):
         parity.compare_surface(got[0], want.surface)
         faces += got[0].num_faces
     assert faces > 100 and batch.stats()["bfs_waves"] > 0
+
+
+def test_registration_builds_the_reference_topology(ctx, volume_ctx):
+    """The face-neighbour table registration builds (sorted faces) equals VolumeMeshTopology (volume_mesh_topology.cc:13-68,
+    the oracle's restatement, itself pinned by the reference's two fixtures) entry for entry -- which neighbour behind
+    which face index -- and the boundary tree has one leaf per triangle of the surface mesh."""
+    from drake_b200 import engine
+    for mesh in (ho.VolumeMesh.sphere(1.0, 0.25, dense=True), ho.VolumeMesh.box_ma(0.06, 0.10, 0.14),
+                 ho.VolumeMesh.ellipsoid(0.3, 0.2, 0.1, 0.05), ho.VolumeMesh.box_grid(0.3, 0.2, 0.1, 0.05)):
+        a = ctx.register_compliant_mesh(mesh.verts, mesh.tets, np.zeros(len(mesh.verts)) + mesh.verts[:, 0])
+        nb, ntri = ctx.asset_topology(a)
+        np.testing.assert_array_equal(nb, mesh.neighbors())
+        assert ntri == len(mesh.to_surface().tris) == int((nb < 0).sum())
+    plain = volume_ctx.register_compliant_mesh(mesh.verts, mesh.tets, mesh.verts[:, 0].copy())
+    with pytest.raises(engine.HydroError):
+        volume_ctx.asset_topology(plain)
+
+
+def test_dense_clutter_is_a_subset_of_the_volume_result(ctx, volume_ctx):
+    """Config 4 (32 soft boxes / ellipsoids dropped into a bin, bodies wholly inside others included), 48 scenes: every
+    surface the surface intersector reports is one of the volume intersector's, every one of its faces one of that
+    surface's faces with the same area bit for bit; most surfaces are complete, and none is invented."""
+    from drake_b200 import workloads as W
+    wl = W.config4(48)
+    results = []
+    for c in (ctx, volume_ctx):
+        batch = wl.register(c)
+        results.append(batch.compute_contact_surfaces(wl.poses.reshape(-1, 12), ho.KPOLYGON))
+    by_surface, by_volume = results
+    total = complete = soft_soft = 0
+    for sc in range(wl.num_scenes):
+        full = {(s.id_M, s.id_N): s for s in by_volume[sc]}
+        for s in by_surface[sc]:
+            f = full[(s.id_M, s.id_N)]            # KeyError = a surface the volume intersector does not have
+            fk, pk = parity.face_keys(f.elem_M, f.elem_N), parity.face_keys(s.elem_M, s.elem_N)
+            assert len(np.unique(pk)) == len(pk) and np.all(np.isin(pk, fk))
+            fo, po = np.argsort(fk, kind="stable"), np.argsort(pk, kind="stable")
+            sel = fo[np.searchsorted(fk[fo], pk[po])]
+            np.testing.assert_array_equal(s.areas[po], f.areas[sel])
+            complete += len(pk) == len(fk)
+            soft_soft += s.grad_eM is not None and s.grad_eN is not None
+        total += len(by_volume[sc])
+    reported = sum(len(x) for x in by_surface)
+    print(f"dense clutter: {reported} of {total} surfaces reported, {complete} complete, {soft_soft} soft-soft")
+    assert total > 1500 and soft_soft > 100
+    assert reported <= total and reported >= 0.98 * total and complete >= 0.9 * reported
