@@ -23,10 +23,12 @@
 //                                                         by atomicCAS, warp-aggregated append) for the next wave.
 //
 // The visit ORDER differs (waves instead of one FIFO) and the seeds are found through per-triangle AABBs instead of
-// 3-triangle OBB leaves, so the set of visited pairs can differ from the reference's in pairs that produce nothing;
-// the polygons are those of every pair reachable from the rim of the contact patch, as in the reference, and equal the
-// volume overload's whenever every component of the contact surface reaches the boundary of both bodies (the
-// reference's own caveat, field_intersection_test.cc:296-344).
+// 3-triangle OBB leaves, so the set of visited pairs can differ from the reference's. What holds: every polygon is one
+// the volume overload produces (same pair, same values); the polygons are those of the pairs the walk reaches from the
+// rim of the contact patch. Like the reference's overload it can miss polygons: a body wholly inside another has no
+// seed (the reference's own caveat, field_intersection_test.cc:296-344), and the walk stops at a pair that produces
+// nothing (filters, slivers), which on dense clutter of grid meshes costs a few faces on a fifth of the surfaces --
+// the oracle's faithful restatement of the reference's overload loses them too (tests/test_oracle_surface_bfs.py).
 #pragma once
 #include "hydro_clip.cuh"
 

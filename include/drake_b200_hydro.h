@@ -81,9 +81,11 @@ dbh_status dbh_context_set_bvh_builder(dbh_context* ctx, int32_t builder);
  * DBH_INTERSECTOR_SURFACE_BFS: the reference's second IntersectFields overload (field_intersection.cc:254-375,
  * volume_mesh_topology.h): tetrahedron pairs seeded where the two boundary surfaces meet, then a breadth-first walk
  * over the face neighbours of every pair that produced a polygon. Its work is proportional to the contact surface,
- * not to the overlap volume (two 2 M-tetrahedron spheres: ~10^5 instead of ~10^7 pairs per scene). Same polygons
- * whenever every component of the contact surface reaches the boundary of both bodies (the reference's own caveat,
- * field_intersection_test.cc:296-344: a body fully inside another may yield no surface). Registration additionally
+ * not to the overlap volume (two 2 M-tetrahedron spheres: ~10^5 instead of ~10^7 pairs per scene). Every polygon it
+ * reports is one the volume intersector reports (same values); like the reference's overload it can miss some: a body
+ * wholly inside another has no seed (field_intersection_test.cc:296-344), and the walk stops at a pair that produces no
+ * polygon (DESIGN.md 4e has the measured rates: none on smooth high-resolution bodies, a few faces on a fifth of the
+ * surfaces in dense clutter of grid meshes -- in the reference's own algorithm too). Registration additionally
  * builds the face-neighbour table and a tree over the boundary triangles. At most 2^21 tetrahedra per mesh and
  * 2^22 - 2 geometry pairs per batch. */
 enum { DBH_INTERSECTOR_VOLUME_BVH = 0, DBH_INTERSECTOR_SURFACE_BFS = 1 };

@@ -119,3 +119,50 @@ def test_dense_spheres_same_surface_through_both_overloads():
     # The BFS visits a small multiple of the emitting pairs, far fewer than the volume hierarchy's candidates.
     cand, _ = ho.candidates(s, s, X_MN, mode=ho.MODE_TREE)
     assert by_volume.num_faces <= len(pairs) < len(cand)
+
+
+def test_the_surface_overload_loses_polygons_in_dense_clutter():
+    """What the reference's equivalence test (field_intersection_test.cc:397-476, one pose of one fixture) does not show:
+    the breadth-first walk stops at a tetrahedron pair that produces no polygon (a gradient filter rejects it, or its
+    sliver dedupes below three vertices), so polygons that are only reachable through such a pair are lost. On a scene of
+    BASELINE config 4 (axis-aligned grid boxes and ellipsoids in a bin) the faithful restatement emits a strict subset
+    of the volume overload's tetrahedron pairs for some body pairs -- never a pair the volume overload does not emit --
+    and about 0.3 % less area. The device intersector shares the property
+    (tests/test_zz_gpu_surface_bfs.py::test_dense_clutter_is_a_subset_of_the_volume_result)."""
+    from drake_b200 import workloads as W
+    from tests import parity
+    wl = W.config4(1)
+    osc, order = parity.oracle_scene_for(wl)
+    poses = wl.poses[0]
+    want, _ = osc.compute(poses[order], ho.KPOLYGON)
+    ids = list(wl.geom_id)
+    meshidx = wl.per_scene_mesh[0] if wl.per_scene_mesh is not None else wl.geom_mesh
+    cache = {}
+
+    def oracle_mesh(mi):
+        if mi not in cache:
+            v, e, p = wl.meshes[mi].arrays()
+            m = ho.VolumeMesh.from_arrays(v, e)
+            cache[mi] = (m, ho.VolumeField.from_values(m, p))
+        return cache[mi]
+
+    soft_soft = incomplete = 0
+    area_volume = area_surface = 0.0
+    for s in want:
+        if s.grad_eM is None or s.grad_eN is None:
+            continue
+        gM, gN = ids.index(s.id_M), ids.index(s.id_N)
+        (mM, fM), (mN, fN) = oracle_mesh(meshidx[gM]), oracle_mesh(meshidx[gN])
+        pairs = ho.surface_bfs_pairs(mM, fM, mN, fN, ho.invert_and_compose(poses[gM], poses[gN]))
+        b = ho.soft_soft(mM, fM, mN, fN, poses[gM], poses[gN], s.id_M, s.id_N, ho.KPOLYGON, pairs=pairs) if len(pairs) else None
+        soft_soft += 1
+        area_volume += s.total_area
+        if b is None:
+            incomplete += 1
+            continue
+        area_surface += b.total_area
+        full, part = set(_multiset(s)), _multiset(b)
+        assert len(set(part)) == len(part) and set(part) <= full       # nothing invented
+        incomplete += len(part) < len(full)
+    assert soft_soft >= 20 and incomplete >= 1
+    assert 0.99 * area_volume < area_surface < area_volume
