@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "drake_b200", "lib", "libdrake_b200_hydro.so")
-HOT = ["k_small_pairs", "k_leaf_undecided", "k_clip", "k_pack", "k_traverse", "k_filter", "k_plane", "k_surface", "k_wrench", "k_discrete", "k_pairs"]
+HOT = ["k_small_pairs", "k_leaf_undecided", "k_bfs", "k_clip", "k_pack", "k_traverse", "k_filter", "k_plane", "k_surface", "k_wrench", "k_discrete", "k_pairs"]
 CLASSES = [("DFMA", r"^DFMA"), ("div/sqrt seeds (MUFU.RCP64H/RSQ64H)", r"^MUFU\.(RCP64H|RSQ64H)"), ("DMUL", r"^DMUL"), ("DADD", r"^DADD"),
            ("DSETP/other fp64", r"^(DSETP|DMNMX|F2F\.F64|I2F\.F64)"),
            ("FFMA", r"^FFMA"), ("FMUL/FADD", r"^(FMUL|FADD)"), ("FSETP/FMNMX", r"^(FSETP|FMNMX)"),
