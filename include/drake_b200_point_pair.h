@@ -8,7 +8,8 @@
 //     through point_distance::DistanceToPoint (distance_to_point_callback.cc:15-77,160-178,406-482);
 //   * FCL's general GJK / EPA collide() for everything else (:145-195) -- an external dependency of the reference
 //     (tools/workspace/fcl_internal), not restated here.
-// This header restates the first half for the shapes the adapter registers (Sphere, Box, HalfSpace). The batched
+// This header restates the first half: Sphere, Box, HalfSpace, Cylinder, Capsule -- every shape the reference has a
+// closed form for (it sends Ellipsoid and Convex to FCL, :273-278). The batched
 // query (dbh_batch_query, DBH_QUERY_WITH_FALLBACK) reports WHICH pairs need it (dbh_batch_copy_fallback_pairs): a
 // handful per scene, so the arithmetic stays on the host next to the shape descriptions the C-ABI never sees.
 // No Eigen: 3-vectors are std::array<double, 3>; operation order follows the reference.
@@ -76,60 +77,123 @@ inline SignedDistanceToPoint DistanceToHalfSpace(const Pose& X_WG, const Vec3& p
   return {{p_GQ[0], p_GQ[1], 0.0}, p_GQ[2], Rotate(X_WG, {0.0, 0.0, 1.0})};
 }
 
-// DistanceToPoint::operator()(Box) = ComputeDistanceToBox (distance_to_point_callback.cc:160-178,384-482); size = full
-// side lengths.
-inline SignedDistanceToPoint DistanceToBox(const Vec3& size, const Pose& X_WG, const Vec3& p_WQ) {
-  const Vec3 p_GQ = ApplyInverse(X_WG, p_WQ);
-  const Vec3 h{size[0] / 2.0, size[1] / 2.0, size[2] / 2.0};
+// DistanceToPoint::ComputeDistanceToBox<dim> (distance_to_point_callback.cc:406-482) with ExtremalAxis (:387-403): the
+// nearest point on the boundary of the box [-h, h]^dim and the gradient, both in the box frame, for a query point p.
+// Three regions: outside (clamp; gradient along p - N), within a relative tolerance of the boundary (normalised sum of
+// the signed axes it touches), inside (the nearest face; ties go to +x, -x, +y, -y, ...).
+template <int dim>
+inline void ComputeDistanceToBox(const std::array<double, dim>& h, const std::array<double, dim>& p,
+                                 std::array<double, dim>* p_GN, std::array<double, dim>* grad_G) {
   enum Location { kInside, kBoundary, kOutside };
-  Location location[3];
-  Vec3 p_GC;
-  for (int i = 0; i < 3; ++i) {
+  Location location[dim];
+  std::array<double, dim> c{};
+  bool any_outside = false, any_boundary = false;
+  for (int i = 0; i < dim; ++i) {
     const double tolerance = RelativeTolerance(h[i]);
-    if (std::abs(p_GQ[i]) > h[i] + tolerance) {
+    if (std::abs(p[i]) > h[i] + tolerance) {
       location[i] = kOutside;
-      p_GC[i] = Sign(p_GQ[i]) * h[i];
-    } else if (std::abs(p_GQ[i]) >= h[i] - tolerance) {
+      c[i] = Sign(p[i]) * h[i];
+      any_outside = true;
+    } else if (std::abs(p[i]) >= h[i] - tolerance) {
       location[i] = kBoundary;
-      p_GC[i] = Sign(p_GQ[i]) * h[i];
+      c[i] = Sign(p[i]) * h[i];
+      any_boundary = true;
     } else {
       location[i] = kInside;
-      p_GC[i] = p_GQ[i];
+      c[i] = p[i];
     }
   }
-  Vec3 p_GN = p_GC;
-  Vec3 grad_G{0.0, 0.0, 0.0};
-  const bool any_outside = location[0] == kOutside || location[1] == kOutside || location[2] == kOutside;
-  const bool any_boundary = location[0] == kBoundary || location[1] == kBoundary || location[2] == kBoundary;
+  *p_GN = c;
+  grad_G->fill(0.0);
   if (any_outside) {
-    const Vec3 p_NQ{p_GQ[0] - p_GN[0], p_GQ[1] - p_GN[1], p_GQ[2] - p_GN[2]};
-    const double distance = Norm(p_NQ);
-    grad_G = {p_NQ[0] / distance, p_NQ[1] / distance, p_NQ[2] / distance};
+    double n2 = 0;
+    for (int i = 0; i < dim; ++i) n2 += (p[i] - c[i]) * (p[i] - c[i]);
+    const double distance = std::sqrt(n2);
+    for (int i = 0; i < dim; ++i) (*grad_G)[i] = (p[i] - c[i]) / distance;
   } else if (any_boundary) {
-    for (int i = 0; i < 3; ++i)
-      if (location[i] == kBoundary) grad_G[i] = Sign(p_GC[i]);
-    const double n = Norm(grad_G);
-    grad_G = {grad_G[0] / n, grad_G[1] / n, grad_G[2] / n};
+    double n2 = 0;
+    for (int i = 0; i < dim; ++i) {
+      if (location[i] == kBoundary) (*grad_G)[i] = Sign(c[i]);
+      n2 += (*grad_G)[i] * (*grad_G)[i];
+    }
+    const double n = std::sqrt(n2);
+    for (int i = 0; i < dim; ++i) (*grad_G)[i] /= n;
   } else {
-    // Inside: project onto the nearest face; ties go to +x, -x, +y, -y, +z, -z (ExtremalAxis, :384-400).
     double min_dist = std::numeric_limits<double>::infinity();
     int axis = -1;
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < dim; ++i)
       for (const double bound : {h[i], -h[i]}) {
-        const double dist = std::abs(bound - p_GQ[i]);
+        const double dist = std::abs(bound - p[i]);
         if (dist < min_dist) {
           min_dist = dist;
           axis = i;
         }
       }
-    const double sign = Sign(p_GQ[axis]);
-    p_GN[axis] = sign * h[axis];
-    grad_G[axis] = sign;
+    const double sign = Sign(p[axis]);
+    (*p_GN)[axis] = sign * h[axis];
+    (*grad_G)[axis] = sign;
   }
+}
+
+// DistanceToPoint::operator()(Box) (distance_to_point_callback.cc:160-178); size = full side lengths.
+inline SignedDistanceToPoint DistanceToBox(const Vec3& size, const Pose& X_WG, const Vec3& p_WQ) {
+  const Vec3 p_GQ = ApplyInverse(X_WG, p_WQ);
+  Vec3 p_GN, grad_G;
+  ComputeDistanceToBox<3>({size[0] / 2.0, size[1] / 2.0, size[2] / 2.0}, p_GQ, &p_GN, &grad_G);
   const Vec3 grad_W = Rotate(X_WG, grad_G);
   const Vec3 p_WN = Apply(X_WG, p_GN);
   const double distance = Dot(grad_W, {p_WQ[0] - p_WN[0], p_WQ[1] - p_WN[1], p_WQ[2] - p_WN[2]});
   return {p_GN, distance, grad_W};
+}
+
+// DistanceToPoint::operator()(Cylinder) (distance_to_point_callback.cc:194-288): the cylinder (axis z, radius r, length
+// L) becomes the 2-D box [-r, r] x [-L/2, L/2] of its cross section through the query point and the axis; a point within
+// a relative tolerance of the axis takes the cross section through +x.
+inline SignedDistanceToPoint DistanceToCylinder(double radius, double length, const Pose& X_WG, const Vec3& p_WQ) {
+  const Vec3 p_GQ = ApplyInverse(X_WG, p_WQ);
+  const double r_Q = std::sqrt(p_GQ[0] * p_GQ[0] + p_GQ[1] * p_GQ[1]);
+  const bool near_center_line = r_Q < RelativeTolerance(radius);
+  const std::array<double, 2> v_GBr = near_center_line ? std::array<double, 2>{1.0, 0.0}
+                                                       : std::array<double, 2>{p_GQ[0] / r_Q, p_GQ[1] / r_Q};
+  std::array<double, 2> p_BN, grad_B;
+  ComputeDistanceToBox<2>({radius, length / 2.0}, {r_Q, p_GQ[2]}, &p_BN, &grad_B);
+  const Vec3 p_GN{p_BN[0] * v_GBr[0], p_BN[0] * v_GBr[1], p_BN[1]};
+  const Vec3 grad_G{grad_B[0] * v_GBr[0], grad_B[0] * v_GBr[1], grad_B[1]};
+  const Vec3 grad_W = Rotate(X_WG, grad_G);
+  const Vec3 p_WN = Apply(X_WG, p_GN);
+  const double distance = Dot(grad_W, {p_WQ[0] - p_WN[0], p_WQ[1] - p_WN[1], p_WQ[2] - p_WN[2]});
+  return {p_GN, distance, grad_W};
+}
+
+// SphereDistanceInSphereFrame (distance_to_point_callback.cc:15-58): nearest point, distance and gradient of a sphere
+// centred on the origin of the frame the query point is given in.
+inline void SphereDistanceInSphereFrame(double radius, const Vec3& p_SQ, Vec3* p_SN, double* distance, Vec3* grad_S) {
+  const double dist = Norm(p_SQ);
+  const double tolerance = RelativeTolerance(radius);
+  *grad_S = dist > tolerance ? Vec3{p_SQ[0] / dist, p_SQ[1] / dist, p_SQ[2] / dist} : Vec3{1.0, 0.0, 0.0};
+  *p_SN = {radius * (*grad_S)[0], radius * (*grad_S)[1], radius * (*grad_S)[2]};
+  *distance = Dot({p_SQ[0] - (*p_SN)[0], p_SQ[1] - (*p_SN)[1], p_SQ[2] - (*p_SN)[2]}, *grad_S);
+}
+
+// ComputeDistanceToPrimitive(Capsule) (distance_to_point_callback.cc:79-160): axis z, radius r, the spine of length L.
+// Beyond the spine's ends the nearest cap is a sphere; beside the spine the problem is that of the query point's
+// projection onto the x-y plane against a sphere at the origin, shifted back along z.
+inline SignedDistanceToPoint DistanceToCapsule(double radius, double length, const Pose& X_WG, const Vec3& p_WQ) {
+  const double half_length = length / 2;
+  const Vec3 p_GQ = ApplyInverse(X_WG, p_WQ);
+  Vec3 p_GN, grad_G;
+  double distance;
+  if (p_GQ[2] >= half_length || p_GQ[2] <= -half_length) {
+    const Vec3 p_GS{0.0, 0.0, p_GQ[2] >= half_length ? half_length : -half_length};
+    Vec3 p_SN;
+    SphereDistanceInSphereFrame(radius, {p_GQ[0] - p_GS[0], p_GQ[1] - p_GS[1], p_GQ[2] - p_GS[2]}, &p_SN, &distance, &grad_G);
+    p_GN = {p_GS[0] + p_SN[0], p_GS[1] + p_SN[1], p_GS[2] + p_SN[2]};
+  } else {
+    Vec3 p_GM;
+    SphereDistanceInSphereFrame(radius, {p_GQ[0], p_GQ[1], 0.0}, &p_GM, &distance, &grad_G);
+    p_GN = {p_GM[0], p_GM[1], p_GQ[2]};
+  }
+  return {p_GN, distance, Rotate(X_WG, grad_G)};
 }
 
 struct Result {  // PenetrationAsPointPair<double> without the ids

@@ -67,6 +67,15 @@ struct Ellipsoid {
   double a, b, c;
 };
 struct HalfSpace {};  // z <= 0 of the geometry frame (shape_specification.h)
+// Cylinder and Capsule (axis z, shape_specification.h): geometries WITHOUT a hydroelastic representation here (their
+// volume-mesh generators, make_cylinder_mesh / make_capsule_mesh, are outside the path) -- they take part in
+// ComputeContactSurfacesWithFallback's point pairs against a Sphere (Drake's closed forms, drake_b200_point_pair.h).
+struct Cylinder {
+  double radius, length;
+};
+struct Capsule {
+  double radius, length;
+};
 struct VolumeMeshShape {  // VolumeMesh<double> + per-vertex pressure
   std::vector<double> vertices;  // [nv*3]
   std::vector<int32_t> tetrahedra;  // [nt*4]
@@ -76,7 +85,7 @@ struct SurfaceMeshShape {  // TriangleSurfaceMesh<double>
   std::vector<double> vertices;
   std::vector<int32_t> triangles;
 };
-using Shape = std::variant<Sphere, Box, Ellipsoid, VolumeMeshShape, SurfaceMeshShape, HalfSpace>;
+using Shape = std::variant<Sphere, Box, Ellipsoid, VolumeMeshShape, SurfaceMeshShape, HalfSpace, Cylinder, Capsule>;
 
 enum class HydroelasticType { kUndefined = DBH_UNDEFINED, kRigid = DBH_RIGID, kCompliant = DBH_COMPLIANT };
 enum class HydroelasticContactRepresentation { kTriangle = DBH_TRIANGLE, kPolygon = DBH_POLYGON };
@@ -415,6 +424,10 @@ class ProximityEngine {
       d = pp::DistanceToBox({bx->width, bx->depth, bx->height}, X_WO, p_WSo);
     } else if (std::holds_alternative<HalfSpace>(shapes_[go])) {
       d = pp::DistanceToHalfSpace(X_WO, p_WSo);
+    } else if (const auto* cy = std::get_if<Cylinder>(&shapes_[go])) {
+      d = pp::DistanceToCylinder(cy->radius, cy->length, X_WO, p_WSo);
+    } else if (const auto* ca = std::get_if<Capsule>(&shapes_[go])) {
+      d = pp::DistanceToCapsule(ca->radius, ca->length, X_WO, p_WSo);
     } else {
       if (skip_unsupported_point_pairs_) return std::nullopt;
       throw std::logic_error("ComputeContactSurfacesWithFallback: the point-pair fallback between a Sphere and the shape of "
@@ -431,6 +444,9 @@ class ProximityEngine {
     last_elements_.clear();
     last_vertices_per_element_ = 0;
     if (p.compliance_type == HydroelasticType::kUndefined) return -1;
+    if (std::holds_alternative<Cylinder>(shape) || std::holds_alternative<Capsule>(shape))
+      throw std::logic_error("a Cylinder or Capsule has no hydroelastic representation in this back end (register it with "
+                             "HydroelasticType::kUndefined: it then takes part in the point-pair fallback)");
     const bool soft = p.compliance_type == HydroelasticType::kCompliant;
     int32_t asset = -1;
     struct MeshHandle {

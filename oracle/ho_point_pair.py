@@ -1,7 +1,7 @@
 """Oracle (test infrastructure): Drake's closed-form point-pair narrow phase for pairs with a sphere, restated in
 numpy -- penetration_as_point_pair_callback.cc:92-118,203-300 (SphereShapePenetration, ComputeNarrowPhasePenetration)
-over point_distance::DistanceToPoint for Sphere, Box and HalfSpace (distance_to_point_callback.cc:15-77,160-178,
-384-482). Pinned by the reference's own test scenes (penetration_as_point_pair_callback_test.cc:119-176,196-230,
+over point_distance::DistanceToPoint for Sphere, Box, HalfSpace, Cylinder and Capsule
+(distance_to_point_callback.cc:15-160,160-288,384-482). Pinned by the reference's own test scenes (penetration_as_point_pair_callback_test.cc:119-176,196-230,
 258-310,430-462), restated in tests/test_point_pair_cpu.py. The general (non-sphere) fallback is FCL's GJK / EPA, an
 external dependency of the reference: not restated.
 
@@ -87,8 +87,85 @@ def distance_to_box(size, X_WG, p_WQ):
     return p_GN, float(grad_W @ (p_WQ - p_WN)), grad_W
 
 
+def _distance_to_box_nd(h, p):
+    """ComputeDistanceToBox<dim> (:406-482) + ExtremalAxis (:387-403) in the box frame: (p_GN, grad_G)."""
+    h, p = np.asarray(h, float), np.asarray(p, float)
+    n = len(h)
+    loc, c = [], np.zeros(n)
+    for i in range(n):
+        tol = relative_tolerance(h[i])
+        if abs(p[i]) > h[i] + tol:
+            loc.append("out")
+            c[i] = sign(p[i]) * h[i]
+        elif abs(p[i]) >= h[i] - tol:
+            loc.append("bnd")
+            c[i] = sign(p[i]) * h[i]
+        else:
+            loc.append("in")
+            c[i] = p[i]
+    p_GN, grad = c.copy(), np.zeros(n)
+    if "out" in loc:
+        d = p - c
+        grad = d / math.sqrt(float(d @ d))
+    elif "bnd" in loc:
+        for i in range(n):
+            if loc[i] == "bnd":
+                grad[i] = sign(c[i])
+        grad = grad / math.sqrt(float(grad @ grad))
+    else:
+        best, axis = math.inf, -1
+        for i in range(n):
+            for bound in (h[i], -h[i]):
+                dist = abs(bound - p[i])
+                if dist < best:
+                    best, axis = dist, i
+        s = sign(p[axis])
+        p_GN[axis] = s * h[axis]
+        grad[axis] = s
+    return p_GN, grad
+
+
+def distance_to_cylinder(radius, length, X_WG, p_WQ):
+    """DistanceToPoint::operator()(Cylinder) (:194-288): the 2-D box [-r, r] x [-L/2, L/2] of the cross section through
+    the query point and the axis (+x for a point on the axis)."""
+    p_WQ = np.asarray(p_WQ, float)
+    p_GQ = _R(X_WG).T @ (p_WQ - _p(X_WG))
+    r_Q = math.sqrt(p_GQ[0] * p_GQ[0] + p_GQ[1] * p_GQ[1])
+    v = np.array([1.0, 0.0]) if r_Q < relative_tolerance(radius) else np.array([p_GQ[0], p_GQ[1]]) / r_Q
+    p_BN, grad_B = _distance_to_box_nd([radius, length / 2.0], [r_Q, p_GQ[2]])
+    p_GN = np.array([p_BN[0] * v[0], p_BN[0] * v[1], p_BN[1]])
+    grad_G = np.array([grad_B[0] * v[0], grad_B[0] * v[1], grad_B[1]])
+    grad_W = _R(X_WG) @ grad_G
+    p_WN = _R(X_WG) @ p_GN + _p(X_WG)
+    return p_GN, float(grad_W @ (p_WQ - p_WN)), grad_W
+
+
+def _sphere_in_its_frame(radius, p_SQ):
+    """SphereDistanceInSphereFrame (:15-58)."""
+    dist = math.sqrt(float(p_SQ @ p_SQ))
+    grad = p_SQ / dist if dist > relative_tolerance(radius) else np.array([1.0, 0.0, 0.0])
+    p_SN = radius * grad
+    return p_SN, float((p_SQ - p_SN) @ grad), grad
+
+
+def distance_to_capsule(radius, length, X_WG, p_WQ):
+    """ComputeDistanceToPrimitive(Capsule) (:79-160): a cap sphere beyond the spine's ends, else the projection onto the
+    x-y plane against a sphere at the origin, shifted back along z."""
+    half = length / 2
+    p_GQ = _R(X_WG).T @ (np.asarray(p_WQ, float) - _p(X_WG))
+    if p_GQ[2] >= half or p_GQ[2] <= -half:
+        p_GS = np.array([0.0, 0.0, half if p_GQ[2] >= half else -half])
+        p_SN, distance, grad_G = _sphere_in_its_frame(radius, p_GQ - p_GS)
+        p_GN = p_GS + p_SN
+    else:
+        p_GM, distance, grad_G = _sphere_in_its_frame(radius, np.array([p_GQ[0], p_GQ[1], 0.0]))
+        p_GN = np.array([p_GM[0], p_GM[1], p_GQ[2]])
+    return p_GN, distance, _R(X_WG) @ grad_G
+
+
 def point_pair(shape_A, X_WA, shape_B, X_WB):
-    """ComputeNarrowPhasePenetration for shapes given as ('sphere', r) | ('box', (x, y, z)) | ('half_space',); A is the
+    """ComputeNarrowPhasePenetration for shapes given as ('sphere', r) | ('box', (x, y, z)) | ('half_space',) |
+    ('cylinder', r, L) | ('capsule', r, L); A is the
     geometry with the smaller id. Returns None (no penetration) or dict(p_WCa, p_WCb, nhat_BA_W, depth). Raises for pairs
     without a sphere (the reference calls FCL there)."""
     a_is_sphere, b_is_sphere = shape_A[0] == "sphere", shape_B[0] == "sphere"
@@ -102,6 +179,10 @@ def point_pair(shape_A, X_WA, shape_B, X_WB):
         p_GN, distance, grad_W = distance_to_box(O[1], X_WO, p_WSo)
     elif O[0] == "half_space":
         p_GN, distance, grad_W = distance_to_half_space(X_WO, p_WSo)
+    elif O[0] == "cylinder":
+        p_GN, distance, grad_W = distance_to_cylinder(O[1], O[2], X_WO, p_WSo)
+    elif O[0] == "capsule":
+        p_GN, distance, grad_W = distance_to_capsule(O[1], O[2], X_WO, p_WSo)
     else:
         raise NotImplementedError(O[0])
     r = S[1]

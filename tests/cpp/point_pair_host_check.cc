@@ -1,5 +1,5 @@
 // Host check of include/drake_b200_point_pair.h (no GPU, no library): reads pairs from stdin, one per line
-//   <kindA> <paramsA...> <poseA x12> <kindB> <paramsB...> <poseB x12>       kind: s r | b x y z | h
+//   <kindA> <paramsA...> <poseA x12> <kindB> <paramsB...> <poseB x12>       kind: s r | b x y z | h | c r L | k r L
 // and prints `none` or `depth p_WCa(3) p_WCb(3) nhat(3)` with 17 significant digits, the way
 // ComputeNarrowPhasePenetration (penetration_as_point_pair_callback.cc:203-300) orders its operands.
 #include <cstdio>
@@ -23,6 +23,7 @@ static bool Read(Geo* g) {
   g->kind = k[0];
   if (g->kind == 's') std::cin >> g->r;
   if (g->kind == 'b') std::cin >> g->size[0] >> g->size[1] >> g->size[2];
+  if (g->kind == 'c' || g->kind == 'k') std::cin >> g->size[0] >> g->size[1];   // cylinder / capsule: radius, length
   for (double& v : g->X) std::cin >> v;
   return true;
 }
@@ -37,6 +38,8 @@ int main() {
     SignedDistanceToPoint d;
     if (o.kind == 's') d = DistanceToSphere(o.r, o.X, p_WSo);
     else if (o.kind == 'b') d = DistanceToBox(o.size, o.X, p_WSo);
+    else if (o.kind == 'c') d = DistanceToCylinder(o.size[0], o.size[1], o.X, p_WSo);
+    else if (o.kind == 'k') d = DistanceToCapsule(o.size[0], o.size[1], o.X, p_WSo);
     else d = DistanceToHalfSpace(o.X, p_WSo);
     auto res = SphereShapePenetration(s.r, s.X, o.X, d);
     if (!res) {

@@ -61,6 +61,32 @@ static int MarginCase(char** argv) {
     EXPECT(std::fabs(poly[0].total_area() - area) <= 1e-10 * area);
     EXPECT(std::fabs(got_p - psum) <= 1e-10 * std::fabs(psum));
   }
+  {  // A rigid sphere against a Cylinder and a Capsule without hydroelastic representation: Drake's closed forms
+     // (penetration_as_point_pair_callback.cc:92-118, distance_to_point_callback.cc:79-160,194-288) fill point_pairs.
+    ProximityProperties none;   // HydroelasticType::kUndefined
+    ProximityEngine e(0);
+    e.AddDynamicGeometry(Sphere{R}, RigidTransformd::Identity(), 1, rigid);
+    e.AddDynamicGeometry(Cylinder{0.1, 0.4}, RigidTransformd::FromTranslation(0.3, 0, 0), 2, none);
+    e.AddDynamicGeometry(Capsule{0.1, 0.4}, RigidTransformd::FromTranslation(0, 0, 0.5), 3, none);
+    e.ExcludeCollisionsBetween(2, 3);   // cylinder x capsule would need FCL
+    std::vector<ContactSurface> surfaces;
+    std::vector<PenetrationAsPointPair> pairs;
+    e.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    EXPECT(surfaces.empty() && pairs.size() == 2);
+    EXPECT(pairs[0].id_A == 1 && pairs[0].id_B == 2 && pairs[1].id_A == 1 && pairs[1].id_B == 3);
+    EXPECT(std::fabs(pairs[0].depth - 0.05) < 1e-15 && std::fabs(pairs[0].nhat_BA_W[0] + 1.0) < 1e-15);
+    EXPECT(std::fabs(pairs[0].p_WCa[0] - R) < 1e-15 && std::fabs(pairs[0].p_WCb[0] - 0.2) < 1e-15);
+    EXPECT(std::fabs(pairs[1].depth - 0.05) < 1e-15 && std::fabs(pairs[1].nhat_BA_W[2] + 1.0) < 1e-15);
+    EXPECT(std::fabs(pairs[1].p_WCa[2] - R) < 1e-15 && std::fabs(pairs[1].p_WCb[2] - 0.2) < 1e-15);
+    bool threw = false;
+    try {
+      ProximityEngine bad(0);
+      bad.AddDynamicGeometry(Cylinder{0.1, 0.4}, RigidTransformd::Identity(), 1, rigid);
+    } catch (const std::logic_error&) {
+      threw = true;
+    }
+    EXPECT(threw);
+  }
   std::printf("ok\n");
   return 0;
 }
