@@ -28,7 +28,7 @@
 // rim of the contact patch. Like the reference's overload it can miss polygons: a body wholly inside another has no
 // seed (the reference's own caveat, field_intersection_test.cc:296-344), and the walk stops at a pair that produces
 // nothing (filters, slivers), which on dense clutter of grid meshes costs a few faces on a fifth of the surfaces --
-// the oracle's faithful restatement of the reference's overload loses them too (tests/test_oracle_surface_bfs.py).
+// a faithful CPU restatement of the reference's overload loses them too (tests/test_zz_gpu_surface_bfs.py).
 #pragma once
 #include "hydro_clip.cuh"
 
