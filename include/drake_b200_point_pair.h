@@ -6,10 +6,17 @@
 //   * Drake's own closed forms, used whenever one of the two shapes is a sphere
 //     (penetration_as_point_pair_callback.cc:92-118,203-300: sphere x {sphere, box, half space, cylinder, capsule})
 //     through point_distance::DistanceToPoint (distance_to_point_callback.cc:15-77,160-178,406-482);
-//   * FCL's general GJK / EPA collide() for everything else (:145-195) -- an external dependency of the reference
-//     (tools/workspace/fcl_internal), not restated here.
-// This header restates the first half: Sphere, Box, HalfSpace, Cylinder, Capsule -- every shape the reference has a
-// closed form for (it sends Ellipsoid and Convex to FCL, :273-278). The batched
+//   * FCL's collide() for everything else (:145-207) -- an external dependency of the reference, absent from its tree
+//     (tools/workspace/fcl_internal/repository.bzl: RobotLocomotion/fcl at commit e5efcc41b57b). Inside FCL that call is
+//     again two things: closed-form primitives for a Halfspace against Box, Capsule, Cylinder, Ellipsoid and Convex
+//     (fcl/narrowphase/detail/primitive_shape_algorithm/halfspace-inl.h), and GJK / EPA over libccd for the rest.
+// This header restates the first half completely -- Sphere against Sphere, Box, HalfSpace, Cylinder, Capsule, every shape
+// the reference has a closed form for (it sends Ellipsoid and Convex to FCL, :273-278) -- and, of the second half, FCL's
+// published half-space primitives with the reference's post-processing of an FCL contact (:164-207): a rigid box,
+// cylinder, capsule, ellipsoid or mesh on a rigid HalfSpace ground is the commonest rigid-rigid fallback pair. The FCL
+// sources are not available here: those functions are pinned by the reference's BoxPenetrationTest TangentPlane scenes
+// (penetration_as_point_pair_callback_test.cc:575-910, 1e-12) and by the shapes' analytic support functions
+// (tests/test_point_pair_cpu.py), not against FCL itself. GJK / EPA and FCL's box-box are NOT restated. The batched
 // query (dbh_batch_query, DBH_QUERY_WITH_FALLBACK) reports WHICH pairs need it (dbh_batch_copy_fallback_pairs): a
 // handful per scene, so the arithmetic stays on the host next to the shape descriptions the C-ABI never sees.
 // No Eigen: 3-vectors are std::array<double, 3>; operation order follows the reference.
@@ -19,6 +26,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstddef>
 #include <limits>
 #include <optional>
 
@@ -220,6 +228,159 @@ inline std::optional<Result> SphereShapePenetration(double radius_A, const Pose&
 inline void SwapAAndB(Result* r) {
   std::swap(r->p_WCa, r->p_WCb);
   r->nhat_BA_W = {-r->nhat_BA_W[0], -r->nhat_BA_W[1], -r->nhat_BA_W[2]};
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FCL's half-space primitives (fcl/narrowphase/detail/primitive_shape_algorithm/halfspace-inl.h at the commit the
+// reference pins), as the reference reaches them: CalcDistanceFallback<double> (penetration_as_point_pair_callback.cc:
+// 145-207) calls fcl::collide() with one contact requested on a pair (Halfspace, X) or (X, Halfspace), X not a sphere.
+// Drake's HalfSpace is fcl::Halfspaced(0, 0, 1, 0) (proximity_engine.cc:667): the solid is z <= 0 of its frame.
+
+// fcl::Contact as CalcDistanceFallback reads it: the position between the two surfaces and the depth. FCL's normal is
+// implied: it points from the shape into the half space, i.e. it is -n_W of the half space.
+struct FclHalfSpaceContact {
+  Vec3 pos;
+  double depth;
+};
+
+// fcl::detail::halfspaceIntersectTolerance<double>().
+inline constexpr double kHalfspaceIntersectTolerance = 0.0000001;
+
+// The half space of frame H posed in World: outward unit normal n_W (the frame's +z) and offset d of n_W . x <= d
+// (fcl::transform(Halfspace, tf): n' = R n, d' = d + n' . t).
+struct WorldHalfSpace {
+  Vec3 n;
+  double d;
+  double SignedDistance(const Vec3& p) const { return Dot(n, p) - d; }
+};
+inline WorldHalfSpace HalfSpaceInWorld(const Pose& X_WH) {
+  const Vec3 n{X_WH[6], X_WH[7], X_WH[8]};
+  return {n, Dot(n, {X_WH[9], X_WH[10], X_WH[11]})};
+}
+inline Vec3 AddScaled(const Vec3& p, const Vec3& v, double s) { return {p[0] + v[0] * s, p[1] + v[1] * s, p[2] + v[2] * s}; }
+
+// boxHalfspaceIntersect: depth from the box's support function; the deepest point is a face centre when the plane is
+// parallel to a face (within the tolerance), else the lowest corner.
+inline std::optional<FclHalfSpaceContact> BoxHalfSpace(const Vec3& size, const Pose& X_WB, const Pose& X_WH) {
+  const WorldHalfSpace hs = HalfSpaceInWorld(X_WH);
+  const Vec3 T{X_WB[9], X_WB[10], X_WB[11]};
+  const Vec3 Q = RotateT(X_WB, hs.n);  // the plane normal in the box frame
+  const Vec3 A{Q[0] * size[0], Q[1] * size[1], Q[2] * size[2]};
+  const double depth = 0.5 * ((std::abs(A[0]) + std::abs(A[1])) + std::abs(A[2])) - hs.SignedDistance(T);
+  if (depth < 0) return std::nullopt;
+  Vec3 p = T;
+  int parallel = -1;
+  for (int i = 0; i < 3 && parallel < 0; ++i)
+    if (std::abs(Q[i] - 1) < kHalfspaceIntersectTolerance || std::abs(Q[i] + 1) < kHalfspaceIntersectTolerance) parallel = i;
+  for (int i = 0; i < 3; ++i) {
+    if (parallel >= 0 && i != parallel) continue;
+    const int sign = A[i] > 0 ? -1 : 1;
+    p = AddScaled(p, {X_WB[3 * i], X_WB[3 * i + 1], X_WB[3 * i + 2]}, 0.5 * size[i] * sign);
+  }
+  return FclHalfSpaceContact{AddScaled(p, hs.n, depth * 0.5), depth};
+}
+
+// capsuleHalfspaceIntersect: axis parallel to the plane -> the point under the centre; else the cap centre at the lower
+// end of the spine.
+inline std::optional<FclHalfSpaceContact> CapsuleHalfSpace(double radius, double length, const Pose& X_WC, const Pose& X_WH) {
+  const WorldHalfSpace hs = HalfSpaceInWorld(X_WH);
+  const Vec3 T{X_WC[9], X_WC[10], X_WC[11]};
+  const Vec3 dir_z{X_WC[6], X_WC[7], X_WC[8]};
+  const double cosa = Dot(dir_z, hs.n);
+  if (std::abs(cosa) < kHalfspaceIntersectTolerance) {
+    const double depth = radius - hs.SignedDistance(T);
+    if (depth < 0) return std::nullopt;
+    return FclHalfSpaceContact{AddScaled(T, hs.n, 0.5 * depth - radius), depth};
+  }
+  const int sign = cosa > 0 ? -1 : 1;
+  const Vec3 p = AddScaled(T, dir_z, length * 0.5 * sign);
+  const double depth = radius - hs.SignedDistance(p);
+  if (depth < 0) return std::nullopt;
+  const Vec3 c = AddScaled(p, hs.n, -radius);  // the deepest point
+  return FclHalfSpaceContact{AddScaled(c, hs.n, 0.5 * depth), depth};
+}
+
+// cylinderHalfspaceIntersect: axis parallel to the plane -> the point under the centre; else the lowest point of the
+// lower rim (the disc's centre when the axis is along the normal).
+inline std::optional<FclHalfSpaceContact> CylinderHalfSpace(double radius, double length, const Pose& X_WC, const Pose& X_WH) {
+  const WorldHalfSpace hs = HalfSpaceInWorld(X_WH);
+  const Vec3 T{X_WC[9], X_WC[10], X_WC[11]};
+  const Vec3 dir_z{X_WC[6], X_WC[7], X_WC[8]};
+  const double cosa = Dot(dir_z, hs.n);
+  if (std::abs(cosa) < kHalfspaceIntersectTolerance) {
+    const double depth = radius - hs.SignedDistance(T);
+    if (depth < 0) return std::nullopt;
+    return FclHalfSpaceContact{AddScaled(T, hs.n, 0.5 * depth - radius), depth};
+  }
+  Vec3 C{dir_z[0] * cosa - hs.n[0], dir_z[1] * cosa - hs.n[1], dir_z[2] * cosa - hs.n[2]};  // -n projected into the disc
+  if (std::abs(cosa + 1) < kHalfspaceIntersectTolerance || std::abs(cosa - 1) < kHalfspaceIntersectTolerance) {
+    C = {0.0, 0.0, 0.0};
+  } else {
+    const double s = radius / Norm(C);
+    C = {C[0] * s, C[1] * s, C[2] * s};
+  }
+  const int sign = cosa > 0 ? -1 : 1;
+  const Vec3 axis_end = AddScaled(T, dir_z, length * 0.5 * sign);
+  const Vec3 p{axis_end[0] + C[0], axis_end[1] + C[1], axis_end[2] + C[2]};  // the deepest point
+  const double depth = -hs.SignedDistance(p);
+  if (depth < 0) return std::nullopt;
+  return FclHalfSpaceContact{AddScaled(p, hs.n, 0.5 * depth), depth};
+}
+
+// ellipsoidHalfspaceIntersect: computed in the ellipsoid's frame. With the plane normal n there, the centre is
+// sqrt(sum (r_i n_i)^2) above the tangent plane; the reported position lies on the ray from the centre through the
+// deepest point, half the depth above it along the normal.
+inline std::optional<FclHalfSpaceContact> EllipsoidHalfSpace(const Vec3& radii, const Pose& X_WE, const Pose& X_WH) {
+  const WorldHalfSpace hs = HalfSpaceInWorld(X_WH);
+  const Vec3 n = RotateT(X_WE, hs.n);
+  const double d = hs.d - Dot(hs.n, {X_WE[9], X_WE[10], X_WE[11]});  // n . x <= d in the ellipsoid's frame
+  const Vec3 radii2{radii[0] * radii[0], radii[1] * radii[1], radii[2] * radii[2]};
+  const double center_to_contact_plane = std::sqrt(Dot({n[0] * n[0], n[1] * n[1], n[2] * n[2]}, radii2));
+  const double depth = center_to_contact_plane + d;
+  if (!(depth >= 0)) return std::nullopt;
+  const double k = 1.0 / center_to_contact_plane;
+  const Vec3 support_vector{k * (radii2[0] * n[0]), k * (radii2[1] * n[1]), k * (radii2[2] * n[2])};
+  const double f = 0.5 * depth / Dot(n, support_vector) - 1.0;
+  return FclHalfSpaceContact{Apply(X_WE, {support_vector[0] * f, support_vector[1] * f, support_vector[2] * f}), depth};
+}
+
+// convexHalfspaceIntersect: the first vertex of smallest signed distance. Drake gives FCL the convex hull of a Mesh or
+// Convex; a linear function takes its minimum over the hull at a vertex of the mesh itself, so the mesh's own vertices
+// give the same depth (and the same vertex except at exact ties). Touching (distance 0) counts as intersecting.
+inline std::optional<FclHalfSpaceContact> VerticesHalfSpace(const double* vertices, std::size_t num_vertices, const Pose& X_WC,
+                                                            const Pose& X_WH) {
+  const WorldHalfSpace hs = HalfSpaceInWorld(X_WH);
+  const Vec3 n = RotateT(X_WC, hs.n);
+  const double d = hs.d - Dot(hs.n, {X_WC[9], X_WC[10], X_WC[11]});
+  double min_signed_distance = std::numeric_limits<double>::max();
+  Vec3 deepest{0.0, 0.0, 0.0};
+  for (std::size_t v = 0; v < num_vertices; ++v) {
+    const Vec3 p{vertices[3 * v], vertices[3 * v + 1], vertices[3 * v + 2]};
+    const double signed_distance = Dot(n, p) - d;
+    if (signed_distance < min_signed_distance) {
+      min_signed_distance = signed_distance;
+      deepest = p;
+    }
+  }
+  if (!(min_signed_distance <= 0)) return std::nullopt;
+  const double depth = -min_signed_distance;
+  return FclHalfSpaceContact{AddScaled(Apply(X_WC, deepest), hs.n, 0.5 * depth), depth};
+}
+
+// CalcDistanceFallback<double> (penetration_as_point_pair_callback.cc:164-207) on such a contact. FCL's normal points
+// from the first object into the second and Drake's nhat_BA_W is its negative; osculation (depth <= epsilon) is no
+// contact; the two witness points sit half the depth either side of FCL's position.
+inline std::optional<Result> HalfSpaceContactToPointPair(const std::optional<FclHalfSpaceContact>& contact, const Pose& X_WH,
+                                                         bool half_space_is_A) {
+  if (!contact) return std::nullopt;
+  if (contact->depth <= std::numeric_limits<double>::epsilon()) return std::nullopt;
+  const Vec3 n{X_WH[6], X_WH[7], X_WH[8]};
+  Result r;
+  r.depth = contact->depth;
+  r.nhat_BA_W = half_space_is_A ? Vec3{-n[0], -n[1], -n[2]} : n;
+  r.p_WCa = AddScaled(contact->pos, r.nhat_BA_W, -0.5 * r.depth);
+  r.p_WCb = AddScaled(contact->pos, r.nhat_BA_W, 0.5 * r.depth);
+  return r;
 }
 
 }  // namespace point_pair

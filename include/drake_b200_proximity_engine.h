@@ -69,7 +69,8 @@ struct Ellipsoid {
 struct HalfSpace {};  // z <= 0 of the geometry frame (shape_specification.h)
 // Cylinder and Capsule (axis z, shape_specification.h): geometries WITHOUT a hydroelastic representation here (their
 // volume-mesh generators, make_cylinder_mesh / make_capsule_mesh, are outside the path) -- they take part in
-// ComputeContactSurfacesWithFallback's point pairs against a Sphere (Drake's closed forms, drake_b200_point_pair.h).
+// ComputeContactSurfacesWithFallback's point pairs against a Sphere (Drake's closed forms) or a HalfSpace (FCL's),
+// drake_b200_point_pair.h.
 struct Cylinder {
   double radius, length;
 };
@@ -102,7 +103,8 @@ struct ProximityProperties {
 };
 
 // geometry::PenetrationAsPointPair<double>, the fallback result (query_results/penetration_as_point_pair.h):
-// filled for the pairs one of whose shapes is a Sphere (Drake's own closed forms, drake_b200_point_pair.h).
+// filled for the pairs one of whose shapes is a Sphere (Drake's own closed forms) or a HalfSpace (FCL's closed-form
+// half-space primitives), drake_b200_point_pair.h.
 struct PenetrationAsPointPair {
   GeometryId id_A, id_B;
   std::array<double, 3> p_WCa, p_WCb, nhat_BA_W;
@@ -290,8 +292,8 @@ class ProximityEngine {
     }
   }
 
-  // What to do with a fallback pair neither of whose shapes is a Sphere: the reference calls FCL's general narrow
-  // phase there (penetration_as_point_pair_callback.cc:145-195), which this back end does not contain. false (the
+  // What to do with a fallback pair neither of whose shapes is a Sphere or a HalfSpace: the reference calls FCL's
+  // general narrow phase there (penetration_as_point_pair_callback.cc:145-195), which this back end does not contain. false (the
   // default): throw std::logic_error naming the pair, so that no contact is lost silently; true: skip such pairs.
   void set_skip_unsupported_point_pairs(bool skip) { skip_unsupported_point_pairs_ = skip; }
 
@@ -404,13 +406,38 @@ class ProximityEngine {
     const Shape& b = shapes_[gb];
     const bool a_is_sphere = std::holds_alternative<Sphere>(a), b_is_sphere = std::holds_alternative<Sphere>(b);
     if (!a_is_sphere && !b_is_sphere) {
-      // The reference rejects half space x half space itself (:525-555 of its test; penetration_as_point_pair_callback.cc
-      // "@pre The pair should not be (Halfspace, X), unless X is Sphere") and hands the rest to FCL.
+      const bool a_is_half_space = std::holds_alternative<HalfSpace>(a), b_is_half_space = std::holds_alternative<HalfSpace>(b);
+      if (a_is_half_space != b_is_half_space) {
+        // FCL's closed-form half-space primitives behind CalcDistanceFallback (:145-207), drake_b200_point_pair.h.
+        const int gh = a_is_half_space ? ga : gb, gx = a_is_half_space ? gb : ga;   // half space, the other shape
+        const pp::Pose& X_WH = poses_[gh].m;
+        const pp::Pose& X_WX = poses_[gx].m;
+        std::optional<pp::FclHalfSpaceContact> contact;
+        if (const auto* bx = std::get_if<Box>(&shapes_[gx])) {
+          contact = pp::BoxHalfSpace({bx->width, bx->depth, bx->height}, X_WX, X_WH);
+        } else if (const auto* cy = std::get_if<Cylinder>(&shapes_[gx])) {
+          contact = pp::CylinderHalfSpace(cy->radius, cy->length, X_WX, X_WH);
+        } else if (const auto* ca = std::get_if<Capsule>(&shapes_[gx])) {
+          contact = pp::CapsuleHalfSpace(ca->radius, ca->length, X_WX, X_WH);
+        } else if (const auto* el = std::get_if<Ellipsoid>(&shapes_[gx])) {
+          contact = pp::EllipsoidHalfSpace({el->a, el->b, el->c}, X_WX, X_WH);
+        } else if (const auto* sm = std::get_if<SurfaceMeshShape>(&shapes_[gx])) {
+          contact = pp::VerticesHalfSpace(sm->vertices.data(), sm->vertices.size() / 3, X_WX, X_WH);
+        } else if (const auto* vm = std::get_if<VolumeMeshShape>(&shapes_[gx])) {
+          contact = pp::VerticesHalfSpace(vm->vertices.data(), vm->vertices.size() / 3, X_WX, X_WH);
+        }
+        auto res = pp::HalfSpaceContactToPointPair(contact, X_WH, a_is_half_space);
+        if (!res) return std::nullopt;
+        return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
+      }
+      // The reference rejects half space x half space itself (:525-555 of its test; ScalarSupport<double>,
+      // penetration_as_point_pair_callback.cc:329-338) and hands the rest to FCL's GJK / EPA (and its box-box).
       if (skip_unsupported_point_pairs_) return std::nullopt;
       throw std::logic_error("ComputeContactSurfacesWithFallback: the point-pair fallback for geometries " +
                              std::to_string(ids_[ga]) + " and " + std::to_string(ids_[gb]) +
-                             " needs FCL's general narrow phase (neither shape is a Sphere), which this back end does not "
-                             "provide; filter the pair or call set_skip_unsupported_point_pairs(true)");
+                             " needs FCL's general narrow phase (neither shape is a Sphere or a HalfSpace, or both are "
+                             "half spaces), which this back end does not provide; filter the pair or call "
+                             "set_skip_unsupported_point_pairs(true)");
     }
     const int gs = a_is_sphere ? ga : gb, go = a_is_sphere ? gb : ga;   // sphere, other
     const pp::Pose& X_WS = poses_[gs].m;
@@ -564,6 +591,55 @@ class ProximityEngine {
     Check(dbh_batch_create(ctx_, num_scenes_, offsets.data(), assets.data(), ids.data(), anchored.data(),
                            static_cast<int32_t>(excluded.size() / 2), excluded.data(), &batch_),
           "batch_create");
+    // Geometries without a hydroelastic representation (asset -1) still take part in the geometry-level broad phase
+    // (FindCollisionCandidates, proximity_engine.cc:867-883): give the library the box FCL's computeLocalAABB gives
+    // each shape, so that only pairs whose world boxes overlap reach the point-pair fallback. A HalfSpace stays
+    // unbounded (non-finite entry: its pairs always count).
+    bool any_unrepresented = false;
+    std::vector<double> boxes(static_cast<size_t>(num_scenes_) * G * 6, std::numeric_limits<double>::quiet_NaN());
+    for (int g = 0; g < G; ++g) {
+      if (assets_[g] >= 0) continue;
+      any_unrepresented = true;
+      std::array<double, 6> box;
+      if (!LocalBox(shapes_[g], &box)) continue;
+      for (int s = 0; s < num_scenes_; ++s) std::copy(box.begin(), box.end(), boxes.begin() + (static_cast<size_t>(s) * G + g) * 6);
+    }
+    if (any_unrepresented) Check(dbh_batch_set_geometry_bounds(batch_, boxes.data()), "set_geometry_bounds");
+  }
+
+  // The shape's axis-aligned box in its own frame as {centre, half widths}; false for a HalfSpace.
+  static bool LocalBox(const Shape& shape, std::array<double, 6>* box) {
+    auto from_vertices = [box](const std::vector<double>& v) {
+      if (v.size() < 3) return false;
+      for (int k = 0; k < 3; ++k) {
+        double lo = v[k], hi = v[k];
+        for (size_t i = k; i < v.size(); i += 3) {
+          lo = std::min(lo, v[i]);
+          hi = std::max(hi, v[i]);
+        }
+        (*box)[k] = 0.5 * (lo + hi);
+        (*box)[3 + k] = 0.5 * (hi - lo);
+      }
+      return true;
+    };
+    if (const auto* sp = std::get_if<Sphere>(&shape)) {
+      *box = {0, 0, 0, sp->radius, sp->radius, sp->radius};
+    } else if (const auto* bx = std::get_if<Box>(&shape)) {
+      *box = {0, 0, 0, bx->width / 2, bx->depth / 2, bx->height / 2};
+    } else if (const auto* el = std::get_if<Ellipsoid>(&shape)) {
+      *box = {0, 0, 0, el->a, el->b, el->c};
+    } else if (const auto* cy = std::get_if<Cylinder>(&shape)) {
+      *box = {0, 0, 0, cy->radius, cy->radius, cy->length / 2};
+    } else if (const auto* ca = std::get_if<Capsule>(&shape)) {
+      *box = {0, 0, 0, ca->radius, ca->radius, ca->length / 2 + ca->radius};
+    } else if (const auto* vm = std::get_if<VolumeMeshShape>(&shape)) {
+      return from_vertices(vm->vertices);
+    } else if (const auto* sm = std::get_if<SurfaceMeshShape>(&shape)) {
+      return from_vertices(sm->vertices);
+    } else {
+      return false;
+    }
+    return true;
   }
 
   std::vector<std::vector<ContactSurface>> Run(HydroelasticContactRepresentation rep, int query_kind,

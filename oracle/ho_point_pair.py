@@ -1,9 +1,18 @@
-"""Oracle (test infrastructure): Drake's closed-form point-pair narrow phase for pairs with a sphere, restated in
-numpy -- penetration_as_point_pair_callback.cc:92-118,203-300 (SphereShapePenetration, ComputeNarrowPhasePenetration)
-over point_distance::DistanceToPoint for Sphere, Box, HalfSpace, Cylinder and Capsule
-(distance_to_point_callback.cc:15-160,160-288,384-482). Pinned by the reference's own test scenes (penetration_as_point_pair_callback_test.cc:119-176,196-230,
-258-310,430-462), restated in tests/test_point_pair_cpu.py. The general (non-sphere) fallback is FCL's GJK / EPA, an
-external dependency of the reference: not restated.
+"""Oracle (test infrastructure): the point-pair narrow phase of ComputeContactSurfacesWithFallback restated in numpy.
+
+(1) Drake's own closed forms for pairs with a sphere -- penetration_as_point_pair_callback.cc:92-118,203-300
+(SphereShapePenetration, ComputeNarrowPhasePenetration) over point_distance::DistanceToPoint for Sphere, Box, HalfSpace,
+Cylinder and Capsule (distance_to_point_callback.cc:15-160,160-288,384-482). Pinned by the reference's own test scenes
+(penetration_as_point_pair_callback_test.cc:119-176,196-230,258-310,430-462), restated in tests/test_point_pair_cpu.py.
+
+(2) Of the FCL half (CalcDistanceFallback<double>, :145-207; FCL is an external dependency of the reference, pinned in
+tools/workspace/fcl_internal/repository.bzl at RobotLocomotion/fcl commit e5efcc41b57b and absent from its tree): FCL's
+published closed-form half-space primitives (fcl/narrowphase/detail/primitive_shape_algorithm/halfspace-inl.h) for a
+HalfSpace against Box, Capsule, Cylinder, Ellipsoid and a vertex cloud (Convex), worked in the HALF SPACE's frame --
+the product header works in World, so the two are independent derivations. PARITY UNPINNED against FCL itself: pinned by
+the reference's BoxPenetrationTest TangentPlane scenes (penetration_as_point_pair_callback_test.cc:575-910) and by the
+shapes' analytic support functions / brute-force surface sampling in tests/test_point_pair_cpu.py. GJK / EPA and FCL's
+box-box are not restated.
 
 Poses are 12 doubles: rotation column-major, then translation (math/rigid_transform.h:1004-1007)."""
 from __future__ import annotations
@@ -163,14 +172,106 @@ def distance_to_capsule(radius, length, X_WG, p_WQ):
     return p_GN, distance, _R(X_WG) @ grad_G
 
 
+HALFSPACE_TOLERANCE = 1e-7   # fcl::detail::halfspaceIntersectTolerance<double>()
+
+
+def _fcl_sign(a: float) -> float:
+    """FCL's `(A > 0) ? -1 : 1`: which end of an axis is the lower one; zero goes to +1."""
+    return -1.0 if a > 0 else 1.0
+
+
+def half_space_contact(shape, X_HS):
+    """FCL's shape x Halfspace primitives in the half space's own frame H (solid z <= 0): shape = ('box', (x, y, z)) |
+    ('capsule', r, L) | ('cylinder', r, L) | ('ellipsoid', (a, b, c)) | ('vertices', [[x, y, z], ...]) posed at X_HS.
+    Returns None or (p_H, depth): FCL's contact position (half the depth above the deepest point) and the depth."""
+    R, t = _R(X_HS), _p(X_HS)
+    ez = np.array([0.0, 0.0, 1.0])
+    kind = shape[0]
+    if kind == "box":
+        h = np.asarray(shape[1], float) / 2.0
+        nz = R[2, :]                                   # the plane normal in the box frame
+        depth = 0.5 * float(abs(nz[0] * 2 * h[0]) + abs(nz[1] * 2 * h[1]) + abs(nz[2] * 2 * h[2])) - t[2]
+        if depth < 0:
+            return None
+        axes = [i for i in range(3) if abs(abs(nz[i]) - 1) < HALFSPACE_TOLERANCE][:1] or [0, 1, 2]
+        p = t.copy()
+        for i in axes:
+            p = p + R[:, i] * (h[i] * _fcl_sign(nz[i] * 2 * h[i]))
+        return p + ez * (0.5 * depth), depth
+    if kind in ("capsule", "cylinder"):
+        r, L = float(shape[1]), float(shape[2])
+        axis = R[:, 2]
+        cosa = float(axis[2])
+        if abs(cosa) < HALFSPACE_TOLERANCE:            # lying on its side: the point under the centre
+            depth = r - t[2]
+            return None if depth < 0 else (t + ez * (0.5 * depth - r), depth)
+        end = t + axis * (0.5 * L * _fcl_sign(cosa))   # the lower end of the axis
+        if kind == "capsule":
+            depth = r - end[2]
+            return None if depth < 0 else ((end - ez * r) + ez * (0.5 * depth), depth)
+        if abs(abs(cosa) - 1) < HALFSPACE_TOLERANCE:
+            rim = np.zeros(3)
+        else:
+            down = axis * cosa - ez                    # -z projected into the end disc
+            rim = down * (r / math.sqrt(float(down @ down)))
+        p = end + rim
+        depth = -float(p[2])
+        return None if depth < 0 else (p + ez * (0.5 * depth), depth)
+    if kind == "ellipsoid":
+        radii2 = np.asarray(shape[1], float) ** 2
+        n = R.T @ ez                                   # plane n . x <= d in the ellipsoid frame
+        d = -float(t[2])
+        c = math.sqrt(float((n * n) @ radii2))         # height of the centre above the tangent plane
+        depth = c + d
+        if not depth >= 0:
+            return None
+        support = (radii2 * n) / c
+        p_E = support * (0.5 * depth / float(n @ support) - 1.0)
+        return R @ p_E + t, depth
+    if kind == "vertices":
+        V = np.asarray(shape[1], float).reshape(-1, 3)
+        n, d = R.T @ ez, -float(t[2])
+        sd = V @ n - d
+        k = int(np.argmin(sd))                         # the first minimum
+        if not sd[k] <= 0:
+            return None
+        depth = -float(sd[k])
+        return (R @ V[k] + t) + ez * (0.5 * depth), depth
+    raise NotImplementedError(kind)
+
+
+def half_space_point_pair(shape_A, X_WA, shape_B, X_WB):
+    """CalcDistanceFallback<double> (:145-207) for a pair exactly one of whose shapes is ('half_space',)."""
+    a_is_hs = shape_A[0] == "half_space"
+    X_WH, (shape, X_WS) = (X_WA, (shape_B, X_WB)) if a_is_hs else (X_WB, (shape_A, X_WA))
+    R_WH, p_WH = _R(X_WH), _p(X_WH)
+    R_HS = R_WH.T @ _R(X_WS)
+    X_HS = np.concatenate([R_HS.T.reshape(-1), R_WH.T @ (_p(X_WS) - p_WH)])
+    hit = half_space_contact(shape, X_HS)
+    if hit is None:
+        return None
+    p_H, depth = hit
+    if depth <= np.finfo(float).eps:                   # osculation is no contact (:179-185)
+        return None
+    n_W = R_WH @ np.array([0.0, 0.0, 1.0])
+    pos = R_WH @ p_H + p_WH
+    # FCL's normal points from object A into object B; nhat_BA_W is its negative (:188-190).
+    nhat_BA_W = -n_W if a_is_hs else n_W
+    return {"depth": depth, "nhat_BA_W": nhat_BA_W, "p_WCa": pos - 0.5 * depth * nhat_BA_W,
+            "p_WCb": pos + 0.5 * depth * nhat_BA_W}
+
+
 def point_pair(shape_A, X_WA, shape_B, X_WB):
     """ComputeNarrowPhasePenetration for shapes given as ('sphere', r) | ('box', (x, y, z)) | ('half_space',) |
-    ('cylinder', r, L) | ('capsule', r, L); A is the
+    ('cylinder', r, L) | ('capsule', r, L) | ('ellipsoid', (a, b, c)) | ('vertices', V); A is the
     geometry with the smaller id. Returns None (no penetration) or dict(p_WCa, p_WCb, nhat_BA_W, depth). Raises for pairs
-    without a sphere (the reference calls FCL there)."""
+    without a sphere or a half space (the reference calls FCL's GJK / EPA or box-box there) and for two half spaces (the
+    reference throws, :329-338)."""
     a_is_sphere, b_is_sphere = shape_A[0] == "sphere", shape_B[0] == "sphere"
     if not (a_is_sphere or b_is_sphere):
-        raise NotImplementedError("no sphere in the pair: FCL's general narrow phase")
+        if (shape_A[0] == "half_space") != (shape_B[0] == "half_space"):
+            return half_space_point_pair(shape_A, X_WA, shape_B, X_WB)
+        raise NotImplementedError("no sphere and not exactly one half space in the pair: FCL's general narrow phase")
     (S, X_WS), (O, X_WO) = ((shape_A, X_WA), (shape_B, X_WB)) if a_is_sphere else ((shape_B, X_WB), (shape_A, X_WA))
     p_WSo = _p(X_WS)
     if O[0] == "sphere":

@@ -245,6 +245,53 @@ int main(int argc, char** argv) {
     b.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
     EXPECT(pairs.empty());
   }
+  {  // Rigid shapes on a rigid HalfSpace ground: rigid-rigid, so the fallback hands them to FCL's closed-form half-space
+     // primitives (drake_b200_point_pair.h). The reference's BoxPenetrationTest TangentPlane2 scene
+     // (penetration_as_point_pair_callback_test.cc:806-820,906-912): a unit box standing on its corner (-.5,-.5,-.5),
+     // 1e-3 under the plane; expected p_WCa = 0, p_WCb = (0, 0, -1e-3), nhat_BA_W = (0, 0, -1), depth 1e-3 to 1e-12.
+    const double kDepth = 1e-3;
+    const double angle = std::atan(std::sqrt(2.0)), ax = std::sqrt(0.5), ay = -std::sqrt(0.5);
+    const double c = std::cos(angle), sn = std::sin(angle), t = 1 - c;
+    // Rodrigues for the axis (ax, ay, 0), column-major.
+    RigidTransformd X_WB;
+    X_WB.m = {t * ax * ax + c, t * ax * ay, -sn * ay, t * ax * ay, t * ay * ay + c, sn * ax, sn * ay, -sn * ax, c, 0, 0, 0};
+    for (int r = 0; r < 3; ++r)   // p_WB = p_WC - R_WB p_BoC_B
+      X_WB.m[9 + r] = (r == 2 ? -kDepth : 0.0) + 0.5 * (X_WB.m[r] + X_WB.m[3 + r] + X_WB.m[6 + r]);
+    ProximityEngine e(0);
+    e.AddAnchoredGeometry(HalfSpace{}, RigidTransformd::Identity(), 1, rigid);
+    e.AddDynamicGeometry(Box{1, 1, 1}, X_WB, 2, rigid);
+    // A capsule standing 0.02 deep, a cylinder lying on its side 0.03 deep, an ellipsoid 0.01 deep, none with a
+    // hydroelastic representation (kUndefined): kUnsupported pairs, same fallback.
+    ProximityProperties none;
+    e.AddDynamicGeometry(Capsule{0.1, 0.4}, RigidTransformd::FromTranslation(3, 0, 0.3 - 0.02), 3, none);
+    RigidTransformd X_prone;   // +90 degrees about x: the cylinder's axis along -y... (z -> y)
+    X_prone.m = {1, 0, 0, 0, 0, 1, 0, -1, 0, 6, 0, 0.2 - 0.03};
+    e.AddDynamicGeometry(Cylinder{0.2, 0.5}, X_prone, 4, none);
+    e.AddDynamicGeometry(Ellipsoid{0.1, 0.2, 0.3}, RigidTransformd::FromTranslation(9, 0, 0.3 - 0.01), 5, none);
+    std::vector<ContactSurface> surfaces;
+    std::vector<PenetrationAsPointPair> pairs;
+    e.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    EXPECT(surfaces.empty());
+    EXPECT(pairs.size() == 4);
+    if (pairs.size() == 4) {
+      const PenetrationAsPointPair& b = pairs[0];
+      EXPECT(b.id_A == 1 && b.id_B == 2 && std::fabs(b.depth - kDepth) < 1e-12);
+      EXPECT(std::fabs(b.nhat_BA_W[0]) < 1e-12 && std::fabs(b.nhat_BA_W[1]) < 1e-12 && std::fabs(b.nhat_BA_W[2] + 1) < 1e-12);
+      for (int r = 0; r < 3; ++r) {
+        EXPECT(std::fabs(b.p_WCa[r]) < 1e-12);
+        EXPECT(std::fabs(b.p_WCb[r] - (r == 2 ? -kDepth : 0.0)) < 1e-12);
+      }
+      const double depths[4] = {kDepth, 0.02, 0.03, 0.01};
+      const double xs[4] = {0, 3, 6, 9};
+      for (int k = 1; k < 4; ++k) {
+        const PenetrationAsPointPair& q = pairs[k];
+        EXPECT(q.id_A == 1 && q.id_B == 3 + (k - 1));
+        EXPECT(std::fabs(q.depth - depths[k]) < 1e-15 && std::fabs(q.nhat_BA_W[2] + 1) < 1e-15);
+        EXPECT(std::fabs(q.p_WCa[0] - xs[k]) < 1e-15 && std::fabs(q.p_WCa[2]) < 1e-15);
+        EXPECT(std::fabs(q.p_WCb[0] - xs[k]) < 1e-15 && std::fabs(q.p_WCb[2] + depths[k]) < 1e-15);
+      }
+    }
+  }
   std::printf("ok\n");
   return 0;
 }

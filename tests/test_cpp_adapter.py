@@ -15,7 +15,9 @@ def build_exe():
     lib = build.build()
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     src = os.path.join(ROOT, "tests", "cpp", "test_proximity_engine.cc")
-    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(lib)):
+    inc = os.path.join(ROOT, "include")
+    newest = max([os.path.getmtime(src), os.path.getmtime(lib)] + [os.path.getmtime(os.path.join(inc, h)) for h in os.listdir(inc)])
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < newest:
         subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src,
                         "-o", EXE, "-L", os.path.dirname(lib), "-ldrake_b200_hydro",
                         "-Wl,-rpath," + os.path.dirname(lib)], check=True)
@@ -93,8 +95,9 @@ def build_deformable_exe():
     exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_deformable_contact")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     src = os.path.join(ROOT, "tests", "cpp", "test_deformable_contact.cc")
-    hdr = os.path.join(ROOT, "include", "drake_b200_deformable_contact.h")
-    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(lib)):
+    inc = os.path.join(ROOT, "include")
+    newest = max([os.path.getmtime(src), os.path.getmtime(lib)] + [os.path.getmtime(os.path.join(inc, h)) for h in os.listdir(inc)])
+    if not os.path.exists(exe) or os.path.getmtime(exe) < newest:
         subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src,
                         "-o", exe, "-L", os.path.dirname(lib), "-ldrake_b200_hydro",
                         "-Wl,-rpath," + os.path.dirname(lib)], check=True)

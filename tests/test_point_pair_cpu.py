@@ -223,3 +223,197 @@ def test_adapter_arithmetic_matches_the_oracle():
         assert np.max(np.abs(got - ref)) <= 4 * K_EPS * scale, (a, b)
         hits += 1
     assert hits > 1500
+
+
+# ---- FCL's half-space primitives behind CalcDistanceFallback (the pairs (HalfSpace, X), X not a sphere) ----------------
+
+def _box_penetration_poses():
+    """BoxPenetrationTest (penetration_as_point_pair_callback_test.cc:575-910): a unit box whose corner (-.5,-.5,-.5) is
+    its lowest point, kDepth = 1e-3 under the z = 0 plane; X_WB_1 (:822-836) and X_WB_2 (:806-820)."""
+    k_depth = 1e-3
+    p_BoC_B, p_WC = np.array([-0.5, -0.5, -0.5]), np.array([0.0, 0.0, -k_depth])
+    R_1 = _angle_axis(-math.pi / 4, [0, 1, 0]) @ _angle_axis(math.pi / 4, [1, 0, 0])
+    R_2 = _angle_axis(math.atan(math.sqrt(2)), [math.sqrt(0.5), -math.sqrt(0.5), 0])
+    return k_depth, [ho.xform(R, p_WC - R @ p_BoC_B) for R in (R_1, R_2)]
+
+
+def test_box_on_tangent_plane_reference_scenes():
+    """TangentPlane1 / TangentPlane2 (:906-912): A = the plane, B = the box; expected p_WCa = 0, p_WCb = (0, 0, -depth),
+    nhat_BA_W = (0, 0, -1), depth = kDepth, all to 1e-12 -- and the reversed encoding (:741-746)."""
+    k_depth, poses = _box_penetration_poses()
+    I = ho.xform(None, [0, 0, 0])
+    for X_WB in poses:
+        R_WB, p_WB = X_WB[:9].reshape(3, 3).T, X_WB[9:]   # the fixture's own check (:661-677): every other corner has z > 0
+        corners = np.array([[x, y, z] for x in (-0.5, 0.5) for y in (-0.5, 0.5) for z in (-0.5, 0.5)])[1:]
+        assert np.all((corners @ R_WB.T + p_WB)[:, 2] > 0)
+        res = pp.point_pair(("half_space",), I, ("box", (1.0, 1.0, 1.0)), X_WB)
+        np.testing.assert_allclose(res["nhat_BA_W"], [0, 0, -1], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(res["p_WCa"], [0, 0, 0], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(res["p_WCb"], [0, 0, -k_depth], rtol=0, atol=1e-12)
+        assert abs(res["depth"] - k_depth) <= 1e-12
+        rev = pp.point_pair(("box", (1.0, 1.0, 1.0)), X_WB, ("half_space",), I)
+        np.testing.assert_array_equal(rev["nhat_BA_W"], -res["nhat_BA_W"])
+        np.testing.assert_array_equal(rev["p_WCa"], res["p_WCb"])
+        np.testing.assert_array_equal(rev["p_WCb"], res["p_WCa"])
+        assert rev["depth"] == res["depth"]
+
+
+def _surface_samples(shape, rng, n=200000):
+    """Points on the boundary of a shape in its own frame (dense enough for a 1e-3 brute-force check of the depth)."""
+    kind = shape[0]
+    if kind == "box":
+        h = np.asarray(shape[1]) / 2
+        P = rng.uniform(-1, 1, (n, 3)) * h
+        ax = rng.integers(0, 3, n)
+        P[np.arange(n), ax] = np.where(rng.random(n) < 0.5, -1, 1) * h[ax]
+        corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]) * h
+        return np.vstack([P, corners])
+    if kind == "ellipsoid":
+        U = rng.normal(size=(n, 3))
+        return U / np.linalg.norm(U, axis=1)[:, None] * np.asarray(shape[1])
+    r, L = shape[1], shape[2]
+    th = rng.uniform(0, 2 * math.pi, n)
+    if kind == "cylinder":
+        z = np.where(rng.random(n) < 0.5, -L / 2, L / 2)   # the extreme is always on a rim (or the barrel's edge lines)
+        return np.stack([r * np.cos(th), r * np.sin(th), z], axis=1)
+    U = rng.normal(size=(n, 3))
+    U = U / np.linalg.norm(U, axis=1)[:, None] * r
+    U[:, 2] += np.where(U[:, 2] >= 0, L / 2, -L / 2)
+    return U
+
+
+def _support_depth(shape, X_WS, X_WH):
+    """Depth from the shape's analytic support function h(-n) - n . c (independent of both restatements)."""
+    R_WS, p_WS = X_WS[:9].reshape(3, 3).T, X_WS[9:]
+    n_W = X_WH[:9].reshape(3, 3).T[:, 2]
+    n = R_WS.T @ n_W
+    height = float(n_W @ (p_WS - X_WH[9:]))
+    kind = shape[0]
+    if kind == "box":
+        sup = float(np.abs(n) @ (np.asarray(shape[1]) / 2))
+    elif kind == "ellipsoid":
+        sup = math.sqrt(float((n * np.asarray(shape[1])) @ (n * np.asarray(shape[1]))))
+    elif kind == "capsule":
+        sup = shape[1] + shape[2] / 2 * abs(n[2])
+    else:
+        sup = shape[1] * math.sqrt(max(0.0, 1 - n[2] * n[2])) + shape[2] / 2 * abs(n[2])
+    return sup - height
+
+
+@pytest.mark.parametrize("kind", ["box", "cylinder", "capsule", "ellipsoid"])
+def test_half_space_primitives_against_support_functions_and_sampling(kind):
+    """What the geometry fixes regardless of FCL's coding: the depth is the support function's, the normal is the plane's,
+    the two witness points are `depth` apart along it, p on the plane side lies ON the plane, the other is a deepest
+    point of the shape (brute force over 2e5 boundary samples)."""
+    from tests import parity
+    rng = np.random.default_rng(7)
+    hits = 0
+    for k in range(40):
+        shape = {"box": ("box", tuple(rng.uniform(0.2, 0.9, 3))), "cylinder": ("cylinder", rng.uniform(0.1, 0.5), rng.uniform(0.2, 1.2)),
+                 "capsule": ("capsule", rng.uniform(0.1, 0.5), rng.uniform(0.2, 1.2)),
+                 "ellipsoid": ("ellipsoid", tuple(rng.uniform(0.1, 0.6, 3)))}[kind]
+        X_WH = parity.random_pose(rng, 0.3)
+        X_WS = parity.random_pose(rng, 0.3)
+        n_W = X_WH[:9].reshape(3, 3).T[:, 2]
+        want_depth = _support_depth(shape, X_WS, X_WH)
+        res = pp.point_pair(("half_space",), X_WH, shape, X_WS)
+        if want_depth < 0:
+            assert res is None
+            continue
+        hits += 1
+        assert abs(res["depth"] - want_depth) <= 1e-13
+        np.testing.assert_allclose(res["nhat_BA_W"], -n_W, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(res["p_WCb"] - res["p_WCa"], res["depth"] * res["nhat_BA_W"], rtol=0, atol=1e-13)
+        assert abs(float(n_W @ (res["p_WCa"] - X_WH[9:]))) <= 1e-13          # A's witness is on the plane
+        S = _surface_samples(shape, rng) @ X_WS[:9].reshape(3, 3) + X_WS[9:]   # rows: R p + t
+        sd = (S - X_WH[9:]) @ n_W
+        assert abs(-sd.min() - res["depth"]) <= 2e-3
+        if kind != "ellipsoid":   # FCL's ellipsoid position is on the centre-to-deepest-point ray, not under the deepest point
+            assert np.linalg.norm(S[np.argmin(sd)] - res["p_WCb"]) <= 0.08
+        else:
+            assert abs(float(n_W @ (res["p_WCb"] - X_WH[9:])) + res["depth"]) <= 1e-13
+    assert hits >= 10
+
+
+def test_half_space_primitives_degenerate_orientations():
+    """The branches FCL takes at its 1e-7 tolerance: a box lying flat reports the face centre, a prone cylinder / capsule
+    the point under its centre, a standing cylinder the disc centre; osculation (depth <= epsilon) is no contact
+    (penetration_as_point_pair_callback.cc:179-185); a vertex cloud reports its first lowest vertex."""
+    I = ho.xform(None, [0, 0, 0])
+    d = 0.01
+    flat = pp.point_pair(("half_space",), I, ("box", (0.4, 0.6, 0.2)), ho.xform(None, [0.3, -0.2, 0.1 - d]))
+    np.testing.assert_allclose(flat["p_WCb"], [0.3, -0.2, -d], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(flat["p_WCa"], [0.3, -0.2, 0.0], rtol=0, atol=1e-15)
+    assert abs(flat["depth"] - d) <= 1e-15
+    prone = ho.xform(rot("x", math.pi / 2), [0.1, 0.2, 0.25 - d])
+    for kind in ("cylinder", "capsule"):
+        res = pp.point_pair((kind, 0.25, 0.8), prone, ("half_space",), I)
+        np.testing.assert_allclose(res["p_WCa"], [0.1, 0.2, -d], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(res["nhat_BA_W"], [0, 0, 1], rtol=0, atol=0)
+    standing = pp.point_pair(("half_space",), I, ("cylinder", 0.25, 0.8), ho.xform(None, [0.1, 0.2, 0.4 - d]))
+    np.testing.assert_allclose(standing["p_WCb"], [0.1, 0.2, -d], rtol=0, atol=1e-15)
+    upside_down = pp.point_pair(("half_space",), I, ("capsule", 0.25, 0.8), ho.xform(rot("x", math.pi), [0.1, 0.2, 0.65 - d]))
+    np.testing.assert_allclose(upside_down["p_WCb"], [0.1, 0.2, -d], rtol=0, atol=1e-15)
+    assert pp.point_pair(("half_space",), I, ("box", (1.0, 1.0, 1.0)), ho.xform(None, [0, 0, 0.5])) is None   # osculation
+    assert pp.point_pair(("half_space",), I, ("box", (1.0, 1.0, 1.0)), ho.xform(None, [0, 0, 0.5 + 1e-9])) is None
+    V = [[0, 0, 0.5], [1, 0, -0.2], [0, 1, -0.2], [1, 1, 0.1]]
+    cloud = pp.point_pair(("half_space",), I, ("vertices", V), I)
+    np.testing.assert_allclose(cloud["p_WCb"], [1, 0, -0.2], rtol=0, atol=1e-16)
+    assert cloud["depth"] == 0.2
+    with pytest.raises(NotImplementedError):
+        pp.point_pair(("half_space",), I, ("half_space",), I)
+    with pytest.raises(NotImplementedError):
+        pp.point_pair(("box", (1.0, 1.0, 1.0)), I, ("box", (1.0, 1.0, 1.0)), I)
+
+
+def test_adapter_half_space_arithmetic_matches_the_oracle():
+    """include/drake_b200_point_pair.h (World-frame formulation) against the oracle (half-space-frame formulation) on 4000
+    random pairs of a half space with a box, cylinder, capsule, ellipsoid or vertex cloud, both operand orders, incl.
+    the axis-aligned orientations that take FCL's tolerance branches, plus the reference's TangentPlane scenes."""
+    from tests import parity
+    rng = np.random.default_rng(43)
+    lines, cases = [], []
+
+    def fmt(shape, X):
+        head = {"box": lambda: "b " + " ".join(repr(float(v)) for v in shape[1]), "half_space": lambda: "h",
+                "cylinder": lambda: f"c {float(shape[1])!r} {float(shape[2])!r}", "capsule": lambda: f"k {float(shape[1])!r} {float(shape[2])!r}",
+                "ellipsoid": lambda: "e " + " ".join(repr(float(v)) for v in shape[1]),
+                "vertices": lambda: f"v {len(shape[1])} " + " ".join(repr(float(v)) for v in np.asarray(shape[1]).reshape(-1))}[shape[0]]()
+        return head + " " + " ".join(repr(float(v)) for v in X)
+
+    k_depth, tangent = _box_penetration_poses()
+    I = ho.xform(None, [0, 0, 0])
+    for X_WB in tangent:
+        cases.append(((("half_space",), I), (("box", (1.0, 1.0, 1.0)), X_WB)))
+    for k in range(4000):
+        kind = ("box", "cylinder", "capsule", "ellipsoid", "vertices")[k % 5]
+        shape = {"box": lambda: ("box", tuple(rng.uniform(0.1, 0.8, 3))), "cylinder": lambda: ("cylinder", rng.uniform(0.05, 0.5), rng.uniform(0.1, 1.0)),
+                 "capsule": lambda: ("capsule", rng.uniform(0.05, 0.5), rng.uniform(0.1, 1.0)),
+                 "ellipsoid": lambda: ("ellipsoid", tuple(rng.uniform(0.1, 0.6, 3))),
+                 "vertices": lambda: ("vertices", rng.uniform(-0.4, 0.4, (int(rng.integers(4, 40)), 3)))}[kind]()
+        X_H = parity.random_pose(rng, 0.4)
+        X_S = parity.random_pose(rng, 0.4)
+        if k % 6 == 0:    # axis-aligned with the plane: quarter turns about x / y relative to the half space
+            Rq = rot("xy"[k % 2], (k // 6 % 4) * math.pi / 2)
+            R_WH = X_H[:9].reshape(3, 3).T
+            X_S = ho.xform(R_WH @ Rq, X_S[9:])
+        pair = ((("half_space",), X_H), (shape, X_S))
+        cases.append(pair[::-1] if k % 2 else pair)
+    for a, b in cases:
+        lines.append(fmt(*a) + " " + fmt(*b))
+    out = subprocess.run([_exe()], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    hits = 0
+    for (a, b), line in zip(cases, out):
+        want = pp.point_pair(a[0], a[1], b[0], b[1])
+        if want is None:
+            assert line.strip() == "none", (a, b, line)
+            continue
+        assert line.strip() != "none", (a, b)
+        got = np.array([float(x) for x in line.split()])
+        ref = np.concatenate([[want["depth"]], want["p_WCa"], want["p_WCb"], want["nhat_BA_W"]])
+        scale = 1.0 + np.max(np.abs(ref))
+        assert np.max(np.abs(got - ref)) <= 16 * K_EPS * scale, (a, b, got - ref)
+        hits += 1
+    assert hits > 1200
+    first = np.array([float(x) for x in out[0].split()])   # TangentPlane1 through the C++: the reference's expectation
+    np.testing.assert_allclose(first, [k_depth, 0, 0, 0, 0, 0, -k_depth, 0, 0, -1], rtol=0, atol=1e-12)
