@@ -435,6 +435,228 @@ void SetBoxPressureField(HostMesh* m, double sx, double sy, double sz, double mo
   }
 }
 
+
+// ---- Cylinder and capsule (make_cylinder_mesh.cc, make_capsule_mesh.cc, meshing_utilities.cc) ------------------------
+namespace {
+
+using Tet = std::array<int, 4>;
+
+// SplitTriangularPrismToTetrahedra (meshing_utilities.cc:21-33): v0 v1 v2 the bottom triangle, v3 v4 v5 above them; the
+// three tetrahedra walk the path v3 -> v4 -> v1 -> v2 and all hold the diagonal v0-v5.
+void AppendPrism(int v0, int v1, int v2, int v3, int v4, int v5, std::vector<Tet>* out) {
+  const int path[4] = {v3, v4, v1, v2};
+  for (int k = 0; k < 3; ++k) out->push_back({path[k], path[k + 1], v0, v5});
+}
+// SplitPyramidToTetrahedra (meshing_utilities.cc:35-46): base v0 v1 v2 v3, apex v4; both tetrahedra hold v0-v2.
+void AppendPyramid(int v0, int v1, int v2, int v3, int v4, std::vector<Tet>* out) {
+  out->push_back({v3, v4, v0, v2});
+  out->push_back({v4, v1, v0, v2});
+}
+
+// The signed distance of DistanceToPoint::operator()(Cylinder) at the identity pose (distance_to_point_callback.cc:
+// 194-288 over ComputeDistanceToBox<2>, :406-482) for a point inside or on the cylinder; mesh vertices are nowhere else.
+double CylinderSignedDistance(double radius, double length, P3 q) {
+  const double r_q = std::sqrt(q.x * q.x + q.y * q.y);
+  const bool on_axis = r_q < RelTol(radius);
+  const double vx = on_axis ? 1.0 : q.x / r_q, vy = on_axis ? 0.0 : q.y / r_q;
+  const double h[2] = {radius, length / 2.0}, p[2] = {r_q, q.z};
+  double nearest[2], grad[2] = {0.0, 0.0};
+  int cls[2];  // 0 inside, 1 boundary, 2 outside
+  for (int k = 0; k < 2; ++k) {
+    const double tol = RelTol(h[k]);
+    const double sgn = p[k] < 0.0 ? -1.0 : 1.0;
+    cls[k] = std::abs(p[k]) > h[k] + tol ? 2 : (std::abs(p[k]) >= h[k] - tol ? 1 : 0);
+    nearest[k] = cls[k] ? sgn * h[k] : p[k];
+  }
+  if (cls[0] == 2 || cls[1] == 2) {
+    const double dx = p[0] - nearest[0], dy = p[1] - nearest[1];
+    const double n = std::sqrt(dx * dx + dy * dy);
+    grad[0] = dx / n;
+    grad[1] = dy / n;
+  } else if (cls[0] == 1 || cls[1] == 1) {
+    for (int k = 0; k < 2; ++k)
+      if (cls[k] == 1) grad[k] = nearest[k] < 0.0 ? -1.0 : 1.0;
+    const double n = std::sqrt(grad[0] * grad[0] + grad[1] * grad[1]);
+    grad[0] = grad[0] / n;
+    grad[1] = grad[1] / n;
+  } else {
+    double best = std::numeric_limits<double>::infinity();
+    int axis = -1;
+    for (int k = 0; k < 2; ++k)
+      for (const double bound : {h[k], -h[k]}) {
+        const double dist = std::abs(bound - p[k]);
+        if (dist < best) {
+          best = dist;
+          axis = k;
+        }
+      }
+    const double sgn = p[axis] < 0.0 ? -1.0 : 1.0;
+    nearest[axis] = sgn * h[axis];
+    grad[axis] = sgn;
+  }
+  const P3 n3{nearest[0] * vx, nearest[0] * vy, nearest[1]};
+  const P3 g3{grad[0] * vx, grad[0] * vy, grad[1]};
+  return dt(g3, sub(q, n3));
+}
+
+// CollectUniqueVertices(IdentifyBoundaryFaces(tetrahedra)) (volume_to_surface_mesh.cc:31-150) as a per-vertex flag.
+std::vector<char> BoundaryVertexFlags(const HostMesh& vol) {
+  static const int kFace[4][3] = {{1, 2, 3}, {3, 2, 0}, {1, 3, 0}, {2, 1, 0}};
+  std::map<std::array<int, 3>, int> seen;
+  for (int t = 0; t < vol.num_elements(); ++t) {
+    const int32_t* e = &vol.elems[4 * t];
+    for (const auto& f : kFace) {
+      std::array<int, 3> key{e[f[0]], e[f[1]], e[f[2]]};
+      std::sort(key.begin(), key.end());
+      ++seen[key];
+    }
+  }
+  std::vector<char> flag(vol.num_vertices(), 0);
+  for (const auto& kv : seen)
+    if (kv.second == 1)
+      for (int v : kv.first) flag[v] = 1;
+  return flag;
+}
+
+}  // namespace
+
+// MakeCylinderVolumeMeshWithMa (make_cylinder_mesh.cc:325-425): the two rim circles (bottom / top vertex interleaved)
+// around the two cap centres, then the medial axis -- two points (long), one (medium) or a disc (short) -- and the
+// fan of tetrahedra of CalcLong / Medium / ShortCylinderVolumeMeshWithMa (:47-95, :127-165, :198-260).
+HostMesh MakeCylinderVolumeMeshWithMa(double radius, double length, double hint) {
+  if (!(radius > 0) || !(length > 0) || !(hint > 0)) throw std::invalid_argument("cylinder mesh: bad parameters");
+  const double top_z = length / 2.0;
+  const double tol = RelTol(std::min(top_z, radius));
+  const int kind = top_z - radius > tol ? 0 : (radius - top_z > tol ? 2 : 1);  // long, medium, short
+  const int n = std::max(3, static_cast<int>(std::ceil(2.0 * M_PI * radius / hint)));
+  std::vector<P3> v;
+  v.push_back({0, 0, -top_z});
+  v.push_back({0, 0, top_z});
+  const int bottom_center = 0, top_center = 1;
+  std::vector<int> bottom(n), top(n);
+  const double step = 2.0 * M_PI / n;
+  for (int i = 0; i < n; ++i) {
+    const double x = radius * std::cos(step * i), y = radius * std::sin(step * i);
+    bottom[i] = static_cast<int>(v.size());
+    v.push_back({x, y, -top_z});
+    top[i] = static_cast<int>(v.size());
+    v.push_back({x, y, top_z});
+  }
+  std::vector<Tet> t;
+  if (kind == 0) {
+    const int m0 = static_cast<int>(v.size());
+    v.push_back({0, 0, -(top_z - radius)});
+    const int m1 = static_cast<int>(v.size());
+    v.push_back({0, 0, top_z - radius});
+    for (int j = 0, i = n - 1; j < n; i = j++) {
+      t.push_back({bottom_center, bottom[i], bottom[j], m0});
+      t.push_back({top_center, top[j], top[i], m1});
+      AppendPrism(m0, bottom[i], bottom[j], m1, top[i], top[j], &t);
+    }
+  } else if (kind == 1) {
+    const int m = static_cast<int>(v.size());
+    v.push_back({0, 0, 0});
+    for (int j = 0, i = n - 1; j < n; i = j++) {
+      t.push_back({bottom_center, bottom[i], bottom[j], m});
+      t.push_back({top_center, top[j], top[i], m});
+      AppendPyramid(top[i], top[j], bottom[j], bottom[i], m, &t);
+    }
+  } else {
+    const int center = static_cast<int>(v.size());
+    v.push_back({0, 0, 0});
+    std::vector<int> medial(n);
+    const double scale = (radius - length / 2.0) / radius;
+    for (int i = 0; i < n; ++i) {
+      medial[i] = static_cast<int>(v.size());
+      v.push_back({v[bottom[i]].x * scale, v[bottom[i]].y * scale, 0});
+    }
+    for (int j = 0, i = n - 1; j < n; i = j++) {
+      AppendPrism(bottom_center, bottom[i], bottom[j], center, medial[i], medial[j], &t);
+      AppendPrism(center, medial[i], medial[j], top_center, top[i], top[j], &t);
+      AppendPrism(bottom[i], medial[i], top[i], bottom[j], medial[j], top[j], &t);
+    }
+  }
+  return FromTables(t, v);
+}
+
+// MakeCapsuleVolumeMesh (make_capsule_mesh.cc:13-180): the two medial end points, the two poles, then per latitude
+// circle (equator first) the top- and bottom-cap vertex interleaved; pyramids under the cap quads, one tetrahedron per
+// pole wedge, a prism per barrel quad.
+HostMesh MakeCapsuleVolumeMesh(double radius, double length, double hint) {
+  if (!(radius > 0) || !(length > 0) || !(hint > 0)) throw std::invalid_argument("capsule mesh: bad parameters");
+  const double medial_top_z = length / 2.0;
+  const double top_z = medial_top_z + radius;
+  const int n = static_cast<int>(std::min(std::max(2.0 * M_PI * radius / hint, 3.0), 706.0));
+  const int circles = n / 2;
+  std::vector<P3> v;
+  const int medial_top = 0, medial_bottom = 1, top = 2, bottom = 3;
+  v.push_back({0, 0, medial_top_z});
+  v.push_back({0, 0, -medial_top_z});
+  v.push_back({0, 0, top_z});
+  v.push_back({0, 0, -top_z});
+  std::vector<int> top_cap(circles * n), bottom_cap(circles * n);
+  const double theta_step = M_PI_2 / circles, phi_step = 2 * M_PI / n;
+  for (int i = 0; i < circles; ++i) {
+    const double theta = M_PI_2 - i * theta_step;
+    const double s = std::sin(theta);
+    const double top_circle_z = radius * std::cos(theta) + medial_top_z;
+    for (int j = 0; j < n; ++j) {
+      const double phi = j * phi_step;
+      const double x = radius * s * std::cos(phi), y = radius * s * std::sin(phi);
+      top_cap[n * i + j] = static_cast<int>(v.size());
+      v.push_back({x, y, top_circle_z});
+      bottom_cap[n * i + j] = static_cast<int>(v.size());
+      v.push_back({x, y, -top_circle_z});
+    }
+  }
+  std::vector<Tet> t;
+  for (int i = 0; i < circles - 1; ++i)
+    for (int j = 0; j < n; ++j) {
+      const int j1 = (j + 1) % n;
+      AppendPyramid(top_cap[(i + 1) * n + j], top_cap[(i + 1) * n + j1], top_cap[i * n + j1], top_cap[i * n + j], medial_top, &t);
+      AppendPyramid(bottom_cap[i * n + j], bottom_cap[i * n + j1], bottom_cap[(i + 1) * n + j1], bottom_cap[(i + 1) * n + j],
+                    medial_bottom, &t);
+    }
+  const int last = (circles - 1) * n;
+  for (int j = 0; j < n; ++j) {
+    const int j1 = (j + 1) % n;
+    t.push_back({top, top_cap[last + j1], top_cap[last + j], medial_top});
+    t.push_back({bottom, bottom_cap[last + j], bottom_cap[last + j1], medial_bottom});
+    AppendPrism(medial_bottom, bottom_cap[j], bottom_cap[j1], medial_top, top_cap[j], top_cap[j1], &t);
+  }
+  return FromTables(t, v);
+}
+
+// MakeCylinderPressureField (make_cylinder_field.cc:18-75): extent = (-signed distance - margin) / (min(r, L/2) - margin)
+// capped at the modulus; every boundary vertex gets the (negative, for margin > 0) surface pressure exactly.
+void SetCylinderPressureField(HostMesh* m, double radius, double length, double modulus, double margin) {
+  if (!(modulus > 0) || !(radius > margin) || !(length > 2 * margin)) throw std::invalid_argument("cylinder field: bad parameters");
+  const double min_half_size = std::min(radius, length / 2.0);
+  m->pressure.resize(m->num_vertices());
+  for (int i = 0; i < m->num_vertices(); ++i) {
+    const double sd = CylinderSignedDistance(radius, length, {m->verts[3 * i], m->verts[3 * i + 1], m->verts[3 * i + 2]});
+    const double extent = (-sd - margin) / (min_half_size - margin);
+    m->pressure[i] = std::min(modulus * extent, modulus);
+  }
+  const double min_pressure = -modulus * margin / (min_half_size - margin);
+  const std::vector<char> boundary = BoundaryVertexFlags(*m);
+  for (int i = 0; i < m->num_vertices(); ++i)
+    if (boundary[i]) m->pressure[i] = min_pressure;
+}
+
+// MakeCapsulePressureField (make_capsule_field.h:55-90): the modulus on the two medial end points (vertices 0 and 1 of
+// MakeCapsuleVolumeMesh), the surface pressure -margin * E / (r - margin) everywhere else.
+void SetCapsulePressureField(HostMesh* m, double radius, double length, double modulus, double margin) {
+  if (!(modulus > 0) || !(radius > margin)) throw std::invalid_argument("capsule field: bad parameters");
+  if (m->num_vertices() < 2 || m->verts[0] != 0 || m->verts[1] != 0 || m->verts[2] != length / 2 || m->verts[3] != 0 ||
+      m->verts[4] != 0 || m->verts[5] != -length / 2)
+    throw std::invalid_argument("capsule field: the first two vertices must be the ends of the medial axis");
+  const double pressure_gradient = modulus / (radius - margin);
+  const double surface_pressure = -margin * pressure_gradient;
+  m->pressure.assign(m->num_vertices(), surface_pressure);
+  m->pressure[0] = m->pressure[1] = modulus;
+}
+
 }  // namespace dbh
 
 // ---------------------------------------------------------------------------
@@ -506,6 +728,32 @@ dbh_status dbh_mesh_set_box_pressure(dbh_mesh* mesh, double x, double y, double 
   if (!mesh) return DBH_ERR_INVALID_ARGUMENT;
   try {
     dbh::SetBoxPressureField(&mesh->m, x, y, z, modulus, margin);
+  } catch (const std::exception& e) {
+    g_shape_error = e.what();
+    return DBH_ERR_INVALID_ARGUMENT;
+  }
+  return DBH_OK;
+}
+dbh_status dbh_mesh_make_cylinder_volume_with_ma(double radius, double length, double resolution_hint, dbh_mesh** out) {
+  return Guard(out, [&] { return dbh::MakeCylinderVolumeMeshWithMa(radius, length, resolution_hint); });
+}
+dbh_status dbh_mesh_make_capsule_volume(double radius, double length, double resolution_hint, dbh_mesh** out) {
+  return Guard(out, [&] { return dbh::MakeCapsuleVolumeMesh(radius, length, resolution_hint); });
+}
+dbh_status dbh_mesh_set_cylinder_pressure(dbh_mesh* mesh, double radius, double length, double modulus, double margin) {
+  if (!mesh) return DBH_ERR_INVALID_ARGUMENT;
+  try {
+    dbh::SetCylinderPressureField(&mesh->m, radius, length, modulus, margin);
+  } catch (const std::exception& e) {
+    g_shape_error = e.what();
+    return DBH_ERR_INVALID_ARGUMENT;
+  }
+  return DBH_OK;
+}
+dbh_status dbh_mesh_set_capsule_pressure(dbh_mesh* mesh, double radius, double length, double modulus, double margin) {
+  if (!mesh) return DBH_ERR_INVALID_ARGUMENT;
+  try {
+    dbh::SetCapsulePressureField(&mesh->m, radius, length, modulus, margin);
   } catch (const std::exception& e) {
     g_shape_error = e.what();
     return DBH_ERR_INVALID_ARGUMENT;

@@ -9,6 +9,8 @@
 //   ConvertVolumeToSurfaceMesh  volume_to_surface_mesh.cc:152-187
 //   Make{Sphere,Ellipsoid,Box}PressureField  make_sphere_field.h:38-73,
 //                               make_ellipsoid_field.h:41-92, make_box_field.cc:15-56
+//   MakeCylinderVolumeMeshWithMa  make_cylinder_mesh.cc:47-425;  MakeCylinderPressureField  make_cylinder_field.cc:18-75
+//   MakeCapsuleVolumeMesh       make_capsule_mesh.cc:13-180;     MakeCapsulePressureField   make_capsule_field.h:55-90
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -34,10 +36,14 @@ HostMesh MakeSphereVolumeMesh(double radius, double resolution_hint, int strateg
 HostMesh MakeEllipsoidVolumeMesh(double a, double b, double c, double resolution_hint, int strategy);
 HostMesh MakeBoxVolumeMeshWithMa(double x, double y, double z);
 HostMesh MakeBoxVolumeMesh(double x, double y, double z, double resolution_hint);
+HostMesh MakeCylinderVolumeMeshWithMa(double radius, double length, double resolution_hint);
+HostMesh MakeCapsuleVolumeMesh(double radius, double length, double resolution_hint);
 HostMesh ConvertVolumeToSurfaceMesh(const HostMesh& volume);
 
 void SetSpherePressureField(HostMesh* mesh, double radius, double modulus, double margin);
 void SetEllipsoidPressureField(HostMesh* mesh, double a, double b, double c, double modulus, double margin);
 void SetBoxPressureField(HostMesh* mesh, double x, double y, double z, double modulus, double margin);
+void SetCylinderPressureField(HostMesh* mesh, double radius, double length, double modulus, double margin);
+void SetCapsulePressureField(HostMesh* mesh, double radius, double length, double modulus, double margin);
 
 }  // namespace dbh

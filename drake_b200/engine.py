@@ -160,10 +160,14 @@ def lib():
     L.dbh_mesh_make_ellipsoid_volume.argtypes = [dbl, dbl, dbl, dbl, C.c_int32, C.POINTER(vp)]
     L.dbh_mesh_make_box_volume_with_ma.argtypes = [dbl, dbl, dbl, C.POINTER(vp)]
     L.dbh_mesh_make_box_volume.argtypes = [dbl, dbl, dbl, dbl, C.POINTER(vp)]
+    L.dbh_mesh_make_cylinder_volume_with_ma.argtypes = [dbl, dbl, dbl, C.POINTER(vp)]
+    L.dbh_mesh_make_capsule_volume.argtypes = [dbl, dbl, dbl, C.POINTER(vp)]
     L.dbh_mesh_convert_volume_to_surface.argtypes = [vp, C.POINTER(vp)]
     L.dbh_mesh_set_sphere_pressure.argtypes = [vp, dbl, dbl, dbl]
     L.dbh_mesh_set_ellipsoid_pressure.argtypes = [vp, dbl, dbl, dbl, dbl, dbl]
     L.dbh_mesh_set_box_pressure.argtypes = [vp, dbl, dbl, dbl, dbl, dbl]
+    L.dbh_mesh_set_cylinder_pressure.argtypes = [vp, dbl, dbl, dbl, dbl]
+    L.dbh_mesh_set_capsule_pressure.argtypes = [vp, dbl, dbl, dbl, dbl]
     L.dbh_mesh_get_sizes.argtypes = [vp, _ip, _ip, _ip, _ip]
     L.dbh_mesh_copy.argtypes = [vp, _dp, _ip, _dp]
     L.dbh_mesh_destroy.argtypes = [vp]
@@ -232,6 +236,14 @@ class Mesh:
     def box_volume(x, y, z, resolution_hint) -> "Mesh":
         return Mesh._make(lib().dbh_mesh_make_box_volume, x, y, z, resolution_hint)
 
+    @staticmethod
+    def cylinder_volume_with_ma(radius, length, resolution_hint) -> "Mesh":
+        return Mesh._make(lib().dbh_mesh_make_cylinder_volume_with_ma, radius, length, resolution_hint)
+
+    @staticmethod
+    def capsule_volume(radius, length, resolution_hint) -> "Mesh":
+        return Mesh._make(lib().dbh_mesh_make_capsule_volume, radius, length, resolution_hint)
+
     def to_surface(self) -> "Mesh":
         return Mesh._make(lib().dbh_mesh_convert_volume_to_surface, self._h)
 
@@ -259,6 +271,16 @@ class Mesh:
 
     def set_box_pressure(self, x, y, z, modulus, margin=0.0) -> "Mesh":
         _check_mesh(lib().dbh_mesh_set_box_pressure(self._h, x, y, z, modulus, margin))
+        self._cache = None
+        return self
+
+    def set_cylinder_pressure(self, radius, length, modulus, margin=0.0) -> "Mesh":
+        _check_mesh(lib().dbh_mesh_set_cylinder_pressure(self._h, radius, length, modulus, margin))
+        self._cache = None
+        return self
+
+    def set_capsule_pressure(self, radius, length, modulus, margin=0.0) -> "Mesh":
+        _check_mesh(lib().dbh_mesh_set_capsule_pressure(self._h, radius, length, modulus, margin))
         self._cache = None
         return self
 

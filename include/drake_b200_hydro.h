@@ -173,7 +173,7 @@ dbh_status dbh_asset_get_derived(dbh_context* ctx, int32_t asset, double* gradie
  *        (make_ellipsoid_mesh.h:50-73), MakeBoxVolumeMeshWithMaAndSymmetricTriangles
  *        (make_box_mesh.cc:475-504), MakeBoxVolumeMesh (make_box_mesh.cc:870-890),
  *        ConvertVolumeToSurfaceMesh (volume_to_surface_mesh.cc:152-187) and
- *        Make{Sphere,Ellipsoid,Box}PressureField. strategy: 0 = kSingleInteriorVertex,
+ *        Make{Sphere,Ellipsoid,Box,Cylinder,Capsule}PressureField. strategy: 0 = kSingleInteriorVertex,
  *        1 = kDenseInteriorVertices (tessellation_strategy.h). ------------------- */
 typedef struct dbh_mesh dbh_mesh;
 const char* dbh_mesh_last_error(void);
@@ -182,12 +182,22 @@ dbh_status dbh_mesh_make_ellipsoid_volume(double a, double b, double c, double r
                                           dbh_mesh** out);
 dbh_status dbh_mesh_make_box_volume_with_ma(double x, double y, double z, dbh_mesh** out);
 dbh_status dbh_mesh_make_box_volume(double x, double y, double z, double resolution_hint, dbh_mesh** out);
+/* MakeCylinderVolumeMeshWithMa (make_cylinder_mesh.cc:325-425) and MakeCapsuleVolumeMesh (make_capsule_mesh.cc:13-180),
+ * both about the z axis; with dbh_mesh_convert_volume_to_surface they are MakeCylinderSurfaceMesh / MakeCapsuleSurfaceMesh
+ * (make_cylinder_mesh.h:678-684, make_capsule_mesh.h:117-123), the rigid representations. */
+dbh_status dbh_mesh_make_cylinder_volume_with_ma(double radius, double length, double resolution_hint, dbh_mesh** out);
+dbh_status dbh_mesh_make_capsule_volume(double radius, double length, double resolution_hint, dbh_mesh** out);
 dbh_status dbh_mesh_convert_volume_to_surface(const dbh_mesh* volume, dbh_mesh** out);
 dbh_status dbh_mesh_set_sphere_pressure(dbh_mesh* mesh, double radius, double hydroelastic_modulus, double margin);
 dbh_status dbh_mesh_set_ellipsoid_pressure(dbh_mesh* mesh, double a, double b, double c, double hydroelastic_modulus,
                                            double margin);
 dbh_status dbh_mesh_set_box_pressure(dbh_mesh* mesh, double x, double y, double z, double hydroelastic_modulus,
                                      double margin);
+/* MakeCylinderPressureField (make_cylinder_field.cc:18-75), MakeCapsulePressureField (make_capsule_field.h:55-90). */
+dbh_status dbh_mesh_set_cylinder_pressure(dbh_mesh* mesh, double radius, double length, double hydroelastic_modulus,
+                                          double margin);
+dbh_status dbh_mesh_set_capsule_pressure(dbh_mesh* mesh, double radius, double length, double hydroelastic_modulus,
+                                         double margin);
 dbh_status dbh_mesh_get_sizes(const dbh_mesh* mesh, int32_t* num_vertices, int32_t* num_elements,
                               int32_t* vertices_per_element, int32_t* has_pressure);
 /* vertices [nv*3], elements [ne*vertices_per_element], pressure [nv]; any may be NULL. */

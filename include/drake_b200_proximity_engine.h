@@ -56,7 +56,8 @@ struct RigidTransformd {
   }
 };
 
-// geometry/shape_specification.h (the primitives the path's mesh generators cover) plus explicit meshes.
+// geometry/shape_specification.h: every primitive the reference gives a hydroelastic representation, plus explicit
+// meshes (its Mesh / Convex arrive here as the vertex and element arrays the caller loaded).
 struct Sphere {
   double radius;
 };
@@ -67,10 +68,10 @@ struct Ellipsoid {
   double a, b, c;
 };
 struct HalfSpace {};  // z <= 0 of the geometry frame (shape_specification.h)
-// Cylinder and Capsule (axis z, shape_specification.h): geometries WITHOUT a hydroelastic representation here (their
-// volume-mesh generators, make_cylinder_mesh / make_capsule_mesh, are outside the path) -- they take part in
-// ComputeContactSurfacesWithFallback's point pairs against a Sphere (Drake's closed forms) or a HalfSpace (FCL's),
-// drake_b200_point_pair.h.
+// Cylinder and Capsule (axis z, shape_specification.h): meshed by MakeCylinderVolumeMeshWithMa / MakeCapsuleVolumeMesh
+// like the reference (hydroelastic_internal.cc:344-363,465-508); registered with HydroelasticType::kUndefined they take
+// part in ComputeContactSurfacesWithFallback's point pairs against a Sphere (Drake's closed forms) or a HalfSpace
+// (FCL's), drake_b200_point_pair.h.
 struct Cylinder {
   double radius, length;
 };
@@ -471,9 +472,6 @@ class ProximityEngine {
     last_elements_.clear();
     last_vertices_per_element_ = 0;
     if (p.compliance_type == HydroelasticType::kUndefined) return -1;
-    if (std::holds_alternative<Cylinder>(shape) || std::holds_alternative<Capsule>(shape))
-      throw std::logic_error("a Cylinder or Capsule has no hydroelastic representation in this back end (register it with "
-                             "HydroelasticType::kUndefined: it then takes part in the point-pair fallback)");
     const bool soft = p.compliance_type == HydroelasticType::kCompliant;
     int32_t asset = -1;
     struct MeshHandle {
@@ -513,6 +511,18 @@ class ProximityEngine {
                 "MakeEllipsoidVolumeMesh");
       if (soft)
         CheckMesh(dbh_mesh_set_ellipsoid_pressure(vol.h, ea, eb, ec, p.hydroelastic_modulus, m), "MakeEllipsoidPressureField");
+    } else if (const auto* cy = std::get_if<Cylinder>(&shape)) {
+      // MakeCylinderVolumeMeshWithMa on Cylinder(radius + margin, length + 2 margin) (hydroelastic_internal.cc:465-486);
+      // rigid: MakeCylinderSurfaceMesh = its boundary (:344-353).
+      const double r = cy->radius + m, l = cy->length + 2.0 * m;
+      CheckMesh(dbh_mesh_make_cylinder_volume_with_ma(r, l, p.resolution_hint, &vol.h), "MakeCylinderVolumeMeshWithMa");
+      if (soft) CheckMesh(dbh_mesh_set_cylinder_pressure(vol.h, r, l, p.hydroelastic_modulus, m), "MakeCylinderPressureField");
+    } else if (const auto* ca = std::get_if<Capsule>(&shape)) {
+      // MakeCapsuleVolumeMesh on Capsule(radius + margin, length) (hydroelastic_internal.cc:488-508); rigid:
+      // MakeCapsuleSurfaceMesh (:355-363).
+      const double r = ca->radius + m;
+      CheckMesh(dbh_mesh_make_capsule_volume(r, ca->length, p.resolution_hint, &vol.h), "MakeCapsuleVolumeMesh");
+      if (soft) CheckMesh(dbh_mesh_set_capsule_pressure(vol.h, r, ca->length, p.hydroelastic_modulus, m), "MakeCapsulePressureField");
     } else if (const auto* v = std::get_if<VolumeMeshShape>(&shape)) {
       if (!soft) throw std::logic_error("a volume mesh can only be registered as a compliant geometry");
       Check(dbh_register_compliant_mesh(ctx_, static_cast<int32_t>(v->vertices.size() / 3), v->vertices.data(),

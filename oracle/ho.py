@@ -52,6 +52,10 @@ def lib():
             "ho_make_ellipsoid_volume": [C.c_double] * 4 + [C.c_int],
             "ho_make_box_volume_ma": [C.c_double] * 3,
             "ho_make_box_volume_grid": [C.c_double] * 4,
+            "ho_make_cylinder_volume_ma": [C.c_double] * 3,
+            "ho_make_capsule_volume": [C.c_double] * 3,
+            "ho_cylinder_field": [C.c_int] + [C.c_double] * 4,
+            "ho_capsule_field": [C.c_int] + [C.c_double] * 4,
             "ho_sphere_field": [C.c_int, C.c_double, C.c_double, C.c_double],
             "ho_ellipsoid_field": [C.c_int] + [C.c_double] * 5,
             "ho_box_field": [C.c_int] + [C.c_double] * 5,
@@ -168,6 +172,16 @@ class VolumeMesh:
     @staticmethod
     def box_grid(x: float, y: float, z: float, hint: float) -> "VolumeMesh":
         return VolumeMesh(lib().ho_make_box_volume_grid(x, y, z, hint))
+
+    @staticmethod
+    def cylinder_ma(radius: float, length: float, hint: float) -> "VolumeMesh":
+        """MakeCylinderVolumeMeshWithMa (make_cylinder_mesh.cc:325-425)."""
+        return VolumeMesh(lib().ho_make_cylinder_volume_ma(radius, length, hint))
+
+    @staticmethod
+    def capsule(radius: float, length: float, hint: float) -> "VolumeMesh":
+        """MakeCapsuleVolumeMesh (make_capsule_mesh.cc:13-180)."""
+        return VolumeMesh(lib().ho_make_capsule_volume(radius, length, hint))
 
     @staticmethod
     def from_arrays(verts, tets) -> "VolumeMesh":
@@ -300,6 +314,16 @@ class VolumeField:
     @staticmethod
     def box(mesh: VolumeMesh, x: float, y: float, z: float, modulus: float, margin: float = 0.0):
         return VolumeField(lib().ho_box_field(mesh.h, x, y, z, modulus, margin), mesh)
+
+    @staticmethod
+    def cylinder(mesh: VolumeMesh, radius: float, length: float, modulus: float, margin: float = 0.0):
+        """MakeCylinderPressureField (make_cylinder_field.cc:18-75)."""
+        return VolumeField(lib().ho_cylinder_field(mesh.h, radius, length, modulus, margin), mesh)
+
+    @staticmethod
+    def capsule(mesh: VolumeMesh, radius: float, length: float, modulus: float, margin: float = 0.0):
+        """MakeCapsulePressureField (make_capsule_field.h:55-90)."""
+        return VolumeField(lib().ho_capsule_field(mesh.h, radius, length, modulus, margin), mesh)
 
     @staticmethod
     def from_values(mesh: VolumeMesh, values) -> "VolumeField":

@@ -21,6 +21,7 @@
 #include "ho_contact.h"
 #include "ho_halfspace.h"
 #include "ho_traction.h"
+#include "ho_cylinder_capsule.h"
 
 using namespace ho;
 
@@ -344,6 +345,14 @@ int ho_make_box_volume_grid(double x, double y, double z, double hint) {
   HO_TRY return AddVol(MakeBoxVolumeMesh({x, y, z}, hint));
   HO_CATCH(-1)
 }
+int ho_make_cylinder_volume_ma(double radius, double length, double hint) {
+  HO_TRY return AddVol(MakeCylinderVolumeMeshWithMa(radius, length, hint));
+  HO_CATCH(-1)
+}
+int ho_make_capsule_volume(double radius, double length, double hint) {
+  HO_TRY return AddVol(MakeCapsuleVolumeMesh(radius, length, hint));
+  HO_CATCH(-1)
+}
 int ho_make_volume(int nv, const double* verts, int nt, const int* tets) {
   HO_TRY
   std::vector<Tet> t(nt);
@@ -425,6 +434,14 @@ int ho_ellipsoid_field(int vol, double a, double b, double c, double modulus, do
 }
 int ho_box_field(int vol, double x, double y, double z, double modulus, double margin) {
   HO_TRY return AddField(MakeBoxPressureField({x, y, z}, g_vols[vol]->mesh, modulus, margin));
+  HO_CATCH(-1)
+}
+int ho_cylinder_field(int vol, double radius, double length, double modulus, double margin) {
+  HO_TRY return AddField(MakeCylinderPressureField(radius, length, g_vols[vol]->mesh, modulus, margin));
+  HO_CATCH(-1)
+}
+int ho_capsule_field(int vol, double radius, double length, double modulus, double margin) {
+  HO_TRY return AddField(MakeCapsulePressureField(radius, length, g_vols[vol]->mesh, modulus, margin));
   HO_CATCH(-1)
 }
 int ho_make_field(int vol, const double* values) {

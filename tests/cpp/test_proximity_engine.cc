@@ -44,11 +44,17 @@ static int MarginCase(char** argv) {
   rigid.resolution_hint = 0.1;
   const RigidTransformd X_WA = RotX(M_PI, 0, 0, 0);
   const RigidTransformd X_WB = RigidTransformd::FromTranslation(0, 0, -(R + R) + 0.125);
-  for (int k = 0; k < 2; ++k) {
+  // Cases 2-4: Capsule and Cylinder get the reference's representations too (MakeCapsuleVolumeMesh /
+  // MakeCylinderVolumeMeshWithMa on the inflated shape, hydroelastic_internal.cc:465-508; rigid: the boundary of the
+  // same mesh, :344-363).
+  for (int k = 0; k < 5; ++k) {
     ProximityEngine e(0);
-    if (k == 0) e.AddDynamicGeometry(Sphere{R}, X_WA, 1, soft);
-    else e.AddDynamicGeometry(Box{0.5, 0.4, 0.5}, X_WA, 1, soft);
-    e.AddDynamicGeometry(Sphere{R}, X_WB, 2, rigid);
+    if (k == 0 || k == 4) e.AddDynamicGeometry(Sphere{R}, X_WA, 1, soft);
+    else if (k == 1) e.AddDynamicGeometry(Box{0.5, 0.4, 0.5}, X_WA, 1, soft);
+    else if (k == 2) e.AddDynamicGeometry(Capsule{0.2, 0.3}, X_WA, 1, soft);
+    else e.AddDynamicGeometry(Cylinder{0.25, 0.4}, X_WA, 1, soft);
+    if (k < 4) e.AddDynamicGeometry(Sphere{R}, X_WB, 2, rigid);
+    else e.AddDynamicGeometry(Cylinder{0.2, 0.3}, X_WB, 2, rigid);
     auto poly = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
     EXPECT(poly.size() == 1);
     const int faces = std::atoi(argv[2 + 3 * k]);
@@ -78,14 +84,6 @@ static int MarginCase(char** argv) {
     EXPECT(std::fabs(pairs[0].p_WCa[0] - R) < 1e-15 && std::fabs(pairs[0].p_WCb[0] - 0.2) < 1e-15);
     EXPECT(std::fabs(pairs[1].depth - 0.05) < 1e-15 && std::fabs(pairs[1].nhat_BA_W[2] + 1.0) < 1e-15);
     EXPECT(std::fabs(pairs[1].p_WCa[2] - R) < 1e-15 && std::fabs(pairs[1].p_WCb[2] - 0.2) < 1e-15);
-    bool threw = false;
-    try {
-      ProximityEngine bad(0);
-      bad.AddDynamicGeometry(Cylinder{0.1, 0.4}, RigidTransformd::Identity(), 1, rigid);
-    } catch (const std::logic_error&) {
-      threw = true;
-    }
-    EXPECT(threw);
   }
   std::printf("ok\n");
   return 0;
@@ -99,7 +97,7 @@ int main(int argc, char** argv) {
     std::printf("no device: %s\n", e.what());
     return 3;
   }
-  if (argc == 8 && std::string(argv[1]) == "margin") return MarginCase(argv);
+  if (argc == 17 && std::string(argv[1]) == "margin") return MarginCase(argv);
   const double R = 0.25;
   ProximityProperties soft;
   soft.compliance_type = HydroelasticType::kCompliant;

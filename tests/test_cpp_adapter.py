@@ -43,8 +43,9 @@ def test_cpp_adapter_known_answers():
 
 @pytest.mark.gpu
 def test_cpp_adapter_inflates_compliant_primitives_by_the_margin():
-    """A compliant Sphere / Box with margin > 0 is meshed and given its pressure field on the shape inflated by the
-    margin (hydroelastic_internal.cc:412-465): the adapter's surfaces must match the oracle's inflated construction."""
+    """A compliant Sphere / Box / Capsule / Cylinder with margin > 0 is meshed and given its pressure field on the shape
+    inflated by the margin (hydroelastic_internal.cc:412-508): the adapter's surfaces must match the oracle's inflated
+    construction; a rigid Cylinder is the boundary of MakeCylinderVolumeMeshWithMa."""
     import math
 
     import numpy as np
@@ -59,8 +60,16 @@ def test_cpp_adapter_inflates_compliant_primitives_by_the_margin():
     fs = ho.VolumeField.sphere(ms, R + margin, E, margin)
     mb = ho.VolumeMesh.box_ma(0.5 + 2 * margin, 0.4 + 2 * margin, 0.5 + 2 * margin)
     fb = ho.VolumeField.box(mb, 0.5 + 2 * margin, 0.4 + 2 * margin, 0.5 + 2 * margin, E, margin)
-    for m, f in ((ms, fs), (mb, fb)):
-        want = ho.soft_rigid(m, f, rigid, X_WA, X_WB, 1, 2, ho.KPOLYGON)
+    # Capsule(0.2, 0.3) -> Capsule(radius + margin, length); Cylinder(0.25, 0.4) -> Cylinder(radius + margin, length +
+    # 2 margin) (hydroelastic_internal.cc:465-508); the last case puts a RIGID Cylinder(0.2, 0.3) (MakeCylinderSurfaceMesh
+    # at the rigid resolution hint 0.1) under the compliant sphere.
+    mc = ho.VolumeMesh.capsule(0.2 + margin, 0.3, 0.25)
+    fc = ho.VolumeField.capsule(mc, 0.2 + margin, 0.3, E, margin)
+    my = ho.VolumeMesh.cylinder_ma(0.25 + margin, 0.4 + 2 * margin, 0.25)
+    fy = ho.VolumeField.cylinder(my, 0.25 + margin, 0.4 + 2 * margin, E, margin)
+    rigid_cylinder = ho.VolumeMesh.cylinder_ma(0.2, 0.3, 0.1).to_surface()
+    for m, f, r in ((ms, fs, rigid), (mb, fb, rigid), (mc, fc, rigid), (my, fy, rigid), (ms, fs, rigid_cylinder)):
+        want = ho.soft_rigid(m, f, r, X_WA, X_WB, 1, 2, ho.KPOLYGON)
         assert want is not None and want.num_faces > 4
         args += [str(want.num_faces), repr(float(want.total_area)), repr(float(np.sum(want.e_centroid)))]
     # The nominal (un-inflated) construction gives a different surface: the test can tell the two apart.
