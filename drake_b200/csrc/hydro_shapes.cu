@@ -657,6 +657,95 @@ void SetCapsulePressureField(HostMesh* m, double radius, double length, double m
   m->pressure[0] = m->pressure[1] = modulus;
 }
 
+
+// ---- Convex / Mesh: MakeConvexVolumeMesh (make_convex_mesh.cc:17-60), MakeVolumeMeshPressureField (make_mesh_field.cc:
+//      45-96) over CalcDistanceToSurfaceMesh (calc_distance_to_surface_mesh.cc:30-120; its BVH only prunes: the result is
+//      the minimum over the boundary triangles, taken here directly) ----------------------------------------------------
+namespace {
+
+double SquaredDistanceToSegment(P3 q, P3 a, P3 b) {
+  const P3 ab = sub(b, a), aq = sub(q, a);
+  if (dt(aq, ab) <= 0.0) return dt(aq, aq);
+  const P3 bq = sub(q, b);
+  if (dt(bq, ab) >= 0.0) return dt(bq, bq);
+  const P3 c = crs(ab, aq);
+  return dt(c, c) / dt(ab, ab);
+}
+
+// In the triangle's frame T (origin A, x along AB, z the normal): inside the triangle's prism the distance is |z|, else
+// it is that to the nearest edge.
+double SquaredDistanceToTriangle(P3 q, P3 a, P3 b, P3 c) {
+  const P3 ab = sub(b, a), ac = sub(c, a);
+  const double lab = len(ab);
+  const P3 tx{ab.x / lab, ab.y / lab, ab.z / lab};
+  const P3 n = crs(ab, ac);
+  const double ln = len(n);
+  const P3 tz{n.x / ln, n.y / ln, n.z / ln};
+  const P3 ty = crs(tz, tx);
+  const P3 aq = sub(q, a);
+  const P3 tb{dt(tx, ab), dt(ty, ab), dt(tz, ab)}, tc{dt(tx, ac), dt(ty, ac), dt(tz, ac)}, tq{dt(tx, aq), dt(ty, aq), dt(tz, aq)};
+  const double det = tb.x * tc.y - tc.x * tb.y;
+  const double b0 = (tq.x * tc.y - tc.x * tq.y) / det, b1 = (tb.x * tq.y - tq.x * tb.y) / det;
+  if (b0 >= 0.0 && b1 >= 0.0 && b0 + b1 <= 1.0) return tq.z * tq.z;
+  const P3 o{0, 0, 0};
+  return std::min({SquaredDistanceToSegment(tq, o, tb), SquaredDistanceToSegment(tq, o, tc), SquaredDistanceToSegment(tq, tb, tc)});
+}
+
+}  // namespace
+
+// The surface's vertices, then the centroid of the enclosed volume; one tetrahedron {centroid, v0, v1, v2} per triangle.
+HostMesh MakeConvexVolumeMesh(const HostMesh& surface) {
+  if (surface.verts_per_elem != 3 || surface.num_elements() < 4) throw std::invalid_argument("convex mesh: not a closed surface");
+  double six_total_volume = 0;
+  P3 centroid{0, 0, 0};
+  auto vertex = [&](int v) { return P3{surface.verts[3 * v], surface.verts[3 * v + 1], surface.verts[3 * v + 2]}; };
+  for (int t = 0; t < surface.num_elements(); ++t) {
+    const P3 p = vertex(surface.elems[3 * t]), q = vertex(surface.elems[3 * t + 1]), r = vertex(surface.elems[3 * t + 2]);
+    const double six_volume = dt(crs(p, q), r);
+    six_total_volume += six_volume;
+    centroid = {centroid.x + six_volume * ((p.x + q.x) + r.x), centroid.y + six_volume * ((p.y + q.y) + r.y),
+                centroid.z + six_volume * ((p.z + q.z) + r.z)};
+  }
+  if (!(six_total_volume > 0)) throw std::invalid_argument("convex mesh: the surface does not enclose a positive volume");
+  const double k = 4 * six_total_volume;
+  HostMesh m;
+  m.verts_per_elem = 4;
+  m.verts = surface.verts;
+  m.verts.push_back(centroid.x / k);
+  m.verts.push_back(centroid.y / k);
+  m.verts.push_back(centroid.z / k);
+  const int c = surface.num_vertices();
+  for (int t = 0; t < surface.num_elements(); ++t)
+    for (int v : {c, surface.elems[3 * t], surface.elems[3 * t + 1], surface.elems[3 * t + 2]}) m.elems.push_back(v);
+  return m;
+}
+
+// Distance of every interior vertex to the boundary surface (+ margin), scaled so that the deepest vertex carries the
+// modulus; boundary vertices sit at -E margin / (max - margin) (0 without margin).
+void SetVolumeMeshPressureField(HostMesh* m, double modulus, double margin) {
+  if (m->verts_per_elem != 4 || !(modulus > 0) || !(margin >= 0)) throw std::invalid_argument("mesh field: bad parameters");
+  const HostMesh surface = ConvertVolumeToSurfaceMesh(*m);
+  const std::vector<char> boundary = BoundaryVertexFlags(*m);
+  auto sv = [&](int v) { return P3{surface.verts[3 * v], surface.verts[3 * v + 1], surface.verts[3 * v + 2]}; };
+  std::vector<double> values(m->num_vertices(), 0.0);
+  double max_value = std::numeric_limits<double>::lowest();
+  for (int v = 0; v < m->num_vertices(); ++v) {
+    if (boundary[v]) continue;
+    const P3 q{m->verts[3 * v], m->verts[3 * v + 1], m->verts[3 * v + 2]};
+    double min_squared = std::numeric_limits<double>::infinity();
+    for (int t = 0; t < surface.num_elements(); ++t)
+      min_squared = std::min(min_squared, SquaredDistanceToTriangle(q, sv(surface.elems[3 * t]), sv(surface.elems[3 * t + 1]),
+                                                                    sv(surface.elems[3 * t + 2])));
+    values[v] = std::sqrt(min_squared) + margin;
+    max_value = std::max(values[v], max_value);
+  }
+  if (!(max_value > 0))
+    throw std::invalid_argument("MakeVolumeMeshPressureField(): the computed max distance to boundary among all mesh vertices "
+                                "is non-positive. Perhaps the mesh lacks interior vertices.");
+  m->pressure.resize(values.size());
+  for (size_t v = 0; v < values.size(); ++v) m->pressure[v] = modulus * (values[v] - margin) / (max_value - margin);
+}
+
 }  // namespace dbh
 
 // ---------------------------------------------------------------------------
@@ -754,6 +843,34 @@ dbh_status dbh_mesh_set_capsule_pressure(dbh_mesh* mesh, double radius, double l
   if (!mesh) return DBH_ERR_INVALID_ARGUMENT;
   try {
     dbh::SetCapsulePressureField(&mesh->m, radius, length, modulus, margin);
+  } catch (const std::exception& e) {
+    g_shape_error = e.what();
+    return DBH_ERR_INVALID_ARGUMENT;
+  }
+  return DBH_OK;
+}
+dbh_status dbh_mesh_from_arrays(int32_t num_vertices, const double* vertices, int32_t num_elements, const int32_t* elements,
+                                int32_t vertices_per_element, dbh_mesh** out) {
+  return Guard(out, [&] {
+    if (num_vertices <= 0 || num_elements <= 0 || !vertices || !elements || (vertices_per_element != 3 && vertices_per_element != 4))
+      throw std::invalid_argument("mesh_from_arrays: bad argument");
+    dbh::HostMesh m;
+    m.verts_per_elem = vertices_per_element;
+    m.verts.assign(vertices, vertices + 3 * static_cast<size_t>(num_vertices));
+    m.elems.assign(elements, elements + static_cast<size_t>(vertices_per_element) * num_elements);
+    for (int32_t v : m.elems)
+      if (v < 0 || v >= num_vertices) throw std::invalid_argument("mesh_from_arrays: vertex index out of range");
+    return m;
+  });
+}
+dbh_status dbh_mesh_make_convex_volume(const dbh_mesh* surface, dbh_mesh** out) {
+  if (!surface) return DBH_ERR_INVALID_ARGUMENT;
+  return Guard(out, [&] { return dbh::MakeConvexVolumeMesh(surface->m); });
+}
+dbh_status dbh_mesh_set_volume_mesh_pressure(dbh_mesh* mesh, double modulus, double margin) {
+  if (!mesh) return DBH_ERR_INVALID_ARGUMENT;
+  try {
+    dbh::SetVolumeMeshPressureField(&mesh->m, modulus, margin);
   } catch (const std::exception& e) {
     g_shape_error = e.what();
     return DBH_ERR_INVALID_ARGUMENT;

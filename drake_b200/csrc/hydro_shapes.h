@@ -39,11 +39,13 @@ HostMesh MakeBoxVolumeMesh(double x, double y, double z, double resolution_hint)
 HostMesh MakeCylinderVolumeMeshWithMa(double radius, double length, double resolution_hint);
 HostMesh MakeCapsuleVolumeMesh(double radius, double length, double resolution_hint);
 HostMesh ConvertVolumeToSurfaceMesh(const HostMesh& volume);
+HostMesh MakeConvexVolumeMesh(const HostMesh& closed_surface);  // make_convex_mesh.cc:17-60
 
 void SetSpherePressureField(HostMesh* mesh, double radius, double modulus, double margin);
 void SetEllipsoidPressureField(HostMesh* mesh, double a, double b, double c, double modulus, double margin);
 void SetBoxPressureField(HostMesh* mesh, double x, double y, double z, double modulus, double margin);
 void SetCylinderPressureField(HostMesh* mesh, double radius, double length, double modulus, double margin);
 void SetCapsulePressureField(HostMesh* mesh, double radius, double length, double modulus, double margin);
+void SetVolumeMeshPressureField(HostMesh* mesh, double modulus, double margin);  // make_mesh_field.cc:45-96
 
 }  // namespace dbh

@@ -168,6 +168,9 @@ def lib():
     L.dbh_mesh_set_box_pressure.argtypes = [vp, dbl, dbl, dbl, dbl, dbl]
     L.dbh_mesh_set_cylinder_pressure.argtypes = [vp, dbl, dbl, dbl, dbl]
     L.dbh_mesh_set_capsule_pressure.argtypes = [vp, dbl, dbl, dbl, dbl]
+    L.dbh_mesh_from_arrays.argtypes = [C.c_int32, _dp, C.c_int32, _ip, C.c_int32, C.POINTER(vp)]
+    L.dbh_mesh_make_convex_volume.argtypes = [vp, C.POINTER(vp)]
+    L.dbh_mesh_set_volume_mesh_pressure.argtypes = [vp, dbl, dbl]
     L.dbh_mesh_get_sizes.argtypes = [vp, _ip, _ip, _ip, _ip]
     L.dbh_mesh_copy.argtypes = [vp, _dp, _ip, _dp]
     L.dbh_mesh_destroy.argtypes = [vp]
@@ -244,6 +247,18 @@ class Mesh:
     def capsule_volume(radius, length, resolution_hint) -> "Mesh":
         return Mesh._make(lib().dbh_mesh_make_capsule_volume, radius, length, resolution_hint)
 
+    @staticmethod
+    def from_arrays(vertices, elements) -> "Mesh":
+        """A caller's tetrahedral ([ne,4]) or triangle ([ne,3]) mesh."""
+        v, e = _d(vertices).reshape(-1, 3), _i(elements)
+        if e.ndim != 2 or e.shape[1] not in (3, 4):
+            raise ValueError("elements must be [ne, 4] (tetrahedra) or [ne, 3] (triangles)")
+        return Mesh._make(lib().dbh_mesh_from_arrays, len(v), _ptr(v, _dp), len(e), _ptr(e, _ip), e.shape[1])
+
+    def to_convex_volume(self) -> "Mesh":
+        """MakeConvexVolumeMesh of a closed triangle surface (make_convex_mesh.cc:17-60)."""
+        return Mesh._make(lib().dbh_mesh_make_convex_volume, self._h)
+
     def to_surface(self) -> "Mesh":
         return Mesh._make(lib().dbh_mesh_convert_volume_to_surface, self._h)
 
@@ -271,6 +286,12 @@ class Mesh:
 
     def set_box_pressure(self, x, y, z, modulus, margin=0.0) -> "Mesh":
         _check_mesh(lib().dbh_mesh_set_box_pressure(self._h, x, y, z, modulus, margin))
+        self._cache = None
+        return self
+
+    def set_volume_mesh_pressure(self, modulus, margin=0.0) -> "Mesh":
+        """MakeVolumeMeshPressureField (make_mesh_field.cc:45-96)."""
+        _check_mesh(lib().dbh_mesh_set_volume_mesh_pressure(self._h, modulus, margin))
         self._cache = None
         return self
 

@@ -193,6 +193,15 @@ dbh_status dbh_mesh_set_ellipsoid_pressure(dbh_mesh* mesh, double a, double b, d
                                            double margin);
 dbh_status dbh_mesh_set_box_pressure(dbh_mesh* mesh, double x, double y, double z, double hydroelastic_modulus,
                                      double margin);
+/* A caller's own mesh as a dbh_mesh: vertices [nv*3], elements [ne*vertices_per_element] (4: tetrahedra, 3: triangles).
+ * With the next two calls this is the reference's compliant Convex / Mesh: MakeConvexVolumeMesh (make_convex_mesh.cc:
+ * 17-60: the closed surface's vertices + the centroid of the enclosed volume, one tetrahedron per triangle) and
+ * MakeVolumeMeshPressureField (make_mesh_field.cc:45-96: distance of every interior vertex to the boundary, scaled so that
+ * the deepest one carries the modulus; throws the reference's error for a mesh without interior vertices). */
+dbh_status dbh_mesh_from_arrays(int32_t num_vertices, const double* vertices, int32_t num_elements, const int32_t* elements,
+                                int32_t vertices_per_element, dbh_mesh** out);
+dbh_status dbh_mesh_make_convex_volume(const dbh_mesh* closed_surface, dbh_mesh** out);
+dbh_status dbh_mesh_set_volume_mesh_pressure(dbh_mesh* mesh, double hydroelastic_modulus, double margin);
 /* MakeCylinderPressureField (make_cylinder_field.cc:18-75), MakeCapsulePressureField (make_capsule_field.h:55-90). */
 dbh_status dbh_mesh_set_cylinder_pressure(dbh_mesh* mesh, double radius, double length, double hydroelastic_modulus,
                                           double margin);

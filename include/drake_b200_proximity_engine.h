@@ -81,9 +81,11 @@ struct Capsule {
 struct VolumeMeshShape {  // VolumeMesh<double> + per-vertex pressure
   std::vector<double> vertices;  // [nv*3]
   std::vector<int32_t> tetrahedra;  // [nt*4]
-  std::vector<double> pressure;  // [nv]
+  std::vector<double> pressure;  // [nv]; empty: MakeVolumeMeshPressureField computes it (the reference's Mesh(.vtk))
 };
-struct SurfaceMeshShape {  // TriangleSurfaceMesh<double>
+// TriangleSurfaceMesh<double>. Rigid: the reference's rigid Mesh / Convex. Compliant: taken to be the convex hull of the
+// reference's compliant Convex (closed, wound outwards): MakeConvexVolumeMesh + MakeVolumeMeshPressureField.
+struct SurfaceMeshShape {
   std::vector<double> vertices;
   std::vector<int32_t> triangles;
 };
@@ -523,6 +525,27 @@ class ProximityEngine {
       const double r = ca->radius + m;
       CheckMesh(dbh_mesh_make_capsule_volume(r, ca->length, p.resolution_hint, &vol.h), "MakeCapsuleVolumeMesh");
       if (soft) CheckMesh(dbh_mesh_set_capsule_pressure(vol.h, r, ca->length, p.hydroelastic_modulus, m), "MakeCapsulePressureField");
+    } else if (const auto* v = std::get_if<VolumeMeshShape>(&shape); v && soft && v->pressure.empty()) {
+      // The reference's compliant Mesh(.vtk): the tetrahedra as given, MakeVolumeMeshPressureField on them
+      // (hydroelastic_internal.cc:579-640). With margin > 0 the reference first inflates the mesh (MakeInflatedMesh, a
+      // QP per vertex): not built here.
+      if (p.margin > 0) throw std::logic_error("a compliant volume mesh with margin > 0 needs MakeInflatedMesh, which this back end does not provide");
+      CheckMesh(dbh_mesh_from_arrays(static_cast<int32_t>(v->vertices.size() / 3), v->vertices.data(),
+                                     static_cast<int32_t>(v->tetrahedra.size() / 4), v->tetrahedra.data(), 4, &vol.h),
+                "mesh_from_arrays");
+      CheckMesh(dbh_mesh_set_volume_mesh_pressure(vol.h, p.hydroelastic_modulus, 0.0), "MakeVolumeMeshPressureField");
+    } else if (const auto* cs = std::get_if<SurfaceMeshShape>(&shape); cs && soft) {
+      // The reference's compliant Convex (and non-.vtk Mesh): MakeConvexVolumeMesh of the convex hull -- here the closed,
+      // outward-wound surface the caller gives IS taken to be that hull (the reference computes it with qhull) -- and
+      // MakeVolumeMeshPressureField (hydroelastic_internal.cc:555-577,598-601). margin > 0 needs the hull re-made with
+      // the margin (MakeConvexHull): not built here.
+      if (p.margin > 0) throw std::logic_error("a compliant convex surface with margin > 0 needs MakeConvexHull, which this back end does not provide");
+      MeshHandle hull;
+      CheckMesh(dbh_mesh_from_arrays(static_cast<int32_t>(cs->vertices.size() / 3), cs->vertices.data(),
+                                     static_cast<int32_t>(cs->triangles.size() / 3), cs->triangles.data(), 3, &hull.h),
+                "mesh_from_arrays");
+      CheckMesh(dbh_mesh_make_convex_volume(hull.h, &vol.h), "MakeConvexVolumeMesh");
+      CheckMesh(dbh_mesh_set_volume_mesh_pressure(vol.h, p.hydroelastic_modulus, 0.0), "MakeVolumeMeshPressureField");
     } else if (const auto* v = std::get_if<VolumeMeshShape>(&shape)) {
       if (!soft) throw std::logic_error("a volume mesh can only be registered as a compliant geometry");
       Check(dbh_register_compliant_mesh(ctx_, static_cast<int32_t>(v->vertices.size() / 3), v->vertices.data(),
@@ -533,7 +556,6 @@ class ProximityEngine {
       last_vertices_per_element_ = 4;
       return asset;
     } else if (const auto* t = std::get_if<SurfaceMeshShape>(&shape)) {
-      if (soft) throw std::logic_error("a surface mesh can only be registered as a rigid geometry");
       Check(dbh_register_rigid_mesh(ctx_, static_cast<int32_t>(t->vertices.size() / 3), t->vertices.data(),
                                     static_cast<int32_t>(t->triangles.size() / 3), t->triangles.data(), &asset),
             "register_rigid_mesh");

@@ -47,6 +47,7 @@ def lib():
         _lib = C.CDLL(_LIB_PATH)
         _lib.ho_last_error.restype = C.c_char_p
         _lib.ho_volume_total_volume.restype = C.c_double
+        _lib.ho_distance_to_surface.restype = C.c_double
         for name, args in {
             "ho_make_sphere_volume": [C.c_double, C.c_double, C.c_int],
             "ho_make_ellipsoid_volume": [C.c_double] * 4 + [C.c_int],
@@ -56,6 +57,9 @@ def lib():
             "ho_make_capsule_volume": [C.c_double] * 3,
             "ho_cylinder_field": [C.c_int] + [C.c_double] * 4,
             "ho_capsule_field": [C.c_int] + [C.c_double] * 4,
+            "ho_mesh_field": [C.c_int, C.c_double, C.c_double],
+            "ho_make_convex_volume": [C.c_int],
+            "ho_distance_to_surface": [C.c_int, _dp],
             "ho_sphere_field": [C.c_int, C.c_double, C.c_double, C.c_double],
             "ho_ellipsoid_field": [C.c_int] + [C.c_double] * 5,
             "ho_box_field": [C.c_int] + [C.c_double] * 5,
@@ -242,6 +246,14 @@ class TriMesh:
         v, t = _d(verts).reshape(-1, 3), _i(tris).reshape(-1, 3)
         return TriMesh(lib().ho_make_tri(len(v), _pd(v), len(t), _pi(t)))
 
+    def to_convex_volume(self) -> "VolumeMesh":
+        """MakeConvexVolumeMesh (make_convex_mesh.cc:17-60): this closed surface's vertices + the centroid of its volume."""
+        return VolumeMesh(lib().ho_make_convex_volume(self.h))
+
+    def distance_to(self, p) -> float:
+        """CalcDistanceToSurfaceMesh (calc_distance_to_surface_mesh.cc:30-200)."""
+        return float(lib().ho_distance_to_surface(self.h, _pd(_d(p))))
+
     def update_vertices(self, verts):
         """DeformableMeshWithBvh::UpdateVertexPositions (deformable_mesh_with_bvh.h:86-93): new vertex positions, derived
         quantities recomputed, BVHs refitted with their topology kept (BvhUpdater::Update, bvh_updater.h:45-103)."""
@@ -324,6 +336,11 @@ class VolumeField:
     def capsule(mesh: VolumeMesh, radius: float, length: float, modulus: float, margin: float = 0.0):
         """MakeCapsulePressureField (make_capsule_field.h:55-90)."""
         return VolumeField(lib().ho_capsule_field(mesh.h, radius, length, modulus, margin), mesh)
+
+    @staticmethod
+    def from_mesh(mesh: VolumeMesh, modulus: float, margin: float = 0.0):
+        """MakeVolumeMeshPressureField (make_mesh_field.cc:45-96)."""
+        return VolumeField(lib().ho_mesh_field(mesh.h, modulus, margin), mesh)
 
     @staticmethod
     def from_values(mesh: VolumeMesh, values) -> "VolumeField":

@@ -291,3 +291,112 @@ inline VolumeField MakeCapsulePressureField(double radius, double length, const 
 }
 
 }  // namespace ho
+
+// ---- Convex / Mesh (oracle, test infrastructure) ------------------------------------------------------------------------
+//   make_convex_mesh.cc:17-60                MakeConvexVolumeMesh (CalcCentroidOfEnclosedVolume)
+//   calc_distance_to_surface_mesh.cc:30-120  CalcSquaredDistanceToLineSegment / ToTriangle (the Bvh<Obb> of :122-200 only
+//                                            prunes; the minimum over all triangles is the same number)
+//   make_mesh_field.cc:45-96                 MakeVolumeMeshPressureField
+// Pinned by make_mesh_field_test.cc (non_convex_mesh.vtk: vertex 0 carries the modulus, 1-5 zero; WithMargin;
+// NoInteriorVertex), calc_distance_to_surface_mesh_test.cc (the seven Voronoi regions of a posed triangle) and
+// make_convex_mesh_test.cc (CoherentVertices), restated in tests/test_oracle_cylinder_capsule.py.
+namespace ho {
+namespace detail {
+
+inline double CalcSquaredDistanceToLineSegment(const Vec3& Q, const Vec3& A, const Vec3& B) {
+  const Vec3 AB = B - A;
+  const Vec3 AQ = Q - A;
+  if (dot(AQ, AB) <= 0.0) return dot(AQ, AQ);
+  const Vec3 BQ = Q - B;
+  if (dot(BQ, AB) >= 0.0) return dot(BQ, BQ);
+  const Vec3 n = cross(AB, AQ);
+  return dot(n, n) / dot(AB, AB);
+}
+
+inline double CalcSquaredDistanceToTriangle(const Vec3& p_WQ, const Vec3& A, const Vec3& B, const Vec3& C) {
+  const Vec3 p_AB_W = B - A;
+  const Vec3 p_AC_W = C - A;
+  const Vec3 Tx_W = p_AB_W / norm(p_AB_W);
+  const Vec3 N = cross(p_AB_W, p_AC_W);
+  const Vec3 Tz_W = N / norm(N);
+  const Vec3 Ty_W = cross(Tz_W, Tx_W);
+  auto to_T = [&](const Vec3& v) { return Vec3(dot(Tx_W, v), dot(Ty_W, v), dot(Tz_W, v)); };
+  const Vec3 p_TB = to_T(p_AB_W);
+  const Vec3 p_TC = to_T(p_AC_W);
+  const Vec3 p_TQ = to_T(p_WQ - A);
+  // IsInTriangle: Q = b0 B + b1 C in the x-y plane of T (Cramer's rule; the reference solves the same 2 x 2 by QR).
+  const double det = p_TB.x * p_TC.y - p_TC.x * p_TB.y;
+  const double b0 = (p_TQ.x * p_TC.y - p_TC.x * p_TQ.y) / det;
+  const double b1 = (p_TB.x * p_TQ.y - p_TQ.x * p_TB.y) / det;
+  if (b0 >= 0.0 && b1 >= 0.0 && b0 + b1 <= 1.0) return p_TQ.z * p_TQ.z;
+  const Vec3 p_TA(0, 0, 0);
+  return std::min({CalcSquaredDistanceToLineSegment(p_TQ, p_TA, p_TB), CalcSquaredDistanceToLineSegment(p_TQ, p_TA, p_TC),
+                   CalcSquaredDistanceToLineSegment(p_TQ, p_TB, p_TC)});
+}
+
+}  // namespace detail
+
+inline double CalcDistanceToSurfaceMesh(const Vec3& p_WQ, const TriMesh& mesh_W) {
+  double min_squared = std::numeric_limits<double>::infinity();
+  for (const Tri& t : mesh_W.tris)
+    min_squared = std::min(min_squared, detail::CalcSquaredDistanceToTriangle(p_WQ, mesh_W.verts[t[0]], mesh_W.verts[t[1]],
+                                                                             mesh_W.verts[t[2]]));
+  return std::sqrt(min_squared);
+}
+
+inline VolumeMesh MakeConvexVolumeMesh(const TriMesh& surface) {
+  double six_total_volume = 0;
+  Vec3 centroid(0, 0, 0);
+  for (const Tri& tri : surface.tris) {
+    const Vec3& p = surface.verts[tri[0]];
+    const Vec3& q = surface.verts[tri[1]];
+    const Vec3& r = surface.verts[tri[2]];
+    const double six_volume = dot(cross(p, q), r);
+    six_total_volume += six_volume;
+    centroid = centroid + six_volume * ((p + q) + r);
+  }
+  if (!(six_total_volume > 0)) throw std::invalid_argument("convex mesh: no enclosed volume");
+  std::vector<Vec3> V(surface.verts.begin(), surface.verts.end());
+  V.push_back(centroid / (4 * six_total_volume));
+  const int c = static_cast<int>(V.size()) - 1;
+  std::vector<Tet> E;
+  for (const Tri& e : surface.tris) E.push_back({c, e[0], e[1], e[2]});
+  return VolumeMesh(std::move(E), std::move(V));
+}
+
+inline VolumeField MakeVolumeMeshPressureField(const VolumeMesh& mesh, double modulus, double margin = 0.0) {
+  if (!(modulus > 0)) throw std::invalid_argument("mesh field");
+  const TriMesh surface = ConvertVolumeToSurfaceMesh(mesh);
+  std::vector<char> on_boundary(mesh.verts.size(), 0);
+  {
+    std::map<std::array<int, 3>, int> face_count;
+    static const int kFaces[4][3] = {{1, 2, 3}, {3, 2, 0}, {1, 3, 0}, {2, 1, 0}};
+    for (const Tet& t : mesh.tets)
+      for (const auto& f : kFaces) {
+        std::array<int, 3> key{t[f[0]], t[f[1]], t[f[2]]};
+        std::sort(key.begin(), key.end());
+        ++face_count[key];
+      }
+    for (const auto& [key, count] : face_count)
+      if (count == 1)
+        for (int bv : key) on_boundary[bv] = 1;
+  }
+  std::vector<double> values;
+  double max_value = std::numeric_limits<double>::lowest();
+  for (size_t v = 0; v < mesh.verts.size(); ++v) {
+    if (on_boundary[v]) {
+      values.push_back(0);
+      continue;
+    }
+    const double distance = CalcDistanceToSurfaceMesh(mesh.verts[v], surface) + margin;
+    values.push_back(distance);
+    max_value = std::max(distance, max_value);
+  }
+  if (max_value <= 0)
+    throw std::runtime_error("MakeVolumeMeshPressureField(): the computed max distance to boundary among all mesh vertices is "
+                             "non-positive. Perhaps the mesh lacks interior vertices.");
+  for (double& p : values) p = modulus * (p - margin) / (max_value - margin);
+  return VolumeField(std::move(values), mesh);
+}
+
+}  // namespace ho

@@ -444,6 +444,17 @@ int ho_capsule_field(int vol, double radius, double length, double modulus, doub
   HO_TRY return AddField(MakeCapsulePressureField(radius, length, g_vols[vol]->mesh, modulus, margin));
   HO_CATCH(-1)
 }
+int ho_mesh_field(int vol, double modulus, double margin) {
+  HO_TRY return AddField(MakeVolumeMeshPressureField(g_vols[vol]->mesh, modulus, margin));
+  HO_CATCH(-1)
+}
+int ho_make_convex_volume(int tri) {
+  HO_TRY return AddVol(MakeConvexVolumeMesh(g_tris[tri]->mesh));
+  HO_CATCH(-1)
+}
+double ho_distance_to_surface(int tri, const double* p) {
+  return CalcDistanceToSurfaceMesh(Vec3(p[0], p[1], p[2]), g_tris[tri]->mesh);
+}
 int ho_make_field(int vol, const double* values) {
   HO_TRY
   const VolumeMesh& m = g_vols[vol]->mesh;

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "drake_b200_proximity_engine.h"
 
@@ -89,6 +90,71 @@ static int MarginCase(char** argv) {
   return 0;
 }
 
+// A generated mesh as plain arrays (what a caller who loaded a .vtk / .obj would hold).
+static void CopyMesh(dbh_mesh* m, std::vector<double>* vertices, std::vector<int32_t>* elements) {
+  int32_t nv = 0, ne = 0, vpe = 0, has_p = 0;
+  dbh_mesh_get_sizes(m, &nv, &ne, &vpe, &has_p);
+  vertices->resize(3 * static_cast<size_t>(nv));
+  elements->resize(static_cast<size_t>(vpe) * ne);
+  dbh_mesh_copy(m, vertices->data(), elements->data(), nullptr);
+}
+
+// The reference's compliant Convex (MakeConvexVolumeMesh of the hull + MakeVolumeMeshPressureField) and compliant
+// Mesh(.vtk) (the tetrahedra as given + MakeVolumeMeshPressureField), hydroelastic_internal.cc:555-640, against a rigid
+// sphere; the expected numbers come from the oracle (tests/test_cpp_adapter.py).
+static int ConvexCase(char** argv) {
+  const double R = 0.25;
+  ProximityProperties soft;
+  soft.compliance_type = HydroelasticType::kCompliant;
+  soft.hydroelastic_modulus = 1e8;
+  ProximityProperties rigid;
+  rigid.compliance_type = HydroelasticType::kRigid;
+  rigid.resolution_hint = 0.1;
+  const RigidTransformd X_WA = RotX(M_PI, 0, 0, 0);
+  const RigidTransformd X_WB = RigidTransformd::FromTranslation(0, 0, -(R + R) + 0.125);
+  for (int k = 0; k < 2; ++k) {
+    ProximityEngine e(0);
+    dbh_mesh *vol = nullptr, *surf = nullptr;
+    if (k == 0) {
+      SurfaceMeshShape hull;
+      EXPECT(dbh_mesh_make_box_volume_with_ma(0.5, 0.4, 0.5, &vol) == DBH_OK);
+      EXPECT(dbh_mesh_convert_volume_to_surface(vol, &surf) == DBH_OK);
+      CopyMesh(surf, &hull.vertices, &hull.triangles);
+      e.AddDynamicGeometry(hull, X_WA, 1, soft);
+    } else {
+      VolumeMeshShape tets;   // no pressure given
+      EXPECT(dbh_mesh_make_box_volume(0.5, 0.4, 0.5, 0.125, &vol) == DBH_OK);
+      CopyMesh(vol, &tets.vertices, &tets.tetrahedra);
+      e.AddDynamicGeometry(tets, X_WA, 1, soft);
+    }
+    if (vol) dbh_mesh_destroy(vol);
+    if (surf) dbh_mesh_destroy(surf);
+    e.AddDynamicGeometry(Sphere{R}, X_WB, 2, rigid);
+    auto poly = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
+    EXPECT(poly.size() == 1);
+    const int faces = std::atoi(argv[2 + 3 * k]);
+    const double area = std::atof(argv[3 + 3 * k]), psum = std::atof(argv[4 + 3 * k]);
+    double got_p = 0;
+    for (int f = 0; f < poly[0].num_faces(); ++f) got_p += poly[0].pressure_at_centroid(f);
+    std::printf("convex case %d: faces %d (want %d) area %.17g (want %.17g) pressure sum %.17g (want %.17g)\n", k,
+                poly[0].num_faces(), faces, poly[0].total_area(), area, got_p, psum);
+    EXPECT(poly[0].num_faces() == faces);
+    EXPECT(std::fabs(poly[0].total_area() - area) <= 1e-10 * area);
+    EXPECT(std::fabs(got_p - psum) <= 1e-10 * std::fabs(psum));
+  }
+  bool threw = false;
+  try {   // margin > 0 would need MakeInflatedMesh / MakeConvexHull
+    ProximityEngine bad(0);
+    soft.margin = 0.01;
+    bad.AddDynamicGeometry(VolumeMeshShape{{0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1}, {0, 1, 2, 3}, {}}, X_WA, 1, soft);
+  } catch (const std::logic_error&) {
+    threw = true;
+  }
+  EXPECT(threw);
+  std::printf("ok\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
   std::unique_ptr<ProximityEngine> engine;
   try {
@@ -98,6 +164,7 @@ int main(int argc, char** argv) {
     return 3;
   }
   if (argc == 17 && std::string(argv[1]) == "margin") return MarginCase(argv);
+  if (argc == 8 && std::string(argv[1]) == "convex") return ConvexCase(argv);
   const double R = 0.25;
   ProximityProperties soft;
   soft.compliance_type = HydroelasticType::kCompliant;

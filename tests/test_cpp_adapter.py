@@ -81,6 +81,32 @@ def test_cpp_adapter_inflates_compliant_primitives_by_the_margin():
     assert res.stdout.strip().endswith("ok")
 
 
+@pytest.mark.gpu
+def test_cpp_adapter_compliant_convex_and_volume_mesh_without_pressure():
+    """The reference's compliant Convex (MakeConvexVolumeMesh + MakeVolumeMeshPressureField) and compliant Mesh(.vtk) (the
+    given tetrahedra + MakeVolumeMeshPressureField), hydroelastic_internal.cc:555-640, through the C++ mirror: surfaces
+    against a rigid sphere equal the oracle's construction."""
+    import math
+
+    import numpy as np
+
+    from oracle import ho
+    R, E = 0.25, 1e8
+    X_WA = ho.xform(ho.rpy_matrix(math.pi, 0, 0))
+    X_WB = ho.xform(None, [0, 0, -(R + R) + 0.125])
+    rigid = ho.TriMesh.sphere(R, 0.1)
+    convex = ho.VolumeMesh.box_ma(0.5, 0.4, 0.5).to_surface().to_convex_volume()
+    grid = ho.VolumeMesh.box_grid(0.5, 0.4, 0.5, 0.125)
+    args = []
+    for m in (convex, grid):
+        want = ho.soft_rigid(m, ho.VolumeField.from_mesh(m, E), rigid, X_WA, X_WB, 1, 2, ho.KPOLYGON)
+        assert want is not None and want.num_faces > 4
+        args += [str(want.num_faces), repr(float(want.total_area)), repr(float(np.sum(want.e_centroid)))]
+    res = subprocess.run([build_exe(), "convex"] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    assert res.stdout.strip().endswith("ok")
+
+
 def test_traction_mirror_compiles():
     """tests/cpp/test_traction_engine.cc (ComputeHydroelasticContactForces of the C++ mirror) compiles against the
     C-ABI with -Werror; without a GPU it must stop at context creation like every other entry point."""

@@ -211,3 +211,92 @@ def test_bad_parameters_are_rejected():
         db.Mesh.cylinder_volume_with_ma(1.0, 1.0, 0.5).set_cylinder_pressure(1.0, 1.0, 1e5, 0.6)   # length <= 2 margin
     with pytest.raises(db.HydroError):
         db.Mesh.box_volume_with_ma(1, 1, 1).set_capsule_pressure(1.0, 1.0, 1e5)   # not a capsule mesh
+
+
+# ---- compliant Convex / Mesh: MakeConvexVolumeMesh, MakeVolumeMeshPressureField -----------------------------------------
+
+# geometry/test/non_convex_mesh.vtk of the reference (6 points, 6 tetrahedra), restated.
+NON_CONVEX_V = [[0.1, 0.1, 0.1], [0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0.2, 0.2, 0.2]]
+NON_CONVEX_T = [[0, 5, 2, 3], [0, 5, 3, 4], [0, 5, 4, 2], [0, 1, 4, 3], [0, 1, 3, 2], [0, 1, 2, 4]]
+
+
+def test_volume_mesh_pressure_field_reference_cases():
+    """MakeVolumeMeshPressureFieldTest (make_mesh_field_test.cc:15-75): vertex 0 carries the modulus, 1-5 are zero; WithMargin
+    through the margin invariants with depth 0.1 + margin; NoInteriorVertex throws the reference's message."""
+    E = 1e7
+    mesh = ho.VolumeMesh.from_arrays(NON_CONVEX_V, NON_CONVEX_T)
+    p = ho.VolumeField.from_mesh(mesh, E).values
+    assert p[0] == E and np.all(p[1:] == 0.0)
+    E, margin, depth = 1.0e5, 0.012, 0.1 + 0.012
+    p0, p1 = ho.VolumeField.from_mesh(mesh, E).values, ho.VolumeField.from_mesh(mesh, E, margin).values
+    want = -margin / (depth - margin) * E
+    assert np.all(p1[1:] < 0)
+    np.testing.assert_allclose(p1[1:], want, rtol=1e-14)
+    np.testing.assert_allclose((p1[0] - want) / p0[0], depth / (depth - margin), rtol=1e-14)
+    one_tet = ho.VolumeMesh.from_arrays([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], [[0, 1, 2, 3]])
+    with pytest.raises(RuntimeError, match="lacks interior vertices"):
+        ho.VolumeField.from_mesh(one_tet, E)
+    with pytest.raises(db.HydroError, match="lacks interior vertices"):
+        db.Mesh.from_arrays([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], [[0, 1, 2, 3]]).set_volume_mesh_pressure(E)
+
+
+def test_distance_to_a_posed_triangle_reference_regions():
+    """CalcDistanceToSurfaceMeshTest.SingleTriangle (calc_distance_to_surface_mesh_test.cc:60-180): the triangle (0,0,0),
+    (1,0,0), (0,1,0) posed at rpy (1, 2, 3), p (4, 5, 6); points of the seven Voronoi regions below / in / above its
+    plane against the analytic distances, 1e-14."""
+    X_WT = ho.xform(ho.rpy_matrix(1, 2, 3), [4, 5, 6])
+    R, t = X_WT[:9].reshape(3, 3).T, X_WT[9:]
+    A, B, C = np.zeros(3), np.array([1.0, 0, 0]), np.array([0, 1.0, 0])
+    tri = ho.TriMesh.from_arrays([R @ v + t for v in (A, B, C)], [[0, 1, 2]])
+
+    def line(Q, P0, P1):
+        d = (P1 - P0) / np.linalg.norm(P1 - P0)
+        return np.linalg.norm(Q - (d @ (Q - P0) * d + P0))
+    cases = [((0.25, 0.25), lambda Q: abs(Q[2])), ((0.25, -0.25), lambda Q: line(Q, A, B)),
+             ((-0.25, -0.25), lambda Q: np.linalg.norm(Q - A)), ((-0.25, 0.25), lambda Q: line(Q, A, C)),
+             ((-0.25, 1.25), lambda Q: np.linalg.norm(Q - C)), ((0.75, 0.75), lambda Q: line(Q, B, C)),
+             ((1.25, -0.25), lambda Q: np.linalg.norm(Q - B))]
+    for (x, y), want in cases:
+        for sz in (-1, 0, 1):
+            Q = np.array([x, y, sz * 0.5])
+            assert abs(tri.distance_to(R @ Q + t) - want(Q)) <= 1e-14, (x, y, sz)
+
+
+def test_convex_volume_mesh_reference_properties_and_product():
+    """MakeConvexMeshTest.CoherentVertices (make_convex_mesh_test.cc:95-125) on a cube's and an octahedron's surface: the
+    surface's vertices in order, then one interior vertex -- the centroid of the enclosed volume -- behind every face;
+    one tetrahedron of positive volume per triangle; the product's generator and field equal the oracle's."""
+    cube = ho.VolumeMesh.box_ma(2.0, 2.0, 2.0).to_surface()                       # the reference's quad_cube.obj is this cube
+    shifted = ho.TriMesh.from_arrays(cube.verts + np.array([0.3, -0.2, 0.5]), cube.tris)
+    for surf, centre in ((cube, np.zeros(3)), (shifted, np.array([0.3, -0.2, 0.5]))):
+        vol = surf.to_convex_volume()
+        assert (vol.num_vertices, vol.num_elements) == (surf.num_vertices + 1, surf.num_elements)
+        np.testing.assert_array_equal(vol.verts[:-1], surf.verts)
+        np.testing.assert_allclose(vol.verts[-1], centre, rtol=0, atol=1e-15)
+        np.testing.assert_array_equal(vol.tets[:, 0], surf.num_vertices)
+        np.testing.assert_array_equal(vol.tets[:, 1:], surf.tris)
+        assert np.all(_tet_volumes(vol.verts, vol.tets) > 0)
+        assert abs(float(np.sum(_tet_volumes(vol.verts, vol.tets))) - 8.0) <= 1e-14
+        m = db.Mesh.from_arrays(surf.verts, surf.tris).to_convex_volume()
+        np.testing.assert_array_equal(m.vertices, vol.verts)
+        np.testing.assert_array_equal(m.elements, vol.tets)
+        field = ho.VolumeField.from_mesh(vol, 1e6)
+        assert field.values[-1] == 1e6 and np.all(field.values[:-1] == 0.0)
+        np.testing.assert_array_equal(m.set_volume_mesh_pressure(1e6).pressure, field.values)
+
+
+def test_product_mesh_field_matches_the_oracle():
+    """MakeVolumeMeshPressureField of the product against the oracle, bit for bit, on meshes WITH many interior vertices
+    (a grid box, a dense-interior sphere, the reference's non-convex mesh), with and without margin."""
+    for o in (ho.VolumeMesh.box_grid(0.4, 0.3, 0.2, 0.05), ho.VolumeMesh.sphere(0.3, 0.1, True),
+              ho.VolumeMesh.from_arrays(NON_CONVEX_V, NON_CONVEX_T)):
+        m = db.Mesh.from_arrays(o.verts, o.tets)
+        for margin in (0.0, 0.004):
+            want = ho.VolumeField.from_mesh(o, 2e5, margin).values
+            np.testing.assert_array_equal(m.set_volume_mesh_pressure(2e5, margin).pressure, want)
+        assert want.max() == 2e5
+    # A grid box: the pressure of an interior grid vertex is its distance to the nearest face over the largest such distance.
+    o = ho.VolumeMesh.box_grid(0.4, 0.4, 0.4, 0.1)
+    p = ho.VolumeField.from_mesh(o, 1.0).values
+    d = np.min(0.2 - np.abs(o.verts), axis=1)
+    np.testing.assert_allclose(p, d / d.max(), rtol=0, atol=1e-14)
