@@ -16,7 +16,8 @@
 // cylinder, capsule, ellipsoid or mesh on a rigid HalfSpace ground is the commonest rigid-rigid fallback pair. The FCL
 // sources are not available here: those functions are pinned by the reference's BoxPenetrationTest TangentPlane scenes
 // (penetration_as_point_pair_callback_test.cc:575-910, 1e-12) and by the shapes' analytic support functions
-// (tests/test_point_pair_cpu.py), not against FCL itself. GJK / EPA and FCL's box-box are NOT restated. The batched
+// (tests/test_point_pair_cpu.py), not against FCL itself; likewise FCL's box x box (ODE's dBoxBox, below), pinned by the
+// TangentBox scenes. GJK / EPA is NOT restated. The batched
 // query (dbh_batch_query, DBH_QUERY_WITH_FALLBACK) reports WHICH pairs need it (dbh_batch_copy_fallback_pairs): a
 // handful per scene, so the arithmetic stays on the host next to the shape descriptions the C-ABI never sees.
 // No Eigen: 3-vectors are std::array<double, 3>; operation order follows the reference.
@@ -378,6 +379,249 @@ inline std::optional<Result> HalfSpaceContactToPointPair(const std::optional<Fcl
   Result r;
   r.depth = contact->depth;
   r.nhat_BA_W = half_space_is_A ? Vec3{-n[0], -n[1], -n[2]} : n;
+  r.p_WCa = AddScaled(contact->pos, r.nhat_BA_W, -0.5 * r.depth);
+  r.p_WCb = AddScaled(contact->pos, r.nhat_BA_W, 0.5 * r.depth);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Box x box: FCL's boxBox2 (fcl/narrowphase/detail/primitive_shape_algorithm/box_box-inl.h, the ODE dBoxBox algorithm),
+// which is what fcl::collide() runs for two fcl::Boxd, as CalcDistanceFallback<double> reads its deepest contact
+// (fcl::collide keeps the contacts of largest depth when fewer are requested than found; Drake requests one).
+//   1. 15 separating axes (3 + 3 face normals, 9 edge x edge), each giving the overlap along it; any positive
+//      separation ends the test. The axis of smallest overlap gives normal and depth; an edge x edge axis only wins when
+//      its overlap is more than 5 % smaller than the best face axis' (fudge_factor 1.05), and parallel edges are skipped.
+//   2. edge x edge: the closest points of the two supporting edges; the contact is their midpoint.
+//   3. face axis: the face of the other box most anti-parallel to the normal (the incident face) is clipped against
+//      the rectangle of the reference face; the deepest of the clipped points is the contact, reported half its depth
+//      back towards the reference face.
+// Pinned by the reference's BoxPenetrationTest TangentBox1 / TangentBox2 scenes (penetration_as_point_pair_callback_test.cc:
+// 914-920: 1e-12) and by an exact 15-axis oracle (oracle/ho_point_pair.py); FCL's choice among EQUALLY deep points (two
+// faces resting flat on each other) is not pinned -- the first of the clipped polygon is taken.
+
+struct FclContact {   // normal: unit, from the first shape into the second
+  Vec3 normal, pos;
+  double depth;
+};
+
+namespace box_box_detail {
+inline Vec3 Col(const Pose& X, int j) { return {X[3 * j], X[3 * j + 1], X[3 * j + 2]}; }
+// Parameters of the closest points pa + alpha ua, pb + beta ub of two lines (ODE's dLineClosestApproach).
+inline void LineClosestApproach(const Vec3& pa, const Vec3& ua, const Vec3& pb, const Vec3& ub, double* alpha, double* beta) {
+  const Vec3 p{pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+  const double uaub = Dot(ua, ub), q1 = Dot(ua, p), q2 = -Dot(ub, p);
+  double d = 1 - uaub * uaub;
+  if (d <= 0.0001) {
+    *alpha = 0;
+    *beta = 0;
+  } else {
+    d = 1.0 / d;
+    *alpha = (q1 + uaub * q2) * d;
+    *beta = (uaub * q1 + q2) * d;
+  }
+}
+// The quadrilateral q (4 points x, y) clipped by the rectangle |x| <= h[0], |y| <= h[1]: up to 8 points (ODE's
+// intersectRectQuad: Sutherland-Hodgman over the four sides in the order -x, +x, -y, +y).
+inline int IntersectRectQuad(const double h[2], const double q_in[8], double ret[16]) {
+  double buffer[16];
+  double* q = const_cast<double*>(q_in);
+  double* r = ret;
+  int nq = 4, nr = 0;
+  for (int dir = 0; dir <= 1; ++dir) {
+    for (int sign = -1; sign <= 1; sign += 2) {
+      double* pq = q;
+      double* pr = r;
+      nr = 0;
+      for (int i = nq; i > 0; --i) {
+        if (sign * pq[dir] < h[dir]) {   // this point is inside the chopping line
+          pr[0] = pq[0];
+          pr[1] = pq[1];
+          pr += 2;
+          ++nr;
+          if (nr & 8) {
+            q = r;
+            goto done;
+          }
+        }
+        double* nextq = (i > 1) ? pq + 2 : q;
+        if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {   // this line crosses the chopping line
+          pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+          pr[dir] = sign * h[dir];
+          pr += 2;
+          ++nr;
+          if (nr & 8) {
+            q = r;
+            goto done;
+          }
+        }
+        pq += 2;
+      }
+      q = r;
+      r = (q == ret) ? buffer : ret;
+      nq = nr;
+    }
+  }
+done:
+  if (q != ret)
+    for (int i = 0; i < 2 * nr; ++i) ret[i] = q[i];
+  return nr;
+}
+}  // namespace box_box_detail
+
+inline std::optional<FclContact> BoxBox(const Vec3& side1, const Pose& X_W1, const Vec3& side2, const Pose& X_W2) {
+  using namespace box_box_detail;
+  const double fudge_factor = 1.05;
+  const Vec3 T1{X_W1[9], X_W1[10], X_W1[11]}, T2{X_W2[9], X_W2[10], X_W2[11]};
+  const Vec3 p{T2[0] - T1[0], T2[1] - T1[1], T2[2] - T1[2]};
+  const Vec3 pp = RotateT(X_W1, p);
+  const double A[3] = {side1[0] * 0.5, side1[1] * 0.5, side1[2] * 0.5}, B[3] = {side2[0] * 0.5, side2[1] * 0.5, side2[2] * 0.5};
+  double R[3][3], Q[3][3];   // R = R1^T R2
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      R[i][j] = Dot(Col(X_W1, i), Col(X_W2, j));
+      Q[i][j] = std::abs(R[i][j]);
+    }
+  double s = -std::numeric_limits<double>::max();
+  int code = 0;
+  bool invert_normal = false;
+  Vec3 normal_face{0, 0, 0}, normalC{0, 0, 0};
+  bool normal_is_face = true;
+  for (int i = 0; i < 3; ++i) {   // u1, u2, u3: the face normals of box 1
+    const double tmp = pp[i];
+    const double s2 = std::abs(tmp) - (((Q[i][0] * B[0] + Q[i][1] * B[1]) + Q[i][2] * B[2]) + A[i]);
+    if (s2 > 0) return std::nullopt;
+    if (s2 > s) {
+      s = s2;
+      normal_face = Col(X_W1, i);
+      normal_is_face = true;
+      invert_normal = tmp < 0;
+      code = 1 + i;
+    }
+  }
+  for (int i = 0; i < 3; ++i) {   // v1, v2, v3: the face normals of box 2
+    const double tmp = Dot(Col(X_W2, i), p);
+    const double s2 = std::abs(tmp) - (((Q[0][i] * A[0] + Q[1][i] * A[1]) + Q[2][i] * A[2]) + B[i]);
+    if (s2 > 0) return std::nullopt;
+    if (s2 > s) {
+      s = s2;
+      normal_face = Col(X_W2, i);
+      normal_is_face = true;
+      invert_normal = tmp < 0;
+      code = 4 + i;
+    }
+  }
+  const double fudge2 = 1.0e-6, eps = std::numeric_limits<double>::epsilon();
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Q[i][j] += fudge2;
+  for (int i = 0; i < 3; ++i) {   // u_i x v_j
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    for (int j = 0; j < 3; ++j) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const double tmp = pp[i2] * R[i1][j] - pp[i1] * R[i2][j];
+      const double s2_raw = std::abs(tmp) - (((A[i1] * Q[i2][j] + A[i2] * Q[i1][j]) + B[j1] * Q[i][j2]) + B[j2] * Q[i][j1]);
+      if (s2_raw > 0) return std::nullopt;
+      double n[3] = {0, 0, 0};
+      n[i1] = -R[i2][j];
+      n[i2] = R[i1][j];
+      const double l = std::sqrt(n[i1] * n[i1] + n[i2] * n[i2]);
+      if (l > eps) {
+        const double s2 = s2_raw / l;
+        if (s2 * fudge_factor > s) {
+          s = s2;
+          normalC = {n[0] / l, n[1] / l, n[2] / l};
+          normal_is_face = false;
+          invert_normal = tmp < 0;
+          code = 7 + 3 * i + j;
+        }
+      }
+    }
+  }
+  if (!code) return std::nullopt;
+  Vec3 normal = normal_is_face ? normal_face : Rotate(X_W1, normalC);
+  if (invert_normal) normal = {-normal[0], -normal[1], -normal[2]};
+  const double depth = -s;
+
+  if (code > 6) {   // edge x edge
+    Vec3 pa = T1, pb = T2;
+    for (int j = 0; j < 3; ++j) {
+      pa = AddScaled(pa, Col(X_W1, j), A[j] * (Dot(Col(X_W1, j), normal) > 0 ? 1.0 : -1.0));
+      pb = AddScaled(pb, Col(X_W2, j), B[j] * (Dot(Col(X_W2, j), normal) > 0 ? -1.0 : 1.0));
+    }
+    const Vec3 ua = Col(X_W1, (code - 7) / 3), ub = Col(X_W2, (code - 7) % 3);
+    double alpha, beta;
+    LineClosestApproach(pa, ua, pb, ub, &alpha, &beta);
+    pa = AddScaled(pa, ua, alpha);
+    pb = AddScaled(pb, ub, beta);
+    return FclContact{normal, {0.5 * (pa[0] + pb[0]), 0.5 * (pa[1] + pb[1]), 0.5 * (pa[2] + pb[2])}, depth};
+  }
+
+  // A face of box a (the reference face, perpendicular to the normal) against the closest face of box b (the incident one).
+  const bool first = code <= 3;
+  const Pose& Xa = first ? X_W1 : X_W2;
+  const Pose& Xb = first ? X_W2 : X_W1;
+  const Vec3& pa = first ? T1 : T2;
+  const Vec3& pb = first ? T2 : T1;
+  const double* Sa = first ? A : B;
+  const double* Sb = first ? B : A;
+  const Vec3 normal2 = first ? normal : Vec3{-normal[0], -normal[1], -normal[2]};
+  const Vec3 nr = RotateT(Xb, normal2);
+  const double anr[3] = {std::abs(nr[0]), std::abs(nr[1]), std::abs(nr[2])};
+  int lanr, a1, a2;   // the incident face's normal axis and its two in-plane axes
+  if (anr[1] > anr[0]) {
+    if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+  } else {
+    if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+  }
+  // Centre of the incident face relative to the centre of box a.
+  const double side = nr[lanr] < 0 ? Sb[lanr] : -Sb[lanr];
+  const Vec3 center = AddScaled({pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, Col(Xb, lanr), side);
+  const int codeN = first ? code - 1 : code - 4;
+  const int code1 = codeN == 0 ? 1 : 0, code2 = codeN == 2 ? 1 : 2;
+  // The incident face's corners in the reference face's 2-D coordinates.
+  const double c1 = Dot(Col(Xa, code1), center), c2 = Dot(Col(Xa, code2), center);
+  double m11 = Dot(Col(Xb, a1), Col(Xa, code1)), m12 = Dot(Col(Xb, a2), Col(Xa, code1));
+  double m21 = Dot(Col(Xb, a1), Col(Xa, code2)), m22 = Dot(Col(Xb, a2), Col(Xa, code2));
+  {
+    const double k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+    const double quad[8] = {c1 - k1 - k3, c2 - k2 - k4, c1 - k1 + k3, c2 - k2 + k4, c1 + k1 + k3, c2 + k2 + k4, c1 + k1 - k3, c2 + k2 - k4};
+    const double rect[2] = {Sa[code1], Sa[code2]};
+    double ret[16];
+    const int n_intersect = IntersectRectQuad(rect, quad, ret);
+    if (n_intersect < 1) return std::nullopt;   // "this should never happen"
+    const double det1 = 1.0 / (m11 * m22 - m12 * m21);
+    m11 *= det1;
+    m12 *= det1;
+    m21 *= det1;
+    m22 *= det1;
+    bool found = false;
+    Vec3 best_point{0, 0, 0};
+    double best_dep = 0;
+    for (int j = 0; j < n_intersect; ++j) {
+      const double k1b = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
+      const double k2b = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
+      const Vec3 point = AddScaled(AddScaled(center, Col(Xb, a1), k1b), Col(Xb, a2), k2b);   // relative to box a's centre
+      const double dep = Sa[codeN] - Dot(normal2, point);
+      if (dep >= 0 && (!found || dep > best_dep)) {
+        found = true;
+        best_dep = dep;
+        best_point = point;
+      }
+    }
+    if (!found) return std::nullopt;
+    // The deepest point of the incident face, moved half its depth back along the reference face's normal.
+    const Vec3 on_b{best_point[0] + pa[0], best_point[1] + pa[1], best_point[2] + pa[2]};
+    return FclContact{normal, AddScaled(on_b, normal2, 0.5 * best_dep), best_dep};
+  }
+}
+
+// CalcDistanceFallback<double> (penetration_as_point_pair_callback.cc:164-207) on a contact whose normal points from A
+// into B.
+inline std::optional<Result> FclContactToPointPair(const std::optional<FclContact>& contact) {
+  if (!contact) return std::nullopt;
+  if (contact->depth <= std::numeric_limits<double>::epsilon()) return std::nullopt;
+  Result r;
+  r.depth = contact->depth;
+  r.nhat_BA_W = {-contact->normal[0], -contact->normal[1], -contact->normal[2]};
   r.p_WCa = AddScaled(contact->pos, r.nhat_BA_W, -0.5 * r.depth);
   r.p_WCb = AddScaled(contact->pos, r.nhat_BA_W, 0.5 * r.depth);
   return r;

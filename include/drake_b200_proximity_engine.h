@@ -107,7 +107,7 @@ struct ProximityProperties {
 
 // geometry::PenetrationAsPointPair<double>, the fallback result (query_results/penetration_as_point_pair.h):
 // filled for the pairs one of whose shapes is a Sphere (Drake's own closed forms) or a HalfSpace (FCL's closed-form
-// half-space primitives), drake_b200_point_pair.h.
+// half-space primitives) and for two boxes (FCL's box-box), drake_b200_point_pair.h.
 struct PenetrationAsPointPair {
   GeometryId id_A, id_B;
   std::array<double, 3> p_WCa, p_WCb, nhat_BA_W;
@@ -295,8 +295,8 @@ class ProximityEngine {
     }
   }
 
-  // What to do with a fallback pair neither of whose shapes is a Sphere or a HalfSpace: the reference calls FCL's
-  // general narrow phase there (penetration_as_point_pair_callback.cc:145-195), which this back end does not contain. false (the
+  // What to do with a fallback pair neither of whose shapes is a Sphere or a HalfSpace and which is not two boxes: the
+  // reference calls FCL's GJK / EPA there (penetration_as_point_pair_callback.cc:145-195), which this back end does not contain. false (the
   // default): throw std::logic_error naming the pair, so that no contact is lost silently; true: skip such pairs.
   void set_skip_unsupported_point_pairs(bool skip) { skip_unsupported_point_pairs_ = skip; }
 
@@ -433,13 +433,20 @@ class ProximityEngine {
         if (!res) return std::nullopt;
         return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
       }
+      if (const auto *ba = std::get_if<Box>(&a), *bb = std::get_if<Box>(&b); ba && bb) {
+        // FCL's box-box (boxBox2) behind CalcDistanceFallback, drake_b200_point_pair.h.
+        auto res = pp::FclContactToPointPair(pp::BoxBox({ba->width, ba->depth, ba->height}, poses_[ga].m,
+                                                        {bb->width, bb->depth, bb->height}, poses_[gb].m));
+        if (!res) return std::nullopt;
+        return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
+      }
       // The reference rejects half space x half space itself (:525-555 of its test; ScalarSupport<double>,
-      // penetration_as_point_pair_callback.cc:329-338) and hands the rest to FCL's GJK / EPA (and its box-box).
+      // penetration_as_point_pair_callback.cc:329-338) and hands the rest to FCL's GJK / EPA.
       if (skip_unsupported_point_pairs_) return std::nullopt;
       throw std::logic_error("ComputeContactSurfacesWithFallback: the point-pair fallback for geometries " +
                              std::to_string(ids_[ga]) + " and " + std::to_string(ids_[gb]) +
-                             " needs FCL's general narrow phase (neither shape is a Sphere or a HalfSpace, or both are "
-                             "half spaces), which this back end does not provide; filter the pair or call "
+                             " needs FCL's GJK / EPA narrow phase (no Sphere or HalfSpace in the pair and not two boxes, or "
+                             "two half spaces), which this back end does not provide; filter the pair or call "
                              "set_skip_unsupported_point_pairs(true)");
     }
     const int gs = a_is_sphere ? ga : gb, go = a_is_sphere ? gb : ga;   // sphere, other

@@ -11,8 +11,11 @@ published closed-form half-space primitives (fcl/narrowphase/detail/primitive_sh
 HalfSpace against Box, Capsule, Cylinder, Ellipsoid and a vertex cloud (Convex), worked in the HALF SPACE's frame --
 the product header works in World, so the two are independent derivations. PARITY UNPINNED against FCL itself: pinned by
 the reference's BoxPenetrationTest TangentPlane scenes (penetration_as_point_pair_callback_test.cc:575-910) and by the
-shapes' analytic support functions / brute-force surface sampling in tests/test_point_pair_cpu.py. GJK / EPA and FCL's
-box-box are not restated.
+shapes' analytic support functions / brute-force surface sampling in tests/test_point_pair_cpu.py.
+
+(3) FCL's box x box (boxBox2, the ODE dBoxBox algorithm): box_box_contact below, pinned by the reference's TangentBox
+scenes and by exact geometry (the minimum-overlap axis over all 15, vertices of one box inside the other). GJK / EPA is
+not restated.
 
 Poses are 12 doubles: rotation column-major, then translation (math/rigid_transform.h:1004-1007)."""
 from __future__ import annotations
@@ -261,6 +264,112 @@ def half_space_point_pair(shape_A, X_WA, shape_B, X_WB):
             "p_WCb": pos + 0.5 * depth * nhat_BA_W}
 
 
+def box_box_contact(size_A, X_WA, size_B, X_WB):
+    """FCL's box-box (boxBox2, the ODE dBoxBox algorithm; fcl/narrowphase/detail/primitive_shape_algorithm/box_box-inl.h)
+    as fcl::collide() reports its deepest contact: None or (normal from A into B, position, depth). The 15 separating
+    axes follow the published algorithm (face axes first; an edge x edge axis wins only by more than 5 %; parallel edges
+    skipped; 1e-6 added to |R| for the edge tests). The contact POINT is derived here in 3-D World coordinates --
+    Sutherland-Hodgman of the incident face against the four side planes of the reference face, deepest vertex, moved
+    half its depth back; edge x edge: midpoint of the closest points of the two lines from the 2 x 2 normal equations --
+    where the product header follows ODE's 2-D route. PARITY UNPINNED against FCL beyond the reference's TangentBox
+    scenes (penetration_as_point_pair_callback_test.cc:914-920)."""
+    R1, T1, R2, T2 = _R(X_WA), _p(X_WA), _R(X_WB), _p(X_WB)
+    A, B = np.asarray(size_A, float) * 0.5, np.asarray(size_B, float) * 0.5
+    p = T2 - T1
+    pp = R1.T @ p
+    R = R1.T @ R2
+    Q = np.abs(R)
+    s, code, normal, invert = -np.finfo(float).max, 0, None, False
+    for i in range(3):
+        tmp = pp[i]
+        s2 = abs(tmp) - (((Q[i, 0] * B[0] + Q[i, 1] * B[1]) + Q[i, 2] * B[2]) + A[i])
+        if s2 > 0:
+            return None
+        if s2 > s:
+            s, code, normal, invert = s2, 1 + i, R1[:, i], tmp < 0
+    for i in range(3):
+        tmp = float(R2[:, i] @ p)
+        s2 = abs(tmp) - (((Q[0, i] * A[0] + Q[1, i] * A[1]) + Q[2, i] * A[2]) + B[i])
+        if s2 > 0:
+            return None
+        if s2 > s:
+            s, code, normal, invert = s2, 4 + i, R2[:, i], tmp < 0
+    Qf = Q + 1.0e-6
+    eps = np.finfo(float).eps
+    for i in range(3):
+        i1, i2 = (i + 1) % 3, (i + 2) % 3
+        for j in range(3):
+            j1, j2 = (j + 1) % 3, (j + 2) % 3
+            tmp = pp[i2] * R[i1, j] - pp[i1] * R[i2, j]
+            s2 = abs(tmp) - (((A[i1] * Qf[i2, j] + A[i2] * Qf[i1, j]) + B[j1] * Qf[i, j2]) + B[j2] * Qf[i, j1])
+            if s2 > 0:
+                return None
+            n = np.zeros(3)
+            n[i1], n[i2] = -R[i2, j], R[i1, j]
+            l = math.sqrt(n[i1] * n[i1] + n[i2] * n[i2])
+            if l > eps:
+                s2 /= l
+                if s2 * 1.05 > s:
+                    s, code, normal, invert = s2, 7 + 3 * i + j, R1 @ (n / l), tmp < 0
+    if code == 0:
+        return None
+    normal = -normal if invert else normal.copy()
+    depth = -s
+    if code > 6:
+        pa = T1 + sum(R1[:, j] * (A[j] * (1.0 if R1[:, j] @ normal > 0 else -1.0)) for j in range(3))
+        pb = T2 + sum(R2[:, j] * (B[j] * (-1.0 if R2[:, j] @ normal > 0 else 1.0)) for j in range(3))
+        ua, ub = R1[:, (code - 7) // 3], R2[:, (code - 7) % 3]
+        c = float(ua @ ub)
+        if 1 - c * c <= 0.0001:
+            alpha = beta = 0.0
+        else:   # minimise |pa + alpha ua - pb - beta ub|^2
+            alpha, beta = np.linalg.solve(np.array([[1.0, -c], [-c, 1.0]]), np.array([ua @ (pb - pa), -(ub @ (pb - pa))]))
+        return normal, 0.5 * ((pa + alpha * ua) + (pb + beta * ub)), depth
+    first = code <= 3
+    (Ra, Ta, Sa), (Rb, Tb, Sb) = ((R1, T1, A), (R2, T2, B)) if first else ((R2, T2, B), (R1, T1, A))
+    normal2 = normal if first else -normal
+    nr = Rb.T @ normal2
+    anr = np.abs(nr)
+    if anr[1] > anr[0]:
+        lanr, a1, a2 = (1, 0, 2) if anr[1] > anr[2] else (2, 0, 1)
+    else:
+        lanr, a1, a2 = (0, 1, 2) if anr[0] > anr[2] else (2, 0, 1)
+    centre = Tb + Rb[:, lanr] * (Sb[lanr] if nr[lanr] < 0 else -Sb[lanr])
+    e1, e2 = Rb[:, a1] * Sb[a1], Rb[:, a2] * Sb[a2]
+    poly = [centre - e1 - e2, centre - e1 + e2, centre + e1 + e2, centre + e1 - e2]
+    codeN = code - 1 if first else code - 4
+    code1, code2 = (1 if codeN == 0 else 0), (1 if codeN == 2 else 2)
+    for axis, h in ((Ra[:, code1], Sa[code1]), (Ra[:, code2], Sa[code2])):
+        for sign in (-1.0, 1.0):
+            out = []
+            for k, P in enumerate(poly):
+                Pn = poly[(k + 1) % len(poly)]
+                dP, dn = sign * float(axis @ (P - Ta)), sign * float(axis @ (Pn - Ta))
+                if dP < h:
+                    out.append(P)
+                if (dP < h) != (dn < h):
+                    out.append(P + (Pn - P) * ((h - dP) / (dn - dP)))
+            poly = out
+    best = None
+    for P in poly:
+        dep = Sa[codeN] - float(normal2 @ (P - Ta))
+        if dep >= 0 and (best is None or dep > best[1]):
+            best = (P, dep)
+    if best is None:
+        return None
+    return normal, best[0] + normal2 * (0.5 * best[1]), best[1]
+
+
+def box_box_point_pair(size_A, X_WA, size_B, X_WB):
+    """CalcDistanceFallback<double> (:164-207) on FCL's box-box contact."""
+    hit = box_box_contact(size_A, X_WA, size_B, X_WB)
+    if hit is None or hit[2] <= np.finfo(float).eps:
+        return None
+    normal, pos, depth = hit
+    nhat_BA_W = -normal
+    return {"depth": depth, "nhat_BA_W": nhat_BA_W, "p_WCa": pos - 0.5 * depth * nhat_BA_W, "p_WCb": pos + 0.5 * depth * nhat_BA_W}
+
+
 def point_pair(shape_A, X_WA, shape_B, X_WB):
     """ComputeNarrowPhasePenetration for shapes given as ('sphere', r) | ('box', (x, y, z)) | ('half_space',) |
     ('cylinder', r, L) | ('capsule', r, L) | ('ellipsoid', (a, b, c)) | ('vertices', V); A is the
@@ -271,6 +380,8 @@ def point_pair(shape_A, X_WA, shape_B, X_WB):
     if not (a_is_sphere or b_is_sphere):
         if (shape_A[0] == "half_space") != (shape_B[0] == "half_space"):
             return half_space_point_pair(shape_A, X_WA, shape_B, X_WB)
+        if shape_A[0] == "box" and shape_B[0] == "box":
+            return box_box_point_pair(shape_A[1], X_WA, shape_B[1], X_WB)
         raise NotImplementedError("no sphere and not exactly one half space in the pair: FCL's general narrow phase")
     (S, X_WS), (O, X_WO) = ((shape_A, X_WA), (shape_B, X_WB)) if a_is_sphere else ((shape_B, X_WB), (shape_A, X_WA))
     p_WSo = _p(X_WS)

@@ -3,7 +3,8 @@
 //   kind: s r | b x y z | h | c r L | k r L | e a b c | v n x0 y0 z0 ... (n vertices)
 // and prints `none` or `depth p_WCa(3) p_WCb(3) nhat(3)` with 17 significant digits, the way
 // ComputeNarrowPhasePenetration (penetration_as_point_pair_callback.cc:203-300) orders its operands; a pair without a
-// sphere must hold exactly one half space (FCL's closed-form half-space primitives behind CalcDistanceFallback).
+// sphere must hold exactly one half space (FCL's closed-form half-space primitives behind CalcDistanceFallback) or be
+// two boxes (FCL's box-box).
 #include <cstdio>
 #include <iostream>
 #include <string>
@@ -42,6 +43,17 @@ int main() {
   Geo a, b;
   while (Read(&a) && Read(&b)) {
     const bool a_is_sphere = a.kind == 's';
+    if (a.kind == 'b' && b.kind == 'b') {   // FCL's box-box behind CalcDistanceFallback
+      const auto res = FclContactToPointPair(BoxBox(a.size, a.X, b.size, b.X));
+      if (!res) {
+        std::printf("none\n");
+        continue;
+      }
+      std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", res->depth, res->p_WCa[0], res->p_WCa[1],
+                  res->p_WCa[2], res->p_WCb[0], res->p_WCb[1], res->p_WCb[2], res->nhat_BA_W[0], res->nhat_BA_W[1],
+                  res->nhat_BA_W[2]);
+      continue;
+    }
     if (!a_is_sphere && b.kind != 's') {
       const bool a_is_half_space = a.kind == 'h';
       const Geo& h = a_is_half_space ? a : b;

@@ -294,10 +294,23 @@ int main(int argc, char** argv) {
     // A is the half space, B the sphere: the normal points from the sphere into the half space, i.e. down.
     EXPECT(std::fabs(pairs[0].nhat_BA_W[2] + 1.0) < 1e-15);
     EXPECT(std::fabs(pairs[0].p_WCa[2]) < 1e-15 && std::fabs(pairs[0].p_WCb[2] - (0.15 - R)) < 1e-15);
-    // Two rigid boxes: FCL's general narrow phase is not part of this back end -- loud unless the caller opts out.
+    // Two rigid boxes, the upper one rotated about z and 0.01 deep in the lower one's top face: FCL's box-box.
+    ProximityEngine bb(0);
+    bb.AddDynamicGeometry(Box{0.4, 0.4, 0.2}, RigidTransformd::Identity(), 1, rigid);
+    RigidTransformd X_top;
+    X_top.m = {std::cos(0.3), std::sin(0.3), 0, -std::sin(0.3), std::cos(0.3), 0, 0, 0, 1, 0.02, -0.01, 0.1 + 0.05 - 0.01};
+    bb.AddDynamicGeometry(Box{0.1, 0.1, 0.1}, X_top, 2, rigid);
+    pairs.clear();
+    bb.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    EXPECT(pairs.size() == 1 && pairs[0].id_A == 1 && pairs[0].id_B == 2);
+    if (pairs.size() == 1) {
+      EXPECT(std::fabs(pairs[0].depth - 0.01) < 1e-15 && std::fabs(pairs[0].nhat_BA_W[2] + 1.0) < 1e-15);
+      EXPECT(std::fabs(pairs[0].p_WCa[2] - 0.1) < 1e-15 && std::fabs(pairs[0].p_WCb[2] - 0.09) < 1e-15);
+    }
+    // A rigid box against a rigid cylinder: FCL's GJK / EPA is not part of this back end -- loud unless the caller opts out.
     ProximityEngine b(0);
     b.AddDynamicGeometry(Box{0.2, 0.2, 0.2}, RigidTransformd::Identity(), 1, rigid);
-    b.AddDynamicGeometry(Box{0.2, 0.2, 0.2}, RigidTransformd::FromTranslation(0, 0, 0.1), 2, rigid);
+    b.AddDynamicGeometry(Cylinder{0.1, 0.2}, RigidTransformd::FromTranslation(0, 0, 0.1), 2, rigid);
     bool threw = false;
     try {
       b.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);

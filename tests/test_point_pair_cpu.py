@@ -363,7 +363,7 @@ def test_half_space_primitives_degenerate_orientations():
     with pytest.raises(NotImplementedError):
         pp.point_pair(("half_space",), I, ("half_space",), I)
     with pytest.raises(NotImplementedError):
-        pp.point_pair(("box", (1.0, 1.0, 1.0)), I, ("box", (1.0, 1.0, 1.0)), I)
+        pp.point_pair(("box", (1.0, 1.0, 1.0)), I, ("capsule", 0.2, 1.0), I)
 
 
 def test_adapter_half_space_arithmetic_matches_the_oracle():
@@ -416,4 +416,151 @@ def test_adapter_half_space_arithmetic_matches_the_oracle():
         hits += 1
     assert hits > 1200
     first = np.array([float(x) for x in out[0].split()])   # TangentPlane1 through the C++: the reference's expectation
+    np.testing.assert_allclose(first, [k_depth, 0, 0, 0, 0, 0, -k_depth, 0, 0, -1], rtol=0, atol=1e-12)
+
+
+# ---- FCL's box x box behind CalcDistanceFallback ----------------------------------------------------------------------
+
+def test_box_on_tangent_box_reference_scenes():
+    """TangentBox1 / TangentBox2 (penetration_as_point_pair_callback_test.cc:914-920): A = a box of side 10 whose top face
+    is the z = 0 plane (:872-876), B = the unit box on its corner; same expectation as the plane scenes, 1e-12."""
+    k_depth, poses = _box_penetration_poses()
+    X_WA = ho.xform(None, [0, 0, -5.0])
+    for X_WB in poses:
+        res = pp.point_pair(("box", (10.0, 10.0, 10.0)), X_WA, ("box", (1.0, 1.0, 1.0)), X_WB)
+        np.testing.assert_allclose(res["nhat_BA_W"], [0, 0, -1], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(res["p_WCa"], [0, 0, 0], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(res["p_WCb"], [0, 0, -k_depth], rtol=0, atol=1e-12)
+        assert abs(res["depth"] - k_depth) <= 1e-12
+        rev = pp.point_pair(("box", (1.0, 1.0, 1.0)), X_WB, ("box", (10.0, 10.0, 10.0)), X_WA)
+        np.testing.assert_allclose(rev["nhat_BA_W"], [0, 0, 1], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(rev["p_WCa"], [0, 0, -k_depth], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(rev["p_WCb"], [0, 0, 0], rtol=0, atol=1e-12)
+
+
+def _box_vertices(size, X):
+    h = np.asarray(size) / 2
+    C = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]) * h
+    return C @ X[:9].reshape(3, 3) + X[9:]
+
+
+def _axis_overlaps(size_A, X_A, size_B, X_B):
+    """Overlap of the two boxes' projections on each of the 15 candidate axes, from their 8 + 8 vertices (no shared code
+    with either restatement). Returns (face overlaps [6], edge overlaps [<= 9])."""
+    RA, RB = X_A[:9].reshape(3, 3).T, X_B[:9].reshape(3, 3).T
+    VA, VB = _box_vertices(size_A, X_A), _box_vertices(size_B, X_B)
+
+    def overlap(L):
+        a, b = VA @ L, VB @ L
+        return min(a.max() - b.min(), b.max() - a.min())
+    faces = [overlap(RA[:, i]) for i in range(3)] + [overlap(RB[:, i]) for i in range(3)]
+    edges = []
+    for i in range(3):
+        for j in range(3):
+            L = np.cross(RA[:, i], RB[:, j])
+            if np.linalg.norm(L) > 1e-6:
+                edges.append(overlap(L / np.linalg.norm(L)))
+    return np.array(faces), np.array(edges)
+
+
+def test_box_box_is_the_minimum_overlap_axis_and_its_witnesses_lie_on_the_boxes():
+    """What the geometry fixes whatever FCL's coding. The contact normal is the axis of smallest overlap over the 15 (an
+    edge axis only when more than 5 % smaller than the best so far). The depth is that overlap whenever the deepest
+    vertex of the incident face lies over the reference face (most poses) -- then moving B by it along the normal
+    separates the boxes -- and otherwise the depth of the deepest point of the incident face that does (ODE reports
+    per-point depths), never more than the overlap. For a face contact both witness points lie on their box (Drake's
+    own DistanceToPoint(Box)), for an edge contact within the 1e-6 fudge."""
+    from tests import parity
+    rng = np.random.default_rng(11)
+    hits = edge_hits = full_depth = 0
+    for k in range(600):
+        sa, sb = tuple(rng.uniform(0.2, 0.9, 3)), tuple(rng.uniform(0.2, 0.9, 3))
+        X_A, X_B = parity.random_pose(rng, 0.25), parity.random_pose(rng, 0.25)
+        faces, edges = _axis_overlaps(sa, X_A, sb, X_B)
+        res = pp.point_pair(("box", sa), X_A, ("box", sb), X_B)
+        if min(faces.min(), edges.min() if len(edges) else np.inf) < -1e-9:
+            assert res is None
+            continue
+        if res is None:
+            continue
+        hits += 1
+        best_face = faces.min()
+        # ODE walks the axes in order; an edge axis replaces the current best only when its overlap is more than 5 %
+        # smaller (so a later, slightly smaller edge overlap does not displace an earlier edge axis).
+        sat, edge_wins, borderline = best_face, False, False
+        for e in edges:
+            borderline = borderline or abs(e * 1.05 - sat) < 1e-4   # within the 1e-6 fudge: either is a faithful answer
+            if e * 1.05 < sat:
+                sat, edge_wins = e, True
+        if borderline:
+            continue
+        tol = 2e-5 if edge_wins else 1e-12
+        assert res["depth"] <= sat + tol, (k, res["depth"], sat)
+        n_AB = -res["nhat_BA_W"]
+        assert abs(np.linalg.norm(n_AB) - 1) <= 1e-12
+        # The normal is the minimum-overlap axis: the overlap along it, measured from the vertices, is `sat`.
+        a, b = _box_vertices(sa, X_A) @ n_AB, _box_vertices(sb, X_B) @ n_AB
+        assert abs((a.max() - b.min()) - sat) <= tol, (k, a.max() - b.min(), sat)
+        if abs(res["depth"] - sat) <= tol:
+            full_depth += 1
+            shifted = X_B.copy()
+            shifted[9:] += (res["depth"] + 1e-5) * n_AB
+            f2, e2 = _axis_overlaps(sa, X_A, sb, shifted)
+            assert min(f2.min(), e2.min() if len(e2) else np.inf) < 0          # separated after the push
+        np.testing.assert_allclose(res["p_WCb"] - res["p_WCa"], res["depth"] * res["nhat_BA_W"], rtol=0, atol=1e-12)
+        # Witnesses on the boxes: always for a face contact; for an edge contact when the axis is the true minimum over
+        # all 15 (ODE takes the closest points of the two edges' LINES: on a non-minimal edge axis, which the 5 % rule can
+        # keep, they may fall outside the edges).
+        if not edge_wins or sat <= min(faces.min(), edges.min()) + 1e-12:
+            assert abs(pp.distance_to_box(sa, X_A, res["p_WCa"])[1]) <= tol
+            assert abs(pp.distance_to_box(sb, X_B, res["p_WCb"])[1]) <= tol
+        edge_hits += edge_wins
+    assert hits > 150 and edge_hits > 5 and full_depth > hits // 2
+
+
+def test_box_box_resting_flat_and_separated():
+    """Two faces flat on each other: depth and normal are the stacking axis', the reported point is a point of the overlap
+    of the two faces (which one FCL picks among the equally deep ones is not pinned); osculation and separation give none;
+    box x cylinder stays FCL's GJK."""
+    I = ho.xform(None, [0, 0, 0])
+    top = ho.xform(rot("z", 0.3), [0.1, -0.05, 0.5 + 0.25 - 0.01])
+    res = pp.point_pair(("box", (1.0, 1.0, 1.0)), I, ("box", (0.5, 0.5, 0.5)), top)
+    assert abs(res["depth"] - 0.01) <= 1e-15
+    np.testing.assert_allclose(res["nhat_BA_W"], [0, 0, -1], rtol=0, atol=1e-15)
+    assert abs(res["p_WCa"][2] - 0.5) <= 1e-15 and abs(res["p_WCb"][2] - 0.49) <= 1e-15
+    assert abs(pp.distance_to_box((0.5, 0.5, 0.5), top, res["p_WCb"])[1]) <= 1e-15
+    assert pp.point_pair(("box", (1.0, 1.0, 1.0)), I, ("box", (0.5, 0.5, 0.5)), ho.xform(None, [0, 0, 0.75])) is None
+    assert pp.point_pair(("box", (1.0, 1.0, 1.0)), I, ("box", (0.5, 0.5, 0.5)), ho.xform(None, [0, 0, 0.8])) is None
+    with pytest.raises(NotImplementedError):
+        pp.point_pair(("box", (1.0, 1.0, 1.0)), I, ("cylinder", 0.2, 0.5), I)
+
+
+def test_adapter_box_box_arithmetic_matches_the_oracle():
+    """include/drake_b200_point_pair.h::BoxBox (ODE's 2-D incident-face route) against the oracle (3-D clipping) on 3000
+    random box pairs, both operand orders, plus the reference's TangentBox scenes through the C++."""
+    from tests import parity
+    rng = np.random.default_rng(44)
+    k_depth, tangent = _box_penetration_poses()
+    cases = [((("box", (10.0, 10.0, 10.0)), ho.xform(None, [0, 0, -5.0])), (("box", (1.0, 1.0, 1.0)), X)) for X in tangent]
+    for k in range(3000):
+        a = (("box", tuple(float(x) for x in rng.uniform(0.15, 0.9, 3))), parity.random_pose(rng, 0.3))
+        b = (("box", tuple(float(x) for x in rng.uniform(0.15, 0.9, 3))), parity.random_pose(rng, 0.3))
+        cases.append((b, a) if k % 2 else (a, b))
+    lines = []
+    for a, b in cases:
+        lines.append(" ".join("b " + " ".join(repr(float(v)) for v in g[0][1]) + " " + " ".join(repr(float(v)) for v in g[1]) for g in (a, b)))
+    out = subprocess.run([_exe()], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    hits = 0
+    for (a, b), line in zip(cases, out):
+        want = pp.point_pair(a[0], a[1], b[0], b[1])
+        if want is None:
+            assert line.strip() == "none", (a, b, line)
+            continue
+        assert line.strip() != "none", (a, b)
+        got = np.array([float(x) for x in line.split()])
+        ref = np.concatenate([[want["depth"]], want["p_WCa"], want["p_WCb"], want["nhat_BA_W"]])
+        assert np.max(np.abs(got - ref)) <= 64 * K_EPS * (1.0 + np.max(np.abs(ref))), (a, b, got - ref)
+        hits += 1
+    assert hits > 800
+    first = np.array([float(x) for x in out[0].split()])
     np.testing.assert_allclose(first, [k_depth, 0, 0, 0, 0, 0, -k_depth, 0, 0, -1], rtol=0, atol=1e-12)
