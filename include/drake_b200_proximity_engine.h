@@ -106,8 +106,8 @@ struct ProximityProperties {
 };
 
 // geometry::PenetrationAsPointPair<double>, the fallback result (query_results/penetration_as_point_pair.h):
-// filled for the pairs one of whose shapes is a Sphere (Drake's own closed forms) or a HalfSpace (FCL's closed-form
-// half-space primitives) and for two boxes (FCL's box-box), drake_b200_point_pair.h.
+// Drake's own closed forms for a Sphere against Sphere / Box / HalfSpace / Cylinder / Capsule, FCL's closed-form half-space
+// primitives, its box-box, and libccd's MPR for every other convex pair (drake_b200_point_pair.h).
 struct PenetrationAsPointPair {
   GeometryId id_A, id_B;
   std::array<double, 3> p_WCa, p_WCb, nhat_BA_W;
@@ -295,9 +295,8 @@ class ProximityEngine {
     }
   }
 
-  // What to do with a fallback pair neither of whose shapes is a Sphere or a HalfSpace and which is not two boxes: the
-  // reference calls FCL's GJK / EPA there (penetration_as_point_pair_callback.cc:145-195), which this back end does not contain. false (the
-  // default): throw std::logic_error naming the pair, so that no contact is lost silently; true: skip such pairs.
+  // What to do with the one pair the reference itself rejects, HalfSpace x HalfSpace (it throws): false (the default)
+  // throws like the reference, true skips the pair.
   void set_skip_unsupported_point_pairs(bool skip) { skip_unsupported_point_pairs_ = skip; }
 
   // Batched form: X_WGs is [num_scenes * num_geometries * 12] doubles, scene-major, geometries in
@@ -440,14 +439,14 @@ class ProximityEngine {
         if (!res) return std::nullopt;
         return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
       }
-      // The reference rejects half space x half space itself (:525-555 of its test; ScalarSupport<double>,
-      // penetration_as_point_pair_callback.cc:329-338) and hands the rest to FCL's GJK / EPA.
-      if (skip_unsupported_point_pairs_) return std::nullopt;
-      throw std::logic_error("ComputeContactSurfacesWithFallback: the point-pair fallback for geometries " +
-                             std::to_string(ids_[ga]) + " and " + std::to_string(ids_[gb]) +
-                             " needs FCL's GJK / EPA narrow phase (no Sphere or HalfSpace in the pair and not two boxes, or "
-                             "two half spaces), which this back end does not provide; filter the pair or call "
-                             "set_skip_unsupported_point_pairs(true)");
+      if (a_is_half_space) {
+        // Two half spaces: the reference rejects the pair itself (ScalarSupport<double>, penetration_as_point_pair_callback.cc:
+        // 329-338,441-449; :525-555 of its test).
+        if (skip_unsupported_point_pairs_) return std::nullopt;
+        throw std::logic_error("Penetration queries between shapes 'HalfSpace' and 'HalfSpace' are not supported for scalar "
+                               "type double (geometries " + std::to_string(ids_[ga]) + " and " + std::to_string(ids_[gb]) + ")");
+      }
+      return MprPointPair(ga, gb);   // every other convex pair: libccd's MPR behind fcl::collide
     }
     const int gs = a_is_sphere ? ga : gb, go = a_is_sphere ? gb : ga;   // sphere, other
     const pp::Pose& X_WS = poses_[gs].m;
@@ -466,14 +465,49 @@ class ProximityEngine {
     } else if (const auto* ca = std::get_if<Capsule>(&shapes_[go])) {
       d = pp::DistanceToCapsule(ca->radius, ca->length, X_WO, p_WSo);
     } else {
-      if (skip_unsupported_point_pairs_) return std::nullopt;
-      throw std::logic_error("ComputeContactSurfacesWithFallback: the point-pair fallback between a Sphere and the shape of "
-                             "geometry " + std::to_string(ids_[go]) + " needs FCL (ellipsoids and meshes have no closed form, "
-                             "penetration_as_point_pair_callback.cc:273-278)");
+      return MprPointPair(ga, gb);   // sphere x ellipsoid / mesh: the reference calls FCL too (:273-278)
     }
     auto res = pp::SphereShapePenetration(r, X_WS, X_WO, d);
     if (!res) return std::nullopt;
     if (!a_is_sphere) pp::SwapAAndB(&*res);
+    return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
+  }
+
+  // The shape as FCL's convex object: primitives as they are, a mesh as its vertex cloud (FCL is given the convex hull of
+  // a Mesh or Convex; the support function of the hull is that of the vertices).
+  point_pair::ConvexShape ToConvex(int g) const {
+    namespace pp = point_pair;
+    pp::ConvexShape sh{};
+    sh.X_WS = poses_[g].m;
+    if (const auto* s = std::get_if<Sphere>(&shapes_[g])) {
+      sh.kind = pp::ConvexShape::kSphere;
+      sh.dims = {s->radius, 0, 0};
+    } else if (const auto* bx = std::get_if<Box>(&shapes_[g])) {
+      sh.kind = pp::ConvexShape::kBox;
+      sh.dims = {bx->width, bx->depth, bx->height};
+    } else if (const auto* cy = std::get_if<Cylinder>(&shapes_[g])) {
+      sh.kind = pp::ConvexShape::kCylinder;
+      sh.dims = {cy->radius, cy->length, 0};
+    } else if (const auto* ca = std::get_if<Capsule>(&shapes_[g])) {
+      sh.kind = pp::ConvexShape::kCapsule;
+      sh.dims = {ca->radius, ca->length, 0};
+    } else if (const auto* el = std::get_if<Ellipsoid>(&shapes_[g])) {
+      sh.kind = pp::ConvexShape::kEllipsoid;
+      sh.dims = {el->a, el->b, el->c};
+    } else {
+      const auto* sm = std::get_if<SurfaceMeshShape>(&shapes_[g]);
+      const auto* vm = std::get_if<VolumeMeshShape>(&shapes_[g]);
+      const std::vector<double>* v = sm ? &sm->vertices : (vm ? &vm->vertices : nullptr);
+      if (v == nullptr || v->size() < 3) throw std::logic_error("point-pair fallback: geometry " + std::to_string(ids_[g]) + " has no convex representation");
+      sh.kind = pp::ConvexShape::kVertices;
+      sh.vertices = v->data();
+      sh.num_vertices = v->size() / 3;
+    }
+    return sh;
+  }
+  std::optional<PenetrationAsPointPair> MprPointPair(int ga, int gb) const {
+    auto res = point_pair::FclContactToPointPair(point_pair::MprPenetration(ToConvex(ga), ToConvex(gb)));
+    if (!res) return std::nullopt;
     return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
   }
 

@@ -14,8 +14,11 @@ the reference's BoxPenetrationTest TangentPlane scenes (penetration_as_point_pai
 shapes' analytic support functions / brute-force surface sampling in tests/test_point_pair_cpu.py.
 
 (3) FCL's box x box (boxBox2, the ODE dBoxBox algorithm): box_box_contact below, pinned by the reference's TangentBox
-scenes and by exact geometry (the minimum-overlap axis over all 15, vertices of one box inside the other). GJK / EPA is
-not restated.
+scenes and by exact geometry (the minimum-overlap axis over all 15, vertices of one box inside the other).
+
+(4) Every other convex pair: libccd's Minkowski Portal Refinement (ccdMPRPenetration, what FCL's GJKCollide calls for a
+contact) over FCL's support functions: mpr_contact below, pinned by the reference's BoxPenetrationTest scenes for
+cylinder / capsule / convex tangent shapes at the tolerances the reference states.
 
 Poses are 12 doubles: rotation column-major, then translation (math/rigid_transform.h:1004-1007)."""
 from __future__ import annotations
@@ -370,6 +373,184 @@ def box_box_point_pair(size_A, X_WA, size_B, X_WB):
     return {"depth": depth, "nhat_BA_W": nhat_BA_W, "p_WCa": pos - 0.5 * depth * nhat_BA_W, "p_WCb": pos + 0.5 * depth * nhat_BA_W}
 
 
+# ---- Minkowski Portal Refinement (libccd's ccdMPRPenetration behind fcl::collide for the remaining convex pairs) -------
+
+def support(shape, X_WS, dir_W):
+    """Farthest point of the shape along a World direction, in World (FCL's per-shape support functions)."""
+    R, t = _R(X_WS), _p(X_WS)
+    d = R.T @ np.asarray(dir_W, float)
+    eps = np.finfo(float).eps
+    sgn = lambda x: 0.0 if abs(x) < eps else (-1.0 if x < 0 else 1.0)
+    kind = shape[0]
+    if kind == "sphere":
+        v = d * (shape[1] / math.sqrt(float(d @ d)))
+    elif kind == "box":
+        v = np.array([sgn(d[k]) * shape[1][k] * 0.5 for k in range(3)])
+    elif kind == "cylinder":
+        zdist = math.sqrt(d[0] * d[0] + d[1] * d[1])
+        if abs(zdist) < eps:
+            v = np.array([0.0, 0.0, sgn(d[2]) * shape[2] * 0.5])
+        else:
+            v = np.array([shape[1] / zdist * d[0], shape[1] / zdist * d[1], sgn(d[2]) * shape[2] * 0.5])
+    elif kind == "capsule":
+        v = d * (shape[1] / math.sqrt(float(d @ d)))
+        v[2] += shape[2] * 0.5 if d[2] > 0 else -shape[2] * 0.5
+    elif kind == "ellipsoid":
+        abc2 = np.asarray(shape[1], float) ** 2 * d
+        v = abc2 / math.sqrt(float(d @ abc2))
+    elif kind == "vertices":
+        V = np.asarray(shape[1], float).reshape(-1, 3)
+        v = V[int(np.argmax(V @ d))]
+    else:
+        raise NotImplementedError(kind)
+    return R @ v + t
+
+
+def _center(shape, X_WS):
+    if shape[0] == "vertices":
+        return _R(X_WS) @ np.mean(np.asarray(shape[1], float).reshape(-1, 3), axis=0) + _p(X_WS)
+    return _p(X_WS)
+
+
+def mpr_contact(shape_A, X_WA, shape_B, X_WB, tolerance=1e-7, max_iterations=500):
+    """G. Snethen's Minkowski Portal Refinement as libccd's ccdMPRPenetration runs it (src/mpr.c; FCL reaches it through
+    GJKCollide for every convex pair without a primitive algorithm): None or (normal from A into B, position, depth).
+    The product header's default tolerance (1e-7, see there) is used; libccd's path through the refinement is not
+    reproduced bit for bit, so the reference anchors are its BoxPenetrationTest scenes at the tolerances they state."""
+    eps = np.finfo(float).eps
+    zero = lambda x: abs(x) < eps
+
+    def sup(d):
+        v1, v2 = support(shape_A, X_WA, d), support(shape_B, X_WB, -d)
+        return [v1 - v2, v1, v2]
+
+    def unit(v):
+        n = math.sqrt(float(v @ v))
+        return v / n if n else v
+    c1, c2 = _center(shape_A, X_WA), _center(shape_B, X_WB)
+    P = [[c1 - c2, c1, c2], None, None, None]
+    if all(zero(x) for x in P[0][0]):
+        P[0][0] = np.array([eps * 10, 0.0, 0.0])
+    d = unit(-P[0][0])
+    P[1] = sup(d)
+    dot = float(P[1][0] @ d)
+    if zero(dot) or dot < 0:
+        return None
+    d = np.cross(P[0][0], P[1][0])
+    mid = lambda s: 0.5 * (s[1] + s[2])
+    if zero(math.sqrt(float(d @ d))):
+        if all(zero(x) for x in P[1][0]):
+            return np.zeros(3), mid(P[1]), 0.0
+        n = P[1][0]
+        return unit(n), mid(P[1]), math.sqrt(float(n @ n))
+    d = unit(d)
+    P[2] = sup(d)
+    dot = float(P[2][0] @ d)
+    if zero(dot) or dot < 0:
+        return None
+    d = unit(np.cross(P[1][0] - P[0][0], P[2][0] - P[0][0]))
+    if float(d @ P[0][0]) > 0:
+        P[1], P[2] = P[2], P[1]
+        d = -d
+    for guard in range(max_iterations + 2):
+        if guard > max_iterations:
+            return None
+        P[3] = sup(d)
+        dot = float(P[3][0] @ d)
+        if zero(dot) or dot < 0:
+            return None
+        if float(np.cross(P[1][0], P[3][0]) @ P[0][0]) < -eps:
+            P[2] = P[3]
+        elif float(np.cross(P[3][0], P[2][0]) @ P[0][0]) < -eps:
+            P[1] = P[3]
+        else:
+            break
+        d = unit(np.cross(P[1][0] - P[0][0], P[2][0] - P[0][0]))
+    portal_dir = lambda: unit(np.cross(P[2][0] - P[1][0], P[3][0] - P[1][0]))
+
+    def expand(v4):
+        v4v0 = np.cross(v4[0], P[0][0])
+        if float(P[1][0] @ v4v0) > 0:
+            if float(P[2][0] @ v4v0) > 0:
+                P[1] = v4
+            else:
+                P[3] = v4
+        elif float(P[3][0] @ v4v0) > 0:
+            P[2] = v4
+        else:
+            P[1] = v4
+
+    def reach(v4, d):
+        d4 = float(v4[0] @ d)
+        return min(d4 - float(P[1][0] @ d), d4 - float(P[2][0] @ d), d4 - float(P[3][0] @ d))
+    guard = 0
+    while True:
+        d = portal_dir()
+        dot = float(P[1][0] @ d)
+        if zero(dot) or dot > 0:
+            break
+        v4 = sup(d)
+        d4 = float(v4[0] @ d)
+        if not (zero(d4) or d4 > 0):
+            return None
+        r = reach(v4, d)
+        if r < tolerance or zero(r - tolerance) or guard > max_iterations:
+            return None
+        expand(v4)
+        guard += 1
+    it = 0
+    while True:
+        d = portal_dir()
+        v4 = sup(d)
+        r = reach(v4, d)
+        if r < tolerance or zero(r - tolerance) or it > max_iterations:
+            a, b, c = P[1][0], P[2][0], P[3][0]
+            d1, d2 = b - a, c - a
+            v, w, p, q, rr = float(d1 @ d1), float(d2 @ d2), float(a @ d1), float(a @ d2), float(d1 @ d2)
+            div = w * v - rr * rr
+            wit = None
+            if not zero(div):
+                s = (q * rr - w * p) / div
+                t = (-s * rr - q) / w
+                ok = lambda x: (zero(x) or x > 0) and (x < 1 or zero(x - 1))
+                if ok(s) and ok(t) and (t + s < 1 or zero(t + s - 1)):
+                    wit = a + s * d1 + t * d2
+            if wit is None:
+                best = None
+                for x0, x1 in ((a, b), (a, c), (b, c)):
+                    e = x1 - x0
+                    k = min(1.0, max(0.0, -float(x0 @ e) / float(e @ e)))
+                    cand = x0 + k * e
+                    if best is None or float(cand @ cand) < float(best @ best):
+                        best = cand
+                wit = best
+            depth = math.sqrt(float(wit @ wit))
+            pdir = d if all(zero(x) for x in wit) else wit
+            pdir = unit(pdir)
+            bc = [float(np.cross(P[1][0], P[2][0]) @ P[3][0]), float(np.cross(P[3][0], P[2][0]) @ P[0][0]),
+                  float(np.cross(P[0][0], P[1][0]) @ P[3][0]), float(np.cross(P[2][0], P[1][0]) @ P[0][0])]
+            total = ((bc[0] + bc[1]) + bc[2]) + bc[3]
+            if zero(total) or total < 0:
+                bc = [0.0, float(np.cross(P[2][0], P[3][0]) @ d), float(np.cross(P[3][0], P[1][0]) @ d),
+                      float(np.cross(P[1][0], P[2][0]) @ d)]
+                total = (bc[1] + bc[2]) + bc[3]
+            p1 = sum(bc[k] * P[k][1] for k in range(4))
+            p2 = sum(bc[k] * P[k][2] for k in range(4))
+            return pdir, 0.5 * (p1 + p2) / total, depth
+        expand(v4)
+        it += 1
+
+
+def mpr_point_pair(shape_A, X_WA, shape_B, X_WB):
+    """CalcDistanceFallback<double> (:164-207) on the MPR contact."""
+    hit = mpr_contact(shape_A, X_WA, shape_B, X_WB)
+    if hit is None or hit[2] <= np.finfo(float).eps:
+        return None
+    normal, pos, depth = hit
+    nhat_BA_W = -normal
+    return {"depth": depth, "nhat_BA_W": nhat_BA_W, "p_WCa": pos - 0.5 * depth * nhat_BA_W, "p_WCb": pos + 0.5 * depth * nhat_BA_W}
+
+
 def point_pair(shape_A, X_WA, shape_B, X_WB):
     """ComputeNarrowPhasePenetration for shapes given as ('sphere', r) | ('box', (x, y, z)) | ('half_space',) |
     ('cylinder', r, L) | ('capsule', r, L) | ('ellipsoid', (a, b, c)) | ('vertices', V); A is the
@@ -380,9 +561,13 @@ def point_pair(shape_A, X_WA, shape_B, X_WB):
     if not (a_is_sphere or b_is_sphere):
         if (shape_A[0] == "half_space") != (shape_B[0] == "half_space"):
             return half_space_point_pair(shape_A, X_WA, shape_B, X_WB)
+        if shape_A[0] == "half_space":
+            raise NotImplementedError("two half spaces: the reference throws (:329-338)")
         if shape_A[0] == "box" and shape_B[0] == "box":
             return box_box_point_pair(shape_A[1], X_WA, shape_B[1], X_WB)
-        raise NotImplementedError("no sphere and not exactly one half space in the pair: FCL's general narrow phase")
+        return mpr_point_pair(shape_A, X_WA, shape_B, X_WB)
+    if (shape_B if a_is_sphere else shape_A)[0] in ("ellipsoid", "vertices"):   # the reference sends these to FCL (:273-278)
+        return mpr_point_pair(shape_A, X_WA, shape_B, X_WB)
     (S, X_WS), (O, X_WO) = ((shape_A, X_WA), (shape_B, X_WB)) if a_is_sphere else ((shape_B, X_WB), (shape_A, X_WA))
     p_WSo = _p(X_WS)
     if O[0] == "sphere":

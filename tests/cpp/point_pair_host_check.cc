@@ -4,7 +4,7 @@
 // and prints `none` or `depth p_WCa(3) p_WCb(3) nhat(3)` with 17 significant digits, the way
 // ComputeNarrowPhasePenetration (penetration_as_point_pair_callback.cc:203-300) orders its operands; a pair without a
 // sphere must hold exactly one half space (FCL's closed-form half-space primitives behind CalcDistanceFallback) or be
-// two boxes (FCL's box-box).
+// two boxes (FCL's box-box); every other pair without a half space goes through MprPenetration.
 #include <cstdio>
 #include <iostream>
 #include <string>
@@ -45,6 +45,30 @@ int main() {
     const bool a_is_sphere = a.kind == 's';
     if (a.kind == 'b' && b.kind == 'b') {   // FCL's box-box behind CalcDistanceFallback
       const auto res = FclContactToPointPair(BoxBox(a.size, a.X, b.size, b.X));
+      if (!res) {
+        std::printf("none\n");
+        continue;
+      }
+      std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", res->depth, res->p_WCa[0], res->p_WCa[1],
+                  res->p_WCa[2], res->p_WCb[0], res->p_WCb[1], res->p_WCb[2], res->nhat_BA_W[0], res->nhat_BA_W[1],
+                  res->nhat_BA_W[2]);
+      continue;
+    }
+    // Neither Drake's closed forms (a sphere against s b h c k) nor a half space: libccd's MPR.
+    const auto drake_has = [](char k) { return k == 's' || k == 'b' || k == 'h' || k == 'c' || k == 'k'; };
+    const bool drake_closed_form = (a_is_sphere && drake_has(b.kind)) || (b.kind == 's' && drake_has(a.kind));
+    if (a.kind != 'h' && b.kind != 'h' && !drake_closed_form) {
+      auto shape = [](const Geo& g) {
+        ConvexShape sh{};
+        sh.kind = g.kind == 's' ? ConvexShape::kSphere : g.kind == 'b' ? ConvexShape::kBox : g.kind == 'c' ? ConvexShape::kCylinder
+                : g.kind == 'k' ? ConvexShape::kCapsule : g.kind == 'e' ? ConvexShape::kEllipsoid : ConvexShape::kVertices;
+        sh.dims = g.kind == 's' ? Vec3{g.r, 0, 0} : g.size;
+        sh.vertices = g.vertices.data();
+        sh.num_vertices = g.vertices.size() / 3;
+        sh.X_WS = g.X;
+        return sh;
+      };
+      const auto res = FclContactToPointPair(MprPenetration(shape(a), shape(b)));
       if (!res) {
         std::printf("none\n");
         continue;

@@ -307,15 +307,27 @@ int main(int argc, char** argv) {
       EXPECT(std::fabs(pairs[0].depth - 0.01) < 1e-15 && std::fabs(pairs[0].nhat_BA_W[2] + 1.0) < 1e-15);
       EXPECT(std::fabs(pairs[0].p_WCa[2] - 0.1) < 1e-15 && std::fabs(pairs[0].p_WCb[2] - 0.09) < 1e-15);
     }
-    // A rigid box against a rigid cylinder: FCL's GJK / EPA is not part of this back end -- loud unless the caller opts out.
+    // A rigid cylinder standing 0.01 deep in a rigid box's top face (the reference's TangentStandingCylinder situation
+    // turned over): libccd's MPR behind fcl::collide.
+    ProximityEngine bc(0);
+    bc.AddDynamicGeometry(Box{0.4, 0.4, 0.2}, RigidTransformd::Identity(), 1, rigid);
+    bc.AddDynamicGeometry(Cylinder{0.1, 0.2}, RigidTransformd::FromTranslation(0.02, -0.01, 0.1 + 0.1 - 0.01), 2, rigid);
+    pairs.clear();
+    bc.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
+    EXPECT(pairs.size() == 1 && pairs[0].id_A == 1 && pairs[0].id_B == 2);
+    if (pairs.size() == 1) {
+      EXPECT(std::fabs(pairs[0].depth - 0.01) < 1e-6 && std::fabs(pairs[0].nhat_BA_W[2] + 1.0) < 1e-6);
+      EXPECT(std::fabs(pairs[0].p_WCa[2] - 0.1) < 1e-3 && std::fabs(pairs[0].p_WCb[2] - 0.09) < 1e-3);
+    }
+    // Two half spaces: the reference rejects the pair itself -- loud unless the caller opts out.
     ProximityEngine b(0);
-    b.AddDynamicGeometry(Box{0.2, 0.2, 0.2}, RigidTransformd::Identity(), 1, rigid);
-    b.AddDynamicGeometry(Cylinder{0.1, 0.2}, RigidTransformd::FromTranslation(0, 0, 0.1), 2, rigid);
+    b.AddAnchoredGeometry(HalfSpace{}, RigidTransformd::Identity(), 1, rigid);
+    b.AddDynamicGeometry(HalfSpace{}, RigidTransformd::FromTranslation(0, 0, 0.1), 2, rigid);
     bool threw = false;
     try {
       b.ComputeContactSurfacesWithFallback(HydroelasticContactRepresentation::kPolygon, {}, &surfaces, &pairs);
     } catch (const std::logic_error& err) {
-      threw = std::string(err.what()).find("FCL") != std::string::npos;
+      threw = std::string(err.what()).find("HalfSpace") != std::string::npos;
     }
     EXPECT(threw);
     b.set_skip_unsupported_point_pairs(true);
