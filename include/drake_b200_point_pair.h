@@ -8,13 +8,13 @@
 //     through point_distance::DistanceToPoint (distance_to_point_callback.cc:15-77,160-178,406-482);
 //   * FCL's collide() for everything else (:145-207) -- an external dependency of the reference, absent from its tree
 //     (tools/workspace/fcl_internal/repository.bzl: RobotLocomotion/fcl at commit e5efcc41b57b). Inside FCL that call is
-//     again two things: closed-form primitives for a Halfspace against Box, Capsule, Cylinder, Ellipsoid and Convex
-//     (fcl/narrowphase/detail/primitive_shape_algorithm/halfspace-inl.h), and GJK / EPA over libccd for the rest.
+//     again three things: closed-form primitives for a Halfspace against Box, Capsule, Cylinder, Ellipsoid and Convex
+//     (fcl/narrowphase/detail/primitive_shape_algorithm/halfspace-inl.h), box x box (box_box-inl.h), and libccd's
+//     Minkowski Portal Refinement for every other convex pair (convexity_based_algorithm/gjk_libccd-inl.h: GJKCollide).
 // This header restates the first half completely -- Sphere against Sphere, Box, HalfSpace, Cylinder, Capsule, every shape
-// the reference has a closed form for (it sends Ellipsoid and Convex to FCL, :273-278) -- and, of the second half, FCL's
-// published half-space primitives with the reference's post-processing of an FCL contact (:164-207): a rigid box,
-// cylinder, capsule, ellipsoid or mesh on a rigid HalfSpace ground is the commonest rigid-rigid fallback pair. The FCL
-// sources are not available here: those functions are pinned by the reference's BoxPenetrationTest TangentPlane scenes
+// the reference has a closed form for (it sends Ellipsoid and Convex to FCL, :273-278) -- and the second half from FCL's
+// and libccd's published algorithms, with the reference's post-processing of an FCL contact (:164-207). The FCL
+// sources are not available here: the half-space functions are pinned by the reference's BoxPenetrationTest TangentPlane scenes
 // (penetration_as_point_pair_callback_test.cc:575-910, 1e-12) and by the shapes' analytic support functions
 // (tests/test_point_pair_cpu.py), not against FCL itself; likewise FCL's box x box (ODE's dBoxBox, below), pinned by the
 // TangentBox scenes, and libccd's Minkowski Portal Refinement for every other convex pair (MprPenetration, below), pinned
