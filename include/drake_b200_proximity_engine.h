@@ -308,6 +308,35 @@ class ProximityEngine {
     return Run(representation, DBH_QUERY_STRICT, X_WGs);
   }
 
+  // ComputeContactSurfacesWithFallback for every scene of the batch: the surfaces per scene and, per scene, the point
+  // pairs of the pairs whose surface cannot be made (proximity_engine.cc:936-977), each list in (id_A, id_B) order.
+  void ComputeContactSurfacesWithFallbackBatched(HydroelasticContactRepresentation representation,
+                                                 const std::vector<double>& X_WGs,
+                                                 std::vector<std::vector<ContactSurface>>* surfaces,
+                                                 std::vector<std::vector<PenetrationAsPointPair>>* point_pairs) {
+    if (surfaces == nullptr || point_pairs == nullptr) throw std::logic_error("ComputeContactSurfacesWithFallbackBatched: null output");
+    const size_t G = ids_.size();
+    if (X_WGs.size() != static_cast<size_t>(num_scenes_) * G * 12)
+      throw std::logic_error("ComputeContactSurfacesWithFallbackBatched: expected num_scenes * num_geometries poses");
+    *surfaces = Run(representation, DBH_QUERY_WITH_FALLBACK, X_WGs);
+    point_pairs->assign(static_cast<size_t>(num_scenes_), {});
+    if (G == 0) return;
+    int64_t n = 0;
+    Check(dbh_batch_copy_fallback_pairs(batch_, nullptr, &n), "copy_fallback_pairs");
+    std::vector<int32_t> quads(static_cast<size_t>(4 * n));
+    if (n) Check(dbh_batch_copy_fallback_pairs(batch_, quads.data(), &n), "copy_fallback_pairs");
+    struct Restore {   // MaybeMakePointPair may throw
+      const double*& p;
+      ~Restore() { p = nullptr; }
+    } restore{scene_poses_};
+    for (int64_t k = 0; k < n; ++k) {
+      const int scene = quads[4 * k];
+      scene_poses_ = X_WGs.data() + static_cast<size_t>(scene) * G * 12;
+      auto pp = MaybeMakePointPair(quads[4 * k + 1] - scene * static_cast<int>(G), quads[4 * k + 2] - scene * static_cast<int>(G));
+      if (pp) (*point_pairs)[scene].push_back(*pp);
+    }
+  }
+
   dbh_stats stats() const {
     dbh_stats s{};
     if (batch_) dbh_batch_stats(batch_, &s);
@@ -402,6 +431,15 @@ class ProximityEngine {
   // hydroelastic::Geometries::MaybeAddGeometry (hydroelastic_internal.cc:145-153, 328-343, 412-536).
   // penetration_as_point_pair::ComputeNarrowPhasePenetration (penetration_as_point_pair_callback.cc:203-300) for the
   // geometries at indices ga, gb (id(ga) < id(gb)) at their current poses.
+  // The pose the point-pair arithmetic sees for geometry g: the engine's own (one scene) or, inside the batched
+  // fallback query, that scene's slice of the caller's pose array.
+  point_pair::Pose PoseOf(int g) const {
+    if (scene_poses_ == nullptr) return poses_[g].m;
+    point_pair::Pose X;
+    std::copy(scene_poses_ + 12 * g, scene_poses_ + 12 * g + 12, X.begin());
+    return X;
+  }
+
   std::optional<PenetrationAsPointPair> MaybeMakePointPair(int ga, int gb) const {
     namespace pp = point_pair;
     const Shape& a = shapes_[ga];
@@ -412,8 +450,8 @@ class ProximityEngine {
       if (a_is_half_space != b_is_half_space) {
         // FCL's closed-form half-space primitives behind CalcDistanceFallback (:145-207), drake_b200_point_pair.h.
         const int gh = a_is_half_space ? ga : gb, gx = a_is_half_space ? gb : ga;   // half space, the other shape
-        const pp::Pose& X_WH = poses_[gh].m;
-        const pp::Pose& X_WX = poses_[gx].m;
+        const pp::Pose X_WH = PoseOf(gh);
+        const pp::Pose X_WX = PoseOf(gx);
         std::optional<pp::FclHalfSpaceContact> contact;
         if (const auto* bx = std::get_if<Box>(&shapes_[gx])) {
           contact = pp::BoxHalfSpace({bx->width, bx->depth, bx->height}, X_WX, X_WH);
@@ -434,8 +472,8 @@ class ProximityEngine {
       }
       if (const auto *ba = std::get_if<Box>(&a), *bb = std::get_if<Box>(&b); ba && bb) {
         // FCL's box-box (boxBox2) behind CalcDistanceFallback, drake_b200_point_pair.h.
-        auto res = pp::FclContactToPointPair(pp::BoxBox({ba->width, ba->depth, ba->height}, poses_[ga].m,
-                                                        {bb->width, bb->depth, bb->height}, poses_[gb].m));
+        auto res = pp::FclContactToPointPair(pp::BoxBox({ba->width, ba->depth, ba->height}, PoseOf(ga),
+                                                        {bb->width, bb->depth, bb->height}, PoseOf(gb)));
         if (!res) return std::nullopt;
         return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
       }
@@ -449,8 +487,8 @@ class ProximityEngine {
       return MprPointPair(ga, gb);   // every other convex pair: libccd's MPR behind fcl::collide
     }
     const int gs = a_is_sphere ? ga : gb, go = a_is_sphere ? gb : ga;   // sphere, other
-    const pp::Pose& X_WS = poses_[gs].m;
-    const pp::Pose& X_WO = poses_[go].m;
+    const pp::Pose X_WS = PoseOf(gs);
+    const pp::Pose X_WO = PoseOf(go);
     const pp::Vec3 p_WSo{X_WS[9], X_WS[10], X_WS[11]};
     const double r = std::get<Sphere>(shapes_[gs]).radius;
     pp::SignedDistanceToPoint d;
@@ -478,7 +516,7 @@ class ProximityEngine {
   point_pair::ConvexShape ToConvex(int g) const {
     namespace pp = point_pair;
     pp::ConvexShape sh{};
-    sh.X_WS = poses_[g].m;
+    sh.X_WS = PoseOf(g);
     if (const auto* s = std::get_if<Sphere>(&shapes_[g])) {
       sh.kind = pp::ConvexShape::kSphere;
       sh.dims = {s->radius, 0, 0};
@@ -863,6 +901,7 @@ class ProximityEngine {
   std::vector<int32_t> last_elements_;
   int last_vertices_per_element_{0};
   bool skip_unsupported_point_pairs_{false};
+  const double* scene_poses_{nullptr};   // set only inside ComputeContactSurfacesWithFallbackBatched
   std::vector<int32_t> assets_;
   std::vector<uint8_t> anchored_;
   std::vector<RigidTransformd> poses_;

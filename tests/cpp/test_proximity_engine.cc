@@ -319,6 +319,38 @@ int main(int argc, char** argv) {
       EXPECT(std::fabs(pairs[0].depth - 0.01) < 1e-6 && std::fabs(pairs[0].nhat_BA_W[2] + 1.0) < 1e-6);
       EXPECT(std::fabs(pairs[0].p_WCa[2] - 0.1) < 1e-3 && std::fabs(pairs[0].p_WCb[2] - 0.09) < 1e-3);
     }
+    // The batched fallback query: 3 scenes of {rigid HalfSpace ground, rigid box, compliant sphere}; the box sits 0.02,
+    // 0.0 (apart by 0.5) and 0.05 deep in the ground, the sphere always rests 0.03 deep: one surface per scene, and a
+    // point pair (FCL's box x half space) in scenes 0 and 2 with that scene's depth.
+    ProximityEngine sc(0);
+    sc.AddAnchoredGeometry(HalfSpace{}, RigidTransformd::Identity(), 1, rigid);
+    sc.AddDynamicGeometry(Box{0.2, 0.2, 0.2}, RigidTransformd::Identity(), 2, rigid);
+    sc.AddDynamicGeometry(Sphere{R}, RigidTransformd::Identity(), 3, soft);
+    sc.ExcludeCollisionsBetween(2, 3);
+    sc.set_num_scenes(3);
+    const double box_z[3] = {0.1 - 0.02, 0.1 + 0.5, 0.1 - 0.05};
+    std::vector<double> scene_poses;
+    for (int sidx = 0; sidx < 3; ++sidx) {
+      const RigidTransformd Xs[3] = {RigidTransformd::Identity(), RigidTransformd::FromTranslation(1.0, 0, box_z[sidx]),
+                                     RigidTransformd::FromTranslation(-1.0, 0, R - 0.03)};
+      for (const auto& X : Xs) scene_poses.insert(scene_poses.end(), X.m.begin(), X.m.end());
+    }
+    std::vector<std::vector<ContactSurface>> batch_surfaces;
+    std::vector<std::vector<PenetrationAsPointPair>> batch_pairs;
+    sc.ComputeContactSurfacesWithFallbackBatched(HydroelasticContactRepresentation::kPolygon, scene_poses, &batch_surfaces,
+                                                 &batch_pairs);
+    EXPECT(batch_surfaces.size() == 3 && batch_pairs.size() == 3);
+    if (batch_pairs.size() == 3) {
+      for (int sidx = 0; sidx < 3; ++sidx) {
+        EXPECT(batch_surfaces[sidx].size() == 1 && batch_surfaces[sidx][0].id_M() == 1 && batch_surfaces[sidx][0].id_N() == 3);
+        EXPECT(batch_pairs[sidx].size() == (sidx == 1 ? 0u : 1u));
+        if (batch_pairs[sidx].size() == 1) {
+          const PenetrationAsPointPair& q = batch_pairs[sidx][0];
+          EXPECT(q.id_A == 1 && q.id_B == 2 && std::fabs(q.depth - (0.1 - box_z[sidx])) < 1e-15);
+          EXPECT(std::fabs(q.nhat_BA_W[2] + 1) < 1e-15 && std::fabs(q.p_WCa[2]) < 1e-15);
+        }
+      }
+    }
     // Two half spaces: the reference rejects the pair itself -- loud unless the caller opts out.
     ProximityEngine b(0);
     b.AddAnchoredGeometry(HalfSpace{}, RigidTransformd::Identity(), 1, rigid);
