@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <limits>
 #include <map>
@@ -306,6 +307,69 @@ class ProximityEngine {
     if (X_WGs.size() != static_cast<size_t>(num_scenes_) * ids_.size() * 12)
       throw std::logic_error("ComputeContactSurfacesBatched: expected num_scenes * num_geometries poses");
     return Run(representation, DBH_QUERY_STRICT, X_WGs);
+  }
+
+  // ProximityEngine::ComputePointPairPenetration (proximity_engine.cc:740-760: FclCollide over dynamic x dynamic and
+  // dynamic x anchored with penetration_as_point_pair::Callback, then std::sort): one PenetrationAsPointPair per
+  // unfiltered pair of penetrating geometries, whatever their hydroelastic types, ordered by (id_A, id_B). Host-side
+  // throughout -- the same narrow phase ComputeContactSurfacesWithFallback uses for its no-surface pairs
+  // (drake_b200_point_pair.h) behind a geometry-level broad phase over FCL's world boxes (computeAABB: the local box
+  // translated under an identity rotation, else the cube around its bounding sphere; a half space bounded only under the
+  // identity). It is the point-contact model's query, next to the path rather than on it: nothing here runs on the GPU.
+  std::vector<PenetrationAsPointPair> ComputePointPairPenetration(const std::unordered_map<GeometryId, RigidTransformd>& X_WGs) {
+    UpdateWorldPoses(X_WGs);
+    const int G = static_cast<int>(ids_.size());
+    std::vector<int> order(G);
+    for (int g = 0; g < G; ++g) order[g] = g;
+    std::sort(order.begin(), order.end(), [this](int x, int y) { return ids_[x] < ids_[y]; });
+    struct WorldBox {
+      double mn[3], mx[3];
+    };
+    std::vector<WorldBox> boxes(G);
+    for (int g = 0; g < G; ++g) {
+      WorldBox& wb = boxes[g];
+      for (int k = 0; k < 3; ++k) {
+        wb.mn[k] = -std::numeric_limits<double>::infinity();
+        wb.mx[k] = std::numeric_limits<double>::infinity();
+      }
+      const auto& X = poses_[g].m;
+      bool identity = true;
+      for (int k = 0; k < 9; ++k) identity = identity && std::abs(X[k] - (k % 4 == 0 ? 1.0 : 0.0)) <= 1e-12;
+      std::array<double, 6> local;
+      if (std::holds_alternative<HalfSpace>(shapes_[g])) {
+        if (identity) wb.mx[2] = X[11];
+      } else if (LocalBox(shapes_[g], &local)) {
+        if (identity) {
+          for (int k = 0; k < 3; ++k) {
+            wb.mn[k] = X[9 + k] + (local[k] - local[3 + k]);
+            wb.mx[k] = X[9 + k] + (local[k] + local[3 + k]);
+          }
+        } else {
+          const point_pair::Vec3 c = point_pair::Apply(X, {local[0], local[1], local[2]});
+          const double r = point_pair::Norm({local[3], local[4], local[5]});
+          for (int k = 0; k < 3; ++k) {
+            wb.mn[k] = c[k] - r;
+            wb.mx[k] = c[k] + r;
+          }
+        }
+      }
+    }
+    std::vector<PenetrationAsPointPair> out;
+    for (int i = 0; i < G; ++i) {
+      for (int j = i + 1; j < G; ++j) {
+        const int ga = order[i], gb = order[j];   // id(ga) < id(gb)
+        if (anchored_[ga] && anchored_[gb]) continue;
+        bool filtered = false;
+        for (const auto& [a, b] : excluded_) filtered = filtered || (a == ga && b == gb) || (a == gb && b == ga);
+        if (filtered) continue;
+        bool overlap = true;
+        for (int k = 0; k < 3; ++k) overlap = overlap && boxes[ga].mn[k] <= boxes[gb].mx[k] && boxes[gb].mn[k] <= boxes[ga].mx[k];
+        if (!overlap) continue;
+        auto pp = MaybeMakePointPair(ga, gb);
+        if (pp) out.push_back(*pp);
+      }
+    }
+    return out;
   }
 
   // ComputeContactSurfacesWithFallback for every scene of the batch: the surfaces per scene and, per scene, the point

@@ -351,6 +351,44 @@ int main(int argc, char** argv) {
         }
       }
     }
+    {  // ProximityEngineTests.ComputePointPairPenetration (geometry/test/proximity_engine_test.cc:1569-1640): spheres of
+       // radius 0.5 with centres 0.9 apart in four clusters -- dynamic x dynamic IS reported, anchored x anchored is not,
+       // dynamic x anchored IS, a filtered dynamic pair is not; results ordered and stable.
+      ProximityEngine pe(0);
+      EXPECT(pe.ComputePointPairPenetration({}).empty());
+      ProximityProperties none;
+      const Sphere sphere{0.5};
+      const double d = 0.9;
+      pe.AddDynamicGeometry(sphere, RigidTransformd::FromTranslation(0, 0, 0), 1, none);      // A
+      pe.AddDynamicGeometry(sphere, RigidTransformd::FromTranslation(d, 0, 0), 2, none);      // B
+      pe.AddAnchoredGeometry(sphere, RigidTransformd::FromTranslation(0, 100, 0), 3, none);
+      pe.AddAnchoredGeometry(sphere, RigidTransformd::FromTranslation(d, 100, 0), 4, none);
+      pe.AddDynamicGeometry(sphere, RigidTransformd::FromTranslation(0, 200, 0), 5, none);    // C
+      pe.AddAnchoredGeometry(sphere, RigidTransformd::FromTranslation(d, 200, 0), 6, none);   // D
+      pe.AddDynamicGeometry(sphere, RigidTransformd::FromTranslation(0, 300, 0), 7, none);    // G
+      pe.AddDynamicGeometry(sphere, RigidTransformd::FromTranslation(d, 300, 0), 8, none);    // H
+      pe.ExcludeCollisionsBetween(7, 8);
+      const auto results = pe.ComputePointPairPenetration({});
+      EXPECT(results.size() == 2);
+      if (results.size() == 2) {
+        EXPECT(results[0].id_A == 1 && results[0].id_B == 2 && results[1].id_A == 5 && results[1].id_B == 6);
+        EXPECT(std::fabs(results[0].depth - 0.1) < 1e-15 && std::fabs(results[1].depth - 0.1) < 1e-15);
+      }
+      const auto again = pe.ComputePointPairPenetration({});
+      EXPECT(again.size() == 2 && again[0].id_A == 1 && again[1].id_A == 5);
+      // A mixed scene: a rigid-hydroelastic box and a cylinder without hydroelastic properties on a half-space ground.
+      ProximityEngine mixed(0);
+      mixed.AddAnchoredGeometry(HalfSpace{}, RigidTransformd::Identity(), 1, rigid);
+      mixed.AddDynamicGeometry(Box{0.2, 0.2, 0.2}, RigidTransformd::FromTranslation(0, 0, 0.09), 2, rigid);
+      mixed.AddDynamicGeometry(Cylinder{0.1, 0.2}, RigidTransformd::FromTranslation(0.15, 0, 0.08), 3, none);
+      const auto mp = mixed.ComputePointPairPenetration({});
+      EXPECT(mp.size() == 3);   // ground x box (0.01), ground x cylinder (0.02), box x cylinder (0.05 of lateral overlap)
+      if (mp.size() == 3) {
+        EXPECT(mp[0].id_A == 1 && mp[0].id_B == 2 && std::fabs(mp[0].depth - 0.01) < 1e-15);
+        EXPECT(mp[1].id_A == 1 && mp[1].id_B == 3 && std::fabs(mp[1].depth - 0.02) < 1e-15);
+        EXPECT(mp[2].id_A == 2 && mp[2].id_B == 3 && std::fabs(mp[2].depth - 0.05) < 1e-4 && std::fabs(mp[2].nhat_BA_W[0] + 1) < 1e-3);
+      }
+    }
     // Two half spaces: the reference rejects the pair itself -- loud unless the caller opts out.
     ProximityEngine b(0);
     b.AddAnchoredGeometry(HalfSpace{}, RigidTransformd::Identity(), 1, rigid);
