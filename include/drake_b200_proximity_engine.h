@@ -689,8 +689,12 @@ class ProximityEngine {
                 "mesh_from_arrays");
       CheckMesh(dbh_mesh_make_convex_volume(hull.h, &vol.h), "MakeConvexVolumeMesh");
       CheckMesh(dbh_mesh_set_volume_mesh_pressure(vol.h, p.hydroelastic_modulus, 0.0), "MakeVolumeMeshPressureField");
+    } else if (const auto* rv = std::get_if<VolumeMeshShape>(&shape); rv && !soft) {
+      // The reference's rigid Mesh(.vtk): the boundary surface of the volume mesh (hydroelastic_internal.cc:375-393).
+      CheckMesh(dbh_mesh_from_arrays(static_cast<int32_t>(rv->vertices.size() / 3), rv->vertices.data(),
+                                     static_cast<int32_t>(rv->tetrahedra.size() / 4), rv->tetrahedra.data(), 4, &vol.h),
+                "mesh_from_arrays");
     } else if (const auto* v = std::get_if<VolumeMeshShape>(&shape)) {
-      if (!soft) throw std::logic_error("a volume mesh can only be registered as a compliant geometry");
       Check(dbh_register_compliant_mesh(ctx_, static_cast<int32_t>(v->vertices.size() / 3), v->vertices.data(),
                                         static_cast<int32_t>(v->tetrahedra.size() / 4), v->tetrahedra.data(),
                                         v->pressure.data(), &asset),

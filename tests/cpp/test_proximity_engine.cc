@@ -112,10 +112,17 @@ static int ConvexCase(char** argv) {
   rigid.resolution_hint = 0.1;
   const RigidTransformd X_WA = RotX(M_PI, 0, 0, 0);
   const RigidTransformd X_WB = RigidTransformd::FromTranslation(0, 0, -(R + R) + 0.125);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 3; ++k) {
     ProximityEngine e(0);
     dbh_mesh *vol = nullptr, *surf = nullptr;
-    if (k == 0) {
+    if (k == 2) {   // the reference's RIGID Mesh(.vtk): the boundary of the given tetrahedra, under a compliant sphere
+      VolumeMeshShape tets;
+      EXPECT(dbh_mesh_make_box_volume(0.5, 0.4, 0.5, 0.125, &vol) == DBH_OK);
+      CopyMesh(vol, &tets.vertices, &tets.tetrahedra);
+      soft.resolution_hint = 0.25;
+      e.AddDynamicGeometry(Sphere{R}, X_WB, 1, soft);
+      e.AddDynamicGeometry(tets, X_WA, 2, rigid);
+    } else if (k == 0) {
       SurfaceMeshShape hull;
       EXPECT(dbh_mesh_make_box_volume_with_ma(0.5, 0.4, 0.5, &vol) == DBH_OK);
       EXPECT(dbh_mesh_convert_volume_to_surface(vol, &surf) == DBH_OK);
@@ -129,7 +136,7 @@ static int ConvexCase(char** argv) {
     }
     if (vol) dbh_mesh_destroy(vol);
     if (surf) dbh_mesh_destroy(surf);
-    e.AddDynamicGeometry(Sphere{R}, X_WB, 2, rigid);
+    if (k < 2) e.AddDynamicGeometry(Sphere{R}, X_WB, 2, rigid);
     auto poly = e.ComputeContactSurfaces(HydroelasticContactRepresentation::kPolygon, {});
     EXPECT(poly.size() == 1);
     const int faces = std::atoi(argv[2 + 3 * k]);
@@ -164,7 +171,7 @@ int main(int argc, char** argv) {
     return 3;
   }
   if (argc == 17 && std::string(argv[1]) == "margin") return MarginCase(argv);
-  if (argc == 8 && std::string(argv[1]) == "convex") return ConvexCase(argv);
+  if (argc == 11 && std::string(argv[1]) == "convex") return ConvexCase(argv);
   const double R = 0.25;
   ProximityProperties soft;
   soft.compliance_type = HydroelasticType::kCompliant;

@@ -102,6 +102,11 @@ def test_cpp_adapter_compliant_convex_and_volume_mesh_without_pressure():
         want = ho.soft_rigid(m, ho.VolumeField.from_mesh(m, E), rigid, X_WA, X_WB, 1, 2, ho.KPOLYGON)
         assert want is not None and want.num_faces > 4
         args += [str(want.num_faces), repr(float(want.total_area)), repr(float(np.sum(want.e_centroid)))]
+    # The reference's RIGID Mesh(.vtk) (hydroelastic_internal.cc:375-393): the boundary of the grid mesh, under a compliant sphere.
+    ball = ho.VolumeMesh.sphere(R, 0.25)
+    want = ho.soft_rigid(ball, ho.VolumeField.sphere(ball, R, E), grid.to_surface(), X_WB, X_WA, 1, 2, ho.KPOLYGON)
+    assert want is not None and want.num_faces > 4
+    args += [str(want.num_faces), repr(float(want.total_area)), repr(float(np.sum(want.e_centroid)))]
     res = subprocess.run([build_exe(), "convex"] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
     assert res.stdout.strip().endswith("ok")
