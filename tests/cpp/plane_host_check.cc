@@ -349,6 +349,13 @@ int phc_clip_triangle_by_tetrahedron(const double* tet_v, const double* tri_v, c
   }
   return n;
 }
+// The exact fp64 box test of the descent's undecided pairs (hydro_math.cuh::boxes_overlap = BoxesOverlap,
+// boxes_overlap.cc:197-255): half widths a, b; X_AB as 12 doubles (R column-major, then p).
+int phc_boxes_overlap(const double* a, const double* b, const double* X_AB) {
+  Xf X;
+  for (int k = 0; k < 12; ++k) X.m[k] = X_AB[k];
+  return boxes_overlap(a, b, X, D3{X_AB[9], X_AB[10], X_AB[11]}) ? 1 : 0;
+}
 int phc_face_normal_along_gradient(const double* ngrad, const double* v) {
   return face_normal_along_gradient(load3(ngrad), load3(v)) ? 1 : 0;
 }

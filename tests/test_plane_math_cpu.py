@@ -807,3 +807,87 @@ def test_tet_pair_polygon_with_face_codes_is_bit_exact():
             polygons += len(want_poly) > 0
             rejected += len(want_poly) == 0
     assert polygons >= 50 and rejected >= 50
+
+
+# ---- BoxesOverlap: the reference's own test, case by case ----------------------------------------------------------------
+
+def _aa(angle, axis):
+    u = np.zeros(3)
+    u[axis] = 1.0
+    K = np.array([[0, -u[2], u[1]], [u[2], 0, -u[0]], [-u[1], u[0], 0]])
+    return np.eye(3) + math.sin(angle) * K + (1 - math.cos(angle)) * K @ K
+
+
+def _corner_transform(a_half, b_half, axis, expect_overlap):
+    """CalcCornerTransform (geometry/test_utilities/boxes_overlap_transforms.cc:12-45): B's lowest corner 0.01 inside /
+    outside the middle of A's face along `axis`."""
+    axis1, axis2 = (axis + 1) % 3, (axis + 2) % 3
+    R_AB = _aa(math.pi / 5, axis1) @ _aa(-math.pi / 5, axis2)
+    p_BqBo_A = R_AB @ b_half
+    assert p_BqBo_A[axis] > 0
+    p_AfBq_A = np.zeros(3)
+    p_AfBq_A[axis] = -0.01 if expect_overlap else 0.01
+    p_AoAf_A = np.array(a_half, float)
+    p_AoAf_A[axis1] /= 2
+    p_AoAf_A[axis2] /= 2
+    return R_AB, p_AoAf_A + p_AfBq_A + p_BqBo_A
+
+
+def _edge_transform(a_half, b_half, a_axis, b_axis, expect_overlap):
+    """CalcEdgeTransform (boxes_overlap_transforms.cc:47-110): an edge of B along b_axis 0.01 inside / outside an edge of
+    A along a_axis -- only the axis a_axis x b_axis separates the two."""
+    a1, a2, b1, b2 = (a_axis + 1) % 3, (a_axis + 2) % 3, (b_axis + 1) % 3, (b_axis + 2) % 3
+    theta = math.pi / 5
+    if a_axis == b_axis:
+        R_AB = _aa(theta, b1) @ _aa(theta, b2)
+    elif a1 == b_axis:
+        R_AB = _aa(theta, b1) @ _aa(-theta, b2)
+    else:
+        R_AB = _aa(-theta, b2) @ _aa(theta, b1)
+    p_BqBo_B = np.array(b_half, float)
+    p_BqBo_B[b_axis] -= b_half[b_axis] / 2
+    p_BqBo_A = R_AB @ p_BqBo_B
+    assert p_BqBo_A[a1] > 0 and p_BqBo_A[a2] > 0
+    offset = -0.01 if expect_overlap else 0.01
+    p_AfBq_A = np.zeros(3)
+    p_AfBq_A[a1] = p_AfBq_A[a2] = offset
+    p_AoAf_A = np.array(a_half, float)
+    p_AoAf_A[a_axis] -= a_half[a_axis] / 2
+    return R_AB, p_AoAf_A + p_AfBq_A + p_BqBo_A
+
+
+def test_boxes_overlap_reference_all_cases():
+    """BoxesOverlapTest.AllCases (geometry/proximity/test/boxes_overlap_test.cc:97-163): parallel and contained; for each
+    of A's and of B's three face normals, and for each of the nine edge x edge axes, a pose where ONLY that axis separates
+    the boxes (expect false) and its colliding twin (expect true); every case both ways round (a, b, X_AB) and
+    (b, a, X_AB^-1). Through the oracle's BoxesOverlap and through the product's fp64 box test compiled for the host."""
+    L = harness()
+    L.phc_boxes_overlap.argtypes = [_dp, _dp, _dp]
+
+    def product(a, b, X):
+        a, b, X = (np.ascontiguousarray(v, float) for v in (a, b, X))
+        return bool(L.phc_boxes_overlap(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), X.ctypes.data_as(_dp)))
+
+    def both_ways(a, b, R, p, expect, label):
+        X = ho.xform(R, p)
+        X_inv = ho.xform(R.T, -R.T @ np.asarray(p, float))
+        for fn in (ho.boxes_overlap, product):
+            assert fn(a, b, X) == expect, (label, fn)
+            assert fn(b, a, X_inv) == expect, (label, "inverse", fn)
+    both_ways([1, 2, 1], [0.5, 1, 0.5], np.eye(3), [0.2, 0.4, 0.2], True, "parallel_and_contained")
+    a, b = np.array([2.0, 4, 3]), np.array([3.5, 2, 1.5])
+    n = 1
+    for axis in range(3):
+        for expect in (False, True):
+            R, p = _corner_transform(a, b, axis, expect)
+            both_ways(a, b, R, p, expect, f"A{axis} {expect}")
+            R, p = _corner_transform(b, a, axis, expect)          # X_BA: invert for X_AB
+            both_ways(a, b, R.T, -R.T @ p, expect, f"B{axis} {expect}")
+            n += 2
+    for a_axis in range(3):
+        for b_axis in range(3):
+            for expect in (False, True):
+                R, p = _edge_transform(a, b, a_axis, b_axis, expect)
+                both_ways(a, b, R, p, expect, f"A{a_axis}-B{b_axis} {expect}")
+                n += 1
+    assert n == 31
