@@ -356,6 +356,20 @@ int phc_boxes_overlap(const double* a, const double* b, const double* X_AB) {
   for (int k = 0; k < 12; ++k) X.m[k] = X_AB[k];
   return boxes_overlap(a, b, X, D3{X_AB[9], X_AB[10], X_AB[11]}) ? 1 : 0;
 }
+// The registration-time derivation of one tetrahedron's record (hydro_derive.cuh::derive_tet: what
+// VolumeMesh::CalcGradBarycentric / MeshFieldLinear's gradient and value at the mesh origin / the inward face normals
+// become on the device): v [12], u [4] -> grad [3], p_mo [1], inward [12]. Returns 0 for a degenerate tetrahedron.
+int phc_derive_tet(const double* v, const double* u, double* grad, double* p_mo, double* inward) {
+  const D3 V[4] = {load3(v), load3(v + 3), load3(v + 6), load3(v + 9)};
+  TetRec rec;
+  TetAux aux;
+  if (!derive_tet(V, u, &rec, &aux)) return 0;
+  for (int k = 0; k < 3; ++k) grad[k] = rec.grad[k];
+  *p_mo = rec.p_mo;
+  for (int f = 0; f < 4; ++f)
+    for (int k = 0; k < 3; ++k) inward[3 * f + k] = aux.inward[f][k];
+  return 1;
+}
 int phc_face_normal_along_gradient(const double* ngrad, const double* v) {
   return face_normal_along_gradient(load3(ngrad), load3(v)) ? 1 : 0;
 }

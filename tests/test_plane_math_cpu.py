@@ -891,3 +891,51 @@ def test_boxes_overlap_reference_all_cases():
                 both_ways(a, b, R, p, expect, f"A{a_axis}-B{b_axis} {expect}")
                 n += 1
     assert n == 31
+
+
+def test_tetrahedron_gradients_reference_known_answers():
+    """VolumeMeshTest.TestCalcGradBarycentric and TestCalcGradientVectorOfLinearField (geometry/proximity/test/
+    volume_mesh_test.cc:290-360,368-385): the tetrahedron (0,0,0), (1,0,0), (0,2,0), (0,0,3) posed at rpy (pi/6, 2pi/3, 5pi/4),
+    p (1,2,3) has grad b_i = R (-1,-1/2,-1/3), R x, R y / 2, R z / 3 (1e-14), summing to zero; the field 2, 3, 4, 5 on the unit
+    tetrahedron has gradient (1, 2, 3) -- through the oracle's MeshFieldLinear and the product's registration-time
+    derivation (derive_tet) compiled for the host. A zero-volume tetrahedron is reported degenerate by both."""
+    L = harness()
+    L.phc_derive_tet.argtypes = [_dp] * 5
+
+    def product(V, u):
+        V, u = np.ascontiguousarray(V, float), np.ascontiguousarray(u, float)
+        g, m, n = np.zeros(3), np.zeros(1), np.zeros(12)
+        ok = L.phc_derive_tet(V.ctypes.data_as(_dp), u.ctypes.data_as(_dp), g.ctypes.data_as(_dp), m.ctypes.data_as(_dp),
+                              n.ctypes.data_as(_dp))
+        return bool(ok), g, float(m[0]), n.reshape(4, 3)
+
+    def oracle(V, u):
+        f = ho.VolumeField.from_values(ho.VolumeMesh.from_arrays(V, [[0, 1, 2, 3]]), u)
+        _, g, m, degenerate = f.arrays()
+        return (not degenerate), g[0], float(m[0]), f.mesh.arrays()[2][0]
+    X_WM = ho.xform(ho.rpy_matrix(math.pi / 6, 2 * math.pi / 3, 5 * math.pi / 4), [1.0, 2.0, 3.0])
+    R, p = X_WM[:9].reshape(3, 3).T, X_WM[9:]
+    V_M = np.array([[0, 0, 0], [1.0, 0, 0], [0, 2.0, 0], [0, 0, 3.0]])
+    V_W = V_M @ R.T + p
+    want = [R @ np.array([-1, -1 / 2, -1 / 3]), R @ np.array([1.0, 0, 0]), R @ np.array([0, 0.5, 0]), R @ np.array([0, 0, 1 / 3])]
+    for fn in (oracle, product):
+        total = np.zeros(3)
+        for i in range(4):
+            ok, g, m, inward = fn(V_W, np.eye(4)[i])
+            assert ok
+            np.testing.assert_allclose(g, want[i], rtol=0, atol=1e-14)
+            assert abs(m + g @ V_W[0] - (1.0 if i == 0 else 0.0)) <= 1e-13      # f(x) = grad . x + f(Mo) at vertex 0
+            total += g
+            # inward_normal(e, f) is the unit normal of the face opposite vertex f, pointing at it: along grad b_f.
+            np.testing.assert_allclose(inward[i], want[i] / np.linalg.norm(want[i]), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(total, 0, atol=1e-14)
+        ok, g, m, _ = fn([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], [2.0, 3.0, 4.0, 5.0])
+        assert ok and m == 2.0
+        np.testing.assert_allclose(g, [1, 2, 3], rtol=0, atol=1e-14)
+        assert not fn([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], [0.0, 0, 0, 1.0])[0]
+    # and the two derivations are the same numbers
+    for i in range(4):
+        a, b = oracle(V_W, np.eye(4)[i]), product(V_W, np.eye(4)[i])
+        np.testing.assert_array_equal(a[1], b[1])
+        assert a[2] == b[2]
+        np.testing.assert_array_equal(a[3], b[3])
