@@ -2093,9 +2093,8 @@ __global__ void __launch_bounds__(128, kPack ? 4 : 1) k_plane(PlaneArgs a) {
 // ShiftSpatialForcesAtCentroidToBodyOrigins (hydroelastic_traction_calculator.cc:24-83) over the packed,
 // device-resident results of the last query: one warp per contact surface, faces strided over the lanes,
 // a shuffle reduction of the six components. A is the body of geometry M (id_M), B of geometry N.
-// Parity-green on the B200 (tests/test_zz_gpu_wrench.py, profiles/r1h_gpu_tests_wrench.log) with the round's last
-// GPU seconds; not yet timed or profiled. The per-face arithmetic is also checked on the host
-// (tests/test_plane_math_cpu.py).
+// Parity-green on the B200 (tests/test_zz_gpu_wrench.py); timed as bench.py's e2e.spatial_forces.
+// The per-face arithmetic is also checked on the host (tests/test_plane_math_cpu.py).
 struct WrenchArgs {
   const int* surf_pair;
   const PairRec* pairs;

@@ -285,8 +285,8 @@ void* dbh_batch_stream(dbh_batch* batch);
  *        fed by HydroelasticEngine::CalcCombinedDissipation (multibody/hydroelastics/hydroelastic_engine.cc:83-104) and
  *        CalcContactFrictionFromSurfaceProperties (coulomb_friction.h:122-139). Body A is the body of geometry
  *        M (id_M), body B the body of geometry N. Data::add_surface_velocity_bias (conveyor-belt surface speeds,
- *        hydroelastic_traction_calculator.h:80-86) is not supported: surfaces move with their bodies. Parity-green on the B200 (tests/test_zz_gpu_wrench.py); not yet
- *        timed. ---------------------------------- */
+ *        hydroelastic_traction_calculator.h:80-86) is not supported: surfaces move with their bodies. Parity-green on the B200 (tests/test_zz_gpu_wrench.py); timed
+ *        as bench.py's e2e.spatial_forces. ---------------------------------- */
 /* p_WBo [G*3]: origin of each geometry's body frame in World (NULL: the geometry frame's origin);
  * V_WB [G*6]: spatial velocity (w, v) of that body at its origin, in World (NULL: at rest). Host pointers. */
 dbh_status dbh_batch_set_body_kinematics(dbh_batch* batch, const double* p_WBo, const double* V_WB);
