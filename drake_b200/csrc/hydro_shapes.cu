@@ -213,6 +213,8 @@ int SphereRefinementLevel(double radius, double resolution_hint) {
 
 HostMesh MakeSphereVolumeMesh(double radius, double resolution_hint, int strategy) {
   if (!(resolution_hint > 0.0) || !(radius > 0.0)) throw std::invalid_argument("sphere: radius and hint must be > 0");
+  if (strategy != kSingleInteriorVertex && strategy != kDenseInteriorVertices)
+    throw std::invalid_argument("sphere: unknown tessellation strategy");  // tessellation_strategy.h has these two only
   SphereTess m = Octahedron();
   const int L = SphereRefinementLevel(radius, resolution_hint);
   for (int l = 0; l < L; ++l) m = (strategy == kDenseInteriorVertices) ? RefineDense(m) : RefineSparse(m);
@@ -222,6 +224,7 @@ HostMesh MakeSphereVolumeMesh(double radius, double resolution_hint, int strateg
 
 HostMesh MakeEllipsoidVolumeMesh(double a, double b, double c, double resolution_hint, int strategy) {
   if (!(resolution_hint > 0.0)) throw std::invalid_argument("ellipsoid: hint must be > 0");
+  if (!(a > 0.0) || !(b > 0.0) || !(c > 0.0)) throw std::invalid_argument("ellipsoid: the semi-axes must be > 0");  // Ellipsoid's constructor
   const double r = std::max({a, b, c});
   HostMesh m = MakeSphereVolumeMesh(1.0, resolution_hint / r, strategy);
   for (int i = 0; i < m.num_vertices(); ++i) {
@@ -233,6 +236,7 @@ HostMesh MakeEllipsoidVolumeMesh(double a, double b, double c, double resolution
 }
 
 HostMesh MakeBoxVolumeMeshWithMa(double sx, double sy, double sz) {
+  if (!(sx > 0.0) || !(sy > 0.0) || !(sz > 0.0)) throw std::invalid_argument("box: the sizes must be > 0");  // Box's constructor
   const double h[3] = {sx / 2., sy / 2., sz / 2.};
   const double hmin = std::min({h[0], h[1], h[2]});
   int zero_axes = 0;
@@ -279,6 +283,7 @@ HostMesh MakeBoxVolumeMeshWithMa(double sx, double sy, double sz) {
 
 HostMesh MakeBoxVolumeMesh(double sx, double sy, double sz, double hint) {
   if (!(hint > 0.)) throw std::invalid_argument("box: hint must be > 0");
+  if (!(sx > 0.0) || !(sy > 0.0) || !(sz > 0.0)) throw std::invalid_argument("box: the sizes must be > 0");
   const double size[3] = {sx, sy, sz};
   int n[3];
   std::vector<double> coord[3];

@@ -26,6 +26,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <initializer_list>
 #include <limits>
 #include <map>
 #include <optional>
@@ -613,10 +614,64 @@ class ProximityEngine {
     return PenetrationAsPointPair{ids_[ga], ids_[gb], res->p_WCa, res->p_WCb, res->nhat_BA_W, res->depth};
   }
 
+  // The property checks of MakeRigidRepresentation / MakeCompliantRepresentation (hydroelastic_internal.cc:236-311, the
+  // PositiveDouble / NonNegativeDouble validators, and the per-shape Extract calls :326-640), with the reference's
+  // messages: a rigid Sphere / Cylinder / Capsule / Ellipsoid needs a positive resolution_hint; a compliant shape a
+  // non-negative margin and a positive hydroelastic_modulus, the curved primitives also a positive resolution_hint,
+  // a HalfSpace a positive slab_thickness. Shape dimensions must be positive (the shape constructors,
+  // shape_specification.cc). Throws std::logic_error like the reference.
+ public:
+  static void ValidateProperties(const Shape& shape, const ProximityProperties& p) {
+    if (p.compliance_type == HydroelasticType::kUndefined) return;
+    const bool soft = p.compliance_type == HydroelasticType::kCompliant;
+    const char* compliance = soft ? "compliant" : "rigid";
+    const char* name = "Shape";
+    bool needs_hint = false;
+    auto positive_size = [](const char* what, std::initializer_list<double> values) {
+      for (double v : values)
+        if (!(v > 0) || !std::isfinite(v)) throw std::logic_error(std::string(what) + " dimensions must all be positive and finite");
+    };
+    if (const auto* s = std::get_if<Sphere>(&shape)) {
+      name = "Sphere", needs_hint = true;
+      if (!(s->radius >= 0) || !std::isfinite(s->radius)) throw std::logic_error("Sphere radius should be >= 0");
+    } else if (const auto* b = std::get_if<Box>(&shape)) {
+      name = "Box";
+      positive_size("Box", {b->width, b->depth, b->height});
+    } else if (const auto* e = std::get_if<Ellipsoid>(&shape)) {
+      name = "Ellipsoid", needs_hint = true;
+      positive_size("Ellipsoid", {e->a, e->b, e->c});
+    } else if (const auto* cy = std::get_if<Cylinder>(&shape)) {
+      name = "Cylinder", needs_hint = true;
+      positive_size("Cylinder", {cy->radius, cy->length});
+    } else if (const auto* ca = std::get_if<Capsule>(&shape)) {
+      name = "Capsule", needs_hint = true;
+      positive_size("Capsule", {ca->radius, ca->length});
+    } else if (std::get_if<HalfSpace>(&shape)) {
+      name = "HalfSpace";
+    } else if (std::get_if<VolumeMeshShape>(&shape)) {
+      name = "Mesh";
+    } else if (std::get_if<SurfaceMeshShape>(&shape)) {
+      name = soft ? "Convex" : "Mesh";
+    }
+    auto fail = [&](const char* property, const char* must_be) {
+      throw std::logic_error(std::string("Cannot create ") + compliance + " " + name + "; the ('hydroelastic', '" + property +
+                             "') property must be " + must_be);
+    };
+    if (needs_hint && !(p.resolution_hint > 0)) fail("resolution_hint", "positive");
+    if (!soft) return;
+    if (!(p.margin >= 0)) fail("margin", "non-negative");
+    if (std::get_if<HalfSpace>(&shape) && !(p.slab_thickness > 0)) fail("slab_thickness", "positive");
+    if (!(p.hydroelastic_modulus > 0)) fail("hydroelastic_modulus", "positive");
+    const int strategy = static_cast<int>(p.tessellation_strategy);
+    if (strategy != 0 && strategy != 1) throw std::logic_error("tessellation_strategy must be kSingleInteriorVertex or kDenseInteriorVertices");
+  }
+
+ private:
   int32_t MakeAsset(const Shape& shape, const ProximityProperties& p) {
     last_elements_.clear();
     last_vertices_per_element_ = 0;
     if (p.compliance_type == HydroelasticType::kUndefined) return -1;
+    ValidateProperties(shape, p);
     const bool soft = p.compliance_type == HydroelasticType::kCompliant;
     int32_t asset = -1;
     struct MeshHandle {

@@ -163,3 +163,19 @@ def test_deformable_mirror_reference_fixtures():
     res = subprocess.run([build_deformable_exe()], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
     assert res.stdout.strip().endswith("ok")
+
+
+def test_registration_property_checks_follow_the_reference():
+    """ProximityEngine::ValidateProperties (static, no device): the reference's BadResolutionHint / BadElasticModulus /
+    BadSlabThickness suites and its NonNegativeDouble margin check, with its messages
+    (hydroelastic_internal_test.cc:905-996,1406-1466; hydroelastic_internal.cc:280-311)."""
+    from drake_b200 import build
+    lib = build.build()
+    src = os.path.join(ROOT, "tests", "cpp", "validate_host_check.cc")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "validate_host_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src,
+                    "-o", exe, "-L", os.path.dirname(lib), "-ldrake_b200_hydro", "-Wl,-rpath," + os.path.dirname(lib)],
+                   check=True)
+    res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout
