@@ -233,6 +233,7 @@ class ProximityEngine {
     elements_.erase(elements_.begin() + g);
     vertices_per_element_.erase(vertices_per_element_.begin() + g);
     assets_.erase(assets_.begin() + g);
+    vanished_.erase(vanished_.begin() + g);
     anchored_.erase(anchored_.begin() + g);
     poses_.erase(poses_.begin() + g);
     index_.clear();
@@ -245,6 +246,12 @@ class ProximityEngine {
     excluded_ = std::move(kept);
     Invalidate();  // the mesh asset stays registered in the context (assets are shared by handle)
   }
+
+  // Geometries::is_vanished (hydroelastic_internal.h): a compliant PRIMITIVE so small that its pressure field has no
+  // gradient (MeshFieldLinear::is_gradient_field_degenerate) is accepted but takes no part in hydroelastic contact:
+  // every pair naming it is "calculated, no surface" -- no surface, no failure, no point pair
+  // (hydroelastic_internal.cc:194-204, hydroelastic_calculator.cc:81-85). A degenerate Mesh / Convex throws instead.
+  bool is_vanished(GeometryId id) const { return vanished_[IndexOf(id)] != 0; }
 
   // CollisionFilter declaration ExcludeBetween for one pair (collision_filter.h:158 CanCollideWith).
   void ExcludeCollisionsBetween(GeometryId a, GeometryId b) {
@@ -670,6 +677,7 @@ class ProximityEngine {
   int32_t MakeAsset(const Shape& shape, const ProximityProperties& p) {
     last_elements_.clear();
     last_vertices_per_element_ = 0;
+    last_vanished_ = false;
     if (p.compliance_type == HydroelasticType::kUndefined) return -1;
     ValidateProperties(shape, p);
     const bool soft = p.compliance_type == HydroelasticType::kCompliant;
@@ -766,7 +774,14 @@ class ProximityEngine {
       return asset;
     }
     if (soft) {
-      Check(dbh_register_mesh(ctx_, vol.h, &asset), "register_mesh");
+      const dbh_status registered = dbh_register_mesh(ctx_, vol.h, &asset);
+      const bool primitive = std::get_if<Sphere>(&shape) || std::get_if<Box>(&shape) || std::get_if<Ellipsoid>(&shape) ||
+                             std::get_if<Cylinder>(&shape) || std::get_if<Capsule>(&shape);
+      if (registered == DBH_ERR_DEGENERATE_FIELD && primitive) {  // vanished (is_vanished above)
+        last_vanished_ = true;
+        return -1;
+      }
+      Check(registered, "register_mesh");
     } else {
       CheckMesh(dbh_mesh_convert_volume_to_surface(vol.h, &surf.h), "ConvertVolumeToSurfaceMesh");
       Check(dbh_register_mesh(ctx_, surf.h, &asset), "register_mesh");
@@ -793,6 +808,7 @@ class ProximityEngine {
     elements_.push_back(std::move(last_elements_));
     vertices_per_element_.push_back(last_vertices_per_element_);
     assets_.push_back(asset);
+    vanished_.push_back(last_vanished_ ? 1 : 0);
     anchored_.push_back(anchored ? 1 : 0);
     poses_.push_back(X_WG);
     Invalidate();
@@ -820,6 +836,14 @@ class ProximityEngine {
       for (const auto& [a, b] : excluded_) {
         excluded.push_back(s * G + a);
         excluded.push_back(s * G + b);
+      }
+      for (int g = 0; g < G; ++g) {  // a vanished geometry meets nothing in the hydroelastic queries
+        if (!vanished_[g]) continue;
+        for (int other = 0; other < G; ++other) {
+          if (other == g || (vanished_[other] && other < g)) continue;
+          excluded.push_back(s * G + g);
+          excluded.push_back(s * G + other);
+        }
       }
     }
     Check(dbh_batch_create(ctx_, num_scenes_, offsets.data(), assets.data(), ids.data(), anchored.data(),
@@ -1026,6 +1050,8 @@ class ProximityEngine {
   bool skip_unsupported_point_pairs_{false};
   const double* scene_poses_{nullptr};   // set only inside ComputeContactSurfacesWithFallbackBatched
   std::vector<int32_t> assets_;
+  std::vector<uint8_t> vanished_;   // per geometry: is_vanished()
+  bool last_vanished_{false};
   std::vector<uint8_t> anchored_;
   std::vector<RigidTransformd> poses_;
   std::vector<std::pair<int, int>> excluded_;

@@ -170,3 +170,52 @@ def test_bad_tessellation_strategy_hints_and_sizes_fail_loudly():
                  lambda: db.Mesh.box_volume_with_ma(0.2, 0.4, 0.8).set_box_pressure(0.2, 0.4, 0.8, 1e5, 0.1)):
         with pytest.raises(db.HydroError):
             make()
+
+
+# ---- HydroelasticVanished (:418-461): is_gradient_field_degenerate of the compliant primitives --------------------------
+
+def _product_field_is_degenerate(mesh, pressure):
+    """The product's registration-time derivation (derive_tet, drake_b200/csrc/hydro_derive.cuh, compiled for the host by
+    tests/test_plane_math_cpu.py's harness) over every tetrahedron: what dbh_register_mesh answers
+    DBH_ERR_DEGENERATE_FIELD on, and the C++ mirror turns into is_vanished() for a primitive."""
+    import ctypes as C
+
+    from tests.test_plane_math_cpu import harness
+    L = harness()
+    dp = C.POINTER(C.c_double)
+    L.phc_derive_tet.argtypes = [dp] * 5
+    V, T = np.ascontiguousarray(mesh.vertices, float), mesh.elements
+    g, m, n = np.zeros(3), np.zeros(1), np.zeros(12)
+    for t in T:
+        v, u = np.ascontiguousarray(V[t]), np.ascontiguousarray(pressure[t], float)
+        if not L.phc_derive_tet(v.ctypes.data_as(dp), u.ctypes.data_as(dp), g.ctypes.data_as(dp), m.ctypes.data_as(dp),
+                                n.ctypes.data_as(dp)):
+            return True
+    return False
+
+
+@pytest.mark.parametrize("shape,size,vanished", [
+    ("sphere", 0.5, False), ("sphere", 1e-6, True), ("box", 0.5, False), ("box", 1e-6, True),
+    ("capsule", 0.5, False), ("capsule", 1e-6, True), ("cylinder", 0.5, False), ("cylinder", 1e-6, True),
+    ("ellipsoid", 0.5, False), ("ellipsoid", 1e-6, True)])
+def test_vanished_primitives(shape, size, vanished):
+    """DoTestVanished: AddCompliantHydroelasticProperties(resolution_hint 1.0, modulus 1e8); a primitive of size 1e-6 has a
+    pressure field without gradient (|signed volume| <= eps, volume_mesh.h:395-446) and vanishes, one of size 0.5 does not."""
+    s, hint = size, 1.0
+    if shape == "sphere":
+        o, p = ho.VolumeMesh.sphere(s, hint), db.Mesh.sphere_volume(s, hint)
+        fo, fp = ho.VolumeField.sphere(o, s, E), p.set_sphere_pressure(s, E).pressure
+    elif shape == "box":
+        o, p = ho.VolumeMesh.box_ma(s, s, s), db.Mesh.box_volume_with_ma(s, s, s)
+        fo, fp = ho.VolumeField.box(o, s, s, s, E), p.set_box_pressure(s, s, s, E).pressure
+    elif shape == "capsule":
+        o, p = ho.VolumeMesh.capsule(s, s, hint), db.Mesh.capsule_volume(s, s, hint)
+        fo, fp = ho.VolumeField.capsule(o, s, s, E), p.set_capsule_pressure(s, s, E).pressure
+    elif shape == "cylinder":
+        o, p = ho.VolumeMesh.cylinder_ma(s, s, hint), db.Mesh.cylinder_volume_with_ma(s, s, hint)
+        fo, fp = ho.VolumeField.cylinder(o, s, s, E), p.set_cylinder_pressure(s, s, E).pressure
+    else:
+        o, p = ho.VolumeMesh.ellipsoid(s, s, s, hint), db.Mesh.ellipsoid_volume(s, s, s, hint)
+        fo, fp = ho.VolumeField.ellipsoid(o, s, s, s, E), p.set_ellipsoid_pressure(s, s, s, E).pressure
+    assert bool(fo.arrays()[3]) == vanished
+    assert _product_field_is_degenerate(p, np.array(fp)) == vanished
