@@ -147,7 +147,9 @@ def test_make_box_pressure_field(G):
 
 @SIDES
 def test_make_box_pressure_field_with_margin(G):
-    # make_box_field_test.cc:57-71
+    # make_box_field_test.cc:57-71. The reference's test meshes with MakeBoxVolumeMeshWithMa; box_ma is the variant the
+    # compliant Box representation uses (MakeBoxVolumeMeshWithMaAndSymmetricTriangles, hydroelastic_internal.cc:451-452):
+    # the same medial axis plus the six face centres, so the same invariants must hold.
     mesh = G.box_ma(1.0, 2.0, 3.0)
     _verify_margin_invariants(G, mesh, G.box_field(mesh, 1.0, 2.0, 3.0, E), G.box_field(mesh, 1.0, 2.0, 3.0, E, 0.12),
                               0.12, 0.5)
@@ -155,7 +157,8 @@ def test_make_box_pressure_field_with_margin(G):
 
 @SIDES
 def test_make_box_pressure_field_in_mesh_with_medial_axis(G):
-    # make_box_field_test.cc:73-126: as above, and no tetrahedron of constant pressure.
+    # make_box_field_test.cc:73-126: as above, and no tetrahedron of constant pressure (on the representation's mesh,
+    # see the note in the test above).
     mesh = G.box_ma(1.0, 2.0, 3.0)
     p = G.box_field(mesh, 1.0, 2.0, 3.0, E)
     _check_min_max_boundary_exact(G, mesh, p, need_centre=False)
